@@ -1,0 +1,266 @@
+"""ctypes binding of the C-ABI in include/c3sc_b200.h (libc3sc_b200.so).
+
+Plumbing for tests / bench only: the product is the shared library.  Loading
+fails loudly when the library has not been built -- there is no Python or CPU
+implementation of the backup to fall back to.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libc3sc_b200.so")
+
+c_f64p = C.POINTER(C.c_double)
+c_i32p = C.POINTER(C.c_int32)
+c_u64p = C.POINTER(C.c_uint64)
+
+
+class ProblemDesc(C.Structure):
+    _fields_ = [
+        ("dx", C.c_uint32), ("du", C.c_uint32), ("dw", C.c_uint32),
+        ("ngrid", c_u64p), ("xgrid", C.POINTER(c_f64p)),
+        ("h2", C.c_double), ("t", c_f64p), ("bc", c_i32p),
+        ("nobs", C.c_uint32), ("obs_lb", c_f64p), ("obs_ub", c_f64p),
+        ("discount", C.c_double),
+        ("nu", C.c_uint32), ("controls", c_f64p),
+        ("model", C.c_int32), ("model_params", c_f64p), ("n_model_params", C.c_uint32),
+        ("arith", C.c_int32),
+    ]
+
+
+class BatchOut(C.Structure):
+    _fields_ = [
+        ("value", C.c_void_p), ("argmin", C.c_void_p), ("absorbed", C.c_void_p),
+        ("costs", C.c_void_p), ("rows", C.c_void_p), ("nbr_vary", C.c_void_p),
+        ("nbr_fixed", C.c_void_p),
+    ]
+
+
+EXPORTS = [
+    "c3sc_cuda_init", "c3sc_cuda_device_count", "c3sc_last_error", "c3sc_version", "c3sc_launch_count",
+    "c3sc_problem_create", "c3sc_problem_destroy", "c3sc_problem_check",
+    "c3sc_valuef_create", "c3sc_valuef_update", "c3sc_valuef_device_buffer", "c3sc_valuef_destroy",
+    "c3sc_vi_batch_dev", "c3sc_pi_batch_dev", "c3sc_vi_batch", "c3sc_vi_batch_debug", "c3sc_pi_batch",
+    "c3sc_transition_batch", "c3sc_model_eval",
+]
+
+_lib = None
+
+
+def lib() -> C.CDLL:
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(make -C c3sc_b200/csrc).  The Bellman backup has no CPU fallback.")
+        L = C.CDLL(LIB_PATH)
+        L.c3sc_last_error.restype = C.c_char_p
+        L.c3sc_version.restype = C.c_char_p
+        L.c3sc_launch_count.restype = C.c_uint64
+        L.c3sc_problem_destroy.restype = None
+        L.c3sc_valuef_destroy.restype = None
+        vp, sz, i32 = C.c_void_p, C.c_size_t, C.c_int
+        L.c3sc_cuda_init.argtypes = [i32]
+        L.c3sc_problem_create.argtypes = [C.POINTER(ProblemDesc), C.POINTER(vp)]
+        L.c3sc_problem_destroy.argtypes = [vp]
+        L.c3sc_problem_check.argtypes = [vp]
+        L.c3sc_valuef_create.argtypes = [C.c_uint32, c_u64p, c_u64p, C.POINTER(c_f64p), C.POINTER(vp)]
+        L.c3sc_valuef_update.argtypes = [vp, C.POINTER(c_f64p)]
+        L.c3sc_valuef_device_buffer.argtypes = [vp, C.POINTER(vp), C.POINTER(sz)]
+        L.c3sc_valuef_destroy.argtypes = [vp]
+        L.c3sc_vi_batch_dev.argtypes = [vp, vp, sz, vp, vp, sz, C.POINTER(BatchOut), vp]
+        L.c3sc_pi_batch_dev.argtypes = [vp, vp, vp, sz, vp, vp, sz, i32, vp, vp, vp, vp]
+        L.c3sc_vi_batch.argtypes = [vp, vp, sz, vp, vp, sz, vp, vp]
+        L.c3sc_vi_batch_debug.argtypes = [vp, vp, sz, vp, vp, sz, vp, vp, vp, vp, vp, vp, vp]
+        L.c3sc_pi_batch.argtypes = [vp, vp, vp, sz, vp, vp, sz, i32, vp, vp, vp]
+        L.c3sc_transition_batch.argtypes = [vp, sz, vp, vp, vp, vp, vp]
+        L.c3sc_model_eval.argtypes = [vp, sz, vp, vp, vp, vp, vp, vp, vp]
+        _lib = L
+    return _lib
+
+
+class C3scError(RuntimeError):
+    pass
+
+
+def check(rc: int) -> None:
+    if rc != 0:
+        raise C3scError(f"c3sc error {rc}: {lib().c3sc_last_error().decode()}")
+
+
+def _ptr(a: np.ndarray | None):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def grid_constants(xgrid: list[np.ndarray], lb: np.ndarray, ub: np.ndarray):
+    """h, hmin, h2, t of c3control_create + mca_add_grid_refs
+    (reference src/bellman.c:1975-1986, :181-186), same operation order."""
+    dx = len(xgrid)
+    h = np.array([xgrid[i][1] - xgrid[i][0] for i in range(dx)], dtype=np.float64)
+    hmin = np.float64(ub[0]) - np.float64(lb[0])
+    for i in range(dx):
+        if h[i] < hmin:
+            hmin = h[i]
+    h2 = np.float64(hmin) * np.float64(hmin)
+    t = np.empty(2 * dx, dtype=np.float64)
+    for i in range(dx):
+        t[2 * i] = h2 / h[i]
+        t[2 * i + 1] = t[2 * i] / h[i]
+    return h, float(hmin), float(h2), t
+
+
+class Problem:
+    """Device mirror of the reference's MCAparam + DPparam + Boundary + brute-force table."""
+
+    def __init__(self, cfg, arith: int = 1, xgrid: list[np.ndarray] | None = None):
+        from .configs import c3_linspace
+        self.cfg = cfg
+        self.dx, self.du, self.dw = cfg.dx, cfg.du, cfg.dw
+        self.ngrid = np.ascontiguousarray(cfg.ngrid, dtype=np.uint64)
+        self.xgrid = xgrid if xgrid is not None else [c3_linspace(cfg.lb[i], cfg.ub[i], int(self.ngrid[i])) for i in range(cfg.dx)]
+        self.xgrid = [np.ascontiguousarray(g, dtype=np.float64) for g in self.xgrid]
+        self.h, self.hmin, self.h2, self.t = grid_constants(self.xgrid, cfg.lb, cfg.ub)
+        self.bc = np.ascontiguousarray(cfg.bc, dtype=np.int32)
+        nobs = int(cfg.obs_center.shape[0]) if cfg.obs_center.size else 0
+        self.nobs = nobs
+        if nobs:
+            # BoundRect: lb = center - len/2, ub = center + len/2 (reference src/boundary.c:264-267)
+            self.obs_lb = np.ascontiguousarray(cfg.obs_center - cfg.obs_width / 2.0, dtype=np.float64)
+            self.obs_ub = np.ascontiguousarray(cfg.obs_center + cfg.obs_width / 2.0, dtype=np.float64)
+        else:
+            self.obs_lb = np.zeros((0, cfg.dx)); self.obs_ub = np.zeros((0, cfg.dx))
+        self.controls = np.ascontiguousarray(cfg.controls, dtype=np.float64)
+        self.params = np.ascontiguousarray(cfg.params, dtype=np.float64)
+        self.nmax = int(self.ngrid.max())
+        self.arith = arith
+        d = ProblemDesc()
+        d.dx, d.du, d.dw = cfg.dx, cfg.du, cfg.dw
+        d.ngrid = self.ngrid.ctypes.data_as(c_u64p)
+        self._xg = (c_f64p * cfg.dx)(*[g.ctypes.data_as(c_f64p) for g in self.xgrid])
+        d.xgrid = C.cast(self._xg, C.POINTER(c_f64p))
+        d.h2 = self.h2
+        d.t = self.t.ctypes.data_as(c_f64p)
+        d.bc = self.bc.ctypes.data_as(c_i32p)
+        d.nobs = nobs
+        d.obs_lb = self.obs_lb.ctypes.data_as(c_f64p)
+        d.obs_ub = self.obs_ub.ctypes.data_as(c_f64p)
+        d.discount = cfg.beta
+        d.nu = cfg.nu
+        d.controls = self.controls.ctypes.data_as(c_f64p)
+        d.model = cfg.model
+        d.model_params = self.params.ctypes.data_as(c_f64p) if self.params.size else None
+        d.n_model_params = int(self.params.size)
+        d.arith = arith
+        self.handle = C.c_void_p()
+        check(lib().c3sc_problem_create(C.byref(d), C.byref(self.handle)))
+
+    def close(self):
+        if getattr(self, "handle", None):
+            lib().c3sc_problem_destroy(self.handle)
+            self.handle = None
+
+    __del__ = close
+
+    def check(self):
+        check(lib().c3sc_problem_check(self.handle))
+
+    # ---- host-buffer entry points -----------------------------------------------
+    def vi_batch(self, vf: "ValueF", dim_vary, fixed_ind, want_argmin=True):
+        dv, fi, F = _fibers(dim_vary, fixed_ind, self.dx)
+        val = np.empty((F, self.nmax), dtype=np.float64)
+        arg = np.empty((F, self.nmax), dtype=np.int32) if want_argmin else None
+        check(lib().c3sc_vi_batch(self.handle, vf.handle, F, _ptr(dv), _ptr(fi), self.nmax, _ptr(val), _ptr(arg)))
+        return (val, arg) if want_argmin else val
+
+    def vi_batch_debug(self, vf: "ValueF", dim_vary, fixed_ind):
+        dv, fi, F = _fibers(dim_vary, fixed_ind, self.dx)
+        n, dx = self.nmax, self.dx
+        out = dict(
+            value=np.empty((F, n)), argmin=np.empty((F, n), np.int32), absorbed=np.empty((F, n), np.int32),
+            costs=np.empty((F, n, 2 * dx + 1)), rows=np.empty((F, n, 2 * dx + 3)),
+            nbr_vary=np.empty((F, n, 2), np.int32), nbr_fixed=np.zeros((F, max(dx - 1, 1), 2), np.int32))
+        check(lib().c3sc_vi_batch_debug(self.handle, vf.handle, F, _ptr(dv), _ptr(fi), n,
+                                        *[_ptr(out[k]) for k in ("value", "argmin", "absorbed", "costs", "rows", "nbr_vary", "nbr_fixed")]))
+        return out
+
+    def pi_batch(self, vf_policy: "ValueF", vf_iter: "ValueF", dim_vary, fixed_ind, rows=None):
+        dv, fi, F = _fibers(dim_vary, fixed_ind, self.dx)
+        n, dx = self.nmax, self.dx
+        have = rows is not None
+        if not have:
+            rows = np.empty((F, n, 2 * dx + 3), dtype=np.float64)
+        arg = np.empty((F, n), dtype=np.int32)
+        val = np.empty((F, n), dtype=np.float64)
+        check(lib().c3sc_pi_batch(self.handle, vf_policy.handle if vf_policy is not None else None, vf_iter.handle,
+                                  F, _ptr(dv), _ptr(fi), n, int(have), _ptr(rows), _ptr(arg), _ptr(val)))
+        return val, rows, (None if have else arg)
+
+    def transition(self, drift: np.ndarray, sigma: np.ndarray):
+        drift = np.ascontiguousarray(drift, np.float64); sigma = np.ascontiguousarray(sigma, np.float64)
+        n = drift.shape[0]
+        prob = np.empty((n, 2 * self.dx + 1)); dt = np.empty(n); st = np.empty(n, np.int32)
+        check(lib().c3sc_transition_batch(self.handle, n, _ptr(drift), _ptr(sigma), _ptr(prob), _ptr(dt), _ptr(st)))
+        return prob, dt, st
+
+    def model_eval(self, x: np.ndarray, u: np.ndarray):
+        x = np.ascontiguousarray(x, np.float64); u = np.ascontiguousarray(u, np.float64)
+        n = x.shape[0]
+        drift = np.empty((n, self.dx)); sig = np.empty((n, self.dx))
+        stage = np.empty(n); bound = np.empty(n); obs = np.empty(n)
+        check(lib().c3sc_model_eval(self.handle, n, _ptr(x), _ptr(u), _ptr(drift), _ptr(sig), _ptr(stage), _ptr(bound), _ptr(obs)))
+        return drift, sig, stage, bound, obs
+
+    # ---- device-pointer entry points (ints are raw device addresses) ---------------
+    def vi_batch_dev(self, vf: "ValueF", F: int, d_dim_vary: int, d_fixed_ind: int, ldo: int, value: int,
+                     argmin: int = 0, stream: int = 0, rows: int = 0):
+        o = BatchOut(value or None, argmin or None, None, None, rows or None, None, None)
+        check(lib().c3sc_vi_batch_dev(self.handle, vf.handle, F, d_dim_vary, d_fixed_ind, ldo, C.byref(o), stream or None))
+
+    def pi_batch_dev(self, vf_policy, vf_iter, F, d_dim_vary, d_fixed_ind, ldo, have_rows, rows, argmin, value, stream=0):
+        check(lib().c3sc_pi_batch_dev(self.handle, vf_policy.handle if vf_policy is not None else None, vf_iter.handle, F,
+                                      d_dim_vary, d_fixed_ind, ldo, int(have_rows), rows, argmin or None, value, stream or None))
+
+
+def _fibers(dim_vary, fixed_ind, dx):
+    dv = np.ascontiguousarray(dim_vary, dtype=np.int32).reshape(-1)
+    fi = np.ascontiguousarray(fixed_ind, dtype=np.int32).reshape(-1, dx)
+    assert fi.shape[0] == dv.shape[0]
+    return dv, fi, int(dv.shape[0])
+
+
+class ValueF:
+    """Device mirror of ValueF::cores (reference src/valuefunc.c:62-78,165-189)."""
+
+    def __init__(self, n, ranks, cores: list[np.ndarray]):
+        self.d = len(cores)
+        self.n = np.ascontiguousarray(n, dtype=np.uint64)
+        self.ranks = np.ascontiguousarray(ranks, dtype=np.uint64)
+        self.cores = [np.ascontiguousarray(c, dtype=np.float64).reshape(-1) for c in cores]
+        for k in range(self.d):
+            assert self.cores[k].size == int(self.n[k] * self.ranks[k] * self.ranks[k + 1])
+        self.handle = C.c_void_p()
+        arr = (c_f64p * self.d)(*[c.ctypes.data_as(c_f64p) for c in self.cores])
+        check(lib().c3sc_valuef_create(self.d, self.n.ctypes.data_as(c_u64p), self.ranks.ctypes.data_as(c_u64p),
+                                       C.cast(arr, C.POINTER(c_f64p)), C.byref(self.handle)))
+
+    def update(self, cores: list[np.ndarray]):
+        self.cores = [np.ascontiguousarray(c, dtype=np.float64).reshape(-1) for c in cores]
+        arr = (c_f64p * self.d)(*[c.ctypes.data_as(c_f64p) for c in self.cores])
+        check(lib().c3sc_valuef_update(self.handle, C.cast(arr, C.POINTER(c_f64p))))
+
+    def device_buffer(self):
+        p = C.c_void_p(); n = C.c_size_t()
+        check(lib().c3sc_valuef_device_buffer(self.handle, C.byref(p), C.byref(n)))
+        return p.value, n.value
+
+    def close(self):
+        if getattr(self, "handle", None):
+            lib().c3sc_valuef_destroy(self.handle)
+            self.handle = None
+
+    __del__ = close

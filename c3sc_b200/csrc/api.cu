@@ -1,0 +1,488 @@
+// api.cu -- the C-ABI of include/c3sc_b200.h: device mirrors + launch wrappers.
+#include <cuda_runtime.h>
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <vector>
+#include "dev_types.h"
+#include "backup_kernel.cuh"   // SmemPlan only (host side)
+
+namespace c3sc {
+int launch_backup_lqg_lo(int dx, int arith, const LaunchArgs &a, cudaStream_t st);
+int launch_backup_lqg_hi(int dx, int arith, const LaunchArgs &a, cudaStream_t st);
+int launch_backup_misc(int model, int dx, int arith, const LaunchArgs &a, cudaStream_t st);
+int launch_model_eval_lqg_lo(int dx, const DevProblem &P, int n, const double *x, const double *u, double *drift,
+                             double *sig, double *stage, double *bound, double *obs, cudaStream_t st);
+int launch_model_eval_lqg_hi(int dx, const DevProblem &P, int n, const double *x, const double *u, double *drift,
+                             double *sig, double *stage, double *bound, double *obs, cudaStream_t st);
+int launch_model_eval_misc(int model, int dx, const DevProblem &P, int n, const double *x, const double *u,
+                           double *drift, double *sig, double *stage, double *bound, double *obs, cudaStream_t st);
+}  // namespace c3sc
+
+using namespace c3sc;
+
+static thread_local char g_err[512] = "";
+static std::atomic<uint64_t> g_launches{0};
+
+static int fail(int code, const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof g_err, fmt, ap);
+    va_end(ap);
+    return code;
+}
+#define CK(call)                                                                              \
+    do {                                                                                      \
+        cudaError_t e_ = (call);                                                              \
+        if (e_ != cudaSuccess) return fail(C3SC_ECUDA, "%s: %s", #call, cudaGetErrorString(e_)); \
+    } while (0)
+
+// grow-only device scratch
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    int reserve(size_t bytes)
+    {
+        if (bytes <= cap) return 0;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        if (cudaMalloc(&p, bytes) != cudaSuccess) return 1;
+        cap = bytes;
+        return 0;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+struct c3sc_problem {
+    DevProblem P;
+    int model, arith;
+    double *d_xgrid = nullptr, *d_obs = nullptr, *d_utab = nullptr;
+    int *d_err = nullptr;
+    cudaStream_t stream = nullptr;           // host-buffer entry points run here
+    DevBuf b_dv, b_fi, b_val, b_arg, b_abs, b_costs, b_rows, b_nv, b_nf, b_misc[8];
+};
+
+struct c3sc_valuef {
+    DevFT ft;
+    double *d_base = nullptr;
+    size_t count = 0;
+    std::vector<size_t> len;
+};
+
+extern "C" {
+
+const char *c3sc_last_error(void) { return g_err; }
+const char *c3sc_version(void) { return "c3sc_b200 0.1 (sm_100a)"; }
+uint64_t c3sc_launch_count(void) { return g_launches.load(); }
+
+int c3sc_cuda_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+    return n;
+}
+
+int c3sc_cuda_init(int device)
+{
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0)
+        return fail(C3SC_ENODEV, "no CUDA device (%s); the Bellman backup has no CPU fallback",
+                    e == cudaSuccess ? "count 0" : cudaGetErrorString(e));
+    if (device < 0 || device >= n) return fail(C3SC_EINVAL, "device %d out of range [0,%d)", device, n);
+    CK(cudaSetDevice(device));
+    CK(cudaFree(0));
+    return C3SC_OK;
+}
+
+int c3sc_problem_create(const c3sc_problem_desc *d, c3sc_problem **out)
+{
+    if (!d || !out) return fail(C3SC_EINVAL, "null argument");
+    if (d->dx < 1 || d->dx > C3SC_MAXD) return fail(C3SC_EINVAL, "dx=%u outside [1,%d]", d->dx, C3SC_MAXD);
+    if (d->nobs > C3SC_MAXOBS) return fail(C3SC_EINVAL, "nobs=%u > %d", d->nobs, C3SC_MAXOBS);
+    if (d->nu < 1 || !d->controls) return fail(C3SC_EINVAL, "empty control table");
+    if (c3sc_cuda_device_count() == 0)
+        return fail(C3SC_ENODEV, "no CUDA device; the Bellman backup has no CPU fallback");
+    c3sc_problem *p = new c3sc_problem();
+    DevProblem &P = p->P;
+    memset(&P, 0, sizeof P);
+    P.dx = (int)d->dx; P.du = (int)d->du; P.dw = (int)d->dw; P.nu = (int)d->nu; P.nobs = (int)d->nobs;
+    P.h2 = d->h2; P.beta = d->discount;
+    p->model = d->model;
+    p->arith = d->arith;
+    size_t total = 0;
+    for (uint32_t i = 0; i < d->dx; i++) {
+        if (d->ngrid[i] < 2) { delete p; return fail(C3SC_EINVAL, "ngrid[%u] < 2", i); }
+        if (d->bc[i] < C3SC_ABSORB || d->bc[i] > C3SC_REFLECT) { delete p; return fail(C3SC_EINVAL, "bc[%u]=%d unknown", i, d->bc[i]); }
+        P.ngrid[i] = (int)d->ngrid[i];
+        P.bc[i] = d->bc[i];
+        P.xoff[i] = (int)total;
+        total += d->ngrid[i];
+        if ((int)d->ngrid[i] > P.nmax) P.nmax = (int)d->ngrid[i];
+        P.t[2 * i] = d->t[2 * i];
+        P.t[2 * i + 1] = d->t[2 * i + 1];
+    }
+    // model parameter defaults = the reference examples' constants
+    static const double defaults[5][8] = {{0}, {1.0, 1.0, 100.0, 0.0}, {1.0, 1.0, 1000.0, 0.0},
+                                          {1.0, 1e-2, 1.0, 10.0, 0.0}, {0.0}};
+    if (d->model < 1 || d->model > 4) { delete p; return fail(C3SC_EUNSUPPORTED, "model %d unknown", d->model); }
+    memcpy(P.mp, defaults[d->model], sizeof P.mp);
+    for (uint32_t i = 0; i < d->n_model_params && i < 8; i++) P.mp[i] = d->model_params[i];
+
+    std::vector<double> xg(total);
+    for (uint32_t i = 0; i < d->dx; i++) memcpy(xg.data() + P.xoff[i], d->xgrid[i], d->ngrid[i] * sizeof(double));
+    std::vector<double> obs((size_t)d->nobs * 2 * d->dx + 1);
+    for (uint32_t o = 0; o < d->nobs; o++) {
+        memcpy(obs.data() + (size_t)o * 2 * d->dx, d->obs_lb + (size_t)o * d->dx, d->dx * sizeof(double));
+        memcpy(obs.data() + (size_t)o * 2 * d->dx + d->dx, d->obs_ub + (size_t)o * d->dx, d->dx * sizeof(double));
+    }
+#define CKP(call)                                                                                    \
+    do {                                                                                             \
+        cudaError_t e_ = (call);                                                                     \
+        if (e_ != cudaSuccess) { c3sc_problem_destroy(p); return fail(C3SC_ECUDA, "%s: %s", #call, cudaGetErrorString(e_)); } \
+    } while (0)
+    CKP(cudaMalloc(&p->d_xgrid, total * sizeof(double)));
+    CKP(cudaMemcpy(p->d_xgrid, xg.data(), total * sizeof(double), cudaMemcpyHostToDevice));
+    CKP(cudaMalloc(&p->d_obs, obs.size() * sizeof(double)));
+    CKP(cudaMemcpy(p->d_obs, obs.data(), obs.size() * sizeof(double), cudaMemcpyHostToDevice));
+    CKP(cudaMalloc(&p->d_utab, (size_t)d->nu * d->du * sizeof(double)));
+    CKP(cudaMemcpy(p->d_utab, d->controls, (size_t)d->nu * d->du * sizeof(double), cudaMemcpyHostToDevice));
+    CKP(cudaMalloc(&p->d_err, sizeof(int)));
+    CKP(cudaMemset(p->d_err, 0, sizeof(int)));
+    CKP(cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking));
+#undef CKP
+    P.xgrid = p->d_xgrid; P.obs = p->d_obs; P.utab = p->d_utab; P.err = p->d_err;
+    *out = p;
+    return C3SC_OK;
+}
+
+void c3sc_problem_destroy(c3sc_problem *p)
+{
+    if (!p) return;
+    cudaFree(p->d_xgrid); cudaFree(p->d_obs); cudaFree(p->d_utab); cudaFree(p->d_err);
+    DevBuf *bufs[] = {&p->b_dv, &p->b_fi, &p->b_val, &p->b_arg, &p->b_abs, &p->b_costs, &p->b_rows, &p->b_nv, &p->b_nf};
+    for (DevBuf *b : bufs) b->release();
+    for (DevBuf &b : p->b_misc) b.release();
+    if (p->stream) cudaStreamDestroy(p->stream);
+    delete p;
+}
+
+int c3sc_problem_check(c3sc_problem *p)
+{
+    if (!p) return fail(C3SC_EINVAL, "null problem");
+    int flag = 0;
+    CK(cudaDeviceSynchronize());
+    CK(cudaMemcpy(&flag, p->d_err, sizeof(int), cudaMemcpyDeviceToHost));
+    if (flag) {
+        cudaMemset(p->d_err, 0, sizeof(int));
+        return fail(C3SC_ENUMERIC, "transition normaliser < 1e-14 at some (node, control): the reference asserts here");
+    }
+    return C3SC_OK;
+}
+
+int c3sc_valuef_create(uint32_t d, const uint64_t *n, const uint64_t *ranks, const double *const *cores,
+                       c3sc_valuef **out)
+{
+    if (!n || !ranks || !out || d < 1 || d > C3SC_MAXD) return fail(C3SC_EINVAL, "bad value-function shape");
+    if (ranks[0] != 1 || ranks[d] != 1) return fail(C3SC_EINVAL, "boundary ranks must be 1");
+    if (c3sc_cuda_device_count() == 0)
+        return fail(C3SC_ENODEV, "no CUDA device; the Bellman backup has no CPU fallback");
+    c3sc_valuef *vf = new c3sc_valuef();
+    DevFT &ft = vf->ft;
+    memset(&ft, 0, sizeof ft);
+    ft.d = (int)d;
+    size_t total = 0;
+    for (uint32_t k = 0; k < d; k++) {
+        ft.n[k] = (int)n[k];
+        ft.r[k] = (int)ranks[k];
+        ft.off[k] = (long long)total;
+        size_t len = n[k] * ranks[k] * ranks[k + 1];
+        vf->len.push_back(len);
+        total += len;
+        if ((int)ranks[k] > ft.rmax) ft.rmax = (int)ranks[k];
+    }
+    ft.r[d] = 1;
+    if (ft.rmax < 1) ft.rmax = 1;
+    vf->count = total;
+    cudaError_t e = cudaMalloc(&vf->d_base, total * sizeof(double));
+    if (e != cudaSuccess) { delete vf; return fail(C3SC_ECUDA, "cudaMalloc cores: %s", cudaGetErrorString(e)); }
+    ft.base = vf->d_base;
+    *out = vf;
+    if (cores) {
+        int rc = c3sc_valuef_update(vf, cores);
+        if (rc) { c3sc_valuef_destroy(vf); *out = nullptr; return rc; }
+    }
+    return C3SC_OK;
+}
+
+int c3sc_valuef_update(c3sc_valuef *vf, const double *const *cores)
+{
+    if (!vf || !cores) return fail(C3SC_EINVAL, "null argument");
+    for (int k = 0; k < vf->ft.d; k++)
+        CK(cudaMemcpy(vf->d_base + vf->ft.off[k], cores[k], vf->len[k] * sizeof(double), cudaMemcpyHostToDevice));
+    return C3SC_OK;
+}
+
+int c3sc_valuef_device_buffer(c3sc_valuef *vf, double **dev, size_t *count)
+{
+    if (!vf || !dev || !count) return fail(C3SC_EINVAL, "null argument");
+    *dev = vf->d_base;
+    *count = vf->count;
+    return C3SC_OK;
+}
+
+void c3sc_valuef_destroy(c3sc_valuef *vf)
+{
+    if (!vf) return;
+    cudaFree(vf->d_base);
+    delete vf;
+}
+
+}  // extern "C"
+
+// ---------------------------------------------------------------------------
+static int dispatch(c3sc_problem *p, const LaunchArgs &a, cudaStream_t st)
+{
+    int rc;
+    if (p->model == C3SC_MODEL_LQGND) rc = (p->P.dx <= 6) ? launch_backup_lqg_lo(p->P.dx, p->arith, a, st)
+                                                          : launch_backup_lqg_hi(p->P.dx, p->arith, a, st);
+    else rc = launch_backup_misc(p->model, p->P.dx, p->arith, a, st);
+    if (rc == -1) return fail(C3SC_EUNSUPPORTED, "model %d with dx=%d is not instantiated", p->model, p->P.dx);
+    if (rc != 0) return fail(C3SC_ECUDA, "kernel launch: %s", cudaGetErrorString((cudaError_t)rc));
+    g_launches++;
+    return C3SC_OK;
+}
+
+static int check_shapes(const c3sc_problem *p, const c3sc_valuef *vf, size_t F, size_t ldo)
+{
+    if (!p || !vf) return fail(C3SC_EINVAL, "null problem / value function");
+    if (vf->ft.d != p->P.dx) return fail(C3SC_EINVAL, "value function has d=%d, problem dx=%d", vf->ft.d, p->P.dx);
+    for (int i = 0; i < p->P.dx; i++)
+        if (vf->ft.n[i] != p->P.ngrid[i]) return fail(C3SC_EINVAL, "grid size mismatch in dim %d", i);
+    if (ldo < (size_t)p->P.nmax) return fail(C3SC_EINVAL, "ldo=%zu < max ngrid=%d", ldo, p->P.nmax);
+    if (F > 0x7fffffffu) return fail(C3SC_EINVAL, "too many fibers in one batch");
+    return C3SC_OK;
+}
+
+extern "C" {
+
+int c3sc_vi_batch_dev(c3sc_problem *p, const c3sc_valuef *vf, size_t F, const int32_t *d_dim_vary,
+                      const int32_t *d_fixed_ind, size_t ldo, const c3sc_batch_out *out, void *stream)
+{
+    int rc = check_shapes(p, vf, F, ldo);
+    if (rc) return rc;
+    if (!out || (!out->value && !out->rows && !out->argmin && !out->costs && !out->absorbed))
+        return fail(C3SC_EINVAL, "no output requested");
+    if (F == 0) return C3SC_OK;
+    LaunchArgs a;
+    memset(&a, 0, sizeof a);
+    a.P = p->P; a.ft = vf->ft; a.F = (int)F; a.dim_vary = d_dim_vary; a.fixed_ind = d_fixed_ind; a.ldo = (int)ldo;
+    a.out.value = out->value; a.out.argmin = out->argmin; a.out.absorbed = out->absorbed;
+    a.out.costs = out->costs; a.out.rows = out->rows; a.out.nbr_vary = out->nbr_vary; a.out.nbr_fixed = out->nbr_fixed;
+    a.mode = MODE_VI;
+    a.write_value = out->value != nullptr;
+    return dispatch(p, a, (cudaStream_t)stream);
+}
+
+int c3sc_pi_batch_dev(c3sc_problem *p, const c3sc_valuef *vf_policy, const c3sc_valuef *vf_iter, size_t F,
+                      const int32_t *d_dim_vary, const int32_t *d_fixed_ind, size_t ldo, int have_rows,
+                      double *d_rows, int32_t *d_argmin, double *d_value, void *stream)
+{
+    int rc = check_shapes(p, vf_iter, F, ldo);
+    if (rc) return rc;
+    if (!d_rows || !d_value) return fail(C3SC_EINVAL, "rows and value buffers are required");
+    if (F == 0) return C3SC_OK;
+    LaunchArgs a;
+    memset(&a, 0, sizeof a);
+    a.P = p->P; a.F = (int)F; a.dim_vary = d_dim_vary; a.fixed_ind = d_fixed_ind; a.ldo = (int)ldo;
+    if (!have_rows) {                       // policy improvement against vf_policy (bellman.c:1831-1860)
+        rc = check_shapes(p, vf_policy, F, ldo);
+        if (rc) return rc;
+        a.ft = vf_policy->ft;
+        a.mode = MODE_VI;
+        a.write_value = 0;
+        a.out.rows = d_rows;
+        a.out.argmin = d_argmin;
+        rc = dispatch(p, a, (cudaStream_t)stream);
+        if (rc) return rc;
+    }
+    a.ft = vf_iter->ft;                     // evaluation against vf_iter (bellman.c:1863-1871)
+    a.mode = MODE_PI_EVAL;
+    memset(&a.out, 0, sizeof a.out);
+    a.out.value = d_value;
+    a.rows_in = d_rows;
+    return dispatch(p, a, (cudaStream_t)stream);
+}
+
+static int upload_fibers(c3sc_problem *p, size_t F, const int32_t *dim_vary, const int32_t *fixed_ind)
+{
+    if (p->b_dv.reserve(F * sizeof(int32_t)) || p->b_fi.reserve(F * p->P.dx * sizeof(int32_t)))
+        return fail(C3SC_ECUDA, "cudaMalloc fiber descriptors failed");
+    CK(cudaMemcpyAsync(p->b_dv.p, dim_vary, F * sizeof(int32_t), cudaMemcpyHostToDevice, p->stream));
+    CK(cudaMemcpyAsync(p->b_fi.p, fixed_ind, F * p->P.dx * sizeof(int32_t), cudaMemcpyHostToDevice, p->stream));
+    return C3SC_OK;
+}
+
+static int finish(c3sc_problem *p)
+{
+    CK(cudaStreamSynchronize(p->stream));
+    int flag = 0;
+    CK(cudaMemcpy(&flag, p->d_err, sizeof(int), cudaMemcpyDeviceToHost));
+    if (flag) {
+        cudaMemset(p->d_err, 0, sizeof(int));
+        return fail(C3SC_ENUMERIC, "transition normaliser < 1e-14 at some (node, control): the reference asserts here");
+    }
+    return C3SC_OK;
+}
+
+int c3sc_vi_batch_debug(c3sc_problem *p, const c3sc_valuef *vf, size_t F, const int32_t *dim_vary,
+                        const int32_t *fixed_ind, size_t ldo, double *value, int32_t *argmin, int32_t *absorbed,
+                        double *costs, double *rows, int32_t *nbr_vary, int32_t *nbr_fixed)
+{
+    int rc = check_shapes(p, vf, F, ldo);
+    if (rc) return rc;
+    if (!dim_vary || !fixed_ind || !value) return fail(C3SC_EINVAL, "null fiber descriptors / value buffer");
+    if (F == 0) return C3SC_OK;
+    const size_t dx = p->P.dx, n = F * ldo;
+    rc = upload_fibers(p, F, dim_vary, fixed_ind);
+    if (rc) return rc;
+    c3sc_batch_out o;
+    memset(&o, 0, sizeof o);
+    int bad = p->b_val.reserve(n * 8);
+    o.value = (double *)p->b_val.p;
+    if (argmin)    { bad |= p->b_arg.reserve(n * 4); o.argmin = (int32_t *)p->b_arg.p; }
+    if (absorbed)  { bad |= p->b_abs.reserve(n * 4); o.absorbed = (int32_t *)p->b_abs.p; }
+    if (costs)     { bad |= p->b_costs.reserve(n * (2 * dx + 1) * 8); o.costs = (double *)p->b_costs.p; }
+    if (rows)      { bad |= p->b_rows.reserve(n * (2 * dx + 3) * 8); o.rows = (double *)p->b_rows.p; }
+    if (nbr_vary)  { bad |= p->b_nv.reserve(n * 2 * 4); o.nbr_vary = (int32_t *)p->b_nv.p; }
+    if (nbr_fixed) { bad |= p->b_nf.reserve(F * 2 * (dx > 1 ? dx - 1 : 1) * 4); o.nbr_fixed = (int32_t *)p->b_nf.p; }
+    if (bad) return fail(C3SC_ECUDA, "cudaMalloc batch outputs failed");
+    // deterministic content for the padding entries j >= ngrid[dim_vary]
+    CK(cudaMemsetAsync(o.value, 0, n * 8, p->stream));
+    if (argmin)   CK(cudaMemsetAsync(o.argmin, 0xff, n * 4, p->stream));
+    if (absorbed) CK(cudaMemsetAsync(o.absorbed, 0, n * 4, p->stream));
+    if (costs)    CK(cudaMemsetAsync(o.costs, 0, n * (2 * dx + 1) * 8, p->stream));
+    if (rows)     CK(cudaMemsetAsync(o.rows, 0, n * (2 * dx + 3) * 8, p->stream));
+    if (nbr_vary) CK(cudaMemsetAsync(o.nbr_vary, 0, n * 2 * 4, p->stream));
+    rc = c3sc_vi_batch_dev(p, vf, F, (const int32_t *)p->b_dv.p, (const int32_t *)p->b_fi.p, ldo, &o, p->stream);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(value, o.value, n * 8, cudaMemcpyDeviceToHost, p->stream));
+    if (argmin)    CK(cudaMemcpyAsync(argmin, o.argmin, n * 4, cudaMemcpyDeviceToHost, p->stream));
+    if (absorbed)  CK(cudaMemcpyAsync(absorbed, o.absorbed, n * 4, cudaMemcpyDeviceToHost, p->stream));
+    if (costs)     CK(cudaMemcpyAsync(costs, o.costs, n * (2 * dx + 1) * 8, cudaMemcpyDeviceToHost, p->stream));
+    if (rows)      CK(cudaMemcpyAsync(rows, o.rows, n * (2 * dx + 3) * 8, cudaMemcpyDeviceToHost, p->stream));
+    if (nbr_vary)  CK(cudaMemcpyAsync(nbr_vary, o.nbr_vary, n * 2 * 4, cudaMemcpyDeviceToHost, p->stream));
+    if (nbr_fixed && dx > 1) CK(cudaMemcpyAsync(nbr_fixed, o.nbr_fixed, F * 2 * (dx - 1) * 4, cudaMemcpyDeviceToHost, p->stream));
+    return finish(p);
+}
+
+int c3sc_vi_batch(c3sc_problem *p, const c3sc_valuef *vf, size_t F, const int32_t *dim_vary,
+                  const int32_t *fixed_ind, size_t ldo, double *value, int32_t *argmin)
+{
+    int rc = check_shapes(p, vf, F, ldo);
+    if (rc) return rc;
+    if (!dim_vary || !fixed_ind || !value) return fail(C3SC_EINVAL, "null fiber descriptors / value buffer");
+    if (F == 0) return C3SC_OK;
+    const size_t n = F * ldo;
+    rc = upload_fibers(p, F, dim_vary, fixed_ind);
+    if (rc) return rc;
+    c3sc_batch_out o;
+    memset(&o, 0, sizeof o);
+    int bad = p->b_val.reserve(n * 8);
+    o.value = (double *)p->b_val.p;
+    if (argmin) { bad |= p->b_arg.reserve(n * 4); o.argmin = (int32_t *)p->b_arg.p; }
+    if (bad) return fail(C3SC_ECUDA, "cudaMalloc batch outputs failed");
+    rc = c3sc_vi_batch_dev(p, vf, F, (const int32_t *)p->b_dv.p, (const int32_t *)p->b_fi.p, ldo, &o, p->stream);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(value, o.value, n * 8, cudaMemcpyDeviceToHost, p->stream));
+    if (argmin) CK(cudaMemcpyAsync(argmin, o.argmin, n * 4, cudaMemcpyDeviceToHost, p->stream));
+    return finish(p);
+}
+
+int c3sc_pi_batch(c3sc_problem *p, const c3sc_valuef *vf_policy, const c3sc_valuef *vf_iter, size_t F,
+                  const int32_t *dim_vary, const int32_t *fixed_ind, size_t ldo, int have_rows, double *rows,
+                  int32_t *argmin, double *value)
+{
+    int rc = check_shapes(p, vf_iter, F, ldo);
+    if (rc) return rc;
+    if (!dim_vary || !fixed_ind || !value || !rows) return fail(C3SC_EINVAL, "null argument");
+    if (F == 0) return C3SC_OK;
+    const size_t dx = p->P.dx, n = F * ldo, rowb = n * (2 * dx + 3) * 8;
+    rc = upload_fibers(p, F, dim_vary, fixed_ind);
+    if (rc) return rc;
+    if (p->b_val.reserve(n * 8) || p->b_rows.reserve(rowb) || p->b_arg.reserve(n * 4))
+        return fail(C3SC_ECUDA, "cudaMalloc batch outputs failed");
+    if (have_rows) CK(cudaMemcpyAsync(p->b_rows.p, rows, rowb, cudaMemcpyHostToDevice, p->stream));
+    else {
+        CK(cudaMemsetAsync(p->b_rows.p, 0, rowb, p->stream));
+        CK(cudaMemsetAsync(p->b_arg.p, 0xff, n * 4, p->stream));
+    }
+    rc = c3sc_pi_batch_dev(p, vf_policy, vf_iter, F, (const int32_t *)p->b_dv.p, (const int32_t *)p->b_fi.p, ldo,
+                           have_rows, (double *)p->b_rows.p, (int32_t *)p->b_arg.p, (double *)p->b_val.p, p->stream);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(value, p->b_val.p, n * 8, cudaMemcpyDeviceToHost, p->stream));
+    if (!have_rows) {
+        CK(cudaMemcpyAsync(rows, p->b_rows.p, rowb, cudaMemcpyDeviceToHost, p->stream));
+        if (argmin) CK(cudaMemcpyAsync(argmin, p->b_arg.p, n * 4, cudaMemcpyDeviceToHost, p->stream));
+    }
+    return finish(p);
+}
+
+int c3sc_transition_batch(c3sc_problem *p, size_t n, const double *drift, const double *sigma_diag,
+                          double *prob, double *dt, int32_t *status)
+{
+    if (!p || !drift || !sigma_diag || !prob || !dt || !status) return fail(C3SC_EINVAL, "null argument");
+    if (n == 0) return C3SC_OK;
+    const size_t dx = p->P.dx;
+    DevBuf *b = p->b_misc;
+    if (b[0].reserve(n * dx * 8) || b[1].reserve(n * dx * 8) || b[2].reserve(n * (2 * dx + 1) * 8) ||
+        b[3].reserve(n * 8) || b[4].reserve(n * 4))
+        return fail(C3SC_ECUDA, "cudaMalloc failed");
+    CK(cudaMemcpyAsync(b[0].p, drift, n * dx * 8, cudaMemcpyHostToDevice, p->stream));
+    CK(cudaMemcpyAsync(b[1].p, sigma_diag, n * dx * 8, cudaMemcpyHostToDevice, p->stream));
+    int rc = launch_transition(p->arith, p->P, (int)n, (const double *)b[0].p, (const double *)b[1].p,
+                               (double *)b[2].p, (double *)b[3].p, (int *)b[4].p, p->stream);
+    if (rc == -1) return fail(C3SC_EUNSUPPORTED, "dx=%d not instantiated for the transition kernel", p->P.dx);
+    if (rc) return fail(C3SC_ECUDA, "kernel launch: %s", cudaGetErrorString((cudaError_t)rc));
+    g_launches++;
+    CK(cudaMemcpyAsync(prob, b[2].p, n * (2 * dx + 1) * 8, cudaMemcpyDeviceToHost, p->stream));
+    CK(cudaMemcpyAsync(dt, b[3].p, n * 8, cudaMemcpyDeviceToHost, p->stream));
+    CK(cudaMemcpyAsync(status, b[4].p, n * 4, cudaMemcpyDeviceToHost, p->stream));
+    CK(cudaStreamSynchronize(p->stream));
+    return C3SC_OK;
+}
+
+int c3sc_model_eval(c3sc_problem *p, size_t n, const double *x, const double *u, double *drift,
+                    double *sigma_diag, double *stage, double *bound, double *obs)
+{
+    if (!p || !x || !u || !drift || !sigma_diag || !stage || !bound || !obs) return fail(C3SC_EINVAL, "null argument");
+    if (n == 0) return C3SC_OK;
+    const size_t dx = p->P.dx, du = p->P.du;
+    DevBuf *b = p->b_misc;
+    if (b[0].reserve(n * dx * 8) || b[1].reserve(n * du * 8) || b[2].reserve(n * dx * 8) || b[3].reserve(n * dx * 8) ||
+        b[4].reserve(n * 8) || b[5].reserve(n * 8) || b[6].reserve(n * 8))
+        return fail(C3SC_ECUDA, "cudaMalloc failed");
+    CK(cudaMemcpyAsync(b[0].p, x, n * dx * 8, cudaMemcpyHostToDevice, p->stream));
+    CK(cudaMemcpyAsync(b[1].p, u, n * du * 8, cudaMemcpyHostToDevice, p->stream));
+    int rc;
+    const double *dxp = (const double *)b[0].p, *dup = (const double *)b[1].p;
+    double *o0 = (double *)b[2].p, *o1 = (double *)b[3].p, *o2 = (double *)b[4].p, *o3 = (double *)b[5].p, *o4 = (double *)b[6].p;
+    if (p->model == C3SC_MODEL_LQGND)
+        rc = (p->P.dx <= 6) ? launch_model_eval_lqg_lo(p->P.dx, p->P, (int)n, dxp, dup, o0, o1, o2, o3, o4, p->stream)
+                            : launch_model_eval_lqg_hi(p->P.dx, p->P, (int)n, dxp, dup, o0, o1, o2, o3, o4, p->stream);
+    else rc = launch_model_eval_misc(p->model, p->P.dx, p->P, (int)n, dxp, dup, o0, o1, o2, o3, o4, p->stream);
+    if (rc == -1) return fail(C3SC_EUNSUPPORTED, "model %d with dx=%d is not instantiated", p->model, p->P.dx);
+    if (rc) return fail(C3SC_ECUDA, "kernel launch: %s", cudaGetErrorString((cudaError_t)rc));
+    g_launches++;
+    CK(cudaMemcpyAsync(drift, o0, n * dx * 8, cudaMemcpyDeviceToHost, p->stream));
+    CK(cudaMemcpyAsync(sigma_diag, o1, n * dx * 8, cudaMemcpyDeviceToHost, p->stream));
+    CK(cudaMemcpyAsync(stage, o2, n * 8, cudaMemcpyDeviceToHost, p->stream));
+    CK(cudaMemcpyAsync(bound, o3, n * 8, cudaMemcpyDeviceToHost, p->stream));
+    CK(cudaMemcpyAsync(obs, o4, n * 8, cudaMemcpyDeviceToHost, p->stream));
+    CK(cudaStreamSynchronize(p->stream));
+    return C3SC_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,64 @@
+// dev_types.h -- POD structs passed BY VALUE to the kernels (constant bank).
+#pragma once
+#include <stdint.h>
+#include "../../include/c3sc_b200.h"
+
+namespace c3sc {
+
+constexpr int MAXD = C3SC_MAXD;
+
+// Device mirror of MCAparam + DPparam + Boundary + the c3opt brute-force table
+// (reference src/bellman.c:118-285, src/boundary.c:353-489).
+struct DevProblem {
+    int dx, du, dw, nu, nobs, nmax;
+    int ngrid[MAXD];
+    int bc[MAXD];
+    int xoff[MAXD];          // offset of xgrid[i] inside `xgrid`
+    double h2, beta;
+    double t[2 * MAXD];      // t[2i]=h2/h_i, t[2i+1]=h2/h_i^2 (bellman.c:181-186)
+    double mp[8];            // model parameters
+    const double *xgrid;     // device, concatenated
+    const double *obs;       // device, [nobs][2][dx]: lb then ub
+    const double *utab;      // device, [nu*du]
+    int *err;                // device error word (norm < 1e-14 seen)
+};
+
+// Device mirror of ValueF::cores (reference src/valuefunc.c:62-78,165-189).
+struct DevFT {
+    int d, rmax;
+    int n[MAXD];
+    int r[MAXD + 1];
+    long long off[MAXD];     // offset of core k inside `base` (doubles)
+    const double *base;
+};
+
+struct DevOut {
+    double *value;
+    int *argmin;
+    int *absorbed;
+    double *costs;
+    double *rows;
+    int *nbr_vary;
+    int *nbr_fixed;
+};
+
+enum Mode { MODE_VI = 0, MODE_PI_EVAL = 1 };
+
+struct LaunchArgs {
+    DevProblem P;
+    DevFT ft;
+    int F;
+    const int *dim_vary;
+    const int *fixed_ind;
+    int ldo;
+    DevOut out;
+    const double *rows_in;   // MODE_PI_EVAL: policy rows
+    int mode;
+    int write_value;         // MODE_VI: 0 when only rows/argmin are wanted
+};
+
+// implemented in inst_misc.cu; returns cudaError_t as int, or -1 if dx is not instantiated
+int launch_transition(int arith, const DevProblem &P, int n, const double *drift, const double *sig,
+                      double *prob, double *dt, int *status, void *stream);
+
+}  // namespace c3sc

@@ -1,0 +1,23 @@
+// explicit instantiations: LQG chain-of-integrators, dx = 8,10,12
+#include "backup_kernel.cuh"
+namespace c3sc {
+int launch_backup_lqg_hi(int dx, int arith, const LaunchArgs &a, cudaStream_t st)
+{
+    switch (dx) {
+    case 8: return launch_backup_m<LqgNd<8>>(arith, a, st);
+    case 10: return launch_backup_m<LqgNd<10>>(arith, a, st);
+    case 12: return launch_backup_m<LqgNd<12>>(arith, a, st);
+    }
+    return -1;
+}
+int launch_model_eval_lqg_hi(int dx, const DevProblem &P, int n, const double *x, const double *u, double *drift,
+                             double *sig, double *stage, double *bound, double *obs, cudaStream_t st)
+{
+    switch (dx) {
+    case 8: return launch_model_eval_t<LqgNd<8>>(P, n, x, u, drift, sig, stage, bound, obs, st);
+    case 10: return launch_model_eval_t<LqgNd<10>>(P, n, x, u, drift, sig, stage, bound, obs, st);
+    case 12: return launch_model_eval_t<LqgNd<12>>(P, n, x, u, drift, sig, stage, bound, obs, st);
+    }
+    return -1;
+}
+}  // namespace c3sc

@@ -1,0 +1,23 @@
+// explicit instantiations: LQG chain-of-integrators, dx = 2,4,6
+#include "backup_kernel.cuh"
+namespace c3sc {
+int launch_backup_lqg_lo(int dx, int arith, const LaunchArgs &a, cudaStream_t st)
+{
+    switch (dx) {
+    case 2: return launch_backup_m<LqgNd<2>>(arith, a, st);
+    case 4: return launch_backup_m<LqgNd<4>>(arith, a, st);
+    case 6: return launch_backup_m<LqgNd<6>>(arith, a, st);
+    }
+    return -1;
+}
+int launch_model_eval_lqg_lo(int dx, const DevProblem &P, int n, const double *x, const double *u, double *drift,
+                             double *sig, double *stage, double *bound, double *obs, cudaStream_t st)
+{
+    switch (dx) {
+    case 2: return launch_model_eval_t<LqgNd<2>>(P, n, x, u, drift, sig, stage, bound, obs, st);
+    case 4: return launch_model_eval_t<LqgNd<4>>(P, n, x, u, drift, sig, stage, bound, obs, st);
+    case 6: return launch_model_eval_t<LqgNd<6>>(P, n, x, u, drift, sig, stage, bound, obs, st);
+    }
+    return -1;
+}
+}  // namespace c3sc

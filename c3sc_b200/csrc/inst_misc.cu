@@ -1,0 +1,63 @@
+// explicit instantiations: double integrator (dx 2,3,4), Dubins car, skidding car; transition test kernel
+#include "backup_kernel.cuh"
+namespace c3sc {
+int launch_backup_misc(int model, int dx, int arith, const LaunchArgs &a, cudaStream_t st)
+{
+    switch (model) {
+    case C3SC_MODEL_DOUBLE_INT:
+        switch (dx) {
+        case 2: return launch_backup_m<DoubleInt<2>>(arith, a, st);
+        case 3: return launch_backup_m<DoubleInt<3>>(arith, a, st);
+        case 4: return launch_backup_m<DoubleInt<4>>(arith, a, st);
+        }
+        return -1;
+    case C3SC_MODEL_DUBINS: return dx == 3 ? launch_backup_m<Dubins>(arith, a, st) : -1;
+    case C3SC_MODEL_SKID5D: return dx == 5 ? launch_backup_m<Skid5d>(arith, a, st) : -1;
+    }
+    return -1;
+}
+int launch_model_eval_misc(int model, int dx, const DevProblem &P, int n, const double *x, const double *u,
+                           double *drift, double *sig, double *stage, double *bound, double *obs, cudaStream_t st)
+{
+    switch (model) {
+    case C3SC_MODEL_DOUBLE_INT:
+        switch (dx) {
+        case 2: return launch_model_eval_t<DoubleInt<2>>(P, n, x, u, drift, sig, stage, bound, obs, st);
+        case 3: return launch_model_eval_t<DoubleInt<3>>(P, n, x, u, drift, sig, stage, bound, obs, st);
+        case 4: return launch_model_eval_t<DoubleInt<4>>(P, n, x, u, drift, sig, stage, bound, obs, st);
+        }
+        return -1;
+    case C3SC_MODEL_DUBINS: return dx == 3 ? launch_model_eval_t<Dubins>(P, n, x, u, drift, sig, stage, bound, obs, st) : -1;
+    case C3SC_MODEL_SKID5D: return dx == 5 ? launch_model_eval_t<Skid5d>(P, n, x, u, drift, sig, stage, bound, obs, st) : -1;
+    }
+    return -1;
+}
+
+template <int DX>
+static int tr(int arith, const DevProblem &P, int n, const double *drift, const double *sig, double *prob,
+              double *dt, int *status, cudaStream_t st)
+{
+    if (n <= 0) return 0;
+    const int g = (n + 127) / 128;
+    if (arith == C3SC_ARITH_EXACT) k_transition<DX, Exact><<<g, 128, 0, st>>>(P, n, drift, sig, prob, dt, status);
+    else k_transition<DX, Fast><<<g, 128, 0, st>>>(P, n, drift, sig, prob, dt, status);
+    return (int)cudaGetLastError();
+}
+int launch_transition(int arith, const DevProblem &P, int n, const double *drift, const double *sig,
+                      double *prob, double *dt, int *status, void *stream)
+{
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (P.dx) {
+    case 1: return tr<1>(arith, P, n, drift, sig, prob, dt, status, st);
+    case 2: return tr<2>(arith, P, n, drift, sig, prob, dt, status, st);
+    case 3: return tr<3>(arith, P, n, drift, sig, prob, dt, status, st);
+    case 4: return tr<4>(arith, P, n, drift, sig, prob, dt, status, st);
+    case 5: return tr<5>(arith, P, n, drift, sig, prob, dt, status, st);
+    case 6: return tr<6>(arith, P, n, drift, sig, prob, dt, status, st);
+    case 8: return tr<8>(arith, P, n, drift, sig, prob, dt, status, st);
+    case 10: return tr<10>(arith, P, n, drift, sig, prob, dt, status, st);
+    case 12: return tr<12>(arith, P, n, drift, sig, prob, dt, status, st);
+    }
+    return -1;
+}
+}  // namespace c3sc

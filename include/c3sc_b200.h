@@ -1,0 +1,177 @@
+/* c3sc_b200.h -- thin C-ABI CUDA layer for the c3sc Bellman-backup hot path.
+ *
+ * Plain pointers and sizes only (no torch / C++ types): this is the surface
+ * the reference's C host code binds (see INTEGRATION.md for the stubs a
+ * maintainer adds to src/bellman.c, src/valuefunc.c).  Every entry point
+ * names the reference interface it replaces (path:line under
+ * /root/reference).  All functions return 0 on success and a non-zero
+ * C3SC_E* code otherwise; c3sc_last_error() gives the message.  There is no
+ * CPU fallback: without a CUDA device every compute entry fails loudly.
+ *
+ * Conventions
+ *   - a FIBER is (dim_vary, fixed_ind[dx]): all nodes of the grid that share
+ *     fixed_ind except along dim_vary (what C3's cross approximation hands
+ *     to bellman_vi as N points, src/bellman.c:1295).  fixed_ind[dim_vary]
+ *     is ignored.
+ *   - per-node outputs of fiber f live at [f*ldo + j], j < ngrid[dim_vary];
+ *     ldo >= max ngrid.
+ *   - index outputs are int32; values fp64.
+ */
+#ifndef C3SC_B200_H
+#define C3SC_B200_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define C3SC_MAXD 16          /* state dimensions supported by the kernels    */
+#define C3SC_MAXOBS 10        /* obstacle boxes (src/boundary.c:393)          */
+
+enum c3sc_status {
+    C3SC_OK = 0,
+    C3SC_EINVAL = 1,          /* bad argument                                 */
+    C3SC_ECUDA = 2,           /* CUDA runtime error (message has the detail)  */
+    C3SC_ENODEV = 3,          /* no usable CUDA device                        */
+    C3SC_ENUMERIC = 4,        /* transition normaliser < 1e-14 somewhere: the
+                                 reference asserts here (src/bellman.c:452,
+                                 src/nodeutil.c:365-367)                      */
+    C3SC_EUNSUPPORTED = 5     /* model / dimension not instantiated           */
+};
+
+/* enum EBTYPE of the reference (src/boundary.h:42-47), same values */
+enum c3sc_bc { C3SC_ABSORB = 1, C3SC_PERIODIC = 2, C3SC_REFLECT = 3 };
+
+/* Device-resident dynamics + cost models.  The reference takes host function
+ * pointers (src/dynamics.c:66,172; src/bellman.c:215-217) that a kernel
+ * cannot call; the examples' definitions are therefore built in and selected
+ * by id next to the unchanged host pointers.
+ *   LQGND      examples/lqgnd/lqgnd.c:80-186 (== examples/lqg2d_new for dx=2)
+ *              params [ss0, ss1, boundcost, obscost]
+ *   DOUBLE_INT examples/double_int/double_int.c:80-162, same params
+ *   DUBINS     examples/dubinscar_new/dubinscar.c:40-121
+ *              params [s_xy, s_theta, stage, boundcost, obscost]
+ *   SKID5D     examples/skidding5d/scar.c:39-176, params [obscost]         */
+enum c3sc_model {
+    C3SC_MODEL_LQGND = 1,
+    C3SC_MODEL_DOUBLE_INT = 2,
+    C3SC_MODEL_DUBINS = 3,
+    C3SC_MODEL_SKID5D = 4
+};
+
+/* EXACT reproduces the reference's operation order without fused
+ * multiply-add and with IEEE division per probability: transition
+ * probabilities and dt are bit-identical to src/nodeutil.c:267-406.
+ * FAST reassociates (one reciprocal per control, FMA, control-independent
+ * dimensions hoisted): <= a few ulp from EXACT, far inside the 1e-12 bar. */
+enum c3sc_arith { C3SC_ARITH_EXACT = 0, C3SC_ARITH_FAST = 1 };
+
+typedef struct c3sc_problem c3sc_problem;   /* device mirror of MCAparam+DPparam+Boundary+c3opt table */
+typedef struct c3sc_valuef c3sc_valuef;     /* device mirror of ValueF::cores */
+
+/* What c3control_create / mca_add_grid_refs / dp_param_* / boundary_* hold on
+ * the host (src/bellman.c:118-285,1962-1999; src/boundary.c:353-489), flattened. */
+typedef struct c3sc_problem_desc {
+    uint32_t dx, du, dw;
+    const uint64_t *ngrid;          /* [dx]                                   */
+    const double *const *xgrid;     /* [dx][ngrid[i]], uploaded as given      */
+    double h2;                      /* MCAparam::h2                           */
+    const double *t;                /* [2dx] MCAparam::t                      */
+    const int32_t *bc;              /* [dx] enum c3sc_bc                      */
+    uint32_t nobs;
+    const double *obs_lb;           /* [nobs*dx] BoundRect::lb                */
+    const double *obs_ub;           /* [nobs*dx] BoundRect::ub                */
+    double discount;                /* DPparam::discount                      */
+    uint32_t nu;                    /* brute-force candidates                 */
+    const double *controls;         /* [nu*du] candidate-major (c3opt table)  */
+    int32_t model;                  /* enum c3sc_model                        */
+    const double *model_params;     /* may be NULL                            */
+    uint32_t n_model_params;
+    int32_t arith;                  /* enum c3sc_arith                        */
+} c3sc_problem_desc;
+
+/* Optional per-batch outputs (device pointers, NULL = not wanted). */
+typedef struct c3sc_batch_out {
+    double  *value;       /* [F*ldo]          backed-up values (bellman_vi `out`)        */
+    int32_t *argmin;      /* [F*ldo]          index into the control table, -1 absorbed  */
+    int32_t *absorbed;    /* [F*ldo]          0 / 1 / -1 (process_fibers_neighbor)        */
+    double  *costs;       /* [F*ldo*(2dx+1)]  neighbour values (valuef_eval_fiber_ind_nn) */
+    double  *rows;        /* [F*ldo*(2dx+3)]  [p(2dx+1), dt, g] at the argmin (bellman_pi) */
+    int32_t *nbr_vary;    /* [F*ldo*2]        neighbours along the fiber                  */
+    int32_t *nbr_fixed;   /* [F*2*(dx-1)]     neighbours in the fixed dimensions          */
+} c3sc_batch_out;
+
+/* ---- runtime ---------------------------------------------------------- */
+int c3sc_cuda_init(int device);                  /* select device, create context */
+int c3sc_cuda_device_count(void);
+const char *c3sc_last_error(void);
+const char *c3sc_version(void);
+/* kernels launched by this library since load (bench.py's gpu_launches) */
+uint64_t c3sc_launch_count(void);
+
+/* ---- problem / value function ------------------------------------------ */
+int  c3sc_problem_create(const c3sc_problem_desc *desc, c3sc_problem **out);
+void c3sc_problem_destroy(c3sc_problem *p);
+/* returns C3SC_ENUMERIC if any launch since the last check hit norm<1e-14;
+ * synchronises the device.                                                 */
+int  c3sc_problem_check(c3sc_problem *p);
+
+/* valuef_precompute_cores layout (src/valuefunc.c:165-189): block j of core k
+ * is an r_k x r_{k+1} column-major matrix at cores[k] + j*r_k*r_{k+1}.      */
+int  c3sc_valuef_create(uint32_t d, const uint64_t *n, const uint64_t *ranks,
+                        const double *const *cores, c3sc_valuef **out);
+/* same shapes, new numbers (next VI iterate); host pointers               */
+int  c3sc_valuef_update(c3sc_valuef *vf, const double *const *cores);
+/* contiguous device buffer holding all cores (for ncclBroadcast)           */
+int  c3sc_valuef_device_buffer(c3sc_valuef *vf, double **dev, size_t *count);
+void c3sc_valuef_destroy(c3sc_valuef *vf);
+
+/* ---- the hot path, device-resident arguments ---------------------------- */
+/* bellman_vi over F fibers (src/bellman.c:1295-1423, memo dropped: backups are
+ * pure).  d_dim_vary [F], d_fixed_ind [F*dx] int32 device arrays.  stream is
+ * a cudaStream_t (NULL = default stream).  Asynchronous.                   */
+int c3sc_vi_batch_dev(c3sc_problem *p, const c3sc_valuef *vf, size_t F,
+                      const int32_t *d_dim_vary, const int32_t *d_fixed_ind,
+                      size_t ldo, const c3sc_batch_out *out, void *stream);
+
+/* bellman_pi over F fibers (src/bellman.c:1702-1886).  have_rows == 0: pick
+ * u* against vf_policy, store the policy rows in d_rows (and argmin if
+ * wanted), then evaluate against vf_iter; have_rows != 0: later sub-iteration,
+ * reuse d_rows.  d_rows [F*ldo*(2dx+3)].                                   */
+int c3sc_pi_batch_dev(c3sc_problem *p, const c3sc_valuef *vf_policy, const c3sc_valuef *vf_iter,
+                      size_t F, const int32_t *d_dim_vary, const int32_t *d_fixed_ind,
+                      size_t ldo, int have_rows, double *d_rows, int32_t *d_argmin,
+                      double *d_value, void *stream);
+
+/* ---- the hot path, host buffers (H2D + kernel + D2H inside) -------------- */
+/* What the reference-facing wrappers call.  value [F*ldo]; argmin may be NULL. */
+int c3sc_vi_batch(c3sc_problem *p, const c3sc_valuef *vf, size_t F,
+                  const int32_t *dim_vary, const int32_t *fixed_ind,
+                  size_t ldo, double *value, int32_t *argmin);
+/* Host-side debugging / parity variant that returns every intermediate.    */
+int c3sc_vi_batch_debug(c3sc_problem *p, const c3sc_valuef *vf, size_t F,
+                        const int32_t *dim_vary, const int32_t *fixed_ind, size_t ldo,
+                        double *value, int32_t *argmin, int32_t *absorbed, double *costs,
+                        double *rows, int32_t *nbr_vary, int32_t *nbr_fixed);
+/* rows: host buffer [F*ldo*(2dx+3)], in/out exactly as d_rows above.       */
+int c3sc_pi_batch(c3sc_problem *p, const c3sc_valuef *vf_policy, const c3sc_valuef *vf_iter,
+                  size_t F, const int32_t *dim_vary, const int32_t *fixed_ind,
+                  size_t ldo, int have_rows, double *rows, int32_t *argmin, double *value);
+
+/* ---- pieces of the path exposed for parity tests -------------------------- */
+/* transition_assemble (src/nodeutil.c:267-406, non-gradient branch) for n
+ * independent (drift[dx], diag sigma[dx]) pairs given on the host;
+ * prob [n*(2dx+1)], dt [n], status [n] (0 ok, 1 norm<1e-14).               */
+int c3sc_transition_batch(c3sc_problem *p, size_t n, const double *drift, const double *sigma_diag,
+                          double *prob, double *dt, int32_t *status);
+/* drift_eval / diff_eval / stagecost / boundcost / obscost of the device model
+ * at n (x,u) pairs: the device-vs-host-callback equality check.
+ * x [n*dx], u [n*du] -> drift [n*dx], sigma_diag [n*dx], stage/bound/obs [n]. */
+int c3sc_model_eval(c3sc_problem *p, size_t n, const double *x, const double *u,
+                    double *drift, double *sigma_diag, double *stage, double *bound, double *obs);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* C3SC_B200_H */
