@@ -1,0 +1,401 @@
+#!/usr/bin/env python
+"""bench.py -- Bellman node-backups/s of the hot path on synthetic fibers.
+
+    python bench.py --gpus N --steps K --warmup W            (N>1: launched under torchrun)
+    python bench.py --impl reference ...                     the reference's own CPU path
+
+One STEP = one pass of the hot path over one batch of synthetic fibers of the headline
+config (BASELINE.json configs[4]): d=10 LQG, 100 nodes/dim, FT rank 20,
+243 discrete controls, F fibers per GPU (weak scaling: per-GPU work fixed as N grows).
+At N>1 a step additionally broadcasts the FT cores from rank 0 and all-gathers the
+backed-up fiber values over NCCL (the path's real exchange).
+
+value    node-backups/s, whole job, fiber descriptors + cores already resident in HBM
+e2e      same metric through the host-buffer C-ABI call (c3sc_vi_batch): pinned host
+         fiber descriptors in, values back out, copies inside the timed region
+roofline FP64 FMA pipe: achieved = node-backups/s x W (SURVEY §8(d) contract flops per
+         node-backup) against the DFMA peak measured in this run
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+
+# --------------------------------------------------------------------------------------
+def contract_flops_per_node(cfg, rank: int) -> float:
+    """W = 8 r^2 + 4 d r + n_u (F_dyn + 12 d + 30)   (contract figure).
+    r^2 is the mean of r_k r_{k+1} over the varying core for dim_vary = f mod d."""
+    d = cfg.dx
+    r = cfg.ranks(rank).astype(np.float64)
+    rbar2 = float(np.mean(r[:-1] * r[1:]))
+    fdyn = {1: 2 * d + 2 * cfg.du, 2: 2 * d + 2, 3: 50, 4: 80}[cfg.model]
+    return 8.0 * rbar2 + 4.0 * d * float(rank) + cfg.nu * (fdyn + 12.0 * d + 30.0)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.05)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [s.strip() for s in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# --------------------------------------------------------------------------------------
+def run_reference(args, cfg, rank_ft):
+    """--impl reference: the reference's own CPU implementation (oracle/_ref = its sources
+    compiled in place; else the oracle port), all host threads, bounded sample per step."""
+    from c3sc_b200 import synthetic
+    from oracle import pyoracle as po
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from helpers import host_problem
+
+    wrank = int(os.environ.get("RANK", "0"))
+    if wrank != 0:
+        return
+    ranks = cfg.ranks(rank_ft)
+    cores = synthetic.random_cores(cfg.ngrid, ranks)
+    ft = po.FT(cfg.ngrid, ranks, cores)
+    F = args.ref_fibers
+    dv, fi = synthetic.random_fibers(cfg.ngrid, F * (args.steps + args.warmup))
+    cores_n = os.cpu_count() or 1
+    if po.have_ref():
+        kind = "reference"
+        ref = po.Ref(cfg)
+        vf = ref.valuef(ft)
+        threads = ref.omp_threads()
+
+        def step(i):
+            s = slice(i * F, (i + 1) * F)
+            _, secs = ref.vi_fibers(vf, dv[s], fi[s], fresh_per_fiber=False)
+            return secs
+    else:
+        kind = "port"
+        if not os.path.exists(po.PORT_PATH):
+            po.build_port()
+        xg, h, hmin, h2, t, olb, oub = host_problem(cfg)
+        port = po.Port(cfg, xg, h2, t, olb, oub)
+        threads = cores_n
+
+        def step(i):
+            s = slice(i * F, (i + 1) * F)
+            t0 = time.perf_counter()
+            port.vi_batch(ft, dv[s], fi[s], nthreads=threads)
+            return time.perf_counter() - t0
+    for i in range(args.warmup):
+        step(i)
+    total = 0.0
+    for i in range(args.steps):
+        total += step(args.warmup + i)
+    nodes = F * cfg.n * args.steps
+    val = nodes / total
+    line = {
+        "impl": "reference", "metric": "bellman_node_backups_per_s", "value": val, "unit": "node-backups/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_config(cfg, rank_ft, F, args),
+        "cpu_baseline": {"value": val, "unit": "node-backups/s", "cores": threads, "kind": kind,
+                         "sample": f"{F} fibers x {cfg.n} nodes per step, one bellman_vi call per fiber, "
+                                   f"OpenMP over the nodes of a fiber ({threads} threads of {cores_n} host cores)"},
+        "e2e": {"value": val, "unit": "node-backups/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+def workload_config(cfg, rank_ft, F, args):
+    return {"workload": f"{cfg.name}: d={cfg.dx} LQG, {cfg.n} nodes/dim, FT rank {rank_ft}, n_u={cfg.nu} "
+                        f"({'x'.join(['3'] * cfg.du)} tensor grid of {{-1,0,1}}), {F} synthetic fibers/GPU/step "
+                        f"(dim_vary = f mod d, 10% of fixed indices on faces)",
+            "fibers_per_gpu": F, "nodes_per_fiber": cfg.n, "rank": rank_ft, "n_controls": cfg.nu,
+            "arith": "fast" if args.arith else "exact",
+            "l2": "256 MiB buffer written between timed steps (L2 flush); each step timed by its own CUDA event pair"}
+
+
+# --------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default="lqgnd_reflect", help="lqgnd_reflect = examples/lqgnd -t 1 (every node a full backup); lqgnd = absorbing faces")
+    ap.add_argument("--fibers", type=int, default=65536, help="fibers per GPU per step")
+    ap.add_argument("--rank", type=int, default=20)
+    ap.add_argument("--arith", type=int, default=1, help="1 = FAST (default), 0 = EXACT reference order")
+    ap.add_argument("--ref-fibers", type=int, default=48, help="fibers per step of the CPU reference arm")
+    ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--sweep", action="store_true", help="also time one synthetic VI sweep (2 x d core batches)")
+    args = ap.parse_args()
+
+    from c3sc_b200 import configs, synthetic
+    cfg = configs.get_config(args.config)
+    rank_ft = args.rank
+
+    if args.impl == "reference":
+        run_reference(args, cfg, rank_ft)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from c3sc_b200 import capi
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the Bellman backup has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    capi.check(capi.lib().c3sc_cuda_init(local))
+
+    F = args.fibers
+    N = cfg.n
+    ranks = cfg.ranks(rank_ft)
+    prob = capi.Problem(cfg, arith=args.arith)
+    cores = synthetic.random_cores(cfg.ngrid, ranks)
+    vf = capi.ValueF(cfg.ngrid, ranks, cores)
+    core_ptr, core_cnt = vf.device_buffer()
+    # torch view over the library's contiguous core buffer (for the NCCL broadcast)
+    core_view = torch.empty(0, dtype=torch.float64, device=dev)
+    if world > 1:
+        import ctypes
+
+        class _Arr:  # __cuda_array_interface__ wrapper, zero copy
+            def __init__(self, ptr, n):
+                self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<f8", "data": (ptr, False), "version": 3}
+        core_view = torch.as_tensor(_Arr(core_ptr, core_cnt), device=dev)
+
+    # every rank draws its own shard of the global fiber list
+    dv_all, fi_all = synthetic.random_fibers(cfg.ngrid, F * world)
+    sl = slice(rank * F, (rank + 1) * F)
+    dv_h = torch.from_numpy(dv_all[sl].copy()).pin_memory()
+    fi_h = torch.from_numpy(fi_all[sl].copy()).pin_memory()
+    dv_d = dv_h.to(dev); fi_d = fi_h.to(dev)
+    out_d = torch.zeros(F * N, dtype=torch.float64, device=dev)
+    gathered = torch.empty(world * F * N, dtype=torch.float64, device=dev) if world > 1 else None
+    out_h = torch.empty(F * N, dtype=torch.float64).pin_memory()
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    stream = torch.cuda.current_stream(dev)
+    sptr = stream.cuda_stream
+
+    def step_resident():
+        if world > 1:
+            dist.broadcast(core_view, src=0)
+        prob.vi_batch_dev(vf, F, dv_d.data_ptr(), fi_d.data_ptr(), N, out_d.data_ptr(), stream=sptr)
+        if world > 1:
+            dist.all_gather_into_tensor(gathered, out_d)
+
+    def step_e2e():
+        capi.check(capi.lib().c3sc_vi_batch(prob.handle, vf.handle, F, dv_h.data_ptr(), fi_h.data_ptr(), N,
+                                            out_h.data_ptr(), None))
+
+    def timed(fn, steps, warmup):
+        for _ in range(warmup):
+            fn()
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+        evs = []
+        for _ in range(steps):
+            flush.fill_(1)
+            e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            fn()
+            e1.record(stream)
+            evs.append((e0, e1))
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+        ms = sum(a.elapsed_time(b) for a, b in evs)
+        if world > 1:
+            t = torch.tensor([ms], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms
+
+    sampler = ClockSampler(local)
+    launches0 = capi.lib().c3sc_launch_count()
+    for _ in range(args.warmup):
+        step_resident()
+    torch.cuda.synchronize(dev)
+    launches0 = capi.lib().c3sc_launch_count()
+    sampler.start()
+    ms_total = timed(step_resident, args.steps, 0)
+    clocks = sampler.stop()
+    launches = capi.lib().c3sc_launch_count() - launches0
+    prob.check()
+
+    # end-to-end through the host-buffer C-ABI entry (wall clock around the blocking call, max over ranks)
+    def timed_host(fn, steps, warmup):
+        for _ in range(warmup):
+            fn()
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            fn()
+        torch.cuda.synchronize(dev)
+        el = (time.perf_counter() - t0) * 1e3
+        if world > 1:
+            t = torch.tensor([el], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            el = float(t.item())
+        return el
+    e2e_steps = max(3, min(args.steps, 10))
+    ms_e2e = timed_host(step_e2e, e2e_steps, 2)
+
+    nodes_per_step = F * N * world
+    value = nodes_per_step * args.steps / (ms_total * 1e-3)
+    e2e_value = nodes_per_step * e2e_steps / (ms_e2e * 1e-3)
+
+    line = None
+    if rank == 0:
+        W = contract_flops_per_node(cfg, rank_ft)
+        peak = capi.measure_fp64_peak()
+        kernel_ms = ms_total / args.steps
+        achieved = (F * N * W) / (kernel_ms * 1e-3) / 1e12 if world == 1 else (value / world) * W / 1e12
+        hbm_bytes = F * N * 8.0 + F * (cfg.dx + 1) * 4.0 + core_cnt * 8.0
+        hbm_peak = None
+        try:
+            hbm_peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
+        except Exception:
+            hbm_peak = 6650.0
+        line = {
+            "metric": "bellman_node_backups_per_s", "value": value, "unit": "node-backups/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": workload_config(cfg, rank_ft, F, args),
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": "node-backups/s",
+                    "h2d_bytes_per_step": int(F * (cfg.dx + 1) * 4 * world), "d2h_bytes_per_step": int(F * N * 8 * world),
+                    "ms_per_step": ms_e2e / e2e_steps, "api": "c3sc_vi_batch (host buffers, pinned)"},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "fp64", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+                         "traffic": None, "flops_per_node_backup": W,
+                         "peak_source": "DFMA loop measured in this run (c3sc_measure_fp64_peak); MEASURED_PEAKS.json has no FP64 figure",
+                         "hbm": {"algorithmic_bytes_per_step": hbm_bytes, "achieved_gbs": hbm_bytes / (kernel_ms * 1e-3) / 1e9,
+                                 "peak_gbs": hbm_peak, "frac": hbm_bytes / (kernel_ms * 1e-3) / 1e9 / hbm_peak,
+                                 "note": "not binding: cores stay in L2/SMEM, HBM sees descriptors in and values out"}},
+        }
+
+    if args.sweep and world == 1:
+        batches = synthetic.sweep_fibers(cfg.ngrid, ranks)
+        dev_b = [(torch.from_numpy(a).to(dev), torch.from_numpy(b).to(dev), len(a)) for a, b in batches]
+
+        def sweep():
+            for a, b, f in dev_b:
+                prob.vi_batch_dev(vf, f, a.data_ptr(), b.data_ptr(), N, out_d.data_ptr(), stream=sptr)
+        ms_sw = timed(sweep, 10, 3) / 10
+        nodes_sw = sum(f for _, _, f in dev_b) * N
+        if line is not None:
+            line["vi_sweep"] = {"seconds": ms_sw * 1e-3, "node_backups": nodes_sw, "launches": len(dev_b),
+                                "node_backups_per_s": nodes_sw / (ms_sw * 1e-3),
+                                "what": "2 x d sequential core batches of r_k*r_{k+1} fibers (SURVEY §8(d))"}
+
+    if rank == 0 and not args.no_cpu_baseline and world == 1:
+        line["cpu_baseline"] = cpu_baseline(cfg, rank_ft, args.cpu_seconds)
+    if rank == 0:
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def cpu_baseline(cfg, rank_ft, budget_s):
+    """The reference's CPU path (oracle/_ref when present, else the oracle port) on a bounded
+    sample of the same workload, on this box's host cores."""
+    from c3sc_b200 import synthetic
+    from oracle import pyoracle as po
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from helpers import host_problem
+    ranks = cfg.ranks(rank_ft)
+    cores = synthetic.random_cores(cfg.ngrid, ranks)
+    ft = po.FT(cfg.ngrid, ranks, cores)
+    ncores = os.cpu_count() or 1
+    dv, fi = synthetic.random_fibers(cfg.ngrid, 4096)
+    if po.have_ref():
+        ref = po.Ref(cfg)
+        vf = ref.valuef(ft)
+        threads = ref.omp_threads()
+        _, s0 = ref.vi_fibers(vf, dv[:8], fi[:8], fresh_per_fiber=False)
+        nf = int(max(8, min(4000, budget_s / max(s0 / 8, 1e-6))))
+        _, secs = ref.vi_fibers(vf, dv[8:8 + nf], fi[8:8 + nf], fresh_per_fiber=False)
+        kind = "reference"
+        how = "oracle/_ref (reference sources compiled in place), one bellman_vi call per fiber, OpenMP over the nodes of a fiber"
+    else:
+        if not os.path.exists(po.PORT_PATH):
+            po.build_port()
+        xg, h, hmin, h2, t, olb, oub = host_problem(cfg)
+        port = po.Port(cfg, xg, h2, t, olb, oub)
+        threads = ncores
+        t0 = time.perf_counter(); port.vi_batch(ft, dv[:32], fi[:32], nthreads=threads); s0 = time.perf_counter() - t0
+        nf = int(max(32, min(4000, budget_s / max(s0 / 32, 1e-6))))
+        t0 = time.perf_counter(); port.vi_batch(ft, dv[32:32 + nf], fi[32:32 + nf], nthreads=threads); secs = time.perf_counter() - t0
+        kind = "port"
+        how = "oracle port (C restatement), OpenMP over fibers"
+    return {"value": nf * cfg.n / secs, "unit": "node-backups/s", "cores": threads, "kind": kind,
+            "sample": f"{nf} fibers x {cfg.n} nodes of the same workload in {secs:.1f} s; {how}; host has {ncores} cores"}
+
+
+if __name__ == "__main__":
+    main()

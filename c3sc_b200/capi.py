@@ -45,7 +45,7 @@ EXPORTS = [
     "c3sc_problem_create", "c3sc_problem_destroy", "c3sc_problem_check",
     "c3sc_valuef_create", "c3sc_valuef_update", "c3sc_valuef_device_buffer", "c3sc_valuef_destroy",
     "c3sc_vi_batch_dev", "c3sc_pi_batch_dev", "c3sc_vi_batch", "c3sc_vi_batch_debug", "c3sc_pi_batch",
-    "c3sc_transition_batch", "c3sc_model_eval",
+    "c3sc_transition_batch", "c3sc_model_eval", "c3sc_measure_fp64_peak",
 ]
 
 _lib = None
@@ -80,8 +80,16 @@ def lib() -> C.CDLL:
         L.c3sc_pi_batch.argtypes = [vp, vp, vp, sz, vp, vp, sz, i32, vp, vp, vp]
         L.c3sc_transition_batch.argtypes = [vp, sz, vp, vp, vp, vp, vp]
         L.c3sc_model_eval.argtypes = [vp, sz, vp, vp, vp, vp, vp, vp, vp]
+        L.c3sc_measure_fp64_peak.argtypes = [C.POINTER(C.c_double), i32, i32]
         _lib = L
     return _lib
+
+
+def measure_fp64_peak(iters: int = 8192, repeats: int = 5) -> float:
+    """TFLOP/s of a pure DFMA loop on the current device (roofline denominator)."""
+    v = C.c_double()
+    check(lib().c3sc_measure_fp64_peak(C.byref(v), iters, repeats))
+    return v.value
 
 
 class C3scError(RuntimeError):

@@ -110,6 +110,10 @@ const char *c3sc_version(void);
 /* kernels launched by this library since load (bench.py's gpu_launches) */
 uint64_t c3sc_launch_count(void);
 
+/* Best-of-`repeats` throughput of a pure DFMA loop on the current device, in
+ * TFLOP/s (FMA = 2 flop): the measured FP64-pipe roofline denominator.      */
+int c3sc_measure_fp64_peak(double *tflops, int iters, int repeats);
+
 /* ---- problem / value function ------------------------------------------ */
 int  c3sc_problem_create(const c3sc_problem_desc *desc, c3sc_problem **out);
 void c3sc_problem_destroy(c3sc_problem *p);

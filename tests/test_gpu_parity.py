@@ -1,0 +1,230 @@
+"""GPU parity: the CUDA path (through the C-ABI) against the CPU oracle on the same seeded
+inputs.  Bars (BASELINE.json north_star / SURVEY.md A8):
+  bit-exact   : absorbed flags, neighbour indices, transition-stencil structure, argmin index
+                (argmin: except ties within tolerance)
+  <= 1e-12 rel: neighbour costs, transition probabilities, dt, backed-up values
+                (relative to max(|ref|, largest magnitude in the same row/fiber) so entries
+                 that cancel to ~0 are judged against the terms that produced them)
+"""
+import numpy as np
+import pytest
+
+from c3sc_b200 import capi, configs, synthetic
+from oracle import pyoracle as po
+from helpers import SMALL, make_ft, make_port, rel_err, valid_mask
+
+pytestmark = pytest.mark.gpu
+RTOL = 1e-12
+
+
+def _argmin_ok(cfg, port, ft, dv, fi, arg, oarg, oval):
+    """identical argmin, or the two candidates' oracle values tie within RTOL"""
+    bad = np.argwhere(arg != oarg)
+    for f, j in bad:
+        if j >= cfg.ngrid[dv[f]]:
+            continue
+        out, ub, ab, costs = port.vi_fiber_full(ft, dv[f], fi[f])
+        x = port.fiber_points(dv[f], fi[f])[j]
+        import ctypes as C
+        vals = []
+        for cand in (arg[f, j], oarg[f, j]):
+            prob = np.zeros(2 * cfg.dx + 1); dt = C.c_double(); g = C.c_double(); st = C.c_int()
+            port.L.orc_control_value.restype = C.c_double
+            u = np.ascontiguousarray(cfg.controls[cand])
+            v = port.L.orc_control_value(C.byref(port.p), po._p(np.ascontiguousarray(x)), po._p(u), po._p(np.ascontiguousarray(costs[j])),
+                                         po._p(prob), C.byref(dt), C.byref(g), C.byref(st))
+            vals.append(v)
+        assert abs(vals[0] - vals[1]) <= RTOL * max(abs(vals[1]), np.abs(oval[f]).max()), (f, j, vals)
+    return len(bad)
+
+
+@pytest.mark.parametrize("arith", [0, 1], ids=["exact", "fast"])
+@pytest.mark.parametrize("name,n,rank,dx", SMALL)
+def test_vi_debug_against_oracle(gpu, name, n, rank, dx, arith):
+    cfg = configs.get_config(name, n=n, rank=rank, dx=dx)
+    prob = capi.Problem(cfg, arith=arith)
+    port = make_port(cfg)
+    ranks, cores, ft = make_ft(cfg)
+    vf = capi.ValueF(cfg.ngrid, ranks, cores)
+    dv, fi = synthetic.random_fibers(cfg.ngrid, 96, face_frac=0.25)
+    out = prob.vi_batch_debug(vf, dv, fi)
+    oval, oarg = port.vi_batch(ft, dv, fi)
+    m = valid_mask(cfg, dv)
+    for f in range(len(dv)):
+        N = int(cfg.ngrid[dv[f]])
+        ab, nv, nf = port.fiber_neighbors(dv[f], fi[f])
+        assert np.array_equal(out["absorbed"][f, :N], ab), f                      # bit-exact
+        assert np.array_equal(out["nbr_vary"][f, :N], nv), f
+        if cfg.dx > 1:
+            assert np.array_equal(out["nbr_fixed"][f, :cfg.dx - 1], nf), f
+        _, costs = port.neighbor_costs(ft, dv[f], fi[f])
+        assert rel_err(out["costs"][f, :N], costs, scale=np.abs(costs).max()) <= RTOL, f
+    assert rel_err(out["value"][m], oval[m], scale=np.abs(oval[m]).max()) <= RTOL
+    nbad = _argmin_ok(cfg, port, ft, dv, fi, out["argmin"], oarg, oval)
+    assert nbad <= 0.01 * m.sum()
+    prob.close(); vf.close()
+
+
+@pytest.mark.parametrize("name,n,rank,dx", SMALL)
+def test_policy_rows_bit_exact_in_exact_mode(gpu, name, n, rank, dx):
+    """EXACT arithmetic reproduces transition_assemble's operation order: p and dt at the
+    argmin are bit-identical to the oracle's policy rows wherever the drift itself is
+    (models without sin/cos); with sin/cos they agree to 1e-14."""
+    cfg = configs.get_config(name, n=n, rank=rank, dx=dx)
+    prob = capi.Problem(cfg, arith=0)
+    port = make_port(cfg)
+    ranks, cores, ft = make_ft(cfg)
+    vf = capi.ValueF(cfg.ngrid, ranks, cores)
+    dv, fi = synthetic.random_fibers(cfg.ngrid, 64, face_frac=0.2)
+    out = prob.vi_batch_debug(vf, dv, fi)
+    _, orows, oarg = port.pi_batch(ft, ft, dv, fi)
+    sel = (out["argmin"] == oarg) & (oarg >= 0) & valid_mask(cfg, dv)
+    assert sel.sum() > 0
+    g, o = out["rows"][sel], orows[sel]
+    if cfg.model in (configs.MODEL_LQGND, configs.MODEL_DOUBLE_INT):
+        assert np.array_equal(g, o)
+    else:
+        assert rel_err(g[:, :-3], o[:, :-3], scale=1e-3) <= 1e-13      # probabilities
+        assert np.abs(g[:, -3] - o[:, -3]).max() <= 1e-15              # p_self: round-off, absolute
+        assert rel_err(g[:, -2:], o[:, -2:]) <= 1e-14                  # dt, g
+    # stencil structure: which side received the drift term
+    assert np.array_equal(g[:, :-3:2] > g[:, 1:-3:2], o[:, :-3:2] > o[:, 1:-3:2])
+    prob.close(); vf.close()
+
+
+@pytest.mark.parametrize("arith", [0, 1], ids=["exact", "fast"])
+@pytest.mark.parametrize("name,n,rank,dx", SMALL)
+def test_pi_two_subiterations(gpu, name, n, rank, dx, arith):
+    cfg = configs.get_config(name, n=n, rank=rank, dx=dx)
+    prob = capi.Problem(cfg, arith=arith)
+    port = make_port(cfg)
+    ranks, c_pol, ft_pol = make_ft(cfg)
+    _, c_it, ft_it = make_ft(cfg, seed=0xABCD00)
+    _, c_it2, ft_it2 = make_ft(cfg, seed=0x777700)
+    vf_pol = capi.ValueF(cfg.ngrid, ranks, c_pol)
+    vf_it = capi.ValueF(cfg.ngrid, ranks, c_it)
+    dv, fi = synthetic.random_fibers(cfg.ngrid, 48, face_frac=0.2)
+    m = valid_mask(cfg, dv)
+    v1, rows, arg = prob.pi_batch(vf_pol, vf_it, dv, fi)
+    o1, orows, oarg = port.pi_batch(ft_pol, ft_it, dv, fi)
+    assert rel_err(v1[m], o1[m]) <= RTOL
+    assert (arg[m] == oarg[m]).mean() > 0.99
+    vf_it.update(c_it2)
+    v2, _, _ = prob.pi_batch(None, vf_it, dv, fi, rows=rows)
+    o2, _, _ = port.pi_batch(ft_pol, ft_it2, dv, fi, rows=orows)
+    assert rel_err(v2[m], o2[m]) <= RTOL
+    prob.close(); vf_pol.close(); vf_it.close()
+
+
+@pytest.mark.parametrize("arith", [0, 1], ids=["exact", "fast"])
+@pytest.mark.parametrize("dx", [2, 3, 5, 10])
+def test_transition_probabilities(gpu, dx, arith):
+    """tprob_test.c:327-364: probabilities >= -1e-15 and sum to 1 +- 1e-15; plus parity."""
+    name = {2: "lqg2d_new", 3: "dubinscar_new", 5: "skidding5d", 10: "lqgnd"}[dx]
+    cfg = configs.get_config(name, n=12, rank=2)
+    prob = capi.Problem(cfg, arith=arith)
+    port = make_port(cfg)
+    n = 4000
+    drift = (synthetic.uniform01(11, n * dx).reshape(n, dx) - 0.5) * 8.0
+    drift[::7, 0] = 0.0
+    drift[::11, dx - 1] = 5e-15                 # inside the 1e-14 dead band
+    drift[::13, dx - 1] = -2e-14                # just outside
+    sig = synthetic.uniform01(12, n * dx).reshape(n, dx) * 2.0
+    sig[::5, 0] = 0.0
+    p, dt, st = prob.transition(drift, sig)
+    op, odt, ost = port.transition(drift, sig)
+    assert np.array_equal(st, ost)
+    ok = ost == 0
+    assert (p[ok] >= -1e-15).all() and np.abs(p[ok].sum(axis=1) - 1.0).max() <= 1e-15
+    if arith == 0:
+        assert np.array_equal(p[ok], op[ok]) and np.array_equal(dt[ok], odt[ok])      # bit-exact
+    else:
+        assert rel_err(p[ok][:, :-1], op[ok][:, :-1], scale=1e-300) <= 1e-14
+        assert np.abs(p[ok][:, -1] - op[ok][:, -1]).max() <= 1e-15
+        assert rel_err(dt[ok], odt[ok], scale=1e-300) <= 1e-14
+    prob.close()
+
+
+@pytest.mark.parametrize("name,n,rank,dx", SMALL)
+def test_device_model_equals_host_callbacks(gpu, name, n, rank, dx):
+    """SURVEY §7 hard part 1: the device-resident model must equal the host callback on the grid."""
+    cfg = configs.get_config(name, n=n, rank=rank, dx=dx)
+    prob = capi.Problem(cfg, arith=0)
+    port = make_port(cfg)
+    ne = 3000
+    u01 = synthetic.uniform01(5, ne * cfg.dx).reshape(ne, cfg.dx)
+    x = cfg.lb + u01 * (cfg.ub - cfg.lb)
+    for i in range(min(ne, cfg.n)):                       # include true grid nodes
+        x[i] = [prob.xgrid[d][(i * (d + 3)) % cfg.n] for d in range(cfg.dx)]
+    u = cfg.controls[np.arange(ne) % cfg.nu]
+    g = prob.model_eval(x, u)
+    o = port.model_eval(x, u)
+    if cfg.model in (configs.MODEL_LQGND, configs.MODEL_DOUBLE_INT):
+        for a, b in zip(g, o):
+            assert np.array_equal(a, b)
+    else:
+        assert rel_err(g[0], o[0], scale=1.0) <= 4e-16 * 30      # sin/cos: <= 2 ulp of |drift| <= 27+10
+        for a, b in zip(g[1:], o[1:]):
+            assert np.array_equal(a, b)
+    prob.close()
+
+
+def test_full_size_configs(gpu):
+    """BASELINE.json full sizes: a few hundred fibers each against the oracle, plus
+    size-independent properties on a larger batch (idempotence, absorbed <-> boundcost,
+    PI(policy=V, iter=V) == VI(V))."""
+    for name in configs.ALL_CONFIGS:
+        cfg = configs.get_config(name)
+        prob = capi.Problem(cfg, arith=1)
+        port = make_port(cfg)
+        ranks, cores, ft = make_ft(cfg)
+        vf = capi.ValueF(cfg.ngrid, ranks, cores)
+        F = 40 if name == "lqgnd" else 200
+        dv, fi = synthetic.random_fibers(cfg.ngrid, F)
+        val, arg = prob.vi_batch(vf, dv, fi)
+        oval, oarg = port.vi_batch(ft, dv, fi)
+        assert rel_err(val, oval) <= RTOL, name
+        assert (arg == oarg).mean() > 0.999, name
+        # properties on a bigger batch
+        dv, fi = synthetic.random_fibers(cfg.ngrid, 2000, seed=99)
+        v1, a1 = prob.vi_batch(vf, dv, fi)
+        v2, a2 = prob.vi_batch(vf, dv, fi)
+        assert np.array_equal(v1, v2) and np.array_equal(a1, a2), "not deterministic"
+        p1, rows, pa = prob.pi_batch(vf, vf, dv, fi)
+        assert np.array_equal(pa, a1)
+        assert rel_err(p1, v1) <= 1e-13
+        prob.close(); vf.close()
+
+
+def test_quadratic_value_function_lqgnd(gpu):
+    """structured case of SURVEY §8(d): exact rank-2 FT of sum x_i^2 on the d=10 grid."""
+    cfg = configs.get_config("lqgnd_reflect", n=30)
+    prob = capi.Problem(cfg, arith=1)
+    port = make_port(cfg)
+    ranks, cores = synthetic.quadratic_cores(prob.xgrid)
+    vf = capi.ValueF(cfg.ngrid, ranks, cores)
+    ft = po.FT(cfg.ngrid, ranks, cores)
+    dv, fi = synthetic.random_fibers(cfg.ngrid, 30)
+    out = prob.vi_batch_debug(vf, dv, fi)
+    # neighbour costs are sums of squares of the neighbour coordinates
+    for f in range(len(dv)):
+        _, costs = port.neighbor_costs(ft, dv[f], fi[f])
+        assert rel_err(out["costs"][f], costs) <= RTOL
+        x = port.fiber_points(dv[f], fi[f])
+        assert rel_err(out["costs"][f][:, -1], (x * x).sum(axis=1)) <= 1e-13
+    oval, oarg = port.vi_batch(ft, dv, fi)
+    assert rel_err(out["value"], oval) <= RTOL
+    prob.close(); vf.close()
+
+
+def test_errors_are_loud(gpu):
+    cfg = configs.get_config("lqg2d_new", n=10, rank=2)
+    prob = capi.Problem(cfg)
+    ranks, cores, ft = make_ft(cfg)
+    bad = configs.get_config("lqg2d_new", n=11, rank=2)
+    r2, c2, _ = make_ft(bad)
+    vf_bad = capi.ValueF(bad.ngrid, r2, c2)
+    dv, fi = synthetic.random_fibers(cfg.ngrid, 4)
+    with pytest.raises(capi.C3scError):
+        prob.vi_batch(vf_bad, dv, fi)
+    prob.close(); vf_bad.close()
