@@ -12,6 +12,9 @@ namespace c3sc {
 int launch_backup_lqg_lo(int dx, int arith, const LaunchArgs &a, cudaStream_t st);
 int launch_backup_lqg_hi(int dx, int arith, const LaunchArgs &a, cudaStream_t st);
 int launch_backup_misc(int model, int dx, int arith, const LaunchArgs &a, cudaStream_t st);
+int build_ctab_lqg_lo(int dx, const DevProblem &P, double *ctab, cudaStream_t st);
+int build_ctab_lqg_hi(int dx, const DevProblem &P, double *ctab, cudaStream_t st);
+int build_ctab_misc(int model, int dx, const DevProblem &P, double *ctab, cudaStream_t st);
 int launch_model_eval_lqg_lo(int dx, const DevProblem &P, int n, const double *x, const double *u, double *drift,
                              double *sig, double *stage, double *bound, double *obs, cudaStream_t st);
 int launch_model_eval_lqg_hi(int dx, const DevProblem &P, int n, const double *x, const double *u, double *drift,
@@ -58,7 +61,7 @@ struct DevBuf {
 struct c3sc_problem {
     DevProblem P;
     int model, arith;
-    double *d_xgrid = nullptr, *d_obs = nullptr, *d_utab = nullptr;
+    double *d_xgrid = nullptr, *d_obs = nullptr, *d_utab = nullptr, *d_ctab = nullptr;
     int *d_err = nullptr;
     cudaStream_t stream = nullptr;           // host-buffer entry points run here
     DevBuf b_dv, b_fi, b_val, b_arg, b_abs, b_costs, b_rows, b_nv, b_nf, b_misc[8];
@@ -152,8 +155,30 @@ int c3sc_problem_create(const c3sc_problem_desc *d, c3sc_problem **out)
     CKP(cudaMalloc(&p->d_err, sizeof(int)));
     CKP(cudaMemset(p->d_err, 0, sizeof(int)));
     CKP(cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking));
-#undef CKP
     P.xgrid = p->d_xgrid; P.obs = p->d_obs; P.utab = p->d_utab; P.err = p->d_err;
+    // candidate table of separable models (row stride 2*NUD+2; NUD = dx/2 for LQG, 1 otherwise)
+    {
+        const int nud = (d->model == C3SC_MODEL_LQGND) ? (int)d->dx / 2 : (d->model == C3SC_MODEL_SKID5D ? 0 : 1);
+        const int ct = 2 * nud + 2;
+        CKP(cudaMalloc(&p->d_ctab, (size_t)d->nu * ct * sizeof(double)));
+        CKP(cudaMemset(p->d_ctab, 0, (size_t)d->nu * ct * sizeof(double)));
+        P.ctab = p->d_ctab;
+        P.amin = 0.0;
+        int rc;
+        if (d->model == C3SC_MODEL_LQGND) rc = (P.dx <= 6) ? build_ctab_lqg_lo(P.dx, P, p->d_ctab, 0) : build_ctab_lqg_hi(P.dx, P, p->d_ctab, 0);
+        else rc = build_ctab_misc(d->model, P.dx, P, p->d_ctab, 0);
+        if (rc == -1) { c3sc_problem_destroy(p); return fail(C3SC_EUNSUPPORTED, "model %d with dx=%u is not instantiated", d->model, d->dx); }
+        if (rc != 0) { c3sc_problem_destroy(p); return fail(C3SC_ECUDA, "candidate table kernel: %s", cudaGetErrorString((cudaError_t)rc)); }
+        if (nud > 0) {
+            g_launches++;
+            std::vector<double> tab((size_t)d->nu * ct);
+            CKP(cudaMemcpy(tab.data(), p->d_ctab, tab.size() * sizeof(double), cudaMemcpyDeviceToHost));
+            double amin = tab[2 * nud];
+            for (uint32_t c = 1; c < d->nu; c++) amin = tab[(size_t)c * ct + 2 * nud] < amin ? tab[(size_t)c * ct + 2 * nud] : amin;
+            P.amin = amin;
+        }
+    }
+#undef CKP
     *out = p;
     return C3SC_OK;
 }
@@ -161,7 +186,7 @@ int c3sc_problem_create(const c3sc_problem_desc *d, c3sc_problem **out)
 void c3sc_problem_destroy(c3sc_problem *p)
 {
     if (!p) return;
-    cudaFree(p->d_xgrid); cudaFree(p->d_obs); cudaFree(p->d_utab); cudaFree(p->d_err);
+    cudaFree(p->d_xgrid); cudaFree(p->d_obs); cudaFree(p->d_utab); cudaFree(p->d_err); cudaFree(p->d_ctab);
     DevBuf *bufs[] = {&p->b_dv, &p->b_fi, &p->b_val, &p->b_arg, &p->b_abs, &p->b_costs, &p->b_rows, &p->b_nv, &p->b_nf};
     for (DevBuf *b : bufs) b->release();
     for (DevBuf &b : p->b_misc) b.release();

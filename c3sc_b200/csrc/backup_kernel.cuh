@@ -29,25 +29,34 @@ __host__ __device__ inline int odd_up(int v) { return v | 1; }
 
 // ---------------------------------------------------------------------------
 // shared-memory carve-up (all offsets in doubles / ints); identical on host+device
+constexpr int PMAX = 8;              // max candidate chunks ("parts") per node
+
 struct SmemPlan {
     int rs;        // padded (odd) vector stride
     int cs;        // cost-row stride (2dx+1, odd already)
-    int oL, oR, oNb, oTmp, oW, oU, oC, oV, oUtab, nDoubles;
+    int ns;        // per-node invariant stride (odd)
+    int oL, oR, oNb, oTmp, oC, oV, oScr, nDoubles;
+    int oW, oU;                    // FT phase view of the scratch region
+    int oNode, oBestV, oBestI;     // control phase view of the scratch region (oBestI in doubles)
     int oAbs, oNv, oAct, oNf, oFix, oMisc, nInts;
-    __host__ __device__ SmemPlan(int dx, int du, int nu, int nmax, int rmax)
+    __host__ __device__ SmemPlan(int dx, int nud, int nmax, int rmax)
     {
         rs = odd_up(rmax);
         cs = 2 * dx + 1;
+        ns = odd_up(2 * nud + 3);
         int o = 0;
         oL = o;    o += (dx + 1) * rs;
         oR = o;    o += (dx + 1) * rs;
         oNb = o;   o += 2 * dx * rs;
         oTmp = o;  o += NW * 2 * rs;
-        oW = o;    o += nmax * rs;
-        oU = o;    o += nmax * rs;
         oC = o;    o += nmax * cs;
         oV = o;    o += nmax;
-        oUtab = o; o += nu * du;
+        oScr = o;
+        oW = oScr; oU = oW + nmax * rs;
+        const int ft_need = 2 * nmax * rs;
+        oNode = oScr; oBestV = oNode + nmax * ns; oBestI = oBestV + PMAX * nmax;
+        const int ctl_need = nmax * ns + PMAX * nmax + (PMAX * nmax + 1) / 2;
+        o += ft_need > ctl_need ? ft_need : ctl_need;
         nDoubles = o;
         int q = 0;
         oAbs = q;  q += nmax;
@@ -60,6 +69,44 @@ struct SmemPlan {
     }
     __host__ __device__ size_t bytes() const { return (size_t)nDoubles * 8 + (size_t)nInts * 4; }
 };
+
+// ---------------------------------------------------------------------------
+// fast reciprocal and exp for the FAST policy (both ~1 ulp)
+__device__ __forceinline__ double rcp_pos(double x)
+{   // x > 0, normal: MUFU.RCP64H seed (~2^-20) + two Newton steps
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    double e = fma(-x, y, 1.0);
+    y = fma(y, e, y);
+    e = fma(-x, y, 1.0);
+    return fma(y, e, y);
+}
+__device__ __forceinline__ double exp_nonpos(double x)
+{   // exp(x) for x <= 0: n = rint(x*log2 e), r = x - n ln2 (Cody-Waite), degree-13 Taylor on
+    // |r| <= ln2/2 (truncation 4e-18), scale by adding n to the exponent field.  No overflow
+    // path is needed for x <= 0; below -708 the result is flushed to 0.
+    const double t = fma(x, 1.4426950408889634, 6755399441055744.0);
+    const double n = t - 6755399441055744.0;
+    double r = fma(n, -6.93147180369123816490e-01, x);
+    r = fma(n, -1.90821492927058770002e-10, r);
+    double p = 1.6059043836821613e-10;            // 1/13!
+    p = fma(p, r, 2.08767569878681e-09);          // 1/12!
+    p = fma(p, r, 2.505210838544172e-08);         // 1/11!
+    p = fma(p, r, 2.755731922398589e-07);         // 1/10!
+    p = fma(p, r, 2.7557319223985893e-06);        // 1/9!
+    p = fma(p, r, 2.48015873015873e-05);          // 1/8!
+    p = fma(p, r, 1.984126984126984e-04);         // 1/7!
+    p = fma(p, r, 1.388888888888889e-03);         // 1/6!
+    p = fma(p, r, 8.333333333333333e-03);         // 1/5!
+    p = fma(p, r, 4.1666666666666664e-02);        // 1/4!
+    p = fma(p, r, 1.6666666666666666e-01);        // 1/3!
+    p = fma(p, r, 0.5);
+    p = fma(p, r, 1.0);
+    p = fma(p, r, 1.0);
+    const int ni = __double2loint(t);
+    const double res = __hiloint2double(__double2hiint(p) + (ni << 20), __double2loint(p));
+    return (x < -708.0) ? 0.0 : res;
+}
 
 // ---------------------------------------------------------------------------
 // transition_assemble (src/nodeutil.c:284-309,365-371,396-402), all dims in order.
@@ -204,7 +251,7 @@ __device__ __forceinline__ void warp_matvec(int m, int n, const double *__restri
 
 // ---------------------------------------------------------------------------
 template <class M, class A>
-__global__ void __launch_bounds__(NT) k_backup(const LaunchArgs a, const int G)
+__global__ void __launch_bounds__(NT) k_backup(const LaunchArgs a)
 {
     constexpr int DX = M::DX, DU = M::DU, CS = 2 * DX + 1, RW = 2 * DX + 3;
     const DevProblem &P = a.P;
@@ -212,16 +259,15 @@ __global__ void __launch_bounds__(NT) k_backup(const LaunchArgs a, const int G)
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
     extern __shared__ double smem[];
-    const SmemPlan sp(DX, DU, P.nu, P.nmax, ft.rmax);
+    const SmemPlan sp(DX, M::NUD, P.nmax, ft.rmax);
     double *sL = smem + sp.oL, *sR = smem + sp.oR, *sNb = smem + sp.oNb, *sTmp = smem + sp.oTmp;
     double *sW = smem + sp.oW, *sU = smem + sp.oU, *sC = smem + sp.oC, *sV = smem + sp.oV;
-    double *sUtab = smem + sp.oUtab;
+    double *sNode = smem + sp.oNode, *sBestV = smem + sp.oBestV;
+    int *sBestI = reinterpret_cast<int *>(smem + sp.oBestI);
     int *ismem = reinterpret_cast<int *>(smem + sp.nDoubles);
     int *sAbs = ismem + sp.oAbs, *sNv = ismem + sp.oNv, *sAct = ismem + sp.oAct, *sNf = ismem + sp.oNf;
     int *sMisc = ismem + sp.oMisc, *sFix = ismem + sp.oFix;
     const int rs = sp.rs;
-
-    for (int i = tid; i < P.nu * DU; i += NT) sUtab[i] = P.utab[i];
 
     for (int f = blockIdx.x; f < a.F; f += gridDim.x) {
         __syncthreads();                       // previous fiber fully consumed
@@ -434,71 +480,174 @@ __global__ void __launch_bounds__(NT) k_backup(const LaunchArgs a, const int G)
             }
         }
 
-        // ---- 3. min over the control table, G lanes per node -------------------
+        // ---- 3. min over the control table -------------------------------------
+        // work item = (candidate chunk "part", active node); a thread walks the candidates of
+        // its chunk sequentially, so the first strict minimum in table order is kept
+        // (bellman.c:539-543 + brute-force c3opt_minimize).  Items are ordered part-major: a warp
+        // sees one chunk, so candidate-table reads are warp-uniform.
         const int nact = sMisc[0];
-        const int ngroups = NT / G, grp = tid / G, gl = tid - grp * G;
-        const unsigned gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << ((lane / G) * G));
-        for (int it = grp; it < nact; it += ngroups) {
-            const int j = sAct[it];
-            double x[DX], c[CS];
+        int parts = nact > 0 ? (2 * NT) / nact : 1;
+        parts = parts < 1 ? 1 : (parts > PMAX ? PMAX : parts);
+        if (parts > P.nu) parts = P.nu;
+        const int chunk = (P.nu + parts - 1) / parts;
+        constexpr bool TAB = M::SEP && !A::exact;
+        constexpr int NUD = M::NUD, CT = 2 * NUD + 2;
+        const int NS = sp.ns;
+        if (TAB) {
+            // per-node invariants: norm0 = sum over all dims of the control-independent part of
+            // (pl+pr), S0 = the matching part of <raw p, V_nbr>, gx = stage_x, then the 2*NUD
+            // neighbour values the candidates weight.
+            __syncthreads();                    // scratch region changes owner (sW/sU -> sNode)
+            for (int idx = tid; idx < nact; idx += NT) {
+                const int j = sAct[idx];
+                double x[DX], u0[DU], b0[DX], s0[DX];
 #pragma unroll
-            for (int i = 0; i < DX; i++) x[i] = P.xgrid[P.xoff[i] + (i == k ? j : fix[i])];
+                for (int i = 0; i < DX; i++) x[i] = P.xgrid[P.xoff[i] + (i == k ? j : fix[i])];
 #pragma unroll
-            for (int m = 0; m < CS; m++) c[m] = sC[j * CS + m];
-            NodeInv<M> inv;
-            node_prepare<M, A>(P, sUtab, x, c, inv);
-            double best = CUDART_INF;
-            int ibest = 0x7fffffff, bad = 0;
-            for (int cand = gl; cand < P.nu; cand += G) {
-                double u[DU];
+                for (int i = 0; i < DU; i++) u0[i] = __ldg(P.utab + i);
+                M::template drift<A>(x, u0, P.mp, b0);
+                M::template sigma<A>(x, u0, P.mp, s0);
+                double norm0 = 0.0, S0 = 0.0;
+                const double *c = sC + j * CS;
 #pragma unroll
-                for (int i = 0; i < DU; i++) u[i] = sUtab[cand * DU + i];
-                const double v = candidate_value<M, A>(P, x, u, c, inv, bad);
-                if (v < best) { best = v; ibest = cand; }
-            }
-            for (int off = G >> 1; off > 0; off >>= 1) {     // first strict minimum in table order
-                const double ov = __shfl_xor_sync(gmask, best, off);
-                const int oi = __shfl_xor_sync(gmask, ibest, off);
-                if (ov < best || (ov == best && oi < ibest)) { best = ov; ibest = oi; }
-            }
-            if (bad) atomicOr(P.err, 1);
-            if (gl == 0) {
-                if (a.write_value) a.out.value[obase + j] = best;
-                if (a.out.argmin) a.out.argmin[obase + j] = ibest;
-                if (a.out.rows) {                           // policy row at u* (bellman.c:1851-1860)
-                    double u[DU], b[DX], s[DX], prob[CS], dt;
-#pragma unroll
-                    for (int i = 0; i < DU; i++) u[i] = sUtab[(ibest < P.nu ? ibest : 0) * DU + i];
-                    M::template drift<A>(x, u, P.mp, b);
-                    M::template sigma<A>(x, u, P.mp, s);
-                    const double g = M::template stage<A>(x, u, P.mp);
-                    if (transition_row<DX, A>(P, b, s, prob, dt)) atomicOr(P.err, 1);
-                    double *row = a.out.rows + (obase + j) * RW;
-#pragma unroll
-                    for (int m = 0; m < CS; m++) row[m] = prob[m];
-                    row[CS] = dt;
-                    row[CS + 1] = g;
+                for (int i = 0; i < DX; i++) {
+                    const double q = (P.t[2 * i + 1] * 0.5) * (s0[i] * s0[i]);
+                    double rl = q, rr = q;
+                    if (!M::u_dep(i)) {
+                        const double tb = P.t[2 * i] * b0[i];
+                        rl = q - ((b0[i] < -1e-14) ? tb : 0.0);
+                        rr = q + ((b0[i] > 1e-14) ? tb : 0.0);
+                    }
+                    norm0 += rl + rr;
+                    S0 = fma(rl, c[2 * i], S0);
+                    S0 = fma(rr, c[2 * i + 1], S0);
                 }
+                double *nd = sNode + idx * NS;
+                nd[0] = norm0; nd[1] = S0; nd[2] = M::stage_x(x, P.mp);
+#pragma unroll
+                for (int m = 0; m < NUD; m++) { nd[3 + 2 * m] = c[2 * M::ud(m)]; nd[4 + 2 * m] = c[2 * M::ud(m) + 1]; }
+                if (norm0 + P.amin < 1e-14) atomicOr(P.err, 1);
+            }
+        }
+        __syncthreads();
+        for (int it = tid; it < nact * parts; it += NT) {
+            const int part = it / nact, idx = it - part * nact;
+            const int c0 = part * chunk, c1 = (c0 + chunk < P.nu) ? c0 + chunk : P.nu;
+            double best = CUDART_INF;
+            int ibest = 0x7fffffff;
+            if (TAB) {
+                const double *nd = sNode + idx * NS;
+                const double norm0 = nd[0], S0 = nd[1], gx = nd[2];
+                double cu[2 * NUD];
+#pragma unroll
+                for (int m = 0; m < 2 * NUD; m++) cu[m] = nd[3 + m];
+                const bool disc = P.beta != 0.0;
+                for (int cand = c0; cand < c1; cand++) {
+                    const double2 *row = reinterpret_cast<const double2 *>(P.ctab + (size_t)cand * CT);
+                    double S = S0;
+#pragma unroll
+                    for (int m = 0; m < NUD; m++) {
+                        const double2 w = __ldg(row + m);
+                        S = fma(w.x, cu[2 * m], S);
+                        S = fma(w.y, cu[2 * m + 1], S);
+                    }
+                    const double2 ag = __ldg(row + NUD);
+                    const double rinv = rcp_pos(norm0 + ag.x);
+                    const double dt = P.h2 * rinv;
+                    const double ebt = disc ? exp_nonpos(-P.beta * dt) : 1.0;
+                    const double v = fma(dt, gx + ag.y, ebt * (S * rinv));
+                    if (v < best) { best = v; ibest = cand; }
+                }
+            } else {
+                const int j = sAct[idx];
+                double x[DX], c[CS];
+#pragma unroll
+                for (int i = 0; i < DX; i++) x[i] = P.xgrid[P.xoff[i] + (i == k ? j : fix[i])];
+#pragma unroll
+                for (int m = 0; m < CS; m++) c[m] = sC[j * CS + m];
+                NodeInv<M> inv;
+                node_prepare<M, A>(P, P.utab, x, c, inv);
+                int bad = 0;
+                for (int cand = c0; cand < c1; cand++) {
+                    double u[DU];
+#pragma unroll
+                    for (int i = 0; i < DU; i++) u[i] = __ldg(P.utab + (size_t)cand * DU + i);
+                    const double v = candidate_value<M, A>(P, x, u, c, inv, bad);
+                    if (v < best) { best = v; ibest = cand; }
+                }
+                if (bad) atomicOr(P.err, 1);
+            }
+            sBestV[part * P.nmax + idx] = best;
+            sBestI[part * P.nmax + idx] = ibest;
+        }
+        __syncthreads();
+        for (int idx = tid; idx < nact; idx += NT) {
+            const int j = sAct[idx];
+            double best = sBestV[idx];
+            int ibest = sBestI[idx];
+            for (int pp = 1; pp < parts; pp++) {          // chunks in table order, strict '<'
+                const double v = sBestV[pp * P.nmax + idx];
+                if (v < best) { best = v; ibest = sBestI[pp * P.nmax + idx]; }
+            }
+            if (a.write_value) a.out.value[obase + j] = best;
+            if (a.out.argmin) a.out.argmin[obase + j] = ibest;
+            if (a.out.rows) {                               // policy row at u* (bellman.c:1851-1860)
+                double x[DX], u[DU], b[DX], s[DX], prob[CS], dt;
+#pragma unroll
+                for (int i = 0; i < DX; i++) x[i] = P.xgrid[P.xoff[i] + (i == k ? j : fix[i])];
+#pragma unroll
+                for (int i = 0; i < DU; i++) u[i] = P.utab[(size_t)(ibest < P.nu ? ibest : 0) * DU + i];
+                M::template drift<A>(x, u, P.mp, b);
+                M::template sigma<A>(x, u, P.mp, s);
+                const double g = M::template stage<A>(x, u, P.mp);
+                if (transition_row<DX, A>(P, b, s, prob, dt)) atomicOr(P.err, 1);
+                double *row = a.out.rows + (obase + j) * RW;
+#pragma unroll
+                for (int m = 0; m < CS; m++) row[m] = prob[m];
+                row[CS] = dt;
+                row[CS + 1] = g;
             }
         }
     }
 }
 
-// ---------------------------------------------------------------------------
-// choose lanes-per-node: minimise rounds(controls) x rounds(nodes), prefer wider groups
-inline int pick_group(int nu, int nmax)
+// Candidate table of a separable model (FAST only): row c = [Wl_0, Wr_0, .., Wl_{NUD-1}, Wr_{NUD-1}, A, gu]
+//   Wl_m / Wr_m = t_i*|b_i(u_c)| on the side the upwind scheme adds it to (0 inside the 1e-14 dead band),
+//   A = sum of the W's (the candidate's share of the normaliser), gu = stage_u(u_c).
+template <class M>
+__global__ void k_build_ctab(const DevProblem P, double *ctab)
 {
-    int best = 32, bestc = 1 << 30;
-    for (int G = 32; G >= 1; G >>= 1) {
-        const int cr = (nu + G - 1) / G, groups = NT / G;
-        const int nodes = (nmax * 9 + 9) / 10;
-        const int nr = (nodes + groups - 1) / groups;
-        const int cost = cr * nr;
-        if (cost < bestc) { bestc = cost; best = G; }
+    constexpr int DX = M::DX, DU = M::DU, NUD = M::NUD, CT = 2 * NUD + 2;
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= P.nu) return;
+    double x[DX], u[DU], b[DX];
+    for (int i = 0; i < DX; i++) x[i] = 0.0;           // SEP: drift of ud(m) does not read x
+    for (int i = 0; i < DU; i++) u[i] = P.utab[(size_t)c * DU + i];
+    M::template drift<Fast>(x, u, P.mp, b);
+    double A = 0.0;
+    for (int m = 0; m < NUD; m++) {
+        const int i = M::ud(m);
+        const double tb = P.t[2 * i] * b[i];
+        const double wl = (b[i] < -1e-14) ? -tb : 0.0, wr = (b[i] > 1e-14) ? tb : 0.0;
+        ctab[(size_t)c * CT + 2 * m] = wl;
+        ctab[(size_t)c * CT + 2 * m + 1] = wr;
+        A += wl + wr;
     }
-    return best;
+    ctab[(size_t)c * CT + 2 * NUD] = A;
+    ctab[(size_t)c * CT + 2 * NUD + 1] = M::stage_u(u, P.mp);
 }
 
+template <class M>
+int build_ctab_t(const DevProblem &P, double *ctab, cudaStream_t st)
+{
+    if (!M::SEP) return 0;
+    k_build_ctab<M><<<(P.nu + 127) / 128, 128, 0, st>>>(P, ctab);
+    return (int)cudaGetLastError();
+}
+template <class M>
+constexpr int ctab_stride() { return 2 * M::NUD + 2; }
+
+// ---------------------------------------------------------------------------
 template <class M, class A>
 int launch_backup_t(const LaunchArgs &a, cudaStream_t st)
 {
@@ -509,7 +658,7 @@ int launch_backup_t(const LaunchArgs &a, cudaStream_t st)
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
         cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
     }
-    const SmemPlan sp(M::DX, M::DU, a.P.nu, a.P.nmax, a.ft.rmax);
+    const SmemPlan sp(M::DX, M::NUD, a.P.nmax, a.ft.rmax);
     const size_t smem = sp.bytes();
     if (smem > (size_t)max_optin) return (int)cudaErrorInvalidValue;
     cudaError_t e = cudaFuncSetAttribute(k_backup<M, A>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -521,8 +670,7 @@ int launch_backup_t(const LaunchArgs &a, cudaStream_t st)
     int grid = sms * per_sm;
     if (grid > a.F) grid = a.F;
     if (grid < 1) return 0;
-    const int G = pick_group(a.P.nu, a.P.nmax);
-    k_backup<M, A><<<grid, NT, smem, st>>>(a, G);
+    k_backup<M, A><<<grid, NT, smem, st>>>(a);
     return (int)cudaGetLastError();
 }
 

@@ -20,6 +20,8 @@ struct DevProblem {
     const double *xgrid;     // device, concatenated
     const double *obs;       // device, [nobs][2][dx]: lb then ub
     const double *utab;      // device, [nu*du]
+    const double *ctab;      // device, candidate table of a separable model (FAST), see k_build_ctab
+    double amin;             // min over candidates of the table's normaliser share
     int *err;                // device error word (norm < 1e-14 seen)
 };
 

@@ -20,4 +20,13 @@ int launch_model_eval_lqg_hi(int dx, const DevProblem &P, int n, const double *x
     }
     return -1;
 }
+int build_ctab_lqg_hi(int dx, const DevProblem &P, double *ctab, cudaStream_t st)
+{
+    switch (dx) {
+    case 8: return build_ctab_t<LqgNd<8>>(P, ctab, st);
+    case 10: return build_ctab_t<LqgNd<10>>(P, ctab, st);
+    case 12: return build_ctab_t<LqgNd<12>>(P, ctab, st);
+    }
+    return -1;
+}
 }  // namespace c3sc

@@ -20,4 +20,13 @@ int launch_model_eval_lqg_lo(int dx, const DevProblem &P, int n, const double *x
     }
     return -1;
 }
+int build_ctab_lqg_lo(int dx, const DevProblem &P, double *ctab, cudaStream_t st)
+{
+    switch (dx) {
+    case 2: return build_ctab_t<LqgNd<2>>(P, ctab, st);
+    case 4: return build_ctab_t<LqgNd<4>>(P, ctab, st);
+    case 6: return build_ctab_t<LqgNd<6>>(P, ctab, st);
+    }
+    return -1;
+}
 }  // namespace c3sc

@@ -33,6 +33,22 @@ int launch_model_eval_misc(int model, int dx, const DevProblem &P, int n, const 
     return -1;
 }
 
+int build_ctab_misc(int model, int dx, const DevProblem &P, double *ctab, cudaStream_t st)
+{
+    switch (model) {
+    case C3SC_MODEL_DOUBLE_INT:
+        switch (dx) {
+        case 2: return build_ctab_t<DoubleInt<2>>(P, ctab, st);
+        case 3: return build_ctab_t<DoubleInt<3>>(P, ctab, st);
+        case 4: return build_ctab_t<DoubleInt<4>>(P, ctab, st);
+        }
+        return -1;
+    case C3SC_MODEL_DUBINS: return dx == 3 ? build_ctab_t<Dubins>(P, ctab, st) : -1;
+    case C3SC_MODEL_SKID5D: return dx == 5 ? 0 : -1;
+    }
+    return -1;
+}
+
 template <int DX>
 static int tr(int arith, const DevProblem &P, int n, const double *drift, const double *sig, double *prob,
               double *dt, int *status, cudaStream_t st)

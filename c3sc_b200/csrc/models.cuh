@@ -8,6 +8,12 @@
 //
 // u_dep(i): does drift_i or sigma_ii depend on the control?  Dimensions with
 // u_dep==false are evaluated once per node instead of once per candidate.
+//
+// Separable models (SEP): for the NUD control-dependent dimensions ud(m) the
+// drift depends on u ONLY, sigma does not depend on u, and the stage cost
+// splits as stage_x(x) + stage_u(u).  Then everything control-dependent is a
+// property of the candidate alone and is tabulated once per problem
+// (k_build_ctab); FAST arithmetic uses the table, EXACT never does.
 #pragma once
 #include "arith.cuh"
 
@@ -18,7 +24,10 @@ namespace c3sc {
 template <int DX_>
 struct LqgNd {
     static constexpr int DX = DX_, DU = DX_ / 2, ID = C3SC_MODEL_LQGND;
+    static constexpr bool SEP = true;            // see "separable models" below
+    static constexpr int NUD = DX_ / 2;
     __host__ __device__ static constexpr bool u_dep(int i) { return (i & 1) != 0; }
+    __host__ __device__ static constexpr int ud(int m) { return 2 * m + 1; }
     template <class A>
     __device__ __forceinline__ static void drift(const double *x, const double *u, const double *, double *b)
     {
@@ -41,6 +50,20 @@ struct LqgNd {
         for (int i = 0; i < DU; i++) g = A::mad(u[i], u[i], g);
         return g;
     }
+    __device__ __forceinline__ static double stage_x(const double *x, const double *)
+    {
+        double g = 0.0;
+#pragma unroll
+        for (int i = 0; i < DX; i++) g = fma(x[i], x[i], g);
+        return g;
+    }
+    __device__ __forceinline__ static double stage_u(const double *u, const double *)
+    {
+        double g = 0.0;
+#pragma unroll
+        for (int i = 0; i < DU; i++) g = fma(u[i], u[i], g);
+        return g;
+    }
     __device__ __forceinline__ static double boundcost(const double *, const double *mp) { return mp[2]; }
     __device__ __forceinline__ static double obscost(const double *, const double *mp) { return mp[3]; }
 };
@@ -49,7 +72,12 @@ struct LqgNd {
 template <int DX_>
 struct DoubleInt {
     static constexpr int DX = DX_, DU = 1, ID = C3SC_MODEL_DOUBLE_INT;
+    static constexpr bool SEP = true;
+    static constexpr int NUD = 1;
     __host__ __device__ static constexpr bool u_dep(int i) { return i == DX_ - 1; }
+    __host__ __device__ static constexpr int ud(int) { return DX_ - 1; }
+    __device__ __forceinline__ static double stage_x(const double *, const double *) { return 1.0; }
+    __device__ __forceinline__ static double stage_u(const double *, const double *) { return 0.0; }
     template <class A>
     __device__ __forceinline__ static void drift(const double *x, const double *u, const double *, double *b)
     {
@@ -73,7 +101,12 @@ struct DoubleInt {
 // examples/dubinscar_new/dubinscar.c:40-121; mp = [s_xy, s_theta, stage, boundcost, obscost]
 struct Dubins {
     static constexpr int DX = 3, DU = 1, ID = C3SC_MODEL_DUBINS;
+    static constexpr bool SEP = true;
+    static constexpr int NUD = 1;
     __host__ __device__ static constexpr bool u_dep(int i) { return i == 2; }
+    __host__ __device__ static constexpr int ud(int) { return 2; }
+    __device__ __forceinline__ static double stage_x(const double *, const double *mp) { return mp[2]; }
+    __device__ __forceinline__ static double stage_u(const double *, const double *) { return 0.0; }
     template <class A>
     __device__ __forceinline__ static void drift(const double *x, const double *u, const double *, double *b)
     {
@@ -95,7 +128,12 @@ struct Dubins {
 // examples/skidding5d/scar.c:39-176 (order = {0,1,2,3,4}); mp = [obscost]
 struct Skid5d {
     static constexpr int DX = 5, DU = 1, ID = C3SC_MODEL_SKID5D;
+    static constexpr bool SEP = false;           // drift_3, drift_4 mix x and u
+    static constexpr int NUD = 2;
     __host__ __device__ static constexpr bool u_dep(int i) { return i >= 3; }
+    __host__ __device__ static constexpr int ud(int m) { return 3 + m; }
+    __device__ __forceinline__ static double stage_x(const double *, const double *) { return 0.0; }
+    __device__ __forceinline__ static double stage_u(const double *, const double *) { return 0.0; }
     template <class A>
     __device__ __forceinline__ static void drift(const double *x, const double *u, const double *, double *b)
     {
