@@ -46,6 +46,8 @@ EXPORTS = [
     "c3sc_valuef_create", "c3sc_valuef_update", "c3sc_valuef_device_buffer", "c3sc_valuef_destroy",
     "c3sc_vi_batch_dev", "c3sc_pi_batch_dev", "c3sc_vi_batch", "c3sc_vi_batch_debug", "c3sc_pi_batch",
     "c3sc_transition_batch", "c3sc_model_eval", "c3sc_measure_fp64_peak",
+    "c3sc_neighbor_costs_batch", "c3sc_node_backup_batch", "c3sc_control_value_batch", "c3sc_rhs_batch",
+    "c3sc_transition_raw", "c3sc_ft_fiber_nn_batch",
 ]
 
 _lib = None
@@ -80,6 +82,12 @@ def lib() -> C.CDLL:
         L.c3sc_pi_batch.argtypes = [vp, vp, vp, sz, vp, vp, sz, i32, vp, vp, vp]
         L.c3sc_transition_batch.argtypes = [vp, sz, vp, vp, vp, vp, vp]
         L.c3sc_model_eval.argtypes = [vp, sz, vp, vp, vp, vp, vp, vp, vp]
+        L.c3sc_neighbor_costs_batch.argtypes = [vp, vp, sz, vp, vp, sz, vp, vp, vp, vp]
+        L.c3sc_node_backup_batch.argtypes = [vp, sz, vp, vp, vp, vp, vp]
+        L.c3sc_control_value_batch.argtypes = [vp, sz, vp, vp, vp, vp]
+        L.c3sc_rhs_batch.argtypes = [i32, C.c_uint32, C.c_double, sz, vp, vp, vp, vp, vp]
+        L.c3sc_transition_raw.argtypes = [i32, C.c_uint32, C.c_double, vp, sz, vp, vp, vp, vp, vp]
+        L.c3sc_ft_fiber_nn_batch.argtypes = [vp, sz, vp, vp, vp, vp, sz, vp]
         L.c3sc_measure_fp64_peak.argtypes = [C.POINTER(C.c_double), i32, i32]
         _lib = L
     return _lib
@@ -207,6 +215,22 @@ class Problem:
         check(lib().c3sc_pi_batch(self.handle, vf_policy.handle if vf_policy is not None else None, vf_iter.handle,
                                   F, _ptr(dv), _ptr(fi), n, int(have), _ptr(rows), _ptr(arg), _ptr(val)))
         return val, rows, (None if have else arg)
+
+    def neighbor_costs(self, vf: "ValueF", dim_vary, fixed_ind):
+        dv, fi, F = _fibers(dim_vary, fixed_ind, self.dx)
+        n, dx = self.nmax, self.dx
+        ab = np.empty((F, n), np.int32); costs = np.empty((F, n, 2 * dx + 1))
+        nv = np.empty((F, n, 2), np.int32); nf = np.zeros((F, max(dx - 1, 1), 2), np.int32)
+        check(lib().c3sc_neighbor_costs_batch(self.handle, vf.handle, F, _ptr(dv), _ptr(fi), n, _ptr(ab), _ptr(costs), _ptr(nv), _ptr(nf)))
+        return ab, costs, nv, nf
+
+    def node_backup(self, x, costs, absorbed=None):
+        x = np.ascontiguousarray(x, np.float64); costs = np.ascontiguousarray(costs, np.float64)
+        n = x.shape[0]
+        ab = None if absorbed is None else np.ascontiguousarray(absorbed, np.int32)
+        val = np.empty(n); arg = np.empty(n, np.int32)
+        check(lib().c3sc_node_backup_batch(self.handle, n, _ptr(x), _ptr(costs), _ptr(ab), _ptr(val), _ptr(arg)))
+        return val, arg
 
     def transition(self, drift: np.ndarray, sigma: np.ndarray):
         drift = np.ascontiguousarray(drift, np.float64); sigma = np.ascontiguousarray(sigma, np.float64)

@@ -12,6 +12,18 @@ namespace c3sc {
 int launch_backup_lqg_lo(int dx, int arith, const LaunchArgs &a, cudaStream_t st);
 int launch_backup_lqg_hi(int dx, int arith, const LaunchArgs &a, cudaStream_t st);
 int launch_backup_misc(int model, int dx, int arith, const LaunchArgs &a, cudaStream_t st);
+int launch_node_backup_lqg_lo(int dx, int arith, const DevProblem &P, int n, const double *x, const double *costs,
+                              const int *absorbed, double *value, int *argmin, cudaStream_t st);
+int launch_node_backup_lqg_hi(int dx, int arith, const DevProblem &P, int n, const double *x, const double *costs,
+                              const int *absorbed, double *value, int *argmin, cudaStream_t st);
+int launch_node_backup_misc(int model, int dx, int arith, const DevProblem &P, int n, const double *x, const double *costs,
+                            const int *absorbed, double *value, int *argmin, cudaStream_t st);
+int launch_control_value_lqg_lo(int dx, int arith, const DevProblem &P, int n, const double *x, const double *u,
+                                const double *costs, double *value, cudaStream_t st);
+int launch_control_value_lqg_hi(int dx, int arith, const DevProblem &P, int n, const double *x, const double *u,
+                                const double *costs, double *value, cudaStream_t st);
+int launch_control_value_misc(int model, int dx, int arith, const DevProblem &P, int n, const double *x, const double *u,
+                              const double *costs, double *value, cudaStream_t st);
 int build_ctab_lqg_lo(int dx, const DevProblem &P, double *ctab, cudaStream_t st);
 int build_ctab_lqg_hi(int dx, const DevProblem &P, double *ctab, cudaStream_t st);
 int build_ctab_misc(int model, int dx, const DevProblem &P, double *ctab, cudaStream_t st);
@@ -453,6 +465,186 @@ int c3sc_pi_batch(c3sc_problem *p, const c3sc_valuef *vf_policy, const c3sc_valu
         if (argmin) CK(cudaMemcpyAsync(argmin, p->b_arg.p, n * 4, cudaMemcpyDeviceToHost, p->stream));
     }
     return finish(p);
+}
+
+int c3sc_neighbor_costs_batch(c3sc_problem *p, const c3sc_valuef *vf, size_t F, const int32_t *dim_vary,
+                              const int32_t *fixed_ind, size_t ldo, int32_t *absorbed, double *costs,
+                              int32_t *nbr_vary, int32_t *nbr_fixed)
+{
+    int rc = check_shapes(p, vf, F, ldo);
+    if (rc) return rc;
+    if (!dim_vary || !fixed_ind || !absorbed || !costs) return fail(C3SC_EINVAL, "null argument");
+    if (F == 0) return C3SC_OK;
+    const size_t dx = p->P.dx, n = F * ldo;
+    rc = upload_fibers(p, F, dim_vary, fixed_ind);
+    if (rc) return rc;
+    int bad = p->b_abs.reserve(n * 4) | p->b_costs.reserve(n * (2 * dx + 1) * 8);
+    if (nbr_vary) bad |= p->b_nv.reserve(n * 2 * 4);
+    if (nbr_fixed) bad |= p->b_nf.reserve(F * 2 * (dx > 1 ? dx - 1 : 1) * 4);
+    if (bad) return fail(C3SC_ECUDA, "cudaMalloc batch outputs failed");
+    CK(cudaMemsetAsync(p->b_abs.p, 0, n * 4, p->stream));
+    CK(cudaMemsetAsync(p->b_costs.p, 0, n * (2 * dx + 1) * 8, p->stream));
+    if (nbr_vary) CK(cudaMemsetAsync(p->b_nv.p, 0, n * 2 * 4, p->stream));
+    LaunchArgs a;
+    memset(&a, 0, sizeof a);
+    a.P = p->P; a.ft = vf->ft; a.F = (int)F; a.dim_vary = (const int *)p->b_dv.p; a.fixed_ind = (const int *)p->b_fi.p;
+    a.ldo = (int)ldo; a.mode = MODE_COSTS;
+    a.out.absorbed = (int *)p->b_abs.p; a.out.costs = (double *)p->b_costs.p;
+    a.out.nbr_vary = nbr_vary ? (int *)p->b_nv.p : nullptr;
+    a.out.nbr_fixed = nbr_fixed ? (int *)p->b_nf.p : nullptr;
+    rc = dispatch(p, a, p->stream);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(absorbed, p->b_abs.p, n * 4, cudaMemcpyDeviceToHost, p->stream));
+    CK(cudaMemcpyAsync(costs, p->b_costs.p, n * (2 * dx + 1) * 8, cudaMemcpyDeviceToHost, p->stream));
+    if (nbr_vary) CK(cudaMemcpyAsync(nbr_vary, p->b_nv.p, n * 2 * 4, cudaMemcpyDeviceToHost, p->stream));
+    if (nbr_fixed && dx > 1) CK(cudaMemcpyAsync(nbr_fixed, p->b_nf.p, F * 2 * (dx - 1) * 4, cudaMemcpyDeviceToHost, p->stream));
+    return finish(p);
+}
+
+int c3sc_node_backup_batch(c3sc_problem *p, size_t n, const double *x, const double *costs, const int32_t *absorbed,
+                           double *value, int32_t *argmin)
+{
+    if (!p || !x || !costs || !value) return fail(C3SC_EINVAL, "null argument");
+    if (n == 0) return C3SC_OK;
+    const size_t dx = p->P.dx;
+    DevBuf *b = p->b_misc;
+    if (b[0].reserve(n * dx * 8) || b[1].reserve(n * (2 * dx + 1) * 8) || b[2].reserve(n * 4) || b[3].reserve(n * 8) || b[4].reserve(n * 4))
+        return fail(C3SC_ECUDA, "cudaMalloc failed");
+    CK(cudaMemcpyAsync(b[0].p, x, n * dx * 8, cudaMemcpyHostToDevice, p->stream));
+    CK(cudaMemcpyAsync(b[1].p, costs, n * (2 * dx + 1) * 8, cudaMemcpyHostToDevice, p->stream));
+    if (absorbed) CK(cudaMemcpyAsync(b[2].p, absorbed, n * 4, cudaMemcpyHostToDevice, p->stream));
+    else CK(cudaMemsetAsync(b[2].p, 0, n * 4, p->stream));
+    int rc;
+    if (p->model == C3SC_MODEL_LQGND)
+        rc = (p->P.dx <= 6) ? launch_node_backup_lqg_lo(p->P.dx, p->arith, p->P, (int)n, (const double *)b[0].p, (const double *)b[1].p, (const int *)b[2].p, (double *)b[3].p, (int *)b[4].p, p->stream)
+                            : launch_node_backup_lqg_hi(p->P.dx, p->arith, p->P, (int)n, (const double *)b[0].p, (const double *)b[1].p, (const int *)b[2].p, (double *)b[3].p, (int *)b[4].p, p->stream);
+    else rc = launch_node_backup_misc(p->model, p->P.dx, p->arith, p->P, (int)n, (const double *)b[0].p, (const double *)b[1].p, (const int *)b[2].p, (double *)b[3].p, (int *)b[4].p, p->stream);
+    if (rc == -1) return fail(C3SC_EUNSUPPORTED, "model %d with dx=%d is not instantiated", p->model, p->P.dx);
+    if (rc) return fail(C3SC_ECUDA, "kernel launch: %s", cudaGetErrorString((cudaError_t)rc));
+    g_launches++;
+    CK(cudaMemcpyAsync(value, b[3].p, n * 8, cudaMemcpyDeviceToHost, p->stream));
+    if (argmin) CK(cudaMemcpyAsync(argmin, b[4].p, n * 4, cudaMemcpyDeviceToHost, p->stream));
+    return finish(p);
+}
+
+int c3sc_control_value_batch(c3sc_problem *p, size_t n, const double *x, const double *u, const double *costs,
+                             double *value)
+{
+    if (!p || !x || !u || !costs || !value) return fail(C3SC_EINVAL, "null argument");
+    if (n == 0) return C3SC_OK;
+    const size_t dx = p->P.dx, du = p->P.du;
+    DevBuf *b = p->b_misc;
+    if (b[0].reserve(n * dx * 8) || b[1].reserve(n * du * 8) || b[2].reserve(n * (2 * dx + 1) * 8) || b[3].reserve(n * 8))
+        return fail(C3SC_ECUDA, "cudaMalloc failed");
+    CK(cudaMemcpyAsync(b[0].p, x, n * dx * 8, cudaMemcpyHostToDevice, p->stream));
+    CK(cudaMemcpyAsync(b[1].p, u, n * du * 8, cudaMemcpyHostToDevice, p->stream));
+    CK(cudaMemcpyAsync(b[2].p, costs, n * (2 * dx + 1) * 8, cudaMemcpyHostToDevice, p->stream));
+    int rc;
+    const double *a0 = (const double *)b[0].p, *a1 = (const double *)b[1].p, *a2 = (const double *)b[2].p;
+    if (p->model == C3SC_MODEL_LQGND)
+        rc = (p->P.dx <= 6) ? launch_control_value_lqg_lo(p->P.dx, p->arith, p->P, (int)n, a0, a1, a2, (double *)b[3].p, p->stream)
+                            : launch_control_value_lqg_hi(p->P.dx, p->arith, p->P, (int)n, a0, a1, a2, (double *)b[3].p, p->stream);
+    else rc = launch_control_value_misc(p->model, p->P.dx, p->arith, p->P, (int)n, a0, a1, a2, (double *)b[3].p, p->stream);
+    if (rc == -1) return fail(C3SC_EUNSUPPORTED, "model %d with dx=%d is not instantiated", p->model, p->P.dx);
+    if (rc) return fail(C3SC_ECUDA, "kernel launch: %s", cudaGetErrorString((cudaError_t)rc));
+    g_launches++;
+    CK(cudaMemcpyAsync(value, b[3].p, n * 8, cudaMemcpyDeviceToHost, p->stream));
+    return finish(p);
+}
+
+// ---- entry points that need no problem handle (raw reference signatures) -------------------
+static DevBuf g_scratch[6];
+
+int c3sc_rhs_batch(int arith, uint32_t dx, double discount, size_t n, const double *prob, const double *dt,
+                   const double *stage, const double *cost, double *out)
+{
+    if (!prob || !dt || !stage || !cost || !out) return fail(C3SC_EINVAL, "null argument");
+    if (c3sc_cuda_device_count() == 0) return fail(C3SC_ENODEV, "no CUDA device; no CPU fallback");
+    if (n == 0) return C3SC_OK;
+    const size_t cs = 2 * (size_t)dx + 1;
+    DevBuf *b = g_scratch;
+    if (b[0].reserve(n * cs * 8) || b[1].reserve(n * 8) || b[2].reserve(n * 8) || b[3].reserve(n * cs * 8) || b[4].reserve(n * 8))
+        return fail(C3SC_ECUDA, "cudaMalloc failed");
+    CK(cudaMemcpy(b[0].p, prob, n * cs * 8, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(b[1].p, dt, n * 8, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(b[2].p, stage, n * 8, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(b[3].p, cost, n * cs * 8, cudaMemcpyHostToDevice));
+    int rc = launch_rhs(arith, (int)dx, discount, (int)n, (const double *)b[0].p, (const double *)b[1].p,
+                        (const double *)b[2].p, (const double *)b[3].p, (double *)b[4].p, nullptr);
+    if (rc) return fail(C3SC_ECUDA, "kernel launch: %s", cudaGetErrorString((cudaError_t)rc));
+    g_launches++;
+    CK(cudaMemcpy(out, b[4].p, n * 8, cudaMemcpyDeviceToHost));
+    return C3SC_OK;
+}
+
+int c3sc_transition_raw(int arith, uint32_t dx, double h2, const double *t, size_t n, const double *drift,
+                        const double *sigma_diag, double *prob, double *dt, int32_t *status)
+{
+    if (!t || !drift || !sigma_diag || !prob || !dt || !status) return fail(C3SC_EINVAL, "null argument");
+    if (dx < 1 || dx > C3SC_MAXD) return fail(C3SC_EINVAL, "dx out of range");
+    if (c3sc_cuda_device_count() == 0) return fail(C3SC_ENODEV, "no CUDA device; no CPU fallback");
+    if (n == 0) return C3SC_OK;
+    DevProblem P;
+    memset(&P, 0, sizeof P);
+    P.dx = (int)dx; P.h2 = h2;
+    for (uint32_t i = 0; i < 2 * dx; i++) P.t[i] = t[i];
+    DevBuf *b = g_scratch;
+    if (b[0].reserve(n * dx * 8) || b[1].reserve(n * dx * 8) || b[2].reserve(n * (2 * dx + 1) * 8) || b[3].reserve(n * 8) || b[4].reserve(n * 4))
+        return fail(C3SC_ECUDA, "cudaMalloc failed");
+    CK(cudaMemcpy(b[0].p, drift, n * dx * 8, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(b[1].p, sigma_diag, n * dx * 8, cudaMemcpyHostToDevice));
+    int rc = launch_transition(arith, P, (int)n, (const double *)b[0].p, (const double *)b[1].p, (double *)b[2].p,
+                               (double *)b[3].p, (int *)b[4].p, nullptr);
+    if (rc == -1) return fail(C3SC_EUNSUPPORTED, "dx=%u not instantiated for the transition kernel", dx);
+    if (rc) return fail(C3SC_ECUDA, "kernel launch: %s", cudaGetErrorString((cudaError_t)rc));
+    g_launches++;
+    CK(cudaMemcpy(prob, b[2].p, n * (2 * dx + 1) * 8, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(dt, b[3].p, n * 8, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(status, b[4].p, n * 4, cudaMemcpyDeviceToHost));
+    return C3SC_OK;
+}
+
+int c3sc_ft_fiber_nn_batch(const c3sc_valuef *vf, size_t F, const int32_t *dim_vary, const int32_t *fixed_ind,
+                           const int32_t *nbr_fixed, const int32_t *nbr_vary, size_t ldo, double *costs)
+{
+    if (!vf || !dim_vary || !fixed_ind || !nbr_fixed || !nbr_vary || !costs) return fail(C3SC_EINVAL, "null argument");
+    if (F == 0) return C3SC_OK;
+    const int dx = vf->ft.d;
+    // any instantiated model of this dimension carries the FT phase; its dynamics are never evaluated
+    int model;
+    if (dx % 2 == 0 && dx <= 12) model = C3SC_MODEL_LQGND;
+    else if (dx == 3) model = C3SC_MODEL_DUBINS;
+    else if (dx == 5) model = C3SC_MODEL_SKID5D;
+    else return fail(C3SC_EUNSUPPORTED, "FT fiber evaluation is instantiated for d in {2,3,4,5,6,8,10,12}, got %d", dx);
+    c3sc_problem tmp;
+    memset(&tmp.P, 0, sizeof tmp.P);
+    tmp.model = model; tmp.arith = C3SC_ARITH_FAST;
+    tmp.P.dx = dx; tmp.P.nu = 0;
+    for (int i = 0; i < dx; i++) { tmp.P.ngrid[i] = vf->ft.n[i]; tmp.P.bc[i] = C3SC_REFLECT; if (vf->ft.n[i] > tmp.P.nmax) tmp.P.nmax = vf->ft.n[i]; }
+    if (ldo < (size_t)tmp.P.nmax) return fail(C3SC_EINVAL, "ldo too small");
+    const size_t n = F * ldo, cs = 2 * (size_t)dx + 1, nfix = 2 * (size_t)(dx > 1 ? dx - 1 : 1);
+    DevBuf *b = g_scratch;
+    if (b[0].reserve(F * 4) || b[1].reserve(F * dx * 4) || b[2].reserve(F * nfix * 4) || b[3].reserve(n * 2 * 4) ||
+        b[4].reserve(n * cs * 8) || b[5].reserve(8 * (size_t)dx * tmp.P.nmax + 64))
+        return fail(C3SC_ECUDA, "cudaMalloc failed");
+    CK(cudaMemcpy(b[0].p, dim_vary, F * 4, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(b[1].p, fixed_ind, F * dx * 4, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(b[2].p, nbr_fixed, F * 2 * (size_t)(dx - 1) * 4, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(b[3].p, nbr_vary, n * 2 * 4, cudaMemcpyHostToDevice));
+    CK(cudaMemset(b[4].p, 0, n * cs * 8));
+    CK(cudaMemset(b[5].p, 0, 8 * (size_t)dx * tmp.P.nmax + 64));
+    tmp.P.xgrid = (const double *)b[5].p;           // coordinates are irrelevant here (no obstacles)
+    for (int i = 0; i < dx; i++) tmp.P.xoff[i] = i * tmp.P.nmax;
+    tmp.P.err = (int *)((char *)b[5].p + 8 * (size_t)dx * tmp.P.nmax);
+    LaunchArgs a;
+    memset(&a, 0, sizeof a);
+    a.P = tmp.P; a.ft = vf->ft; a.F = (int)F; a.dim_vary = (const int *)b[0].p; a.fixed_ind = (const int *)b[1].p;
+    a.ldo = (int)ldo; a.mode = MODE_COSTS; a.out.costs = (double *)b[4].p;
+    a.nbr_fixed_in = (const int *)b[2].p; a.nbr_vary_in = (const int *)b[3].p;
+    int rc = dispatch(&tmp, a, nullptr);
+    if (rc) return rc;
+    CK(cudaMemcpy(costs, b[4].p, n * cs * 8, cudaMemcpyDeviceToHost));
+    return C3SC_OK;
 }
 
 int c3sc_transition_batch(c3sc_problem *p, size_t n, const double *drift, const double *sigma_diag,

@@ -332,6 +332,11 @@ __global__ void __launch_bounds__(NT) k_backup(const LaunchArgs a)
             sNv[2 * j + 1] = hi;
         }
 
+        if (a.nbr_fixed_in) {                  // valuef_eval_fiber_ind_nn: indices come from the caller
+            __syncthreads();
+            for (int e = tid; e < 2 * (DX - 1); e += NT) sNf[e] = a.nbr_fixed_in[(size_t)f * 2 * (DX - 1) + e];
+            for (int e = tid; e < 2 * N; e += NT) sNv[e] = a.nbr_vary_in[2 * obase + e];
+        }
         __syncthreads();                       // sFix / sNf / flags visible
 
         // ---- 2. function-train neighbour values (valuefunc.c:369-585) ---------
@@ -441,6 +446,8 @@ __global__ void __launch_bounds__(NT) k_backup(const LaunchArgs a)
         if (a.out.nbr_vary) for (int e = tid; e < 2 * N; e += NT) a.out.nbr_vary[2 * obase + e] = sNv[e];
         if (a.out.nbr_fixed) for (int e = tid; e < 2 * (DX - 1); e += NT) a.out.nbr_fixed[(size_t)f * 2 * (DX - 1) + e] = sNf[e];
         if (a.out.costs) for (int e = tid; e < N * CS; e += NT) a.out.costs[obase * CS + e] = sC[e];
+
+        if (a.mode == MODE_COSTS) continue;      // mca_get_neighbor_costs only (nodeutil.c:647-713)
 
         if (a.mode == MODE_PI_EVAL) {
             // ---- policy evaluation (bellman.c:1774-1828,1863-1871) ------------
@@ -679,6 +686,93 @@ int launch_backup_m(int arith, const LaunchArgs &a, cudaStream_t st)
 {
     if (arith == C3SC_ARITH_EXACT) return launch_backup_t<M, Exact>(a, st);
     return launch_backup_t<M, Fast>(a, st);
+}
+
+// ---- node-level entry: bellman_optimal on caller-supplied (x, neighbour costs, flag) --------
+// One thread per node, candidates walked in table order (bellman.c:504-543).
+template <class M, class A>
+__global__ void k_node_backup(const DevProblem P, int n, const double *x, const double *costs, const int *absorbed,
+                              double *value, int *argmin)
+{
+    constexpr int DX = M::DX, DU = M::DU, CS = 2 * DX + 1;
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n) return;
+    double xx[DX], c[CS];
+#pragma unroll
+    for (int i = 0; i < DX; i++) xx[i] = x[(size_t)e * DX + i];
+    const int ab = absorbed ? absorbed[e] : 0;
+    if (ab == 1) { value[e] = M::boundcost(xx, P.mp); if (argmin) argmin[e] = -1; return; }
+    if (ab == -1) { value[e] = M::obscost(xx, P.mp); if (argmin) argmin[e] = -1; return; }
+#pragma unroll
+    for (int m = 0; m < CS; m++) c[m] = costs[(size_t)e * CS + m];
+    NodeInv<M> inv;
+    node_prepare<M, A>(P, P.utab, xx, c, inv);
+    double best = CUDART_INF;
+    int ibest = 0x7fffffff, bad = 0;
+    for (int cand = 0; cand < P.nu; cand++) {
+        double u[DU];
+#pragma unroll
+        for (int i = 0; i < DU; i++) u[i] = P.utab[(size_t)cand * DU + i];
+        const double v = candidate_value<M, A>(P, xx, u, c, inv, bad);
+        if (v < best) { best = v; ibest = cand; }
+    }
+    if (bad) atomicOr(P.err, 1);
+    value[e] = best;
+    if (argmin) argmin[e] = ibest;
+}
+
+template <class M>
+int launch_node_backup_t(int arith, const DevProblem &P, int n, const double *x, const double *costs,
+                         const int *absorbed, double *value, int *argmin, cudaStream_t st)
+{
+    if (n <= 0) return 0;
+    const int g = (n + 127) / 128;
+    if (arith == C3SC_ARITH_EXACT) k_node_backup<M, Exact><<<g, 128, 0, st>>>(P, n, x, costs, absorbed, value, argmin);
+    else k_node_backup<M, Fast><<<g, 128, 0, st>>>(P, n, x, costs, absorbed, value, argmin);
+    return (int)cudaGetLastError();
+}
+
+// bellman_control (bellman.c:367-480, grad_u == NULL) at n (x, u, costs) triples, any u
+template <class M, class A>
+__global__ void k_control_value(const DevProblem P, int n, const double *x, const double *u, const double *costs,
+                                double *value)
+{
+    constexpr int DX = M::DX, DU = M::DU, CS = 2 * DX + 1;
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n) return;
+    double xx[DX], uu[DU], c[CS], b[DX], s[DX], prob[CS], dt;
+    for (int i = 0; i < DX; i++) xx[i] = x[(size_t)e * DX + i];
+    for (int i = 0; i < DU; i++) uu[i] = u[(size_t)e * DU + i];
+    for (int m = 0; m < CS; m++) c[m] = costs[(size_t)e * CS + m];
+    M::template drift<A>(xx, uu, P.mp, b);
+    M::template sigma<A>(xx, uu, P.mp, s);
+    const double g = M::template stage<A>(xx, uu, P.mp);
+    if (transition_row<DX, A>(P, b, s, prob, dt)) { atomicOr(P.err, 1); value[e] = CUDART_NAN; return; }
+    value[e] = rhs<DX, A>(P, prob, dt, g, c);
+}
+template <class M>
+int launch_control_value_t(int arith, const DevProblem &P, int n, const double *x, const double *u, const double *costs,
+                           double *value, cudaStream_t st)
+{
+    if (n <= 0) return 0;
+    const int g = (n + 127) / 128;
+    if (arith == C3SC_ARITH_EXACT) k_control_value<M, Exact><<<g, 128, 0, st>>>(P, n, x, u, costs, value);
+    else k_control_value<M, Fast><<<g, 128, 0, st>>>(P, n, x, u, costs, value);
+    return (int)cudaGetLastError();
+}
+
+// bellmanrhs on raw tuples (runtime dx)
+template <class A>
+__global__ void k_rhs(int dx, double beta, int n, const double *prob, const double *dt, const double *stage,
+                      const double *cost, double *out)
+{
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n) return;
+    const int cs = 2 * dx + 1;
+    const double ebt = exp(A::mul(-beta, dt[e]));
+    double ctg = 0.0;
+    for (int m = 0; m < cs; m++) ctg = A::mad(prob[(size_t)e * cs + m], cost[(size_t)e * cs + m], ctg);
+    out[e] = A::add(A::mul(dt[e], stage[e]), A::mul(ebt, ctg));
 }
 
 // ---- small test kernels -------------------------------------------------------

@@ -44,7 +44,7 @@ struct DevOut {
     int *nbr_fixed;
 };
 
-enum Mode { MODE_VI = 0, MODE_PI_EVAL = 1 };
+enum Mode { MODE_VI = 0, MODE_PI_EVAL = 1, MODE_COSTS = 2 };
 
 struct LaunchArgs {
     DevProblem P;
@@ -57,10 +57,15 @@ struct LaunchArgs {
     const double *rows_in;   // MODE_PI_EVAL: policy rows
     int mode;
     int write_value;         // MODE_VI: 0 when only rows/argmin are wanted
+    const int *nbr_fixed_in; // MODE_COSTS: caller-supplied neighbour indices (valuef_eval_fiber_ind_nn)
+    const int *nbr_vary_in;  //             [F*2*(dx-1)] and [F*ldo*2]; NULL = derive from the boundary
 };
 
 // implemented in inst_misc.cu; returns cudaError_t as int, or -1 if dx is not instantiated
 int launch_transition(int arith, const DevProblem &P, int n, const double *drift, const double *sig,
                       double *prob, double *dt, int *status, void *stream);
+// bellmanrhs (bellman.c:88-112) for n independent (prob[2dx+1], dt, stage, cost[2dx+1]) tuples
+int launch_rhs(int arith, int dx, double beta, int n, const double *prob, const double *dt, const double *stage,
+               const double *cost, double *out, void *stream);
 
 }  // namespace c3sc

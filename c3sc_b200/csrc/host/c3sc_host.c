@@ -1,0 +1,731 @@
+/* c3sc_host.c -- C host mirror of the reference API (include/c3sc_host.h).
+ *
+ * Containers and index decoding live here; every floating-point result of the
+ * path comes back from the GPU through include/c3sc_b200.h.  Written from the
+ * behaviour documented in SURVEY.md / the reference headers, not transcribed.
+ */
+#define _POSIX_C_SOURCE 200809L
+#include <math.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include "../../../include/c3sc_host.h"
+
+static void *xalloc(size_t n, size_t sz)
+{
+    void *p = calloc(n ? n : 1, sz);
+    if (!p) { fprintf(stderr, "c3sc_b200: out of host memory\n"); exit(1); }
+    return p;
+}
+static double *dupd(const double *s, size_t n)
+{
+    double *p = xalloc(n, sizeof(double));
+    if (s) memcpy(p, s, n * sizeof(double));
+    return p;
+}
+static void die(const char *what)
+{
+    fprintf(stderr, "c3sc_b200: %s: %s\n", what, c3sc_last_error());
+    abort();                      /* the reference asserts on every failure of the path */
+}
+
+/* ========================== boundary ======================================= */
+struct Boundary {
+    size_t d, nobs;
+    double *lo, *hi;              /* domain bounds                       */
+    int *type;                    /* enum EBTYPE per dimension           */
+    double *obs_lb[C3SC_MAXOBS], *obs_ub[C3SC_MAXOBS];
+};
+static int parse_type(const char *s)
+{
+    if (!strcmp(s, "absorb")) return ABSORB;
+    if (!strcmp(s, "periodic")) return PERIODIC;
+    if (!strcmp(s, "reflect")) return REFLECT;
+    fprintf(stderr, "External boundary of type %s is unknown\n", s);
+    exit(1);
+}
+struct Boundary *boundary_alloc(size_t d, double *lb, double *ub)
+{
+    struct Boundary *b = xalloc(1, sizeof *b);
+    b->d = d;
+    b->lo = dupd(lb, d);
+    b->hi = dupd(ub, d);
+    b->type = xalloc(d, sizeof(int));
+    for (size_t i = 0; i < d; i++) b->type[i] = ABSORB;     /* default, boundary.c:386-388 */
+    return b;
+}
+struct Boundary *boundary_copy_deep(struct Boundary *o)
+{
+    if (!o) return NULL;
+    struct Boundary *b = boundary_alloc(o->d, o->lo, o->hi);
+    memcpy(b->type, o->type, o->d * sizeof(int));
+    b->nobs = o->nobs;
+    for (size_t k = 0; k < o->nobs; k++) { b->obs_lb[k] = dupd(o->obs_lb[k], o->d); b->obs_ub[k] = dupd(o->obs_ub[k], o->d); }
+    return b;
+}
+void boundary_free(struct Boundary *b)
+{
+    if (!b) return;
+    for (size_t k = 0; k < b->nobs; k++) { free(b->obs_lb[k]); free(b->obs_ub[k]); }
+    free(b->lo); free(b->hi); free(b->type); free(b);
+}
+size_t boundary_get_nobs(struct Boundary *b) { return b->nobs; }
+double *boundary_obstacle_get_lb(struct Boundary *b, size_t k) { return b->obs_lb[k]; }
+double *boundary_obstacle_get_ub(struct Boundary *b, size_t k) { return b->obs_ub[k]; }
+void boundary_add_obstacle(struct Boundary *b, double *center, double *lengths)
+{
+    if (b->nobs == C3SC_MAXOBS) { fprintf(stderr, "Not enough space allocated for obstacles in boundary\n"); exit(1); }
+    double *lb = xalloc(b->d, sizeof(double)), *ub = xalloc(b->d, sizeof(double));
+    for (size_t i = 0; i < b->d; i++) {            /* boundary.c:264-267 */
+        lb[i] = center[i] - lengths[i] / 2.0;
+        ub[i] = center[i] + lengths[i] / 2.0;
+    }
+    b->obs_lb[b->nobs] = lb; b->obs_ub[b->nobs] = ub;
+    b->nobs++;
+}
+void boundary_external_set_type(struct Boundary *b, size_t dim, char *type) { b->type[dim] = parse_type(type); }
+enum EBTYPE boundary_type_dim(const struct Boundary *b, size_t dim, int right) { (void)right; return (enum EBTYPE)b->type[dim]; }
+int boundary_in_obstacle(const struct Boundary *b, const double *x)
+{   /* geometric predicate (closed boxes, first hit), boundary.c:329-344,668-680 */
+    for (size_t k = 0; k < b->nobs; k++) {
+        int in = 1;
+        for (size_t i = 0; i < b->d && in; i++) in = !(x[i] < b->obs_lb[k][i] || x[i] > b->obs_ub[k][i]);
+        if (in) return 1;
+    }
+    return 0;
+}
+
+/* ========================== dynamics containers ============================ */
+struct Drift { size_t dx, du; c3sc_dyn_cb b; void *bargs; };
+struct Diff  { size_t dx, du, dw; c3sc_dyn_cb s; void *sargs; };
+struct Dyn   { struct Drift *drift; struct Diff *diff; };
+struct Drift *drift_alloc(size_t dx, size_t du) { struct Drift *d = xalloc(1, sizeof *d); d->dx = dx; d->du = du; return d; }
+struct Drift *drift_copy(struct Drift *o) { if (!o) return NULL; struct Drift *d = xalloc(1, sizeof *d); *d = *o; return d; }
+void drift_free(struct Drift *d) { free(d); }
+void drift_add_func(struct Drift *d, c3sc_dyn_cb b, void *a) { d->b = b; d->bargs = a; }
+size_t drift_get_dx(struct Drift *d) { return d->dx; }
+int drift_eval(struct Drift *d, double t, const double *x, const double *u, double *out, double *jac)
+{
+    if (!d->b) { fprintf(stderr, "Warning: drift dynamics (Drift->b) are not\n         yet specified\n"); return 1; }
+    return d->b(t, x, u, out, jac, d->bargs);
+}
+struct Diff *diff_alloc(size_t dx, size_t du, size_t dw) { struct Diff *d = xalloc(1, sizeof *d); d->dx = dx; d->du = du; d->dw = dw; return d; }
+struct Diff *diff_copy(struct Diff *o) { if (!o) return NULL; struct Diff *d = xalloc(1, sizeof *d); *d = *o; return d; }
+void diff_free(struct Diff *d) { free(d); }
+void diff_add_func(struct Diff *d, c3sc_dyn_cb s, void *a) { d->s = s; d->sargs = a; }
+int diff_eval(struct Diff *d, double t, const double *x, const double *u, double *out, double *jac)
+{
+    if (!d->s) { fprintf(stderr, "Warning: Diff dynamics (Diff->s) are not\n         yet specified\n"); return 1; }
+    return d->s(t, x, u, out, jac, d->sargs);
+}
+size_t diff_get_dw(struct Diff *d) { return d->dw; }
+struct Dyn *dyn_alloc(struct Drift *a, struct Diff *b) { struct Dyn *d = xalloc(1, sizeof *d); d->drift = a; d->diff = b; return d; }
+void dyn_free(struct Dyn *d) { free(d); }
+void dyn_free_deep(struct Dyn *d) { if (d) { drift_free(d->drift); diff_free(d->diff); free(d); } }
+size_t dyn_get_dx(struct Dyn *d) { return d->drift->dx; }
+size_t dyn_get_dw(struct Dyn *d) { return d->diff->dw; }
+size_t dyn_get_du(struct Dyn *d) { return d->drift->du; }
+int dyn_eval(struct Dyn *d, double t, const double *x, const double *u, double *drift, double *jd, double *diff, double *jf)
+{
+    int rc = drift_eval(d->drift, t, x, u, drift, jd);
+    return rc ? rc : diff_eval(d->diff, t, x, u, diff, jf);
+}
+
+/* ========================== c3opt (brute force) ============================ */
+struct c3Opt { enum c3opt_alg alg; size_t d, n; double *vals; };
+struct c3Opt *c3opt_alloc(enum c3opt_alg alg, size_t d) { struct c3Opt *o = xalloc(1, sizeof *o); o->alg = alg; o->d = d; return o; }
+struct c3Opt *c3opt_copy(struct c3Opt *s) { if (!s) return NULL; struct c3Opt *o = xalloc(1, sizeof *o); *o = *s; o->vals = s->vals ? dupd(s->vals, s->n * s->d) : NULL; return o; }
+void c3opt_free(struct c3Opt *o) { if (o) { free(o->vals); free(o); } }
+int c3opt_is_bruteforce(const struct c3Opt *o) { return o->alg == BRUTEFORCE; }
+void c3opt_set_brute_force_vals(struct c3Opt *o, size_t n, double *vals) { free(o->vals); o->n = n; o->vals = dupd(vals, n * o->d); }
+size_t c3opt_get_d(const struct c3Opt *o) { return o->d; }
+
+/* ========================== value function ================================= */
+struct ValueF {
+    size_t d, *N, *ranks;
+    double **cores;               /* host copy, valuef_precompute_cores layout */
+    c3sc_valuef *dev;
+};
+struct ValueF *valuef_from_cores(size_t d, const size_t *N, const size_t *ranks, double *const *cores)
+{
+    struct ValueF *v = xalloc(1, sizeof *v);
+    v->d = d;
+    v->N = xalloc(d, sizeof(size_t));
+    v->ranks = xalloc(d + 1, sizeof(size_t));
+    v->cores = xalloc(d, sizeof(double *));
+    memcpy(v->N, N, d * sizeof(size_t));
+    memcpy(v->ranks, ranks, (d + 1) * sizeof(size_t));
+    uint64_t n64[C3SC_MAXD], r64[C3SC_MAXD + 1];
+    for (size_t k = 0; k < d; k++) { v->cores[k] = dupd(cores[k], N[k] * ranks[k] * ranks[k + 1]); n64[k] = N[k]; }
+    for (size_t k = 0; k <= d; k++) r64[k] = ranks[k];
+    if (c3sc_valuef_create((uint32_t)d, n64, r64, (const double *const *)v->cores, &v->dev)) die("valuef_from_cores");
+    return v;
+}
+int valuef_update_cores(struct ValueF *v, double *const *cores)
+{
+    for (size_t k = 0; k < v->d; k++) memcpy(v->cores[k], cores[k], v->N[k] * v->ranks[k] * v->ranks[k + 1] * sizeof(double));
+    return c3sc_valuef_update(v->dev, (const double *const *)v->cores);
+}
+void valuef_destroy(struct ValueF *v)
+{
+    if (!v) return;
+    c3sc_valuef_destroy(v->dev);
+    for (size_t k = 0; k < v->d; k++) free(v->cores[k]);
+    free(v->cores); free(v->N); free(v->ranks); free(v);
+}
+struct ValueF *valuef_copy(struct ValueF *v) { return valuef_from_cores(v->d, v->N, v->ranks, v->cores); }
+size_t *valuef_get_ranks(struct ValueF *v) { return v->ranks; }
+
+int valuef_eval_fiber_ind_nn(struct ValueF *vf, const size_t *fixed_ind, size_t dim_vary,
+                             const size_t *neighbors, const size_t *neighbors_vary, double *out)
+{
+    const size_t d = vf->d, N = vf->N[dim_vary];
+    size_t nmax = 0;
+    for (size_t i = 0; i < d; i++) if (vf->N[i] > nmax) nmax = vf->N[i];
+    int32_t fi[C3SC_MAXD], nf[2 * C3SC_MAXD], dv = (int32_t)dim_vary;
+    for (size_t i = 0; i < d; i++) fi[i] = (int32_t)fixed_ind[i];
+    for (size_t i = 0; i + 2 < 2 * d; i++) nf[i] = (int32_t)neighbors[i];
+    int32_t *nv = xalloc(2 * nmax, sizeof(int32_t));
+    for (size_t j = 0; j < 2 * N; j++) nv[j] = (int32_t)neighbors_vary[j];
+    double *tmp = xalloc(nmax * (2 * d + 1), sizeof(double));
+    int rc = c3sc_ft_fiber_nn_batch(vf->dev, 1, &dv, fi, nf, nv, nmax, tmp);
+    if (!rc) memcpy(out, tmp, N * (2 * d + 1) * sizeof(double));
+    free(nv); free(tmp);
+    return rc;
+}
+
+/* ========================== workspace ====================================== */
+struct RowEntry { uint64_t hash; size_t pi_iter; int32_t key[C3SC_MAXD + 1]; double *rows; int32_t *argmin; struct RowEntry *next; };
+struct Workspace {
+    size_t dx, du, dw, N;
+    size_t vi_iter, pi_iter, pi_subiter;
+    double *costs;                /* N*(2dx+1): neighbour costs of the fiber in flight */
+    int *absorbed;                /* N */
+    double *u;                    /* N*du */
+    struct RowEntry **rows;       /* policy rows per fiber (replaces pi_prob_htable) */
+    size_t nbuckets;
+};
+struct Workspace *workspace_alloc(size_t dx, size_t du, size_t dw, size_t N)
+{
+    struct Workspace *w = xalloc(1, sizeof *w);
+    w->dx = dx; w->du = du; w->dw = dw; w->N = N;
+    w->costs = xalloc(N * (2 * dx + 1), sizeof(double));
+    w->absorbed = xalloc(N, sizeof(int));
+    w->u = xalloc(N * (du ? du : 1), sizeof(double));
+    w->nbuckets = 1 << 16;
+    w->rows = xalloc(w->nbuckets, sizeof(struct RowEntry *));
+    return w;
+}
+void workspace_reset_pi_prob_htable(struct Workspace *w)
+{
+    for (size_t b = 0; b < w->nbuckets; b++) {
+        struct RowEntry *e = w->rows[b];
+        while (e) { struct RowEntry *n = e->next; free(e->rows); free(e->argmin); free(e); e = n; }
+        w->rows[b] = NULL;
+    }
+}
+void workspace_reset_pi_htable(struct Workspace *w) { (void)w; }   /* value memo: dropped, backups are pure */
+void workspace_reset_vi_htable(struct Workspace *w) { (void)w; }
+void workspace_free(struct Workspace *w)
+{
+    if (!w) return;
+    workspace_reset_pi_prob_htable(w);
+    free(w->rows); free(w->costs); free(w->absorbed); free(w->u); free(w);
+}
+void workspace_increment_vi_iter(struct Workspace *w) { w->vi_iter++; }
+size_t workspace_get_vi_iter(const struct Workspace *w) { return w->vi_iter; }
+void workspace_increment_pi_iter(struct Workspace *w) { w->pi_iter++; }
+size_t workspace_get_pi_iter(const struct Workspace *w) { return w->pi_iter; }
+void workspace_increment_pi_subiter(struct Workspace *w) { w->pi_subiter++; }
+size_t workspace_get_pi_subiter(const struct Workspace *w) { return w->pi_subiter; }
+double *workspace_get_costs(struct Workspace *w, size_t node) { return w->costs + node * (2 * w->dx + 1); }
+int *workspace_get_absorbed(struct Workspace *w, size_t node) { return w->absorbed + node; }
+double *workspace_get_u(struct Workspace *w, size_t node) { return w->u + node * w->du; }
+
+static uint64_t fiber_hash(size_t pi_iter, int32_t k, const int32_t *fi, size_t d)
+{
+    uint64_t h = 1469598103934665603ull ^ pi_iter;
+    h = (h ^ (uint64_t)(uint32_t)k) * 1099511628211ull;
+    for (size_t i = 0; i < d; i++) h = (h ^ (uint64_t)(uint32_t)((size_t)k == i ? 0 : fi[i])) * 1099511628211ull;
+    return h;
+}
+static struct RowEntry *rows_find(struct Workspace *w, int32_t k, const int32_t *fi)
+{
+    uint64_t h = fiber_hash(w->pi_iter, k, fi, w->dx);
+    for (struct RowEntry *e = w->rows[h % w->nbuckets]; e; e = e->next) {
+        if (e->hash != h || e->pi_iter != w->pi_iter || e->key[w->dx] != k) continue;
+        int same = 1;
+        for (size_t i = 0; i < w->dx && same; i++) same = ((size_t)k == i) || e->key[i] == fi[i];
+        if (same) return e;
+    }
+    return NULL;
+}
+static struct RowEntry *rows_add(struct Workspace *w, int32_t k, const int32_t *fi, size_t nrow)
+{
+    struct RowEntry *e = xalloc(1, sizeof *e);
+    e->hash = fiber_hash(w->pi_iter, k, fi, w->dx);
+    e->pi_iter = w->pi_iter;
+    memcpy(e->key, fi, w->dx * sizeof(int32_t));
+    e->key[w->dx] = k;
+    e->rows = xalloc(nrow * (2 * w->dx + 3), sizeof(double));
+    e->argmin = xalloc(nrow, sizeof(int32_t));
+    e->next = w->rows[e->hash % w->nbuckets];
+    w->rows[e->hash % w->nbuckets] = e;
+    return e;
+}
+
+/* ========================== MCA / DP / ControlParams ======================= */
+struct MCAparam { size_t dx, du; size_t *ngrid; double **xgrid; double hmin, *hvec, h2, *t; };
+struct MCAparam *mca_param_create(size_t dx, size_t du) { struct MCAparam *m = xalloc(1, sizeof *m); m->dx = dx; m->du = du; return m; }
+void mca_add_grid_refs(struct MCAparam *m, size_t *ngrid, double **xgrid, double hmin, double *hvec)
+{   /* grid is BORROWED (bellman.c:171-178); derived constants as bellman.c:181-186 -- two divisions
+       per dimension done once on the host and uploaded, never recomputed on the device */
+    m->ngrid = ngrid; m->xgrid = xgrid; m->hmin = hmin; m->hvec = hvec;
+    m->h2 = hmin * hmin;
+    free(m->t);
+    m->t = xalloc(2 * m->dx, sizeof(double));
+    for (size_t i = 0; i < m->dx; i++) { m->t[2 * i] = m->h2 / hvec[i]; m->t[2 * i + 1] = m->t[2 * i] / hvec[i]; }
+}
+void mca_param_destroy(struct MCAparam *m) { if (m) { free(m->t); free(m); } }
+
+struct DPparam {
+    struct Drift *drift; struct Diff *diff; struct Boundary *bound;
+    double discount;
+    int (*stagecost)(double, const double *, const double *, double *, double *);
+    int (*boundcost)(double, const double *, double *);
+    int (*obscost)(const double *, double *);
+    int model, arith; double params[8]; size_t nparams;
+};
+struct DPparam *dp_param_create(size_t dx, size_t du, size_t dw, double discount)
+{
+    struct DPparam *dp = xalloc(1, sizeof *dp);
+    dp->drift = drift_alloc(dx, du);
+    dp->diff = diff_alloc(dx, du, dw);
+    dp->discount = discount;
+    dp->arith = C3SC_ARITH_FAST;
+    return dp;
+}
+void dp_param_destroy(struct DPparam *dp) { if (dp) { drift_free(dp->drift); diff_free(dp->diff); free(dp); } }
+void dp_param_add_drift(struct DPparam *dp, c3sc_dyn_cb b, void *a) { drift_add_func(dp->drift, b, a); }
+void dp_param_add_diff(struct DPparam *dp, c3sc_dyn_cb s, void *a) { diff_add_func(dp->diff, s, a); }
+void dp_param_add_boundary(struct DPparam *dp, struct Boundary *b) { dp->bound = b; }
+void dp_param_add_stagecost(struct DPparam *dp, int (*f)(double, const double *, const double *, double *, double *)) { dp->stagecost = f; }
+void dp_param_add_boundcost(struct DPparam *dp, int (*f)(double, const double *, double *)) { dp->boundcost = f; }
+void dp_param_add_obscost(struct DPparam *dp, int (*f)(const double *, double *)) { dp->obscost = f; }
+void dp_param_set_device_model(struct DPparam *dp, int model, const double *params, size_t n)
+{
+    dp->model = model;
+    dp->nparams = n > 8 ? 8 : n;
+    if (params) memcpy(dp->params, params, dp->nparams * sizeof(double));
+}
+void dp_param_set_arith(struct DPparam *dp, int arith) { dp->arith = arith; }
+
+static c3sc_problem *make_problem(struct DPparam *dp, struct MCAparam *m, struct c3Opt *opt, size_t dw)
+{
+    if (!dp->model) { fprintf(stderr, "c3sc_b200: no device model registered (dp_param_set_device_model): host callbacks cannot run inside a kernel\n"); abort(); }
+    if (!opt || !c3opt_is_bruteforce(opt) || !opt->n) { fprintf(stderr, "c3sc_b200: only the BRUTEFORCE control set is supported on the device\n"); abort(); }
+    if (!dp->bound || !m->xgrid) { fprintf(stderr, "c3sc_b200: boundary / grid missing\n"); abort(); }
+    const size_t dx = m->dx;
+    uint64_t ng[C3SC_MAXD]; int32_t bc[C3SC_MAXD];
+    double lb[C3SC_MAXOBS * C3SC_MAXD], ub[C3SC_MAXOBS * C3SC_MAXD];
+    for (size_t i = 0; i < dx; i++) { ng[i] = m->ngrid[i]; bc[i] = dp->bound->type[i]; }
+    for (size_t k = 0; k < dp->bound->nobs; k++) {
+        memcpy(lb + k * dx, dp->bound->obs_lb[k], dx * sizeof(double));
+        memcpy(ub + k * dx, dp->bound->obs_ub[k], dx * sizeof(double));
+    }
+    c3sc_problem_desc d;
+    memset(&d, 0, sizeof d);
+    d.dx = (uint32_t)dx; d.du = (uint32_t)m->du; d.dw = (uint32_t)dw;
+    d.ngrid = ng; d.xgrid = (const double *const *)m->xgrid; d.h2 = m->h2; d.t = m->t; d.bc = bc;
+    d.nobs = (uint32_t)dp->bound->nobs; d.obs_lb = lb; d.obs_ub = ub;
+    d.discount = dp->discount; d.nu = (uint32_t)opt->n; d.controls = opt->vals;
+    d.model = dp->model; d.model_params = dp->nparams ? dp->params : NULL; d.n_model_params = (uint32_t)dp->nparams;
+    d.arith = dp->arith;
+    c3sc_problem *p = NULL;
+    if (c3sc_problem_create(&d, &p)) die("c3sc_problem_create");
+    return p;
+}
+
+struct ControlParams {
+    double time; size_t dx, dw, N; const double *x;
+    struct DPparam *dp; struct MCAparam *mca; struct Workspace *work; struct c3Opt *opt;
+    int res_last_grad;
+    c3sc_problem *dev;            /* built on first use from everything above */
+};
+struct ControlParams *control_params_create(size_t dx, size_t dw, struct DPparam *dp, struct MCAparam *mca,
+                                            struct Workspace *work, struct c3Opt *opt)
+{
+    struct ControlParams *c = xalloc(1, sizeof *c);
+    c->dx = dx; c->dw = dw; c->dp = dp; c->mca = mca; c->work = work; c->opt = opt;
+    return c;
+}
+static c3sc_problem *cp_dev(struct ControlParams *c)
+{
+    if (!c->dev) c->dev = make_problem(c->dp, c->mca, c->opt, c->dw);
+    return c->dev;
+}
+void control_params_add_time_and_states(struct ControlParams *c, double t, size_t N, const double *x) { c->time = t; c->N = N; c->x = x; }
+int control_params_get_last_res(const struct ControlParams *c) { return c->res_last_grad; }
+void control_params_destroy(struct ControlParams *c) { if (c) { c3sc_problem_destroy(c->dev); free(c); } }
+
+size_t dp_param_check_device_model(struct DPparam *dp, struct MCAparam *m, struct c3Opt *opt, size_t n, double tol)
+{
+    const size_t dx = m->dx, du = m->du, dw = dp->diff->dw;
+    c3sc_problem *p = make_problem(dp, m, opt, dw);
+    double *x = xalloc(n * dx, 8), *u = xalloc(n * du, 8), *dr = xalloc(n * dx, 8), *sg = xalloc(n * dx, 8);
+    double *st = xalloc(n, 8), *bd = xalloc(n, 8), *ob = xalloc(n, 8), *hd = xalloc(dx, 8), *hs = xalloc(dx * dw + 64, 8);
+    for (size_t e = 0; e < n; e++) {
+        for (size_t i = 0; i < dx; i++) x[e * dx + i] = m->xgrid[i][(e * (2 * i + 3) + i) % m->ngrid[i]];
+        memcpy(u + e * du, opt->vals + (e % opt->n) * du, du * sizeof(double));
+    }
+    if (c3sc_model_eval(p, n, x, u, dr, sg, st, bd, ob)) die("c3sc_model_eval");
+    size_t bad = 0;
+    for (size_t e = 0; e < n; e++) {
+        double v;
+        drift_eval(dp->drift, 0.0, x + e * dx, u + e * du, hd, NULL);
+        diff_eval(dp->diff, 0.0, x + e * dx, u + e * du, hs, NULL);
+        for (size_t i = 0; i < dx; i++) {
+            bad += fabs(hd[i] - dr[e * dx + i]) > tol * fmax(1.0, fabs(hd[i]));
+            bad += fabs(hs[i * dx + i] - sg[e * dx + i]) > tol * fmax(1.0, fabs(hs[i * dx + i]));
+        }
+        if (dp->stagecost) { dp->stagecost(0.0, x + e * dx, u + e * du, &v, NULL); bad += fabs(v - st[e]) > tol * fmax(1.0, fabs(v)); }
+        if (dp->boundcost) { dp->boundcost(0.0, x + e * dx, &v); bad += fabs(v - bd[e]) > tol * fmax(1.0, fabs(v)); }
+        if (dp->obscost) { dp->obscost(x + e * dx, &v); bad += fabs(v - ob[e]) > tol * fmax(1.0, fabs(v)); }
+    }
+    free(x); free(u); free(dr); free(sg); free(st); free(bd); free(ob); free(hd); free(hs);
+    c3sc_problem_destroy(p);
+    return bad;
+}
+
+/* ========================== scalar pieces of the path ====================== */
+double bellmanrhs(size_t dx, size_t du, double stage, const double *stage_grad, double discount, const double *prob,
+                  const double *prob_grad, double dt, const double *dtgrad, const double *cost, double *grad)
+{
+    (void)du; (void)stage_grad; (void)prob_grad; (void)dtgrad;
+    if (grad) { fprintf(stderr, "c3sc_b200: bellmanrhs gradient (BFGS path) is out of scope\n"); abort(); }
+    double out;
+    if (c3sc_rhs_batch(C3SC_ARITH_EXACT, (uint32_t)dx, discount, 1, prob, &dt, &stage, cost, &out)) die("bellmanrhs");
+    return out;
+}
+int transition_assemble(size_t dx, size_t du, size_t dw, double h, const double *hvec, const double *drift,
+                        const double *grad_drift, const double *ddiff, const double *grad_ddiff, double *prob,
+                        double *grad_prob, double *dt, double *grad_dt, double *space)
+{
+    (void)du; (void)dw; (void)grad_drift; (void)grad_ddiff; (void)grad_dt; (void)space;
+    if (grad_prob) { fprintf(stderr, "c3sc_b200: transition_assemble gradients (BFGS path) are out of scope\n"); abort(); }
+    double sig[C3SC_MAXD];
+    for (size_t i = 0; i < dx; i++) sig[i] = ddiff[i * dx + i];         /* only the diagonal is read, nodeutil.c:294 */
+    int32_t st;
+    if (c3sc_transition_raw(C3SC_ARITH_EXACT, (uint32_t)dx, h, hvec, 1, drift, sig, prob, dt, &st)) die("transition_assemble");
+    return st;
+}
+int convert_fiber_to_ind(size_t d, size_t N, const double *x, const size_t *Ngrid, double **xgrid,
+                         size_t *fixed_ind, size_t *dim_vary)
+{   /* index decode only: first point -> indices, second point -> first differing dimension */
+    for (size_t i = 0; i < d; i++) {
+        size_t hit = Ngrid[i];
+        for (size_t j = 0; j < Ngrid[i]; j++) if (fabs(x[i] - xgrid[i][j]) < 1e-14) { hit = j; break; }
+        if (hit == Ngrid[i]) {
+            fprintf(stderr, "Error: evaluation is not on the grid\nx[%zu] = %3.15E\n", i, x[i]);
+            return 1;
+        }
+        fixed_ind[i] = hit;
+    }
+    *dim_vary = d;
+    for (size_t i = 0; i < d && *dim_vary == d; i++) {
+        size_t hit = Ngrid[i];
+        for (size_t j = 0; j < Ngrid[i]; j++) if (fabs(x[d + i] - xgrid[i][j]) < 1e-14) { hit = j; break; }
+        if (hit != fixed_ind[i]) *dim_vary = i;
+    }
+    if (*dim_vary == d) return 1;
+    return N != Ngrid[*dim_vary] ? 2 : 0;
+}
+
+/* node-level objective / argmin (struct Memory protocol of bellman.c:59-63,367,504) */
+static void node_args(void *arg, struct ControlParams **cp, size_t *node, const double **x, int *ab, double **costs)
+{
+    struct c3sc_memory *mem = arg;
+    *cp = mem->shared; *node = mem->private_;
+    *x = (*cp)->x + *node * (*cp)->dx;
+    *ab = *workspace_get_absorbed((*cp)->work, *node);
+    *costs = workspace_get_costs((*cp)->work, *node);
+}
+double bellman_control(size_t du, const double *u, double *grad_u, void *args)
+{
+    struct ControlParams *cp; size_t node; const double *x; int ab; double *costs, val;
+    (void)du;
+    if (grad_u) { fprintf(stderr, "c3sc_b200: bellman_control gradient (BFGS path) is out of scope\n"); abort(); }
+    node_args(args, &cp, &node, &x, &ab, &costs);
+    if (ab != 0) {
+        int32_t a32 = ab;
+        if (c3sc_node_backup_batch(cp_dev(cp), 1, x, costs, &a32, &val, NULL)) die("bellman_control");
+        return val;
+    }
+    if (c3sc_control_value_batch(cp_dev(cp), 1, x, u, costs, &val)) die("bellman_control");
+    return val;
+}
+int bellman_optimal(size_t du, double *u, double *val, void *arg)
+{
+    struct ControlParams *cp; size_t node; const double *x; int ab; double *costs;
+    node_args(arg, &cp, &node, &x, &ab, &costs);
+    int32_t a32 = ab, best = -1;
+    int rc = c3sc_node_backup_batch(cp_dev(cp), 1, x, costs, &a32, val, &best);
+    if (rc) return rc;
+    for (size_t i = 0; i < du; i++) u[i] = best >= 0 ? cp->opt->vals[(size_t)best * du + i] : 0.0;
+    return 0;
+}
+
+/* ========================== fiber operators ================================ */
+struct VIparam { struct ControlParams *cp; struct ValueF *vf; size_t nstate_evals, nnode_evals; double convergence; };
+struct VIparam *vi_param_create(double conv) { struct VIparam *v = xalloc(1, sizeof *v); v->convergence = conv; return v; }
+void vi_param_destroy(struct VIparam *v) { free(v); }
+void vi_param_add_cp(struct VIparam *v, struct ControlParams *cp) { v->cp = cp; }
+void vi_param_add_value(struct VIparam *v, struct ValueF *vf) { v->vf = vf; v->nstate_evals = 0; v->nnode_evals = 0; }
+size_t vi_param_get_nstate_evals(const struct VIparam *v) { return v->nstate_evals; }
+
+struct PIparam { struct ControlParams *cp; struct ValueF *vf_iteration, *vf_policy; size_t npol_evals, niter_evals; double convergence; };
+struct PIparam *pi_param_create(double conv, struct ValueF *policy)
+{
+    struct PIparam *p = xalloc(1, sizeof *p);
+    p->convergence = conv; p->vf_policy = policy;
+    return p;
+}
+void pi_param_destroy(struct PIparam *p) { free(p); }
+void pi_param_add_cp(struct PIparam *p, struct ControlParams *cp) { p->cp = cp; }
+void pi_param_add_value(struct PIparam *p, struct ValueF *vf) { p->vf_iteration = vf; p->niter_evals = 0; }
+size_t pi_param_get_npol_evals(const struct PIparam *p) { return p->npol_evals; }
+
+static size_t grid_nmax(const struct MCAparam *m)
+{
+    size_t n = 0;
+    for (size_t i = 0; i < m->dx; i++) if (m->ngrid[i] > n) n = m->ngrid[i];
+    return n;
+}
+/* decode F point-described fibers laid back to back; returns total node count or 0 on error */
+static size_t decode_fibers(const struct MCAparam *m, size_t F, const double *x, int32_t *dv, int32_t *fi, size_t *offs)
+{
+    const size_t d = m->dx;
+    size_t pos = 0, fixed[C3SC_MAXD], k;
+    for (size_t f = 0; f < F; f++) {
+        /* N is implied by the varying dimension: decode with the two leading points */
+        size_t Ntry = 0;
+        int rc = convert_fiber_to_ind(d, 0, x + pos * d, m->ngrid, m->xgrid, fixed, &k);
+        if (rc == 1) return 0;
+        Ntry = m->ngrid[k];
+        for (size_t i = 0; i < d; i++) fi[f * d + i] = (int32_t)fixed[i];
+        dv[f] = (int32_t)k;
+        offs[f] = pos;
+        pos += Ntry;
+    }
+    offs[F] = pos;
+    return pos;
+}
+
+int bellman_vi_batch_ind(size_t F, const int32_t *dv, const int32_t *fi, double *out, void *arg)
+{
+    struct VIparam *v = arg;
+    struct ControlParams *cp = v->cp;
+    const size_t nmax = grid_nmax(cp->mca);
+    int rc = c3sc_vi_batch(cp_dev(cp), v->vf->dev, F, dv, fi, nmax, out, NULL);
+    if (rc) { fprintf(stderr, "c3sc_b200: bellman_vi: %s\n", c3sc_last_error()); return rc; }
+    for (size_t f = 0; f < F; f++) { v->nstate_evals += cp->mca->ngrid[dv[f]]; v->nnode_evals += cp->mca->ngrid[dv[f]]; }
+    return 0;
+}
+int bellman_vi_batch(size_t F, const double *x, double *out, void *arg)
+{
+    struct VIparam *v = arg;
+    const struct MCAparam *m = v->cp->mca;
+    const size_t d = m->dx, nmax = grid_nmax(m);
+    int32_t *dv = xalloc(F, 4), *fi = xalloc(F * d, 4);
+    size_t *offs = xalloc(F + 1, sizeof(size_t));
+    double *tmp = xalloc(F * nmax, 8);
+    int rc = decode_fibers(m, F, x, dv, fi, offs) ? 0 : 1;
+    if (!rc) rc = bellman_vi_batch_ind(F, dv, fi, tmp, arg);
+    for (size_t f = 0; f < F && !rc; f++) memcpy(out + offs[f], tmp + f * nmax, (offs[f + 1] - offs[f]) * sizeof(double));
+    free(dv); free(fi); free(offs); free(tmp);
+    return rc;
+}
+int bellman_vi(size_t N, const double *x, double *out, void *arg)
+{
+    struct VIparam *v = arg;
+    const struct MCAparam *m = v->cp->mca;
+    size_t fixed[C3SC_MAXD], k;
+    int rc = convert_fiber_to_ind(m->dx, N, x, m->ngrid, m->xgrid, fixed, &k);
+    if (rc) return rc;
+    control_params_add_time_and_states(v->cp, 0.0, N, x);
+    return bellman_vi_batch(1, x, out, arg);
+}
+
+int bellman_pi_batch_ind(size_t F, const int32_t *dv, const int32_t *fi, double *out, void *arg)
+{
+    struct PIparam *p = arg;
+    struct ControlParams *cp = p->cp;
+    struct Workspace *w = cp->work;
+    const size_t d = cp->mca->dx, nmax = grid_nmax(cp->mca), R = 2 * d + 3;
+    /* split the batch into fibers whose policy rows exist (this pi_iter) and new ones */
+    size_t nh = 0, nm = 0;
+    size_t *ih = xalloc(F, sizeof(size_t)), *im = xalloc(F, sizeof(size_t));
+    struct RowEntry **ent = xalloc(F, sizeof *ent);
+    for (size_t f = 0; f < F; f++) {
+        ent[f] = rows_find(w, dv[f], fi + f * d);
+        if (ent[f]) ih[nh++] = f; else im[nm++] = f;
+    }
+    int rc = 0;
+    for (int pass = 0; pass < 2 && !rc; pass++) {
+        const size_t n = pass ? nh : nm, *idx = pass ? ih : im;
+        if (!n) continue;
+        int32_t *bdv = xalloc(n, 4), *bfi = xalloc(n * d, 4), *barg = xalloc(n * nmax, 4);
+        double *rows = xalloc(n * nmax * R, 8), *val = xalloc(n * nmax, 8);
+        for (size_t q = 0; q < n; q++) {
+            bdv[q] = dv[idx[q]];
+            memcpy(bfi + q * d, fi + idx[q] * d, d * 4);
+            if (pass) memcpy(rows + q * nmax * R, ent[idx[q]]->rows, nmax * R * 8);
+        }
+        rc = c3sc_pi_batch(cp_dev(cp), p->vf_policy->dev, p->vf_iteration->dev, n, bdv, bfi, nmax, pass, rows, barg, val);
+        for (size_t q = 0; q < n && !rc; q++) {
+            memcpy(out + idx[q] * nmax, val + q * nmax, nmax * 8);
+            if (!pass) {
+                struct RowEntry *e = rows_add(w, bdv[q], bfi + q * d, nmax);
+                memcpy(e->rows, rows + q * nmax * R, nmax * R * 8);
+                memcpy(e->argmin, barg + q * nmax, nmax * 4);
+                p->npol_evals += cp->mca->ngrid[bdv[q]];
+            }
+            p->niter_evals += cp->mca->ngrid[bdv[q]];
+        }
+        free(bdv); free(bfi); free(barg); free(rows); free(val);
+    }
+    if (rc) fprintf(stderr, "c3sc_b200: bellman_pi: %s\n", c3sc_last_error());
+    free(ih); free(im); free(ent);
+    return rc;
+}
+int bellman_pi_batch(size_t F, const double *x, double *out, void *arg)
+{
+    struct PIparam *p = arg;
+    const struct MCAparam *m = p->cp->mca;
+    const size_t d = m->dx, nmax = grid_nmax(m);
+    int32_t *dv = xalloc(F, 4), *fi = xalloc(F * d, 4);
+    size_t *offs = xalloc(F + 1, sizeof(size_t));
+    double *tmp = xalloc(F * nmax, 8);
+    int rc = decode_fibers(m, F, x, dv, fi, offs) ? 0 : 1;
+    if (!rc) rc = bellman_pi_batch_ind(F, dv, fi, tmp, arg);
+    for (size_t f = 0; f < F && !rc; f++) memcpy(out + offs[f], tmp + f * nmax, (offs[f + 1] - offs[f]) * sizeof(double));
+    free(dv); free(fi); free(offs); free(tmp);
+    return rc;
+}
+int bellman_pi(size_t N, const double *x, double *out, void *arg)
+{
+    struct PIparam *p = arg;
+    const struct MCAparam *m = p->cp->mca;
+    size_t fixed[C3SC_MAXD], k;
+    int rc = convert_fiber_to_ind(m->dx, N, x, m->ngrid, m->xgrid, fixed, &k);
+    if (rc) return rc;
+    control_params_add_time_and_states(p->cp, 0.0, N, x);
+    return bellman_pi_batch(1, x, out, arg);
+}
+
+int mca_get_neighbor_costs(size_t d, size_t N, const double *x, struct Boundary *bound, struct ValueF *vf,
+                           const size_t *ngrid, double **xgrid, size_t *fixed_ind, size_t *dim_vary,
+                           int *absorbed, double *out)
+{
+    int rc = convert_fiber_to_ind(d, N, x, ngrid, xgrid, fixed_ind, dim_vary);
+    if (rc) return rc;
+    /* geometry-only device problem: any instantiated model of this dimension carries the
+       flag + FT phases; its dynamics are not evaluated in this mode */
+    struct MCAparam m = { d, 1, (size_t *)ngrid, xgrid, 1.0, NULL, 1.0, NULL };
+    double t[2 * C3SC_MAXD], u0[C3SC_MAXD] = { 0 };
+    for (size_t i = 0; i < 2 * d; i++) t[i] = 1.0;
+    m.t = t;
+    struct DPparam dp;
+    memset(&dp, 0, sizeof dp);
+    dp.bound = bound;
+    dp.arith = C3SC_ARITH_FAST;
+    dp.model = (d % 2 == 0) ? C3SC_MODEL_LQGND : (d == 3 ? C3SC_MODEL_DUBINS : C3SC_MODEL_SKID5D);
+    m.du = (dp.model == C3SC_MODEL_LQGND) ? d / 2 : 1;
+    struct c3Opt opt = { BRUTEFORCE, m.du, 1, u0 };
+    c3sc_problem *p = make_problem(&dp, &m, &opt, d);
+    size_t nmax = 0;
+    for (size_t i = 0; i < d; i++) if (ngrid[i] > nmax) nmax = ngrid[i];
+    int32_t dv = (int32_t)*dim_vary, fi[C3SC_MAXD];
+    for (size_t i = 0; i < d; i++) fi[i] = (int32_t)fixed_ind[i];
+    int32_t *ab = xalloc(nmax, 4);
+    double *costs = xalloc(nmax * (2 * d + 1), 8);
+    rc = c3sc_neighbor_costs_batch(p, vf->dev, 1, &dv, fi, nmax, ab, costs, NULL, NULL);
+    if (!rc) {
+        for (size_t j = 0; j < N; j++) absorbed[j] = ab[j];
+        memcpy(out, costs, N * (2 * d + 1) * sizeof(double));
+    }
+    free(ab); free(costs);
+    c3sc_problem_destroy(p);
+    return rc;
+}
+
+/* ========================== C3Control facade =============================== */
+struct C3Control {
+    size_t dx, du, dw;
+    size_t *ngrid; double **xgrid, *h, hmin;
+    struct Boundary *bound; struct MCAparam *mca; struct DPparam *dp; struct Workspace *work;
+};
+struct C3Control *c3control_create(size_t dx, size_t du, size_t dw, double *lb, double *ub, size_t *ngrid, double discount)
+{
+    struct C3Control *c = xalloc(1, sizeof *c);
+    c->dx = dx; c->du = du; c->dw = dw; c->ngrid = ngrid;
+    c->xgrid = xalloc(dx, sizeof(double *));
+    c->h = xalloc(dx, sizeof(double));
+    c->hmin = ub[0] - lb[0];
+    size_t nmax = ngrid[0];
+    for (size_t i = 0; i < dx; i++) {
+        /* C3 linspace: running sum of the interval (bellman.c:1979) */
+        double *g = xalloc(ngrid[i], sizeof(double));
+        const double step = (ub[i] - lb[i]) / (double)(ngrid[i] - 1);
+        g[0] = lb[i];
+        for (size_t j = 1; j < ngrid[i]; j++) g[j] = g[j - 1] + step;
+        c->xgrid[i] = g;
+        c->h[i] = g[1] - g[0];
+        if (c->h[i] < c->hmin) c->hmin = c->h[i];
+        if (ngrid[i] > nmax) nmax = ngrid[i];
+    }
+    c->bound = boundary_alloc(dx, lb, ub);
+    c->mca = mca_param_create(dx, du);
+    mca_add_grid_refs(c->mca, c->ngrid, c->xgrid, c->hmin, c->h);
+    c->dp = dp_param_create(dx, du, dw, discount);
+    dp_param_add_boundary(c->dp, c->bound);
+    c->work = workspace_alloc(dx, du, dw, nmax);
+    return c;
+}
+void c3control_destroy(struct C3Control *c)
+{
+    if (!c) return;
+    boundary_free(c->bound); mca_param_destroy(c->mca); dp_param_destroy(c->dp); workspace_free(c->work);
+    for (size_t i = 0; i < c->dx; i++) free(c->xgrid[i]);
+    free(c->xgrid); free(c->h); free(c);
+}
+size_t *c3control_get_ngrid(struct C3Control *c) { return c ? c->ngrid : NULL; }
+double **c3control_get_xgrid(struct C3Control *c) { return c ? c->xgrid : NULL; }
+void c3control_set_external_boundary(struct C3Control *c, size_t dim, char *type) { boundary_external_set_type(c->bound, dim, type); }
+void c3control_add_obstacle(struct C3Control *c, double *center, double *widths) { boundary_add_obstacle(c->bound, center, widths); }
+void c3control_add_drift(struct C3Control *c, c3sc_dyn_cb b, void *a) { dp_param_add_drift(c->dp, b, a); }
+void c3control_add_diff(struct C3Control *c, c3sc_dyn_cb s, void *a) { dp_param_add_diff(c->dp, s, a); }
+void c3control_add_stagecost(struct C3Control *c, int (*f)(double, const double *, const double *, double *, double *)) { dp_param_add_stagecost(c->dp, f); }
+void c3control_add_boundcost(struct C3Control *c, int (*f)(double, const double *, double *)) { dp_param_add_boundcost(c->dp, f); }
+void c3control_add_obscost(struct C3Control *c, int (*f)(const double *, double *)) { dp_param_add_obscost(c->dp, f); }
+void c3control_set_device_model(struct C3Control *c, int model, const double *params, size_t n) { dp_param_set_device_model(c->dp, model, params, n); }
+struct DPparam *c3control_get_dp(struct C3Control *c) { return c->dp; }
+struct MCAparam *c3control_get_mca(struct C3Control *c) { return c->mca; }
+struct Workspace *c3control_get_work(struct C3Control *c) { return c->work; }
+struct Boundary *c3control_get_boundary(struct C3Control *c) { return c->bound; }
+
+int c3control_vi_fibers(struct C3Control *c, struct ValueF *vf, struct c3Opt *opt, size_t F, const int32_t *dv,
+                        const int32_t *fi, double *out, size_t *nevals)
+{
+    struct ControlParams *cp = control_params_create(c->dx, c->dw, c->dp, c->mca, c->work, opt);
+    struct VIparam *vi = vi_param_create(1e-10);
+    vi_param_add_cp(vi, cp);
+    vi_param_add_value(vi, vf);
+    workspace_increment_vi_iter(c->work);
+    int rc = bellman_vi_batch_ind(F, dv, fi, out, vi);
+    if (nevals) *nevals = vi->nnode_evals;
+    vi_param_destroy(vi);
+    control_params_destroy(cp);
+    return rc;
+}

@@ -29,4 +29,24 @@ int build_ctab_lqg_lo(int dx, const DevProblem &P, double *ctab, cudaStream_t st
     }
     return -1;
 }
+int launch_node_backup_lqg_lo(int dx, int arith, const DevProblem &P, int n, const double *x, const double *costs,
+                              const int *absorbed, double *value, int *argmin, cudaStream_t st)
+{
+    switch (dx) {
+    case 2: return launch_node_backup_t<LqgNd<2>>(arith, P, n, x, costs, absorbed, value, argmin, st);
+    case 4: return launch_node_backup_t<LqgNd<4>>(arith, P, n, x, costs, absorbed, value, argmin, st);
+    case 6: return launch_node_backup_t<LqgNd<6>>(arith, P, n, x, costs, absorbed, value, argmin, st);
+    }
+    return -1;
+}
+int launch_control_value_lqg_lo(int dx, int arith, const DevProblem &P, int n, const double *x, const double *u,
+                                const double *costs, double *value, cudaStream_t st)
+{
+    switch (dx) {
+    case 2: return launch_control_value_t<LqgNd<2>>(arith, P, n, x, u, costs, value, st);
+    case 4: return launch_control_value_t<LqgNd<4>>(arith, P, n, x, u, costs, value, st);
+    case 6: return launch_control_value_t<LqgNd<6>>(arith, P, n, x, u, costs, value, st);
+    }
+    return -1;
+}
 }  // namespace c3sc

@@ -49,6 +49,50 @@ int build_ctab_misc(int model, int dx, const DevProblem &P, double *ctab, cudaSt
     return -1;
 }
 
+int launch_node_backup_misc(int model, int dx, int arith, const DevProblem &P, int n, const double *x, const double *costs,
+                            const int *absorbed, double *value, int *argmin, cudaStream_t st)
+{
+    switch (model) {
+    case C3SC_MODEL_DOUBLE_INT:
+        switch (dx) {
+        case 2: return launch_node_backup_t<DoubleInt<2>>(arith, P, n, x, costs, absorbed, value, argmin, st);
+        case 3: return launch_node_backup_t<DoubleInt<3>>(arith, P, n, x, costs, absorbed, value, argmin, st);
+        case 4: return launch_node_backup_t<DoubleInt<4>>(arith, P, n, x, costs, absorbed, value, argmin, st);
+        }
+        return -1;
+    case C3SC_MODEL_DUBINS: return dx == 3 ? launch_node_backup_t<Dubins>(arith, P, n, x, costs, absorbed, value, argmin, st) : -1;
+    case C3SC_MODEL_SKID5D: return dx == 5 ? launch_node_backup_t<Skid5d>(arith, P, n, x, costs, absorbed, value, argmin, st) : -1;
+    }
+    return -1;
+}
+
+int launch_control_value_misc(int model, int dx, int arith, const DevProblem &P, int n, const double *x, const double *u,
+                              const double *costs, double *value, cudaStream_t st)
+{
+    switch (model) {
+    case C3SC_MODEL_DOUBLE_INT:
+        switch (dx) {
+        case 2: return launch_control_value_t<DoubleInt<2>>(arith, P, n, x, u, costs, value, st);
+        case 3: return launch_control_value_t<DoubleInt<3>>(arith, P, n, x, u, costs, value, st);
+        case 4: return launch_control_value_t<DoubleInt<4>>(arith, P, n, x, u, costs, value, st);
+        }
+        return -1;
+    case C3SC_MODEL_DUBINS: return dx == 3 ? launch_control_value_t<Dubins>(arith, P, n, x, u, costs, value, st) : -1;
+    case C3SC_MODEL_SKID5D: return dx == 5 ? launch_control_value_t<Skid5d>(arith, P, n, x, u, costs, value, st) : -1;
+    }
+    return -1;
+}
+int launch_rhs(int arith, int dx, double beta, int n, const double *prob, const double *dt, const double *stage,
+               const double *cost, double *out, void *stream)
+{
+    if (n <= 0) return 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int g = (n + 127) / 128;
+    if (arith == C3SC_ARITH_EXACT) k_rhs<Exact><<<g, 128, 0, st>>>(dx, beta, n, prob, dt, stage, cost, out);
+    else k_rhs<Fast><<<g, 128, 0, st>>>(dx, beta, n, prob, dt, stage, cost, out);
+    return (int)cudaGetLastError();
+}
+
 template <int DX>
 static int tr(int arith, const DevProblem &P, int n, const double *drift, const double *sig, double *prob,
               double *dt, int *status, cudaStream_t st)

@@ -163,6 +163,36 @@ int c3sc_pi_batch(c3sc_problem *p, const c3sc_valuef *vf_policy, const c3sc_valu
                   size_t F, const int32_t *dim_vary, const int32_t *fixed_ind,
                   size_t ldo, int have_rows, double *rows, int32_t *argmin, double *value);
 
+/* mca_get_neighbor_costs (src/nodeutil.c:647-713) over F fibers: flags, neighbour
+ * indices and FT neighbour values only (process_fibers_neighbor + 
+ * valuef_eval_fiber_ind_nn).  nbr_vary / nbr_fixed may be NULL.               */
+int c3sc_neighbor_costs_batch(c3sc_problem *p, const c3sc_valuef *vf, size_t F,
+                              const int32_t *dim_vary, const int32_t *fixed_ind, size_t ldo,
+                              int32_t *absorbed, double *costs, int32_t *nbr_vary, int32_t *nbr_fixed);
+/* bellman_optimal (src/bellman.c:504-543) at n nodes with caller-supplied
+ * neighbour costs [n*(2dx+1)] and flags (NULL = all 0): the building block of
+ * the online controller (src/bellman.c:2105-2175).                           */
+int c3sc_node_backup_batch(c3sc_problem *p, size_t n, const double *x, const double *costs,
+                           const int32_t *absorbed, double *value, int32_t *argmin);
+
+/* bellman_control (src/bellman.c:367-480, grad_u == NULL) at n (x, u, costs)
+ * triples; u need not be in the control table.                               */
+int c3sc_control_value_batch(c3sc_problem *p, size_t n, const double *x, const double *u,
+                             const double *costs, double *value);
+/* bellmanrhs (src/bellman.c:88-112, no gradient) on n raw tuples; no problem handle. */
+int c3sc_rhs_batch(int arith, uint32_t dx, double discount, size_t n, const double *prob,
+                   const double *dt, const double *stage, const double *cost, double *out);
+/* transition_assemble (src/nodeutil.c:267-406, non-gradient branch) with the raw
+ * (h2, t[2dx]) of its signature; no problem handle.                          */
+int c3sc_transition_raw(int arith, uint32_t dx, double h2, const double *t, size_t n,
+                        const double *drift, const double *sigma_diag, double *prob, double *dt,
+                        int32_t *status);
+/* valuef_eval_fiber_ind_nn (src/valuefunc.c:369-585) with caller-supplied neighbour
+ * indices: nbr_fixed [F*2*(d-1)], nbr_vary [F*ldo*2]; costs [F*ldo*(2d+1)].  */
+int c3sc_ft_fiber_nn_batch(const c3sc_valuef *vf, size_t F, const int32_t *dim_vary,
+                           const int32_t *fixed_ind, const int32_t *nbr_fixed,
+                           const int32_t *nbr_vary, size_t ldo, double *costs);
+
 /* ---- pieces of the path exposed for parity tests -------------------------- */
 /* transition_assemble (src/nodeutil.c:267-406, non-gradient branch) for n
  * independent (drift[dx], diag sigma[dx]) pairs given on the host;
