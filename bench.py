@@ -222,11 +222,13 @@ def main():
                 self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<f8", "data": (ptr, False), "version": 3}
         core_view = torch.as_tensor(_Arr(core_ptr, core_cnt), device=dev)
 
-    # every rank draws its own shard of the global fiber list
+    # one global fiber list of F*world fibers; rank g owns the contiguous block g (stable map)
+    from c3sc_b200 import sharding
     dv_all, fi_all = synthetic.random_fibers(cfg.ngrid, F * world)
-    sl = slice(rank * F, (rank + 1) * F)
-    dv_h = torch.from_numpy(dv_all[sl].copy()).pin_memory()
-    fi_h = torch.from_numpy(fi_all[sl].copy()).pin_memory()
+    dv_s, fi_s, nreal = sharding.shard_fibers(dv_all, fi_all, world, rank)
+    assert nreal == F
+    dv_h = torch.from_numpy(dv_s).pin_memory()
+    fi_h = torch.from_numpy(fi_s).pin_memory()
     dv_d = dv_h.to(dev); fi_d = fi_h.to(dev)
     out_d = torch.zeros(F * N, dtype=torch.float64, device=dev)
     gathered = torch.empty(world * F * N, dtype=torch.float64, device=dev) if world > 1 else None
@@ -237,10 +239,10 @@ def main():
 
     def step_resident():
         if world > 1:
-            dist.broadcast(core_view, src=0)
+            sharding.broadcast_cores(core_view, src=0)
         prob.vi_batch_dev(vf, F, dv_d.data_ptr(), fi_d.data_ptr(), N, out_d.data_ptr(), stream=sptr)
         if world > 1:
-            dist.all_gather_into_tensor(gathered, out_d)
+            sharding.gather_values(out_d, F * world, N, out=gathered)
 
     def step_e2e():
         capi.check(capi.lib().c3sc_vi_batch(prob.handle, vf.handle, F, dv_h.data_ptr(), fi_h.data_ptr(), N,
