@@ -47,7 +47,7 @@ EXPORTS = [
     "c3sc_vi_batch_dev", "c3sc_pi_batch_dev", "c3sc_vi_batch", "c3sc_vi_batch_debug", "c3sc_pi_batch",
     "c3sc_transition_batch", "c3sc_model_eval", "c3sc_measure_fp64_peak",
     "c3sc_neighbor_costs_batch", "c3sc_node_backup_batch", "c3sc_control_value_batch", "c3sc_rhs_batch",
-    "c3sc_transition_raw", "c3sc_ft_fiber_nn_batch",
+    "c3sc_transition_raw", "c3sc_ft_fiber_nn_batch", "c3sc_debug_phase_profile",
 ]
 
 _lib = None

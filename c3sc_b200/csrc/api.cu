@@ -303,7 +303,18 @@ static int check_shapes(const c3sc_problem *p, const c3sc_valuef *vf, size_t F, 
     return C3SC_OK;
 }
 
+static unsigned long long *g_prof = nullptr;
+
 extern "C" {
+
+/* debug: per-phase cycle counters of k_backup (8 slots), summed over CTAs; enable=0 turns it off */
+int c3sc_debug_phase_profile(int enable, unsigned long long *out8)
+{
+    if (enable && !g_prof) { CK(cudaMalloc(&g_prof, 64)); CK(cudaMemset(g_prof, 0, 64)); }
+    if (out8 && g_prof) { CK(cudaDeviceSynchronize()); CK(cudaMemcpy(out8, g_prof, 64, cudaMemcpyDeviceToHost)); CK(cudaMemset(g_prof, 0, 64)); }
+    if (!enable && g_prof) { cudaFree(g_prof); g_prof = nullptr; }
+    return C3SC_OK;
+}
 
 int c3sc_vi_batch_dev(c3sc_problem *p, const c3sc_valuef *vf, size_t F, const int32_t *d_dim_vary,
                       const int32_t *d_fixed_ind, size_t ldo, const c3sc_batch_out *out, void *stream)
@@ -320,6 +331,7 @@ int c3sc_vi_batch_dev(c3sc_problem *p, const c3sc_valuef *vf, size_t F, const in
     a.out.costs = out->costs; a.out.rows = out->rows; a.out.nbr_vary = out->nbr_vary; a.out.nbr_fixed = out->nbr_fixed;
     a.mode = MODE_VI;
     a.write_value = out->value != nullptr;
+    a.prof = g_prof;
     return dispatch(p, a, (cudaStream_t)stream);
 }
 

@@ -15,6 +15,7 @@
 // Only the N values (and optional diagnostics) go back to HBM.
 #pragma once
 #include <cuda_runtime.h>
+#include <cstdlib>
 #include <math_constants.h>
 #include "dev_types.h"
 #include "arith.cuh"
@@ -30,33 +31,44 @@ __host__ __device__ inline int odd_up(int v) { return v | 1; }
 // ---------------------------------------------------------------------------
 // shared-memory carve-up (all offsets in doubles / ints); identical on host+device
 constexpr int PMAX = 8;              // max candidate chunks ("parts") per node
+constexpr int TMAX = 16;             // max nodes per FT tile
+constexpr int NSTAGE = 3;            // depth of the TMA staging ring
 
 struct SmemPlan {
     int rs;        // padded (odd) vector stride
     int cs;        // cost-row stride (2dx+1, odd already)
     int ns;        // per-node invariant stride (odd)
-    int oL, oR, oNb, oTmp, oC, oV, oScr, nDoubles;
-    int oW, oU;                    // FT phase view of the scratch region
+    int nv;        // vectors per chain set: 1 + 2(dx-1)
+    int wst;       // stride of one node's (w,u) pair in the FT tile
+    int oVL, oVR, oC, oV, oScr, nDoubles;
+    int oWt;                       // FT phase view of the scratch region
     int oNode, oBestV, oBestI;     // control phase view of the scratch region (oBestI in doubles)
+    int oRing, oBar, cb, slot;     // TMA staging ring (staged plan only): NSTAGE slots of `slot` doubles
     int oAbs, oNv, oAct, oNf, oFix, oMisc, nInts;
-    __host__ __device__ SmemPlan(int dx, int nud, int nmax, int rmax)
+    __host__ __device__ SmemPlan(int dx, int nud, int nmax, int rmax, bool staged)
     {
         rs = odd_up(rmax);
         cs = 2 * dx + 1;
         ns = odd_up(2 * nud + 3);
+        nv = 2 * dx - 1;
+        wst = 2 * rs + 1 - ((2 * rs + 1) & 1) + 1;     // odd
         int o = 0;
-        oL = o;    o += (dx + 1) * rs;
-        oR = o;    o += (dx + 1) * rs;
-        oNb = o;   o += 2 * dx * rs;
-        oTmp = o;  o += NW * 2 * rs;
+        oVL = o;   o += 2 * nv * rs;
+        oVR = o;   o += 2 * nv * rs;
         oC = o;    o += nmax * cs;
         oV = o;    o += nmax;
         oScr = o;
-        oW = oScr; oU = oW + nmax * rs;
-        const int ft_need = 2 * nmax * rs;
+        oWt = oScr;
+        const int ft_need = TMAX * wst;
         oNode = oScr; oBestV = oNode + nmax * ns; oBestI = oBestV + PMAX * nmax;
         const int ctl_need = nmax * ns + PMAX * nmax + (PMAX * nmax + 1) / 2;
         o += ft_need > ctl_need ? ft_need : ctl_need;
+        o += o & 1;                                     // 16-byte alignment of the ring
+        cb = (rmax * rmax + 2 + 1) & ~1;               // one block + alignment slack, even
+        slot = 6 * cb;                                  // a chain step stages <= 6 blocks
+        oRing = o;
+        oBar = o;
+        if (staged) { o += NSTAGE * slot; oBar = o; o += NSTAGE + (NSTAGE & 1); }
         nDoubles = o;
         int q = 0;
         oAbs = q;  q += nmax;
@@ -69,6 +81,51 @@ struct SmemPlan {
     }
     __host__ __device__ size_t bytes() const { return (size_t)nDoubles * 8 + (size_t)nInts * 4; }
 };
+
+// ---- TMA bulk copy (cp.async.bulk, SASS UBLKCP) + mbarrier helpers -------------------------
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long *b, unsigned count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(b)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *b, unsigned bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(b)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, unsigned bytes, unsigned long long *b)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(b)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *b, unsigned parity)
+{
+    asm volatile("{\n"
+                 ".reg .pred P1;\n"
+                 "LAB_WAIT:\n"
+                 "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+                 "@P1 bra DONE;\n"
+                 "bra LAB_WAIT;\n"
+                 "DONE:\n"
+                 "}" ::"r"(smem_u32(b)), "r"(parity) : "memory");
+}
+// length-n dot with strides, four independent partial sums (breaks the DFMA dependency chain so
+// the shared-memory loads of four terms are in flight together)
+__device__ __forceinline__ double dot4(const double *x, int sx, const double *y, int sy, int n)
+{
+    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+    int i = 0;
+    for (; i + 4 <= n; i += 4) {
+        a0 = fma(x[i * sx], y[i * sy], a0);
+        a1 = fma(x[(i + 1) * sx], y[(i + 1) * sy], a1);
+        a2 = fma(x[(i + 2) * sx], y[(i + 2) * sy], a2);
+        a3 = fma(x[(i + 3) * sx], y[(i + 3) * sy], a3);
+    }
+    for (; i < n; i++) a0 = fma(x[i * sx], y[i * sy], a0);
+    return (a0 + a1) + (a2 + a3);
+}
+__host__ __device__ inline int gcd16(int r) { int g = 1; while (g < 16 && (r % (2 * g)) == 0) g *= 2; return g; }
+
+__device__ __forceinline__ void prefetch_l1(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 
 // ---------------------------------------------------------------------------
 // fast reciprocal and exp for the FAST policy (both ~1 ulp)
@@ -227,41 +284,80 @@ __device__ __forceinline__ double candidate_value(const DevProblem &P, const dou
 }
 
 // ---------------------------------------------------------------------------
-// y[b] = sum_a v[a] * G[a + b*m]   (row vector times column-major m x n block), one warp
-__device__ __forceinline__ void warp_vecmat(int m, int n, const double *__restrict__ G,
-                                            const double *v, double *y, int lane)
+#define PHASE_MARK(slot)                                                        \
+    do {                                                                        \
+        if (a.prof && tid == 0) {                                               \
+            const long long now_ = clock64();                                   \
+            pacc[slot] += (unsigned long long)(now_ - tmark);                   \
+            tmark = now_;                                                       \
+        }                                                                       \
+    } while (0)
+
+// Arm one ring slot: the bulk copies of item `item` of the current fiber (thread 0 only).
+// Chain step s stages, per active side, the centre block and the two neighbour blocks of the
+// dimension it consumes; a node tile stages nt consecutive blocks of the varying core.  Sources
+// are widened to 16-byte boundaries (cp.async.bulk needs it); consumers add (offset & 1).
+__device__ __forceinline__ void ring_issue(const DevFT &ft, int item, int nsteps, int k, int DX, int N, int T,
+                                        const int *sFix, const int *sNf, double *dst, int cb,
+                                        unsigned long long *bar)
 {
-    for (int b = lane; b < n; b += 32) {
-        const double *col = G + (size_t)b * m;
-        double acc = 0.0;
-        for (int a = 0; a < m; a++) acc = fma(v[a], __ldg(col + a), acc);
-        y[b] = acc;
-    }
-}
-// y[a] = sum_b G[a + b*m] * v[b], one warp
-__device__ __forceinline__ void warp_matvec(int m, int n, const double *__restrict__ G,
-                                            const double *v, double *y, int lane)
-{
-    for (int a = lane; a < m; a += 32) {
-        double acc = 0.0;
-        for (int b = 0; b < n; b++) acc = fma(__ldg(G + a + (size_t)b * m), v[b], acc);
-        y[a] = acc;
+    unsigned total = 0;
+#pragma unroll 1
+    for (int pass = 0; pass < 2; pass++) {
+        if (pass == 1) mbar_expect_tx(bar, total);
+        if (item < nsteps) {
+#pragma unroll 1
+            for (int c = 0; c < 6; c++) {
+                const int side = c / 3, w = c - 3 * side;
+                const bool on = side == 0 ? (item < k) : (item < DX - 1 - k);
+                if (!on) continue;
+                const int m = side == 0 ? item : DX - 1 - item;
+                const int bl = ft.r[m] * ft.r[m + 1];
+                const int slotn = m < k ? m : m - 1;
+                const int jn = w == 0 ? sFix[m] : sNf[2 * slotn + (w - 1)];
+                const long long s0 = ft.off[m] + (long long)jn * bl;
+                const long long sa = s0 & ~1LL, ea = (s0 + bl + 1) & ~1LL;
+                if (pass == 0) total += (unsigned)((ea - sa) * 8);
+                else bulk_g2s(dst + c * cb, ft.base + sa, (unsigned)((ea - sa) * 8), bar);
+            }
+        } else {
+            const int blk = ft.r[k] * ft.r[k + 1];
+            const int j0 = (item - nsteps) * T;
+            const int nt = (N - j0 < T) ? N - j0 : T;
+            const long long s0 = ft.off[k] + (long long)j0 * blk;
+            const long long sa = s0 & ~1LL, ea = (s0 + (long long)nt * blk + 1) & ~1LL;
+            if (pass == 0) total += (unsigned)((ea - sa) * 8);
+            else bulk_g2s(dst, ft.base + sa, (unsigned)((ea - sa) * 8), bar);
+        }
     }
 }
 
-// ---------------------------------------------------------------------------
 template <class M, class A>
-__global__ void __launch_bounds__(NT) k_backup(const LaunchArgs a)
+__global__ void __launch_bounds__(NT, A::exact ? 1 : 2) k_backup(const LaunchArgs a)
 {
+    unsigned long long pacc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    long long tmark = clock64();
     constexpr int DX = M::DX, DU = M::DU, CS = 2 * DX + 1, RW = 2 * DX + 3;
     const DevProblem &P = a.P;
     const DevFT &ft = a.ft;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
-    extern __shared__ double smem[];
-    const SmemPlan sp(DX, M::NUD, P.nmax, ft.rmax);
-    double *sL = smem + sp.oL, *sR = smem + sp.oR, *sNb = smem + sp.oNb, *sTmp = smem + sp.oTmp;
-    double *sW = smem + sp.oW, *sU = smem + sp.oU, *sC = smem + sp.oC, *sV = smem + sp.oV;
+    extern __shared__ __align__(16) double smem[];
+    const SmemPlan sp(DX, M::NUD, P.nmax, ft.rmax, a.staged != 0);
+    double *sVL = smem + sp.oVL, *sVR = smem + sp.oVR, *sC = smem + sp.oC, *sV = smem + sp.oV;
+    double *sWt = smem + sp.oWt;
+    const double *sLset = sVL, *sRset = sVR;
+    const int NV = sp.nv, wst = sp.wst;
+    double *ring = smem + sp.oRing;
+    unsigned long long *mbar = reinterpret_cast<unsigned long long *>(smem + sp.oBar);
+    unsigned git = 0;                      // running item counter of the staging ring (CTA-uniform)
+    if (a.staged) {
+        if (tid == 0) {
+            for (int q = 0; q < NSTAGE; q++) mbar_init(mbar + q, 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncthreads();
+    }
     double *sNode = smem + sp.oNode, *sBestV = smem + sp.oBestV;
     int *sBestI = reinterpret_cast<int *>(smem + sp.oBestI);
     int *ismem = reinterpret_cast<int *>(smem + sp.nDoubles);
@@ -338,101 +434,240 @@ __global__ void __launch_bounds__(NT) k_backup(const LaunchArgs a)
             for (int e = tid; e < 2 * N; e += NT) sNv[e] = a.nbr_vary_in[2 * obase + e];
         }
         __syncthreads();                       // sFix / sNf / flags visible
+        PHASE_MARK(0);
 
-        // ---- 2. function-train neighbour values (valuefunc.c:369-585) ---------
+        // ---- 2. function-train neighbour values (valuefunc.c:369-585, re-associated) ----
+        // 2a. stepped chains.  Left set after step m:  {L_{m+1}} U {a_i^-, a_i^+ : i <= m}, all row
+        //     vectors of length r_{m+1};  a_i^s = L_i G_i[nb_s] G_{i+1}[f] .. G_m[f].
+        //     Right set (dimensions walked from d-1 down): {R_m} U {c_i^s : i >= m}, columns of
+        //     length r_m;  c_i^s = G_m[f] .. G_{i-1}[f] G_i[nb_s] R_{i+1}.
+        //     One step = every vector of a set times one centre block + two neighbour blocks of
+        //     the prefix/suffix vector: a small GEMM spread over all threads, depth max(k, d-1-k).
         const int rk = ft.r[k], rk1 = ft.r[k + 1];
 #define CORE_BLK(i, j) (ft.base + ft.off[i] + (size_t)(j) * ft.r[i] * ft.r[(i) + 1])
-        // 2a. prefix row vectors L_i = G_0[f]..G_{i-1}[f] (warp 0), suffix columns R_i = G_i[f]..G_{d-1}[f] (warp 1)
-        if (warp == 0) {
-            if (lane == 0) sL[0] = 1.0;
-            __syncwarp();
-            for (int i = 0; i < k; i++) {
-                warp_vecmat(ft.r[i], ft.r[i + 1], CORE_BLK(i, sFix[i]), sL + i * rs, sL + (i + 1) * rs, lane);
-                __syncwarp();
+        if (a.staged) {
+            // ---- staged plan: every FT operand arrives in shared memory by TMA bulk copy --------
+            // item stream of a fiber = chain steps 0..nsteps-1, then node tiles; item i lives in ring
+            // slot (git0+i) % NSTAGE; thread 0 re-arms a slot as soon as the CTA is done with it.
+            const int nsteps = (k > DX - 1 - k) ? k : DX - 1 - k;
+            const int blk = rk * rk1, CBs = sp.cb, SL = sp.slot;
+            int T = (SL - 2) / blk;
+            T = T < 1 ? 1 : (T > TMAX ? TMAX : T);
+            const int ntiles = (N + T - 1) / T, nitems = nsteps + ntiles;
+            const unsigned git0 = git;
+            auto issue = [&](int item) {
+                const unsigned g = git0 + (unsigned)item;
+                ring_issue(ft, item, nsteps, k, DX, N, T, sFix, sNf, ring + (g % NSTAGE) * SL, CBs, mbar + (g % NSTAGE));
+            };
+            if (tid == 0) {
+                sVL[0] = 1.0; sVR[0] = 1.0;
+                for (int it = 0; it < NSTAGE && it < nitems; it++) issue(it);
             }
-        } else if (warp == 1) {
-            if (lane == 0) sR[DX * rs] = 1.0;
-            __syncwarp();
-            for (int i = DX - 1; i > k; i--) {
-                warp_matvec(ft.r[i], ft.r[i + 1], CORE_BLK(i, sFix[i]), sR + (i + 1) * rs, sR + i * rs, lane);
-                __syncwarp();
-            }
-        }
-        __syncthreads();
-        // 2b. neighbour vectors: for i<k  a_i^s = L_i G_i[nb] G_{i+1}[f]..G_{k-1}[f]   (length r_k)
-        //                        for i>k  c_i^s = G_{k+1}[f]..G_{i-1}[f] G_i[nb] R_{i+1} (length r_{k+1})
-        for (int task = warp; task < 2 * (DX - 1); task += NW) {
-            const int slot = task >> 1, side = task & 1;
-            const int i = slot < k ? slot : slot + 1;
-            const int nb = sNf[2 * slot + side];
-            double *t0 = sTmp + (warp * 2) * rs, *t1 = t0 + rs;
-            double *dst = sNb + (2 * i + side) * rs;
-            if (i < k) {
-                double *cur = (i + 1 == k) ? dst : t0;
-                warp_vecmat(ft.r[i], ft.r[i + 1], CORE_BLK(i, nb), sL + i * rs, cur, lane);
-                __syncwarp();
-                for (int m = i + 1; m < k; m++) {
-                    double *nxt = (m + 1 == k) ? dst : (cur == t0 ? t1 : t0);
-                    warp_vecmat(ft.r[m], ft.r[m + 1], CORE_BLK(m, sFix[m]), cur, nxt, lane);
-                    __syncwarp();
-                    cur = nxt;
+            int cur = 0;
+            __syncthreads();
+            for (int s = 0; s < nsteps; s++, git++) {
+                const double *inL = sVL + cur * NV * rs, *inR = sVR + cur * NV * rs;
+                double *outL = sVL + (cur ^ 1) * NV * rs, *outR = sVR + (cur ^ 1) * NV * rs;
+                const bool doL = s < k, doR = s < DX - 1 - k;
+                const int mL = s, mR = DX - 1 - s, nin = 1 + 2 * s;
+                const int nl = doL ? (nin + 2) * ft.r[mL + 1] : 0;
+                const int nr = doR ? (nin + 2) * ft.r[mR] : 0;
+                const double *sl = ring + (git % NSTAGE) * SL;
+                mbar_wait(mbar + (git % NSTAGE), (git / NSTAGE) & 1);
+                for (int e = tid; e < nl + nr; e += NT) {
+                    if (e < nl) {
+                        const int m = mL, rm = ft.r[m], nout = nin + 2, bl = rm * ft.r[m + 1];
+                        const int b = e / nout, v = e - b * nout;
+                        const int w = v < nin ? 0 : 1 + (v - nin);
+                        const int jn = w == 0 ? sFix[m] : sNf[2 * m + (w - 1)];
+                        const double *G = sl + w * CBs + (int)((ft.off[m] + (long long)jn * bl) & 1);
+                        const double *vec = inL + (v < nin ? v : 0) * rs;
+                        outL[v * rs + b] = dot4(vec, 1, G + b * rm, 1, rm);
+                    } else {
+                        const int e2 = e - nl, m = mR, rm = ft.r[m], rm1 = ft.r[m + 1], nout = nin + 2, bl = rm * rm1;
+                        const int aa = e2 / nout, v = e2 - aa * nout;
+                        const int w = v < nin ? 0 : 1 + (v - nin);
+                        const int jn = w == 0 ? sFix[m] : sNf[2 * (m - 1) + (w - 1)];
+                        const double *G = sl + (3 + w) * CBs + (int)((ft.off[m] + (long long)jn * bl) & 1);
+                        const double *vec = inR + (v < nin ? v : 0) * rs;
+                        outR[v * rs + aa] = dot4(G + aa, rm, vec, 1, rm1);
+                    }
                 }
-            } else {
-                double *cur = (i - 1 == k) ? dst : t0;
-                warp_matvec(ft.r[i], ft.r[i + 1], CORE_BLK(i, nb), sR + (i + 1) * rs, cur, lane);
-                __syncwarp();
-                for (int m = i - 1; m > k; m--) {
-                    double *nxt = (m - 1 == k) ? dst : (cur == t0 ? t1 : t0);
-                    warp_matvec(ft.r[m], ft.r[m + 1], CORE_BLK(m, sFix[m]), cur, nxt, lane);
-                    __syncwarp();
-                    cur = nxt;
+                if (!doL && k > 0) for (int e = tid; e < (1 + 2 * k) * rs; e += NT) outL[e] = inL[e];
+                if (!doR && DX - 1 - k > 0) for (int e = tid; e < (1 + 2 * (DX - 1 - k)) * rs; e += NT) outR[e] = inR[e];
+                if (!doL && k == 0 && tid == 0) outL[0] = 1.0;
+                if (!doR && DX - 1 - k == 0 && tid == 0) outR[0] = 1.0;
+                cur ^= 1;
+                __syncthreads();
+                if (tid == 0 && s + NSTAGE < nitems) issue(s + NSTAGE);
+            }
+            sLset = sVL + cur * NV * rs;
+            sRset = sVR + cur * NV * rs;
+            PHASE_MARK(1);
+            {
+                const double *Lk = sLset, *Rk1 = sRset;
+                const int gk = gcd16(rk), per16 = 16 / gk;
+                for (int t = 0; t < ntiles; t++, git++) {
+                    const int j0 = t * T, nt = (N - j0 < T) ? N - j0 : T;
+                    const double *gt = ring + (git % NSTAGE) * SL + (int)((ft.off[k] + (long long)j0 * blk) & 1);
+                    long long t0_ = (a.prof && tid == 0) ? clock64() : 0;
+                    mbar_wait(mbar + (git % NSTAGE), (git / NSTAGE) & 1);
+                    if (a.prof && tid == 0) { const long long t1_ = clock64(); pacc[6] += (unsigned long long)(t1_ - t0_); t0_ = t1_; }
+                    for (int e = tid; e < nt * rk; e += NT) {          // w[a] = sum_b G[a + b*rk] R[b]
+                        const int jl = e / rk, aa = e - jl * rk;
+                        sWt[jl * wst + aa] = dot4(gt + jl * blk + aa, rk, Rk1, 1, rk1);
+                    }
+                    for (int e = tid; e < nt * rk1; e += NT) {         // u[b] = sum_a L[a] G[a + b*rk]
+                        const int jl = e / rk1, b = e - jl * rk1;
+                        const double *col = gt + jl * blk + b * rk;
+                        const int q = (b / per16) % gk;                 // start skew: conflict-free column walks
+                        sWt[jl * wst + rs + b] = dot4(Lk + q, 1, col + q, 1, rk - q) + dot4(Lk, 1, col, 1, q);
+                    }
+                    __syncthreads();
+                    if (a.prof && tid == 0) { pacc[7] += (unsigned long long)(clock64() - t0_); }
+                    if (tid == 0 && nsteps + t + NSTAGE < nitems) issue(nsteps + t + NSTAGE);
+                    for (int e = tid; e < nt * (2 * DX - 1); e += NT) {
+                        const int q = e / nt, jl = e - q * nt, j = j0 + jl;
+                        const double *w = sWt + jl * wst, *u = w + rs;
+                        double acc = 0.0;
+                        int oslot;
+                        if (q == 0) {
+                            acc = dot4(Lk, 1, w, 1, rk);
+                            oslot = 2 * DX;
+                            sV[j] = acc;
+                        } else {
+                            const int fs = q - 1, slot = fs >> 1, side = fs & 1;
+                            const int i = slot < k ? slot : slot + 1;
+                            if (i < k) acc = dot4(sLset + (1 + 2 * i + side) * rs, 1, w, 1, rk);
+                            else       acc = dot4(u, 1, sRset + (1 + 2 * (DX - 1 - i) + side) * rs, 1, rk1);
+                            oslot = 2 * i + side;
+                        }
+                        sC[j * CS + oslot] = acc;
+                    }
+                    __syncthreads();
                 }
             }
-        }
-        // 2c. per node: w_j = G_k[j] R_{k+1} (length r_k), u_j = L_k G_k[j] (length r_{k+1})
+        } else {
         {
-            const double *Lk = sL + k * rs, *Rk1 = sR + (k + 1) * rs;
+            if (tid == 0) { sVL[0] = 1.0; sVR[0] = 1.0; }
+            const int nsteps = (k > DX - 1 - k) ? k : DX - 1 - k;
+            int cur = 0;
+            __syncthreads();
+            for (int s = 0; s < nsteps; s++) {
+                const double *inL = sVL + cur * NV * rs, *inR = sVR + cur * NV * rs;
+                double *outL = sVL + (cur ^ 1) * NV * rs, *outR = sVR + (cur ^ 1) * NV * rs;
+                // left side, dimension m = s
+                const bool doL = s < k, doR = s < DX - 1 - k;
+                const int mL = s, mR = DX - 1 - s;
+                const int ninL = 1 + 2 * s, ninR = 1 + 2 * s;
+                const int nl = doL ? (ninL + 2) * ft.r[mL + 1] : 0;
+                const int nr = doR ? (ninR + 2) * ft.r[mR] : 0;
+                if (s + 1 < nsteps) {              // pull the next step's blocks towards L1
+                    const int nxt = s + 1;
+                    if (nxt < k) {
+                        const int bl = ft.r[nxt] * ft.r[nxt + 1];
+                        const int slot = nxt;     // nxt < k
+                        const double *b0 = CORE_BLK(nxt, sFix[nxt]), *b1 = CORE_BLK(nxt, sNf[2 * slot]), *b2 = CORE_BLK(nxt, sNf[2 * slot + 1]);
+                        for (int e = tid * 16; e < bl; e += NT * 16) { prefetch_l1(b0 + e); prefetch_l1(b1 + e); prefetch_l1(b2 + e); }
+                    }
+                    const int nxr = DX - 1 - nxt;
+                    if (nxt < DX - 1 - k) {
+                        const int bl = ft.r[nxr] * ft.r[nxr + 1];
+                        const int slot = nxr - 1;  // nxr > k
+                        const double *b0 = CORE_BLK(nxr, sFix[nxr]), *b1 = CORE_BLK(nxr, sNf[2 * slot]), *b2 = CORE_BLK(nxr, sNf[2 * slot + 1]);
+                        for (int e = tid * 16; e < bl; e += NT * 16) { prefetch_l1(b0 + e); prefetch_l1(b1 + e); prefetch_l1(b2 + e); }
+                    }
+                }
+                for (int e = tid; e < nl + nr; e += NT) {
+                    if (e < nl) {
+                        const int m = mL, rm = ft.r[m], nout = ninL + 2;
+                        const int b = e / nout, v = e - b * nout;            // v fastest: block reads broadcast
+                        const double *G = (v < ninL) ? CORE_BLK(m, sFix[m]) : CORE_BLK(m, sNf[2 * m + (v - ninL)]);
+                        const double *vec = inL + ((v < ninL) ? v : 0) * rs;
+                        const double *col = G + (size_t)b * rm;
+                        double acc = 0.0;
+                        for (int a = 0; a < rm; a++) acc = fma(vec[a], __ldg(col + a), acc);
+                        outL[v * rs + b] = acc;
+                    } else {
+                        const int e2 = e - nl, m = mR, rm = ft.r[m], rm1 = ft.r[m + 1], nout = ninR + 2;
+                        const int aa = e2 / nout, v = e2 - aa * nout;
+                        const double *G = (v < ninR) ? CORE_BLK(m, sFix[m]) : CORE_BLK(m, sNf[2 * (m - 1) + (v - ninR)]);
+                        const double *vec = inR + ((v < ninR) ? v : 0) * rs;
+                        double acc = 0.0;
+                        for (int b = 0; b < rm1; b++) acc = fma(__ldg(G + aa + (size_t)b * rm), vec[b], acc);
+                        outR[v * rs + aa] = acc;
+                    }
+                }
+                // a side that is already finished carries its set over unchanged
+                if (!doL && k > 0) for (int e = tid; e < (1 + 2 * k) * rs; e += NT) outL[e] = inL[e];
+                if (!doR && DX - 1 - k > 0) for (int e = tid; e < (1 + 2 * (DX - 1 - k)) * rs; e += NT) outR[e] = inR[e];
+                if (!doL && k == 0 && tid == 0) outL[0] = 1.0;
+                if (!doR && DX - 1 - k == 0 && tid == 0) outR[0] = 1.0;
+                cur ^= 1;
+                __syncthreads();
+            }
+            sLset = sVL + cur * NV * rs;
+            sRset = sVR + cur * NV * rs;
+        }
+        PHASE_MARK(1);
+        // 2b. per node tile: w_j = G_k[j] R (length r_k), u_j = L G_k[j] (length r_{k+1}), then the dots.
+        //     left set index of dim i<k:  1+2i+side;  right set index of dim i>k: 1+2(d-1-i)+side
+        {
+            const double *Lk = sLset, *Rk1 = sRset;
             const double *Gk = ft.base + ft.off[k];
-            const int blk = rk * rk1;
-            for (int e = tid; e < N * rk; e += NT) {
-                const int j = e / rk, aa = e - j * rk;
-                const double *g = Gk + (size_t)j * blk + aa;
-                double acc = 0.0;
-                for (int b = 0; b < rk1; b++) acc = fma(__ldg(g + (size_t)b * rk), Rk1[b], acc);
-                sW[j * rs + aa] = acc;
-            }
-            for (int e = tid; e < N * rk1; e += NT) {
-                const int j = e / rk1, bb = e - j * rk1;
-                const double *g = Gk + (size_t)j * blk + (size_t)bb * rk;
-                double acc = 0.0;
-                for (int aa = 0; aa < rk; aa++) acc = fma(Lk[aa], __ldg(g + aa), acc);
-                sU[j * rs + bb] = acc;
-            }
-        }
-        __syncthreads();
-        // 2d. dots: slot 2d = self, slots of fixed dims; slots 2k,2k+1 gathered below
-        {
-            const double *Lk = sL + k * rs;
-            for (int e = tid; e < N * (2 * DX - 1); e += NT) {
-                const int q = e / N, j = e - q * N;        // q: 0 = self, then fixed-dim slots in order
-                double acc = 0.0;
-                int oslot;
-                if (q == 0) {
-                    for (int aa = 0; aa < rk; aa++) acc = fma(Lk[aa], sW[j * rs + aa], acc);
-                    oslot = 2 * DX;
-                    sV[j] = acc;
-                } else {
-                    const int fs = q - 1, slot = fs >> 1, side = fs & 1;
-                    const int i = slot < k ? slot : slot + 1;
-                    const double *nbv = sNb + (2 * i + side) * rs;
-                    if (i < k) for (int aa = 0; aa < rk; aa++) acc = fma(nbv[aa], sW[j * rs + aa], acc);
-                    else       for (int bb = 0; bb < rk1; bb++) acc = fma(sU[j * rs + bb], nbv[bb], acc);
-                    oslot = 2 * i + side;
+            const int blk = rk * rk1, per = rk + rk1;
+            int T = (2 * NT) / per;
+            T = T < 1 ? 1 : (T > TMAX ? TMAX : T);
+            for (int j0 = 0; j0 < N; j0 += T) {
+                const int nt = (N - j0 < T) ? N - j0 : T;
+                if (j0 + T < N) {                   // next tile towards L1
+                    const double *nx = Gk + (size_t)(j0 + T) * blk;
+                    const int cnt = ((N - j0 - T < T) ? N - j0 - T : T) * blk;
+                    for (int e = tid * 16; e < cnt; e += NT * 16) prefetch_l1(nx + e);
                 }
-                sC[j * CS + oslot] = acc;
+                for (int e = tid; e < nt * per; e += NT) {
+                    const int jl = e / per, q = e - jl * per;
+                    const double *g = Gk + (size_t)(j0 + jl) * blk;
+                    double acc = 0.0;
+                    if (q < rk) {                   // w[q] = sum_b G[q + b*rk] R[b]
+                        for (int b = 0; b < rk1; b++) acc = fma(__ldg(g + q + (size_t)b * rk), Rk1[b], acc);
+                        sWt[jl * wst + q] = acc;
+                    } else {                        // u[b] = sum_a L[a] G[a + b*rk]
+                        const int b = q - rk;
+                        const double *col = g + (size_t)b * rk;
+                        for (int a = 0; a < rk; a++) acc = fma(Lk[a], __ldg(col + a), acc);
+                        sWt[jl * wst + rs + b] = acc;
+                    }
+                }
+                __syncthreads();
+                for (int e = tid; e < nt * (2 * DX - 1); e += NT) {
+                    const int q = e / nt, jl = e - q * nt, j = j0 + jl;    // q: 0 = self, then fixed-dim slots
+                    const double *w = sWt + jl * wst, *u = w + rs;
+                    double acc = 0.0;
+                    int oslot;
+                    if (q == 0) {
+                        for (int a = 0; a < rk; a++) acc = fma(Lk[a], w[a], acc);
+                        oslot = 2 * DX;
+                        sV[j] = acc;
+                    } else {
+                        const int fs = q - 1, slot = fs >> 1, side = fs & 1;
+                        const int i = slot < k ? slot : slot + 1;
+                        if (i < k) {
+                            const double *av = sLset + (1 + 2 * i + side) * rs;
+                            for (int a = 0; a < rk; a++) acc = fma(av[a], w[a], acc);
+                        } else {
+                            const double *cv = sRset + (1 + 2 * (DX - 1 - i) + side) * rs;
+                            for (int b = 0; b < rk1; b++) acc = fma(u[b], cv[b], acc);
+                        }
+                        oslot = 2 * i + side;
+                    }
+                    sC[j * CS + oslot] = acc;
+                }
+                __syncthreads();
             }
         }
-        __syncthreads();
+        }   // direct plan
+
         for (int j = tid; j < N; j += NT) {                 // along the fiber (valuefunc.c:514-519)
             sC[j * CS + 2 * k] = sV[sNv[2 * j]];
             sC[j * CS + 2 * k + 1] = sV[sNv[2 * j + 1]];
@@ -441,6 +676,7 @@ __global__ void __launch_bounds__(NT) k_backup(const LaunchArgs a)
         __syncthreads();
 #undef CORE_BLK
 
+        PHASE_MARK(2);
         // optional diagnostics
         if (a.out.absorbed) for (int j = tid; j < N; j += NT) a.out.absorbed[obase + j] = sAbs[j];
         if (a.out.nbr_vary) for (int e = tid; e < 2 * N; e += NT) a.out.nbr_vary[2 * obase + e] = sNv[e];
@@ -537,6 +773,7 @@ __global__ void __launch_bounds__(NT) k_backup(const LaunchArgs a)
             }
         }
         __syncthreads();
+        PHASE_MARK(3);
         for (int it = tid; it < nact * parts; it += NT) {
             const int part = it / nact, idx = it - part * nact;
             const int c0 = part * chunk, c1 = (c0 + chunk < P.nu) ? c0 + chunk : P.nu;
@@ -588,6 +825,7 @@ __global__ void __launch_bounds__(NT) k_backup(const LaunchArgs a)
             sBestI[part * P.nmax + idx] = ibest;
         }
         __syncthreads();
+        PHASE_MARK(4);
         for (int idx = tid; idx < nact; idx += NT) {
             const int j = sAct[idx];
             double best = sBestV[idx];
@@ -615,7 +853,10 @@ __global__ void __launch_bounds__(NT) k_backup(const LaunchArgs a)
                 row[CS + 1] = g;
             }
         }
+        PHASE_MARK(5);
     }
+    if (a.prof && tid == 0)
+        for (int q = 0; q < 8; q++) atomicAdd(a.prof + q, pacc[q]);
 }
 
 // Candidate table of a separable model (FAST only): row c = [Wl_0, Wr_0, .., Wl_{NUD-1}, Wr_{NUD-1}, A, gu]
@@ -656,17 +897,25 @@ constexpr int ctab_stride() { return 2 * M::NUD + 2; }
 
 // ---------------------------------------------------------------------------
 template <class M, class A>
-int launch_backup_t(const LaunchArgs &a, cudaStream_t st)
+int launch_backup_t(const LaunchArgs &a_in, cudaStream_t st)
 {
-    static int sms = 0, max_optin = 0;
+    static int sms = 0, max_optin = 0, max_sm = 0;
     if (!sms) {
         int dev = 0;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
         cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+        cudaDeviceGetAttribute(&max_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, dev);
     }
-    const SmemPlan sp(M::DX, M::NUD, a.P.nmax, a.ft.rmax);
-    const size_t smem = sp.bytes();
+    // staged plan (TMA ring) when two CTAs of it fit on an SM, else the direct-load plan
+    LaunchArgs a = a_in;
+    a.staged = 1;
+    size_t smem = SmemPlan(M::DX, M::NUD, a.P.nmax, a.ft.rmax, true).bytes();
+    static const bool want_staged = getenv("C3SC_STAGED") != nullptr;   // experiment: measured slower than direct loads
+    if (!want_staged || a.force_direct || 2 * (smem + 1024) > (size_t)max_sm) {
+        a.staged = 0;
+        smem = SmemPlan(M::DX, M::NUD, a.P.nmax, a.ft.rmax, false).bytes();
+    }
     if (smem > (size_t)max_optin) return (int)cudaErrorInvalidValue;
     cudaError_t e = cudaFuncSetAttribute(k_backup<M, A>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
@@ -674,6 +923,7 @@ int launch_backup_t(const LaunchArgs &a, cudaStream_t st)
     e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_backup<M, A>, NT, smem);
     if (e != cudaSuccess) return (int)e;
     if (per_sm < 1) per_sm = 1;
+    if (const char *env = getenv("C3SC_CTAS_PER_SM")) { int v = atoi(env); if (v >= 1 && v < per_sm) per_sm = v; }   // experiments only
     int grid = sms * per_sm;
     if (grid > a.F) grid = a.F;
     if (grid < 1) return 0;

@@ -57,6 +57,9 @@ struct LaunchArgs {
     const double *rows_in;   // MODE_PI_EVAL: policy rows
     int mode;
     int write_value;         // MODE_VI: 0 when only rows/argmin are wanted
+    int staged;              // set by the launcher: FT operands via the TMA staging ring
+    int force_direct;        // debug / test: never use the staged plan
+    unsigned long long *prof; // optional [8] per-phase cycle counters (summed over CTAs), NULL = off
     const int *nbr_fixed_in; // MODE_COSTS: caller-supplied neighbour indices (valuef_eval_fiber_ind_nn)
     const int *nbr_vary_in;  //             [F*2*(dx-1)] and [F*ldo*2]; NULL = derive from the boundary
 };

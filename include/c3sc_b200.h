@@ -110,6 +110,11 @@ const char *c3sc_version(void);
 /* kernels launched by this library since load (bench.py's gpu_launches) */
 uint64_t c3sc_launch_count(void);
 
+/* Debug aid: accumulate k_backup's per-phase SM cycles (thread 0 of every CTA, summed):
+ * [0] flags, [1] FT chains, [2] FT node tiles, [3] node invariants, [4] control loop,
+ * [5] merge + write.  enable != 0 arms it; out8 (may be NULL) receives and clears.   */
+int c3sc_debug_phase_profile(int enable, unsigned long long *out8);
+
 /* Best-of-`repeats` throughput of a pure DFMA loop on the current device, in
  * TFLOP/s (FMA = 2 flop): the measured FP64-pipe roofline denominator.      */
 int c3sc_measure_fp64_peak(double *tflops, int iters, int repeats);
