@@ -240,6 +240,7 @@ def main():
     def step_resident():
         if world > 1:
             sharding.broadcast_cores(core_view, src=0)
+            vf.commit(stream=sptr)
         prob.vi_batch_dev(vf, F, dv_d.data_ptr(), fi_d.data_ptr(), N, out_d.data_ptr(), stream=sptr)
         if world > 1:
             sharding.gather_values(out_d, F * world, N, out=gathered)

@@ -47,7 +47,7 @@ EXPORTS = [
     "c3sc_vi_batch_dev", "c3sc_pi_batch_dev", "c3sc_vi_batch", "c3sc_vi_batch_debug", "c3sc_pi_batch",
     "c3sc_transition_batch", "c3sc_model_eval", "c3sc_measure_fp64_peak",
     "c3sc_neighbor_costs_batch", "c3sc_node_backup_batch", "c3sc_control_value_batch", "c3sc_rhs_batch",
-    "c3sc_transition_raw", "c3sc_ft_fiber_nn_batch", "c3sc_debug_phase_profile",
+    "c3sc_transition_raw", "c3sc_ft_fiber_nn_batch", "c3sc_valuef_commit",
 ]
 
 _lib = None
@@ -75,6 +75,7 @@ def lib() -> C.CDLL:
         L.c3sc_valuef_update.argtypes = [vp, C.POINTER(c_f64p)]
         L.c3sc_valuef_device_buffer.argtypes = [vp, C.POINTER(vp), C.POINTER(sz)]
         L.c3sc_valuef_destroy.argtypes = [vp]
+        L.c3sc_valuef_commit.argtypes = [vp, vp]
         L.c3sc_vi_batch_dev.argtypes = [vp, vp, sz, vp, vp, sz, C.POINTER(BatchOut), vp]
         L.c3sc_pi_batch_dev.argtypes = [vp, vp, vp, sz, vp, vp, sz, i32, vp, vp, vp, vp]
         L.c3sc_vi_batch.argtypes = [vp, vp, sz, vp, vp, sz, vp, vp]
@@ -176,7 +177,7 @@ class Problem:
         check(lib().c3sc_problem_create(C.byref(d), C.byref(self.handle)))
 
     def close(self):
-        if getattr(self, "handle", None):
+        if getattr(self, "handle", None) and lib is not None:
             lib().c3sc_problem_destroy(self.handle)
             self.handle = None
 
@@ -290,8 +291,12 @@ class ValueF:
         check(lib().c3sc_valuef_device_buffer(self.handle, C.byref(p), C.byref(n)))
         return p.value, n.value
 
+    def commit(self, stream: int = 0):
+        """Rebuild the transposed core copy after the device buffer was written directly."""
+        check(lib().c3sc_valuef_commit(self.handle, stream or None))
+
     def close(self):
-        if getattr(self, "handle", None):
+        if getattr(self, "handle", None) and lib is not None:
             lib().c3sc_valuef_destroy(self.handle)
             self.handle = None
 

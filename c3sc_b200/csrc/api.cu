@@ -6,12 +6,18 @@
 #include <cstring>
 #include <vector>
 #include "dev_types.h"
-#include "backup_kernel.cuh"   // SmemPlan only (host side)
+#define C3SC_FT_TYPES_ONLY
+#include "ft_kernel.cuh"        // FtArgs (host side; the kernels are compiled in ft.cu)
+#include "control_kernel.cuh"   // CtlArgs
 
 namespace c3sc {
-int launch_backup_lqg_lo(int dx, int arith, const LaunchArgs &a, cudaStream_t st);
-int launch_backup_lqg_hi(int dx, int arith, const LaunchArgs &a, cudaStream_t st);
-int launch_backup_misc(int model, int dx, int arith, const LaunchArgs &a, cudaStream_t st);
+int launch_control_lqg_lo(int dx, int arith, const CtlArgs &a, int pi_eval, cudaStream_t st);
+int launch_control_lqg_hi(int dx, int arith, const CtlArgs &a, int pi_eval, cudaStream_t st);
+int launch_control_misc(int model, int dx, int arith, const CtlArgs &a, int pi_eval, cudaStream_t st);
+int launch_group_fibers(int F, int d, const int *dim_vary, int *perm, int *kcount, int *kstart, int *act_count,
+                        cudaStream_t st);
+int launch_transpose_cores(const DevFT &ft, double *baseT, cudaStream_t st);
+int launch_ft_costs(const FtArgs &a, cudaStream_t st);
 int launch_node_backup_lqg_lo(int dx, int arith, const DevProblem &P, int n, const double *x, const double *costs,
                               const int *absorbed, double *value, int *argmin, cudaStream_t st);
 int launch_node_backup_lqg_hi(int dx, int arith, const DevProblem &P, int n, const double *x, const double *costs,
@@ -70,9 +76,17 @@ struct DevBuf {
     void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
 };
 
+// per-problem scratch of the two-stage pipeline (one batch in flight per problem, like the
+// reference's Workspace, src/util.c:689-964)
+struct Scratch {
+    DevBuf cst, flag, act, perm, cnt;
+    void release() { cst.release(); flag.release(); act.release(); perm.release(); cnt.release(); }
+};
+
 struct c3sc_problem {
     DevProblem P;
     int model, arith;
+    Scratch scr;
     double *d_xgrid = nullptr, *d_obs = nullptr, *d_utab = nullptr, *d_ctab = nullptr;
     int *d_err = nullptr;
     cudaStream_t stream = nullptr;           // host-buffer entry points run here
@@ -81,7 +95,7 @@ struct c3sc_problem {
 
 struct c3sc_valuef {
     DevFT ft;
-    double *d_base = nullptr;
+    double *d_base = nullptr, *d_baseT = nullptr;
     size_t count = 0;
     std::vector<size_t> len;
 };
@@ -202,6 +216,7 @@ void c3sc_problem_destroy(c3sc_problem *p)
     DevBuf *bufs[] = {&p->b_dv, &p->b_fi, &p->b_val, &p->b_arg, &p->b_abs, &p->b_costs, &p->b_rows, &p->b_nv, &p->b_nf};
     for (DevBuf *b : bufs) b->release();
     for (DevBuf &b : p->b_misc) b.release();
+    p->scr.release();
     if (p->stream) cudaStreamDestroy(p->stream);
     delete p;
 }
@@ -244,8 +259,10 @@ int c3sc_valuef_create(uint32_t d, const uint64_t *n, const uint64_t *ranks, con
     if (ft.rmax < 1) ft.rmax = 1;
     vf->count = total;
     cudaError_t e = cudaMalloc(&vf->d_base, total * sizeof(double));
-    if (e != cudaSuccess) { delete vf; return fail(C3SC_ECUDA, "cudaMalloc cores: %s", cudaGetErrorString(e)); }
+    if (e == cudaSuccess) e = cudaMalloc(&vf->d_baseT, total * sizeof(double));
+    if (e != cudaSuccess) { cudaFree(vf->d_base); delete vf; return fail(C3SC_ECUDA, "cudaMalloc cores: %s", cudaGetErrorString(e)); }
     ft.base = vf->d_base;
+    ft.baseT = vf->d_baseT;
     *out = vf;
     if (cores) {
         int rc = c3sc_valuef_update(vf, cores);
@@ -259,6 +276,18 @@ int c3sc_valuef_update(c3sc_valuef *vf, const double *const *cores)
     if (!vf || !cores) return fail(C3SC_EINVAL, "null argument");
     for (int k = 0; k < vf->ft.d; k++)
         CK(cudaMemcpy(vf->d_base + vf->ft.off[k], cores[k], vf->len[k] * sizeof(double), cudaMemcpyHostToDevice));
+    int rc = c3sc_valuef_commit(vf, nullptr);
+    if (rc) return rc;
+    CK(cudaDeviceSynchronize());
+    return C3SC_OK;
+}
+
+int c3sc_valuef_commit(c3sc_valuef *vf, void *stream)
+{
+    if (!vf) return fail(C3SC_EINVAL, "null argument");
+    int rc = launch_transpose_cores(vf->ft, vf->d_baseT, (cudaStream_t)stream);
+    if (rc) return fail(C3SC_ECUDA, "transpose kernel: %s", cudaGetErrorString((cudaError_t)rc));
+    g_launches++;
     return C3SC_OK;
 }
 
@@ -274,21 +303,82 @@ void c3sc_valuef_destroy(c3sc_valuef *vf)
 {
     if (!vf) return;
     cudaFree(vf->d_base);
+    cudaFree(vf->d_baseT);
     delete vf;
 }
 
 }  // extern "C"
 
 // ---------------------------------------------------------------------------
-static int dispatch(c3sc_problem *p, const LaunchArgs &a, cudaStream_t st)
+enum Mode { MODE_VI = 0, MODE_PI_EVAL = 1, MODE_COSTS = 2 };
+
+// One batch through the two-stage pipeline, in chunks whose slot-major cost scratch stays L2-sized:
+//   k_group_fibers -> k_ft_costs -> k_control (MODE_VI) | k_pi_eval (MODE_PI_EVAL) | nothing (MODE_COSTS)
+struct BatchArgs {
+    size_t F, ldo;
+    const int *dim_vary, *fixed_ind;      // device
+    DevOut out;                           // device, optional
+    const double *rows_in;                // MODE_PI_EVAL
+    const int *nbr_fixed_in, *nbr_vary_in;
+    int mode;
+};
+
+static size_t g_chunk_bytes = (size_t)64 << 20;
+
+static int run_batch(const DevProblem &P, int model, int arith, Scratch &scr, const DevFT &ft, const BatchArgs &b,
+                     cudaStream_t st)
 {
-    int rc;
-    if (p->model == C3SC_MODEL_LQGND) rc = (p->P.dx <= 6) ? launch_backup_lqg_lo(p->P.dx, p->arith, a, st)
-                                                          : launch_backup_lqg_hi(p->P.dx, p->arith, a, st);
-    else rc = launch_backup_misc(p->model, p->P.dx, p->arith, a, st);
-    if (rc == -1) return fail(C3SC_EUNSUPPORTED, "model %d with dx=%d is not instantiated", p->model, p->P.dx);
-    if (rc != 0) return fail(C3SC_ECUDA, "kernel launch: %s", cudaGetErrorString((cudaError_t)rc));
-    g_launches++;
+    const size_t d = (size_t)P.dx, CS = 2 * d + 1, RW = 2 * d + 3;
+    size_t FC = g_chunk_bytes / (b.ldo * CS * 8);
+    if (FC < 1) FC = 1;
+    if (FC > b.F) FC = b.F;
+    const size_t NSmax = FC * b.ldo;
+    const bool need_cst = b.mode != MODE_COSTS;
+    if ((need_cst && scr.cst.reserve(NSmax * CS * 8)) || scr.flag.reserve(NSmax) || scr.act.reserve(NSmax * 4) ||
+        scr.perm.reserve(FC * 4) || scr.cnt.reserve(64 * 4))
+        return fail(C3SC_ECUDA, "cudaMalloc pipeline scratch failed");
+    int *cnt = (int *)scr.cnt.p;                  // [0,16) kcount, [16,32) kstart, [32] act_count
+    for (size_t c0 = 0; c0 < b.F; c0 += FC) {
+        const size_t Fc = (b.F - c0 < FC) ? b.F - c0 : FC;
+        const size_t n0 = c0 * b.ldo;
+        int rc = launch_group_fibers((int)Fc, (int)d, b.dim_vary + c0, (int *)scr.perm.p, cnt, cnt + 16, cnt + 32, st);
+        if (rc) return fail(C3SC_ECUDA, "grouping kernel: %s", cudaGetErrorString((cudaError_t)rc));
+        FtArgs a;
+        memset(&a, 0, sizeof a);
+        a.P = P; a.ft = ft; a.F = (int)Fc; a.dim_vary = b.dim_vary + c0; a.fixed_ind = b.fixed_ind + c0 * d;
+        a.ldo = (int)b.ldo; a.FB = 0;
+        a.perm = (const int *)scr.perm.p; a.kcount = cnt; a.kstart = cnt + 16;
+        a.NS = (long long)(Fc * b.ldo);
+        a.cst = need_cst ? (double *)scr.cst.p : nullptr;
+        a.flag = need_cst ? (signed char *)scr.flag.p : nullptr;
+        a.act = b.mode == MODE_VI ? (int *)scr.act.p : nullptr;
+        a.act_count = cnt + 32;
+        a.costs = b.out.costs ? b.out.costs + n0 * CS : nullptr;
+        a.absorbed = b.out.absorbed ? b.out.absorbed + n0 : nullptr;
+        a.nbr_vary = b.out.nbr_vary ? b.out.nbr_vary + 2 * n0 : nullptr;
+        a.nbr_fixed = (b.out.nbr_fixed && d > 1) ? b.out.nbr_fixed + c0 * 2 * (d - 1) : nullptr;
+        a.nbr_fixed_in = (b.nbr_fixed_in && d > 1) ? b.nbr_fixed_in + c0 * 2 * (d - 1) : nullptr;
+        a.nbr_vary_in = b.nbr_vary_in ? b.nbr_vary_in + 2 * n0 : nullptr;
+        rc = launch_ft_costs(a, st);
+        if (rc) return fail(C3SC_ECUDA, "FT kernel launch: %s", cudaGetErrorString((cudaError_t)rc));
+        g_launches += 2;
+        if (b.mode == MODE_COSTS) continue;
+        CtlArgs c;
+        memset(&c, 0, sizeof c);
+        c.P = P; c.F = (int)Fc; c.dim_vary = a.dim_vary; c.fixed_ind = a.fixed_ind; c.ldo = (int)b.ldo; c.NS = a.NS;
+        c.cst = a.cst; c.flag = a.flag; c.act = a.act; c.act_count = cnt + 32;
+        c.value = b.out.value ? b.out.value + n0 : nullptr;
+        c.argmin = b.out.argmin ? b.out.argmin + n0 : nullptr;
+        c.rows = b.out.rows ? b.out.rows + n0 * RW : nullptr;
+        c.rows_in = b.rows_in ? b.rows_in + n0 * RW : nullptr;
+        const int pe = b.mode == MODE_PI_EVAL;
+        if (model == C3SC_MODEL_LQGND) rc = (P.dx <= 6) ? launch_control_lqg_lo(P.dx, arith, c, pe, st)
+                                                        : launch_control_lqg_hi(P.dx, arith, c, pe, st);
+        else rc = launch_control_misc(model, P.dx, arith, c, pe, st);
+        if (rc == -1) return fail(C3SC_EUNSUPPORTED, "model %d with dx=%d is not instantiated", model, P.dx);
+        if (rc != 0) return fail(C3SC_ECUDA, "control kernel launch: %s", cudaGetErrorString((cudaError_t)rc));
+        g_launches++;
+    }
     return C3SC_OK;
 }
 
@@ -303,18 +393,7 @@ static int check_shapes(const c3sc_problem *p, const c3sc_valuef *vf, size_t F, 
     return C3SC_OK;
 }
 
-static unsigned long long *g_prof = nullptr;
-
 extern "C" {
-
-/* debug: per-phase cycle counters of k_backup (8 slots), summed over CTAs; enable=0 turns it off */
-int c3sc_debug_phase_profile(int enable, unsigned long long *out8)
-{
-    if (enable && !g_prof) { CK(cudaMalloc(&g_prof, 64)); CK(cudaMemset(g_prof, 0, 64)); }
-    if (out8 && g_prof) { CK(cudaDeviceSynchronize()); CK(cudaMemcpy(out8, g_prof, 64, cudaMemcpyDeviceToHost)); CK(cudaMemset(g_prof, 0, 64)); }
-    if (!enable && g_prof) { cudaFree(g_prof); g_prof = nullptr; }
-    return C3SC_OK;
-}
 
 int c3sc_vi_batch_dev(c3sc_problem *p, const c3sc_valuef *vf, size_t F, const int32_t *d_dim_vary,
                       const int32_t *d_fixed_ind, size_t ldo, const c3sc_batch_out *out, void *stream)
@@ -324,15 +403,13 @@ int c3sc_vi_batch_dev(c3sc_problem *p, const c3sc_valuef *vf, size_t F, const in
     if (!out || (!out->value && !out->rows && !out->argmin && !out->costs && !out->absorbed))
         return fail(C3SC_EINVAL, "no output requested");
     if (F == 0) return C3SC_OK;
-    LaunchArgs a;
-    memset(&a, 0, sizeof a);
-    a.P = p->P; a.ft = vf->ft; a.F = (int)F; a.dim_vary = d_dim_vary; a.fixed_ind = d_fixed_ind; a.ldo = (int)ldo;
-    a.out.value = out->value; a.out.argmin = out->argmin; a.out.absorbed = out->absorbed;
-    a.out.costs = out->costs; a.out.rows = out->rows; a.out.nbr_vary = out->nbr_vary; a.out.nbr_fixed = out->nbr_fixed;
-    a.mode = MODE_VI;
-    a.write_value = out->value != nullptr;
-    a.prof = g_prof;
-    return dispatch(p, a, (cudaStream_t)stream);
+    BatchArgs b;
+    memset(&b, 0, sizeof b);
+    b.F = F; b.ldo = ldo; b.dim_vary = d_dim_vary; b.fixed_ind = d_fixed_ind;
+    b.out.value = out->value; b.out.argmin = out->argmin; b.out.absorbed = out->absorbed;
+    b.out.costs = out->costs; b.out.rows = out->rows; b.out.nbr_vary = out->nbr_vary; b.out.nbr_fixed = out->nbr_fixed;
+    b.mode = (out->value || out->argmin || out->rows) ? MODE_VI : MODE_COSTS;
+    return run_batch(p->P, p->model, p->arith, p->scr, vf->ft, b, (cudaStream_t)stream);
 }
 
 int c3sc_pi_batch_dev(c3sc_problem *p, const c3sc_valuef *vf_policy, const c3sc_valuef *vf_iter, size_t F,
@@ -343,26 +420,23 @@ int c3sc_pi_batch_dev(c3sc_problem *p, const c3sc_valuef *vf_policy, const c3sc_
     if (rc) return rc;
     if (!d_rows || !d_value) return fail(C3SC_EINVAL, "rows and value buffers are required");
     if (F == 0) return C3SC_OK;
-    LaunchArgs a;
-    memset(&a, 0, sizeof a);
-    a.P = p->P; a.F = (int)F; a.dim_vary = d_dim_vary; a.fixed_ind = d_fixed_ind; a.ldo = (int)ldo;
+    BatchArgs b;
+    memset(&b, 0, sizeof b);
+    b.F = F; b.ldo = ldo; b.dim_vary = d_dim_vary; b.fixed_ind = d_fixed_ind;
     if (!have_rows) {                       // policy improvement against vf_policy (bellman.c:1831-1860)
         rc = check_shapes(p, vf_policy, F, ldo);
         if (rc) return rc;
-        a.ft = vf_policy->ft;
-        a.mode = MODE_VI;
-        a.write_value = 0;
-        a.out.rows = d_rows;
-        a.out.argmin = d_argmin;
-        rc = dispatch(p, a, (cudaStream_t)stream);
+        b.mode = MODE_VI;
+        b.out.rows = d_rows;
+        b.out.argmin = d_argmin;
+        rc = run_batch(p->P, p->model, p->arith, p->scr, vf_policy->ft, b, (cudaStream_t)stream);
         if (rc) return rc;
     }
-    a.ft = vf_iter->ft;                     // evaluation against vf_iter (bellman.c:1863-1871)
-    a.mode = MODE_PI_EVAL;
-    memset(&a.out, 0, sizeof a.out);
-    a.out.value = d_value;
-    a.rows_in = d_rows;
-    return dispatch(p, a, (cudaStream_t)stream);
+    memset(&b.out, 0, sizeof b.out);        // evaluation against vf_iter (bellman.c:1863-1871)
+    b.mode = MODE_PI_EVAL;
+    b.out.value = d_value;
+    b.rows_in = d_rows;
+    return run_batch(p->P, p->model, p->arith, p->scr, vf_iter->ft, b, (cudaStream_t)stream);
 }
 
 static int upload_fibers(c3sc_problem *p, size_t F, const int32_t *dim_vary, const int32_t *fixed_ind)
@@ -497,14 +571,14 @@ int c3sc_neighbor_costs_batch(c3sc_problem *p, const c3sc_valuef *vf, size_t F, 
     CK(cudaMemsetAsync(p->b_abs.p, 0, n * 4, p->stream));
     CK(cudaMemsetAsync(p->b_costs.p, 0, n * (2 * dx + 1) * 8, p->stream));
     if (nbr_vary) CK(cudaMemsetAsync(p->b_nv.p, 0, n * 2 * 4, p->stream));
-    LaunchArgs a;
-    memset(&a, 0, sizeof a);
-    a.P = p->P; a.ft = vf->ft; a.F = (int)F; a.dim_vary = (const int *)p->b_dv.p; a.fixed_ind = (const int *)p->b_fi.p;
-    a.ldo = (int)ldo; a.mode = MODE_COSTS;
-    a.out.absorbed = (int *)p->b_abs.p; a.out.costs = (double *)p->b_costs.p;
-    a.out.nbr_vary = nbr_vary ? (int *)p->b_nv.p : nullptr;
-    a.out.nbr_fixed = nbr_fixed ? (int *)p->b_nf.p : nullptr;
-    rc = dispatch(p, a, p->stream);
+    BatchArgs b;
+    memset(&b, 0, sizeof b);
+    b.F = F; b.ldo = ldo; b.dim_vary = (const int *)p->b_dv.p; b.fixed_ind = (const int *)p->b_fi.p;
+    b.mode = MODE_COSTS;
+    b.out.absorbed = (int *)p->b_abs.p; b.out.costs = (double *)p->b_costs.p;
+    b.out.nbr_vary = nbr_vary ? (int *)p->b_nv.p : nullptr;
+    b.out.nbr_fixed = nbr_fixed ? (int *)p->b_nf.p : nullptr;
+    rc = run_batch(p->P, p->model, p->arith, p->scr, vf->ft, b, p->stream);
     if (rc) return rc;
     CK(cudaMemcpyAsync(absorbed, p->b_abs.p, n * 4, cudaMemcpyDeviceToHost, p->stream));
     CK(cudaMemcpyAsync(costs, p->b_costs.p, n * (2 * dx + 1) * 8, cudaMemcpyDeviceToHost, p->stream));
@@ -622,15 +696,9 @@ int c3sc_ft_fiber_nn_batch(const c3sc_valuef *vf, size_t F, const int32_t *dim_v
     if (!vf || !dim_vary || !fixed_ind || !nbr_fixed || !nbr_vary || !costs) return fail(C3SC_EINVAL, "null argument");
     if (F == 0) return C3SC_OK;
     const int dx = vf->ft.d;
-    // any instantiated model of this dimension carries the FT phase; its dynamics are never evaluated
-    int model;
-    if (dx % 2 == 0 && dx <= 12) model = C3SC_MODEL_LQGND;
-    else if (dx == 3) model = C3SC_MODEL_DUBINS;
-    else if (dx == 5) model = C3SC_MODEL_SKID5D;
-    else return fail(C3SC_EUNSUPPORTED, "FT fiber evaluation is instantiated for d in {2,3,4,5,6,8,10,12}, got %d", dx);
-    c3sc_problem tmp;
+    const int model = 0;   // stage 1 is independent of the dynamics model
+    struct { DevProblem P; } tmp;
     memset(&tmp.P, 0, sizeof tmp.P);
-    tmp.model = model; tmp.arith = C3SC_ARITH_FAST;
     tmp.P.dx = dx; tmp.P.nu = 0;
     for (int i = 0; i < dx; i++) { tmp.P.ngrid[i] = vf->ft.n[i]; tmp.P.bc[i] = C3SC_REFLECT; if (vf->ft.n[i] > tmp.P.nmax) tmp.P.nmax = vf->ft.n[i]; }
     if (ldo < (size_t)tmp.P.nmax) return fail(C3SC_EINVAL, "ldo too small");
@@ -648,13 +716,15 @@ int c3sc_ft_fiber_nn_batch(const c3sc_valuef *vf, size_t F, const int32_t *dim_v
     tmp.P.xgrid = (const double *)b[5].p;           // coordinates are irrelevant here (no obstacles)
     for (int i = 0; i < dx; i++) tmp.P.xoff[i] = i * tmp.P.nmax;
     tmp.P.err = (int *)((char *)b[5].p + 8 * (size_t)dx * tmp.P.nmax);
-    LaunchArgs a;
-    memset(&a, 0, sizeof a);
-    a.P = tmp.P; a.ft = vf->ft; a.F = (int)F; a.dim_vary = (const int *)b[0].p; a.fixed_ind = (const int *)b[1].p;
-    a.ldo = (int)ldo; a.mode = MODE_COSTS; a.out.costs = (double *)b[4].p;
-    a.nbr_fixed_in = (const int *)b[2].p; a.nbr_vary_in = (const int *)b[3].p;
-    int rc = dispatch(&tmp, a, nullptr);
+    BatchArgs ba;
+    memset(&ba, 0, sizeof ba);
+    ba.F = F; ba.ldo = ldo; ba.dim_vary = (const int *)b[0].p; ba.fixed_ind = (const int *)b[1].p;
+    ba.mode = MODE_COSTS; ba.out.costs = (double *)b[4].p;
+    ba.nbr_fixed_in = (const int *)b[2].p; ba.nbr_vary_in = (const int *)b[3].p;
+    static Scratch scr;
+    int rc = run_batch(tmp.P, model, C3SC_ARITH_FAST, scr, vf->ft, ba, nullptr);
     if (rc) return rc;
+    CK(cudaDeviceSynchronize());
     CK(cudaMemcpy(costs, b[4].p, n * cs * 8, cudaMemcpyDeviceToHost));
     return C3SC_OK;
 }

@@ -1,0 +1,624 @@
+// control_kernel.cuh -- stage 2 of the Bellman backup: per node, the min over the discretised
+// control set of
+//        dt*g + exp(-beta*dt) * <p, V_nbr>        bellman_control / bellmanrhs
+//                                                 src/bellman.c:88-112,367-480,504-543
+// with p, dt from the upwind Kushner-Dupuis construction (transition_assemble,
+// src/nodeutil.c:267-406) and V_nbr the neighbour values stage 1 left in the slot-major
+// scratch.  One thread owns one (node, candidate chunk); the chunks of a node sit in adjacent
+// lanes and are merged in table order with strict '<', so the result is the FIRST strict
+// minimum in table order -- the brute-force c3opt_minimize rule (bellman.c:539-543).
+// Absorbed nodes take boundcost / obscost (bellman.c:513-532).
+#pragma once
+#include <cuda_runtime.h>
+#include <math_constants.h>
+#include "dev_types.h"
+#include "arith.cuh"
+#include "models.cuh"
+
+namespace c3sc {
+
+constexpr int CT_NT = 256;
+
+struct CtlArgs {
+    DevProblem P;
+    int F;                    // fibers of this chunk
+    const int *dim_vary;      // [F]
+    const int *fixed_ind;     // [F*dx]
+    int ldo;
+    long long NS;             // F*ldo
+    const double *cst;        // [(2dx+1)*NS] slot-major neighbour values
+    const signed char *flag;  // [NS]
+    const int *act;           // [NS] non-absorbed node ids
+    const int *act_count;
+    int parts_log2;           // candidate chunks per node = 1 << parts_log2 (<= 32)
+    int tab_in_smem;          // candidate table staged in shared memory
+    double *value;            // outputs, any may be NULL
+    int *argmin;
+    double *rows;
+    const double *rows_in;    // k_pi_eval
+};
+
+// ---------------------------------------------------------------------------
+// fast reciprocal and exp for the FAST policy (both ~1 ulp)
+__device__ __forceinline__ double rcp_pos(double x)
+{   // x > 0, normal: MUFU.RCP64H seed (~2^-20) + two Newton steps
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    double e = fma(-x, y, 1.0);
+    y = fma(y, e, y);
+    e = fma(-x, y, 1.0);
+    return fma(y, e, y);
+}
+__device__ __forceinline__ double exp_nonpos(double x)
+{   // exp(x) for x <= 0: n = rint(x*log2 e), r = x - n ln2 (Cody-Waite), degree-13 Taylor on
+    // |r| <= ln2/2 (truncation 4e-18), scale by adding n to the exponent field.  No overflow
+    // path is needed for x <= 0; below -708 the result is flushed to 0.
+    const double t = fma(x, 1.4426950408889634, 6755399441055744.0);
+    const double n = t - 6755399441055744.0;
+    double r = fma(n, -6.93147180369123816490e-01, x);
+    r = fma(n, -1.90821492927058770002e-10, r);
+    double p = 1.6059043836821613e-10;            // 1/13!
+    p = fma(p, r, 2.08767569878681e-09);          // 1/12!
+    p = fma(p, r, 2.505210838544172e-08);         // 1/11!
+    p = fma(p, r, 2.755731922398589e-07);         // 1/10!
+    p = fma(p, r, 2.7557319223985893e-06);        // 1/9!
+    p = fma(p, r, 2.48015873015873e-05);          // 1/8!
+    p = fma(p, r, 1.984126984126984e-04);         // 1/7!
+    p = fma(p, r, 1.388888888888889e-03);         // 1/6!
+    p = fma(p, r, 8.333333333333333e-03);         // 1/5!
+    p = fma(p, r, 4.1666666666666664e-02);        // 1/4!
+    p = fma(p, r, 1.6666666666666666e-01);        // 1/3!
+    p = fma(p, r, 0.5);
+    p = fma(p, r, 1.0);
+    p = fma(p, r, 1.0);
+    const int ni = __double2loint(t);
+    const double res = __hiloint2double(__double2hiint(p) + (ni << 20), __double2loint(p));
+    return (x < -708.0) ? 0.0 : res;
+}
+__device__ __forceinline__ double exp_tiny(double x)
+{   // exp(x) for -2^-8 <= x <= 0: degree-5 Taylor, truncation x^6/720 < 5e-18 (relative, e^x ~ 1)
+    double p = 8.333333333333333e-03;
+    p = fma(p, x, 4.1666666666666664e-02);
+    p = fma(p, x, 1.6666666666666666e-01);
+    p = fma(p, x, 0.5);
+    p = fma(p, x, 1.0);
+    return fma(p, x, 1.0);
+}
+
+// ---------------------------------------------------------------------------
+// transition_assemble (src/nodeutil.c:284-309,365-371,396-402), all dims in order.
+// prob = [pl_0, pr_0, ..., pl_{d-1}, pr_{d-1}, pself]; returns 0 or 1 (norm < 1e-14).
+template <int DX, class A>
+__device__ __forceinline__ int transition_row(const DevProblem &P, const double *b, const double *s,
+                                              double *prob, double &dt)
+{
+    double norm = 0.0;
+#pragma unroll
+    for (int i = 0; i < DX; i++) {
+        const double s2 = A::mul(s[i], s[i]);
+        const double q = A::mul(A::mul(P.t[2 * i + 1], s2), 0.5);     // t2*diff/2.0
+        double pl = q, pr = q;
+        if (b[i] < -1e-14)      pl = A::sub(pl, A::mul(P.t[2 * i], b[i]));
+        else if (b[i] > 1e-14)  pr = A::add(pr, A::mul(P.t[2 * i], b[i]));
+        prob[2 * i] = pl;
+        prob[2 * i + 1] = pr;
+        norm = A::add(norm, pl);
+        norm = A::add(norm, pr);
+    }
+    if (norm < 1e-14) { dt = 0.0; return 1; }
+    dt = A::div(P.h2, norm);
+    double ps = 1.0;
+#pragma unroll
+    for (int i = 0; i < DX; i++) {
+        prob[2 * i] = A::div(prob[2 * i], norm);
+        prob[2 * i + 1] = A::div(prob[2 * i + 1], norm);
+        ps = A::sub(ps, prob[2 * i]);
+        ps = A::sub(ps, prob[2 * i + 1]);
+    }
+    prob[2 * DX] = ps;
+    return 0;
+}
+
+// bellmanrhs (src/bellman.c:88-112): dt*g + exp(-beta*dt) * <p, c>, sequential dot.
+template <int DX, class A>
+__device__ __forceinline__ double rhs(const DevProblem &P, const double *prob, double dt, double g,
+                                      const double *c)
+{
+    const double ebt = exp(A::mul(-P.beta, dt));
+    double ctg = 0.0;
+#pragma unroll
+    for (int m = 0; m < 2 * DX + 1; m++) ctg = A::mad(prob[m], c[m], ctg);
+    return A::add(A::mul(dt, g), A::mul(ebt, ctg));
+}
+
+// Per-node state hoisted out of the candidate loop.
+template <class M>
+struct NodeInv {
+    double b0[M::DX], s0[M::DX];   // drift / sigma at the first candidate (valid for !u_dep dims)
+    double norm0, S0;              // Fast: partial normaliser and partial <raw, c>
+};
+
+template <class M, class A>
+__device__ __forceinline__ void node_prepare(const DevProblem &P, const double *utab, const double *x,
+                                             const double *c, NodeInv<M> &inv)
+{
+    constexpr int DX = M::DX;
+    double u0[M::DU];
+#pragma unroll
+    for (int i = 0; i < M::DU; i++) u0[i] = utab[i];
+    M::template drift<A>(x, u0, P.mp, inv.b0);
+    M::template sigma<A>(x, u0, P.mp, inv.s0);
+    inv.norm0 = 0.0;
+    inv.S0 = 0.0;
+    if (!A::exact) {
+#pragma unroll
+        for (int i = 0; i < DX; i++) {
+            if (M::u_dep(i)) continue;
+            const double q = (P.t[2 * i + 1] * 0.5) * (inv.s0[i] * inv.s0[i]);
+            const double tb = P.t[2 * i] * inv.b0[i];
+            const double rl = q - ((inv.b0[i] < -1e-14) ? tb : 0.0);
+            const double rr = q + ((inv.b0[i] > 1e-14) ? tb : 0.0);
+            inv.norm0 += rl + rr;
+            inv.S0 = fma(rl, c[2 * i], inv.S0);
+            inv.S0 = fma(rr, c[2 * i + 1], inv.S0);
+        }
+    }
+}
+
+// value of one candidate control (bellman_control, src/bellman.c:367-480, absorbed==0 branch)
+template <class M, class A>
+__device__ __forceinline__ double candidate_value(const DevProblem &P, const double *x, const double *u,
+                                                  const double *c, const NodeInv<M> &inv, int &bad)
+{
+    constexpr int DX = M::DX;
+    double b[DX], s[DX];
+    M::template drift<A>(x, u, P.mp, b);
+    M::template sigma<A>(x, u, P.mp, s);
+    const double g = M::template stage<A>(x, u, P.mp);
+    if (A::exact) {
+#pragma unroll
+        for (int i = 0; i < DX; i++)
+            if (!M::u_dep(i)) { b[i] = inv.b0[i]; s[i] = inv.s0[i]; }
+        double prob[2 * DX + 1], dt;
+        if (transition_row<DX, A>(P, b, s, prob, dt)) { bad = 1; return CUDART_INF; }
+        return rhs<DX, A>(P, prob, dt, g, c);
+    } else {
+        double norm = inv.norm0, S = inv.S0;
+#pragma unroll
+        for (int i = 0; i < DX; i++) {
+            if (!M::u_dep(i)) continue;
+            const double q = (P.t[2 * i + 1] * 0.5) * (s[i] * s[i]);
+            const double tb = P.t[2 * i] * b[i];
+            const double rl = q - ((b[i] < -1e-14) ? tb : 0.0);
+            const double rr = q + ((b[i] > 1e-14) ? tb : 0.0);
+            norm += rl + rr;
+            S = fma(rl, c[2 * i], S);
+            S = fma(rr, c[2 * i + 1], S);
+        }
+        if (norm < 1e-14) { bad = 1; return CUDART_INF; }
+        const double rinv = rcp_pos(norm);
+        const double dt = P.h2 * rinv;
+        const double ebt = exp_nonpos(-P.beta * dt);
+        return fma(dt, g, ebt * (S * rinv));
+    }
+}
+
+// node id -> state
+template <int DX>
+__device__ __forceinline__ void node_state(const CtlArgs &c, int id, double *x)
+{
+    const int f = id / c.ldo, j = id - f * c.ldo;
+    const int k = c.dim_vary[f];
+#pragma unroll
+    for (int i = 0; i < DX; i++) x[i] = c.P.xgrid[c.P.xoff[i] + (i == k ? j : c.fixed_ind[(size_t)f * DX + i])];
+}
+
+// ---------------------------------------------------------------------------
+template <class M, class A>
+__global__ void __launch_bounds__(CT_NT) k_control(const CtlArgs c)
+{
+    constexpr int DX = M::DX, DU = M::DU, CS = 2 * DX + 1, RW = 2 * DX + 3;
+    constexpr bool TAB = M::SEP && !A::exact;
+    constexpr int NUD = M::NUD, CTW = 2 * NUD + 2;
+    const DevProblem &P = c.P;
+    const int tid = threadIdx.x, lane = tid & 31;
+    extern __shared__ __align__(16) double smem[];
+
+    // candidate table (separable models, FAST) or the raw control table, staged once per CTA
+    const double *tab = TAB ? P.ctab : P.utab;
+    {
+        const int cnt = P.nu * (TAB ? CTW : DU);
+        if (c.tab_in_smem) {
+            for (int e = tid; e < cnt; e += CT_NT) smem[e] = tab[e];
+            __syncthreads();
+            tab = smem;
+        }
+    }
+
+    const int pl2 = c.parts_log2, parts = 1 << pl2;
+    const int chunk = (P.nu + parts - 1) >> pl2;
+    const int nact = *c.act_count;
+    const long long total = (long long)nact << pl2;
+    const long long stride = (long long)gridDim.x * CT_NT;
+    // warp-uniform trip count: every lane of a warp stays in the loop for the shuffles
+    for (long long it0 = (long long)blockIdx.x * CT_NT + (tid & ~31); it0 < total; it0 += stride) {
+        const long long it = it0 + lane;
+        const bool valid = it < total;
+        const int idx = valid ? (int)(it >> pl2) : 0, part = (int)(it & (parts - 1));
+        const int id = c.act[idx];
+        const int c0 = part * chunk, c1 = valid ? ((c0 + chunk < P.nu) ? c0 + chunk : P.nu) : c0;
+        double x[DX], cc[CS];
+        node_state<DX>(c, id, x);
+#pragma unroll
+        for (int m = 0; m < CS; m++) cc[m] = c.cst[(size_t)m * c.NS + id];
+        double best = CUDART_INF;
+        int ibest = 0x7fffffff;
+        if (TAB) {
+            // per-node invariants: norm0 = control-independent part of the normaliser, S0 = the
+            // matching part of <raw p, V_nbr>, gx = stage_x; cu = the 2*NUD neighbour values the
+            // candidates weight.
+            double u0[DU], b0[DX], s0[DX];
+#pragma unroll
+            for (int i = 0; i < DU; i++) u0[i] = P.utab[i];
+            M::template drift<A>(x, u0, P.mp, b0);
+            M::template sigma<A>(x, u0, P.mp, s0);
+            double norm0 = 0.0, S0 = 0.0;
+#pragma unroll
+            for (int i = 0; i < DX; i++) {
+                const double q = (P.t[2 * i + 1] * 0.5) * (s0[i] * s0[i]);
+                double rl = q, rr = q;
+                if (!M::u_dep(i)) {
+                    const double tb = P.t[2 * i] * b0[i];
+                    rl = q - ((b0[i] < -1e-14) ? tb : 0.0);
+                    rr = q + ((b0[i] > 1e-14) ? tb : 0.0);
+                }
+                norm0 += rl + rr;
+                S0 = fma(rl, cc[2 * i], S0);
+                S0 = fma(rr, cc[2 * i + 1], S0);
+            }
+            const double gx = M::stage_x(x, P.mp);
+            double cu[2 * NUD];
+#pragma unroll
+            for (int m = 0; m < NUD; m++) { cu[2 * m] = cc[2 * M::ud(m)]; cu[2 * m + 1] = cc[2 * M::ud(m) + 1]; }
+            if (valid && norm0 + P.amin < 1e-14) atomicOr(P.err, 1);
+            const double nbh = -P.beta * P.h2;
+            const bool disc = P.beta != 0.0;
+            // exp(-beta*dt) with dt <= h2/(norm0+amin): short series when every lane's bound is tiny
+            const bool tiny = __all_sync(0xffffffffu, !valid || (P.beta * P.h2 <= 0.00390625 * (norm0 + P.amin)));
+            if (tiny) {
+#pragma unroll 2
+                for (int cand = c0; cand < c1; cand++) {
+                    const double2 *row = reinterpret_cast<const double2 *>(tab + (size_t)cand * CTW);
+                    double S = S0;
+#pragma unroll
+                    for (int m = 0; m < NUD; m++) {
+                        const double2 w = row[m];
+                        S = fma(w.x, cu[2 * m], S);
+                        S = fma(w.y, cu[2 * m + 1], S);
+                    }
+                    const double2 ag = row[NUD];
+                    const double rinv = rcp_pos(norm0 + ag.x);
+                    const double ebt = disc ? exp_tiny(nbh * rinv) : 1.0;
+                    const double v = rinv * fma(P.h2, gx + ag.y, ebt * S);
+                    if (v < best) { best = v; ibest = cand; }
+                }
+            } else {
+                for (int cand = c0; cand < c1; cand++) {
+                    const double2 *row = reinterpret_cast<const double2 *>(tab + (size_t)cand * CTW);
+                    double S = S0;
+#pragma unroll
+                    for (int m = 0; m < NUD; m++) {
+                        const double2 w = row[m];
+                        S = fma(w.x, cu[2 * m], S);
+                        S = fma(w.y, cu[2 * m + 1], S);
+                    }
+                    const double2 ag = row[NUD];
+                    const double rinv = rcp_pos(norm0 + ag.x);
+                    const double ebt = disc ? exp_nonpos(nbh * rinv) : 1.0;
+                    const double v = rinv * fma(P.h2, gx + ag.y, ebt * S);
+                    if (v < best) { best = v; ibest = cand; }
+                }
+            }
+        } else {
+            NodeInv<M> inv;
+            node_prepare<M, A>(P, P.utab, x, cc, inv);
+            int bad = 0;
+            for (int cand = c0; cand < c1; cand++) {
+                double u[DU];
+#pragma unroll
+                for (int i = 0; i < DU; i++) u[i] = tab[(size_t)cand * DU + i];
+                const double v = candidate_value<M, A>(P, x, u, cc, inv, bad);
+                if (v < best) { best = v; ibest = cand; }
+            }
+            if (bad) atomicOr(P.err, 1);
+        }
+        // merge the chunks of a node: lower part = earlier in the table, wins ties
+        for (int o = 1; o < parts; o <<= 1) {
+            const double vb = __shfl_down_sync(0xffffffffu, best, o);
+            const int ib = __shfl_down_sync(0xffffffffu, ibest, o);
+            if (vb < best) { best = vb; ibest = ib; }
+        }
+        if (!valid || part != 0) continue;
+        if (c.value) c.value[id] = best;
+        if (c.argmin) c.argmin[id] = ibest;
+        if (c.rows) {                               // policy row at u* (bellman.c:1851-1860)
+            double u[DU], b[DX], s[DX], prob[CS], dt;
+#pragma unroll
+            for (int i = 0; i < DU; i++) u[i] = P.utab[(size_t)(ibest < P.nu ? ibest : 0) * DU + i];
+            M::template drift<A>(x, u, P.mp, b);
+            M::template sigma<A>(x, u, P.mp, s);
+            const double g = M::template stage<A>(x, u, P.mp);
+            if (transition_row<DX, A>(P, b, s, prob, dt)) atomicOr(P.err, 1);
+            double *row = c.rows + (size_t)id * RW;
+#pragma unroll
+            for (int m = 0; m < CS; m++) row[m] = prob[m];
+            row[CS] = dt;
+            row[CS + 1] = g;
+        }
+    }
+
+    // absorbed nodes (bellman.c:513-532): boundary / obstacle cost, u = 0
+    for (long long id = (long long)blockIdx.x * CT_NT + tid; id < c.NS; id += stride) {
+        const int ab = c.flag[id];
+        if (ab != 1 && ab != -1) continue;
+        double x[DX];
+        node_state<DX>(c, (int)id, x);
+        const double v = (ab == 1) ? M::boundcost(x, P.mp) : M::obscost(x, P.mp);
+        if (c.value) c.value[id] = v;
+        if (c.argmin) c.argmin[id] = -1;
+        if (c.rows) {
+            double *row = c.rows + (size_t)id * RW;
+            for (int m = 0; m < RW; m++) row[m] = 0.0;
+        }
+    }
+}
+
+// policy evaluation (bellman.c:1774-1828,1863-1871): stored rows against the new neighbour values
+template <class M, class A>
+__global__ void __launch_bounds__(CT_NT) k_pi_eval(const CtlArgs c)
+{
+    constexpr int DX = M::DX, CS = 2 * DX + 1, RW = 2 * DX + 3;
+    const DevProblem &P = c.P;
+    const long long stride = (long long)gridDim.x * CT_NT;
+    for (long long id = (long long)blockIdx.x * CT_NT + threadIdx.x; id < c.NS; id += stride) {
+        const int ab = c.flag[id];
+        if (ab == 2) continue;
+        double v;
+        if (ab != 0) {
+            double x[DX];
+            node_state<DX>(c, (int)id, x);
+            v = (ab == 1) ? M::boundcost(x, P.mp) : M::obscost(x, P.mp);
+        } else {
+            const double *row = c.rows_in + (size_t)id * RW;
+            double prob[CS], cc[CS];
+#pragma unroll
+            for (int m = 0; m < CS; m++) { prob[m] = row[m]; cc[m] = c.cst[(size_t)m * c.NS + id]; }
+            v = rhs<DX, A>(P, prob, row[CS], row[CS + 1], cc);
+        }
+        c.value[id] = v;
+    }
+}
+
+// Candidate table of a separable model (FAST only): row c = [Wl_0, Wr_0, .., Wl_{NUD-1}, Wr_{NUD-1}, A, gu]
+//   Wl_m / Wr_m = t_i*|b_i(u_c)| on the side the upwind scheme adds it to (0 inside the 1e-14 dead band),
+//   A = sum of the W's (the candidate's share of the normaliser), gu = h2-free stage_u(u_c).
+template <class M>
+__global__ void k_build_ctab(const DevProblem P, double *ctab)
+{
+    constexpr int DX = M::DX, DU = M::DU, NUD = M::NUD, CT = 2 * NUD + 2;
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= P.nu) return;
+    double x[DX], u[DU], b[DX];
+    for (int i = 0; i < DX; i++) x[i] = 0.0;           // SEP: drift of ud(m) does not read x
+    for (int i = 0; i < DU; i++) u[i] = P.utab[(size_t)c * DU + i];
+    M::template drift<Fast>(x, u, P.mp, b);
+    double A = 0.0;
+    for (int m = 0; m < NUD; m++) {
+        const int i = M::ud(m);
+        const double tb = P.t[2 * i] * b[i];
+        const double wl = (b[i] < -1e-14) ? -tb : 0.0, wr = (b[i] > 1e-14) ? tb : 0.0;
+        ctab[(size_t)c * CT + 2 * m] = wl;
+        ctab[(size_t)c * CT + 2 * m + 1] = wr;
+        A += wl + wr;
+    }
+    ctab[(size_t)c * CT + 2 * NUD] = A;
+    ctab[(size_t)c * CT + 2 * NUD + 1] = M::stage_u(u, P.mp);
+}
+
+template <class M>
+int build_ctab_t(const DevProblem &P, double *ctab, cudaStream_t st)
+{
+    if (!M::SEP) return 0;
+    k_build_ctab<M><<<(P.nu + 127) / 128, 128, 0, st>>>(P, ctab);
+    return (int)cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------
+struct CtlLaunchInfo { int sms, max_optin; };
+inline const CtlLaunchInfo &ctl_info()
+{
+    static CtlLaunchInfo info = {0, 0};
+    if (!info.sms) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&info.sms, cudaDevAttrMultiProcessorCount, dev);
+        cudaDeviceGetAttribute(&info.max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+    }
+    return info;
+}
+
+template <class M, class A>
+int launch_control_t(const CtlArgs &c_in, int pi_eval, cudaStream_t st)
+{
+    const CtlLaunchInfo &info = ctl_info();
+    CtlArgs c = c_in;
+    if (pi_eval) {
+        long long g = (c.NS + CT_NT - 1) / CT_NT;
+        if (g > (long long)info.sms * 16) g = (long long)info.sms * 16;
+        if (g < 1) return 0;
+        k_pi_eval<M, A><<<(int)g, CT_NT, 0, st>>>(c);
+        return (int)cudaGetLastError();
+    }
+    constexpr bool TAB = M::SEP && !A::exact;
+    const size_t tabBytes = (size_t)c.P.nu * (TAB ? 2 * M::NUD + 2 : M::DU) * sizeof(double);
+    c.tab_in_smem = tabBytes <= 96 * 1024;
+    const size_t smem = c.tab_in_smem ? tabBytes : 0;
+    static size_t attr_set = 0;
+    if (smem > 48 * 1024 && smem > attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(k_control<M, A>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+        if (e != cudaSuccess) return (int)e;
+        attr_set = 96 * 1024;
+    }
+    // candidate chunks per node: enough (node, chunk) items to occupy every SM; 1 for large batches
+    int pl2 = 0;
+    while (pl2 < 5 && (c.NS << pl2) < (long long)info.sms * CT_NT * 4 && (2 << pl2) <= c.P.nu) pl2++;
+    c.parts_log2 = pl2;
+    int per_sm = 1;
+    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_control<M, A>, CT_NT, smem);
+    if (e != cudaSuccess) return (int)e;
+    if (per_sm < 1) per_sm = 1;
+    long long need = ((c.NS << pl2) + CT_NT - 1) / CT_NT;
+    long long g = (long long)info.sms * per_sm;
+    if (g > need) g = need;
+    if (g < 1) return 0;
+    k_control<M, A><<<(int)g, CT_NT, smem, st>>>(c);
+    return (int)cudaGetLastError();
+}
+
+template <class M>
+int launch_control_m(int arith, const CtlArgs &c, int pi_eval, cudaStream_t st)
+{
+    if (arith == C3SC_ARITH_EXACT) return launch_control_t<M, Exact>(c, pi_eval, st);
+    return launch_control_t<M, Fast>(c, pi_eval, st);
+}
+
+// ---- node-level entry: bellman_optimal on caller-supplied (x, neighbour costs, flag) --------
+// One thread per node, candidates walked in table order (bellman.c:504-543).
+template <class M, class A>
+__global__ void k_node_backup(const DevProblem P, int n, const double *x, const double *costs, const int *absorbed,
+                              double *value, int *argmin)
+{
+    constexpr int DX = M::DX, DU = M::DU, CS = 2 * DX + 1;
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n) return;
+    double xx[DX], c[CS];
+#pragma unroll
+    for (int i = 0; i < DX; i++) xx[i] = x[(size_t)e * DX + i];
+    const int ab = absorbed ? absorbed[e] : 0;
+    if (ab == 1) { value[e] = M::boundcost(xx, P.mp); if (argmin) argmin[e] = -1; return; }
+    if (ab == -1) { value[e] = M::obscost(xx, P.mp); if (argmin) argmin[e] = -1; return; }
+#pragma unroll
+    for (int m = 0; m < CS; m++) c[m] = costs[(size_t)e * CS + m];
+    NodeInv<M> inv;
+    node_prepare<M, A>(P, P.utab, xx, c, inv);
+    double best = CUDART_INF;
+    int ibest = 0x7fffffff, bad = 0;
+    for (int cand = 0; cand < P.nu; cand++) {
+        double u[DU];
+#pragma unroll
+        for (int i = 0; i < DU; i++) u[i] = P.utab[(size_t)cand * DU + i];
+        const double v = candidate_value<M, A>(P, xx, u, c, inv, bad);
+        if (v < best) { best = v; ibest = cand; }
+    }
+    if (bad) atomicOr(P.err, 1);
+    value[e] = best;
+    if (argmin) argmin[e] = ibest;
+}
+
+template <class M>
+int launch_node_backup_t(int arith, const DevProblem &P, int n, const double *x, const double *costs,
+                         const int *absorbed, double *value, int *argmin, cudaStream_t st)
+{
+    if (n <= 0) return 0;
+    const int g = (n + 127) / 128;
+    if (arith == C3SC_ARITH_EXACT) k_node_backup<M, Exact><<<g, 128, 0, st>>>(P, n, x, costs, absorbed, value, argmin);
+    else k_node_backup<M, Fast><<<g, 128, 0, st>>>(P, n, x, costs, absorbed, value, argmin);
+    return (int)cudaGetLastError();
+}
+
+// bellman_control (bellman.c:367-480, grad_u == NULL) at n (x, u, costs) triples, any u
+template <class M, class A>
+__global__ void k_control_value(const DevProblem P, int n, const double *x, const double *u, const double *costs,
+                                double *value)
+{
+    constexpr int DX = M::DX, DU = M::DU, CS = 2 * DX + 1;
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n) return;
+    double xx[DX], uu[DU], c[CS], b[DX], s[DX], prob[CS], dt;
+    for (int i = 0; i < DX; i++) xx[i] = x[(size_t)e * DX + i];
+    for (int i = 0; i < DU; i++) uu[i] = u[(size_t)e * DU + i];
+    for (int m = 0; m < CS; m++) c[m] = costs[(size_t)e * CS + m];
+    M::template drift<A>(xx, uu, P.mp, b);
+    M::template sigma<A>(xx, uu, P.mp, s);
+    const double g = M::template stage<A>(xx, uu, P.mp);
+    if (transition_row<DX, A>(P, b, s, prob, dt)) { atomicOr(P.err, 1); value[e] = CUDART_NAN; return; }
+    value[e] = rhs<DX, A>(P, prob, dt, g, c);
+}
+template <class M>
+int launch_control_value_t(int arith, const DevProblem &P, int n, const double *x, const double *u, const double *costs,
+                           double *value, cudaStream_t st)
+{
+    if (n <= 0) return 0;
+    const int g = (n + 127) / 128;
+    if (arith == C3SC_ARITH_EXACT) k_control_value<M, Exact><<<g, 128, 0, st>>>(P, n, x, u, costs, value);
+    else k_control_value<M, Fast><<<g, 128, 0, st>>>(P, n, x, u, costs, value);
+    return (int)cudaGetLastError();
+}
+
+// bellmanrhs on raw tuples (runtime dx)
+template <class A>
+__global__ void k_rhs(int dx, double beta, int n, const double *prob, const double *dt, const double *stage,
+                      const double *cost, double *out)
+{
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n) return;
+    const int cs = 2 * dx + 1;
+    const double ebt = exp(A::mul(-beta, dt[e]));
+    double ctg = 0.0;
+    for (int m = 0; m < cs; m++) ctg = A::mad(prob[(size_t)e * cs + m], cost[(size_t)e * cs + m], ctg);
+    out[e] = A::add(A::mul(dt[e], stage[e]), A::mul(ebt, ctg));
+}
+
+// ---- small test kernels -------------------------------------------------------
+template <class M>
+__global__ void k_model_eval(const DevProblem P, int n, const double *x, const double *u, double *drift,
+                             double *sig, double *stage, double *bound, double *obs)
+{
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n) return;
+    double xx[M::DX], uu[M::DU], b[M::DX], s[M::DX];
+    for (int i = 0; i < M::DX; i++) xx[i] = x[(size_t)e * M::DX + i];
+    for (int i = 0; i < M::DU; i++) uu[i] = u[(size_t)e * M::DU + i];
+    M::template drift<Exact>(xx, uu, P.mp, b);
+    M::template sigma<Exact>(xx, uu, P.mp, s);
+    for (int i = 0; i < M::DX; i++) { drift[(size_t)e * M::DX + i] = b[i]; sig[(size_t)e * M::DX + i] = s[i]; }
+    stage[e] = M::template stage<Exact>(xx, uu, P.mp);
+    bound[e] = M::boundcost(xx, P.mp);
+    obs[e] = M::obscost(xx, P.mp);
+}
+
+template <class M>
+int launch_model_eval_t(const DevProblem &P, int n, const double *x, const double *u, double *drift,
+                        double *sig, double *stage, double *bound, double *obs, cudaStream_t st)
+{
+    if (n <= 0) return 0;
+    k_model_eval<M><<<(n + 127) / 128, 128, 0, st>>>(P, n, x, u, drift, sig, stage, bound, obs);
+    return (int)cudaGetLastError();
+}
+
+// transition_assemble on caller-supplied (drift, diag sigma) pairs: parity-test entry
+template <int DX, class A>
+__global__ void k_transition(const DevProblem P, int n, const double *drift, const double *sig,
+                             double *prob, double *dt, int *status)
+{
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n) return;
+    double b[DX], s[DX], p[2 * DX + 1], t;
+    for (int i = 0; i < DX; i++) { b[i] = drift[(size_t)e * DX + i]; s[i] = sig[(size_t)e * DX + i]; }
+    const int st = transition_row<DX, A>(P, b, s, p, t);
+    for (int m = 0; m < 2 * DX + 1; m++) prob[(size_t)e * (2 * DX + 1) + m] = p[m];
+    dt[e] = t;
+    status[e] = st;
+}
+
+}  // namespace c3sc

@@ -32,6 +32,7 @@ struct DevFT {
     int r[MAXD + 1];
     long long off[MAXD];     // offset of core k inside `base` (doubles)
     const double *base;
+    const double *baseT;     // same offsets, every block transposed (b + a*r_{k+1}); see k_transpose_cores
 };
 
 struct DevOut {
@@ -42,26 +43,6 @@ struct DevOut {
     double *rows;
     int *nbr_vary;
     int *nbr_fixed;
-};
-
-enum Mode { MODE_VI = 0, MODE_PI_EVAL = 1, MODE_COSTS = 2 };
-
-struct LaunchArgs {
-    DevProblem P;
-    DevFT ft;
-    int F;
-    const int *dim_vary;
-    const int *fixed_ind;
-    int ldo;
-    DevOut out;
-    const double *rows_in;   // MODE_PI_EVAL: policy rows
-    int mode;
-    int write_value;         // MODE_VI: 0 when only rows/argmin are wanted
-    int staged;              // set by the launcher: FT operands via the TMA staging ring
-    int force_direct;        // debug / test: never use the staged plan
-    unsigned long long *prof; // optional [8] per-phase cycle counters (summed over CTAs), NULL = off
-    const int *nbr_fixed_in; // MODE_COSTS: caller-supplied neighbour indices (valuef_eval_fiber_ind_nn)
-    const int *nbr_vary_in;  //             [F*2*(dx-1)] and [F*ldo*2]; NULL = derive from the boundary
 };
 
 // implemented in inst_misc.cu; returns cudaError_t as int, or -1 if dx is not instantiated

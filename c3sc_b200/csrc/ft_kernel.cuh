@@ -1,0 +1,532 @@
+// ft_kernel.cuh -- stage 1 of the Bellman backup: flags, neighbour indices and the
+// function-train neighbour values of every node of every fiber of a batch.
+//
+//   process_fibers_neighbor   src/nodeutil.c:489-627   (flags + neighbour indices)
+//   valuef_eval_fiber_ind_nn  src/valuefunc.c:369-585  (FT values at the node and its 2d
+//                                                       axis neighbours, re-associated)
+//   = mca_get_neighbor_costs  src/nodeutil.c:647-713   for F fibers at once.
+//
+// Independent of the dynamics / cost model.  Fibers are first grouped by their varying
+// dimension k (k_group_fibers); one CTA then evaluates up to FB fibers that share k, so the
+// blocks G_k[j] of the varying core are brought on chip once per group.
+//
+//   chains   (per fiber)  L = G_0[f_0]..G_{k-1}[f_{k-1}], R = G_{k+1}[f_{k+1}]..G_{d-1}[f_{d-1}] and the
+//            2(d-1) neighbour variants of them (one centre block replaced by a neighbour's),
+//            built as stepped vector-set x block products.  Operands come straight from
+//            L2 with coalesced loads: the right side walks G (a + b r_m, lanes over a), the
+//            left side walks the TRANSPOSED copy of the cores (b + a r_{m+1}, lanes over b)
+//            that the value function keeps next to the original.
+//   nodes    per tile of T nodes: stage G_k[j] in shared memory (odd column stride, so both
+//            orientations are bank-conflict free), w_j = G_k[j] R and u_j = L G_k[j] for
+//            all fibers of the group, then the (2d-1) length-r dots per (fiber, node).
+//   output   costs in a slot-major scratch  cst[slot*NS + node]  (what the control kernel
+//            reads coalesced), optionally the reference's node-major rows, flags, the
+//            compacted list of non-absorbed nodes.
+#pragma once
+#include <cuda_runtime.h>
+#include "dev_types.h"
+
+namespace c3sc {
+
+constexpr int FT_NT = 256;        // threads per CTA
+constexpr int FT_FBMAX = 8;       // fibers per group
+constexpr int FT_TMAX = 8;        // nodes per tile
+constexpr int FT_VG = 8;          // chain: vectors per work item
+constexpr int FT_DG = 4;          // dots: vectors per work item
+
+struct FtArgs {
+    DevProblem P;             // grid, boundary types, obstacles (model fields unused)
+    DevFT ft;
+    int F;                    // fibers in this launch (a chunk of the caller's batch)
+    const int *dim_vary;      // [F]
+    const int *fixed_ind;     // [F*d]
+    int ldo;
+    int FB;                   // fibers per group (<= FT_FBMAX)
+    const int *perm;          // [F] fiber ids grouped by k
+    const int *kcount;        // [d] fibers per k
+    const int *kstart;        // [d] first position of k in perm
+    // outputs
+    double *cst;              // [(2d+1) * NS] slot-major scratch, may be NULL
+    long long NS;             // F*ldo
+    signed char *flag;        // [NS] 0 / 1 / -1, 2 = padding (j >= ngrid[k]); may be NULL
+    int *act;                 // [NS] ids of nodes with flag 0; may be NULL
+    int *act_count;
+    double *costs;            // optional node-major rows [NS*(2d+1)]
+    int *absorbed;            // optional [NS]
+    int *nbr_vary;            // optional [NS*2]
+    int *nbr_fixed;           // optional [F*2*(d-1)]
+    const int *nbr_fixed_in;  // caller-supplied neighbour indices (valuef_eval_fiber_ind_nn)
+    const int *nbr_vary_in;
+};
+
+__host__ __device__ inline int ft_even_up(int v) { return (v + 1) & ~1; }
+
+// node-tile size for a varying core with block r_k x r_{k+1}
+__host__ __device__ inline int ft_tile_nodes(int rk, int rk1)
+{
+    int T = FT_NT / (rk + rk1);
+    return T < 1 ? 1 : (T > FT_TMAX ? FT_TMAX : T);
+}
+
+// shared-memory carve-up; identical on host and device
+struct FtPlan {
+    int d, FB, rs, nvt, tp, nmax;
+    int oSetA, oUni, oLt, oRt, oV, nDoubles;      // doubles
+    int setDoubles, gTile, oW, oU;                // inside the union region
+    int oFix, oNf, oAbs, oNv, oFid, oWall, nInts; // ints
+    __host__ __device__ FtPlan(const DevFT &ft, int nmax_, int FB_)
+    {
+        d = ft.d; FB = FB_; nmax = nmax_;
+        rs = 1;
+        for (int i = 0; i <= d; i++) rs = ft.r[i] > rs ? ft.r[i] : rs;
+        nvt = 2 * d + 2;                          // vectors of both chain sets of one fiber (even-padded)
+        tp = FT_TMAX | 1;                         // odd stride of a (fiber, rank index) row of w / u
+        setDoubles = FB * rs * nvt;
+        gTile = 0;
+        int wu = 0;
+        for (int k = 0; k < d; k++) {
+            const int rk = ft.r[k], rk1 = ft.r[k + 1];
+            const int g = ft_tile_nodes(rk, rk1) * (rk | 1) * rk1;
+            gTile = g > gTile ? g : gTile;
+            wu = (rk + rk1) > wu ? (rk + rk1) : wu;
+        }
+        gTile = ft_even_up(gTile);
+        int o = 0;
+        oSetA = o; o += setDoubles;
+        oUni = o;
+        oW = gTile;                                // union region: [G tile][w rows][u rows]  or  chain buffer B
+        oU = oW;                                   // u rows follow the w rows (offset set per group: rk*FB*tp)
+        const int node_need = gTile + wu * FB * tp;
+        o += node_need > setDoubles ? node_need : setDoubles;
+        o = ft_even_up(o);
+        oLt = o; o += rs * FT_FBMAX;
+        oRt = o; o += rs * FT_FBMAX;
+        oV = o;  o += FB * nmax;
+        nDoubles = ft_even_up(o);
+        int q = 0;
+        oFix = q;  q += FB * d;
+        oNf = q;   q += FB * 2 * d;
+        oAbs = q;  q += FB * nmax;
+        oNv = q;   q += FB * 2 * nmax;
+        oFid = q;  q += FT_FBMAX;
+        oWall = q; q += FT_FBMAX;
+        nInts = q;
+    }
+    __host__ __device__ size_t bytes() const { return (size_t)nDoubles * 8 + (size_t)nInts * 4; }
+};
+
+#ifndef C3SC_FT_TYPES_ONLY
+// ---------------------------------------------------------------------------
+// Group the fibers of a chunk by varying dimension: perm = fiber ids, k-major.  One CTA.
+// Also clears the active-node counter of the chunk.
+__global__ void __launch_bounds__(1024) k_group_fibers(int F, int d, const int *dim_vary, int *perm, int *kcount,
+                                                       int *kstart, int *act_count)
+{
+    __shared__ int cnt[MAXD], pos[MAXD];
+    const int tid = threadIdx.x;
+    if (tid < MAXD) cnt[tid] = 0;
+    __syncthreads();
+    for (int f = tid; f < F; f += blockDim.x) {
+        int k = dim_vary[f];
+        k = k < 0 ? 0 : (k >= d ? d - 1 : k);
+        atomicAdd(&cnt[k], 1);
+    }
+    __syncthreads();
+    if (tid == 0) {
+        int run = 0;
+        for (int k = 0; k < d; k++) { pos[k] = run; kstart[k] = run; kcount[k] = cnt[k]; run += cnt[k]; }
+        if (act_count) *act_count = 0;
+    }
+    __syncthreads();
+    // stable within a thread's stride; the order inside a group does not change any result
+    for (int f = tid; f < F; f += blockDim.x) {
+        int k = dim_vary[f];
+        k = k < 0 ? 0 : (k >= d ? d - 1 : k);
+        perm[atomicAdd(&pos[k], 1)] = f;
+    }
+}
+
+// Transposed copy of every core block: baseT[off_k + j*blk + b + a*r_{k+1}] = base[off_k + j*blk + a + b*r_k].
+__global__ void k_transpose_cores(DevFT ft, double *baseT)
+{
+    const int k = blockIdx.y;
+    const int rk = ft.r[k], rk1 = ft.r[k + 1], blk = rk * rk1;
+    const long long total = (long long)ft.n[k] * blk;
+    for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+        const long long j = e / blk;
+        const int rem = (int)(e - j * blk);
+        const int a = rem / rk1, b = rem - a * rk1;            // e enumerates the transposed layout
+        baseT[ft.off[k] + e] = ft.base[ft.off[k] + j * blk + a + (long long)b * rk];
+    }
+}
+
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(FT_NT, 2) k_ft_costs(const FtArgs a)
+{
+    const DevProblem &P = a.P;
+    const DevFT &ft = a.ft;
+    const int d = ft.d, CS = 2 * d + 1;
+    const int tid = threadIdx.x;
+    const int FB = a.FB;
+
+    // ---- which group is this CTA ------------------------------------------------
+    int k = -1, gstart = 0, nf = 0;
+    {
+        int b = blockIdx.x;
+        for (int kk = 0; kk < d; kk++) {
+            const int c = a.kcount[kk];
+            const int ng = (c + FB - 1) / FB;
+            if (b < ng) { k = kk; gstart = a.kstart[kk] + b * FB; nf = c - b * FB; nf = nf > FB ? FB : nf; break; }
+            b -= ng;
+        }
+    }
+    if (k < 0) return;
+
+    extern __shared__ __align__(16) double smem[];
+    const FtPlan sp(ft, P.nmax, FB);
+    const int rs = sp.rs, TP = sp.tp, nmax = sp.nmax;
+    double *bufA = smem + sp.oSetA, *bufB = smem + sp.oUni;
+    double *sLt = smem + sp.oLt, *sRt = smem + sp.oRt, *sV = smem + sp.oV;
+    int *ismem = reinterpret_cast<int *>(smem + sp.nDoubles);
+    int *sFix = ismem + sp.oFix, *sNf = ismem + sp.oNf, *sAbs = ismem + sp.oAbs, *sNv = ismem + sp.oNv;
+    int *sFid = ismem + sp.oFid, *sWall = ismem + sp.oWall;
+
+    const int N = P.ngrid[k];
+    const int NVL = ft_even_up(1 + 2 * k), NVR = ft_even_up(1 + 2 * (d - 1 - k));
+    const int setStride = rs * sp.nvt;                 // one fiber's two sets inside a buffer
+    const int offR = rs * NVL;                         // right set follows the left set
+
+    // ---- 0. descriptors, flags, neighbour indices (nodeutil.c:489-627) ------------
+    if (tid < FT_FBMAX) { sFid[tid] = tid < nf ? a.perm[gstart + tid] : -1; sWall[tid] = 0; }
+    __syncthreads();
+    for (int e = tid; e < nf * d; e += FT_NT) {
+        const int g = e / d, i = e - g * d;
+        sFix[g * d + i] = a.fixed_ind[(size_t)sFid[g] * d + i];
+    }
+    __syncthreads();
+    for (int e = tid; e < nf * d; e += FT_NT) {        // fixed-dimension neighbour pairs
+        const int g = e / d, i = e - g * d;
+        if (i == k) continue;
+        const int slot = i < k ? i : i - 1;
+        const int i0 = sFix[g * d + i], last = P.ngrid[i] - 1, bc = P.bc[i];
+        int lo, hi;
+        if (i0 == 0) {
+            if (bc == C3SC_ABSORB)        { lo = i0; hi = i0; sWall[g] = 1; }
+            else if (bc == C3SC_REFLECT)  { lo = i0; hi = i0 + 1; }
+            else                          { lo = P.ngrid[i] - 2; hi = i0 + 1; }
+        } else if (i0 == last) {
+            if (bc == C3SC_ABSORB)        { lo = i0; hi = i0; sWall[g] = 1; }
+            else if (bc == C3SC_REFLECT)  { lo = i0 - 1; hi = i0; }
+            else                          { lo = i0 - 1; hi = 1; }
+        } else { lo = i0 - 1; hi = i0 + 1; }
+        if (a.nbr_fixed_in) {
+            lo = a.nbr_fixed_in[(size_t)sFid[g] * 2 * (d - 1) + 2 * slot];
+            hi = a.nbr_fixed_in[(size_t)sFid[g] * 2 * (d - 1) + 2 * slot + 1];
+        }
+        sNf[g * 2 * d + 2 * slot] = lo;
+        sNf[g * 2 * d + 2 * slot + 1] = hi;
+        if (a.nbr_fixed) {
+            a.nbr_fixed[(size_t)sFid[g] * 2 * (d - 1) + 2 * slot] = lo;
+            a.nbr_fixed[(size_t)sFid[g] * 2 * (d - 1) + 2 * slot + 1] = hi;
+        }
+    }
+    __syncthreads();
+    for (int e = tid; e < nf * N; e += FT_NT) {
+        const int g = e / N, j = e - g * N;
+        int ab = 0;
+        for (int o = 0; o < P.nobs && ab == 0; o++) {                   // boundary.c:329-344,668-680
+            const double *lb = P.obs + (size_t)o * 2 * d, *ub = lb + d;
+            bool inside = true;
+            for (int i = 0; i < d; i++) {
+                const double x = P.xgrid[P.xoff[i] + (i == k ? j : sFix[g * d + i])];
+                inside = inside && !(x < lb[i] || x > ub[i]);
+            }
+            if (inside) ab = -1;
+        }
+        if (sWall[g]) ab = 1;
+        int lo = j - 1, hi = j + 1;
+        const int bk = P.bc[k];
+        if (j == 0) {                                                   // ends overwrite (nodeutil.c:570-612)
+            if (bk == C3SC_ABSORB)       { lo = 0; hi = 0; ab = 1; }
+            else if (bk == C3SC_REFLECT) { lo = 0; hi = 1; ab = 0; }
+            else                         { lo = N - 2; hi = 1; ab = 0; }
+        } else if (j == N - 1) {
+            if (bk == C3SC_ABSORB)       { lo = N - 1; hi = N - 1; ab = 1; }
+            else if (bk == C3SC_REFLECT) { lo = N - 2; hi = N - 1; ab = 0; }
+            else                         { lo = N - 2; hi = 1; ab = 0; }
+        } else if (ab != 0) { lo = j; hi = j; }
+        const size_t id = (size_t)sFid[g] * a.ldo + j;
+        if (a.nbr_vary_in) { lo = a.nbr_vary_in[2 * id]; hi = a.nbr_vary_in[2 * id + 1]; }
+        sAbs[g * nmax + j] = ab;
+        sNv[g * 2 * nmax + 2 * j] = lo;
+        sNv[g * 2 * nmax + 2 * j + 1] = hi;
+        if (a.flag) a.flag[id] = (signed char)ab;
+        if (a.absorbed) a.absorbed[id] = ab;
+        if (a.nbr_vary) { a.nbr_vary[2 * id] = lo; a.nbr_vary[2 * id + 1] = hi; }
+    }
+    if (a.flag)
+        for (int e = tid; e < nf * (a.ldo - N); e += FT_NT) {           // padding entries of ragged grids
+            const int g = e / (a.ldo - N), j = N + (e - g * (a.ldo - N));
+            a.flag[(size_t)sFid[g] * a.ldo + j] = 2;
+        }
+
+    // ---- 1. chains -----------------------------------------------------------------
+    // set layout: element (q, v) of a set at q*NV + v  (q = rank index, v = vector, v fastest).
+    // left set after step m:  v=0 the prefix L_{m+1}, v=1+2i+s the variant with G_i[nb_s], i<=m.
+    // right set after step m' (dimension d-1-m'): v=0 the suffix, v=1+2m''+s the variant of
+    // dimension d-1-m''.
+    for (int e = tid; e < nf; e += FT_NT) {
+        bufA[e * setStride] = 1.0;
+        bufA[e * setStride + offR] = 1.0;
+    }
+    __syncthreads();
+    const int nsteps = (k > d - 1 - k) ? k : d - 1 - k;
+    for (int s = 0; s < nsteps; s++) {
+        const bool doL = s < k, doR = s < d - 1 - k;
+        const int nin = 1 + 2 * s, nvg = (nin + FT_VG - 1) / FT_VG;
+        const double *in = (s & 1) ? bufB : bufA;
+        double *out = (s & 1) ? bufA : bufB;
+        const int mL = s, mR = d - 1 - s;
+        const int roL = doL ? ft.r[mL + 1] : 0, roR = doR ? ft.r[mR] : 0;
+        const int perL = nvg * roL, perR = nvg * roR;
+        const int nitems = nf * (perL + perR);
+        for (int e = tid; e < nitems; e += FT_NT) {
+            const int g = e / (perL + perR);
+            int rem = e - g * (perL + perR);
+            const bool left = rem < perL;
+            if (!left) rem -= perL;
+            const int ro = left ? roL : roR;
+            const int vg = rem / ro, o = rem - vg * ro;
+            const int m = left ? mL : mR;
+            const int rq = left ? ft.r[m] : ft.r[m + 1];
+            const int NV = left ? NVL : NVR;
+            const int blk = ft.r[m] * ft.r[m + 1];
+            const double *base = (left ? ft.baseT : ft.base) + ft.off[m];
+            const int slot = m < k ? m : m - 1;
+            const double *gc = base + (size_t)sFix[g * d + m] * blk + o;
+            const double *vin = in + g * setStride + (left ? 0 : offR);
+            double *vout = out + g * setStride + (left ? 0 : offR);
+            const int v0 = vg * FT_VG;
+            double acc[FT_VG];
+#pragma unroll
+            for (int i = 0; i < FT_VG; i++) acc[i] = 0.0;
+            if (vg == 0) {
+                const double *glo = base + (size_t)sNf[g * 2 * d + 2 * slot] * blk + o;
+                const double *ghi = base + (size_t)sNf[g * 2 * d + 2 * slot + 1] * blk + o;
+                double alo = 0.0, ahi = 0.0;
+#pragma unroll 4
+                for (int q = 0; q < rq; q++) {
+                    const double c = __ldg(gc + (size_t)q * ro), l = __ldg(glo + (size_t)q * ro), h = __ldg(ghi + (size_t)q * ro);
+                    const double2 *row = reinterpret_cast<const double2 *>(vin + q * NV);
+#pragma unroll
+                    for (int i = 0; i < FT_VG / 2; i++) {
+                        const double2 x = row[i];
+                        acc[2 * i] = fma(x.x, c, acc[2 * i]);
+                        acc[2 * i + 1] = fma(x.y, c, acc[2 * i + 1]);
+                        if (i == 0) { alo = fma(x.x, l, alo); ahi = fma(x.x, h, ahi); }
+                    }
+                }
+                vout[o * NV + nin] = alo;
+                vout[o * NV + nin + 1] = ahi;
+            } else {
+#pragma unroll 4
+                for (int q = 0; q < rq; q++) {
+                    const double c = __ldg(gc + (size_t)q * ro);
+                    const double2 *row = reinterpret_cast<const double2 *>(vin + q * NV + v0);
+#pragma unroll
+                    for (int i = 0; i < FT_VG / 2; i++) {
+                        const double2 x = row[i];
+                        acc[2 * i] = fma(x.x, c, acc[2 * i]);
+                        acc[2 * i + 1] = fma(x.y, c, acc[2 * i + 1]);
+                    }
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < FT_VG; i++)
+                if (v0 + i < nin) vout[o * NV + v0 + i] = acc[i];
+        }
+        // a side that has already finished carries its set over unchanged
+        if (!doL) {
+            const int cnt = ft.r[k] * NVL;
+            for (int e = tid; e < nf * cnt; e += FT_NT) { const int g = e / cnt, q = e - g * cnt; out[g * setStride + q] = in[g * setStride + q]; }
+        }
+        if (!doR) {
+            const int cnt = ft.r[k + 1] * NVR;
+            for (int e = tid; e < nf * cnt; e += FT_NT) { const int g = e / cnt, q = e - g * cnt; out[g * setStride + offR + q] = in[g * setStride + offR + q]; }
+        }
+        __syncthreads();
+    }
+    if (nsteps & 1) {                                   // final sets must live in buffer A (B is the node scratch)
+        for (int e = tid; e < nf * setStride; e += FT_NT) bufA[e] = bufB[e];
+        __syncthreads();
+    }
+    const int rk = ft.r[k], rk1 = ft.r[k + 1];
+    // transposed prefix / suffix for the node mat-vecs: Lt[a*FBMAX + g], Rt[b*FBMAX + g] (0 for g >= nf)
+    for (int e = tid; e < rk * FT_FBMAX; e += FT_NT) {
+        const int aa = e / FT_FBMAX, g = e - aa * FT_FBMAX;
+        sLt[e] = g < nf ? bufA[g * setStride + aa * NVL] : 0.0;
+    }
+    for (int e = tid; e < rk1 * FT_FBMAX; e += FT_NT) {
+        const int b = e / FT_FBMAX, g = e - b * FT_FBMAX;
+        sRt[e] = g < nf ? bufA[g * setStride + offR + b * NVR] : 0.0;
+    }
+    __syncthreads();
+
+    // ---- 2. node tiles ----------------------------------------------------------------
+    {
+        const int ldk = rk | 1, blk = rk * rk1;
+        const int T = ft_tile_nodes(rk, rk1);
+        double *sG = bufB, *sW = bufB + sp.gTile, *sU = sW + rk * FB * TP;
+        const double *Gk = ft.base + ft.off[k];
+        const unsigned magic = (unsigned)((0x100000000ULL + rk - 1) / rk);        // e / rk for e < 2^32 / rk
+        const int ngL = (1 + 2 * k + FT_DG - 1) / FT_DG;
+        const int ngR = (d - 1 - k > 0) ? (1 + 2 * (d - 1 - k) + FT_DG - 1) / FT_DG : 0;
+        for (int j0 = 0; j0 < N; j0 += T) {
+            const int nt = (N - j0 < T) ? N - j0 : T;
+            // stage the tile: column c = jl*rk1 + b of length rk -> sG[c*ldk + a]
+            {
+                const double *src = Gk + (size_t)j0 * blk;
+                const int cnt = nt * blk;
+                for (int e = tid; e < cnt; e += FT_NT) {
+                    const int c = rk == 1 ? e : (int)__umulhi((unsigned)e, magic);
+                    const int aa = e - c * rk;
+                    sG[c * ldk + aa] = __ldg(src + e);
+                }
+            }
+            __syncthreads();
+            // w[g] = G_k[j] R_g (row a), u[g] = L_g G_k[j] (column b), all fibers of the group at once
+            {
+                const int per = rk + rk1;
+                for (int e = tid; e < nt * per; e += FT_NT) {
+                    const int jl = e / per, q = e - jl * per;
+                    double acc[FT_FBMAX];
+#pragma unroll
+                    for (int g = 0; g < FT_FBMAX; g++) acc[g] = 0.0;
+                    if (q < rk) {
+                        const double *gp = sG + jl * rk1 * ldk + q;
+#pragma unroll 2
+                        for (int b = 0; b < rk1; b++) {
+                            const double gv = gp[b * ldk];
+                            const double2 *rr = reinterpret_cast<const double2 *>(sRt + b * FT_FBMAX);
+#pragma unroll
+                            for (int g = 0; g < FT_FBMAX / 2; g++) {
+                                const double2 x = rr[g];
+                                acc[2 * g] = fma(gv, x.x, acc[2 * g]);
+                                acc[2 * g + 1] = fma(gv, x.y, acc[2 * g + 1]);
+                            }
+                        }
+#pragma unroll
+                        for (int g = 0; g < FT_FBMAX; g++)
+                            if (g < nf) sW[(g * rk + q) * TP + jl] = acc[g];
+                    } else {
+                        const int b = q - rk;
+                        const double *gp = sG + (jl * rk1 + b) * ldk;
+#pragma unroll 2
+                        for (int aa = 0; aa < rk; aa++) {
+                            const double gv = gp[aa];
+                            const double2 *ll = reinterpret_cast<const double2 *>(sLt + aa * FT_FBMAX);
+#pragma unroll
+                            for (int g = 0; g < FT_FBMAX / 2; g++) {
+                                const double2 x = ll[g];
+                                acc[2 * g] = fma(gv, x.x, acc[2 * g]);
+                                acc[2 * g + 1] = fma(gv, x.y, acc[2 * g + 1]);
+                            }
+                        }
+#pragma unroll
+                        for (int g = 0; g < FT_FBMAX; g++)
+                            if (g < nf) sU[(g * rk1 + b) * TP + jl] = acc[g];
+                    }
+                }
+            }
+            __syncthreads();
+            // dots: left variants against w, right variants against u
+            {
+                const int perf = (ngL + ngR) * nt;
+                for (int e = tid; e < nf * perf; e += FT_NT) {
+                    const int g = e / perf;
+                    int rem = e - g * perf;
+                    const int grp = rem / nt, jl = rem - grp * nt, j = j0 + jl;
+                    const bool left = grp < ngL;
+                    const int v0 = (left ? grp : grp - ngL) * FT_DG;
+                    const int NV = left ? NVL : NVR, rr = left ? rk : rk1;
+                    const double *vec = bufA + g * setStride + (left ? 0 : offR) + v0;
+                    const double *wu = (left ? sW + g * rk * TP : sU + g * rk1 * TP) + jl;
+                    double acc[FT_DG];
+#pragma unroll
+                    for (int i = 0; i < FT_DG; i++) acc[i] = 0.0;
+#pragma unroll 2
+                    for (int q = 0; q < rr; q++) {
+                        const double x = wu[q * TP];
+                        const double2 *row = reinterpret_cast<const double2 *>(vec + q * NV);
+#pragma unroll
+                        for (int i = 0; i < FT_DG / 2; i++) {
+                            const double2 y = row[i];
+                            acc[2 * i] = fma(y.x, x, acc[2 * i]);
+                            acc[2 * i + 1] = fma(y.y, x, acc[2 * i + 1]);
+                        }
+                    }
+                    const size_t id = (size_t)sFid[g] * a.ldo + j;
+                    const int nvec = left ? 1 + 2 * k : 1 + 2 * (d - 1 - k);
+#pragma unroll
+                    for (int i = 0; i < FT_DG; i++) {
+                        const int v = v0 + i;
+                        if (v >= nvec) continue;
+                        int slot;
+                        if (v == 0) {
+                            if (!left) continue;                       // suffix . u == self again
+                            slot = 2 * d;
+                            sV[g * nmax + j] = acc[i];
+                        } else {
+                            const int st = (v - 1) >> 1, side = (v - 1) & 1;
+                            slot = 2 * (left ? st : d - 1 - st) + side;
+                        }
+                        if (a.cst) a.cst[(size_t)slot * a.NS + id] = acc[i];
+                        if (a.costs) a.costs[id * CS + slot] = acc[i];
+                    }
+                }
+            }
+            __syncthreads();
+        }
+    }
+
+    // ---- 3. neighbours along the fiber (valuefunc.c:514-519) + active-node list ----------
+    for (int e = tid; e < nf * N; e += FT_NT) {
+        const int g = e / N, j = e - g * N;
+        const size_t id = (size_t)sFid[g] * a.ldo + j;
+        const double lo = sV[g * nmax + sNv[g * 2 * nmax + 2 * j]], hi = sV[g * nmax + sNv[g * 2 * nmax + 2 * j + 1]];
+        if (a.cst) { a.cst[(size_t)(2 * k) * a.NS + id] = lo; a.cst[(size_t)(2 * k + 1) * a.NS + id] = hi; }
+        if (a.costs) { a.costs[id * CS + 2 * k] = lo; a.costs[id * CS + 2 * k + 1] = hi; }
+    }
+    if (a.act) {
+        // one warp per fiber: count, reserve a run of the list, write ids in node order
+        const int warp = tid >> 5, lane = tid & 31;
+        for (int g = warp; g < nf; g += FT_NT / 32) {
+            int cnt = 0;
+            for (int j = lane; j < N; j += 32) cnt += sAbs[g * nmax + j] == 0;
+            for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+            int base = 0;
+            if (lane == 0 && cnt > 0) base = atomicAdd(a.act_count, cnt);
+            base = __shfl_sync(0xffffffffu, base, 0);
+            for (int j0 = 0; j0 < N; j0 += 32) {
+                const int j = j0 + lane;
+                const bool on = j < N && sAbs[g * nmax + j] == 0;
+                const unsigned m = __ballot_sync(0xffffffffu, on);
+                if (on) a.act[base + __popc(m & ((1u << lane) - 1))] = sFid[g] * a.ldo + j;
+                base += __popc(m);
+            }
+        }
+    }
+}
+
+#endif  // C3SC_FT_TYPES_ONLY
+
+inline int ft_pick_fb(const DevFT &ft, int nmax, int F, int sms, size_t smem_budget)
+{
+    // enough groups to fill the machine twice over, and a carve-up that lets two CTAs share an SM
+    int fb = FT_FBMAX;
+    while (fb > 1 && (F / fb) < 2 * sms) fb >>= 1;
+    while (fb > 1 && FtPlan(ft, nmax, fb).bytes() > smem_budget) fb >>= 1;
+    return fb;
+}
+
+}  // namespace c3sc

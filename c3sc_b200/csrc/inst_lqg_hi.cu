@@ -1,12 +1,12 @@
 // explicit instantiations: LQG chain-of-integrators, dx = 8,10,12
-#include "backup_kernel.cuh"
+#include "control_kernel.cuh"
 namespace c3sc {
-int launch_backup_lqg_hi(int dx, int arith, const LaunchArgs &a, cudaStream_t st)
+int launch_control_lqg_hi(int dx, int arith, const CtlArgs &a, int pi_eval, cudaStream_t st)
 {
     switch (dx) {
-    case 8: return launch_backup_m<LqgNd<8>>(arith, a, st);
-    case 10: return launch_backup_m<LqgNd<10>>(arith, a, st);
-    case 12: return launch_backup_m<LqgNd<12>>(arith, a, st);
+    case 8: return launch_control_m<LqgNd<8>>(arith, a, pi_eval, st);
+    case 10: return launch_control_m<LqgNd<10>>(arith, a, pi_eval, st);
+    case 12: return launch_control_m<LqgNd<12>>(arith, a, pi_eval, st);
     }
     return -1;
 }

@@ -1,12 +1,12 @@
 // explicit instantiations: LQG chain-of-integrators, dx = 2,4,6
-#include "backup_kernel.cuh"
+#include "control_kernel.cuh"
 namespace c3sc {
-int launch_backup_lqg_lo(int dx, int arith, const LaunchArgs &a, cudaStream_t st)
+int launch_control_lqg_lo(int dx, int arith, const CtlArgs &a, int pi_eval, cudaStream_t st)
 {
     switch (dx) {
-    case 2: return launch_backup_m<LqgNd<2>>(arith, a, st);
-    case 4: return launch_backup_m<LqgNd<4>>(arith, a, st);
-    case 6: return launch_backup_m<LqgNd<6>>(arith, a, st);
+    case 2: return launch_control_m<LqgNd<2>>(arith, a, pi_eval, st);
+    case 4: return launch_control_m<LqgNd<4>>(arith, a, pi_eval, st);
+    case 6: return launch_control_m<LqgNd<6>>(arith, a, pi_eval, st);
     }
     return -1;
 }

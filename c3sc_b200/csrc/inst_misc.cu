@@ -1,18 +1,18 @@
 // explicit instantiations: double integrator (dx 2,3,4), Dubins car, skidding car; transition test kernel
-#include "backup_kernel.cuh"
+#include "control_kernel.cuh"
 namespace c3sc {
-int launch_backup_misc(int model, int dx, int arith, const LaunchArgs &a, cudaStream_t st)
+int launch_control_misc(int model, int dx, int arith, const CtlArgs &a, int pi_eval, cudaStream_t st)
 {
     switch (model) {
     case C3SC_MODEL_DOUBLE_INT:
         switch (dx) {
-        case 2: return launch_backup_m<DoubleInt<2>>(arith, a, st);
-        case 3: return launch_backup_m<DoubleInt<3>>(arith, a, st);
-        case 4: return launch_backup_m<DoubleInt<4>>(arith, a, st);
+        case 2: return launch_control_m<DoubleInt<2>>(arith, a, pi_eval, st);
+        case 3: return launch_control_m<DoubleInt<3>>(arith, a, pi_eval, st);
+        case 4: return launch_control_m<DoubleInt<4>>(arith, a, pi_eval, st);
         }
         return -1;
-    case C3SC_MODEL_DUBINS: return dx == 3 ? launch_backup_m<Dubins>(arith, a, st) : -1;
-    case C3SC_MODEL_SKID5D: return dx == 5 ? launch_backup_m<Skid5d>(arith, a, st) : -1;
+    case C3SC_MODEL_DUBINS: return dx == 3 ? launch_control_m<Dubins>(arith, a, pi_eval, st) : -1;
+    case C3SC_MODEL_SKID5D: return dx == 5 ? launch_control_m<Skid5d>(arith, a, pi_eval, st) : -1;
     }
     return -1;
 }

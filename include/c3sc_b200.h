@@ -110,11 +110,6 @@ const char *c3sc_version(void);
 /* kernels launched by this library since load (bench.py's gpu_launches) */
 uint64_t c3sc_launch_count(void);
 
-/* Debug aid: accumulate k_backup's per-phase SM cycles (thread 0 of every CTA, summed):
- * [0] flags, [1] FT chains, [2] FT node tiles, [3] node invariants, [4] control loop,
- * [5] merge + write.  enable != 0 arms it; out8 (may be NULL) receives and clears.   */
-int c3sc_debug_phase_profile(int enable, unsigned long long *out8);
-
 /* Best-of-`repeats` throughput of a pure DFMA loop on the current device, in
  * TFLOP/s (FMA = 2 flop): the measured FP64-pipe roofline denominator.      */
 int c3sc_measure_fp64_peak(double *tflops, int iters, int repeats);
@@ -134,6 +129,9 @@ int  c3sc_valuef_create(uint32_t d, const uint64_t *n, const uint64_t *ranks,
 int  c3sc_valuef_update(c3sc_valuef *vf, const double *const *cores);
 /* contiguous device buffer holding all cores (for ncclBroadcast)           */
 int  c3sc_valuef_device_buffer(c3sc_valuef *vf, double **dev, size_t *count);
+/* after writing that buffer on the device (e.g. a broadcast): rebuild the
+ * transposed copy the chain kernels read; asynchronous on `stream`.         */
+int  c3sc_valuef_commit(c3sc_valuef *vf, void *stream);
 void c3sc_valuef_destroy(c3sc_valuef *vf);
 
 /* ---- the hot path, device-resident arguments ---------------------------- */
