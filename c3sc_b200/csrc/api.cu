@@ -83,10 +83,19 @@ struct Scratch {
     void release() { cst.release(); flag.release(); act.release(); perm.release(); cnt.release(); }
 };
 
+// candidates of a separable model regrouped by normaliser share (see k_control)
+struct CtlGroups {
+    int ng = 0;
+    int gstart[CT_NGMAX + 1];
+    double gA[CT_NGMAX];
+};
+
 struct c3sc_problem {
     DevProblem P;
     int model, arith;
     Scratch scr;
+    CtlGroups grp;
+    double *d_gtab = nullptr;
     double *d_xgrid = nullptr, *d_obs = nullptr, *d_utab = nullptr, *d_ctab = nullptr;
     int *d_err = nullptr;
     cudaStream_t stream = nullptr;           // host-buffer entry points run here
@@ -202,6 +211,39 @@ int c3sc_problem_create(const c3sc_problem_desc *d, c3sc_problem **out)
             double amin = tab[2 * nud];
             for (uint32_t c = 1; c < d->nu; c++) amin = tab[(size_t)c * ct + 2 * nud] < amin ? tab[(size_t)c * ct + 2 * nud] : amin;
             P.amin = amin;
+            // regroup by normaliser share A_c (exact equality, first-appearance order); rows of a group
+            // keep table order.  Grouped row: [Wl_0, Wr_0, .., h2*gu_c, table index in the low word].
+            std::vector<double> shares;
+            std::vector<int> gid(d->nu);
+            for (uint32_t c = 0; c < d->nu; c++) {
+                const double a = tab[(size_t)c * ct + 2 * nud];
+                size_t g = 0;
+                while (g < shares.size() && shares[g] != a) g++;
+                if (g == shares.size()) shares.push_back(a);
+                gid[c] = (int)g;
+            }
+            if (shares.size() <= (size_t)CT_NGMAX) {
+                std::vector<double> gt((size_t)d->nu * ct);
+                CtlGroups &G = p->grp;
+                size_t pos = 0;
+                for (size_t g = 0; g < shares.size(); g++) {
+                    G.gstart[g] = (int)pos;
+                    G.gA[g] = shares[g];
+                    for (uint32_t c = 0; c < d->nu; c++) {
+                        if (gid[c] != (int)g) continue;
+                        memcpy(&gt[pos * ct], &tab[(size_t)c * ct], 2 * nud * sizeof(double));
+                        gt[pos * ct + 2 * nud] = d->h2 * tab[(size_t)c * ct + 2 * nud + 1];
+                        const long long idx = (long long)c;
+                        memcpy(&gt[pos * ct + 2 * nud + 1], &idx, sizeof(double));
+                        pos++;
+                    }
+                }
+                G.gstart[shares.size()] = (int)pos;
+                G.ng = (int)shares.size();
+                CKP(cudaMalloc(&p->d_gtab, gt.size() * sizeof(double)));
+                CKP(cudaMemcpy(p->d_gtab, gt.data(), gt.size() * sizeof(double), cudaMemcpyHostToDevice));
+                P.gtab = p->d_gtab;
+            }
         }
     }
 #undef CKP
@@ -212,7 +254,7 @@ int c3sc_problem_create(const c3sc_problem_desc *d, c3sc_problem **out)
 void c3sc_problem_destroy(c3sc_problem *p)
 {
     if (!p) return;
-    cudaFree(p->d_xgrid); cudaFree(p->d_obs); cudaFree(p->d_utab); cudaFree(p->d_err); cudaFree(p->d_ctab);
+    cudaFree(p->d_xgrid); cudaFree(p->d_obs); cudaFree(p->d_utab); cudaFree(p->d_err); cudaFree(p->d_ctab); cudaFree(p->d_gtab);
     DevBuf *bufs[] = {&p->b_dv, &p->b_fi, &p->b_val, &p->b_arg, &p->b_abs, &p->b_costs, &p->b_rows, &p->b_nv, &p->b_nf};
     for (DevBuf *b : bufs) b->release();
     for (DevBuf &b : p->b_misc) b.release();
@@ -323,15 +365,16 @@ struct BatchArgs {
     int mode;
 };
 
-static size_t g_chunk_bytes = (size_t)64 << 20;
+static size_t g_chunk_bytes = (size_t)96 << 20;    // slot-major cost scratch per chunk: stays inside the 126 MB L2
 
-static int run_batch(const DevProblem &P, int model, int arith, Scratch &scr, const DevFT &ft, const BatchArgs &b,
-                     cudaStream_t st)
+static int run_batch(const DevProblem &P, int model, int arith, Scratch &scr, const CtlGroups *grp, const DevFT &ft,
+                     const BatchArgs &b, cudaStream_t st)
 {
     const size_t d = (size_t)P.dx, CS = 2 * d + 1, RW = 2 * d + 3;
     size_t FC = g_chunk_bytes / (b.ldo * CS * 8);
     if (FC < 1) FC = 1;
     if (FC > b.F) FC = b.F;
+    FC = (b.F + (b.F + FC - 1) / FC - 1) / ((b.F + FC - 1) / FC);      // equal chunks
     const size_t NSmax = FC * b.ldo;
     const bool need_cst = b.mode != MODE_COSTS;
     if ((need_cst && scr.cst.reserve(NSmax * CS * 8)) || scr.flag.reserve(NSmax) || scr.act.reserve(NSmax * 4) ||
@@ -371,6 +414,11 @@ static int run_batch(const DevProblem &P, int model, int arith, Scratch &scr, co
         c.argmin = b.out.argmin ? b.out.argmin + n0 : nullptr;
         c.rows = b.out.rows ? b.out.rows + n0 * RW : nullptr;
         c.rows_in = b.rows_in ? b.rows_in + n0 * RW : nullptr;
+        if (grp && grp->ng > 0 && P.gtab) {
+            c.ng = grp->ng;
+            memcpy(c.gstart, grp->gstart, sizeof c.gstart);
+            memcpy(c.gA, grp->gA, sizeof c.gA);
+        }
         const int pe = b.mode == MODE_PI_EVAL;
         if (model == C3SC_MODEL_LQGND) rc = (P.dx <= 6) ? launch_control_lqg_lo(P.dx, arith, c, pe, st)
                                                         : launch_control_lqg_hi(P.dx, arith, c, pe, st);
@@ -409,7 +457,7 @@ int c3sc_vi_batch_dev(c3sc_problem *p, const c3sc_valuef *vf, size_t F, const in
     b.out.value = out->value; b.out.argmin = out->argmin; b.out.absorbed = out->absorbed;
     b.out.costs = out->costs; b.out.rows = out->rows; b.out.nbr_vary = out->nbr_vary; b.out.nbr_fixed = out->nbr_fixed;
     b.mode = (out->value || out->argmin || out->rows) ? MODE_VI : MODE_COSTS;
-    return run_batch(p->P, p->model, p->arith, p->scr, vf->ft, b, (cudaStream_t)stream);
+    return run_batch(p->P, p->model, p->arith, p->scr, &p->grp, vf->ft, b, (cudaStream_t)stream);
 }
 
 int c3sc_pi_batch_dev(c3sc_problem *p, const c3sc_valuef *vf_policy, const c3sc_valuef *vf_iter, size_t F,
@@ -429,14 +477,14 @@ int c3sc_pi_batch_dev(c3sc_problem *p, const c3sc_valuef *vf_policy, const c3sc_
         b.mode = MODE_VI;
         b.out.rows = d_rows;
         b.out.argmin = d_argmin;
-        rc = run_batch(p->P, p->model, p->arith, p->scr, vf_policy->ft, b, (cudaStream_t)stream);
+        rc = run_batch(p->P, p->model, p->arith, p->scr, &p->grp, vf_policy->ft, b, (cudaStream_t)stream);
         if (rc) return rc;
     }
     memset(&b.out, 0, sizeof b.out);        // evaluation against vf_iter (bellman.c:1863-1871)
     b.mode = MODE_PI_EVAL;
     b.out.value = d_value;
     b.rows_in = d_rows;
-    return run_batch(p->P, p->model, p->arith, p->scr, vf_iter->ft, b, (cudaStream_t)stream);
+    return run_batch(p->P, p->model, p->arith, p->scr, &p->grp, vf_iter->ft, b, (cudaStream_t)stream);
 }
 
 static int upload_fibers(c3sc_problem *p, size_t F, const int32_t *dim_vary, const int32_t *fixed_ind)
@@ -578,7 +626,7 @@ int c3sc_neighbor_costs_batch(c3sc_problem *p, const c3sc_valuef *vf, size_t F, 
     b.out.absorbed = (int *)p->b_abs.p; b.out.costs = (double *)p->b_costs.p;
     b.out.nbr_vary = nbr_vary ? (int *)p->b_nv.p : nullptr;
     b.out.nbr_fixed = nbr_fixed ? (int *)p->b_nf.p : nullptr;
-    rc = run_batch(p->P, p->model, p->arith, p->scr, vf->ft, b, p->stream);
+    rc = run_batch(p->P, p->model, p->arith, p->scr, &p->grp, vf->ft, b, p->stream);
     if (rc) return rc;
     CK(cudaMemcpyAsync(absorbed, p->b_abs.p, n * 4, cudaMemcpyDeviceToHost, p->stream));
     CK(cudaMemcpyAsync(costs, p->b_costs.p, n * (2 * dx + 1) * 8, cudaMemcpyDeviceToHost, p->stream));
@@ -722,7 +770,7 @@ int c3sc_ft_fiber_nn_batch(const c3sc_valuef *vf, size_t F, const int32_t *dim_v
     ba.mode = MODE_COSTS; ba.out.costs = (double *)b[4].p;
     ba.nbr_fixed_in = (const int *)b[2].p; ba.nbr_vary_in = (const int *)b[3].p;
     static Scratch scr;
-    int rc = run_batch(tmp.P, model, C3SC_ARITH_FAST, scr, vf->ft, ba, nullptr);
+    int rc = run_batch(tmp.P, model, C3SC_ARITH_FAST, scr, nullptr, vf->ft, ba, nullptr);
     if (rc) return rc;
     CK(cudaDeviceSynchronize());
     CK(cudaMemcpy(costs, b[4].p, n * cs * 8, cudaMemcpyDeviceToHost));

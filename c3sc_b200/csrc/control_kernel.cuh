@@ -18,6 +18,7 @@
 namespace c3sc {
 
 constexpr int CT_NT = 256;
+constexpr int CT_NGMAX = 32;       // candidate groups (distinct normaliser shares) handled by the grouped walk
 
 struct CtlArgs {
     DevProblem P;
@@ -31,7 +32,10 @@ struct CtlArgs {
     const int *act;           // [NS] non-absorbed node ids
     const int *act_count;
     int parts_log2;           // candidate chunks per node = 1 << parts_log2 (<= 32)
-    int tab_in_smem;          // candidate table staged in shared memory
+    // separable models, FAST: candidates regrouped by their share of the normaliser (DevProblem::gtab)
+    int ng;                   // number of groups, 0 = plain table walk
+    int gstart[CT_NGMAX + 1]; // first grouped position of every group
+    double gA[CT_NGMAX];      // the group's normaliser share
     double *value;            // outputs, any may be NULL
     int *argmin;
     double *rows;
@@ -215,7 +219,7 @@ __device__ __forceinline__ void node_state(const CtlArgs &c, int id, double *x)
 
 // ---------------------------------------------------------------------------
 template <class M, class A>
-__global__ void __launch_bounds__(CT_NT) k_control(const CtlArgs c)
+__global__ void __launch_bounds__(CT_NT, 3) k_control(const CtlArgs c)
 {
     constexpr int DX = M::DX, DU = M::DU, CS = 2 * DX + 1, RW = 2 * DX + 3;
     constexpr bool TAB = M::SEP && !A::exact;
@@ -225,15 +229,14 @@ __global__ void __launch_bounds__(CT_NT) k_control(const CtlArgs c)
     extern __shared__ __align__(16) double smem[];
 
     // candidate table (separable models, FAST) or the raw control table, staged once per CTA
-    const double *tab = TAB ? P.ctab : P.utab;
+    const bool grouped = TAB && c.ng > 0;
     {
+        const double *src = TAB ? (grouped ? P.gtab : P.ctab) : P.utab;
         const int cnt = P.nu * (TAB ? CTW : DU);
-        if (c.tab_in_smem) {
-            for (int e = tid; e < cnt; e += CT_NT) smem[e] = tab[e];
-            __syncthreads();
-            tab = smem;
-        }
+        for (int e = tid; e < cnt; e += CT_NT) smem[e] = src[e];
+        __syncthreads();
     }
+    const double *tab = smem;
 
     const int pl2 = c.parts_log2, parts = 1 << pl2;
     const int chunk = (P.nu + parts - 1) >> pl2;
@@ -285,10 +288,41 @@ __global__ void __launch_bounds__(CT_NT) k_control(const CtlArgs c)
             const bool disc = P.beta != 0.0;
             // exp(-beta*dt) with dt <= h2/(norm0+amin): short series when every lane's bound is tiny
             const bool tiny = __all_sync(0xffffffffu, !valid || (P.beta * P.h2 <= 0.00390625 * (norm0 + P.amin)));
-            if (tiny) {
+            if (grouped) {
+                // Candidates with the same normaliser share A_g share dt and the discount: per group
+                // one reciprocal + one exp, per candidate only S_c and  t_c = ebt*S_c + h2*gu_c.
+                // value_c = rinv_g * (t_c + h2*gx).  Rows of a group keep table order (strict '<'),
+                // groups are merged on (value, table index).
+                const double hgx = P.h2 * gx;
+                for (int g = 0; g < c.ng; g++) {
+                    const int lo = c.gstart[g] > c0 ? c.gstart[g] : c0;
+                    const int hi = c.gstart[g + 1] < c1 ? c.gstart[g + 1] : c1;
+                    if (lo >= hi) continue;
+                    const double rinv = rcp_pos(norm0 + c.gA[g]);
+                    const double ebt = !disc ? 1.0 : (tiny ? exp_tiny(nbh * rinv) : exp_nonpos(nbh * rinv));
+                    double bt = CUDART_INF;
+                    int bi = 0x7fffffff;
+#pragma unroll 2
+                    for (int pos = lo; pos < hi; pos++) {
+                        const double2 *row = reinterpret_cast<const double2 *>(tab + pos * CTW);
+                        double Sa = S0, Sb = 0.0;
+#pragma unroll
+                        for (int m = 0; m < NUD; m++) {
+                            const double2 w = row[m];
+                            Sa = fma(w.x, cu[2 * m], Sa);
+                            Sb = fma(w.y, cu[2 * m + 1], Sb);
+                        }
+                        const double2 hi2 = row[NUD];           // (h2*gu_c, table index in the low word)
+                        const double t = fma(ebt, Sa + Sb, hi2.x);
+                        if (t < bt) { bt = t; bi = __double2loint(hi2.y); }
+                    }
+                    const double v = rinv * (bt + hgx);
+                    if (v < best || (v == best && bi < ibest)) { best = v; ibest = bi; }
+                }
+            } else if (tiny) {
 #pragma unroll 2
                 for (int cand = c0; cand < c1; cand++) {
-                    const double2 *row = reinterpret_cast<const double2 *>(tab + (size_t)cand * CTW);
+                    const double2 *row = reinterpret_cast<const double2 *>(tab + cand * CTW);
                     double S = S0;
 #pragma unroll
                     for (int m = 0; m < NUD; m++) {
@@ -304,7 +338,7 @@ __global__ void __launch_bounds__(CT_NT) k_control(const CtlArgs c)
                 }
             } else {
                 for (int cand = c0; cand < c1; cand++) {
-                    const double2 *row = reinterpret_cast<const double2 *>(tab + (size_t)cand * CTW);
+                    const double2 *row = reinterpret_cast<const double2 *>(tab + cand * CTW);
                     double S = S0;
 #pragma unroll
                     for (int m = 0; m < NUD; m++) {
@@ -336,13 +370,14 @@ __global__ void __launch_bounds__(CT_NT) k_control(const CtlArgs c)
         for (int o = 1; o < parts; o <<= 1) {
             const double vb = __shfl_down_sync(0xffffffffu, best, o);
             const int ib = __shfl_down_sync(0xffffffffu, ibest, o);
-            if (vb < best) { best = vb; ibest = ib; }
+            if (vb < best || (vb == best && ib < ibest)) { best = vb; ibest = ib; }
         }
         if (!valid || part != 0) continue;
         if (c.value) c.value[id] = best;
         if (c.argmin) c.argmin[id] = ibest;
         if (c.rows) {                               // policy row at u* (bellman.c:1851-1860)
             double u[DU], b[DX], s[DX], prob[CS], dt;
+            node_state<DX>(c, id, x);               // recomputed: keeps x out of the candidate loop's live set
 #pragma unroll
             for (int i = 0; i < DU; i++) u[i] = P.utab[(size_t)(ibest < P.nu ? ibest : 0) * DU + i];
             M::template drift<A>(x, u, P.mp, b);
@@ -460,14 +495,13 @@ int launch_control_t(const CtlArgs &c_in, int pi_eval, cudaStream_t st)
         return (int)cudaGetLastError();
     }
     constexpr bool TAB = M::SEP && !A::exact;
-    const size_t tabBytes = (size_t)c.P.nu * (TAB ? 2 * M::NUD + 2 : M::DU) * sizeof(double);
-    c.tab_in_smem = tabBytes <= 96 * 1024;
-    const size_t smem = c.tab_in_smem ? tabBytes : 0;
-    static size_t attr_set = 0;
-    if (smem > 48 * 1024 && smem > attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(k_control<M, A>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+    const size_t smem = (size_t)c.P.nu * (TAB ? 2 * M::NUD + 2 : M::DU) * sizeof(double);
+    if (smem > (size_t)info.max_optin) return (int)cudaErrorInvalidValue;      // control table must fit on chip
+    static size_t attr_set = 48 * 1024;
+    if (smem > attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(k_control<M, A>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return (int)e;
-        attr_set = 96 * 1024;
+        attr_set = smem;
     }
     // candidate chunks per node: enough (node, chunk) items to occupy every SM; 1 for large batches
     int pl2 = 0;

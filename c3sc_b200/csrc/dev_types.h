@@ -21,6 +21,7 @@ struct DevProblem {
     const double *obs;       // device, [nobs][2][dx]: lb then ub
     const double *utab;      // device, [nu*du]
     const double *ctab;      // device, candidate table of a separable model (FAST), see k_build_ctab
+    const double *gtab;      // device, the same rows regrouped by normaliser share: [W.., h2*gu, table index]; NULL = not grouped
     double amin;             // min over candidates of the table's normaliser share
     int *err;                // device error word (norm < 1e-14 seen)
 };

@@ -394,15 +394,16 @@ __global__ void __launch_bounds__(FT_NT, 2) k_ft_costs(const FtArgs a)
                 }
             }
             __syncthreads();
-            // w[g] = G_k[j] R_g (row a), u[g] = L_g G_k[j] (column b), all fibers of the group at once
+            // w[g] = G_k[j] R_g (row a), u[g] = L_g G_k[j] (column b), all fibers of the group at once.
+            // Items are ordered all-w then all-u so a warp runs one of the two loops, not both.
             {
-                const int per = rk + rk1;
-                for (int e = tid; e < nt * per; e += FT_NT) {
-                    const int jl = e / per, q = e - jl * per;
+                const int nW = nt * rk, nU = nt * rk1;
+                for (int e = tid; e < nW + nU; e += FT_NT) {
                     double acc[FT_FBMAX];
 #pragma unroll
                     for (int g = 0; g < FT_FBMAX; g++) acc[g] = 0.0;
-                    if (q < rk) {
+                    if (e < nW) {
+                        const int jl = e / rk, q = e - jl * rk;
                         const double *gp = sG + jl * rk1 * ldk + q;
 #pragma unroll 2
                         for (int b = 0; b < rk1; b++) {
@@ -419,7 +420,8 @@ __global__ void __launch_bounds__(FT_NT, 2) k_ft_costs(const FtArgs a)
                         for (int g = 0; g < FT_FBMAX; g++)
                             if (g < nf) sW[(g * rk + q) * TP + jl] = acc[g];
                     } else {
-                        const int b = q - rk;
+                        const int e2 = e - nW;
+                        const int jl = e2 / rk1, b = e2 - jl * rk1;
                         const double *gp = sG + (jl * rk1 + b) * ldk;
 #pragma unroll 2
                         for (int aa = 0; aa < rk; aa++) {
