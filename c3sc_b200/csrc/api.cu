@@ -16,8 +16,11 @@ int launch_control_lqg_hi(int dx, int arith, const CtlArgs &a, int pi_eval, cuda
 int launch_control_misc(int model, int dx, int arith, const CtlArgs &a, int pi_eval, cudaStream_t st);
 int launch_group_fibers(int F, int d, const int *dim_vary, int *perm, int *kcount, int *kstart, int *act_count,
                         cudaStream_t st);
-int launch_transpose_cores(const DevFT &ft, double *baseT, cudaStream_t st);
+int launch_pack_cores(const DevFT &ft, double *baseT, double *baseP, cudaStream_t st);
+long long ft_padded_layout(DevFT &ft);
 int launch_ft_costs(const FtArgs &a, cudaStream_t st);
+int ft_uses_mma(const DevFT &ft);
+size_t ft_sets_bytes(const DevFT &ft, size_t F);
 int launch_node_backup_lqg_lo(int dx, int arith, const DevProblem &P, int n, const double *x, const double *costs,
                               const int *absorbed, double *value, int *argmin, cudaStream_t st);
 int launch_node_backup_lqg_hi(int dx, int arith, const DevProblem &P, int n, const double *x, const double *costs,
@@ -79,8 +82,8 @@ struct DevBuf {
 // per-problem scratch of the two-stage pipeline (one batch in flight per problem, like the
 // reference's Workspace, src/util.c:689-964)
 struct Scratch {
-    DevBuf cst, flag, act, perm, cnt;
-    void release() { cst.release(); flag.release(); act.release(); perm.release(); cnt.release(); }
+    DevBuf cst, flag, act, perm, cnt, sets;
+    void release() { cst.release(); flag.release(); act.release(); perm.release(); cnt.release(); sets.release(); }
 };
 
 // candidates of a separable model regrouped by normaliser share (see k_control)
@@ -104,7 +107,7 @@ struct c3sc_problem {
 
 struct c3sc_valuef {
     DevFT ft;
-    double *d_base = nullptr, *d_baseT = nullptr;
+    double *d_base = nullptr, *d_baseT = nullptr, *d_baseP = nullptr;
     size_t count = 0;
     std::vector<size_t> len;
 };
@@ -305,6 +308,12 @@ int c3sc_valuef_create(uint32_t d, const uint64_t *n, const uint64_t *ranks, con
     if (e != cudaSuccess) { cudaFree(vf->d_base); delete vf; return fail(C3SC_ECUDA, "cudaMalloc cores: %s", cudaGetErrorString(e)); }
     ft.base = vf->d_base;
     ft.baseT = vf->d_baseT;
+    if (ft_uses_mma(ft)) {
+        const long long np = ft_padded_layout(ft);
+        e = cudaMalloc(&vf->d_baseP, (size_t)np * sizeof(double));
+        if (e != cudaSuccess) { cudaFree(vf->d_base); cudaFree(vf->d_baseT); delete vf; return fail(C3SC_ECUDA, "cudaMalloc padded cores: %s", cudaGetErrorString(e)); }
+        ft.baseP = vf->d_baseP;
+    }
     *out = vf;
     if (cores) {
         int rc = c3sc_valuef_update(vf, cores);
@@ -327,8 +336,8 @@ int c3sc_valuef_update(c3sc_valuef *vf, const double *const *cores)
 int c3sc_valuef_commit(c3sc_valuef *vf, void *stream)
 {
     if (!vf) return fail(C3SC_EINVAL, "null argument");
-    int rc = launch_transpose_cores(vf->ft, vf->d_baseT, (cudaStream_t)stream);
-    if (rc) return fail(C3SC_ECUDA, "transpose kernel: %s", cudaGetErrorString((cudaError_t)rc));
+    int rc = launch_pack_cores(vf->ft, vf->d_baseT, vf->d_baseP, (cudaStream_t)stream);
+    if (rc) return fail(C3SC_ECUDA, "core packing kernel: %s", cudaGetErrorString((cudaError_t)rc));
     g_launches++;
     return C3SC_OK;
 }
@@ -346,6 +355,7 @@ void c3sc_valuef_destroy(c3sc_valuef *vf)
     if (!vf) return;
     cudaFree(vf->d_base);
     cudaFree(vf->d_baseT);
+    cudaFree(vf->d_baseP);
     delete vf;
 }
 
@@ -380,6 +390,8 @@ static int run_batch(const DevProblem &P, int model, int arith, Scratch &scr, co
     if ((need_cst && scr.cst.reserve(NSmax * CS * 8)) || scr.flag.reserve(NSmax) || scr.act.reserve(NSmax * 4) ||
         scr.perm.reserve(FC * 4) || scr.cnt.reserve(64 * 4))
         return fail(C3SC_ECUDA, "cudaMalloc pipeline scratch failed");
+    const int mma = ft_uses_mma(ft);
+    if (mma && scr.sets.reserve(ft_sets_bytes(ft, FC))) return fail(C3SC_ECUDA, "cudaMalloc chain scratch failed");
     int *cnt = (int *)scr.cnt.p;                  // [0,16) kcount, [16,32) kstart, [32] act_count
     for (size_t c0 = 0; c0 < b.F; c0 += FC) {
         const size_t Fc = (b.F - c0 < FC) ? b.F - c0 : FC;
@@ -402,9 +414,10 @@ static int run_batch(const DevProblem &P, int model, int arith, Scratch &scr, co
         a.nbr_fixed = (b.out.nbr_fixed && d > 1) ? b.out.nbr_fixed + c0 * 2 * (d - 1) : nullptr;
         a.nbr_fixed_in = (b.nbr_fixed_in && d > 1) ? b.nbr_fixed_in + c0 * 2 * (d - 1) : nullptr;
         a.nbr_vary_in = b.nbr_vary_in ? b.nbr_vary_in + 2 * n0 : nullptr;
+        a.sets = mma ? (double *)scr.sets.p : nullptr;
         rc = launch_ft_costs(a, st);
         if (rc) return fail(C3SC_ECUDA, "FT kernel launch: %s", cudaGetErrorString((cudaError_t)rc));
-        g_launches += 2;
+        g_launches += 2 + mma;
         if (b.mode == MODE_COSTS) continue;
         CtlArgs c;
         memset(&c, 0, sizeof c);

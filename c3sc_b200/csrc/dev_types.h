@@ -33,7 +33,12 @@ struct DevFT {
     int r[MAXD + 1];
     long long off[MAXD];     // offset of core k inside `base` (doubles)
     const double *base;
-    const double *baseT;     // same offsets, every block transposed (b + a*r_{k+1}); see k_transpose_cores
+    const double *baseT;     // same offsets, every block transposed (b + a*r_{k+1}); see k_pack_cores
+    // zero-padded tile copy for the tensor-core node kernel (ranks <= 32, else NULL): block j of core k
+    // at baseP + offP[k] + j*cpp[k]*ldp[k], element (a,b) at b*ldp[k] + a, rows a >= r_k / cols b >= r_{k+1} zero
+    const double *baseP;
+    long long offP[MAXD];
+    int ldp[MAXD], cpp[MAXD];
 };
 
 struct DevOut {

@@ -1,5 +1,6 @@
 // ft.cu -- host launchers of the model-independent stage-1 kernels (ft_kernel.cuh)
-#include "ft_kernel.cuh"
+#include <cstdlib>
+#include "ft_mma_kernel.cuh"
 
 namespace c3sc {
 
@@ -25,18 +26,92 @@ int launch_group_fibers(int F, int d, const int *dim_vary, int *perm, int *kcoun
     return (int)cudaGetLastError();
 }
 
-int launch_transpose_cores(const DevFT &ft, double *baseT, cudaStream_t st)
+int launch_pack_cores(const DevFT &ft, double *baseT, double *baseP, cudaStream_t st)
 {
     long long most = 0;
     for (int k = 0; k < ft.d; k++) {
-        const long long len = (long long)ft.n[k] * ft.r[k] * ft.r[k + 1];
+        long long len = (long long)ft.n[k] * ft.r[k] * ft.r[k + 1];
+        if (baseP) { const long long pl = (long long)ft.n[k] * ft.ldp[k] * ft.cpp[k]; len = pl > len ? pl : len; }
         most = len > most ? len : most;
     }
     if (most <= 0) return 0;
     long long gx = (most + 255) / 256;
     if (gx > 1024) gx = 1024;
-    k_transpose_cores<<<dim3((unsigned)gx, (unsigned)ft.d), 256, 0, st>>>(ft, baseT);
+    k_pack_cores<<<dim3((unsigned)gx, (unsigned)ft.d), 256, 0, st>>>(ft, baseT, baseP);
     return (int)cudaGetLastError();
+}
+
+// padded-tile geometry of core k for the tensor-core node kernel: leading dimension = 4 (mod 8) and
+// >= 8*ceil(r_k/8) (fragment rows, conflict-free in both orientations, 16-byte columns), columns
+// padded to 8*ceil(r_{k+1}/8).  Fills ft.ldp / cpp / offP, returns the doubles needed.
+long long ft_padded_layout(DevFT &ft)
+{
+    long long total = 0;
+    for (int k = 0; k < ft.d; k++) {
+        const int r8 = 8 * ((ft.r[k] + 7) / 8), c8 = 8 * ((ft.r[k + 1] + 7) / 8);
+        ft.ldp[k] = r8 + 4;
+        ft.cpp[k] = c8;
+        ft.offP[k] = total;
+        total += (long long)ft.n[k] * ft.ldp[k] * ft.cpp[k];
+    }
+    return total;
+}
+
+// ranks <= 32: chains by warp tasks + DMMA node kernel; larger ranks (or C3SC_FT_GENERAL=1): k_ft_costs
+int ft_uses_mma(const DevFT &ft)
+{
+    static const bool general = getenv("C3SC_FT_GENERAL") != nullptr;
+    if (general) return 0;
+    for (int i = 0; i <= ft.d; i++)
+        if (ft.r[i] > 32) return 0;
+    return 1;
+}
+size_t ft_sets_bytes(const DevFT &ft, size_t F) { return (size_t)ft_set_width(ft) * F * sizeof(double); }
+
+template <int RMAX>
+static int launch_nodes_t(const FtArgs &a, cudaStream_t st)
+{
+    const size_t smem = FtNodePlan<RMAX>(a.ft, a.P.nmax).bytes();
+    if (smem > (size_t)g_max_optin) return (int)cudaErrorInvalidValue;
+    static size_t attr = 0;
+    if (smem > attr) {
+        cudaError_t e = cudaFuncSetAttribute(k_ft_nodes<RMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return (int)e;
+        attr = smem;
+    }
+    const int grid = (a.F + a.FB - 1) / a.FB + a.ft.d;
+    k_ft_nodes<RMAX><<<grid, FTN_NT, smem, st>>>(a, a.sets);
+    return (int)cudaGetLastError();
+}
+
+static int launch_ft_mma(FtArgs a, cudaStream_t st)
+{
+    // group size: 8 fibers fill the DMMA tile; fewer when the batch is too small to cover the SMs
+    int fb = FT_FBMAX;
+    while (fb > 1 && (a.F / fb) < 2 * g_sms) fb >>= 1;
+    a.FB = fb;
+    const size_t csm = FtChainPlan(a.ft).bytes();
+    if (csm > (size_t)g_max_optin) return (int)cudaErrorInvalidValue;
+    static size_t cattr = 0;
+    if (csm > cattr) {
+        cudaError_t e = cudaFuncSetAttribute(k_ft_chains, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)csm);
+        if (e != cudaSuccess) return (int)e;
+        cattr = csm;
+    }
+    int per_sm = 1;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_ft_chains, FTC_NT, csm);
+    if (per_sm < 1) per_sm = 1;
+    int cgrid = (2 * a.F + FTC_NT / 32 - 1) / (FTC_NT / 32);
+    if (cgrid > g_sms * per_sm) cgrid = g_sms * per_sm;
+    k_ft_chains<<<cgrid, FTC_NT, csm, st>>>(a, a.sets);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return (int)e;
+    int rmax = 1;
+    for (int i = 0; i <= a.ft.d; i++) rmax = a.ft.r[i] > rmax ? a.ft.r[i] : rmax;
+    if (rmax <= 8) return launch_nodes_t<8>(a, st);
+    if (rmax <= 16) return launch_nodes_t<16>(a, st);
+    if (rmax <= 24) return launch_nodes_t<24>(a, st);
+    return launch_nodes_t<32>(a, st);
 }
 
 // Stage 1 over one chunk.  a.FB == 0: pick the group size here.  1 launch.
@@ -45,6 +120,7 @@ int launch_ft_costs(const FtArgs &a_in, cudaStream_t st)
     ft_device_info();
     FtArgs a = a_in;
     if (a.F <= 0) return 0;
+    if (a.sets && ft_uses_mma(a.ft)) return launch_ft_mma(a, st);
     // two CTAs per SM when the carve-up allows it
     const size_t budget = (size_t)g_max_sm / 2 - 1024;
     if (a.FB <= 0) a.FB = ft_pick_fb(a.ft, a.P.nmax, a.F, g_sms, budget);

@@ -57,6 +57,7 @@ struct FtArgs {
     int *nbr_fixed;           // optional [F*2*(d-1)]
     const int *nbr_fixed_in;  // caller-supplied neighbour indices (valuef_eval_fiber_ind_nn)
     const int *nbr_vary_in;
+    double *sets;             // [F * ft_set_width] chain scratch of the tensor-core path; NULL = general kernel
 };
 
 __host__ __device__ inline int ft_even_up(int v) { return (v + 1) & ~1; }
@@ -146,79 +147,88 @@ __global__ void __launch_bounds__(1024) k_group_fibers(int F, int d, const int *
     }
 }
 
-// Transposed copy of every core block: baseT[off_k + j*blk + b + a*r_{k+1}] = base[off_k + j*blk + a + b*r_k].
-__global__ void k_transpose_cores(DevFT ft, double *baseT)
+// Derived copies of the cores, rebuilt whenever the cores change (c3sc_valuef_commit):
+//   baseT  every block transposed: baseT[off_k + j*blk + b + a*r_{k+1}] = base[off_k + j*blk + a + b*r_k]
+//   baseP  (optional) zero-padded blocks, leading dimension ldp[k], cpp[k] columns
+__global__ void k_pack_cores(DevFT ft, double *baseT, double *baseP)
 {
     const int k = blockIdx.y;
     const int rk = ft.r[k], rk1 = ft.r[k + 1], blk = rk * rk1;
     const long long total = (long long)ft.n[k] * blk;
-    for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    const long long step = (long long)gridDim.x * blockDim.x, t0 = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    for (long long e = t0; e < total; e += step) {
         const long long j = e / blk;
         const int rem = (int)(e - j * blk);
         const int a = rem / rk1, b = rem - a * rk1;            // e enumerates the transposed layout
         baseT[ft.off[k] + e] = ft.base[ft.off[k] + j * blk + a + (long long)b * rk];
     }
+    if (baseP) {
+        const int ld = ft.ldp[k], cp = ft.cpp[k], pb = ld * cp;
+        const long long ptotal = (long long)ft.n[k] * pb;
+        for (long long e = t0; e < ptotal; e += step) {
+            const long long j = e / pb;
+            const int rem = (int)(e - j * pb);
+            const int b = rem / ld, a = rem - b * ld;
+            baseP[ft.offP[k] + e] = (a < rk && b < rk1) ? ft.base[ft.off[k] + j * blk + a + (long long)b * rk] : 0.0;
+        }
+    }
 }
 
 // ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(FT_NT, 2) k_ft_costs(const FtArgs a)
+// pieces shared by the general kernel (k_ft_costs) and the tensor-core pair (ft_mma_kernel.cuh)
+
+// which same-k group does this CTA own: groups are enumerated k-major, FB fibers each
+__device__ __forceinline__ void ft_find_group(const FtArgs &a, int &k, int &gstart, int &nf)
+{
+    k = -1; gstart = 0; nf = 0;
+    int b = blockIdx.x;
+    for (int kk = 0; kk < a.ft.d; kk++) {
+        const int c = a.kcount[kk];
+        const int ng = (c + a.FB - 1) / a.FB;
+        if (b < ng) { k = kk; gstart = a.kstart[kk] + b * a.FB; nf = c - b * a.FB; nf = nf > a.FB ? a.FB : nf; return; }
+        b -= ng;
+    }
+}
+
+// neighbour pair of a FIXED dimension i at index i0 (nodeutil.c:527-565); returns true when the
+// index sits on an ABSORB face ("wall": every node of the fiber is absorbed)
+__device__ __forceinline__ bool ft_fixed_pair(const DevProblem &P, int i, int i0, int &lo, int &hi)
+{
+    const int last = P.ngrid[i] - 1, bc = P.bc[i];
+    bool wall = false;
+    if (i0 == 0) {
+        if (bc == C3SC_ABSORB)        { lo = i0; hi = i0; wall = true; }
+        else if (bc == C3SC_REFLECT)  { lo = i0; hi = i0 + 1; }
+        else                          { lo = P.ngrid[i] - 2; hi = i0 + 1; }
+    } else if (i0 == last) {
+        if (bc == C3SC_ABSORB)        { lo = i0; hi = i0; wall = true; }
+        else if (bc == C3SC_REFLECT)  { lo = i0 - 1; hi = i0; }
+        else                          { lo = i0 - 1; hi = 1; }
+    } else { lo = i0 - 1; hi = i0 + 1; }
+    return wall;
+}
+
+// descriptors, flags, neighbour indices of the nf fibers of a group (nodeutil.c:489-627).
+// Whole CTA; ends with a barrier.
+__device__ __forceinline__ void ft_flags_and_indices(const FtArgs &a, int k, int nf, int gstart, int *sFid, int *sWall,
+                                                     int *sFix, int *sNf, int *sAbs, int *sNv, int nmax)
 {
     const DevProblem &P = a.P;
-    const DevFT &ft = a.ft;
-    const int d = ft.d, CS = 2 * d + 1;
-    const int tid = threadIdx.x;
-    const int FB = a.FB;
-
-    // ---- which group is this CTA ------------------------------------------------
-    int k = -1, gstart = 0, nf = 0;
-    {
-        int b = blockIdx.x;
-        for (int kk = 0; kk < d; kk++) {
-            const int c = a.kcount[kk];
-            const int ng = (c + FB - 1) / FB;
-            if (b < ng) { k = kk; gstart = a.kstart[kk] + b * FB; nf = c - b * FB; nf = nf > FB ? FB : nf; break; }
-            b -= ng;
-        }
-    }
-    if (k < 0) return;
-
-    extern __shared__ __align__(16) double smem[];
-    const FtPlan sp(ft, P.nmax, FB);
-    const int rs = sp.rs, TP = sp.tp, nmax = sp.nmax;
-    double *bufA = smem + sp.oSetA, *bufB = smem + sp.oUni;
-    double *sLt = smem + sp.oLt, *sRt = smem + sp.oRt, *sV = smem + sp.oV;
-    int *ismem = reinterpret_cast<int *>(smem + sp.nDoubles);
-    int *sFix = ismem + sp.oFix, *sNf = ismem + sp.oNf, *sAbs = ismem + sp.oAbs, *sNv = ismem + sp.oNv;
-    int *sFid = ismem + sp.oFid, *sWall = ismem + sp.oWall;
-
+    const int d = a.ft.d, tid = threadIdx.x, NT = blockDim.x;
     const int N = P.ngrid[k];
-    const int NVL = ft_even_up(1 + 2 * k), NVR = ft_even_up(1 + 2 * (d - 1 - k));
-    const int setStride = rs * sp.nvt;                 // one fiber's two sets inside a buffer
-    const int offR = rs * NVL;                         // right set follows the left set
-
-    // ---- 0. descriptors, flags, neighbour indices (nodeutil.c:489-627) ------------
     if (tid < FT_FBMAX) { sFid[tid] = tid < nf ? a.perm[gstart + tid] : -1; sWall[tid] = 0; }
     __syncthreads();
-    for (int e = tid; e < nf * d; e += FT_NT) {
+    for (int e = tid; e < nf * d; e += NT) {
         const int g = e / d, i = e - g * d;
         sFix[g * d + i] = a.fixed_ind[(size_t)sFid[g] * d + i];
     }
     __syncthreads();
-    for (int e = tid; e < nf * d; e += FT_NT) {        // fixed-dimension neighbour pairs
+    for (int e = tid; e < nf * d; e += NT) {          // fixed-dimension neighbour pairs
         const int g = e / d, i = e - g * d;
         if (i == k) continue;
         const int slot = i < k ? i : i - 1;
-        const int i0 = sFix[g * d + i], last = P.ngrid[i] - 1, bc = P.bc[i];
         int lo, hi;
-        if (i0 == 0) {
-            if (bc == C3SC_ABSORB)        { lo = i0; hi = i0; sWall[g] = 1; }
-            else if (bc == C3SC_REFLECT)  { lo = i0; hi = i0 + 1; }
-            else                          { lo = P.ngrid[i] - 2; hi = i0 + 1; }
-        } else if (i0 == last) {
-            if (bc == C3SC_ABSORB)        { lo = i0; hi = i0; sWall[g] = 1; }
-            else if (bc == C3SC_REFLECT)  { lo = i0 - 1; hi = i0; }
-            else                          { lo = i0 - 1; hi = 1; }
-        } else { lo = i0 - 1; hi = i0 + 1; }
+        if (ft_fixed_pair(P, i, sFix[g * d + i], lo, hi)) sWall[g] = 1;
         if (a.nbr_fixed_in) {
             lo = a.nbr_fixed_in[(size_t)sFid[g] * 2 * (d - 1) + 2 * slot];
             hi = a.nbr_fixed_in[(size_t)sFid[g] * 2 * (d - 1) + 2 * slot + 1];
@@ -231,7 +241,7 @@ __global__ void __launch_bounds__(FT_NT, 2) k_ft_costs(const FtArgs a)
         }
     }
     __syncthreads();
-    for (int e = tid; e < nf * N; e += FT_NT) {
+    for (int e = tid; e < nf * N; e += NT) {
         const int g = e / N, j = e - g * N;
         int ab = 0;
         for (int o = 0; o < P.nobs && ab == 0; o++) {                   // boundary.c:329-344,668-680
@@ -265,10 +275,76 @@ __global__ void __launch_bounds__(FT_NT, 2) k_ft_costs(const FtArgs a)
         if (a.nbr_vary) { a.nbr_vary[2 * id] = lo; a.nbr_vary[2 * id + 1] = hi; }
     }
     if (a.flag)
-        for (int e = tid; e < nf * (a.ldo - N); e += FT_NT) {           // padding entries of ragged grids
+        for (int e = tid; e < nf * (a.ldo - N); e += NT) {              // padding entries of ragged grids
             const int g = e / (a.ldo - N), j = N + (e - g * (a.ldo - N));
             a.flag[(size_t)sFid[g] * a.ldo + j] = 2;
         }
+    __syncthreads();
+}
+
+// neighbours along the fiber (valuefunc.c:514-519) from the self values sV, and the compacted list
+// of non-absorbed nodes.  Whole CTA; sV / sAbs / sNv must be visible (barrier before the call).
+__device__ __forceinline__ void ft_along_fiber_and_active(const FtArgs &a, int k, int nf, const int *sFid, const int *sAbs,
+                                                          const int *sNv, const double *sV, int nmax)
+{
+    const int d = a.ft.d, CS = 2 * d + 1, tid = threadIdx.x, NT = blockDim.x;
+    const int N = a.P.ngrid[k];
+    for (int e = tid; e < nf * N; e += NT) {
+        const int g = e / N, j = e - g * N;
+        const size_t id = (size_t)sFid[g] * a.ldo + j;
+        const double lo = sV[g * nmax + sNv[g * 2 * nmax + 2 * j]], hi = sV[g * nmax + sNv[g * 2 * nmax + 2 * j + 1]];
+        if (a.cst) { a.cst[(size_t)(2 * k) * a.NS + id] = lo; a.cst[(size_t)(2 * k + 1) * a.NS + id] = hi; }
+        if (a.costs) { a.costs[id * CS + 2 * k] = lo; a.costs[id * CS + 2 * k + 1] = hi; }
+    }
+    if (a.act) {
+        // one warp per fiber: count, reserve a run of the list, write ids in node order
+        const int warp = tid >> 5, lane = tid & 31;
+        for (int g = warp; g < nf; g += NT / 32) {
+            int cnt = 0;
+            for (int j = lane; j < N; j += 32) cnt += sAbs[g * nmax + j] == 0;
+            for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+            int base = 0;
+            if (lane == 0 && cnt > 0) base = atomicAdd(a.act_count, cnt);
+            base = __shfl_sync(0xffffffffu, base, 0);
+            for (int j0 = 0; j0 < N; j0 += 32) {
+                const int j = j0 + lane;
+                const bool on = j < N && sAbs[g * nmax + j] == 0;
+                const unsigned m = __ballot_sync(0xffffffffu, on);
+                if (on) a.act[base + __popc(m & ((1u << lane) - 1))] = sFid[g] * a.ldo + j;
+                base += __popc(m);
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(FT_NT, 2) k_ft_costs(const FtArgs a)
+{
+    const DevProblem &P = a.P;
+    const DevFT &ft = a.ft;
+    const int d = ft.d, CS = 2 * d + 1;
+    const int tid = threadIdx.x;
+    const int FB = a.FB;
+
+    int k, gstart, nf;
+    ft_find_group(a, k, gstart, nf);
+    if (k < 0) return;
+
+    extern __shared__ __align__(16) double smem[];
+    const FtPlan sp(ft, P.nmax, FB);
+    const int rs = sp.rs, TP = sp.tp, nmax = sp.nmax;
+    double *bufA = smem + sp.oSetA, *bufB = smem + sp.oUni;
+    double *sLt = smem + sp.oLt, *sRt = smem + sp.oRt, *sV = smem + sp.oV;
+    int *ismem = reinterpret_cast<int *>(smem + sp.nDoubles);
+    int *sFix = ismem + sp.oFix, *sNf = ismem + sp.oNf, *sAbs = ismem + sp.oAbs, *sNv = ismem + sp.oNv;
+    int *sFid = ismem + sp.oFid, *sWall = ismem + sp.oWall;
+
+    const int N = P.ngrid[k];
+    const int NVL = ft_even_up(1 + 2 * k), NVR = ft_even_up(1 + 2 * (d - 1 - k));
+    const int setStride = rs * sp.nvt;                 // one fiber's two sets inside a buffer
+    const int offR = rs * NVL;                         // right set follows the left set
+
+    ft_flags_and_indices(a, k, nf, gstart, sFid, sWall, sFix, sNf, sAbs, sNv, nmax);
 
     // ---- 1. chains -----------------------------------------------------------------
     // set layout: element (q, v) of a set at q*NV + v  (q = rank index, v = vector, v fastest).
@@ -491,33 +567,7 @@ __global__ void __launch_bounds__(FT_NT, 2) k_ft_costs(const FtArgs a)
         }
     }
 
-    // ---- 3. neighbours along the fiber (valuefunc.c:514-519) + active-node list ----------
-    for (int e = tid; e < nf * N; e += FT_NT) {
-        const int g = e / N, j = e - g * N;
-        const size_t id = (size_t)sFid[g] * a.ldo + j;
-        const double lo = sV[g * nmax + sNv[g * 2 * nmax + 2 * j]], hi = sV[g * nmax + sNv[g * 2 * nmax + 2 * j + 1]];
-        if (a.cst) { a.cst[(size_t)(2 * k) * a.NS + id] = lo; a.cst[(size_t)(2 * k + 1) * a.NS + id] = hi; }
-        if (a.costs) { a.costs[id * CS + 2 * k] = lo; a.costs[id * CS + 2 * k + 1] = hi; }
-    }
-    if (a.act) {
-        // one warp per fiber: count, reserve a run of the list, write ids in node order
-        const int warp = tid >> 5, lane = tid & 31;
-        for (int g = warp; g < nf; g += FT_NT / 32) {
-            int cnt = 0;
-            for (int j = lane; j < N; j += 32) cnt += sAbs[g * nmax + j] == 0;
-            for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
-            int base = 0;
-            if (lane == 0 && cnt > 0) base = atomicAdd(a.act_count, cnt);
-            base = __shfl_sync(0xffffffffu, base, 0);
-            for (int j0 = 0; j0 < N; j0 += 32) {
-                const int j = j0 + lane;
-                const bool on = j < N && sAbs[g * nmax + j] == 0;
-                const unsigned m = __ballot_sync(0xffffffffu, on);
-                if (on) a.act[base + __popc(m & ((1u << lane) - 1))] = sFid[g] * a.ldo + j;
-                base += __popc(m);
-            }
-        }
-    }
+    ft_along_fiber_and_active(a, k, nf, sFid, sAbs, sNv, sV, nmax);
 }
 
 #endif  // C3SC_FT_TYPES_ONLY

@@ -1,0 +1,418 @@
+// ft_mma_kernel.cuh -- stage 1 for ranks <= 32, as two kernels:
+//
+//   k_ft_chains   one WARP per (fiber, side): the prefix / suffix vector sets of
+//                 valuef_eval_fiber_ind_nn (src/valuefunc.c:414-446 and the neighbour variants
+//                 of :522-582), stepped block by block with coalesced loads straight from L2
+//                 (right side: G, left side: the transposed copy).  No CTA barrier anywhere;
+//                 results go to a per-fiber global scratch  sets[f][SETW].
+//   k_ft_nodes    one CTA per group of <= 8 fibers that share dim_vary k.  Fibers of a group share
+//                 all but the fixed coordinates, so the per-node work is a dense contraction and
+//                 runs on the FP64 tensor cores (DMMA, mma.sync m8n8k4):
+//                     W[a][g] = sum_b G_k[j][a,b] R_g[b]      (r_k x r_{k+1}) x (r_{k+1} x 8 fibers)
+//                     U[g][b] = sum_a L_g[a] G_k[j][a,b]      (8 fibers x r_k) x (r_k x r_{k+1})
+//                     left  variants:  C[v][j] = sum_a A_g[v][a] W_g[a][j]     per fiber, 8 nodes a tile
+//                     right variants:  C[j][v] = sum_b U_g[j][b] C_g[b][v]
+//                 G_k tiles are staged in shared memory with an odd column stride (both fragment
+//                 orientations conflict-light) and prefetched one tile ahead through registers.
+//
+// Same outputs as k_ft_costs (ft_kernel.cuh), which stays the general path for larger ranks.
+#pragma once
+#include "ft_kernel.cuh"
+
+namespace c3sc {
+
+constexpr int FTC_NT = 256;      // chain kernel: 8 warps = 8 tasks in flight per CTA
+constexpr int FTN_NT = 256;      // node kernel: 8 warps
+constexpr int FTN_T = 8;         // nodes per tile (one per warp in the w/u phase)
+constexpr int FTN_TP = 12;       // row stride of a (rank index) row of w / u: 8 nodes padded to 12 (fragment reads conflict-free)
+
+// width of one fiber's record in the chain scratch: both sets, [q][v] with v fastest
+__host__ __device__ inline int ft_set_width(const DevFT &ft)
+{
+    int rs = 1;
+    for (int i = 0; i <= ft.d; i++) rs = ft.r[i] > rs ? ft.r[i] : rs;
+    return rs * (2 * ft.d + 2);
+}
+
+struct FtChainPlan {            // shared memory of k_ft_chains, per warp: two set buffers + indices
+    int rs, nvm, bufDoubles, perWarpDoubles, perWarpInts;
+    __host__ __device__ FtChainPlan(const DevFT &ft)
+    {
+        rs = 1;
+        for (int i = 0; i <= ft.d; i++) rs = ft.r[i] > rs ? ft.r[i] : rs;
+        nvm = 2 * ft.d;                              // vectors of one side, even
+        bufDoubles = rs * nvm;
+        perWarpDoubles = 2 * bufDoubles;
+        perWarpInts = 4 * ft.d;                      // fixed indices + neighbour pairs
+    }
+    __host__ __device__ size_t bytes() const { return (size_t)(FTC_NT / 32) * (perWarpDoubles * 8 + perWarpInts * 4); }
+};
+
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(FTC_NT) k_ft_chains(const FtArgs a, double *sets)
+{
+    const DevProblem &P = a.P;
+    const DevFT &ft = a.ft;
+    const int d = ft.d;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    constexpr int NW = FTC_NT / 32;
+    extern __shared__ __align__(16) double smem[];
+    const FtChainPlan cp(ft);
+    double *buf0 = smem + warp * cp.perWarpDoubles, *buf1 = buf0 + cp.bufDoubles;
+    int *iw = reinterpret_cast<int *>(smem + NW * cp.perWarpDoubles) + warp * cp.perWarpInts;
+    int *sFix = iw, *sNf = iw + d;                   // sNf[2*i], sNf[2*i+1]: pair of dimension i
+    const int SETW = cp.rs * (2 * d + 2);
+
+    for (int task = blockIdx.x * NW + warp; task < 2 * a.F; task += gridDim.x * NW) {
+        const int f = task >> 1;
+        const bool left = (task & 1) == 0;
+        int k = a.dim_vary[f];
+        k = k < 0 ? 0 : (k >= d ? d - 1 : k);
+        const int NVL = ft_even_up(1 + 2 * k), NVR = ft_even_up(1 + 2 * (d - 1 - k));
+        const int NV = left ? NVL : NVR;
+        const int nsteps = left ? k : d - 1 - k;
+        __syncwarp();
+        if (lane < d) {
+            const int i = lane, i0 = a.fixed_ind[(size_t)f * d + i];
+            sFix[i] = i0;
+            if (i != k) {
+                int lo, hi;
+                ft_fixed_pair(P, i, i0, lo, hi);
+                if (a.nbr_fixed_in) {
+                    const int slot = i < k ? i : i - 1;
+                    lo = a.nbr_fixed_in[(size_t)f * 2 * (d - 1) + 2 * slot];
+                    hi = a.nbr_fixed_in[(size_t)f * 2 * (d - 1) + 2 * slot + 1];
+                }
+                sNf[2 * i] = lo;
+                sNf[2 * i + 1] = hi;
+            }
+        }
+        if (lane == 0) buf0[0] = 1.0;
+        __syncwarp();
+        double *in = buf0, *out = buf1;
+        for (int s = 0; s < nsteps; s++) {
+            const int m = left ? s : d - 1 - s;
+            const int rq = left ? ft.r[m] : ft.r[m + 1], ro = left ? ft.r[m + 1] : ft.r[m];
+            const int blk = ft.r[m] * ft.r[m + 1];
+            const double *base = (left ? ft.baseT : ft.base) + ft.off[m];
+            const double *bc = base + (size_t)sFix[m] * blk;
+            const double *bl = base + (size_t)sNf[2 * m] * blk, *bh = base + (size_t)sNf[2 * m + 1] * blk;
+            const int nin = 1 + 2 * s, nvg = (nin + FT_VG - 1) / FT_VG;
+            for (int o = lane; o < ro; o += 32) {
+                for (int vg = 0; vg < nvg; vg++) {
+                    const int v0 = vg * FT_VG;
+                    double acc[FT_VG];
+#pragma unroll
+                    for (int i = 0; i < FT_VG; i++) acc[i] = 0.0;
+                    if (vg == 0) {
+                        double alo = 0.0, ahi = 0.0;
+#pragma unroll 4
+                        for (int q = 0; q < rq; q++) {
+                            const double c = __ldg(bc + o + (size_t)q * ro), l = __ldg(bl + o + (size_t)q * ro),
+                                         h = __ldg(bh + o + (size_t)q * ro);
+                            const double2 *row = reinterpret_cast<const double2 *>(in + q * NV);
+#pragma unroll
+                            for (int i = 0; i < FT_VG / 2; i++) {
+                                if (2 * i >= NV) break;                 // rows are NV wide (NV even)
+                                const double2 x = row[i];
+                                acc[2 * i] = fma(x.x, c, acc[2 * i]);
+                                acc[2 * i + 1] = fma(x.y, c, acc[2 * i + 1]);
+                                if (i == 0) { alo = fma(x.x, l, alo); ahi = fma(x.x, h, ahi); }
+                            }
+                        }
+                        out[o * NV + nin] = alo;
+                        out[o * NV + nin + 1] = ahi;
+                    } else {
+#pragma unroll 4
+                        for (int q = 0; q < rq; q++) {
+                            const double c = __ldg(bc + o + (size_t)q * ro);
+                            const double2 *row = reinterpret_cast<const double2 *>(in + q * NV + v0);
+#pragma unroll
+                            for (int i = 0; i < FT_VG / 2; i++) {
+                                if (v0 + 2 * i >= NV) break;
+                                const double2 x = row[i];
+                                acc[2 * i] = fma(x.x, c, acc[2 * i]);
+                                acc[2 * i + 1] = fma(x.y, c, acc[2 * i + 1]);
+                            }
+                        }
+                    }
+#pragma unroll
+                    for (int i = 0; i < FT_VG; i++)
+                        if (v0 + i < nin) out[o * NV + v0 + i] = acc[i];
+                }
+            }
+            __syncwarp();
+            double *t = in; in = out; out = t;
+        }
+        // final set -> global record of the fiber ([q][v], v fastest; right set after the left one)
+        {
+            const int rl = left ? ft.r[k] : ft.r[k + 1];
+            double *dst = sets + (size_t)f * SETW + (left ? 0 : cp.rs * NVL);
+            for (int e = lane; e < rl * NV; e += 32) dst[e] = in[e];
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ void dmma_m8n8k4(double &d0, double &d1, double a, double b)
+{
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
+}
+
+// ---- TMA bulk copy (cp.async.bulk, SASS UBLKCP) + mbarrier helpers -------------------------
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long *b, unsigned count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(b)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *b, unsigned bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(b)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, unsigned bytes, unsigned long long *b)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(b)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *b, unsigned parity)
+{
+    asm volatile("{\n"
+                 ".reg .pred P1;\n"
+                 "LAB_WAIT:\n"
+                 "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+                 "@P1 bra DONE;\n"
+                 "bra LAB_WAIT;\n"
+                 "DONE:\n"
+                 "}" ::"r"(smem_u32(b)), "r"(parity) : "memory");
+}
+
+// Shared memory of k_ft_nodes.  Everything the MMA fragments read is zero-padded to the fragment
+// shape, so no fragment load is predicated.
+template <int RMAX>
+struct FtNodePlan {
+    int rs4, setw, nmax, sw;
+    int oG, oW, oU, oSets, oV, oBar, nDoubles;
+    int oFix, oNf, oAbs, oNv, oFid, oWall, nInts;
+    __host__ __device__ FtNodePlan(const DevFT &ft, int nmax_)
+    {
+        nmax = nmax_;
+        int rs = 1;
+        for (int i = 0; i <= ft.d; i++) rs = ft.r[i] > rs ? ft.r[i] : rs;
+        rs4 = (rs + 3) & ~3;                         // rank rows padded to the MMA k-step
+        setw = rs4 * (2 * ft.d + 2) + 8;             // + slack: fragment rows may overrun a set by < 8
+        sw = RMAX * FTN_TP + 2;                      // one fiber's w (or u) tile: [rank index][8 nodes]
+        int gt = 0;
+        for (int k = 0; k < ft.d; k++) {
+            const int g = FTN_T * ft.ldp[k] * ft.cpp[k];
+            gt = g > gt ? g : gt;
+        }
+        int o = 0;
+        oG = o;    o += gt;                          // multiple of 8 doubles: 16-byte aligned
+        oW = o;    o += FT_FBMAX * sw;
+        oU = o;    o += FT_FBMAX * sw;
+        oSets = o; o += FT_FBMAX * setw;
+        oV = o;    o += FT_FBMAX * nmax;
+        o = ft_even_up(o);
+        oBar = o;  o += 2;
+        nDoubles = o;
+        int q = 0;
+        oFix = q;  q += FT_FBMAX * ft.d;
+        oNf = q;   q += FT_FBMAX * 2 * ft.d;
+        oAbs = q;  q += FT_FBMAX * nmax;
+        oNv = q;   q += FT_FBMAX * 2 * nmax;
+        oFid = q;  q += FT_FBMAX;
+        oWall = q; q += FT_FBMAX;
+        nInts = q;
+    }
+    __host__ __device__ size_t bytes() const { return (size_t)nDoubles * 8 + (size_t)nInts * 4; }
+};
+
+template <int RMAX>
+__global__ void __launch_bounds__(FTN_NT, 2) k_ft_nodes(const FtArgs a, const double *sets)
+{
+    constexpr int KS = RMAX / 4, MT = RMAX / 8, VT = (2 * MAXD + 7) / 8;
+    const DevProblem &P = a.P;
+    const DevFT &ft = a.ft;
+    const int d = ft.d, CS = 2 * d + 1;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int gid = lane >> 2, tig = lane & 3;
+
+    int k, gstart, nf;
+    ft_find_group(a, k, gstart, nf);
+    if (k < 0) return;
+
+    extern __shared__ __align__(16) double smem[];
+    const FtNodePlan<RMAX> sp(ft, P.nmax);
+    const int nmax = sp.nmax, SW = sp.sw, SETW = sp.setw;
+    double *sG = smem + sp.oG, *sW = smem + sp.oW, *sU = smem + sp.oU, *sSets = smem + sp.oSets, *sV = smem + sp.oV;
+    unsigned long long *mbar = reinterpret_cast<unsigned long long *>(smem + sp.oBar);
+    int *ismem = reinterpret_cast<int *>(smem + sp.nDoubles);
+    int *sFix = ismem + sp.oFix, *sNf = ismem + sp.oNf, *sAbs = ismem + sp.oAbs, *sNv = ismem + sp.oNv;
+    int *sFid = ismem + sp.oFid, *sWall = ismem + sp.oWall;
+
+    const int N = P.ngrid[k];
+    const int rk = ft.r[k], rk1 = ft.r[k + 1];
+    const int ldk = ft.ldp[k], pblk = ft.ldp[k] * ft.cpp[k];          // padded block
+    const int NVL = ft_even_up(1 + 2 * k), NVR = ft_even_up(1 + 2 * (d - 1 - k));
+    const int nvL = 1 + 2 * k, nvR = 1 + 2 * (d - 1 - k);
+    int rsG = 1;
+    for (int i = 0; i <= d; i++) rsG = ft.r[i] > rsG ? ft.r[i] : rsG;
+    const int SETWG = rsG * (2 * d + 2), offRG = rsG * NVL;           // layout of the chain kernel's records
+    const int offR = sp.rs4 * NVL;                                    // layout of the zero-padded shared copy
+    const int nksA = (rk + 3) >> 2, nksB = (rk1 + 3) >> 2;            // k-steps over a / over b
+    const int mtA = (rk + 7) >> 3, ntB = (rk1 + 7) >> 3;              // 8-wide tiles over a / over b
+    const int mtL = (nvL + 7) >> 3, ntR = nvR > 1 ? (nvR + 7) >> 3 : 0;   // 8-wide tiles over the variant vectors
+
+    // ---- tile 0 on its way while the flags are computed ---------------------------------------
+    const double *Gp = ft.baseP + ft.offP[k];
+    if (tid == 0) {
+        mbar_init(mbar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        const int nt0 = N < FTN_T ? N : FTN_T;
+        mbar_expect_tx(mbar, (unsigned)(nt0 * pblk * 8));
+        bulk_g2s(sG, Gp, (unsigned)(nt0 * pblk * 8), mbar);
+    }
+
+    ft_flags_and_indices(a, k, nf, gstart, sFid, sWall, sFix, sNf, sAbs, sNv, nmax);
+
+    // the group's chain records -> shared memory, rank rows zero-padded to a multiple of 4
+    for (int e = tid; e < FT_FBMAX * SETW; e += FTN_NT) {
+        const int g = e / SETW, q = e - g * SETW;
+        double v = 0.0;
+        if (g < nf) {
+            if (q < offR) { if (q < rk * NVL) v = sets[(size_t)sFid[g] * SETWG + q]; }
+            else { const int q2 = q - offR; if (q2 < rk1 * NVR) v = sets[(size_t)sFid[g] * SETWG + offRG + q2]; }
+        }
+        sSets[e] = v;
+    }
+    for (int e = tid; e < 2 * FT_FBMAX * SW; e += FTN_NT) sW[e] = 0.0;       // sW and sU are adjacent
+    __syncthreads();
+
+    // operands of the w/u products that do not change with the node:
+    // B fragment of R (row b = 4ks+tig, col fiber gid), A fragment of L (row fiber gid, col a = 4ks+tig)
+    double Rf[KS], Lf[KS];
+#pragma unroll
+    for (int ks = 0; ks < KS; ks++) {
+        Rf[ks] = (ks < nksB) ? sSets[gid * SETW + offR + (4 * ks + tig) * NVR] : 0.0;
+        Lf[ks] = (ks < nksA) ? sSets[gid * SETW + (4 * ks + tig) * NVL] : 0.0;
+    }
+    // output slots of this lane's accumulator rows / columns
+    int slotL[VT], slotR[VT][2];
+#pragma unroll
+    for (int t = 0; t < VT; t++) {
+        const int v = 8 * t + gid;
+        slotL[t] = v >= nvL ? -1 : (v == 0 ? 2 * d : 2 * ((v - 1) >> 1) + ((v - 1) & 1));
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            const int vv = 8 * t + 2 * tig + h;
+            slotR[t][h] = (vv < 1 || vv >= nvR) ? -1 : 2 * (d - 1 - ((vv - 1) >> 1)) + ((vv - 1) & 1);
+        }
+    }
+    const int offW = tig * ldk + gid, offU = gid * ldk + tig;           // fragment origins inside a node block
+    const double *setL = sSets + warp * SETW, *setR = setL + offR;      // dots phase: fiber g = warp
+    const double *wg = sW + warp * SW + tig * FTN_TP + gid, *ug = sU + warp * SW + tig * FTN_TP + gid;
+    const size_t idf = warp < nf ? (size_t)sFid[warp] * a.ldo : 0;
+
+    unsigned phase = 0;
+    for (int j0 = 0; j0 < N; j0 += FTN_T) {
+        const int nt = (N - j0 < FTN_T) ? N - j0 : FTN_T;
+        mbar_wait(mbar, phase);
+        phase ^= 1;
+        // ---- w / u of node jl = warp, all fibers of the group --------------------------------
+        if (warp < nt) {
+            const double *gj = sG + warp * pblk;
+#pragma unroll
+            for (int mt = 0; mt < MT; mt++) {
+                if (mt < mtA) {
+                    double d0 = 0.0, d1 = 0.0;
+#pragma unroll
+                    for (int ks = 0; ks < KS; ks++)
+                        if (ks < nksB) dmma_m8n8k4(d0, d1, gj[offW + ks * 4 * ldk + mt * 8], Rf[ks]);
+                    // D: row a = 8mt+gid, cols fiber 2*tig, 2*tig+1
+                    sW[(2 * tig) * SW + (8 * mt + gid) * FTN_TP + warp] = d0;
+                    sW[(2 * tig + 1) * SW + (8 * mt + gid) * FTN_TP + warp] = d1;
+                }
+            }
+#pragma unroll
+            for (int nb = 0; nb < MT; nb++) {
+                if (nb < ntB) {
+                    double d0 = 0.0, d1 = 0.0;
+#pragma unroll
+                    for (int ks = 0; ks < KS; ks++)
+                        if (ks < nksA) dmma_m8n8k4(d0, d1, Lf[ks], gj[offU + nb * 8 * ldk + ks * 4]);
+                    // D: row fiber gid, cols b = 8nb+2tig, +1
+                    sU[gid * SW + (8 * nb + 2 * tig) * FTN_TP + warp] = d0;
+                    sU[gid * SW + (8 * nb + 2 * tig + 1) * FTN_TP + warp] = d1;
+                }
+            }
+        }
+        __syncthreads();
+        if (tid == 0 && j0 + FTN_T < N) {                                // G tile is free: fetch the next one
+            const int j1 = j0 + FTN_T, nt1 = (N - j1 < FTN_T) ? N - j1 : FTN_T;
+            mbar_expect_tx(mbar, (unsigned)(nt1 * pblk * 8));
+            bulk_g2s(sG, Gp + (size_t)j1 * pblk, (unsigned)(nt1 * pblk * 8), mbar);
+        }
+        // ---- variant dots of fiber g = warp over the tile's nodes -----------------------------
+        if (warp < nf) {
+            const size_t idb = idf + j0;
+            double bfr[KS];
+            // left: C[v][jl] = sum_a A[v][a] W[a][jl];  B fragment (row a, col jl) shared by the v tiles
+#pragma unroll
+            for (int ks = 0; ks < KS; ks++) bfr[ks] = (ks < nksA) ? wg[ks * 4 * FTN_TP] : 0.0;
+#pragma unroll
+            for (int mt = 0; mt < VT; mt++) {
+                if (mt < mtL) {
+                    double d0 = 0.0, d1 = 0.0;
+#pragma unroll
+                    for (int ks = 0; ks < KS; ks++)
+                        if (ks < nksA) dmma_m8n8k4(d0, d1, setL[(4 * ks + tig) * NVL + 8 * mt + gid], bfr[ks]);
+                    const int slot = slotL[mt];
+                    if (slot >= 0) {                                     // D: row v, cols jl = 2tig, 2tig+1
+                        const int jl = 2 * tig;
+                        if (mt == 0 && gid == 0) {
+                            if (jl < nt) sV[warp * nmax + j0 + jl] = d0;
+                            if (jl + 1 < nt) sV[warp * nmax + j0 + jl + 1] = d1;
+                        }
+                        if (a.cst) {
+                            double *o = a.cst + (size_t)slot * a.NS + idb + jl;
+                            if (jl < nt) o[0] = d0;
+                            if (jl + 1 < nt) o[1] = d1;
+                        }
+                        if (a.costs) {
+                            if (jl < nt) a.costs[(idb + jl) * CS + slot] = d0;
+                            if (jl + 1 < nt) a.costs[(idb + jl + 1) * CS + slot] = d1;
+                        }
+                    }
+                }
+            }
+            // right: C[jl][v] = sum_b U[jl][b] Cv[b][v];  A fragment (row jl, col b) shared by the v tiles
+#pragma unroll
+            for (int ks = 0; ks < KS; ks++) bfr[ks] = (ks < nksB) ? ug[ks * 4 * FTN_TP] : 0.0;
+#pragma unroll
+            for (int nb = 0; nb < VT; nb++) {
+                if (nb < ntR) {
+                    double d0 = 0.0, d1 = 0.0;
+#pragma unroll
+                    for (int ks = 0; ks < KS; ks++)
+                        if (ks < nksB) dmma_m8n8k4(d0, d1, bfr[ks], setR[(4 * ks + tig) * NVR + 8 * nb + gid]);
+                    if (gid < nt) {                                      // D: row jl = gid, cols v = 8nb+2tig, +1
+#pragma unroll
+                        for (int h = 0; h < 2; h++) {
+                            const int slot = slotR[nb][h];
+                            if (slot < 0) continue;
+                            const double val = h ? d1 : d0;
+                            if (a.cst) a.cst[(size_t)slot * a.NS + idb + gid] = val;
+                            if (a.costs) a.costs[(idb + gid) * CS + slot] = val;
+                        }
+                    }
+                }
+            }
+        }
+        __syncthreads();
+    }
+
+    ft_along_fiber_and_active(a, k, nf, sFid, sAbs, sNv, sV, nmax);
+}
+
+}  // namespace c3sc
