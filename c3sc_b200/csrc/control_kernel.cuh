@@ -408,6 +408,148 @@ __global__ void __launch_bounds__(CT_NT, 3) k_control(const CtlArgs c)
     }
 }
 
+// Large batches of a separable model (FAST, grouped candidates): TWO nodes per thread, so every
+// candidate row read from shared memory feeds two independent FMA chains (half the LDS traffic per
+// candidate-node, twice the instruction-level parallelism).  Same arithmetic as k_control's grouped
+// walk; nodes it and it+ceil(nact/2) of the active list share a thread.
+template <class M>
+struct Node2 {
+    double S0, norm0, hgx, cu[2 * M::NUD];
+    double best;
+    int ibest;
+};
+template <class M>
+__device__ __forceinline__ void node2_prepare(const CtlArgs &c, int id, Node2<M> &n)
+{
+    constexpr int DX = M::DX, DU = M::DU, NUD = M::NUD;
+    const DevProblem &P = c.P;
+    double x[DX], u0[DU], b0[DX], s0[DX];
+    node_state<DX>(c, id, x);
+#pragma unroll
+    for (int i = 0; i < DU; i++) u0[i] = P.utab[i];
+    M::template drift<Fast>(x, u0, P.mp, b0);
+    M::template sigma<Fast>(x, u0, P.mp, s0);
+    double norm0 = 0.0, S0 = 0.0;
+#pragma unroll
+    for (int i = 0; i < DX; i++) {
+        const double cl = c.cst[(size_t)(2 * i) * c.NS + id], cr = c.cst[(size_t)(2 * i + 1) * c.NS + id];
+        const double q = (P.t[2 * i + 1] * 0.5) * (s0[i] * s0[i]);
+        double rl = q, rr = q;
+        if (!M::u_dep(i)) {
+            const double tb = P.t[2 * i] * b0[i];
+            rl = q - ((b0[i] < -1e-14) ? tb : 0.0);
+            rr = q + ((b0[i] > 1e-14) ? tb : 0.0);
+        }
+        norm0 += rl + rr;
+        S0 = fma(rl, cl, S0);
+        S0 = fma(rr, cr, S0);
+#pragma unroll
+        for (int m = 0; m < NUD; m++)
+            if (M::ud(m) == i) { n.cu[2 * m] = cl; n.cu[2 * m + 1] = cr; }
+    }
+    n.S0 = S0; n.norm0 = norm0; n.hgx = P.h2 * M::stage_x(x, P.mp);
+    n.best = CUDART_INF; n.ibest = 0x7fffffff;
+}
+
+template <class M>
+__global__ void __launch_bounds__(CT_NT, 2) k_control2(const CtlArgs c)
+{
+    constexpr int DX = M::DX, DU = M::DU, CS = 2 * DX + 1, RW = 2 * DX + 3;
+    constexpr int NUD = M::NUD, CTW = 2 * NUD + 2;
+    const DevProblem &P = c.P;
+    const int tid = threadIdx.x, lane = tid & 31;
+    extern __shared__ __align__(16) double smem[];
+    {
+        const int cnt = P.nu * CTW;
+        for (int e = tid; e < cnt; e += CT_NT) smem[e] = P.gtab[e];
+        __syncthreads();
+    }
+    const double *tab = smem;
+    const int nact = *c.act_count, nhalf = (nact + 1) >> 1;
+    const long long stride = (long long)gridDim.x * CT_NT;
+    const double nbh = -P.beta * P.h2;
+    const bool disc = P.beta != 0.0;
+    for (long long it0 = (long long)blockIdx.x * CT_NT + (tid & ~31); it0 < nhalf; it0 += stride) {
+        const int it = (int)it0 + lane;
+        const bool validA = it < nhalf, validB = it + nhalf < nact;
+        const int idA = c.act[validA ? it : 0], idB = c.act[validB ? it + nhalf : (validA ? it : 0)];
+        Node2<M> A, B;
+        node2_prepare<M>(c, idA, A);
+        node2_prepare<M>(c, idB, B);
+        if ((validA && A.norm0 + P.amin < 1e-14) || (validB && B.norm0 + P.amin < 1e-14)) atomicOr(P.err, 1);
+        const double nmin = A.norm0 < B.norm0 ? A.norm0 : B.norm0;
+        const bool tiny = __all_sync(0xffffffffu, !validA || (P.beta * P.h2 <= 0.00390625 * (nmin + P.amin)));
+        for (int g = 0; g < c.ng; g++) {
+            const int lo = c.gstart[g], hi = validA ? c.gstart[g + 1] : lo;
+            const double rinvA = rcp_pos(A.norm0 + c.gA[g]), rinvB = rcp_pos(B.norm0 + c.gA[g]);
+            double ebtA = 1.0, ebtB = 1.0;
+            if (disc) {
+                if (tiny) { ebtA = exp_tiny(nbh * rinvA); ebtB = exp_tiny(nbh * rinvB); }
+                else { ebtA = exp_nonpos(nbh * rinvA); ebtB = exp_nonpos(nbh * rinvB); }
+            }
+            double btA = CUDART_INF, btB = CUDART_INF;
+            int biA = 0x7fffffff, biB = 0x7fffffff;
+#pragma unroll 2
+            for (int pos = lo; pos < hi; pos++) {
+                const double2 *row = reinterpret_cast<const double2 *>(tab + pos * CTW);
+                double SA0 = A.S0, SA1 = 0.0, SB0 = B.S0, SB1 = 0.0;
+#pragma unroll
+                for (int m = 0; m < NUD; m++) {
+                    const double2 w = row[m];
+                    SA0 = fma(w.x, A.cu[2 * m], SA0);
+                    SA1 = fma(w.y, A.cu[2 * m + 1], SA1);
+                    SB0 = fma(w.x, B.cu[2 * m], SB0);
+                    SB1 = fma(w.y, B.cu[2 * m + 1], SB1);
+                }
+                const double2 hi2 = row[NUD];                   // (h2*gu_c, table index in the low word)
+                const int ci = __double2loint(hi2.y);
+                const double tA = fma(ebtA, SA0 + SA1, hi2.x), tB = fma(ebtB, SB0 + SB1, hi2.x);
+                if (tA < btA) { btA = tA; biA = ci; }
+                if (tB < btB) { btB = tB; biB = ci; }
+            }
+            const double vA = rinvA * (btA + A.hgx), vB = rinvB * (btB + B.hgx);
+            if (vA < A.best || (vA == A.best && biA < A.ibest)) { A.best = vA; A.ibest = biA; }
+            if (vB < B.best || (vB == B.best && biB < B.ibest)) { B.best = vB; B.ibest = biB; }
+        }
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            if (!(h ? validB : validA)) continue;
+            const int id = h ? idB : idA, ibest = h ? B.ibest : A.ibest;
+            if (c.value) c.value[id] = h ? B.best : A.best;
+            if (c.argmin) c.argmin[id] = ibest;
+            if (c.rows) {                               // policy row at u* (bellman.c:1851-1860)
+                double x[DX], u[DU], b[DX], s[DX], prob[CS], dt;
+                node_state<DX>(c, id, x);
+#pragma unroll
+                for (int i = 0; i < DU; i++) u[i] = P.utab[(size_t)(ibest < P.nu ? ibest : 0) * DU + i];
+                M::template drift<Fast>(x, u, P.mp, b);
+                M::template sigma<Fast>(x, u, P.mp, s);
+                const double g = M::template stage<Fast>(x, u, P.mp);
+                if (transition_row<DX, Fast>(P, b, s, prob, dt)) atomicOr(P.err, 1);
+                double *row = c.rows + (size_t)id * RW;
+#pragma unroll
+                for (int m = 0; m < CS; m++) row[m] = prob[m];
+                row[CS] = dt;
+                row[CS + 1] = g;
+            }
+        }
+    }
+    // absorbed nodes (bellman.c:513-532): boundary / obstacle cost, u = 0
+    for (long long id = (long long)blockIdx.x * CT_NT + tid; id < c.NS; id += stride) {
+        const int ab = c.flag[id];
+        if (ab != 1 && ab != -1) continue;
+        double x[DX];
+        node_state<DX>(c, (int)id, x);
+        const double v = (ab == 1) ? M::boundcost(x, P.mp) : M::obscost(x, P.mp);
+        if (c.value) c.value[id] = v;
+        if (c.argmin) c.argmin[id] = -1;
+        if (c.rows) {
+            double *row = c.rows + (size_t)id * RW;
+            for (int m = 0; m < RW; m++) row[m] = 0.0;
+        }
+    }
+}
+
 // policy evaluation (bellman.c:1774-1828,1863-1871): stored rows against the new neighbour values
 template <class M, class A>
 __global__ void __launch_bounds__(CT_NT) k_pi_eval(const CtlArgs c)
@@ -507,6 +649,24 @@ int launch_control_t(const CtlArgs &c_in, int pi_eval, cudaStream_t st)
     int pl2 = 0;
     while (pl2 < 5 && (c.NS << pl2) < (long long)info.sms * CT_NT * 4 && (2 << pl2) <= c.P.nu) pl2++;
     c.parts_log2 = pl2;
+    if (TAB && c.ng > 0 && pl2 == 0) {          // large batch of a separable model: two nodes per thread
+        static size_t attr2 = 48 * 1024;
+        if (smem > attr2) {
+            cudaError_t e2 = cudaFuncSetAttribute(k_control2<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e2 != cudaSuccess) return (int)e2;
+            attr2 = smem;
+        }
+        int per2 = 1;
+        cudaError_t e2 = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per2, k_control2<M>, CT_NT, smem);
+        if (e2 != cudaSuccess) return (int)e2;
+        if (per2 < 1) per2 = 1;
+        long long need2 = ((c.NS + 1) / 2 + CT_NT - 1) / CT_NT;
+        long long g2 = (long long)info.sms * per2;
+        if (g2 > need2) g2 = need2;
+        if (g2 < 1) return 0;
+        k_control2<M><<<(int)g2, CT_NT, smem, st>>>(c);
+        return (int)cudaGetLastError();
+    }
     int per_sm = 1;
     cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_control<M, A>, CT_NT, smem);
     if (e != cudaSuccess) return (int)e;

@@ -74,7 +74,7 @@ struct FtPlan {
     int d, FB, rs, nvt, tp, nmax;
     int oSetA, oUni, oLt, oRt, oV, nDoubles;      // doubles
     int setDoubles, gTile, oW, oU;                // inside the union region
-    int oFix, oNf, oAbs, oNv, oFid, oWall, nInts; // ints
+    int oFix, oNf, oFid, oWall, nInts;            // ints
     __host__ __device__ FtPlan(const DevFT &ft, int nmax_, int FB_)
     {
         d = ft.d; FB = FB_; nmax = nmax_;
@@ -107,13 +107,11 @@ struct FtPlan {
         int q = 0;
         oFix = q;  q += FB * d;
         oNf = q;   q += FB * 2 * d;
-        oAbs = q;  q += FB * nmax;
-        oNv = q;   q += FB * 2 * nmax;
         oFid = q;  q += FT_FBMAX;
         oWall = q; q += FT_FBMAX;
-        nInts = q;
+        nInts = q;                                 // then FB*2*nmax shorts (sNv) and FB*nmax bytes (sAbs)
     }
-    __host__ __device__ size_t bytes() const { return (size_t)nDoubles * 8 + (size_t)nInts * 4; }
+    __host__ __device__ size_t bytes() const { return (size_t)nDoubles * 8 + (size_t)nInts * 4 + (((size_t)FB * nmax * 5 + 7) & ~(size_t)7); }
 };
 
 #ifndef C3SC_FT_TYPES_ONLY
@@ -211,7 +209,7 @@ __device__ __forceinline__ bool ft_fixed_pair(const DevProblem &P, int i, int i0
 // descriptors, flags, neighbour indices of the nf fibers of a group (nodeutil.c:489-627).
 // Whole CTA; ends with a barrier.
 __device__ __forceinline__ void ft_flags_and_indices(const FtArgs &a, int k, int nf, int gstart, int *sFid, int *sWall,
-                                                     int *sFix, int *sNf, int *sAbs, int *sNv, int nmax)
+                                                     int *sFix, int *sNf, signed char *sAbs, short *sNv, int nmax)
 {
     const DevProblem &P = a.P;
     const int d = a.ft.d, tid = threadIdx.x, NT = blockDim.x;
@@ -267,9 +265,9 @@ __device__ __forceinline__ void ft_flags_and_indices(const FtArgs &a, int k, int
         } else if (ab != 0) { lo = j; hi = j; }
         const size_t id = (size_t)sFid[g] * a.ldo + j;
         if (a.nbr_vary_in) { lo = a.nbr_vary_in[2 * id]; hi = a.nbr_vary_in[2 * id + 1]; }
-        sAbs[g * nmax + j] = ab;
-        sNv[g * 2 * nmax + 2 * j] = lo;
-        sNv[g * 2 * nmax + 2 * j + 1] = hi;
+        sAbs[g * nmax + j] = (signed char)ab;
+        sNv[g * 2 * nmax + 2 * j] = (short)lo;
+        sNv[g * 2 * nmax + 2 * j + 1] = (short)hi;
         if (a.flag) a.flag[id] = (signed char)ab;
         if (a.absorbed) a.absorbed[id] = ab;
         if (a.nbr_vary) { a.nbr_vary[2 * id] = lo; a.nbr_vary[2 * id + 1] = hi; }
@@ -284,8 +282,8 @@ __device__ __forceinline__ void ft_flags_and_indices(const FtArgs &a, int k, int
 
 // neighbours along the fiber (valuefunc.c:514-519) from the self values sV, and the compacted list
 // of non-absorbed nodes.  Whole CTA; sV / sAbs / sNv must be visible (barrier before the call).
-__device__ __forceinline__ void ft_along_fiber_and_active(const FtArgs &a, int k, int nf, const int *sFid, const int *sAbs,
-                                                          const int *sNv, const double *sV, int nmax)
+__device__ __forceinline__ void ft_along_fiber_and_active(const FtArgs &a, int k, int nf, const int *sFid, const signed char *sAbs,
+                                                          const short *sNv, const double *sV, int nmax)
 {
     const int d = a.ft.d, CS = 2 * d + 1, tid = threadIdx.x, NT = blockDim.x;
     const int N = a.P.ngrid[k];
@@ -336,8 +334,10 @@ __global__ void __launch_bounds__(FT_NT, 2) k_ft_costs(const FtArgs a)
     double *bufA = smem + sp.oSetA, *bufB = smem + sp.oUni;
     double *sLt = smem + sp.oLt, *sRt = smem + sp.oRt, *sV = smem + sp.oV;
     int *ismem = reinterpret_cast<int *>(smem + sp.nDoubles);
-    int *sFix = ismem + sp.oFix, *sNf = ismem + sp.oNf, *sAbs = ismem + sp.oAbs, *sNv = ismem + sp.oNv;
+    int *sFix = ismem + sp.oFix, *sNf = ismem + sp.oNf;
     int *sFid = ismem + sp.oFid, *sWall = ismem + sp.oWall;
+    short *sNv = reinterpret_cast<short *>(ismem + sp.nInts);
+    signed char *sAbs = reinterpret_cast<signed char *>(sNv + FB * 2 * nmax);
 
     const int N = P.ngrid[k];
     const int NVL = ft_even_up(1 + 2 * k), NVR = ft_even_up(1 + 2 * (d - 1 - k));

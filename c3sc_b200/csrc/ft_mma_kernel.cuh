@@ -24,7 +24,7 @@ namespace c3sc {
 constexpr int FTC_NT = 256;      // chain kernel: 8 warps = 8 tasks in flight per CTA
 constexpr int FTN_NT = 256;      // node kernel: 8 warps
 constexpr int FTN_T = 8;         // nodes per tile (one per warp in the w/u phase)
-constexpr int FTN_TP = 12;       // row stride of a (rank index) row of w / u: 8 nodes padded to 12 (fragment reads conflict-free)
+constexpr int FTN_TP = 8;        // row stride of a (rank index) row of w / u: 8 nodes padded to 12 (fragment reads conflict-free)
 
 // width of one fiber's record in the chain scratch: both sets, [q][v] with v fastest
 __host__ __device__ inline int ft_set_width(const DevFT &ft)
@@ -156,8 +156,8 @@ __global__ void __launch_bounds__(FTC_NT) k_ft_chains(const FtArgs a, double *se
 // ---------------------------------------------------------------------------
 __device__ __forceinline__ void dmma_m8n8k4(double &d0, double &d1, double a, double b)
 {
-    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
-                 : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
+    asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+        : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
 }
 
 // ---- TMA bulk copy (cp.async.bulk, SASS UBLKCP) + mbarrier helpers -------------------------
@@ -193,7 +193,7 @@ template <int RMAX>
 struct FtNodePlan {
     int rs4, setw, nmax, sw;
     int oG, oW, oU, oSets, oV, oBar, nDoubles;
-    int oFix, oNf, oAbs, oNv, oFid, oWall, nInts;
+    int oFix, oNf, oFid, oWall, nInts;
     __host__ __device__ FtNodePlan(const DevFT &ft, int nmax_)
     {
         nmax = nmax_;
@@ -219,13 +219,11 @@ struct FtNodePlan {
         int q = 0;
         oFix = q;  q += FT_FBMAX * ft.d;
         oNf = q;   q += FT_FBMAX * 2 * ft.d;
-        oAbs = q;  q += FT_FBMAX * nmax;
-        oNv = q;   q += FT_FBMAX * 2 * nmax;
         oFid = q;  q += FT_FBMAX;
         oWall = q; q += FT_FBMAX;
-        nInts = q;
+        nInts = q;                                   // then 8*2*nmax shorts (sNv) and 8*nmax bytes (sAbs)
     }
-    __host__ __device__ size_t bytes() const { return (size_t)nDoubles * 8 + (size_t)nInts * 4; }
+    __host__ __device__ size_t bytes() const { return (size_t)nDoubles * 8 + (size_t)nInts * 4 + (size_t)FT_FBMAX * nmax * 5; }
 };
 
 template <int RMAX>
@@ -248,8 +246,10 @@ __global__ void __launch_bounds__(FTN_NT, 2) k_ft_nodes(const FtArgs a, const do
     double *sG = smem + sp.oG, *sW = smem + sp.oW, *sU = smem + sp.oU, *sSets = smem + sp.oSets, *sV = smem + sp.oV;
     unsigned long long *mbar = reinterpret_cast<unsigned long long *>(smem + sp.oBar);
     int *ismem = reinterpret_cast<int *>(smem + sp.nDoubles);
-    int *sFix = ismem + sp.oFix, *sNf = ismem + sp.oNf, *sAbs = ismem + sp.oAbs, *sNv = ismem + sp.oNv;
+    int *sFix = ismem + sp.oFix, *sNf = ismem + sp.oNf;
     int *sFid = ismem + sp.oFid, *sWall = ismem + sp.oWall;
+    short *sNv = reinterpret_cast<short *>(ismem + sp.nInts);
+    signed char *sAbs = reinterpret_cast<signed char *>(sNv + FT_FBMAX * 2 * nmax);
 
     const int N = P.ngrid[k];
     const int rk = ft.r[k], rk1 = ft.r[k + 1];
@@ -277,14 +277,16 @@ __global__ void __launch_bounds__(FTN_NT, 2) k_ft_nodes(const FtArgs a, const do
     ft_flags_and_indices(a, k, nf, gstart, sFid, sWall, sFix, sNf, sAbs, sNv, nmax);
 
     // the group's chain records -> shared memory, rank rows zero-padded to a multiple of 4
-    for (int e = tid; e < FT_FBMAX * SETW; e += FTN_NT) {
-        const int g = e / SETW, q = e - g * SETW;
-        double v = 0.0;
-        if (g < nf) {
-            if (q < offR) { if (q < rk * NVL) v = sets[(size_t)sFid[g] * SETWG + q]; }
-            else { const int q2 = q - offR; if (q2 < rk1 * NVR) v = sets[(size_t)sFid[g] * SETWG + offRG + q2]; }
+    for (int e = tid; e < FT_FBMAX * SETW; e += FTN_NT) sSets[e] = 0.0;
+    __syncthreads();
+    {
+        const int nl = rk * NVL, nr = rk1 * NVR;                      // valid doubles of the left / right set
+        for (int g = 0; g < nf; g++) {
+            const double *src = sets + (size_t)sFid[g] * SETWG;
+            double *dst = sSets + g * SETW;
+            for (int q = tid; q < nl; q += FTN_NT) dst[q] = src[q];
+            for (int q = tid; q < nr; q += FTN_NT) dst[offR + q] = src[offRG + q];
         }
-        sSets[e] = v;
     }
     for (int e = tid; e < 2 * FT_FBMAX * SW; e += FTN_NT) sW[e] = 0.0;       // sW and sU are adjacent
     __syncthreads();
@@ -320,30 +322,34 @@ __global__ void __launch_bounds__(FTN_NT, 2) k_ft_nodes(const FtArgs a, const do
         mbar_wait(mbar, phase);
         phase ^= 1;
         // ---- w / u of node jl = warp, all fibers of the group --------------------------------
+        // k-step outermost: the MT (resp. ntB) accumulator tiles are independent DMMA chains
         if (warp < nt) {
             const double *gj = sG + warp * pblk;
+            double dw[MT][2], du[MT][2];
 #pragma unroll
-            for (int mt = 0; mt < MT; mt++) {
-                if (mt < mtA) {
-                    double d0 = 0.0, d1 = 0.0;
+            for (int t = 0; t < MT; t++) { dw[t][0] = dw[t][1] = 0.0; du[t][0] = du[t][1] = 0.0; }
 #pragma unroll
-                    for (int ks = 0; ks < KS; ks++)
-                        if (ks < nksB) dmma_m8n8k4(d0, d1, gj[offW + ks * 4 * ldk + mt * 8], Rf[ks]);
-                    // D: row a = 8mt+gid, cols fiber 2*tig, 2*tig+1
-                    sW[(2 * tig) * SW + (8 * mt + gid) * FTN_TP + warp] = d0;
-                    sW[(2 * tig + 1) * SW + (8 * mt + gid) * FTN_TP + warp] = d1;
+            for (int ks = 0; ks < KS; ks++) {
+                if (ks < nksB) {
+#pragma unroll
+                    for (int mt = 0; mt < MT; mt++)
+                        if (mt < mtA) dmma_m8n8k4(dw[mt][0], dw[mt][1], gj[offW + ks * 4 * ldk + mt * 8], Rf[ks]);
+                }
+                if (ks < nksA) {
+#pragma unroll
+                    for (int nb = 0; nb < MT; nb++)
+                        if (nb < ntB) dmma_m8n8k4(du[nb][0], du[nb][1], Lf[ks], gj[offU + nb * 8 * ldk + ks * 4]);
                 }
             }
 #pragma unroll
-            for (int nb = 0; nb < MT; nb++) {
-                if (nb < ntB) {
-                    double d0 = 0.0, d1 = 0.0;
-#pragma unroll
-                    for (int ks = 0; ks < KS; ks++)
-                        if (ks < nksA) dmma_m8n8k4(d0, d1, Lf[ks], gj[offU + nb * 8 * ldk + ks * 4]);
-                    // D: row fiber gid, cols b = 8nb+2tig, +1
-                    sU[gid * SW + (8 * nb + 2 * tig) * FTN_TP + warp] = d0;
-                    sU[gid * SW + (8 * nb + 2 * tig + 1) * FTN_TP + warp] = d1;
+            for (int mt = 0; mt < MT; mt++) {
+                if (mt < mtA) {                                      // D: row a = 8mt+gid, cols fiber 2*tig, 2*tig+1
+                    sW[(2 * tig) * SW + (8 * mt + gid) * FTN_TP + warp] = dw[mt][0];
+                    sW[(2 * tig + 1) * SW + (8 * mt + gid) * FTN_TP + warp] = dw[mt][1];
+                }
+                if (mt < ntB) {                                      // D: row fiber gid, cols b = 8nb+2tig, +1
+                    sU[gid * SW + (8 * mt + 2 * tig) * FTN_TP + warp] = du[mt][0];
+                    sU[gid * SW + (8 * mt + 2 * tig + 1) * FTN_TP + warp] = du[mt][1];
                 }
             }
         }
@@ -356,52 +362,55 @@ __global__ void __launch_bounds__(FTN_NT, 2) k_ft_nodes(const FtArgs a, const do
         // ---- variant dots of fiber g = warp over the tile's nodes -----------------------------
         if (warp < nf) {
             const size_t idb = idf + j0;
-            double bfr[KS];
-            // left: C[v][jl] = sum_a A[v][a] W[a][jl];  B fragment (row a, col jl) shared by the v tiles
+            // left: C[v][jl] = sum_a A[v][a] W[a][jl];  right: C[jl][v] = sum_b U[jl][b] Cv[b][v]
+            double dl[VT][2], dr[VT][2];
 #pragma unroll
-            for (int ks = 0; ks < KS; ks++) bfr[ks] = (ks < nksA) ? wg[ks * 4 * FTN_TP] : 0.0;
+            for (int t = 0; t < VT; t++) { dl[t][0] = dl[t][1] = 0.0; dr[t][0] = dr[t][1] = 0.0; }
+#pragma unroll
+            for (int ks = 0; ks < KS; ks++) {
+                if (ks < nksA) {
+                    const double bw = wg[ks * 4 * FTN_TP];               // B fragment (row a, col jl), shared by the v tiles
+#pragma unroll
+                    for (int mt = 0; mt < VT; mt++)
+                        if (mt < mtL) dmma_m8n8k4(dl[mt][0], dl[mt][1], setL[(4 * ks + tig) * NVL + 8 * mt + gid], bw);
+                }
+                if (ks < nksB) {
+                    const double au = ug[ks * 4 * FTN_TP];               // A fragment (row jl, col b)
+#pragma unroll
+                    for (int nb = 0; nb < VT; nb++)
+                        if (nb < ntR) dmma_m8n8k4(dr[nb][0], dr[nb][1], au, setR[(4 * ks + tig) * NVR + 8 * nb + gid]);
+                }
+            }
 #pragma unroll
             for (int mt = 0; mt < VT; mt++) {
-                if (mt < mtL) {
-                    double d0 = 0.0, d1 = 0.0;
-#pragma unroll
-                    for (int ks = 0; ks < KS; ks++)
-                        if (ks < nksA) dmma_m8n8k4(d0, d1, setL[(4 * ks + tig) * NVL + 8 * mt + gid], bfr[ks]);
-                    const int slot = slotL[mt];
-                    if (slot >= 0) {                                     // D: row v, cols jl = 2tig, 2tig+1
-                        const int jl = 2 * tig;
-                        if (mt == 0 && gid == 0) {
-                            if (jl < nt) sV[warp * nmax + j0 + jl] = d0;
-                            if (jl + 1 < nt) sV[warp * nmax + j0 + jl + 1] = d1;
-                        }
-                        if (a.cst) {
-                            double *o = a.cst + (size_t)slot * a.NS + idb + jl;
-                            if (jl < nt) o[0] = d0;
-                            if (jl + 1 < nt) o[1] = d1;
-                        }
-                        if (a.costs) {
-                            if (jl < nt) a.costs[(idb + jl) * CS + slot] = d0;
-                            if (jl + 1 < nt) a.costs[(idb + jl + 1) * CS + slot] = d1;
-                        }
+                const int slot = slotL[mt];
+                if (mt < mtL && slot >= 0) {                             // D: row v, cols jl = 2tig, 2tig+1
+                    const int jl = 2 * tig;
+                    const double d0 = dl[mt][0], d1 = dl[mt][1];
+                    if (mt == 0 && gid == 0) {
+                        if (jl < nt) sV[warp * nmax + j0 + jl] = d0;
+                        if (jl + 1 < nt) sV[warp * nmax + j0 + jl + 1] = d1;
+                    }
+                    if (a.cst) {
+                        double *o = a.cst + (size_t)slot * a.NS + idb + jl;
+                        if (jl < nt) o[0] = d0;
+                        if (jl + 1 < nt) o[1] = d1;
+                    }
+                    if (a.costs) {
+                        if (jl < nt) a.costs[(idb + jl) * CS + slot] = d0;
+                        if (jl + 1 < nt) a.costs[(idb + jl + 1) * CS + slot] = d1;
                     }
                 }
             }
-            // right: C[jl][v] = sum_b U[jl][b] Cv[b][v];  A fragment (row jl, col b) shared by the v tiles
+            if (gid < nt) {
 #pragma unroll
-            for (int ks = 0; ks < KS; ks++) bfr[ks] = (ks < nksB) ? ug[ks * 4 * FTN_TP] : 0.0;
-#pragma unroll
-            for (int nb = 0; nb < VT; nb++) {
-                if (nb < ntR) {
-                    double d0 = 0.0, d1 = 0.0;
-#pragma unroll
-                    for (int ks = 0; ks < KS; ks++)
-                        if (ks < nksB) dmma_m8n8k4(d0, d1, bfr[ks], setR[(4 * ks + tig) * NVR + 8 * nb + gid]);
-                    if (gid < nt) {                                      // D: row jl = gid, cols v = 8nb+2tig, +1
+                for (int nb = 0; nb < VT; nb++) {
+                    if (nb < ntR) {                                      // D: row jl = gid, cols v = 8nb+2tig, +1
 #pragma unroll
                         for (int h = 0; h < 2; h++) {
                             const int slot = slotR[nb][h];
                             if (slot < 0) continue;
-                            const double val = h ? d1 : d0;
+                            const double val = dr[nb][h];
                             if (a.cst) a.cst[(size_t)slot * a.NS + idb + gid] = val;
                             if (a.costs) a.costs[(idb + gid) * CS + slot] = val;
                         }
