@@ -69,13 +69,31 @@ int ft_uses_mma(const DevFT &ft)
 size_t ft_sets_bytes(const DevFT &ft, size_t F) { return (size_t)ft_set_width(ft) * F * sizeof(double); }
 
 template <int RMAX>
-static int launch_nodes_t(const FtArgs &a, cudaStream_t st)
+static int launch_mma_t(const FtArgs &a, cudaStream_t st)
 {
+    // chains: one warp per (fiber, side)
+    const size_t csm = FtChainPlan<RMAX>(a.ft).bytes();
+    if (csm > (size_t)g_max_optin) return (int)cudaErrorInvalidValue;
+    static size_t cattr = 0;
+    if (csm > cattr) {
+        cudaError_t e = cudaFuncSetAttribute(k_ft_chains<RMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)csm);
+        if (e != cudaSuccess) return (int)e;
+        cattr = csm;
+    }
+    int per_sm = 1;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_ft_chains<RMAX>, FTC_NT, csm);
+    if (per_sm < 1) per_sm = 1;
+    int cgrid = (2 * a.F + FTC_NT / 32 - 1) / (FTC_NT / 32);
+    if (cgrid > g_sms * per_sm) cgrid = g_sms * per_sm;
+    k_ft_chains<RMAX><<<cgrid, FTC_NT, csm, st>>>(a, a.sets);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return (int)e;
+    // nodes: one CTA per same-k group
     const size_t smem = FtNodePlan<RMAX>(a.ft, a.P.nmax).bytes();
     if (smem > (size_t)g_max_optin) return (int)cudaErrorInvalidValue;
     static size_t attr = 0;
     if (smem > attr) {
-        cudaError_t e = cudaFuncSetAttribute(k_ft_nodes<RMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        e = cudaFuncSetAttribute(k_ft_nodes<RMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return (int)e;
         attr = smem;
     }
@@ -90,28 +108,12 @@ static int launch_ft_mma(FtArgs a, cudaStream_t st)
     int fb = FT_FBMAX;
     while (fb > 1 && (a.F / fb) < 2 * g_sms) fb >>= 1;
     a.FB = fb;
-    const size_t csm = FtChainPlan(a.ft).bytes();
-    if (csm > (size_t)g_max_optin) return (int)cudaErrorInvalidValue;
-    static size_t cattr = 0;
-    if (csm > cattr) {
-        cudaError_t e = cudaFuncSetAttribute(k_ft_chains, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)csm);
-        if (e != cudaSuccess) return (int)e;
-        cattr = csm;
-    }
-    int per_sm = 1;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_ft_chains, FTC_NT, csm);
-    if (per_sm < 1) per_sm = 1;
-    int cgrid = (2 * a.F + FTC_NT / 32 - 1) / (FTC_NT / 32);
-    if (cgrid > g_sms * per_sm) cgrid = g_sms * per_sm;
-    k_ft_chains<<<cgrid, FTC_NT, csm, st>>>(a, a.sets);
-    cudaError_t e = cudaGetLastError();
-    if (e != cudaSuccess) return (int)e;
     int rmax = 1;
     for (int i = 0; i <= a.ft.d; i++) rmax = a.ft.r[i] > rmax ? a.ft.r[i] : rmax;
-    if (rmax <= 8) return launch_nodes_t<8>(a, st);
-    if (rmax <= 16) return launch_nodes_t<16>(a, st);
-    if (rmax <= 24) return launch_nodes_t<24>(a, st);
-    return launch_nodes_t<32>(a, st);
+    if (rmax <= 8) return launch_mma_t<8>(a, st);
+    if (rmax <= 16) return launch_mma_t<16>(a, st);
+    if (rmax <= 24) return launch_mma_t<24>(a, st);
+    return launch_mma_t<32>(a, st);
 }
 
 // Stage 1 over one chunk.  a.FB == 0: pick the group size here.  1 launch.

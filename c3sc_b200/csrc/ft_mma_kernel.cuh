@@ -34,14 +34,22 @@ __host__ __device__ inline int ft_set_width(const DevFT &ft)
     return rs * (2 * ft.d + 2);
 }
 
+// vectors-per-row stride of the chain sets in shared memory: >= 2d and = 4 (mod 8), so the A-fragment
+// reads (row v, col q) of the stepped products are bank-conflict free
+__host__ __device__ inline int ft_chain_nvp(int d)
+{
+    int n = 2 * d;
+    while ((n & 7) != 4) n++;
+    return n;
+}
+
+template <int RMAX>
 struct FtChainPlan {            // shared memory of k_ft_chains, per warp: two set buffers + indices
-    int rs, nvm, bufDoubles, perWarpDoubles, perWarpInts;
+    int nvp, bufDoubles, perWarpDoubles, perWarpInts;
     __host__ __device__ FtChainPlan(const DevFT &ft)
     {
-        rs = 1;
-        for (int i = 0; i <= ft.d; i++) rs = ft.r[i] > rs ? ft.r[i] : rs;
-        nvm = 2 * ft.d;                              // vectors of one side, even
-        bufDoubles = rs * nvm;
+        nvp = ft_chain_nvp(ft.d);
+        bufDoubles = RMAX * nvp;                     // [rank row q][vector v], rows padded to the MMA tile
         perWarpDoubles = 2 * bufDoubles;
         perWarpInts = 4 * ft.d;                      // fixed indices + neighbour pairs
     }
@@ -49,19 +57,38 @@ struct FtChainPlan {            // shared memory of k_ft_chains, per warp: two s
 };
 
 // ---------------------------------------------------------------------------
+__device__ __forceinline__ void dmma_m8n8k4(double &d0, double &d1, double a, double b)
+{
+    asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+        : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
+}
+
+// One warp per (fiber, side).  A step multiplies the whole vector set by one core block on the
+// tensor cores:  out[v][o] = sum_q in[v][q] B[q][o]  (left: B = G_m[f_m], right: B = G_m[f_m]^T),
+// B fragments straight from the zero-padded core copy in L2 (all loads of a step are independent),
+// and appends the two neighbour variants  in[0] . G_m[nb]  with plain FMAs.
+template <int RMAX>
 __global__ void __launch_bounds__(FTC_NT) k_ft_chains(const FtArgs a, double *sets)
 {
+    constexpr int KS = RMAX / 4, NTL = RMAX / 8, VT = (2 * MAXD + 7) / 8;
     const DevProblem &P = a.P;
     const DevFT &ft = a.ft;
     const int d = ft.d;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int gid = lane >> 2, tig = lane & 3;
     constexpr int NW = FTC_NT / 32;
     extern __shared__ __align__(16) double smem[];
-    const FtChainPlan cp(ft);
+    const FtChainPlan<RMAX> cp(ft);
+    const int NVP = cp.nvp;
     double *buf0 = smem + warp * cp.perWarpDoubles, *buf1 = buf0 + cp.bufDoubles;
     int *iw = reinterpret_cast<int *>(smem + NW * cp.perWarpDoubles) + warp * cp.perWarpInts;
     int *sFix = iw, *sNf = iw + d;                   // sNf[2*i], sNf[2*i+1]: pair of dimension i
-    const int SETW = cp.rs * (2 * d + 2);
+    int rsG = 1;
+    for (int i = 0; i <= d; i++) rsG = ft.r[i] > rsG ? ft.r[i] : rsG;
+    const int SETW = rsG * (2 * d + 2);
+
+    // every value a fragment may touch must be finite (padding rows meet zero rows of the block)
+    for (int e = lane; e < cp.perWarpDoubles; e += 32) buf0[e] = 0.0;
 
     for (int task = blockIdx.x * NW + warp; task < 2 * a.F; task += gridDim.x * NW) {
         const int f = task >> 1;
@@ -93,72 +120,76 @@ __global__ void __launch_bounds__(FTC_NT) k_ft_chains(const FtArgs a, double *se
         for (int s = 0; s < nsteps; s++) {
             const int m = left ? s : d - 1 - s;
             const int rq = left ? ft.r[m] : ft.r[m + 1], ro = left ? ft.r[m + 1] : ft.r[m];
-            const int blk = ft.r[m] * ft.r[m + 1];
-            const double *base = (left ? ft.baseT : ft.base) + ft.off[m];
-            const double *bc = base + (size_t)sFix[m] * blk;
-            const double *bl = base + (size_t)sNf[2 * m] * blk, *bh = base + (size_t)sNf[2 * m + 1] * blk;
-            const int nin = 1 + 2 * s, nvg = (nin + FT_VG - 1) / FT_VG;
-            for (int o = lane; o < ro; o += 32) {
-                for (int vg = 0; vg < nvg; vg++) {
-                    const int v0 = vg * FT_VG;
-                    double acc[FT_VG];
+            const int ld = ft.ldp[m], pblk = ft.ldp[m] * ft.cpp[m];
+            const double *base = ft.baseP + ft.offP[m];
+            const double *bc = base + (size_t)sFix[m] * pblk;
+            const double *bl = base + (size_t)sNf[2 * m] * pblk, *bh = base + (size_t)sNf[2 * m + 1] * pblk;
+            const int nin = 1 + 2 * s;
+            const int nks = (rq + 3) >> 2, ntl = (ro + 7) >> 3, mtn = (nin + 7) >> 3;
+            // B fragments (row q = 4ks+tig, col o = 8nt+gid); element (a,b) of a padded block at b*ld + a
+            const int sq = left ? 1 : ld, so = left ? ld : 1;        // strides of q and of o inside the block
+            double Bf[KS][NTL];
 #pragma unroll
-                    for (int i = 0; i < FT_VG; i++) acc[i] = 0.0;
-                    if (vg == 0) {
-                        double alo = 0.0, ahi = 0.0;
+            for (int ks = 0; ks < KS; ks++)
+#pragma unroll
+                for (int nt = 0; nt < NTL; nt++)
+                    Bf[ks][nt] = (ks < nks && nt < ntl) ? __ldg(bc + (4 * ks + tig) * sq + (8 * nt + gid) * so) : 0.0;
+            // the two new variants: in[0] against the neighbour blocks, output index o = lane
+            if (lane < ro) {
+                const double *pl = bl + lane * so, *ph = bh + lane * so;
+                double alo = 0.0, ahi = 0.0;
 #pragma unroll 4
-                        for (int q = 0; q < rq; q++) {
-                            const double c = __ldg(bc + o + (size_t)q * ro), l = __ldg(bl + o + (size_t)q * ro),
-                                         h = __ldg(bh + o + (size_t)q * ro);
-                            const double2 *row = reinterpret_cast<const double2 *>(in + q * NV);
+                for (int q = 0; q < rq; q++) {
+                    const double x = in[q * NVP];
+                    alo = fma(x, __ldg(pl + q * sq), alo);
+                    ahi = fma(x, __ldg(ph + q * sq), ahi);
+                }
+                out[lane * NVP + nin] = alo;
+                out[lane * NVP + nin + 1] = ahi;
+            }
+            // the existing vectors against the centre block
 #pragma unroll
-                            for (int i = 0; i < FT_VG / 2; i++) {
-                                if (2 * i >= NV) break;                 // rows are NV wide (NV even)
-                                const double2 x = row[i];
-                                acc[2 * i] = fma(x.x, c, acc[2 * i]);
-                                acc[2 * i + 1] = fma(x.y, c, acc[2 * i + 1]);
-                                if (i == 0) { alo = fma(x.x, l, alo); ahi = fma(x.x, h, ahi); }
-                            }
+            for (int mt = 0; mt < VT; mt++) {
+                if (mt < mtn) {
+                    double acc[NTL][2];
+#pragma unroll
+                    for (int nt = 0; nt < NTL; nt++) acc[nt][0] = acc[nt][1] = 0.0;
+#pragma unroll
+                    for (int ks = 0; ks < KS; ks++) {
+                        if (ks < nks) {
+                            const double af = in[(4 * ks + tig) * NVP + 8 * mt + gid];   // A: row v, col q
+#pragma unroll
+                            for (int nt = 0; nt < NTL; nt++)
+                                if (nt < ntl) dmma_m8n8k4(acc[nt][0], acc[nt][1], af, Bf[ks][nt]);
                         }
-                        out[o * NV + nin] = alo;
-                        out[o * NV + nin + 1] = ahi;
-                    } else {
-#pragma unroll 4
-                        for (int q = 0; q < rq; q++) {
-                            const double c = __ldg(bc + o + (size_t)q * ro);
-                            const double2 *row = reinterpret_cast<const double2 *>(in + q * NV + v0);
+                    }
+                    const int v = 8 * mt + gid;                      // D: row v, cols o = 8nt+2tig, +1
+                    if (v < nin) {
 #pragma unroll
-                            for (int i = 0; i < FT_VG / 2; i++) {
-                                if (v0 + 2 * i >= NV) break;
-                                const double2 x = row[i];
-                                acc[2 * i] = fma(x.x, c, acc[2 * i]);
-                                acc[2 * i + 1] = fma(x.y, c, acc[2 * i + 1]);
+                        for (int nt = 0; nt < NTL; nt++) {
+                            if (nt < ntl) {
+                                out[(8 * nt + 2 * tig) * NVP + v] = acc[nt][0];
+                                out[(8 * nt + 2 * tig + 1) * NVP + v] = acc[nt][1];
                             }
                         }
                     }
-#pragma unroll
-                    for (int i = 0; i < FT_VG; i++)
-                        if (v0 + i < nin) out[o * NV + v0 + i] = acc[i];
                 }
             }
             __syncwarp();
             double *t = in; in = out; out = t;
         }
-        // final set -> global record of the fiber ([q][v], v fastest; right set after the left one)
+        // final set -> global record of the fiber ([q][v] with stride NV; right set after the left one)
         {
             const int rl = left ? ft.r[k] : ft.r[k + 1];
-            double *dst = sets + (size_t)f * SETW + (left ? 0 : cp.rs * NVL);
-            for (int e = lane; e < rl * NV; e += 32) dst[e] = in[e];
+            double *dst = sets + (size_t)f * SETW + (left ? 0 : rsG * NVL);
+            for (int e = lane; e < rl * NV; e += 32) {
+                const int q = e / NV, v = e - q * NV;
+                dst[e] = in[q * NVP + v];
+            }
         }
     }
 }
 
-// ---------------------------------------------------------------------------
-__device__ __forceinline__ void dmma_m8n8k4(double &d0, double &d1, double a, double b)
-{
-    asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
-        : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
-}
 
 // ---- TMA bulk copy (cp.async.bulk, SASS UBLKCP) + mbarrier helpers -------------------------
 __device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
