@@ -68,7 +68,7 @@ __device__ __forceinline__ void dmma_m8n8k4(double &d0, double &d1, double a, do
 // B fragments straight from the zero-padded core copy in L2 (all loads of a step are independent),
 // and appends the two neighbour variants  in[0] . G_m[nb]  with plain FMAs.
 template <int RMAX>
-__global__ void __launch_bounds__(FTC_NT) k_ft_chains(const FtArgs a, double *sets)
+__global__ void __launch_bounds__(FTC_NT, RMAX <= 24 ? 2 : 1) k_ft_chains(const FtArgs a, double *sets)
 {
     constexpr int KS = RMAX / 4, NTL = RMAX / 8, VT = (2 * MAXD + 7) / 8;
     const DevProblem &P = a.P;
@@ -126,28 +126,25 @@ __global__ void __launch_bounds__(FTC_NT) k_ft_chains(const FtArgs a, double *se
             const double *bl = base + (size_t)sNf[2 * m] * pblk, *bh = base + (size_t)sNf[2 * m + 1] * pblk;
             const int nin = 1 + 2 * s;
             const int nks = (rq + 3) >> 2, ntl = (ro + 7) >> 3, mtn = (nin + 7) >> 3;
-            // B fragments (row q = 4ks+tig, col o = 8nt+gid); element (a,b) of a padded block at b*ld + a
+            // B fragments (row q = 4ks+tig, col o = 8nt+gid); element (a,b) of a padded block at b*ld + a.
+            // All loads of the centre and the first neighbour block are issued before any use.
             const int sq = left ? 1 : ld, so = left ? ld : 1;        // strides of q and of o inside the block
-            double Bf[KS][NTL];
+            const int foff = tig * sq + gid * so;
+            double Bc[KS][NTL], Bl[KS][NTL], Bh[KS][NTL];
 #pragma unroll
             for (int ks = 0; ks < KS; ks++)
 #pragma unroll
                 for (int nt = 0; nt < NTL; nt++)
-                    Bf[ks][nt] = (ks < nks && nt < ntl) ? __ldg(bc + (4 * ks + tig) * sq + (8 * nt + gid) * so) : 0.0;
-            // the two new variants: in[0] against the neighbour blocks, output index o = lane
-            if (lane < ro) {
-                const double *pl = bl + lane * so, *ph = bh + lane * so;
-                double alo = 0.0, ahi = 0.0;
-#pragma unroll 4
-                for (int q = 0; q < rq; q++) {
-                    const double x = in[q * NVP];
-                    alo = fma(x, __ldg(pl + q * sq), alo);
-                    ahi = fma(x, __ldg(ph + q * sq), ahi);
-                }
-                out[lane * NVP + nin] = alo;
-                out[lane * NVP + nin + 1] = ahi;
-            }
+                    Bc[ks][nt] = (ks < nks && nt < ntl) ? __ldg(bc + foff + 4 * ks * sq + 8 * nt * so) : 0.0;
+#pragma unroll
+            for (int ks = 0; ks < KS; ks++)
+#pragma unroll
+                for (int nt = 0; nt < NTL; nt++)
+                    Bl[ks][nt] = (ks < nks && nt < ntl) ? __ldg(bl + foff + 4 * ks * sq + 8 * nt * so) : 0.0;
             // the existing vectors against the centre block
+            double Af0[KS];                                          // A fragments of the first vector tile (row v = gid)
+#pragma unroll
+            for (int ks = 0; ks < KS; ks++) Af0[ks] = (ks < nks) ? in[(4 * ks + tig) * NVP + gid] : 0.0;
 #pragma unroll
             for (int mt = 0; mt < VT; mt++) {
                 if (mt < mtn) {
@@ -157,10 +154,10 @@ __global__ void __launch_bounds__(FTC_NT) k_ft_chains(const FtArgs a, double *se
 #pragma unroll
                     for (int ks = 0; ks < KS; ks++) {
                         if (ks < nks) {
-                            const double af = in[(4 * ks + tig) * NVP + 8 * mt + gid];   // A: row v, col q
+                            const double af = mt == 0 ? Af0[ks] : in[(4 * ks + tig) * NVP + 8 * mt + gid];   // A: row v, col q
 #pragma unroll
                             for (int nt = 0; nt < NTL; nt++)
-                                if (nt < ntl) dmma_m8n8k4(acc[nt][0], acc[nt][1], af, Bf[ks][nt]);
+                                if (nt < ntl) dmma_m8n8k4(acc[nt][0], acc[nt][1], af, Bc[ks][nt]);
                         }
                     }
                     const int v = 8 * mt + gid;                      // D: row v, cols o = 8nt+2tig, +1
@@ -171,6 +168,36 @@ __global__ void __launch_bounds__(FTC_NT) k_ft_chains(const FtArgs a, double *se
                                 out[(8 * nt + 2 * tig) * NVP + v] = acc[nt][0];
                                 out[(8 * nt + 2 * tig + 1) * NVP + v] = acc[nt][1];
                             }
+                        }
+                    }
+                }
+            }
+#pragma unroll
+            for (int ks = 0; ks < KS; ks++)
+#pragma unroll
+                for (int nt = 0; nt < NTL; nt++)
+                    Bh[ks][nt] = (ks < nks && nt < ntl) ? __ldg(bh + foff + 4 * ks * sq + 8 * nt * so) : 0.0;
+            // the two new variants: row 0 of the first vector tile (the prefix / suffix itself) against the
+            // neighbour blocks; only D row 0 (lanes with gid == 0) is kept
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+                double acc[NTL][2];
+#pragma unroll
+                for (int nt = 0; nt < NTL; nt++) acc[nt][0] = acc[nt][1] = 0.0;
+#pragma unroll
+                for (int ks = 0; ks < KS; ks++) {
+                    if (ks < nks) {
+#pragma unroll
+                        for (int nt = 0; nt < NTL; nt++)
+                            if (nt < ntl) dmma_m8n8k4(acc[nt][0], acc[nt][1], Af0[ks], h ? Bh[ks][nt] : Bl[ks][nt]);
+                    }
+                }
+                if (gid == 0) {
+#pragma unroll
+                    for (int nt = 0; nt < NTL; nt++) {
+                        if (nt < ntl) {
+                            out[(8 * nt + 2 * tig) * NVP + nin + h] = acc[nt][0];
+                            out[(8 * nt + 2 * tig + 1) * NVP + nin + h] = acc[nt][1];
                         }
                     }
                 }
