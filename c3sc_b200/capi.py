@@ -12,7 +12,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libc3sc_b200.so")
+LIB_PATH = os.environ.get("C3SC_LIB") or os.path.join(_HERE, "lib", "libc3sc_b200.so")   # C3SC_LIB: kernel experiments only
 
 c_f64p = C.POINTER(C.c_double)
 c_i32p = C.POINTER(C.c_int32)

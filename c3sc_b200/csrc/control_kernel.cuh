@@ -451,8 +451,15 @@ __device__ __forceinline__ void node2_prepare(const CtlArgs &c, int id, Node2<M>
     n.best = CUDART_INF; n.ibest = 0x7fffffff;
 }
 
+#ifndef C3SC_C2_UNROLL
+#define C3SC_C2_UNROLL 2
+#endif
+#ifndef C3SC_C2_MINB
+#define C3SC_C2_MINB 2
+#endif
+constexpr int C2U = C3SC_C2_UNROLL;
 template <class M>
-__global__ void __launch_bounds__(CT_NT, 2) k_control2(const CtlArgs c)
+__global__ void __launch_bounds__(CT_NT, C3SC_C2_MINB) k_control2(const CtlArgs c)
 {
     constexpr int DX = M::DX, DU = M::DU, CS = 2 * DX + 1, RW = 2 * DX + 3;
     constexpr int NUD = M::NUD, CTW = 2 * NUD + 2;
@@ -489,7 +496,7 @@ __global__ void __launch_bounds__(CT_NT, 2) k_control2(const CtlArgs c)
             }
             double btA = CUDART_INF, btB = CUDART_INF;
             int biA = 0x7fffffff, biB = 0x7fffffff;
-#pragma unroll 2
+#pragma unroll C2U
             for (int pos = lo; pos < hi; pos++) {
                 const double2 *row = reinterpret_cast<const double2 *>(tab + pos * CTW);
                 double SA0 = A.S0, SA1 = 0.0, SB0 = B.S0, SB1 = 0.0;
