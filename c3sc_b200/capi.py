@@ -40,6 +40,14 @@ class BatchOut(C.Structure):
     ]
 
 
+class CrossOpts(C.Structure):
+    _fields_ = [("maxiter", C.c_uint32), ("tol", C.c_double), ("verbose", C.c_int)]
+
+
+# int f(size_t F, const int32_t *dim_vary, const int32_t *fixed_ind, size_t ldo, double *out, void *arg)
+FIBER_FN = C.CFUNCTYPE(C.c_int, C.c_size_t, c_i32p, c_i32p, C.c_size_t, c_f64p, C.c_void_p)
+
+
 EXPORTS = [
     "c3sc_cuda_init", "c3sc_cuda_device_count", "c3sc_last_error", "c3sc_version", "c3sc_launch_count",
     "c3sc_problem_create", "c3sc_problem_destroy", "c3sc_problem_check",
@@ -48,6 +56,7 @@ EXPORTS = [
     "c3sc_transition_batch", "c3sc_model_eval", "c3sc_measure_fp64_peak",
     "c3sc_neighbor_costs_batch", "c3sc_node_backup_batch", "c3sc_control_value_batch", "c3sc_rhs_batch",
     "c3sc_transition_raw", "c3sc_ft_fiber_nn_batch", "c3sc_valuef_commit",
+    "c3sc_cross_create", "c3sc_cross_destroy", "c3sc_cross_ranks", "c3sc_cross_run", "c3sc_cross_run_vi", "c3sc_cross_run_pi",
 ]
 
 _lib = None
@@ -90,6 +99,13 @@ def lib() -> C.CDLL:
         L.c3sc_transition_raw.argtypes = [i32, C.c_uint32, C.c_double, vp, sz, vp, vp, vp, vp, vp]
         L.c3sc_ft_fiber_nn_batch.argtypes = [vp, sz, vp, vp, vp, vp, sz, vp]
         L.c3sc_measure_fp64_peak.argtypes = [C.POINTER(C.c_double), i32, i32]
+        L.c3sc_cross_create.argtypes = [C.c_uint32, c_u64p, c_u64p, C.POINTER(vp)]
+        L.c3sc_cross_destroy.argtypes = [vp]
+        L.c3sc_cross_destroy.restype = None
+        L.c3sc_cross_ranks.argtypes = [vp, c_u64p]
+        L.c3sc_cross_run.argtypes = [vp, FIBER_FN, vp, C.POINTER(CrossOpts), C.POINTER(c_f64p), c_u64p, c_f64p]
+        L.c3sc_cross_run_vi.argtypes = [vp, vp, vp, C.POINTER(CrossOpts), C.POINTER(c_f64p), c_u64p, c_f64p]
+        L.c3sc_cross_run_pi.argtypes = [vp, vp, vp, vp, C.c_uint32, C.POINTER(CrossOpts), C.POINTER(c_f64p), c_u64p, c_f64p]
         _lib = L
     return _lib
 
@@ -298,6 +314,68 @@ class ValueF:
     def close(self):
         if getattr(self, "handle", None) and lib is not None:
             lib().c3sc_valuef_destroy(self.handle)
+            self.handle = None
+
+    __del__ = close
+
+
+class Cross:
+    """Host cross-approximation driver with batched fiber requests (include/c3sc_cross.h):
+    the stand-in for what valuef_interp gets from C3 (reference src/valuefunc.c:603-767)."""
+
+    def __init__(self, n, ranks):
+        self.n = np.ascontiguousarray(n, dtype=np.uint64)
+        self.d = int(self.n.size)
+        r = np.ascontiguousarray(ranks, dtype=np.uint64)
+        self.handle = C.c_void_p()
+        check(lib().c3sc_cross_create(self.d, self.n.ctypes.data_as(c_u64p), r.ctypes.data_as(c_u64p), C.byref(self.handle)))
+        self.ranks = np.zeros(self.d + 1, dtype=np.uint64)
+        check(lib().c3sc_cross_ranks(self.handle, self.ranks.ctypes.data_as(c_u64p)))
+
+    def _cores(self):
+        cores = [np.zeros(int(self.n[k] * self.ranks[k] * self.ranks[k + 1])) for k in range(self.d)]
+        arr = (c_f64p * self.d)(*[c.ctypes.data_as(c_f64p) for c in cores])
+        return cores, arr
+
+    def run_vi(self, prob: "Problem", vf: "ValueF", maxiter=5, tol=0.0, verbose=0):
+        """one c3control_step_vi on the GPU path: cores of cross(bellman_vi(.; vf))"""
+        cores, arr = self._cores()
+        o = CrossOpts(maxiter, tol, verbose)
+        nf = C.c_uint64(); ch = C.c_double()
+        check(lib().c3sc_cross_run_vi(self.handle, prob.handle, vf.handle, C.byref(o), arr, C.byref(nf), C.byref(ch)))
+        return cores, int(nf.value), float(ch.value)
+
+    def run_pi(self, prob: "Problem", vf_policy: "ValueF", vf_iter: "ValueF", maxiter=5, tol=0.0, verbose=0):
+        cores, arr = self._cores()
+        o = CrossOpts(maxiter, tol, verbose)
+        nf = C.c_uint64(); ch = C.c_double()
+        check(lib().c3sc_cross_run_pi(self.handle, prob.handle, vf_policy.handle, vf_iter.handle, prob.dx, C.byref(o), arr,
+                                      C.byref(nf), C.byref(ch)))
+        return cores, int(nf.value), float(ch.value)
+
+    def run(self, fn, maxiter=5, tol=0.0, verbose=0):
+        """same driver, operator = Python callable fn(dim_vary[F], fixed_ind[F,d]) -> values[F, nmax]"""
+        nmax = int(self.n.max())
+        d = self.d
+
+        def _cb(F, dv, fi, ldo, out, _arg):
+            dvn = np.ctypeslib.as_array(dv, shape=(F,)).copy()
+            fin = np.ctypeslib.as_array(fi, shape=(F * d,)).reshape(F, d).copy()
+            vals = np.asarray(fn(dvn, fin), dtype=np.float64).reshape(F, -1)
+            dst = np.ctypeslib.as_array(out, shape=(F * ldo,)).reshape(F, ldo)
+            dst[:, :vals.shape[1]] = vals[:, :ldo]
+            return 0
+        cb = FIBER_FN(_cb)
+        cores, arr = self._cores()
+        o = CrossOpts(maxiter, tol, verbose)
+        nf = C.c_uint64(); ch = C.c_double()
+        check(lib().c3sc_cross_run(self.handle, cb, None, C.byref(o), arr, C.byref(nf), C.byref(ch)))
+        assert nmax >= 1
+        return cores, int(nf.value), float(ch.value)
+
+    def close(self):
+        if getattr(self, "handle", None) and lib is not None:
+            lib().c3sc_cross_destroy(self.handle)
             self.handle = None
 
     __del__ = close

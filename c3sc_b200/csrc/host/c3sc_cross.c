@@ -1,0 +1,417 @@
+/* c3sc_cross.c -- host driver that asks the Bellman operator for fibers in BATCHES.
+ *
+ * What the reference does here: valuef_interp (src/valuefunc.c:603-767) hands bellman_vi /
+ * bellman_pi to C3's ftapprox_cross, which calls the operator one fiber at a time.  C3 is not
+ * vendored (README.md:17-39), so this file restates the published algorithm it implements --
+ * alternating TT-cross with QR + maxvol pivoting (Oseledets & Tyrtyshnikov 2010; the C3 paper,
+ * Gorodetsky et al. 2018, Alg. 3) -- with the reference's set-up:
+ *   - start index sets from uniform_stride (src/util.c:995-1006, src/valuefunc.c:676-690)
+ *   - ft_cross_args maxiter 5 (src/valuefunc.c:632), fixed ranks (the adapt == 0 branch, :732)
+ *   - the result in the valuef_precompute_cores layout (src/valuefunc.c:165-189)
+ * The one difference that matters for the GPU: every core step requests ALL r_k * r_{k+1} fibers of
+ * the core in one call (c3sc_fiber_batch_fn), which is what lets stage 1 of the backup share the
+ * core tiles between fibers.
+ *
+ * Plain C, no arithmetic of the backup itself: the operator is a callback (the GPU path through
+ * c3sc_vi_batch / c3sc_pi_batch in c3sc_cross_run_vi / _pi; the parity tests plug the CPU oracle
+ * into the same driver).
+ */
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include "../../../include/c3sc_cross.h"
+
+struct c3sc_cross {
+    uint32_t d;
+    uint64_t n[C3SC_MAXD], r[C3SC_MAXD + 1], nmax;
+    /* left index sets I[k]: r[k] multi-indices over dims 0..k-1 (row-major, stride d);
+       right index sets J[k]: r[k] multi-indices over dims k..d-1 (stored at their dims) */
+    int32_t *I[C3SC_MAXD + 1], *J[C3SC_MAXD + 1];
+};
+
+/* src/util.c:995-1006 */
+static uint64_t uniform_stride(uint64_t N, uint64_t M)
+{
+    uint64_t stride = 1;
+    if (M < 2) return 0;
+    while (stride * (M - 1) < N - 1) stride++;
+    return stride - 1;
+}
+
+int c3sc_cross_create(uint32_t d, const uint64_t *n, const uint64_t *ranks, c3sc_cross **out)
+{
+    if (!n || !ranks || !out || d < 1 || d > C3SC_MAXD) return C3SC_EINVAL;
+    if (ranks[0] != 1 || ranks[d] != 1) return C3SC_EINVAL;
+    c3sc_cross *c = (c3sc_cross *)calloc(1, sizeof *c);
+    if (!c) return C3SC_EINVAL;
+    c->d = d;
+    for (uint32_t k = 0; k < d; k++) {
+        c->n[k] = n[k];
+        if (n[k] > c->nmax) c->nmax = n[k];
+    }
+    for (uint32_t k = 0; k <= d; k++) c->r[k] = ranks[k];
+    /* a rank cannot exceed the size of either unfolding it indexes */
+    for (uint32_t k = 1; k < d; k++) {
+        uint64_t cap = c->r[k - 1] * n[k - 1];
+        if (c->r[k] > cap) c->r[k] = cap;
+    }
+    for (uint32_t k = d - 1; k >= 1; k--) {
+        uint64_t cap = c->r[k + 1] * n[k];
+        if (c->r[k] > cap) c->r[k] = cap;
+    }
+    for (uint32_t k = 0; k <= d; k++) {
+        c->I[k] = (int32_t *)calloc(c->r[k] * d + 1, sizeof(int32_t));
+        c->J[k] = (int32_t *)calloc(c->r[k] * d + 1, sizeof(int32_t));
+        if (!c->I[k] || !c->J[k]) { c3sc_cross_destroy(c); return C3SC_EINVAL; }
+    }
+    /* start sets: element j of a set takes node (stride_i * j) mod N_i in every dimension i it spans,
+       stride_i = uniform_stride(N_i, rank) -- the "diagonal" start of src/valuefunc.c:676-690 */
+    for (uint32_t k = 0; k <= d; k++)
+        for (uint64_t j = 0; j < c->r[k]; j++)
+            for (uint32_t i = 0; i < d; i++) {
+                const uint64_t st = uniform_stride(n[i], c->r[k] < n[i] ? c->r[k] : n[i]);
+                const int32_t node = (int32_t)(((st ? st : 1) * j) % n[i]);
+                if (i < k) c->I[k][j * d + i] = node;
+                else c->J[k][j * d + i] = node;
+            }
+    *out = c;
+    return C3SC_OK;
+}
+
+void c3sc_cross_destroy(c3sc_cross *c)
+{
+    if (!c) return;
+    for (uint32_t k = 0; k <= c->d; k++) { free(c->I[k]); free(c->J[k]); }
+    free(c);
+}
+
+int c3sc_cross_ranks(const c3sc_cross *c, uint64_t *ranks)
+{
+    if (!c || !ranks) return C3SC_EINVAL;
+    for (uint32_t k = 0; k <= c->d; k++) ranks[k] = c->r[k];
+    return C3SC_OK;
+}
+
+/* ---- small dense linear algebra (column-major) --------------------------------------------- */
+/* Householder QR of A (m x n, m >= n): Q (m x n, explicit, orthonormal columns) overwrites A. */
+static void qr_explicit_q(double *A, size_t m, size_t n, double *work /* n + m */)
+{
+    double *tau = work, *v = work + n;
+    for (size_t k = 0; k < n; k++) {
+        double nrm = 0.0;
+        for (size_t i = k; i < m; i++) nrm += A[i + k * m] * A[i + k * m];
+        nrm = sqrt(nrm);
+        if (nrm == 0.0) { tau[k] = 0.0; continue; }
+        const double alpha = A[k + k * m] >= 0.0 ? -nrm : nrm;
+        const double v0 = A[k + k * m] - alpha;
+        for (size_t i = k + 1; i < m; i++) A[i + k * m] /= v0;
+        tau[k] = -v0 / alpha;
+        A[k + k * m] = alpha;
+        for (size_t j = k + 1; j < n; j++) {
+            double s = A[k + j * m];
+            for (size_t i = k + 1; i < m; i++) s += A[i + k * m] * A[i + j * m];
+            s *= tau[k];
+            A[k + j * m] -= s;
+            for (size_t i = k + 1; i < m; i++) A[i + j * m] -= s * A[i + k * m];
+        }
+    }
+    /* accumulate Q = H_0 .. H_{n-1} [I; 0] in place, last reflector first */
+    for (size_t kk = n; kk-- > 0;) {
+        v[kk] = 1.0;
+        for (size_t i = kk + 1; i < m; i++) v[i] = A[i + kk * m];
+        for (size_t i = 0; i < m; i++) A[i + kk * m] = 0.0;
+        A[kk + kk * m] = 1.0;
+        if (tau[kk] == 0.0) continue;
+        for (size_t j = kk; j < n; j++) {
+            double s = 0.0;
+            for (size_t i = kk; i < m; i++) s += v[i] * A[i + j * m];
+            s *= tau[kk];
+            for (size_t i = kk; i < m; i++) A[i + j * m] -= s * v[i];
+        }
+    }
+}
+
+/* maxvol: rows P (n of m) of Q (m x n) whose submatrix has (locally) maximal |det|; on return
+ * B = Q * inv(Q[P,:]) (m x n), so B[P,:] = I.  Deterministic: first maximum in scan order. */
+static int maxvol(const double *Q, size_t m, size_t n, size_t *P, double *B, double *work /* n*n + n */)
+{
+    /* start rows: Gaussian elimination with row pivoting on a copy */
+    memcpy(B, Q, m * n * sizeof(double));
+    char *used = (char *)calloc(m, 1);
+    if (!used) return 1;
+    for (size_t j = 0; j < n; j++) {
+        size_t piv = 0; double best = -1.0;
+        for (size_t i = 0; i < m; i++)
+            if (!used[i] && fabs(B[i + j * m]) > best) { best = fabs(B[i + j * m]); piv = i; }
+        P[j] = piv; used[piv] = 1;
+        const double pv = B[piv + j * m];
+        if (pv == 0.0) continue;
+        for (size_t c = j + 1; c < n; c++) {
+            const double f = B[piv + c * m] / pv;
+            if (f == 0.0) continue;
+            for (size_t i = 0; i < m; i++)
+                if (!used[i]) B[i + c * m] -= f * B[i + j * m];
+        }
+    }
+    free(used);
+    /* B = Q inv(Q[P]): invert the n x n block by Gauss-Jordan with partial pivoting on [S | I] */
+    double *S = work, *col = work + n * n;
+    {
+        double *aug = (double *)malloc(2 * n * n * sizeof(double));      /* row-major n x 2n */
+        if (!aug) return 1;
+        for (size_t a = 0; a < n; a++)
+            for (size_t b = 0; b < n; b++) {
+                aug[a * 2 * n + b] = Q[P[a] + b * m];
+                aug[a * 2 * n + n + b] = a == b ? 1.0 : 0.0;
+            }
+        for (size_t k = 0; k < n; k++) {
+            size_t piv = k; double best = fabs(aug[k * 2 * n + k]);
+            for (size_t i = k + 1; i < n; i++)
+                if (fabs(aug[i * 2 * n + k]) > best) { best = fabs(aug[i * 2 * n + k]); piv = i; }
+            if (best == 0.0) { free(aug); return 2; }
+            if (piv != k)
+                for (size_t jx = 0; jx < 2 * n; jx++) { double t = aug[k * 2 * n + jx]; aug[k * 2 * n + jx] = aug[piv * 2 * n + jx]; aug[piv * 2 * n + jx] = t; }
+            const double pv = 1.0 / aug[k * 2 * n + k];
+            for (size_t jx = 0; jx < 2 * n; jx++) aug[k * 2 * n + jx] *= pv;
+            for (size_t i = 0; i < n; i++) {
+                if (i == k) continue;
+                const double fct = aug[i * 2 * n + k];
+                if (fct == 0.0) continue;
+                for (size_t jx = 0; jx < 2 * n; jx++) aug[i * 2 * n + jx] -= fct * aug[k * 2 * n + jx];
+            }
+        }
+        for (size_t a = 0; a < n; a++)
+            for (size_t b = 0; b < n; b++) S[a + b * n] = aug[a * 2 * n + n + b];
+        free(aug);
+    }
+    for (size_t i = 0; i < m; i++) {
+        for (size_t b = 0; b < n; b++) {
+            double s = 0.0;
+            for (size_t a = 0; a < n; a++) s += Q[i + a * m] * S[a + b * n];
+            col[b] = s;
+        }
+        for (size_t b = 0; b < n; b++) B[i + b * m] = col[b];
+    }
+    /* swaps while some |B[i,j]| > 1 + delta */
+    for (int it = 0; it < 200; it++) {
+        size_t bi = 0, bj = 0; double best = 0.0;
+        for (size_t j = 0; j < n; j++)
+            for (size_t i = 0; i < m; i++)
+                if (fabs(B[i + j * m]) > best) { best = fabs(B[i + j * m]); bi = i; bj = j; }
+        if (best <= 1.0 + 1e-2) break;
+        /* row bi replaces P[bj]:  B <- B - B[:,bj] (B[bi,:] - e_bj) / B[bi,bj] */
+        const double pv = B[bi + bj * m];
+        for (size_t b = 0; b < n; b++) col[b] = (B[bi + b * m] - (b == bj ? 1.0 : 0.0)) / pv;
+        for (size_t b = 0; b < n; b++) {
+            const double f = col[b];
+            if (f == 0.0 || b == bj) continue;
+            for (size_t i = 0; i < m; i++) B[i + b * m] -= B[i + bj * m] * f;
+        }
+        {
+            const double f = col[bj];
+            for (size_t i = 0; i < m; i++) B[i + bj * m] -= B[i + bj * m] * f;
+        }
+        P[bj] = bi;
+    }
+    return 0;
+}
+
+/* ---- one core step: all fibers of core k in ONE operator call --------------------------------- */
+static int eval_core(const c3sc_cross *c, uint32_t k, c3sc_fiber_batch_fn f, void *arg, int32_t *dv, int32_t *fi,
+                     double *vals, double *T /* [r_k][N][r_{k+1}] as a + j*rk + b*rk*N */, uint64_t *nfib)
+{
+    const uint32_t d = c->d;
+    const size_t rk = c->r[k], rk1 = c->r[k + 1], N = c->n[k], ldo = c->nmax;
+    const size_t F = rk * rk1;
+    for (size_t a = 0; a < rk; a++)
+        for (size_t b = 0; b < rk1; b++) {
+            const size_t fidx = a + b * rk;
+            dv[fidx] = (int32_t)k;
+            for (uint32_t i = 0; i < d; i++)
+                fi[fidx * d + i] = i < k ? c->I[k][a * d + i] : (i > k ? c->J[k + 1][b * d + i] : 0);
+        }
+    int rc = f(F, dv, fi, ldo, vals, arg);
+    if (rc) return rc;
+    *nfib += F;
+    for (size_t a = 0; a < rk; a++)
+        for (size_t b = 0; b < rk1; b++)
+            for (size_t j = 0; j < N; j++) T[a + j * rk + b * rk * N] = vals[(a + b * rk) * ldo + j];
+    return 0;
+}
+
+/* core tensor T[a + j*rk + b*rk*N] -> valuef_precompute_cores layout: block j column-major */
+static void store_core(const double *T, size_t rk, size_t N, size_t rk1, double *core)
+{
+    for (size_t j = 0; j < N; j++)
+        for (size_t b = 0; b < rk1; b++)
+            for (size_t a = 0; a < rk; a++) core[j * rk * rk1 + a + b * rk] = T[a + j * rk + b * rk * N];
+}
+
+/* <A, B> of two trains in the ValueF layout (discrete inner product over the grid) */
+static double tt_dot(uint32_t d, const uint64_t *n, const uint64_t *r, double *const *A, double *const *B, double *w1, double *w2)
+{
+    /* M (r_k x r_k) <- sum_j A_k[j]^T M B_k[j] */
+    size_t rk = 1;
+    w1[0] = 1.0;
+    for (uint32_t k = 0; k < d; k++) {
+        const size_t r0 = r[k], r1 = r[k + 1], blk = r0 * r1;
+        for (size_t e = 0; e < r1 * r1; e++) w2[e] = 0.0;
+        for (size_t j = 0; j < n[k]; j++) {
+            const double *a = A[k] + j * blk, *b = B[k] + j * blk;
+            /* tmp = M * b  (r0 x r1), then w2 += a^T tmp */
+            for (size_t q = 0; q < r1; q++)
+                for (size_t p = 0; p < r1; p++) {
+                    double s = 0.0;
+                    for (size_t x = 0; x < r0; x++) {
+                        double t = 0.0;
+                        for (size_t y = 0; y < r0; y++) t += w1[x + y * r0] * b[y + q * r0];
+                        s += a[x + p * r0] * t;
+                    }
+                    w2[p + q * r1] += s;
+                }
+        }
+        memcpy(w1, w2, r1 * r1 * sizeof(double));
+        rk = r1;
+    }
+    (void)rk;
+    return w1[0];
+}
+
+int c3sc_cross_run(c3sc_cross *c, c3sc_fiber_batch_fn f, void *arg, const c3sc_cross_opts *opts, double *const *cores,
+                   uint64_t *nfibers, double *rel_change)
+{
+    if (!c || !f || !cores) return C3SC_EINVAL;
+    const uint32_t d = c->d;
+    const uint32_t maxiter = opts && opts->maxiter ? opts->maxiter : 5;       /* src/valuefunc.c:632 */
+    const double tol = opts ? opts->tol : 0.0;
+    const int verbose = opts ? opts->verbose : 0;
+    size_t rmax = 1, fmax = 1, tmax = 1;
+    for (uint32_t k = 0; k < d; k++) {
+        if (c->r[k + 1] > rmax) rmax = c->r[k + 1];
+        if (c->r[k] * c->r[k + 1] > fmax) fmax = c->r[k] * c->r[k + 1];
+        if (c->r[k] * c->n[k] * c->r[k + 1] > tmax) tmax = c->r[k] * c->n[k] * c->r[k + 1];
+    }
+    int32_t *dv = (int32_t *)malloc(fmax * sizeof(int32_t));
+    int32_t *fi = (int32_t *)malloc(fmax * d * sizeof(int32_t));
+    double *vals = (double *)malloc(fmax * c->nmax * sizeof(double));
+    double *T = (double *)malloc(tmax * sizeof(double)), *Q = (double *)malloc(tmax * sizeof(double));
+    double *B = (double *)malloc(tmax * sizeof(double));
+    size_t *P = (size_t *)malloc(rmax * sizeof(size_t));
+    double *work = (double *)malloc((rmax * rmax * 2 + rmax + rmax * c->nmax * rmax + 16) * sizeof(double));
+    double **prev = (double **)calloc(d, sizeof(double *));
+    int32_t *tmpI = (int32_t *)malloc(rmax * d * sizeof(int32_t));
+    int rc = C3SC_OK;
+    uint64_t nfib = 0;
+    double change = 1.0;
+    if (!dv || !fi || !vals || !T || !Q || !B || !P || !work || !prev || !tmpI) { rc = C3SC_EINVAL; goto done; }
+    for (uint32_t k = 0; k < d; k++) {
+        prev[k] = (double *)calloc(c->r[k] * c->n[k] * c->r[k + 1], sizeof(double));
+        if (!prev[k]) { rc = C3SC_EINVAL; goto done; }
+    }
+    for (uint32_t it = 0; it < maxiter; it++) {
+        /* ---- left -> right: fix the left index sets I[1..d-1] ---------------------------------- */
+        for (uint32_t k = 0; k + 1 < d; k++) {
+            const size_t rk = c->r[k], rk1 = c->r[k + 1], N = c->n[k], m = rk * N;
+            rc = eval_core(c, k, f, arg, dv, fi, vals, T, &nfib);
+            if (rc) goto done;
+            memcpy(Q, T, m * rk1 * sizeof(double));                 /* unfolding (a,j) x b is already column-major */
+            qr_explicit_q(Q, m, rk1, work);
+            if (maxvol(Q, m, rk1, P, B, work)) { rc = C3SC_ENUMERIC; goto done; }
+            for (size_t b = 0; b < rk1; b++) {                      /* new left set: row (a,j) = a + j*rk */
+                const size_t a = P[b] % rk, j = P[b] / rk;
+                for (uint32_t i = 0; i < k; i++) tmpI[b * d + i] = c->I[k][a * d + i];
+                tmpI[b * d + k] = (int32_t)j;
+            }
+            for (size_t b = 0; b < rk1; b++)
+                for (uint32_t i = 0; i <= k; i++) c->I[k + 1][b * d + i] = tmpI[b * d + i];
+            store_core(B, rk, N, rk1, cores[k]);
+        }
+        rc = eval_core(c, d - 1, f, arg, dv, fi, vals, T, &nfib);
+        if (rc) goto done;
+        store_core(T, c->r[d - 1], c->n[d - 1], 1, cores[d - 1]);
+        /* ---- right -> left: fix the right index sets J[1..d-1] ---------------------------------- */
+        for (uint32_t k = d - 1; k >= 1; k--) {
+            const size_t rk = c->r[k], rk1 = c->r[k + 1], N = c->n[k], m = N * rk1;
+            rc = eval_core(c, k, f, arg, dv, fi, vals, T, &nfib);
+            if (rc) goto done;
+            for (size_t a = 0; a < rk; a++)                         /* transpose: rows (j,b) = j + b*N, cols a */
+                for (size_t j = 0; j < N; j++)
+                    for (size_t b = 0; b < rk1; b++) Q[(j + b * N) + a * m] = T[a + j * rk + b * rk * N];
+            qr_explicit_q(Q, m, rk, work);
+            if (maxvol(Q, m, rk, P, B, work)) { rc = C3SC_ENUMERIC; goto done; }
+            for (size_t a = 0; a < rk; a++) {
+                const size_t j = P[a] % N, b = P[a] / N;
+                tmpI[a * d + k] = (int32_t)j;
+                for (uint32_t i = k + 1; i < d; i++) tmpI[a * d + i] = c->J[k + 1][b * d + i];
+            }
+            for (size_t a = 0; a < rk; a++)
+                for (uint32_t i = k; i < d; i++) c->J[k][a * d + i] = tmpI[a * d + i];
+            for (size_t a = 0; a < rk; a++)                         /* back to [a][j][b] */
+                for (size_t j = 0; j < N; j++)
+                    for (size_t b = 0; b < rk1; b++) T[a + j * rk + b * rk * N] = B[(j + b * N) + a * m];
+            store_core(T, rk, N, rk1, cores[k]);
+        }
+        rc = eval_core(c, 0, f, arg, dv, fi, vals, T, &nfib);
+        if (rc) goto done;
+        store_core(T, 1, c->n[0], c->r[1], cores[0]);
+        /* ---- change of the train against the previous sweep pair (valuef_norm2diff idea) -------- */
+        {
+            double *w1 = work, *w2 = work + rmax * rmax;
+            const double aa = tt_dot(d, c->n, c->r, cores, cores, w1, w2);
+            const double ab = tt_dot(d, c->n, c->r, cores, prev, w1, w2);
+            const double bb = tt_dot(d, c->n, c->r, prev, prev, w1, w2);
+            const double diff2 = aa - 2.0 * ab + bb;
+            change = aa > 0.0 ? sqrt(fabs(diff2) / aa) : 0.0;
+            if (verbose) fprintf(stderr, "c3sc_cross: sweep %u, |T|=%g, rel change %g, fibers %llu\n", it, sqrt(aa), change, (unsigned long long)nfib);
+            for (uint32_t k = 0; k < d; k++) memcpy(prev[k], cores[k], c->r[k] * c->n[k] * c->r[k + 1] * sizeof(double));
+            if (tol > 0.0 && change < tol) break;
+        }
+    }
+done:
+    if (nfibers) *nfibers = nfib;
+    if (rel_change) *rel_change = change;
+    if (prev) for (uint32_t k = 0; k < d; k++) free(prev[k]);
+    free(prev); free(dv); free(fi); free(vals); free(T); free(Q); free(B); free(P); free(work); free(tmpI);
+    return rc;
+}
+
+/* ---- the GPU operators behind the driver ---------------------------------------------------------- */
+struct vi_ctx { c3sc_problem *p; const c3sc_valuef *vf; };
+static int vi_cb(size_t F, const int32_t *dv, const int32_t *fi, size_t ldo, double *out, void *arg)
+{
+    struct vi_ctx *x = (struct vi_ctx *)arg;
+    return c3sc_vi_batch(x->p, x->vf, F, dv, fi, ldo, out, NULL);
+}
+
+struct pi_ctx { c3sc_problem *p; const c3sc_valuef *pol, *iter; double *rows; size_t cap; };
+static int pi_cb(size_t F, const int32_t *dv, const int32_t *fi, size_t ldo, double *out, void *arg)
+{
+    struct pi_ctx *x = (struct pi_ctx *)arg;
+    /* the index sets move between sweeps, so the policy rows are rebuilt for every request
+       (improvement against `pol`, evaluation against `iter`, src/bellman.c:1831-1871) */
+    return c3sc_pi_batch(x->p, x->pol, x->iter, F, dv, fi, ldo, 0, x->rows, NULL, out);
+}
+
+/* one c3control_step_pi (src/bellman.c:2214-2262): next = cross(bellman_pi(.; policy of vf_policy, vf_iter)) */
+int c3sc_cross_run_pi(c3sc_cross *c, c3sc_problem *p, const c3sc_valuef *vf_policy, const c3sc_valuef *vf_iter,
+                      uint32_t dx, const c3sc_cross_opts *opts, double *const *cores, uint64_t *nfibers, double *rel_change)
+{
+    size_t fmax = 1;
+    for (uint32_t k = 0; k < c->d; k++)
+        if (c->r[k] * c->r[k + 1] > fmax) fmax = c->r[k] * c->r[k + 1];
+    struct pi_ctx x = {p, vf_policy, vf_iter, NULL, 0};
+    x.rows = (double *)malloc(fmax * c->nmax * (2 * (size_t)dx + 3) * sizeof(double));
+    if (!x.rows) return C3SC_EINVAL;
+    int rc = c3sc_cross_run(c, pi_cb, &x, opts, cores, nfibers, rel_change);
+    free(x.rows);
+    return rc;
+}
+
+/* one c3control_step_vi (src/bellman.c:2177-2211): next = cross(bellman_vi(.; vf)) */
+int c3sc_cross_run_vi(c3sc_cross *c, c3sc_problem *p, const c3sc_valuef *vf, const c3sc_cross_opts *opts,
+                      double *const *cores, uint64_t *nfibers, double *rel_change)
+{
+    struct vi_ctx x = {p, vf};
+    return c3sc_cross_run(c, vi_cb, &x, opts, cores, nfibers, rel_change);
+}

@@ -1,0 +1,49 @@
+/* c3sc_cross.h -- host cross-approximation driver with BATCHED fiber requests.
+ *
+ * Replaces, for the Bellman path, what the reference obtains from the (un-vendored) C3 library in
+ * valuef_interp (src/valuefunc.c:603-767): ftapprox_cross on a nodal (LINELM) discretisation,
+ * maxiter 5, index sets started from uniform_stride (src/util.c:995-1006).  The operator handed to
+ * the driver is called once per CORE with all r_k*r_{k+1} fibers of that core, instead of once per
+ * fiber (bellman_vi's signature, src/bellman.h:96); the result is in ValueF::cores layout
+ * (src/valuefunc.c:165-189) and goes straight into c3sc_valuef_update.
+ */
+#ifndef C3SC_CROSS_H
+#define C3SC_CROSS_H
+#include "c3sc_b200.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* F fibers (dim_vary[F], fixed_ind[F*d]) -> out[F*ldo]; 0 on success.  Same contract as c3sc_vi_batch. */
+typedef int (*c3sc_fiber_batch_fn)(size_t F, const int32_t *dim_vary, const int32_t *fixed_ind, size_t ldo,
+                                   double *out, void *arg);
+
+typedef struct c3sc_cross_opts {
+    uint32_t maxiter;     /* sweep pairs (left->right + right->left); 0 = the reference's 5 */
+    double tol;           /* stop when the relative change of the train drops below it; 0 = run maxiter */
+    int verbose;
+} c3sc_cross_opts;
+
+typedef struct c3sc_cross c3sc_cross;   /* ranks + left/right index sets, kept between value-iteration steps */
+
+/* ranks[d+1] with ranks[0] = ranks[d] = 1 (clipped to what the unfoldings allow) */
+int  c3sc_cross_create(uint32_t d, const uint64_t *n, const uint64_t *ranks, c3sc_cross **out);
+void c3sc_cross_destroy(c3sc_cross *c);
+int  c3sc_cross_ranks(const c3sc_cross *c, uint64_t *ranks);
+
+/* cores[k]: caller-allocated n[k]*r[k]*r[k+1] doubles.  nfibers / rel_change may be NULL. */
+int c3sc_cross_run(c3sc_cross *c, c3sc_fiber_batch_fn f, void *arg, const c3sc_cross_opts *opts,
+                   double *const *cores, uint64_t *nfibers, double *rel_change);
+
+/* c3control_step_vi / c3control_step_pi (src/bellman.c:2177-2262) on the GPU path */
+int c3sc_cross_run_vi(c3sc_cross *c, c3sc_problem *p, const c3sc_valuef *vf, const c3sc_cross_opts *opts,
+                      double *const *cores, uint64_t *nfibers, double *rel_change);
+int c3sc_cross_run_pi(c3sc_cross *c, c3sc_problem *p, const c3sc_valuef *vf_policy, const c3sc_valuef *vf_iter,
+                      uint32_t dx, const c3sc_cross_opts *opts, double *const *cores, uint64_t *nfibers,
+                      double *rel_change);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* C3SC_CROSS_H */

@@ -1,0 +1,101 @@
+"""The host cross driver (include/c3sc_cross.h): CPU tests of the driver itself on analytic
+tensors, and the end-to-end parity bar of BASELINE.json -- value iteration through the SAME driver
+with the GPU operator and with the CPU oracle must agree to 1e-10 (sup norm, held-out points)."""
+import numpy as np
+import pytest
+
+from c3sc_b200 import capi, configs, synthetic
+from oracle import pyoracle as po
+from helpers import make_port
+
+
+def _tt_full(n, ranks, cores):
+    """dense tensor of a train in ValueF::cores layout"""
+    d = len(n)
+    out = np.ones((1, 1))
+    for k in range(d):
+        g = np.asarray(cores[k]).reshape(int(n[k]), int(ranks[k + 1]), int(ranks[k])).transpose(2, 0, 1)   # [a][j][b]
+        out = np.tensordot(out, g, axes=([-1], [0]))
+    return out.reshape([int(x) for x in n])
+
+
+def test_cross_recovers_low_rank_tensor():
+    """a tensor of exact TT rank 3 is reproduced to round-off with ranks >= 3"""
+    n = [9, 7, 8, 6]
+    grids = [np.linspace(-1, 1, m) for m in n]
+    X = np.meshgrid(*grids, indexing="ij")
+    full = np.sin(X[0] + X[1] + X[2] + X[3]) + 0.3 * X[0] * X[3]          # rank <= 2 + 1
+
+    def fn(dv, fi):
+        F = len(dv)
+        out = np.zeros((F, max(n)))
+        for f in range(F):
+            idx = [int(v) for v in fi[f]]
+            k = int(dv[f])
+            for j in range(n[k]):
+                idx[k] = j
+                out[f, j] = full[tuple(idx)]
+        return out
+    cr = capi.Cross(n, [1, 4, 4, 4, 1])
+    cores, nfib, change = cr.run(fn, maxiter=3)
+    approx = _tt_full(n, cr.ranks, cores)
+    assert np.abs(approx - full).max() <= 1e-11 * np.abs(full).max()
+    assert nfib == 3 * 2 * (4 + 16 + 16 + 4)
+    assert change < 1e-6          # the norm-difference formula bottoms out at sqrt(eps)
+    cr.close()
+
+
+def test_cross_batches_are_whole_cores():
+    """every operator call asks for r_k * r_{k+1} fibers that all vary the same dimension"""
+    n = [6, 5, 7]
+    seen = []
+
+    def fn(dv, fi):
+        seen.append((len(dv), set(int(v) for v in dv)))
+        return np.ones((len(dv), max(n)))
+    cr = capi.Cross(n, [1, 3, 2, 1])
+    cr.run(fn, maxiter=1)
+    sizes = {0: 3, 1: 6, 2: 2}
+    assert all(len(ks) == 1 and F == sizes[next(iter(ks))] for F, ks in seen)
+    cr.close()
+
+
+def test_rank_is_clipped_to_unfolding():
+    cr = capi.Cross([3, 50, 50], [1, 10, 10, 1])
+    assert list(cr.ranks) == [1, 3, 10, 1]
+    cr.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name,n,rank,dx,iters", [("lqg2d_reflect", 24, 6, None, 6), ("lqgnd", 12, 4, 4, 4),
+                                                    ("dubinscar_new", 14, 5, None, 4)])
+def test_value_iteration_gpu_equals_oracle(gpu, name, n, rank, dx, iters):
+    """north_star: the value function after K value-iteration steps matches the CPU reference
+    restatement within 1e-10 in sup norm on a held-out (off-grid) point set."""
+    cfg = configs.get_config(name, n=n, rank=rank, dx=dx)
+    prob = capi.Problem(cfg, arith=1)
+    port = make_port(cfg)
+    ranks, cores0 = synthetic.quadratic_cores(prob.xgrid) if cfg.model == configs.MODEL_LQGND else (cfg.ranks(), synthetic.random_cores(cfg.ngrid, cfg.ranks()))
+    cr_g = capi.Cross(cfg.ngrid, cfg.ranks())
+    cr_o = capi.Cross(cfg.ngrid, cfg.ranks())
+    cg, co = cores0, cores0
+    rg = ro = np.asarray(ranks, dtype=np.uint64)
+    vf = None
+    for it in range(iters):
+        if vf is not None:
+            vf.close()
+        vf = capi.ValueF(cfg.ngrid, rg, cg)
+        cg, _, _ = cr_g.run_vi(prob, vf, maxiter=2)
+        rg = cr_g.ranks
+        ft_o = po.FT(cfg.ngrid, ro, co)
+        co, _, _ = cr_o.run(lambda dv, fi: port.vi_batch(ft_o, dv, fi)[0], maxiter=2)
+        ro = cr_o.ranks
+    # held-out grid: random off-grid points, piecewise-linear FT evaluation (valuef_eval, src/valuefunc.c:345-350)
+    ft_g, ft_o = po.FT(cfg.ngrid, rg, cg), po.FT(cfg.ngrid, ro, co)
+    u = synthetic.uniform01(77, 400 * cfg.dx).reshape(400, cfg.dx)
+    pts = cfg.lb + u * (cfg.ub - cfg.lb)
+    vg = np.array([port.ft_eval_linear(ft_g, np.ascontiguousarray(x)) for x in pts])
+    vo = np.array([port.ft_eval_linear(ft_o, np.ascontiguousarray(x)) for x in pts])
+    scale = max(np.abs(vo).max(), 1.0)
+    assert np.abs(vg - vo).max() <= 1e-10 * scale, np.abs(vg - vo).max() / scale
+    prob.close(); vf.close(); cr_g.close(); cr_o.close()

@@ -1,0 +1,101 @@
+"""GPU parity of the stage-1 code paths the standard configs do not reach by themselves:
+the general (rank > 32) kernel, odd and mixed ranks on the tensor-core path, group sizes that do
+not fill a DMMA tile, chunked batches, and the device-buffer + commit route of the cores."""
+import numpy as np
+import pytest
+
+from c3sc_b200 import capi, configs, synthetic
+from oracle import pyoracle as po
+from helpers import make_port, rel_err, valid_mask
+
+pytestmark = pytest.mark.gpu
+RTOL = 1e-12
+
+
+def _check_costs_and_values(cfg, ranks, F, seed=5, face_frac=0.2):
+    prob = capi.Problem(cfg, arith=1)
+    port = make_port(cfg)
+    cores = synthetic.random_cores(cfg.ngrid, ranks)
+    ft = po.FT(cfg.ngrid, ranks, cores)
+    vf = capi.ValueF(cfg.ngrid, ranks, cores)
+    dv, fi = synthetic.random_fibers(cfg.ngrid, F, seed=seed, face_frac=face_frac)
+    out = prob.vi_batch_debug(vf, dv, fi)
+    oval, oarg = port.vi_batch(ft, dv, fi)
+    m = valid_mask(cfg, dv)
+    for f in range(len(dv)):
+        N = int(cfg.ngrid[dv[f]])
+        ab, nv, nf = port.fiber_neighbors(dv[f], fi[f])
+        assert np.array_equal(out["absorbed"][f, :N], ab), f
+        assert np.array_equal(out["nbr_vary"][f, :N], nv), f
+        _, costs = port.neighbor_costs(ft, dv[f], fi[f])
+        assert rel_err(out["costs"][f, :N], costs, scale=np.abs(costs).max()) <= RTOL, f
+    assert rel_err(out["value"][m], oval[m], scale=np.abs(oval[m]).max()) <= RTOL
+    assert (out["argmin"][m] == oarg[m]).mean() > 0.99
+    prob.close(); vf.close()
+
+
+@pytest.mark.parametrize("name,n,rank", [("dubinscar_new", 14, 40), ("lqgnd_reflect", 10, 36), ("double_int", 48, 40)])
+def test_general_kernel_large_ranks(gpu, name, n, rank):
+    """ranks above 32 take k_ft_costs (shared-memory staged DFMA kernel), not the DMMA pair"""
+    cfg = configs.get_config(name, n=n, rank=rank, dx=4 if name.startswith("lqgnd") else None)
+    _check_costs_and_values(cfg, cfg.ranks(), 40)
+
+
+@pytest.mark.parametrize("rank", [1, 5, 7, 9, 15, 17, 23, 25, 31, 32])
+def test_tensor_core_path_rank_sweep(gpu, rank):
+    """every DMMA instantiation (RMAX 8/16/24/32), ranks that are not multiples of the 8x8x4 tile"""
+    cfg = configs.get_config("skidding5d", n=12, rank=rank)
+    _check_costs_and_values(cfg, cfg.ranks(), 24)
+
+
+def test_mixed_ranks_and_ragged_groups(gpu):
+    """different rank per core; fiber counts that leave partial groups for some dim_vary"""
+    cfg = configs.get_config("lqgnd", n=9, dx=6)
+    ranks = np.array([1, 3, 8, 5, 12, 2, 1], dtype=np.uint64)
+    for F in (1, 3, 13, 67):
+        _check_costs_and_values(cfg, ranks, F, seed=F)
+
+
+def test_large_batch_is_chunked_consistently(gpu):
+    """a batch larger than one pipeline chunk gives the same numbers as its pieces"""
+    cfg = configs.get_config("lqgnd_reflect", n=20, rank=6, dx=8)
+    prob = capi.Problem(cfg, arith=1)
+    ranks = cfg.ranks()
+    cores = synthetic.random_cores(cfg.ngrid, ranks)
+    vf = capi.ValueF(cfg.ngrid, ranks, cores)
+    F = 60000                                   # 60000 * 20 * 17 * 8 B = 163 MB of cost scratch -> 2 chunks
+    dv, fi = synthetic.random_fibers(cfg.ngrid, F, seed=3)
+    val, arg = prob.vi_batch(vf, dv, fi)
+    for lo, hi in ((0, 500), (29990, 30400), (F - 300, F)):
+        v2, a2 = prob.vi_batch(vf, dv[lo:hi], fi[lo:hi])
+        assert np.array_equal(val[lo:hi], v2) and np.array_equal(arg[lo:hi], a2)
+    prob.close(); vf.close()
+
+
+def test_device_buffer_commit(gpu):
+    """cores written straight into the library's device buffer (what the NCCL broadcast does)
+    take effect after c3sc_valuef_commit"""
+    import torch
+    cfg = configs.get_config("dubinscar_new", n=16, rank=6)
+    prob = capi.Problem(cfg, arith=1)
+    ranks = cfg.ranks()
+    cores_a = synthetic.random_cores(cfg.ngrid, ranks, seed=1)
+    cores_b = synthetic.random_cores(cfg.ngrid, ranks, seed=2)
+    vf = capi.ValueF(cfg.ngrid, ranks, cores_a)
+    ref = capi.ValueF(cfg.ngrid, ranks, cores_b)
+    dv, fi = synthetic.random_fibers(cfg.ngrid, 50)
+    want, _ = prob.vi_batch(ref, dv, fi)
+    ptr, cnt = vf.device_buffer()
+
+    class _Arr:
+        def __init__(self, p, n):
+            self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<f8", "data": (p, False), "version": 3}
+    view = torch.as_tensor(_Arr(ptr, cnt), device="cuda")
+    flat = np.concatenate([np.asarray(c, dtype=np.float64).reshape(-1) for c in cores_b])
+    assert flat.size == cnt
+    view.copy_(torch.from_numpy(flat).cuda())
+    torch.cuda.synchronize()
+    vf.commit()
+    got, _ = prob.vi_batch(vf, dv, fi)
+    assert np.array_equal(got, want)
+    prob.close(); vf.close(); ref.close()
