@@ -14,7 +14,11 @@ value    node-backups/s, whole job, fiber descriptors + cores already resident i
 e2e      same metric through the host-buffer C-ABI call (c3sc_vi_batch): pinned host
          fiber descriptors in, values back out, copies inside the timed region
 roofline FP64 FMA pipe: achieved = node-backups/s x W (SURVEY §8(d) contract flops per
-         node-backup) against the DFMA peak measured in this run
+         node-backup) against the DFMA peak measured in this run.  One step = per chunk of the
+         batch three kernels of ours (k_ft_chains, k_ft_nodes, k_control2) after a 1-CTA grouping
+         kernel; their ncu numbers are in profiles/.
+vi_sweep seconds per synthetic VI sweep: 2 x d sequential core batches of r_k*r_{k+1} fibers,
+         the request pattern of the cross driver (include/c3sc_cross.h)
 """
 from __future__ import annotations
 
@@ -154,6 +158,16 @@ def run_reference(args, cfg, rank_ft):
     print(json.dumps(line))
 
 
+def ncu_traffic(F):
+    """dram__bytes_read.sum + dram__bytes_write.sum of one step, from the committed `ncu --set full`
+    capture (profiles/r01_traffic.json: bytes per fiber of the three pipeline kernels), or None."""
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
+        return float(t["dram_bytes_per_fiber"]) * F
+    except Exception:
+        return None
+
+
 def workload_config(cfg, rank_ft, F, args):
     return {"workload": f"{cfg.name}: d={cfg.dx} LQG, {cfg.n} nodes/dim, FT rank {rank_ft}, n_u={cfg.nu} "
                         f"({'x'.join(['3'] * cfg.du)} tensor grid of {{-1,0,1}}), {F} synthetic fibers/GPU/step "
@@ -177,7 +191,7 @@ def main():
     ap.add_argument("--ref-fibers", type=int, default=48, help="fibers per step of the CPU reference arm")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--sweep", action="store_true", help="also time one synthetic VI sweep (2 x d core batches)")
+    ap.add_argument("--no-sweep", action="store_true", help="skip the synthetic VI sweep (2 x d core batches, one launch set per core)")
     args = ap.parse_args()
 
     from c3sc_b200 import configs, synthetic
@@ -334,14 +348,14 @@ def main():
                     "ms_per_step": ms_e2e / e2e_steps, "api": "c3sc_vi_batch (host buffers, pinned)"},
             "gpu_launches": int(launches),
             "roofline": {"bound": "fp64", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                         "traffic": None, "flops_per_node_backup": W,
+                         "traffic": ncu_traffic(F), "flops_per_node_backup": W,
                          "peak_source": "DFMA loop measured in this run (c3sc_measure_fp64_peak); MEASURED_PEAKS.json has no FP64 figure",
                          "hbm": {"algorithmic_bytes_per_step": hbm_bytes, "achieved_gbs": hbm_bytes / (kernel_ms * 1e-3) / 1e9,
                                  "peak_gbs": hbm_peak, "frac": hbm_bytes / (kernel_ms * 1e-3) / 1e9 / hbm_peak,
                                  "note": "not binding: cores stay in L2/SMEM, HBM sees descriptors in and values out"}},
         }
 
-    if args.sweep and world == 1:
+    if not args.no_sweep and world == 1:
         batches = synthetic.sweep_fibers(cfg.ngrid, ranks)
         dev_b = [(torch.from_numpy(a).to(dev), torch.from_numpy(b).to(dev), len(a)) for a, b in batches]
 

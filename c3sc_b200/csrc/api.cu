@@ -102,6 +102,8 @@ struct c3sc_problem {
     double *d_xgrid = nullptr, *d_obs = nullptr, *d_utab = nullptr, *d_ctab = nullptr;
     int *d_err = nullptr;
     cudaStream_t stream = nullptr;           // host-buffer entry points run here
+    cudaStream_t copy_stream = nullptr;      // device->host copies of finished chunks
+    cudaEvent_t chunk_done = nullptr;
     DevBuf b_dv, b_fi, b_val, b_arg, b_abs, b_costs, b_rows, b_nv, b_nf, b_misc[8];
 };
 
@@ -193,6 +195,8 @@ int c3sc_problem_create(const c3sc_problem_desc *d, c3sc_problem **out)
     CKP(cudaMalloc(&p->d_err, sizeof(int)));
     CKP(cudaMemset(p->d_err, 0, sizeof(int)));
     CKP(cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking));
+    CKP(cudaStreamCreateWithFlags(&p->copy_stream, cudaStreamNonBlocking));
+    CKP(cudaEventCreateWithFlags(&p->chunk_done, cudaEventDisableTiming));
     P.xgrid = p->d_xgrid; P.obs = p->d_obs; P.utab = p->d_utab; P.err = p->d_err;
     // candidate table of separable models (row stride 2*NUD+2; NUD = dx/2 for LQG, 1 otherwise)
     {
@@ -263,6 +267,8 @@ void c3sc_problem_destroy(c3sc_problem *p)
     for (DevBuf &b : p->b_misc) b.release();
     p->scr.release();
     if (p->stream) cudaStreamDestroy(p->stream);
+    if (p->copy_stream) cudaStreamDestroy(p->copy_stream);
+    if (p->chunk_done) cudaEventDestroy(p->chunk_done);
     delete p;
 }
 
@@ -373,6 +379,11 @@ struct BatchArgs {
     const double *rows_in;                // MODE_PI_EVAL
     const int *nbr_fixed_in, *nbr_vary_in;
     int mode;
+    // host-buffer entries: copy each chunk's results out on a second stream while the next chunk computes
+    cudaStream_t copy_stream;
+    cudaEvent_t chunk_done;
+    double *h_value;
+    int32_t *h_argmin;
 };
 
 static size_t g_chunk_bytes = (size_t)96 << 20;    // slot-major cost scratch per chunk: stays inside the 126 MB L2
@@ -439,6 +450,12 @@ static int run_batch(const DevProblem &P, int model, int arith, Scratch &scr, co
         if (rc == -1) return fail(C3SC_EUNSUPPORTED, "model %d with dx=%d is not instantiated", model, P.dx);
         if (rc != 0) return fail(C3SC_ECUDA, "control kernel launch: %s", cudaGetErrorString((cudaError_t)rc));
         g_launches++;
+        if (b.copy_stream && b.chunk_done) {
+            CK(cudaEventRecord(b.chunk_done, st));
+            CK(cudaStreamWaitEvent(b.copy_stream, b.chunk_done, 0));
+            if (b.h_value && c.value) CK(cudaMemcpyAsync(b.h_value + n0, c.value, Fc * b.ldo * 8, cudaMemcpyDeviceToHost, b.copy_stream));
+            if (b.h_argmin && c.argmin) CK(cudaMemcpyAsync(b.h_argmin + n0, c.argmin, Fc * b.ldo * 4, cudaMemcpyDeviceToHost, b.copy_stream));
+        }
     }
     return C3SC_OK;
 }
@@ -578,10 +595,15 @@ int c3sc_vi_batch(c3sc_problem *p, const c3sc_valuef *vf, size_t F, const int32_
     o.value = (double *)p->b_val.p;
     if (argmin) { bad |= p->b_arg.reserve(n * 4); o.argmin = (int32_t *)p->b_arg.p; }
     if (bad) return fail(C3SC_ECUDA, "cudaMalloc batch outputs failed");
-    rc = c3sc_vi_batch_dev(p, vf, F, (const int32_t *)p->b_dv.p, (const int32_t *)p->b_fi.p, ldo, &o, p->stream);
+    BatchArgs b;
+    memset(&b, 0, sizeof b);
+    b.F = F; b.ldo = ldo; b.dim_vary = (const int *)p->b_dv.p; b.fixed_ind = (const int *)p->b_fi.p;
+    b.out.value = o.value; b.out.argmin = o.argmin;
+    b.mode = MODE_VI;
+    b.copy_stream = p->copy_stream; b.chunk_done = p->chunk_done; b.h_value = value; b.h_argmin = argmin;
+    rc = run_batch(p->P, p->model, p->arith, p->scr, &p->grp, vf->ft, b, p->stream);
     if (rc) return rc;
-    CK(cudaMemcpyAsync(value, o.value, n * 8, cudaMemcpyDeviceToHost, p->stream));
-    if (argmin) CK(cudaMemcpyAsync(argmin, o.argmin, n * 4, cudaMemcpyDeviceToHost, p->stream));
+    CK(cudaStreamSynchronize(p->copy_stream));
     return finish(p);
 }
 
