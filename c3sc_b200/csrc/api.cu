@@ -416,7 +416,7 @@ static int run_batch(const DevProblem &P, int model, int arith, Scratch &scr, co
         a.perm = (const int *)scr.perm.p; a.kcount = cnt; a.kstart = cnt + 16;
         a.NS = (long long)(Fc * b.ldo);
         a.cst = need_cst ? (double *)scr.cst.p : nullptr;
-        a.flag = need_cst ? (signed char *)scr.flag.p : nullptr;
+        a.flag = (signed char *)scr.flag.p;
         a.act = b.mode == MODE_VI ? (int *)scr.act.p : nullptr;
         a.act_count = cnt + 32;
         a.costs = b.out.costs ? b.out.costs + n0 * CS : nullptr;

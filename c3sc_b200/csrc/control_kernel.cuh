@@ -217,6 +217,26 @@ __device__ __forceinline__ void node_state(const CtlArgs &c, int id, double *x)
     for (int i = 0; i < DX; i++) x[i] = c.P.xgrid[c.P.xoff[i] + (i == k ? j : c.fixed_ind[(size_t)f * DX + i])];
 }
 
+// Neighbour values of node `id` from the slot-major scratch.  Stage 1 stores the fixed-dimension
+// neighbours and the node's own value (slot 2dx); the two neighbours ALONG the fiber are the own
+// values of other nodes of the same fiber (valuefunc.c:514-519) and are fetched here.
+template <int DX>
+__device__ __forceinline__ void load_costs(const CtlArgs &c, int id, double *cc)
+{
+    const int f = id / c.ldo, j = id - f * c.ldo;
+    const int k = c.dim_vary[f];
+    int lo, hi;
+    ft_vary_pair(c.P.bc[k], c.P.ngrid[k], j, c.flag[id], lo, hi);
+    const double *self = c.cst + (size_t)(2 * DX) * c.NS + (size_t)f * c.ldo;
+    const double vlo = self[lo], vhi = self[hi];
+#pragma unroll
+    for (int i = 0; i < DX; i++) {
+        cc[2 * i] = i == k ? vlo : c.cst[(size_t)(2 * i) * c.NS + id];
+        cc[2 * i + 1] = i == k ? vhi : c.cst[(size_t)(2 * i + 1) * c.NS + id];
+    }
+    cc[2 * DX] = self[j];
+}
+
 // ---------------------------------------------------------------------------
 template <class M, class A>
 __global__ void __launch_bounds__(CT_NT, 3) k_control(const CtlArgs c)
@@ -252,8 +272,7 @@ __global__ void __launch_bounds__(CT_NT, 3) k_control(const CtlArgs c)
         const int c0 = part * chunk, c1 = valid ? ((c0 + chunk < P.nu) ? c0 + chunk : P.nu) : c0;
         double x[DX], cc[CS];
         node_state<DX>(c, id, x);
-#pragma unroll
-        for (int m = 0; m < CS; m++) cc[m] = c.cst[(size_t)m * c.NS + id];
+        load_costs<DX>(c, id, cc);
         double best = CUDART_INF;
         int ibest = 0x7fffffff;
         if (TAB) {
@@ -423,8 +442,9 @@ __device__ __forceinline__ void node2_prepare(const CtlArgs &c, int id, Node2<M>
 {
     constexpr int DX = M::DX, DU = M::DU, NUD = M::NUD;
     const DevProblem &P = c.P;
-    double x[DX], u0[DU], b0[DX], s0[DX];
+    double x[DX], u0[DU], b0[DX], s0[DX], cc[2 * DX + 1];
     node_state<DX>(c, id, x);
+    load_costs<DX>(c, id, cc);
 #pragma unroll
     for (int i = 0; i < DU; i++) u0[i] = P.utab[i];
     M::template drift<Fast>(x, u0, P.mp, b0);
@@ -432,7 +452,7 @@ __device__ __forceinline__ void node2_prepare(const CtlArgs &c, int id, Node2<M>
     double norm0 = 0.0, S0 = 0.0;
 #pragma unroll
     for (int i = 0; i < DX; i++) {
-        const double cl = c.cst[(size_t)(2 * i) * c.NS + id], cr = c.cst[(size_t)(2 * i + 1) * c.NS + id];
+        const double cl = cc[2 * i], cr = cc[2 * i + 1];
         const double q = (P.t[2 * i + 1] * 0.5) * (s0[i] * s0[i]);
         double rl = q, rr = q;
         if (!M::u_dep(i)) {
@@ -468,15 +488,15 @@ __global__ void __launch_bounds__(CT_NT, C3SC_C2_MINB) k_control2(const CtlArgs 
     extern __shared__ __align__(16) double smem[];
     {
         const int cnt = P.nu * CTW;
-        for (int e = tid; e < cnt; e += CT_NT) smem[e] = P.gtab[e];
+        for (int e = tid; e < cnt; e += (int)blockDim.x) smem[e] = P.gtab[e];
         __syncthreads();
     }
     const double *tab = smem;
     const int nact = *c.act_count, nhalf = (nact + 1) >> 1;
-    const long long stride = (long long)gridDim.x * CT_NT;
+    const long long stride = (long long)gridDim.x * blockDim.x;      // launched with 256 or (small batches) 128 threads
     const double nbh = -P.beta * P.h2;
     const bool disc = P.beta != 0.0;
-    for (long long it0 = (long long)blockIdx.x * CT_NT + (tid & ~31); it0 < nhalf; it0 += stride) {
+    for (long long it0 = (long long)blockIdx.x * blockDim.x + (tid & ~31); it0 < nhalf; it0 += stride) {
         const int it = (int)it0 + lane;
         const bool validA = it < nhalf, validB = it + nhalf < nact;
         const int idA = c.act[validA ? it : 0], idB = c.act[validB ? it + nhalf : (validA ? it : 0)];
@@ -542,7 +562,7 @@ __global__ void __launch_bounds__(CT_NT, C3SC_C2_MINB) k_control2(const CtlArgs 
         }
     }
     // absorbed nodes (bellman.c:513-532): boundary / obstacle cost, u = 0
-    for (long long id = (long long)blockIdx.x * CT_NT + tid; id < c.NS; id += stride) {
+    for (long long id = (long long)blockIdx.x * blockDim.x + tid; id < c.NS; id += stride) {
         const int ab = c.flag[id];
         if (ab != 1 && ab != -1) continue;
         double x[DX];
@@ -575,8 +595,9 @@ __global__ void __launch_bounds__(CT_NT) k_pi_eval(const CtlArgs c)
         } else {
             const double *row = c.rows_in + (size_t)id * RW;
             double prob[CS], cc[CS];
+            load_costs<DX>(c, (int)id, cc);
 #pragma unroll
-            for (int m = 0; m < CS; m++) { prob[m] = row[m]; cc[m] = c.cst[(size_t)m * c.NS + id]; }
+            for (int m = 0; m < CS; m++) prob[m] = row[m];
             v = rhs<DX, A>(P, prob, row[CS], row[CS + 1], cc);
         }
         c.value[id] = v;
@@ -654,24 +675,28 @@ int launch_control_t(const CtlArgs &c_in, int pi_eval, cudaStream_t st)
     }
     // candidate chunks per node: enough (node, chunk) items to occupy every SM; 1 for large batches
     int pl2 = 0;
-    while (pl2 < 5 && (c.NS << pl2) < (long long)info.sms * CT_NT * 4 && (2 << pl2) <= c.P.nu) pl2++;
+    while (pl2 < 5 && (c.NS << pl2) < (long long)info.sms * CT_NT * 8 && (2 << pl2) <= c.P.nu) pl2++;
     c.parts_log2 = pl2;
-    if (TAB && c.ng > 0 && pl2 == 0) {          // large batch of a separable model: two nodes per thread
+    if (TAB && c.ng > 0 && c.NS >= (long long)info.sms * 128) {
+        // separable model, at least ~a warp pair of nodes per SM: two nodes per thread walk the whole
+        // grouped table (no per-chunk re-derivation of the node invariants); 128-thread CTAs while the
+        // batch is too small to give every SM a 256-thread one
         static size_t attr2 = 48 * 1024;
         if (smem > attr2) {
             cudaError_t e2 = cudaFuncSetAttribute(k_control2<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             if (e2 != cudaSuccess) return (int)e2;
             attr2 = smem;
         }
+        const int nt2 = (c.NS / 2 >= (long long)info.sms * 2 * CT_NT) ? CT_NT : 128;
         int per2 = 1;
-        cudaError_t e2 = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per2, k_control2<M>, CT_NT, smem);
+        cudaError_t e2 = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per2, k_control2<M>, nt2, smem);
         if (e2 != cudaSuccess) return (int)e2;
         if (per2 < 1) per2 = 1;
-        long long need2 = ((c.NS + 1) / 2 + CT_NT - 1) / CT_NT;
+        long long need2 = ((c.NS + 1) / 2 + nt2 - 1) / nt2;
         long long g2 = (long long)info.sms * per2;
         if (g2 > need2) g2 = need2;
         if (g2 < 1) return 0;
-        k_control2<M><<<(int)g2, CT_NT, smem, st>>>(c);
+        k_control2<M><<<(int)g2, nt2, smem, st>>>(c);
         return (int)cudaGetLastError();
     }
     int per_sm = 1;

@@ -51,6 +51,22 @@ struct DevOut {
     int *nbr_fixed;
 };
 
+// neighbour pair of node j ALONG the fiber (nodeutil.c:570-624); ab = the node's flag after the
+// end-node overwrite (0 / 1 / -1).  Interior absorbed nodes point at themselves.
+__host__ __device__ inline void ft_vary_pair(int bk, int N, int j, int ab, int &lo, int &hi)
+{
+    lo = j - 1; hi = j + 1;
+    if (j == 0) {
+        if (bk == C3SC_ABSORB)       { lo = 0; hi = 0; }
+        else if (bk == C3SC_REFLECT) { lo = 0; hi = 1; }
+        else                         { lo = N - 2; hi = 1; }
+    } else if (j == N - 1) {
+        if (bk == C3SC_ABSORB)       { lo = N - 1; hi = N - 1; }
+        else if (bk == C3SC_REFLECT) { lo = N - 2; hi = N - 1; }
+        else                         { lo = N - 2; hi = 1; }
+    } else if (ab != 0) { lo = j; hi = j; }
+}
+
 // implemented in inst_misc.cu; returns cudaError_t as int, or -1 if dx is not instantiated
 int launch_transition(int arith, const DevProblem &P, int n, const double *drift, const double *sig,
                       double *prob, double *dt, int *status, void *stream);

@@ -98,16 +98,22 @@ static int launch_mma_t(const FtArgs &a, cudaStream_t st)
         attr = smem;
     }
     const int grid = (a.F + a.FB - 1) / a.FB + a.ft.d;
-    k_ft_nodes<RMAX><<<grid, FTN_NT, smem, st>>>(a, a.sets);
+    // small batches: several CTAs per group, each a range of node tiles, until the machine is covered twice
+    FtArgs b = a;
+    int ntl = 1;
+    for (int k = 0; k < a.ft.d; k++) { const int t = (a.P.ngrid[k] + FTN_T - 1) / FTN_T; ntl = t > ntl ? t : ntl; }
+    b.nsplit = 1;
+    while (b.nsplit < ntl && grid * b.nsplit < 4 * g_sms) b.nsplit *= 2;
+    if (b.nsplit > ntl) b.nsplit = ntl;
+    k_ft_nodes<RMAX><<<dim3((unsigned)grid, (unsigned)b.nsplit), FTN_NT, smem, st>>>(b, b.sets);
     return (int)cudaGetLastError();
 }
 
 static int launch_ft_mma(FtArgs a, cudaStream_t st)
 {
-    // group size: 8 fibers fill the DMMA tile; fewer when the batch is too small to cover the SMs
-    int fb = FT_FBMAX;
-    while (fb > 1 && (a.F / fb) < 2 * g_sms) fb >>= 1;
-    a.FB = fb;
+    // group size: 8 fibers fill the DMMA tile (a tile costs the same for 1 fiber as for 8); small
+    // batches cover the SMs by splitting every group over node-tile ranges instead (nsplit)
+    a.FB = FT_FBMAX;
     int rmax = 1;
     for (int i = 0; i <= a.ft.d; i++) rmax = a.ft.r[i] > rmax ? a.ft.r[i] : rmax;
     if (rmax <= 8) return launch_mma_t<8>(a, st);
@@ -116,8 +122,20 @@ static int launch_ft_mma(FtArgs a, cudaStream_t st)
     return launch_mma_t<32>(a, st);
 }
 
-// Stage 1 over one chunk.  a.FB == 0: pick the group size here.  1 launch.
+static int launch_ft_stage(const FtArgs &a_in, cudaStream_t st);
+
+// Stage 1 over one chunk.  a.FB == 0: pick the group size here.
 int launch_ft_costs(const FtArgs &a_in, cudaStream_t st)
+{
+    int rc = launch_ft_stage(a_in, st);
+    if (rc || !a_in.costs || a_in.F <= 0) return rc;
+    long long g = (a_in.NS + 255) / 256;
+    if (g > 4096) g = 4096;
+    k_costs_along<<<(unsigned)g, 256, 0, st>>>(a_in);
+    return (int)cudaGetLastError();
+}
+
+static int launch_ft_stage(const FtArgs &a_in, cudaStream_t st)
 {
     ft_device_info();
     FtArgs a = a_in;

@@ -58,6 +58,7 @@ struct FtArgs {
     const int *nbr_fixed_in;  // caller-supplied neighbour indices (valuef_eval_fiber_ind_nn)
     const int *nbr_vary_in;
     double *sets;             // [F * ft_set_width] chain scratch of the tensor-core path; NULL = general kernel
+    int nsplit;               // k_ft_nodes: CTAs per group, each owning a contiguous range of node tiles (blockIdx.y)
 };
 
 __host__ __device__ inline int ft_even_up(int v) { return (v + 1) & ~1; }
@@ -72,7 +73,7 @@ __host__ __device__ inline int ft_tile_nodes(int rk, int rk1)
 // shared-memory carve-up; identical on host and device
 struct FtPlan {
     int d, FB, rs, nvt, tp, nmax;
-    int oSetA, oUni, oLt, oRt, oV, nDoubles;      // doubles
+    int oSetA, oUni, oLt, oRt, nDoubles;          // doubles
     int setDoubles, gTile, oW, oU;                // inside the union region
     int oFix, oNf, oFid, oWall, nInts;            // ints
     __host__ __device__ FtPlan(const DevFT &ft, int nmax_, int FB_)
@@ -102,16 +103,15 @@ struct FtPlan {
         o = ft_even_up(o);
         oLt = o; o += rs * FT_FBMAX;
         oRt = o; o += rs * FT_FBMAX;
-        oV = o;  o += FB * nmax;
         nDoubles = ft_even_up(o);
         int q = 0;
         oFix = q;  q += FB * d;
         oNf = q;   q += FB * 2 * d;
         oFid = q;  q += FT_FBMAX;
         oWall = q; q += FT_FBMAX;
-        nInts = q;                                 // then FB*2*nmax shorts (sNv) and FB*nmax bytes (sAbs)
+        nInts = q;                                 // then FB*nmax bytes (sAbs)
     }
-    __host__ __device__ size_t bytes() const { return (size_t)nDoubles * 8 + (size_t)nInts * 4 + (((size_t)FB * nmax * 5 + 7) & ~(size_t)7); }
+    __host__ __device__ size_t bytes() const { return (size_t)nDoubles * 8 + (size_t)nInts * 4 + (((size_t)FB * nmax + 7) & ~(size_t)7); }
 };
 
 #ifndef C3SC_FT_TYPES_ONLY
@@ -208,12 +208,13 @@ __device__ __forceinline__ bool ft_fixed_pair(const DevProblem &P, int i, int i0
 
 // descriptors, flags, neighbour indices of the nf fibers of a group (nodeutil.c:489-627).
 // Whole CTA; ends with a barrier.
-__device__ __forceinline__ void ft_flags_and_indices(const FtArgs &a, int k, int nf, int gstart, int *sFid, int *sWall,
-                                                     int *sFix, int *sNf, signed char *sAbs, short *sNv, int nmax)
+__device__ __forceinline__ void ft_flags_and_indices(const FtArgs &a, int k, int nf, int gstart, int jb, int je,
+                                                     int *sFid, int *sWall, int *sFix, int *sNf, signed char *sAbs, int nmax)
 {
+    // nodes [jb, je) of every fiber of the group; the CTA that owns node 0 also marks the padding entries
     const DevProblem &P = a.P;
     const int d = a.ft.d, tid = threadIdx.x, NT = blockDim.x;
-    const int N = P.ngrid[k];
+    const int N = P.ngrid[k], nj = je - jb;
     if (tid < FT_FBMAX) { sFid[tid] = tid < nf ? a.perm[gstart + tid] : -1; sWall[tid] = 0; }
     __syncthreads();
     for (int e = tid; e < nf * d; e += NT) {
@@ -233,14 +234,14 @@ __device__ __forceinline__ void ft_flags_and_indices(const FtArgs &a, int k, int
         }
         sNf[g * 2 * d + 2 * slot] = lo;
         sNf[g * 2 * d + 2 * slot + 1] = hi;
-        if (a.nbr_fixed) {
+        if (a.nbr_fixed && jb == 0) {
             a.nbr_fixed[(size_t)sFid[g] * 2 * (d - 1) + 2 * slot] = lo;
             a.nbr_fixed[(size_t)sFid[g] * 2 * (d - 1) + 2 * slot + 1] = hi;
         }
     }
     __syncthreads();
-    for (int e = tid; e < nf * N; e += NT) {
-        const int g = e / N, j = e - g * N;
+    for (int e = tid; e < nf * nj; e += NT) {
+        const int g = e / nj, j = jb + (e - g * nj);
         int ab = 0;
         for (int o = 0; o < P.nobs && ab == 0; o++) {                   // boundary.c:329-344,668-680
             const double *lb = P.obs + (size_t)o * 2 * d, *ub = lb + d;
@@ -252,27 +253,20 @@ __device__ __forceinline__ void ft_flags_and_indices(const FtArgs &a, int k, int
             if (inside) ab = -1;
         }
         if (sWall[g]) ab = 1;
-        int lo = j - 1, hi = j + 1;
         const int bk = P.bc[k];
-        if (j == 0) {                                                   // ends overwrite (nodeutil.c:570-612)
-            if (bk == C3SC_ABSORB)       { lo = 0; hi = 0; ab = 1; }
-            else if (bk == C3SC_REFLECT) { lo = 0; hi = 1; ab = 0; }
-            else                         { lo = N - 2; hi = 1; ab = 0; }
-        } else if (j == N - 1) {
-            if (bk == C3SC_ABSORB)       { lo = N - 1; hi = N - 1; ab = 1; }
-            else if (bk == C3SC_REFLECT) { lo = N - 2; hi = N - 1; ab = 0; }
-            else                         { lo = N - 2; hi = 1; ab = 0; }
-        } else if (ab != 0) { lo = j; hi = j; }
+        if (j == 0 || j == N - 1) ab = bk == C3SC_ABSORB ? 1 : 0;       // ends overwrite (nodeutil.c:570-612)
         const size_t id = (size_t)sFid[g] * a.ldo + j;
-        if (a.nbr_vary_in) { lo = a.nbr_vary_in[2 * id]; hi = a.nbr_vary_in[2 * id + 1]; }
         sAbs[g * nmax + j] = (signed char)ab;
-        sNv[g * 2 * nmax + 2 * j] = (short)lo;
-        sNv[g * 2 * nmax + 2 * j + 1] = (short)hi;
         if (a.flag) a.flag[id] = (signed char)ab;
         if (a.absorbed) a.absorbed[id] = ab;
-        if (a.nbr_vary) { a.nbr_vary[2 * id] = lo; a.nbr_vary[2 * id + 1] = hi; }
+        if (a.nbr_vary) {
+            int lo, hi;
+            ft_vary_pair(bk, N, j, ab, lo, hi);
+            if (a.nbr_vary_in) { lo = a.nbr_vary_in[2 * id]; hi = a.nbr_vary_in[2 * id + 1]; }
+            a.nbr_vary[2 * id] = lo; a.nbr_vary[2 * id + 1] = hi;
+        }
     }
-    if (a.flag)
+    if (a.flag && jb == 0)
         for (int e = tid; e < nf * (a.ldo - N); e += NT) {              // padding entries of ragged grids
             const int g = e / (a.ldo - N), j = N + (e - g * (a.ldo - N));
             a.flag[(size_t)sFid[g] * a.ldo + j] = 2;
@@ -280,38 +274,49 @@ __device__ __forceinline__ void ft_flags_and_indices(const FtArgs &a, int k, int
     __syncthreads();
 }
 
-// neighbours along the fiber (valuefunc.c:514-519) from the self values sV, and the compacted list
-// of non-absorbed nodes.  Whole CTA; sV / sAbs / sNv must be visible (barrier before the call).
-__device__ __forceinline__ void ft_along_fiber_and_active(const FtArgs &a, int k, int nf, const int *sFid, const signed char *sAbs,
-                                                          const short *sNv, const double *sV, int nmax)
+// Compacted list of the non-absorbed nodes [jb, je) of the group's fibers: one warp per fiber counts,
+// reserves a run of the list and writes the ids in node order.  sAbs must be visible.
+__device__ __forceinline__ void ft_active_list(const FtArgs &a, int nf, int jb, int je, const int *sFid,
+                                               const signed char *sAbs, int nmax)
 {
-    const int d = a.ft.d, CS = 2 * d + 1, tid = threadIdx.x, NT = blockDim.x;
-    const int N = a.P.ngrid[k];
-    for (int e = tid; e < nf * N; e += NT) {
-        const int g = e / N, j = e - g * N;
-        const size_t id = (size_t)sFid[g] * a.ldo + j;
-        const double lo = sV[g * nmax + sNv[g * 2 * nmax + 2 * j]], hi = sV[g * nmax + sNv[g * 2 * nmax + 2 * j + 1]];
-        if (a.cst) { a.cst[(size_t)(2 * k) * a.NS + id] = lo; a.cst[(size_t)(2 * k + 1) * a.NS + id] = hi; }
-        if (a.costs) { a.costs[id * CS + 2 * k] = lo; a.costs[id * CS + 2 * k + 1] = hi; }
-    }
-    if (a.act) {
-        // one warp per fiber: count, reserve a run of the list, write ids in node order
-        const int warp = tid >> 5, lane = tid & 31;
-        for (int g = warp; g < nf; g += NT / 32) {
-            int cnt = 0;
-            for (int j = lane; j < N; j += 32) cnt += sAbs[g * nmax + j] == 0;
-            for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
-            int base = 0;
-            if (lane == 0 && cnt > 0) base = atomicAdd(a.act_count, cnt);
-            base = __shfl_sync(0xffffffffu, base, 0);
-            for (int j0 = 0; j0 < N; j0 += 32) {
-                const int j = j0 + lane;
-                const bool on = j < N && sAbs[g * nmax + j] == 0;
-                const unsigned m = __ballot_sync(0xffffffffu, on);
-                if (on) a.act[base + __popc(m & ((1u << lane) - 1))] = sFid[g] * a.ldo + j;
-                base += __popc(m);
-            }
+    if (!a.act) return;
+    const int tid = threadIdx.x, NT = blockDim.x;
+    const int warp = tid >> 5, lane = tid & 31;
+    for (int g = warp; g < nf; g += NT / 32) {
+        int cnt = 0;
+        for (int j = jb + lane; j < je; j += 32) cnt += sAbs[g * nmax + j] == 0;
+        for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+        int base = 0;
+        if (lane == 0 && cnt > 0) base = atomicAdd(a.act_count, cnt);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        for (int j0 = jb; j0 < je; j0 += 32) {
+            const int j = j0 + lane;
+            const bool on = j < je && sAbs[g * nmax + j] == 0;
+            const unsigned m = __ballot_sync(0xffffffffu, on);
+            if (on) a.act[base + __popc(m & ((1u << lane) - 1))] = sFid[g] * a.ldo + j;
+            base += __popc(m);
         }
+    }
+}
+
+// The two neighbours ALONG the fiber (valuefunc.c:514-519) are the fiber's own values at other
+// nodes: stage 1 stores only the self value (slot 2d); the slot-major scratch is completed by its
+// consumer (control_kernel.cuh: load_costs), the node-major `costs` output by this kernel.
+__global__ void k_costs_along(const FtArgs a)
+{
+    const int d = a.ft.d, CS = 2 * d + 1;
+    for (long long id = blockIdx.x * (long long)blockDim.x + threadIdx.x; id < a.NS; id += (long long)gridDim.x * blockDim.x) {
+        const int f = (int)(id / a.ldo), j = (int)(id - (long long)f * a.ldo);
+        int k = a.dim_vary[f];
+        k = k < 0 ? 0 : (k >= d ? d - 1 : k);
+        const int N = a.P.ngrid[k];
+        if (j >= N) continue;
+        int lo, hi;
+        if (a.nbr_vary_in) { lo = a.nbr_vary_in[2 * id]; hi = a.nbr_vary_in[2 * id + 1]; }
+        else ft_vary_pair(a.P.bc[k], N, j, a.flag ? a.flag[id] : a.absorbed[id], lo, hi);
+        const size_t fb = (size_t)f * a.ldo;
+        a.costs[id * CS + 2 * k] = a.costs[(fb + lo) * CS + 2 * d];
+        a.costs[id * CS + 2 * k + 1] = a.costs[(fb + hi) * CS + 2 * d];
     }
 }
 
@@ -332,19 +337,18 @@ __global__ void __launch_bounds__(FT_NT, 2) k_ft_costs(const FtArgs a)
     const FtPlan sp(ft, P.nmax, FB);
     const int rs = sp.rs, TP = sp.tp, nmax = sp.nmax;
     double *bufA = smem + sp.oSetA, *bufB = smem + sp.oUni;
-    double *sLt = smem + sp.oLt, *sRt = smem + sp.oRt, *sV = smem + sp.oV;
+    double *sLt = smem + sp.oLt, *sRt = smem + sp.oRt;
     int *ismem = reinterpret_cast<int *>(smem + sp.nDoubles);
     int *sFix = ismem + sp.oFix, *sNf = ismem + sp.oNf;
     int *sFid = ismem + sp.oFid, *sWall = ismem + sp.oWall;
-    short *sNv = reinterpret_cast<short *>(ismem + sp.nInts);
-    signed char *sAbs = reinterpret_cast<signed char *>(sNv + FB * 2 * nmax);
+    signed char *sAbs = reinterpret_cast<signed char *>(ismem + sp.nInts);
 
     const int N = P.ngrid[k];
     const int NVL = ft_even_up(1 + 2 * k), NVR = ft_even_up(1 + 2 * (d - 1 - k));
     const int setStride = rs * sp.nvt;                 // one fiber's two sets inside a buffer
     const int offR = rs * NVL;                         // right set follows the left set
 
-    ft_flags_and_indices(a, k, nf, gstart, sFid, sWall, sFix, sNf, sAbs, sNv, nmax);
+    ft_flags_and_indices(a, k, nf, gstart, 0, N, sFid, sWall, sFix, sNf, sAbs, nmax);
 
     // ---- 1. chains -----------------------------------------------------------------
     // set layout: element (q, v) of a set at q*NV + v  (q = rank index, v = vector, v fastest).
@@ -553,7 +557,6 @@ __global__ void __launch_bounds__(FT_NT, 2) k_ft_costs(const FtArgs a)
                         if (v == 0) {
                             if (!left) continue;                       // suffix . u == self again
                             slot = 2 * d;
-                            sV[g * nmax + j] = acc[i];
                         } else {
                             const int st = (v - 1) >> 1, side = (v - 1) & 1;
                             slot = 2 * (left ? st : d - 1 - st) + side;
@@ -567,7 +570,7 @@ __global__ void __launch_bounds__(FT_NT, 2) k_ft_costs(const FtArgs a)
         }
     }
 
-    ft_along_fiber_and_active(a, k, nf, sFid, sAbs, sNv, sV, nmax);
+    ft_active_list(a, nf, 0, N, sFid, sAbs, nmax);
 }
 
 #endif  // C3SC_FT_TYPES_ONLY

@@ -250,7 +250,7 @@ __device__ __forceinline__ void mbar_wait(unsigned long long *b, unsigned parity
 template <int RMAX>
 struct FtNodePlan {
     int rs4, setw, nmax, sw;
-    int oG, oW, oU, oSets, oV, oBar, nDoubles;
+    int oG, oW, oU, oSets, oBar, nDoubles;
     int oFix, oNf, oFid, oWall, nInts;
     __host__ __device__ FtNodePlan(const DevFT &ft, int nmax_)
     {
@@ -270,7 +270,6 @@ struct FtNodePlan {
         oW = o;    o += FT_FBMAX * sw;
         oU = o;    o += FT_FBMAX * sw;
         oSets = o; o += FT_FBMAX * setw;
-        oV = o;    o += FT_FBMAX * nmax;
         o = ft_even_up(o);
         oBar = o;  o += 2;
         nDoubles = o;
@@ -279,9 +278,9 @@ struct FtNodePlan {
         oNf = q;   q += FT_FBMAX * 2 * ft.d;
         oFid = q;  q += FT_FBMAX;
         oWall = q; q += FT_FBMAX;
-        nInts = q;                                   // then 8*2*nmax shorts (sNv) and 8*nmax bytes (sAbs)
+        nInts = q;                                   // then 8*nmax bytes (sAbs)
     }
-    __host__ __device__ size_t bytes() const { return (size_t)nDoubles * 8 + (size_t)nInts * 4 + (size_t)FT_FBMAX * nmax * 5; }
+    __host__ __device__ size_t bytes() const { return (size_t)nDoubles * 8 + (size_t)nInts * 4 + (size_t)FT_FBMAX * nmax; }
 };
 
 template <int RMAX>
@@ -301,13 +300,12 @@ __global__ void __launch_bounds__(FTN_NT, 2) k_ft_nodes(const FtArgs a, const do
     extern __shared__ __align__(16) double smem[];
     const FtNodePlan<RMAX> sp(ft, P.nmax);
     const int nmax = sp.nmax, SW = sp.sw, SETW = sp.setw;
-    double *sG = smem + sp.oG, *sW = smem + sp.oW, *sU = smem + sp.oU, *sSets = smem + sp.oSets, *sV = smem + sp.oV;
+    double *sG = smem + sp.oG, *sW = smem + sp.oW, *sU = smem + sp.oU, *sSets = smem + sp.oSets;
     unsigned long long *mbar = reinterpret_cast<unsigned long long *>(smem + sp.oBar);
     int *ismem = reinterpret_cast<int *>(smem + sp.nDoubles);
     int *sFix = ismem + sp.oFix, *sNf = ismem + sp.oNf;
     int *sFid = ismem + sp.oFid, *sWall = ismem + sp.oWall;
-    short *sNv = reinterpret_cast<short *>(ismem + sp.nInts);
-    signed char *sAbs = reinterpret_cast<signed char *>(sNv + FT_FBMAX * 2 * nmax);
+    signed char *sAbs = reinterpret_cast<signed char *>(ismem + sp.nInts);
 
     const int N = P.ngrid[k];
     const int rk = ft.r[k], rk1 = ft.r[k + 1];
@@ -322,28 +320,37 @@ __global__ void __launch_bounds__(FTN_NT, 2) k_ft_nodes(const FtArgs a, const do
     const int mtA = (rk + 7) >> 3, ntB = (rk1 + 7) >> 3;              // 8-wide tiles over a / over b
     const int mtL = (nvL + 7) >> 3, ntR = nvR > 1 ? (nvR + 7) >> 3 : 0;   // 8-wide tiles over the variant vectors
 
-    // ---- tile 0 on its way while the flags are computed ---------------------------------------
+    // this CTA's share of the fiber: a contiguous range of node tiles
+    const int ntiles = (N + FTN_T - 1) / FTN_T, nsp = a.nsplit > 0 ? a.nsplit : 1;
+    const int tper = (ntiles + nsp - 1) / nsp;
+    const int jb = (int)blockIdx.y * tper * FTN_T, je = (jb + tper * FTN_T < N) ? jb + tper * FTN_T : N;
+    if (jb >= N) return;
+
+    // ---- first tile on its way while the flags are computed -----------------------------------
     const double *Gp = ft.baseP + ft.offP[k];
     if (tid == 0) {
         mbar_init(mbar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        const int nt0 = N < FTN_T ? N : FTN_T;
+        const int nt0 = je - jb < FTN_T ? je - jb : FTN_T;
         mbar_expect_tx(mbar, (unsigned)(nt0 * pblk * 8));
-        bulk_g2s(sG, Gp, (unsigned)(nt0 * pblk * 8), mbar);
+        bulk_g2s(sG, Gp + (size_t)jb * pblk, (unsigned)(nt0 * pblk * 8), mbar);
     }
 
-    ft_flags_and_indices(a, k, nf, gstart, sFid, sWall, sFix, sNf, sAbs, sNv, nmax);
+    ft_flags_and_indices(a, k, nf, gstart, jb, je, sFid, sWall, sFix, sNf, sAbs, nmax);
 
-    // the group's chain records -> shared memory, rank rows zero-padded to a multiple of 4
-    for (int e = tid; e < FT_FBMAX * SETW; e += FTN_NT) sSets[e] = 0.0;
-    __syncthreads();
+    // the group's chain records -> shared memory, rank rows zero-padded to a multiple of 4.
+    // One flat loop: every thread has all its loads in flight at once.
     {
         const int nl = rk * NVL, nr = rk1 * NVR;                      // valid doubles of the left / right set
-        for (int g = 0; g < nf; g++) {
-            const double *src = sets + (size_t)sFid[g] * SETWG;
-            double *dst = sSets + g * SETW;
-            for (int q = tid; q < nl; q += FTN_NT) dst[q] = src[q];
-            for (int q = tid; q < nr; q += FTN_NT) dst[offR + q] = src[offRG + q];
+        for (int e = tid; e < FT_FBMAX * SETW; e += FTN_NT) {
+            const int g = e / SETW, q = e - g * SETW;
+            double v = 0.0;
+            if (g < nf) {
+                const double *src = sets + (size_t)sFid[g] * SETWG;
+                if (q < nl) v = __ldg(src + q);
+                else if (q >= offR && q - offR < nr) v = __ldg(src + offRG + (q - offR));
+            }
+            sSets[e] = v;
         }
     }
     for (int e = tid; e < 2 * FT_FBMAX * SW; e += FTN_NT) sW[e] = 0.0;       // sW and sU are adjacent
@@ -375,8 +382,8 @@ __global__ void __launch_bounds__(FTN_NT, 2) k_ft_nodes(const FtArgs a, const do
     const size_t idf = warp < nf ? (size_t)sFid[warp] * a.ldo : 0;
 
     unsigned phase = 0;
-    for (int j0 = 0; j0 < N; j0 += FTN_T) {
-        const int nt = (N - j0 < FTN_T) ? N - j0 : FTN_T;
+    for (int j0 = jb; j0 < je; j0 += FTN_T) {
+        const int nt = (je - j0 < FTN_T) ? je - j0 : FTN_T;
         mbar_wait(mbar, phase);
         phase ^= 1;
         // ---- w / u of node jl = warp, all fibers of the group --------------------------------
@@ -412,8 +419,8 @@ __global__ void __launch_bounds__(FTN_NT, 2) k_ft_nodes(const FtArgs a, const do
             }
         }
         __syncthreads();
-        if (tid == 0 && j0 + FTN_T < N) {                                // G tile is free: fetch the next one
-            const int j1 = j0 + FTN_T, nt1 = (N - j1 < FTN_T) ? N - j1 : FTN_T;
+        if (tid == 0 && j0 + FTN_T < je) {                               // G tile is free: fetch the next one
+            const int j1 = j0 + FTN_T, nt1 = (je - j1 < FTN_T) ? je - j1 : FTN_T;
             mbar_expect_tx(mbar, (unsigned)(nt1 * pblk * 8));
             bulk_g2s(sG, Gp + (size_t)j1 * pblk, (unsigned)(nt1 * pblk * 8), mbar);
         }
@@ -445,10 +452,6 @@ __global__ void __launch_bounds__(FTN_NT, 2) k_ft_nodes(const FtArgs a, const do
                 if (mt < mtL && slot >= 0) {                             // D: row v, cols jl = 2tig, 2tig+1
                     const int jl = 2 * tig;
                     const double d0 = dl[mt][0], d1 = dl[mt][1];
-                    if (mt == 0 && gid == 0) {
-                        if (jl < nt) sV[warp * nmax + j0 + jl] = d0;
-                        if (jl + 1 < nt) sV[warp * nmax + j0 + jl + 1] = d1;
-                    }
                     if (a.cst) {
                         double *o = a.cst + (size_t)slot * a.NS + idb + jl;
                         if (jl < nt) o[0] = d0;
@@ -479,7 +482,7 @@ __global__ void __launch_bounds__(FTN_NT, 2) k_ft_nodes(const FtArgs a, const do
         __syncthreads();
     }
 
-    ft_along_fiber_and_active(a, k, nf, sFid, sAbs, sNv, sV, nmax);
+    ft_active_list(a, nf, jb, je, sFid, sAbs, nmax);
 }
 
 }  // namespace c3sc
