@@ -103,7 +103,7 @@ static int launch_mma_t(const FtArgs &a, cudaStream_t st)
     int ntl = 1;
     for (int k = 0; k < a.ft.d; k++) { const int t = (a.P.ngrid[k] + FTN_T - 1) / FTN_T; ntl = t > ntl ? t : ntl; }
     b.nsplit = 1;
-    while (b.nsplit < ntl && grid * b.nsplit < 4 * g_sms) b.nsplit *= 2;
+    while (b.nsplit < ntl && grid * b.nsplit * 2 <= 2 * g_sms) b.nsplit *= 2;      // stay within one wave of 2 CTAs/SM
     if (b.nsplit > ntl) b.nsplit = ntl;
     k_ft_nodes<RMAX><<<dim3((unsigned)grid, (unsigned)b.nsplit), FTN_NT, smem, st>>>(b, b.sets);
     return (int)cudaGetLastError();

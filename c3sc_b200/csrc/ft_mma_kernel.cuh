@@ -339,18 +339,30 @@ __global__ void __launch_bounds__(FTN_NT, 2) k_ft_nodes(const FtArgs a, const do
     ft_flags_and_indices(a, k, nf, gstart, jb, je, sFid, sWall, sFix, sNf, sAbs, nmax);
 
     // the group's chain records -> shared memory, rank rows zero-padded to a multiple of 4.
-    // One flat loop: every thread has all its loads in flight at once.
+    // Loads are issued four at a time before the first store, so their latencies overlap.
     {
         const int nl = rk * NVL, nr = rk1 * NVR;                      // valid doubles of the left / right set
-        for (int e = tid; e < FT_FBMAX * SETW; e += FTN_NT) {
-            const int g = e / SETW, q = e - g * SETW;
-            double v = 0.0;
-            if (g < nf) {
-                const double *src = sets + (size_t)sFid[g] * SETWG;
-                if (q < nl) v = __ldg(src + q);
-                else if (q >= offR && q - offR < nr) v = __ldg(src + offRG + (q - offR));
+        const int total = FT_FBMAX * SETW;
+        for (int e0 = tid; e0 < total; e0 += 4 * FTN_NT) {
+            double v[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const int e = e0 + u * FTN_NT;
+                v[u] = 0.0;
+                if (e < total) {
+                    const int g = e / SETW, q = e - g * SETW;
+                    if (g < nf) {
+                        const double *src = sets + (size_t)sFid[g] * SETWG;
+                        if (q < nl) v[u] = __ldg(src + q);
+                        else if (q >= offR && q - offR < nr) v[u] = __ldg(src + offRG + (q - offR));
+                    }
+                }
             }
-            sSets[e] = v;
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const int e = e0 + u * FTN_NT;
+                if (e < total) sSets[e] = v[u];
+            }
         }
     }
     for (int e = tid; e < 2 * FT_FBMAX * SW; e += FTN_NT) sW[e] = 0.0;       // sW and sU are adjacent
