@@ -41,16 +41,18 @@ int launch_pack_cores(const DevFT &ft, double *baseT, double *baseP, cudaStream_
     return (int)cudaGetLastError();
 }
 
-// padded-tile geometry of core k for the tensor-core node kernel: leading dimension = 4 (mod 8) and
-// >= 8*ceil(r_k/8) (fragment rows, conflict-free in both orientations, 16-byte columns), columns
-// padded to 8*ceil(r_{k+1}/8).  Fills ft.ldp / cpp / offP, returns the doubles needed.
+// padded-tile geometry for the tensor-core kernels, the same for every core: 8*MT columns of 8*MT+4
+// rows (leading dimension = 4 mod 8: fragment reads conflict-free in both orientations, 16-byte
+// columns for TMA).  Fills ft.ldp / cpp / offP, returns the doubles needed.
 long long ft_padded_layout(DevFT &ft)
 {
     long long total = 0;
+    int rmax = 1;
+    for (int k = 0; k <= ft.d; k++) rmax = ft.r[k] > rmax ? ft.r[k] : rmax;
+    const int m8 = 8 * (((rmax + 3) / 4 + 1) / 2);          // 8*MT, MT = ceil(KS/2), KS = ceil(rmax/4): one geometry for all cores
     for (int k = 0; k < ft.d; k++) {
-        const int r8 = 8 * ((ft.r[k] + 7) / 8), c8 = 8 * ((ft.r[k + 1] + 7) / 8);
-        ft.ldp[k] = r8 + 4;
-        ft.cpp[k] = c8;
+        ft.ldp[k] = m8 + 4;
+        ft.cpp[k] = m8;
         ft.offP[k] = total;
         total += (long long)ft.n[k] * ft.ldp[k] * ft.cpp[k];
     }
@@ -68,32 +70,32 @@ int ft_uses_mma(const DevFT &ft)
 }
 size_t ft_sets_bytes(const DevFT &ft, size_t F) { return (size_t)ft_set_width(ft) * F * sizeof(double); }
 
-template <int RMAX>
+template <int KS>
 static int launch_mma_t(const FtArgs &a, cudaStream_t st)
 {
     // chains: one warp per (fiber, side)
-    const size_t csm = FtChainPlan<RMAX>(a.ft).bytes();
+    const size_t csm = FtChainPlan<KS>(a.ft).bytes();
     if (csm > (size_t)g_max_optin) return (int)cudaErrorInvalidValue;
     static size_t cattr = 0;
     if (csm > cattr) {
-        cudaError_t e = cudaFuncSetAttribute(k_ft_chains<RMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)csm);
+        cudaError_t e = cudaFuncSetAttribute(k_ft_chains<KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)csm);
         if (e != cudaSuccess) return (int)e;
         cattr = csm;
     }
     int per_sm = 1;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_ft_chains<RMAX>, FTC_NT, csm);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_ft_chains<KS>, FTC_NT, csm);
     if (per_sm < 1) per_sm = 1;
     int cgrid = (2 * a.F + FTC_NT / 32 - 1) / (FTC_NT / 32);
     if (cgrid > g_sms * per_sm) cgrid = g_sms * per_sm;
-    k_ft_chains<RMAX><<<cgrid, FTC_NT, csm, st>>>(a, a.sets);
+    k_ft_chains<KS><<<cgrid, FTC_NT, csm, st>>>(a, a.sets);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return (int)e;
     // nodes: one CTA per same-k group
-    const size_t smem = FtNodePlan<RMAX>(a.ft, a.P.nmax).bytes();
+    const size_t smem = FtNodePlan<KS>(a.ft, a.P.nmax).bytes();
     if (smem > (size_t)g_max_optin) return (int)cudaErrorInvalidValue;
     static size_t attr = 0;
     if (smem > attr) {
-        e = cudaFuncSetAttribute(k_ft_nodes<RMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        e = cudaFuncSetAttribute(k_ft_nodes<KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return (int)e;
         attr = smem;
     }
@@ -105,7 +107,7 @@ static int launch_mma_t(const FtArgs &a, cudaStream_t st)
     b.nsplit = 1;
     while (b.nsplit < ntl && grid * b.nsplit * 2 <= 2 * g_sms) b.nsplit *= 2;      // stay within one wave of 2 CTAs/SM
     if (b.nsplit > ntl) b.nsplit = ntl;
-    k_ft_nodes<RMAX><<<dim3((unsigned)grid, (unsigned)b.nsplit), FTN_NT, smem, st>>>(b, b.sets);
+    k_ft_nodes<KS><<<dim3((unsigned)grid, (unsigned)b.nsplit), FTN_NT, smem, st>>>(b, b.sets);
     return (int)cudaGetLastError();
 }
 
@@ -116,10 +118,16 @@ static int launch_ft_mma(FtArgs a, cudaStream_t st)
     a.FB = FT_FBMAX;
     int rmax = 1;
     for (int i = 0; i <= a.ft.d; i++) rmax = a.ft.r[i] > rmax ? a.ft.r[i] : rmax;
-    if (rmax <= 8) return launch_mma_t<8>(a, st);
-    if (rmax <= 16) return launch_mma_t<16>(a, st);
-    if (rmax <= 24) return launch_mma_t<24>(a, st);
-    return launch_mma_t<32>(a, st);
+    switch ((rmax + 3) / 4) {                                // KS
+    case 1: return launch_mma_t<1>(a, st);
+    case 2: return launch_mma_t<2>(a, st);
+    case 3: return launch_mma_t<3>(a, st);
+    case 4: return launch_mma_t<4>(a, st);
+    case 5: return launch_mma_t<5>(a, st);
+    case 6: return launch_mma_t<6>(a, st);
+    case 7: return launch_mma_t<7>(a, st);
+    default: return launch_mma_t<8>(a, st);
+    }
 }
 
 static int launch_ft_stage(const FtArgs &a_in, cudaStream_t st);

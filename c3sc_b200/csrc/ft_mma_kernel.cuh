@@ -43,13 +43,16 @@ __host__ __device__ inline int ft_chain_nvp(int d)
     return n;
 }
 
-template <int RMAX>
+// Both kernels are instantiated on KS = ceil(rmax/4), the number of MMA k-steps a rank index needs;
+// MT = ceil(KS/2) 8-wide tiles.  Every core is padded to that geometry (ft_padded_layout), so all
+// fragment loops have compile-time trip counts and no predicates (zero padding does the masking).
+template <int KS>
 struct FtChainPlan {            // shared memory of k_ft_chains, per warp: two set buffers + indices
     int nvp, bufDoubles, perWarpDoubles, perWarpInts;
     __host__ __device__ FtChainPlan(const DevFT &ft)
     {
         nvp = ft_chain_nvp(ft.d);
-        bufDoubles = RMAX * nvp;                     // [rank row q][vector v], rows padded to the MMA tile
+        bufDoubles = 8 * ((KS + 1) / 2) * nvp;       // [rank row q][vector v], rows padded to the MMA tile
         perWarpDoubles = 2 * bufDoubles;
         perWarpInts = 4 * ft.d;                      // fixed indices + neighbour pairs
     }
@@ -67,10 +70,10 @@ __device__ __forceinline__ void dmma_m8n8k4(double &d0, double &d1, double a, do
 // tensor cores:  out[v][o] = sum_q in[v][q] B[q][o]  (left: B = G_m[f_m], right: B = G_m[f_m]^T),
 // B fragments straight from the zero-padded core copy in L2 (all loads of a step are independent),
 // and appends the two neighbour variants  in[0] . G_m[nb]  with plain FMAs.
-template <int RMAX>
-__global__ void __launch_bounds__(FTC_NT, RMAX <= 24 ? 2 : 1) k_ft_chains(const FtArgs a, double *sets)
+template <int KS>
+__global__ void __launch_bounds__(FTC_NT, KS <= 6 ? 2 : 1) k_ft_chains(const FtArgs a, double *sets)
 {
-    constexpr int KS = RMAX / 4, NTL = RMAX / 8, VT = (2 * MAXD + 7) / 8;
+    constexpr int NTL = (KS + 1) / 2, VT = (2 * MAXD + 7) / 8;
     const DevProblem &P = a.P;
     const DevFT &ft = a.ft;
     const int d = ft.d;
@@ -78,7 +81,7 @@ __global__ void __launch_bounds__(FTC_NT, RMAX <= 24 ? 2 : 1) k_ft_chains(const 
     const int gid = lane >> 2, tig = lane & 3;
     constexpr int NW = FTC_NT / 32;
     extern __shared__ __align__(16) double smem[];
-    const FtChainPlan<RMAX> cp(ft);
+    const FtChainPlan<KS> cp(ft);
     const int NVP = cp.nvp;
     double *buf0 = smem + warp * cp.perWarpDoubles, *buf1 = buf0 + cp.bufDoubles;
     int *iw = reinterpret_cast<int *>(smem + NW * cp.perWarpDoubles) + warp * cp.perWarpInts;
@@ -125,7 +128,9 @@ __global__ void __launch_bounds__(FTC_NT, RMAX <= 24 ? 2 : 1) k_ft_chains(const 
             const double *bc = base + (size_t)sFix[m] * pblk;
             const double *bl = base + (size_t)sNf[2 * m] * pblk, *bh = base + (size_t)sNf[2 * m + 1] * pblk;
             const int nin = 1 + 2 * s;
-            const int nks = (rq + 3) >> 2, ntl = (ro + 7) >> 3, mtn = (nin + 7) >> 3;
+            constexpr int nks = KS, ntl = NTL;
+            const int mtn = (nin + 7) >> 3;
+            (void)rq; (void)ro;
             // B fragments (row q = 4ks+tig, col o = 8nt+gid); element (a,b) of a padded block at b*ld + a.
             // All loads of the centre and the first neighbour block are issued before any use.
             const int sq = left ? 1 : ld, so = left ? ld : 1;        // strides of q and of o inside the block
@@ -247,7 +252,7 @@ __device__ __forceinline__ void mbar_wait(unsigned long long *b, unsigned parity
 
 // Shared memory of k_ft_nodes.  Everything the MMA fragments read is zero-padded to the fragment
 // shape, so no fragment load is predicated.
-template <int RMAX>
+template <int KS>
 struct FtNodePlan {
     int rs4, setw, nmax, sw;
     int oG, oW, oU, oSets, oBar, nDoubles;
@@ -259,7 +264,7 @@ struct FtNodePlan {
         for (int i = 0; i <= ft.d; i++) rs = ft.r[i] > rs ? ft.r[i] : rs;
         rs4 = (rs + 3) & ~3;                         // rank rows padded to the MMA k-step
         setw = rs4 * (2 * ft.d + 2) + 8;             // + slack: fragment rows may overrun a set by < 8
-        sw = RMAX * FTN_TP + 2;                      // one fiber's w (or u) tile: [rank index][8 nodes]
+        sw = 8 * ((KS + 1) / 2) * FTN_TP + 2;        // one fiber's w (or u) tile: [rank index][8 nodes]
         int gt = 0;
         for (int k = 0; k < ft.d; k++) {
             const int g = FTN_T * ft.ldp[k] * ft.cpp[k];
@@ -283,10 +288,10 @@ struct FtNodePlan {
     __host__ __device__ size_t bytes() const { return (size_t)nDoubles * 8 + (size_t)nInts * 4 + (size_t)FT_FBMAX * nmax; }
 };
 
-template <int RMAX>
+template <int KS>
 __global__ void __launch_bounds__(FTN_NT, 2) k_ft_nodes(const FtArgs a, const double *sets)
 {
-    constexpr int KS = RMAX / 4, MT = RMAX / 8, VT = (2 * MAXD + 7) / 8;
+    constexpr int MT = (KS + 1) / 2, VT = (2 * MAXD + 7) / 8;
     const DevProblem &P = a.P;
     const DevFT &ft = a.ft;
     const int d = ft.d, CS = 2 * d + 1;
@@ -298,7 +303,7 @@ __global__ void __launch_bounds__(FTN_NT, 2) k_ft_nodes(const FtArgs a, const do
     if (k < 0) return;
 
     extern __shared__ __align__(16) double smem[];
-    const FtNodePlan<RMAX> sp(ft, P.nmax);
+    const FtNodePlan<KS> sp(ft, P.nmax);
     const int nmax = sp.nmax, SW = sp.sw, SETW = sp.setw;
     double *sG = smem + sp.oG, *sW = smem + sp.oW, *sU = smem + sp.oU, *sSets = smem + sp.oSets;
     unsigned long long *mbar = reinterpret_cast<unsigned long long *>(smem + sp.oBar);
@@ -316,8 +321,8 @@ __global__ void __launch_bounds__(FTN_NT, 2) k_ft_nodes(const FtArgs a, const do
     for (int i = 0; i <= d; i++) rsG = ft.r[i] > rsG ? ft.r[i] : rsG;
     const int SETWG = rsG * (2 * d + 2), offRG = rsG * NVL;           // layout of the chain kernel's records
     const int offR = sp.rs4 * NVL;                                    // layout of the zero-padded shared copy
-    const int nksA = (rk + 3) >> 2, nksB = (rk1 + 3) >> 2;            // k-steps over a / over b
-    const int mtA = (rk + 7) >> 3, ntB = (rk1 + 7) >> 3;              // 8-wide tiles over a / over b
+    constexpr int nksA = KS, nksB = KS;                               // k-steps over a / over b (padded geometry)
+    constexpr int mtA = MT, ntB = MT;                                 // 8-wide tiles over a / over b
     const int mtL = (nvL + 7) >> 3, ntR = nvR > 1 ? (nvR + 7) >> 3 : 0;   // 8-wide tiles over the variant vectors
 
     // this CTA's share of the fiber: a contiguous range of node tiles
