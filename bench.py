@@ -369,6 +369,22 @@ def main():
                                 "node_backups_per_s": nodes_sw / (ms_sw * 1e-3),
                                 "what": "2 x d sequential core batches of r_k*r_{k+1} fibers (SURVEY §8(d))"}
 
+    if not args.no_sweep and world == 1 and line is not None:
+        # one value-iteration step through the host cross driver (include/c3sc_cross.h): 2 sweeps over the
+        # d cores, every core step = H2D fiber descriptors + pipeline + D2H values + host QR/maxvol
+        cr = capi.Cross(cfg.ngrid, ranks)
+        cr.run_vi(prob, vf, maxiter=1)
+        t0 = time.perf_counter()
+        reps = 3
+        nf = 0
+        for _ in range(reps):
+            _, nf, _ = cr.run_vi(prob, vf, maxiter=1)
+        dt = (time.perf_counter() - t0) / reps
+        line["vi_cross_step"] = {"seconds": dt, "fibers": nf, "node_backups": nf * N, "node_backups_per_s": nf * N / dt,
+                                 "what": "c3sc_cross_run_vi, one left-right + right-left sweep (host TT-cross with QR + maxvol, "
+                                         "one batched operator call per core, host buffers)"}
+        cr.close()
+
     if rank == 0 and not args.no_cpu_baseline and world == 1:
         line["cpu_baseline"] = cpu_baseline(cfg, rank_ft, args.cpu_seconds)
     if rank == 0:

@@ -16,10 +16,12 @@
  * c3sc_vi_batch / c3sc_pi_batch in c3sc_cross_run_vi / _pi; the parity tests plug the CPU oracle
  * into the same driver).
  */
+#define _POSIX_C_SOURCE 199309L
 #include <math.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <time.h>
 #include "../../../include/c3sc_cross.h"
 
 struct c3sc_cross {
@@ -218,6 +220,9 @@ static int maxvol(const double *Q, size_t m, size_t n, size_t *P, double *B, dou
 }
 
 /* ---- one core step: all fibers of core k in ONE operator call --------------------------------- */
+static double g_t_eval, g_t_qr, g_t_mv, g_t_dot;
+static double now_s(void) { struct timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec + 1e-9 * ts.tv_nsec; }
+
 static int eval_core(const c3sc_cross *c, uint32_t k, c3sc_fiber_batch_fn f, void *arg, int32_t *dv, int32_t *fi,
                      double *vals, double *T /* [r_k][N][r_{k+1}] as a + j*rk + b*rk*N */, uint64_t *nfib)
 {
@@ -231,7 +236,9 @@ static int eval_core(const c3sc_cross *c, uint32_t k, c3sc_fiber_batch_fn f, voi
             for (uint32_t i = 0; i < d; i++)
                 fi[fidx * d + i] = i < k ? c->I[k][a * d + i] : (i > k ? c->J[k + 1][b * d + i] : 0);
         }
+    const double t0_ = now_s();
     int rc = f(F, dv, fi, ldo, vals, arg);
+    g_t_eval += now_s() - t0_;
     if (rc) return rc;
     *nfib += F;
     for (size_t a = 0; a < rk; a++)
@@ -248,33 +255,32 @@ static void store_core(const double *T, size_t rk, size_t N, size_t rk1, double 
             for (size_t a = 0; a < rk; a++) core[j * rk * rk1 + a + b * rk] = T[a + j * rk + b * rk * N];
 }
 
-/* <A, B> of two trains in the ValueF layout (discrete inner product over the grid) */
-static double tt_dot(uint32_t d, const uint64_t *n, const uint64_t *r, double *const *A, double *const *B, double *w1, double *w2)
+/* <A, B> of two trains in the ValueF layout (discrete inner product over the grid):
+ * M (r_k x r_k) <- sum_j A_k[j]^T M B_k[j], two r^3 products per node.  w1, w2: rmax^2 each, w3: rmax^2. */
+static double tt_dot(uint32_t d, const uint64_t *n, const uint64_t *r, double *const *A, double *const *B, double *w1, double *w2,
+                     double *w3)
 {
-    /* M (r_k x r_k) <- sum_j A_k[j]^T M B_k[j] */
-    size_t rk = 1;
     w1[0] = 1.0;
     for (uint32_t k = 0; k < d; k++) {
         const size_t r0 = r[k], r1 = r[k + 1], blk = r0 * r1;
         for (size_t e = 0; e < r1 * r1; e++) w2[e] = 0.0;
         for (size_t j = 0; j < n[k]; j++) {
             const double *a = A[k] + j * blk, *b = B[k] + j * blk;
-            /* tmp = M * b  (r0 x r1), then w2 += a^T tmp */
-            for (size_t q = 0; q < r1; q++)
+            for (size_t q = 0; q < r1; q++)                    /* w3 = M b  (r0 x r1) */
+                for (size_t x = 0; x < r0; x++) {
+                    double t = 0.0;
+                    for (size_t y = 0; y < r0; y++) t += w1[x + y * r0] * b[y + q * r0];
+                    w3[x + q * r0] = t;
+                }
+            for (size_t q = 0; q < r1; q++)                    /* w2 += a^T w3  (r1 x r1) */
                 for (size_t p = 0; p < r1; p++) {
-                    double s = 0.0;
-                    for (size_t x = 0; x < r0; x++) {
-                        double t = 0.0;
-                        for (size_t y = 0; y < r0; y++) t += w1[x + y * r0] * b[y + q * r0];
-                        s += a[x + p * r0] * t;
-                    }
-                    w2[p + q * r1] += s;
+                    double t = 0.0;
+                    for (size_t x = 0; x < r0; x++) t += a[x + p * r0] * w3[x + q * r0];
+                    w2[p + q * r1] += t;
                 }
         }
         memcpy(w1, w2, r1 * r1 * sizeof(double));
-        rk = r1;
     }
-    (void)rk;
     return w1[0];
 }
 
@@ -298,12 +304,12 @@ int c3sc_cross_run(c3sc_cross *c, c3sc_fiber_batch_fn f, void *arg, const c3sc_c
     double *T = (double *)malloc(tmax * sizeof(double)), *Q = (double *)malloc(tmax * sizeof(double));
     double *B = (double *)malloc(tmax * sizeof(double));
     size_t *P = (size_t *)malloc(rmax * sizeof(size_t));
-    double *work = (double *)malloc((rmax * rmax * 2 + rmax + rmax * c->nmax * rmax + 16) * sizeof(double));
+    double *work = (double *)malloc((rmax * rmax * 3 + rmax + rmax * c->nmax * rmax + 16) * sizeof(double));
     double **prev = (double **)calloc(d, sizeof(double *));
     int32_t *tmpI = (int32_t *)malloc(rmax * d * sizeof(int32_t));
     int rc = C3SC_OK;
     uint64_t nfib = 0;
-    double change = 1.0;
+    double change = 1.0, prev_norm2 = 0.0;
     if (!dv || !fi || !vals || !T || !Q || !B || !P || !work || !prev || !tmpI) { rc = C3SC_EINVAL; goto done; }
     for (uint32_t k = 0; k < d; k++) {
         prev[k] = (double *)calloc(c->r[k] * c->n[k] * c->r[k + 1], sizeof(double));
@@ -316,8 +322,8 @@ int c3sc_cross_run(c3sc_cross *c, c3sc_fiber_batch_fn f, void *arg, const c3sc_c
             rc = eval_core(c, k, f, arg, dv, fi, vals, T, &nfib);
             if (rc) goto done;
             memcpy(Q, T, m * rk1 * sizeof(double));                 /* unfolding (a,j) x b is already column-major */
-            qr_explicit_q(Q, m, rk1, work);
-            if (maxvol(Q, m, rk1, P, B, work)) { rc = C3SC_ENUMERIC; goto done; }
+            { const double t_ = now_s(); qr_explicit_q(Q, m, rk1, work); g_t_qr += now_s() - t_; }
+            { const double t_ = now_s(); const int mv = maxvol(Q, m, rk1, P, B, work); g_t_mv += now_s() - t_; if (mv) { rc = C3SC_ENUMERIC; goto done; } }
             for (size_t b = 0; b < rk1; b++) {                      /* new left set: row (a,j) = a + j*rk */
                 const size_t a = P[b] % rk, j = P[b] / rk;
                 for (uint32_t i = 0; i < k; i++) tmpI[b * d + i] = c->I[k][a * d + i];
@@ -338,8 +344,8 @@ int c3sc_cross_run(c3sc_cross *c, c3sc_fiber_batch_fn f, void *arg, const c3sc_c
             for (size_t a = 0; a < rk; a++)                         /* transpose: rows (j,b) = j + b*N, cols a */
                 for (size_t j = 0; j < N; j++)
                     for (size_t b = 0; b < rk1; b++) Q[(j + b * N) + a * m] = T[a + j * rk + b * rk * N];
-            qr_explicit_q(Q, m, rk, work);
-            if (maxvol(Q, m, rk, P, B, work)) { rc = C3SC_ENUMERIC; goto done; }
+            { const double t_ = now_s(); qr_explicit_q(Q, m, rk, work); g_t_qr += now_s() - t_; }
+            { const double t_ = now_s(); const int mv = maxvol(Q, m, rk, P, B, work); g_t_mv += now_s() - t_; if (mv) { rc = C3SC_ENUMERIC; goto done; } }
             for (size_t a = 0; a < rk; a++) {
                 const size_t j = P[a] % N, b = P[a] / N;
                 tmpI[a * d + k] = (int32_t)j;
@@ -357,13 +363,17 @@ int c3sc_cross_run(c3sc_cross *c, c3sc_fiber_batch_fn f, void *arg, const c3sc_c
         store_core(T, 1, c->n[0], c->r[1], cores[0]);
         /* ---- change of the train against the previous sweep pair (valuef_norm2diff idea) -------- */
         {
-            double *w1 = work, *w2 = work + rmax * rmax;
-            const double aa = tt_dot(d, c->n, c->r, cores, cores, w1, w2);
-            const double ab = tt_dot(d, c->n, c->r, cores, prev, w1, w2);
-            const double bb = tt_dot(d, c->n, c->r, prev, prev, w1, w2);
+            double *w1 = work, *w2 = work + rmax * rmax, *w3 = work + 2 * rmax * rmax;
+            const double t_ = now_s();
+            const double aa = tt_dot(d, c->n, c->r, cores, cores, w1, w2, w3);
+            const double ab = it == 0 ? 0.0 : tt_dot(d, c->n, c->r, cores, prev, w1, w2, w3);
+            const double bb = prev_norm2;                            /* <prev, prev> is last sweep's <cores, cores> */
+            prev_norm2 = aa;
+            g_t_dot += now_s() - t_;
             const double diff2 = aa - 2.0 * ab + bb;
             change = aa > 0.0 ? sqrt(fabs(diff2) / aa) : 0.0;
-            if (verbose) fprintf(stderr, "c3sc_cross: sweep %u, |T|=%g, rel change %g, fibers %llu\n", it, sqrt(aa), change, (unsigned long long)nfib);
+            if (verbose) fprintf(stderr, "c3sc_cross: sweep %u, |T|=%g, rel change %g, fibers %llu; cumulative s: operator %.4f qr %.4f maxvol %.4f norms %.4f\n",
+                                 it, sqrt(aa), change, (unsigned long long)nfib, g_t_eval, g_t_qr, g_t_mv, g_t_dot);
             for (uint32_t k = 0; k < d; k++) memcpy(prev[k], cores[k], c->r[k] * c->n[k] * c->r[k + 1] * sizeof(double));
             if (tol > 0.0 && change < tol) break;
         }
