@@ -57,6 +57,7 @@ EXPORTS = [
     "c3sc_neighbor_costs_batch", "c3sc_node_backup_batch", "c3sc_control_value_batch", "c3sc_rhs_batch",
     "c3sc_transition_raw", "c3sc_ft_fiber_nn_batch", "c3sc_valuef_commit",
     "c3sc_cross_create", "c3sc_cross_destroy", "c3sc_cross_ranks", "c3sc_cross_run", "c3sc_cross_run_vi", "c3sc_cross_run_pi",
+    "c3sc_vi_solve", "c3sc_cores_dot", "c3sc_cores_norm", "c3sc_cores_norm2diff",
 ]
 
 _lib = None
@@ -106,6 +107,13 @@ def lib() -> C.CDLL:
         L.c3sc_cross_run.argtypes = [vp, FIBER_FN, vp, C.POINTER(CrossOpts), C.POINTER(c_f64p), c_u64p, c_f64p]
         L.c3sc_cross_run_vi.argtypes = [vp, vp, vp, C.POINTER(CrossOpts), C.POINTER(c_f64p), c_u64p, c_f64p]
         L.c3sc_cross_run_pi.argtypes = [vp, vp, vp, vp, C.c_uint32, C.POINTER(CrossOpts), C.POINTER(c_f64p), c_u64p, c_f64p]
+        L.c3sc_vi_solve.argtypes = [vp, vp, c_u64p, C.POINTER(c_f64p), C.c_uint32, C.c_double, C.POINTER(CrossOpts), C.POINTER(c_f64p),
+                                    C.POINTER(C.c_uint32), c_f64p, c_u64p]
+        for fn in (L.c3sc_cores_dot, L.c3sc_cores_norm, L.c3sc_cores_norm2diff):
+            fn.restype = C.c_double
+        L.c3sc_cores_dot.argtypes = [C.c_uint32, c_u64p, c_u64p, C.POINTER(c_f64p), c_u64p, C.POINTER(c_f64p)]
+        L.c3sc_cores_norm.argtypes = [C.c_uint32, c_u64p, c_u64p, C.POINTER(c_f64p)]
+        L.c3sc_cores_norm2diff.argtypes = [C.c_uint32, c_u64p, c_u64p, C.POINTER(c_f64p), c_u64p, C.POINTER(c_f64p)]
         _lib = L
     return _lib
 
@@ -353,6 +361,18 @@ class Cross:
                                       C.byref(nf), C.byref(ch)))
         return cores, int(nf.value), float(ch.value)
 
+    def vi_solve(self, prob: "Problem", ranks0, cores0, maxiter, abs_conv_tol=0.0, sweeps=5, verbose=0):
+        """c3control_vi_solve on the GPU path; returns (cores, iterations, last l2 difference, fibers)"""
+        r0 = np.ascontiguousarray(ranks0, dtype=np.uint64)
+        c0 = [np.ascontiguousarray(c, dtype=np.float64).reshape(-1) for c in cores0]
+        a0 = (c_f64p * self.d)(*[c.ctypes.data_as(c_f64p) for c in c0])
+        cores, arr = self._cores()
+        o = CrossOpts(sweeps, 0.0, verbose)
+        it = C.c_uint32(); diff = C.c_double(); nf = C.c_uint64()
+        check(lib().c3sc_vi_solve(self.handle, prob.handle, r0.ctypes.data_as(c_u64p), a0, maxiter, abs_conv_tol, C.byref(o), arr,
+                                  C.byref(it), C.byref(diff), C.byref(nf)))
+        return cores, int(it.value), float(diff.value), int(nf.value)
+
     def run(self, fn, maxiter=5, tol=0.0, verbose=0):
         """same driver, operator = Python callable fn(dim_vary[F], fixed_ind[F,d]) -> values[F, nmax]"""
         nmax = int(self.n.max())
@@ -379,3 +399,21 @@ class Cross:
             self.handle = None
 
     __del__ = close
+
+
+def cores_norm2diff(n, ranks_a, cores_a, ranks_b, cores_b) -> float:
+    """valuef_norm2diff on nodal cores (discrete l2 over the grid nodes)"""
+    n = np.ascontiguousarray(n, dtype=np.uint64); d = int(n.size)
+    ra = np.ascontiguousarray(ranks_a, dtype=np.uint64); rb = np.ascontiguousarray(ranks_b, dtype=np.uint64)
+    ca = [np.ascontiguousarray(c, dtype=np.float64).reshape(-1) for c in cores_a]
+    cb = [np.ascontiguousarray(c, dtype=np.float64).reshape(-1) for c in cores_b]
+    aa = (c_f64p * d)(*[c.ctypes.data_as(c_f64p) for c in ca]); ab = (c_f64p * d)(*[c.ctypes.data_as(c_f64p) for c in cb])
+    return float(lib().c3sc_cores_norm2diff(d, n.ctypes.data_as(c_u64p), ra.ctypes.data_as(c_u64p), aa, rb.ctypes.data_as(c_u64p), ab))
+
+
+def cores_norm(n, ranks, cores) -> float:
+    n = np.ascontiguousarray(n, dtype=np.uint64); d = int(n.size)
+    r = np.ascontiguousarray(ranks, dtype=np.uint64)
+    ca = [np.ascontiguousarray(c, dtype=np.float64).reshape(-1) for c in cores]
+    aa = (c_f64p * d)(*[c.ctypes.data_as(c_f64p) for c in ca])
+    return float(lib().c3sc_cores_norm(d, n.ctypes.data_as(c_u64p), r.ctypes.data_as(c_u64p), aa))

@@ -255,33 +255,63 @@ static void store_core(const double *T, size_t rk, size_t N, size_t rk1, double 
             for (size_t a = 0; a < rk; a++) core[j * rk * rk1 + a + b * rk] = T[a + j * rk + b * rk * N];
 }
 
-/* <A, B> of two trains in the ValueF layout (discrete inner product over the grid):
- * M (r_k x r_k) <- sum_j A_k[j]^T M B_k[j], two r^3 products per node.  w1, w2: rmax^2 each, w3: rmax^2. */
-static double tt_dot(uint32_t d, const uint64_t *n, const uint64_t *r, double *const *A, double *const *B, double *w1, double *w2,
-                     double *w3)
+/* <A, B> of two trains in the ValueF layout (discrete inner product over the grid nodes):
+ * M (rA_k x rB_k) <- sum_j A_k[j]^T M B_k[j], two r^3 products per node.  w1, w2, w3: rmax^2 each. */
+static double tt_dot2(uint32_t d, const uint64_t *n, const uint64_t *ra, double *const *A, const uint64_t *rb, double *const *B,
+                      double *w1, double *w2, double *w3)
 {
     w1[0] = 1.0;
     for (uint32_t k = 0; k < d; k++) {
-        const size_t r0 = r[k], r1 = r[k + 1], blk = r0 * r1;
-        for (size_t e = 0; e < r1 * r1; e++) w2[e] = 0.0;
+        const size_t a0 = ra[k], a1 = ra[k + 1], b0 = rb[k], b1 = rb[k + 1];
+        for (size_t e = 0; e < a1 * b1; e++) w2[e] = 0.0;
         for (size_t j = 0; j < n[k]; j++) {
-            const double *a = A[k] + j * blk, *b = B[k] + j * blk;
-            for (size_t q = 0; q < r1; q++)                    /* w3 = M b  (r0 x r1) */
-                for (size_t x = 0; x < r0; x++) {
+            const double *a = A[k] + j * a0 * a1, *b = B[k] + j * b0 * b1;
+            for (size_t q = 0; q < b1; q++)                    /* w3 = M b  (a0 x b1), M is a0 x b0 */
+                for (size_t x = 0; x < a0; x++) {
                     double t = 0.0;
-                    for (size_t y = 0; y < r0; y++) t += w1[x + y * r0] * b[y + q * r0];
-                    w3[x + q * r0] = t;
+                    for (size_t y = 0; y < b0; y++) t += w1[x + y * a0] * b[y + q * b0];
+                    w3[x + q * a0] = t;
                 }
-            for (size_t q = 0; q < r1; q++)                    /* w2 += a^T w3  (r1 x r1) */
-                for (size_t p = 0; p < r1; p++) {
+            for (size_t q = 0; q < b1; q++)                    /* w2 += a^T w3  (a1 x b1) */
+                for (size_t p = 0; p < a1; p++) {
                     double t = 0.0;
-                    for (size_t x = 0; x < r0; x++) t += a[x + p * r0] * w3[x + q * r0];
-                    w2[p + q * r1] += t;
+                    for (size_t x = 0; x < a0; x++) t += a[x + p * a0] * w3[x + q * a0];
+                    w2[p + q * a1] += t;
                 }
         }
-        memcpy(w1, w2, r1 * r1 * sizeof(double));
+        memcpy(w1, w2, a1 * b1 * sizeof(double));
     }
     return w1[0];
+}
+static double tt_dot(uint32_t d, const uint64_t *n, const uint64_t *r, double *const *A, double *const *B, double *w1, double *w2,
+                     double *w3)
+{
+    return tt_dot2(d, n, r, A, r, B, w1, w2, w3);
+}
+
+/* valuef_norm / valuef_norm2diff (src/valuefunc.c:315-335) on nodal cores: the discrete l2 norm over the
+ * grid nodes (C3's function_train_norm2 integrates the piecewise-linear interpolant instead; the
+ * solvers only use these numbers as a Cauchy criterion, src/bellman.c:2307-2338). */
+double c3sc_cores_dot(uint32_t d, const uint64_t *n, const uint64_t *ra, const double *const *A, const uint64_t *rb,
+                      const double *const *B)
+{
+    size_t rmax = 1;
+    for (uint32_t k = 0; k <= d; k++) { if (ra[k] > rmax) rmax = ra[k]; if (rb[k] > rmax) rmax = rb[k]; }
+    double *w = (double *)malloc(3 * rmax * rmax * sizeof(double));
+    if (!w) return NAN;
+    const double v = tt_dot2(d, n, ra, (double *const *)A, rb, (double *const *)B, w, w + rmax * rmax, w + 2 * rmax * rmax);
+    free(w);
+    return v;
+}
+double c3sc_cores_norm(uint32_t d, const uint64_t *n, const uint64_t *r, const double *const *A)
+{
+    return sqrt(fabs(c3sc_cores_dot(d, n, r, A, r, A)));
+}
+double c3sc_cores_norm2diff(uint32_t d, const uint64_t *n, const uint64_t *ra, const double *const *A, const uint64_t *rb,
+                            const double *const *B)
+{
+    const double aa = c3sc_cores_dot(d, n, ra, A, ra, A), ab = c3sc_cores_dot(d, n, ra, A, rb, B), bb = c3sc_cores_dot(d, n, rb, B, rb, B);
+    return sqrt(fabs(aa - 2.0 * ab + bb));
 }
 
 int c3sc_cross_run(c3sc_cross *c, c3sc_fiber_batch_fn f, void *arg, const c3sc_cross_opts *opts, double *const *cores,
@@ -424,4 +454,56 @@ int c3sc_cross_run_vi(c3sc_cross *c, c3sc_problem *p, const c3sc_valuef *vf, con
 {
     struct vi_ctx x = {p, vf};
     return c3sc_cross_run(c, vi_cb, &x, opts, cores, nfibers, rel_change);
+}
+
+/* c3control_vi_solve (src/bellman.c:2282-2340): iterate next = cross(bellman_vi(.; current)) until the l2
+ * difference between iterates drops below abs_conv_tol or maxiter steps were taken.  cores0 / ranks0: the
+ * start value function (any ranks); cores_out: n[k]*r[k]*r[k+1] doubles each with the driver's ranks. */
+int c3sc_vi_solve(c3sc_cross *c, c3sc_problem *p, const uint64_t *ranks0, const double *const *cores0, uint32_t maxiter,
+                  double abs_conv_tol, const c3sc_cross_opts *opts, double *const *cores_out, uint32_t *iters_done,
+                  double *last_diff, uint64_t *nfibers)
+{
+    if (!c || !p || !ranks0 || !cores0 || !cores_out) return C3SC_EINVAL;
+    const uint32_t d = c->d;
+    c3sc_valuef *vf = NULL;
+    int rc = c3sc_valuef_create(d, c->n, ranks0, cores0, &vf);
+    if (rc) return rc;
+    double **cur = (double **)calloc(d, sizeof(double *));
+    uint64_t rcur[C3SC_MAXD + 1], total = 0;
+    if (!cur) { c3sc_valuef_destroy(vf); return C3SC_EINVAL; }
+    for (uint32_t k = 0; k <= d; k++) rcur[k] = ranks0[k];
+    for (uint32_t k = 0; k < d; k++) {
+        size_t len0 = c->n[k] * ranks0[k] * ranks0[k + 1], len1 = c->n[k] * c->r[k] * c->r[k + 1];
+        cur[k] = (double *)malloc((len0 > len1 ? len0 : len1) * sizeof(double));
+        if (!cur[k]) { rc = C3SC_EINVAL; goto out; }
+        memcpy(cur[k], cores0[k], len0 * sizeof(double));
+    }
+    uint32_t it = 0;
+    double diff = 0.0;
+    for (; it < maxiter; it++) {
+        uint64_t nf = 0;
+        rc = c3sc_cross_run_vi(c, p, vf, opts, cores_out, &nf, NULL);
+        if (rc) goto out;
+        total += nf;
+        diff = c3sc_cores_norm2diff(d, c->n, rcur, (const double *const *)cur, c->r, (const double *const *)cores_out);
+        if (opts && opts->verbose)
+            fprintf(stderr, "c3sc_vi_solve: iteration %u, l2 difference %.5e, l2 norm %.5e\n", it + 1, diff,
+                    c3sc_cores_norm(d, c->n, c->r, (const double *const *)cores_out));
+        int same = 1;
+        for (uint32_t k = 0; k <= d; k++) same = same && rcur[k] == c->r[k];
+        for (uint32_t k = 0; k < d; k++) memcpy(cur[k], cores_out[k], c->n[k] * c->r[k] * c->r[k + 1] * sizeof(double));
+        for (uint32_t k = 0; k <= d; k++) rcur[k] = c->r[k];
+        if (same) rc = c3sc_valuef_update(vf, (const double *const *)cur);
+        else { c3sc_valuef_destroy(vf); vf = NULL; rc = c3sc_valuef_create(d, c->n, c->r, (const double *const *)cur, &vf); }
+        if (rc) goto out;
+        if (diff < abs_conv_tol) { it++; break; }
+    }
+    if (iters_done) *iters_done = it;
+    if (last_diff) *last_diff = diff;
+    if (nfibers) *nfibers = total;
+out:
+    for (uint32_t k = 0; k < d; k++) free(cur[k]);
+    free(cur);
+    c3sc_valuef_destroy(vf);
+    return rc;
 }

@@ -43,6 +43,21 @@ int c3sc_cross_run_pi(c3sc_cross *c, c3sc_problem *p, const c3sc_valuef *vf_poli
                       uint32_t dx, const c3sc_cross_opts *opts, double *const *cores, uint64_t *nfibers,
                       double *rel_change);
 
+/* c3control_vi_solve (src/bellman.c:2282-2340) on the GPU path: value iteration from the start train
+ * (ranks0, cores0) until ||V_{t+1} - V_t|| < abs_conv_tol (nodal l2) or maxiter steps.  cores_out in the
+ * driver's ranks (c3sc_cross_ranks).  iters_done / last_diff / nfibers may be NULL. */
+int c3sc_vi_solve(c3sc_cross *c, c3sc_problem *p, const uint64_t *ranks0, const double *const *cores0,
+                  uint32_t maxiter, double abs_conv_tol, const c3sc_cross_opts *opts, double *const *cores_out,
+                  uint32_t *iters_done, double *last_diff, uint64_t *nfibers);
+
+/* valuef_norm / valuef_norm2diff (src/valuefunc.c:315-335) on nodal cores in ValueF::cores layout:
+ * discrete l2 over the grid nodes; the two trains may have different ranks. */
+double c3sc_cores_dot(uint32_t d, const uint64_t *n, const uint64_t *ranks_a, const double *const *a,
+                      const uint64_t *ranks_b, const double *const *b);
+double c3sc_cores_norm(uint32_t d, const uint64_t *n, const uint64_t *ranks, const double *const *a);
+double c3sc_cores_norm2diff(uint32_t d, const uint64_t *n, const uint64_t *ranks_a, const double *const *a,
+                            const uint64_t *ranks_b, const double *const *b);
+
 #ifdef __cplusplus
 }
 #endif

@@ -66,6 +66,39 @@ def test_rank_is_clipped_to_unfolding():
     cr.close()
 
 
+def test_core_norms_against_dense():
+    """valuef_norm / valuef_norm2diff stand-ins: discrete l2 of trains with different ranks"""
+    n = [5, 6, 4]
+    ra, rb = [1, 3, 2, 1], [1, 2, 4, 1]
+    ca = synthetic.random_cores(np.array(n, dtype=np.uint64), np.array(ra, dtype=np.uint64), seed=3)
+    cb = synthetic.random_cores(np.array(n, dtype=np.uint64), np.array(rb, dtype=np.uint64), seed=4)
+    A, B = _tt_full(n, ra, ca), _tt_full(n, rb, cb)
+    assert abs(capi.cores_norm(n, ra, ca) - np.linalg.norm(A)) <= 1e-13 * np.linalg.norm(A)
+    assert abs(capi.cores_norm2diff(n, ra, ca, rb, cb) - np.linalg.norm(A - B)) <= 1e-12 * np.linalg.norm(A - B)
+
+
+@pytest.mark.gpu
+def test_vi_solve_converges_like_the_python_loop(gpu):
+    """c3sc_vi_solve == the step-by-step loop over c3sc_cross_run_vi (same driver state evolution)"""
+    cfg = configs.get_config("lqg2d_reflect", n=20, rank=5)
+    prob = capi.Problem(cfg, arith=1)
+    ranks0, cores0 = synthetic.quadratic_cores(prob.xgrid)
+    cr1, cr2 = capi.Cross(cfg.ngrid, cfg.ranks()), capi.Cross(cfg.ngrid, cfg.ranks())
+    cores, iters, diff, nfib = cr1.vi_solve(prob, ranks0, cores0, maxiter=5, abs_conv_tol=0.0, sweeps=2)
+    assert iters == 5 and nfib > 0 and np.isfinite(diff)
+    cg, rg = cores0, np.asarray(ranks0, dtype=np.uint64)
+    for _ in range(5):
+        vf = capi.ValueF(cfg.ngrid, rg, cg)
+        prev, rprev = cg, rg
+        cg, _, _ = cr2.run_vi(prob, vf, maxiter=2)
+        rg = cr2.ranks
+        vf.close()
+    for a, b in zip(cores, cg):
+        assert np.array_equal(a, b)
+    assert abs(diff - capi.cores_norm2diff(cfg.ngrid, rprev, prev, rg, cg)) <= 1e-12 * max(diff, 1e-300)
+    prob.close(); cr1.close(); cr2.close()
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("name,n,rank,dx,iters", [("lqg2d_reflect", 24, 6, None, 6), ("lqgnd", 12, 4, 4, 4),
                                                     ("dubinscar_new", 14, 5, None, 4)])
