@@ -132,3 +132,27 @@ def test_value_iteration_gpu_equals_oracle(gpu, name, n, rank, dx, iters):
     scale = max(np.abs(vo).max(), 1.0)
     assert np.abs(vg - vo).max() <= 1e-10 * scale, np.abs(vg - vo).max() / scale
     prob.close(); vf.close(); cr_g.close(); cr_o.close()
+
+
+@pytest.mark.gpu
+def test_policy_iteration_step_gpu_equals_oracle(gpu):
+    """c3control_step_pi through the driver: policy from one train, evaluation against another"""
+    cfg = configs.get_config("lqgnd", n=12, rank=4, dx=4)
+    prob = capi.Problem(cfg, arith=1)
+    port = make_port(cfg)
+    ranks = cfg.ranks()
+    c_pol = synthetic.random_cores(cfg.ngrid, ranks, seed=11)
+    c_it = synthetic.random_cores(cfg.ngrid, ranks, seed=12)
+    vf_pol, vf_it = capi.ValueF(cfg.ngrid, ranks, c_pol), capi.ValueF(cfg.ngrid, ranks, c_it)
+    ft_pol, ft_it = po.FT(cfg.ngrid, ranks, c_pol), po.FT(cfg.ngrid, ranks, c_it)
+    cr_g, cr_o = capi.Cross(cfg.ngrid, ranks), capi.Cross(cfg.ngrid, ranks)
+    cg, nf_g, _ = cr_g.run_pi(prob, vf_pol, vf_it, maxiter=2)
+    co, nf_o, _ = cr_o.run(lambda dv, fi: port.pi_batch(ft_pol, ft_it, dv, fi)[0], maxiter=2)
+    assert nf_g == nf_o
+    ft_g, ft_o = po.FT(cfg.ngrid, cr_g.ranks, cg), po.FT(cfg.ngrid, cr_o.ranks, co)
+    u = synthetic.uniform01(5, 300 * cfg.dx).reshape(300, cfg.dx)
+    pts = cfg.lb + u * (cfg.ub - cfg.lb)
+    vg = np.array([port.ft_eval_linear(ft_g, np.ascontiguousarray(x)) for x in pts])
+    vo = np.array([port.ft_eval_linear(ft_o, np.ascontiguousarray(x)) for x in pts])
+    assert np.abs(vg - vo).max() <= 1e-10 * max(np.abs(vo).max(), 1.0)
+    prob.close(); vf_pol.close(); vf_it.close(); cr_g.close(); cr_o.close()
