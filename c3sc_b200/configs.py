@@ -46,9 +46,12 @@ class Config:
     obs_center: np.ndarray = field(default_factory=lambda: np.zeros((0, 0)))
     obs_width: np.ndarray = field(default_factory=lambda: np.zeros((0, 0)))
     params: np.ndarray = field(default_factory=lambda: np.zeros(0))
+    nvec: np.ndarray | None = None   # per-dimension node counts when they differ (tests); n = their maximum
 
     @property
     def ngrid(self) -> np.ndarray:
+        if self.nvec is not None:
+            return np.asarray(self.nvec, dtype=np.uint64)
         return np.full(self.dx, self.n, dtype=np.uint64)
 
     @property

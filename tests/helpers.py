@@ -23,7 +23,7 @@ SMALL = [
 def host_problem(cfg):
     """xgrid, h2, t, obstacle boxes computed on the host exactly as the reference does
     (c3control_create / mca_add_grid_refs / bound_rect_init)."""
-    xg = [configs.c3_linspace(cfg.lb[i], cfg.ub[i], cfg.n) for i in range(cfg.dx)]
+    xg = [configs.c3_linspace(cfg.lb[i], cfg.ub[i], int(cfg.ngrid[i])) for i in range(cfg.dx)]
     h, hmin, h2, t = grid_constants(xg, cfg.lb, cfg.ub)
     if cfg.obs_center.size:
         olb = cfg.obs_center - cfg.obs_width / 2.0

@@ -56,6 +56,19 @@ def test_mixed_ranks_and_ragged_groups(gpu):
         _check_costs_and_values(cfg, ranks, F, seed=F)
 
 
+def test_ragged_grids_and_twelve_dimensions(gpu):
+    """different node counts per dimension (ldo = the largest; shorter fibers leave padding entries
+    untouched) and the largest instantiated LQG dimension"""
+    cfg = configs.get_config("dubinscar_new", n=17, rank=5)
+    cfg.nvec = np.array([11, 17, 13], dtype=np.uint64)
+    _check_costs_and_values(cfg, cfg.ranks(), 45)
+    cfg = configs.get_config("skidding5d", n=12, rank=4)
+    cfg.nvec = np.array([9, 12, 8, 10, 11], dtype=np.uint64)
+    _check_costs_and_values(cfg, cfg.ranks(), 45)
+    cfg = configs.get_config("lqgnd_reflect", n=5, rank=3, dx=12)
+    _check_costs_and_values(cfg, cfg.ranks(), 36)
+
+
 def test_large_batch_is_chunked_consistently(gpu):
     """a batch larger than one pipeline chunk gives the same numbers as its pieces"""
     cfg = configs.get_config("lqgnd_reflect", n=20, rank=6, dx=8)
