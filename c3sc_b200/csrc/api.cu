@@ -14,8 +14,7 @@ namespace c3sc {
 int launch_control_lqg_lo(int dx, int arith, const CtlArgs &a, int pi_eval, cudaStream_t st);
 int launch_control_lqg_hi(int dx, int arith, const CtlArgs &a, int pi_eval, cudaStream_t st);
 int launch_control_misc(int model, int dx, int arith, const CtlArgs &a, int pi_eval, cudaStream_t st);
-int launch_group_fibers(int F, int d, const int *dim_vary, int *perm, int *kcount, int *kstart, int *act_count,
-                        cudaStream_t st);
+int launch_group_fibers(int F, int FC, int d, const int *dim_vary, int *perm, int *cnt_all, cudaStream_t st);
 int launch_pack_cores(const DevFT &ft, double *baseT, double *baseP, cudaStream_t st);
 long long ft_padded_layout(DevFT &ft);
 int launch_ft_costs(const FtArgs &a, cudaStream_t st);
@@ -399,21 +398,25 @@ static int run_batch(const DevProblem &P, int model, int arith, Scratch &scr, co
     const size_t NSmax = FC * b.ldo;
     const bool need_cst = b.mode != MODE_COSTS;
     if ((need_cst && scr.cst.reserve(NSmax * CS * 8)) || scr.flag.reserve(NSmax) || scr.act.reserve(NSmax * 4) ||
-        scr.perm.reserve(FC * 4) || scr.cnt.reserve(64 * 4))
+        scr.perm.reserve(b.F * 4) || scr.cnt.reserve(((b.F + FC - 1) / FC) * 64 * 4))
         return fail(C3SC_ECUDA, "cudaMalloc pipeline scratch failed");
     const int mma = ft_uses_mma(ft);
     if (mma && scr.sets.reserve(ft_sets_bytes(ft, FC))) return fail(C3SC_ECUDA, "cudaMalloc chain scratch failed");
-    int *cnt = (int *)scr.cnt.p;                  // [0,16) kcount, [16,32) kstart, [32] act_count
+    {   // every chunk's grouping in one launch
+        int rc = launch_group_fibers((int)b.F, (int)FC, (int)d, b.dim_vary, (int *)scr.perm.p, (int *)scr.cnt.p, st);
+        if (rc) return fail(C3SC_ECUDA, "grouping kernel: %s", cudaGetErrorString((cudaError_t)rc));
+        g_launches++;
+    }
     for (size_t c0 = 0; c0 < b.F; c0 += FC) {
         const size_t Fc = (b.F - c0 < FC) ? b.F - c0 : FC;
         const size_t n0 = c0 * b.ldo;
-        int rc = launch_group_fibers((int)Fc, (int)d, b.dim_vary + c0, (int *)scr.perm.p, cnt, cnt + 16, cnt + 32, st);
-        if (rc) return fail(C3SC_ECUDA, "grouping kernel: %s", cudaGetErrorString((cudaError_t)rc));
+        int *cnt = (int *)scr.cnt.p + 64 * (c0 / FC);   // [0,16) kcount, [16,32) kstart, [32] act_count
+        int rc;
         FtArgs a;
         memset(&a, 0, sizeof a);
         a.P = P; a.ft = ft; a.F = (int)Fc; a.dim_vary = b.dim_vary + c0; a.fixed_ind = b.fixed_ind + c0 * d;
         a.ldo = (int)b.ldo; a.FB = 0;
-        a.perm = (const int *)scr.perm.p; a.kcount = cnt; a.kstart = cnt + 16;
+        a.perm = (const int *)scr.perm.p + c0; a.kcount = cnt; a.kstart = cnt + 16;
         a.NS = (long long)(Fc * b.ldo);
         a.cst = need_cst ? (double *)scr.cst.p : nullptr;
         a.flag = (signed char *)scr.flag.p;
@@ -428,7 +431,7 @@ static int run_batch(const DevProblem &P, int model, int arith, Scratch &scr, co
         a.sets = mma ? (double *)scr.sets.p : nullptr;
         rc = launch_ft_costs(a, st);
         if (rc) return fail(C3SC_ECUDA, "FT kernel launch: %s", cudaGetErrorString((cudaError_t)rc));
-        g_launches += 2 + mma;
+        g_launches += 1 + mma;
         if (b.mode == MODE_COSTS) continue;
         CtlArgs c;
         memset(&c, 0, sizeof c);

@@ -17,12 +17,11 @@ static void ft_device_info()
 
 int ft_sm_count() { ft_device_info(); return g_sms; }
 
-// perm / kcount / kstart of one chunk; clears *act_count.  1 launch.
-int launch_group_fibers(int F, int d, const int *dim_vary, int *perm, int *kcount, int *kstart, int *act_count,
-                        cudaStream_t st)
+// perm / kcount / kstart / cleared active counters of ALL chunks of a batch.  1 launch.
+int launch_group_fibers(int F, int FC, int d, const int *dim_vary, int *perm, int *cnt_all, cudaStream_t st)
 {
     if (F <= 0) return 0;
-    k_group_fibers<<<1, 1024, 0, st>>>(F, d, dim_vary, perm, kcount, kstart, act_count);
+    k_group_fibers<<<(F + FC - 1) / FC, 1024, 0, st>>>(F, FC, d, dim_vary, perm, cnt_all);
     return (int)cudaGetLastError();
 }
 

@@ -116,16 +116,19 @@ struct FtPlan {
 
 #ifndef C3SC_FT_TYPES_ONLY
 // ---------------------------------------------------------------------------
-// Group the fibers of a chunk by varying dimension: perm = fiber ids, k-major.  One CTA.
-// Also clears the active-node counter of the chunk.
-__global__ void __launch_bounds__(1024) k_group_fibers(int F, int d, const int *dim_vary, int *perm, int *kcount,
-                                                       int *kstart, int *act_count)
+// Group the fibers of every chunk of a batch by varying dimension: perm = fiber ids (relative to the
+// chunk), k-major.  One CTA per chunk (blockIdx.x); chunk c covers fibers [c*FC, min(F, (c+1)*FC)) and
+// owns perm[c*FC ..], and 64 ints of `cnt`: [0,16) kcount, [16,32) kstart, [32] active-node counter (cleared).
+__global__ void __launch_bounds__(1024) k_group_fibers(int F, int FC, int d, const int *dim_vary, int *perm, int *cnt_all)
 {
     __shared__ int cnt[MAXD], pos[MAXD];
     const int tid = threadIdx.x;
+    const int c0 = blockIdx.x * FC, Fc = (F - c0 < FC) ? F - c0 : FC;
+    dim_vary += c0; perm += c0;
+    int *kcount = cnt_all + 64 * blockIdx.x, *kstart = kcount + 16, *act_count = kcount + 32;
     if (tid < MAXD) cnt[tid] = 0;
     __syncthreads();
-    for (int f = tid; f < F; f += blockDim.x) {
+    for (int f = tid; f < Fc; f += blockDim.x) {
         int k = dim_vary[f];
         k = k < 0 ? 0 : (k >= d ? d - 1 : k);
         atomicAdd(&cnt[k], 1);
@@ -134,11 +137,11 @@ __global__ void __launch_bounds__(1024) k_group_fibers(int F, int d, const int *
     if (tid == 0) {
         int run = 0;
         for (int k = 0; k < d; k++) { pos[k] = run; kstart[k] = run; kcount[k] = cnt[k]; run += cnt[k]; }
-        if (act_count) *act_count = 0;
+        *act_count = 0;
     }
     __syncthreads();
-    // stable within a thread's stride; the order inside a group does not change any result
-    for (int f = tid; f < F; f += blockDim.x) {
+    // the order inside a group does not change any result
+    for (int f = tid; f < Fc; f += blockDim.x) {
         int k = dim_vary[f];
         k = k < 0 ? 0 : (k >= d ? d - 1 : k);
         perm[atomicAdd(&pos[k], 1)] = f;

@@ -86,6 +86,22 @@ __global__ void __launch_bounds__(256) k_mix(double *sink, int iters, double a, 
     for (int i = 0; i < CH; i++) s += c[i][0] + c[i][1] + f[i];
     if (s == 123.456) sink[0] = s;
 }
+// DMMA with distinct operand registers per instruction (what a real fragment loop issues)
+template <int CH>
+__global__ void __launch_bounds__(256) k_dmma_ops(double *sink, const double *src, int iters)
+{
+    double c[CH][2], a[CH], b[CH];
+#pragma unroll
+    for (int i = 0; i < CH; i++) { c[i][0] = threadIdx.x; c[i][1] = i; a[i] = src[(threadIdx.x + i) & 63]; b[i] = src[(threadIdx.x * 5 + i) & 63]; }
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+        for (int i = 0; i < CH; i++) dmma(c[i][0], c[i][1], a[i], b[(i + 3) % CH]);
+    }
+    double s = 0;
+#pragma unroll
+    for (int i = 0; i < CH; i++) s += c[i][0] + c[i][1];
+    if (s == 123.456) sink[0] = s;
+}
 int main()
 {
     double *sink; cudaMalloc(&sink, 8);
@@ -129,6 +145,19 @@ int main()
         cudaEventElapsedTime(&ms, e0, e1);
         double fl_t = 2.0 * 256 * 8.0 * iters * (double)sms * ctas * 8, fl_f = 2.0 * 256 * 8.0 * 4 * iters * (double)sms * ctas;
         printf("MIX 1 DMMA : 4 DFMA  %d CTA/SM: tensor %.2f + fma %.2f = %.2f TFLOP/s\n", ctas, fl_t / ms / 1e9, fl_f / ms / 1e9, (fl_t + fl_f) / ms / 1e9);
+    }
+    {
+        double *src; cudaMalloc(&src, 64 * 8);
+        double h[64]; for (int i = 0; i < 64; i++) h[i] = 1.0 + 1e-9 * i;
+        cudaMemcpy(src, h, sizeof h, cudaMemcpyHostToDevice);
+        for (int ctas = 1; ctas <= 4; ctas *= 2) {
+            float ms;
+            k_dmma_ops<8><<<sms * ctas, 256>>>(sink, src, 100);
+            cudaEventRecord(e0); k_dmma_ops<8><<<sms * ctas, 256>>>(sink, src, iters); cudaEventRecord(e1); cudaEventSynchronize(e1);
+            cudaEventElapsedTime(&ms, e0, e1);
+            double fl = 2.0 * 256 * 8.0 * iters * (double)sms * ctas * 8;
+            printf("DMMA distinct operand registers %d CTA/SM: %.2f TFLOP/s\n", ctas, fl / ms / 1e9);
+        }
     }
     // dependent-chain latency: one chain per warp, one warp per SM
     {
