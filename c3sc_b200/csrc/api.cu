@@ -15,8 +15,9 @@ int launch_control_lqg_lo(int dx, int arith, const CtlArgs &a, int pi_eval, cuda
 int launch_control_lqg_hi(int dx, int arith, const CtlArgs &a, int pi_eval, cudaStream_t st);
 int launch_control_misc(int model, int dx, int arith, const CtlArgs &a, int pi_eval, cudaStream_t st);
 int launch_group_fibers(int F, int FC, int d, const int *dim_vary, int *perm, int *cnt_all, cudaStream_t st);
-int launch_pack_cores(const DevFT &ft, double *baseT, double *baseP, cudaStream_t st);
+int launch_pack_cores(const DevFT &ft, double *baseT, double *baseP, double *baseQ, cudaStream_t st);
 long long ft_padded_layout(DevFT &ft);
+long long ft_compact_layout(DevFT &ft);
 int launch_ft_costs(const FtArgs &a, cudaStream_t st);
 int ft_uses_mma(const DevFT &ft);
 size_t ft_sets_bytes(const DevFT &ft, size_t F);
@@ -108,7 +109,7 @@ struct c3sc_problem {
 
 struct c3sc_valuef {
     DevFT ft;
-    double *d_base = nullptr, *d_baseT = nullptr, *d_baseP = nullptr;
+    double *d_base = nullptr, *d_baseT = nullptr, *d_baseP = nullptr, *d_baseQ = nullptr;
     size_t count = 0;
     std::vector<size_t> len;
 };
@@ -318,6 +319,11 @@ int c3sc_valuef_create(uint32_t d, const uint64_t *n, const uint64_t *ranks, con
         e = cudaMalloc(&vf->d_baseP, (size_t)np * sizeof(double));
         if (e != cudaSuccess) { cudaFree(vf->d_base); cudaFree(vf->d_baseT); delete vf; return fail(C3SC_ECUDA, "cudaMalloc padded cores: %s", cudaGetErrorString(e)); }
         ft.baseP = vf->d_baseP;
+        const long long nq = ft_compact_layout(ft);
+        e = cudaMalloc(&vf->d_baseQ, (size_t)nq * sizeof(double));
+        if (e == cudaSuccess) e = cudaMemset(vf->d_baseQ, 0, (size_t)nq * sizeof(double));
+        if (e != cudaSuccess) { cudaFree(vf->d_base); cudaFree(vf->d_baseT); cudaFree(vf->d_baseP); delete vf; return fail(C3SC_ECUDA, "cudaMalloc tile cores: %s", cudaGetErrorString(e)); }
+        ft.baseQ = vf->d_baseQ;
     }
     *out = vf;
     if (cores) {
@@ -341,7 +347,7 @@ int c3sc_valuef_update(c3sc_valuef *vf, const double *const *cores)
 int c3sc_valuef_commit(c3sc_valuef *vf, void *stream)
 {
     if (!vf) return fail(C3SC_EINVAL, "null argument");
-    int rc = launch_pack_cores(vf->ft, vf->d_baseT, vf->d_baseP, (cudaStream_t)stream);
+    int rc = launch_pack_cores(vf->ft, vf->d_baseT, vf->d_baseP, vf->d_baseQ, (cudaStream_t)stream);
     if (rc) return fail(C3SC_ECUDA, "core packing kernel: %s", cudaGetErrorString((cudaError_t)rc));
     g_launches++;
     return C3SC_OK;
@@ -361,6 +367,7 @@ void c3sc_valuef_destroy(c3sc_valuef *vf)
     cudaFree(vf->d_base);
     cudaFree(vf->d_baseT);
     cudaFree(vf->d_baseP);
+    cudaFree(vf->d_baseQ);
     delete vf;
 }
 

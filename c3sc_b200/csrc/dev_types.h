@@ -39,6 +39,12 @@ struct DevFT {
     const double *baseP;
     long long offP[MAXD];
     int ldp[MAXD], cpp[MAXD];
+    // compact tile copy for the node kernel's TMA: block j of core k at baseQ + offQ[k] + j*ldq[k]*r_{k+1},
+    // element (a,b) at b*ldq[k] + a with ldq = r_k rounded up to even, so every block starts 16-byte aligned.
+    // Fragment reads past r_k / r_{k+1} land in neighbouring finite data and meet zero operands.
+    const double *baseQ;
+    long long offQ[MAXD];
+    int ldq[MAXD];
 };
 
 struct DevOut {

@@ -25,7 +25,7 @@ int launch_group_fibers(int F, int FC, int d, const int *dim_vary, int *perm, in
     return (int)cudaGetLastError();
 }
 
-int launch_pack_cores(const DevFT &ft, double *baseT, double *baseP, cudaStream_t st)
+int launch_pack_cores(const DevFT &ft, double *baseT, double *baseP, double *baseQ, cudaStream_t st)
 {
     long long most = 0;
     for (int k = 0; k < ft.d; k++) {
@@ -36,7 +36,7 @@ int launch_pack_cores(const DevFT &ft, double *baseT, double *baseP, cudaStream_
     if (most <= 0) return 0;
     long long gx = (most + 255) / 256;
     if (gx > 1024) gx = 1024;
-    k_pack_cores<<<dim3((unsigned)gx, (unsigned)ft.d), 256, 0, st>>>(ft, baseT, baseP);
+    k_pack_cores<<<dim3((unsigned)gx, (unsigned)ft.d), 256, 0, st>>>(ft, baseT, baseP, baseQ);
     return (int)cudaGetLastError();
 }
 
@@ -56,6 +56,19 @@ long long ft_padded_layout(DevFT &ft)
         total += (long long)ft.n[k] * ft.ldp[k] * ft.cpp[k];
     }
     return total;
+}
+
+// compact tile copy (baseQ): rows padded to even only; + one zero block of slack at the end
+long long ft_compact_layout(DevFT &ft)
+{
+    long long total = 0;
+    for (int k = 0; k < ft.d; k++) {
+        ft.ldq[k] = (ft.r[k] + 1) & ~1;
+        ft.offQ[k] = total;
+        total += (long long)ft.n[k] * ft.ldq[k] * ft.r[k + 1];
+        total = (total + 1) & ~1LL;
+    }
+    return total + 2;
 }
 
 // ranks <= 32: chains by warp tasks + DMMA node kernel; larger ranks (or C3SC_FT_GENERAL=1): k_ft_costs

@@ -151,7 +151,7 @@ __global__ void __launch_bounds__(1024) k_group_fibers(int F, int FC, int d, con
 // Derived copies of the cores, rebuilt whenever the cores change (c3sc_valuef_commit):
 //   baseT  every block transposed: baseT[off_k + j*blk + b + a*r_{k+1}] = base[off_k + j*blk + a + b*r_k]
 //   baseP  (optional) zero-padded blocks, leading dimension ldp[k], cpp[k] columns
-__global__ void k_pack_cores(DevFT ft, double *baseT, double *baseP)
+__global__ void k_pack_cores(DevFT ft, double *baseT, double *baseP, double *baseQ)
 {
     const int k = blockIdx.y;
     const int rk = ft.r[k], rk1 = ft.r[k + 1], blk = rk * rk1;
@@ -171,6 +171,16 @@ __global__ void k_pack_cores(DevFT ft, double *baseT, double *baseP)
             const int rem = (int)(e - j * pb);
             const int b = rem / ld, a = rem - b * ld;
             baseP[ft.offP[k] + e] = (a < rk && b < rk1) ? ft.base[ft.off[k] + j * blk + a + (long long)b * rk] : 0.0;
+        }
+    }
+    if (baseQ) {
+        const int ld = ft.ldq[k], pb = ld * rk1;
+        const long long qtotal = (long long)ft.n[k] * pb;
+        for (long long e = t0; e < qtotal; e += step) {
+            const long long j = e / pb;
+            const int rem = (int)(e - j * pb);
+            const int b = rem / ld, a = rem - b * ld;
+            baseQ[ft.offQ[k] + e] = a < rk ? ft.base[ft.off[k] + j * blk + a + (long long)b * rk] : 0.0;
         }
     }
 }

@@ -254,7 +254,7 @@ __device__ __forceinline__ void mbar_wait(unsigned long long *b, unsigned parity
 // shape, so no fragment load is predicated.
 template <int KS>
 struct FtNodePlan {
-    int rs4, setw, nmax, sw;
+    int rs4, setw, nmax, sw, gbuf;
     int oG, oW, oU, oSets, oBar, nDoubles;
     int oFix, oNf, oFid, oWall, nInts;
     __host__ __device__ FtNodePlan(const DevFT &ft, int nmax_)
@@ -267,16 +267,18 @@ struct FtNodePlan {
         sw = 8 * ((KS + 1) / 2) * FTN_TP + 2;        // one fiber's w (or u) tile: [rank index][8 nodes]
         int gt = 0;
         for (int k = 0; k < ft.d; k++) {
-            const int g = FTN_T * ft.ldp[k] * ft.cpp[k];
+            const int g = (FTN_T + 1) * ft.ldq[k] * (int)ft.r[k + 1];    // 8 blocks + one block of zero slack
             gt = g > gt ? g : gt;
         }
+        gt = (gt + 1) & ~1;
+        gbuf = gt;
         int o = 0;
-        oG = o;    o += gt;                          // multiple of 8 doubles: 16-byte aligned
+        oG = o;    o += 2 * gt;                      // two tile buffers, each 16-byte aligned
         oW = o;    o += FT_FBMAX * sw;
         oU = o;    o += FT_FBMAX * sw;
         oSets = o; o += FT_FBMAX * setw;
         o = ft_even_up(o);
-        oBar = o;  o += 2;
+        oBar = o;  o += 2;                           // two mbarriers
         nDoubles = o;
         int q = 0;
         oFix = q;  q += FT_FBMAX * ft.d;
@@ -314,7 +316,7 @@ __global__ void __launch_bounds__(FTN_NT, 2) k_ft_nodes(const FtArgs a, const do
 
     const int N = P.ngrid[k];
     const int rk = ft.r[k], rk1 = ft.r[k + 1];
-    const int ldk = ft.ldp[k], pblk = ft.ldp[k] * ft.cpp[k];          // padded block
+    const int ldk = ft.ldq[k], pblk = ft.ldq[k] * rk1;                // compact block (rows even-padded)
     const int NVL = ft_even_up(1 + 2 * k), NVR = ft_even_up(1 + 2 * (d - 1 - k));
     const int nvL = 1 + 2 * k, nvR = 1 + 2 * (d - 1 - k);
     int rsG = 1;
@@ -331,14 +333,25 @@ __global__ void __launch_bounds__(FTN_NT, 2) k_ft_nodes(const FtArgs a, const do
     const int jb = (int)blockIdx.y * tper * FTN_T, je = (jb + tper * FTN_T < N) ? jb + tper * FTN_T : N;
     if (jb >= N) return;
 
-    // ---- first tile on its way while the flags are computed -----------------------------------
-    const double *Gp = ft.baseP + ft.offP[k];
+    // ---- tile buffers: zero once (fragment rows / columns past the ranks read finite data that meets
+    //      zero operands), then the first two tiles are on their way while the flags are computed -----
+    const double *Gp = ft.baseQ + ft.offQ[k];
+    const int GB = sp.gbuf;
+    for (int e = tid; e < 2 * GB; e += FTN_NT) sG[e] = 0.0;
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncthreads();
+    auto fetch = [&](int j1, int buf) {                     // tid 0: tile starting at node j1 -> buffer buf
+        const int nt1 = (je - j1 < FTN_T) ? je - j1 : FTN_T;
+        const unsigned bytes = (unsigned)(((size_t)nt1 * pblk * 8 + 15) & ~(size_t)15);
+        mbar_expect_tx(mbar + buf, bytes);
+        bulk_g2s(sG + buf * GB, Gp + (size_t)j1 * pblk, bytes, mbar + buf);
+    };
     if (tid == 0) {
         mbar_init(mbar, 1);
+        mbar_init(mbar + 1, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        const int nt0 = je - jb < FTN_T ? je - jb : FTN_T;
-        mbar_expect_tx(mbar, (unsigned)(nt0 * pblk * 8));
-        bulk_g2s(sG, Gp + (size_t)jb * pblk, (unsigned)(nt0 * pblk * 8), mbar);
+        fetch(jb, 0);
+        if (jb + FTN_T < je) fetch(jb + FTN_T, 1);
     }
 
     ft_flags_and_indices(a, k, nf, gstart, jb, je, sFid, sWall, sFix, sNf, sAbs, nmax);
@@ -398,15 +411,16 @@ __global__ void __launch_bounds__(FTN_NT, 2) k_ft_nodes(const FtArgs a, const do
     const double *wg = sW + warp * SW + tig * FTN_TP + gid, *ug = sU + warp * SW + tig * FTN_TP + gid;
     const size_t idf = warp < nf ? (size_t)sFid[warp] * a.ldo : 0;
 
-    unsigned phase = 0;
-    for (int j0 = jb; j0 < je; j0 += FTN_T) {
+    unsigned ph0 = 0, ph1 = 0;                             // mbarrier phase parity of the two buffers
+    int buf = 0;
+    for (int j0 = jb; j0 < je; j0 += FTN_T, buf ^= 1) {
         const int nt = (je - j0 < FTN_T) ? je - j0 : FTN_T;
-        mbar_wait(mbar, phase);
-        phase ^= 1;
+        mbar_wait(mbar + buf, buf ? ph1 : ph0);
+        if (buf) ph1 ^= 1; else ph0 ^= 1;
         // ---- w / u of node jl = warp, all fibers of the group --------------------------------
         // k-step outermost: the MT (resp. ntB) accumulator tiles are independent DMMA chains
         if (warp < nt) {
-            const double *gj = sG + warp * pblk;
+            const double *gj = sG + buf * GB + warp * pblk;
             double dw[MT][2], du[MT][2];
 #pragma unroll
             for (int t = 0; t < MT; t++) { dw[t][0] = dw[t][1] = 0.0; du[t][0] = du[t][1] = 0.0; }
@@ -436,11 +450,7 @@ __global__ void __launch_bounds__(FTN_NT, 2) k_ft_nodes(const FtArgs a, const do
             }
         }
         __syncthreads();
-        if (tid == 0 && j0 + FTN_T < je) {                               // G tile is free: fetch the next one
-            const int j1 = j0 + FTN_T, nt1 = (je - j1 < FTN_T) ? je - j1 : FTN_T;
-            mbar_expect_tx(mbar, (unsigned)(nt1 * pblk * 8));
-            bulk_g2s(sG, Gp + (size_t)j1 * pblk, (unsigned)(nt1 * pblk * 8), mbar);
-        }
+        if (tid == 0 && j0 + 2 * FTN_T < je) fetch(j0 + 2 * FTN_T, buf);     // this buffer is free: fetch the tile after next
         // ---- variant dots of fiber g = warp over the tile's nodes -----------------------------
         if (warp < nf) {
             const size_t idb = idf + j0;
