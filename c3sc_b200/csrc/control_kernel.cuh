@@ -477,9 +477,17 @@ __device__ __forceinline__ void node2_prepare(const CtlArgs &c, int id, Node2<M>
 #ifndef C3SC_C2_MINB
 #define C3SC_C2_MINB 2
 #endif
+#ifndef C3SC_C2_NODES
+#define C3SC_C2_NODES 2
+#endif
+#ifndef C3SC_C2_NT
+#define C3SC_C2_NT CT_NT
+#endif
 constexpr int C2U = C3SC_C2_UNROLL;
+constexpr int C2N = C3SC_C2_NODES;         // nodes per thread
+constexpr int C2_NT = C3SC_C2_NT;          // threads per CTA for large batches
 template <class M>
-__global__ void __launch_bounds__(CT_NT, C3SC_C2_MINB) k_control2(const CtlArgs c)
+__global__ void __launch_bounds__(C2_NT, C3SC_C2_MINB) k_control2(const CtlArgs c)
 {
     constexpr int DX = M::DX, DU = M::DU, CS = 2 * DX + 1, RW = 2 * DX + 3;
     constexpr int NUD = M::NUD, CTW = 2 * NUD + 2;
@@ -492,68 +500,82 @@ __global__ void __launch_bounds__(CT_NT, C3SC_C2_MINB) k_control2(const CtlArgs 
         __syncthreads();
     }
     const double *tab = smem;
-    const int nact = *c.act_count, nhalf = (nact + 1) >> 1;
-    const long long stride = (long long)gridDim.x * blockDim.x;      // launched with 256 or (small batches) 128 threads
+    const int nact = *c.act_count, nper = (nact + C2N - 1) / C2N;    // node q of a thread: active position it + q*nper
+    const long long stride = (long long)gridDim.x * blockDim.x;      // launched with C2_NT or (small batches) 128 threads
     const double nbh = -P.beta * P.h2;
     const bool disc = P.beta != 0.0;
-    for (long long it0 = (long long)blockIdx.x * blockDim.x + (tid & ~31); it0 < nhalf; it0 += stride) {
+    for (long long it0 = (long long)blockIdx.x * blockDim.x + (tid & ~31); it0 < nper; it0 += stride) {
         const int it = (int)it0 + lane;
-        const bool validA = it < nhalf, validB = it + nhalf < nact;
-        const int idA = c.act[validA ? it : 0], idB = c.act[validB ? it + nhalf : (validA ? it : 0)];
-        Node2<M> A, B;
-        node2_prepare<M>(c, idA, A);
-        node2_prepare<M>(c, idB, B);
-        if ((validA && A.norm0 + P.amin < 1e-14) || (validB && B.norm0 + P.amin < 1e-14)) atomicOr(P.err, 1);
-        const double nmin = A.norm0 < B.norm0 ? A.norm0 : B.norm0;
-        const bool tiny = __all_sync(0xffffffffu, !validA || (P.beta * P.h2 <= 0.00390625 * (nmin + P.amin)));
+        bool valid[C2N];
+        int id[C2N];
+        Node2<M> nd[C2N];
+        bool bad = false, small = true;
+#pragma unroll
+        for (int q = 0; q < C2N; q++) {
+            valid[q] = it < nper && it + q * nper < nact;
+            id[q] = c.act[valid[q] ? it + q * nper : 0];
+            node2_prepare<M>(c, id[q], nd[q]);
+            bad = bad || (valid[q] && nd[q].norm0 + P.amin < 1e-14);
+            small = small && (!valid[q] || P.beta * P.h2 <= 0.00390625 * (nd[q].norm0 + P.amin));
+        }
+        if (bad) atomicOr(P.err, 1);
+        const bool tiny = __all_sync(0xffffffffu, small);
         for (int g = 0; g < c.ng; g++) {
-            const int lo = c.gstart[g], hi = validA ? c.gstart[g + 1] : lo;
-            const double rinvA = rcp_pos(A.norm0 + c.gA[g]), rinvB = rcp_pos(B.norm0 + c.gA[g]);
-            double ebtA = 1.0, ebtB = 1.0;
-            if (disc) {
-                if (tiny) { ebtA = exp_tiny(nbh * rinvA); ebtB = exp_tiny(nbh * rinvB); }
-                else { ebtA = exp_nonpos(nbh * rinvA); ebtB = exp_nonpos(nbh * rinvB); }
+            const int lo = c.gstart[g], hi = valid[0] ? c.gstart[g + 1] : lo;
+            double rinv[C2N], ebt[C2N], bt[C2N];
+            int bi[C2N];
+#pragma unroll
+            for (int q = 0; q < C2N; q++) {
+                rinv[q] = rcp_pos(nd[q].norm0 + c.gA[g]);
+                ebt[q] = !disc ? 1.0 : (tiny ? exp_tiny(nbh * rinv[q]) : exp_nonpos(nbh * rinv[q]));
+                bt[q] = CUDART_INF;
+                bi[q] = 0x7fffffff;
             }
-            double btA = CUDART_INF, btB = CUDART_INF;
-            int biA = 0x7fffffff, biB = 0x7fffffff;
 #pragma unroll C2U
             for (int pos = lo; pos < hi; pos++) {
                 const double2 *row = reinterpret_cast<const double2 *>(tab + pos * CTW);
-                double SA0 = A.S0, SA1 = 0.0, SB0 = B.S0, SB1 = 0.0;
+                double S0[C2N], S1[C2N];
+#pragma unroll
+                for (int q = 0; q < C2N; q++) { S0[q] = nd[q].S0; S1[q] = 0.0; }
 #pragma unroll
                 for (int m = 0; m < NUD; m++) {
                     const double2 w = row[m];
-                    SA0 = fma(w.x, A.cu[2 * m], SA0);
-                    SA1 = fma(w.y, A.cu[2 * m + 1], SA1);
-                    SB0 = fma(w.x, B.cu[2 * m], SB0);
-                    SB1 = fma(w.y, B.cu[2 * m + 1], SB1);
+#pragma unroll
+                    for (int q = 0; q < C2N; q++) {
+                        S0[q] = fma(w.x, nd[q].cu[2 * m], S0[q]);
+                        S1[q] = fma(w.y, nd[q].cu[2 * m + 1], S1[q]);
+                    }
                 }
                 const double2 hi2 = row[NUD];                   // (h2*gu_c, table index in the low word)
                 const int ci = __double2loint(hi2.y);
-                const double tA = fma(ebtA, SA0 + SA1, hi2.x), tB = fma(ebtB, SB0 + SB1, hi2.x);
-                if (tA < btA) { btA = tA; biA = ci; }
-                if (tB < btB) { btB = tB; biB = ci; }
+#pragma unroll
+                for (int q = 0; q < C2N; q++) {
+                    const double t = fma(ebt[q], S0[q] + S1[q], hi2.x);
+                    if (t < bt[q]) { bt[q] = t; bi[q] = ci; }
+                }
             }
-            const double vA = rinvA * (btA + A.hgx), vB = rinvB * (btB + B.hgx);
-            if (vA < A.best || (vA == A.best && biA < A.ibest)) { A.best = vA; A.ibest = biA; }
-            if (vB < B.best || (vB == B.best && biB < B.ibest)) { B.best = vB; B.ibest = biB; }
+#pragma unroll
+            for (int q = 0; q < C2N; q++) {
+                const double v = rinv[q] * (bt[q] + nd[q].hgx);
+                if (v < nd[q].best || (v == nd[q].best && bi[q] < nd[q].ibest)) { nd[q].best = v; nd[q].ibest = bi[q]; }
+            }
         }
 #pragma unroll
-        for (int h = 0; h < 2; h++) {
-            if (!(h ? validB : validA)) continue;
-            const int id = h ? idB : idA, ibest = h ? B.ibest : A.ibest;
-            if (c.value) c.value[id] = h ? B.best : A.best;
-            if (c.argmin) c.argmin[id] = ibest;
+        for (int q = 0; q < C2N; q++) {
+            if (!valid[q]) continue;
+            const int ibest = nd[q].ibest;
+            if (c.value) c.value[id[q]] = nd[q].best;
+            if (c.argmin) c.argmin[id[q]] = ibest;
             if (c.rows) {                               // policy row at u* (bellman.c:1851-1860)
                 double x[DX], u[DU], b[DX], s[DX], prob[CS], dt;
-                node_state<DX>(c, id, x);
+                node_state<DX>(c, id[q], x);
 #pragma unroll
                 for (int i = 0; i < DU; i++) u[i] = P.utab[(size_t)(ibest < P.nu ? ibest : 0) * DU + i];
                 M::template drift<Fast>(x, u, P.mp, b);
                 M::template sigma<Fast>(x, u, P.mp, s);
                 const double g = M::template stage<Fast>(x, u, P.mp);
                 if (transition_row<DX, Fast>(P, b, s, prob, dt)) atomicOr(P.err, 1);
-                double *row = c.rows + (size_t)id * RW;
+                double *row = c.rows + (size_t)id[q] * RW;
 #pragma unroll
                 for (int m = 0; m < CS; m++) row[m] = prob[m];
                 row[CS] = dt;
@@ -687,12 +709,12 @@ int launch_control_t(const CtlArgs &c_in, int pi_eval, cudaStream_t st)
             if (e2 != cudaSuccess) return (int)e2;
             attr2 = smem;
         }
-        const int nt2 = (c.NS / 2 >= (long long)info.sms * 2 * CT_NT) ? CT_NT : 128;
+        const int nt2 = (c.NS / C2N >= (long long)info.sms * 2 * C2_NT) ? C2_NT : (C2_NT < 128 ? C2_NT : 128);
         int per2 = 1;
         cudaError_t e2 = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per2, k_control2<M>, nt2, smem);
         if (e2 != cudaSuccess) return (int)e2;
         if (per2 < 1) per2 = 1;
-        long long need2 = ((c.NS + 1) / 2 + nt2 - 1) / nt2;
+        long long need2 = ((c.NS + C2N - 1) / C2N + nt2 - 1) / nt2;
         long long g2 = (long long)info.sms * per2;
         if (g2 > need2) g2 = need2;
         if (g2 < 1) return 0;
