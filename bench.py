@@ -158,14 +158,18 @@ def run_reference(args, cfg, rank_ft):
     print(json.dumps(line))
 
 
+def _ncu_record():
+    try:
+        return json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
+    except Exception:
+        return None
+
+
 def ncu_traffic(F):
     """dram__bytes_read.sum + dram__bytes_write.sum of one step, from the committed `ncu --set full`
     capture (profiles/r01_traffic.json: bytes per fiber of the three pipeline kernels), or None."""
-    try:
-        t = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
-        return float(t["dram_bytes_per_fiber"]) * F
-    except Exception:
-        return None
+    t = _ncu_record()
+    return float(t["dram_bytes_per_fiber"]) * F if t else None
 
 
 def workload_config(cfg, rank_ft, F, args):
@@ -350,6 +354,11 @@ def main():
             "roofline": {"bound": "fp64", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
                          "traffic": ncu_traffic(F), "flops_per_node_backup": W,
                          "peak_source": "DFMA loop measured in this run (c3sc_measure_fp64_peak); MEASURED_PEAKS.json has no FP64 figure",
+                         "note": "achieved counts the CONTRACT flops per node-backup (SURVEY 8(d): the reference's ~180 flops per candidate); "
+                                 "the kernels execute 12 FP64 instructions per candidate, so frac > 1 is algebra, not pipe utilisation -- "
+                                 "see dominant_kernel for the ncu pipe counters",
+                         "dominant_kernel": (_ncu_record() or {}).get("dominant_kernel"),
+                         "other_kernels": (_ncu_record() or {}).get("other_kernels"),
                          "hbm": {"algorithmic_bytes_per_step": hbm_bytes, "achieved_gbs": hbm_bytes / (kernel_ms * 1e-3) / 1e9,
                                  "peak_gbs": hbm_peak, "frac": hbm_bytes / (kernel_ms * 1e-3) / 1e9 / hbm_peak,
                                  "note": "not binding: cores stay in L2/SMEM, HBM sees descriptors in and values out"}},
