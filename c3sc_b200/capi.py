@@ -58,6 +58,7 @@ EXPORTS = [
     "c3sc_transition_raw", "c3sc_ft_fiber_nn_batch", "c3sc_valuef_commit",
     "c3sc_cross_create", "c3sc_cross_destroy", "c3sc_cross_ranks", "c3sc_cross_run", "c3sc_cross_run_vi", "c3sc_cross_run_pi",
     "c3sc_vi_solve", "c3sc_cores_dot", "c3sc_cores_norm", "c3sc_cores_norm2diff",
+    "c3sc_valuef_eval_batch", "c3sc_policy_eval_batch",
 ]
 
 _lib = None
@@ -100,6 +101,8 @@ def lib() -> C.CDLL:
         L.c3sc_transition_raw.argtypes = [i32, C.c_uint32, C.c_double, vp, sz, vp, vp, vp, vp, vp]
         L.c3sc_ft_fiber_nn_batch.argtypes = [vp, sz, vp, vp, vp, vp, sz, vp]
         L.c3sc_measure_fp64_peak.argtypes = [C.POINTER(C.c_double), i32, i32]
+        L.c3sc_valuef_eval_batch.argtypes = [vp, vp, sz, vp, vp]
+        L.c3sc_policy_eval_batch.argtypes = [vp, vp, sz, vp, vp, vp, vp, vp]
         L.c3sc_cross_create.argtypes = [C.c_uint32, c_u64p, c_u64p, C.POINTER(vp)]
         L.c3sc_cross_destroy.argtypes = [vp]
         L.c3sc_cross_destroy.restype = None
@@ -271,6 +274,21 @@ class Problem:
         stage = np.empty(n); bound = np.empty(n); obs = np.empty(n)
         check(lib().c3sc_model_eval(self.handle, n, _ptr(x), _ptr(u), _ptr(drift), _ptr(sig), _ptr(stage), _ptr(bound), _ptr(obs)))
         return drift, sig, stage, bound, obs
+
+    def valuef_eval(self, vf: "ValueF", x):
+        """valuef_eval at arbitrary points (piecewise-linear FT interpolation)"""
+        x = np.ascontiguousarray(x, np.float64).reshape(-1, self.dx)
+        out = np.empty(x.shape[0])
+        check(lib().c3sc_valuef_eval_batch(self.handle, vf.handle, x.shape[0], _ptr(x), _ptr(out)))
+        return out
+
+    def policy_eval(self, vf: "ValueF", x):
+        """c3control_policy_eval at n states: (u [n,du], value [n], absorbed [n], costs [n,2dx+1])"""
+        x = np.ascontiguousarray(x, np.float64).reshape(-1, self.dx)
+        n = x.shape[0]
+        u = np.empty((n, self.du)); val = np.empty(n); ab = np.empty(n, np.int32); costs = np.empty((n, 2 * self.dx + 1))
+        check(lib().c3sc_policy_eval_batch(self.handle, vf.handle, n, _ptr(x), _ptr(u), _ptr(val), _ptr(ab), _ptr(costs)))
+        return u, val, ab, costs
 
     # ---- device-pointer entry points (ints are raw device addresses) ---------------
     def vi_batch_dev(self, vf: "ValueF", F: int, d_dim_vary: int, d_fixed_ind: int, ldo: int, value: int,

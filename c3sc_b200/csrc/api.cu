@@ -20,6 +20,8 @@ long long ft_padded_layout(DevFT &ft);
 long long ft_compact_layout(DevFT &ft);
 int launch_ft_costs(const FtArgs &a, cudaStream_t st);
 int ft_uses_mma(const DevFT &ft);
+int launch_ft_eval_points(const DevProblem &P, const DevFT &ft, int npts, const double *pts, double *out, cudaStream_t st);
+int launch_policy_points(const DevProblem &P, int n, const double *x, double *pts, int *absorbed, cudaStream_t st);
 size_t ft_sets_bytes(const DevFT &ft, size_t F);
 int launch_node_backup_lqg_lo(int dx, int arith, const DevProblem &P, int n, const double *x, const double *costs,
                               const int *absorbed, double *value, int *argmin, cudaStream_t st);
@@ -99,6 +101,7 @@ struct c3sc_problem {
     Scratch scr;
     CtlGroups grp;
     double *d_gtab = nullptr;
+    std::vector<double> h_utab;              // host copy of the control table (policy entry returns u, not its index)
     double *d_xgrid = nullptr, *d_obs = nullptr, *d_utab = nullptr, *d_ctab = nullptr;
     int *d_err = nullptr;
     cudaStream_t stream = nullptr;           // host-buffer entry points run here
@@ -198,6 +201,7 @@ int c3sc_problem_create(const c3sc_problem_desc *d, c3sc_problem **out)
     CKP(cudaStreamCreateWithFlags(&p->copy_stream, cudaStreamNonBlocking));
     CKP(cudaEventCreateWithFlags(&p->chunk_done, cudaEventDisableTiming));
     P.xgrid = p->d_xgrid; P.obs = p->d_obs; P.utab = p->d_utab; P.err = p->d_err;
+    p->h_utab.assign(d->controls, d->controls + (size_t)d->nu * d->du);
     // candidate table of separable models (row stride 2*NUD+2; NUD = dx/2 for LQG, 1 otherwise)
     {
         const int nud = (d->model == C3SC_MODEL_LQGND) ? (int)d->dx / 2 : (d->model == C3SC_MODEL_SKID5D ? 0 : 1);
@@ -704,6 +708,63 @@ int c3sc_node_backup_batch(c3sc_problem *p, size_t n, const double *x, const dou
     CK(cudaMemcpyAsync(value, b[3].p, n * 8, cudaMemcpyDeviceToHost, p->stream));
     if (argmin) CK(cudaMemcpyAsync(argmin, b[4].p, n * 4, cudaMemcpyDeviceToHost, p->stream));
     return finish(p);
+}
+
+/* valuef_eval (src/valuefunc.c:345-350) at n arbitrary points */
+int c3sc_valuef_eval_batch(c3sc_problem *p, const c3sc_valuef *vf, size_t n, const double *x, double *out)
+{
+    if (!p || !vf || !x || !out) return fail(C3SC_EINVAL, "null argument");
+    if (vf->ft.d != p->P.dx) return fail(C3SC_EINVAL, "value function has d=%d, problem dx=%d", vf->ft.d, p->P.dx);
+    if (n == 0) return C3SC_OK;
+    const size_t dx = p->P.dx;
+    DevBuf *b = p->b_misc;
+    if (b[0].reserve(n * dx * 8) || b[1].reserve(n * 8)) return fail(C3SC_ECUDA, "cudaMalloc failed");
+    CK(cudaMemcpyAsync(b[0].p, x, n * dx * 8, cudaMemcpyHostToDevice, p->stream));
+    int rc = launch_ft_eval_points(p->P, vf->ft, (int)n, (const double *)b[0].p, (double *)b[1].p, p->stream);
+    if (rc) return fail(C3SC_ECUDA, "kernel launch: %s", cudaGetErrorString((cudaError_t)rc));
+    g_launches++;
+    CK(cudaMemcpyAsync(out, b[1].p, n * 8, cudaMemcpyDeviceToHost, p->stream));
+    CK(cudaStreamSynchronize(p->stream));
+    return C3SC_OK;
+}
+
+/* c3control_policy_eval (src/bellman.c:2105-2151) at n states: mca_get_neighbor_node_costs
+ * (src/nodeutil.c:718-816) + bellman_optimal.  u [n*du]; value / absorbed / costs may be NULL. */
+int c3sc_policy_eval_batch(c3sc_problem *p, const c3sc_valuef *vf, size_t n, const double *x, double *u, double *value,
+                           int32_t *absorbed, double *costs)
+{
+    if (!p || !vf || !x || !u) return fail(C3SC_EINVAL, "null argument");
+    if (vf->ft.d != p->P.dx) return fail(C3SC_EINVAL, "value function has d=%d, problem dx=%d", vf->ft.d, p->P.dx);
+    if (n == 0) return C3SC_OK;
+    const size_t dx = p->P.dx, du = p->P.du, np = 2 * dx + 1;
+    DevBuf *b = p->b_misc;
+    if (b[0].reserve(n * dx * 8) || b[1].reserve(n * np * dx * 8) || b[2].reserve(n * 4) || b[3].reserve(n * np * 8) ||
+        b[4].reserve(n * 8) || b[5].reserve(n * 4))
+        return fail(C3SC_ECUDA, "cudaMalloc failed");
+    const double *d_x = (const double *)b[0].p;
+    double *d_pts = (double *)b[1].p, *d_costs = (double *)b[3].p, *d_val = (double *)b[4].p;
+    int *d_abs = (int *)b[2].p, *d_arg = (int *)b[5].p;
+    CK(cudaMemcpyAsync(b[0].p, x, n * dx * 8, cudaMemcpyHostToDevice, p->stream));
+    int rc = launch_policy_points(p->P, (int)n, d_x, d_pts, d_abs, p->stream);
+    if (!rc) rc = launch_ft_eval_points(p->P, vf->ft, (int)(n * np), d_pts, d_costs, p->stream);
+    if (rc) return fail(C3SC_ECUDA, "kernel launch: %s", cudaGetErrorString((cudaError_t)rc));
+    if (p->model == C3SC_MODEL_LQGND)
+        rc = (p->P.dx <= 6) ? launch_node_backup_lqg_lo(p->P.dx, p->arith, p->P, (int)n, d_x, d_costs, d_abs, d_val, d_arg, p->stream)
+                            : launch_node_backup_lqg_hi(p->P.dx, p->arith, p->P, (int)n, d_x, d_costs, d_abs, d_val, d_arg, p->stream);
+    else rc = launch_node_backup_misc(p->model, p->P.dx, p->arith, p->P, (int)n, d_x, d_costs, d_abs, d_val, d_arg, p->stream);
+    if (rc == -1) return fail(C3SC_EUNSUPPORTED, "model %d with dx=%d is not instantiated", p->model, p->P.dx);
+    if (rc) return fail(C3SC_ECUDA, "kernel launch: %s", cudaGetErrorString((cudaError_t)rc));
+    g_launches += 3;
+    std::vector<int> arg(n);
+    CK(cudaMemcpyAsync(arg.data(), d_arg, n * 4, cudaMemcpyDeviceToHost, p->stream));
+    if (value) CK(cudaMemcpyAsync(value, d_val, n * 8, cudaMemcpyDeviceToHost, p->stream));
+    if (absorbed) CK(cudaMemcpyAsync(absorbed, d_abs, n * 4, cudaMemcpyDeviceToHost, p->stream));
+    if (costs) CK(cudaMemcpyAsync(costs, d_costs, n * np * 8, cudaMemcpyDeviceToHost, p->stream));
+    rc = finish(p);
+    if (rc) return rc;
+    for (size_t e = 0; e < n; e++)
+        for (size_t i = 0; i < du; i++) u[e * du + i] = arg[e] >= 0 ? p->h_utab[(size_t)arg[e] * du + i] : 0.0;   /* absorbed: u = 0 */
+    return C3SC_OK;
 }
 
 int c3sc_control_value_batch(c3sc_problem *p, size_t n, const double *x, const double *u, const double *costs,

@@ -1,6 +1,7 @@
 // ft.cu -- host launchers of the model-independent stage-1 kernels (ft_kernel.cuh)
 #include <cstdlib>
 #include "ft_mma_kernel.cuh"
+#include "policy_kernel.cuh"
 
 namespace c3sc {
 
@@ -175,6 +176,28 @@ static int launch_ft_stage(const FtArgs &a_in, cudaStream_t st)
     }
     const int grid = (a.F + a.FB - 1) / a.FB + a.ft.d;       // upper bound on the number of groups
     k_ft_costs<<<grid, FT_NT, smem, st>>>(a);
+    return (int)cudaGetLastError();
+}
+
+// valuef_eval at npts points (device arrays): piecewise-linear interpolation of the nodal cores
+int launch_ft_eval_points(const DevProblem &P, const DevFT &ft, int npts, const double *pts, double *out, cudaStream_t st)
+{
+    if (npts <= 0) return 0;
+    int rs = 1;
+    for (int i = 0; i <= ft.d; i++) rs = ft.r[i] > rs ? ft.r[i] : rs;
+    const size_t smem = (size_t)8 * 2 * rs * sizeof(double);
+    int grid = (npts + 7) / 8;
+    ft_device_info();
+    if (grid > g_sms * 8) grid = g_sms * 8;
+    k_ft_eval_points<<<grid, 256, smem, st>>>(P, ft, npts, pts, out);
+    return (int)cudaGetLastError();
+}
+
+// flags + the 2d+1 evaluation points of n states (mca_get_neighbor_node_costs)
+int launch_policy_points(const DevProblem &P, int n, const double *x, double *pts, int *absorbed, cudaStream_t st)
+{
+    if (n <= 0) return 0;
+    k_policy_points<<<(n + 127) / 128, 128, 0, st>>>(P, n, x, pts, absorbed);
     return (int)cudaGetLastError();
 }
 

@@ -178,6 +178,17 @@ int c3sc_neighbor_costs_batch(c3sc_problem *p, const c3sc_valuef *vf, size_t F,
 int c3sc_node_backup_batch(c3sc_problem *p, size_t n, const double *x, const double *costs,
                            const int32_t *absorbed, double *value, int32_t *argmin);
 
+/* ---- the implicit policy at off-grid states (online controller) ------------- */
+/* valuef_eval (src/valuefunc.c:345-350 -> C3 function_train_eval on LINELM cores): piecewise-
+ * linear interpolation of the nodal cores at n points x[n*dx]; 0 outside the grid.            */
+int c3sc_valuef_eval_batch(c3sc_problem *p, const c3sc_valuef *vf, size_t n, const double *x, double *out);
+/* c3control_policy_eval (src/bellman.c:2105-2151) at n states: mca_get_neighbor_node_costs
+ * (src/nodeutil.c:718-816: V at x -+ h e_i with the boundary stand-ins, all V(x) and flag -1 inside
+ * an obstacle) then bellman_optimal.  u [n*du]; value [n], absorbed [n], costs [n*(2dx+1)] may be
+ * NULL.  costs[2dx] (the state itself, left unset by the reference) is V(x).                   */
+int c3sc_policy_eval_batch(c3sc_problem *p, const c3sc_valuef *vf, size_t n, const double *x, double *u,
+                           double *value, int32_t *absorbed, double *costs);
+
 /* bellman_control (src/bellman.c:367-480, grad_u == NULL) at n (x, u, costs)
  * triples; u need not be in the control table.                               */
 int c3sc_control_value_batch(c3sc_problem *p, size_t n, const double *x, const double *u,

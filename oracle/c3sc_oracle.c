@@ -448,3 +448,62 @@ double orc_ft_eval_linear(const orc_ft *ft, double *const *xgrid, const double *
     free(v);
     return res;
 }
+
+
+/* ---- implicit policy at an arbitrary state (online controller) -------------------------------
+ * mca_get_neighbor_node_costs, src/nodeutil.c:718-816: the value function at x -+ h e_i with the
+ * boundary type deciding what stands in when the step leaves the grid; inside an obstacle every
+ * entry is V(x) and absorbed = -1.  The reference leaves out[2d] (the node itself) unset outside
+ * obstacles; it only meets the round-off probability p_self, and is set to V(x) here.        */
+int orc_neighbor_node_costs(const orc_problem *p, const orc_ft *ft, const double *x, int *absorbed, double *out)
+{
+    const size_t d = p->dx;
+    if (orc_in_obstacle(p, x)) {
+        *absorbed = -1;
+        const double val = orc_ft_eval_linear(ft, p->xgrid, x);
+        for (size_t i = 0; i < 2 * d + 1; i++) out[i] = val;
+        return 0;
+    }
+    *absorbed = 0;
+    double xt[64];
+    for (size_t i = 0; i < d; i++) xt[i] = x[i];
+    for (size_t i = 0; i < d; i++) {
+        const double lb = p->xgrid[i][0], ub = p->xgrid[i][p->ngrid[i] - 1];
+        const double h = p->xgrid[i][1] - p->xgrid[i][0];
+        if (((x[i] + h) < ub) && (x[i] - h > lb)) {                 /* standard case, :741-747 */
+            xt[i] = x[i] - h; out[2 * i] = orc_ft_eval_linear(ft, p->xgrid, xt);
+            xt[i] = x[i] + h; out[2 * i + 1] = orc_ft_eval_linear(ft, p->xgrid, xt);
+        } else if ((x[i] - h) <= lb) {                              /* left boundary, :748-775 */
+            xt[i] = x[i] + h; out[2 * i + 1] = orc_ft_eval_linear(ft, p->xgrid, xt);
+            if (p->bc[i] == ORC_ABSORB || p->bc[i] == ORC_REFLECT) xt[i] = lb;
+            else if (x[i] > lb) xt[i] = ub - (h - (x[i] - lb));
+            else xt[i] = (ub - (lb - x[i])) - h;
+            out[2 * i] = orc_ft_eval_linear(ft, p->xgrid, xt);
+        } else {                                                    /* right boundary, :776-806 */
+            xt[i] = x[i] - h; out[2 * i] = orc_ft_eval_linear(ft, p->xgrid, xt);
+            if (p->bc[i] == ORC_ABSORB || p->bc[i] == ORC_REFLECT) xt[i] = ub;
+            else if (x[i] < ub) xt[i] = lb + (h - (ub - x[i]));
+            else xt[i] = (lb + (x[i] - ub)) + h;
+            out[2 * i + 1] = orc_ft_eval_linear(ft, p->xgrid, xt);
+        }
+        xt[i] = x[i];
+    }
+    out[2 * d] = orc_ft_eval_linear(ft, p->xgrid, x);
+    return 0;
+}
+
+/* c3control_policy_eval, src/bellman.c:2105-2151: neighbour values at x, then bellman_optimal
+ * (brute force over the control table; absorbed = -1 gives the obstacle cost and u = 0).   */
+int orc_policy_eval(const orc_problem *p, const orc_ft *ft, const double *x, double *u, double *val, int *absorbed,
+                    double *costs)
+{
+    double cbuf[2 * 64 + 1];
+    double *c = costs ? costs : cbuf;
+    int ab = 0, ub = -1;
+    int rc = orc_neighbor_node_costs(p, ft, x, &ab, c);
+    if (rc) return rc;
+    rc = orc_node_backup(p, ab, x, c, val, &ub);
+    for (size_t i = 0; i < p->du; i++) u[i] = ub >= 0 ? p->utab[(size_t)ub * p->du + i] : 0.0;
+    if (absorbed) *absorbed = ab;
+    return rc;
+}

@@ -127,6 +127,11 @@ int orc_pi_batch(const orc_problem *p, const orc_ft *ft_policy, const orc_ft *ft
  * nodal cores (valuefunc.c:345-350 -> C3).  Used for held-out-grid checks. */
 double orc_ft_eval_linear(const orc_ft *ft, double *const *xgrid, const double *x);
 
+/* nodeutil.c:718-816 and bellman.c:2105-2151: the implicit policy at an off-grid state. */
+int orc_neighbor_node_costs(const orc_problem *p, const orc_ft *ft, const double *x, int *absorbed, double *out);
+int orc_policy_eval(const orc_problem *p, const orc_ft *ft, const double *x, double *u, double *val, int *absorbed,
+                    double *costs);
+
 #ifdef __cplusplus
 }
 #endif

@@ -210,6 +210,20 @@ class Port:
             raise RuntimeError(f"oracle pi_batch rc={rc}")
         return out, rows, ub
 
+    def neighbor_node_costs(self, ft: FT, x):
+        x = np.ascontiguousarray(x, np.float64)
+        ab = C.c_int(); out = np.zeros(2 * self.dx + 1)
+        rc = self.L.orc_neighbor_node_costs(C.byref(self.p), C.byref(ft.c), _p(x), C.byref(ab), _p(out))
+        assert rc == 0
+        return ab.value, out
+
+    def policy_eval(self, ft: FT, x):
+        x = np.ascontiguousarray(x, np.float64)
+        u = np.zeros(self.cfg.du); val = C.c_double(); ab = C.c_int(); costs = np.zeros(2 * self.dx + 1)
+        rc = self.L.orc_policy_eval(C.byref(self.p), C.byref(ft.c), _p(x), _p(u), C.byref(val), C.byref(ab), _p(costs))
+        assert rc == 0
+        return u, val.value, ab.value, costs
+
     def ft_eval_linear(self, ft: FT, x):
         x = np.ascontiguousarray(x, np.float64)
         return self.L.orc_ft_eval_linear(C.byref(ft.c), C.cast(self._xg, C.POINTER(f64p)), _p(x))
@@ -305,6 +319,13 @@ class Ref:
         rc = self.L.ref_neighbor_costs(self.h, vf, int(k), _p(fixed), _p(ab), _p(costs))
         assert rc == 0
         return ab, costs
+
+    def neighbor_node_costs(self, vf, x):
+        x = np.ascontiguousarray(x, np.float64)
+        ab = C.c_int(); out = np.zeros(2 * self.dx + 1)
+        rc = self.L.ref_neighbor_node_costs(self.h, vf, _p(x), C.byref(ab), _p(out))
+        assert rc == 0
+        return ab.value, out
 
     def transition(self, drift, sigma_diag):
         drift = np.ascontiguousarray(drift, np.float64); sigma_diag = np.ascontiguousarray(sigma_diag, np.float64)

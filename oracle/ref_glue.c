@@ -248,6 +248,12 @@ int ref_neighbor_costs(ref_ctx *c, struct ValueF *vf, int dim_vary, const int *f
                                   c->xgrid, fi, &k, absorbed, costs);
 }
 
+/* mca_get_neighbor_node_costs (nodeutil.c:718) at one off-grid state */
+int ref_neighbor_node_costs(ref_ctx *c, struct ValueF *vf, const double *x, int *absorbed, double *costs)
+{
+    return mca_get_neighbor_node_costs(c->dx, x, c->bound, vf, c->ngrid, c->xgrid, absorbed, costs);
+}
+
 /* transition_assemble (nodeutil.c:267), non-gradient branch, with the grid's h2/t */
 int ref_transition(ref_ctx *c, const double *drift, const double *ddiff, double *prob, double *dt)
 {
