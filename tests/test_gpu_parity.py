@@ -228,3 +228,36 @@ def test_errors_are_loud(gpu):
     with pytest.raises(capi.C3scError):
         prob.vi_batch(vf_bad, dv, fi)
     prob.close(); vf_bad.close()
+
+
+import os as _os
+_GOLD = _os.path.join(_os.path.dirname(__file__), "golden")
+
+
+@pytest.mark.parametrize("arith", [0, 1], ids=["exact", "fast"])
+@pytest.mark.parametrize("fname", sorted(f for f in _os.listdir(_GOLD) if f.endswith(".npz")) if _os.path.isdir(_GOLD) else [])
+def test_cuda_path_against_golden_fixtures(gpu, fname, arith):
+    """the CUDA path directly against the committed outputs of the reference's own object code
+    (tests/golden/make_golden.py): flags and neighbour indices bit-exact, neighbour values,
+    bellman_vi and both bellman_pi sub-iterations within 1e-12"""
+    z = np.load(_os.path.join(_GOLD, fname))
+    name, n, rank, dx = str(z["name"]), int(z["n"]), int(z["rank"]), int(z["dx"])
+    cfg = configs.get_config(name, n=n, rank=rank, dx=dx if name.startswith("lqgnd") else None)
+    prob = capi.Problem(cfg, arith=arith)
+    ranks, cores, _ = make_ft(cfg)
+    _, cores2, _ = make_ft(cfg, seed=0xABCD00)
+    vf, vf2 = capi.ValueF(cfg.ngrid, ranks, cores), capi.ValueF(cfg.ngrid, ranks, cores2)
+    dv, fi = z["dim_vary"], z["fixed_ind"]
+    m = valid_mask(cfg, dv)
+    out = prob.vi_batch_debug(vf, dv, fi)
+    assert np.array_equal(out["absorbed"][m], z["absorbed"][m])
+    assert np.array_equal(out["nbr_vary"][m], z["nbr_vary"][m])
+    if cfg.dx > 1:
+        assert np.array_equal(out["nbr_fixed"][:, :cfg.dx - 1].reshape(len(dv), -1), z["nbr_fixed"].reshape(len(dv), -1))
+    assert rel_err(out["costs"][m], z["costs"][m], scale=np.abs(z["costs"][m]).max()) <= RTOL
+    assert rel_err(out["value"][m], z["vi"][m], scale=np.abs(z["vi"][m]).max()) <= RTOL
+    p1, rows, _ = prob.pi_batch(vf, vf2, dv, fi)
+    p2, _, _ = prob.pi_batch(None, vf, dv, fi, rows=rows)
+    assert rel_err(p1[m], z["pi1"][m], scale=np.abs(z["pi1"][m]).max()) <= RTOL
+    assert rel_err(p2[m], z["pi2"][m], scale=np.abs(z["pi2"][m]).max()) <= RTOL
+    prob.close(); vf.close(); vf2.close()
