@@ -14,11 +14,14 @@
  * batched fiber entries, and ValueF construction from nodal cores (the
  * reference builds ValueF only through the absent C3 library).
  *
- * NOT mirrored (out of scope): valuef_interp / c3control_step_* /
- * c3control_*_solve (C3 cross approximation driver), valuef_norm / save / load / eval
- * (C3 file formats and inner products), BoundInfo, HashGrid, process_fibers,
- * mca_get_neighbor_node_costs, the BFGS branch of bellman_optimal and every
- * gradient output (grad_* arguments must be NULL).
+ * Beside this header: include/c3sc_cross.h restates what valuef_interp / c3control_step_vi / _pi /
+ * c3control_vi_solve obtain from C3's cross approximation (batched core requests), valuef_norm /
+ * valuef_norm2diff on nodal cores; include/c3sc_b200.h has valuef_eval and c3control_policy_eval
+ * for batches of off-grid states (c3sc_valuef_eval_batch, c3sc_policy_eval_batch).
+ *
+ * NOT mirrored (out of scope): valuef save / load (C3 file formats), BoundInfo,
+ * HashGrid, process_fibers, rank adaptation and rounding of the cross, the BFGS branch of
+ * bellman_optimal and every gradient output (grad_* arguments must be NULL).
  */
 #ifndef C3SC_HOST_H
 #define C3SC_HOST_H
