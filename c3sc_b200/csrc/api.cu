@@ -138,6 +138,11 @@ int c3sc_cuda_init(int device)
         return fail(C3SC_ENODEV, "no CUDA device (%s); the Bellman backup has no CPU fallback",
                     e == cudaSuccess ? "count 0" : cudaGetErrorString(e));
     if (device < 0 || device >= n) return fail(C3SC_EINVAL, "device %d out of range [0,%d)", device, n);
+    // one device per process (one process per GPU): launch geometry and function attributes are cached
+    static int bound_device = -1;
+    if (bound_device >= 0 && bound_device != device)
+        return fail(C3SC_EINVAL, "this process is bound to device %d; use one process per GPU", bound_device);
+    bound_device = device;
     CK(cudaSetDevice(device));
     CK(cudaFree(0));
     return C3SC_OK;

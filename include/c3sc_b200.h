@@ -103,7 +103,8 @@ typedef struct c3sc_batch_out {
 } c3sc_batch_out;
 
 /* ---- runtime ---------------------------------------------------------- */
-int c3sc_cuda_init(int device);                  /* select device, create context */
+int c3sc_cuda_init(int device);                  /* select device, create context; ONE device per
+                                                    process (multi-GPU = one process per GPU)     */
 int c3sc_cuda_device_count(void);
 const char *c3sc_last_error(void);
 const char *c3sc_version(void);
