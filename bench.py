@@ -8,7 +8,8 @@ One STEP = one pass of the hot path over one batch of synthetic fibers of the he
 config (BASELINE.json configs[4]): d=10 LQG, 100 nodes/dim, FT rank 20,
 243 discrete controls, F fibers per GPU (weak scaling: per-GPU work fixed as N grows).
 At N>1 a step additionally broadcasts the FT cores from rank 0 and all-gathers the
-backed-up fiber values over NCCL (the path's real exchange).
+backed-up fiber values over NCCL (the path's real exchange); the gather of one
+quarter of the rank's fibers overlaps the backup of the next quarter on a second stream.
 
 value    node-backups/s, whole job, fiber descriptors + cores already resident in HBM
 e2e      same metric through the host-buffer C-ABI call (c3sc_vi_batch): pinned host
@@ -255,13 +256,29 @@ def main():
     stream = torch.cuda.current_stream(dev)
     sptr = stream.cuda_stream
 
+    # N > 1: the rank's fibers go through the pipeline in NSUB sub-batches; the all-gather of sub-batch s
+    # runs on a second stream while sub-batch s+1 computes (gathered layout: [sub-batch][rank][fiber][node])
+    NSUB = 4 if (world > 1 and F % 4 == 0 and F >= 4096) else 1
+    Fs = F // NSUB
+    comm = torch.cuda.Stream(device=dev) if world > 1 else None
+    sub_done = [torch.cuda.Event() for _ in range(NSUB)] if world > 1 else []
+
     def step_resident():
-        if world > 1:
-            sharding.broadcast_cores(core_view, src=0)
-            vf.commit(stream=sptr)
-        prob.vi_batch_dev(vf, F, dv_d.data_ptr(), fi_d.data_ptr(), N, out_d.data_ptr(), stream=sptr)
-        if world > 1:
-            sharding.gather_values(out_d, F * world, N, out=gathered)
+        if world == 1:
+            prob.vi_batch_dev(vf, F, dv_d.data_ptr(), fi_d.data_ptr(), N, out_d.data_ptr(), stream=sptr)
+            return
+        sharding.broadcast_cores(core_view, src=0)
+        vf.commit(stream=sptr)
+        comm.wait_stream(stream)                      # the previous step's gathers are ordered before reuse
+        for sb in range(NSUB):
+            prob.vi_batch_dev(vf, Fs, dv_d[sb * Fs:].data_ptr(), fi_d[sb * Fs:].data_ptr(), N,
+                              out_d[sb * Fs * N:].data_ptr(), stream=sptr)
+            sub_done[sb].record(stream)
+            comm.wait_event(sub_done[sb])
+            with torch.cuda.stream(comm):
+                dist.all_gather_into_tensor(gathered[sb * world * Fs * N:(sb + 1) * world * Fs * N],
+                                            out_d[sb * Fs * N:(sb + 1) * Fs * N])
+        stream.wait_stream(comm)                      # the step ends when the last gather has landed
 
     def step_e2e():
         capi.check(capi.lib().c3sc_vi_batch(prob.handle, vf.handle, F, dv_h.data_ptr(), fi_h.data_ptr(), N,
