@@ -439,6 +439,12 @@ def cpu_baseline(cfg, rank_ft, budget_s):
         _, s0 = ref.vi_fibers(vf, dv[:8], fi[:8], fresh_per_fiber=False)
         nf = int(max(8, min(4000, budget_s / max(s0 / 8, 1e-6))))
         _, secs = ref.vi_fibers(vf, dv[8:8 + nf], fi[8:8 + nf], fresh_per_fiber=False)
+        # single-thread figure: a short sample with OpenMP limited to one thread
+        ref.set_omp_threads(1)
+        n1 = int(max(4, min(400, 3.0 / max(s0 / 8 * threads, 1e-6))))
+        _, s1 = ref.vi_fibers(vf, dv[8:8 + n1], fi[8:8 + n1], fresh_per_fiber=False)
+        ref.set_omp_threads(threads)
+        one_thread = n1 * cfg.n / s1
         kind = "reference"
         how = "oracle/_ref (reference sources compiled in place), one bellman_vi call per fiber, OpenMP over the nodes of a fiber"
     else:
@@ -452,7 +458,8 @@ def cpu_baseline(cfg, rank_ft, budget_s):
         t0 = time.perf_counter(); port.vi_batch(ft, dv[32:32 + nf], fi[32:32 + nf], nthreads=threads); secs = time.perf_counter() - t0
         kind = "port"
         how = "oracle port (C restatement), OpenMP over fibers"
-    return {"value": nf * cfg.n / secs, "unit": "node-backups/s", "cores": threads, "kind": kind,
+    extra = {"value_1_thread": one_thread} if kind == "reference" else {}
+    return {"value": nf * cfg.n / secs, "unit": "node-backups/s", "cores": threads, "kind": kind, **extra,
             "sample": f"{nf} fibers x {cfg.n} nodes of the same workload in {secs:.1f} s; {how}; host has {ncores} cores"}
 
 

@@ -367,3 +367,6 @@ class Ref:
 
     def omp_threads(self):
         return int(self.L.ref_omp_threads())
+
+    def set_omp_threads(self, n: int):
+        self.L.ref_set_omp_threads(int(n))

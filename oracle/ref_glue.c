@@ -339,6 +339,15 @@ double ref_pi_fibers(ref_ctx *c, struct ValueF *vf_iter, size_t F, const int *di
     return secs;
 }
 
+void ref_set_omp_threads(int n)
+{
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
+
 int ref_omp_threads(void)
 {
 #ifdef _OPENMP
