@@ -256,6 +256,28 @@ def main():
     stream = torch.cuda.current_stream(dev)
     sptr = stream.cuda_stream
 
+    # N > 1, fused all-gather: every rank's gathered buffer is peer-mapped (CUDA IPC) and the control kernel
+    # stores each value into all of them over NVLink while it computes; a step ends with a barrier.
+    # C3SC_GATHER=nccl keeps the NCCL all-gather (sub-batches overlapped on a second stream) instead.
+    peers = None
+    if world > 1 and os.environ.get("C3SC_GATHER", "p2p") == "p2p":
+        try:
+            def _exchange(h):
+                got = [None] * world
+                dist.all_gather_object(got, h)
+                return got
+            peers = capi.PeerBuffers(world * F * N * 8, rank, world, _exchange)
+
+            class _Arr:  # zero-copy torch view of the rank's own gathered buffer
+                def __init__(self, ptr, n):
+                    self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<f8", "data": (ptr, False), "version": 3}
+            gathered_p2p = torch.as_tensor(_Arr(peers.own, world * F * N), device=dev)
+            sync_flag = torch.zeros(1, device=dev)
+        except Exception as exc:           # no peer access on this box: fall back to NCCL
+            if rank == 0:
+                print(f"bench: fused all-gather unavailable ({exc}); using NCCL", file=sys.stderr)
+            peers = None
+
     # N > 1: the rank's fibers go through the pipeline in NSUB sub-batches; the all-gather of sub-batch s
     # runs on a second stream while sub-batch s+1 computes (gathered layout: [sub-batch][rank][fiber][node])
     NSUB = 4 if (world > 1 and F % 4 == 0 and F >= 4096) else 1
@@ -269,6 +291,11 @@ def main():
             return
         sharding.broadcast_cores(core_view, src=0)
         vf.commit(stream=sptr)
+        if peers is not None:
+            prob.vi_batch_dev(vf, F, dv_d.data_ptr(), fi_d.data_ptr(), N, out_d.data_ptr(), stream=sptr,
+                              peers=peers.ptrs, peer_offset=rank * F * N)
+            dist.all_reduce(sync_flag)                # barrier on the stream: every rank's stores have landed
+            return
         comm.wait_stream(stream)                      # the previous step's gathers are ordered before reuse
         for sb in range(NSUB):
             prob.vi_batch_dev(vf, Fs, dv_d[sb * Fs:].data_ptr(), fi_d[sb * Fs:].data_ptr(), N,
@@ -309,6 +336,16 @@ def main():
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             ms = float(t.item())
         return ms
+
+    if peers is not None:                               # the fused gather must equal an NCCL all-gather
+        step_resident()
+        torch.cuda.synchronize(dev)
+        ref_g = torch.empty(world * F * N, dtype=torch.float64, device=dev)
+        dist.all_gather_into_tensor(ref_g, out_d)
+        torch.cuda.synchronize(dev)
+        if not torch.equal(ref_g, gathered_p2p):
+            raise SystemExit("fused all-gather differs from the NCCL all-gather")
+        del ref_g
 
     sampler = ClockSampler(local)
     launches0 = capi.lib().c3sc_launch_count()
@@ -362,7 +399,10 @@ def main():
             "metric": "bellman_node_backups_per_s", "value": value, "unit": "node-backups/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": workload_config(cfg, rank_ft, F, args),
+            "config": dict(workload_config(cfg, rank_ft, F, args),
+                           **({"gather": "fused: control kernel stores into every rank's peer-mapped buffer (CUDA IPC over NVLink) + barrier"
+                               if peers is not None else "nccl all_gather_into_tensor, 4 sub-batches overlapped on a second stream"}
+                              if world > 1 else {})),
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "node-backups/s",
                     "h2d_bytes_per_step": int(F * (cfg.dx + 1) * 4 * world), "d2h_bytes_per_step": int(F * N * 8 * world),

@@ -37,6 +37,7 @@ class BatchOut(C.Structure):
         ("value", C.c_void_p), ("argmin", C.c_void_p), ("absorbed", C.c_void_p),
         ("costs", C.c_void_p), ("rows", C.c_void_p), ("nbr_vary", C.c_void_p),
         ("nbr_fixed", C.c_void_p),
+        ("value_peers", C.c_void_p * 8), ("n_peers", C.c_uint32), ("peer_offset", C.c_uint64),
     ]
 
 
@@ -59,6 +60,7 @@ EXPORTS = [
     "c3sc_cross_create", "c3sc_cross_destroy", "c3sc_cross_ranks", "c3sc_cross_run", "c3sc_cross_run_vi", "c3sc_cross_run_pi",
     "c3sc_vi_solve", "c3sc_cores_dot", "c3sc_cores_norm", "c3sc_cores_norm2diff",
     "c3sc_valuef_eval_batch", "c3sc_policy_eval_batch",
+    "c3sc_peer_buffer_create", "c3sc_peer_buffer_open", "c3sc_peer_buffer_close",
 ]
 
 _lib = None
@@ -101,6 +103,9 @@ def lib() -> C.CDLL:
         L.c3sc_transition_raw.argtypes = [i32, C.c_uint32, C.c_double, vp, sz, vp, vp, vp, vp, vp]
         L.c3sc_ft_fiber_nn_batch.argtypes = [vp, sz, vp, vp, vp, vp, sz, vp]
         L.c3sc_measure_fp64_peak.argtypes = [C.POINTER(C.c_double), i32, i32]
+        L.c3sc_peer_buffer_create.argtypes = [sz, C.POINTER(vp), C.c_char_p]
+        L.c3sc_peer_buffer_open.argtypes = [C.c_char_p, C.POINTER(vp)]
+        L.c3sc_peer_buffer_close.argtypes = [vp, i32]
         L.c3sc_valuef_eval_batch.argtypes = [vp, vp, sz, vp, vp]
         L.c3sc_policy_eval_batch.argtypes = [vp, vp, sz, vp, vp, vp, vp, vp]
         L.c3sc_cross_create.argtypes = [C.c_uint32, c_u64p, c_u64p, C.POINTER(vp)]
@@ -292,8 +297,14 @@ class Problem:
 
     # ---- device-pointer entry points (ints are raw device addresses) ---------------
     def vi_batch_dev(self, vf: "ValueF", F: int, d_dim_vary: int, d_fixed_ind: int, ldo: int, value: int,
-                     argmin: int = 0, stream: int = 0, rows: int = 0):
+                     argmin: int = 0, stream: int = 0, rows: int = 0, peers=None, peer_offset: int = 0):
+        """peers: device addresses of every rank's gathered buffer (peer-mapped) for the fused all-gather"""
         o = BatchOut(value or None, argmin or None, None, None, rows or None, None, None)
+        if peers:
+            o.n_peers = len(peers)
+            for g, ptr in enumerate(peers):
+                o.value_peers[g] = ptr
+            o.peer_offset = peer_offset
         check(lib().c3sc_vi_batch_dev(self.handle, vf.handle, F, d_dim_vary, d_fixed_ind, ldo, C.byref(o), stream or None))
 
     def pi_batch_dev(self, vf_policy, vf_iter, F, d_dim_vary, d_fixed_ind, ldo, have_rows, rows, argmin, value, stream=0):
@@ -435,3 +446,30 @@ def cores_norm(n, ranks, cores) -> float:
     ca = [np.ascontiguousarray(c, dtype=np.float64).reshape(-1) for c in cores]
     aa = (c_f64p * d)(*[c.ctypes.data_as(c_f64p) for c in ca])
     return float(lib().c3sc_cores_norm(d, n.ctypes.data_as(c_u64p), r.ctypes.data_as(c_u64p), aa))
+
+
+class PeerBuffers:
+    """Every rank's gathered buffer, peer-mapped into this process (fused all-gather).
+    `exchange(handle_bytes) -> list of every rank's handle` is the out-of-band step
+    (torch.distributed.all_gather_object in bench.py)."""
+
+    def __init__(self, nbytes: int, rank: int, world: int, exchange):
+        self.rank, self.world = rank, world
+        own = C.c_void_p()
+        hbuf = C.create_string_buffer(64)
+        check(lib().c3sc_peer_buffer_create(nbytes, C.byref(own), hbuf))
+        self.own = own.value
+        handles = exchange(hbuf.raw)
+        self.ptrs = []
+        for g in range(world):
+            if g == rank:
+                self.ptrs.append(self.own)
+            else:
+                p = C.c_void_p()
+                check(lib().c3sc_peer_buffer_open(C.create_string_buffer(handles[g], 64), C.byref(p)))
+                self.ptrs.append(p.value)
+
+    def close(self):
+        for g, p in enumerate(getattr(self, "ptrs", [])):
+            lib().c3sc_peer_buffer_close(p, int(g != self.rank))
+        self.ptrs = []

@@ -148,6 +148,38 @@ int c3sc_cuda_init(int device)
     return C3SC_OK;
 }
 
+/* ---- peer-mapped buffers for the fused all-gather (one process per GPU) --------------------------- */
+int c3sc_peer_buffer_create(size_t bytes, void **dev, unsigned char handle[64])
+{
+    if (!dev || !handle || bytes == 0) return fail(C3SC_EINVAL, "null argument");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+    void *p = nullptr;
+    CK(cudaMalloc(&p, bytes));
+    cudaIpcMemHandle_t h;
+    cudaError_t e = cudaIpcGetMemHandle(&h, p);
+    if (e != cudaSuccess) { cudaFree(p); return fail(C3SC_ECUDA, "cudaIpcGetMemHandle: %s", cudaGetErrorString(e)); }
+    memcpy(handle, &h, 64);
+    *dev = p;
+    return C3SC_OK;
+}
+
+int c3sc_peer_buffer_open(const unsigned char handle[64], void **dev)
+{
+    if (!dev || !handle) return fail(C3SC_EINVAL, "null argument");
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, 64);
+    CK(cudaIpcOpenMemHandle(dev, h, cudaIpcMemLazyEnablePeerAccess));     /* maps the peer's allocation, enables P2P */
+    return C3SC_OK;
+}
+
+int c3sc_peer_buffer_close(void *dev, int opened)
+{
+    if (!dev) return C3SC_OK;
+    if (opened) CK(cudaIpcCloseMemHandle(dev));
+    else CK(cudaFree(dev));
+    return C3SC_OK;
+}
+
 int c3sc_problem_create(const c3sc_problem_desc *d, c3sc_problem **out)
 {
     if (!d || !out) return fail(C3SC_EINVAL, "null argument");
@@ -399,6 +431,10 @@ struct BatchArgs {
     cudaEvent_t chunk_done;
     double *h_value;
     int32_t *h_argmin;
+    // fused all-gather into peer-mapped buffers
+    double *value_peers[C3SC_MAXPEERS];
+    int n_peers;
+    size_t peer_offset;
 };
 
 static size_t g_chunk_bytes = (size_t)96 << 20;    // slot-major cost scratch per chunk: stays inside the 126 MB L2
@@ -457,6 +493,9 @@ static int run_batch(const DevProblem &P, int model, int arith, Scratch &scr, co
         c.argmin = b.out.argmin ? b.out.argmin + n0 : nullptr;
         c.rows = b.out.rows ? b.out.rows + n0 * RW : nullptr;
         c.rows_in = b.rows_in ? b.rows_in + n0 * RW : nullptr;
+        c.npeer = b.n_peers;
+        for (int g = 0; g < b.n_peers; g++) c.vpeer[g] = b.value_peers[g];
+        c.peer_off = (long long)(b.peer_offset + n0);
         if (grp && grp->ng > 0 && P.gtab) {
             c.ng = grp->ng;
             memcpy(c.gstart, grp->gstart, sizeof c.gstart);
@@ -497,7 +536,7 @@ int c3sc_vi_batch_dev(c3sc_problem *p, const c3sc_valuef *vf, size_t F, const in
 {
     int rc = check_shapes(p, vf, F, ldo);
     if (rc) return rc;
-    if (!out || (!out->value && !out->rows && !out->argmin && !out->costs && !out->absorbed))
+    if (!out || (!out->value && !out->rows && !out->argmin && !out->costs && !out->absorbed && !out->n_peers))
         return fail(C3SC_EINVAL, "no output requested");
     if (F == 0) return C3SC_OK;
     BatchArgs b;
@@ -505,7 +544,11 @@ int c3sc_vi_batch_dev(c3sc_problem *p, const c3sc_valuef *vf, size_t F, const in
     b.F = F; b.ldo = ldo; b.dim_vary = d_dim_vary; b.fixed_ind = d_fixed_ind;
     b.out.value = out->value; b.out.argmin = out->argmin; b.out.absorbed = out->absorbed;
     b.out.costs = out->costs; b.out.rows = out->rows; b.out.nbr_vary = out->nbr_vary; b.out.nbr_fixed = out->nbr_fixed;
-    b.mode = (out->value || out->argmin || out->rows) ? MODE_VI : MODE_COSTS;
+    b.mode = (out->value || out->argmin || out->rows || out->n_peers) ? MODE_VI : MODE_COSTS;
+    if (out->n_peers > C3SC_MAXPEERS) return fail(C3SC_EINVAL, "n_peers=%u > %d", out->n_peers, C3SC_MAXPEERS);
+    b.n_peers = (int)out->n_peers;
+    for (uint32_t g = 0; g < out->n_peers; g++) b.value_peers[g] = out->value_peers[g];
+    b.peer_offset = (size_t)out->peer_offset;
     return run_batch(p->P, p->model, p->arith, p->scr, &p->grp, vf->ft, b, (cudaStream_t)stream);
 }
 

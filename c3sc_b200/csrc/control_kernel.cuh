@@ -40,7 +40,18 @@ struct CtlArgs {
     int *argmin;
     double *rows;
     const double *rows_in;    // k_pi_eval
+    // fused all-gather: values also go to every peer's gathered buffer (peer-mapped memory over NVLink)
+    double *vpeer[C3SC_MAXPEERS];
+    int npeer;
+    long long peer_off;       // element offset of this chunk inside a gathered buffer
 };
+
+// backed-up value of node `id`: the local output and, when the all-gather is fused, every rank's copy
+__device__ __forceinline__ void store_value(const CtlArgs &c, long long id, double v)
+{
+    if (c.value) c.value[id] = v;
+    for (int g = 0; g < c.npeer; g++) c.vpeer[g][c.peer_off + id] = v;
+}
 
 // ---------------------------------------------------------------------------
 // fast reciprocal and exp for the FAST policy (both ~1 ulp)
@@ -392,7 +403,7 @@ __global__ void __launch_bounds__(CT_NT, 3) k_control(const CtlArgs c)
             if (vb < best || (vb == best && ib < ibest)) { best = vb; ibest = ib; }
         }
         if (!valid || part != 0) continue;
-        if (c.value) c.value[id] = best;
+        store_value(c, id, best);
         if (c.argmin) c.argmin[id] = ibest;
         if (c.rows) {                               // policy row at u* (bellman.c:1851-1860)
             double u[DU], b[DX], s[DX], prob[CS], dt;
@@ -418,7 +429,7 @@ __global__ void __launch_bounds__(CT_NT, 3) k_control(const CtlArgs c)
         double x[DX];
         node_state<DX>(c, (int)id, x);
         const double v = (ab == 1) ? M::boundcost(x, P.mp) : M::obscost(x, P.mp);
-        if (c.value) c.value[id] = v;
+        store_value(c, id, v);
         if (c.argmin) c.argmin[id] = -1;
         if (c.rows) {
             double *row = c.rows + (size_t)id * RW;
@@ -564,7 +575,7 @@ __global__ void __launch_bounds__(C2_NT, C3SC_C2_MINB) k_control2(const CtlArgs 
         for (int q = 0; q < C2N; q++) {
             if (!valid[q]) continue;
             const int ibest = nd[q].ibest;
-            if (c.value) c.value[id[q]] = nd[q].best;
+            store_value(c, id[q], nd[q].best);
             if (c.argmin) c.argmin[id[q]] = ibest;
             if (c.rows) {                               // policy row at u* (bellman.c:1851-1860)
                 double x[DX], u[DU], b[DX], s[DX], prob[CS], dt;
@@ -590,7 +601,7 @@ __global__ void __launch_bounds__(C2_NT, C3SC_C2_MINB) k_control2(const CtlArgs 
         double x[DX];
         node_state<DX>(c, (int)id, x);
         const double v = (ab == 1) ? M::boundcost(x, P.mp) : M::obscost(x, P.mp);
-        if (c.value) c.value[id] = v;
+        store_value(c, id, v);
         if (c.argmin) c.argmin[id] = -1;
         if (c.rows) {
             double *row = c.rows + (size_t)id * RW;
@@ -622,7 +633,7 @@ __global__ void __launch_bounds__(CT_NT) k_pi_eval(const CtlArgs c)
             for (int m = 0; m < CS; m++) prob[m] = row[m];
             v = rhs<DX, A>(P, prob, row[CS], row[CS + 1], cc);
         }
-        c.value[id] = v;
+        store_value(c, id, v);
     }
 }
 

@@ -28,6 +28,7 @@ extern "C" {
 
 #define C3SC_MAXD 16          /* state dimensions supported by the kernels    */
 #define C3SC_MAXOBS 10        /* obstacle boxes (src/boundary.c:393)          */
+#define C3SC_MAXPEERS 8       /* GPUs of one box for the fused value all-gather */
 
 enum c3sc_status {
     C3SC_OK = 0,
@@ -100,6 +101,13 @@ typedef struct c3sc_batch_out {
     double  *rows;        /* [F*ldo*(2dx+3)]  [p(2dx+1), dt, g] at the argmin (bellman_pi) */
     int32_t *nbr_vary;    /* [F*ldo*2]        neighbours along the fiber                  */
     int32_t *nbr_fixed;   /* [F*2*(dx-1)]     neighbours in the fixed dimensions          */
+    /* Fused all-gather (one process per GPU, peer-mapped device buffers, e.g. cudaIpcOpenMemHandle):
+     * the control kernel stores every backed-up value ALSO to value_peers[g][peer_offset + f*ldo + j]
+     * for g < n_peers, i.e. straight into every rank's gathered buffer over NVLink while it computes.
+     * The caller orders completion across ranks (a barrier) before reading.  n_peers = 0: off.      */
+    double  *value_peers[C3SC_MAXPEERS];
+    uint32_t n_peers;
+    uint64_t peer_offset;
 } c3sc_batch_out;
 
 /* ---- runtime ---------------------------------------------------------- */
@@ -114,6 +122,14 @@ uint64_t c3sc_launch_count(void);
 /* Best-of-`repeats` throughput of a pure DFMA loop on the current device, in
  * TFLOP/s (FMA = 2 flop): the measured FP64-pipe roofline denominator.      */
 int c3sc_measure_fp64_peak(double *tflops, int iters, int repeats);
+
+/* Peer-mapped device buffers for the fused all-gather (c3sc_batch_out::value_peers), one process per
+ * GPU: every rank creates its gathered buffer (cudaMalloc + cudaIpcGetMemHandle), exchanges the 64-byte
+ * handles out of band, and opens the other ranks' buffers (cudaIpcOpenMemHandle with lazy peer access).
+ * close: opened != 0 for buffers obtained from _open, 0 for the rank's own.                          */
+int c3sc_peer_buffer_create(size_t bytes, void **dev, unsigned char handle[64]);
+int c3sc_peer_buffer_open(const unsigned char handle[64], void **dev);
+int c3sc_peer_buffer_close(void *dev, int opened);
 
 /* ---- problem / value function ------------------------------------------ */
 int  c3sc_problem_create(const c3sc_problem_desc *desc, c3sc_problem **out);

@@ -114,3 +114,33 @@ def test_device_buffer_commit(gpu):
     got, _ = prob.vi_batch(vf, dv, fi)
     assert np.array_equal(got, want)
     prob.close(); vf.close(); ref.close()
+
+
+def test_fused_gather_stores(gpu):
+    """c3sc_batch_out::value_peers: the control kernels store each value into every listed buffer at
+    peer_offset (the fused all-gather; here both 'peers' live on the one device)"""
+    import torch
+    cfg = configs.get_config("lqgnd_reflect", n=12, rank=5, dx=4)
+    prob = capi.Problem(cfg, arith=1)
+    ranks = cfg.ranks()
+    vf = capi.ValueF(cfg.ngrid, ranks, synthetic.random_cores(cfg.ngrid, ranks))
+    F, N = 300, cfg.n
+    dv, fi = synthetic.random_fibers(cfg.ngrid, F, seed=11)
+    want, _ = prob.vi_batch(vf, dv, fi)
+    dv_d = torch.from_numpy(np.ascontiguousarray(dv)).cuda()
+    fi_d = torch.from_numpy(np.ascontiguousarray(fi)).cuda()
+    off = 2 * F * N
+    bufs = [torch.full((4 * F * N,), -7.0, dtype=torch.float64, device="cuda") for _ in range(2)]
+    for own in (True, False):                     # with and without the rank's private value buffer
+        out = torch.zeros(F * N, dtype=torch.float64, device="cuda")
+        prob.vi_batch_dev(vf, F, dv_d.data_ptr(), fi_d.data_ptr(), N, out.data_ptr() if own else 0,
+                          peers=[b.data_ptr() for b in bufs], peer_offset=off)
+        torch.cuda.synchronize()
+        for b in bufs:
+            got = b.cpu().numpy()
+            assert np.array_equal(got[off:off + F * N].reshape(F, N), want)
+            assert (got[:off] == -7.0).all() and (got[off + F * N:] == -7.0).all()
+            b.fill_(-7.0)
+        if own:
+            assert np.array_equal(out.cpu().numpy().reshape(F, N), want)
+    prob.close(); vf.close()
