@@ -45,6 +45,10 @@ class CrossOpts(C.Structure):
     _fields_ = [("maxiter", C.c_uint32), ("tol", C.c_double), ("verbose", C.c_int)]
 
 
+class AdaptOpts(C.Structure):
+    _fields_ = [("kickrank", C.c_uint32), ("maxrank", C.c_uint32), ("round_tol", C.c_double), ("maxiter_adapt", C.c_uint32)]
+
+
 # int f(size_t F, const int32_t *dim_vary, const int32_t *fixed_ind, size_t ldo, double *out, void *arg)
 FIBER_FN = C.CFUNCTYPE(C.c_int, C.c_size_t, c_i32p, c_i32p, C.c_size_t, c_f64p, C.c_void_p)
 
@@ -60,6 +64,7 @@ EXPORTS = [
     "c3sc_cross_create", "c3sc_cross_destroy", "c3sc_cross_ranks", "c3sc_cross_run", "c3sc_cross_run_vi", "c3sc_cross_run_pi",
     "c3sc_vi_solve", "c3sc_cores_dot", "c3sc_cores_norm", "c3sc_cores_norm2diff",
     "c3sc_valuef_eval_batch", "c3sc_policy_eval_batch",
+    "c3sc_cores_round", "c3sc_cross_adapt_capacity", "c3sc_cross_set_ranks", "c3sc_cross_run_adapt", "c3sc_cross_run_vi_adapt",
     "c3sc_peer_buffer_create", "c3sc_peer_buffer_open", "c3sc_peer_buffer_close",
 ]
 
@@ -117,6 +122,13 @@ def lib() -> C.CDLL:
         L.c3sc_cross_run_pi.argtypes = [vp, vp, vp, vp, C.c_uint32, C.POINTER(CrossOpts), C.POINTER(c_f64p), c_u64p, c_f64p]
         L.c3sc_vi_solve.argtypes = [vp, vp, c_u64p, C.POINTER(c_f64p), C.c_uint32, C.c_double, C.POINTER(CrossOpts), C.POINTER(c_f64p),
                                     C.POINTER(C.c_uint32), c_f64p, c_u64p]
+        L.c3sc_cores_round.argtypes = [C.c_uint32, c_u64p, c_u64p, C.POINTER(c_f64p), C.c_double, c_u64p, C.POINTER(c_f64p)]
+        L.c3sc_cross_adapt_capacity.argtypes = [vp, C.POINTER(AdaptOpts), c_u64p]
+        L.c3sc_cross_set_ranks.argtypes = [vp, c_u64p]
+        L.c3sc_cross_run_adapt.argtypes = [vp, FIBER_FN, vp, C.POINTER(CrossOpts), C.POINTER(AdaptOpts), c_u64p, C.POINTER(c_f64p),
+                                           c_u64p, c_f64p]
+        L.c3sc_cross_run_vi_adapt.argtypes = [vp, vp, vp, C.POINTER(CrossOpts), C.POINTER(AdaptOpts), c_u64p, C.POINTER(c_f64p),
+                                              c_u64p, c_f64p]
         for fn in (L.c3sc_cores_dot, L.c3sc_cores_norm, L.c3sc_cores_norm2diff):
             fn.restype = C.c_double
         L.c3sc_cores_dot.argtypes = [C.c_uint32, c_u64p, c_u64p, C.POINTER(c_f64p), c_u64p, C.POINTER(c_f64p)]
@@ -422,6 +434,57 @@ class Cross:
         assert nmax >= 1
         return cores, int(nf.value), float(ch.value)
 
+    # ---- rank adaptation (the adapt == 1 branch of valuef_interp) ----
+    def _adapt_buffers(self, a):
+        cap = np.zeros(self.d + 1, dtype=np.uint64)
+        check(lib().c3sc_cross_adapt_capacity(self.handle, C.byref(a), cap.ctypes.data_as(c_u64p)))
+        cores = [np.zeros(int(self.n[k] * cap[k] * cap[k + 1])) for k in range(self.d)]
+        arr = (c_f64p * self.d)(*[c.ctypes.data_as(c_f64p) for c in cores])
+        return cores, arr
+
+    def _adapt_result(self, cores, rout):
+        check(lib().c3sc_cross_ranks(self.handle, self.ranks.ctypes.data_as(c_u64p)))
+        return [cores[k][:int(self.n[k] * rout[k] * rout[k + 1])].copy() for k in range(self.d)], rout
+
+    def set_ranks(self, ranks):
+        r = np.ascontiguousarray(ranks, dtype=np.uint64)
+        check(lib().c3sc_cross_set_ranks(self.handle, r.ctypes.data_as(c_u64p)))
+        check(lib().c3sc_cross_ranks(self.handle, self.ranks.ctypes.data_as(c_u64p)))
+
+    def run_vi_adapt(self, prob, vf, kickrank=2, maxrank=0, round_tol=1e-8, maxiter_adapt=0, maxiter=5, tol=0.0, verbose=0):
+        """cross -> round -> kick -> cross ... of bellman_vi(.; vf); returns (cores, ranks, fibers, change)"""
+        a = AdaptOpts(kickrank, maxrank, round_tol, maxiter_adapt)
+        cores, arr = self._adapt_buffers(a)
+        o = CrossOpts(maxiter, tol, verbose)
+        rout = np.zeros(self.d + 1, dtype=np.uint64)
+        nf = C.c_uint64(); ch = C.c_double()
+        check(lib().c3sc_cross_run_vi_adapt(self.handle, prob.handle, vf.handle, C.byref(o), C.byref(a),
+                                            rout.ctypes.data_as(c_u64p), arr, C.byref(nf), C.byref(ch)))
+        cores, rout = self._adapt_result(cores, rout)
+        return cores, rout, int(nf.value), float(ch.value)
+
+    def run_adapt(self, fn, kickrank=2, maxrank=0, round_tol=1e-8, maxiter_adapt=0, maxiter=5, tol=0.0, verbose=0):
+        """same with a Python operator fn(dim_vary[F], fixed_ind[F,d]) -> values[F, nmax]"""
+        d = self.d
+
+        def _cb(F, dv, fi, ldo, out, _arg):
+            dvn = np.ctypeslib.as_array(dv, shape=(F,)).copy()
+            fin = np.ctypeslib.as_array(fi, shape=(F * d,)).reshape(F, d).copy()
+            vals = np.asarray(fn(dvn, fin), dtype=np.float64).reshape(F, -1)
+            dst = np.ctypeslib.as_array(out, shape=(F * ldo,)).reshape(F, ldo)
+            dst[:, :vals.shape[1]] = vals[:, :ldo]
+            return 0
+        cb = FIBER_FN(_cb)
+        a = AdaptOpts(kickrank, maxrank, round_tol, maxiter_adapt)
+        cores, arr = self._adapt_buffers(a)
+        o = CrossOpts(maxiter, tol, verbose)
+        rout = np.zeros(self.d + 1, dtype=np.uint64)
+        nf = C.c_uint64(); ch = C.c_double()
+        check(lib().c3sc_cross_run_adapt(self.handle, cb, None, C.byref(o), C.byref(a), rout.ctypes.data_as(c_u64p), arr,
+                                         C.byref(nf), C.byref(ch)))
+        cores, rout = self._adapt_result(cores, rout)
+        return cores, rout, int(nf.value), float(ch.value)
+
     def close(self):
         if getattr(self, "handle", None) and lib is not None:
             lib().c3sc_cross_destroy(self.handle)
@@ -473,3 +536,17 @@ class PeerBuffers:
         for g, p in enumerate(getattr(self, "ptrs", [])):
             lib().c3sc_peer_buffer_close(p, int(g != self.rank))
         self.ptrs = []
+
+
+def cores_round(n, ranks, cores, eps):
+    """function_train_round on nodal cores (c3sc_cores_round): returns (ranks, cores)"""
+    n = np.ascontiguousarray(n, dtype=np.uint64); d = int(n.size)
+    r = np.ascontiguousarray(ranks, dtype=np.uint64)
+    cin = [np.ascontiguousarray(c, dtype=np.float64).reshape(-1) for c in cores]
+    ain = (c_f64p * d)(*[c.ctypes.data_as(c_f64p) for c in cin])
+    cout = [np.zeros_like(c) for c in cin]
+    aout = (c_f64p * d)(*[c.ctypes.data_as(c_f64p) for c in cout])
+    rout = np.zeros(d + 1, dtype=np.uint64)
+    check(lib().c3sc_cores_round(d, n.ctypes.data_as(c_u64p), r.ctypes.data_as(c_u64p), ain, float(eps),
+                                 rout.ctypes.data_as(c_u64p), aout))
+    return rout, [cout[k][:int(n[k] * rout[k] * rout[k + 1])].copy() for k in range(d)]

@@ -416,6 +416,299 @@ done:
     return rc;
 }
 
+/* ---- rank adaptation: TT rounding + kicked ranks ------------------------------------------------------
+ * The adapt == 1 branch of valuef_interp (src/valuefunc.c:637-648,:706-730) calls C3's
+ * ftapprox_cross_rankadapt with cross_tol / round_tol / kickrank / maxrank.  C3 is not vendored; the
+ * published algorithm (C3 paper, Alg. 4; Oseledets 2011 TT-rounding) is restated here on nodal cores:
+ *   run the fixed-rank cross; round the result to round_tol; every interior rank the rounding did NOT
+ *   reduce (and that is below maxrank) is kicked by kickrank and the cross is run again; the rounded
+ *   train is the answer.
+ * Inner products are the discrete l2 ones over the grid nodes (like c3sc_cores_norm).              */
+
+/* one-sided Jacobi SVD of A (m x n, column-major, m >= n): A <- U (orthonormal columns where s > 0),
+ * s[n] descending, V (n x n). */
+static void svd_jacobi(double *A, size_t m, size_t n, double *s, double *V)
+{
+    for (size_t i = 0; i < n * n; i++) V[i] = 0.0;
+    for (size_t i = 0; i < n; i++) V[i + i * n] = 1.0;
+    for (int sweep = 0; sweep < 60; sweep++) {
+        int rotated = 0;
+        for (size_t p = 0; p + 1 < n; p++)
+            for (size_t q = p + 1; q < n; q++) {
+                double al = 0.0, be = 0.0, ga = 0.0;
+                for (size_t i = 0; i < m; i++) {
+                    const double x = A[i + p * m], y = A[i + q * m];
+                    al += x * x; be += y * y; ga += x * y;
+                }
+                if (ga == 0.0 || fabs(ga) <= 1e-15 * sqrt(al * be)) continue;
+                rotated = 1;
+                const double zeta = (be - al) / (2.0 * ga);
+                const double t = (zeta >= 0.0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
+                const double cs = 1.0 / sqrt(1.0 + t * t), sn = cs * t;
+                for (size_t i = 0; i < m; i++) {
+                    const double x = A[i + p * m], y = A[i + q * m];
+                    A[i + p * m] = cs * x - sn * y; A[i + q * m] = sn * x + cs * y;
+                }
+                for (size_t i = 0; i < n; i++) {
+                    const double x = V[i + p * n], y = V[i + q * n];
+                    V[i + p * n] = cs * x - sn * y; V[i + q * n] = sn * x + cs * y;
+                }
+            }
+        if (!rotated) break;
+    }
+    for (size_t j = 0; j < n; j++) {
+        double nr = 0.0;
+        for (size_t i = 0; i < m; i++) nr += A[i + j * m] * A[i + j * m];
+        s[j] = sqrt(nr);
+        if (s[j] > 0.0) for (size_t i = 0; i < m; i++) A[i + j * m] /= s[j];
+    }
+    for (size_t j = 0; j + 1 < n; j++) {                               /* selection sort, descending */
+        size_t b = j;
+        for (size_t q = j + 1; q < n; q++) if (s[q] > s[b]) b = q;
+        if (b == j) continue;
+        double t = s[j]; s[j] = s[b]; s[b] = t;
+        for (size_t i = 0; i < m; i++) { t = A[i + j * m]; A[i + j * m] = A[i + b * m]; A[i + b * m] = t; }
+        for (size_t i = 0; i < n; i++) { t = V[i + j * n]; V[i + j * n] = V[i + b * n]; V[i + b * n] = t; }
+    }
+}
+
+/* function_train_round on nodal cores: right-to-left QR, then left-to-right truncated SVD with the
+ * tail of every unfolding below eps * |T| / sqrt(d-1).  cores_out[k] needs the capacity of cores_in[k]. */
+int c3sc_cores_round(uint32_t d, const uint64_t *n, const uint64_t *rin, const double *const *cin, double eps,
+                     uint64_t *rout, double *const *cout)
+{
+    if (!n || !rin || !cin || !rout || !cout || d < 1 || d > C3SC_MAXD || rin[0] != 1 || rin[d] != 1 || eps < 0.0)
+        return C3SC_EINVAL;
+    for (uint32_t k = 1; k < d; k++)
+        if (rin[k] > rin[k - 1] * n[k - 1] || rin[k] > rin[k + 1] * n[k]) return C3SC_EINVAL;   /* ranks beyond an unfolding */
+    uint64_t r[C3SC_MAXD + 1];
+    size_t tmax = 1, rmax = 1;
+    for (uint32_t k = 0; k <= d; k++) { r[k] = rin[k]; if (rin[k] > rmax) rmax = rin[k]; }
+    for (uint32_t k = 0; k < d; k++) if (rin[k] * n[k] * rin[k + 1] > tmax) tmax = rin[k] * n[k] * rin[k + 1];
+    double *W[C3SC_MAXD] = {0};
+    double *Q = (double *)malloc(tmax * sizeof(double)), *A0 = (double *)malloc(tmax * sizeof(double));
+    double *R = (double *)malloc(rmax * rmax * sizeof(double)), *V = (double *)malloc(rmax * rmax * sizeof(double));
+    double *sv = (double *)malloc(rmax * sizeof(double));
+    double *work = (double *)malloc((tmax + rmax + 16) * sizeof(double));
+    int rc = C3SC_OK;
+    if (!Q || !A0 || !R || !V || !sv || !work) { rc = C3SC_EINVAL; goto done; }
+    for (uint32_t k = 0; k < d; k++) {                                  /* ValueF layout -> [a + j*rk + b*rk*N] */
+        const size_t rk = r[k], rk1 = r[k + 1], N = n[k];
+        W[k] = (double *)malloc(rk * N * rk1 * sizeof(double));
+        if (!W[k]) { rc = C3SC_EINVAL; goto done; }
+        for (size_t j = 0; j < N; j++)
+            for (size_t b = 0; b < rk1; b++)
+                for (size_t a = 0; a < rk; a++) W[k][a + j * rk + b * rk * N] = cin[k][j * rk * rk1 + a + b * rk];
+    }
+    for (uint32_t k = d - 1; k >= 1; k--) {                             /* rows of core k orthonormal */
+        const size_t rk = r[k], rk1 = r[k + 1], N = n[k], m = N * rk1;
+        for (size_t a = 0; a < rk; a++)
+            for (size_t j = 0; j < N; j++)
+                for (size_t b = 0; b < rk1; b++) Q[(j + b * N) + a * m] = W[k][a + j * rk + b * rk * N];
+        memcpy(A0, Q, m * rk * sizeof(double));
+        qr_explicit_q(Q, m, rk, work);
+        for (size_t a = 0; a < rk; a++)                                 /* R = Q^T A0 */
+            for (size_t c2 = 0; c2 < rk; c2++) {
+                double t = 0.0;
+                for (size_t i = 0; i < m; i++) t += Q[i + a * m] * A0[i + c2 * m];
+                R[a + c2 * rk] = t;
+            }
+        for (size_t a = 0; a < rk; a++)
+            for (size_t j = 0; j < N; j++)
+                for (size_t b = 0; b < rk1; b++) W[k][a + j * rk + b * rk * N] = Q[(j + b * N) + a * m];
+        const size_t rp = r[k - 1], Np = n[k - 1], mp = rp * Np;         /* core k-1 <- core k-1 x R^T */
+        for (size_t x = 0; x < mp; x++) {
+            for (size_t a2 = 0; a2 < rk; a2++) {
+                double t = 0.0;
+                for (size_t a = 0; a < rk; a++) t += W[k - 1][x + a * mp] * R[a2 + a * rk];
+                work[a2] = t;
+            }
+            for (size_t a2 = 0; a2 < rk; a2++) W[k - 1][x + a2 * mp] = work[a2];
+        }
+    }
+    if (d > 1) {
+        double nrm2 = 0.0;
+        for (size_t e = 0; e < r[0] * n[0] * r[1]; e++) nrm2 += W[0][e] * W[0][e];
+        const double delta2 = eps * eps * nrm2 / (double)(d - 1);
+        for (uint32_t k = 0; k + 1 < d; k++) {
+            const size_t rk = r[k], rk1 = r[k + 1], N = n[k], m = rk * N;
+            size_t p, rnew;
+            double *U, *G;                                                /* U: m x rnew, G = diag(s) Vt: rnew x rk1 */
+            if (m >= rk1) {
+                p = rk1;
+                svd_jacobi(W[k], m, rk1, sv, V);                          /* W[k] <- U, V: rk1 x rk1 */
+                U = W[k];
+            } else {                                                      /* wide unfolding: SVD of the transpose */
+                p = m;
+                for (size_t i = 0; i < m; i++)
+                    for (size_t b = 0; b < rk1; b++) Q[b + i * rk1] = W[k][i + b * m];
+                svd_jacobi(Q, rk1, m, sv, V);                             /* Q <- V' (rk1 x m), V <- U' (m x m) */
+                U = V;
+            }
+            double tail = 0.0;
+            rnew = p;
+            while (rnew > 1 && tail + sv[rnew - 1] * sv[rnew - 1] <= delta2) { tail += sv[rnew - 1] * sv[rnew - 1]; rnew--; }
+            G = A0;
+            for (size_t a2 = 0; a2 < rnew; a2++)
+                for (size_t b = 0; b < rk1; b++)
+                    G[a2 + b * rnew] = sv[a2] * (m >= rk1 ? V[b + a2 * rk1] : Q[b + a2 * rk1]);
+            if (m < rk1)
+                for (size_t a2 = 0; a2 < rnew; a2++)
+                    for (size_t i = 0; i < m; i++) W[k][i + a2 * m] = U[i + a2 * m];
+            /* core k keeps its first rnew columns (already in place); core k+1 <- G x core k+1 */
+            const size_t N1 = n[k + 1], r2 = r[k + 2];
+            double *Wn = (double *)malloc(rnew * N1 * r2 * sizeof(double));
+            if (!Wn) { rc = C3SC_EINVAL; goto done; }
+            for (size_t c2 = 0; c2 < N1 * r2; c2++)
+                for (size_t a2 = 0; a2 < rnew; a2++) {
+                    double t = 0.0;
+                    for (size_t b = 0; b < rk1; b++) t += G[a2 + b * rnew] * W[k + 1][b + c2 * rk1];
+                    Wn[a2 + c2 * rnew] = t;
+                }
+            free(W[k + 1]);
+            W[k + 1] = Wn;
+            r[k + 1] = rnew;
+        }
+    }
+    for (uint32_t k = 0; k < d; k++) {
+        const size_t rk = r[k], rk1 = r[k + 1], N = n[k];
+        for (size_t j = 0; j < N; j++)
+            for (size_t b = 0; b < rk1; b++)
+                for (size_t a = 0; a < rk; a++) cout[k][j * rk * rk1 + a + b * rk] = W[k][a + j * rk + b * rk * N];
+    }
+    for (uint32_t k = 0; k <= d; k++) rout[k] = r[k];
+done:
+    for (uint32_t k = 0; k < d; k++) free(W[k]);
+    free(Q); free(A0); free(R); free(V); free(sv); free(work);
+    return rc;
+}
+
+/* SplitMix64, for the index nodes a kicked rank starts from */
+static uint64_t mix64(uint64_t *st)
+{
+    uint64_t z = (*st += 0x9E3779B97F4A7C15ull);
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+
+/* change interior rank k to rnew.  Shrinking keeps the first rnew multi-indices of both sets.  Growing
+ * appends right multi-indices not yet in J[k] (C3's cross_index_copylast repeats the last one instead,
+ * which makes the next maxvol matrix singular by construction; fresh nodes serve the same purpose);
+ * the left set I[k] only needs the room -- the next left-to-right sweep rebuilds it. */
+static int cross_resize(c3sc_cross *c, uint32_t k, uint64_t rnew)
+{
+    const uint32_t d = c->d;
+    const uint64_t rold = c->r[k];
+    if (rnew == rold) return 0;
+    int32_t *I = (int32_t *)realloc(c->I[k], (rnew * d + 1) * sizeof(int32_t));
+    if (!I) return 1;
+    c->I[k] = I;
+    int32_t *J = (int32_t *)realloc(c->J[k], (rnew * d + 1) * sizeof(int32_t));
+    if (!J) return 1;
+    c->J[k] = J;
+    uint64_t st = 0xC35CA0DA00000000ull + ((uint64_t)k << 20) + rold;
+    for (uint64_t j = rold; j < rnew; j++) {
+        for (uint32_t i = 0; i < d; i++) { I[j * d + i] = 0; J[j * d + i] = 0; }
+        for (int attempt = 0; attempt < 64; attempt++) {
+            for (uint32_t i = k; i < d; i++) J[j * d + i] = (int32_t)(mix64(&st) % c->n[i]);
+            int dup = 0;
+            for (uint64_t q = 0; q < j && !dup; q++) {
+                int same = 1;
+                for (uint32_t i = k; i < d && same; i++) same = J[q * d + i] == J[j * d + i];
+                dup = same;
+            }
+            if (!dup) break;
+        }
+        for (uint32_t i = 0; i < k; i++) I[j * d + i] = (int32_t)(mix64(&st) % c->n[i]);
+    }
+    c->r[k] = rnew;
+    return 0;
+}
+
+/* start ranks of the next solver step from the ranks the last one found: min(r+1, maxrank), the
+ * vref branch of valuef_interp (src/valuefunc.c:637-648); index sets are kept (:706-712). */
+int c3sc_cross_set_ranks(c3sc_cross *c, const uint64_t *ranks)
+{
+    if (!c || !ranks || ranks[0] != 1 || ranks[c->d] != 1) return C3SC_EINVAL;
+    uint64_t r[C3SC_MAXD + 1];
+    for (uint32_t k = 0; k <= c->d; k++) r[k] = ranks[k] ? ranks[k] : 1;
+    for (uint32_t k = 1; k < c->d; k++) if (r[k] > r[k - 1] * c->n[k - 1]) r[k] = r[k - 1] * c->n[k - 1];
+    for (uint32_t k = c->d - 1; k >= 1; k--) if (r[k] > r[k + 1] * c->n[k]) r[k] = r[k + 1] * c->n[k];
+    for (uint32_t k = 1; k < c->d; k++)
+        if (cross_resize(c, k, r[k])) return C3SC_EINVAL;
+    return C3SC_OK;
+}
+
+/* ftapprox_cross_rankadapt: see the section header.  cores[k] needs n[k]*cap[k]*cap[k+1] doubles with
+ * cap = min(maxrank, unfolding bounds) -- c3sc_cross_adapt_capacity() gives cap[]. */
+static uint64_t adapt_maxrank(const c3sc_cross *c, const c3sc_adapt_opts *a)
+{
+    uint64_t minN = c->n[0];
+    for (uint32_t k = 1; k < c->d; k++) if (c->n[k] < minN) minN = c->n[k];
+    uint64_t mr = a && a->maxrank ? a->maxrank : minN;
+    return mr < minN ? mr : minN;                                        /* src/valuefunc.c:625-631 */
+}
+
+int c3sc_cross_adapt_capacity(const c3sc_cross *c, const c3sc_adapt_opts *a, uint64_t *cap)
+{
+    if (!c || !cap) return C3SC_EINVAL;
+    const uint64_t mr = adapt_maxrank(c, a);
+    for (uint32_t k = 0; k <= c->d; k++) cap[k] = (k == 0 || k == c->d) ? 1 : (c->r[k] > mr ? c->r[k] : mr);
+    return C3SC_OK;
+}
+
+int c3sc_cross_run_adapt(c3sc_cross *c, c3sc_fiber_batch_fn f, void *arg, const c3sc_cross_opts *opts,
+                         const c3sc_adapt_opts *aopts, uint64_t *ranks_out, double *const *cores, uint64_t *nfibers,
+                         double *rel_change)
+{
+    if (!c || !f || !aopts || !ranks_out || !cores) return C3SC_EINVAL;
+    const uint32_t d = c->d;
+    const uint64_t maxrank = adapt_maxrank(c, aopts);
+    const uint32_t rounds = aopts->maxiter_adapt ? aopts->maxiter_adapt : 5;
+    const int verbose = opts ? opts->verbose : 0;
+    uint64_t cap[C3SC_MAXD + 1], total = 0;
+    c3sc_cross_adapt_capacity(c, aopts, cap);
+    double *raw[C3SC_MAXD] = {0};
+    int rc = C3SC_OK;
+    for (uint32_t k = 0; k < d; k++) {
+        raw[k] = (double *)malloc(c->n[k] * cap[k] * cap[k + 1] * sizeof(double));
+        if (!raw[k]) { rc = C3SC_EINVAL; goto done; }
+    }
+    for (uint32_t round = 0;; round++) {
+        uint64_t nf = 0;
+        rc = c3sc_cross_run(c, f, arg, opts, raw, &nf, rel_change);
+        total += nf;
+        if (rc) goto done;
+        rc = c3sc_cores_round(d, c->n, c->r, (const double *const *)raw, aopts->round_tol, ranks_out, cores);
+        if (rc) goto done;
+        if (verbose) {
+            fprintf(stderr, "c3sc_cross_run_adapt: round %u, cross ranks", round);
+            for (uint32_t k = 0; k <= d; k++) fprintf(stderr, " %llu", (unsigned long long)c->r[k]);
+            fprintf(stderr, " -> rounded");
+            for (uint32_t k = 0; k <= d; k++) fprintf(stderr, " %llu", (unsigned long long)ranks_out[k]);
+            fprintf(stderr, "\n");
+        }
+        if (aopts->kickrank == 0 || round + 1 >= rounds) break;
+        int adapt = 0;
+        for (uint32_t k = 1; k < d; k++) {
+            if (ranks_out[k] != c->r[k] || c->r[k] >= maxrank) continue;  /* rounding cut it, or at the cap */
+            uint64_t rnew = c->r[k] + aopts->kickrank;
+            if (rnew > maxrank) rnew = maxrank;
+            if (rnew > c->r[k - 1] * c->n[k - 1]) rnew = c->r[k - 1] * c->n[k - 1];
+            if (rnew > c->r[k + 1] * c->n[k]) rnew = c->r[k + 1] * c->n[k];
+            if (rnew <= c->r[k]) continue;
+            if (cross_resize(c, k, rnew)) { rc = C3SC_EINVAL; goto done; }
+            adapt = 1;
+        }
+        if (!adapt) break;
+    }
+done:
+    if (nfibers) *nfibers = total;
+    for (uint32_t k = 0; k < d; k++) free(raw[k]);
+    return rc;
+}
+
 /* ---- the GPU operators behind the driver ---------------------------------------------------------- */
 struct vi_ctx { c3sc_problem *p; const c3sc_valuef *vf; };
 static int vi_cb(size_t F, const int32_t *dv, const int32_t *fi, size_t ldo, double *out, void *arg)
@@ -506,4 +799,13 @@ out:
     free(cur);
     c3sc_valuef_destroy(vf);
     return rc;
+}
+
+/* c3control_step_vi with the adapt == 1 branch of valuef_interp */
+int c3sc_cross_run_vi_adapt(c3sc_cross *c, c3sc_problem *p, const c3sc_valuef *vf, const c3sc_cross_opts *opts,
+                            const c3sc_adapt_opts *aopts, uint64_t *ranks_out, double *const *cores, uint64_t *nfibers,
+                            double *rel_change)
+{
+    struct vi_ctx x = {p, vf};
+    return c3sc_cross_run_adapt(c, vi_cb, &x, opts, aopts, ranks_out, cores, nfibers, rel_change);
 }

@@ -43,6 +43,32 @@ int c3sc_cross_run_pi(c3sc_cross *c, c3sc_problem *p, const c3sc_valuef *vf_poli
                       uint32_t dx, const c3sc_cross_opts *opts, double *const *cores, uint64_t *nfibers,
                       double *rel_change);
 
+/* ---- rank adaptation (the adapt == 1 branch of valuef_interp, src/valuefunc.c:637-648,:706-730:
+ * C3's ftapprox_cross_rankadapt with round_tol / kickrank / maxrank) ------------------------------- */
+typedef struct c3sc_adapt_opts {
+    uint32_t kickrank;       /* ranks the rounding did not reduce grow by this much; 0 = round only */
+    uint32_t maxrank;        /* cap; 0 or > min N = min N (src/valuefunc.c:625-631) */
+    double round_tol;        /* relative accuracy of the rounding */
+    uint32_t maxiter_adapt;  /* cross runs at most; 0 = 5 */
+} c3sc_adapt_opts;
+
+/* function_train_round on nodal cores (discrete l2): ranks_out[d+1], cores_out[k] with the capacity of
+ * cores_in[k].  ranks_in must respect the unfolding bounds (r_k <= r_{k-1} n_{k-1}, r_k <= r_{k+1} n_k). */
+int c3sc_cores_round(uint32_t d, const uint64_t *n, const uint64_t *ranks_in, const double *const *cores_in,
+                     double eps, uint64_t *ranks_out, double *const *cores_out);
+
+/* largest rank per bond an adaptive run can return (sizes the caller's cores: n[k]*cap[k]*cap[k+1]) */
+int c3sc_cross_adapt_capacity(const c3sc_cross *c, const c3sc_adapt_opts *aopts, uint64_t *cap);
+/* resize the driver's ranks / index sets, e.g. to min(found+1, maxrank) before the next solver step */
+int c3sc_cross_set_ranks(c3sc_cross *c, const uint64_t *ranks);
+/* cross -> round -> kick -> cross ...; returns the ROUNDED train (ranks_out, cores) */
+int c3sc_cross_run_adapt(c3sc_cross *c, c3sc_fiber_batch_fn f, void *arg, const c3sc_cross_opts *opts,
+                         const c3sc_adapt_opts *aopts, uint64_t *ranks_out, double *const *cores, uint64_t *nfibers,
+                         double *rel_change);
+int c3sc_cross_run_vi_adapt(c3sc_cross *c, c3sc_problem *p, const c3sc_valuef *vf, const c3sc_cross_opts *opts,
+                            const c3sc_adapt_opts *aopts, uint64_t *ranks_out, double *const *cores, uint64_t *nfibers,
+                            double *rel_change);
+
 /* c3control_vi_solve (src/bellman.c:2282-2340) on the GPU path: value iteration from the start train
  * (ranks0, cores0) until ||V_{t+1} - V_t|| < abs_conv_tol (nodal l2) or maxiter steps.  cores_out in the
  * driver's ranks (c3sc_cross_ranks).  iters_done / last_diff / nfibers may be NULL. */

@@ -156,3 +156,159 @@ def test_policy_iteration_step_gpu_equals_oracle(gpu):
     vo = np.array([port.ft_eval_linear(ft_o, np.ascontiguousarray(x)) for x in pts])
     assert np.abs(vg - vo).max() <= 1e-10 * max(np.abs(vo).max(), 1.0)
     prob.close(); vf_pol.close(); vf_it.close(); cr_g.close(); cr_o.close()
+
+
+# ---- rank adaptation: TT rounding + kicked ranks (the adapt == 1 branch of valuef_interp) -------------
+def _u64(x):
+    return np.array(x, dtype=np.uint64)
+
+
+def test_round_keeps_a_full_rank_train():
+    n = [6, 7, 5, 6]
+    r = [1, 4, 5, 3, 1]
+    c = synthetic.random_cores(_u64(n), _u64(r), seed=9)
+    rr, cc = capi.cores_round(n, r, c, 1e-14)
+    assert list(rr) == r
+    A = _tt_full(n, r, c)
+    assert np.abs(_tt_full(n, rr, cc) - A).max() <= 1e-13 * np.abs(A).max()
+
+
+def test_round_finds_the_exact_rank():
+    """a rank-2 function written with padded rank-5/6 cores (sum of a train with itself and zeros)"""
+    n = [8, 9, 7, 8, 6]
+    grids = [np.linspace(-1, 1, m) for m in n]
+    r2, c2 = synthetic.quadratic_cores(grids)                            # sum x_i^2: exact rank 2
+    d = len(n)
+    big = [1] + [5, 6, 5, 6] + [1]
+    noise = synthetic.random_cores(_u64(n), _u64(big), seed=21)
+    cores = []
+    for k in range(d):
+        g = np.zeros((n[k], big[k + 1], big[k]))                        # [j][b][a] (block j column-major)
+        src = np.asarray(c2[k]).reshape(n[k], int(r2[k + 1]), int(r2[k]))
+        g[:, :src.shape[1], :src.shape[2]] = src
+        if 0 < k < d - 1:                                               # a block the neighbours never reach
+            g[:, 2:, 2:] = np.asarray(noise[k]).reshape(n[k], big[k + 1], big[k])[:, 2:, 2:]
+        cores.append(g.reshape(-1))
+    # make the junk unreachable: the first core feeds only the first two ranks
+    A = _tt_full(n, r2, c2)
+    assert np.abs(_tt_full(n, big, cores) - A).max() <= 1e-12 * np.abs(A).max()
+    rr, cc = capi.cores_round(n, big, cores, 1e-10)
+    assert list(rr) == [1, 2, 2, 2, 2, 1]
+    assert np.abs(_tt_full(n, rr, cc) - A).max() <= 1e-9 * np.abs(A).max()
+
+
+@pytest.mark.parametrize("eps", [1e-2, 1e-4, 1e-7])
+def test_round_error_is_below_eps(eps):
+    """|A - round(A, eps)| <= eps |A| (Frobenius), ranks non-increasing in eps; decaying singular values"""
+    n = [10, 9, 11, 8]
+    grids = [np.linspace(0, 1, m) for m in n]
+    X = np.meshgrid(*grids, indexing="ij")
+    full = 1.0 / (1.0 + X[0] + 2 * X[1] + 3 * X[2] + 0.5 * X[3])
+
+    def fn(dv, fi):
+        out = np.zeros((len(dv), max(n)))
+        for f in range(len(dv)):
+            idx = [int(v) for v in fi[f]]; k = int(dv[f])
+            for j in range(n[k]):
+                idx[k] = j
+                out[f, j] = full[tuple(idx)]
+        return out
+    cr = capi.Cross(n, [1, 8, 8, 8, 1])
+    cores, _, _ = cr.run(fn, maxiter=3)
+    A = _tt_full(n, cr.ranks, cores)
+    rr, cc = capi.cores_round(n, cr.ranks, cores, eps)
+    err = np.linalg.norm(_tt_full(n, rr, cc) - A) / np.linalg.norm(A)
+    assert err <= eps
+    assert all(int(a) <= int(b) for a, b in zip(rr, cr.ranks))
+    assert capi.cores_norm2diff(n, cr.ranks, cores, rr, cc) <= 1.01 * eps * capi.cores_norm(n, cr.ranks, cores) + 1e-12
+    cr.close()
+
+
+def test_round_handles_wide_unfoldings_and_bad_ranks():
+    n = [2, 3, 9, 3, 2]
+    r = [1, 2, 6, 6, 2, 1]
+    c = synthetic.random_cores(_u64(n), _u64(r), seed=2)
+    A = _tt_full(n, r, c)
+    rr, cc = capi.cores_round(n, r, c, 1e-13)
+    assert np.abs(_tt_full(n, rr, cc) - A).max() <= 1e-12 * np.abs(A).max()
+    with pytest.raises(capi.C3scError):
+        capi.cores_round([2, 9, 9], [1, 5, 3, 1], synthetic.random_cores(_u64([2, 9, 9]), _u64([1, 5, 3, 1])), 1e-8)
+
+
+def test_adaptive_cross_grows_to_the_needed_rank():
+    """start at rank 2 on a rank-4 tensor: kicks until the rounding cuts every bond, returns rank 4"""
+    n = [9, 8, 10, 7]
+    grids = [np.linspace(-1, 1, m) for m in n]
+    X = np.meshgrid(*grids, indexing="ij")
+    full = np.sin(X[0] + X[1] + X[2] + X[3]) + np.cos(2 * (X[0] - X[1] + X[2] - X[3]))     # TT rank 4
+    calls = []
+
+    def fn(dv, fi):
+        calls.append(len(dv))
+        out = np.zeros((len(dv), max(n)))
+        for f in range(len(dv)):
+            idx = [int(v) for v in fi[f]]; k = int(dv[f])
+            for j in range(n[k]):
+                idx[k] = j
+                out[f, j] = full[tuple(idx)]
+        return out
+    cr = capi.Cross(n, [1, 2, 2, 2, 1])
+    cores, ranks, nfib, _ = cr.run_adapt(fn, kickrank=2, maxrank=7, round_tol=1e-10, maxiter=3)
+    assert list(ranks) == [1, 4, 4, 4, 1]
+    assert all(int(x) > 4 for x in cr.ranks[1:-1])                       # the cross ran above the rank it returned
+    assert np.abs(_tt_full(n, ranks, cores) - full).max() <= 1e-9
+    assert nfib == sum(calls)
+    # the next solver step starts from found + 1 (src/valuefunc.c:637-648)
+    cr.set_ranks([1] + [int(x) + 1 for x in ranks[1:-1]] + [1])
+    assert list(cr.ranks) == [1, 5, 5, 5, 1]
+    cores2, ranks2, _, _ = cr.run_adapt(fn, kickrank=2, maxrank=7, round_tol=1e-10, maxiter=2)
+    assert list(ranks2) == [1, 4, 4, 4, 1] and list(cr.ranks) == [1, 5, 5, 5, 1]     # nothing to kick this time
+    assert np.abs(_tt_full(n, ranks2, cores2) - full).max() <= 1e-9
+    cr.close()
+
+
+def test_adaptive_cross_respects_maxrank_and_kick_zero():
+    n = [6, 6, 6]
+    rng = np.random.default_rng(4)
+    full = rng.standard_normal(n)                                        # full rank: 6, 6
+
+    def fn(dv, fi):
+        out = np.zeros((len(dv), 6))
+        for f in range(len(dv)):
+            idx = [int(v) for v in fi[f]]; k = int(dv[f])
+            for j in range(6):
+                idx[k] = j
+                out[f, j] = full[tuple(idx)]
+        return out
+    cr = capi.Cross(n, [1, 2, 2, 1])
+    _, ranks, _, _ = cr.run_adapt(fn, kickrank=3, maxrank=4, round_tol=1e-12, maxiter=2, maxiter_adapt=6)
+    assert list(cr.ranks) == [1, 4, 4, 1] and list(ranks) == [1, 4, 4, 1]
+    cr.close()
+    cr = capi.Cross(n, [1, 2, 2, 1])
+    _, ranks, _, _ = cr.run_adapt(fn, kickrank=0, maxrank=4, round_tol=1e-12, maxiter=2)
+    assert list(cr.ranks) == [1, 2, 2, 1] and list(ranks) == [1, 2, 2, 1]
+    cr.close()
+
+
+@pytest.mark.gpu
+def test_adaptive_value_iteration_matches_fixed_rank(gpu):
+    """value iteration with rank adaptation (start rank 2, kick 2) against the fixed-rank driver at a
+    generous rank: same value function to the rounding tolerance, with smaller ranks"""
+    cfg = configs.get_config("lqgnd", n=16, rank=8, dx=3)
+    prob = capi.Problem(cfg, arith=1)
+    port = make_port(cfg)
+    r0, c0 = synthetic.quadratic_cores(prob.xgrid)
+    fixed = capi.Cross(cfg.ngrid, cfg.ranks())
+    adapt = capi.Cross(cfg.ngrid, [1, 2, 2, 1])
+    cf, rf = c0, np.asarray(r0, dtype=np.uint64)
+    ca, ra = c0, np.asarray(r0, dtype=np.uint64)
+    for it in range(4):
+        vf = capi.ValueF(cfg.ngrid, rf, cf)
+        cf, _, _ = fixed.run_vi(prob, vf, maxiter=3); rf = fixed.ranks.copy(); vf.close()
+        va = capi.ValueF(cfg.ngrid, ra, ca)
+        ca, ra, _, _ = adapt.run_vi_adapt(prob, va, kickrank=2, maxrank=10, round_tol=1e-9, maxiter=3); va.close()
+        adapt.set_ranks([1] + [min(int(x) + 1, 10) for x in ra[1:-1]] + [1])
+    nf = capi.cores_norm(cfg.ngrid, rf, cf)
+    assert capi.cores_norm2diff(cfg.ngrid, rf, cf, ra, ca) <= 1e-6 * nf
+    assert max(int(x) for x in ra) <= 8
+    prob.close(); fixed.close(); adapt.close()
