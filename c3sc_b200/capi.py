@@ -64,7 +64,7 @@ EXPORTS = [
     "c3sc_cross_create", "c3sc_cross_destroy", "c3sc_cross_ranks", "c3sc_cross_run", "c3sc_cross_run_vi", "c3sc_cross_run_pi",
     "c3sc_vi_solve", "c3sc_cores_dot", "c3sc_cores_norm", "c3sc_cores_norm2diff",
     "c3sc_valuef_eval_batch", "c3sc_policy_eval_batch",
-    "c3sc_cores_round", "c3sc_cross_adapt_capacity", "c3sc_cross_set_ranks", "c3sc_cross_run_adapt", "c3sc_cross_run_vi_adapt",
+    "c3sc_cross_index_sets", "c3sc_cores_round", "c3sc_cross_adapt_capacity", "c3sc_cross_set_ranks", "c3sc_cross_run_adapt", "c3sc_cross_run_vi_adapt",
     "c3sc_peer_buffer_create", "c3sc_peer_buffer_open", "c3sc_peer_buffer_close",
 ]
 
@@ -125,6 +125,7 @@ def lib() -> C.CDLL:
         L.c3sc_cores_round.argtypes = [C.c_uint32, c_u64p, c_u64p, C.POINTER(c_f64p), C.c_double, c_u64p, C.POINTER(c_f64p)]
         L.c3sc_cross_adapt_capacity.argtypes = [vp, C.POINTER(AdaptOpts), c_u64p]
         L.c3sc_cross_set_ranks.argtypes = [vp, c_u64p]
+        L.c3sc_cross_index_sets.argtypes = [vp, C.c_uint32, vp, vp]
         L.c3sc_cross_run_adapt.argtypes = [vp, FIBER_FN, vp, C.POINTER(CrossOpts), C.POINTER(AdaptOpts), c_u64p, C.POINTER(c_f64p),
                                            c_u64p, c_f64p]
         L.c3sc_cross_run_vi_adapt.argtypes = [vp, vp, vp, C.POINTER(CrossOpts), C.POINTER(AdaptOpts), c_u64p, C.POINTER(c_f64p),
@@ -445,6 +446,14 @@ class Cross:
     def _adapt_result(self, cores, rout):
         check(lib().c3sc_cross_ranks(self.handle, self.ranks.ctypes.data_as(c_u64p)))
         return [cores[k][:int(self.n[k] * rout[k] * rout[k + 1])].copy() for k in range(self.d)], rout
+
+    def index_sets(self, k):
+        """(left, right) multi-index sets at bond k, each [r_k, d]"""
+        check(lib().c3sc_cross_ranks(self.handle, self.ranks.ctypes.data_as(c_u64p)))
+        r = int(self.ranks[k])
+        left = np.zeros((r, self.d), dtype=np.int32); right = np.zeros((r, self.d), dtype=np.int32)
+        check(lib().c3sc_cross_index_sets(self.handle, k, left.ctypes.data, right.ctypes.data))
+        return left, right
 
     def set_ranks(self, ranks):
         r = np.ascontiguousarray(ranks, dtype=np.uint64)

@@ -95,6 +95,19 @@ int c3sc_cross_ranks(const c3sc_cross *c, uint64_t *ranks)
     return C3SC_OK;
 }
 
+/* the driver's index sets at bond k (ValueF keeps them as isl / isr between solver steps,
+ * src/valuefunc.c:706-712): left[r_k * d] uses dims 0..k-1, right[r_k * d] dims k..d-1, others 0 */
+int c3sc_cross_index_sets(const c3sc_cross *c, uint32_t k, int32_t *left, int32_t *right)
+{
+    if (!c || k > c->d) return C3SC_EINVAL;
+    for (uint64_t j = 0; j < c->r[k]; j++)
+        for (uint32_t i = 0; i < c->d; i++) {
+            if (left) left[j * c->d + i] = i < k ? c->I[k][j * c->d + i] : 0;
+            if (right) right[j * c->d + i] = i >= k ? c->J[k][j * c->d + i] : 0;
+        }
+    return C3SC_OK;
+}
+
 /* ---- small dense linear algebra (column-major) --------------------------------------------- */
 /* Householder QR of A (m x n, m >= n): Q (m x n, explicit, orthonormal columns) overwrites A. */
 static void qr_explicit_q(double *A, size_t m, size_t n, double *work /* n + m */)
@@ -136,7 +149,45 @@ static void qr_explicit_q(double *A, size_t m, size_t n, double *work /* n + m *
 
 /* maxvol: rows P (n of m) of Q (m x n) whose submatrix has (locally) maximal |det|; on return
  * B = Q * inv(Q[P,:]) (m x n), so B[P,:] = I.  Deterministic: first maximum in scan order. */
-static int maxvol(const double *Q, size_t m, size_t n, size_t *P, double *B, double *work /* n*n + n */)
+/* Rows of the unfolding A (m x n, before the QR) that repeat an earlier row to round-off carry no
+ * information for the pivoting (absorbing faces with a constant boundary cost produce whole families of
+ * them); when the unfolding is rank-deficient the QR completes Q with arbitrary directions and maxvol would
+ * happily pick such twins, which makes the NEXT unfolding rank-deficient as well.  skip[i] = 1 withholds
+ * row i from the pivoting.  Twins are found through two fixed random projections of the rows. */
+typedef struct { double k1, k2; size_t row; } rowkey;
+static int rowkey_cmp(const void *a, const void *b)
+{
+    const rowkey *x = (const rowkey *)a, *y = (const rowkey *)b;
+    if (x->k1 != y->k1) return x->k1 < y->k1 ? -1 : 1;
+    return x->row < y->row ? -1 : (x->row > y->row);
+}
+static void mark_twin_rows(const double *A, size_t m, size_t n, char *skip)
+{
+    rowkey *key = (rowkey *)malloc(m * sizeof(rowkey));
+    memset(skip, 0, m);
+    if (!key) return;
+    double scale = 0.0;
+    for (size_t e = 0; e < m * n; e++) if (fabs(A[e]) > scale) scale = fabs(A[e]);
+    for (size_t i = 0; i < m; i++) { key[i].k1 = key[i].k2 = 0.0; key[i].row = i; }
+    uint64_t st = 0x7F1BE7ull;
+    for (size_t j = 0; j < n; j++) {
+        st = st * 6364136223846793005ull + 1442695040888963407ull;
+        const double w1 = 0.5 + (double)(st >> 11) / 9007199254740992.0;
+        st = st * 6364136223846793005ull + 1442695040888963407ull;
+        const double w2 = 0.5 + (double)(st >> 11) / 9007199254740992.0;
+        for (size_t i = 0; i < m; i++) { key[i].k1 += w1 * A[i + j * m]; key[i].k2 += w2 * A[i + j * m]; }
+    }
+    qsort(key, m, sizeof(rowkey), rowkey_cmp);
+    const double tol = 1e-12 * scale * (double)n;
+    size_t eligible = m;
+    for (size_t i = 1; i < m; i++)
+        for (size_t q = i; q-- > 0 && key[i].k1 - key[q].k1 <= tol;)
+            if (!skip[key[q].row] && fabs(key[i].k2 - key[q].k2) <= tol) { skip[key[i].row] = 1; eligible--; break; }
+    if (eligible < n) memset(skip, 0, m);                              /* not enough distinct rows: no restriction */
+    free(key);
+}
+
+static int maxvol(const double *Q, size_t m, size_t n, const char *skip, size_t *P, double *B, double *work /* n*n + n */)
 {
     /* start rows: Gaussian elimination with row pivoting on a copy */
     memcpy(B, Q, m * n * sizeof(double));
@@ -145,7 +196,7 @@ static int maxvol(const double *Q, size_t m, size_t n, size_t *P, double *B, dou
     for (size_t j = 0; j < n; j++) {
         size_t piv = 0; double best = -1.0;
         for (size_t i = 0; i < m; i++)
-            if (!used[i] && fabs(B[i + j * m]) > best) { best = fabs(B[i + j * m]); piv = i; }
+            if (!used[i] && !(skip && skip[i]) && fabs(B[i + j * m]) > best) { best = fabs(B[i + j * m]); piv = i; }
         P[j] = piv; used[piv] = 1;
         const double pv = B[piv + j * m];
         if (pv == 0.0) continue;
@@ -200,7 +251,7 @@ static int maxvol(const double *Q, size_t m, size_t n, size_t *P, double *B, dou
         size_t bi = 0, bj = 0; double best = 0.0;
         for (size_t j = 0; j < n; j++)
             for (size_t i = 0; i < m; i++)
-                if (fabs(B[i + j * m]) > best) { best = fabs(B[i + j * m]); bi = i; bj = j; }
+                if (!(skip && skip[i]) && fabs(B[i + j * m]) > best) { best = fabs(B[i + j * m]); bi = i; bj = j; }
         if (best <= 1.0 + 1e-2) break;
         /* row bi replaces P[bj]:  B <- B - B[:,bj] (B[bi,:] - e_bj) / B[bi,bj] */
         const double pv = B[bi + bj * m];
@@ -337,10 +388,11 @@ int c3sc_cross_run(c3sc_cross *c, c3sc_fiber_batch_fn f, void *arg, const c3sc_c
     double *work = (double *)malloc((rmax * rmax * 3 + rmax + rmax * c->nmax * rmax + 16) * sizeof(double));
     double **prev = (double **)calloc(d, sizeof(double *));
     int32_t *tmpI = (int32_t *)malloc(rmax * d * sizeof(int32_t));
+    char *skip = (char *)malloc(rmax * c->nmax + 1);
     int rc = C3SC_OK;
     uint64_t nfib = 0;
     double change = 1.0, prev_norm2 = 0.0;
-    if (!dv || !fi || !vals || !T || !Q || !B || !P || !work || !prev || !tmpI) { rc = C3SC_EINVAL; goto done; }
+    if (!dv || !fi || !vals || !T || !Q || !B || !P || !work || !prev || !tmpI || !skip) { rc = C3SC_EINVAL; goto done; }
     for (uint32_t k = 0; k < d; k++) {
         prev[k] = (double *)calloc(c->r[k] * c->n[k] * c->r[k + 1], sizeof(double));
         if (!prev[k]) { rc = C3SC_EINVAL; goto done; }
@@ -352,8 +404,9 @@ int c3sc_cross_run(c3sc_cross *c, c3sc_fiber_batch_fn f, void *arg, const c3sc_c
             rc = eval_core(c, k, f, arg, dv, fi, vals, T, &nfib);
             if (rc) goto done;
             memcpy(Q, T, m * rk1 * sizeof(double));                 /* unfolding (a,j) x b is already column-major */
+            mark_twin_rows(Q, m, rk1, skip);
             { const double t_ = now_s(); qr_explicit_q(Q, m, rk1, work); g_t_qr += now_s() - t_; }
-            { const double t_ = now_s(); const int mv = maxvol(Q, m, rk1, P, B, work); g_t_mv += now_s() - t_; if (mv) { rc = C3SC_ENUMERIC; goto done; } }
+            { const double t_ = now_s(); const int mv = maxvol(Q, m, rk1, skip, P, B, work); g_t_mv += now_s() - t_; if (mv) { rc = C3SC_ENUMERIC; goto done; } }
             for (size_t b = 0; b < rk1; b++) {                      /* new left set: row (a,j) = a + j*rk */
                 const size_t a = P[b] % rk, j = P[b] / rk;
                 for (uint32_t i = 0; i < k; i++) tmpI[b * d + i] = c->I[k][a * d + i];
@@ -374,8 +427,9 @@ int c3sc_cross_run(c3sc_cross *c, c3sc_fiber_batch_fn f, void *arg, const c3sc_c
             for (size_t a = 0; a < rk; a++)                         /* transpose: rows (j,b) = j + b*N, cols a */
                 for (size_t j = 0; j < N; j++)
                     for (size_t b = 0; b < rk1; b++) Q[(j + b * N) + a * m] = T[a + j * rk + b * rk * N];
+            mark_twin_rows(Q, m, rk, skip);
             { const double t_ = now_s(); qr_explicit_q(Q, m, rk, work); g_t_qr += now_s() - t_; }
-            { const double t_ = now_s(); const int mv = maxvol(Q, m, rk, P, B, work); g_t_mv += now_s() - t_; if (mv) { rc = C3SC_ENUMERIC; goto done; } }
+            { const double t_ = now_s(); const int mv = maxvol(Q, m, rk, skip, P, B, work); g_t_mv += now_s() - t_; if (mv) { rc = C3SC_ENUMERIC; goto done; } }
             for (size_t a = 0; a < rk; a++) {
                 const size_t j = P[a] % N, b = P[a] / N;
                 tmpI[a * d + k] = (int32_t)j;
@@ -412,7 +466,7 @@ done:
     if (nfibers) *nfibers = nfib;
     if (rel_change) *rel_change = change;
     if (prev) for (uint32_t k = 0; k < d; k++) free(prev[k]);
-    free(prev); free(dv); free(fi); free(vals); free(T); free(Q); free(B); free(P); free(work); free(tmpI);
+    free(prev); free(dv); free(fi); free(vals); free(T); free(Q); free(B); free(P); free(work); free(tmpI); free(skip);
     return rc;
 }
 
@@ -611,7 +665,9 @@ static int cross_resize(c3sc_cross *c, uint32_t k, uint64_t rnew)
     for (uint64_t j = rold; j < rnew; j++) {
         for (uint32_t i = 0; i < d; i++) { I[j * d + i] = 0; J[j * d + i] = 0; }
         for (int attempt = 0; attempt < 64; attempt++) {
-            for (uint32_t i = k; i < d; i++) J[j * d + i] = (int32_t)(mix64(&st) % c->n[i]);
+            for (uint32_t i = k; i < d; i++)                              /* interior nodes: the end nodes are the */
+                J[j * d + i] = c->n[i] > 2 ? 1 + (int32_t)(mix64(&st) % (c->n[i] - 2))   /* faces, where an absorbing */
+                                           : (int32_t)(mix64(&st) % c->n[i]);            /* problem is degenerate    */
             int dup = 0;
             for (uint64_t q = 0; q < j && !dup; q++) {
                 int same = 1;

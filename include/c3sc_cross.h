@@ -31,6 +31,9 @@ typedef struct c3sc_cross c3sc_cross;   /* ranks + left/right index sets, kept b
 int  c3sc_cross_create(uint32_t d, const uint64_t *n, const uint64_t *ranks, c3sc_cross **out);
 void c3sc_cross_destroy(c3sc_cross *c);
 int  c3sc_cross_ranks(const c3sc_cross *c, uint64_t *ranks);
+/* index sets at bond k (0..d): left[r_k*d] over dims 0..k-1, right[r_k*d] over dims k..d-1 (others 0);
+ * what ValueF keeps as isl / isr between solver steps (src/valuefunc.c:706-712).  Either may be NULL. */
+int  c3sc_cross_index_sets(const c3sc_cross *c, uint32_t k, int32_t *left, int32_t *right);
 
 /* cores[k]: caller-allocated n[k]*r[k]*r[k+1] doubles.  nfibers / rel_change may be NULL. */
 int c3sc_cross_run(c3sc_cross *c, c3sc_fiber_batch_fn f, void *arg, const c3sc_cross_opts *opts,
