@@ -19,6 +19,7 @@
 #define _POSIX_C_SOURCE 199309L
 #include <math.h>
 #include <stdio.h>
+#include <stdint.h>
 #include <stdlib.h>
 #include <string.h>
 #include <time.h>
@@ -109,82 +110,122 @@ int c3sc_cross_index_sets(const c3sc_cross *c, uint32_t k, int32_t *left, int32_
 }
 
 /* ---- small dense linear algebra (column-major) --------------------------------------------- */
+#if defined(__x86_64__) && defined(__GNUC__) && !defined(__clang__)
+#define C3SC_CLONES __attribute__((target_clones("avx2", "default")))   /* same arithmetic, wider registers (no FMA) */
+#else
+#define C3SC_CLONES
+#endif
+/* Stride-1 kernels with a fixed association order (eight partial sums), so the compiler can keep them in
+ * vector registers without -ffast-math and the result does not depend on the vector width it picks. */
+C3SC_CLONES static double dot8(const double *x, const double *y, size_t n)
+{
+    double s0 = 0, s1 = 0, s2 = 0, s3 = 0, s4 = 0, s5 = 0, s6 = 0, s7 = 0;
+    size_t i = 0;
+    for (; i + 8 <= n; i += 8) {
+        s0 += x[i] * y[i];         s1 += x[i + 1] * y[i + 1]; s2 += x[i + 2] * y[i + 2]; s3 += x[i + 3] * y[i + 3];
+        s4 += x[i + 4] * y[i + 4]; s5 += x[i + 5] * y[i + 5]; s6 += x[i + 6] * y[i + 6]; s7 += x[i + 7] * y[i + 7];
+    }
+    for (; i < n; i++) s0 += x[i] * y[i];
+    return ((s0 + s1) + (s2 + s3)) + ((s4 + s5) + (s6 + s7));
+}
+C3SC_CLONES static void axpy(double a, const double *restrict x, double *restrict y, size_t n)
+{
+    for (size_t i = 0; i < n; i++) y[i] += a * x[i];
+}
+C3SC_CLONES static double absmax(const double *x, size_t n)
+{
+    double m0 = 0, m1 = 0, m2 = 0, m3 = 0;
+    size_t i = 0;
+    for (; i + 4 <= n; i += 4) {
+        const double a = fabs(x[i]), b = fabs(x[i + 1]), c = fabs(x[i + 2]), e = fabs(x[i + 3]);
+        m0 = a > m0 ? a : m0; m1 = b > m1 ? b : m1; m2 = c > m2 ? c : m2; m3 = e > m3 ? e : m3;
+    }
+    for (; i < n; i++) { const double a = fabs(x[i]); m0 = a > m0 ? a : m0; }
+    m0 = m1 > m0 ? m1 : m0; m2 = m3 > m2 ? m3 : m2;
+    return m2 > m0 ? m2 : m0;
+}
+
 /* Householder QR of A (m x n, m >= n): Q (m x n, explicit, orthonormal columns) overwrites A. */
 static void qr_explicit_q(double *A, size_t m, size_t n, double *work /* n + m */)
 {
     double *tau = work, *v = work + n;
     for (size_t k = 0; k < n; k++) {
-        double nrm = 0.0;
-        for (size_t i = k; i < m; i++) nrm += A[i + k * m] * A[i + k * m];
-        nrm = sqrt(nrm);
+        double *ak = A + k * m;
+        const double nrm = sqrt(dot8(ak + k, ak + k, m - k));
         if (nrm == 0.0) { tau[k] = 0.0; continue; }
-        const double alpha = A[k + k * m] >= 0.0 ? -nrm : nrm;
-        const double v0 = A[k + k * m] - alpha;
-        for (size_t i = k + 1; i < m; i++) A[i + k * m] /= v0;
+        const double alpha = ak[k] >= 0.0 ? -nrm : nrm;
+        const double v0 = ak[k] - alpha;
+        for (size_t i = k + 1; i < m; i++) ak[i] /= v0;
         tau[k] = -v0 / alpha;
-        A[k + k * m] = alpha;
+        ak[k] = alpha;
         for (size_t j = k + 1; j < n; j++) {
-            double s = A[k + j * m];
-            for (size_t i = k + 1; i < m; i++) s += A[i + k * m] * A[i + j * m];
-            s *= tau[k];
-            A[k + j * m] -= s;
-            for (size_t i = k + 1; i < m; i++) A[i + j * m] -= s * A[i + k * m];
+            double *aj = A + j * m;
+            const double sc = (aj[k] + dot8(ak + k + 1, aj + k + 1, m - k - 1)) * tau[k];
+            aj[k] -= sc;
+            axpy(-sc, ak + k + 1, aj + k + 1, m - k - 1);
         }
     }
     /* accumulate Q = H_0 .. H_{n-1} [I; 0] in place, last reflector first */
     for (size_t kk = n; kk-- > 0;) {
+        double *ak = A + kk * m;
         v[kk] = 1.0;
-        for (size_t i = kk + 1; i < m; i++) v[i] = A[i + kk * m];
-        for (size_t i = 0; i < m; i++) A[i + kk * m] = 0.0;
-        A[kk + kk * m] = 1.0;
+        for (size_t i = kk + 1; i < m; i++) v[i] = ak[i];
+        for (size_t i = 0; i < m; i++) ak[i] = 0.0;
+        ak[kk] = 1.0;
         if (tau[kk] == 0.0) continue;
         for (size_t j = kk; j < n; j++) {
-            double s = 0.0;
-            for (size_t i = kk; i < m; i++) s += v[i] * A[i + j * m];
-            s *= tau[kk];
-            for (size_t i = kk; i < m; i++) A[i + j * m] -= s * v[i];
+            double *aj = A + j * m;
+            const double sc = dot8(v + kk, aj + kk, m - kk) * tau[kk];
+            axpy(-sc, v + kk, aj + kk, m - kk);
         }
     }
 }
 
-/* maxvol: rows P (n of m) of Q (m x n) whose submatrix has (locally) maximal |det|; on return
- * B = Q * inv(Q[P,:]) (m x n), so B[P,:] = I.  Deterministic: first maximum in scan order. */
 /* Rows of the unfolding A (m x n, before the QR) that repeat an earlier row to round-off carry no
  * information for the pivoting (absorbing faces with a constant boundary cost produce whole families of
  * them); when the unfolding is rank-deficient the QR completes Q with arbitrary directions and maxvol would
  * happily pick such twins, which makes the NEXT unfolding rank-deficient as well.  skip[i] = 1 withholds
  * row i from the pivoting.  Twins are found through two fixed random projections of the rows. */
-typedef struct { double k1, k2; size_t row; } rowkey;
-static int rowkey_cmp(const void *a, const void *b)
-{
-    const rowkey *x = (const rowkey *)a, *y = (const rowkey *)b;
-    if (x->k1 != y->k1) return x->k1 < y->k1 ? -1 : 1;
-    return x->row < y->row ? -1 : (x->row > y->row);
-}
 static void mark_twin_rows(const double *A, size_t m, size_t n, char *skip)
 {
-    rowkey *key = (rowkey *)malloc(m * sizeof(rowkey));
     memset(skip, 0, m);
-    if (!key) return;
-    double scale = 0.0;
-    for (size_t e = 0; e < m * n; e++) if (fabs(A[e]) > scale) scale = fabs(A[e]);
-    for (size_t i = 0; i < m; i++) { key[i].k1 = key[i].k2 = 0.0; key[i].row = i; }
+    size_t H = 16;
+    while (H < 4 * m) H <<= 1;
+    double *k1 = (double *)calloc(2 * m, sizeof(double));
+    uint32_t *slot = (uint32_t *)calloc(H, sizeof(uint32_t));          /* row + 1, keyed by the quantised k1 */
+    int64_t *qk = (int64_t *)malloc(m * sizeof(int64_t));
+    if (!k1 || !slot || !qk) { free(k1); free(slot); free(qk); return; }
+    double *k2 = k1 + m, scale = 0.0;
     uint64_t st = 0x7F1BE7ull;
     for (size_t j = 0; j < n; j++) {
+        const double mx = absmax(A + j * m, m);
+        if (mx > scale) scale = mx;
         st = st * 6364136223846793005ull + 1442695040888963407ull;
-        const double w1 = 0.5 + (double)(st >> 11) / 9007199254740992.0;
+        axpy(0.5 + (double)(st >> 11) / 9007199254740992.0, A + j * m, k1, m);
         st = st * 6364136223846793005ull + 1442695040888963407ull;
-        const double w2 = 0.5 + (double)(st >> 11) / 9007199254740992.0;
-        for (size_t i = 0; i < m; i++) { key[i].k1 += w1 * A[i + j * m]; key[i].k2 += w2 * A[i + j * m]; }
+        axpy(0.5 + (double)(st >> 11) / 9007199254740992.0, A + j * m, k2, m);
     }
-    qsort(key, m, sizeof(rowkey), rowkey_cmp);
-    const double tol = 1e-12 * scale * (double)n;
+    const double tol = 1e-12 * scale * (double)n, quantum = 1024.0 * tol;
     size_t eligible = m;
-    for (size_t i = 1; i < m; i++)
-        for (size_t q = i; q-- > 0 && key[i].k1 - key[q].k1 <= tol;)
-            if (!skip[key[q].row] && fabs(key[i].k2 - key[q].k2) <= tol) { skip[key[i].row] = 1; eligible--; break; }
+    if (!(tol > 0.0)) goto out;                                         /* all-zero unfolding */
+    for (size_t i = 0; i < m; i++) {                                    /* earlier rows stay eligible */
+        qk[i] = (int64_t)floor(k1[i] / quantum);
+        int twin = 0;
+        for (int64_t dq = -1; dq <= 1 && !twin; dq++) {
+            const int64_t q = qk[i] + dq;
+            for (size_t h = (size_t)((uint64_t)q * 0x9E3779B97F4A7C15ull) & (H - 1); slot[h]; h = (h + 1) & (H - 1)) {
+                const size_t r = slot[h] - 1;
+                if (qk[r] == q && fabs(k1[i] - k1[r]) <= tol && fabs(k2[i] - k2[r]) <= tol) { twin = 1; break; }
+            }
+        }
+        if (twin) { skip[i] = 1; eligible--; continue; }
+        size_t h = (size_t)((uint64_t)qk[i] * 0x9E3779B97F4A7C15ull) & (H - 1);
+        while (slot[h]) h = (h + 1) & (H - 1);
+        slot[h] = (uint32_t)(i + 1);
+    }
     if (eligible < n) memset(skip, 0, m);                              /* not enough distinct rows: no restriction */
-    free(key);
+out:
+    free(k1); free(slot); free(qk);
 }
 
 static int maxvol(const double *Q, size_t m, size_t n, const char *skip, size_t *P, double *B, double *work /* n*n + n */)
@@ -203,8 +244,7 @@ static int maxvol(const double *Q, size_t m, size_t n, const char *skip, size_t 
         for (size_t c = j + 1; c < n; c++) {
             const double f = B[piv + c * m] / pv;
             if (f == 0.0) continue;
-            for (size_t i = 0; i < m; i++)
-                if (!used[i]) B[i + c * m] -= f * B[i + j * m];
+            axpy(-f, B + j * m, B + c * m, m);                           /* rows already used are never read again */
         }
     }
     free(used);
@@ -238,32 +278,38 @@ static int maxvol(const double *Q, size_t m, size_t n, const char *skip, size_t 
             for (size_t b = 0; b < n; b++) S[a + b * n] = aug[a * 2 * n + n + b];
         free(aug);
     }
-    for (size_t i = 0; i < m; i++) {
-        for (size_t b = 0; b < n; b++) {
-            double s = 0.0;
-            for (size_t a = 0; a < n; a++) s += Q[i + a * m] * S[a + b * n];
-            col[b] = s;
-        }
-        for (size_t b = 0; b < n; b++) B[i + b * m] = col[b];
+    for (size_t b = 0; b < n; b++) {                                    /* B[:,b] = sum_a S[a,b] Q[:,a] */
+        double *bb = B + b * m;
+        for (size_t i = 0; i < m; i++) bb[i] = 0.0;
+        for (size_t a = 0; a < n; a++) axpy(S[a + b * n], Q + a * m, bb, m);
     }
     /* swaps while some |B[i,j]| > 1 + delta */
     for (int it = 0; it < 200; it++) {
         size_t bi = 0, bj = 0; double best = 0.0;
-        for (size_t j = 0; j < n; j++)
-            for (size_t i = 0; i < m; i++)
-                if (!(skip && skip[i]) && fabs(B[i + j * m]) > best) { best = fabs(B[i + j * m]); bi = i; bj = j; }
+        for (size_t j = 0; j < n; j++) {
+            const double mx = absmax(B + j * m, m);
+            if (mx > best) { best = mx; bj = j; }
+        }
         if (best <= 1.0 + 1e-2) break;
+        for (size_t i = 0; i < m; i++) if (fabs(B[i + bj * m]) == best) { bi = i; break; }
+        if (skip && skip[bi]) {                                          /* the maximum sits on a withheld row: masked scan */
+            best = 0.0;
+            for (size_t j = 0; j < n; j++)
+                for (size_t i = 0; i < m; i++)
+                    if (!skip[i] && fabs(B[i + j * m]) > best) { best = fabs(B[i + j * m]); bi = i; bj = j; }
+            if (best <= 1.0 + 1e-2) break;
+        }
         /* row bi replaces P[bj]:  B <- B - B[:,bj] (B[bi,:] - e_bj) / B[bi,bj] */
         const double pv = B[bi + bj * m];
         for (size_t b = 0; b < n; b++) col[b] = (B[bi + b * m] - (b == bj ? 1.0 : 0.0)) / pv;
         for (size_t b = 0; b < n; b++) {
-            const double f = col[b];
-            if (f == 0.0 || b == bj) continue;
-            for (size_t i = 0; i < m; i++) B[i + b * m] -= B[i + bj * m] * f;
+            if (col[b] == 0.0 || b == bj) continue;
+            axpy(-col[b], B + bj * m, B + b * m, m);
         }
         {
-            const double f = col[bj];
-            for (size_t i = 0; i < m; i++) B[i + bj * m] -= B[i + bj * m] * f;
+            const double f = 1.0 - col[bj];
+            double *bb = B + bj * m;
+            for (size_t i = 0; i < m; i++) bb[i] *= f;
         }
         P[bj] = bi;
     }
@@ -311,27 +357,38 @@ static void store_core(const double *T, size_t rk, size_t N, size_t rk1, double 
 static double tt_dot2(uint32_t d, const uint64_t *n, const uint64_t *ra, double *const *A, const uint64_t *rb, double *const *B,
                       double *w1, double *w2, double *w3)
 {
+    /* per core: At[j + e*N] = A_k[j][e] (nodes contiguous), likewise Bt; W[(j + x*N) + q*a0*N] = sum_y M[x,y] Bt[j + (y + q*b0)*N]
+       (axpys of length N); new M[p,q] = <At[:, (x,p)], W[:, (x,q)]> over (j,x) (dots of length a0*N).  w3 unused. */
+    (void)w3;
+    size_t cap = 1;
+    for (uint32_t k = 0; k < d; k++) {
+        const size_t ea = n[k] * ra[k] * ra[k + 1], eb = n[k] * rb[k] * rb[k + 1], ew = n[k] * ra[k] * rb[k + 1];
+        if (ea > cap) cap = ea;
+        if (eb > cap) cap = eb;
+        if (ew > cap) cap = ew;
+    }
+    double *At = (double *)malloc(3 * cap * sizeof(double));
+    if (!At) return NAN;
+    double *Bt = At + cap, *W = At + 2 * cap;
     w1[0] = 1.0;
     for (uint32_t k = 0; k < d; k++) {
-        const size_t a0 = ra[k], a1 = ra[k + 1], b0 = rb[k], b1 = rb[k + 1];
-        for (size_t e = 0; e < a1 * b1; e++) w2[e] = 0.0;
-        for (size_t j = 0; j < n[k]; j++) {
-            const double *a = A[k] + j * a0 * a1, *b = B[k] + j * b0 * b1;
-            for (size_t q = 0; q < b1; q++)                    /* w3 = M b  (a0 x b1), M is a0 x b0 */
-                for (size_t x = 0; x < a0; x++) {
-                    double t = 0.0;
-                    for (size_t y = 0; y < b0; y++) t += w1[x + y * a0] * b[y + q * b0];
-                    w3[x + q * a0] = t;
-                }
-            for (size_t q = 0; q < b1; q++)                    /* w2 += a^T w3  (a1 x b1) */
-                for (size_t p = 0; p < a1; p++) {
-                    double t = 0.0;
-                    for (size_t x = 0; x < a0; x++) t += a[x + p * a0] * w3[x + q * a0];
-                    w2[p + q * a1] += t;
-                }
-        }
+        const size_t a0 = ra[k], a1 = ra[k + 1], b0 = rb[k], b1 = rb[k + 1], N = n[k];
+        const int same = A[k] == B[k] && a0 == b0 && a1 == b1;
+        for (size_t j = 0; j < N; j++)
+            for (size_t e = 0; e < a0 * a1; e++) At[j + e * N] = A[k][j * a0 * a1 + e];
+        if (!same)
+            for (size_t j = 0; j < N; j++)
+                for (size_t e = 0; e < b0 * b1; e++) Bt[j + e * N] = B[k][j * b0 * b1 + e];
+        const double *Bu = same ? At : Bt;
+        for (size_t e = 0; e < a0 * N * b1; e++) W[e] = 0.0;
+        for (size_t q = 0; q < b1; q++)
+            for (size_t y = 0; y < b0; y++)
+                for (size_t x = 0; x < a0; x++) axpy(w1[x + y * a0], Bu + (y + q * b0) * N, W + x * N + q * a0 * N, N);
+        for (size_t q = 0; q < b1; q++)
+            for (size_t p = 0; p < a1; p++) w2[p + q * a1] = dot8(At + p * a0 * N, W + q * a0 * N, a0 * N);
         memcpy(w1, w2, a1 * b1 * sizeof(double));
     }
+    free(At);
     return w1[0];
 }
 static double tt_dot(uint32_t d, const uint64_t *n, const uint64_t *r, double *const *A, double *const *B, double *w1, double *w2,
