@@ -181,6 +181,62 @@ static void qr_explicit_q(double *A, size_t m, size_t n, double *work /* n + m *
     }
 }
 
+/* Orthonormal basis Q (m x n) of the column space of A, by Householder QR with column pivoting; Q
+ * overwrites A (column order is immaterial: the cross core B = Q inv(Q[P,:]) only depends on span(Q)).
+ * Columns whose remaining norm falls below RANK_EPS times the largest column norm are numerically dependent:
+ * a reflector built from them would point wherever the round-off of the operator's values points, and the
+ * pivoting after it would follow.  They get no reflector, so their Q columns are H_0..H_{rank-1} e_k -- a
+ * completion that depends on the well-determined part only.  Returns the numerical rank. */
+#define RANK_EPS 1e-11
+#define TIE_EPS 1e-8     /* see maxvol */
+static size_t qr_basis(double *A, size_t m, size_t n, double *work /* n + m */)
+{
+    double *tau = work, *v = work + n;
+    size_t rank = n;
+    double ref = 0.0;
+    for (size_t k = 0; k < n; k++) {
+        size_t p = k; double best = -1.0;
+        for (size_t j = k; j < n; j++) {
+            const double c2 = dot8(A + j * m + k, A + j * m + k, m - k);
+            v[j] = c2;
+            if (c2 > best) { best = c2; p = j; }
+        }
+        for (size_t j = k; j < p; j++) if (v[j] >= best * (1.0 - TIE_EPS)) { p = j; break; }
+        if (p != k)
+            for (size_t i = 0; i < m; i++) { const double t = A[i + k * m]; A[i + k * m] = A[i + p * m]; A[i + p * m] = t; }
+        double *ak = A + k * m;
+        const double nrm = sqrt(v[p]);
+        if (k == 0) ref = nrm;
+        if (nrm <= RANK_EPS * ref || nrm == 0.0) { rank = k; break; }
+        const double alpha = ak[k] >= 0.0 ? -nrm : nrm;
+        const double v0 = ak[k] - alpha;
+        for (size_t i = k + 1; i < m; i++) ak[i] /= v0;
+        tau[k] = -v0 / alpha;
+        ak[k] = alpha;
+        for (size_t j = k + 1; j < n; j++) {
+            double *aj = A + j * m;
+            const double sc = (aj[k] + dot8(ak + k + 1, aj + k + 1, m - k - 1)) * tau[k];
+            aj[k] -= sc;
+            axpy(-sc, ak + k + 1, aj + k + 1, m - k - 1);
+        }
+    }
+    for (size_t k = rank; k < n; k++) tau[k] = 0.0;
+    for (size_t kk = n; kk-- > 0;) {
+        double *ak = A + kk * m;
+        v[kk] = 1.0;
+        for (size_t i = kk + 1; i < m; i++) v[i] = ak[i];
+        for (size_t i = 0; i < m; i++) ak[i] = 0.0;
+        ak[kk] = 1.0;
+        if (tau[kk] == 0.0) continue;
+        for (size_t j = kk; j < n; j++) {
+            double *aj = A + j * m;
+            const double sc = dot8(v + kk, aj + kk, m - kk) * tau[kk];
+            axpy(-sc, v + kk, aj + kk, m - kk);
+        }
+    }
+    return rank;
+}
+
 /* Rows of the unfolding A (m x n, before the QR) that repeat an earlier row to round-off carry no
  * information for the pivoting (absorbing faces with a constant boundary cost produce whole families of
  * them); when the unfolding is rank-deficient the QR completes Q with arbitrary directions and maxvol would
@@ -228,6 +284,9 @@ out:
     free(k1); free(slot); free(qk);
 }
 
+/* Symmetric problems (V(x) = V(-x)) make mirrored rows tie exactly in exact arithmetic; which one wins would
+ * then depend on the last bits of the operator's values.  Entries within TIE_EPS of the maximum count as
+ * tied and the first in scan order wins, so two operators that agree to round-off pick the same rows. */
 static int maxvol(const double *Q, size_t m, size_t n, const char *skip, size_t *P, double *B, double *work /* n*n + n */)
 {
     /* start rows: Gaussian elimination with row pivoting on a copy */
@@ -235,9 +294,21 @@ static int maxvol(const double *Q, size_t m, size_t n, const char *skip, size_t 
     char *used = (char *)calloc(m, 1);
     if (!used) return 1;
     for (size_t j = 0; j < n; j++) {
-        size_t piv = 0; double best = -1.0;
-        for (size_t i = 0; i < m; i++)
-            if (!used[i] && !(skip && skip[i]) && fabs(B[i + j * m]) > best) { best = fabs(B[i + j * m]); piv = i; }
+        size_t piv = 0; double best = -1.0, best_any = 0.0;
+        for (size_t i = 0; i < m; i++) {
+            if (used[i]) continue;
+            const double a = fabs(B[i + j * m]);
+            if (a > best_any) best_any = a;
+            if (!(skip && skip[i]) && a > best) { best = a; piv = i; }
+        }
+        const int all_rows = !skip || best < 1e-6 * best_any;             /* the distinct rows do not reach this direction */
+        if (all_rows && skip) {
+            best = -1.0;
+            for (size_t i = 0; i < m; i++)
+                if (!used[i] && fabs(B[i + j * m]) > best) { best = fabs(B[i + j * m]); piv = i; }
+        }
+        for (size_t i = 0; i < piv; i++)                                 /* TIE_EPS: first row among the near-maximal ones */
+            if (!used[i] && (all_rows || !skip[i]) && fabs(B[i + j * m]) >= best * (1.0 - TIE_EPS)) { piv = i; break; }
         P[j] = piv; used[piv] = 1;
         const double pv = B[piv + j * m];
         if (pv == 0.0) continue;
@@ -288,15 +359,20 @@ static int maxvol(const double *Q, size_t m, size_t n, const char *skip, size_t 
         size_t bi = 0, bj = 0; double best = 0.0;
         for (size_t j = 0; j < n; j++) {
             const double mx = absmax(B + j * m, m);
-            if (mx > best) { best = mx; bj = j; }
+            if (mx > best) best = mx;
         }
         if (best <= 1.0 + 1e-2) break;
-        for (size_t i = 0; i < m; i++) if (fabs(B[i + bj * m]) == best) { bi = i; break; }
-        if (skip && skip[bi]) {                                          /* the maximum sits on a withheld row: masked scan */
+        int found = 0;                                                   /* first near-maximal entry, column-major order */
+        for (size_t j = 0; j < n && !found; j++) {
+            if (absmax(B + j * m, m) < best * (1.0 - TIE_EPS)) continue;
+            for (size_t i = 0; i < m; i++)
+                if (fabs(B[i + j * m]) >= best * (1.0 - TIE_EPS) && !(skip && skip[i])) { bi = i; bj = j; found = 1; break; }
+        }
+        if (!found) {                                                    /* the maxima sit on withheld rows: masked scan */
             best = 0.0;
             for (size_t j = 0; j < n; j++)
                 for (size_t i = 0; i < m; i++)
-                    if (!skip[i] && fabs(B[i + j * m]) > best) { best = fabs(B[i + j * m]); bi = i; bj = j; }
+                    if (!skip[i] && fabs(B[i + j * m]) > best * (1.0 + TIE_EPS)) { best = fabs(B[i + j * m]); bi = i; bj = j; }
             if (best <= 1.0 + 1e-2) break;
         }
         /* row bi replaces P[bj]:  B <- B - B[:,bj] (B[bi,:] - e_bj) / B[bi,bj] */
@@ -462,7 +538,7 @@ int c3sc_cross_run(c3sc_cross *c, c3sc_fiber_batch_fn f, void *arg, const c3sc_c
             if (rc) goto done;
             memcpy(Q, T, m * rk1 * sizeof(double));                 /* unfolding (a,j) x b is already column-major */
             mark_twin_rows(Q, m, rk1, skip);
-            { const double t_ = now_s(); qr_explicit_q(Q, m, rk1, work); g_t_qr += now_s() - t_; }
+            { const double t_ = now_s(); qr_basis(Q, m, rk1, work); g_t_qr += now_s() - t_; }
             { const double t_ = now_s(); const int mv = maxvol(Q, m, rk1, skip, P, B, work); g_t_mv += now_s() - t_; if (mv) { rc = C3SC_ENUMERIC; goto done; } }
             for (size_t b = 0; b < rk1; b++) {                      /* new left set: row (a,j) = a + j*rk */
                 const size_t a = P[b] % rk, j = P[b] / rk;
@@ -485,7 +561,7 @@ int c3sc_cross_run(c3sc_cross *c, c3sc_fiber_batch_fn f, void *arg, const c3sc_c
                 for (size_t j = 0; j < N; j++)
                     for (size_t b = 0; b < rk1; b++) Q[(j + b * N) + a * m] = T[a + j * rk + b * rk * N];
             mark_twin_rows(Q, m, rk, skip);
-            { const double t_ = now_s(); qr_explicit_q(Q, m, rk, work); g_t_qr += now_s() - t_; }
+            { const double t_ = now_s(); qr_basis(Q, m, rk, work); g_t_qr += now_s() - t_; }
             { const double t_ = now_s(); const int mv = maxvol(Q, m, rk, skip, P, B, work); g_t_mv += now_s() - t_; if (mv) { rc = C3SC_ENUMERIC; goto done; } }
             for (size_t a = 0; a < rk; a++) {
                 const size_t j = P[a] % N, b = P[a] / N;

@@ -343,3 +343,16 @@ def test_adaptive_value_iteration_tracks_the_dense_backup(gpu):
         adapt.set_ranks([1] + [min(int(x) + 1, 12) for x in ra[1:-1]] + [1])
     assert int(ra[1]) < 12
     prob.close(); adapt.close()
+
+
+@pytest.mark.parametrize("name,n,rank,dx,iters", [("lqg2d_new", 30, 5, None, 3), ("lqg2d_reflect", 24, 6, None, 3),
+                                                    ("lqgnd", 8, 6, 4, 2)])
+def test_pivoting_ignores_round_off_of_the_operator(built, name, n, rank, dx, iters):
+    """two operators that agree to round-off (the GPU and the CPU oracle do) must drive the cross to the
+    same index sets: symmetric problems tie mirrored rows exactly, and over-specified ranks leave
+    numerically dependent columns whose QR directions are pure round-off (tools/pivot_stability.py)"""
+    import sys, os
+    sys.path.insert(0, os.path.join(os.path.dirname(__file__), "..", "tools"))
+    import pivot_stability as ps
+    for seed in (2, 5):
+        assert ps.run(name, n, rank, dx, iters, seed) <= 1e-10
