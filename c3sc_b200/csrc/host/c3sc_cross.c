@@ -89,6 +89,27 @@ void c3sc_cross_destroy(c3sc_cross *c)
     free(c);
 }
 
+/* ranks + index sets of `src` (ValueF keeps isl / isr and hands copies to the next step, src/valuefunc.c:706-712) */
+int c3sc_cross_copy(const c3sc_cross *src, c3sc_cross **out)
+{
+    if (!src || !out) return C3SC_EINVAL;
+    c3sc_cross *c = (c3sc_cross *)calloc(1, sizeof *c);
+    if (!c) return C3SC_EINVAL;
+    c->d = src->d; c->nmax = src->nmax;
+    memcpy(c->n, src->n, sizeof c->n);
+    memcpy(c->r, src->r, sizeof c->r);
+    for (uint32_t k = 0; k <= c->d; k++) {
+        const size_t len = c->r[k] * c->d + 1;
+        c->I[k] = (int32_t *)malloc(len * sizeof(int32_t));
+        c->J[k] = (int32_t *)malloc(len * sizeof(int32_t));
+        if (!c->I[k] || !c->J[k]) { c3sc_cross_destroy(c); return C3SC_EINVAL; }
+        memcpy(c->I[k], src->I[k], len * sizeof(int32_t));
+        memcpy(c->J[k], src->J[k], len * sizeof(int32_t));
+    }
+    *out = c;
+    return C3SC_OK;
+}
+
 int c3sc_cross_ranks(const c3sc_cross *c, uint64_t *ranks)
 {
     if (!c || !ranks) return C3SC_EINVAL;

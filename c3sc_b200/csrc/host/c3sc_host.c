@@ -11,6 +11,7 @@
 #include <stdlib.h>
 #include <string.h>
 #include "../../../include/c3sc_host.h"
+#include "../../../include/c3sc_cross.h"
 
 static void *xalloc(size_t n, size_t sz)
 {
@@ -146,6 +147,10 @@ struct ValueF {
     size_t d, *N, *ranks;
     double **cores;               /* host copy, valuef_precompute_cores layout */
     c3sc_valuef *dev;
+    c3sc_cross *cross;            /* isl / isr of the reference (src/valuefunc.c:62-78): ranks + index sets of the
+                                     cross run that produced this function; NULL for valuef_from_cores */
+    double **xgrid;               /* owned copy of the nodes (the reference keeps them inside the LINELM cores) */
+    c3sc_problem *eval_dev;       /* geometry-only device problem for valuef_eval, built on first use */
 };
 struct ValueF *valuef_from_cores(size_t d, const size_t *N, const size_t *ranks, double *const *cores)
 {
@@ -171,10 +176,26 @@ void valuef_destroy(struct ValueF *v)
 {
     if (!v) return;
     c3sc_valuef_destroy(v->dev);
+    c3sc_cross_destroy(v->cross);
+    c3sc_problem_destroy(v->eval_dev);
+    if (v->xgrid) { for (size_t k = 0; k < v->d; k++) free(v->xgrid[k]); free(v->xgrid); }
     for (size_t k = 0; k < v->d; k++) free(v->cores[k]);
     free(v->cores); free(v->N); free(v->ranks); free(v);
 }
-struct ValueF *valuef_copy(struct ValueF *v) { return valuef_from_cores(v->d, v->N, v->ranks, v->cores); }
+void valuef_set_grid(struct ValueF *v, double *const *xgrid)
+{
+    if (v->xgrid) { for (size_t k = 0; k < v->d; k++) free(v->xgrid[k]); free(v->xgrid); }
+    v->xgrid = xalloc(v->d, sizeof(double *));
+    for (size_t k = 0; k < v->d; k++) v->xgrid[k] = dupd(xgrid[k], v->N[k]);
+    c3sc_problem_destroy(v->eval_dev); v->eval_dev = NULL;
+}
+struct ValueF *valuef_copy(struct ValueF *v)
+{
+    struct ValueF *c = valuef_from_cores(v->d, v->N, v->ranks, v->cores);
+    if (v->cross && c3sc_cross_copy(v->cross, &c->cross)) die("valuef_copy");
+    if (v->xgrid) valuef_set_grid(c, v->xgrid);
+    return c;
+}
 size_t *valuef_get_ranks(struct ValueF *v) { return v->ranks; }
 
 int valuef_eval_fiber_ind_nn(struct ValueF *vf, const size_t *fixed_ind, size_t dim_vary,
@@ -665,6 +686,8 @@ struct C3Control {
     size_t dx, du, dw;
     size_t *ngrid; double **xgrid, *h, hmin;
     struct Boundary *bound; struct MCAparam *mca; struct DPparam *dp; struct Workspace *work;
+    struct ValueF *policy_sim; struct c3Opt *opt_sim; void (*transform_sim)(size_t, const double *, double *);
+    struct ControlParams *cp_sim; double *prevpol;
 };
 struct C3Control *c3control_create(size_t dx, size_t du, size_t dw, double *lb, double *ub, size_t *ngrid, double discount)
 {
@@ -696,6 +719,7 @@ struct C3Control *c3control_create(size_t dx, size_t du, size_t dw, double *lb, 
 void c3control_destroy(struct C3Control *c)
 {
     if (!c) return;
+    control_params_destroy(c->cp_sim); free(c->prevpol);
     boundary_free(c->bound); mca_param_destroy(c->mca); dp_param_destroy(c->dp); workspace_free(c->work);
     for (size_t i = 0; i < c->dx; i++) free(c->xgrid[i]);
     free(c->xgrid); free(c->h); free(c);
@@ -728,4 +752,310 @@ int c3control_vi_fibers(struct C3Control *c, struct ValueF *vf, struct c3Opt *op
     vi_param_destroy(vi);
     control_params_destroy(cp);
     return rc;
+}
+
+
+/* ========================== approximation arguments (src/util.c:105-230) ==== */
+struct ApproxArgs { double cross_tol, round_tol; size_t kickrank, startrank, maxrank; int adapt; enum function_class fc; };
+struct ApproxArgs *approx_args_init(void)
+{
+    struct ApproxArgs *a = xalloc(1, sizeof *a);
+    a->cross_tol = 1e-10; a->round_tol = 1e-10; a->kickrank = 10; a->startrank = 5; a->maxrank = 40; a->adapt = 1; a->fc = LINELM;
+    return a;
+}
+void approx_args_free(struct ApproxArgs *a) { free(a); }
+void approx_args_set_function_class(struct ApproxArgs *a, enum function_class fc) { a->fc = fc; }
+enum function_class approx_args_get_function_class(const struct ApproxArgs *a) { return a->fc; }
+void approx_args_set_cross_tol(struct ApproxArgs *a, double v) { a->cross_tol = v; }
+double approx_args_get_cross_tol(const struct ApproxArgs *a) { return a->cross_tol; }
+void approx_args_set_round_tol(struct ApproxArgs *a, double v) { a->round_tol = v; }
+double approx_args_get_round_tol(const struct ApproxArgs *a) { return a->round_tol; }
+void approx_args_set_kickrank(struct ApproxArgs *a, size_t v) { a->kickrank = v; }
+size_t approx_args_get_kickrank(const struct ApproxArgs *a) { return a->kickrank; }
+void approx_args_set_maxrank(struct ApproxArgs *a, size_t v) { a->maxrank = v; }
+size_t approx_args_get_maxrank(const struct ApproxArgs *a) { return a->maxrank; }
+void approx_args_set_startrank(struct ApproxArgs *a, size_t v) { a->startrank = v; }
+size_t approx_args_get_startrank(const struct ApproxArgs *a) { return a->startrank; }
+void approx_args_set_adapt(struct ApproxArgs *a, int v) { a->adapt = v; }
+int approx_args_get_adapt(const struct ApproxArgs *a) { return a->adapt; }
+
+/* ========================== valuef_interp and friends ======================= */
+/* The operator behind a cross run: bellman_vi / bellman_pi go to the device as whole-core batches; any other
+ * fiber function (a start cost handed to c3control_init_value) is the caller's own host code and is called
+ * once per fiber with the points the reference would hand it. */
+struct interp_ctx {
+    int (*f)(size_t, const double *, double *, void *); void *args;
+    size_t d; const size_t *N; double **grid;
+};
+static int interp_cb(size_t F, const int32_t *dv, const int32_t *fi, size_t ldo, double *out, void *arg)
+{
+    struct interp_ctx *c = arg;
+    if (c->f == bellman_vi) return bellman_vi_batch_ind(F, dv, fi, out, c->args);
+    if (c->f == bellman_pi) return bellman_pi_batch_ind(F, dv, fi, out, c->args);
+    double *x = xalloc(ldo * c->d, sizeof(double));
+    int rc = 0;
+    for (size_t f = 0; f < F && !rc; f++) {
+        const size_t k = (size_t)dv[f], n = c->N[k];
+        for (size_t j = 0; j < n; j++)
+            for (size_t i = 0; i < c->d; i++) x[j * c->d + i] = c->grid[i][i == k ? j : (size_t)fi[f * c->d + i]];
+        rc = c->f(n, x, out + f * ldo, c->args);
+    }
+    free(x);
+    return rc;
+}
+
+/* valuef_interp (src/valuefunc.c:603-767) over the batched cross driver */
+struct ValueF *valuef_interp(size_t d, int (*f)(size_t, const double *, double *, void *), void *args, const size_t *N,
+                             double **grid, struct ValueF *vref, struct ApproxArgs *aargs, int verbose)
+{
+    if (aargs->fc != LINELM) die("valuef_interp: only nodal LINELM value functions are supported");
+    uint64_t n64[C3SC_MAXD], r64[C3SC_MAXD + 1], minN = N[0];
+    for (size_t k = 0; k < d; k++) { n64[k] = N[k]; if (N[k] < minN) minN = N[k]; }
+    const uint64_t maxrank = aargs->maxrank < minN ? aargs->maxrank : minN;          /* :625-631 */
+    c3sc_cross *cr = NULL;
+    r64[0] = r64[d] = 1;
+    if (vref && aargs->adapt == 1) {                                                  /* :637-648, :706-712 */
+        for (size_t k = 1; k < d; k++) r64[k] = vref->ranks[k] + 1 >= maxrank ? maxrank : vref->ranks[k] + 1;
+        if (vref->cross) {
+            if (c3sc_cross_copy(vref->cross, &cr) || c3sc_cross_set_ranks(cr, r64)) die("valuef_interp: index sets");
+        }
+    } else {
+        for (size_t k = 1; k < d; k++) r64[k] = aargs->startrank;
+    }
+    if (!cr && c3sc_cross_create((uint32_t)d, n64, r64, &cr)) die("valuef_interp: c3sc_cross_create");
+    if (verbose > 0) {
+        c3sc_cross_ranks(cr, r64);
+        printf("Starting Ranks: ");
+        for (size_t k = 0; k <= d; k++) printf("%llu ", (unsigned long long)r64[k]);
+        printf("\n");
+    }
+    struct interp_ctx ctx = { f, args, d, N, grid };
+    c3sc_cross_opts o = { 5, aargs->cross_tol, verbose > 1 };                          /* maxiter 5, :632 */
+    c3sc_adapt_opts ao = { aargs->adapt == 1 ? (uint32_t)aargs->kickrank : 0, (uint32_t)maxrank, aargs->round_tol, 0 };
+    uint64_t cap[C3SC_MAXD + 1], rout[C3SC_MAXD + 1];
+    double *cores[C3SC_MAXD];
+    if (aargs->adapt == 1) c3sc_cross_adapt_capacity(cr, &ao, cap);
+    else c3sc_cross_ranks(cr, cap);
+    for (size_t k = 0; k < d; k++) cores[k] = xalloc(N[k] * cap[k] * cap[k + 1], sizeof(double));
+    int rc;
+    if (aargs->adapt == 1) rc = c3sc_cross_run_adapt(cr, interp_cb, &ctx, &o, &ao, rout, cores, NULL, NULL);
+    else { rc = c3sc_cross_run(cr, interp_cb, &ctx, &o, cores, NULL, NULL); c3sc_cross_ranks(cr, rout); }
+    if (rc) die("valuef_interp: cross approximation failed");
+    size_t ranks[C3SC_MAXD + 1];
+    for (size_t k = 0; k <= d; k++) ranks[k] = (size_t)rout[k];
+    if (verbose > 0) {
+        printf("Final Ranks: ");
+        for (size_t k = 0; k <= d; k++) printf("%zu ", ranks[k]);
+        printf("\n");
+    }
+    struct ValueF *vf = valuef_from_cores(d, N, ranks, cores);
+    vf->cross = cr;
+    valuef_set_grid(vf, grid);
+    for (size_t k = 0; k < d; k++) free(cores[k]);
+    return vf;
+}
+
+static void vf_u64(const struct ValueF *v, uint64_t *n, uint64_t *r)
+{
+    for (size_t k = 0; k < v->d; k++) n[k] = v->N[k];
+    for (size_t k = 0; k <= v->d; k++) r[k] = v->ranks[k];
+}
+/* valuef_norm / valuef_norm2diff (src/valuefunc.c:315-335); discrete l2 over the grid nodes */
+double valuef_norm(struct ValueF *v)
+{
+    uint64_t n[C3SC_MAXD], r[C3SC_MAXD + 1];
+    vf_u64(v, n, r);
+    return c3sc_cores_norm((uint32_t)v->d, n, r, (const double *const *)v->cores);
+}
+double valuef_norm2diff(struct ValueF *a, struct ValueF *b)
+{
+    uint64_t n[C3SC_MAXD], ra[C3SC_MAXD + 1], rb[C3SC_MAXD + 1];
+    vf_u64(a, n, ra); vf_u64(b, n, rb);
+    return c3sc_cores_norm2diff((uint32_t)a->d, n, ra, (const double *const *)a->cores, rb, (const double *const *)b->cores);
+}
+/* valuef_eval (src/valuefunc.c:345-350): piecewise-linear interpolation of the nodal cores, on the device */
+double valuef_eval(struct ValueF *v, const double *x)
+{
+    if (!v->xgrid) die("valuef_eval: the value function has no grid (valuef_set_grid)");
+    if (!v->eval_dev) {
+        double lo[C3SC_MAXD], hi[C3SC_MAXD];
+        for (size_t i = 0; i < v->d; i++) { lo[i] = v->xgrid[i][0]; hi[i] = v->xgrid[i][v->N[i] - 1]; }
+        struct Boundary *b = boundary_alloc(v->d, lo, hi);
+        struct MCAparam m = { v->d, 1, v->N, v->xgrid, 1.0, NULL, 1.0, NULL };
+        double t[2 * C3SC_MAXD], u0[C3SC_MAXD] = { 0 };
+        for (size_t i = 0; i < 2 * v->d; i++) t[i] = 1.0;
+        m.t = t;
+        struct DPparam dp;
+        memset(&dp, 0, sizeof dp);
+        dp.bound = b;
+        dp.arith = C3SC_ARITH_FAST;
+        dp.model = (v->d % 2 == 0) ? C3SC_MODEL_LQGND : (v->d == 3 ? C3SC_MODEL_DUBINS : C3SC_MODEL_SKID5D);
+        m.du = (dp.model == C3SC_MODEL_LQGND) ? v->d / 2 : 1;
+        struct c3Opt opt = { BRUTEFORCE, m.du, 1, u0 };
+        v->eval_dev = make_problem(&dp, &m, &opt, v->d);
+        boundary_free(b);
+    }
+    double out = 0.0;
+    if (c3sc_valuef_eval_batch(v->eval_dev, v->dev, 1, x, &out)) die("valuef_eval");
+    return out;
+}
+
+/* ========================== solver loops (src/bellman.c:2105-2420) ========== */
+void c3control_add_policy_sim(struct C3Control *c, struct ValueF *pol, struct c3Opt *opt_sim,
+                              void (*transform)(size_t, const double *, double *))
+{
+    c->policy_sim = pol; c->opt_sim = opt_sim; c->transform_sim = transform;
+    control_params_destroy(c->cp_sim); c->cp_sim = NULL;
+}
+int c3control_policy_eval(struct C3Control *c, double t, const double *x, double *u)
+{
+    if (!c->policy_sim || !c->opt_sim) die("c3control_policy_eval: no policy (c3control_add_policy_sim)");
+    if (!c->cp_sim) c->cp_sim = control_params_create(c->dx, c->dw, c->dp, c->mca, c->work, c->opt_sim);
+    if (!c->prevpol) c->prevpol = xalloc(c->du, sizeof(double));
+    control_params_add_time_and_states(c->cp_sim, t, 1, x);
+    int ab = 0;
+    int rc = c3sc_policy_eval_batch(cp_dev(c->cp_sim), c->policy_sim->dev, 1, x, u, NULL, &ab,
+                                    workspace_get_costs(c->work, 0));
+    if (rc) { fprintf(stderr, "c3sc_b200: c3control_policy_eval: %s\n", c3sc_last_error()); return rc; }
+    workspace_get_absorbed(c->work, 0)[0] = ab;
+    memcpy(c->prevpol, u, c->du * sizeof(double));
+    return 0;
+}
+int c3control_controller(double t, const double *x, double *u, void *args)
+{
+    struct C3Control *c = args;
+    if (!c->transform_sim) return c3control_policy_eval(c, t, x, u);
+    double *xin = xalloc(c->dx, sizeof(double));
+    c->transform_sim(c->dx, x, xin);
+    int rc = c3control_policy_eval(c, t, xin, u);
+    free(xin);
+    return rc;
+}
+
+struct ValueF *c3control_step_vi(struct C3Control *c, struct ValueF *vf, struct ApproxArgs *apargs, struct c3Opt *opt,
+                                 int verbose, size_t *nevals)
+{
+    struct ControlParams *cp = control_params_create(c->dx, c->dw, c->dp, c->mca, c->work, opt);
+    struct VIparam *vi = vi_param_create(1e-10);
+    vi_param_add_cp(vi, cp);
+    vi_param_add_value(vi, vf);
+    workspace_increment_vi_iter(c->work);
+    struct ValueF *next = valuef_interp(c->dx, bellman_vi, vi, c->ngrid, c->xgrid, vf, apargs, verbose);
+    if (nevals) *nevals = vi->nnode_evals;
+    vi_param_destroy(vi);
+    control_params_destroy(cp);
+    return next;
+}
+struct ValueF *c3control_step_pi(struct C3Control *c, struct ValueF *vf, struct PIparam *poli, struct ApproxArgs *apargs,
+                                 struct c3Opt *opt, int verbose, size_t *niter_evals)
+{
+    struct ControlParams *cp = control_params_create(c->dx, c->dw, c->dp, c->mca, c->work, opt);
+    pi_param_add_cp(poli, cp);
+    pi_param_add_value(poli, vf);
+    workspace_increment_pi_subiter(c->work);
+    struct ValueF *next = valuef_interp(c->dx, bellman_pi, poli, c->ngrid, c->xgrid, vf, apargs, verbose);
+    if (niter_evals) *niter_evals = poli->niter_evals;
+    pi_param_add_cp(poli, NULL);
+    control_params_destroy(cp);
+    return next;
+}
+struct ValueF *c3control_init_value(struct C3Control *c, int (*f)(size_t, const double *, double *, void *), void *args,
+                                    struct ApproxArgs *aargs, int verbose)
+{
+    return valuef_interp(c->dx, f, args, c->ngrid, c->xgrid, NULL, aargs, verbose);
+}
+
+/* ---- Diag: the per-iteration record list (src/bellman.c:2408-2540) ---- */
+struct Diag { size_t iter; int type; double norm, abs_diff; size_t dim, *ranks; double frac; struct Diag *next; };
+struct Diag *diag_create(size_t iter, int type, double norm, double abs_diff, size_t dim, size_t *ranks, double frac)
+{
+    struct Diag *g = xalloc(1, sizeof *g);
+    g->iter = iter; g->type = type; g->norm = norm; g->abs_diff = abs_diff; g->dim = dim; g->frac = frac;
+    g->ranks = xalloc(dim + 1, sizeof(size_t));
+    memcpy(g->ranks, ranks, (dim + 1) * sizeof(size_t));
+    return g;
+}
+void diag_destroy(struct Diag **head)
+{
+    if (!head) return;
+    for (struct Diag *g = *head; g;) { struct Diag *nx = g->next; free(g->ranks); free(g); g = nx; }
+    *head = NULL;
+}
+void diag_append(struct Diag **head, size_t iter, int type, double norm, double abs_diff, size_t dim, size_t *ranks, double frac)
+{
+    struct Diag *g = diag_create(iter, type, norm, abs_diff, dim, ranks, frac);
+    if (!*head) { *head = g; return; }
+    struct Diag *t = *head;
+    while (t->next) t = t->next;
+    t->next = g;
+}
+void diag_print(struct Diag *head, FILE *fp)
+{
+    fprintf(fp, "Type Iter Norm AbsDiff RelDiff FracEval AvgRank\n");
+    for (struct Diag *g = head; g; g = g->next) {
+        double avg = 0.0;
+        for (size_t k = 1; k < g->dim; k++) avg += (double)g->ranks[k];
+        if (g->dim > 1) avg /= (double)(g->dim - 1);
+        fprintf(fp, "%d %zu %3.5E %3.5E %3.5E %3.5E %3.5E\n", g->type, g->iter, g->norm, g->abs_diff,
+                g->norm != 0.0 ? g->abs_diff / g->norm : 0.0, g->frac, avg);
+    }
+}
+int diag_save(struct Diag *head, char *filename)
+{
+    FILE *fp = fopen(filename, "w");
+    if (!fp) return 1;
+    diag_print(head, fp);
+    fclose(fp);
+    return 0;
+}
+
+static void solve_report(const char *what, size_t ii, size_t maxiter, double diff, double norm, double frac)
+{
+    printf("\t %s (%zu\\%zu):\n", what, ii + 1, maxiter);
+    printf("\t \t L2 Difference between iterates    = %3.5E\n ", diff);
+    printf("\t \t L2 Norm of current value function = %3.5E\n", norm);
+    printf("\t \t Relative L2 Cauchy difference     = %3.5E\n", diff / norm);
+    printf("\t \t Fraction of states evaluated      = %3.5E\n", frac);
+}
+struct ValueF *c3control_vi_solve(struct C3Control *c, size_t maxiter, double abs_conv_tol, struct ValueF *vo,
+                                  struct ApproxArgs *apargs, struct c3Opt *opt, int verbose, struct Diag **diag)
+{
+    struct ValueF *start = valuef_copy(vo);
+    workspace_reset_vi_htable(c->work);
+    double stot = 1.0;
+    for (size_t j = 0; j < c->dx; j++) stot *= (double)c->ngrid[j];
+    for (size_t ii = 0; ii < maxiter; ii++) {
+        size_t nev = 0;
+        struct ValueF *next = c3control_step_vi(c, start, apargs, opt, verbose - 1, &nev);
+        const double diff = valuef_norm2diff(start, next), norm = valuef_norm(next), frac = (double)nev / stot;
+        if (verbose > 0) solve_report("Value Iteration", ii, maxiter, diff, norm, frac);
+        if (diag) diag_append(diag, ii, 1, norm, diff, c->dx, valuef_get_ranks(next), frac);
+        valuef_destroy(start);
+        start = next;
+        if (diff < abs_conv_tol) break;
+    }
+    return start;
+}
+struct ValueF *c3control_pi_solve(struct C3Control *c, size_t maxiter, double abs_conv_tol, struct ValueF *policy,
+                                  struct ApproxArgs *apargs, struct c3Opt *opt, int verbose, struct Diag **diag)
+{
+    struct ValueF *start = valuef_copy(policy);
+    struct PIparam *poli = pi_param_create(1e-10, policy);
+    workspace_increment_pi_iter(c->work);
+    workspace_reset_pi_prob_htable(c->work);
+    workspace_reset_pi_htable(c->work);
+    double stot = 1.0;
+    for (size_t j = 0; j < c->dx; j++) stot *= (double)c->ngrid[j];
+    for (size_t ii = 0; ii < maxiter; ii++) {
+        size_t nev = 0;
+        struct ValueF *next = c3control_step_pi(c, start, poli, apargs, opt, verbose - 1, &nev);
+        const double diff = valuef_norm2diff(start, next), norm = valuef_norm(next), frac = (double)nev / stot;
+        if (verbose > 0) solve_report("POLICY ITERATION", ii, maxiter, diff, norm, frac);
+        if (diag) diag_append(diag, ii, 0, norm, diff, c->dx, valuef_get_ranks(next), frac);
+        valuef_destroy(start);
+        start = next;
+        if (diff < abs_conv_tol) break;
+    }
+    pi_param_destroy(poli);
+    return start;
 }

@@ -29,6 +29,7 @@ typedef struct c3sc_cross c3sc_cross;   /* ranks + left/right index sets, kept b
 
 /* ranks[d+1] with ranks[0] = ranks[d] = 1 (clipped to what the unfoldings allow) */
 int  c3sc_cross_create(uint32_t d, const uint64_t *n, const uint64_t *ranks, c3sc_cross **out);
+int  c3sc_cross_copy(const c3sc_cross *src, c3sc_cross **out);    /* ranks + index sets */
 void c3sc_cross_destroy(c3sc_cross *c);
 int  c3sc_cross_ranks(const c3sc_cross *c, uint64_t *ranks);
 /* index sets at bond k (0..d): left[r_k*d] over dims 0..k-1, right[r_k*d] over dims k..d-1 (others 0);

@@ -210,6 +210,60 @@ struct Boundary *c3control_get_boundary(struct C3Control *);
 int c3control_vi_fibers(struct C3Control *, struct ValueF *, struct c3Opt *, size_t F,
                         const int32_t *dim_vary, const int32_t *fixed_ind, double *out, size_t *nevals);
 
+/* ---- approximation arguments (src/util.h:50-66, defaults src/util.c:116-132) ---- */
+enum function_class { CONSTANT, PIECEWISE, POLYNOMIAL, LINELM, CONSTELM, KERNEL };   /* C3's enum; LINELM (nodal) only */
+struct ApproxArgs;
+struct ApproxArgs *approx_args_init(void);
+void approx_args_free(struct ApproxArgs *);
+void approx_args_set_function_class(struct ApproxArgs *, enum function_class);
+enum function_class approx_args_get_function_class(const struct ApproxArgs *);
+void approx_args_set_cross_tol(struct ApproxArgs *, double);
+double approx_args_get_cross_tol(const struct ApproxArgs *);
+void approx_args_set_round_tol(struct ApproxArgs *, double);
+double approx_args_get_round_tol(const struct ApproxArgs *);
+void approx_args_set_kickrank(struct ApproxArgs *, size_t);
+size_t approx_args_get_kickrank(const struct ApproxArgs *);
+void approx_args_set_maxrank(struct ApproxArgs *, size_t);
+size_t approx_args_get_maxrank(const struct ApproxArgs *);
+void approx_args_set_startrank(struct ApproxArgs *, size_t);
+size_t approx_args_get_startrank(const struct ApproxArgs *);
+void approx_args_set_adapt(struct ApproxArgs *, int);
+int approx_args_get_adapt(const struct ApproxArgs *);
+
+/* ---- value function: interpolation, norms, evaluation (src/valuefunc.h:57-76) ---- */
+/* f == bellman_vi / bellman_pi: every core of the cross is ONE device batch; any other f is called per
+ * fiber on the host, as the reference does.  Cross approximation: include/c3sc_cross.h.          */
+struct ValueF *valuef_interp(size_t d, int (*f)(size_t, const double *, double *, void *), void *args, const size_t *N,
+                             double **grid, struct ValueF *vref, struct ApproxArgs *aargs, int verbose);   /* :603 */
+double valuef_norm(struct ValueF *);                                      /* :315, discrete l2 over the nodes */
+double valuef_norm2diff(struct ValueF *, struct ValueF *);                /* :325 */
+double valuef_eval(struct ValueF *, const double *);                      /* :345 */
+/* NEW: the nodes a train built with valuef_from_cores lives on (needed by valuef_eval) */
+void valuef_set_grid(struct ValueF *, double *const *xgrid);
+
+/* ---- solver loops and the online controller (src/bellman.h:129-194) ---- */
+#include <stdio.h>
+struct Diag;
+void diag_destroy(struct Diag **);
+struct Diag *diag_create(size_t iter, int type, double norm, double abs_diff, size_t dim, size_t *ranks, double frac);
+void diag_append(struct Diag **, size_t iter, int type, double norm, double abs_diff, size_t dim, size_t *ranks, double frac);
+void diag_print(struct Diag *, FILE *);
+int diag_save(struct Diag *, char *filename);
+void c3control_add_policy_sim(struct C3Control *, struct ValueF *, struct c3Opt *opt_sim,
+                              void (*transform)(size_t, const double *, double *));
+int c3control_policy_eval(struct C3Control *, double t, const double *x, double *u);     /* src/bellman.c:2105 */
+int c3control_controller(double, const double *, double *, void *);                      /* :2158 */
+struct ValueF *c3control_step_vi(struct C3Control *, struct ValueF *, struct ApproxArgs *, struct c3Opt *, int verbose,
+                                 size_t *nevals);                                         /* :2177 */
+struct ValueF *c3control_step_pi(struct C3Control *, struct ValueF *, struct PIparam *, struct ApproxArgs *,
+                                 struct c3Opt *, int verbose, size_t *nevals_iter);       /* :2214 */
+struct ValueF *c3control_init_value(struct C3Control *, int (*f)(size_t, const double *, double *, void *), void *args,
+                                    struct ApproxArgs *, int verbose);                    /* :2264 */
+struct ValueF *c3control_vi_solve(struct C3Control *, size_t maxiter, double abs_conv_tol, struct ValueF *vo,
+                                  struct ApproxArgs *, struct c3Opt *, int verbose, struct Diag **);   /* :2282 */
+struct ValueF *c3control_pi_solve(struct C3Control *, size_t maxiter, double abs_conv_tol, struct ValueF *policy,
+                                  struct ApproxArgs *, struct c3Opt *, int verbose, struct Diag **);   /* :2342 */
+
 #ifdef __cplusplus
 }
 #endif

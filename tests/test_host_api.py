@@ -221,3 +221,152 @@ def test_host_containers_without_gpu():
     x[0, 0] += 1e-9
     assert L.convert_fiber_to_ind(3, 11, po._p(x), po._p(ng), xg, po._p(fi), C.byref(kk)) == 1
     L.c3control_destroy(c3c)
+
+
+# ---- the solver facade: ApproxArgs, valuef_interp, c3control_step_* / *_solve, policy_eval, Diag --------
+def solver_lib():
+    L = host_lib()
+    for name in ("approx_args_init", "c3control_step_vi", "c3control_step_pi", "c3control_init_value", "c3control_vi_solve",
+                 "c3control_pi_solve", "valuef_interp"):
+        getattr(L, name).restype = vp
+    for name in ("valuef_norm", "valuef_norm2diff", "valuef_eval", "approx_args_get_cross_tol", "approx_args_get_round_tol"):
+        getattr(L, name).restype = dbl
+    for name in ("approx_args_get_kickrank", "approx_args_get_maxrank", "approx_args_get_startrank"):
+        getattr(L, name).restype = sz
+        getattr(L, name).argtypes = [vp]
+    L.approx_args_free.argtypes = [vp]
+    L.approx_args_get_cross_tol.argtypes = [vp]; L.approx_args_get_round_tol.argtypes = [vp]; L.approx_args_get_adapt.argtypes = [vp]
+    L.approx_args_set_cross_tol.argtypes = [vp, dbl]; L.approx_args_set_round_tol.argtypes = [vp, dbl]
+    for name in ("approx_args_set_kickrank", "approx_args_set_maxrank", "approx_args_set_startrank"):
+        getattr(L, name).argtypes = [vp, sz]
+    L.approx_args_set_adapt.argtypes = [vp, C.c_int]
+    L.valuef_norm.argtypes = [vp]; L.valuef_norm2diff.argtypes = [vp, vp]; L.valuef_eval.argtypes = [vp, vp]
+    L.valuef_set_grid.argtypes = [vp, vp]
+    L.c3control_step_vi.argtypes = [vp, vp, vp, vp, C.c_int, vp]
+    L.c3control_step_pi.argtypes = [vp, vp, vp, vp, vp, C.c_int, vp]
+    L.c3control_vi_solve.argtypes = [vp, sz, dbl, vp, vp, vp, C.c_int, vp]
+    L.c3control_pi_solve.argtypes = [vp, sz, dbl, vp, vp, vp, C.c_int, vp]
+    L.c3control_init_value.argtypes = [vp, vp, vp, vp, C.c_int]
+    L.c3control_add_policy_sim.argtypes = [vp, vp, vp, vp]
+    L.c3control_policy_eval.argtypes = [vp, dbl, vp, vp]
+    L.c3control_controller.argtypes = [dbl, vp, vp, vp]
+    L.diag_destroy.argtypes = [vp]; L.diag_save.argtypes = [vp, C.c_char_p]
+    L.diag_append.argtypes = [vp, sz, C.c_int, dbl, dbl, sz, vp, dbl]
+    return L
+
+
+def _host_cores(L, vf, n):
+    """(ranks, cores) of a host-mirror ValueF (struct: d, N*, ranks*, cores**)"""
+    class VF(C.Structure):
+        _fields_ = [("d", sz), ("N", C.POINTER(sz)), ("ranks", C.POINTER(sz)), ("cores", C.POINTER(C.POINTER(dbl)))]
+    v = C.cast(vf, C.POINTER(VF)).contents
+    d = v.d
+    ranks = np.array([v.ranks[k] for k in range(d + 1)], dtype=np.uint64)
+    cores = [np.ctypeslib.as_array(v.cores[k], shape=(int(n[k] * ranks[k] * ranks[k + 1]),)).copy() for k in range(d)]
+    return ranks, cores
+
+
+def test_approx_args_defaults_and_diag(tmp_path):
+    """src/util.c:116-132 defaults; Diag list round trip (no device needed)"""
+    L = solver_lib()
+    a = L.approx_args_init()
+    assert L.approx_args_get_cross_tol(a) == 1e-10 and L.approx_args_get_round_tol(a) == 1e-10
+    assert (L.approx_args_get_kickrank(a), L.approx_args_get_startrank(a), L.approx_args_get_maxrank(a)) == (10, 5, 40)
+    assert L.approx_args_get_adapt(a) == 1
+    L.approx_args_set_kickrank(a, 3); L.approx_args_set_adapt(a, 0); L.approx_args_set_round_tol(a, 1e-6)
+    assert L.approx_args_get_kickrank(a) == 3 and L.approx_args_get_adapt(a) == 0 and L.approx_args_get_round_tol(a) == 1e-6
+    L.approx_args_free(a)
+    head = vp()
+    ranks = np.array([1, 4, 6, 1], dtype=np.uintp)
+    for it in range(3):
+        L.diag_append(C.byref(head), it, 1, 10.0 + it, 0.5 / (it + 1), 3, po._p(ranks), 0.25)
+    f = tmp_path / "diag.txt"
+    assert L.diag_save(head, str(f).encode()) == 0
+    rows = f.read_text().strip().splitlines()
+    assert len(rows) == 4 and rows[1].split()[:2] == ["1", "0"] and float(rows[3].split()[2]) == 12.0
+    assert float(rows[1].split()[-1]) == 5.0                                  # mean interior rank
+    L.diag_destroy(C.byref(head))
+    assert not head.value
+
+
+@pytest.mark.gpu
+def test_vi_solve_fixed_rank_equals_the_cross_driver(gpu):
+    """c3control_vi_solve with adapt = 0 is a fresh startrank cross of bellman_vi per iteration
+    (src/valuefunc.c:713-733): same cores as driving include/c3sc_cross.h by hand"""
+    L = solver_lib()
+    cfg = configs.get_config("lqg2d_reflect", n=20, rank=4)
+    hp = HostProblem(L, cfg, arith=1)
+    prob = capi.Problem(cfg, arith=1)
+    r0, c0 = synthetic.quadratic_cores(prob.xgrid)
+    v0 = hp.valuef(r0, c0)
+    a = L.approx_args_init()
+    L.approx_args_set_adapt(a, 0); L.approx_args_set_startrank(a, 4); L.approx_args_set_cross_tol(a, 1e-12)
+    head = vp()
+    out = L.c3control_vi_solve(hp.c3c, 3, 0.0, v0, a, hp.opt, 0, C.byref(head))
+    ranks, cores = _host_cores(L, out, cfg.ngrid)
+    cg, rg = c0, np.asarray(r0, dtype=np.uint64)
+    for _ in range(3):
+        vf = capi.ValueF(cfg.ngrid, rg, cg)
+        cr = capi.Cross(cfg.ngrid, [1, 4, 1])
+        cg, _, _ = cr.run_vi(prob, vf, maxiter=5, tol=1e-12)
+        rg = cr.ranks.copy(); vf.close(); cr.close()
+    assert list(ranks) == list(rg)
+    for x, y in zip(cores, cg):
+        assert np.array_equal(x, y)
+    assert abs(L.valuef_norm(out) - capi.cores_norm(cfg.ngrid, rg, cg)) <= 1e-12 * L.valuef_norm(out)
+    assert L.valuef_norm2diff(out, v0) > 0
+    f = C.create_string_buffer(b"/dev/null")
+    assert L.diag_save(head, f) == 0
+    L.diag_destroy(C.byref(head)); L.valuef_destroy(out); L.valuef_destroy(v0); L.approx_args_free(a)
+    hp.close(); prob.close()
+
+
+@pytest.mark.gpu
+def test_adaptive_vi_solve_pi_solve_and_controller(gpu):
+    """the example main() flow (examples/lqgnd/lqgnd.c:300-420): init value from a host start cost,
+    value iteration with rank adaptation, a policy-iteration solve on top, then the online controller"""
+    L = solver_lib()
+    cfg = configs.get_config("lqgnd", n=12, rank=6, dx=4)
+    hp = HostProblem(L, cfg, arith=1)
+    prob = capi.Problem(cfg, arith=1)
+    port = make_port(cfg)
+    START = C.CFUNCTYPE(C.c_int, sz, C.POINTER(dbl), C.POINTER(dbl), vp)
+
+    def _start(N, x, out, _):                                                # startcost of lqgnd.c:200-215: sum x_i^2
+        xs = np.ctypeslib.as_array(x, shape=(N * cfg.dx,)).reshape(N, cfg.dx)
+        np.ctypeslib.as_array(out, shape=(N,))[:] = (xs ** 2).sum(axis=1)
+        return 0
+    start = START(_start)
+    a = L.approx_args_init()
+    L.approx_args_set_startrank(a, 3); L.approx_args_set_kickrank(a, 2); L.approx_args_set_maxrank(a, 10)
+    L.approx_args_set_round_tol(a, 1e-6); L.approx_args_set_cross_tol(a, 1e-8)
+    v0 = L.c3control_init_value(hp.c3c, start, None, a, 0)
+    r0, c0 = _host_cores(L, v0, cfg.ngrid)
+    assert list(r0) == [1, 2, 2, 2, 1]                                        # sum of squares has TT rank 2
+    pt = np.array([0.3, -0.7, 1.1, 0.05])
+    assert abs(L.valuef_eval(v0, po._p(pt)) - port.ft_eval_linear(po.FT(cfg.ngrid, r0, c0), pt)) <= 1e-12
+    head = vp()
+    v1 = L.c3control_vi_solve(hp.c3c, 4, 1e-12, v0, a, hp.opt, 0, C.byref(head))
+    r1, c1 = _host_cores(L, v1, cfg.ngrid)
+    assert max(int(x) for x in r1) <= 10 and L.valuef_norm(v1) > 0
+    # one more step by hand must move the function less than the first one did (contraction)
+    nev = sz(0)
+    v2 = L.c3control_step_vi(hp.c3c, v1, a, hp.opt, 0, C.byref(nev))
+    assert nev.value > 0
+    assert L.valuef_norm2diff(v2, v1) < L.valuef_norm2diff(v1, v0)
+    # policy iteration on the policy of v2
+    v3 = L.c3control_pi_solve(hp.c3c, 2, 1e-12, v2, a, hp.opt, 0, C.byref(head))
+    assert np.isfinite(L.valuef_norm(v3)) and L.valuef_norm2diff(v3, v2) < 0.5 * L.valuef_norm(v2)
+    # online controller: same control as the batched device entry at a few states
+    L.c3control_add_policy_sim(hp.c3c, v3, hp.opt, None)
+    r3, c3 = _host_cores(L, v3, cfg.ngrid)
+    vf3 = capi.ValueF(cfg.ngrid, r3, c3)
+    xs = np.array([[0.3, -0.7, 1.1, 0.05], [-1.2, 0.4, 0.0, 0.9], [1.9, 1.9, -1.9, 0.2]])
+    want = prob.policy_eval(vf3, xs)
+    for i, x in enumerate(xs):
+        u = np.zeros(cfg.du)
+        assert L.c3control_controller(0.0, po._p(np.ascontiguousarray(x)), po._p(u), hp.c3c) == 0
+        assert np.array_equal(u, np.asarray(want[0])[i])
+    for v in (v0, v1, v2, v3):
+        L.valuef_destroy(v)
+    L.diag_destroy(C.byref(head)); L.approx_args_free(a); vf3.close(); hp.close(); prob.close()
