@@ -55,7 +55,7 @@ FIBER_FN = C.CFUNCTYPE(C.c_int, C.c_size_t, c_i32p, c_i32p, C.c_size_t, c_f64p, 
 
 EXPORTS = [
     "c3sc_cuda_init", "c3sc_cuda_device_count", "c3sc_last_error", "c3sc_version", "c3sc_launch_count",
-    "c3sc_problem_create", "c3sc_problem_destroy", "c3sc_problem_check",
+    "c3sc_problem_create", "c3sc_problem_destroy", "c3sc_problem_check", "c3sc_problem_control_path",
     "c3sc_valuef_create", "c3sc_valuef_update", "c3sc_valuef_device_buffer", "c3sc_valuef_destroy",
     "c3sc_vi_batch_dev", "c3sc_pi_batch_dev", "c3sc_vi_batch", "c3sc_vi_batch_debug", "c3sc_pi_batch",
     "c3sc_transition_batch", "c3sc_model_eval", "c3sc_measure_fp64_peak",
@@ -89,6 +89,7 @@ def lib() -> C.CDLL:
         L.c3sc_problem_create.argtypes = [C.POINTER(ProblemDesc), C.POINTER(vp)]
         L.c3sc_problem_destroy.argtypes = [vp]
         L.c3sc_problem_check.argtypes = [vp]
+        L.c3sc_problem_control_path.argtypes = [vp]
         L.c3sc_valuef_create.argtypes = [C.c_uint32, c_u64p, c_u64p, C.POINTER(c_f64p), C.POINTER(vp)]
         L.c3sc_valuef_update.argtypes = [vp, C.POINTER(c_f64p)]
         L.c3sc_valuef_device_buffer.argtypes = [vp, C.POINTER(vp), C.POINTER(sz)]

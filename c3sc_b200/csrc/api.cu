@@ -93,7 +93,65 @@ struct CtlGroups {
     int ng = 0;
     int gstart[CT_NGMAX + 1];
     double gA[CT_NGMAX];
+    // full {lo, 0, hi}^nud control grid in C order (k_control_grid)
+    int grid_on = 0;
+    double gWlo[CT_NUDMAX], gWhi[CT_NUDMAX], gAg[CT_NUDMAX + 1], gHg[CT_NUDMAX + 1];
 };
+
+/* Is the control table the full grid {lo_m, mid_m, hi_m}^nud, candidate c = sum_m k_m 3^(nud-1-m), whose
+ * middle level sits in the dead band of the upwind scheme (no extra weight), whose lo / hi levels load only
+ * the left / right neighbour, and whose normaliser share and stage cost depend on the number of non-middle
+ * levels only?  tab: the candidate table read back from the device (row stride ct).  All comparisons are
+ * exact: the shared-prefix walk must reproduce the per-candidate numbers, not approximate them. */
+static void detect_control_grid(const c3sc_problem_desc *d, const std::vector<double> &tab, int nud, int ct, CtlGroups &G)
+{
+    G.grid_on = 0;
+    if (nud < 1 || nud > CT_NUDMAX || (int)d->du != nud) return;
+    size_t want = 1;
+    for (int m = 0; m < nud; m++) want *= 3;
+    if (d->nu != want) return;
+    double lev[CT_NUDMAX][3];
+    for (int m = 0; m < nud; m++) {
+        int nl = 0;
+        for (uint32_t c = 0; c < d->nu; c++) {
+            const double u = d->controls[(size_t)c * d->du + m];
+            int k = 0;
+            while (k < nl && lev[m][k] != u) k++;
+            if (k < nl) continue;
+            if (nl == 3) return;
+            lev[m][nl++] = u;
+        }
+        if (nl != 3) return;
+        for (int a = 0; a < 3; a++)
+            for (int b = a + 1; b < 3; b++)
+                if (lev[m][b] < lev[m][a]) { const double t = lev[m][a]; lev[m][a] = lev[m][b]; lev[m][b] = t; }
+    }
+    bool haveW[CT_NUDMAX][2] = {}, haveG[CT_NUDMAX + 1] = {};
+    for (uint32_t c = 0; c < d->nu; c++) {
+        size_t idx = 0;
+        int cnt = 0;
+        for (int m = 0; m < nud; m++) {
+            const double u = d->controls[(size_t)c * d->du + m];
+            const int k = u == lev[m][0] ? 0 : (u == lev[m][1] ? 1 : 2);
+            idx = idx * 3 + (size_t)k;
+            const double wl = tab[(size_t)c * ct + 2 * m], wr = tab[(size_t)c * ct + 2 * m + 1];
+            if (k == 1) { if (wl != 0.0 || wr != 0.0) return; continue; }
+            cnt++;
+            if (k == 0) {
+                if (wr != 0.0 || !(wl > 0.0)) return;
+                if (!haveW[m][0]) { G.gWlo[m] = wl; haveW[m][0] = true; } else if (G.gWlo[m] != wl) return;
+            } else {
+                if (wl != 0.0 || !(wr > 0.0)) return;
+                if (!haveW[m][1]) { G.gWhi[m] = wr; haveW[m][1] = true; } else if (G.gWhi[m] != wr) return;
+            }
+        }
+        if (idx != c) return;
+        const double A = tab[(size_t)c * ct + 2 * nud], H = d->h2 * tab[(size_t)c * ct + 2 * nud + 1];
+        if (!haveG[cnt]) { G.gAg[cnt] = A; G.gHg[cnt] = H; haveG[cnt] = true; }
+        else if (G.gAg[cnt] != A || G.gHg[cnt] != H) return;
+    }
+    G.grid_on = 1;
+}
 
 struct c3sc_problem {
     DevProblem P;
@@ -270,6 +328,7 @@ int c3sc_problem_create(const c3sc_problem_desc *d, c3sc_problem **out)
                 if (g == shares.size()) shares.push_back(a);
                 gid[c] = (int)g;
             }
+            detect_control_grid(d, tab, nud, ct, p->grp);
             if (shares.size() <= (size_t)CT_NGMAX) {
                 std::vector<double> gt((size_t)d->nu * ct);
                 CtlGroups &G = p->grp;
@@ -311,6 +370,13 @@ void c3sc_problem_destroy(c3sc_problem *p)
     if (p->copy_stream) cudaStreamDestroy(p->copy_stream);
     if (p->chunk_done) cudaEventDestroy(p->chunk_done);
     delete p;
+}
+
+int c3sc_problem_control_path(const c3sc_problem *p)
+{
+    if (!p) return -1;
+    if (p->arith != C3SC_ARITH_FAST) return 0;
+    return p->grp.grid_on ? 2 : (p->grp.ng > 0 ? 1 : 0);
 }
 
 int c3sc_problem_check(c3sc_problem *p)
@@ -496,6 +562,11 @@ static int run_batch(const DevProblem &P, int model, int arith, Scratch &scr, co
         c.npeer = b.n_peers;
         for (int g = 0; g < b.n_peers; g++) c.vpeer[g] = b.value_peers[g];
         c.peer_off = (long long)(b.peer_offset + n0);
+        if (grp && grp->grid_on) {
+            c.grid_on = 1;
+            memcpy(c.gWlo, grp->gWlo, sizeof c.gWlo); memcpy(c.gWhi, grp->gWhi, sizeof c.gWhi);
+            memcpy(c.gAg, grp->gAg, sizeof c.gAg); memcpy(c.gHg, grp->gHg, sizeof c.gHg);
+        }
         if (grp && grp->ng > 0 && P.gtab) {
             c.ng = grp->ng;
             memcpy(c.gstart, grp->gstart, sizeof c.gstart);

@@ -18,6 +18,7 @@
 namespace c3sc {
 
 constexpr int CT_NT = 256;
+constexpr int CT_NUDMAX = 6;       // control dimensions of a grid-structured table (3^6 = 729 candidates)
 constexpr int CT_NGMAX = 32;       // candidate groups (distinct normaliser shares) handled by the grouped walk
 
 struct CtlArgs {
@@ -36,6 +37,12 @@ struct CtlArgs {
     int ng;                   // number of groups, 0 = plain table walk
     int gstart[CT_NGMAX + 1]; // first grouped position of every group
     double gA[CT_NGMAX];      // the group's normaliser share
+    // ... and, when the control table is a full {lo, 0, hi}^NUD grid in C order (last control fastest), its
+    // per-control description for the shared-prefix walk (k_control_grid): candidate (k_0..k_{NUD-1}) adds
+    // gWlo[m]*cost_left(ud m) if k_m = 0, nothing if k_m = 1, gWhi[m]*cost_right if k_m = 2; its normaliser
+    // share and h2*stage_u depend on the number of non-zero controls only (gAg, gHg).
+    int grid_on;
+    double gWlo[CT_NUDMAX], gWhi[CT_NUDMAX], gAg[CT_NUDMAX + 1], gHg[CT_NUDMAX + 1];
     double *value;            // outputs, any may be NULL
     int *argmin;
     double *rows;
@@ -610,6 +617,124 @@ __global__ void __launch_bounds__(C2_NT, C3SC_C2_MINB) k_control2(const CtlArgs 
     }
 }
 
+// ---------------------------------------------------------------------------
+// Grid-structured control tables ({lo, 0, hi}^NUD, C order): every candidate is still formed and compared,
+// but candidates that share their first controls share the partial sum S0 + sum_{m' < m} T_{m'}(k_{m'}), so a
+// candidate costs one DADD (amortised 2/3 of one: the zero level adds nothing) and one compare instead of
+// 2*NUD DFMAs.  The walk is fully unrolled (3^NUD leaves, every index static), candidates are visited in
+// table order, and the running minimum is kept per number of non-zero controls -- the groups of the
+// grouped walk, whose reciprocal/exp are shared.  ARG = false (value iteration: no argmin, no policy rows)
+// drops the index bookkeeping.
+template <int NUD, int m, int cnt, int idx, bool ARG>
+struct GridWalk {
+    static __device__ __forceinline__ void go(double s, const double (&Tl)[NUD], const double (&Th)[NUD],
+                                              double (&mn)[NUD + 1], int (&am)[NUD + 1])
+    {
+        if constexpr (m == NUD) {
+            if (s < mn[cnt]) {                   // DSETP + predicated moves (fmin's NaN handling costs three more slots)
+                mn[cnt] = s;
+                if constexpr (ARG) am[cnt] = idx;
+            }
+        } else {
+            constexpr int stride = GridWalk<NUD, m + 1, 0, 0, ARG>::SPAN;      // 3^(NUD-1-m): last control fastest
+            GridWalk<NUD, m + 1, cnt + 1, idx, ARG>::go(s + Tl[m], Tl, Th, mn, am);
+            GridWalk<NUD, m + 1, cnt, idx + stride, ARG>::go(s, Tl, Th, mn, am);
+            GridWalk<NUD, m + 1, cnt + 1, idx + 2 * stride, ARG>::go(s + Th[m], Tl, Th, mn, am);
+        }
+    }
+    static constexpr int span()
+    {
+        int v = 1;
+        for (int i = m; i < NUD; i++) v *= 3;
+        return v;
+    }
+    static constexpr int SPAN = span();      // candidates below a node of depth m
+};
+
+template <class M, bool ARG, int Q>
+__global__ void __launch_bounds__(CT_NT, 2) k_control_grid(const CtlArgs c)
+{
+    constexpr int DX = M::DX, DU = M::DU, CS = 2 * DX + 1, RW = 2 * DX + 3;
+    constexpr int NUD = M::NUD, NG = NUD + 1;
+    const DevProblem &P = c.P;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int nact = *c.act_count, nper = (nact + Q - 1) / Q;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    const double nbh = -P.beta * P.h2;
+    const bool disc = P.beta != 0.0;
+    for (long long it0 = (long long)blockIdx.x * blockDim.x + (tid & ~31); it0 < nper; it0 += stride) {
+        const int it = (int)it0 + lane;
+        bool valid[Q], bad = false, small = true;
+        int id[Q];
+        Node2<M> nd[Q];
+#pragma unroll
+        for (int q = 0; q < Q; q++) {
+            valid[q] = it < nper && it + q * nper < nact;
+            id[q] = c.act[valid[q] ? it + q * nper : 0];
+            node2_prepare<M>(c, id[q], nd[q]);
+            bad = bad || (valid[q] && nd[q].norm0 + P.amin < 1e-14);
+            small = small && (!valid[q] || P.beta * P.h2 <= 0.00390625 * (nd[q].norm0 + P.amin));
+        }
+        if (bad) atomicOr(P.err, 1);
+        const bool tiny = __all_sync(0xffffffffu, small);
+#pragma unroll
+        for (int q = 0; q < Q; q++) {
+            double Tl[NUD], Th[NUD], mn[NG];
+            int am[NG];
+#pragma unroll
+            for (int m = 0; m < NUD; m++) { Tl[m] = c.gWlo[m] * nd[q].cu[2 * m]; Th[m] = c.gWhi[m] * nd[q].cu[2 * m + 1]; }
+#pragma unroll
+            for (int g = 0; g < NG; g++) { mn[g] = CUDART_INF; am[g] = 0x7fffffff; }
+            GridWalk<NUD, 0, 0, 0, ARG>::go(nd[q].S0, Tl, Th, mn, am);
+#pragma unroll
+            for (int g = 0; g < NG; g++) {
+                const double rinv = rcp_pos(nd[q].norm0 + c.gAg[g]);
+                const double ebt = !disc ? 1.0 : (tiny ? exp_tiny(nbh * rinv) : exp_nonpos(nbh * rinv));
+                const double v = rinv * (fma(ebt, mn[g], c.gHg[g]) + nd[q].hgx);
+                if (v < nd[q].best || (ARG && v == nd[q].best && am[g] < nd[q].ibest)) { nd[q].best = v; nd[q].ibest = am[g]; }
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < Q; q++) {
+            if (!valid[q]) continue;
+            store_value(c, id[q], nd[q].best);
+            if constexpr (ARG) {
+                const int ibest = nd[q].ibest;
+                if (c.argmin) c.argmin[id[q]] = ibest;
+                if (c.rows) {                               // policy row at u* (bellman.c:1851-1860)
+                    double x[DX], u[DU], b[DX], sg[DX], prob[CS], dt;
+                    node_state<DX>(c, id[q], x);
+#pragma unroll
+                    for (int i = 0; i < DU; i++) u[i] = P.utab[(size_t)(ibest < P.nu ? ibest : 0) * DU + i];
+                    M::template drift<Fast>(x, u, P.mp, b);
+                    M::template sigma<Fast>(x, u, P.mp, sg);
+                    const double g = M::template stage<Fast>(x, u, P.mp);
+                    if (transition_row<DX, Fast>(P, b, sg, prob, dt)) atomicOr(P.err, 1);
+                    double *row = c.rows + (size_t)id[q] * RW;
+#pragma unroll
+                    for (int m = 0; m < CS; m++) row[m] = prob[m];
+                    row[CS] = dt;
+                    row[CS + 1] = g;
+                }
+            }
+        }
+    }
+    // absorbed nodes (bellman.c:513-532): boundary / obstacle cost, u = 0
+    for (long long id = (long long)blockIdx.x * blockDim.x + tid; id < c.NS; id += stride) {
+        const int ab = c.flag[id];
+        if (ab != 1 && ab != -1) continue;
+        double x[DX];
+        node_state<DX>(c, (int)id, x);
+        const double v = (ab == 1) ? M::boundcost(x, P.mp) : M::obscost(x, P.mp);
+        store_value(c, id, v);
+        if (c.argmin) c.argmin[id] = -1;
+        if (c.rows) {
+            double *row = c.rows + (size_t)id * RW;
+            for (int m = 0; m < RW; m++) row[m] = 0.0;
+        }
+    }
+}
+
 // policy evaluation (bellman.c:1774-1828,1863-1871): stored rows against the new neighbour values
 template <class M, class A>
 __global__ void __launch_bounds__(CT_NT) k_pi_eval(const CtlArgs c)
@@ -710,6 +835,22 @@ int launch_control_t(const CtlArgs &c_in, int pi_eval, cudaStream_t st)
     int pl2 = 0;
     while (pl2 < 5 && (c.NS << pl2) < (long long)info.sms * CT_NT * 8 && (2 << pl2) <= c.P.nu) pl2++;
     c.parts_log2 = pl2;
+    if constexpr (TAB && M::NUD >= 1 && M::NUD <= CT_NUDMAX) {
+        if (c.grid_on && !getenv("C3SC_NO_GRID")) {
+            // grid-structured table: the shared-prefix walk, one node per thread until the batch fills the part twice
+            const bool arg = c.argmin || c.rows;
+            const bool two = c.NS >= (long long)info.sms * 4 * CT_NT;
+            const int q = two ? 2 : 1;
+            const int nt = (c.NS / q >= (long long)info.sms * 2 * CT_NT) ? CT_NT : 128;
+            long long need = ((c.NS + q - 1) / q + nt - 1) / nt;
+            long long g = (long long)info.sms * 2 * (CT_NT / nt);
+            if (g > need) g = need;
+            if (g < 1) return 0;
+            if (arg) { if (two) k_control_grid<M, true, 2><<<(int)g, nt, 0, st>>>(c); else k_control_grid<M, true, 1><<<(int)g, nt, 0, st>>>(c); }
+            else     { if (two) k_control_grid<M, false, 2><<<(int)g, nt, 0, st>>>(c); else k_control_grid<M, false, 1><<<(int)g, nt, 0, st>>>(c); }
+            return (int)cudaGetLastError();
+        }
+    }
     if (TAB && c.ng > 0 && c.NS >= (long long)info.sms * 128) {
         // separable model, at least ~a warp pair of nodes per SM: two nodes per thread walk the whole
         // grouped table (no per-chunk re-derivation of the node invariants); 128-thread CTAs while the

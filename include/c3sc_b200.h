@@ -137,6 +137,9 @@ void c3sc_problem_destroy(c3sc_problem *p);
 /* returns C3SC_ENUMERIC if any launch since the last check hit norm<1e-14;
  * synchronises the device.                                                 */
 int  c3sc_problem_check(c3sc_problem *p);
+/* how stage 2 walks the control table in FAST arithmetic: 0 = plain table walk, 1 = candidates grouped by
+ * their share of the normaliser, 2 = shared-prefix walk of a full {lo, 0, hi}^du grid */
+int  c3sc_problem_control_path(const c3sc_problem *p);
 
 /* valuef_precompute_cores layout (src/valuefunc.c:165-189): block j of core k
  * is an r_k x r_{k+1} column-major matrix at cores[k] + j*r_k*r_{k+1}.      */

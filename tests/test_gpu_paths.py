@@ -144,3 +144,38 @@ def test_fused_gather_stores(gpu):
         if own:
             assert np.array_equal(out.cpu().numpy().reshape(F, N), want)
     prob.close(); vf.close()
+
+
+@pytest.mark.parametrize("name,n,rank,dx,F", [("lqgnd", 10, 4, 6, 700), ("lqgnd_reflect", 7, 3, 10, 300), ("lqg2d_new", 40, 5, None, 60),
+                                               ("double_int", 30, 4, None, 50), ("dubinscar_new", 14, 4, None, 120)])
+def test_grid_walk_equals_table_walk(gpu, name, n, rank, dx, F):
+    """full {lo, 0, hi}^du control grids take the shared-prefix walk (k_control_grid); it must give the
+    brute-force walk's value and argmin -- checked against the oracle and against the library's own
+    grouped walk (C3SC_NO_GRID=1), VI and the PI pair (policy rows from the argmin)"""
+    import os
+    cfg = configs.get_config(name, n=n, rank=rank, dx=dx)
+    prob = capi.Problem(cfg, arith=1)
+    assert capi.lib().c3sc_problem_control_path(prob.handle) == 2
+    port = make_port(cfg)
+    ranks = cfg.ranks()
+    cores = synthetic.random_cores(cfg.ngrid, ranks)
+    cores2 = synthetic.random_cores(cfg.ngrid, ranks, seed=0xABCD00)
+    ft, ft2 = po.FT(cfg.ngrid, ranks, cores), po.FT(cfg.ngrid, ranks, cores2)
+    vf, vf2 = capi.ValueF(cfg.ngrid, ranks, cores), capi.ValueF(cfg.ngrid, ranks, cores2)
+    dv, fi = synthetic.random_fibers(cfg.ngrid, F, seed=9, face_frac=0.1)
+    m = valid_mask(cfg, dv)
+    val, arg = prob.vi_batch(vf, dv, fi)
+    oval, oarg = port.vi_batch(ft, dv, fi, nthreads=4)
+    assert rel_err(val[m], oval[m], scale=np.abs(oval[m]).max()) <= RTOL
+    assert (arg[m] == oarg[m]).mean() > 0.99
+    p1, rows, _ = prob.pi_batch(vf, vf2, dv, fi)
+    o1, orows, _ = port.pi_batch(ft, ft2, dv, fi)
+    assert rel_err(p1[m], o1[m], scale=np.abs(o1[m]).max()) <= RTOL
+    os.environ["C3SC_NO_GRID"] = "1"
+    try:
+        val2, arg2 = prob.vi_batch(vf, dv, fi)
+    finally:
+        del os.environ["C3SC_NO_GRID"]
+    assert rel_err(val[m], val2[m], scale=np.abs(val2[m]).max()) <= 1e-13
+    assert (arg[m] == arg2[m]).mean() > 0.999
+    prob.close(); vf.close(); vf2.close()
