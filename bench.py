@@ -411,9 +411,10 @@ def main():
             "roofline": {"bound": "fp64", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
                          "traffic": ncu_traffic(F), "flops_per_node_backup": W,
                          "peak_source": "DFMA loop measured in this run (c3sc_measure_fp64_peak); MEASURED_PEAKS.json has no FP64 figure",
-                         "note": "achieved counts the CONTRACT flops per node-backup (SURVEY 8(d): the reference's ~180 flops per candidate); "
-                                 "the kernels execute 12 FP64 instructions per candidate, so frac > 1 is algebra, not pipe utilisation -- "
-                                 "see dominant_kernel for the ncu pipe counters",
+                         "note": "achieved counts the CONTRACT flops per node-backup (SURVEY 8(d): 8r^2+4dr for the neighbour values + "
+                                 "~180 flops per candidate control) over the whole step (all pipeline kernels); stage 2 forms every candidate "
+                                 "from shared partial sums (~2 FP64 instructions per candidate), so frac > 1 is algebra, not pipe utilisation -- "
+                                 "see dominant_kernel / other_kernels for the ncu pipe counters and the stage-1 fraction",
                          "dominant_kernel": (_ncu_record() or {}).get("dominant_kernel"),
                          "other_kernels": (_ncu_record() or {}).get("other_kernels"),
                          "hbm": {"algorithmic_bytes_per_step": hbm_bytes, "achieved_gbs": hbm_bytes / (kernel_ms * 1e-3) / 1e9,
