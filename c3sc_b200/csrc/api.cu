@@ -83,9 +83,23 @@ struct DevBuf {
 
 // per-problem scratch of the two-stage pipeline (one batch in flight per problem, like the
 // reference's Workspace, src/util.c:689-964)
+// Pipeline scratch.  perm / cnt belong to the batch; cst / flag / act / sets belong to a chunk and exist once
+// per LANE: consecutive chunks of a large batch alternate between the caller's stream and a second one, so
+// the latency-bound chain kernel of one chunk and the tails of every kernel overlap the other chunk's work.
 struct Scratch {
     DevBuf cst, flag, act, perm, cnt, sets;
-    void release() { cst.release(); flag.release(); act.release(); perm.release(); cnt.release(); sets.release(); }
+    DevBuf cst1, flag1, act1, sets1;
+    cudaStream_t lane = nullptr;
+    cudaEvent_t fork = nullptr, join = nullptr;
+    void release()
+    {
+        cst.release(); flag.release(); act.release(); perm.release(); cnt.release(); sets.release();
+        cst1.release(); flag1.release(); act1.release(); sets1.release();
+        if (lane) cudaStreamDestroy(lane);
+        if (fork) cudaEventDestroy(fork);
+        if (join) cudaEventDestroy(join);
+        lane = nullptr; fork = join = nullptr;
+    }
 };
 
 // candidates of a separable model regrouped by normaliser share (see k_control)
@@ -503,16 +517,30 @@ struct BatchArgs {
     size_t peer_offset;
 };
 
-static size_t g_chunk_bytes = (size_t)96 << 20;    // slot-major cost scratch per chunk: stays inside the 126 MB L2
+static size_t g_chunk_bytes = (size_t)192 << 20;   // slot-major cost scratch in flight (all lanes); measured optimum, see profiles/r01_lanes.md
+
+static int g_lanes = -1;                            // 2 = alternate chunks between two streams (default), 1 = one stream
 
 static int run_batch(const DevProblem &P, int model, int arith, Scratch &scr, const CtlGroups *grp, const DevFT &ft,
                      const BatchArgs &b, cudaStream_t st)
 {
     const size_t d = (size_t)P.dx, CS = 2 * d + 1, RW = 2 * d + 3;
-    size_t FC = g_chunk_bytes / (b.ldo * CS * 8);
-    if (FC < 1) FC = 1;
-    if (FC > b.F) FC = b.F;
-    FC = (b.F + (b.F + FC - 1) / FC - 1) / ((b.F + FC - 1) / FC);      // equal chunks
+    if (g_lanes < 0) {
+        const char *e = getenv("C3SC_LANES");
+        g_lanes = (e && atoi(e) == 1) ? 1 : 2;
+        const char *m = getenv("C3SC_CHUNK_MB");                      // tuning aid: cost scratch of all lanes together
+        if (m && atoi(m) > 0) g_chunk_bytes = (size_t)atoi(m) << 20;
+    }
+    // chunks: at most g_chunk_bytes of cost scratch in flight (half per lane).  Two lanes as soon as each of two
+    // chunks still fills the machine; an even number of equal chunks then, so both lanes carry the same load.
+    size_t per_lane = g_chunk_bytes / 2 / (b.ldo * CS * 8);
+    if (per_lane < 1) per_lane = 1;
+    const bool two = g_lanes == 2 && b.mode != MODE_COSTS && b.F * b.ldo >= (size_t)2 * 148 * 1024;
+    size_t nch = two ? (b.F + per_lane - 1) / per_lane : (b.F + 2 * per_lane - 1) / (2 * per_lane);
+    if (two && nch < 2) nch = 2;
+    if (two && (nch & 1)) nch++;
+    if (nch < 1) nch = 1;
+    size_t FC = (b.F + nch - 1) / nch;
     const size_t NSmax = FC * b.ldo;
     const bool need_cst = b.mode != MODE_COSTS;
     if ((need_cst && scr.cst.reserve(NSmax * CS * 8)) || scr.flag.reserve(NSmax) || scr.act.reserve(NSmax * 4) ||
@@ -520,14 +548,33 @@ static int run_batch(const DevProblem &P, int model, int arith, Scratch &scr, co
         return fail(C3SC_ECUDA, "cudaMalloc pipeline scratch failed");
     const int mma = ft_uses_mma(ft);
     if (mma && scr.sets.reserve(ft_sets_bytes(ft, FC))) return fail(C3SC_ECUDA, "cudaMalloc chain scratch failed");
+    if (two) {
+        if (scr.cst1.reserve(NSmax * CS * 8) || scr.flag1.reserve(NSmax) || scr.act1.reserve(NSmax * 4) ||
+            (mma && scr.sets1.reserve(ft_sets_bytes(ft, FC))))
+            return fail(C3SC_ECUDA, "cudaMalloc pipeline scratch (second lane) failed");
+        if (!scr.lane) {
+            CK(cudaStreamCreateWithFlags(&scr.lane, cudaStreamNonBlocking));
+            CK(cudaEventCreateWithFlags(&scr.fork, cudaEventDisableTiming));
+            CK(cudaEventCreateWithFlags(&scr.join, cudaEventDisableTiming));
+        }
+    }
     {   // every chunk's grouping in one launch
         int rc = launch_group_fibers((int)b.F, (int)FC, (int)d, b.dim_vary, (int *)scr.perm.p, (int *)scr.cnt.p, st);
         if (rc) return fail(C3SC_ECUDA, "grouping kernel: %s", cudaGetErrorString((cudaError_t)rc));
         g_launches++;
     }
+    if (two) {                                              // the second lane starts after everything queued on st so far
+        CK(cudaEventRecord(scr.fork, st));
+        CK(cudaStreamWaitEvent(scr.lane, scr.fork, 0));
+    }
+    const cudaStream_t st0 = st;
     for (size_t c0 = 0; c0 < b.F; c0 += FC) {
         const size_t Fc = (b.F - c0 < FC) ? b.F - c0 : FC;
         const size_t n0 = c0 * b.ldo;
+        const bool odd = two && ((c0 / FC) & 1);
+        st = odd ? scr.lane : st0;
+        DevBuf &bcst = odd ? scr.cst1 : scr.cst, &bflag = odd ? scr.flag1 : scr.flag, &bact = odd ? scr.act1 : scr.act,
+               &bsets = odd ? scr.sets1 : scr.sets;
         int *cnt = (int *)scr.cnt.p + 64 * (c0 / FC);   // [0,16) kcount, [16,32) kstart, [32] act_count
         int rc;
         FtArgs a;
@@ -536,9 +583,9 @@ static int run_batch(const DevProblem &P, int model, int arith, Scratch &scr, co
         a.ldo = (int)b.ldo; a.FB = 0;
         a.perm = (const int *)scr.perm.p + c0; a.kcount = cnt; a.kstart = cnt + 16;
         a.NS = (long long)(Fc * b.ldo);
-        a.cst = need_cst ? (double *)scr.cst.p : nullptr;
-        a.flag = (signed char *)scr.flag.p;
-        a.act = b.mode == MODE_VI ? (int *)scr.act.p : nullptr;
+        a.cst = need_cst ? (double *)bcst.p : nullptr;
+        a.flag = (signed char *)bflag.p;
+        a.act = b.mode == MODE_VI ? (int *)bact.p : nullptr;
         a.act_count = cnt + 32;
         a.costs = b.out.costs ? b.out.costs + n0 * CS : nullptr;
         a.absorbed = b.out.absorbed ? b.out.absorbed + n0 : nullptr;
@@ -546,7 +593,7 @@ static int run_batch(const DevProblem &P, int model, int arith, Scratch &scr, co
         a.nbr_fixed = (b.out.nbr_fixed && d > 1) ? b.out.nbr_fixed + c0 * 2 * (d - 1) : nullptr;
         a.nbr_fixed_in = (b.nbr_fixed_in && d > 1) ? b.nbr_fixed_in + c0 * 2 * (d - 1) : nullptr;
         a.nbr_vary_in = b.nbr_vary_in ? b.nbr_vary_in + 2 * n0 : nullptr;
-        a.sets = mma ? (double *)scr.sets.p : nullptr;
+        a.sets = mma ? (double *)bsets.p : nullptr;
         rc = launch_ft_costs(a, st);
         if (rc) return fail(C3SC_ECUDA, "FT kernel launch: %s", cudaGetErrorString((cudaError_t)rc));
         g_launches += 1 + mma;
@@ -585,6 +632,10 @@ static int run_batch(const DevProblem &P, int model, int arith, Scratch &scr, co
             if (b.h_value && c.value) CK(cudaMemcpyAsync(b.h_value + n0, c.value, Fc * b.ldo * 8, cudaMemcpyDeviceToHost, b.copy_stream));
             if (b.h_argmin && c.argmin) CK(cudaMemcpyAsync(b.h_argmin + n0, c.argmin, Fc * b.ldo * 4, cudaMemcpyDeviceToHost, b.copy_stream));
         }
+    }
+    if (two) {                                              // the caller's stream continues after both lanes
+        CK(cudaEventRecord(scr.join, scr.lane));
+        CK(cudaStreamWaitEvent(st0, scr.join, 0));
     }
     return C3SC_OK;
 }
