@@ -86,19 +86,29 @@ struct DevBuf {
 // Pipeline scratch.  perm / cnt belong to the batch; cst / flag / act / sets belong to a chunk and exist once
 // per LANE: consecutive chunks of a large batch alternate between the caller's stream and a second one, so
 // the latency-bound chain kernel of one chunk and the tails of every kernel overlap the other chunk's work.
-struct Scratch {
-    DevBuf cst, flag, act, perm, cnt, sets;
-    DevBuf cst1, flag1, act1, sets1;
-    cudaStream_t lane = nullptr;
-    cudaEvent_t fork = nullptr, join = nullptr;
+constexpr int MAXLANES = 4;
+struct LaneScratch {
+    DevBuf cst, flag, act, sets;
+    cudaStream_t stream = nullptr;          // lane 0 runs on the caller's stream
+    cudaEvent_t join = nullptr;
     void release()
     {
-        cst.release(); flag.release(); act.release(); perm.release(); cnt.release(); sets.release();
-        cst1.release(); flag1.release(); act1.release(); sets1.release();
-        if (lane) cudaStreamDestroy(lane);
-        if (fork) cudaEventDestroy(fork);
+        cst.release(); flag.release(); act.release(); sets.release();
+        if (stream) cudaStreamDestroy(stream);
         if (join) cudaEventDestroy(join);
-        lane = nullptr; fork = join = nullptr;
+        stream = nullptr; join = nullptr;
+    }
+};
+struct Scratch {
+    DevBuf perm, cnt;
+    LaneScratch lane[MAXLANES];
+    cudaEvent_t fork = nullptr;
+    void release()
+    {
+        perm.release(); cnt.release();
+        for (LaneScratch &l : lane) l.release();
+        if (fork) cudaEventDestroy(fork);
+        fork = nullptr;
     }
 };
 
@@ -527,54 +537,55 @@ static int run_batch(const DevProblem &P, int model, int arith, Scratch &scr, co
     const size_t d = (size_t)P.dx, CS = 2 * d + 1, RW = 2 * d + 3;
     if (g_lanes < 0) {
         const char *e = getenv("C3SC_LANES");
-        g_lanes = (e && atoi(e) == 1) ? 1 : 2;
+        g_lanes = e ? atoi(e) : 2;
+        if (g_lanes < 1) g_lanes = 1;
+        if (g_lanes > MAXLANES) g_lanes = MAXLANES;
         const char *m = getenv("C3SC_CHUNK_MB");                      // tuning aid: cost scratch of all lanes together
         if (m && atoi(m) > 0) g_chunk_bytes = (size_t)atoi(m) << 20;
     }
-    // chunks: at most g_chunk_bytes of cost scratch in flight (half per lane).  Two lanes as soon as each of two
-    // chunks still fills the machine; an even number of equal chunks then, so both lanes carry the same load.
-    size_t per_lane = g_chunk_bytes / 2 / (b.ldo * CS * 8);
-    if (per_lane < 1) per_lane = 1;
-    const bool two = g_lanes == 2 && b.mode != MODE_COSTS && b.F * b.ldo >= (size_t)2 * 148 * 1024;
-    size_t nch = two ? (b.F + per_lane - 1) / per_lane : (b.F + 2 * per_lane - 1) / (2 * per_lane);
-    if (two && nch < 2) nch = 2;
-    if (two && (nch & 1)) nch++;
-    if (nch < 1) nch = 1;
+    // chunks: at most g_chunk_bytes of cost scratch in flight, shared by the lanes.  Several lanes as soon as each
+    // chunk still fills the machine; the chunk count is then a multiple of the lane count (equal load per lane).
+    const bool multi = g_lanes > 1 && b.mode != MODE_COSTS && b.F * b.ldo >= (size_t)g_lanes * 148 * 1024;
+    const size_t L = multi ? (size_t)g_lanes : 1;
+    size_t per_chunk = g_chunk_bytes / (size_t)g_lanes / (b.ldo * CS * 8);
+    if (!multi) per_chunk *= (size_t)g_lanes;
+    if (per_chunk < 1) per_chunk = 1;
+    size_t nch = (b.F + per_chunk - 1) / per_chunk;
+    if (nch < L) nch = L;
+    nch = (nch + L - 1) / L * L;
     size_t FC = (b.F + nch - 1) / nch;
     const size_t NSmax = FC * b.ldo;
     const bool need_cst = b.mode != MODE_COSTS;
-    if ((need_cst && scr.cst.reserve(NSmax * CS * 8)) || scr.flag.reserve(NSmax) || scr.act.reserve(NSmax * 4) ||
-        scr.perm.reserve(b.F * 4) || scr.cnt.reserve(((b.F + FC - 1) / FC) * 64 * 4))
-        return fail(C3SC_ECUDA, "cudaMalloc pipeline scratch failed");
     const int mma = ft_uses_mma(ft);
-    if (mma && scr.sets.reserve(ft_sets_bytes(ft, FC))) return fail(C3SC_ECUDA, "cudaMalloc chain scratch failed");
-    if (two) {
-        if (scr.cst1.reserve(NSmax * CS * 8) || scr.flag1.reserve(NSmax) || scr.act1.reserve(NSmax * 4) ||
-            (mma && scr.sets1.reserve(ft_sets_bytes(ft, FC))))
-            return fail(C3SC_ECUDA, "cudaMalloc pipeline scratch (second lane) failed");
-        if (!scr.lane) {
-            CK(cudaStreamCreateWithFlags(&scr.lane, cudaStreamNonBlocking));
-            CK(cudaEventCreateWithFlags(&scr.fork, cudaEventDisableTiming));
-            CK(cudaEventCreateWithFlags(&scr.join, cudaEventDisableTiming));
+    if (scr.perm.reserve(b.F * 4) || scr.cnt.reserve(((b.F + FC - 1) / FC) * 64 * 4))
+        return fail(C3SC_ECUDA, "cudaMalloc pipeline scratch failed");
+    for (size_t l = 0; l < L; l++) {
+        LaneScratch &ln = scr.lane[l];
+        if ((need_cst && ln.cst.reserve(NSmax * CS * 8)) || ln.flag.reserve(NSmax) || ln.act.reserve(NSmax * 4) ||
+            (mma && ln.sets.reserve(ft_sets_bytes(ft, FC))))
+            return fail(C3SC_ECUDA, "cudaMalloc pipeline scratch failed");
+        if (l > 0 && !ln.stream) {
+            CK(cudaStreamCreateWithFlags(&ln.stream, cudaStreamNonBlocking));
+            CK(cudaEventCreateWithFlags(&ln.join, cudaEventDisableTiming));
         }
     }
+    if (L > 1 && !scr.fork) CK(cudaEventCreateWithFlags(&scr.fork, cudaEventDisableTiming));
     {   // every chunk's grouping in one launch
         int rc = launch_group_fibers((int)b.F, (int)FC, (int)d, b.dim_vary, (int *)scr.perm.p, (int *)scr.cnt.p, st);
         if (rc) return fail(C3SC_ECUDA, "grouping kernel: %s", cudaGetErrorString((cudaError_t)rc));
         g_launches++;
     }
-    if (two) {                                              // the second lane starts after everything queued on st so far
+    if (L > 1) {                                            // the other lanes start after everything queued on st so far
         CK(cudaEventRecord(scr.fork, st));
-        CK(cudaStreamWaitEvent(scr.lane, scr.fork, 0));
+        for (size_t l = 1; l < L; l++) CK(cudaStreamWaitEvent(scr.lane[l].stream, scr.fork, 0));
     }
     const cudaStream_t st0 = st;
     for (size_t c0 = 0; c0 < b.F; c0 += FC) {
         const size_t Fc = (b.F - c0 < FC) ? b.F - c0 : FC;
         const size_t n0 = c0 * b.ldo;
-        const bool odd = two && ((c0 / FC) & 1);
-        st = odd ? scr.lane : st0;
-        DevBuf &bcst = odd ? scr.cst1 : scr.cst, &bflag = odd ? scr.flag1 : scr.flag, &bact = odd ? scr.act1 : scr.act,
-               &bsets = odd ? scr.sets1 : scr.sets;
+        LaneScratch &ln = scr.lane[(c0 / FC) % L];
+        st = ln.stream ? ln.stream : st0;
+        DevBuf &bcst = ln.cst, &bflag = ln.flag, &bact = ln.act, &bsets = ln.sets;
         int *cnt = (int *)scr.cnt.p + 64 * (c0 / FC);   // [0,16) kcount, [16,32) kstart, [32] act_count
         int rc;
         FtArgs a;
@@ -633,9 +644,9 @@ static int run_batch(const DevProblem &P, int model, int arith, Scratch &scr, co
             if (b.h_argmin && c.argmin) CK(cudaMemcpyAsync(b.h_argmin + n0, c.argmin, Fc * b.ldo * 4, cudaMemcpyDeviceToHost, b.copy_stream));
         }
     }
-    if (two) {                                              // the caller's stream continues after both lanes
-        CK(cudaEventRecord(scr.join, scr.lane));
-        CK(cudaStreamWaitEvent(st0, scr.join, 0));
+    for (size_t l = 1; l < L; l++) {                        // the caller's stream continues after every lane
+        CK(cudaEventRecord(scr.lane[l].join, scr.lane[l].stream));
+        CK(cudaStreamWaitEvent(st0, scr.lane[l].join, 0));
     }
     return C3SC_OK;
 }
