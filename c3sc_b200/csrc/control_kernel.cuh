@@ -651,8 +651,18 @@ struct GridWalk {
     static constexpr int SPAN = span();      // candidates below a node of depth m
 };
 
+// Occupancy beats registers here: the walk has no loop-carried state beyond the du+1 running minima, and the
+// 21 neighbour values of a node arrive from L2 -- one node per thread at 4 CTAs/SM (64 registers, ~100 B of
+// spills) measured 4 % faster end to end than two nodes per thread at 2 CTAs/SM (profiles/r01_lanes.md).
+#ifndef C3SC_GRID_MINB
+#define C3SC_GRID_MINB 4
+#endif
+#ifndef C3SC_GRID_Q
+#define C3SC_GRID_Q 1          // nodes per thread for large batches
+#endif
+constexpr int grid_minb(bool arg) { return arg && C3SC_GRID_MINB > 3 ? 3 : C3SC_GRID_MINB; }   // the index bookkeeping needs more registers
 template <class M, bool ARG, int Q>
-__global__ void __launch_bounds__(CT_NT, 2) k_control_grid(const CtlArgs c)
+__global__ void __launch_bounds__(CT_NT, grid_minb(ARG)) k_control_grid(const CtlArgs c)
 {
     constexpr int DX = M::DX, DU = M::DU, CS = 2 * DX + 1, RW = 2 * DX + 3;
     constexpr int NUD = M::NUD, NG = NUD + 1;
@@ -839,11 +849,11 @@ int launch_control_t(const CtlArgs &c_in, int pi_eval, cudaStream_t st)
         if (c.grid_on && !getenv("C3SC_NO_GRID")) {
             // grid-structured table: the shared-prefix walk, one node per thread until the batch fills the part twice
             const bool arg = c.argmin || c.rows;
-            const bool two = c.NS >= (long long)info.sms * 4 * CT_NT;
+            const bool two = C3SC_GRID_Q == 2 && c.NS >= (long long)info.sms * 4 * CT_NT;
             const int q = two ? 2 : 1;
             const int nt = (c.NS / q >= (long long)info.sms * 2 * CT_NT) ? CT_NT : 128;
             long long need = ((c.NS + q - 1) / q + nt - 1) / nt;
-            long long g = (long long)info.sms * 2 * (CT_NT / nt);
+            long long g = (long long)info.sms * grid_minb(arg) * (CT_NT / nt);
             if (g > need) g = need;
             if (g < 1) return 0;
             if (arg) { if (two) k_control_grid<M, true, 2><<<(int)g, nt, 0, st>>>(c); else k_control_grid<M, true, 1><<<(int)g, nt, 0, st>>>(c); }
