@@ -70,8 +70,11 @@ __device__ __forceinline__ void dmma_m8n8k4(double &d0, double &d1, double a, do
 // tensor cores:  out[v][o] = sum_q in[v][q] B[q][o]  (left: B = G_m[f_m], right: B = G_m[f_m]^T),
 // B fragments straight from the zero-padded core copy in L2 (all loads of a step are independent),
 // and appends the two neighbour variants  in[0] . G_m[nb]  with plain FMAs.
+#ifndef C3SC_FTC_MINB
+#define C3SC_FTC_MINB 2
+#endif
 template <int KS>
-__global__ void __launch_bounds__(FTC_NT, KS <= 6 ? 2 : 1) k_ft_chains(const FtArgs a, double *sets)
+__global__ void __launch_bounds__(FTC_NT, KS <= 6 ? C3SC_FTC_MINB : 1) k_ft_chains(const FtArgs a, double *sets)
 {
     constexpr int NTL = (KS + 1) / 2, VT = (2 * MAXD + 7) / 8;
     const DevProblem &P = a.P;
