@@ -370,3 +370,44 @@ def test_adaptive_vi_solve_pi_solve_and_controller(gpu):
     for v in (v0, v1, v2, v3):
         L.valuef_destroy(v)
     L.diag_destroy(C.byref(head)); L.approx_args_free(a); vf3.close(); hp.close(); prob.close()
+
+
+@pytest.mark.gpu
+def test_pi_regression_norm_from_the_paper(gpu):
+    """Test_bellman_pi_25 (tprob_test.c:1996-2357, "FROM PAPER!! This is a regression test"): 2-D LQG,
+    reflecting boundaries, discount 0.1, 25 x 25 nodes, start value 0.2, outer loop pi_solve(10) + vi_solve(1)
+    until the iterates differ by < 1e-5; the L2 norm of the value function is 100 within 10 %.  The
+    reference minimises over u in [-1, 1] with BFGS; here the control set is {-1, 0, 1}."""
+    L = solver_lib()
+    N = 25
+    cfg = configs.get_config("lqg2d_reflect", n=N, rank=3)
+    hp = HostProblem(L, cfg, arith=1)
+    START = C.CFUNCTYPE(C.c_int, sz, C.POINTER(dbl), C.POINTER(dbl), vp)
+
+    def _quad2d(n, x, out, _):                                    # tprob_test.c:1389-1398
+        np.ctypeslib.as_array(out, shape=(n,))[:] = 0.2
+        return 0
+    quad2d = START(_quad2d)
+    a = L.approx_args_init()                                      # tprob_test.c:2025-2031
+    L.approx_args_set_cross_tol(a, 1e-8); L.approx_args_set_round_tol(a, 1e-7); L.approx_args_set_kickrank(a, 5)
+    L.approx_args_set_adapt(a, 0); L.approx_args_set_startrank(a, 3); L.approx_args_set_maxrank(a, 20)
+    cost = L.c3control_init_value(hp.c3c, quad2d, None, a, 0)
+    diff = 1.0
+    for it in range(2000):
+        nxt = L.c3control_pi_solve(hp.c3c, 10, 1e-5, cost, a, hp.opt, 0, None)
+        tmp = L.c3control_vi_solve(hp.c3c, 1, 1e-5, nxt, a, hp.opt, 0, None)
+        diff = L.valuef_norm2diff(nxt, tmp)
+        L.valuef_destroy(nxt); L.valuef_destroy(cost)
+        cost = tmp
+        if diff < 1e-5:
+            break
+    assert diff < 1e-5, (it, diff)
+    ranks, cores = _host_cores(L, cost, cfg.ngrid)
+    g0 = np.asarray(cores[0]).reshape(N, int(ranks[1]))            # [j][b] (r_0 = 1)
+    g1 = np.asarray(cores[1]).reshape(N, int(ranks[1]))            # [j][a] (r_2 = 1)
+    V = g0 @ g1.T
+    w = np.full(N, 4.0 / (N - 1)); w[0] = w[-1] = 2.0 / (N - 1)    # trapezoid rule on [-2, 2]
+    l2 = float(np.sqrt(np.einsum("i,j,ij->", w, w, V * V)))
+    assert abs(100.0 - l2) / 100.0 < 0.1, l2
+    assert V.min() > 0 and abs(V[N // 2, N // 2] - V.min()) < 0.05 * V.max()      # bowl centred at the origin
+    L.valuef_destroy(cost); L.approx_args_free(a); hp.close()
