@@ -14,14 +14,15 @@
  * batched fiber entries, and ValueF construction from nodal cores (the
  * reference builds ValueF only through the absent C3 library).
  *
- * Beside this header: include/c3sc_cross.h restates what valuef_interp / c3control_step_vi / _pi /
- * c3control_vi_solve obtain from C3's cross approximation (batched core requests), valuef_norm /
- * valuef_norm2diff on nodal cores; include/c3sc_b200.h has valuef_eval and c3control_policy_eval
- * for batches of off-grid states (c3sc_valuef_eval_batch, c3sc_policy_eval_batch).
+ * The solver loops (valuef_interp, c3control_init_value / step_vi / step_pi / vi_solve / pi_solve, ApproxArgs,
+ * Diag) and the online controller (c3control_add_policy_sim / policy_eval / controller) are here too; what they
+ * obtain from C3's cross approximation in the reference is restated in include/c3sc_cross.h (batched core
+ * requests, TT rounding, rank adaptation, nodal norms).  examples/lqg2d_b200.c is an examples/lqg2d_new-style
+ * main() written against this header.
  *
- * NOT mirrored (out of scope): valuef save / load (C3 file formats), BoundInfo,
- * HashGrid, process_fibers, rank adaptation and rounding of the cross, the BFGS branch of
- * bellman_optimal and every gradient output (grad_* arguments must be NULL).
+ * NOT mirrored (out of scope): valuef save / load (C3 file formats), the CONSTELM function
+ * class, BoundInfo, HashGrid, process_fibers, the BFGS branch of bellman_optimal and every gradient output
+ * (grad_* arguments must be NULL), the trajectory simulation of the example tails (cdyn).
  */
 #ifndef C3SC_HOST_H
 #define C3SC_HOST_H
