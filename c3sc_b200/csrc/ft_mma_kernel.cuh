@@ -253,6 +253,73 @@ __device__ __forceinline__ void mbar_wait(unsigned long long *b, unsigned parity
                  "}" ::"r"(smem_u32(b)), "r"(parity) : "memory");
 }
 
+// Variant dots of one fiber over one 8-node tile (second phase of k_ft_nodes) with compile-time tile counts:
+// left  C[v][jl] = sum_a A[v][a] W[a][jl]  (ML tiles of 8 variant vectors),
+// right C[jl][v] = sum_b U[jl][b] Cv[b][v] (NR tiles).
+template <int KS>
+struct NodeDots {
+    static constexpr int VT = (2 * MAXD + 7) / 8;
+    const double *setL, *setR, *wg, *ug;
+    int NVL, NVR;
+    const int (&slotL)[VT];
+    const int (&slotR)[VT][2];
+    double *cst, *costs;
+    long long NS;
+    size_t idb;
+    int CS, nt, tig, gid;
+
+    template <int ML, int NR>
+    __device__ __forceinline__ void run() const
+    {
+        double dl[ML][2], dr[NR > 0 ? NR : 1][2];
+#pragma unroll
+        for (int t = 0; t < ML; t++) dl[t][0] = dl[t][1] = 0.0;
+#pragma unroll
+        for (int t = 0; t < NR; t++) dr[t][0] = dr[t][1] = 0.0;
+#pragma unroll
+        for (int ks = 0; ks < KS; ks++) {
+            const double bw = wg[ks * 4 * FTN_TP];                   // B fragment (row a, col jl), shared by the v tiles
+#pragma unroll
+            for (int mt = 0; mt < ML; mt++) dmma_m8n8k4(dl[mt][0], dl[mt][1], setL[(4 * ks + tig) * NVL + 8 * mt + gid], bw);
+            if constexpr (NR > 0) {
+                const double au = ug[ks * 4 * FTN_TP];               // A fragment (row jl, col b)
+#pragma unroll
+                for (int nb = 0; nb < NR; nb++) dmma_m8n8k4(dr[nb][0], dr[nb][1], au, setR[(4 * ks + tig) * NVR + 8 * nb + gid]);
+            }
+        }
+#pragma unroll
+        for (int mt = 0; mt < ML; mt++) {
+            const int slot = slotL[mt];
+            if (slot >= 0) {                                         // D: row v, cols jl = 2tig, 2tig+1
+                const int jl = 2 * tig;
+                const double d0 = dl[mt][0], d1 = dl[mt][1];
+                if (cst) {
+                    double *o = cst + (size_t)slot * NS + idb + jl;
+                    if (jl < nt) o[0] = d0;
+                    if (jl + 1 < nt) o[1] = d1;
+                }
+                if (costs) {
+                    if (jl < nt) costs[(idb + jl) * CS + slot] = d0;
+                    if (jl + 1 < nt) costs[(idb + jl + 1) * CS + slot] = d1;
+                }
+            }
+        }
+        if (gid < nt) {
+#pragma unroll
+            for (int nb = 0; nb < NR; nb++) {                        // D: row jl = gid, cols v = 8nb+2tig, +1
+#pragma unroll
+                for (int h = 0; h < 2; h++) {
+                    const int slot = slotR[nb][h];
+                    if (slot < 0) continue;
+                    const double val = dr[nb][h];
+                    if (cst) cst[(size_t)slot * NS + idb + gid] = val;
+                    if (costs) costs[(idb + gid) * CS + slot] = val;
+                }
+            }
+        }
+    }
+};
+
 // Shared memory of k_ft_nodes.  Everything the MMA fragments read is zero-padded to the fragment
 // shape, so no fragment load is predicated.
 template <int KS>
@@ -457,56 +524,16 @@ __global__ void __launch_bounds__(FTN_NT, 2) k_ft_nodes(const FtArgs a, const do
         // ---- variant dots of fiber g = warp over the tile's nodes -----------------------------
         if (warp < nf) {
             const size_t idb = idf + j0;
-            // left: C[v][jl] = sum_a A[v][a] W[a][jl];  right: C[jl][v] = sum_b U[jl][b] Cv[b][v]
-            double dl[VT][2], dr[VT][2];
-#pragma unroll
-            for (int t = 0; t < VT; t++) { dl[t][0] = dl[t][1] = 0.0; dr[t][0] = dr[t][1] = 0.0; }
-#pragma unroll
-            for (int ks = 0; ks < KS; ks++) {
-                if (ks < nksA) {
-                    const double bw = wg[ks * 4 * FTN_TP];               // B fragment (row a, col jl), shared by the v tiles
-#pragma unroll
-                    for (int mt = 0; mt < VT; mt++)
-                        if (mt < mtL) dmma_m8n8k4(dl[mt][0], dl[mt][1], setL[(4 * ks + tig) * NVL + 8 * mt + gid], bw);
-                }
-                if (ks < nksB) {
-                    const double au = ug[ks * 4 * FTN_TP];               // A fragment (row jl, col b)
-#pragma unroll
-                    for (int nb = 0; nb < VT; nb++)
-                        if (nb < ntR) dmma_m8n8k4(dr[nb][0], dr[nb][1], au, setR[(4 * ks + tig) * NVR + 8 * nb + gid]);
-                }
-            }
-#pragma unroll
-            for (int mt = 0; mt < VT; mt++) {
-                const int slot = slotL[mt];
-                if (mt < mtL && slot >= 0) {                             // D: row v, cols jl = 2tig, 2tig+1
-                    const int jl = 2 * tig;
-                    const double d0 = dl[mt][0], d1 = dl[mt][1];
-                    if (a.cst) {
-                        double *o = a.cst + (size_t)slot * a.NS + idb + jl;
-                        if (jl < nt) o[0] = d0;
-                        if (jl + 1 < nt) o[1] = d1;
-                    }
-                    if (a.costs) {
-                        if (jl < nt) a.costs[(idb + jl) * CS + slot] = d0;
-                        if (jl + 1 < nt) a.costs[(idb + jl + 1) * CS + slot] = d1;
-                    }
-                }
-            }
-            if (gid < nt) {
-#pragma unroll
-                for (int nb = 0; nb < VT; nb++) {
-                    if (nb < ntR) {                                      // D: row jl = gid, cols v = 8nb+2tig, +1
-#pragma unroll
-                        for (int h = 0; h < 2; h++) {
-                            const int slot = slotR[nb][h];
-                            if (slot < 0) continue;
-                            const double val = dr[nb][h];
-                            if (a.cst) a.cst[(size_t)slot * a.NS + idb + gid] = val;
-                            if (a.costs) a.costs[(idb + gid) * CS + slot] = val;
-                        }
-                    }
-                }
+            // the tile counts of the variant sets are warp-uniform run-time values: dispatch to a body with
+            // compile-time counts, so that no predicated-off DMMA (and its fragment load) is issued at all
+            const NodeDots<KS> nd{setL, setR, wg, ug, NVL, NVR, slotL, slotR, a.cst, a.costs, a.NS, idb, CS, nt, tig, gid};
+            switch (mtL * 8 + ntR) {
+#define C3SC_ND(L, R) case (L) * 8 + (R): nd.template run<L, R>(); break;
+                C3SC_ND(1, 0) C3SC_ND(1, 1) C3SC_ND(1, 2) C3SC_ND(1, 3) C3SC_ND(1, 4)
+                C3SC_ND(2, 0) C3SC_ND(2, 1) C3SC_ND(2, 2) C3SC_ND(2, 3) C3SC_ND(2, 4)
+                C3SC_ND(3, 0) C3SC_ND(3, 1) C3SC_ND(3, 2) C3SC_ND(3, 3) C3SC_ND(3, 4)
+                C3SC_ND(4, 0) C3SC_ND(4, 1) C3SC_ND(4, 2) C3SC_ND(4, 3) C3SC_ND(4, 4)
+#undef C3SC_ND
             }
         }
         __syncthreads();
