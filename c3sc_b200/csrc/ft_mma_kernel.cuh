@@ -253,6 +253,41 @@ __device__ __forceinline__ void mbar_wait(unsigned long long *b, unsigned parity
                  "}" ::"r"(smem_u32(b)), "r"(parity) : "memory");
 }
 
+// w / u of one node for the (up to) 8 fibers of the group (first phase of k_ft_nodes):
+//   W[a][g] = sum_b G[a,b] R_g[b],  U[g][b] = sum_a L_g[a] G[a,b];  k-step outermost, so the MT accumulator
+//   tiles of either product are independent DMMA chains.
+template <int KS, bool DO_W, bool DO_U>
+__device__ __forceinline__ void node_wu(const double *gj, int offW, int offU, int ldk, const double (&Rf)[KS], const double (&Lf)[KS],
+                                        double *sW, double *sU, int SW, int tig, int gid, int warp)
+{
+    constexpr int MT = (KS + 1) / 2;
+    double dw[MT][2], du[MT][2];
+#pragma unroll
+    for (int t = 0; t < MT; t++) { dw[t][0] = dw[t][1] = 0.0; du[t][0] = du[t][1] = 0.0; }
+#pragma unroll
+    for (int ks = 0; ks < KS; ks++) {
+        if constexpr (DO_W) {
+#pragma unroll
+            for (int mt = 0; mt < MT; mt++) dmma_m8n8k4(dw[mt][0], dw[mt][1], gj[offW + ks * 4 * ldk + mt * 8], Rf[ks]);
+        }
+        if constexpr (DO_U) {
+#pragma unroll
+            for (int nb = 0; nb < MT; nb++) dmma_m8n8k4(du[nb][0], du[nb][1], Lf[ks], gj[offU + nb * 8 * ldk + ks * 4]);
+        }
+    }
+#pragma unroll
+    for (int mt = 0; mt < MT; mt++) {
+        if constexpr (DO_W) {                                    // D: row a = 8mt+gid, cols fiber 2*tig, 2*tig+1
+            sW[(2 * tig) * SW + (8 * mt + gid) * FTN_TP + warp] = dw[mt][0];
+            sW[(2 * tig + 1) * SW + (8 * mt + gid) * FTN_TP + warp] = dw[mt][1];
+        }
+        if constexpr (DO_U) {                                    // D: row fiber gid, cols b = 8nb+2tig, +1
+            sU[gid * SW + (8 * mt + 2 * tig) * FTN_TP + warp] = du[mt][0];
+            sU[gid * SW + (8 * mt + 2 * tig + 1) * FTN_TP + warp] = du[mt][1];
+        }
+    }
+}
+
 // Variant dots of one fiber over one 8-node tile (second phase of k_ft_nodes) with compile-time tile counts:
 // left  C[v][jl] = sum_a A[v][a] W[a][jl]  (ML tiles of 8 variant vectors),
 // right C[jl][v] = sum_b U[jl][b] Cv[b][v] (NR tiles).
@@ -271,16 +306,18 @@ struct NodeDots {
     template <int ML, int NR>
     __device__ __forceinline__ void run() const
     {
-        double dl[ML][2], dr[NR > 0 ? NR : 1][2];
+        double dl[ML > 0 ? ML : 1][2], dr[NR > 0 ? NR : 1][2];
 #pragma unroll
         for (int t = 0; t < ML; t++) dl[t][0] = dl[t][1] = 0.0;
 #pragma unroll
         for (int t = 0; t < NR; t++) dr[t][0] = dr[t][1] = 0.0;
 #pragma unroll
         for (int ks = 0; ks < KS; ks++) {
-            const double bw = wg[ks * 4 * FTN_TP];                   // B fragment (row a, col jl), shared by the v tiles
+            if constexpr (ML > 0) {
+                const double bw = wg[ks * 4 * FTN_TP];               // B fragment (row a, col jl), shared by the v tiles
 #pragma unroll
-            for (int mt = 0; mt < ML; mt++) dmma_m8n8k4(dl[mt][0], dl[mt][1], setL[(4 * ks + tig) * NVL + 8 * mt + gid], bw);
+                for (int mt = 0; mt < ML; mt++) dmma_m8n8k4(dl[mt][0], dl[mt][1], setL[(4 * ks + tig) * NVL + 8 * mt + gid], bw);
+            }
             if constexpr (NR > 0) {
                 const double au = ug[ks * 4 * FTN_TP];               // A fragment (row jl, col b)
 #pragma unroll
@@ -395,7 +432,8 @@ __global__ void __launch_bounds__(FTN_NT, 2) k_ft_nodes(const FtArgs a, const do
     const int offR = sp.rs4 * NVL;                                    // layout of the zero-padded shared copy
     constexpr int nksA = KS, nksB = KS;                               // k-steps over a / over b (padded geometry)
     constexpr int mtA = MT, ntB = MT;                                 // 8-wide tiles over a / over b
-    const int mtL = (nvL + 7) >> 3, ntR = nvR > 1 ? (nvR + 7) >> 3 : 0;   // 8-wide tiles over the variant vectors
+    const bool needU = nvR > 1, needW = nvL > 1 || !needU;           // sides that have neighbour variants (or carry the self value)
+    const int mtL = needW ? (nvL + 7) >> 3 : 0, ntR = needU ? (nvR + 7) >> 3 : 0;   // 8-wide tiles over the variant vectors
 
     // this CTA's share of the fiber: a contiguous range of node tiles
     const int ntiles = (N + FTN_T - 1) / FTN_T, nsp = a.nsplit > 0 ? a.nsplit : 1;
@@ -473,7 +511,8 @@ __global__ void __launch_bounds__(FTN_NT, 2) k_ft_nodes(const FtArgs a, const do
 #pragma unroll
         for (int h = 0; h < 2; h++) {
             const int vv = 8 * t + 2 * tig + h;
-            slotR[t][h] = (vv < 1 || vv >= nvR) ? -1 : 2 * (d - 1 - ((vv - 1) >> 1)) + ((vv - 1) & 1);
+            slotR[t][h] = vv >= nvR ? -1 : (vv == 0 ? (needW ? -1 : 2 * d)          // vector 0 is R itself: the self value when w is skipped
+                                                     : 2 * (d - 1 - ((vv - 1) >> 1)) + ((vv - 1) & 1));
         }
     }
     const int offW = tig * ldk + gid, offU = gid * ldk + tig;           // fragment origins inside a node block
@@ -491,33 +530,11 @@ __global__ void __launch_bounds__(FTN_NT, 2) k_ft_nodes(const FtArgs a, const do
         // k-step outermost: the MT (resp. ntB) accumulator tiles are independent DMMA chains
         if (warp < nt) {
             const double *gj = sG + buf * GB + warp * pblk;
-            double dw[MT][2], du[MT][2];
-#pragma unroll
-            for (int t = 0; t < MT; t++) { dw[t][0] = dw[t][1] = 0.0; du[t][0] = du[t][1] = 0.0; }
-#pragma unroll
-            for (int ks = 0; ks < KS; ks++) {
-                if (ks < nksB) {
-#pragma unroll
-                    for (int mt = 0; mt < MT; mt++)
-                        if (mt < mtA) dmma_m8n8k4(dw[mt][0], dw[mt][1], gj[offW + ks * 4 * ldk + mt * 8], Rf[ks]);
-                }
-                if (ks < nksA) {
-#pragma unroll
-                    for (int nb = 0; nb < MT; nb++)
-                        if (nb < ntB) dmma_m8n8k4(du[nb][0], du[nb][1], Lf[ks], gj[offU + nb * 8 * ldk + ks * 4]);
-                }
-            }
-#pragma unroll
-            for (int mt = 0; mt < MT; mt++) {
-                if (mt < mtA) {                                      // D: row a = 8mt+gid, cols fiber 2*tig, 2*tig+1
-                    sW[(2 * tig) * SW + (8 * mt + gid) * FTN_TP + warp] = dw[mt][0];
-                    sW[(2 * tig + 1) * SW + (8 * mt + gid) * FTN_TP + warp] = dw[mt][1];
-                }
-                if (mt < ntB) {                                      // D: row fiber gid, cols b = 8nb+2tig, +1
-                    sU[gid * SW + (8 * mt + 2 * tig) * FTN_TP + warp] = du[mt][0];
-                    sU[gid * SW + (8 * mt + 2 * tig + 1) * FTN_TP + warp] = du[mt][1];
-                }
-            }
+            // w only feeds the left variant set, u only the right one: a side without variants is skipped
+            // (k = 0 takes the self value from u . R, k = d-1 from L . w)
+            if (needW && needU) node_wu<KS, true, true>(gj, offW, offU, ldk, Rf, Lf, sW, sU, SW, tig, gid, warp);
+            else if (needW) node_wu<KS, true, false>(gj, offW, offU, ldk, Rf, Lf, sW, sU, SW, tig, gid, warp);
+            else node_wu<KS, false, true>(gj, offW, offU, ldk, Rf, Lf, sW, sU, SW, tig, gid, warp);
         }
         __syncthreads();
         if (tid == 0 && j0 + 2 * FTN_T < je) fetch(j0 + 2 * FTN_T, buf);     // this buffer is free: fetch the tile after next
@@ -529,6 +546,7 @@ __global__ void __launch_bounds__(FTN_NT, 2) k_ft_nodes(const FtArgs a, const do
             const NodeDots<KS> nd{setL, setR, wg, ug, NVL, NVR, slotL, slotR, a.cst, a.costs, a.NS, idb, CS, nt, tig, gid};
             switch (mtL * 8 + ntR) {
 #define C3SC_ND(L, R) case (L) * 8 + (R): nd.template run<L, R>(); break;
+                C3SC_ND(0, 1) C3SC_ND(0, 2) C3SC_ND(0, 3) C3SC_ND(0, 4)
                 C3SC_ND(1, 0) C3SC_ND(1, 1) C3SC_ND(1, 2) C3SC_ND(1, 3) C3SC_ND(1, 4)
                 C3SC_ND(2, 0) C3SC_ND(2, 1) C3SC_ND(2, 2) C3SC_ND(2, 3) C3SC_ND(2, 4)
                 C3SC_ND(3, 0) C3SC_ND(3, 1) C3SC_ND(3, 2) C3SC_ND(3, 3) C3SC_ND(3, 4)
