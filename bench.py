@@ -388,6 +388,21 @@ def main():
         W = contract_flops_per_node(cfg, rank_ft)
         peak = capi.measure_fp64_peak()
         kernel_ms = ms_total / args.steps
+        # stage 1 alone (chains + nodes = the neighbour values, 8r^2 + 4dr algorithmic flops per node): the same
+        # kernels with the node-major cost output instead of the scratch, timed live on a sample of the batch
+        stage1 = None
+        if world == 1:
+            F1 = min(F, 8192)
+            costs_d = torch.empty(F1 * N * (2 * cfg.dx + 1), dtype=torch.float64, device=dev)
+
+            def step_stage1():
+                prob.vi_batch_dev(vf, F1, dv_d.data_ptr(), fi_d.data_ptr(), N, 0, stream=sptr, costs=costs_d.data_ptr())
+            ms1 = timed(step_stage1, max(3, min(args.steps, 10)), 3) / max(3, min(args.steps, 10))
+            rbar2 = float(np.mean([ranks[k] * ranks[k + 1] for k in range(cfg.dx)]))
+            W1 = 8.0 * rbar2 + 4.0 * cfg.dx * float(max(ranks))
+            stage1 = {"kernels": "k_ft_chains + k_ft_nodes", "fibers": F1, "ms": ms1, "flops_per_node": W1,
+                      "achieved": F1 * N * W1 / (ms1 * 1e-3) / 1e12, "unit": "TFLOP/s"}
+            del costs_d
         achieved = (F * N * W) / (kernel_ms * 1e-3) / 1e12 if world == 1 else (value / world) * W / 1e12
         hbm_bytes = F * N * 8.0 + F * (cfg.dx + 1) * 4.0 + core_cnt * 8.0
         hbm_peak = None
@@ -415,6 +430,7 @@ def main():
                                  "~180 flops per candidate control) over the whole step (all pipeline kernels); stage 2 forms every candidate "
                                  "from shared partial sums (~2 FP64 instructions per candidate), so frac > 1 is algebra, not pipe utilisation -- "
                                  "see dominant_kernel / other_kernels for the ncu pipe counters and the stage-1 fraction",
+                         "stage1_live": (dict(stage1, peak=peak, frac=stage1["achieved"] / peak) if stage1 else None),
                          "dominant_kernel": (_ncu_record() or {}).get("dominant_kernel"),
                          "other_kernels": (_ncu_record() or {}).get("other_kernels"),
                          "hbm": {"algorithmic_bytes_per_step": hbm_bytes, "achieved_gbs": hbm_bytes / (kernel_ms * 1e-3) / 1e9,

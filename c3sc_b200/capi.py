@@ -312,9 +312,10 @@ class Problem:
 
     # ---- device-pointer entry points (ints are raw device addresses) ---------------
     def vi_batch_dev(self, vf: "ValueF", F: int, d_dim_vary: int, d_fixed_ind: int, ldo: int, value: int,
-                     argmin: int = 0, stream: int = 0, rows: int = 0, peers=None, peer_offset: int = 0):
-        """peers: device addresses of every rank's gathered buffer (peer-mapped) for the fused all-gather"""
-        o = BatchOut(value or None, argmin or None, None, None, rows or None, None, None)
+                     argmin: int = 0, stream: int = 0, rows: int = 0, peers=None, peer_offset: int = 0, costs: int = 0):
+        """peers: device addresses of every rank's gathered buffer (peer-mapped) for the fused all-gather;
+        costs alone (no value / argmin / rows): stage 1 only, node-major neighbour values"""
+        o = BatchOut(value or None, argmin or None, None, costs or None, rows or None, None, None)
         if peers:
             o.n_peers = len(peers)
             for g, ptr in enumerate(peers):
