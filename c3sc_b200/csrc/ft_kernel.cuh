@@ -228,30 +228,32 @@ __device__ __forceinline__ void ft_flags_and_indices(const FtArgs &a, int k, int
     const DevProblem &P = a.P;
     const int d = a.ft.d, tid = threadIdx.x, NT = blockDim.x;
     const int N = P.ngrid[k], nj = je - jb;
-    if (tid < FT_FBMAX) { sFid[tid] = tid < nf ? a.perm[gstart + tid] : -1; sWall[tid] = 0; }
+    // one thread per (fiber, dimension): fiber id, fixed index and the neighbour pair of that dimension in one
+    // dependent chain of loads (perm -> fixed_ind), one barrier before anything is consumed
+    if (tid < FT_FBMAX) sWall[tid] = 0;
     __syncthreads();
     for (int e = tid; e < nf * d; e += NT) {
         const int g = e / d, i = e - g * d;
-        sFix[g * d + i] = a.fixed_ind[(size_t)sFid[g] * d + i];
-    }
-    __syncthreads();
-    for (int e = tid; e < nf * d; e += NT) {          // fixed-dimension neighbour pairs
-        const int g = e / d, i = e - g * d;
+        const int fid = a.perm[gstart + g];
+        const int i0 = a.fixed_ind[(size_t)fid * d + i];
+        if (i == 0) sFid[g] = fid;
+        sFix[g * d + i] = i0;
         if (i == k) continue;
         const int slot = i < k ? i : i - 1;
         int lo, hi;
-        if (ft_fixed_pair(P, i, sFix[g * d + i], lo, hi)) sWall[g] = 1;
+        if (ft_fixed_pair(P, i, i0, lo, hi)) sWall[g] = 1;
         if (a.nbr_fixed_in) {
-            lo = a.nbr_fixed_in[(size_t)sFid[g] * 2 * (d - 1) + 2 * slot];
-            hi = a.nbr_fixed_in[(size_t)sFid[g] * 2 * (d - 1) + 2 * slot + 1];
+            lo = a.nbr_fixed_in[(size_t)fid * 2 * (d - 1) + 2 * slot];
+            hi = a.nbr_fixed_in[(size_t)fid * 2 * (d - 1) + 2 * slot + 1];
         }
         sNf[g * 2 * d + 2 * slot] = lo;
         sNf[g * 2 * d + 2 * slot + 1] = hi;
         if (a.nbr_fixed && jb == 0) {
-            a.nbr_fixed[(size_t)sFid[g] * 2 * (d - 1) + 2 * slot] = lo;
-            a.nbr_fixed[(size_t)sFid[g] * 2 * (d - 1) + 2 * slot + 1] = hi;
+            a.nbr_fixed[(size_t)fid * 2 * (d - 1) + 2 * slot] = lo;
+            a.nbr_fixed[(size_t)fid * 2 * (d - 1) + 2 * slot + 1] = hi;
         }
     }
+    if (tid >= nf && tid < FT_FBMAX) sFid[tid] = -1;
     __syncthreads();
     for (int e = tid; e < nf * nj; e += NT) {
         const int g = e / nj, j = jb + (e - g * nj);

@@ -464,30 +464,29 @@ __global__ void __launch_bounds__(FTN_NT, 2) k_ft_nodes(const FtArgs a, const do
 
     ft_flags_and_indices(a, k, nf, gstart, jb, je, sFid, sWall, sFix, sNf, sAbs, nmax);
 
-    // the group's chain records -> shared memory, rank rows zero-padded to a multiple of 4.
-    // Loads are issued four at a time before the first store, so their latencies overlap.
+    // the group's chain records -> shared memory, rank rows zero-padded to a multiple of 4: warp g copies
+    // fiber g's record, eight independent loads per lane in flight before the first store
     {
         const int nl = rk * NVL, nr = rk1 * NVR;                      // valid doubles of the left / right set
-        const int total = FT_FBMAX * SETW;
-        for (int e0 = tid; e0 < total; e0 += 4 * FTN_NT) {
-            double v[4];
+        for (int g = warp; g < FT_FBMAX; g += FTN_NT / 32) {
+            const double *src = g < nf ? sets + (size_t)sFid[g] * SETWG : nullptr;
+            double *dst = sSets + g * SETW;
+            for (int q0 = lane; q0 < SETW; q0 += 8 * 32) {
+                double v[8];
 #pragma unroll
-            for (int u = 0; u < 4; u++) {
-                const int e = e0 + u * FTN_NT;
-                v[u] = 0.0;
-                if (e < total) {
-                    const int g = e / SETW, q = e - g * SETW;
-                    if (g < nf) {
-                        const double *src = sets + (size_t)sFid[g] * SETWG;
+                for (int u = 0; u < 8; u++) {
+                    const int q = q0 + 32 * u;
+                    v[u] = 0.0;
+                    if (src && q < SETW) {
                         if (q < nl) v[u] = __ldg(src + q);
                         else if (q >= offR && q - offR < nr) v[u] = __ldg(src + offRG + (q - offR));
                     }
                 }
-            }
 #pragma unroll
-            for (int u = 0; u < 4; u++) {
-                const int e = e0 + u * FTN_NT;
-                if (e < total) sSets[e] = v[u];
+                for (int u = 0; u < 8; u++) {
+                    const int q = q0 + 32 * u;
+                    if (q < SETW) dst[q] = v[u];
+                }
             }
         }
     }
