@@ -605,6 +605,7 @@ static int run_batch(const DevProblem &P, int model, int arith, Scratch &scr, co
         a.nbr_fixed_in = (b.nbr_fixed_in && d > 1) ? b.nbr_fixed_in + c0 * 2 * (d - 1) : nullptr;
         a.nbr_vary_in = b.nbr_vary_in ? b.nbr_vary_in + 2 * n0 : nullptr;
         a.sets = mma ? (double *)bsets.p : nullptr;
+        a.task_count = cnt + 33;
         rc = launch_ft_costs(a, st);
         if (rc) return fail(C3SC_ECUDA, "FT kernel launch: %s", cudaGetErrorString((cudaError_t)rc));
         g_launches += 1 + mma;

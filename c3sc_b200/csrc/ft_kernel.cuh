@@ -58,6 +58,7 @@ struct FtArgs {
     const int *nbr_fixed_in;  // caller-supplied neighbour indices (valuef_eval_fiber_ind_nn)
     const int *nbr_vary_in;
     double *sets;             // [F * ft_set_width] chain scratch of the tensor-core path; NULL = general kernel
+    int *task_count;          // chain kernel: next (fiber, side) task, zeroed by k_group_fibers
     int nsplit;               // k_ft_nodes: CTAs per group, each owning a contiguous range of node tiles (blockIdx.y)
 };
 
@@ -138,6 +139,7 @@ __global__ void __launch_bounds__(1024) k_group_fibers(int F, int FC, int d, con
         int run = 0;
         for (int k = 0; k < d; k++) { pos[k] = run; kstart[k] = run; kcount[k] = cnt[k]; run += cnt[k]; }
         *act_count = 0;
+        kcount[33] = 0;                                     // task counter of the chain kernel (FtArgs::task_count)
     }
     __syncthreads();
     // the order inside a group does not change any result

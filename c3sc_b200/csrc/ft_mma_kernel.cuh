@@ -96,9 +96,16 @@ __global__ void __launch_bounds__(FTC_NT, KS <= 6 ? C3SC_FTC_MINB : 1) k_ft_chai
     // every value a fragment may touch must be finite (padding rows meet zero rows of the block)
     for (int e = lane; e < cp.perWarpDoubles; e += 32) buf0[e] = 0.0;
 
-    for (int task = blockIdx.x * NW + warp; task < 2 * a.F; task += gridDim.x * NW) {
-        const int f = task >> 1;
-        const bool left = (task & 1) == 0;
+    // Tasks differ in length (a left chain has k steps, a right chain d-1-k): warps take them from a counter,
+    // longest first -- even tasks are right chains over the k-grouped order ascending (k = 0 first), odd tasks
+    // left chains over it descending (k = d-1 first).
+    for (;;) {
+        int task = 0;
+        if (lane == 0) task = atomicAdd(a.task_count, 1);
+        task = __shfl_sync(0xffffffffu, task, 0);
+        if (task >= 2 * a.F) break;
+        const bool left = (task & 1) != 0;
+        const int f = a.perm[left ? a.F - 1 - (task >> 1) : (task >> 1)];
         int k = a.dim_vary[f];
         k = k < 0 ? 0 : (k >= d ? d - 1 : k);
         const int NVL = ft_even_up(1 + 2 * k), NVR = ft_even_up(1 + 2 * (d - 1 - k));
