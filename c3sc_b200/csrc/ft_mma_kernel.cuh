@@ -305,6 +305,9 @@ struct NodeDots {
     int NVL, NVR;
     const int (&slotL)[VT];
     const int (&slotR)[VT][2];
+    const int (&offL)[VT];
+    const int (&offR)[VT][2];
+    bool fast;
     double *cst, *costs;
     long long NS;
     size_t idb;
@@ -330,6 +333,21 @@ struct NodeDots {
 #pragma unroll
                 for (int nb = 0; nb < NR; nb++) dmma_m8n8k4(dr[nb][0], dr[nb][1], au, setR[(4 * ks + tig) * NVR + 8 * nb + gid]);
             }
+        }
+        if (fast) {
+            // full tile, slot-major scratch only (the pipeline's case): one 32-bit element offset per output,
+            // prepared once per CTA; -1 = no such variant
+            double *cb = cst + idb;
+#pragma unroll
+            for (int mt = 0; mt < ML; mt++)
+                if (offL[mt] >= 0) *reinterpret_cast<double2 *>(cb + offL[mt]) = make_double2(dl[mt][0], dl[mt][1]);
+#pragma unroll
+            for (int nb = 0; nb < NR; nb++) {
+#pragma unroll
+                for (int h = 0; h < 2; h++)
+                    if (offR[nb][h] >= 0) cb[offR[nb][h]] = dr[nb][h];
+            }
+            return;
         }
 #pragma unroll
         for (int mt = 0; mt < ML; mt++) {
@@ -521,6 +539,17 @@ __global__ void __launch_bounds__(FTN_NT, 2) k_ft_nodes(const FtArgs a, const do
                                                      : 2 * (d - 1 - ((vv - 1) >> 1)) + ((vv - 1) & 1));
         }
     }
+    // element offsets of this lane's outputs inside the slot-major scratch, relative to cst + fiber row + tile
+    // start (left: nodes 2tig, 2tig+1 of variant row gid; right: node gid of variant columns 2tig, 2tig+1)
+    int outL[VT], outR[VT][2];
+    const bool off32 = a.cst && (long long)CS * a.NS < 0x7fffffffLL && !a.costs && ((a.NS | (long long)a.ldo) & 1) == 0 &&
+                       ((size_t)a.cst & 15) == 0;
+#pragma unroll
+    for (int t = 0; t < VT; t++) {
+        outL[t] = (off32 && slotL[t] >= 0) ? (int)(slotL[t] * a.NS) + 2 * tig : -1;
+#pragma unroll
+        for (int h = 0; h < 2; h++) outR[t][h] = (off32 && slotR[t][h] >= 0) ? (int)(slotR[t][h] * a.NS) + gid : -1;
+    }
     const int offW = tig * ldk + gid, offU = gid * ldk + tig;           // fragment origins inside a node block
     const double *setL = sSets + warp * SETW, *setR = setL + offR;      // dots phase: fiber g = warp
     const double *wg = sW + warp * SW + tig * FTN_TP + gid, *ug = sU + warp * SW + tig * FTN_TP + gid;
@@ -549,7 +578,8 @@ __global__ void __launch_bounds__(FTN_NT, 2) k_ft_nodes(const FtArgs a, const do
             const size_t idb = idf + j0;
             // the tile counts of the variant sets are warp-uniform run-time values: dispatch to a body with
             // compile-time counts, so that no predicated-off DMMA (and its fragment load) is issued at all
-            const NodeDots<KS> nd{setL, setR, wg, ug, NVL, NVR, slotL, slotR, a.cst, a.costs, a.NS, idb, CS, nt, tig, gid};
+            const NodeDots<KS> nd{setL, setR, wg, ug, NVL, NVR, slotL, slotR, outL, outR, off32 && nt == FTN_T && (j0 & 1) == 0,
+                                  a.cst, a.costs, a.NS, idb, CS, nt, tig, gid};
             switch (mtL * 8 + ntR) {
 #define C3SC_ND(L, R) case (L) * 8 + (R): nd.template run<L, R>(); break;
                 C3SC_ND(0, 1) C3SC_ND(0, 2) C3SC_ND(0, 3) C3SC_ND(0, 4)
