@@ -785,10 +785,24 @@ int c3sc_vi_batch(c3sc_problem *p, const c3sc_valuef *vf, size_t F, const int32_
     const size_t n = F * ldo;
     rc = upload_fibers(p, F, dim_vary, fixed_ind);
     if (rc) return rc;
+    // Results are staged on the device and copied chunk by chunk while later chunks compute.  With
+    // C3SC_ZEROCOPY=1 and a page-locked, device-mapped result buffer (cudaHostAlloc / cudaHostRegister, e.g.
+    // torch pin_memory) the control kernels store the values straight into it over PCIe instead -- no
+    // staging buffer, no copy tail; measured SLOWER on B200 + PCIe 5 (2.16 vs 2.45 G node-backups/s end to
+    // end: the stores of a control kernel arrive in bursts of ~100 GB/s and stall it), so it is opt-in.
+    double *mapped = nullptr;
+    {
+        const char *zc = getenv("C3SC_ZEROCOPY");
+        cudaPointerAttributes at;
+        if (zc && zc[0] == '1' && cudaPointerGetAttributes(&at, value) == cudaSuccess && at.type == cudaMemoryTypeHost &&
+            at.devicePointer)
+            mapped = (double *)at.devicePointer;
+        cudaGetLastError();
+    }
     c3sc_batch_out o;
     memset(&o, 0, sizeof o);
-    int bad = p->b_val.reserve(n * 8);
-    o.value = (double *)p->b_val.p;
+    int bad = 0;
+    if (!mapped) { bad |= p->b_val.reserve(n * 8); o.value = (double *)p->b_val.p; }
     if (argmin) { bad |= p->b_arg.reserve(n * 4); o.argmin = (int32_t *)p->b_arg.p; }
     if (bad) return fail(C3SC_ECUDA, "cudaMalloc batch outputs failed");
     BatchArgs b;
@@ -796,7 +810,8 @@ int c3sc_vi_batch(c3sc_problem *p, const c3sc_valuef *vf, size_t F, const int32_
     b.F = F; b.ldo = ldo; b.dim_vary = (const int *)p->b_dv.p; b.fixed_ind = (const int *)p->b_fi.p;
     b.out.value = o.value; b.out.argmin = o.argmin;
     b.mode = MODE_VI;
-    b.copy_stream = p->copy_stream; b.chunk_done = p->chunk_done; b.h_value = value; b.h_argmin = argmin;
+    if (mapped) { b.value_peers[0] = mapped; b.n_peers = 1; b.peer_offset = 0; }
+    b.copy_stream = p->copy_stream; b.chunk_done = p->chunk_done; b.h_value = mapped ? nullptr : value; b.h_argmin = argmin;
     rc = run_batch(p->P, p->model, p->arith, p->scr, &p->grp, vf->ft, b, p->stream);
     if (rc) return rc;
     CK(cudaStreamSynchronize(p->copy_stream));

@@ -179,3 +179,28 @@ def test_grid_walk_equals_table_walk(gpu, name, n, rank, dx, F):
     assert rel_err(val[m], val2[m], scale=np.abs(val2[m]).max()) <= 1e-13
     assert (arg[m] == arg2[m]).mean() > 0.999
     prob.close(); vf.close(); vf2.close()
+
+
+def test_pinned_result_buffer_is_written_in_place(gpu, monkeypatch):
+    """c3sc_vi_batch with C3SC_ZEROCOPY=1 and a page-locked (device-mapped) result buffer: the control
+    kernels store into it directly; same numbers as the staged copy into pageable memory"""
+    import torch
+    monkeypatch.setenv("C3SC_ZEROCOPY", "1")
+    cfg = configs.get_config("lqgnd_reflect", n=14, rank=5, dx=4)
+    prob = capi.Problem(cfg, arith=1)
+    ranks = cfg.ranks()
+    vf = capi.ValueF(cfg.ngrid, ranks, synthetic.random_cores(cfg.ngrid, ranks))
+    F, N = 9000, cfg.n                                         # > 2 * 148 * 1024 nodes / 14: both lanes
+    dv, fi = synthetic.random_fibers(cfg.ngrid, F, seed=21)
+    dv = np.ascontiguousarray(dv, dtype=np.int32); fi = np.ascontiguousarray(fi, dtype=np.int32)
+    want, warg = prob.vi_batch(vf, dv, fi)                     # numpy (pageable) buffers
+    out = torch.full((F * N,), -3.0, dtype=torch.float64).pin_memory()
+    arg = torch.full((F * N,), -9, dtype=torch.int32).pin_memory()
+    for with_arg in (False, True):
+        out.fill_(-3.0)
+        capi.check(capi.lib().c3sc_vi_batch(prob.handle, vf.handle, F, dv.ctypes.data, fi.ctypes.data, N,
+                                            out.data_ptr(), arg.data_ptr() if with_arg else None))
+        assert np.array_equal(out.numpy().reshape(F, N), want)
+        if with_arg:
+            assert np.array_equal(arg.numpy().reshape(F, N), warg)
+    prob.close(); vf.close()
