@@ -153,6 +153,21 @@ C3SC_CLONES static void axpy(double a, const double *restrict x, double *restric
 {
     for (size_t i = 0; i < n; i++) y[i] += a * x[i];
 }
+/* y += a x, returning max |y| of the updated vector (same four-lane maximum as absmax) */
+C3SC_CLONES static double axpy_absmax(double a, const double *restrict x, double *restrict y, size_t n)
+{
+    double m0 = 0, m1 = 0, m2 = 0, m3 = 0;
+    size_t i = 0;
+    for (; i + 4 <= n; i += 4) {
+        const double y0 = y[i] + a * x[i], y1 = y[i + 1] + a * x[i + 1], y2 = y[i + 2] + a * x[i + 2], y3 = y[i + 3] + a * x[i + 3];
+        y[i] = y0; y[i + 1] = y1; y[i + 2] = y2; y[i + 3] = y3;
+        const double b0 = fabs(y0), b1 = fabs(y1), b2 = fabs(y2), b3 = fabs(y3);
+        m0 = b0 > m0 ? b0 : m0; m1 = b1 > m1 ? b1 : m1; m2 = b2 > m2 ? b2 : m2; m3 = b3 > m3 ? b3 : m3;
+    }
+    for (; i < n; i++) { y[i] += a * x[i]; const double b = fabs(y[i]); m0 = b > m0 ? b : m0; }
+    m0 = m1 > m0 ? m1 : m0; m2 = m3 > m2 ? m3 : m2;
+    return m2 > m0 ? m2 : m0;
+}
 C3SC_CLONES static double absmax(const double *x, size_t n)
 {
     double m0 = 0, m1 = 0, m2 = 0, m3 = 0;
@@ -210,23 +225,25 @@ static void qr_explicit_q(double *A, size_t m, size_t n, double *work /* n + m *
  * completion that depends on the well-determined part only.  Returns the numerical rank. */
 #define RANK_EPS 1e-11
 #define TIE_EPS 1e-8     /* see maxvol */
-static size_t qr_basis(double *A, size_t m, size_t n, double *work /* n + m */)
+static size_t qr_basis(double *A, size_t m, size_t n, double *work /* 3n + m */)
 {
-    double *tau = work, *v = work + n;
+    double *tau = work, *vn2 = work + n, *vref = work + 2 * n, *v = work + 3 * n;
     size_t rank = n;
     double ref = 0.0;
+    /* remaining squared column norms, downdated after every reflector (as in LAPACK's dgeqp3) and recomputed
+       exactly once they have lost six digits; the pivot's own norm is always recomputed exactly */
+    for (size_t j = 0; j < n; j++) vn2[j] = vref[j] = dot8(A + j * m, A + j * m, m);
     for (size_t k = 0; k < n; k++) {
         size_t p = k; double best = -1.0;
-        for (size_t j = k; j < n; j++) {
-            const double c2 = dot8(A + j * m + k, A + j * m + k, m - k);
-            v[j] = c2;
-            if (c2 > best) { best = c2; p = j; }
-        }
-        for (size_t j = k; j < p; j++) if (v[j] >= best * (1.0 - TIE_EPS)) { p = j; break; }
-        if (p != k)
+        for (size_t j = k; j < n; j++) if (vn2[j] > best) { best = vn2[j]; p = j; }
+        for (size_t j = k; j < p; j++) if (vn2[j] >= best * (1.0 - TIE_EPS)) { p = j; break; }
+        if (p != k) {
             for (size_t i = 0; i < m; i++) { const double t = A[i + k * m]; A[i + k * m] = A[i + p * m]; A[i + p * m] = t; }
+            double t = vn2[k]; vn2[k] = vn2[p]; vn2[p] = t;
+            t = vref[k]; vref[k] = vref[p]; vref[p] = t;
+        }
         double *ak = A + k * m;
-        const double nrm = sqrt(v[p]);
+        const double nrm = sqrt(dot8(ak + k, ak + k, m - k));
         if (k == 0) ref = nrm;
         if (nrm <= RANK_EPS * ref || nrm == 0.0) { rank = k; break; }
         const double alpha = ak[k] >= 0.0 ? -nrm : nrm;
@@ -239,6 +256,8 @@ static size_t qr_basis(double *A, size_t m, size_t n, double *work /* n + m */)
             const double sc = (aj[k] + dot8(ak + k + 1, aj + k + 1, m - k - 1)) * tau[k];
             aj[k] -= sc;
             axpy(-sc, ak + k + 1, aj + k + 1, m - k - 1);
+            vn2[j] -= aj[k] * aj[k];
+            if (!(vn2[j] > 1e-6 * vref[j])) vn2[j] = vref[j] = dot8(aj + k + 1, aj + k + 1, m - k - 1);
         }
     }
     for (size_t k = rank; k < n; k++) tau[k] = 0.0;
@@ -308,7 +327,7 @@ out:
 /* Symmetric problems (V(x) = V(-x)) make mirrored rows tie exactly in exact arithmetic; which one wins would
  * then depend on the last bits of the operator's values.  Entries within TIE_EPS of the maximum count as
  * tied and the first in scan order wins, so two operators that agree to round-off pick the same rows. */
-static int maxvol(const double *Q, size_t m, size_t n, const char *skip, size_t *P, double *B, double *work /* n*n + n */)
+static int maxvol(const double *Q, size_t m, size_t n, const char *skip, size_t *P, double *B, double *work /* n*n + 2n */)
 {
     /* start rows: Gaussian elimination with row pivoting on a copy */
     memcpy(B, Q, m * n * sizeof(double));
@@ -375,17 +394,16 @@ static int maxvol(const double *Q, size_t m, size_t n, const char *skip, size_t 
         for (size_t i = 0; i < m; i++) bb[i] = 0.0;
         for (size_t a = 0; a < n; a++) axpy(S[a + b * n], Q + a * m, bb, m);
     }
-    /* swaps while some |B[i,j]| > 1 + delta */
+    /* swaps while some |B[i,j]| > 1 + delta; cmax[j] = max |B[:,j]| is kept up to date by the update pass */
+    double *cmax = col + n;
+    for (size_t j = 0; j < n; j++) cmax[j] = absmax(B + j * m, m);
     for (int it = 0; it < 200; it++) {
         size_t bi = 0, bj = 0; double best = 0.0;
-        for (size_t j = 0; j < n; j++) {
-            const double mx = absmax(B + j * m, m);
-            if (mx > best) best = mx;
-        }
+        for (size_t j = 0; j < n; j++) if (cmax[j] > best) best = cmax[j];
         if (best <= 1.0 + 1e-2) break;
         int found = 0;                                                   /* first near-maximal entry, column-major order */
         for (size_t j = 0; j < n && !found; j++) {
-            if (absmax(B + j * m, m) < best * (1.0 - TIE_EPS)) continue;
+            if (cmax[j] < best * (1.0 - TIE_EPS)) continue;
             for (size_t i = 0; i < m; i++)
                 if (fabs(B[i + j * m]) >= best * (1.0 - TIE_EPS) && !(skip && skip[i])) { bi = i; bj = j; found = 1; break; }
         }
@@ -401,12 +419,13 @@ static int maxvol(const double *Q, size_t m, size_t n, const char *skip, size_t 
         for (size_t b = 0; b < n; b++) col[b] = (B[bi + b * m] - (b == bj ? 1.0 : 0.0)) / pv;
         for (size_t b = 0; b < n; b++) {
             if (col[b] == 0.0 || b == bj) continue;
-            axpy(-col[b], B + bj * m, B + b * m, m);
+            cmax[b] = axpy_absmax(-col[b], B + bj * m, B + b * m, m);
         }
         {
             const double f = 1.0 - col[bj];
             double *bb = B + bj * m;
             for (size_t i = 0; i < m; i++) bb[i] *= f;
+            cmax[bj] *= fabs(f);
         }
         P[bj] = bi;
     }
