@@ -24,7 +24,10 @@ namespace c3sc {
 constexpr int FTC_NT = 256;      // chain kernel: 8 warps = 8 tasks in flight per CTA
 constexpr int FTN_NT = 256;      // node kernel: 8 warps
 constexpr int FTN_T = 8;         // nodes per tile (one per warp in the w/u phase)
-constexpr int FTN_TP = 8;        // row stride of a (rank index) row of w / u: 8 nodes padded to 12 (fragment reads conflict-free)
+constexpr int FTN_TP = 9;        // row stride of a (rank index) row of w / u (8 nodes + 1).  With the odd per-fiber stride
+                                 // sw below, a fragment load and the D-fragment stores of w and u take 4 shared-memory
+                                 // wavefronts each, against 4 / 8 / 8 for stride 8; stride 12 would take 2 / 4 / 4 but its
+                                 // 12 kB no longer let two CTAs share an SM (enumerated over strides 8..13, paddings 0..15)
 
 // width of one fiber's record in the chain scratch: both sets, [q][v] with v fastest
 __host__ __device__ inline int ft_set_width(const DevFT &ft)
@@ -396,10 +399,12 @@ struct FtNodePlan {
         for (int i = 0; i <= ft.d; i++) rs = ft.r[i] > rs ? ft.r[i] : rs;
         rs4 = (rs + 3) & ~3;                         // rank rows padded to the MMA k-step
         setw = rs4 * (2 * ft.d + 2) + 8;             // + slack: fragment rows may overrun a set by < 8
-        sw = 8 * ((KS + 1) / 2) * FTN_TP + 2;        // one fiber's w (or u) tile: [rank index][8 nodes]
+        sw = 8 * ((KS + 1) / 2) * FTN_TP + 1;        // one fiber's w (or u) tile: [rank index][8 nodes], odd stride
         int gt = 0;
         for (int k = 0; k < ft.d; k++) {
-            const int g = (FTN_T + 1) * ft.ldq[k] * (int)ft.r[k + 1];    // 8 blocks + one block of zero slack
+            // 8 blocks + zero slack for the fragment rows / columns that run past the last block: the padded
+            // MMA geometry reads at most 7 columns and 4 rows beyond a block (ranks 17..24 on 24-wide tiles)
+            const int g = FTN_T * ft.ldq[k] * (int)ft.r[k + 1] + 8 * ft.ldq[k] + 8;
             gt = g > gt ? g : gt;
         }
         gt = (gt + 1) & ~1;
