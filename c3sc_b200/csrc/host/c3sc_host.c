@@ -900,6 +900,124 @@ double valuef_eval(struct ValueF *v, const double *x)
     return out;
 }
 
+/* ========================== checkpoint / resume (src/valuefunc.c:226-295) === */
+/* The reference saves through C3's function_train_save / _savetxt; those formats belong to the absent
+ * library, so the files written here are this library's own (not interchangeable with .c3 files): ranks, the
+ * nodes the cores live on and the nodal cores, binary (valuef_save) or text with 21 digits (valuef_savetxt).
+ * Loading re-samples the cores on the caller's grid when it differs from the saved one, which is what
+ * function_train_create_nodal does in valuef_load (piecewise-linear cores, zero outside the saved nodes). */
+static const char VF_MAGIC[8] = { 'C', '3', 'S', 'C', 'V', 'F', '0', '1' };
+static int vf_write(struct ValueF *v, FILE *fp, int text)
+{
+    if (!v->xgrid) return 1;
+    if (text) {
+        fprintf(fp, "C3SCVF01 %zu\n", v->d);
+        for (size_t k = 0; k < v->d; k++) fprintf(fp, "%zu ", v->N[k]);
+        fprintf(fp, "\n");
+        for (size_t k = 0; k <= v->d; k++) fprintf(fp, "%zu ", v->ranks[k]);
+        fprintf(fp, "\n");
+        for (size_t k = 0; k < v->d; k++) {
+            for (size_t j = 0; j < v->N[k]; j++) fprintf(fp, "%.21g ", v->xgrid[k][j]);
+            fprintf(fp, "\n");
+            const size_t len = v->N[k] * v->ranks[k] * v->ranks[k + 1];
+            for (size_t e = 0; e < len; e++) fprintf(fp, "%.21g ", v->cores[k][e]);
+            fprintf(fp, "\n");
+        }
+        return ferror(fp) ? 1 : 0;
+    }
+    uint64_t hd = v->d;
+    if (fwrite(VF_MAGIC, 1, 8, fp) != 8 || fwrite(&hd, 8, 1, fp) != 1) return 1;
+    for (size_t k = 0; k < v->d; k++) { uint64_t n = v->N[k]; if (fwrite(&n, 8, 1, fp) != 1) return 1; }
+    for (size_t k = 0; k <= v->d; k++) { uint64_t r = v->ranks[k]; if (fwrite(&r, 8, 1, fp) != 1) return 1; }
+    for (size_t k = 0; k < v->d; k++) {
+        const size_t len = v->N[k] * v->ranks[k] * v->ranks[k + 1];
+        if (fwrite(v->xgrid[k], 8, v->N[k], fp) != v->N[k] || fwrite(v->cores[k], 8, len, fp) != len) return 1;
+    }
+    return 0;
+}
+static struct ValueF *vf_read(FILE *fp, int text, size_t *ngrid, double **xgrid)
+{
+    size_t d = 0, N[C3SC_MAXD], ranks[C3SC_MAXD + 1];
+    double *g[C3SC_MAXD] = { 0 }, *c[C3SC_MAXD] = { 0 }, *cn[C3SC_MAXD] = { 0 };
+    struct ValueF *out = NULL;
+    int ok = 1;
+    if (text) {
+        char magic[16];
+        ok = fscanf(fp, "%15s %zu", magic, &d) == 2 && !strcmp(magic, "C3SCVF01") && d >= 1 && d <= C3SC_MAXD;
+        for (size_t k = 0; ok && k < d; k++) ok = fscanf(fp, "%zu", &N[k]) == 1;
+        for (size_t k = 0; ok && k <= d; k++) ok = fscanf(fp, "%zu", &ranks[k]) == 1;
+    } else {
+        char magic[8];
+        uint64_t t;
+        ok = fread(magic, 1, 8, fp) == 8 && !memcmp(magic, VF_MAGIC, 8) && fread(&t, 8, 1, fp) == 1 && t >= 1 && t <= C3SC_MAXD;
+        d = ok ? (size_t)t : 0;
+        for (size_t k = 0; ok && k < d; k++) { ok = fread(&t, 8, 1, fp) == 1; N[k] = (size_t)t; }
+        for (size_t k = 0; ok && k <= d; k++) { ok = fread(&t, 8, 1, fp) == 1; ranks[k] = (size_t)t; }
+    }
+    for (size_t k = 0; ok && k < d; k++) {
+        ok = N[k] >= 2 && N[k] < ((size_t)1 << 24) && ranks[k] >= 1 && ranks[k + 1] >= 1 && ranks[k] < 4096 && ranks[k + 1] < 4096;
+        if (!ok) break;
+        const size_t len = N[k] * ranks[k] * ranks[k + 1];
+        g[k] = xalloc(N[k], 8); c[k] = xalloc(len, 8);
+        if (text) {
+            for (size_t j = 0; ok && j < N[k]; j++) ok = fscanf(fp, "%lf", &g[k][j]) == 1;
+            for (size_t e = 0; ok && e < len; e++) ok = fscanf(fp, "%lf", &c[k][e]) == 1;
+        } else ok = fread(g[k], 8, N[k], fp) == N[k] && fread(c[k], 8, len, fp) == len;
+    }
+    if (ok) {
+        /* cores on the caller's grid: copied when the nodes agree, else piecewise-linear in the node */
+        for (size_t k = 0; k < d; k++) {
+            const size_t blk = ranks[k] * ranks[k + 1], Nn = ngrid[k];
+            int same = Nn == N[k];
+            for (size_t j = 0; same && j < Nn; j++) same = xgrid[k][j] == g[k][j];
+            cn[k] = xalloc(Nn * blk, 8);
+            if (same) { memcpy(cn[k], c[k], Nn * blk * 8); continue; }
+            for (size_t j = 0; j < Nn; j++) {
+                const double x = xgrid[k][j];
+                if (x < g[k][0] || x > g[k][N[k] - 1]) continue;               /* zero outside the saved nodes */
+                size_t i = 0;
+                while (i + 2 < N[k] && x > g[k][i + 1]) i++;
+                const double w = (x - g[k][i]) / (g[k][i + 1] - g[k][i]);
+                for (size_t e = 0; e < blk; e++) cn[k][j * blk + e] = (1.0 - w) * c[k][i * blk + e] + w * c[k][(i + 1) * blk + e];
+            }
+        }
+        out = valuef_from_cores(d, ngrid, ranks, cn);
+        valuef_set_grid(out, xgrid);
+    }
+    for (size_t k = 0; k < C3SC_MAXD; k++) { free(g[k]); free(c[k]); free(cn[k]); }
+    return out;
+}
+int valuef_save(struct ValueF *v, char *filename)
+{
+    FILE *fp = fopen(filename, "wb");
+    if (!fp) return 1;
+    const int rc = vf_write(v, fp, 0);
+    return fclose(fp) || rc;
+}
+int valuef_savetxt(struct ValueF *v, char *filename)
+{
+    FILE *fp = fopen(filename, "w");
+    if (!fp) return 1;
+    const int rc = vf_write(v, fp, 1);
+    return fclose(fp) || rc;
+}
+struct ValueF *valuef_load(char *filename, size_t *ngrid, double **xgrid)
+{
+    FILE *fp = fopen(filename, "rb");
+    if (!fp) return NULL;                                   /* the examples test for NULL to start afresh */
+    struct ValueF *v = vf_read(fp, 0, ngrid, xgrid);
+    fclose(fp);
+    return v;
+}
+struct ValueF *valuef_loadtxt(char *filename, size_t *ngrid, double **xgrid)
+{
+    FILE *fp = fopen(filename, "r");
+    if (!fp) return NULL;
+    struct ValueF *v = vf_read(fp, 1, ngrid, xgrid);
+    fclose(fp);
+    return v;
+}
+
 /* ========================== solver loops (src/bellman.c:2105-2420) ========== */
 void c3control_add_policy_sim(struct C3Control *c, struct ValueF *pol, struct c3Opt *opt_sim,
                               void (*transform)(size_t, const double *, double *))

@@ -20,8 +20,8 @@
  * requests, TT rounding, rank adaptation, nodal norms).  examples/lqg2d_b200.c is an examples/lqg2d_new-style
  * main() written against this header.
  *
- * NOT mirrored (out of scope): valuef save / load (C3 file formats), the CONSTELM function
- * class, BoundInfo, HashGrid, process_fibers, the BFGS branch of bellman_optimal and every gradient output
+ * NOT mirrored (out of scope): C3's own .c3 file formats (valuef_save / load write this
+ * library's format), the CONSTELM function class, BoundInfo, HashGrid, process_fibers, the BFGS branch of bellman_optimal and every gradient output
  * (grad_* arguments must be NULL), the trajectory simulation of the example tails (cdyn).
  */
 #ifndef C3SC_HOST_H
@@ -239,6 +239,13 @@ struct ValueF *valuef_interp(size_t d, int (*f)(size_t, const double *, double *
 double valuef_norm(struct ValueF *);                                      /* :315, discrete l2 over the nodes */
 double valuef_norm2diff(struct ValueF *, struct ValueF *);                /* :325 */
 double valuef_eval(struct ValueF *, const double *);                      /* :345 */
+/* checkpoint / resume (src/valuefunc.h:51-54).  Own file formats (the reference's are C3's): binary and a
+ * 21-digit text form; loading re-samples the cores on the given grid like function_train_create_nodal.
+ * save: 0 on success.  load: NULL when the file is missing or not one of ours. */
+int valuef_save(struct ValueF *, char *filename);
+struct ValueF *valuef_load(char *filename, size_t *ngrid, double **xgrid);
+int valuef_savetxt(struct ValueF *, char *filename);
+struct ValueF *valuef_loadtxt(char *filename, size_t *ngrid, double **xgrid);
 /* NEW: the nodes a train built with valuef_from_cores lives on (needed by valuef_eval) */
 void valuef_set_grid(struct ValueF *, double *const *xgrid);
 

@@ -411,3 +411,47 @@ def test_pi_regression_norm_from_the_paper(gpu):
     assert abs(100.0 - l2) / 100.0 < 0.1, l2
     assert V.min() > 0 and abs(V[N // 2, N // 2] - V.min()) < 0.05 * V.max()      # bowl centred at the origin
     L.valuef_destroy(cost); L.approx_args_free(a); hp.close()
+
+
+@pytest.mark.gpu
+def test_valuef_save_and_load_round_trip(gpu, tmp_path):
+    """checkpoint / resume (src/valuefunc.c:226-295): binary and text files reproduce the function bit for
+    bit on the same grid; on a finer grid the load re-samples the piecewise-linear cores; a missing file is
+    NULL (the examples then start afresh)"""
+    L = solver_lib()
+    L.valuef_save.argtypes = [vp, C.c_char_p]; L.valuef_savetxt.argtypes = [vp, C.c_char_p]
+    L.valuef_load.argtypes = [C.c_char_p, vp, vp]; L.valuef_load.restype = vp
+    L.valuef_loadtxt.argtypes = [C.c_char_p, vp, vp]; L.valuef_loadtxt.restype = vp
+    cfg = configs.get_config("dubinscar_new", n=12, rank=4)
+    hp = HostProblem(L, cfg, arith=1)
+    port = make_port(cfg)
+    ranks = cfg.ranks()
+    cores = synthetic.random_cores(cfg.ngrid, ranks, seed=31)
+    vf = hp.valuef(ranks, cores)
+    xg = [np.ascontiguousarray(g) for g in port.xgrid]
+    garr = (vp * cfg.dx)(*[g.ctypes.data for g in xg])
+    L.valuef_set_grid(vf, garr)
+    ng = np.ascontiguousarray(cfg.ngrid, np.uintp)
+    for save, load, name in ((L.valuef_save, L.valuef_load, "v.bin"), (L.valuef_savetxt, L.valuef_loadtxt, "v.txt")):
+        f = str(tmp_path / name).encode()
+        assert save(vf, f) == 0
+        back = load(f, po._p(ng), garr)
+        assert back
+        r2, c2 = _host_cores(L, back, cfg.ngrid)
+        assert list(r2) == [int(x) for x in ranks]
+        for a, b in zip(cores, c2):
+            assert np.array_equal(np.asarray(a).reshape(-1), b)
+        assert L.valuef_norm2diff(vf, back) == 0.0
+        L.valuef_destroy(back)
+    assert not L.valuef_load(str(tmp_path / "missing.bin").encode(), po._p(ng), garr)
+    # finer grid: every old node is a new node (2n-1 nodes), so the function agrees there and is linear between
+    fine_n = np.array([2 * int(n) - 1 for n in cfg.ngrid], dtype=np.uintp)
+    fine = [np.ascontiguousarray(np.interp(np.arange(2 * len(g) - 1) / 2.0, np.arange(len(g)), g)) for g in xg]
+    farr = (vp * cfg.dx)(*[g.ctypes.data for g in fine])
+    back = L.valuef_load(str(tmp_path / "v.bin").encode(), po._p(fine_n), farr)
+    assert back
+    ft = po.FT(cfg.ngrid, ranks, cores)
+    for pt in (np.array([0.3, -1.1, 2.0]), np.array([xg[0][3], xg[1][5], xg[2][7]]), np.array([-2.2, 1.7, 0.4])):
+        want = port.ft_eval_linear(ft, np.ascontiguousarray(pt))
+        assert abs(L.valuef_eval(back, po._p(np.ascontiguousarray(pt))) - want) <= 1e-12 * max(1.0, abs(want))
+    L.valuef_destroy(back); L.valuef_destroy(vf); hp.close()
