@@ -6,7 +6,10 @@
  *
  *   gcc -std=c99 -O2 -Iinclude examples/lqg2d_b200.c -Lc3sc_b200/lib -lc3sc_b200 \
  *       -Wl,-rpath,$PWD/c3sc_b200/lib -lm -o build/lqg2d_b200
- *   build/lqg2d_b200 [nodes per dimension] [outer iterations]
+ *   build/lqg2d_b200 [nodes per dimension] [outer iterations] [checkpoint file]
+ *
+ * With a checkpoint file the program resumes from it when it exists and saves the value function into it
+ * at the end, the way the reference examples handle their cost.c3 (examples/dubinscar_new/dubinscar.c:324-354).
  *
  * Prints one line per outer iteration and a final "RESULT norm <nodal l2> u0 <control at (0.5,-0.5)>".
  */
@@ -81,7 +84,10 @@ int main(int argc, char **argv)
     approx_args_set_maxrank(aargs, 12);
     approx_args_set_adapt(aargs, 1);
 
-    struct ValueF *cost = c3control_init_value(c3c, startcost, NULL, aargs, 0);
+    char *checkpoint = argc > 3 ? argv[3] : NULL;
+    struct ValueF *cost = checkpoint ? valuef_load(checkpoint, ngrid, c3control_get_xgrid(c3c)) : NULL;
+    if (cost) printf("resumed from %s\n", checkpoint);
+    else cost = c3control_init_value(c3c, startcost, NULL, aargs, 0);
     struct Diag *diag = NULL;
     for (size_t it = 0; it < outer; it++) {
         struct ValueF *next = c3control_pi_solve(c3c, 5, 1e-7, cost, aargs, opt, 0, &diag);
@@ -96,6 +102,7 @@ int main(int argc, char **argv)
     double x[2] = { 0.5, -0.5 }, u[1] = { 0.0 };
     if (c3control_controller(0.0, x, u, c3c)) return 4;
     printf("RESULT norm %.12e u0 %.3f\n", valuef_norm(cost), u[0]);
+    if (checkpoint && valuef_save(cost, checkpoint)) fprintf(stderr, "lqg2d_b200: could not write %s\n", checkpoint);
 
     diag_destroy(&diag);
     valuef_destroy(cost);

@@ -62,3 +62,21 @@ def test_example_program_runs_the_reference_call_sequence(gpu):
         cost = tmp
     assert abs(L.valuef_norm(cost) - norm) <= 1e-9 * norm
     L.valuef_destroy(cost); L.approx_args_free(a); hp.close()
+
+
+@pytest.mark.gpu
+def test_example_program_resumes_from_its_checkpoint(gpu, tmp_path):
+    """second run with the same checkpoint file continues where the first stopped: its first outer
+    iteration moves the function less than the first run's last one did"""
+    _build()
+    ck = str(tmp_path / "cost.c3sc")
+    r1 = subprocess.run([EXE, "20", "3", ck], capture_output=True, text=True, timeout=300)
+    assert r1.returncode == 0 and os.path.exists(ck), r1.stderr
+    r2 = subprocess.run([EXE, "20", "1", ck], capture_output=True, text=True, timeout=300)
+    assert r2.returncode == 0 and "resumed from" in r2.stdout, r2.stderr
+    d1 = [float(x) for x in re.findall(r"diff (\S+)", r1.stdout)]
+    d2 = [float(x) for x in re.findall(r"diff (\S+)", r2.stdout)]
+    assert len(d1) == 3 and len(d2) == 1 and d2[0] < d1[-1]
+    n1 = float(re.search(r"RESULT norm (\S+)", r1.stdout).group(1))
+    n2 = float(re.search(r"RESULT norm (\S+)", r2.stdout).group(1))
+    assert n2 > n1                      # the cost-to-go keeps growing towards its fixed point
