@@ -24,10 +24,12 @@ namespace c3sc {
 constexpr int FTC_NT = 256;      // chain kernel: 8 warps = 8 tasks in flight per CTA
 constexpr int FTN_NT = 256;      // node kernel: 8 warps
 constexpr int FTN_T = 8;         // nodes per tile (one per warp in the w/u phase)
-constexpr int FTN_TP = 9;        // row stride of a (rank index) row of w / u (8 nodes + 1).  With the odd per-fiber stride
-                                 // sw below, a fragment load and the D-fragment stores of w and u take 4 shared-memory
-                                 // wavefronts each, against 4 / 8 / 8 for stride 8; stride 12 would take 2 / 4 / 4 but its
-                                 // 12 kB no longer let two CTAs share an SM (enumerated over strides 8..13, paddings 0..15)
+constexpr int FTN_TP = 8;        // row stride of a (rank index) row of w / u: 8 nodes, XOR-swizzled (ftn_swz): element
+                                 // (rank row a, node j) of a fiber's tile sits at a*8 + (j ^ swz(a)).  With the odd
+                                 // per-fiber stride sw below, the D-fragment stores of w take 2 shared-memory wavefronts
+                                 // (the minimum for 64-bit accesses), those of u 4, a fragment load 2 -- against 8 / 8 / 4
+                                 // unswizzled and 4 / 4 / 4 for a plain stride of 9 (layouts enumerated off line)
+__host__ __device__ constexpr int ftn_swz(int a) { return (5 * ((a >> 1) & 1)) ^ ((a >> 2) & 1); }
 
 // width of one fiber's record in the chain scratch: both sets, [q][v] with v fastest
 __host__ __device__ inline int ft_set_width(const DevFT &ft)
@@ -288,12 +290,14 @@ __device__ __forceinline__ void node_wu(const double *gj, int offW, int offU, in
 #pragma unroll
     for (int mt = 0; mt < MT; mt++) {
         if constexpr (DO_W) {                                    // D: row a = 8mt+gid, cols fiber 2*tig, 2*tig+1
-            sW[(2 * tig) * SW + (8 * mt + gid) * FTN_TP + warp] = dw[mt][0];
-            sW[(2 * tig + 1) * SW + (8 * mt + gid) * FTN_TP + warp] = dw[mt][1];
+            const int jw = warp ^ ftn_swz(gid);                  // swz(8mt + gid) = swz(gid)
+            sW[(2 * tig) * SW + (8 * mt + gid) * FTN_TP + jw] = dw[mt][0];
+            sW[(2 * tig + 1) * SW + (8 * mt + gid) * FTN_TP + jw] = dw[mt][1];
         }
         if constexpr (DO_U) {                                    // D: row fiber gid, cols b = 8nb+2tig, +1
-            sU[gid * SW + (8 * mt + 2 * tig) * FTN_TP + warp] = du[mt][0];
-            sU[gid * SW + (8 * mt + 2 * tig + 1) * FTN_TP + warp] = du[mt][1];
+            const int ju = warp ^ ftn_swz(2 * tig);              // swz(8mt + 2tig + h) = swz(2tig)
+            sU[gid * SW + (8 * mt + 2 * tig) * FTN_TP + ju] = du[mt][0];
+            sU[gid * SW + (8 * mt + 2 * tig + 1) * FTN_TP + ju] = du[mt][1];
         }
     }
 }
@@ -304,7 +308,8 @@ __device__ __forceinline__ void node_wu(const double *gj, int offW, int offU, in
 template <int KS>
 struct NodeDots {
     static constexpr int VT = (2 * MAXD + 7) / 8;
-    const double *setL, *setR, *wg, *ug;
+    const double *setL, *setR, *wg, *ug;     // wg / ug: row tig of this fiber's w / u tile (node column added per k-step)
+    int jl0, jl1;                            // swizzled node column of this lane for even / odd k-steps: gid ^ swz(4ks + tig)
     int NVL, NVR;
     const int (&slotL)[VT];
     const int (&slotR)[VT][2];
@@ -327,12 +332,12 @@ struct NodeDots {
 #pragma unroll
         for (int ks = 0; ks < KS; ks++) {
             if constexpr (ML > 0) {
-                const double bw = wg[ks * 4 * FTN_TP];               // B fragment (row a, col jl), shared by the v tiles
+                const double bw = wg[ks * 4 * FTN_TP + ((ks & 1) ? jl1 : jl0)];   // B fragment (row a = 4ks+tig, col jl = gid)
 #pragma unroll
                 for (int mt = 0; mt < ML; mt++) dmma_m8n8k4(dl[mt][0], dl[mt][1], setL[(4 * ks + tig) * NVL + 8 * mt + gid], bw);
             }
             if constexpr (NR > 0) {
-                const double au = ug[ks * 4 * FTN_TP];               // A fragment (row jl, col b)
+                const double au = ug[ks * 4 * FTN_TP + ((ks & 1) ? jl1 : jl0)];   // A fragment (row jl = gid, col b = 4ks+tig)
 #pragma unroll
                 for (int nb = 0; nb < NR; nb++) dmma_m8n8k4(dr[nb][0], dr[nb][1], au, setR[(4 * ks + tig) * NVR + 8 * nb + gid]);
             }
@@ -399,7 +404,7 @@ struct FtNodePlan {
         for (int i = 0; i <= ft.d; i++) rs = ft.r[i] > rs ? ft.r[i] : rs;
         rs4 = (rs + 3) & ~3;                         // rank rows padded to the MMA k-step
         setw = rs4 * (2 * ft.d + 2) + 8;             // + slack: fragment rows may overrun a set by < 8
-        sw = 8 * ((KS + 1) / 2) * FTN_TP + 1;        // one fiber's w (or u) tile: [rank index][8 nodes], odd stride
+        sw = 8 * ((KS + 1) / 2) * FTN_TP + 1;        // one fiber's w (or u) tile: [rank index][8 nodes, swizzled], odd stride
         int gt = 0;
         for (int k = 0; k < ft.d; k++) {
             // 8 blocks + zero slack for the fragment rows / columns that run past the last block: the padded
@@ -557,7 +562,8 @@ __global__ void __launch_bounds__(FTN_NT, 2) k_ft_nodes(const FtArgs a, const do
     }
     const int offW = tig * ldk + gid, offU = gid * ldk + tig;           // fragment origins inside a node block
     const double *setL = sSets + warp * SETW, *setR = setL + offR;      // dots phase: fiber g = warp
-    const double *wg = sW + warp * SW + tig * FTN_TP + gid, *ug = sU + warp * SW + tig * FTN_TP + gid;
+    const double *wg = sW + warp * SW + tig * FTN_TP, *ug = sU + warp * SW + tig * FTN_TP;
+    const int jl0 = gid ^ ftn_swz(tig), jl1 = gid ^ ftn_swz(4 + tig);
     const size_t idf = warp < nf ? (size_t)sFid[warp] * a.ldo : 0;
 
     unsigned ph0 = 0, ph1 = 0;                             // mbarrier phase parity of the two buffers
@@ -583,7 +589,7 @@ __global__ void __launch_bounds__(FTN_NT, 2) k_ft_nodes(const FtArgs a, const do
             const size_t idb = idf + j0;
             // the tile counts of the variant sets are warp-uniform run-time values: dispatch to a body with
             // compile-time counts, so that no predicated-off DMMA (and its fragment load) is issued at all
-            const NodeDots<KS> nd{setL, setR, wg, ug, NVL, NVR, slotL, slotR, outL, outR, off32 && nt == FTN_T && (j0 & 1) == 0,
+            const NodeDots<KS> nd{setL, setR, wg, ug, jl0, jl1, NVL, NVR, slotL, slotR, outL, outR, off32 && nt == FTN_T && (j0 & 1) == 0,
                                   a.cst, a.costs, a.NS, idb, CS, nt, tig, gid};
             switch (mtL * 8 + ntR) {
 #define C3SC_ND(L, R) case (L) * 8 + (R): nd.template run<L, R>(); break;
