@@ -618,8 +618,9 @@ int c3sc_cross_run(c3sc_cross *c, c3sc_fiber_batch_fn f, void *arg, const c3sc_c
         rc = eval_core(c, 0, f, arg, dv, fi, vals, T, &nfib);
         if (rc) goto done;
         store_core(T, 1, c->n[0], c->r[1], cores[0]);
-        /* ---- change of the train against the previous sweep pair (valuef_norm2diff idea) -------- */
-        {
+        /* ---- change of the train against the previous sweep pair (valuef_norm2diff idea); skipped when
+                nobody asks for it (no tolerance, no output, not verbose): a fifth of a sweep's host time ---- */
+        if (tol > 0.0 || rel_change || verbose) {
             double *w1 = work, *w2 = work + rmax * rmax, *w3 = work + 2 * rmax * rmax;
             const double t_ = now_s();
             const double aa = tt_dot(d, c->n, c->r, cores, cores, w1, w2, w3);
