@@ -66,6 +66,7 @@ EXPORTS = [
     "c3sc_valuef_eval_batch", "c3sc_policy_eval_batch",
     "c3sc_cross_index_sets", "c3sc_cores_round", "c3sc_cross_adapt_capacity", "c3sc_cross_set_ranks", "c3sc_cross_run_adapt", "c3sc_cross_run_vi_adapt",
     "c3sc_peer_buffer_create", "c3sc_peer_buffer_open", "c3sc_peer_buffer_close",
+    "c3sc_fibers_check",
 ]
 
 _lib = None
@@ -99,6 +100,7 @@ def lib() -> C.CDLL:
         L.c3sc_pi_batch_dev.argtypes = [vp, vp, vp, sz, vp, vp, sz, i32, vp, vp, vp, vp]
         L.c3sc_vi_batch.argtypes = [vp, vp, sz, vp, vp, sz, vp, vp]
         L.c3sc_vi_batch_debug.argtypes = [vp, vp, sz, vp, vp, sz, vp, vp, vp, vp, vp, vp, vp]
+        L.c3sc_fibers_check.argtypes = [vp, sz, vp, vp]
         L.c3sc_pi_batch.argtypes = [vp, vp, vp, sz, vp, vp, sz, i32, vp, vp, vp]
         L.c3sc_transition_batch.argtypes = [vp, sz, vp, vp, vp, vp, vp]
         L.c3sc_model_eval.argtypes = [vp, sz, vp, vp, vp, vp, vp, vp, vp]
@@ -232,6 +234,11 @@ class Problem:
 
     def check(self):
         check(lib().c3sc_problem_check(self.handle))
+
+    def fibers_check(self, dim_vary, fixed_ind):
+        """c3sc_fibers_check: raises C3scError naming the first descriptor outside the grid."""
+        dv, fi, F = _fibers(dim_vary, fixed_ind, self.dx)
+        check(lib().c3sc_fibers_check(self.handle, F, _ptr(dv), _ptr(fi)))
 
     # ---- host-buffer entry points -----------------------------------------------
     def vi_batch(self, vf: "ValueF", dim_vary, fixed_ind, want_argmin=True):

@@ -734,6 +734,25 @@ static int finish(c3sc_problem *p)
     return C3SC_OK;
 }
 
+int c3sc_fibers_check(const c3sc_problem *p, size_t F, const int32_t *dim_vary, const int32_t *fixed_ind)
+{
+    if (!p) return fail(C3SC_EINVAL, "null problem");
+    if (F && (!dim_vary || !fixed_ind)) return fail(C3SC_EINVAL, "null fiber descriptors");
+    const uint32_t d = (uint32_t)p->P.dx;
+    for (size_t f = 0; f < F; f++) {
+        unsigned bad = (uint32_t)dim_vary[f] >= d;
+        const int32_t *fi = fixed_ind + f * d;
+        for (uint32_t i = 0; i < d; i++) bad |= (uint32_t)fi[i] >= (uint32_t)p->P.ngrid[i];
+        if (!bad) continue;
+        if ((uint32_t)dim_vary[f] >= d)
+            return fail(C3SC_EINVAL, "fiber %zu: dim_vary=%d outside [0, %u)", f, (int)dim_vary[f], d);
+        for (uint32_t i = 0; i < d; i++)
+            if ((uint32_t)fi[i] >= (uint32_t)p->P.ngrid[i])
+                return fail(C3SC_EINVAL, "fiber %zu: fixed_ind[%u]=%d outside [0, %d)", f, i, (int)fi[i], p->P.ngrid[i]);
+    }
+    return C3SC_OK;
+}
+
 int c3sc_vi_batch_debug(c3sc_problem *p, const c3sc_valuef *vf, size_t F, const int32_t *dim_vary,
                         const int32_t *fixed_ind, size_t ldo, double *value, int32_t *argmin, int32_t *absorbed,
                         double *costs, double *rows, int32_t *nbr_vary, int32_t *nbr_fixed)
@@ -742,6 +761,8 @@ int c3sc_vi_batch_debug(c3sc_problem *p, const c3sc_valuef *vf, size_t F, const 
     if (rc) return rc;
     if (!dim_vary || !fixed_ind || !value) return fail(C3SC_EINVAL, "null fiber descriptors / value buffer");
     if (F == 0) return C3SC_OK;
+    rc = c3sc_fibers_check(p, F, dim_vary, fixed_ind);
+    if (rc) return rc;
     const size_t dx = p->P.dx, n = F * ldo;
     rc = upload_fibers(p, F, dim_vary, fixed_ind);
     if (rc) return rc;

@@ -154,6 +154,18 @@ int  c3sc_valuef_device_buffer(c3sc_valuef *vf, double **dev, size_t *count);
 int  c3sc_valuef_commit(c3sc_valuef *vf, void *stream);
 void c3sc_valuef_destroy(c3sc_valuef *vf);
 
+/* ---- fiber descriptors --------------------------------------------------- */
+/* A fiber is (dim_vary, fixed_ind[dx]): what convert_fiber_to_ind (src/nodeutil.c:437-470) decodes from
+ * the reference's point list.  PRECONDITION of every batch entry below: 0 <= dim_vary < dx and
+ * 0 <= fixed_ind[i] < ngrid[i] (the slot of the varying dimension is ignored by the kernels but must be
+ * in range too; the reference stores the first node's index there, i.e. 0).  The reference-facing
+ * wrappers (bellman_vi / bellman_pi in c3sc_host.h) produce descriptors by decoding and so cannot
+ * violate it; the batch entries do NOT re-check -- a scan of F*(dx+1) integers ahead of the first launch
+ * costs 5-15 % of a 65 536-fiber step -- except c3sc_vi_batch_debug.  c3sc_fibers_check is that scan for
+ * callers who build descriptors themselves: HOST arrays, no device work; C3SC_EINVAL names the first
+ * offending fiber in c3sc_last_error().                                                              */
+int c3sc_fibers_check(const c3sc_problem *p, size_t F, const int32_t *dim_vary, const int32_t *fixed_ind);
+
 /* ---- the hot path, device-resident arguments ---------------------------- */
 /* bellman_vi over F fibers (src/bellman.c:1295-1423, memo dropped: backups are
  * pure).  d_dim_vary [F], d_fixed_ind [F*dx] int32 device arrays.  stream is

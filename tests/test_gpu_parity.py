@@ -230,6 +230,34 @@ def test_errors_are_loud(gpu):
     prob.close(); vf_bad.close()
 
 
+def test_fiber_descriptors_outside_the_grid_are_refused(gpu):
+    """c3sc_fibers_check / the debug entry: the batch analogue of convert_fiber_to_ind's non-zero
+    returns (src/nodeutil.c:437-470) -- a descriptor that names no grid node is an error, not a read
+    outside the cores."""
+    cfg = configs.get_config("dubinscar_new", n=12, rank=3)
+    prob = capi.Problem(cfg)
+    ranks, cores, ft = make_ft(cfg)
+    vf = capi.ValueF(cfg.ngrid, ranks, cores)
+    dv, fi = synthetic.random_fibers(cfg.ngrid, 9)
+    prob.fibers_check(dv, fi)
+    prob.fibers_check(dv[:0], fi[:0])                                  # empty batch
+    for f, (bad_dv, slot, bad_fi) in enumerate([(3, None, None), (-1, None, None), (None, 1, 12), (None, 2, -1)]):
+        dv2, fi2 = dv.copy(), fi.copy()
+        if bad_dv is not None:
+            dv2[4 + f] = bad_dv
+        else:
+            fi2[4 + f, slot] = bad_fi
+        with pytest.raises(capi.C3scError, match=f"fiber {4 + f}"):
+            prob.fibers_check(dv2, fi2)
+        with pytest.raises(capi.C3scError, match=f"fiber {4 + f}"):
+            prob.vi_batch_debug(vf, dv2, fi2)
+    out = prob.vi_batch_debug(vf, dv, fi)                              # the refusals left the problem usable
+    port = po.Port(cfg, prob.xgrid, prob.h2, prob.t, prob.obs_lb, prob.obs_ub)
+    oval, _ = port.vi_batch(ft, dv, fi)
+    assert rel_err(out["value"], oval) <= RTOL
+    prob.close(); vf.close()
+
+
 import os as _os
 _GOLD = _os.path.join(_os.path.dirname(__file__), "golden")
 
