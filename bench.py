@@ -65,7 +65,7 @@ class ClockSampler:
         self.proc = None
         self.lines = []
         self.nvml = None
-        self.sm, self.mask, self.max_mhz = [], 0, None
+        self.sm, self.ts, self.mask, self.max_mhz = [], [], 0, None
         self.running = False
         try:
             import pynvml
@@ -81,14 +81,22 @@ class ClockSampler:
     def _poll(self):
         while self.running:
             try:
-                self.sm.append(float(self.nvml.nvmlDeviceGetClockInfo(self.handle, self.nvml.NVML_CLOCK_SM)))
+                mhz = float(self.nvml.nvmlDeviceGetClockInfo(self.handle, self.nvml.NVML_CLOCK_SM))
                 self.mask |= int(self.reasons_fn(self.handle))
+                self.sm.append(mhz)
+                self.ts.append(time.perf_counter())         # when the answer arrived
             except Exception:
                 pass
             time.sleep(0.002)
 
     def count(self) -> int:
         return len(self.sm) if self.nvml is not None else len(self.lines)
+
+    def count_between(self, t0: float, t1: float, before: int) -> int:
+        """samples answered inside the wall-clock window [t0, t1] (nvidia-smi fallback: lines read since `before`)"""
+        if self.nvml is None:
+            return max(0, len(self.lines) - before)
+        return sum(1 for t in list(self.ts) if t0 <= t <= t1)
 
     def start(self):
         if self.nvml is not None:
@@ -265,7 +273,7 @@ def workload_config(cfg, rank_ft, F, args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default="lqgnd_reflect", help="lqgnd_reflect = examples/lqgnd -t 1 (every node a full backup); lqgnd = absorbing faces")
@@ -426,18 +434,21 @@ def main():
             raise SystemExit("fused all-gather differs from the NCCL all-gather")
         del ref_g
 
+    # The sampler runs from the warm-up on (one NVML query takes ~20 ms on these boxes, about the whole timed
+    # region at the default K: a query has to be in flight when the region starts to be answered inside it);
+    # warm-up, timed steps and the steps below are the identical load.
     sampler = ClockSampler(local)
-    launches0 = capi.lib().c3sc_launch_count()
+    sampler.start()
     for _ in range(args.warmup):
         step_resident()
     torch.cuda.synchronize(dev)
     launches0 = capi.lib().c3sc_launch_count()
-    sampler.start()
+    seen0, wall0 = sampler.count(), time.perf_counter()
     ms_total = timed(step_resident, args.steps, 0)
+    wall1 = time.perf_counter()
     launches = capi.lib().c3sc_launch_count() - launches0
-    # one NVML query takes ~20 ms on these boxes, about the whole timed region: keep the identical load
-    # running (untimed) until the sampler has seen it a few times
-    in_region, extra = sampler.count(), 0
+    # keep the same load running (untimed) until the sampler has seen it a few times
+    in_region, extra = sampler.count_between(wall0, wall1, seen0), 0
     while (extra < 40) if world > 1 else (sampler.count() < 5 and extra < 400):   # fixed count under torchrun: the step has collectives
         step_resident()
         extra += 1
