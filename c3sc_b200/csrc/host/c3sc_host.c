@@ -97,6 +97,17 @@ int boundary_in_obstacle(const struct Boundary *b, const double *x)
     return 0;
 }
 
+double outer_bound_dim(const struct Boundary *b, size_t dim, double x, int *map)
+{   /* boundary.c:577-597: only a PERIODIC face maps; left is tested first */
+    *map = 0;
+    if (x <= b->lo[dim]) {
+        if (b->type[dim] == PERIODIC) { *map = 1; return b->hi[dim]; }
+    } else if (x >= b->hi[dim]) {
+        if (b->type[dim] == PERIODIC) { *map = 2; return b->lo[dim]; }
+    }
+    return x;
+}
+
 /* ========================== dynamics containers ============================ */
 struct Drift { size_t dx, du; c3sc_dyn_cb b; void *bargs; };
 struct Diff  { size_t dx, du, dw; c3sc_dyn_cb s; void *sargs; };
@@ -124,6 +135,8 @@ size_t diff_get_dw(struct Diff *d) { return d->dw; }
 struct Dyn *dyn_alloc(struct Drift *a, struct Diff *b) { struct Dyn *d = xalloc(1, sizeof *d); d->drift = a; d->diff = b; return d; }
 void dyn_free(struct Dyn *d) { free(d); }
 void dyn_free_deep(struct Dyn *d) { if (d) { drift_free(d->drift); diff_free(d->diff); free(d); } }
+struct Dyn *dyn_copy_deep(struct Dyn *o) { return o ? dyn_alloc(drift_copy(o->drift), diff_copy(o->diff)) : NULL; }
+void dyn_init_ref(struct Dyn *d, struct Drift *a, struct Diff *b) { d->drift = a; d->diff = b; }
 size_t dyn_get_dx(struct Dyn *d) { return d->drift->dx; }
 size_t dyn_get_dw(struct Dyn *d) { return d->diff->dw; }
 size_t dyn_get_du(struct Dyn *d) { return d->drift->du; }
@@ -214,6 +227,15 @@ int valuef_eval_fiber_ind_nn(struct ValueF *vf, const size_t *fixed_ind, size_t 
     if (!rc) memcpy(out, tmp, N * (2 * d + 1) * sizeof(double));
     free(nv); free(tmp);
     return rc;
+}
+
+/* src/util.c:995-1006 */
+size_t uniform_stride(size_t N, size_t M)
+{
+    size_t stride = 1;
+    if (M < 2) return 0;
+    while (stride * (M - 1) < N - 1) stride++;
+    return stride - 1;
 }
 
 /* ========================== workspace ====================================== */

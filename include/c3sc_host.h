@@ -47,6 +47,8 @@ void boundary_add_obstacle(struct Boundary *, double *, double *);       /* :470
 void boundary_external_set_type(struct Boundary *, size_t, char *);      /* :486 */
 enum EBTYPE boundary_type_dim(const struct Boundary *, size_t, int);     /* :604 */
 int boundary_in_obstacle(const struct Boundary *, const double *);       /* :668 */
+/* x mapped through a PERIODIC face: the opposite bound and *map = 1 (x <= left) / 2 (x >= right); else x, 0 */
+double outer_bound_dim(const struct Boundary *, size_t, double, int *);  /* :577 */
 
 /* ---- dynamics.h ------------------------------------------------------------ */
 struct Drift;
@@ -68,11 +70,17 @@ size_t diff_get_dw(struct Diff *);
 struct Dyn *dyn_alloc(struct Drift *, struct Diff *);                    /* :265 */
 void dyn_free(struct Dyn *);
 void dyn_free_deep(struct Dyn *);
+struct Dyn *dyn_copy_deep(struct Dyn *);                                 /* :279 */
+void dyn_init_ref(struct Dyn *, struct Drift *, struct Diff *);          /* :307 */
 size_t dyn_get_dx(struct Dyn *);
 size_t dyn_get_dw(struct Dyn *);
 size_t dyn_get_du(struct Dyn *);
 int dyn_eval(struct Dyn *, double, const double *, const double *, double *, double *, double *, double *);
 
+/* ---- util.h --------------------------------------------------------------- */
+/* largest stride s with s*(M-1) <= N-1 reached by the reference's search: the start index sets of the
+ * cross approximation (src/util.c:995-1006).  M < 2 returns 0 (the reference does not terminate there). */
+size_t uniform_stride(size_t, size_t);
 /* ---- util.h: Workspace (iteration counters; the memo tables are dropped) ------ */
 struct Workspace;
 struct Workspace *workspace_alloc(size_t, size_t, size_t, size_t);       /* src/util.c:717 */

@@ -220,6 +220,35 @@ def test_host_containers_without_gpu():
     assert L.convert_fiber_to_ind(3, 10, po._p(x), po._p(ng), xg, po._p(fi), C.byref(kk)) == 2
     x[0, 0] += 1e-9
     assert L.convert_fiber_to_ind(3, 11, po._p(x), po._p(ng), xg, po._p(fi), C.byref(kk)) == 1
+    # outer_bound_dim (src/boundary.c:577-597): only the periodic dimension maps, left face first
+    L.outer_bound_dim.restype = dbl
+    L.outer_bound_dim.argtypes = [vp, sz, dbl, C.POINTER(C.c_int)]
+    mp = C.c_int(7)
+    assert L.outer_bound_dim(b, 2, cfg.lb[2], C.byref(mp)) == cfg.ub[2] and mp.value == 1
+    assert L.outer_bound_dim(b, 2, cfg.ub[2] + 0.5, C.byref(mp)) == cfg.lb[2] and mp.value == 2
+    assert L.outer_bound_dim(b, 2, 0.25, C.byref(mp)) == 0.25 and mp.value == 0
+    assert L.outer_bound_dim(b, 0, cfg.lb[0] - 1.0, C.byref(mp)) == cfg.lb[0] - 1.0 and mp.value == 0   # absorbing: no map
+    # uniform_stride (src/util.c:995-1006)
+    L.uniform_stride.restype = sz
+    L.uniform_stride.argtypes = [sz, sz]
+    assert [L.uniform_stride(100, m) for m in (2, 5, 20, 100)] == [98, 24, 5, 0]
+    assert L.uniform_stride(60, 3) == 29 and L.uniform_stride(7, 1) == 0
+    # dyn_copy_deep / dyn_init_ref (src/dynamics.c:279-312)
+    for name in ("drift_alloc", "diff_alloc", "dyn_alloc", "dyn_copy_deep"):
+        getattr(L, name).restype = vp
+    L.drift_alloc.argtypes = [sz, sz]; L.diff_alloc.argtypes = [sz, sz, sz]; L.dyn_alloc.argtypes = [vp, vp]
+    L.dyn_copy_deep.argtypes = [vp]; L.dyn_init_ref.argtypes = [vp, vp, vp]; L.dyn_free_deep.argtypes = [vp]; L.dyn_free.argtypes = [vp]
+    for name in ("dyn_get_dx", "dyn_get_du", "dyn_get_dw"):
+        getattr(L, name).restype = sz; getattr(L, name).argtypes = [vp]
+    dyn = L.dyn_alloc(L.drift_alloc(3, 1), L.diff_alloc(3, 1, 3))
+    cp = L.dyn_copy_deep(dyn)
+    assert cp and cp != dyn and (L.dyn_get_dx(cp), L.dyn_get_du(cp), L.dyn_get_dw(cp)) == (3, 1, 3)
+    assert L.dyn_copy_deep(None) is None
+    shell = L.dyn_alloc(None, None)
+    d5, f5 = L.drift_alloc(5, 2), L.diff_alloc(5, 2, 4)
+    L.dyn_init_ref(shell, d5, f5)
+    assert (L.dyn_get_dx(shell), L.dyn_get_du(shell), L.dyn_get_dw(shell)) == (5, 2, 4)
+    L.dyn_free_deep(shell); L.dyn_free_deep(cp); L.dyn_free_deep(dyn)
     L.c3control_destroy(c3c)
 
 
