@@ -4,6 +4,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <mutex>
 #include <vector>
 #include "dev_types.h"
 #define C3SC_FT_TYPES_ONLY
@@ -14,7 +15,8 @@ namespace c3sc {
 int launch_control_lqg_lo(int dx, int arith, const CtlArgs &a, int pi_eval, cudaStream_t st);
 int launch_control_lqg_hi(int dx, int arith, const CtlArgs &a, int pi_eval, cudaStream_t st);
 int launch_control_misc(int model, int dx, int arith, const CtlArgs &a, int pi_eval, cudaStream_t st);
-int launch_group_fibers(int F, int FC, int d, const int *dim_vary, int *perm, int *cnt_all, cudaStream_t st);
+int launch_group_fibers(const DevProblem &P, int F, int FC, const int *dim_vary, const int *fixed_ind, int *perm, int *cnt_all,
+                        cudaStream_t st);
 int launch_pack_cores(const DevFT &ft, double *baseT, double *baseP, double *baseQ, cudaStream_t st);
 long long ft_padded_layout(DevFT &ft);
 long long ft_compact_layout(DevFT &ft);
@@ -190,6 +192,7 @@ struct c3sc_problem {
     cudaStream_t copy_stream = nullptr;      // device->host copies of finished chunks
     cudaEvent_t chunk_done = nullptr;
     DevBuf b_dv, b_fi, b_val, b_arg, b_abs, b_costs, b_rows, b_nv, b_nf, b_misc[8];
+    c3sc_valuef *vf_flags = nullptr;         // rank-1 zero train for the flags-only entry (c3sc_fiber_flags_batch)
 };
 
 struct c3sc_valuef {
@@ -198,6 +201,21 @@ struct c3sc_valuef {
     size_t count = 0;
     std::vector<size_t> len;
 };
+
+// device error word of a problem: [0] transition normaliser < 1e-14 seen, [1] a fiber descriptor outside the
+// grid seen (k_group_fibers), [2] smallest such fiber id, [3] spare
+static const int k_err_clear[4] = {0, 0, 0x7fffffff, 0};
+static int read_error_word(c3sc_problem *p)
+{
+    int w[4] = {0, 0, 0, 0};
+    CK(cudaMemcpy(w, p->d_err, sizeof w, cudaMemcpyDeviceToHost));
+    if (!w[0] && !w[1]) return C3SC_OK;
+    cudaMemcpy(p->d_err, k_err_clear, sizeof k_err_clear, cudaMemcpyHostToDevice);
+    if (w[1])
+        return fail(C3SC_EINVAL, "fiber %d: dim_vary or a fixed index lies outside the grid (src/nodeutil.c:437-470 returns non-zero here); "
+                    "the batch's results are undefined", w[2]);
+    return fail(C3SC_ENUMERIC, "transition normaliser < 1e-14 at some (node, control): the reference asserts here");
+}
 
 extern "C" {
 
@@ -267,7 +285,8 @@ int c3sc_problem_create(const c3sc_problem_desc *d, c3sc_problem **out)
     if (!d || !out) return fail(C3SC_EINVAL, "null argument");
     if (d->dx < 1 || d->dx > C3SC_MAXD) return fail(C3SC_EINVAL, "dx=%u outside [1,%d]", d->dx, C3SC_MAXD);
     if (d->nobs > C3SC_MAXOBS) return fail(C3SC_EINVAL, "nobs=%u > %d", d->nobs, C3SC_MAXOBS);
-    if (d->nu < 1 || !d->controls) return fail(C3SC_EINVAL, "empty control table");
+    const bool geometry_only = d->model == C3SC_MODEL_NONE;       // flags + neighbour values only: no dynamics, no control set
+    if (!geometry_only && (d->nu < 1 || !d->controls)) return fail(C3SC_EINVAL, "empty control table");
     if (c3sc_cuda_device_count() == 0)
         return fail(C3SC_ENODEV, "no CUDA device; the Bellman backup has no CPU fallback");
     c3sc_problem *p = new c3sc_problem();
@@ -292,7 +311,8 @@ int c3sc_problem_create(const c3sc_problem_desc *d, c3sc_problem **out)
     // model parameter defaults = the reference examples' constants
     static const double defaults[5][8] = {{0}, {1.0, 1.0, 100.0, 0.0}, {1.0, 1.0, 1000.0, 0.0},
                                           {1.0, 1e-2, 1.0, 10.0, 0.0}, {0.0}};
-    if (d->model < 1 || d->model > 4) { delete p; return fail(C3SC_EUNSUPPORTED, "model %d unknown", d->model); }
+    if (d->model < 0 || d->model > 4) { delete p; return fail(C3SC_EUNSUPPORTED, "model %d unknown", d->model); }
+    if (geometry_only) P.nu = 0;
     memcpy(P.mp, defaults[d->model], sizeof P.mp);
     for (uint32_t i = 0; i < d->n_model_params && i < 8; i++) P.mp[i] = d->model_params[i];
 
@@ -312,17 +332,19 @@ int c3sc_problem_create(const c3sc_problem_desc *d, c3sc_problem **out)
     CKP(cudaMemcpy(p->d_xgrid, xg.data(), total * sizeof(double), cudaMemcpyHostToDevice));
     CKP(cudaMalloc(&p->d_obs, obs.size() * sizeof(double)));
     CKP(cudaMemcpy(p->d_obs, obs.data(), obs.size() * sizeof(double), cudaMemcpyHostToDevice));
-    CKP(cudaMalloc(&p->d_utab, (size_t)d->nu * d->du * sizeof(double)));
-    CKP(cudaMemcpy(p->d_utab, d->controls, (size_t)d->nu * d->du * sizeof(double), cudaMemcpyHostToDevice));
-    CKP(cudaMalloc(&p->d_err, sizeof(int)));
-    CKP(cudaMemset(p->d_err, 0, sizeof(int)));
+    if (!geometry_only) {
+        CKP(cudaMalloc(&p->d_utab, (size_t)d->nu * d->du * sizeof(double)));
+        CKP(cudaMemcpy(p->d_utab, d->controls, (size_t)d->nu * d->du * sizeof(double), cudaMemcpyHostToDevice));
+    }
+    CKP(cudaMalloc(&p->d_err, 4 * sizeof(int)));
+    CKP(cudaMemcpy(p->d_err, k_err_clear, sizeof k_err_clear, cudaMemcpyHostToDevice));
     CKP(cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking));
     CKP(cudaStreamCreateWithFlags(&p->copy_stream, cudaStreamNonBlocking));
     CKP(cudaEventCreateWithFlags(&p->chunk_done, cudaEventDisableTiming));
     P.xgrid = p->d_xgrid; P.obs = p->d_obs; P.utab = p->d_utab; P.err = p->d_err;
-    p->h_utab.assign(d->controls, d->controls + (size_t)d->nu * d->du);
+    if (!geometry_only) p->h_utab.assign(d->controls, d->controls + (size_t)d->nu * d->du);
     // candidate table of separable models (row stride 2*NUD+2; NUD = dx/2 for LQG, 1 otherwise)
-    {
+    if (!geometry_only) {
         const int nud = (d->model == C3SC_MODEL_LQGND) ? (int)d->dx / 2 : (d->model == C3SC_MODEL_SKID5D ? 0 : 1);
         const int ct = 2 * nud + 2;
         CKP(cudaMalloc(&p->d_ctab, (size_t)d->nu * ct * sizeof(double)));
@@ -390,6 +412,7 @@ void c3sc_problem_destroy(c3sc_problem *p)
     for (DevBuf *b : bufs) b->release();
     for (DevBuf &b : p->b_misc) b.release();
     p->scr.release();
+    if (p->vf_flags) c3sc_valuef_destroy(p->vf_flags);
     if (p->stream) cudaStreamDestroy(p->stream);
     if (p->copy_stream) cudaStreamDestroy(p->copy_stream);
     if (p->chunk_done) cudaEventDestroy(p->chunk_done);
@@ -406,14 +429,8 @@ int c3sc_problem_control_path(const c3sc_problem *p)
 int c3sc_problem_check(c3sc_problem *p)
 {
     if (!p) return fail(C3SC_EINVAL, "null problem");
-    int flag = 0;
     CK(cudaDeviceSynchronize());
-    CK(cudaMemcpy(&flag, p->d_err, sizeof(int), cudaMemcpyDeviceToHost));
-    if (flag) {
-        cudaMemset(p->d_err, 0, sizeof(int));
-        return fail(C3SC_ENUMERIC, "transition normaliser < 1e-14 at some (node, control): the reference asserts here");
-    }
-    return C3SC_OK;
+    return read_error_word(p);
 }
 
 int c3sc_valuef_create(uint32_t d, const uint64_t *n, const uint64_t *ranks, const double *const *cores,
@@ -571,7 +588,7 @@ static int run_batch(const DevProblem &P, int model, int arith, Scratch &scr, co
     }
     if (L > 1 && !scr.fork) CK(cudaEventCreateWithFlags(&scr.fork, cudaEventDisableTiming));
     {   // every chunk's grouping in one launch
-        int rc = launch_group_fibers((int)b.F, (int)FC, (int)d, b.dim_vary, (int *)scr.perm.p, (int *)scr.cnt.p, st);
+        int rc = launch_group_fibers(P, (int)b.F, (int)FC, b.dim_vary, b.fixed_ind, (int *)scr.perm.p, (int *)scr.cnt.p, st);
         if (rc) return fail(C3SC_ECUDA, "grouping kernel: %s", cudaGetErrorString((cudaError_t)rc));
         g_launches++;
     }
@@ -652,6 +669,13 @@ static int run_batch(const DevProblem &P, int model, int arith, Scratch &scr, co
     return C3SC_OK;
 }
 
+static int need_model(const c3sc_problem *p)
+{
+    if (p && p->model == C3SC_MODEL_NONE)
+        return fail(C3SC_EUNSUPPORTED, "geometry-only problem (C3SC_MODEL_NONE): no dynamics / control set for a backup");
+    return C3SC_OK;
+}
+
 static int check_shapes(const c3sc_problem *p, const c3sc_valuef *vf, size_t F, size_t ldo)
 {
     if (!p || !vf) return fail(C3SC_EINVAL, "null problem / value function");
@@ -679,6 +703,7 @@ int c3sc_vi_batch_dev(c3sc_problem *p, const c3sc_valuef *vf, size_t F, const in
     b.out.value = out->value; b.out.argmin = out->argmin; b.out.absorbed = out->absorbed;
     b.out.costs = out->costs; b.out.rows = out->rows; b.out.nbr_vary = out->nbr_vary; b.out.nbr_fixed = out->nbr_fixed;
     b.mode = (out->value || out->argmin || out->rows || out->n_peers) ? MODE_VI : MODE_COSTS;
+    if (b.mode == MODE_VI && (rc = need_model(p))) return rc;
     if (out->n_peers > C3SC_MAXPEERS) return fail(C3SC_EINVAL, "n_peers=%u > %d", out->n_peers, C3SC_MAXPEERS);
     b.n_peers = (int)out->n_peers;
     for (uint32_t g = 0; g < out->n_peers; g++) b.value_peers[g] = out->value_peers[g];
@@ -691,6 +716,7 @@ int c3sc_pi_batch_dev(c3sc_problem *p, const c3sc_valuef *vf_policy, const c3sc_
                       double *d_rows, int32_t *d_argmin, double *d_value, void *stream)
 {
     int rc = check_shapes(p, vf_iter, F, ldo);
+    if (!rc) rc = need_model(p);
     if (rc) return rc;
     if (!d_rows || !d_value) return fail(C3SC_EINVAL, "rows and value buffers are required");
     if (F == 0) return C3SC_OK;
@@ -725,13 +751,7 @@ static int upload_fibers(c3sc_problem *p, size_t F, const int32_t *dim_vary, con
 static int finish(c3sc_problem *p)
 {
     CK(cudaStreamSynchronize(p->stream));
-    int flag = 0;
-    CK(cudaMemcpy(&flag, p->d_err, sizeof(int), cudaMemcpyDeviceToHost));
-    if (flag) {
-        cudaMemset(p->d_err, 0, sizeof(int));
-        return fail(C3SC_ENUMERIC, "transition normaliser < 1e-14 at some (node, control): the reference asserts here");
-    }
-    return C3SC_OK;
+    return read_error_word(p);
 }
 
 int c3sc_fibers_check(const c3sc_problem *p, size_t F, const int32_t *dim_vary, const int32_t *fixed_ind)
@@ -800,6 +820,7 @@ int c3sc_vi_batch(c3sc_problem *p, const c3sc_valuef *vf, size_t F, const int32_
                   const int32_t *fixed_ind, size_t ldo, double *value, int32_t *argmin)
 {
     int rc = check_shapes(p, vf, F, ldo);
+    if (!rc) rc = need_model(p);
     if (rc) return rc;
     if (!dim_vary || !fixed_ind || !value) return fail(C3SC_EINVAL, "null fiber descriptors / value buffer");
     if (F == 0) return C3SC_OK;
@@ -902,10 +923,53 @@ int c3sc_neighbor_costs_batch(c3sc_problem *p, const c3sc_valuef *vf, size_t F, 
     return finish(p);
 }
 
+/* process_fibers_neighbor (src/nodeutil.c:489-627) over F fibers: flags and neighbour indices only.  The flags are
+ * produced by the stage-1 kernels, which want a value function: a rank-1 zero train of the problem's shape is kept
+ * inside the problem for this entry. */
+int c3sc_fiber_flags_batch(c3sc_problem *p, size_t F, const int32_t *dim_vary, const int32_t *fixed_ind, size_t ldo,
+                           int32_t *absorbed, int32_t *nbr_vary, int32_t *nbr_fixed)
+{
+    if (!p || !dim_vary || !fixed_ind || !absorbed) return fail(C3SC_EINVAL, "null argument");
+    if (ldo < (size_t)p->P.nmax) return fail(C3SC_EINVAL, "ldo=%zu < max ngrid=%d", ldo, p->P.nmax);
+    if (F == 0) return C3SC_OK;
+    if (!p->vf_flags) {
+        uint64_t n[C3SC_MAXD], r[C3SC_MAXD + 1];
+        std::vector<std::vector<double>> z(p->P.dx);
+        const double *cp[C3SC_MAXD];
+        for (int i = 0; i < p->P.dx; i++) { n[i] = (uint64_t)p->P.ngrid[i]; r[i] = 1; z[i].assign(n[i], 0.0); cp[i] = z[i].data(); }
+        r[p->P.dx] = 1;
+        int rc = c3sc_valuef_create((uint32_t)p->P.dx, n, r, cp, &p->vf_flags);
+        if (rc) return rc;
+    }
+    const size_t dx = p->P.dx, n = F * ldo;
+    int rc = upload_fibers(p, F, dim_vary, fixed_ind);
+    if (rc) return rc;
+    int bad = p->b_abs.reserve(n * 4);
+    if (nbr_vary) bad |= p->b_nv.reserve(n * 2 * 4);
+    if (nbr_fixed) bad |= p->b_nf.reserve(F * 2 * (dx > 1 ? dx - 1 : 1) * 4);
+    if (bad) return fail(C3SC_ECUDA, "cudaMalloc batch outputs failed");
+    CK(cudaMemsetAsync(p->b_abs.p, 0, n * 4, p->stream));
+    if (nbr_vary) CK(cudaMemsetAsync(p->b_nv.p, 0, n * 2 * 4, p->stream));
+    BatchArgs b;
+    memset(&b, 0, sizeof b);
+    b.F = F; b.ldo = ldo; b.dim_vary = (const int *)p->b_dv.p; b.fixed_ind = (const int *)p->b_fi.p;
+    b.mode = MODE_COSTS;
+    b.out.absorbed = (int *)p->b_abs.p;
+    b.out.nbr_vary = nbr_vary ? (int *)p->b_nv.p : nullptr;
+    b.out.nbr_fixed = nbr_fixed ? (int *)p->b_nf.p : nullptr;
+    rc = run_batch(p->P, p->model, p->arith, p->scr, &p->grp, p->vf_flags->ft, b, p->stream);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(absorbed, p->b_abs.p, n * 4, cudaMemcpyDeviceToHost, p->stream));
+    if (nbr_vary) CK(cudaMemcpyAsync(nbr_vary, p->b_nv.p, n * 2 * 4, cudaMemcpyDeviceToHost, p->stream));
+    if (nbr_fixed && dx > 1) CK(cudaMemcpyAsync(nbr_fixed, p->b_nf.p, F * 2 * (dx - 1) * 4, cudaMemcpyDeviceToHost, p->stream));
+    return finish(p);
+}
+
 int c3sc_node_backup_batch(c3sc_problem *p, size_t n, const double *x, const double *costs, const int32_t *absorbed,
                            double *value, int32_t *argmin)
 {
     if (!p || !x || !costs || !value) return fail(C3SC_EINVAL, "null argument");
+    if (need_model(p)) return C3SC_EUNSUPPORTED;
     if (n == 0) return C3SC_OK;
     const size_t dx = p->P.dx;
     DevBuf *b = p->b_misc;
@@ -946,6 +1010,29 @@ int c3sc_valuef_eval_batch(c3sc_problem *p, const c3sc_valuef *vf, size_t n, con
     return C3SC_OK;
 }
 
+/* mca_get_neighbor_node_costs (src/nodeutil.c:718-816) at n off-grid states: V at x -+ h e_i with the boundary
+ * stand-ins, all V(x) and flag -1 inside an obstacle.  Needs no dynamics: works on a geometry-only problem. */
+int c3sc_neighbor_node_costs_batch(c3sc_problem *p, const c3sc_valuef *vf, size_t n, const double *x, int32_t *absorbed,
+                                   double *costs)
+{
+    if (!p || !vf || !x || !absorbed || !costs) return fail(C3SC_EINVAL, "null argument");
+    if (vf->ft.d != p->P.dx) return fail(C3SC_EINVAL, "value function has d=%d, problem dx=%d", vf->ft.d, p->P.dx);
+    if (n == 0) return C3SC_OK;
+    const size_t dx = p->P.dx, np = 2 * dx + 1;
+    DevBuf *b = p->b_misc;
+    if (b[0].reserve(n * dx * 8) || b[1].reserve(n * np * dx * 8) || b[2].reserve(n * 4) || b[3].reserve(n * np * 8))
+        return fail(C3SC_ECUDA, "cudaMalloc failed");
+    CK(cudaMemcpyAsync(b[0].p, x, n * dx * 8, cudaMemcpyHostToDevice, p->stream));
+    int rc = launch_policy_points(p->P, (int)n, (const double *)b[0].p, (double *)b[1].p, (int *)b[2].p, p->stream);
+    if (!rc) rc = launch_ft_eval_points(p->P, vf->ft, (int)(n * np), (const double *)b[1].p, (double *)b[3].p, p->stream);
+    if (rc) return fail(C3SC_ECUDA, "kernel launch: %s", cudaGetErrorString((cudaError_t)rc));
+    g_launches += 2;
+    CK(cudaMemcpyAsync(absorbed, b[2].p, n * 4, cudaMemcpyDeviceToHost, p->stream));
+    CK(cudaMemcpyAsync(costs, b[3].p, n * np * 8, cudaMemcpyDeviceToHost, p->stream));
+    CK(cudaStreamSynchronize(p->stream));
+    return C3SC_OK;
+}
+
 /* c3control_policy_eval (src/bellman.c:2105-2151) at n states: mca_get_neighbor_node_costs
  * (src/nodeutil.c:718-816) + bellman_optimal.  u [n*du]; value / absorbed / costs may be NULL. */
 int c3sc_policy_eval_batch(c3sc_problem *p, const c3sc_valuef *vf, size_t n, const double *x, double *u, double *value,
@@ -953,6 +1040,7 @@ int c3sc_policy_eval_batch(c3sc_problem *p, const c3sc_valuef *vf, size_t n, con
 {
     if (!p || !vf || !x || !u) return fail(C3SC_EINVAL, "null argument");
     if (vf->ft.d != p->P.dx) return fail(C3SC_EINVAL, "value function has d=%d, problem dx=%d", vf->ft.d, p->P.dx);
+    if (need_model(p)) return C3SC_EUNSUPPORTED;
     if (n == 0) return C3SC_OK;
     const size_t dx = p->P.dx, du = p->P.du, np = 2 * dx + 1;
     DevBuf *b = p->b_misc;
@@ -989,6 +1077,7 @@ int c3sc_control_value_batch(c3sc_problem *p, size_t n, const double *x, const d
                              double *value)
 {
     if (!p || !x || !u || !costs || !value) return fail(C3SC_EINVAL, "null argument");
+    if (need_model(p)) return C3SC_EUNSUPPORTED;
     if (n == 0) return C3SC_OK;
     const size_t dx = p->P.dx, du = p->P.du;
     DevBuf *b = p->b_misc;
@@ -1011,11 +1100,14 @@ int c3sc_control_value_batch(c3sc_problem *p, size_t n, const double *x, const d
 }
 
 // ---- entry points that need no problem handle (raw reference signatures) -------------------
+// They share static scratch: one call at a time (g_scratch_mu).
 static DevBuf g_scratch[6];
+static std::mutex g_scratch_mu;
 
 int c3sc_rhs_batch(int arith, uint32_t dx, double discount, size_t n, const double *prob, const double *dt,
                    const double *stage, const double *cost, double *out)
 {
+    std::lock_guard<std::mutex> lock(g_scratch_mu);
     if (!prob || !dt || !stage || !cost || !out) return fail(C3SC_EINVAL, "null argument");
     if (c3sc_cuda_device_count() == 0) return fail(C3SC_ENODEV, "no CUDA device; no CPU fallback");
     if (n == 0) return C3SC_OK;
@@ -1038,6 +1130,7 @@ int c3sc_rhs_batch(int arith, uint32_t dx, double discount, size_t n, const doub
 int c3sc_transition_raw(int arith, uint32_t dx, double h2, const double *t, size_t n, const double *drift,
                         const double *sigma_diag, double *prob, double *dt, int32_t *status)
 {
+    std::lock_guard<std::mutex> lock(g_scratch_mu);
     if (!t || !drift || !sigma_diag || !prob || !dt || !status) return fail(C3SC_EINVAL, "null argument");
     if (dx < 1 || dx > C3SC_MAXD) return fail(C3SC_EINVAL, "dx out of range");
     if (c3sc_cuda_device_count() == 0) return fail(C3SC_ENODEV, "no CUDA device; no CPU fallback");
@@ -1065,6 +1158,7 @@ int c3sc_transition_raw(int arith, uint32_t dx, double h2, const double *t, size
 int c3sc_ft_fiber_nn_batch(const c3sc_valuef *vf, size_t F, const int32_t *dim_vary, const int32_t *fixed_ind,
                            const int32_t *nbr_fixed, const int32_t *nbr_vary, size_t ldo, double *costs)
 {
+    std::lock_guard<std::mutex> lock(g_scratch_mu);
     if (!vf || !dim_vary || !fixed_ind || !nbr_fixed || !nbr_vary || !costs) return fail(C3SC_EINVAL, "null argument");
     if (F == 0) return C3SC_OK;
     const int dx = vf->ft.d;
@@ -1088,6 +1182,7 @@ int c3sc_ft_fiber_nn_batch(const c3sc_valuef *vf, size_t F, const int32_t *dim_v
     tmp.P.xgrid = (const double *)b[5].p;           // coordinates are irrelevant here (no obstacles)
     for (int i = 0; i < dx; i++) tmp.P.xoff[i] = i * tmp.P.nmax;
     tmp.P.err = (int *)((char *)b[5].p + 8 * (size_t)dx * tmp.P.nmax);
+    CK(cudaMemcpy(tmp.P.err, k_err_clear, sizeof k_err_clear, cudaMemcpyHostToDevice));
     BatchArgs ba;
     memset(&ba, 0, sizeof ba);
     ba.F = F; ba.ldo = ldo; ba.dim_vary = (const int *)b[0].p; ba.fixed_ind = (const int *)b[1].p;
@@ -1097,6 +1192,9 @@ int c3sc_ft_fiber_nn_batch(const c3sc_valuef *vf, size_t F, const int32_t *dim_v
     int rc = run_batch(tmp.P, model, C3SC_ARITH_FAST, scr, nullptr, vf->ft, ba, nullptr);
     if (rc) return rc;
     CK(cudaDeviceSynchronize());
+    int w[4];
+    CK(cudaMemcpy(w, tmp.P.err, sizeof w, cudaMemcpyDeviceToHost));
+    if (w[1]) return fail(C3SC_EINVAL, "fiber %d: dim_vary or a fixed index lies outside the grid", w[2]);
     CK(cudaMemcpy(costs, b[4].p, n * cs * 8, cudaMemcpyDeviceToHost));
     return C3SC_OK;
 }
@@ -1105,6 +1203,7 @@ int c3sc_transition_batch(c3sc_problem *p, size_t n, const double *drift, const 
                           double *prob, double *dt, int32_t *status)
 {
     if (!p || !drift || !sigma_diag || !prob || !dt || !status) return fail(C3SC_EINVAL, "null argument");
+    if (need_model(p)) return C3SC_EUNSUPPORTED;
     if (n == 0) return C3SC_OK;
     const size_t dx = p->P.dx;
     DevBuf *b = p->b_misc;
@@ -1129,6 +1228,7 @@ int c3sc_model_eval(c3sc_problem *p, size_t n, const double *x, const double *u,
                     double *sigma_diag, double *stage, double *bound, double *obs)
 {
     if (!p || !x || !u || !drift || !sigma_diag || !stage || !bound || !obs) return fail(C3SC_EINVAL, "null argument");
+    if (need_model(p)) return C3SC_EUNSUPPORTED;
     if (n == 0) return C3SC_OK;
     const size_t dx = p->P.dx, du = p->P.du;
     DevBuf *b = p->b_misc;

@@ -230,9 +230,14 @@ template <int DX>
 __device__ __forceinline__ void node_state(const CtlArgs &c, int id, double *x)
 {
     const int f = id / c.ldo, j = id - f * c.ldo;
-    const int k = c.dim_vary[f];
+    int k = c.dim_vary[f];
+    k = k < 0 ? 0 : (k >= DX ? DX - 1 : k);                     // stage 1 clamps the same way
 #pragma unroll
-    for (int i = 0; i < DX; i++) x[i] = c.P.xgrid[c.P.xoff[i] + (i == k ? j : c.fixed_ind[(size_t)f * DX + i])];
+    for (int i = 0; i < DX; i++) {
+        int i0 = c.fixed_ind[(size_t)f * DX + i];                   // clamped like stage 1 (bad descriptors are reported by k_group_fibers)
+        i0 = i0 < 0 ? 0 : (i0 >= c.P.ngrid[i] ? c.P.ngrid[i] - 1 : i0);
+        x[i] = c.P.xgrid[c.P.xoff[i] + (i == k ? j : i0)];
+    }
 }
 
 // Neighbour values of node `id` from the slot-major scratch.  Stage 1 stores the fixed-dimension
@@ -242,7 +247,8 @@ template <int DX>
 __device__ __forceinline__ void load_costs(const CtlArgs &c, int id, double *cc)
 {
     const int f = id / c.ldo, j = id - f * c.ldo;
-    const int k = c.dim_vary[f];
+    int k = c.dim_vary[f];
+    k = k < 0 ? 0 : (k >= DX ? DX - 1 : k);                     // stage 1 clamps the same way
     int lo, hi;
     ft_vary_pair(c.P.bc[k], c.P.ngrid[k], j, c.flag[id], lo, hi);
     const double *self = c.cst + (size_t)(2 * DX) * c.NS + (size_t)f * c.ldo;
@@ -323,8 +329,10 @@ __global__ void __launch_bounds__(CT_NT, 3) k_control(const CtlArgs c)
             if (valid && norm0 + P.amin < 1e-14) atomicOr(P.err, 1);
             const double nbh = -P.beta * P.h2;
             const bool disc = P.beta != 0.0;
-            // exp(-beta*dt) with dt <= h2/(norm0+amin): short series when every lane's bound is tiny
-            const bool tiny = __all_sync(0xffffffffu, !valid || (P.beta * P.h2 <= 0.00390625 * (norm0 + P.amin)));
+            // exp(-beta*dt) with dt <= h2/(norm0+amin): short series when the node's bound is tiny.  Decided per
+            // NODE (not by a warp vote): which nodes share a warp depends on the atomically filled active list,
+            // and the result of a node must not depend on its neighbours in the list.
+            const bool tiny = !valid || (P.beta * P.h2 <= 0.00390625 * (norm0 + P.amin));
             if (grouped) {
                 // Candidates with the same normaliser share A_g share dt and the discount: per group
                 // one reciprocal + one exp, per candidate only S_c and  t_c = ebt*S_c + h2*gu_c.
@@ -432,10 +440,13 @@ __global__ void __launch_bounds__(CT_NT, 3) k_control(const CtlArgs c)
     // absorbed nodes (bellman.c:513-532): boundary / obstacle cost, u = 0
     for (long long id = (long long)blockIdx.x * CT_NT + tid; id < c.NS; id += stride) {
         const int ab = c.flag[id];
-        if (ab != 1 && ab != -1) continue;
-        double x[DX];
-        node_state<DX>(c, (int)id, x);
-        const double v = (ab == 1) ? M::boundcost(x, P.mp) : M::obscost(x, P.mp);
+        if (ab == 0) continue;
+        double v = 0.0;                                     // ab == 2: padding entry j >= ngrid[dim_vary], defined as 0 / -1
+        if (ab != 2) {
+            double x[DX];
+            node_state<DX>(c, (int)id, x);
+            v = (ab == 1) ? M::boundcost(x, P.mp) : M::obscost(x, P.mp);
+        }
         store_value(c, id, v);
         if (c.argmin) c.argmin[id] = -1;
         if (c.rows) {
@@ -527,17 +538,16 @@ __global__ void __launch_bounds__(C2_NT, C3SC_C2_MINB) k_control2(const CtlArgs 
         bool valid[C2N];
         int id[C2N];
         Node2<M> nd[C2N];
-        bool bad = false, small = true;
+        bool bad = false, tiny[C2N];
 #pragma unroll
         for (int q = 0; q < C2N; q++) {
             valid[q] = it < nper && it + q * nper < nact;
             id[q] = c.act[valid[q] ? it + q * nper : 0];
             node2_prepare<M>(c, id[q], nd[q]);
             bad = bad || (valid[q] && nd[q].norm0 + P.amin < 1e-14);
-            small = small && (!valid[q] || P.beta * P.h2 <= 0.00390625 * (nd[q].norm0 + P.amin));
+            tiny[q] = !valid[q] || P.beta * P.h2 <= 0.00390625 * (nd[q].norm0 + P.amin);      // per node: see k_control
         }
         if (bad) atomicOr(P.err, 1);
-        const bool tiny = __all_sync(0xffffffffu, small);
         for (int g = 0; g < c.ng; g++) {
             const int lo = c.gstart[g], hi = valid[0] ? c.gstart[g + 1] : lo;
             double rinv[C2N], ebt[C2N], bt[C2N];
@@ -545,7 +555,7 @@ __global__ void __launch_bounds__(C2_NT, C3SC_C2_MINB) k_control2(const CtlArgs 
 #pragma unroll
             for (int q = 0; q < C2N; q++) {
                 rinv[q] = rcp_pos(nd[q].norm0 + c.gA[g]);
-                ebt[q] = !disc ? 1.0 : (tiny ? exp_tiny(nbh * rinv[q]) : exp_nonpos(nbh * rinv[q]));
+                ebt[q] = !disc ? 1.0 : (tiny[q] ? exp_tiny(nbh * rinv[q]) : exp_nonpos(nbh * rinv[q]));
                 bt[q] = CUDART_INF;
                 bi[q] = 0x7fffffff;
             }
@@ -604,10 +614,13 @@ __global__ void __launch_bounds__(C2_NT, C3SC_C2_MINB) k_control2(const CtlArgs 
     // absorbed nodes (bellman.c:513-532): boundary / obstacle cost, u = 0
     for (long long id = (long long)blockIdx.x * blockDim.x + tid; id < c.NS; id += stride) {
         const int ab = c.flag[id];
-        if (ab != 1 && ab != -1) continue;
-        double x[DX];
-        node_state<DX>(c, (int)id, x);
-        const double v = (ab == 1) ? M::boundcost(x, P.mp) : M::obscost(x, P.mp);
+        if (ab == 0) continue;
+        double v = 0.0;                                     // ab == 2: padding entry j >= ngrid[dim_vary], defined as 0 / -1
+        if (ab != 2) {
+            double x[DX];
+            node_state<DX>(c, (int)id, x);
+            v = (ab == 1) ? M::boundcost(x, P.mp) : M::obscost(x, P.mp);
+        }
         store_value(c, id, v);
         if (c.argmin) c.argmin[id] = -1;
         if (c.rows) {
@@ -674,7 +687,7 @@ __global__ void __launch_bounds__(CT_NT, grid_minb(ARG)) k_control_grid(const Ct
     const bool disc = P.beta != 0.0;
     for (long long it0 = (long long)blockIdx.x * blockDim.x + (tid & ~31); it0 < nper; it0 += stride) {
         const int it = (int)it0 + lane;
-        bool valid[Q], bad = false, small = true;
+        bool valid[Q], bad = false, tiny[Q];
         int id[Q];
         Node2<M> nd[Q];
 #pragma unroll
@@ -683,10 +696,9 @@ __global__ void __launch_bounds__(CT_NT, grid_minb(ARG)) k_control_grid(const Ct
             id[q] = c.act[valid[q] ? it + q * nper : 0];
             node2_prepare<M>(c, id[q], nd[q]);
             bad = bad || (valid[q] && nd[q].norm0 + P.amin < 1e-14);
-            small = small && (!valid[q] || P.beta * P.h2 <= 0.00390625 * (nd[q].norm0 + P.amin));
+            tiny[q] = !valid[q] || P.beta * P.h2 <= 0.00390625 * (nd[q].norm0 + P.amin);      // per node: see k_control
         }
         if (bad) atomicOr(P.err, 1);
-        const bool tiny = __all_sync(0xffffffffu, small);
 #pragma unroll
         for (int q = 0; q < Q; q++) {
             double Tl[NUD], Th[NUD], mn[NG];
@@ -699,7 +711,7 @@ __global__ void __launch_bounds__(CT_NT, grid_minb(ARG)) k_control_grid(const Ct
 #pragma unroll
             for (int g = 0; g < NG; g++) {
                 const double rinv = rcp_pos(nd[q].norm0 + c.gAg[g]);
-                const double ebt = !disc ? 1.0 : (tiny ? exp_tiny(nbh * rinv) : exp_nonpos(nbh * rinv));
+                const double ebt = !disc ? 1.0 : (tiny[q] ? exp_tiny(nbh * rinv) : exp_nonpos(nbh * rinv));
                 const double v = rinv * (fma(ebt, mn[g], c.gHg[g]) + nd[q].hgx);
                 if (v < nd[q].best || (ARG && v == nd[q].best && am[g] < nd[q].ibest)) { nd[q].best = v; nd[q].ibest = am[g]; }
             }
@@ -732,10 +744,13 @@ __global__ void __launch_bounds__(CT_NT, grid_minb(ARG)) k_control_grid(const Ct
     // absorbed nodes (bellman.c:513-532): boundary / obstacle cost, u = 0
     for (long long id = (long long)blockIdx.x * blockDim.x + tid; id < c.NS; id += stride) {
         const int ab = c.flag[id];
-        if (ab != 1 && ab != -1) continue;
-        double x[DX];
-        node_state<DX>(c, (int)id, x);
-        const double v = (ab == 1) ? M::boundcost(x, P.mp) : M::obscost(x, P.mp);
+        if (ab == 0) continue;
+        double v = 0.0;                                     // ab == 2: padding entry j >= ngrid[dim_vary], defined as 0 / -1
+        if (ab != 2) {
+            double x[DX];
+            node_state<DX>(c, (int)id, x);
+            v = (ab == 1) ? M::boundcost(x, P.mp) : M::obscost(x, P.mp);
+        }
         store_value(c, id, v);
         if (c.argmin) c.argmin[id] = -1;
         if (c.rows) {
@@ -754,9 +769,9 @@ __global__ void __launch_bounds__(CT_NT) k_pi_eval(const CtlArgs c)
     const long long stride = (long long)gridDim.x * CT_NT;
     for (long long id = (long long)blockIdx.x * CT_NT + threadIdx.x; id < c.NS; id += stride) {
         const int ab = c.flag[id];
-        if (ab == 2) continue;
         double v;
-        if (ab != 0) {
+        if (ab == 2) v = 0.0;                               // padding entry: defined content
+        else if (ab != 0) {
             double x[DX];
             node_state<DX>(c, (int)id, x);
             v = (ab == 1) ? M::boundcost(x, P.mp) : M::obscost(x, P.mp);

@@ -19,10 +19,13 @@ static void ft_device_info()
 int ft_sm_count() { ft_device_info(); return g_sms; }
 
 // perm / kcount / kstart / cleared active counters of ALL chunks of a batch.  1 launch.
-int launch_group_fibers(int F, int FC, int d, const int *dim_vary, int *perm, int *cnt_all, cudaStream_t st)
+int launch_group_fibers(const DevProblem &P, int F, int FC, const int *dim_vary, const int *fixed_ind, int *perm, int *cnt_all,
+                        cudaStream_t st)
 {
     if (F <= 0) return 0;
-    k_group_fibers<<<(F + FC - 1) / FC, 1024, 0, st>>>(F, FC, d, dim_vary, perm, cnt_all);
+    GridDims ng;
+    for (int i = 0; i < MAXD; i++) ng.n[i] = P.ngrid[i];
+    k_group_fibers<<<(F + FC - 1) / FC, 1024, 0, st>>>(F, FC, P.dx, dim_vary, fixed_ind, ng, P.err, perm, cnt_all);
     return (int)cudaGetLastError();
 }
 

@@ -120,11 +120,30 @@ struct FtPlan {
 // Group the fibers of every chunk of a batch by varying dimension: perm = fiber ids (relative to the
 // chunk), k-major.  One CTA per chunk (blockIdx.x); chunk c covers fibers [c*FC, min(F, (c+1)*FC)) and
 // owns perm[c*FC ..], and 64 ints of `cnt`: [0,16) kcount, [16,32) kstart, [32] active-node counter (cleared).
-__global__ void __launch_bounds__(1024) k_group_fibers(int F, int FC, int d, const int *dim_vary, int *perm, int *cnt_all)
+//
+// The same pass validates the descriptors (the batch analogue of convert_fiber_to_ind's error returns,
+// src/nodeutil.c:437-470): a dim_vary outside [0, d) or a fixed index outside its grid sets err[1] and records
+// the smallest offending fiber id in err[2]; every consumer clamps what it loads, so a bad descriptor is an
+// error return of the batch, never a read outside the cores.
+struct GridDims { int n[MAXD]; };
+__device__ __forceinline__ int ft_clamp_index(int i0, int n) { return i0 < 0 ? 0 : (i0 >= n ? n - 1 : i0); }
+__global__ void __launch_bounds__(1024) k_group_fibers(int F, int FC, int d, const int *dim_vary, const int *fixed_ind,
+                                                       GridDims ng, int *err, int *perm, int *cnt_all)
 {
     __shared__ int cnt[MAXD], pos[MAXD];
     const int tid = threadIdx.x;
     const int c0 = blockIdx.x * FC, Fc = (F - c0 < FC) ? F - c0 : FC;
+    if (err && fixed_ind) {
+        int bad = 0x7fffffff;
+        for (int e = tid; e < Fc * d; e += blockDim.x) {
+            const int f = e / d, i = e - f * d;
+            const int v = fixed_ind[(size_t)c0 * d + e];
+            bool b = (unsigned)v >= (unsigned)ng.n[i];
+            if (i == 0) b = b || (unsigned)dim_vary[c0 + f] >= (unsigned)d;
+            if (b && c0 + f < bad) bad = c0 + f;
+        }
+        if (bad != 0x7fffffff) { atomicOr(err + 1, 1); atomicMin(err + 2, bad); }
+    }
     dim_vary += c0; perm += c0;
     int *kcount = cnt_all + 64 * blockIdx.x, *kstart = kcount + 16, *act_count = kcount + 32;
     if (tid < MAXD) cnt[tid] = 0;
@@ -237,7 +256,7 @@ __device__ __forceinline__ void ft_flags_and_indices(const FtArgs &a, int k, int
     for (int e = tid; e < nf * d; e += NT) {
         const int g = e / d, i = e - g * d;
         const int fid = a.perm[gstart + g];
-        const int i0 = a.fixed_ind[(size_t)fid * d + i];
+        const int i0 = ft_clamp_index(a.fixed_ind[(size_t)fid * d + i], P.ngrid[i]);
         if (i == 0) sFid[g] = fid;
         sFix[g * d + i] = i0;
         if (i == k) continue;

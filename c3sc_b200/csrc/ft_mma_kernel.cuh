@@ -118,7 +118,7 @@ __global__ void __launch_bounds__(FTC_NT, KS <= 6 ? C3SC_FTC_MINB : 1) k_ft_chai
         const int nsteps = left ? k : d - 1 - k;
         __syncwarp();
         if (lane < d) {
-            const int i = lane, i0 = a.fixed_ind[(size_t)f * d + i];
+            const int i = lane, i0 = ft_clamp_index(a.fixed_ind[(size_t)f * d + i], P.ngrid[i]);
             sFix[i] = i0;
             if (i != k) {
                 int lo, hi;

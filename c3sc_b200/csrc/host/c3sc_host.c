@@ -164,7 +164,9 @@ struct ValueF {
                                      cross run that produced this function; NULL for valuef_from_cores */
     double **xgrid;               /* owned copy of the nodes (the reference keeps them inside the LINELM cores) */
     c3sc_problem *eval_dev;       /* geometry-only device problem for valuef_eval, built on first use */
+    struct CrossIndex **isl;      /* valuef_get_isl's view of cross's left index sets, rebuilt per call */
 };
+static void isl_free(struct ValueF *v);
 struct ValueF *valuef_from_cores(size_t d, const size_t *N, const size_t *ranks, double *const *cores)
 {
     struct ValueF *v = xalloc(1, sizeof *v);
@@ -188,6 +190,7 @@ int valuef_update_cores(struct ValueF *v, double *const *cores)
 void valuef_destroy(struct ValueF *v)
 {
     if (!v) return;
+    isl_free(v);
     c3sc_valuef_destroy(v->dev);
     c3sc_cross_destroy(v->cross);
     c3sc_problem_destroy(v->eval_dev);
@@ -210,6 +213,42 @@ struct ValueF *valuef_copy(struct ValueF *v)
     return c;
 }
 size_t *valuef_get_ranks(struct ValueF *v) { return v->ranks; }
+
+/* src/valuefunc.c:218: the left index sets the cross run that produced vf ended with.  isl[k], k = 0..d-1, holds the
+   r_k multi-indices over dimensions 0..k-1 that core k's fibers were sampled at (isl[0] is the empty prefix).
+   C3's struct CrossIndex is absent; the stand-in in c3sc_host.h carries grid indices and, when the value function
+   knows its grid, the node coordinates C3 stores.  NULL for a value function that did not come from a cross run. */
+static void isl_free(struct ValueF *v)
+{
+    if (!v->isl) return;
+    for (size_t k = 0; k < v->d; k++) if (v->isl[k]) { free(v->isl[k]->inds); free(v->isl[k]->vals); free(v->isl[k]); }
+    free(v->isl); v->isl = NULL;
+}
+struct CrossIndex **valuef_get_isl(const struct ValueF *cv)
+{
+    struct ValueF *v = (struct ValueF *)cv;
+    if (!v || !v->cross) return NULL;
+    isl_free(v);
+    uint64_t r[C3SC_MAXD + 1];
+    if (c3sc_cross_ranks(v->cross, r)) return NULL;
+    v->isl = xalloc(v->d, sizeof *v->isl);
+    for (size_t k = 0; k < v->d; k++) {
+        struct CrossIndex *ci = xalloc(1, sizeof *ci);
+        ci->d = k; ci->n = (size_t)r[k];
+        ci->inds = xalloc(ci->n * (k ? k : 1), sizeof(size_t));
+        ci->vals = v->xgrid ? xalloc(ci->n * (k ? k : 1), sizeof(double)) : NULL;
+        int32_t *left = xalloc(ci->n * v->d, sizeof(int32_t));
+        if (c3sc_cross_index_sets(v->cross, (uint32_t)k, left, NULL)) die("valuef_get_isl");
+        for (size_t a = 0; a < ci->n; a++)
+            for (size_t i = 0; i < k; i++) {
+                ci->inds[a * k + i] = (size_t)left[a * v->d + i];
+                if (ci->vals) ci->vals[a * k + i] = v->xgrid[i][left[a * v->d + i]];
+            }
+        free(left);
+        v->isl[k] = ci;
+    }
+    return v->isl;
+}
 
 int valuef_eval_fiber_ind_nn(struct ValueF *vf, const size_t *fixed_ind, size_t dim_vary,
                              const size_t *neighbors, const size_t *neighbors_vary, double *out)
@@ -242,6 +281,11 @@ size_t uniform_stride(size_t N, size_t M)
 struct RowEntry { uint64_t hash; size_t pi_iter; int32_t key[C3SC_MAXD + 1]; double *rows; int32_t *argmin; struct RowEntry *next; };
 struct Workspace {
     size_t dx, du, dw, N;
+    size_t active;                /* src/util.c: workspace_set_active */
+    size_t index[11];             /* offsets of the slab fields, src/util.c:738-748 */
+    double **mem;                 /* N per-node slabs: drift, grad_drift, diff, grad_diff, dt, grad_dt, prob, grad_prob,
+                                     grad_stage, extra, u -- filled by the scalar entries bellman_control / bellman_optimal
+                                     (one node per call); the batched kernels keep these quantities in registers */
     size_t vi_iter, pi_iter, pi_subiter;
     double *costs;                /* N*(2dx+1): neighbour costs of the fiber in flight */
     int *absorbed;                /* N */
@@ -256,6 +300,20 @@ struct Workspace *workspace_alloc(size_t dx, size_t du, size_t dw, size_t N)
     w->costs = xalloc(N * (2 * dx + 1), sizeof(double));
     w->absorbed = xalloc(N, sizeof(int));
     w->u = xalloc(N * (du ? du : 1), sizeof(double));
+    /* slab layout of src/util.c:738-748 */
+    w->index[0] = dx;                                   /* drift */
+    w->index[1] = w->index[0] + dx * du;                /* grad_drift */
+    w->index[2] = w->index[1] + dx * dw;                /* diff */
+    w->index[3] = w->index[2] + dx * dw * du;           /* grad_diff */
+    w->index[4] = w->index[3] + 1;                      /* dt */
+    w->index[5] = w->index[4] + du;                     /* grad_dt */
+    w->index[6] = w->index[5] + 2 * dx + 1;             /* prob */
+    w->index[7] = w->index[6] + du * (2 * dx + 1);      /* grad_prob */
+    w->index[8] = w->index[7] + du;                     /* grad_stage */
+    w->index[9] = w->index[8] + du;                     /* extra */
+    w->index[10] = w->index[9] + du;                    /* u */
+    w->mem = xalloc(N ? N : 1, sizeof(double *));
+    for (size_t i = 0; i < N; i++) w->mem[i] = xalloc(w->index[10] ? w->index[10] : 1, sizeof(double));
     w->nbuckets = 1 << 16;
     w->rows = xalloc(w->nbuckets, sizeof(struct RowEntry *));
     return w;
@@ -274,6 +332,8 @@ void workspace_free(struct Workspace *w)
 {
     if (!w) return;
     workspace_reset_pi_prob_htable(w);
+    for (size_t i = 0; i < w->N; i++) free(w->mem[i]);
+    free(w->mem);
     free(w->rows); free(w->costs); free(w->absorbed); free(w->u); free(w);
 }
 void workspace_increment_vi_iter(struct Workspace *w) { w->vi_iter++; }
@@ -284,7 +344,20 @@ void workspace_increment_pi_subiter(struct Workspace *w) { w->pi_subiter++; }
 size_t workspace_get_pi_subiter(const struct Workspace *w) { return w->pi_subiter; }
 double *workspace_get_costs(struct Workspace *w, size_t node) { return w->costs + node * (2 * w->dx + 1); }
 int *workspace_get_absorbed(struct Workspace *w, size_t node) { return w->absorbed + node; }
-double *workspace_get_u(struct Workspace *w, size_t node) { return w->u + node * w->du; }
+double *workspace_get_u(struct Workspace *w, size_t node) { return w->mem[node] + w->index[9]; }
+/* src/util.c:843-906: the per-node scratch slabs */
+void workspace_set_active(struct Workspace *w, size_t active) { w->active = active; }
+size_t workspace_get_active(struct Workspace *w) { return w->active; }
+double *workspace_get_drift(struct Workspace *w, size_t node) { return w->mem[node]; }
+double *workspace_get_grad_drift(struct Workspace *w, size_t node) { return w->mem[node] + w->index[0]; }
+double *workspace_get_diff(struct Workspace *w, size_t node) { return w->mem[node] + w->index[1]; }
+double *workspace_get_grad_diff(struct Workspace *w, size_t node) { return w->mem[node] + w->index[2]; }
+double *workspace_get_dt(struct Workspace *w, size_t node) { return w->mem[node] + w->index[3]; }
+double *workspace_get_grad_dt(struct Workspace *w, size_t node) { return w->mem[node] + w->index[4]; }
+double *workspace_get_prob(struct Workspace *w, size_t node) { return w->mem[node] + w->index[5]; }
+double *workspace_get_grad_prob(struct Workspace *w, size_t node) { return w->mem[node] + w->index[6]; }
+double *workspace_get_grad_stage(struct Workspace *w, size_t node) { return w->mem[node] + w->index[7]; }
+double *workspace_get_control_size_extra(struct Workspace *w, size_t node) { return w->mem[node] + w->index[8]; }
 
 static uint64_t fiber_hash(size_t pi_iter, int32_t k, const int32_t *fi, size_t d)
 {
@@ -370,6 +443,7 @@ static c3sc_problem *make_problem(struct DPparam *dp, struct MCAparam *m, struct
     if (!opt || !c3opt_is_bruteforce(opt) || !opt->n) { fprintf(stderr, "c3sc_b200: only the BRUTEFORCE control set is supported on the device\n"); abort(); }
     if (!dp->bound || !m->xgrid) { fprintf(stderr, "c3sc_b200: boundary / grid missing\n"); abort(); }
     const size_t dx = m->dx;
+    if (dx < 1 || dx > C3SC_MAXD || dp->bound->nobs > C3SC_MAXOBS) { fprintf(stderr, "c3sc_b200: dx=%zu outside [1,%d] or more than %d obstacles\n", dx, C3SC_MAXD, C3SC_MAXOBS); abort(); }
     uint64_t ng[C3SC_MAXD]; int32_t bc[C3SC_MAXD];
     double lb[C3SC_MAXOBS * C3SC_MAXD], ub[C3SC_MAXOBS * C3SC_MAXD];
     for (size_t i = 0; i < dx; i++) { ng[i] = m->ngrid[i]; bc[i] = dp->bound->type[i]; }
@@ -506,6 +580,21 @@ double bellman_control(size_t du, const double *u, double *grad_u, void *args)
         return val;
     }
     if (c3sc_control_value_batch(cp_dev(cp), 1, x, u, costs, &val)) die("bellman_control");
+    {   /* the node's slab as the reference leaves it (src/bellman.c:400-449): drift, diffusion (column-major
+           dx x dw, diagonal), dt, probabilities -- from the device model and the device transition kernel */
+        struct Workspace *w = cp->work;
+        const size_t dx = cp->dx, dw = cp->dw;
+        double sg[C3SC_MAXD], st, bd, ob;
+        int32_t status;
+        if (node < w->N && !c3sc_model_eval(cp_dev(cp), 1, x, u, workspace_get_drift(w, node), sg, &st, &bd, &ob) &&
+            !c3sc_transition_batch(cp_dev(cp), 1, workspace_get_drift(w, node), sg, workspace_get_prob(w, node),
+                                   workspace_get_dt(w, node), &status)) {
+            double *df = workspace_get_diff(w, node);
+            memset(df, 0, dx * dw * sizeof(double));
+            for (size_t i = 0; i < dx && i < dw; i++) df[i * dx + i] = sg[i];
+            cp->res_last_grad = status;
+        }
+    }
     return val;
 }
 int bellman_optimal(size_t du, double *u, double *val, void *arg)
@@ -516,6 +605,7 @@ int bellman_optimal(size_t du, double *u, double *val, void *arg)
     int rc = c3sc_node_backup_batch(cp_dev(cp), 1, x, costs, &a32, val, &best);
     if (rc) return rc;
     for (size_t i = 0; i < du; i++) u[i] = best >= 0 ? cp->opt->vals[(size_t)best * du + i] : 0.0;
+    if (node < cp->work->N) memcpy(workspace_get_u(cp->work, node), u, du * sizeof(double));
     return 0;
 }
 
@@ -667,26 +757,38 @@ int bellman_pi(size_t N, const double *x, double *out, void *arg)
     return bellman_pi_batch(1, x, out, arg);
 }
 
+/* geometry-only device problem (C3SC_MODEL_NONE): grid, boundary types, obstacle boxes -- what the flag and
+   neighbour-value entries need; no dynamics, no control set */
+static c3sc_problem *geometry_problem(size_t d, const struct Boundary *bound, const size_t *ngrid, double *const *xgrid)
+{
+    if (d < 1 || d > C3SC_MAXD || !bound || bound->nobs > C3SC_MAXOBS) return NULL;
+    uint64_t ng[C3SC_MAXD]; int32_t bc[C3SC_MAXD];
+    double t[2 * C3SC_MAXD], lb[C3SC_MAXOBS * C3SC_MAXD], ub[C3SC_MAXOBS * C3SC_MAXD];
+    for (size_t i = 0; i < d; i++) { ng[i] = ngrid[i]; bc[i] = bound->type[i]; t[2 * i] = t[2 * i + 1] = 1.0; }
+    for (size_t k = 0; k < bound->nobs; k++) {
+        memcpy(lb + k * d, bound->obs_lb[k], d * sizeof(double));
+        memcpy(ub + k * d, bound->obs_ub[k], d * sizeof(double));
+    }
+    c3sc_problem_desc ds;
+    memset(&ds, 0, sizeof ds);
+    ds.dx = (uint32_t)d; ds.du = 1; ds.dw = (uint32_t)d;
+    ds.ngrid = ng; ds.xgrid = (const double *const *)xgrid; ds.h2 = 1.0; ds.t = t; ds.bc = bc;
+    ds.nobs = (uint32_t)bound->nobs; ds.obs_lb = lb; ds.obs_ub = ub;
+    ds.model = C3SC_MODEL_NONE; ds.arith = C3SC_ARITH_FAST;
+    c3sc_problem *p = NULL;
+    if (c3sc_problem_create(&ds, &p)) return NULL;
+    return p;
+}
+
+/* src/nodeutil.c:647-713 */
 int mca_get_neighbor_costs(size_t d, size_t N, const double *x, struct Boundary *bound, struct ValueF *vf,
                            const size_t *ngrid, double **xgrid, size_t *fixed_ind, size_t *dim_vary,
                            int *absorbed, double *out)
 {
     int rc = convert_fiber_to_ind(d, N, x, ngrid, xgrid, fixed_ind, dim_vary);
     if (rc) return rc;
-    /* geometry-only device problem: any instantiated model of this dimension carries the
-       flag + FT phases; its dynamics are not evaluated in this mode */
-    struct MCAparam m = { d, 1, (size_t *)ngrid, xgrid, 1.0, NULL, 1.0, NULL };
-    double t[2 * C3SC_MAXD], u0[C3SC_MAXD] = { 0 };
-    for (size_t i = 0; i < 2 * d; i++) t[i] = 1.0;
-    m.t = t;
-    struct DPparam dp;
-    memset(&dp, 0, sizeof dp);
-    dp.bound = bound;
-    dp.arith = C3SC_ARITH_FAST;
-    dp.model = (d % 2 == 0) ? C3SC_MODEL_LQGND : (d == 3 ? C3SC_MODEL_DUBINS : C3SC_MODEL_SKID5D);
-    m.du = (dp.model == C3SC_MODEL_LQGND) ? d / 2 : 1;
-    struct c3Opt opt = { BRUTEFORCE, m.du, 1, u0 };
-    c3sc_problem *p = make_problem(&dp, &m, &opt, d);
+    c3sc_problem *p = geometry_problem(d, bound, ngrid, xgrid);
+    if (!p) { fprintf(stderr, "c3sc_b200: mca_get_neighbor_costs: %s\n", c3sc_last_error()); return 1; }
     size_t nmax = 0;
     for (size_t i = 0; i < d; i++) if (ngrid[i] > nmax) nmax = ngrid[i];
     int32_t dv = (int32_t)*dim_vary, fi[C3SC_MAXD];
@@ -699,6 +801,54 @@ int mca_get_neighbor_costs(size_t d, size_t N, const double *x, struct Boundary 
         memcpy(out, costs, N * (2 * d + 1) * sizeof(double));
     }
     free(ab); free(costs);
+    c3sc_problem_destroy(p);
+    return rc;
+}
+
+/* src/nodeutil.c:489-627.  The reference signature carries the fiber's points but no grids: the coordinates the
+   obstacle test needs are all in x (the fixed ones in its first point, the varying one in every point), so a
+   geometry-only problem is built whose grids hold exactly those coordinates at the fiber's indices. */
+int process_fibers_neighbor(size_t d, const size_t *fixed_ind, size_t dim_vary, const double *x, int *absorbed,
+                            size_t *neighbors_vary, size_t *neighbors_fixed, const size_t *ngrid,
+                            const struct Boundary *bound)
+{
+    if (d < 1 || d > C3SC_MAXD || dim_vary >= d || !bound) return 1;
+    const size_t N = ngrid[dim_vary];
+    size_t nmax = 0;
+    for (size_t i = 0; i < d; i++) if (ngrid[i] > nmax) nmax = ngrid[i];
+    double *xg[C3SC_MAXD];
+    for (size_t i = 0; i < d; i++) {
+        xg[i] = xalloc(ngrid[i], sizeof(double));
+        if (i == dim_vary) for (size_t j = 0; j < N; j++) xg[i][j] = x[j * d + i];
+        else for (size_t j = 0; j < ngrid[i]; j++) xg[i][j] = x[i];        /* only entry fixed_ind[i] is read */
+    }
+    c3sc_problem *p = geometry_problem(d, bound, ngrid, xg);
+    int rc = p ? 0 : 1;
+    int32_t dv = (int32_t)dim_vary, fi[C3SC_MAXD];
+    for (size_t i = 0; i < d; i++) fi[i] = (int32_t)(i == dim_vary ? 0 : fixed_ind[i]);
+    int32_t *ab = xalloc(nmax, 4), *nv = xalloc(2 * nmax, 4), *nf = xalloc(2 * d, 4);
+    if (!rc) rc = c3sc_fiber_flags_batch(p, 1, &dv, fi, nmax, ab, nv, nf);
+    if (rc) fprintf(stderr, "c3sc_b200: process_fibers_neighbor: %s\n", c3sc_last_error());
+    else {
+        for (size_t j = 0; j < N; j++) { absorbed[j] = ab[j]; neighbors_vary[2 * j] = (size_t)nv[2 * j]; neighbors_vary[2 * j + 1] = (size_t)nv[2 * j + 1]; }
+        for (size_t q = 0; q + 2 < 2 * d; q++) neighbors_fixed[q] = (size_t)nf[q];
+    }
+    free(ab); free(nv); free(nf);
+    for (size_t i = 0; i < d; i++) free(xg[i]);
+    c3sc_problem_destroy(p);
+    return rc;
+}
+
+/* src/nodeutil.c:718-816 */
+int mca_get_neighbor_node_costs(size_t d, const double *x, struct Boundary *bound, struct ValueF *vf,
+                                const size_t *ngrid, double **xgrid, int *absorbed, double *out)
+{
+    c3sc_problem *p = geometry_problem(d, bound, ngrid, xgrid);
+    if (!p) { fprintf(stderr, "c3sc_b200: mca_get_neighbor_node_costs: %s\n", c3sc_last_error()); return 1; }
+    int32_t ab = 0;
+    int rc = c3sc_neighbor_node_costs_batch(p, vf->dev, 1, x, &ab, out);
+    if (rc) fprintf(stderr, "c3sc_b200: mca_get_neighbor_node_costs: %s\n", c3sc_last_error());
+    *absorbed = ab;
     c3sc_problem_destroy(p);
     return rc;
 }

@@ -55,6 +55,9 @@ enum c3sc_bc { C3SC_ABSORB = 1, C3SC_PERIODIC = 2, C3SC_REFLECT = 3 };
  *              params [s_xy, s_theta, stage, boundcost, obscost]
  *   SKID5D     examples/skidding5d/scar.c:39-176, params [obscost]         */
 enum c3sc_model {
+    C3SC_MODEL_NONE = 0,      /* geometry only: grid, boundary types, obstacles.  Enough for the entries that do
+                                 not evaluate dynamics (c3sc_neighbor_costs_batch, c3sc_neighbor_node_costs_batch,
+                                 c3sc_valuef_eval_batch); nu / controls may be 0 / NULL; backups are refused   */
     C3SC_MODEL_LQGND = 1,
     C3SC_MODEL_DOUBLE_INT = 2,
     C3SC_MODEL_DUBINS = 3,
@@ -134,8 +137,8 @@ int c3sc_peer_buffer_close(void *dev, int opened);
 /* ---- problem / value function ------------------------------------------ */
 int  c3sc_problem_create(const c3sc_problem_desc *desc, c3sc_problem **out);
 void c3sc_problem_destroy(c3sc_problem *p);
-/* returns C3SC_ENUMERIC if any launch since the last check hit norm<1e-14;
- * synchronises the device.                                                 */
+/* returns C3SC_ENUMERIC if any launch since the last check hit norm<1e-14, C3SC_EINVAL if
+ * one was given a fiber descriptor outside the grid; synchronises the device.               */
 int  c3sc_problem_check(c3sc_problem *p);
 /* how stage 2 walks the control table in FAST arithmetic: 0 = plain table walk, 1 = candidates grouped by
  * their share of the normaliser, 2 = shared-prefix walk of a full {lo, 0, hi}^du grid */
@@ -156,17 +159,24 @@ void c3sc_valuef_destroy(c3sc_valuef *vf);
 
 /* ---- fiber descriptors --------------------------------------------------- */
 /* A fiber is (dim_vary, fixed_ind[dx]): what convert_fiber_to_ind (src/nodeutil.c:437-470) decodes from
- * the reference's point list.  PRECONDITION of every batch entry below: 0 <= dim_vary < dx and
- * 0 <= fixed_ind[i] < ngrid[i] (the slot of the varying dimension is ignored by the kernels but must be
- * in range too; the reference stores the first node's index there, i.e. 0).  The reference-facing
- * wrappers (bellman_vi / bellman_pi in c3sc_host.h) produce descriptors by decoding and so cannot
- * violate it; the batch entries do NOT re-check -- a scan of F*(dx+1) integers ahead of the first launch
- * costs 5-15 % of a 65 536-fiber step -- except c3sc_vi_batch_debug.  c3sc_fibers_check is that scan for
- * callers who build descriptors themselves: HOST arrays, no device work; C3SC_EINVAL names the first
- * offending fiber in c3sc_last_error().                                                              */
+ * the reference's point list.  Valid means 0 <= dim_vary < dx and 0 <= fixed_ind[i] < ngrid[i] (the slot of
+ * the varying dimension is ignored by the kernels but must be in range too; the reference stores the first
+ * node's index there, i.e. 0).  EVERY batch entry validates its descriptors ON THE DEVICE, in the grouping
+ * kernel that reads them anyway (no host scan, no extra pass): an invalid descriptor makes the call return
+ * C3SC_EINVAL with the smallest offending fiber id in c3sc_last_error() -- the batch analogue of
+ * convert_fiber_to_ind's non-zero return -- and is clamped into the grid wherever a kernel uses it, so it is
+ * never a read outside the cores.  The host-buffer entries report it from the call itself; the asynchronous
+ * *_dev entries report it from the next c3sc_problem_check().  c3sc_fibers_check is the same test as a scan
+ * of HOST arrays, with no device work, for callers who want the answer before queueing anything.        */
 int c3sc_fibers_check(const c3sc_problem *p, size_t F, const int32_t *dim_vary, const int32_t *fixed_ind);
 
 /* ---- the hot path, device-resident arguments ---------------------------- */
+/* Concurrency contract (as for the reference's Workspace, src/util.c:689-964, which one C3Control owns and
+ * bellman_vi / bellman_pi mutate): ONE batch in flight per c3sc_problem.  A problem owns the pipeline scratch
+ * (grouping, cost scratch, lanes) that its batches reuse; queueing a second batch of the SAME problem on another
+ * stream or thread before the first has finished is a data race.  Different problems are independent.  The
+ * handle-free entries further down (c3sc_rhs_batch, c3sc_transition_raw, c3sc_ft_fiber_nn_batch) share static
+ * scratch and serialise themselves on a mutex.  c3sc_last_error() is per thread.                        */
 /* bellman_vi over F fibers (src/bellman.c:1295-1423, memo dropped: backups are
  * pure).  d_dim_vary [F], d_fixed_ind [F*dx] int32 device arrays.  stream is
  * a cudaStream_t (NULL = default stream).  Asynchronous.                   */
@@ -204,6 +214,10 @@ int c3sc_pi_batch(c3sc_problem *p, const c3sc_valuef *vf_policy, const c3sc_valu
 int c3sc_neighbor_costs_batch(c3sc_problem *p, const c3sc_valuef *vf, size_t F,
                               const int32_t *dim_vary, const int32_t *fixed_ind, size_t ldo,
                               int32_t *absorbed, double *costs, int32_t *nbr_vary, int32_t *nbr_fixed);
+/* process_fibers_neighbor (src/nodeutil.c:489-627) over F fibers: absorbed [F*ldo] (0 / 1 / -1), nbr_vary
+ * [F*ldo*2], nbr_fixed [F*2*(dx-1)] (either may be NULL).  No value function, no dynamics (C3SC_MODEL_NONE ok). */
+int c3sc_fiber_flags_batch(c3sc_problem *p, size_t F, const int32_t *dim_vary, const int32_t *fixed_ind,
+                           size_t ldo, int32_t *absorbed, int32_t *nbr_vary, int32_t *nbr_fixed);
 /* bellman_optimal (src/bellman.c:504-543) at n nodes with caller-supplied
  * neighbour costs [n*(2dx+1)] and flags (NULL = all 0): the building block of
  * the online controller (src/bellman.c:2105-2175).                           */
@@ -214,6 +228,11 @@ int c3sc_node_backup_batch(c3sc_problem *p, size_t n, const double *x, const dou
 /* valuef_eval (src/valuefunc.c:345-350 -> C3 function_train_eval on LINELM cores): piecewise-
  * linear interpolation of the nodal cores at n points x[n*dx]; 0 outside the grid.            */
 int c3sc_valuef_eval_batch(c3sc_problem *p, const c3sc_valuef *vf, size_t n, const double *x, double *out);
+/* mca_get_neighbor_node_costs (src/nodeutil.c:718-816) at n off-grid states x[n*dx]: absorbed [n],
+ * costs [n*(2dx+1)] (slot 2i / 2i+1 = V at x -+ h_i e_i with the boundary stand-ins; everything V(x) and
+ * flag -1 inside an obstacle; slot 2dx = V(x)).  No dynamics involved: a C3SC_MODEL_NONE problem will do. */
+int c3sc_neighbor_node_costs_batch(c3sc_problem *p, const c3sc_valuef *vf, size_t n, const double *x,
+                                   int32_t *absorbed, double *costs);
 /* c3control_policy_eval (src/bellman.c:2105-2151) at n states: mca_get_neighbor_node_costs
  * (src/nodeutil.c:718-816: V at x -+ h e_i with the boundary stand-ins, all V(x) and flag -1 inside
  * an obstacle) then bellman_optimal.  u [n*du]; value [n], absorbed [n], costs [n*(2dx+1)] may be

@@ -97,6 +97,22 @@ size_t workspace_get_pi_subiter(const struct Workspace *);
 double *workspace_get_costs(struct Workspace *, size_t);
 int *workspace_get_absorbed(struct Workspace *, size_t);
 double *workspace_get_u(struct Workspace *, size_t);
+/* per-node scratch slabs in the reference's layout (src/util.c:738-748,843-906).  The batched kernels keep these
+ * quantities in registers; the slabs are filled by the scalar entries bellman_control (drift, diff, dt, prob of the
+ * (node, u) it was called with) and bellman_optimal (u), which is how the reference's callers read them
+ * (src/bellman.c:400-449).  The gradient slabs exist for layout compatibility and stay zero (BFGS path out of scope). */
+void workspace_set_active(struct Workspace *, size_t);
+size_t workspace_get_active(struct Workspace *);
+double *workspace_get_drift(struct Workspace *, size_t);
+double *workspace_get_grad_drift(struct Workspace *, size_t);
+double *workspace_get_diff(struct Workspace *, size_t);
+double *workspace_get_grad_diff(struct Workspace *, size_t);
+double *workspace_get_dt(struct Workspace *, size_t);
+double *workspace_get_grad_dt(struct Workspace *, size_t);
+double *workspace_get_prob(struct Workspace *, size_t);
+double *workspace_get_grad_prob(struct Workspace *, size_t);
+double *workspace_get_grad_stage(struct Workspace *, size_t);
+double *workspace_get_control_size_extra(struct Workspace *, size_t);
 
 /* ---- minimal c3opt (brute force only; C3's lib_optimization.h is absent) ------- */
 enum c3opt_alg { BFGS, LBFGS, BATCHGRAD, BRUTEFORCE, SGD };
@@ -118,6 +134,10 @@ int valuef_update_cores(struct ValueF *, double *const *cores);
 void valuef_destroy(struct ValueF *);                                     /* src/valuefunc.c:104 */
 struct ValueF *valuef_copy(struct ValueF *);                              /* :194 */
 size_t *valuef_get_ranks(struct ValueF *);                                /* :300 */
+/* Stand-in for C3's struct CrossIndex (absent): n multi-indices over the d leading dimensions, as grid indices
+ * (inds[a*d + i]) and, when the value function knows its grid, node coordinates (vals, what C3 stores). */
+struct CrossIndex { size_t d, n; size_t *inds; double *vals; };
+struct CrossIndex **valuef_get_isl(const struct ValueF *);               /* :218; owned by the value function */
 int valuef_eval_fiber_ind_nn(struct ValueF *, const size_t *, size_t, const size_t *, const size_t *,
                              double *);                                   /* :369 */
 
@@ -128,6 +148,11 @@ int transition_assemble(size_t dx, size_t du, size_t dw, double h, const double 
                         double *grad_dt, double *space);                  /* src/nodeutil.c:267 */
 int convert_fiber_to_ind(size_t d, size_t N, const double *x, const size_t *Ngrid, double **xgrid,
                          size_t *fixed_ind, size_t *dim_vary);            /* :437 (host: index decode) */
+int process_fibers_neighbor(size_t d, const size_t *fixed_ind, size_t dim_vary, const double *x, int *absorbed,
+                            size_t *neighbors_vary, size_t *neighbors_fixed, const size_t *ngrid,
+                            const struct Boundary *bound);                /* :489 */
+int mca_get_neighbor_node_costs(size_t d, const double *x, struct Boundary *bound, struct ValueF *vf,
+                                const size_t *ngrid, double **xgrid, int *absorbed, double *out);   /* :718 */
 
 /* ---- bellman.h ----------------------------------------------------------------- */
 double bellmanrhs(size_t dx, size_t du, double stage_cost, const double *stage_grad, double discount,

@@ -91,7 +91,8 @@ class Port:
         self.cfg = cfg
         self.dx = cfg.dx
         params = np.ascontiguousarray(cfg.params, dtype=np.float64)
-        if L.orc_model_select(cfg.model, cfg.dx, _p(params) if params.size else None, params.size):
+        # model 0 = geometry only (flags, neighbour indices, neighbour values): no dynamics callbacks
+        if cfg.model and L.orc_model_select(cfg.model, cfg.dx, _p(params) if params.size else None, params.size):
             raise ValueError("oracle: unknown model")
         self.ngrid = np.ascontiguousarray(cfg.ngrid, dtype=np.uintp)
         self.nmax = int(self.ngrid.max())
@@ -115,8 +116,9 @@ class Port:
         p.beta = cfg.beta
         p.nu = cfg.nu
         p.utab = self.utab.ctypes.data_as(f64p)
-        p.drift = L.orc_model_drift(); p.diff = L.orc_model_diff(); p.diff_arg = L.orc_model_diff_arg()
-        p.stage = L.orc_model_stage(); p.boundcost = L.orc_model_boundcost(); p.obscost = L.orc_model_obscost()
+        if cfg.model:
+            p.drift = L.orc_model_drift(); p.diff = L.orc_model_diff(); p.diff_arg = L.orc_model_diff_arg()
+            p.stage = L.orc_model_stage(); p.boundcost = L.orc_model_boundcost(); p.obscost = L.orc_model_obscost()
 
     def fiber_points(self, k, fixed):
         fixed = np.ascontiguousarray(fixed, dtype=np.intc)

@@ -11,7 +11,8 @@ import pytest
 
 from c3sc_b200 import capi, configs, synthetic
 from oracle import pyoracle as po
-from helpers import SMALL, make_ft, make_port, rel_err, valid_mask
+from helpers import (SMALL, make_ft, make_port, rel_err, valid_mask, elem_err_costs, elem_err_values,
+                     argmin_mismatches_are_ties)
 
 pytestmark = pytest.mark.gpu
 RTOL = 1e-12
@@ -60,8 +61,14 @@ def test_vi_debug_against_oracle(gpu, name, n, rank, dx, arith):
         _, costs = port.neighbor_costs(ft, dv[f], fi[f])
         assert rel_err(out["costs"][f, :N], costs, scale=np.abs(costs).max()) <= RTOL, f
     assert rel_err(out["value"][m], oval[m], scale=np.abs(oval[m]).max()) <= RTOL
-    nbad = _argmin_ok(cfg, port, ft, dv, fi, out["argmin"], oarg, oval)
+    nbad = argmin_mismatches_are_ties(cfg, port, ft, dv, fi, out["argmin"], oarg)
     assert nbad <= 0.01 * m.sum()
+    # per-element errors (scale = sum|terms| of the element) beside the batch-max figure above
+    for f in range(0, len(dv), 7):
+        N = int(cfg.ngrid[dv[f]])
+        ec, _, scale = elem_err_costs(port, ft, dv[f], fi[f], out["costs"][f, :N])
+        assert ec <= RTOL, (f, ec)
+        assert elem_err_values(out["value"][f, :N], oval[f, :N], scale) <= RTOL, f
     prob.close(); vf.close()
 
 
@@ -108,7 +115,7 @@ def test_pi_two_subiterations(gpu, name, n, rank, dx, arith):
     v1, rows, arg = prob.pi_batch(vf_pol, vf_it, dv, fi)
     o1, orows, oarg = port.pi_batch(ft_pol, ft_it, dv, fi)
     assert rel_err(v1[m], o1[m]) <= RTOL
-    assert (arg[m] == oarg[m]).mean() > 0.99
+    argmin_mismatches_are_ties(cfg, port, ft_pol, dv, fi, arg, oarg)
     vf_it.update(c_it2)
     v2, _, _ = prob.pi_batch(None, vf_it, dv, fi, rows=rows)
     o2, _, _ = port.pi_batch(ft_pol, ft_it2, dv, fi, rows=orows)
@@ -184,7 +191,7 @@ def test_full_size_configs(gpu):
         val, arg = prob.vi_batch(vf, dv, fi)
         oval, oarg = port.vi_batch(ft, dv, fi)
         assert rel_err(val, oval) <= RTOL, name
-        assert (arg == oarg).mean() > 0.999, name
+        assert argmin_mismatches_are_ties(cfg, port, ft, dv, fi, arg, oarg) <= 1e-3 * arg.size, name
         # properties on a bigger batch
         dv, fi = synthetic.random_fibers(cfg.ngrid, 2000, seed=99)
         v1, a1 = prob.vi_batch(vf, dv, fi)
@@ -288,4 +295,60 @@ def test_cuda_path_against_golden_fixtures(gpu, fname, arith):
     p2, _, _ = prob.pi_batch(None, vf, dv, fi, rows=rows)
     assert rel_err(p1[m], z["pi1"][m], scale=np.abs(z["pi1"][m]).max()) <= RTOL
     assert rel_err(p2[m], z["pi2"][m], scale=np.abs(z["pi2"][m]).max()) <= RTOL
+    prob.close(); vf.close(); vf2.close()
+
+
+def test_timed_workload_full_size_against_oracle(gpu, capsys):
+    """The workload bench.py times -- lqgnd_reflect, d = 10, N = 100, r = 20, 243 controls -- at a batch large
+    enough for the pipeline the bench runs (two lanes, several chunks: >= 2*148*1024 nodes), all ten varying
+    dimensions, faces included: values and argmin of all 4096 fibers against the oracle; flags, neighbour
+    indices and neighbour values of a 320-fiber subset through the debug entry.  Errors are judged per
+    ELEMENT against sum|terms| of that element, and the batch-max figure is printed beside it."""
+    cfg = configs.get_config("lqgnd_reflect")
+    assert (cfg.dx, cfg.n, cfg.rank, cfg.nu) == (10, 100, 20, 243)
+    prob = capi.Problem(cfg, arith=1)
+    assert capi.lib().c3sc_problem_control_path(prob.handle) == 2            # the grid walk, as in the bench
+    port = make_port(cfg)
+    ranks, cores, ft = make_ft(cfg)
+    vf = capi.ValueF(cfg.ngrid, ranks, cores)
+    F = 4096
+    assert F * cfg.n >= 2 * 148 * 1024
+    dv, fi = synthetic.random_fibers(cfg.ngrid, F)
+    assert set(dv.tolist()) == set(range(10))
+    val, arg = prob.vi_batch(vf, dv, fi)                                   # the timed entry point
+    oval, oarg = port.vi_batch(ft, dv, fi)
+    # debug entry (every intermediate) on a subset that covers every dimension and the face fibers
+    sub = np.arange(0, F, F // 320)[:320]
+    dbg = prob.vi_batch_debug(vf, dv[sub], fi[sub])
+    worst_c = worst_v = 0.0
+    for q, f in enumerate(sub):
+        ab, nv, nf = port.fiber_neighbors(dv[f], fi[f])
+        assert np.array_equal(dbg["absorbed"][q], ab), f
+        assert np.array_equal(dbg["nbr_vary"][q], nv), f
+        assert np.array_equal(dbg["nbr_fixed"][q, :cfg.dx - 1], nf), f
+        ec, ocost, scale = elem_err_costs(port, ft, dv[f], fi[f], dbg["costs"][q])
+        worst_c = max(worst_c, ec)
+        worst_v = max(worst_v, elem_err_values(val[f], oval[f], scale), elem_err_values(dbg["value"][q], oval[f], scale))
+    batch_rel = rel_err(val, oval, scale=np.abs(oval).max())
+    # per-element figure over ALL fibers with the node's own magnitude as scale (no batch max involved)
+    own = float((np.abs(val - oval) / np.maximum(np.abs(oval), 1e-300)).max())
+    nties = argmin_mismatches_are_ties(cfg, port, ft, dv, fi, arg, oarg)
+    with capsys.disabled():
+        print(f"\n[full size lqgnd_reflect F={F}] costs per-element {worst_c:.2e}; values per-element (sum|terms| scale) "
+              f"{worst_v:.2e}, (own magnitude) {own:.2e}, (batch max scale) {batch_rel:.2e}; argmin mismatches {nties} (all ties)")
+    assert worst_c <= RTOL and worst_v <= RTOL and batch_rel <= RTOL
+    assert own <= 1e-9                               # a value that cancels to ~0 may lose digits; nothing does here
+    assert nties <= 1e-4 * F * cfg.n
+    # bellman_pi at the same size: improvement against vf, evaluation against a second train, then a sub-iteration
+    _, cores2, ft2 = make_ft(cfg, seed=0xABCD00)
+    vf2 = capi.ValueF(cfg.ngrid, ranks, cores2)
+    p1, rows, parg = prob.pi_batch(vf, vf2, dv, fi)
+    o1, orows, opa = port.pi_batch(ft, ft2, dv, fi)
+    assert rel_err(p1, o1, scale=np.abs(o1).max()) <= RTOL
+    assert argmin_mismatches_are_ties(cfg, port, ft, dv, fi, parg, opa) <= 1e-4 * F * cfg.n
+    p2, _, _ = prob.pi_batch(None, vf, dv, fi, rows=rows)
+    same = parg == opa
+    o2, _, _ = port.pi_batch(ft, ft, dv, fi, rows=orows)
+    assert rel_err(p2[same], o2[same], scale=np.abs(o2).max()) <= RTOL
+    assert np.array_equal(parg, arg)                                       # same argmin as value iteration on vf
     prob.close(); vf.close(); vf2.close()

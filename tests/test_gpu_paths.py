@@ -6,7 +6,7 @@ import pytest
 
 from c3sc_b200 import capi, configs, synthetic
 from oracle import pyoracle as po
-from helpers import make_port, rel_err, valid_mask
+from helpers import make_port, rel_err, valid_mask, argmin_mismatches_are_ties, elem_err_costs, elem_err_values
 
 pytestmark = pytest.mark.gpu
 RTOL = 1e-12
@@ -27,10 +27,12 @@ def _check_costs_and_values(cfg, ranks, F, seed=5, face_frac=0.2):
         ab, nv, nf = port.fiber_neighbors(dv[f], fi[f])
         assert np.array_equal(out["absorbed"][f, :N], ab), f
         assert np.array_equal(out["nbr_vary"][f, :N], nv), f
-        _, costs = port.neighbor_costs(ft, dv[f], fi[f])
+        ec, costs, scale = elem_err_costs(port, ft, dv[f], fi[f], out["costs"][f, :N])      # per element, scale = sum|terms|
+        assert ec <= RTOL, (f, ec)
         assert rel_err(out["costs"][f, :N], costs, scale=np.abs(costs).max()) <= RTOL, f
+        assert elem_err_values(out["value"][f, :N], oval[f, :N], scale) <= RTOL, f
     assert rel_err(out["value"][m], oval[m], scale=np.abs(oval[m]).max()) <= RTOL
-    assert (out["argmin"][m] == oarg[m]).mean() > 0.99
+    assert argmin_mismatches_are_ties(cfg, port, ft, dv, fi, out["argmin"], oarg) <= 0.01 * m.sum()
     prob.close(); vf.close()
 
 
@@ -73,8 +75,10 @@ def test_large_batch_is_chunked_consistently(gpu):
     """a batch larger than one pipeline chunk gives the same numbers as its pieces"""
     cfg = configs.get_config("lqgnd_reflect", n=20, rank=6, dx=8)
     prob = capi.Problem(cfg, arith=1)
+    port = make_port(cfg)
     ranks = cfg.ranks()
     cores = synthetic.random_cores(cfg.ngrid, ranks)
+    ft = po.FT(cfg.ngrid, ranks, cores)
     vf = capi.ValueF(cfg.ngrid, ranks, cores)
     F = 60000                                   # 60000 * 20 * 17 * 8 B = 163 MB of cost scratch -> 2 chunks
     dv, fi = synthetic.random_fibers(cfg.ngrid, F, seed=3)
@@ -83,7 +87,7 @@ def test_large_batch_is_chunked_consistently(gpu):
         v2, a2 = prob.vi_batch(vf, dv[lo:hi], fi[lo:hi])
         # large and small batches take different stage-2 kernels: same numbers to round-off, same argmin
         assert rel_err(val[lo:hi], v2) <= 1e-13
-        assert (arg[lo:hi] == a2).mean() > 0.999
+        assert argmin_mismatches_are_ties(cfg, port, ft, dv[lo:hi], fi[lo:hi], arg[lo:hi], a2) <= 1e-3 * a2.size
     prob.close(); vf.close()
 
 
@@ -167,7 +171,7 @@ def test_grid_walk_equals_table_walk(gpu, name, n, rank, dx, F):
     val, arg = prob.vi_batch(vf, dv, fi)
     oval, oarg = port.vi_batch(ft, dv, fi, nthreads=4)
     assert rel_err(val[m], oval[m], scale=np.abs(oval[m]).max()) <= RTOL
-    assert (arg[m] == oarg[m]).mean() > 0.99
+    assert argmin_mismatches_are_ties(cfg, port, ft, dv, fi, arg, oarg) <= 0.01 * m.sum()
     p1, rows, _ = prob.pi_batch(vf, vf2, dv, fi)
     o1, orows, _ = port.pi_batch(ft, ft2, dv, fi)
     assert rel_err(p1[m], o1[m], scale=np.abs(o1[m]).max()) <= RTOL
@@ -177,7 +181,7 @@ def test_grid_walk_equals_table_walk(gpu, name, n, rank, dx, F):
     finally:
         del os.environ["C3SC_NO_GRID"]
     assert rel_err(val[m], val2[m], scale=np.abs(val2[m]).max()) <= 1e-13
-    assert (arg[m] == arg2[m]).mean() > 0.999
+    assert argmin_mismatches_are_ties(cfg, port, ft, dv, fi, arg, arg2) <= 1e-3 * m.sum()
     prob.close(); vf.close(); vf2.close()
 
 

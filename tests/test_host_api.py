@@ -484,3 +484,194 @@ def test_valuef_save_and_load_round_trip(gpu, tmp_path):
         want = port.ft_eval_linear(ft, np.ascontiguousarray(pt))
         assert abs(L.valuef_eval(back, po._p(np.ascontiguousarray(pt))) - want) <= 1e-12 * max(1.0, abs(want))
     L.valuef_destroy(back); L.valuef_destroy(vf); hp.close()
+
+
+# ---- reference names added in round 2: process_fibers_neighbor, mca_get_neighbor_node_costs,
+# ---- valuef_get_isl, the per-node workspace slabs -------------------------------------------------------
+def _geom_config(name, n, rank, dx):
+    """a BASELINE config, or "geom7": a 7-dimensional grid with mixed boundary types and an obstacle but NO
+    dynamics model (model id 0) -- for the entries of the path that are pure geometry + FT evaluation"""
+    if name != "geom7":
+        return configs.get_config(name, n=n, rank=rank, dx=dx)
+    d = 7
+    bc = np.array([configs.ABSORB, configs.REFLECT, configs.PERIODIC, configs.ABSORB, configs.REFLECT, configs.ABSORB, configs.PERIODIC], np.int32)
+    return configs.Config("geom7", 0, d, 1, d, n, np.full(d, -1.0), np.linspace(1.0, 2.0, d), bc, 0.1, np.zeros((1, 1)), rank,
+                          obs_center=np.full((1, d), 0.1), obs_width=np.full((1, d), 0.9))
+
+
+def _r2_lib():
+    L = solver_lib()
+    L.process_fibers_neighbor.argtypes = [sz, vp, sz, vp, vp, vp, vp, vp, vp]
+    L.mca_get_neighbor_node_costs.argtypes = [sz, vp, vp, vp, vp, vp, vp, vp]
+    L.valuef_get_isl.restype = vp
+    L.valuef_get_isl.argtypes = [vp]
+    for n in ("workspace_get_drift", "workspace_get_diff", "workspace_get_dt", "workspace_get_prob", "workspace_get_u",
+              "workspace_get_grad_drift", "workspace_get_grad_prob"):
+        getattr(L, n).restype = vp
+        getattr(L, n).argtypes = [vp, sz]
+    return L
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name,n,rank,dx", [("double_int", 24, 5, None), ("dubinscar_new", 16, 4, None),
+                                             ("skidding5d", 10, 3, None), ("lqgnd_reflect", 8, 3, 6), ("geom7", 6, 2, 7)])
+def test_process_fibers_neighbor_reference_signature(gpu, name, n, rank, dx):
+    """process_fibers_neighbor (src/nodeutil.c:489-627) with the reference's own argument list (no grids: the
+    coordinates come from x), every varying dimension, faces and obstacle fibers: bit-exact flags and indices.
+    d = 7 has no device dynamics model and must still work (the entry is geometry only)."""
+    L = _r2_lib()
+    cfg = _geom_config(name, n, rank, dx)
+    port = make_port(cfg)
+    lb = np.ascontiguousarray(cfg.lb); ub = np.ascontiguousarray(cfg.ub); ng = np.ascontiguousarray(cfg.ngrid, np.uintp)
+    L.c3control_create.restype = vp
+    c3c = L.c3control_create(cfg.dx, cfg.du, cfg.dw, po._p(lb), po._p(ub), po._p(ng), cfg.beta)
+    for i in range(cfg.dx):
+        if cfg.bc[i] != configs.ABSORB:
+            L.c3control_set_external_boundary(c3c, i, BC_NAME[int(cfg.bc[i])])
+    for o in range(cfg.obs_center.shape[0] if cfg.obs_center.size else 0):
+        L.c3control_add_obstacle(c3c, po._p(np.ascontiguousarray(cfg.obs_center[o])), po._p(np.ascontiguousarray(cfg.obs_width[o])))
+    bound = L.c3control_get_boundary(c3c)
+    dv, fi = synthetic.random_fibers(cfg.ngrid, 3 * cfg.dx, face_frac=0.3)
+    if cfg.obs_center.size:                                               # a fiber through the obstacle's centre
+        fi[0] = [int(np.argmin(np.abs(port.xgrid[i] - cfg.obs_center[0][i]))) for i in range(cfg.dx)]
+    for f in range(len(dv)):
+        k = int(dv[f]); N = int(cfg.ngrid[k])
+        x = port.fiber_points(k, fi[f])
+        fz = np.ascontiguousarray(fi[f], np.uintp); fz[k] = 0
+        ab = np.full(N, 9, np.intc); nv = np.zeros(2 * N, np.uintp); nf = np.zeros(max(2 * (cfg.dx - 1), 1), np.uintp)
+        assert L.process_fibers_neighbor(cfg.dx, po._p(fz), k, po._p(x), po._p(ab), po._p(nv), po._p(nf), po._p(ng), bound) == 0
+        oab, onv, onf = port.fiber_neighbors(k, fi[f])
+        assert np.array_equal(ab, oab), (f, k)
+        assert np.array_equal(nv.reshape(N, 2), onv), (f, k)
+        assert np.array_equal(nf.reshape(-1, 2)[:cfg.dx - 1], onf[:cfg.dx - 1]), (f, k)
+    L.c3control_destroy(c3c)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name,n,rank,dx", [("dubinscar_new", 14, 4, None), ("skidding5d", 10, 3, None), ("geom7", 6, 2, 7)])
+def test_mca_get_neighbor_costs_and_node_costs_are_model_free(gpu, name, n, rank, dx):
+    """mca_get_neighbor_costs (src/nodeutil.c:647) and mca_get_neighbor_node_costs (:718) with the reference's
+    signatures on a geometry-only device problem -- including d = 7, which has no instantiated dynamics model."""
+    L = _r2_lib()
+    cfg = _geom_config(name, n, rank, dx)
+    port = make_port(cfg)
+    ranks, cores, ft = make_ft(cfg)
+    lb = np.ascontiguousarray(cfg.lb); ub = np.ascontiguousarray(cfg.ub); ng = np.ascontiguousarray(cfg.ngrid, np.uintp)
+    L.c3control_create.restype = vp
+    c3c = L.c3control_create(cfg.dx, cfg.du, cfg.dw, po._p(lb), po._p(ub), po._p(ng), cfg.beta)
+    for i in range(cfg.dx):
+        if cfg.bc[i] != configs.ABSORB:
+            L.c3control_set_external_boundary(c3c, i, BC_NAME[int(cfg.bc[i])])
+    for o in range(cfg.obs_center.shape[0] if cfg.obs_center.size else 0):
+        L.c3control_add_obstacle(c3c, po._p(np.ascontiguousarray(cfg.obs_center[o])), po._p(np.ascontiguousarray(cfg.obs_width[o])))
+    bound, xg = L.c3control_get_boundary(c3c), L.c3control_get_xgrid(c3c)
+    nn = np.ascontiguousarray(cfg.ngrid, np.uintp); rr = np.ascontiguousarray(ranks, np.uintp)
+    cs = [np.ascontiguousarray(c, np.float64) for c in cores]
+    arr = (vp * len(cs))(*[c.ctypes.data for c in cs])
+    vf = L.valuef_from_cores(len(cs), po._p(nn), po._p(rr), arr)
+    dv, fi = synthetic.random_fibers(cfg.ngrid, 6, face_frac=0.3)
+    for f in range(len(dv)):
+        k = int(dv[f]); N = int(cfg.ngrid[k])
+        x = port.fiber_points(k, fi[f])
+        fo = np.zeros(cfg.dx, np.uintp); kk = sz(); ab = np.zeros(N, np.intc); costs = np.zeros((N, 2 * cfg.dx + 1))
+        assert L.mca_get_neighbor_costs(cfg.dx, N, po._p(x), bound, vf, po._p(ng), xg, po._p(fo), C.byref(kk), po._p(ab), po._p(costs)) == 0
+        oab, oc = port.neighbor_costs(ft, k, fi[f])
+        assert kk.value == k and np.array_equal(ab, oab)
+        assert rel_err(costs, oc, scale=np.abs(oc).max()) <= 1e-12
+    u = synthetic.uniform01(5, 40 * cfg.dx).reshape(40, cfg.dx)
+    pts = cfg.lb + u * (cfg.ub - cfg.lb)
+    pts[::5] = cfg.lb; pts[1::5] = cfg.ub
+    if cfg.obs_center.size:
+        pts[2::7] = cfg.obs_center[0]
+    for x in pts:
+        x = np.ascontiguousarray(x)
+        ab = C.c_int(5); out = np.zeros(2 * cfg.dx + 1)
+        assert L.mca_get_neighbor_node_costs(cfg.dx, po._p(x), bound, vf, po._p(ng), xg, C.byref(ab), po._p(out)) == 0
+        oab, oout = port.neighbor_node_costs(ft, x)
+        assert ab.value == oab
+        m = 2 * cfg.dx                                                    # slot 2dx is left unset by the reference
+        assert rel_err(out[:m], oout[:m], scale=max(np.abs(oout[:m]).max(), 1e-300)) <= 1e-12
+    L.valuef_destroy(vf); L.c3control_destroy(c3c)
+
+
+@pytest.mark.gpu
+def test_workspace_slabs_after_bellman_control(gpu):
+    """workspace_get_{drift,diff,dt,prob,u} (src/util.c:876-906): after bellman_control(node, u) the node's slab holds
+    what the reference leaves there (src/bellman.c:400-449) -- checked against the oracle's transition row"""
+    L = _r2_lib()
+    cfg = configs.get_config("skidding5d", n=10, rank=3)
+    hp = HostProblem(L, cfg, arith=0)
+    port = make_port(cfg)
+    ranks, cores, ft = make_ft(cfg)
+    dx = cfg.dx
+    k, fixed = 1, np.array([3, 0, 2, 4, 6], np.int32)
+    x = port.fiber_points(k, fixed)
+    oab, ocosts = port.neighbor_costs(ft, k, fixed)
+    work = L.c3control_get_work(hp.c3c)
+    L.control_params_add_time_and_states(hp.cp, 0.0, cfg.n, po._p(x))
+    wc = np.ctypeslib.as_array(C.cast(L.workspace_get_costs(work, 0), C.POINTER(dbl)), shape=(cfg.n, 2 * dx + 1))
+    wa = np.ctypeslib.as_array(C.cast(L.workspace_get_absorbed(work, 0), C.POINTER(C.c_int)), shape=(cfg.n,))
+    wc[:] = ocosts; wa[:] = 0
+
+    class Mem(C.Structure):
+        _fields_ = [("shared", vp), ("private_", sz)]
+    for j in (1, 4, 8):
+        for cand in (0, cfg.nu // 2, cfg.nu - 1):
+            u = np.ascontiguousarray(cfg.controls[cand])
+            mem = Mem(hp.cp, j)
+            L.bellman_control(cfg.du, po._p(u), None, C.byref(mem))
+            od, osg, *_ = port.model_eval(x[j:j + 1], u[None, :])
+            op, odt, ost = port.transition(od, osg)
+            drift = np.ctypeslib.as_array(C.cast(L.workspace_get_drift(work, j), C.POINTER(dbl)), shape=(dx,))
+            diff = np.ctypeslib.as_array(C.cast(L.workspace_get_diff(work, j), C.POINTER(dbl)), shape=(dx, cfg.dw))
+            dt = C.cast(L.workspace_get_dt(work, j), C.POINTER(dbl))[0]
+            prob = np.ctypeslib.as_array(C.cast(L.workspace_get_prob(work, j), C.POINTER(dbl)), shape=(2 * dx + 1,))
+            assert rel_err(drift, od[0], scale=1.0) <= 1e-14
+            assert np.array_equal(np.diag(diff), osg[0]) and np.count_nonzero(diff - np.diag(np.diag(diff))) == 0
+            assert rel_err(prob[:-1], op[0][:-1], scale=1e-3) <= 1e-13 and abs(prob[-1] - op[0][-1]) <= 1e-15
+            assert abs(dt - odt[0]) <= 1e-14 * odt[0]
+        uo = np.zeros(cfg.du); val = dbl()
+        mem = Mem(hp.cp, j)
+        assert L.bellman_optimal(cfg.du, po._p(uo), C.byref(val), C.byref(mem)) == 0
+        wu = np.ctypeslib.as_array(C.cast(L.workspace_get_u(work, j), C.POINTER(dbl)), shape=(cfg.du,))
+        assert np.array_equal(wu, uo)
+    # slab layout of src/util.c:738-748: grad_drift follows drift, grad_prob follows prob
+    assert L.workspace_get_grad_drift(work, 2) - L.workspace_get_drift(work, 2) == 8 * dx
+    assert L.workspace_get_grad_prob(work, 2) - L.workspace_get_prob(work, 2) == 8 * (2 * dx + 1)
+    hp.close()
+
+
+@pytest.mark.gpu
+def test_valuef_get_isl_after_a_cross_run(gpu):
+    """valuef_get_isl (src/valuefunc.c:218): the left index sets of the cross run that produced the value function,
+    r_k multi-indices over dimensions 0..k-1, equal to c3sc_cross_index_sets of the same run"""
+    L = _r2_lib()
+    cfg = configs.get_config("lqgnd", n=10, rank=3, dx=4)
+    hp = HostProblem(L, cfg, arith=1)
+    prob = capi.Problem(cfg, arith=1)
+    r0, c0 = synthetic.quadratic_cores(prob.xgrid)
+    v0 = hp.valuef(r0, c0)
+    assert not L.valuef_get_isl(v0)                                         # not produced by a cross run
+    a = L.approx_args_init()
+    L.approx_args_set_adapt(a, 0); L.approx_args_set_startrank(a, 3); L.approx_args_set_cross_tol(a, 1e-10)
+    nev = sz(0)
+    v1 = L.c3control_step_vi(hp.c3c, v0, a, hp.opt, 0, C.byref(nev))
+    ranks, _ = _host_cores(L, v1, cfg.ngrid)
+
+    class CI(C.Structure):
+        _fields_ = [("d", sz), ("n", sz), ("inds", C.POINTER(sz)), ("vals", C.POINTER(dbl))]
+    isl = C.cast(L.valuef_get_isl(v1), C.POINTER(C.POINTER(CI)))
+    assert isl
+    for k in range(cfg.dx):
+        ci = isl[k].contents
+        assert ci.d == k and ci.n == int(ranks[k])
+        for a_ in range(ci.n):
+            for i in range(k):
+                idx = ci.inds[a_ * k + i]
+                assert idx < cfg.ngrid[i]
+                if ci.vals:
+                    assert ci.vals[a_ * k + i] == prob.xgrid[i][idx]
+        if k >= 1:                                                          # multi-indices of a set are distinct
+            rows = {tuple(ci.inds[a_ * k + i] for i in range(k)) for a_ in range(ci.n)}
+            assert len(rows) == ci.n
+    L.valuef_destroy(v0); L.valuef_destroy(v1); L.approx_args_free(a); hp.close(); prob.close()
