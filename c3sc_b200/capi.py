@@ -66,7 +66,7 @@ EXPORTS = [
     "c3sc_valuef_eval_batch", "c3sc_policy_eval_batch",
     "c3sc_cross_index_sets", "c3sc_cores_round", "c3sc_cross_adapt_capacity", "c3sc_cross_set_ranks", "c3sc_cross_run_adapt", "c3sc_cross_run_vi_adapt",
     "c3sc_peer_buffer_create", "c3sc_peer_buffer_open", "c3sc_peer_buffer_close",
-    "c3sc_fibers_check", "c3sc_fiber_flags_batch", "c3sc_neighbor_node_costs_batch",
+    "c3sc_fibers_check", "c3sc_fiber_flags_batch", "c3sc_neighbor_node_costs_batch", "c3sc_stage1_batch_dev",
 ]
 
 _lib = None
@@ -101,6 +101,7 @@ def lib() -> C.CDLL:
         L.c3sc_vi_batch.argtypes = [vp, vp, sz, vp, vp, sz, vp, vp]
         L.c3sc_vi_batch_debug.argtypes = [vp, vp, sz, vp, vp, sz, vp, vp, vp, vp, vp, vp, vp]
         L.c3sc_fibers_check.argtypes = [vp, sz, vp, vp]
+        L.c3sc_stage1_batch_dev.argtypes = [vp, vp, sz, vp, vp, sz, vp]
         L.c3sc_fiber_flags_batch.argtypes = [vp, sz, vp, vp, sz, vp, vp, vp]
         L.c3sc_neighbor_node_costs_batch.argtypes = [vp, vp, sz, vp, vp, vp]
         L.c3sc_pi_batch.argtypes = [vp, vp, vp, sz, vp, vp, sz, i32, vp, vp, vp]

@@ -8,7 +8,7 @@
 #include <vector>
 #include "dev_types.h"
 #define C3SC_FT_TYPES_ONLY
-#include "ft_kernel.cuh"        // FtArgs (host side; the kernels are compiled in ft.cu)
+#include "chain_kernel.cuh"     // FtArgs, ChainArgs (host side; the kernels are compiled in ft.cu)
 #include "control_kernel.cuh"   // CtlArgs
 
 namespace c3sc {
@@ -25,6 +25,11 @@ int ft_uses_mma(const DevFT &ft);
 int launch_ft_eval_points(const DevProblem &P, const DevFT &ft, int npts, const double *pts, double *out, cudaStream_t st);
 int launch_policy_points(const DevProblem &P, int n, const double *x, double *pts, int *absorbed, cudaStream_t st);
 size_t ft_sets_bytes(const DevFT &ft, size_t F);
+void ft_record_geometry(const DevFT &ft, int *setw, int *rs);
+void chain_plan_sizes(const DevFT &ft, int nmax, size_t FC, size_t *kst, size_t *tst, size_t *ent);
+int chain_bucketed_ok(const DevFT &ft, int nmax);
+int launch_chain_plan(const ChainArgs &a, int FC, cudaStream_t st);
+int launch_chain_steps(const ChainArgs &a, cudaStream_t st, int *n);
 int launch_node_backup_lqg_lo(int dx, int arith, const DevProblem &P, int n, const double *x, const double *costs,
                               const int *absorbed, double *value, int *argmin, cudaStream_t st);
 int launch_node_backup_lqg_hi(int dx, int arith, const DevProblem &P, int n, const double *x, const double *costs,
@@ -102,12 +107,12 @@ struct LaneScratch {
     }
 };
 struct Scratch {
-    DevBuf perm, cnt;
+    DevBuf perm, cnt, plan_k, plan_t, plan_e;
     LaneScratch lane[MAXLANES];
     cudaEvent_t fork = nullptr;
     void release()
     {
-        perm.release(); cnt.release();
+        perm.release(); cnt.release(); plan_k.release(); plan_t.release(); plan_e.release();
         for (LaneScratch &l : lane) l.release();
         if (fork) cudaEventDestroy(fork);
         fork = nullptr;
@@ -522,7 +527,7 @@ void c3sc_valuef_destroy(c3sc_valuef *vf)
 }  // extern "C"
 
 // ---------------------------------------------------------------------------
-enum Mode { MODE_VI = 0, MODE_PI_EVAL = 1, MODE_COSTS = 2 };
+enum Mode { MODE_VI = 0, MODE_PI_EVAL = 1, MODE_COSTS = 2, MODE_STAGE1 = 3 };   // STAGE1: stage 1 into the pipeline's scratch, no stage 2 (measurement)
 
 // One batch through the two-stage pipeline, in chunks whose slot-major cost scratch stays L2-sized:
 //   k_group_fibers -> k_ft_costs -> k_control (MODE_VI) | k_pi_eval (MODE_PI_EVAL) | nothing (MODE_COSTS)
@@ -544,42 +549,72 @@ struct BatchArgs {
     size_t peer_offset;
 };
 
-static size_t g_chunk_bytes = (size_t)192 << 20;   // slot-major cost scratch in flight (all lanes); measured optimum, see profiles/r01_lanes.md
+static size_t g_chunk_bytes = (size_t)192 << 20;   // slot-major cost scratch in flight (all lanes) when stage 1a runs per fiber
+static size_t g_chunk_bytes_b = (size_t)64 << 20;  // ... when it runs bucketed: the chain stage spans several chunks, so a chunk can be
+                                                    // small enough for its scratch to stay in L2 between stage 1 and stage 2
+static size_t g_chain_fibers = 8192;                // fibers per chain super-chunk (bucketed stage 1a)
+static size_t g_chain_min = 4096;                   // smaller batches keep the per-fiber chain kernel
+static int g_lanes = -1;                            // 2 = alternate (super-)chunks between two streams (default), 1 = one stream
 
-static int g_lanes = -1;                            // 2 = alternate chunks between two streams (default), 1 = one stream
+static void read_tuning()
+{   // re-read on every batch (four getenv calls): tests and tuning runs switch paths inside one process
+    const char *e = getenv("C3SC_LANES");
+    g_lanes = e ? atoi(e) : 2;
+    if (g_lanes < 1) g_lanes = 1;
+    if (g_lanes > MAXLANES) g_lanes = MAXLANES;
+    const char *m = getenv("C3SC_CHUNK_MB");                          // tuning aids: cost scratch of all lanes together
+    g_chunk_bytes = (size_t)192 << 20; g_chunk_bytes_b = (size_t)64 << 20;
+    if (m && atoi(m) > 0) { g_chunk_bytes = (size_t)atoi(m) << 20; g_chunk_bytes_b = g_chunk_bytes; }
+    const char *cf = getenv("C3SC_CHAIN_FIBERS");
+    g_chain_fibers = (cf && atoi(cf) > 0) ? (size_t)atoi(cf) : 8192;
+    const char *cm = getenv("C3SC_CHAIN_MIN");
+    g_chain_min = (cm && atoi(cm) >= 0) ? (size_t)atoi(cm) : 4096;
+}
 
+// One batch through the pipeline.  Units:
+//   chunk        FC fibers: grouping by varying dimension, node kernel, control kernel, cost scratch
+//   super-chunk  SC consecutive chunks: the bucketed chain stage (chain_kernel.cuh) works on all of them at once,
+//                its records stay in L2 until the node kernels of its chunks have consumed them
+//   lane         consecutive super-chunks alternate between the caller's stream and a second one
 static int run_batch(const DevProblem &P, int model, int arith, Scratch &scr, const CtlGroups *grp, const DevFT &ft,
                      const BatchArgs &b, cudaStream_t st)
 {
     const size_t d = (size_t)P.dx, CS = 2 * d + 1, RW = 2 * d + 3;
-    if (g_lanes < 0) {
-        const char *e = getenv("C3SC_LANES");
-        g_lanes = e ? atoi(e) : 2;
-        if (g_lanes < 1) g_lanes = 1;
-        if (g_lanes > MAXLANES) g_lanes = MAXLANES;
-        const char *m = getenv("C3SC_CHUNK_MB");                      // tuning aid: cost scratch of all lanes together
-        if (m && atoi(m) > 0) g_chunk_bytes = (size_t)atoi(m) << 20;
-    }
-    // chunks: at most g_chunk_bytes of cost scratch in flight, shared by the lanes.  Several lanes as soon as each
-    // chunk still fills the machine; the chunk count is then a multiple of the lane count (equal load per lane).
-    const bool multi = g_lanes > 1 && b.mode != MODE_COSTS && b.F * b.ldo >= (size_t)g_lanes * 148 * 1024;
-    const size_t L = multi ? (size_t)g_lanes : 1;
-    size_t per_chunk = g_chunk_bytes / (size_t)g_lanes / (b.ldo * CS * 8);
-    if (!multi) per_chunk *= (size_t)g_lanes;
-    if (per_chunk < 1) per_chunk = 1;
-    size_t nch = (b.F + per_chunk - 1) / per_chunk;
-    if (nch < L) nch = L;
-    nch = (nch + L - 1) / L * L;
-    size_t FC = (b.F + nch - 1) / nch;
-    const size_t NSmax = FC * b.ldo;
+    read_tuning();
     const bool need_cst = b.mode != MODE_COSTS;
     const int mma = ft_uses_mma(ft);
+    const bool bucketed = mma && chain_bucketed_ok(ft, P.nmax) && b.F >= g_chain_min && !getenv("C3SC_NO_BUCKETS");
+    // several lanes as soon as each (super-)chunk still fills the machine
+    const bool multi = g_lanes > 1 && b.mode != MODE_COSTS && b.F * b.ldo >= (size_t)g_lanes * 148 * 1024;
+    const size_t L = multi ? (size_t)g_lanes : 1;
+    size_t per_chunk = (bucketed ? g_chunk_bytes_b : g_chunk_bytes) / (size_t)g_lanes / (b.ldo * CS * 8);
+    if (!multi) per_chunk *= (size_t)g_lanes;
+    { const char *pf = getenv("C3SC_CHUNK_FIBERS"); if (pf && atoi(pf) > 0) per_chunk = (size_t)atoi(pf); }    // tests: exact chunk size
+    if (per_chunk < 1) per_chunk = 1;
+    size_t SC = 1;                                          // chunks per super-chunk
+    if (bucketed) { SC = (g_chain_fibers + per_chunk / 2) / per_chunk; if (SC < 1) SC = 1; }
+    // super-chunks: a multiple of the lane count (equal load per lane), then equal chunks inside
+    size_t nsup = (b.F + per_chunk * SC - 1) / (per_chunk * SC);
+    if (nsup < L) nsup = L;
+    nsup = (nsup + L - 1) / L * L;
+    const size_t FC = ((b.F + nsup - 1) / nsup + SC - 1) / SC;        // fibers per chunk
+    const size_t FS = FC * SC;                                        // fibers per super-chunk
+    nsup = (b.F + FS - 1) / FS;
+    const size_t NSmax = FC * b.ldo;
+    int setw = 0, rs = 0;
+    if (mma) ft_record_geometry(ft, &setw, &rs);
     if (scr.perm.reserve(b.F * 4) || scr.cnt.reserve(((b.F + FC - 1) / FC) * 64 * 4))
         return fail(C3SC_ECUDA, "cudaMalloc pipeline scratch failed");
+    size_t pk = 0, pt = 0, pe = 0;
+    if (bucketed) {
+        chain_plan_sizes(ft, P.nmax, FS, &pk, &pt, &pe);
+        if (scr.plan_k.reserve(nsup * pk * 4) || scr.plan_t.reserve(nsup * pt * 4) || scr.plan_e.reserve(nsup * pe * 4))
+            return fail(C3SC_ECUDA, "cudaMalloc chain plan failed");
+    }
     for (size_t l = 0; l < L; l++) {
         LaneScratch &ln = scr.lane[l];
         if ((need_cst && ln.cst.reserve(NSmax * CS * 8)) || ln.flag.reserve(NSmax) || ln.act.reserve(NSmax * 4) ||
-            (mma && ln.sets.reserve(ft_sets_bytes(ft, FC))))
+            (mma && ln.sets.reserve((size_t)setw * FS * 8)))
             return fail(C3SC_ECUDA, "cudaMalloc pipeline scratch failed");
         if (l > 0 && !ln.stream) {
             CK(cudaStreamCreateWithFlags(&ln.stream, cudaStreamNonBlocking));
@@ -587,21 +622,46 @@ static int run_batch(const DevProblem &P, int model, int arith, Scratch &scr, co
         }
     }
     if (L > 1 && !scr.fork) CK(cudaEventCreateWithFlags(&scr.fork, cudaEventDisableTiming));
-    {   // every chunk's grouping in one launch
+    {   // every chunk's grouping in one launch; every super-chunk's chain plan in another
         int rc = launch_group_fibers(P, (int)b.F, (int)FC, b.dim_vary, b.fixed_ind, (int *)scr.perm.p, (int *)scr.cnt.p, st);
         if (rc) return fail(C3SC_ECUDA, "grouping kernel: %s", cudaGetErrorString((cudaError_t)rc));
         g_launches++;
+        if (bucketed) {
+            ChainArgs ca;
+            memset(&ca, 0, sizeof ca);
+            ca.P = P; ca.ft = ft; ca.F = (int)b.F; ca.dim_vary = b.dim_vary; ca.fixed_ind = b.fixed_ind;
+            ca.nbr_fixed_in = (b.nbr_fixed_in && d > 1) ? b.nbr_fixed_in : nullptr;
+            ca.setw = setw; ca.rs = rs; ca.kst = (int *)scr.plan_k.p; ca.tst = (int *)scr.plan_t.p; ca.ent = (int *)scr.plan_e.p;
+            ca.nmax = P.nmax; ca.entstride = (int)(3 * FS);
+            rc = launch_chain_plan(ca, (int)FS, st);
+            if (rc) return fail(C3SC_ECUDA, "chain plan kernel: %s", cudaGetErrorString((cudaError_t)rc));
+            g_launches++;
+        }
     }
     if (L > 1) {                                            // the other lanes start after everything queued on st so far
         CK(cudaEventRecord(scr.fork, st));
         for (size_t l = 1; l < L; l++) CK(cudaStreamWaitEvent(scr.lane[l].stream, scr.fork, 0));
     }
     const cudaStream_t st0 = st;
-    for (size_t c0 = 0; c0 < b.F; c0 += FC) {
-        const size_t Fc = (b.F - c0 < FC) ? b.F - c0 : FC;
-        const size_t n0 = c0 * b.ldo;
-        LaneScratch &ln = scr.lane[(c0 / FC) % L];
+    for (size_t s0 = 0, si = 0; s0 < b.F; s0 += FS, si++) {
+        const size_t Fs = (b.F - s0 < FS) ? b.F - s0 : FS;
+        LaneScratch &ln = scr.lane[si % L];
         st = ln.stream ? ln.stream : st0;
+        if (bucketed) {
+            ChainArgs ca;
+            memset(&ca, 0, sizeof ca);
+            ca.P = P; ca.ft = ft; ca.F = (int)Fs; ca.dim_vary = b.dim_vary + s0; ca.fixed_ind = b.fixed_ind + s0 * d;
+            ca.sets = (double *)ln.sets.p; ca.setw = setw; ca.rs = rs;
+            ca.kst = (int *)scr.plan_k.p + si * pk; ca.tst = (int *)scr.plan_t.p + si * pt; ca.ent = (int *)scr.plan_e.p + si * pe;
+            ca.nmax = P.nmax; ca.entstride = (int)(3 * FS);
+            int nl = 0;
+            int rc = launch_chain_steps(ca, st, &nl);
+            if (rc) return fail(C3SC_ECUDA, "chain step kernel: %s", cudaGetErrorString((cudaError_t)rc));
+            g_launches += nl;
+        }
+        for (size_t c0 = s0; c0 < s0 + Fs; c0 += FC) {
+        const size_t Fc = (s0 + Fs - c0 < FC) ? s0 + Fs - c0 : FC;
+        const size_t n0 = c0 * b.ldo;
         DevBuf &bcst = ln.cst, &bflag = ln.flag, &bact = ln.act, &bsets = ln.sets;
         int *cnt = (int *)scr.cnt.p + 64 * (c0 / FC);   // [0,16) kcount, [16,32) kstart, [32] act_count
         int rc;
@@ -621,12 +681,13 @@ static int run_batch(const DevProblem &P, int model, int arith, Scratch &scr, co
         a.nbr_fixed = (b.out.nbr_fixed && d > 1) ? b.out.nbr_fixed + c0 * 2 * (d - 1) : nullptr;
         a.nbr_fixed_in = (b.nbr_fixed_in && d > 1) ? b.nbr_fixed_in + c0 * 2 * (d - 1) : nullptr;
         a.nbr_vary_in = b.nbr_vary_in ? b.nbr_vary_in + 2 * n0 : nullptr;
-        a.sets = mma ? (double *)bsets.p : nullptr;
+        a.sets = mma ? (double *)bsets.p + (c0 - s0) * (size_t)setw : nullptr;
+        a.setw = setw; a.rs = rs; a.chains_done = bucketed ? 1 : 0;
         a.task_count = cnt + 33;
         rc = launch_ft_costs(a, st);
         if (rc) return fail(C3SC_ECUDA, "FT kernel launch: %s", cudaGetErrorString((cudaError_t)rc));
-        g_launches += 1 + mma;
-        if (b.mode == MODE_COSTS) continue;
+        g_launches += 1 + (mma && !bucketed);
+        if (b.mode == MODE_COSTS || b.mode == MODE_STAGE1) continue;
         CtlArgs c;
         memset(&c, 0, sizeof c);
         c.P = P; c.F = (int)Fc; c.dim_vary = a.dim_vary; c.fixed_ind = a.fixed_ind; c.ldo = (int)b.ldo; c.NS = a.NS;
@@ -648,10 +709,10 @@ static int run_batch(const DevProblem &P, int model, int arith, Scratch &scr, co
             memcpy(c.gstart, grp->gstart, sizeof c.gstart);
             memcpy(c.gA, grp->gA, sizeof c.gA);
         }
-        const int pe = b.mode == MODE_PI_EVAL;
-        if (model == C3SC_MODEL_LQGND) rc = (P.dx <= 6) ? launch_control_lqg_lo(P.dx, arith, c, pe, st)
-                                                        : launch_control_lqg_hi(P.dx, arith, c, pe, st);
-        else rc = launch_control_misc(model, P.dx, arith, c, pe, st);
+        const int pe_ = b.mode == MODE_PI_EVAL;
+        if (model == C3SC_MODEL_LQGND) rc = (P.dx <= 6) ? launch_control_lqg_lo(P.dx, arith, c, pe_, st)
+                                                        : launch_control_lqg_hi(P.dx, arith, c, pe_, st);
+        else rc = launch_control_misc(model, P.dx, arith, c, pe_, st);
         if (rc == -1) return fail(C3SC_EUNSUPPORTED, "model %d with dx=%d is not instantiated", model, P.dx);
         if (rc != 0) return fail(C3SC_ECUDA, "control kernel launch: %s", cudaGetErrorString((cudaError_t)rc));
         g_launches++;
@@ -660,6 +721,7 @@ static int run_batch(const DevProblem &P, int model, int arith, Scratch &scr, co
             CK(cudaStreamWaitEvent(b.copy_stream, b.chunk_done, 0));
             if (b.h_value && c.value) CK(cudaMemcpyAsync(b.h_value + n0, c.value, Fc * b.ldo * 8, cudaMemcpyDeviceToHost, b.copy_stream));
             if (b.h_argmin && c.argmin) CK(cudaMemcpyAsync(b.h_argmin + n0, c.argmin, Fc * b.ldo * 4, cudaMemcpyDeviceToHost, b.copy_stream));
+        }
         }
     }
     for (size_t l = 1; l < L; l++) {                        // the caller's stream continues after every lane
@@ -708,6 +770,21 @@ int c3sc_vi_batch_dev(c3sc_problem *p, const c3sc_valuef *vf, size_t F, const in
     b.n_peers = (int)out->n_peers;
     for (uint32_t g = 0; g < out->n_peers; g++) b.value_peers[g] = out->value_peers[g];
     b.peer_offset = (size_t)out->peer_offset;
+    return run_batch(p->P, p->model, p->arith, p->scr, &p->grp, vf->ft, b, (cudaStream_t)stream);
+}
+
+/* Stage 1 alone, exactly as the pipeline runs it (grouping, chain stage, node kernel into the lanes' slot-major
+ * scratch; no stage 2, no output): the measurement entry behind bench.py's roofline.stage1_live. */
+int c3sc_stage1_batch_dev(c3sc_problem *p, const c3sc_valuef *vf, size_t F, const int32_t *d_dim_vary,
+                          const int32_t *d_fixed_ind, size_t ldo, void *stream)
+{
+    int rc = check_shapes(p, vf, F, ldo);
+    if (rc) return rc;
+    if (F == 0) return C3SC_OK;
+    BatchArgs b;
+    memset(&b, 0, sizeof b);
+    b.F = F; b.ldo = ldo; b.dim_vary = d_dim_vary; b.fixed_ind = d_fixed_ind;
+    b.mode = MODE_STAGE1;
     return run_batch(p->P, p->model, p->arith, p->scr, &p->grp, vf->ft, b, (cudaStream_t)stream);
 }
 

@@ -84,7 +84,73 @@ int ft_uses_mma(const DevFT &ft)
         if (ft.r[i] > 32) return 0;
     return 1;
 }
-size_t ft_sets_bytes(const DevFT &ft, size_t F) { return (size_t)ft_set_width(ft) * F * sizeof(double); }
+static int ft_rmax(const DevFT &ft)
+{
+    int rmax = 1;
+    for (int i = 0; i <= ft.d; i++) rmax = ft.r[i] > rmax ? ft.r[i] : rmax;
+    return rmax;
+}
+size_t ft_sets_bytes(const DevFT &ft, size_t F) { return (size_t)ft_rec_width(ft.d, ft_rmax(ft)) * F * sizeof(double); }
+void ft_record_geometry(const DevFT &ft, int *setw, int *rs) { *setw = ft_rec_width(ft.d, ft_rmax(ft)); *rs = ft_rec_rs(ft_rmax(ft)); }
+
+// ---- bucketed chain stage (chain_kernel.cuh) ------------------------------------------------------------------
+// ints of plan storage per chunk of FC fibers
+void chain_plan_sizes(const DevFT &ft, int nmax, size_t FC, size_t *kst, size_t *tst, size_t *ent)
+{
+    *kst = (size_t)ft.d * 2 * ((size_t)nmax * 3 + 1);
+    *tst = (size_t)ft.d * 2 * ((size_t)nmax + 1);
+    *ent = (size_t)ft.d * 3 * FC;
+}
+int chain_bucketed_ok(const DevFT &ft, int nmax) { return ft.d >= 2 && nmax <= CH_NMAX && ft_uses_mma(ft); }
+
+// plan of every chunk of a batch in one launch: a.F = fibers of the batch, FC = fibers per chunk; a.kst / tst / ent /
+// sets point at chunk 0's slices, consecutive chunks follow at the strides of chain_plan_sizes / FC * setw
+int launch_chain_plan(const ChainArgs &a, int FC, cudaStream_t st)
+{
+    if (a.F <= 0) return 0;
+    size_t k, t, e;
+    chain_plan_sizes(a.ft, a.nmax, (size_t)FC, &k, &t, &e);
+    ChainPlanStrides S = {(long long)k, (long long)t, (long long)e};
+    const size_t smem = (size_t)14 * a.nmax * sizeof(int);
+    k_chain_plan<<<dim3((unsigned)((a.F + FC - 1) / FC), (unsigned)a.ft.d), 1024, smem, st>>>(a, FC, S);
+    return (int)cudaGetLastError();
+}
+
+template <int KS>
+static int launch_chain_steps_t(const ChainArgs &a, cudaStream_t st)
+{
+    ft_device_info();
+    const int grid = g_sms * 2;
+    {
+        long long gi = ((long long)a.F * 4 * a.rs + 255) / 256;
+        if (gi > g_sms * 8) gi = g_sms * 8;
+        k_chain_init<<<(unsigned)gi, 256, 0, st>>>(a);
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) return (int)e;
+    }
+    for (int t = 0; t + 1 < a.ft.d; t++) {
+        k_chain_step<KS><<<grid, CH_NT, 0, st>>>(a, t);
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) return (int)e;
+    }
+    return 0;
+}
+
+// the d-1 steps of one chunk (a.F = fibers of the chunk, pointers at the chunk's slices); returns the launches via *n
+int launch_chain_steps(const ChainArgs &a, cudaStream_t st, int *n)
+{
+    *n = a.ft.d;                                            // init + d-1 steps
+    switch ((ft_rmax(a.ft) + 3) / 4) {
+    case 1: return launch_chain_steps_t<1>(a, st);
+    case 2: return launch_chain_steps_t<2>(a, st);
+    case 3: return launch_chain_steps_t<3>(a, st);
+    case 4: return launch_chain_steps_t<4>(a, st);
+    case 5: return launch_chain_steps_t<5>(a, st);
+    case 6: return launch_chain_steps_t<6>(a, st);
+    case 7: return launch_chain_steps_t<7>(a, st);
+    default: return launch_chain_steps_t<8>(a, st);
+    }
+}
 
 template <int KS>
 static int launch_mma_t(const FtArgs &a, cudaStream_t st)
@@ -103,9 +169,12 @@ static int launch_mma_t(const FtArgs &a, cudaStream_t st)
     if (per_sm < 1) per_sm = 1;
     int cgrid = (2 * a.F + FTC_NT / 32 - 1) / (FTC_NT / 32);
     if (cgrid > g_sms * per_sm) cgrid = g_sms * per_sm;
-    k_ft_chains<KS><<<cgrid, FTC_NT, csm, st>>>(a, a.sets);
-    cudaError_t e = cudaGetLastError();
-    if (e != cudaSuccess) return (int)e;
+    cudaError_t e = cudaSuccess;
+    if (!a.chains_done) {
+        k_ft_chains<KS><<<cgrid, FTC_NT, csm, st>>>(a, a.sets);
+        e = cudaGetLastError();
+        if (e != cudaSuccess) return (int)e;
+    }
     // nodes: one CTA per same-k group
     const size_t smem = FtNodePlan<KS>(a.ft, a.P.nmax).bytes();
     if (smem > (size_t)g_max_optin) return (int)cudaErrorInvalidValue;

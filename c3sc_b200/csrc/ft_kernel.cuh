@@ -57,7 +57,9 @@ struct FtArgs {
     int *nbr_fixed;           // optional [F*2*(d-1)]
     const int *nbr_fixed_in;  // caller-supplied neighbour indices (valuef_eval_fiber_ind_nn)
     const int *nbr_vary_in;
-    double *sets;             // [F * ft_set_width] chain scratch of the tensor-core path; NULL = general kernel
+    double *sets;             // [F * setw] chain records of the tensor-core path (chain_kernel.cuh); NULL = general kernel
+    int setw, rs;             // record width and row stride in doubles
+    int chains_done;          // the records were filled by the bucketed chain steps: skip k_ft_chains
     int *task_count;          // chain kernel: next (fiber, side) task, zeroed by k_group_fibers
     int nsplit;               // k_ft_nodes: CTAs per group, each owning a contiguous range of node tiles (blockIdx.y)
 };

@@ -18,6 +18,7 @@
 // Same outputs as k_ft_costs (ft_kernel.cuh), which stays the general path for larger ranks.
 #pragma once
 #include "ft_kernel.cuh"
+#include "chain_kernel.cuh"
 
 namespace c3sc {
 
@@ -30,14 +31,6 @@ constexpr int FTN_TP = 8;        // row stride of a (rank index) row of w / u: 8
                                  // (the minimum for 64-bit accesses), those of u 4, a fragment load 2 -- against 8 / 8 / 4
                                  // unswizzled and 4 / 4 / 4 for a plain stride of 9 (layouts enumerated off line)
 __host__ __device__ constexpr int ftn_swz(int a) { return (5 * ((a >> 1) & 1)) ^ ((a >> 2) & 1); }
-
-// width of one fiber's record in the chain scratch: both sets, [q][v] with v fastest
-__host__ __device__ inline int ft_set_width(const DevFT &ft)
-{
-    int rs = 1;
-    for (int i = 0; i <= ft.d; i++) rs = ft.r[i] > rs ? ft.r[i] : rs;
-    return rs * (2 * ft.d + 2);
-}
 
 // vectors-per-row stride of the chain sets in shared memory: >= 2d and = 4 (mod 8), so the A-fragment
 // reads (row v, col q) of the stepped products are bank-conflict free
@@ -94,9 +87,7 @@ __global__ void __launch_bounds__(FTC_NT, KS <= 6 ? C3SC_FTC_MINB : 1) k_ft_chai
     double *buf0 = smem + warp * cp.perWarpDoubles, *buf1 = buf0 + cp.bufDoubles;
     int *iw = reinterpret_cast<int *>(smem + NW * cp.perWarpDoubles) + warp * cp.perWarpInts;
     int *sFix = iw, *sNf = iw + d;                   // sNf[2*i], sNf[2*i+1]: pair of dimension i
-    int rsG = 1;
-    for (int i = 0; i <= d; i++) rsG = ft.r[i] > rsG ? ft.r[i] : rsG;
-    const int SETW = rsG * (2 * d + 2);
+    const int SETW = a.setw, RS = a.rs;
 
     // every value a fragment may touch must be finite (padding rows meet zero rows of the block)
     for (int e = lane; e < cp.perWarpDoubles; e += 32) buf0[e] = 0.0;
@@ -113,8 +104,6 @@ __global__ void __launch_bounds__(FTC_NT, KS <= 6 ? C3SC_FTC_MINB : 1) k_ft_chai
         const int f = a.perm[left ? a.F - 1 - (task >> 1) : (task >> 1)];
         int k = a.dim_vary[f];
         k = k < 0 ? 0 : (k >= d ? d - 1 : k);
-        const int NVL = ft_even_up(1 + 2 * k), NVR = ft_even_up(1 + 2 * (d - 1 - k));
-        const int NV = left ? NVL : NVR;
         const int nsteps = left ? k : d - 1 - k;
         __syncwarp();
         if (lane < d) {
@@ -225,13 +214,15 @@ __global__ void __launch_bounds__(FTC_NT, KS <= 6 ? C3SC_FTC_MINB : 1) k_ft_chai
             __syncwarp();
             double *t = in; in = out; out = t;
         }
-        // final set -> global record of the fiber ([q][v] with stride NV; right set after the left one)
+        // final set -> global record of the fiber (chain_kernel.cuh: row v = vector v, RS doubles, zero beyond the
+        // rank; the right set follows the 1 + 2k rows of the left one)
         {
             const int rl = left ? ft.r[k] : ft.r[k + 1];
-            double *dst = sets + (size_t)f * SETW + (left ? 0 : rsG * NVL);
-            for (int e = lane; e < rl * NV; e += 32) {
-                const int q = e / NV, v = e - q * NV;
-                dst[e] = in[q * NVP + v];
+            const int nv = left ? 1 + 2 * k : 1 + 2 * (d - 1 - k);
+            double *dst = sets + (size_t)f * SETW + (size_t)(left ? 0 : 1 + 2 * k) * RS;
+            for (int e = lane; e < nv * RS; e += 32) {
+                const int v = e / RS, q = e - v * RS;
+                dst[e] = q < rl ? in[q * NVP + v] : 0.0;
             }
         }
     }
@@ -302,108 +293,17 @@ __device__ __forceinline__ void node_wu(const double *gj, int offW, int offU, in
     }
 }
 
-// Variant dots of one fiber over one 8-node tile (second phase of k_ft_nodes) with compile-time tile counts:
-// left  C[v][jl] = sum_a A[v][a] W[a][jl]  (ML tiles of 8 variant vectors),
-// right C[jl][v] = sum_b U[jl][b] Cv[b][v] (NR tiles).
-template <int KS>
-struct NodeDots {
-    static constexpr int VT = (2 * MAXD + 7) / 8;
-    const double *setL, *setR, *wg, *ug;     // wg / ug: row tig of this fiber's w / u tile (node column added per k-step)
-    int jl0, jl1;                            // swizzled node column of this lane for even / odd k-steps: gid ^ swz(4ks + tig)
-    int NVL, NVR;
-    const int (&slotL)[VT];
-    const int (&slotR)[VT][2];
-    const int (&offL)[VT];
-    const int (&offR)[VT][2];
-    bool fast;
-    double *cst, *costs;
-    long long NS;
-    size_t idb;
-    int CS, nt, tig, gid;
-
-    template <int ML, int NR>
-    __device__ __forceinline__ void run() const
-    {
-        double dl[ML > 0 ? ML : 1][2], dr[NR > 0 ? NR : 1][2];
-#pragma unroll
-        for (int t = 0; t < ML; t++) dl[t][0] = dl[t][1] = 0.0;
-#pragma unroll
-        for (int t = 0; t < NR; t++) dr[t][0] = dr[t][1] = 0.0;
-#pragma unroll
-        for (int ks = 0; ks < KS; ks++) {
-            if constexpr (ML > 0) {
-                const double bw = wg[ks * 4 * FTN_TP + ((ks & 1) ? jl1 : jl0)];   // B fragment (row a = 4ks+tig, col jl = gid)
-#pragma unroll
-                for (int mt = 0; mt < ML; mt++) dmma_m8n8k4(dl[mt][0], dl[mt][1], setL[(4 * ks + tig) * NVL + 8 * mt + gid], bw);
-            }
-            if constexpr (NR > 0) {
-                const double au = ug[ks * 4 * FTN_TP + ((ks & 1) ? jl1 : jl0)];   // A fragment (row jl = gid, col b = 4ks+tig)
-#pragma unroll
-                for (int nb = 0; nb < NR; nb++) dmma_m8n8k4(dr[nb][0], dr[nb][1], au, setR[(4 * ks + tig) * NVR + 8 * nb + gid]);
-            }
-        }
-        if (fast) {
-            // full tile, slot-major scratch only (the pipeline's case): one 32-bit element offset per output,
-            // prepared once per CTA; -1 = no such variant
-            double *cb = cst + idb;
-#pragma unroll
-            for (int mt = 0; mt < ML; mt++)
-                if (offL[mt] >= 0) *reinterpret_cast<double2 *>(cb + offL[mt]) = make_double2(dl[mt][0], dl[mt][1]);
-#pragma unroll
-            for (int nb = 0; nb < NR; nb++) {
-#pragma unroll
-                for (int h = 0; h < 2; h++)
-                    if (offR[nb][h] >= 0) cb[offR[nb][h]] = dr[nb][h];
-            }
-            return;
-        }
-#pragma unroll
-        for (int mt = 0; mt < ML; mt++) {
-            const int slot = slotL[mt];
-            if (slot >= 0) {                                         // D: row v, cols jl = 2tig, 2tig+1
-                const int jl = 2 * tig;
-                const double d0 = dl[mt][0], d1 = dl[mt][1];
-                if (cst) {
-                    double *o = cst + (size_t)slot * NS + idb + jl;
-                    if (jl < nt) o[0] = d0;
-                    if (jl + 1 < nt) o[1] = d1;
-                }
-                if (costs) {
-                    if (jl < nt) costs[(idb + jl) * CS + slot] = d0;
-                    if (jl + 1 < nt) costs[(idb + jl + 1) * CS + slot] = d1;
-                }
-            }
-        }
-        if (gid < nt) {
-#pragma unroll
-            for (int nb = 0; nb < NR; nb++) {                        // D: row jl = gid, cols v = 8nb+2tig, +1
-#pragma unroll
-                for (int h = 0; h < 2; h++) {
-                    const int slot = slotR[nb][h];
-                    if (slot < 0) continue;
-                    const double val = dr[nb][h];
-                    if (cst) cst[(size_t)slot * NS + idb + gid] = val;
-                    if (costs) costs[(idb + gid) * CS + slot] = val;
-                }
-            }
-        }
-    }
-};
-
 // Shared memory of k_ft_nodes.  Everything the MMA fragments read is zero-padded to the fragment
-// shape, so no fragment load is predicated.
+// shape, so no fragment load is predicated.  The chain records are NOT staged: every fragment of a fiber's
+// variant sets is loaded from L2 once per CTA and lives in registers for all node tiles.
 template <int KS>
 struct FtNodePlan {
-    int rs4, setw, nmax, sw, gbuf;
-    int oG, oW, oU, oSets, oBar, nDoubles;
+    int nmax, sw, gbuf;
+    int oG, oW, oU, oBar, nDoubles;
     int oFix, oNf, oFid, oWall, nInts;
     __host__ __device__ FtNodePlan(const DevFT &ft, int nmax_)
     {
         nmax = nmax_;
-        int rs = 1;
-        for (int i = 0; i <= ft.d; i++) rs = ft.r[i] > rs ? ft.r[i] : rs;
-        rs4 = (rs + 3) & ~3;                         // rank rows padded to the MMA k-step
-        setw = rs4 * (2 * ft.d + 2) + 8;             // + slack: fragment rows may overrun a set by < 8
         sw = 8 * ((KS + 1) / 2) * FTN_TP + 1;        // one fiber's w (or u) tile: [rank index][8 nodes, swizzled], odd stride
         int gt = 0;
         for (int k = 0; k < ft.d; k++) {
@@ -418,7 +318,6 @@ struct FtNodePlan {
         oG = o;    o += 2 * gt;                      // two tile buffers, each 16-byte aligned
         oW = o;    o += FT_FBMAX * sw;
         oU = o;    o += FT_FBMAX * sw;
-        oSets = o; o += FT_FBMAX * setw;
         o = ft_even_up(o);
         oBar = o;  o += 2;                           // two mbarriers
         nDoubles = o;
@@ -432,15 +331,192 @@ struct FtNodePlan {
     __host__ __device__ size_t bytes() const { return (size_t)nDoubles * 8 + (size_t)nInts * 4 + (size_t)FT_FBMAX * nmax; }
 };
 
+// Everything the tile loop of k_ft_nodes needs besides its compile-time tile counts.
+struct FtNodeCtx {
+    const double *sG; double *sW, *sU;
+    unsigned long long *mbar;
+    const double *Gp;
+    const int *sFid;
+    int GB, SW, pblk, ldk, jb, je, nf, nvL, nvR, d, CS, RS, setw;
+    long long NS;
+    double *cst, *costs;
+    const double *sets;
+    int ldo;
+    bool needSelfFromU;      // k = 0: the self value comes from u . R (vector 0 of the right set)
+};
+
+// The node-tile loop with compile-time numbers of 8-wide variant tiles: ML over the left set (1 + 2k vectors, 0 when
+// the left side has no variants and the self value comes from the right), NR over the right set.  A DMMA that is
+// merely predicated off still costs its issue slot and fragment load, hence the dispatch on (ML, NR).
+//   phase 1 (warp = node of the tile)   W[a][g] = sum_b G[a,b] R_g[b],  U[g][b] = sum_a L_g[a] G[a,b]   for the 8 fibers
+//   phase 2 (warp = fiber of the group) left  C[v][jl] = sum_a A[v][a] W[a][jl],  right C[jl][v] = sum_b U[jl][b] Cv[b][v]
+// The A / Cv fragments (the fiber's variant sets) and R / L are loaded from the chain records ONCE and stay in
+// registers; per tile phase 2 reads only the w / u fragments from shared memory.
+template <int KS, int ML, int NR>
+__device__ __forceinline__ void ftn_tile_loop(const FtNodeCtx &c)
+{
+    constexpr int VT = (2 * MAXD + 7) / 8;
+    constexpr bool DO_W = ML > 0, DO_U = NR > 0;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int gid = lane >> 2, tig = lane & 3;
+    const int d = c.d, RS = c.RS;
+
+    // ---- register-resident operands ---------------------------------------------------------------
+    // phase 1: B fragment of R (row b = 4ks+tig, col fiber gid), A fragment of L (row fiber gid, col a = 4ks+tig)
+    double Rf[KS], Lf[KS];
+    {
+        const bool on = gid < c.nf;
+        const double *rec = c.sets + (size_t)(on ? c.sFid[gid] : 0) * c.setw;
+#pragma unroll
+        for (int ks = 0; ks < KS; ks++) {
+            Rf[ks] = on ? __ldg(rec + (size_t)c.nvL * RS + 4 * ks + tig) : 0.0;
+            Lf[ks] = on ? __ldg(rec + 4 * ks + tig) : 0.0;
+        }
+    }
+    // phase 2, fiber g = warp: A fragments of the left set (row v = 8mt+gid, col a = 4ks+tig), B fragments of the
+    // right set (row b = 4ks+tig, col v = 8nb+gid); both are rows v of the record, element 4ks+tig
+    double aL[ML > 0 ? ML : 1][KS], bR[NR > 0 ? NR : 1][KS];
+    {
+        const bool on = warp < c.nf;
+        const double *rec = c.sets + (size_t)(on ? c.sFid[warp] : 0) * c.setw;
+#pragma unroll
+        for (int mt = 0; mt < ML; mt++) {
+            const int v = 8 * mt + gid;
+#pragma unroll
+            for (int ks = 0; ks < KS; ks++) aL[mt][ks] = (on && v < c.nvL) ? __ldg(rec + (size_t)v * RS + 4 * ks + tig) : 0.0;
+        }
+#pragma unroll
+        for (int nb = 0; nb < NR; nb++) {
+            const int v = 8 * nb + gid;
+#pragma unroll
+            for (int ks = 0; ks < KS; ks++) bR[nb][ks] = (on && v < c.nvR) ? __ldg(rec + (size_t)(c.nvL + v) * RS + 4 * ks + tig) : 0.0;
+        }
+    }
+    // output slots of this lane's accumulator rows / columns (-1 = no such variant)
+    int slotL[VT], slotR[VT][2];
+#pragma unroll
+    for (int t = 0; t < VT; t++) {
+        const int v = 8 * t + gid;
+        slotL[t] = v >= c.nvL ? -1 : (v == 0 ? 2 * d : 2 * ((v - 1) >> 1) + ((v - 1) & 1));
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            const int vv = 8 * t + 2 * tig + h;
+            slotR[t][h] = vv >= c.nvR ? -1 : (vv == 0 ? (c.needSelfFromU ? 2 * d : -1)      // vector 0 is R itself
+                                                       : 2 * (d - 1 - ((vv - 1) >> 1)) + ((vv - 1) & 1));
+        }
+    }
+    // element offsets of this lane's outputs inside the slot-major scratch, relative to cst + fiber row + tile
+    // start (left: nodes 2tig, 2tig+1 of variant row gid; right: node gid of variant columns 2tig, 2tig+1)
+    int outL[VT], outR[VT][2];
+    const bool off32 = c.cst && (long long)c.CS * c.NS < 0x7fffffffLL && !c.costs && ((c.NS | (long long)c.ldo) & 1) == 0 &&
+                       ((size_t)c.cst & 15) == 0;
+#pragma unroll
+    for (int t = 0; t < VT; t++) {
+        outL[t] = (off32 && slotL[t] >= 0) ? (int)(slotL[t] * c.NS) + 2 * tig : -1;
+#pragma unroll
+        for (int h = 0; h < 2; h++) outR[t][h] = (off32 && slotR[t][h] >= 0) ? (int)(slotR[t][h] * c.NS) + gid : -1;
+    }
+    const int ldk = c.ldk, SW = c.SW, pblk = c.pblk, GB = c.GB;
+    const int offW = tig * ldk + gid, offU = gid * ldk + tig;           // fragment origins inside a node block
+    const double *wg = c.sW + warp * SW + tig * FTN_TP, *ug = c.sU + warp * SW + tig * FTN_TP;
+    const int jl0 = gid ^ ftn_swz(tig), jl1 = gid ^ ftn_swz(4 + tig);
+    const size_t idf = warp < c.nf ? (size_t)c.sFid[warp] * c.ldo : 0;
+    const int CS = c.CS;
+
+    auto fetch = [&](int j1, int buf) {                     // tid 0: tile starting at node j1 -> buffer buf
+        const int nt1 = (c.je - j1 < FTN_T) ? c.je - j1 : FTN_T;
+        const unsigned bytes = (unsigned)(((size_t)nt1 * pblk * 8 + 15) & ~(size_t)15);
+        mbar_expect_tx(c.mbar + buf, bytes);
+        bulk_g2s(const_cast<double *>(c.sG) + buf * GB, c.Gp + (size_t)j1 * pblk, bytes, c.mbar + buf);
+    };
+
+    unsigned ph0 = 0, ph1 = 0;                             // mbarrier phase parity of the two buffers
+    int buf = 0;
+    for (int j0 = c.jb; j0 < c.je; j0 += FTN_T, buf ^= 1) {
+        const int nt = (c.je - j0 < FTN_T) ? c.je - j0 : FTN_T;
+        mbar_wait(c.mbar + buf, buf ? ph1 : ph0);
+        if (buf) ph1 ^= 1; else ph0 ^= 1;
+        // ---- w / u of node jl = warp, all fibers of the group (k-step outermost: independent DMMA chains) ----
+        if (warp < nt) node_wu<KS, DO_W, DO_U>(c.sG + buf * GB + warp * pblk, offW, offU, ldk, Rf, Lf, c.sW, c.sU, SW, tig, gid, warp);
+        __syncthreads();
+        if (tid == 0 && j0 + 2 * FTN_T < c.je) fetch(j0 + 2 * FTN_T, buf);     // this buffer is free: fetch the tile after next
+        // ---- variant dots of fiber g = warp over the tile's nodes -----------------------------
+        if (warp < c.nf) {
+            double dl[ML > 0 ? ML : 1][2], dr[NR > 0 ? NR : 1][2];
+#pragma unroll
+            for (int t = 0; t < ML; t++) dl[t][0] = dl[t][1] = 0.0;
+#pragma unroll
+            for (int t = 0; t < NR; t++) dr[t][0] = dr[t][1] = 0.0;
+#pragma unroll
+            for (int ks = 0; ks < KS; ks++) {
+                if constexpr (ML > 0) {
+                    const double bw = wg[ks * 4 * FTN_TP + ((ks & 1) ? jl1 : jl0)];   // B fragment (row a = 4ks+tig, col jl = gid)
+#pragma unroll
+                    for (int mt = 0; mt < ML; mt++) dmma_m8n8k4(dl[mt][0], dl[mt][1], aL[mt][ks], bw);
+                }
+                if constexpr (NR > 0) {
+                    const double au = ug[ks * 4 * FTN_TP + ((ks & 1) ? jl1 : jl0)];   // A fragment (row jl = gid, col b = 4ks+tig)
+#pragma unroll
+                    for (int nb = 0; nb < NR; nb++) dmma_m8n8k4(dr[nb][0], dr[nb][1], au, bR[nb][ks]);
+                }
+            }
+            const size_t idb = idf + j0;
+            if (off32 && nt == FTN_T && (j0 & 1) == 0) {
+                // full tile, slot-major scratch only (the pipeline's case): one 32-bit element offset per output
+                double *cb = c.cst + idb;
+#pragma unroll
+                for (int mt = 0; mt < ML; mt++)
+                    if (outL[mt] >= 0) *reinterpret_cast<double2 *>(cb + outL[mt]) = make_double2(dl[mt][0], dl[mt][1]);
+#pragma unroll
+                for (int nb = 0; nb < NR; nb++) {
+#pragma unroll
+                    for (int h = 0; h < 2; h++)
+                        if (outR[nb][h] >= 0) cb[outR[nb][h]] = dr[nb][h];
+                }
+            } else {
+#pragma unroll
+                for (int mt = 0; mt < ML; mt++) {
+                    const int slot = slotL[mt];
+                    if (slot >= 0) {                                         // D: row v, cols jl = 2tig, 2tig+1
+                        const int jl = 2 * tig;
+                        const double d0 = dl[mt][0], d1 = dl[mt][1];
+                        if (c.cst) {
+                            double *o = c.cst + (size_t)slot * c.NS + idb + jl;
+                            if (jl < nt) o[0] = d0;
+                            if (jl + 1 < nt) o[1] = d1;
+                        }
+                        if (c.costs) {
+                            if (jl < nt) c.costs[(idb + jl) * CS + slot] = d0;
+                            if (jl + 1 < nt) c.costs[(idb + jl + 1) * CS + slot] = d1;
+                        }
+                    }
+                }
+                if (gid < nt) {
+#pragma unroll
+                    for (int nb = 0; nb < NR; nb++) {                        // D: row jl = gid, cols v = 8nb+2tig, +1
+#pragma unroll
+                        for (int h = 0; h < 2; h++) {
+                            const int slot = slotR[nb][h];
+                            if (slot < 0) continue;
+                            const double val = dr[nb][h];
+                            if (c.cst) c.cst[(size_t)slot * c.NS + idb + gid] = val;
+                            if (c.costs) c.costs[(idb + gid) * CS + slot] = val;
+                        }
+                    }
+                }
+            }
+        }
+        __syncthreads();
+    }
+}
+
 template <int KS>
 __global__ void __launch_bounds__(FTN_NT, 2) k_ft_nodes(const FtArgs a, const double *sets)
 {
-    constexpr int MT = (KS + 1) / 2, VT = (2 * MAXD + 7) / 8;
     const DevProblem &P = a.P;
     const DevFT &ft = a.ft;
-    const int d = ft.d, CS = 2 * d + 1;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int gid = lane >> 2, tig = lane & 3;
+    const int d = ft.d;
+    const int tid = threadIdx.x;
 
     int k, gstart, nf;
     ft_find_group(a, k, gstart, nf);
@@ -448,8 +524,8 @@ __global__ void __launch_bounds__(FTN_NT, 2) k_ft_nodes(const FtArgs a, const do
 
     extern __shared__ __align__(16) double smem[];
     const FtNodePlan<KS> sp(ft, P.nmax);
-    const int nmax = sp.nmax, SW = sp.sw, SETW = sp.setw;
-    double *sG = smem + sp.oG, *sW = smem + sp.oW, *sU = smem + sp.oU, *sSets = smem + sp.oSets;
+    const int nmax = sp.nmax;
+    double *sG = smem + sp.oG, *sW = smem + sp.oW, *sU = smem + sp.oU;
     unsigned long long *mbar = reinterpret_cast<unsigned long long *>(smem + sp.oBar);
     int *ismem = reinterpret_cast<int *>(smem + sp.nDoubles);
     int *sFix = ismem + sp.oFix, *sNf = ismem + sp.oNf;
@@ -457,17 +533,10 @@ __global__ void __launch_bounds__(FTN_NT, 2) k_ft_nodes(const FtArgs a, const do
     signed char *sAbs = reinterpret_cast<signed char *>(ismem + sp.nInts);
 
     const int N = P.ngrid[k];
-    const int rk = ft.r[k], rk1 = ft.r[k + 1];
-    const int ldk = ft.ldq[k], pblk = ft.ldq[k] * rk1;                // compact block (rows even-padded)
-    const int NVL = ft_even_up(1 + 2 * k), NVR = ft_even_up(1 + 2 * (d - 1 - k));
+    const int rk1 = ft.r[k + 1];
+    const int pblk = ft.ldq[k] * rk1;                                  // compact block (rows even-padded)
     const int nvL = 1 + 2 * k, nvR = 1 + 2 * (d - 1 - k);
-    int rsG = 1;
-    for (int i = 0; i <= d; i++) rsG = ft.r[i] > rsG ? ft.r[i] : rsG;
-    const int SETWG = rsG * (2 * d + 2), offRG = rsG * NVL;           // layout of the chain kernel's records
-    const int offR = sp.rs4 * NVL;                                    // layout of the zero-padded shared copy
-    constexpr int nksA = KS, nksB = KS;                               // k-steps over a / over b (padded geometry)
-    constexpr int mtA = MT, ntB = MT;                                 // 8-wide tiles over a / over b
-    const bool needU = nvR > 1, needW = nvL > 1 || !needU;           // sides that have neighbour variants (or carry the self value)
+    const bool needU = nvR > 1, needW = nvL > 1 || !needU;            // sides that have neighbour variants (or carry the self value)
     const int mtL = needW ? (nvL + 7) >> 3 : 0, ntR = needU ? (nvR + 7) >> 3 : 0;   // 8-wide tiles over the variant vectors
 
     // this CTA's share of the fiber: a contiguous range of node tiles
@@ -481,127 +550,41 @@ __global__ void __launch_bounds__(FTN_NT, 2) k_ft_nodes(const FtArgs a, const do
     const double *Gp = ft.baseQ + ft.offQ[k];
     const int GB = sp.gbuf;
     for (int e = tid; e < 2 * GB; e += FTN_NT) sG[e] = 0.0;
+    for (int e = tid; e < 2 * FT_FBMAX * sp.sw; e += FTN_NT) sW[e] = 0.0;       // sW and sU are adjacent
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     __syncthreads();
-    auto fetch = [&](int j1, int buf) {                     // tid 0: tile starting at node j1 -> buffer buf
-        const int nt1 = (je - j1 < FTN_T) ? je - j1 : FTN_T;
-        const unsigned bytes = (unsigned)(((size_t)nt1 * pblk * 8 + 15) & ~(size_t)15);
-        mbar_expect_tx(mbar + buf, bytes);
-        bulk_g2s(sG + buf * GB, Gp + (size_t)j1 * pblk, bytes, mbar + buf);
-    };
     if (tid == 0) {
         mbar_init(mbar, 1);
         mbar_init(mbar + 1, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        fetch(jb, 0);
-        if (jb + FTN_T < je) fetch(jb + FTN_T, 1);
-    }
-
-    ft_flags_and_indices(a, k, nf, gstart, jb, je, sFid, sWall, sFix, sNf, sAbs, nmax);
-
-    // the group's chain records -> shared memory, rank rows zero-padded to a multiple of 4: warp g copies
-    // fiber g's record, eight independent loads per lane in flight before the first store
-    {
-        const int nl = rk * NVL, nr = rk1 * NVR;                      // valid doubles of the left / right set
-        for (int g = warp; g < FT_FBMAX; g += FTN_NT / 32) {
-            const double *src = g < nf ? sets + (size_t)sFid[g] * SETWG : nullptr;
-            double *dst = sSets + g * SETW;
-            for (int q0 = lane; q0 < SETW; q0 += 8 * 32) {
-                double v[8];
-#pragma unroll
-                for (int u = 0; u < 8; u++) {
-                    const int q = q0 + 32 * u;
-                    v[u] = 0.0;
-                    if (src && q < SETW) {
-                        if (q < nl) v[u] = __ldg(src + q);
-                        else if (q >= offR && q - offR < nr) v[u] = __ldg(src + offRG + (q - offR));
-                    }
-                }
-#pragma unroll
-                for (int u = 0; u < 8; u++) {
-                    const int q = q0 + 32 * u;
-                    if (q < SETW) dst[q] = v[u];
-                }
-            }
+        for (int b = 0; b < 2; b++) {
+            const int j1 = jb + b * FTN_T;
+            if (j1 >= je) break;
+            const int nt1 = (je - j1 < FTN_T) ? je - j1 : FTN_T;
+            const unsigned bytes = (unsigned)(((size_t)nt1 * pblk * 8 + 15) & ~(size_t)15);
+            mbar_expect_tx(mbar + b, bytes);
+            bulk_g2s(sG + b * GB, Gp + (size_t)j1 * pblk, bytes, mbar + b);
         }
     }
-    for (int e = tid; e < 2 * FT_FBMAX * SW; e += FTN_NT) sW[e] = 0.0;       // sW and sU are adjacent
-    __syncthreads();
 
-    // operands of the w/u products that do not change with the node:
-    // B fragment of R (row b = 4ks+tig, col fiber gid), A fragment of L (row fiber gid, col a = 4ks+tig)
-    double Rf[KS], Lf[KS];
-#pragma unroll
-    for (int ks = 0; ks < KS; ks++) {
-        Rf[ks] = (ks < nksB) ? sSets[gid * SETW + offR + (4 * ks + tig) * NVR] : 0.0;
-        Lf[ks] = (ks < nksA) ? sSets[gid * SETW + (4 * ks + tig) * NVL] : 0.0;
-    }
-    // output slots of this lane's accumulator rows / columns
-    int slotL[VT], slotR[VT][2];
-#pragma unroll
-    for (int t = 0; t < VT; t++) {
-        const int v = 8 * t + gid;
-        slotL[t] = v >= nvL ? -1 : (v == 0 ? 2 * d : 2 * ((v - 1) >> 1) + ((v - 1) & 1));
-#pragma unroll
-        for (int h = 0; h < 2; h++) {
-            const int vv = 8 * t + 2 * tig + h;
-            slotR[t][h] = vv >= nvR ? -1 : (vv == 0 ? (needW ? -1 : 2 * d)          // vector 0 is R itself: the self value when w is skipped
-                                                     : 2 * (d - 1 - ((vv - 1) >> 1)) + ((vv - 1) & 1));
-        }
-    }
-    // element offsets of this lane's outputs inside the slot-major scratch, relative to cst + fiber row + tile
-    // start (left: nodes 2tig, 2tig+1 of variant row gid; right: node gid of variant columns 2tig, 2tig+1)
-    int outL[VT], outR[VT][2];
-    const bool off32 = a.cst && (long long)CS * a.NS < 0x7fffffffLL && !a.costs && ((a.NS | (long long)a.ldo) & 1) == 0 &&
-                       ((size_t)a.cst & 15) == 0;
-#pragma unroll
-    for (int t = 0; t < VT; t++) {
-        outL[t] = (off32 && slotL[t] >= 0) ? (int)(slotL[t] * a.NS) + 2 * tig : -1;
-#pragma unroll
-        for (int h = 0; h < 2; h++) outR[t][h] = (off32 && slotR[t][h] >= 0) ? (int)(slotR[t][h] * a.NS) + gid : -1;
-    }
-    const int offW = tig * ldk + gid, offU = gid * ldk + tig;           // fragment origins inside a node block
-    const double *setL = sSets + warp * SETW, *setR = setL + offR;      // dots phase: fiber g = warp
-    const double *wg = sW + warp * SW + tig * FTN_TP, *ug = sU + warp * SW + tig * FTN_TP;
-    const int jl0 = gid ^ ftn_swz(tig), jl1 = gid ^ ftn_swz(4 + tig);
-    const size_t idf = warp < nf ? (size_t)sFid[warp] * a.ldo : 0;
+    ft_flags_and_indices(a, k, nf, gstart, jb, je, sFid, sWall, sFix, sNf, sAbs, nmax);      // ends with a barrier
 
-    unsigned ph0 = 0, ph1 = 0;                             // mbarrier phase parity of the two buffers
-    int buf = 0;
-    for (int j0 = jb; j0 < je; j0 += FTN_T, buf ^= 1) {
-        const int nt = (je - j0 < FTN_T) ? je - j0 : FTN_T;
-        mbar_wait(mbar + buf, buf ? ph1 : ph0);
-        if (buf) ph1 ^= 1; else ph0 ^= 1;
-        // ---- w / u of node jl = warp, all fibers of the group --------------------------------
-        // k-step outermost: the MT (resp. ntB) accumulator tiles are independent DMMA chains
-        if (warp < nt) {
-            const double *gj = sG + buf * GB + warp * pblk;
-            // w only feeds the left variant set, u only the right one: a side without variants is skipped
-            // (k = 0 takes the self value from u . R, k = d-1 from L . w)
-            if (needW && needU) node_wu<KS, true, true>(gj, offW, offU, ldk, Rf, Lf, sW, sU, SW, tig, gid, warp);
-            else if (needW) node_wu<KS, true, false>(gj, offW, offU, ldk, Rf, Lf, sW, sU, SW, tig, gid, warp);
-            else node_wu<KS, false, true>(gj, offW, offU, ldk, Rf, Lf, sW, sU, SW, tig, gid, warp);
-        }
-        __syncthreads();
-        if (tid == 0 && j0 + 2 * FTN_T < je) fetch(j0 + 2 * FTN_T, buf);     // this buffer is free: fetch the tile after next
-        // ---- variant dots of fiber g = warp over the tile's nodes -----------------------------
-        if (warp < nf) {
-            const size_t idb = idf + j0;
-            // the tile counts of the variant sets are warp-uniform run-time values: dispatch to a body with
-            // compile-time counts, so that no predicated-off DMMA (and its fragment load) is issued at all
-            const NodeDots<KS> nd{setL, setR, wg, ug, jl0, jl1, NVL, NVR, slotL, slotR, outL, outR, off32 && nt == FTN_T && (j0 & 1) == 0,
-                                  a.cst, a.costs, a.NS, idb, CS, nt, tig, gid};
-            switch (mtL * 8 + ntR) {
-#define C3SC_ND(L, R) case (L) * 8 + (R): nd.template run<L, R>(); break;
-                C3SC_ND(0, 1) C3SC_ND(0, 2) C3SC_ND(0, 3) C3SC_ND(0, 4)
-                C3SC_ND(1, 0) C3SC_ND(1, 1) C3SC_ND(1, 2) C3SC_ND(1, 3) C3SC_ND(1, 4)
-                C3SC_ND(2, 0) C3SC_ND(2, 1) C3SC_ND(2, 2) C3SC_ND(2, 3) C3SC_ND(2, 4)
-                C3SC_ND(3, 0) C3SC_ND(3, 1) C3SC_ND(3, 2) C3SC_ND(3, 3) C3SC_ND(3, 4)
-                C3SC_ND(4, 0) C3SC_ND(4, 1) C3SC_ND(4, 2) C3SC_ND(4, 3) C3SC_ND(4, 4)
+    FtNodeCtx c;
+    c.sG = sG; c.sW = sW; c.sU = sU; c.mbar = mbar; c.Gp = Gp; c.sFid = sFid;
+    c.GB = GB; c.SW = sp.sw; c.pblk = pblk; c.ldk = ft.ldq[k]; c.jb = jb; c.je = je; c.nf = nf;
+    c.nvL = nvL; c.nvR = nvR; c.d = d; c.CS = 2 * d + 1; c.RS = a.rs; c.setw = a.setw;
+    c.NS = a.NS; c.cst = a.cst; c.costs = a.costs; c.sets = sets; c.ldo = a.ldo;
+    c.needSelfFromU = !needW;
+    // the tile counts of the variant sets are CTA-uniform run-time values: dispatch to a loop with compile-time
+    // counts, so that no predicated-off DMMA (and its fragment load) is issued at all
+    switch (mtL * 8 + ntR) {
+#define C3SC_ND(L, R) case (L) * 8 + (R): ftn_tile_loop<KS, L, R>(c); break;
+        C3SC_ND(0, 1) C3SC_ND(0, 2) C3SC_ND(0, 3) C3SC_ND(0, 4)
+        C3SC_ND(1, 0) C3SC_ND(1, 1) C3SC_ND(1, 2) C3SC_ND(1, 3) C3SC_ND(1, 4)
+        C3SC_ND(2, 0) C3SC_ND(2, 1) C3SC_ND(2, 2) C3SC_ND(2, 3) C3SC_ND(2, 4)
+        C3SC_ND(3, 0) C3SC_ND(3, 1) C3SC_ND(3, 2) C3SC_ND(3, 3) C3SC_ND(3, 4)
+        C3SC_ND(4, 0) C3SC_ND(4, 1) C3SC_ND(4, 2) C3SC_ND(4, 3) C3SC_ND(4, 4)
 #undef C3SC_ND
-            }
-        }
-        __syncthreads();
     }
 
     ft_active_list(a, nf, jb, je, sFid, sAbs, nmax);

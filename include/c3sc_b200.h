@@ -184,6 +184,11 @@ int c3sc_vi_batch_dev(c3sc_problem *p, const c3sc_valuef *vf, size_t F,
                       const int32_t *d_dim_vary, const int32_t *d_fixed_ind,
                       size_t ldo, const c3sc_batch_out *out, void *stream);
 
+/* Measurement entry: stage 1 of the pipeline alone (neighbour values into the library's own scratch, nothing
+ * returned), launched exactly as c3sc_vi_batch_dev launches it.  bench.py times it for roofline.stage1_live. */
+int c3sc_stage1_batch_dev(c3sc_problem *p, const c3sc_valuef *vf, size_t F,
+                          const int32_t *d_dim_vary, const int32_t *d_fixed_ind, size_t ldo, void *stream);
+
 /* bellman_pi over F fibers (src/bellman.c:1702-1886).  have_rows == 0: pick
  * u* against vf_policy, store the policy rows in d_rows (and argmin if
  * wanted), then evaluate against vf_iter; have_rows != 0: later sub-iteration,

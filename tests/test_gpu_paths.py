@@ -208,3 +208,47 @@ def test_pinned_result_buffer_is_written_in_place(gpu, monkeypatch):
         if with_arg:
             assert np.array_equal(arg.numpy().reshape(F, N), warg)
     prob.close(); vf.close()
+
+
+@pytest.mark.parametrize("case", ["skid_r7", "lqg6_mixed", "dubins_r12", "lqg10_r20", "ragged", "double_int"])
+def test_bucketed_chain_stage_equals_oracle(gpu, monkeypatch, case):
+    """the bucketed chain stage (chain_kernel.cuh: counting sort by core block + streaming DMMA steps) forced on small
+    batches (it normally starts at 4096 fibers): same flags, indices, neighbour values, values and argmin as the oracle,
+    odd / mixed ranks, ragged grids, every boundary type, one and several super-chunks"""
+    monkeypatch.setenv("C3SC_CHAIN_MIN", "1")
+    if case == "skid_r7":
+        cfg = configs.get_config("skidding5d", n=12, rank=7); _check_costs_and_values(cfg, cfg.ranks(), 150)
+    elif case == "lqg6_mixed":
+        cfg = configs.get_config("lqgnd", n=9, dx=6)
+        for F in (1, 13, 67, 400):
+            _check_costs_and_values(cfg, np.array([1, 3, 8, 5, 12, 2, 1], dtype=np.uint64), F, seed=F)
+    elif case == "dubins_r12":
+        cfg = configs.get_config("dubinscar_new", n=14, rank=12); _check_costs_and_values(cfg, cfg.ranks(), 200)
+    elif case == "lqg10_r20":
+        monkeypatch.setenv("C3SC_CHAIN_FIBERS", "96")                       # 48-fiber chunks, 2 per super-chunk, 4 super-chunks
+        monkeypatch.setenv("C3SC_CHUNK_FIBERS", "48")
+        cfg = configs.get_config("lqgnd_reflect", n=16, rank=20, dx=10); _check_costs_and_values(cfg, cfg.ranks(), 300, face_frac=0.3)
+    elif case == "ragged":
+        cfg = configs.get_config("skidding5d", n=12, rank=4)
+        cfg.nvec = np.array([9, 12, 8, 10, 11], dtype=np.uint64)
+        _check_costs_and_values(cfg, cfg.ranks(), 90)
+    else:
+        cfg = configs.get_config("double_int", n=30, rank=9); _check_costs_and_values(cfg, cfg.ranks(), 120)
+
+
+def test_bucketed_and_per_fiber_chain_stages_agree(gpu, monkeypatch):
+    """the two implementations of stage 1a on the same batch: values agree to round-off (different association of the
+    same products), flags and argmin identical up to ties"""
+    cfg = configs.get_config("lqgnd_reflect", n=20, rank=11, dx=8)
+    prob = capi.Problem(cfg, arith=1)
+    ranks = cfg.ranks()
+    cores = synthetic.random_cores(cfg.ngrid, ranks)
+    vf = capi.ValueF(cfg.ngrid, ranks, cores)
+    dv, fi = synthetic.random_fibers(cfg.ngrid, 5000, seed=4)
+    monkeypatch.setenv("C3SC_NO_BUCKETS", "1")
+    v0, a0 = prob.vi_batch(vf, dv, fi)
+    monkeypatch.delenv("C3SC_NO_BUCKETS")
+    v1, a1 = prob.vi_batch(vf, dv, fi)
+    assert rel_err(v1, v0) <= 1e-13
+    assert (a0 != a1).mean() <= 1e-4
+    prob.close(); vf.close()
