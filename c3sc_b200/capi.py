@@ -333,6 +333,10 @@ class Problem:
             o.peer_offset = peer_offset
         check(lib().c3sc_vi_batch_dev(self.handle, vf.handle, F, d_dim_vary, d_fixed_ind, ldo, C.byref(o), stream or None))
 
+    def stage1_batch_dev(self, vf: "ValueF", F: int, d_dim_vary: int, d_fixed_ind: int, ldo: int, stream: int = 0):
+        """stage 1 of the pipeline alone, into the library's own scratch (measurement entry)"""
+        check(lib().c3sc_stage1_batch_dev(self.handle, vf.handle, F, d_dim_vary, d_fixed_ind, ldo, stream or None))
+
     def pi_batch_dev(self, vf_policy, vf_iter, F, d_dim_vary, d_fixed_ind, ldo, have_rows, rows, argmin, value, stream=0):
         check(lib().c3sc_pi_batch_dev(self.handle, vf_policy.handle if vf_policy is not None else None, vf_iter.handle, F,
                                       d_dim_vary, d_fixed_ind, ldo, int(have_rows), rows, argmin or None, value, stream or None))

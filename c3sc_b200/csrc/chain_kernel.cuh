@@ -15,7 +15,6 @@
 //
 //   k_chain_plan   counting sort of the chunk's (fiber, role) entries by (side, dimension, block); roles: centre,
 //                  lower neighbour, upper neighbour.  One CTA per (chunk, dimension).
-//   k_chain_init   row 0 of both sets and the prefix buffers of every record := e_1.
 //   k_chain_step   launch t = 0..d-2 advances the left sets through dimension t and the right sets through d-1-t.
 //
 // Record of fiber f (FtArgs::sets + f*setw, rows of RS = 4*KS doubles, zero beyond the rank):
@@ -110,12 +109,20 @@ __global__ void __launch_bounds__(1024) k_chain_plan(ChainArgs a, int FC, ChainP
         }
         return k;
     };
-    for (int f = tid; f < Fc; f += NT) {
-        int side, i0, lo, hi;
-        if (roles(f, side, i0, lo, hi) < 0) continue;
-        atomicAdd(&cnt[(side * N + i0) * 3], 1);
-        atomicAdd(&cnt[(side * N + lo) * 3 + 1], 1);
-        atomicAdd(&cnt[(side * N + hi) * 3 + 2], 1);
+    // four fibers per thread and trip: the descriptor loads (a dependent pair per fiber, strided by d) are what this
+    // kernel waits for
+    constexpr int U = 4;
+    for (int f0 = tid; f0 < Fc; f0 += U * NT) {
+        int kk[U], side[U], i0[U], lo[U], hi[U];
+#pragma unroll
+        for (int u = 0; u < U; u++) kk[u] = (f0 + u * NT < Fc) ? roles(f0 + u * NT, side[u], i0[u], lo[u], hi[u]) : -1;
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            if (kk[u] < 0) continue;
+            atomicAdd(&cnt[(side[u] * N + i0[u]) * 3], 1);
+            atomicAdd(&cnt[(side[u] * N + lo[u]) * 3 + 1], 1);
+            atomicAdd(&cnt[(side[u] * N + hi[u]) * 3 + 2], 1);
+        }
     }
     __syncthreads();
     // tiles per block: ceil((centre * nin + lo + hi) / 8), nin = 1 + 2s vectors before the step; the left sets
@@ -137,32 +144,21 @@ __global__ void __launch_bounds__(1024) k_chain_plan(ChainArgs a, int FC, ChainP
     for (int e = tid; e < nb; e += NT) { fill[e] = cnt[e]; kst[(e / (3 * N)) * (nmax * 3 + 1) + (e % (3 * N))] = cnt[e]; }
     if (tid == 0) kst[3 * N] = cnt[3 * N];                  // end of side 0 = start of side 1
     __syncthreads();
-    for (int f = tid; f < Fc; f += NT) {
-        int side, i0, lo, hi;
-        const int k = roles(f, side, i0, lo, hi);
-        if (k < 0) continue;
-        const int tag = f | (k << 24);
-        ent[atomicAdd(&fill[(side * N + i0) * 3], 1)] = tag;
-        ent[atomicAdd(&fill[(side * N + lo) * 3 + 1], 1)] = tag;
-        ent[atomicAdd(&fill[(side * N + hi) * 3 + 2], 1)] = tag;
+    for (int f0 = tid; f0 < Fc; f0 += U * NT) {
+        int kk[U], side[U], i0[U], lo[U], hi[U];
+#pragma unroll
+        for (int u = 0; u < U; u++) kk[u] = (f0 + u * NT < Fc) ? roles(f0 + u * NT, side[u], i0[u], lo[u], hi[u]) : -1;
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            if (kk[u] < 0) continue;
+            const int tag = (f0 + u * NT) | (kk[u] << 24);
+            ent[atomicAdd(&fill[(side[u] * N + i0[u]) * 3], 1)] = tag;
+            ent[atomicAdd(&fill[(side[u] * N + lo[u]) * 3 + 1], 1)] = tag;
+            ent[atomicAdd(&fill[(side[u] * N + hi[u]) * 3 + 2], 1)] = tag;
+        }
     }
     __syncthreads();
     if (tid == 0) kst[(nmax * 3 + 1) + 3 * N] = fill[(2 * N - 1) * 3 + 2];       // end of side 1's last bucket
-}
-
-// Records of a chunk before its first step: row 0 of both sets and both P[.][0] buffers start as e_1 (the empty
-// product).  Launched per chunk on the chunk's stream (the record buffer is reused by the lane's next chunk).
-__global__ void __launch_bounds__(256) k_chain_init(const ChainArgs a)
-{
-    const int d = a.ft.d, RS = a.rs;
-    const long long total = (long long)a.F * 4 * RS, step = (long long)gridDim.x * blockDim.x;
-    for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += step) {
-        const int f = (int)(e / (4 * RS)), rem = (int)(e - (long long)f * 4 * RS), w = rem / RS, q = rem - w * RS;
-        int k = a.dim_vary[f];
-        k = k < 0 ? 0 : (k >= d ? d - 1 : k);
-        const int row = w == 0 ? 0 : (w == 1 ? 1 + 2 * k : (w == 2 ? 2 * d : 2 * d + 2));   // L row 0, R row 0, P[0][0], P[1][0]
-        a.sets[(size_t)f * a.setw + (size_t)row * RS + q] = q == 0 ? 1.0 : 0.0;
-    }
 }
 
 __device__ __forceinline__ void ch_dmma(double &d0, double &d1, double a, double b)
@@ -172,50 +168,131 @@ __device__ __forceinline__ void ch_dmma(double &d0, double &d1, double a, double
 }
 
 // One launch = one step of both sides.  Warps own contiguous ranges of 8-row tiles of the concatenated tile list
-// [left buckets of dimension t | right buckets of dimension d-1-t].
+// [left buckets of dimension t | right buckets of dimension d-1-t].  The bucket tables of the two dimensions are
+// staged in shared memory once per CTA (one coalesced round trip instead of a dependent chain of L2 loads per warp);
+// a warp's loop is software-pipelined: the entry of tile i+2 and the rows of tile i+1 are in flight while the
+// products of tile i run.
+struct ChainDec { int e, v, sj; unsigned flags; };          // entry position, vector / new row, side*65536 + bucket; flags: 1 valid, 2 centre
+
 template <int KS>
 __global__ void __launch_bounds__(CH_NT, 2) k_chain_step(const ChainArgs a, int t)
 {
     constexpr int NT8 = (KS + 1) / 2;                       // 8-wide output tiles
+    extern __shared__ int shs[];
     const DevFT &ft = a.ft;
     const int d = ft.d, nmax = a.nmax, RS = a.rs;
     const int lane = threadIdx.x & 31, gid = lane >> 2, tig = lane & 3;
     const int W = gridDim.x * (CH_NT / 32), w = blockIdx.x * (CH_NT / 32) + (threadIdx.x >> 5);
-    const int mS[2] = {t, d - 1 - t};
+    const int mL = t, mR = d - 1 - t;
+    const int NL = a.P.ngrid[mL], NR = a.P.ngrid[mR];
     const int nin = 1 + 2 * t, par = t & 1;
-    const int TL = a.tst[((size_t)mS[0] * 2 + 0) * (nmax + 1) + a.P.ngrid[mS[0]]];
-    const int TR = a.tst[((size_t)mS[1] * 2 + 1) * (nmax + 1) + a.P.ngrid[mS[1]]];
+    // shared: tst of both sides (N+1 each), kst of both sides (3N+1 each)
+    int *sT[2], *sK[2];
+    sT[0] = shs; sT[1] = sT[0] + NL + 1; sK[0] = sT[1] + NR + 1; sK[1] = sK[0] + 3 * NL + 1;
+    {
+        const int *gT0 = a.tst + ((size_t)mL * 2 + 0) * (nmax + 1), *gT1 = a.tst + ((size_t)mR * 2 + 1) * (nmax + 1);
+        const int *gK0 = a.kst + ((size_t)mL * 2 + 0) * (nmax * 3 + 1), *gK1 = a.kst + ((size_t)mR * 2 + 1) * (nmax * 3 + 1);
+        for (int e = threadIdx.x; e <= NL; e += CH_NT) sT[0][e] = __ldg(gT0 + e);
+        for (int e = threadIdx.x; e <= NR; e += CH_NT) sT[1][e] = __ldg(gT1 + e);
+        for (int e = threadIdx.x; e <= 3 * NL; e += CH_NT) sK[0][e] = __ldg(gK0 + e);
+        for (int e = threadIdx.x; e <= 3 * NR; e += CH_NT) sK[1][e] = __ldg(gK1 + e);
+    }
+    if (t == 0) {
+        // records whose side takes no step at all keep the empty product e_1 in row 0: the left set of k = 0, the
+        // right set of k = d-1 (rows that no step of this or a later launch touches)
+        const long long total = (long long)a.F * RS, stride = (long long)gridDim.x * CH_NT;
+        for (long long e = blockIdx.x * (long long)CH_NT + threadIdx.x; e < total; e += stride) {
+            const int f = (int)(e / RS), q = (int)(e - (long long)f * RS);
+            int k = a.dim_vary[f];
+            k = k < 0 ? 0 : (k >= d ? d - 1 : k);
+            if (k == 0) a.sets[(size_t)f * a.setw + q] = q == 0 ? 1.0 : 0.0;
+            if (k == d - 1) a.sets[(size_t)f * a.setw + (size_t)(1 + 2 * k) * RS + q] = q == 0 ? 1.0 : 0.0;
+        }
+    }
+    __syncthreads();
+    const int TL = sT[0][NL], TR = sT[1][NR];
     const long long T = (long long)TL + TR;
     int tile = (int)(T * w / W);
     const int tend = (int)(T * (w + 1) / W);
     if (tile >= tend) return;
-    const unsigned magic = (unsigned)((0x100000000ULL + nin - 1) / nin);          // r / nin for r < 2^32 / nin
+    const unsigned magic = (unsigned)((0x100000000ULL + nin - 1) / nin);          // r / nin for r < 2^32 / nin (nin > 1)
 
-    int side = -1, j = 0, N = 0, m = 0, rin = 0, rout = 0;
-    const int *tst = nullptr, *kst = nullptr, *ent = nullptr;
-    int jt0 = 0, jt1 = 0;                                   // tile range of the current bucket (side-relative)
-    int sc = 0, slo = 0, shi = 0, send = 0;                 // entry ranges of the bucket: centre, lo, hi
-    double B[KS][NT8];
-    for (; tile < tend; tile++) {
-        const int sd = tile < TL ? 0 : 1;
-        const int tl = tile - (sd ? TL : 0);
+    // cursor of the decoder: the bucket that holds the tile most recently decoded
+    int cside = -1, cj = 0, cjt0 = 0, cjt1 = 0, csc = 0, cslo = 0, cshi = 0, csend = 0;
+    auto decode = [&](int tl_abs) -> ChainDec {
+        const int sd = tl_abs < TL ? 0 : 1;
+        const int tl = tl_abs - (sd ? TL : 0);
         bool newb = false;
-        if (sd != side) {
-            side = sd; m = mS[side]; N = a.P.ngrid[m];
-            tst = a.tst + ((size_t)m * 2 + side) * (nmax + 1);
-            kst = a.kst + ((size_t)m * 2 + side) * (nmax * 3 + 1);
-            ent = a.ent + (size_t)m * a.entstride;
-            rin = side ? ft.r[m + 1] : ft.r[m];
-            rout = side ? ft.r[m] : ft.r[m + 1];
+        if (sd != cside) {
+            cside = sd;
+            const int N = sd ? NR : NL;
             int lo = 0, hi = N;                             // largest j with tst[j] <= tl
-            while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (__ldg(tst + mid) <= tl) lo = mid; else hi = mid; }
-            j = lo; newb = true;
-        }
-        if (!newb && tl >= jt1) { j++; newb = true; }
+            while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (sT[sd][mid] <= tl) lo = mid; else hi = mid; }
+            cj = lo; newb = true;
+        } else if (tl >= cjt1) { cj++; newb = true; }
         if (newb) {
-            jt0 = __ldg(tst + j); jt1 = __ldg(tst + j + 1);
-            while (tl >= jt1) { j++; jt0 = jt1; jt1 = __ldg(tst + j + 1); }       // empty buckets
-            sc = __ldg(kst + 3 * j); slo = __ldg(kst + 3 * j + 1); shi = __ldg(kst + 3 * j + 2); send = __ldg(kst + 3 * j + 3);
+            cjt0 = sT[sd][cj]; cjt1 = sT[sd][cj + 1];
+            while (tl >= cjt1) { cj++; cjt0 = cjt1; cjt1 = sT[sd][cj + 1]; }      // empty buckets
+            csc = sK[sd][3 * cj]; cslo = sK[sd][3 * cj + 1]; cshi = sK[sd][3 * cj + 2]; csend = sK[sd][3 * cj + 3];
+        }
+        const int r = (tl - cjt0) * 8 + gid;
+        const int nc = (cslo - csc) * nin, rows = nc + (csend - cslo);
+        ChainDec D;
+        D.flags = (r < rows ? 1u : 0u) | (r < nc ? 2u : 0u);
+        if (r < nc) { const int q = nin == 1 ? r : (int)__umulhi((unsigned)r, magic); D.e = csc + q; D.v = r - q * nin; }
+        else { D.e = cslo + (r - nc); D.v = D.e < cshi ? nin : nin + 1; }
+        D.sj = sd * 65536 + cj;
+        return D;
+    };
+    const int *entS[2] = {a.ent + (size_t)mL * a.entstride, a.ent + (size_t)mR * a.entstride};
+    auto load_tag = [&](const ChainDec &D) -> int { return (D.flags & 1u) ? __ldg(entS[D.sj >> 16] + D.e) : 0; };
+    // pointers of a row: src (read), dst (written), and for the prefix row also row 0 of the set
+    auto row_ptrs = [&](const ChainDec &D, int tag, const double *&src, double *&dst, double *&dst0) {
+        const int f = tag & 0xffffff, k = tag >> 24, side = D.sj >> 16;
+        double *rec = a.sets + (size_t)f * a.setw;
+        double *set = rec + (size_t)(side ? 1 + 2 * k : 0) * RS;
+        const bool centre = (D.flags & 2u) != 0;
+        src = (centre && D.v > 0) ? set + (size_t)D.v * RS : rec + (size_t)(2 * d + 2 * side + par) * RS;
+        dst = (centre && D.v == 0) ? rec + (size_t)(2 * d + 2 * side + (par ^ 1)) * RS : set + (size_t)D.v * RS;
+        dst0 = (centre && D.v == 0) ? set : nullptr;
+    };
+    auto load_rows = [&](const ChainDec &D, const double *src, double (&A)[KS]) {
+#pragma unroll
+        for (int ks = 0; ks < KS; ks++) {
+            if (t == 0) A[ks] = (4 * ks + tig == 0 && (D.flags & 1u)) ? 1.0 : 0.0;       // every vector of step 0 is e_1
+            else A[ks] = (D.flags & 1u) ? src[4 * ks + tig] : 0.0;
+        }
+    };
+
+    double B[KS][NT8];
+    int Bsj = -1;
+    // pipeline fill: tile i decoded + tag + rows; tile i+1 decoded + tag
+    ChainDec D0 = decode(tile), D1;
+    int tag0 = load_tag(D0), tag1 = 0;
+    const double *src0; double *dst0, *dsz0;
+    row_ptrs(D0, tag0, src0, dst0, dsz0);
+    double A0[KS];
+    load_rows(D0, src0, A0);
+    bool have1 = tile + 1 < tend;
+    if (have1) { D1 = decode(tile + 1); tag1 = load_tag(D1); }
+    for (; tile < tend; tile++) {
+        // next tile: pointers from its tag, rows in flight; the tile after: decode + tag in flight
+        const double *src1 = nullptr; double *dst1 = nullptr, *dsz1 = nullptr;
+        double A1[KS];
+        ChainDec D2;
+        int tag2 = 0;
+        bool have2 = false;
+        if (have1) {
+            row_ptrs(D1, tag1, src1, dst1, dsz1);
+            load_rows(D1, src1, A1);
+            have2 = tile + 2 < tend;
+            if (have2) { D2 = decode(tile + 2); tag2 = load_tag(D2); }
+        }
+        // current tile
+        if (D0.sj != Bsj) {
+            Bsj = D0.sj;
+            const int side = Bsj >> 16, j = Bsj & 0xffff, m = side ? mR : mL;
+            const int rin = side ? ft.r[m + 1] : ft.r[m], rout = side ? ft.r[m] : ft.r[m + 1];
             // B fragments (row q = 4ks+tig of the contraction, column o = 8nt+gid of the output) of block G_m[j]
             // (element (a,b) at a + b*r_m): left  out[o=b] = sum_a in[a] G[a,b],  right  out[o=a] = sum_b G[a,b] in[b]
             const double *g = ft.base + ft.off[m] + (size_t)j * ft.r[m] * ft.r[m + 1];
@@ -228,42 +305,29 @@ __global__ void __launch_bounds__(CH_NT, 2) k_chain_step(const ChainArgs a, int 
                     B[ks][nt] = (q < rin && o < rout) ? __ldg(g + (side ? o + q * rm : q + o * rm)) : 0.0;
                 }
         }
-        // this lane's row of the tile
-        const int r = (tl - jt0) * 8 + gid;
-        const int nc = (slo - sc) * nin, rows = nc + (send - slo);
-        const bool valid = r < rows;
-        int e, v;                                           // entry position, vector index (centre) / new row (neighbours)
-        if (r < nc) { const int q = (int)__umulhi((unsigned)r, magic); e = sc + q; v = r - q * nin; }
-        else { e = slo + (r - nc); v = e < shi ? nin : nin + 1; }
-        const int tag = valid ? __ldg(ent + e) : 0;
-        const int f = tag & 0xffffff, k = tag >> 24;
-        double *rec = a.sets + (size_t)f * a.setw;
-        double *set = rec + (size_t)(side ? 1 + 2 * k : 0) * RS;
-        double *Pc = rec + (size_t)(2 * d + 2 * side + par) * RS, *Pn = rec + (size_t)(2 * d + 2 * side + (par ^ 1)) * RS;
-        const bool centre = r < nc;
-        const double *src = (centre && v > 0) ? set + (size_t)v * RS : Pc;
-        double *dst = (centre && v == 0) ? Pn : set + (size_t)v * RS;
-        double A[KS];
-#pragma unroll
-        for (int ks = 0; ks < KS; ks++) A[ks] = valid ? src[4 * ks + tig] : 0.0;
         double acc[NT8][2];
 #pragma unroll
         for (int nt = 0; nt < NT8; nt++) acc[nt][0] = acc[nt][1] = 0.0;
 #pragma unroll
         for (int ks = 0; ks < KS; ks++)
 #pragma unroll
-            for (int nt = 0; nt < NT8; nt++) ch_dmma(acc[nt][0], acc[nt][1], A[ks], B[ks][nt]);
-        if (valid) {
+            for (int nt = 0; nt < NT8; nt++) ch_dmma(acc[nt][0], acc[nt][1], A0[ks], B[ks][nt]);
+        if (D0.flags & 1u) {
 #pragma unroll
             for (int nt = 0; nt < NT8; nt++) {
                 const int o = 8 * nt + 2 * tig;                 // D: row r, columns o, o+1; zero beyond the rank
                 if (o < RS) {
                     const double2 val = make_double2(acc[nt][0], acc[nt][1]);
-                    *reinterpret_cast<double2 *>(dst + o) = val;
-                    if (centre && v == 0) *reinterpret_cast<double2 *>(set + o) = val;      // the prefix also lives in row 0
+                    *reinterpret_cast<double2 *>(dst0 + o) = val;
+                    if (dsz0) *reinterpret_cast<double2 *>(dsz0 + o) = val;                   // the prefix also lives in row 0
                 }
             }
         }
+        // shift the pipeline
+        D0 = D1; tag0 = tag1; src0 = src1; dst0 = dst1; dsz0 = dsz1;
+#pragma unroll
+        for (int ks = 0; ks < KS; ks++) A0[ks] = A1[ks];
+        D1 = D2; tag1 = tag2; have1 = have2;
     }
 }
 

@@ -25,7 +25,9 @@ int launch_group_fibers(const DevProblem &P, int F, int FC, const int *dim_vary,
     if (F <= 0) return 0;
     GridDims ng;
     for (int i = 0; i < MAXD; i++) ng.n[i] = P.ngrid[i];
-    k_group_fibers<<<(F + FC - 1) / FC, 1024, 0, st>>>(F, FC, P.dx, dim_vary, fixed_ind, ng, P.err, perm, cnt_all);
+    const int vy = (FC * P.dx + 8191) / 8192 > 16 ? 16 : (FC * P.dx + 8191) / 8192;     // CTAs per chunk for the descriptor check
+    k_group_fibers<<<dim3((unsigned)((F + FC - 1) / FC), (unsigned)(vy < 1 ? 1 : vy)), 1024, 0, st>>>(F, FC, P.dx, dim_vary, fixed_ind, ng, P.err, perm,
+                                                                                                  cnt_all);
     return (int)cudaGetLastError();
 }
 
@@ -121,15 +123,9 @@ static int launch_chain_steps_t(const ChainArgs &a, cudaStream_t st)
 {
     ft_device_info();
     const int grid = g_sms * 2;
-    {
-        long long gi = ((long long)a.F * 4 * a.rs + 255) / 256;
-        if (gi > g_sms * 8) gi = g_sms * 8;
-        k_chain_init<<<(unsigned)gi, 256, 0, st>>>(a);
-        cudaError_t e = cudaGetLastError();
-        if (e != cudaSuccess) return (int)e;
-    }
     for (int t = 0; t + 1 < a.ft.d; t++) {
-        k_chain_step<KS><<<grid, CH_NT, 0, st>>>(a, t);
+        const size_t smem = (size_t)(4 * (a.P.ngrid[t] + a.P.ngrid[a.ft.d - 1 - t]) + 4) * sizeof(int);
+        k_chain_step<KS><<<grid, CH_NT, smem, st>>>(a, t);
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) return (int)e;
     }
@@ -139,7 +135,7 @@ static int launch_chain_steps_t(const ChainArgs &a, cudaStream_t st)
 // the d-1 steps of one chunk (a.F = fibers of the chunk, pointers at the chunk's slices); returns the launches via *n
 int launch_chain_steps(const ChainArgs &a, cudaStream_t st, int *n)
 {
-    *n = a.ft.d;                                            // init + d-1 steps
+    *n = a.ft.d - 1;
     switch ((ft_rmax(a.ft) + 3) / 4) {
     case 1: return launch_chain_steps_t<1>(a, st);
     case 2: return launch_chain_steps_t<2>(a, st);

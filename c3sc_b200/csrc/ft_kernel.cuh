@@ -135,9 +135,9 @@ __global__ void __launch_bounds__(1024) k_group_fibers(int F, int FC, int d, con
     __shared__ int cnt[MAXD], pos[MAXD];
     const int tid = threadIdx.x;
     const int c0 = blockIdx.x * FC, Fc = (F - c0 < FC) ? F - c0 : FC;
-    if (err && fixed_ind) {
+    if (err && fixed_ind) {                                 // validation: the gridDim.y CTAs of a chunk share the scan
         int bad = 0x7fffffff;
-        for (int e = tid; e < Fc * d; e += blockDim.x) {
+        for (int e = blockIdx.y * blockDim.x + tid; e < Fc * d; e += gridDim.y * blockDim.x) {
             const int f = e / d, i = e - f * d;
             const int v = fixed_ind[(size_t)c0 * d + e];
             bool b = (unsigned)v >= (unsigned)ng.n[i];
@@ -146,6 +146,7 @@ __global__ void __launch_bounds__(1024) k_group_fibers(int F, int FC, int d, con
         }
         if (bad != 0x7fffffff) { atomicOr(err + 1, 1); atomicMin(err + 2, bad); }
     }
+    if (blockIdx.y != 0) return;
     dim_vary += c0; perm += c0;
     int *kcount = cnt_all + 64 * blockIdx.x, *kstart = kcount + 16, *act_count = kcount + 32;
     if (tid < MAXD) cnt[tid] = 0;
