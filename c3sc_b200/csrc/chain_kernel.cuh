@@ -197,6 +197,10 @@ __global__ void __launch_bounds__(CH_NT, 2) k_chain_step(const ChainArgs a, int 
         for (int e = threadIdx.x; e <= 3 * NL; e += CH_NT) sK[0][e] = __ldg(gK0 + e);
         for (int e = threadIdx.x; e <= 3 * NR; e += CH_NT) sK[1][e] = __ldg(gK1 + e);
     }
+    // Programmatic dependent launch: steps t >= 1 are launched while step t-1 still runs (ft.cu); everything above
+    // reads the plan only.  Let the next step start its own prologue, then wait for the previous step's rows.
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     if (t == 0) {
         // records whose side takes no step at all keep the empty product e_1 in row 0: the left set of k = 0, the
         // right set of k = d-1 (rows that no step of this or a later launch touches)

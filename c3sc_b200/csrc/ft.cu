@@ -122,11 +122,20 @@ template <int KS>
 static int launch_chain_steps_t(const ChainArgs &a, cudaStream_t st)
 {
     ft_device_info();
+    const bool g_no_pdl = getenv("C3SC_NO_PDL") != nullptr;
     const int grid = g_sms * 2;
     for (int t = 0; t + 1 < a.ft.d; t++) {
         const size_t smem = (size_t)(4 * (a.P.ngrid[t] + a.P.ngrid[a.ft.d - 1 - t]) + 4) * sizeof(int);
-        k_chain_step<KS><<<grid, CH_NT, smem, st>>>(a, t);
-        cudaError_t e = cudaGetLastError();
+        // steps t >= 1 overlap their launch and table prologue with the tail of step t-1 (programmatic dependent
+        // launch; the kernel waits with griddepcontrol.wait before it touches the records)
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(CH_NT); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = (t > 0 && !g_no_pdl) ? 1 : 0;
+        cudaError_t e = cudaLaunchKernelEx(&cfg, k_chain_step<KS>, a, t);
         if (e != cudaSuccess) return (int)e;
     }
     return 0;

@@ -316,8 +316,8 @@ struct FtNodePlan {
         gbuf = gt;
         int o = 0;
         oG = o;    o += 2 * gt;                      // two tile buffers, each 16-byte aligned
-        oW = o;    o += FT_FBMAX * sw;
-        oU = o;    o += FT_FBMAX * sw;
+        oW = o;    o += 2 * FT_FBMAX * sw;           // w tiles of two consecutive node tiles (one barrier per tile, see the loop)
+        oU = o;    o += 2 * FT_FBMAX * sw;
         o = ft_even_up(o);
         oBar = o;  o += 2;                           // two mbarriers
         nDoubles = o;
@@ -418,7 +418,8 @@ __device__ __forceinline__ void ftn_tile_loop(const FtNodeCtx &c)
     }
     const int ldk = c.ldk, SW = c.SW, pblk = c.pblk, GB = c.GB;
     const int offW = tig * ldk + gid, offU = gid * ldk + tig;           // fragment origins inside a node block
-    const double *wg = c.sW + warp * SW + tig * FTN_TP, *ug = c.sU + warp * SW + tig * FTN_TP;
+    const double *wg0 = c.sW + warp * SW + tig * FTN_TP, *ug0 = c.sU + warp * SW + tig * FTN_TP;
+    const int WB = FT_FBMAX * SW;                           // one buffer of w (or u) tiles
     const int jl0 = gid ^ ftn_swz(tig), jl1 = gid ^ ftn_swz(4 + tig);
     const size_t idf = warp < c.nf ? (size_t)c.sFid[warp] * c.ldo : 0;
     const int CS = c.CS;
@@ -437,8 +438,12 @@ __device__ __forceinline__ void ftn_tile_loop(const FtNodeCtx &c)
         mbar_wait(c.mbar + buf, buf ? ph1 : ph0);
         if (buf) ph1 ^= 1; else ph0 ^= 1;
         // ---- w / u of node jl = warp, all fibers of the group (k-step outermost: independent DMMA chains) ----
-        if (warp < nt) node_wu<KS, DO_W, DO_U>(c.sG + buf * GB + warp * pblk, offW, offU, ldk, Rf, Lf, c.sW, c.sU, SW, tig, gid, warp);
+        // The w / u tiles are double-buffered like the G tiles: phase 1 of tile i+1 writes the other buffer, so the
+        // barrier after phase 1 of tile i+1 is also the one that orders phase 2 of tile i before phase 1 of tile i+2
+        // re-uses its buffer: ONE CTA barrier per node tile.
+        if (warp < nt) node_wu<KS, DO_W, DO_U>(c.sG + buf * GB + warp * pblk, offW, offU, ldk, Rf, Lf, c.sW + buf * WB, c.sU + buf * WB, SW, tig, gid, warp);
         __syncthreads();
+        const double *wg = wg0 + buf * WB, *ug = ug0 + buf * WB;
         if (tid == 0 && j0 + 2 * FTN_T < c.je) fetch(j0 + 2 * FTN_T, buf);     // this buffer is free: fetch the tile after next
         // ---- variant dots of fiber g = warp over the tile's nodes -----------------------------
         if (warp < c.nf) {
@@ -506,7 +511,6 @@ __device__ __forceinline__ void ftn_tile_loop(const FtNodeCtx &c)
                 }
             }
         }
-        __syncthreads();
     }
 }
 
@@ -550,7 +554,7 @@ __global__ void __launch_bounds__(FTN_NT, 2) k_ft_nodes(const FtArgs a, const do
     const double *Gp = ft.baseQ + ft.offQ[k];
     const int GB = sp.gbuf;
     for (int e = tid; e < 2 * GB; e += FTN_NT) sG[e] = 0.0;
-    for (int e = tid; e < 2 * FT_FBMAX * sp.sw; e += FTN_NT) sW[e] = 0.0;       // sW and sU are adjacent
+    for (int e = tid; e < 4 * FT_FBMAX * sp.sw; e += FTN_NT) sW[e] = 0.0;       // sW and sU are adjacent
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     __syncthreads();
     if (tid == 0) {

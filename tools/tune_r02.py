@@ -49,12 +49,11 @@ def main():
 
     ref = None
     combos = [dict(C3SC_NO_BUCKETS="1")]
-    for mb, cf, lanes in itertools.product((32, 48, 64, 96, 128, 192), (4096, 8192, 16384), (2,)):
+    for mb, cf, lanes in ((96, 8192, 2), (96, 16384, 2), (128, 16384, 2), (192, 8192, 2), (192, 16384, 2), (192, 32768, 2), (256, 16384, 2),
+                          (192, 16384, 3), (288, 16384, 3)):
         combos.append(dict(C3SC_CHUNK_MB=str(mb), C3SC_CHAIN_FIBERS=str(cf), C3SC_LANES=str(lanes)))
-    combos += [dict(C3SC_CHUNK_MB="64", C3SC_CHAIN_FIBERS="8192", C3SC_LANES="1"),
-               dict(C3SC_CHUNK_MB="96", C3SC_CHAIN_FIBERS="8192", C3SC_LANES="3"),
-               dict(C3SC_CHUNK_MB="128", C3SC_CHAIN_FIBERS="16384", C3SC_LANES="4")]
-    keys = ("C3SC_NO_BUCKETS", "C3SC_CHUNK_MB", "C3SC_CHAIN_FIBERS", "C3SC_LANES")
+    combos.append(dict(C3SC_CHUNK_MB="192", C3SC_CHAIN_FIBERS="16384", C3SC_LANES="2", C3SC_NO_PDL="1"))
+    keys = ("C3SC_NO_BUCKETS", "C3SC_CHUNK_MB", "C3SC_CHAIN_FIBERS", "C3SC_LANES", "C3SC_NO_PDL")
     for c in combos:
         for k in keys:
             os.environ.pop(k, None)
