@@ -37,7 +37,7 @@ class BatchOut(C.Structure):
         ("value", C.c_void_p), ("argmin", C.c_void_p), ("absorbed", C.c_void_p),
         ("costs", C.c_void_p), ("rows", C.c_void_p), ("nbr_vary", C.c_void_p),
         ("nbr_fixed", C.c_void_p),
-        ("value_peers", C.c_void_p * 8), ("n_peers", C.c_uint32), ("peer_offset", C.c_uint64),
+        ("value_peers", C.c_void_p * 8), ("n_peers", C.c_uint32), ("peer_offset", C.c_uint64), ("peer_mode", C.c_uint32),
     ]
 
 
@@ -58,7 +58,7 @@ EXPORTS = [
     "c3sc_problem_create", "c3sc_problem_destroy", "c3sc_problem_check", "c3sc_problem_control_path",
     "c3sc_valuef_create", "c3sc_valuef_update", "c3sc_valuef_device_buffer", "c3sc_valuef_destroy",
     "c3sc_vi_batch_dev", "c3sc_pi_batch_dev", "c3sc_vi_batch", "c3sc_vi_batch_debug", "c3sc_pi_batch",
-    "c3sc_transition_batch", "c3sc_model_eval", "c3sc_measure_fp64_peak",
+    "c3sc_transition_batch", "c3sc_model_eval", "c3sc_measure_fp64_peak", "c3sc_measure_fp64_tensor_peak",
     "c3sc_neighbor_costs_batch", "c3sc_node_backup_batch", "c3sc_control_value_batch", "c3sc_rhs_batch",
     "c3sc_transition_raw", "c3sc_ft_fiber_nn_batch", "c3sc_valuef_commit",
     "c3sc_cross_create", "c3sc_cross_copy", "c3sc_cross_destroy", "c3sc_cross_ranks", "c3sc_cross_run", "c3sc_cross_run_vi", "c3sc_cross_run_pi",
@@ -66,7 +66,11 @@ EXPORTS = [
     "c3sc_valuef_eval_batch", "c3sc_policy_eval_batch",
     "c3sc_cross_index_sets", "c3sc_cores_round", "c3sc_cross_adapt_capacity", "c3sc_cross_set_ranks", "c3sc_cross_run_adapt", "c3sc_cross_run_vi_adapt",
     "c3sc_peer_buffer_create", "c3sc_peer_buffer_open", "c3sc_peer_buffer_close",
-    "c3sc_fibers_check", "c3sc_fiber_flags_batch", "c3sc_neighbor_node_costs_batch", "c3sc_stage1_batch_dev",
+    "c3sc_fibers_check", "c3sc_fiber_flags_batch", "c3sc_neighbor_node_costs_batch", "c3sc_stage1_batch_dev", "c3sc_pi_batch_resident", "c3sc_pi_store_reserve", "c3sc_pi_batch_store",
+    "c3sc_multi_create", "c3sc_multi_destroy", "c3sc_multi_device_count", "c3sc_multi_uses_nccl", "c3sc_multi_problem",
+    "c3sc_multi_valuef_create", "c3sc_multi_valuef_update", "c3sc_multi_valuef_destroy", "c3sc_multi_valuef_get", "c3sc_multi_shard",
+    "c3sc_multi_vi_batch", "c3sc_multi_pi_batch", "c3sc_multi_pi_reset", "c3sc_multi_gathered_count", "c3sc_multi_vi_batch_gathered",
+    "c3sc_cross_run_vi_multi", "c3sc_cross_run_pi_multi",
 ]
 
 _lib = None
@@ -102,6 +106,25 @@ def lib() -> C.CDLL:
         L.c3sc_vi_batch_debug.argtypes = [vp, vp, sz, vp, vp, sz, vp, vp, vp, vp, vp, vp, vp]
         L.c3sc_fibers_check.argtypes = [vp, sz, vp, vp]
         L.c3sc_stage1_batch_dev.argtypes = [vp, vp, sz, vp, vp, sz, vp]
+        L.c3sc_pi_batch_resident.argtypes = [vp, vp, vp, sz, vp, vp, sz, i32, vp, vp]
+        L.c3sc_pi_store_reserve.argtypes = [vp, sz, sz]
+        L.c3sc_multi_create.argtypes = [C.POINTER(ProblemDesc), i32, vp, C.POINTER(vp)]
+        L.c3sc_multi_destroy.argtypes = [vp]; L.c3sc_multi_destroy.restype = None
+        L.c3sc_multi_device_count.argtypes = [vp]; L.c3sc_multi_uses_nccl.argtypes = [vp]
+        L.c3sc_multi_problem.argtypes = [vp, i32]; L.c3sc_multi_problem.restype = vp
+        L.c3sc_multi_valuef_create.argtypes = [vp, C.c_uint32, c_u64p, c_u64p, C.POINTER(c_f64p), C.POINTER(vp)]
+        L.c3sc_multi_valuef_update.argtypes = [vp, C.POINTER(c_f64p)]
+        L.c3sc_multi_valuef_destroy.argtypes = [vp]; L.c3sc_multi_valuef_destroy.restype = None
+        L.c3sc_multi_valuef_get.argtypes = [vp, i32]; L.c3sc_multi_valuef_get.restype = vp
+        L.c3sc_multi_shard.argtypes = [sz, i32, i32, C.POINTER(sz), C.POINTER(sz)]; L.c3sc_multi_shard.restype = None
+        L.c3sc_multi_vi_batch.argtypes = [vp, vp, sz, vp, vp, sz, vp, vp]
+        L.c3sc_multi_pi_batch.argtypes = [vp, vp, vp, C.c_uint32, sz, vp, vp, sz, i32, vp]
+        L.c3sc_multi_pi_reset.argtypes = [vp]
+        L.c3sc_multi_gathered_count.argtypes = [sz, i32, sz]; L.c3sc_multi_gathered_count.restype = sz
+        L.c3sc_multi_vi_batch_gathered.argtypes = [vp, vp, sz, vp, vp, sz, vp]
+        L.c3sc_cross_run_vi_multi.argtypes = [vp, vp, vp, C.POINTER(CrossOpts), C.POINTER(c_f64p), c_u64p, c_f64p]
+        L.c3sc_cross_run_pi_multi.argtypes = [vp, vp, vp, vp, C.POINTER(CrossOpts), C.POINTER(c_f64p), c_u64p, c_f64p]
+        L.c3sc_pi_batch_store.argtypes = [vp, vp, vp, sz, vp, vp, sz, i32, vp, vp]
         L.c3sc_fiber_flags_batch.argtypes = [vp, sz, vp, vp, sz, vp, vp, vp]
         L.c3sc_neighbor_node_costs_batch.argtypes = [vp, vp, sz, vp, vp, vp]
         L.c3sc_pi_batch.argtypes = [vp, vp, vp, sz, vp, vp, sz, i32, vp, vp, vp]
@@ -114,6 +137,7 @@ def lib() -> C.CDLL:
         L.c3sc_transition_raw.argtypes = [i32, C.c_uint32, C.c_double, vp, sz, vp, vp, vp, vp, vp]
         L.c3sc_ft_fiber_nn_batch.argtypes = [vp, sz, vp, vp, vp, vp, sz, vp]
         L.c3sc_measure_fp64_peak.argtypes = [C.POINTER(C.c_double), i32, i32]
+        L.c3sc_measure_fp64_tensor_peak.argtypes = [C.POINTER(C.c_double), i32, i32]
         L.c3sc_peer_buffer_create.argtypes = [sz, C.POINTER(vp), C.c_char_p]
         L.c3sc_peer_buffer_open.argtypes = [C.c_char_p, C.POINTER(vp)]
         L.c3sc_peer_buffer_close.argtypes = [vp, i32]
@@ -150,6 +174,13 @@ def measure_fp64_peak(iters: int = 8192, repeats: int = 5) -> float:
     """TFLOP/s of a pure DFMA loop on the current device (roofline denominator)."""
     v = C.c_double()
     check(lib().c3sc_measure_fp64_peak(C.byref(v), iters, repeats))
+    return v.value
+
+
+def measure_fp64_tensor_peak(iters: int = 4096, repeats: int = 5) -> float:
+    """TFLOP/s of a pure DMMA (mma.sync m8n8k4 f64) loop on the current device."""
+    v = C.c_double()
+    check(lib().c3sc_measure_fp64_tensor_peak(C.byref(v), iters, repeats))
     return v.value
 
 
@@ -322,7 +353,8 @@ class Problem:
 
     # ---- device-pointer entry points (ints are raw device addresses) ---------------
     def vi_batch_dev(self, vf: "ValueF", F: int, d_dim_vary: int, d_fixed_ind: int, ldo: int, value: int,
-                     argmin: int = 0, stream: int = 0, rows: int = 0, peers=None, peer_offset: int = 0, costs: int = 0):
+                     argmin: int = 0, stream: int = 0, rows: int = 0, peers=None, peer_offset: int = 0, costs: int = 0,
+                     peer_mode: int = 0):
         """peers: device addresses of every rank's gathered buffer (peer-mapped) for the fused all-gather;
         costs alone (no value / argmin / rows): stage 1 only, node-major neighbour values"""
         o = BatchOut(value or None, argmin or None, None, costs or None, rows or None, None, None)
@@ -331,6 +363,7 @@ class Problem:
             for g, ptr in enumerate(peers):
                 o.value_peers[g] = ptr
             o.peer_offset = peer_offset
+            o.peer_mode = peer_mode
         check(lib().c3sc_vi_batch_dev(self.handle, vf.handle, F, d_dim_vary, d_fixed_ind, ldo, C.byref(o), stream or None))
 
     def stage1_batch_dev(self, vf: "ValueF", F: int, d_dim_vary: int, d_fixed_ind: int, ldo: int, stream: int = 0):

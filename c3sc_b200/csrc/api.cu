@@ -30,6 +30,7 @@ void chain_plan_sizes(const DevFT &ft, int nmax, size_t FC, size_t *kst, size_t 
 int chain_bucketed_ok(const DevFT &ft, int nmax);
 int launch_chain_plan(const ChainArgs &a, int FC, cudaStream_t st);
 int launch_chain_steps(const ChainArgs &a, cudaStream_t st, int *n);
+int launch_rows_move(double *dst, const double *src, const int *idx, int F, long long per, int scatter, cudaStream_t st);
 int launch_node_backup_lqg_lo(int dx, int arith, const DevProblem &P, int n, const double *x, const double *costs,
                               const int *absorbed, double *value, int *argmin, cudaStream_t st);
 int launch_node_backup_lqg_hi(int dx, int arith, const DevProblem &P, int n, const double *x, const double *costs,
@@ -187,6 +188,7 @@ static void detect_control_grid(const c3sc_problem_desc *d, const std::vector<do
 struct c3sc_problem {
     DevProblem P;
     int model, arith;
+    int device = 0;                          // the device the problem lives on (current device at creation)
     Scratch scr;
     CtlGroups grp;
     double *d_gtab = nullptr;
@@ -195,16 +197,26 @@ struct c3sc_problem {
     int *d_err = nullptr;
     cudaStream_t stream = nullptr;           // host-buffer entry points run here
     cudaStream_t copy_stream = nullptr;      // device->host copies of finished chunks
-    cudaEvent_t chunk_done = nullptr;
+    cudaEvent_t chunk_done = nullptr, copies_done = nullptr;
     DevBuf b_dv, b_fi, b_val, b_arg, b_abs, b_costs, b_rows, b_nv, b_nf, b_misc[8];
     c3sc_valuef *vf_flags = nullptr;         // rank-1 zero train for the flags-only entry (c3sc_fiber_flags_batch)
+    DevBuf rows_store;                       // device-resident policy rows per fiber slot (c3sc_pi_batch_store)
+    size_t store_ldo = 0;
 };
 
 struct c3sc_valuef {
     DevFT ft;
+    int device = 0;
     double *d_base = nullptr, *d_baseT = nullptr, *d_baseP = nullptr, *d_baseQ = nullptr;
     size_t count = 0;
     std::vector<size_t> len;
+};
+
+// switch the calling thread to a handle's device for the duration of an entry point
+struct DeviceScope {
+    int prev = -1;
+    explicit DeviceScope(int dev) { cudaGetDevice(&prev); if (prev != dev) cudaSetDevice(dev); else prev = -1; }
+    ~DeviceScope() { if (prev >= 0) cudaSetDevice(prev); }
 };
 
 // device error word of a problem: [0] transition normaliser < 1e-14 seen, [1] a fiber descriptor outside the
@@ -225,6 +237,8 @@ static int read_error_word(c3sc_problem *p)
 extern "C" {
 
 const char *c3sc_last_error(void) { return g_err; }
+/* internal (multi.cu): set the calling thread's message */
+int c3sc_set_error(int code, const char *msg) { return fail(code, "%s", msg ? msg : ""); }
 const char *c3sc_version(void) { return "c3sc_b200 0.1 (sm_100a)"; }
 uint64_t c3sc_launch_count(void) { return g_launches.load(); }
 
@@ -243,11 +257,8 @@ int c3sc_cuda_init(int device)
         return fail(C3SC_ENODEV, "no CUDA device (%s); the Bellman backup has no CPU fallback",
                     e == cudaSuccess ? "count 0" : cudaGetErrorString(e));
     if (device < 0 || device >= n) return fail(C3SC_EINVAL, "device %d out of range [0,%d)", device, n);
-    // one device per process (one process per GPU): launch geometry and function attributes are cached
-    static int bound_device = -1;
-    if (bound_device >= 0 && bound_device != device)
-        return fail(C3SC_EINVAL, "this process is bound to device %d; use one process per GPU", bound_device);
-    bound_device = device;
+    // a process may use several devices (include/c3sc_multi.h: one host thread per device); every handle remembers the
+    // device it was created on and its entry points switch to it
     CK(cudaSetDevice(device));
     CK(cudaFree(0));
     return C3SC_OK;
@@ -295,6 +306,7 @@ int c3sc_problem_create(const c3sc_problem_desc *d, c3sc_problem **out)
     if (c3sc_cuda_device_count() == 0)
         return fail(C3SC_ENODEV, "no CUDA device; the Bellman backup has no CPU fallback");
     c3sc_problem *p = new c3sc_problem();
+    cudaGetDevice(&p->device);
     DevProblem &P = p->P;
     memset(&P, 0, sizeof P);
     P.dx = (int)d->dx; P.du = (int)d->du; P.dw = (int)d->dw; P.nu = (int)d->nu; P.nobs = (int)d->nobs;
@@ -346,6 +358,7 @@ int c3sc_problem_create(const c3sc_problem_desc *d, c3sc_problem **out)
     CKP(cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking));
     CKP(cudaStreamCreateWithFlags(&p->copy_stream, cudaStreamNonBlocking));
     CKP(cudaEventCreateWithFlags(&p->chunk_done, cudaEventDisableTiming));
+    CKP(cudaEventCreateWithFlags(&p->copies_done, cudaEventDisableTiming));
     P.xgrid = p->d_xgrid; P.obs = p->d_obs; P.utab = p->d_utab; P.err = p->d_err;
     if (!geometry_only) p->h_utab.assign(d->controls, d->controls + (size_t)d->nu * d->du);
     // candidate table of separable models (row stride 2*NUD+2; NUD = dx/2 for LQG, 1 otherwise)
@@ -412,15 +425,18 @@ int c3sc_problem_create(const c3sc_problem_desc *d, c3sc_problem **out)
 void c3sc_problem_destroy(c3sc_problem *p)
 {
     if (!p) return;
+    DeviceScope ds_(p->device);
     cudaFree(p->d_xgrid); cudaFree(p->d_obs); cudaFree(p->d_utab); cudaFree(p->d_err); cudaFree(p->d_ctab); cudaFree(p->d_gtab);
     DevBuf *bufs[] = {&p->b_dv, &p->b_fi, &p->b_val, &p->b_arg, &p->b_abs, &p->b_costs, &p->b_rows, &p->b_nv, &p->b_nf};
     for (DevBuf *b : bufs) b->release();
     for (DevBuf &b : p->b_misc) b.release();
     p->scr.release();
+    p->rows_store.release();
     if (p->vf_flags) c3sc_valuef_destroy(p->vf_flags);
     if (p->stream) cudaStreamDestroy(p->stream);
     if (p->copy_stream) cudaStreamDestroy(p->copy_stream);
     if (p->chunk_done) cudaEventDestroy(p->chunk_done);
+    if (p->copies_done) cudaEventDestroy(p->copies_done);
     delete p;
 }
 
@@ -433,6 +449,7 @@ int c3sc_problem_control_path(const c3sc_problem *p)
 
 int c3sc_problem_check(c3sc_problem *p)
 {
+    DeviceScope ds_(p ? p->device : c3sc_cur_dev());
     if (!p) return fail(C3SC_EINVAL, "null problem");
     CK(cudaDeviceSynchronize());
     return read_error_word(p);
@@ -446,6 +463,7 @@ int c3sc_valuef_create(uint32_t d, const uint64_t *n, const uint64_t *ranks, con
     if (c3sc_cuda_device_count() == 0)
         return fail(C3SC_ENODEV, "no CUDA device; the Bellman backup has no CPU fallback");
     c3sc_valuef *vf = new c3sc_valuef();
+    cudaGetDevice(&vf->device);
     DevFT &ft = vf->ft;
     memset(&ft, 0, sizeof ft);
     ft.d = (int)d;
@@ -488,6 +506,7 @@ int c3sc_valuef_create(uint32_t d, const uint64_t *n, const uint64_t *ranks, con
 
 int c3sc_valuef_update(c3sc_valuef *vf, const double *const *cores)
 {
+    DeviceScope ds_(vf ? vf->device : c3sc_cur_dev());
     if (!vf || !cores) return fail(C3SC_EINVAL, "null argument");
     for (int k = 0; k < vf->ft.d; k++)
         CK(cudaMemcpy(vf->d_base + vf->ft.off[k], cores[k], vf->len[k] * sizeof(double), cudaMemcpyHostToDevice));
@@ -499,6 +518,7 @@ int c3sc_valuef_update(c3sc_valuef *vf, const double *const *cores)
 
 int c3sc_valuef_commit(c3sc_valuef *vf, void *stream)
 {
+    DeviceScope ds_(vf ? vf->device : c3sc_cur_dev());
     if (!vf) return fail(C3SC_EINVAL, "null argument");
     int rc = launch_pack_cores(vf->ft, vf->d_baseT, vf->d_baseP, vf->d_baseQ, (cudaStream_t)stream);
     if (rc) return fail(C3SC_ECUDA, "core packing kernel: %s", cudaGetErrorString((cudaError_t)rc));
@@ -517,6 +537,7 @@ int c3sc_valuef_device_buffer(c3sc_valuef *vf, double **dev, size_t *count)
 void c3sc_valuef_destroy(c3sc_valuef *vf)
 {
     if (!vf) return;
+    DeviceScope ds_(vf->device);
     cudaFree(vf->d_base);
     cudaFree(vf->d_baseT);
     cudaFree(vf->d_baseP);
@@ -547,14 +568,16 @@ struct BatchArgs {
     double *value_peers[C3SC_MAXPEERS];
     int n_peers;
     size_t peer_offset;
+    int peer_copy;                        // 1: one bulk copy per chunk and peer on copy_stream (copy engines) instead of stores from the kernel
+    cudaEvent_t copies_done;
 };
 
-static size_t g_chunk_bytes = (size_t)192 << 20;   // slot-major cost scratch in flight (all lanes) when stage 1a runs per fiber
-static size_t g_chunk_bytes_b = (size_t)64 << 20;  // ... when it runs bucketed: the chain stage spans several chunks, so a chunk can be
-                                                    // small enough for its scratch to stay in L2 between stage 1 and stage 2
-static size_t g_chain_fibers = 8192;                // fibers per chain super-chunk (bucketed stage 1a)
-static size_t g_chain_min = 4096;                   // smaller batches keep the per-fiber chain kernel
-static int g_lanes = -1;                            // 2 = alternate (super-)chunks between two streams (default), 1 = one stream
+static thread_local size_t g_chunk_bytes = (size_t)192 << 20;   // slot-major cost scratch in flight (all lanes) when stage 1a runs per fiber
+static thread_local size_t g_chunk_bytes_b = (size_t)192 << 20; // ... when it runs bucketed (measured: smaller, L2-resident scratch chunks lose more to launch
+                                                    // granularity than they gain, gpurun_out/r02_tune*.log -> profiles/r02_tuning.md)
+static thread_local size_t g_chain_fibers = 16384;               // fibers per chain super-chunk (bucketed stage 1a): 63 MB of records, about half the L2
+static thread_local size_t g_chain_min = 4096;                   // smaller batches keep the per-fiber chain kernel
+static thread_local int g_lanes = -1;                            // 2 = alternate (super-)chunks between two streams (default), 1 = one stream
 
 static void read_tuning()
 {   // re-read on every batch (four getenv calls): tests and tuning runs switch paths inside one process
@@ -563,10 +586,10 @@ static void read_tuning()
     if (g_lanes < 1) g_lanes = 1;
     if (g_lanes > MAXLANES) g_lanes = MAXLANES;
     const char *m = getenv("C3SC_CHUNK_MB");                          // tuning aids: cost scratch of all lanes together
-    g_chunk_bytes = (size_t)192 << 20; g_chunk_bytes_b = (size_t)64 << 20;
+    g_chunk_bytes = (size_t)192 << 20; g_chunk_bytes_b = (size_t)192 << 20;
     if (m && atoi(m) > 0) { g_chunk_bytes = (size_t)atoi(m) << 20; g_chunk_bytes_b = g_chunk_bytes; }
     const char *cf = getenv("C3SC_CHAIN_FIBERS");
-    g_chain_fibers = (cf && atoi(cf) > 0) ? (size_t)atoi(cf) : 8192;
+    g_chain_fibers = (cf && atoi(cf) > 0) ? (size_t)atoi(cf) : 16384;
     const char *cm = getenv("C3SC_CHAIN_MIN");
     g_chain_min = (cm && atoi(cm) >= 0) ? (size_t)atoi(cm) : 4096;
 }
@@ -696,7 +719,7 @@ static int run_batch(const DevProblem &P, int model, int arith, Scratch &scr, co
         c.argmin = b.out.argmin ? b.out.argmin + n0 : nullptr;
         c.rows = b.out.rows ? b.out.rows + n0 * RW : nullptr;
         c.rows_in = b.rows_in ? b.rows_in + n0 * RW : nullptr;
-        c.npeer = b.n_peers;
+        c.npeer = b.peer_copy ? 0 : b.n_peers;
         for (int g = 0; g < b.n_peers; g++) c.vpeer[g] = b.value_peers[g];
         c.peer_off = (long long)(b.peer_offset + n0);
         if (grp && grp->grid_on) {
@@ -719,6 +742,11 @@ static int run_batch(const DevProblem &P, int model, int arith, Scratch &scr, co
         if (b.copy_stream && b.chunk_done) {
             CK(cudaEventRecord(b.chunk_done, st));
             CK(cudaStreamWaitEvent(b.copy_stream, b.chunk_done, 0));
+            if (b.peer_copy && c.value)                     // the chunk's values into every peer's gathered buffer, off the SMs
+                for (int g = 0; g < b.n_peers; g++) {
+                    double *dst = b.value_peers[g] + b.peer_offset + n0;
+                    if (dst != c.value) CK(cudaMemcpyAsync(dst, c.value, Fc * b.ldo * 8, cudaMemcpyDefault, b.copy_stream));
+                }
             if (b.h_value && c.value) CK(cudaMemcpyAsync(b.h_value + n0, c.value, Fc * b.ldo * 8, cudaMemcpyDeviceToHost, b.copy_stream));
             if (b.h_argmin && c.argmin) CK(cudaMemcpyAsync(b.h_argmin + n0, c.argmin, Fc * b.ldo * 4, cudaMemcpyDeviceToHost, b.copy_stream));
         }
@@ -727,6 +755,10 @@ static int run_batch(const DevProblem &P, int model, int arith, Scratch &scr, co
     for (size_t l = 1; l < L; l++) {                        // the caller's stream continues after every lane
         CK(cudaEventRecord(scr.lane[l].join, scr.lane[l].stream));
         CK(cudaStreamWaitEvent(st0, scr.lane[l].join, 0));
+    }
+    if (b.peer_copy && b.copy_stream && b.copies_done) {    // ... and after the last peer copy
+        CK(cudaEventRecord(b.copies_done, b.copy_stream));
+        CK(cudaStreamWaitEvent(st0, b.copies_done, 0));
     }
     return C3SC_OK;
 }
@@ -754,6 +786,7 @@ extern "C" {
 int c3sc_vi_batch_dev(c3sc_problem *p, const c3sc_valuef *vf, size_t F, const int32_t *d_dim_vary,
                       const int32_t *d_fixed_ind, size_t ldo, const c3sc_batch_out *out, void *stream)
 {
+    DeviceScope ds_(p ? p->device : c3sc_cur_dev());
     int rc = check_shapes(p, vf, F, ldo);
     if (rc) return rc;
     if (!out || (!out->value && !out->rows && !out->argmin && !out->costs && !out->absorbed && !out->n_peers))
@@ -770,6 +803,12 @@ int c3sc_vi_batch_dev(c3sc_problem *p, const c3sc_valuef *vf, size_t F, const in
     b.n_peers = (int)out->n_peers;
     for (uint32_t g = 0; g < out->n_peers; g++) b.value_peers[g] = out->value_peers[g];
     b.peer_offset = (size_t)out->peer_offset;
+    if (out->n_peers && out->peer_mode == 1) {
+        if (!out->value) return fail(C3SC_EINVAL, "peer_mode 1 (bulk copies) needs the local value buffer");
+        b.peer_copy = 1;
+        b.copy_stream = p->copy_stream; b.chunk_done = p->chunk_done; b.copies_done = p->copies_done;
+        // the copy stream must not run ahead of work queued earlier on the caller's stream that still reads the peers' buffers
+    }
     return run_batch(p->P, p->model, p->arith, p->scr, &p->grp, vf->ft, b, (cudaStream_t)stream);
 }
 
@@ -778,6 +817,7 @@ int c3sc_vi_batch_dev(c3sc_problem *p, const c3sc_valuef *vf, size_t F, const in
 int c3sc_stage1_batch_dev(c3sc_problem *p, const c3sc_valuef *vf, size_t F, const int32_t *d_dim_vary,
                           const int32_t *d_fixed_ind, size_t ldo, void *stream)
 {
+    DeviceScope ds_(p ? p->device : c3sc_cur_dev());
     int rc = check_shapes(p, vf, F, ldo);
     if (rc) return rc;
     if (F == 0) return C3SC_OK;
@@ -792,6 +832,7 @@ int c3sc_pi_batch_dev(c3sc_problem *p, const c3sc_valuef *vf_policy, const c3sc_
                       const int32_t *d_dim_vary, const int32_t *d_fixed_ind, size_t ldo, int have_rows,
                       double *d_rows, int32_t *d_argmin, double *d_value, void *stream)
 {
+    DeviceScope ds_(p ? p->device : c3sc_cur_dev());
     int rc = check_shapes(p, vf_iter, F, ldo);
     if (!rc) rc = need_model(p);
     if (rc) return rc;
@@ -854,6 +895,7 @@ int c3sc_vi_batch_debug(c3sc_problem *p, const c3sc_valuef *vf, size_t F, const 
                         const int32_t *fixed_ind, size_t ldo, double *value, int32_t *argmin, int32_t *absorbed,
                         double *costs, double *rows, int32_t *nbr_vary, int32_t *nbr_fixed)
 {
+    DeviceScope ds_(p ? p->device : c3sc_cur_dev());
     int rc = check_shapes(p, vf, F, ldo);
     if (rc) return rc;
     if (!dim_vary || !fixed_ind || !value) return fail(C3SC_EINVAL, "null fiber descriptors / value buffer");
@@ -896,6 +938,7 @@ int c3sc_vi_batch_debug(c3sc_problem *p, const c3sc_valuef *vf, size_t F, const 
 int c3sc_vi_batch(c3sc_problem *p, const c3sc_valuef *vf, size_t F, const int32_t *dim_vary,
                   const int32_t *fixed_ind, size_t ldo, double *value, int32_t *argmin)
 {
+    DeviceScope ds_(p ? p->device : c3sc_cur_dev());
     int rc = check_shapes(p, vf, F, ldo);
     if (!rc) rc = need_model(p);
     if (rc) return rc;
@@ -941,6 +984,7 @@ int c3sc_pi_batch(c3sc_problem *p, const c3sc_valuef *vf_policy, const c3sc_valu
                   const int32_t *dim_vary, const int32_t *fixed_ind, size_t ldo, int have_rows, double *rows,
                   int32_t *argmin, double *value)
 {
+    DeviceScope ds_(p ? p->device : c3sc_cur_dev());
     int rc = check_shapes(p, vf_iter, F, ldo);
     if (rc) return rc;
     if (!dim_vary || !fixed_ind || !value || !rows) return fail(C3SC_EINVAL, "null argument");
@@ -966,10 +1010,94 @@ int c3sc_pi_batch(c3sc_problem *p, const c3sc_valuef *vf_policy, const c3sc_valu
     return finish(p);
 }
 
+/* bellman_pi with the policy rows RESIDENT on the device: host fiber descriptors in, host values out, rows in a
+ * caller-owned device buffer d_rows [F*ldo*(2dx+3)] that is written when have_rows == 0 and only read otherwise.
+ * Nothing of the 184 B/node row record crosses PCIe (the reference keeps it in pi_prob_htable, src/bellman.c:1803-1880). */
+int c3sc_pi_batch_resident(c3sc_problem *p, const c3sc_valuef *vf_policy, const c3sc_valuef *vf_iter, size_t F,
+                           const int32_t *dim_vary, const int32_t *fixed_ind, size_t ldo, int have_rows, double *d_rows,
+                           double *value)
+{
+    DeviceScope ds_(p ? p->device : c3sc_cur_dev());
+    int rc = check_shapes(p, vf_iter, F, ldo);
+    if (!rc) rc = need_model(p);
+    if (rc) return rc;
+    if (!dim_vary || !fixed_ind || !value || !d_rows) return fail(C3SC_EINVAL, "null argument");
+    if (F == 0) return C3SC_OK;
+    const size_t n = F * ldo;
+    rc = upload_fibers(p, F, dim_vary, fixed_ind);
+    if (rc) return rc;
+    if (p->b_val.reserve(n * 8)) return fail(C3SC_ECUDA, "cudaMalloc batch outputs failed");
+    rc = c3sc_pi_batch_dev(p, vf_policy, vf_iter, F, (const int32_t *)p->b_dv.p, (const int32_t *)p->b_fi.p, ldo, have_rows,
+                           d_rows, nullptr, (double *)p->b_val.p, p->stream);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(value, p->b_val.p, n * 8, cudaMemcpyDeviceToHost, p->stream));
+    return finish(p);
+}
+
+/* Device-resident policy-row store of a problem, addressed per fiber: capacity fibers x ldo nodes x (2dx+3).
+ * c3sc_pi_batch_store runs one bellman_pi batch whose fiber f owns row slot row_id[f] of the store: have_rows == 0
+ * computes the rows and files them there, have_rows != 0 evaluates against the filed rows.  This is what the host
+ * mirror's bellman_pi uses in place of pi_prob_htable. */
+int c3sc_pi_store_reserve(c3sc_problem *p, size_t capacity_fibers, size_t ldo)
+{
+    DeviceScope ds_(p ? p->device : c3sc_cur_dev());
+    if (!p) return fail(C3SC_EINVAL, "null problem");
+    const size_t RW = 2 * (size_t)p->P.dx + 3, need = capacity_fibers * ldo * RW * 8;
+    if (need <= p->rows_store.cap && ldo == p->store_ldo) return C3SC_OK;
+    // grow, keeping what is filed (same ldo) -- a changed ldo drops the store
+    DevBuf nb;
+    if (nb.reserve(need)) return fail(C3SC_ECUDA, "cudaMalloc policy-row store (%zu MB) failed", need >> 20);
+    if (p->rows_store.p && ldo == p->store_ldo)
+        CK(cudaMemcpyAsync(nb.p, p->rows_store.p, p->rows_store.cap < need ? p->rows_store.cap : need, cudaMemcpyDeviceToDevice, p->stream));
+    CK(cudaStreamSynchronize(p->stream));
+    p->rows_store.release();
+    p->rows_store = nb;
+    p->store_ldo = ldo;
+    return C3SC_OK;
+}
+
+int c3sc_pi_batch_store(c3sc_problem *p, const c3sc_valuef *vf_policy, const c3sc_valuef *vf_iter, size_t F,
+                        const int32_t *dim_vary, const int32_t *fixed_ind, size_t ldo, int have_rows,
+                        const int32_t *row_id, double *value)
+{
+    DeviceScope ds_(p ? p->device : c3sc_cur_dev());
+    int rc = check_shapes(p, vf_iter, F, ldo);
+    if (!rc) rc = need_model(p);
+    if (rc) return rc;
+    if (!dim_vary || !fixed_ind || !value || !row_id) return fail(C3SC_EINVAL, "null argument");
+    if (F == 0) return C3SC_OK;
+    if (!p->rows_store.p || ldo != p->store_ldo) return fail(C3SC_EINVAL, "policy-row store not reserved for ldo=%zu (c3sc_pi_store_reserve)", ldo);
+    const size_t RW = 2 * (size_t)p->P.dx + 3, per = ldo * RW, n = F * ldo;
+    const size_t capf = p->rows_store.cap / (per * 8);
+    for (size_t f = 0; f < F; f++)
+        if (row_id[f] < 0 || (size_t)row_id[f] >= capf) return fail(C3SC_EINVAL, "fiber %zu: row slot %d outside the store (%zu)", f, row_id[f], capf);
+    rc = upload_fibers(p, F, dim_vary, fixed_ind);
+    if (rc) return rc;
+    if (p->b_val.reserve(n * 8) || p->b_rows.reserve(n * RW * 8) || p->b_misc[7].reserve(F * 4))
+        return fail(C3SC_ECUDA, "cudaMalloc batch outputs failed");
+    CK(cudaMemcpyAsync(p->b_misc[7].p, row_id, F * 4, cudaMemcpyHostToDevice, p->stream));
+    if (have_rows) {
+        rc = launch_rows_move((double *)p->b_rows.p, (const double *)p->rows_store.p, (const int *)p->b_misc[7].p, (int)F, (long long)per, 0, p->stream);
+        if (rc) return fail(C3SC_ECUDA, "row gather kernel: %s", cudaGetErrorString((cudaError_t)rc));
+        g_launches++;
+    }
+    rc = c3sc_pi_batch_dev(p, vf_policy, vf_iter, F, (const int32_t *)p->b_dv.p, (const int32_t *)p->b_fi.p, ldo, have_rows,
+                           (double *)p->b_rows.p, nullptr, (double *)p->b_val.p, p->stream);
+    if (rc) return rc;
+    if (!have_rows) {
+        rc = launch_rows_move((double *)p->rows_store.p, (const double *)p->b_rows.p, (const int *)p->b_misc[7].p, (int)F, (long long)per, 1, p->stream);
+        if (rc) return fail(C3SC_ECUDA, "row scatter kernel: %s", cudaGetErrorString((cudaError_t)rc));
+        g_launches++;
+    }
+    CK(cudaMemcpyAsync(value, p->b_val.p, n * 8, cudaMemcpyDeviceToHost, p->stream));
+    return finish(p);
+}
+
 int c3sc_neighbor_costs_batch(c3sc_problem *p, const c3sc_valuef *vf, size_t F, const int32_t *dim_vary,
                               const int32_t *fixed_ind, size_t ldo, int32_t *absorbed, double *costs,
                               int32_t *nbr_vary, int32_t *nbr_fixed)
 {
+    DeviceScope ds_(p ? p->device : c3sc_cur_dev());
     int rc = check_shapes(p, vf, F, ldo);
     if (rc) return rc;
     if (!dim_vary || !fixed_ind || !absorbed || !costs) return fail(C3SC_EINVAL, "null argument");
@@ -1006,6 +1134,7 @@ int c3sc_neighbor_costs_batch(c3sc_problem *p, const c3sc_valuef *vf, size_t F, 
 int c3sc_fiber_flags_batch(c3sc_problem *p, size_t F, const int32_t *dim_vary, const int32_t *fixed_ind, size_t ldo,
                            int32_t *absorbed, int32_t *nbr_vary, int32_t *nbr_fixed)
 {
+    DeviceScope ds_(p ? p->device : c3sc_cur_dev());
     if (!p || !dim_vary || !fixed_ind || !absorbed) return fail(C3SC_EINVAL, "null argument");
     if (ldo < (size_t)p->P.nmax) return fail(C3SC_EINVAL, "ldo=%zu < max ngrid=%d", ldo, p->P.nmax);
     if (F == 0) return C3SC_OK;
@@ -1045,6 +1174,7 @@ int c3sc_fiber_flags_batch(c3sc_problem *p, size_t F, const int32_t *dim_vary, c
 int c3sc_node_backup_batch(c3sc_problem *p, size_t n, const double *x, const double *costs, const int32_t *absorbed,
                            double *value, int32_t *argmin)
 {
+    DeviceScope ds_(p ? p->device : c3sc_cur_dev());
     if (!p || !x || !costs || !value) return fail(C3SC_EINVAL, "null argument");
     if (need_model(p)) return C3SC_EUNSUPPORTED;
     if (n == 0) return C3SC_OK;
@@ -1072,6 +1202,7 @@ int c3sc_node_backup_batch(c3sc_problem *p, size_t n, const double *x, const dou
 /* valuef_eval (src/valuefunc.c:345-350) at n arbitrary points */
 int c3sc_valuef_eval_batch(c3sc_problem *p, const c3sc_valuef *vf, size_t n, const double *x, double *out)
 {
+    DeviceScope ds_(p ? p->device : c3sc_cur_dev());
     if (!p || !vf || !x || !out) return fail(C3SC_EINVAL, "null argument");
     if (vf->ft.d != p->P.dx) return fail(C3SC_EINVAL, "value function has d=%d, problem dx=%d", vf->ft.d, p->P.dx);
     if (n == 0) return C3SC_OK;
@@ -1092,6 +1223,7 @@ int c3sc_valuef_eval_batch(c3sc_problem *p, const c3sc_valuef *vf, size_t n, con
 int c3sc_neighbor_node_costs_batch(c3sc_problem *p, const c3sc_valuef *vf, size_t n, const double *x, int32_t *absorbed,
                                    double *costs)
 {
+    DeviceScope ds_(p ? p->device : c3sc_cur_dev());
     if (!p || !vf || !x || !absorbed || !costs) return fail(C3SC_EINVAL, "null argument");
     if (vf->ft.d != p->P.dx) return fail(C3SC_EINVAL, "value function has d=%d, problem dx=%d", vf->ft.d, p->P.dx);
     if (n == 0) return C3SC_OK;
@@ -1115,6 +1247,7 @@ int c3sc_neighbor_node_costs_batch(c3sc_problem *p, const c3sc_valuef *vf, size_
 int c3sc_policy_eval_batch(c3sc_problem *p, const c3sc_valuef *vf, size_t n, const double *x, double *u, double *value,
                            int32_t *absorbed, double *costs)
 {
+    DeviceScope ds_(p ? p->device : c3sc_cur_dev());
     if (!p || !vf || !x || !u) return fail(C3SC_EINVAL, "null argument");
     if (vf->ft.d != p->P.dx) return fail(C3SC_EINVAL, "value function has d=%d, problem dx=%d", vf->ft.d, p->P.dx);
     if (need_model(p)) return C3SC_EUNSUPPORTED;
@@ -1153,6 +1286,7 @@ int c3sc_policy_eval_batch(c3sc_problem *p, const c3sc_valuef *vf, size_t n, con
 int c3sc_control_value_batch(c3sc_problem *p, size_t n, const double *x, const double *u, const double *costs,
                              double *value)
 {
+    DeviceScope ds_(p ? p->device : c3sc_cur_dev());
     if (!p || !x || !u || !costs || !value) return fail(C3SC_EINVAL, "null argument");
     if (need_model(p)) return C3SC_EUNSUPPORTED;
     if (n == 0) return C3SC_OK;
@@ -1235,6 +1369,7 @@ int c3sc_transition_raw(int arith, uint32_t dx, double h2, const double *t, size
 int c3sc_ft_fiber_nn_batch(const c3sc_valuef *vf, size_t F, const int32_t *dim_vary, const int32_t *fixed_ind,
                            const int32_t *nbr_fixed, const int32_t *nbr_vary, size_t ldo, double *costs)
 {
+    DeviceScope ds_(vf ? vf->device : c3sc_cur_dev());
     std::lock_guard<std::mutex> lock(g_scratch_mu);
     if (!vf || !dim_vary || !fixed_ind || !nbr_fixed || !nbr_vary || !costs) return fail(C3SC_EINVAL, "null argument");
     if (F == 0) return C3SC_OK;
@@ -1279,6 +1414,7 @@ int c3sc_ft_fiber_nn_batch(const c3sc_valuef *vf, size_t F, const int32_t *dim_v
 int c3sc_transition_batch(c3sc_problem *p, size_t n, const double *drift, const double *sigma_diag,
                           double *prob, double *dt, int32_t *status)
 {
+    DeviceScope ds_(p ? p->device : c3sc_cur_dev());
     if (!p || !drift || !sigma_diag || !prob || !dt || !status) return fail(C3SC_EINVAL, "null argument");
     if (need_model(p)) return C3SC_EUNSUPPORTED;
     if (n == 0) return C3SC_OK;
@@ -1304,6 +1440,7 @@ int c3sc_transition_batch(c3sc_problem *p, size_t n, const double *drift, const 
 int c3sc_model_eval(c3sc_problem *p, size_t n, const double *x, const double *u, double *drift,
                     double *sigma_diag, double *stage, double *bound, double *obs)
 {
+    DeviceScope ds_(p ? p->device : c3sc_cur_dev());
     if (!p || !x || !u || !drift || !sigma_diag || !stage || !bound || !obs) return fail(C3SC_EINVAL, "null argument");
     if (need_model(p)) return C3SC_EUNSUPPORTED;
     if (n == 0) return C3SC_OK;

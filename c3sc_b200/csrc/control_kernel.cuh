@@ -850,7 +850,9 @@ int launch_control_t(const CtlArgs &c_in, int pi_eval, cudaStream_t st)
     constexpr bool TAB = M::SEP && !A::exact;
     const size_t smem = (size_t)c.P.nu * (TAB ? 2 * M::NUD + 2 : M::DU) * sizeof(double);
     if (smem > (size_t)info.max_optin) return (int)cudaErrorInvalidValue;      // control table must fit on chip
-    static size_t attr_set = 48 * 1024;
+    static size_t attr_dev[C3SC_MAXDEV] = {0};
+    size_t &attr_set = attr_dev[c3sc_cur_dev()];
+    if (attr_set == 0) attr_set = 48 * 1024;
     if (smem > attr_set) {
         cudaError_t e = cudaFuncSetAttribute(k_control<M, A>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return (int)e;
@@ -880,7 +882,9 @@ int launch_control_t(const CtlArgs &c_in, int pi_eval, cudaStream_t st)
         // separable model, at least ~a warp pair of nodes per SM: two nodes per thread walk the whole
         // grouped table (no per-chunk re-derivation of the node invariants); 128-thread CTAs while the
         // batch is too small to give every SM a 256-thread one
-        static size_t attr2 = 48 * 1024;
+        static size_t attr2_dev[C3SC_MAXDEV] = {0};
+        size_t &attr2 = attr2_dev[c3sc_cur_dev()];
+        if (attr2 == 0) attr2 = 48 * 1024;
         if (smem > attr2) {
             cudaError_t e2 = cudaFuncSetAttribute(k_control2<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             if (e2 != cudaSuccess) return (int)e2;

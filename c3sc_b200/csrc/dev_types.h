@@ -1,6 +1,7 @@
 // dev_types.h -- POD structs passed BY VALUE to the kernels (constant bank).
 #pragma once
 #include <stdint.h>
+#include <cuda_runtime.h>
 #include "../../include/c3sc_b200.h"
 
 namespace c3sc {
@@ -56,6 +57,15 @@ struct DevOut {
     int *nbr_vary;
     int *nbr_fixed;
 };
+
+// Per-device caches (function attributes are per device; one process may drive several GPUs, one host thread each)
+constexpr int C3SC_MAXDEV = 16;
+inline int c3sc_cur_dev()
+{
+    int dv = 0;
+    cudaGetDevice(&dv);
+    return dv < 0 ? 0 : (dv >= C3SC_MAXDEV ? C3SC_MAXDEV - 1 : dv);
+}
 
 // neighbour pair of node j ALONG the fiber (nodeutil.c:570-624); ab = the node's flag after the
 // end-node overwrite (0 / 1 / -1).  Interior absorbed nodes point at themselves.

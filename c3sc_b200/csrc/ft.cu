@@ -123,7 +123,10 @@ static int launch_chain_steps_t(const ChainArgs &a, cudaStream_t st)
 {
     ft_device_info();
     const bool g_no_pdl = getenv("C3SC_NO_PDL") != nullptr;
-    const int grid = g_sms * 2;
+    // CTAs of a step: the kernel is latency-bound (dependent L2 round trips, a handful of tiles per warp), and while it
+    // holds an SM's registers the other lane's node kernel cannot use that SM
+    int grid = g_sms * 2;
+    { const char *e = getenv("C3SC_CHAIN_GRID"); if (e && atoi(e) > 0) grid = atoi(e); }
     for (int t = 0; t + 1 < a.ft.d; t++) {
         const size_t smem = (size_t)(4 * (a.P.ngrid[t] + a.P.ngrid[a.ft.d - 1 - t]) + 4) * sizeof(int);
         // steps t >= 1 overlap their launch and table prologue with the tail of step t-1 (programmatic dependent
@@ -163,7 +166,8 @@ static int launch_mma_t(const FtArgs &a, cudaStream_t st)
     // chains: one warp per (fiber, side)
     const size_t csm = FtChainPlan<KS>(a.ft).bytes();
     if (csm > (size_t)g_max_optin) return (int)cudaErrorInvalidValue;
-    static size_t cattr = 0;
+    static size_t cattr_dev[C3SC_MAXDEV] = {0};
+    size_t &cattr = cattr_dev[c3sc_cur_dev()];
     if (csm > cattr) {
         cudaError_t e = cudaFuncSetAttribute(k_ft_chains<KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)csm);
         if (e != cudaSuccess) return (int)e;
@@ -183,7 +187,8 @@ static int launch_mma_t(const FtArgs &a, cudaStream_t st)
     // nodes: one CTA per same-k group
     const size_t smem = FtNodePlan<KS>(a.ft, a.P.nmax).bytes();
     if (smem > (size_t)g_max_optin) return (int)cudaErrorInvalidValue;
-    static size_t attr = 0;
+    static size_t attr_dev[C3SC_MAXDEV] = {0};
+    size_t &attr = attr_dev[c3sc_cur_dev()];
     if (smem > attr) {
         e = cudaFuncSetAttribute(k_ft_nodes<KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return (int)e;
@@ -245,7 +250,8 @@ static int launch_ft_stage(const FtArgs &a_in, cudaStream_t st)
     size_t smem = FtPlan(a.ft, a.P.nmax, a.FB).bytes();
     while (smem > (size_t)g_max_optin && a.FB > 1) { a.FB >>= 1; smem = FtPlan(a.ft, a.P.nmax, a.FB).bytes(); }
     if (smem > (size_t)g_max_optin) return (int)cudaErrorInvalidValue;
-    static size_t attr = 0;
+    static size_t attr_dev[C3SC_MAXDEV] = {0};
+    size_t &attr = attr_dev[c3sc_cur_dev()];
     if (smem > attr) {
         cudaError_t e = cudaFuncSetAttribute(k_ft_costs, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return (int)e;
@@ -253,6 +259,26 @@ static int launch_ft_stage(const FtArgs &a_in, cudaStream_t st)
     }
     const int grid = (a.F + a.FB - 1) / a.FB + a.ft.d;       // upper bound on the number of groups
     k_ft_costs<<<grid, FT_NT, smem, st>>>(a);
+    return (int)cudaGetLastError();
+}
+
+// policy rows between a batch-contiguous buffer and the per-fiber row store: fiber f <-> slot idx[f], `per` doubles each
+__global__ void k_rows_move(double *dst, const double *src, const int *idx, int F, long long per, int scatter)
+{
+    const long long total = (long long)F * per, step = (long long)gridDim.x * blockDim.x;
+    for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += step) {
+        const long long f = e / per, q = e - f * per;
+        const long long s = (long long)idx[f] * per + q;
+        if (scatter) dst[s] = src[e]; else dst[e] = src[s];
+    }
+}
+int launch_rows_move(double *dst, const double *src, const int *idx, int F, long long per, int scatter, cudaStream_t st)
+{
+    if (F <= 0) return 0;
+    ft_device_info();
+    long long g = ((long long)F * per + 255) / 256;
+    if (g > g_sms * 8) g = g_sms * 8;
+    k_rows_move<<<(unsigned)g, 256, 0, st>>>(dst, src, idx, F, per, scatter);
     return (int)cudaGetLastError();
 }
 

@@ -111,6 +111,11 @@ typedef struct c3sc_batch_out {
     double  *value_peers[C3SC_MAXPEERS];
     uint32_t n_peers;
     uint64_t peer_offset;
+    /* how the values reach the peers: 0 = stores from the control kernel (each value crosses NVLink once per peer as
+     * an 8-byte store; no extra pass); 1 = one bulk copy per pipeline chunk and peer on the library's copy stream
+     * (copy engines, no SM involvement, overlapped with the next chunk's kernels; needs `value`).  A peer pointer that
+     * equals value - peer_offset (the rank's own gathered buffer used as its output) is skipped.                 */
+    uint32_t peer_mode;
 } c3sc_batch_out;
 
 /* ---- runtime ---------------------------------------------------------- */
@@ -125,6 +130,10 @@ uint64_t c3sc_launch_count(void);
 /* Best-of-`repeats` throughput of a pure DFMA loop on the current device, in
  * TFLOP/s (FMA = 2 flop): the measured FP64-pipe roofline denominator.      */
 int c3sc_measure_fp64_peak(double *tflops, int iters, int repeats);
+/* The same for the FP64 tensor path: a pure DMMA (mma.sync.m8n8k4.f64) loop.  On B200 the two figures are within
+ * 10 % of each other and do not add up (one execution resource, profiles/r01_fp64_pipe_microbench.md); this one is
+ * the denominator for kernels whose flops run as DMMAs (stage 1).                                            */
+int c3sc_measure_fp64_tensor_peak(double *tflops, int iters, int repeats);
 
 /* Peer-mapped device buffers for the fused all-gather (c3sc_batch_out::value_peers), one process per
  * GPU: every rank creates its gathered buffer (cudaMalloc + cudaIpcGetMemHandle), exchanges the 64-byte
@@ -212,6 +221,19 @@ int c3sc_vi_batch_debug(c3sc_problem *p, const c3sc_valuef *vf, size_t F,
 int c3sc_pi_batch(c3sc_problem *p, const c3sc_valuef *vf_policy, const c3sc_valuef *vf_iter,
                   size_t F, const int32_t *dim_vary, const int32_t *fixed_ind,
                   size_t ldo, int have_rows, double *rows, int32_t *argmin, double *value);
+
+/* bellman_pi with the policy rows RESIDENT on the device.  _resident: rows of the whole batch in a caller-owned
+ * DEVICE buffer d_rows [F*ldo*(2dx+3)] (written when have_rows == 0, read otherwise).  _store: rows filed per fiber
+ * in the problem's own device store (c3sc_pi_store_reserve(capacity in fibers, ldo); growing keeps what is filed);
+ * fiber f of a call owns slot row_id[f].  Either way only descriptors go up and values come down: the 184 B/node
+ * row record of src/bellman.c:1810 never crosses PCIe.                                                          */
+int c3sc_pi_batch_resident(c3sc_problem *p, const c3sc_valuef *vf_policy, const c3sc_valuef *vf_iter, size_t F,
+                           const int32_t *dim_vary, const int32_t *fixed_ind, size_t ldo, int have_rows,
+                           double *d_rows, double *value);
+int c3sc_pi_store_reserve(c3sc_problem *p, size_t capacity_fibers, size_t ldo);
+int c3sc_pi_batch_store(c3sc_problem *p, const c3sc_valuef *vf_policy, const c3sc_valuef *vf_iter, size_t F,
+                        const int32_t *dim_vary, const int32_t *fixed_ind, size_t ldo, int have_rows,
+                        const int32_t *row_id, double *value);
 
 /* mca_get_neighbor_costs (src/nodeutil.c:647-713) over F fibers: flags, neighbour
  * indices and FT neighbour values only (process_fibers_neighbor + 

@@ -185,7 +185,7 @@ def test_c_abi_exports_every_declared_symbol():
     from c3sc_b200 import capi
     L = capi.lib()
     inc = os.path.join(os.path.dirname(GOLD), "..", "include")
-    hdr = open(os.path.join(inc, "c3sc_b200.h")).read() + open(os.path.join(inc, "c3sc_cross.h")).read()
+    hdr = "".join(open(os.path.join(inc, h)).read() for h in ("c3sc_b200.h", "c3sc_cross.h", "c3sc_multi.h"))
     declared = set(re.findall(r"\b(c3sc_[a-z_0-9]+)\s*\(", hdr)) - {"c3sc_fiber_batch_fn"}
     assert declared, "no declarations parsed"
     assert declared == set(capi.EXPORTS)

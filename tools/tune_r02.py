@@ -48,12 +48,11 @@ def main():
         prob.stage1_batch_dev(vf, F, dv_d.data_ptr(), fi_d.data_ptr(), cfg.n, stream=st.cuda_stream)
 
     ref = None
-    combos = [dict(C3SC_NO_BUCKETS="1")]
-    for mb, cf, lanes in ((96, 8192, 2), (96, 16384, 2), (128, 16384, 2), (192, 8192, 2), (192, 16384, 2), (192, 32768, 2), (256, 16384, 2),
-                          (192, 16384, 3), (288, 16384, 3)):
-        combos.append(dict(C3SC_CHUNK_MB=str(mb), C3SC_CHAIN_FIBERS=str(cf), C3SC_LANES=str(lanes)))
-    combos.append(dict(C3SC_CHUNK_MB="192", C3SC_CHAIN_FIBERS="16384", C3SC_LANES="2", C3SC_NO_PDL="1"))
-    keys = ("C3SC_NO_BUCKETS", "C3SC_CHUNK_MB", "C3SC_CHAIN_FIBERS", "C3SC_LANES", "C3SC_NO_PDL")
+    # combos from the command line: "K=V,K=V;K=V,..." (argv[2]); default: the pipeline's defaults and the per-fiber chains
+    combos = [dict(), dict(C3SC_NO_BUCKETS="1")]
+    if len(sys.argv) > 2:
+        combos = [dict(kv.split("=") for kv in grp.split(",") if kv) for grp in sys.argv[2].split(";")]
+    keys = sorted({k for c in combos for k in c} | {"C3SC_NO_BUCKETS"})
     for c in combos:
         for k in keys:
             os.environ.pop(k, None)
