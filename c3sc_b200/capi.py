@@ -66,11 +66,11 @@ EXPORTS = [
     "c3sc_valuef_eval_batch", "c3sc_policy_eval_batch",
     "c3sc_cross_index_sets", "c3sc_cores_round", "c3sc_cross_adapt_capacity", "c3sc_cross_set_ranks", "c3sc_cross_run_adapt", "c3sc_cross_run_vi_adapt",
     "c3sc_peer_buffer_create", "c3sc_peer_buffer_open", "c3sc_peer_buffer_close",
-    "c3sc_fibers_check", "c3sc_fiber_flags_batch", "c3sc_neighbor_node_costs_batch", "c3sc_stage1_batch_dev", "c3sc_pi_batch_resident", "c3sc_pi_store_reserve", "c3sc_pi_batch_store",
+    "c3sc_fibers_check", "c3sc_fiber_flags_batch", "c3sc_neighbor_node_costs_batch", "c3sc_stage1_batch_dev", "c3sc_pi_batch_resident", "c3sc_rowstore_create", "c3sc_rowstore_reserve", "c3sc_rowstore_destroy", "c3sc_pi_batch_store",
     "c3sc_multi_create", "c3sc_multi_destroy", "c3sc_multi_device_count", "c3sc_multi_uses_nccl", "c3sc_multi_problem",
     "c3sc_multi_valuef_create", "c3sc_multi_valuef_update", "c3sc_multi_valuef_destroy", "c3sc_multi_valuef_get", "c3sc_multi_shard",
     "c3sc_multi_vi_batch", "c3sc_multi_pi_batch", "c3sc_multi_pi_reset", "c3sc_multi_gathered_count", "c3sc_multi_vi_batch_gathered",
-    "c3sc_cross_run_vi_multi", "c3sc_cross_run_pi_multi",
+    "c3sc_cross_run_vi_multi", "c3sc_cross_run_pi_multi", "c3sc_host_alloc", "c3sc_host_free",
 ]
 
 _lib = None
@@ -107,7 +107,9 @@ def lib() -> C.CDLL:
         L.c3sc_fibers_check.argtypes = [vp, sz, vp, vp]
         L.c3sc_stage1_batch_dev.argtypes = [vp, vp, sz, vp, vp, sz, vp]
         L.c3sc_pi_batch_resident.argtypes = [vp, vp, vp, sz, vp, vp, sz, i32, vp, vp]
-        L.c3sc_pi_store_reserve.argtypes = [vp, sz, sz]
+        L.c3sc_rowstore_create.argtypes = [C.c_uint32, sz, C.POINTER(vp)]
+        L.c3sc_rowstore_reserve.argtypes = [vp, sz]
+        L.c3sc_rowstore_destroy.argtypes = [vp]; L.c3sc_rowstore_destroy.restype = None
         L.c3sc_multi_create.argtypes = [C.POINTER(ProblemDesc), i32, vp, C.POINTER(vp)]
         L.c3sc_multi_destroy.argtypes = [vp]; L.c3sc_multi_destroy.restype = None
         L.c3sc_multi_device_count.argtypes = [vp]; L.c3sc_multi_uses_nccl.argtypes = [vp]
@@ -120,11 +122,12 @@ def lib() -> C.CDLL:
         L.c3sc_multi_vi_batch.argtypes = [vp, vp, sz, vp, vp, sz, vp, vp]
         L.c3sc_multi_pi_batch.argtypes = [vp, vp, vp, C.c_uint32, sz, vp, vp, sz, i32, vp]
         L.c3sc_multi_pi_reset.argtypes = [vp]
+        L.c3sc_host_alloc.argtypes = [sz, C.POINTER(vp)]; L.c3sc_host_free.argtypes = [vp]
         L.c3sc_multi_gathered_count.argtypes = [sz, i32, sz]; L.c3sc_multi_gathered_count.restype = sz
         L.c3sc_multi_vi_batch_gathered.argtypes = [vp, vp, sz, vp, vp, sz, vp]
         L.c3sc_cross_run_vi_multi.argtypes = [vp, vp, vp, C.POINTER(CrossOpts), C.POINTER(c_f64p), c_u64p, c_f64p]
         L.c3sc_cross_run_pi_multi.argtypes = [vp, vp, vp, vp, C.POINTER(CrossOpts), C.POINTER(c_f64p), c_u64p, c_f64p]
-        L.c3sc_pi_batch_store.argtypes = [vp, vp, vp, sz, vp, vp, sz, i32, vp, vp]
+        L.c3sc_pi_batch_store.argtypes = [vp, vp, vp, sz, vp, vp, sz, i32, vp, vp, vp]
         L.c3sc_fiber_flags_batch.argtypes = [vp, sz, vp, vp, sz, vp, vp, vp]
         L.c3sc_neighbor_node_costs_batch.argtypes = [vp, vp, sz, vp, vp, vp]
         L.c3sc_pi_batch.argtypes = [vp, vp, vp, sz, vp, vp, sz, i32, vp, vp, vp]

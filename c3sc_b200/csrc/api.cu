@@ -200,8 +200,6 @@ struct c3sc_problem {
     cudaEvent_t chunk_done = nullptr, copies_done = nullptr;
     DevBuf b_dv, b_fi, b_val, b_arg, b_abs, b_costs, b_rows, b_nv, b_nf, b_misc[8];
     c3sc_valuef *vf_flags = nullptr;         // rank-1 zero train for the flags-only entry (c3sc_fiber_flags_batch)
-    DevBuf rows_store;                       // device-resident policy rows per fiber slot (c3sc_pi_batch_store)
-    size_t store_ldo = 0;
 };
 
 struct c3sc_valuef {
@@ -261,6 +259,20 @@ int c3sc_cuda_init(int device)
     // device it was created on and its entry points switch to it
     CK(cudaSetDevice(device));
     CK(cudaFree(0));
+    return C3SC_OK;
+}
+
+/* page-locked host memory, usable from every device of the process: host buffers handed to the batch entries
+ * move at PCIe speed only when they are page-locked (pageable memory goes through the driver's staging copies) */
+int c3sc_host_alloc(size_t bytes, void **ptr)
+{
+    if (!ptr || bytes == 0) return fail(C3SC_EINVAL, "null argument");
+    CK(cudaHostAlloc(ptr, bytes, cudaHostAllocPortable));
+    return C3SC_OK;
+}
+int c3sc_host_free(void *ptr)
+{
+    if (ptr) CK(cudaFreeHost(ptr));
     return C3SC_OK;
 }
 
@@ -431,7 +443,6 @@ void c3sc_problem_destroy(c3sc_problem *p)
     for (DevBuf *b : bufs) b->release();
     for (DevBuf &b : p->b_misc) b.release();
     p->scr.release();
-    p->rows_store.release();
     if (p->vf_flags) c3sc_valuef_destroy(p->vf_flags);
     if (p->stream) cudaStreamDestroy(p->stream);
     if (p->copy_stream) cudaStreamDestroy(p->copy_stream);
@@ -1034,50 +1045,79 @@ int c3sc_pi_batch_resident(c3sc_problem *p, const c3sc_valuef *vf_policy, const 
     return finish(p);
 }
 
-/* Device-resident policy-row store of a problem, addressed per fiber: capacity fibers x ldo nodes x (2dx+3).
- * c3sc_pi_batch_store runs one bellman_pi batch whose fiber f owns row slot row_id[f] of the store: have_rows == 0
- * computes the rows and files them there, have_rows != 0 evaluates against the filed rows.  This is what the host
- * mirror's bellman_pi uses in place of pi_prob_htable. */
-int c3sc_pi_store_reserve(c3sc_problem *p, size_t capacity_fibers, size_t ldo)
+/* Device-resident policy-row store, addressed per fiber: capacity fibers x ldo nodes x (2dx+3) doubles.  It is an
+ * object of its own because it outlives the per-step device problems: the reference keeps the rows of a policy in
+ * the Workspace (pi_prob_htable) across the c3control_step_pi calls of one c3control_pi_solve.
+ * c3sc_pi_batch_store runs one bellman_pi batch whose fiber f owns row slot row_id[f]: have_rows == 0 computes the
+ * rows and files them there, have_rows != 0 evaluates against the filed rows. */
+struct c3sc_rowstore {
+    int device = 0;
+    uint32_t dx = 0;
+    size_t ldo = 0, cap_fibers = 0;
+    double *p = nullptr;
+};
+
+int c3sc_rowstore_create(uint32_t dx, size_t ldo, c3sc_rowstore **out)
 {
-    DeviceScope ds_(p ? p->device : c3sc_cur_dev());
-    if (!p) return fail(C3SC_EINVAL, "null problem");
-    const size_t RW = 2 * (size_t)p->P.dx + 3, need = capacity_fibers * ldo * RW * 8;
-    if (need <= p->rows_store.cap && ldo == p->store_ldo) return C3SC_OK;
-    // grow, keeping what is filed (same ldo) -- a changed ldo drops the store
-    DevBuf nb;
-    if (nb.reserve(need)) return fail(C3SC_ECUDA, "cudaMalloc policy-row store (%zu MB) failed", need >> 20);
-    if (p->rows_store.p && ldo == p->store_ldo)
-        CK(cudaMemcpyAsync(nb.p, p->rows_store.p, p->rows_store.cap < need ? p->rows_store.cap : need, cudaMemcpyDeviceToDevice, p->stream));
-    CK(cudaStreamSynchronize(p->stream));
-    p->rows_store.release();
-    p->rows_store = nb;
-    p->store_ldo = ldo;
+    if (!out || dx < 1 || dx > C3SC_MAXD || ldo < 1) return fail(C3SC_EINVAL, "bad row-store shape");
+    if (c3sc_cuda_device_count() == 0) return fail(C3SC_ENODEV, "no CUDA device; the Bellman backup has no CPU fallback");
+    c3sc_rowstore *s = new c3sc_rowstore();
+    cudaGetDevice(&s->device);
+    s->dx = dx; s->ldo = ldo;
+    *out = s;
     return C3SC_OK;
+}
+
+int c3sc_rowstore_reserve(c3sc_rowstore *s, size_t capacity_fibers)
+{
+    if (!s) return fail(C3SC_EINVAL, "null row store");
+    if (capacity_fibers <= s->cap_fibers) return C3SC_OK;
+    DeviceScope ds_(s->device);
+    const size_t per = s->ldo * (2 * (size_t)s->dx + 3) * sizeof(double);
+    double *np = nullptr;
+    if (cudaMalloc(&np, capacity_fibers * per) != cudaSuccess) {
+        cudaGetLastError();
+        return fail(C3SC_ECUDA, "cudaMalloc of the policy-row store (%zu MB) failed", (capacity_fibers * per) >> 20);
+    }
+    if (s->p) {                                             // growing keeps what is filed
+        CK(cudaMemcpy(np, s->p, s->cap_fibers * per, cudaMemcpyDeviceToDevice));
+        cudaFree(s->p);
+    }
+    s->p = np; s->cap_fibers = capacity_fibers;
+    return C3SC_OK;
+}
+
+void c3sc_rowstore_destroy(c3sc_rowstore *s)
+{
+    if (!s) return;
+    DeviceScope ds_(s->device);
+    cudaFree(s->p);
+    delete s;
 }
 
 int c3sc_pi_batch_store(c3sc_problem *p, const c3sc_valuef *vf_policy, const c3sc_valuef *vf_iter, size_t F,
                         const int32_t *dim_vary, const int32_t *fixed_ind, size_t ldo, int have_rows,
-                        const int32_t *row_id, double *value)
+                        c3sc_rowstore *store, const int32_t *row_id, double *value)
 {
     DeviceScope ds_(p ? p->device : c3sc_cur_dev());
     int rc = check_shapes(p, vf_iter, F, ldo);
     if (!rc) rc = need_model(p);
     if (rc) return rc;
-    if (!dim_vary || !fixed_ind || !value || !row_id) return fail(C3SC_EINVAL, "null argument");
+    if (!dim_vary || !fixed_ind || !value || !row_id || !store) return fail(C3SC_EINVAL, "null argument");
     if (F == 0) return C3SC_OK;
-    if (!p->rows_store.p || ldo != p->store_ldo) return fail(C3SC_EINVAL, "policy-row store not reserved for ldo=%zu (c3sc_pi_store_reserve)", ldo);
+    if (store->ldo != ldo || (int)store->dx != p->P.dx || store->device != p->device)
+        return fail(C3SC_EINVAL, "policy-row store was created for dx=%u, ldo=%zu on device %d", store->dx, store->ldo, store->device);
     const size_t RW = 2 * (size_t)p->P.dx + 3, per = ldo * RW, n = F * ldo;
-    const size_t capf = p->rows_store.cap / (per * 8);
     for (size_t f = 0; f < F; f++)
-        if (row_id[f] < 0 || (size_t)row_id[f] >= capf) return fail(C3SC_EINVAL, "fiber %zu: row slot %d outside the store (%zu)", f, row_id[f], capf);
+        if (row_id[f] < 0 || (size_t)row_id[f] >= store->cap_fibers)
+            return fail(C3SC_EINVAL, "fiber %zu: row slot %d outside the store (%zu)", f, row_id[f], store->cap_fibers);
     rc = upload_fibers(p, F, dim_vary, fixed_ind);
     if (rc) return rc;
     if (p->b_val.reserve(n * 8) || p->b_rows.reserve(n * RW * 8) || p->b_misc[7].reserve(F * 4))
         return fail(C3SC_ECUDA, "cudaMalloc batch outputs failed");
     CK(cudaMemcpyAsync(p->b_misc[7].p, row_id, F * 4, cudaMemcpyHostToDevice, p->stream));
     if (have_rows) {
-        rc = launch_rows_move((double *)p->b_rows.p, (const double *)p->rows_store.p, (const int *)p->b_misc[7].p, (int)F, (long long)per, 0, p->stream);
+        rc = launch_rows_move((double *)p->b_rows.p, store->p, (const int *)p->b_misc[7].p, (int)F, (long long)per, 0, p->stream);
         if (rc) return fail(C3SC_ECUDA, "row gather kernel: %s", cudaGetErrorString((cudaError_t)rc));
         g_launches++;
     }
@@ -1085,7 +1125,7 @@ int c3sc_pi_batch_store(c3sc_problem *p, const c3sc_valuef *vf_policy, const c3s
                            (double *)p->b_rows.p, nullptr, (double *)p->b_val.p, p->stream);
     if (rc) return rc;
     if (!have_rows) {
-        rc = launch_rows_move((double *)p->rows_store.p, (const double *)p->b_rows.p, (const int *)p->b_misc[7].p, (int)F, (long long)per, 1, p->stream);
+        rc = launch_rows_move(store->p, (const double *)p->b_rows.p, (const int *)p->b_misc[7].p, (int)F, (long long)per, 1, p->stream);
         if (rc) return fail(C3SC_ECUDA, "row scatter kernel: %s", cudaGetErrorString((cudaError_t)rc));
         g_launches++;
     }

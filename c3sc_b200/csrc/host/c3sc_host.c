@@ -278,7 +278,7 @@ size_t uniform_stride(size_t N, size_t M)
 }
 
 /* ========================== workspace ====================================== */
-struct RowEntry { uint64_t hash; size_t pi_iter; int32_t key[C3SC_MAXD + 1]; double *rows; int32_t *argmin; struct RowEntry *next; };
+struct RowEntry { uint64_t hash; size_t pi_iter; int32_t key[C3SC_MAXD + 1]; int32_t slot; struct RowEntry *next; };   /* slot: the fiber's rows in the device store */
 struct Workspace {
     size_t dx, du, dw, N;
     size_t active;                /* src/util.c: workspace_set_active */
@@ -290,8 +290,11 @@ struct Workspace {
     double *costs;                /* N*(2dx+1): neighbour costs of the fiber in flight */
     int *absorbed;                /* N */
     double *u;                    /* N*du */
-    struct RowEntry **rows;       /* policy rows per fiber (replaces pi_prob_htable) */
+    struct RowEntry **rows;       /* fiber -> slot of its policy rows (replaces pi_prob_htable); the rows themselves
+                                     stay on the device, in `store` */
     size_t nbuckets;
+    c3sc_rowstore *store;         /* created on first use (needs the grid's nmax) */
+    size_t nslots;                /* slots handed out for the current policy */
 };
 struct Workspace *workspace_alloc(size_t dx, size_t du, size_t dw, size_t N)
 {
@@ -322,9 +325,10 @@ void workspace_reset_pi_prob_htable(struct Workspace *w)
 {
     for (size_t b = 0; b < w->nbuckets; b++) {
         struct RowEntry *e = w->rows[b];
-        while (e) { struct RowEntry *n = e->next; free(e->rows); free(e->argmin); free(e); e = n; }
+        while (e) { struct RowEntry *n = e->next; free(e); e = n; }
         w->rows[b] = NULL;
     }
+    w->nslots = 0;                /* the store keeps its memory; its slots are handed out again */
 }
 void workspace_reset_pi_htable(struct Workspace *w) { (void)w; }   /* value memo: dropped, backups are pure */
 void workspace_reset_vi_htable(struct Workspace *w) { (void)w; }
@@ -332,6 +336,7 @@ void workspace_free(struct Workspace *w)
 {
     if (!w) return;
     workspace_reset_pi_prob_htable(w);
+    c3sc_rowstore_destroy(w->store);
     for (size_t i = 0; i < w->N; i++) free(w->mem[i]);
     free(w->mem);
     free(w->rows); free(w->costs); free(w->absorbed); free(w->u); free(w);
@@ -377,15 +382,14 @@ static struct RowEntry *rows_find(struct Workspace *w, int32_t k, const int32_t 
     }
     return NULL;
 }
-static struct RowEntry *rows_add(struct Workspace *w, int32_t k, const int32_t *fi, size_t nrow)
+static struct RowEntry *rows_add(struct Workspace *w, int32_t k, const int32_t *fi)
 {
     struct RowEntry *e = xalloc(1, sizeof *e);
     e->hash = fiber_hash(w->pi_iter, k, fi, w->dx);
     e->pi_iter = w->pi_iter;
     memcpy(e->key, fi, w->dx * sizeof(int32_t));
     e->key[w->dx] = k;
-    e->rows = xalloc(nrow * (2 * w->dx + 3), sizeof(double));
-    e->argmin = xalloc(nrow, sizeof(int32_t));
+    e->slot = (int32_t)w->nslots++;
     e->next = w->rows[e->hash % w->nbuckets];
     w->rows[e->hash % w->nbuckets] = e;
     return e;
@@ -695,8 +699,11 @@ int bellman_pi_batch_ind(size_t F, const int32_t *dv, const int32_t *fi, double 
     struct PIparam *p = arg;
     struct ControlParams *cp = p->cp;
     struct Workspace *w = cp->work;
-    const size_t d = cp->mca->dx, nmax = grid_nmax(cp->mca), R = 2 * d + 3;
-    /* split the batch into fibers whose policy rows exist (this pi_iter) and new ones */
+    const size_t d = cp->mca->dx, nmax = grid_nmax(cp->mca);
+    /* The policy rows [p(2dx+1), dt, g] of src/bellman.c:1810 live in a device store owned by the Workspace, one slot
+       per fiber of the current policy (pi_iter); only fiber descriptors go up and values come down.  Split the batch
+       into fibers whose rows are filed (this pi_iter) and new ones. */
+    if (!w->store && c3sc_rowstore_create((uint32_t)d, nmax, &w->store)) die("c3sc_rowstore_create");
     size_t nh = 0, nm = 0;
     size_t *ih = xalloc(F, sizeof(size_t)), *im = xalloc(F, sizeof(size_t));
     struct RowEntry **ent = xalloc(F, sizeof *ent);
@@ -708,25 +715,31 @@ int bellman_pi_batch_ind(size_t F, const int32_t *dv, const int32_t *fi, double 
     for (int pass = 0; pass < 2 && !rc; pass++) {
         const size_t n = pass ? nh : nm, *idx = pass ? ih : im;
         if (!n) continue;
-        int32_t *bdv = xalloc(n, 4), *bfi = xalloc(n * d, 4), *barg = xalloc(n * nmax, 4);
-        double *rows = xalloc(n * nmax * R, 8), *val = xalloc(n * nmax, 8);
+        int32_t *bdv = xalloc(n, 4), *bfi = xalloc(n * d, 4), *slot = xalloc(n, 4);
+        double *val = xalloc(n * nmax, 8);
         for (size_t q = 0; q < n; q++) {
             bdv[q] = dv[idx[q]];
             memcpy(bfi + q * d, fi + idx[q] * d, d * 4);
-            if (pass) memcpy(rows + q * nmax * R, ent[idx[q]]->rows, nmax * R * 8);
+            if (pass) slot[q] = ent[idx[q]]->slot;
+            else {
+                /* a fiber requested twice in one batch files its rows once */
+                struct RowEntry *e = rows_find(w, bdv[q], bfi + q * d);
+                if (!e) e = rows_add(w, bdv[q], bfi + q * d);
+                slot[q] = e->slot;
+            }
         }
-        rc = c3sc_pi_batch(cp_dev(cp), p->vf_policy->dev, p->vf_iteration->dev, n, bdv, bfi, nmax, pass, rows, barg, val);
+        if (!pass) {
+            size_t cap = 1024;
+            while (cap < w->nslots) cap *= 2;
+            rc = c3sc_rowstore_reserve(w->store, cap);
+        }
+        if (!rc) rc = c3sc_pi_batch_store(cp_dev(cp), p->vf_policy->dev, p->vf_iteration->dev, n, bdv, bfi, nmax, pass, w->store, slot, val);
         for (size_t q = 0; q < n && !rc; q++) {
             memcpy(out + idx[q] * nmax, val + q * nmax, nmax * 8);
-            if (!pass) {
-                struct RowEntry *e = rows_add(w, bdv[q], bfi + q * d, nmax);
-                memcpy(e->rows, rows + q * nmax * R, nmax * R * 8);
-                memcpy(e->argmin, barg + q * nmax, nmax * 4);
-                p->npol_evals += cp->mca->ngrid[bdv[q]];
-            }
+            if (!pass) p->npol_evals += cp->mca->ngrid[bdv[q]];
             p->niter_evals += cp->mca->ngrid[bdv[q]];
         }
-        free(bdv); free(bfi); free(barg); free(rows); free(val);
+        free(bdv); free(bfi); free(slot); free(val);
     }
     if (rc) fprintf(stderr, "c3sc_b200: bellman_pi: %s\n", c3sc_last_error());
     free(ih); free(im); free(ent);

@@ -90,7 +90,10 @@ int main(int argc, char **argv)
         cores[k] = malloc(len * sizeof(double)); cores2[k] = malloc(len * sizeof(double));
         for (size_t e = 0; e < len; e++) { cores[k][e] = (2.0 * u01() - 1.0) / sqrt((double)ranks[k]); cores2[k][e] = (2.0 * u01() - 1.0) / sqrt((double)ranks[k]); }
     }
-    int32_t *dv = malloc(F * sizeof(int32_t)), *fi = malloc(F * d * sizeof(int32_t));
+    /* descriptors and results of the timed calls in page-locked memory (c3sc_host_alloc): PCIe speed, overlapped copies */
+    int32_t *dv, *fi;
+    CHECK(c3sc_host_alloc(F * sizeof(int32_t), (void **)&dv));
+    CHECK(c3sc_host_alloc(F * d * sizeof(int32_t), (void **)&fi));
     for (size_t f = 0; f < F; f++) {
         dv[f] = (int32_t)(f % d);
         for (uint32_t i = 0; i < d; i++) {
@@ -119,7 +122,8 @@ int main(int argc, char **argv)
     CHECK(c3sc_multi_valuef_create(m, d, ngrid, ranks, (const double *const *)cores2, &mv));     /* wrong numbers first ... */
     CHECK(c3sc_multi_valuef_update(mv, (const double *const *)cores));                           /* ... the update broadcasts the right ones */
     CHECK(c3sc_multi_valuef_create(m, d, ngrid, ranks, (const double *const *)cores2, &mvb));
-    double *got = malloc(nval * 8);
+    double *got;
+    CHECK(c3sc_host_alloc(nval * 8, (void **)&got));
     memset(got, 0xff, nval * 8);
     CHECK(c3sc_multi_vi_batch(m, mv, F, dv, fi, ldo, got, NULL));
     if (memcmp(got, ref, nval * 8)) { fprintf(stderr, "sharded bellman_vi differs from one device\n"); return 1; }
@@ -167,6 +171,7 @@ int main(int argc, char **argv)
     if (!same) { fprintf(stderr, "cross step over all devices differs from one device\n"); return 1; }
     printf("OK devices %d nccl %d fibers %zu nodes %zu sharded_vi_seconds %.6f node_backups_per_s %.4e cross_fibers %llu\n", G,
            c3sc_multi_uses_nccl(m), F, nval, best, (double)nval / best, (unsigned long long)nfb);
+    c3sc_host_free(dv); c3sc_host_free(fi); c3sc_host_free(got);
     c3sc_cross_destroy(ca); c3sc_cross_destroy(cb);
     c3sc_multi_valuef_destroy(mv); c3sc_multi_valuef_destroy(mvb); c3sc_multi_destroy(m);
     c3sc_valuef_destroy(v1); c3sc_valuef_destroy(v1b); c3sc_problem_destroy(p1);

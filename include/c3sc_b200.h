@@ -135,6 +135,12 @@ int c3sc_measure_fp64_peak(double *tflops, int iters, int repeats);
  * the denominator for kernels whose flops run as DMMAs (stage 1).                                            */
 int c3sc_measure_fp64_tensor_peak(double *tflops, int iters, int repeats);
 
+/* Page-locked (pinned, portable) host memory.  The host-buffer entries accept any host pointer, but only page-locked
+ * buffers move at PCIe speed and overlap with the kernels (cudaMemcpyAsync from pageable memory is staged by the
+ * driver): allocate the fiber descriptors and result arrays of large batches with these.                     */
+int c3sc_host_alloc(size_t bytes, void **ptr);
+int c3sc_host_free(void *ptr);
+
 /* Peer-mapped device buffers for the fused all-gather (c3sc_batch_out::value_peers), one process per
  * GPU: every rank creates its gathered buffer (cudaMalloc + cudaIpcGetMemHandle), exchanges the 64-byte
  * handles out of band, and opens the other ranks' buffers (cudaIpcOpenMemHandle with lazy peer access).
@@ -222,18 +228,24 @@ int c3sc_pi_batch(c3sc_problem *p, const c3sc_valuef *vf_policy, const c3sc_valu
                   size_t F, const int32_t *dim_vary, const int32_t *fixed_ind,
                   size_t ldo, int have_rows, double *rows, int32_t *argmin, double *value);
 
-/* bellman_pi with the policy rows RESIDENT on the device.  _resident: rows of the whole batch in a caller-owned
- * DEVICE buffer d_rows [F*ldo*(2dx+3)] (written when have_rows == 0, read otherwise).  _store: rows filed per fiber
- * in the problem's own device store (c3sc_pi_store_reserve(capacity in fibers, ldo); growing keeps what is filed);
- * fiber f of a call owns slot row_id[f].  Either way only descriptors go up and values come down: the 184 B/node
- * row record of src/bellman.c:1810 never crosses PCIe.                                                          */
+/* bellman_pi with the policy rows RESIDENT on the device: only descriptors go up and values come down, the
+ * 184 B/node row record of src/bellman.c:1810 never crosses PCIe.
+ *   _resident  rows of the whole batch in a caller-owned DEVICE buffer d_rows [F*ldo*(2dx+3)] (written when
+ *              have_rows == 0, read otherwise);
+ *   _store     rows filed per fiber in a c3sc_rowstore -- a device object of its own, because it outlives the
+ *              per-step problems: the reference keeps a policy's rows in the Workspace (pi_prob_htable) across the
+ *              c3control_step_pi calls of one c3control_pi_solve.  Fiber f of a call owns slot row_id[f]
+ *              (< reserved capacity; reserving more keeps what is filed).                                        */
 int c3sc_pi_batch_resident(c3sc_problem *p, const c3sc_valuef *vf_policy, const c3sc_valuef *vf_iter, size_t F,
                            const int32_t *dim_vary, const int32_t *fixed_ind, size_t ldo, int have_rows,
                            double *d_rows, double *value);
-int c3sc_pi_store_reserve(c3sc_problem *p, size_t capacity_fibers, size_t ldo);
+typedef struct c3sc_rowstore c3sc_rowstore;
+int  c3sc_rowstore_create(uint32_t dx, size_t ldo, c3sc_rowstore **out);
+int  c3sc_rowstore_reserve(c3sc_rowstore *s, size_t capacity_fibers);
+void c3sc_rowstore_destroy(c3sc_rowstore *s);
 int c3sc_pi_batch_store(c3sc_problem *p, const c3sc_valuef *vf_policy, const c3sc_valuef *vf_iter, size_t F,
                         const int32_t *dim_vary, const int32_t *fixed_ind, size_t ldo, int have_rows,
-                        const int32_t *row_id, double *value);
+                        c3sc_rowstore *store, const int32_t *row_id, double *value);
 
 /* mca_get_neighbor_costs (src/nodeutil.c:647-713) over F fibers: flags, neighbour
  * indices and FT neighbour values only (process_fibers_neighbor + 
