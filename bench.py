@@ -170,6 +170,9 @@ def run_reference(args, cfg, rank_ft):
         kind = "reference"
         ref = po.Ref(cfg)
         vf = ref.valuef(ft)
+        # torch.distributed.run exports OMP_NUM_THREADS=1 to every rank; rank 0 alone runs this arm (the other ranks
+        # have exited), so it takes every core of the box
+        ref.set_omp_threads(cores_n)
         threads = ref.omp_threads()
 
         def step(i):
@@ -210,63 +213,71 @@ def run_reference(args, cfg, rank_ft):
 
 
 def _ncu_record():
-    try:
-        return json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
-    except Exception:
-        return None
+    for name in ("r02_traffic.json", "r01_traffic.json"):
+        try:
+            return json.load(open(os.path.join(ROOT, "profiles", name)))
+        except Exception:
+            continue
+    return None
 
 
-def ncu_traffic(F):
-    """dram__bytes_read.sum + dram__bytes_write.sum of one step, from the committed `ncu --set full`
-    capture (profiles/r01_traffic.json: bytes per fiber of the three pipeline kernels), or None."""
-    t = _ncu_record()
-    return float(t["dram_bytes_per_fiber"]) * F if t else None
-
-
-def roofline_record(stage1, whole_achieved, peak, W, F, kernel_ms, hbm_bytes, hbm_peak):
-    """The `roofline` object of the bench line.
-
-    Top level = the dominant kernels: stage 1 (k_ft_chains + k_ft_nodes, 3/4 of a step, FP64 tensor path), timed live
-    by `main` with CUDA events on the launching stream against their ALGORITHMIC 8r^2 + 4dr flops per node
-    (DESIGN 3.6).  `contract_whole_step` keeps SURVEY 8(d)'s whole-step figure (node-backups/s x W): W charges
-    ~180 flops per candidate control, the grid walk of stage 2 spends ~2 FP64 instructions per candidate, so that
-    ratio exceeds 1 -- algebra, not pipe utilisation -- and is not the headline fraction.  With more than one rank
-    stage 1 is not re-timed and the top level falls back to the whole-step figure, flagged in `basis`."""
+def roofline_record(stage1, whole, peak_dmma, peak_dfma, W, W1, F, kernel_ms, hbm_bytes, hbm_peak):
+    """The `roofline` object of the bench line.  Top level = the dominant kernels: stage 1 (chain stage + node kernel, FP64
+    tensor path), timed live by `main` with CUDA events on the launching stream against its ALGORITHMIC 8r^2 + 4dr flops per
+    node, over the DMMA peak measured in the same run (both measured FP64 peaks are printed).
+    `contract_whole_step` keeps SURVEY 8(d)'s whole-step figure: it exceeds 1 because stage 2 shares partial sums between
+    candidates -- algebra, not utilisation.  With more than one rank stage 1 is not re-timed (flagged in `basis`)."""
     rec = _ncu_record() or {}
-    whole = {"achieved": whole_achieved, "peak": peak, "unit": "TFLOP/s", "frac": whole_achieved / peak,
-             "flops_per_node_backup": W,
-             "note": "SURVEY 8(d) contract flops per node-backup (8r^2+4dr for the neighbour values + ~180 flops per candidate "
-                     "control) over the whole step (all pipeline kernels); stage 2 forms every candidate from shared partial "
-                     "sums (~2 FP64 instructions per candidate), so frac > 1 is algebra, not pipe utilisation"}
+    traffic = rec.get("dram_bytes_per_fiber")
+    roof = {"bound": "tensor", "unit": "TFLOP/s", "peak": peak_dmma,
+            "peaks_measured_in_this_run": {"fp64_dmma_tflops": peak_dmma, "fp64_dfma_tflops": peak_dfma,
+                                           "note": "one execution resource on B200 (they do not add up); the DMMA figure is the denominator "
+                                                   "because stage 1's flops run as DMMAs; MEASURED_PEAKS.json has no FP64 figure"}}
     if stage1:
-        top = {"bound": "tensor", "achieved": stage1["achieved"], "peak": peak, "unit": "TFLOP/s",
-               "frac": stage1["achieved"] / peak, "basis": "stage 1 (k_ft_chains + k_ft_nodes), timed alone in this run",
-               "kernels": stage1["kernels"], "fibers_per_launch": stage1["fibers"], "ms_per_launch": stage1["ms"],
-               "flops_per_node": stage1["flops_per_node"],
-               "stage1_live": dict(stage1, peak=peak, frac=stage1["achieved"] / peak)}
+        roof.update({"achieved": stage1["achieved"], "frac": stage1["achieved"] / peak_dmma,
+                     "basis": "stage 1 (chain stage + node kernel) timed alone in this run against its ALGORITHMIC 8r^2 + 4dr flops per node",
+                     "kernels": stage1["kernels"], "fibers_per_launch_set": stage1["fibers"], "ms_per_launch_set": stage1["ms"],
+                     "flops_per_node": W1, "frac_of_dfma_peak": stage1["achieved"] / peak_dfma, "stage1_live": stage1})
     else:
-        top = {"bound": "tensor", "achieved": whole_achieved, "peak": peak, "unit": "TFLOP/s", "frac": whole_achieved / peak,
-               "basis": "whole step against the contract flops (stage 1 is timed alone only at --gpus 1)", "stage1_live": None}
-    top.update({
-        "traffic": ncu_traffic(F),
-        "peak_source": "FP64 pipe: DFMA loop measured in this run (c3sc_measure_fp64_peak); DMMA and DFMA share the unit on "
-                       "this part (profiles/r01_fp64_pipe_microbench.md); MEASURED_PEAKS.json has no FP64 figure",
-        "contract_whole_step": whole,
-        "dominant_kernel": rec.get("dominant_kernel"),
-        "other_kernels": rec.get("other_kernels"),
-        "hbm": {"algorithmic_bytes_per_step": hbm_bytes, "achieved_gbs": hbm_bytes / (kernel_ms * 1e-3) / 1e9,
-                "peak_gbs": hbm_peak, "frac": hbm_bytes / (kernel_ms * 1e-3) / 1e9 / hbm_peak,
+        roof.update({"achieved": whole, "frac": whole / peak_dmma, "stage1_live": None,
+                     "basis": "whole step against the contract flops (stage 1 is timed alone only at --gpus 1)"})
+    roof.update({
+        "traffic": float(traffic) * F if traffic else None,
+        "traffic_source": rec.get("source"),
+        "contract_whole_step": {"achieved": whole, "frac": whole / peak_dmma, "flops_per_node_backup": W,
+                                "note": "SURVEY 8(d) contract flops per node-backup over the whole step; stage 2 forms every candidate "
+                                        "from shared partial sums (~2 FP64 instructions per candidate), so frac > 1 is algebra, not utilisation"},
+        "dominant_kernel": rec.get("dominant_kernel"), "other_kernels": rec.get("other_kernels"),
+        "hbm": {"algorithmic_bytes_per_step": hbm_bytes, "achieved_gbs": hbm_bytes / (kernel_ms * 1e-3) / 1e9, "peak_gbs": hbm_peak,
+                "frac": hbm_bytes / (kernel_ms * 1e-3) / 1e9 / hbm_peak,
                 "note": "not binding: cores stay in L2/SMEM, HBM sees descriptors in and values out"}})
-    return top
+    return roof
 
 
 def workload_config(cfg, rank_ft, F, args):
-    return {"workload": f"{cfg.name}: d={cfg.dx} LQG, {cfg.n} nodes/dim, FT rank {rank_ft}, n_u={cfg.nu} "
-                        f"({'x'.join(['3'] * cfg.du)} tensor grid of {{-1,0,1}}), {F} synthetic fibers/GPU/step "
-                        f"(dim_vary = f mod d, 10% of fixed indices on faces)",
+    return {"workload": f"{cfg.name}: d={cfg.dx}, {cfg.n} nodes/dim, FT rank {rank_ft}, n_u={cfg.nu} discrete controls, "
+                        f"{F} synthetic fibers/GPU/step (dim_vary = f mod d, 10% of fixed indices on faces)",
             "fibers_per_gpu": F, "nodes_per_fiber": cfg.n, "rank": rank_ft, "n_controls": cfg.nu,
             "arith": "fast" if args.arith else "exact",
             "l2": "256 MiB buffer written between timed steps (L2 flush); each step timed by its own CUDA event pair"}
+
+
+def pin_to_gpu_numa_node(index: int):
+    """bind this process (and so its first-touch page-locked allocations) to the CPUs next to its GPU: with eight
+    ranks copying results to the host at once, buffers on the far socket halve the D2H rate"""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        n = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, n)
+        cpus = [64 * w + b for w, word in enumerate(mask) for b in range(64) if (int(word) >> b) & 1]
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return len(cpus)
+    except Exception:
+        pass
+    return 0
 
 
 # --------------------------------------------------------------------------------------
@@ -283,24 +294,27 @@ def main():
     ap.add_argument("--ref-fibers", type=int, default=48, help="fibers per step of the CPU reference arm")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-sweep", action="store_true", help="skip the synthetic VI sweep (2 x d core batches, one launch set per core)")
+    ap.add_argument("--no-sweep", action="store_true", help="skip the synthetic VI sweep, the cross step, the PI step and the other configs")
     args = ap.parse_args()
 
     from c3sc_b200 import configs, synthetic
     cfg = configs.get_config(args.config)
-    rank_ft = args.rank
+    rank_ft = args.rank if args.config.startswith("lqgnd") else cfg.rank
 
     if args.impl == "reference":
         run_reference(args, cfg, rank_ft)
         return
 
-    import torch
-    import torch.distributed as dist
-    from c3sc_b200 import capi
-
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    ncpus = pin_to_gpu_numa_node(local) if world > 1 else 0
+
+    import ctypes
+    import torch
+    import torch.distributed as dist
+    from c3sc_b200 import capi, sharding
+
     if world != args.gpus and world > 1:
         raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
     if not torch.cuda.is_available():
@@ -309,7 +323,8 @@ def main():
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    capi.check(capi.lib().c3sc_cuda_init(local))
+    L = capi.lib()
+    capi.check(L.c3sc_cuda_init(local))
 
     F = args.fibers
     N = cfg.n
@@ -318,59 +333,58 @@ def main():
     cores = synthetic.random_cores(cfg.ngrid, ranks)
     vf = capi.ValueF(cfg.ngrid, ranks, cores)
     core_ptr, core_cnt = vf.device_buffer()
-    # torch view over the library's contiguous core buffer (for the NCCL broadcast)
-    core_view = torch.empty(0, dtype=torch.float64, device=dev)
-    if world > 1:
-        import ctypes
 
-        class _Arr:  # __cuda_array_interface__ wrapper, zero copy
-            def __init__(self, ptr, n):
-                self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<f8", "data": (ptr, False), "version": 3}
-        core_view = torch.as_tensor(_Arr(core_ptr, core_cnt), device=dev)
+    class _Arr:  # __cuda_array_interface__ wrapper, zero copy
+        def __init__(self, ptr, n):
+            self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<f8", "data": (ptr, False), "version": 3}
+    core_view = torch.as_tensor(_Arr(core_ptr, core_cnt), device=dev) if world > 1 else None
 
     # one global fiber list of F*world fibers; rank g owns the contiguous block g (stable map)
-    from c3sc_b200 import sharding
     dv_all, fi_all = synthetic.random_fibers(cfg.ngrid, F * world)
     dv_s, fi_s, nreal = sharding.shard_fibers(dv_all, fi_all, world, rank)
     assert nreal == F
     dv_h = torch.from_numpy(dv_s).pin_memory()
     fi_h = torch.from_numpy(fi_s).pin_memory()
     dv_d = dv_h.to(dev); fi_d = fi_h.to(dev)
-    out_d = torch.zeros(F * N, dtype=torch.float64, device=dev)
-    gathered = torch.empty(world * F * N, dtype=torch.float64, device=dev) if world > 1 else None
     out_h = torch.empty(F * N, dtype=torch.float64).pin_memory()
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     stream = torch.cuda.current_stream(dev)
     sptr = stream.cuda_stream
 
-    # N > 1, fused all-gather: every rank's gathered buffer is peer-mapped (CUDA IPC) and the control kernel
-    # stores each value into all of them over NVLink while it computes; a step ends with a barrier.
-    # C3SC_GATHER=nccl keeps the NCCL all-gather (sub-batches overlapped on a second stream) instead.
+    # N > 1: every rank's gathered buffer is peer-mapped (CUDA IPC); a rank's values reach the others either as stores
+    # from the control kernel (C3SC_GATHER=p2p) or as one bulk copy per pipeline chunk on the copy engines, overlapped with
+    # the next chunk (C3SC_GATHER=copy, default); a step ends with a barrier.  C3SC_GATHER=nccl: NCCL all-gather.
+    gather_mode = os.environ.get("C3SC_GATHER", "copy") if world > 1 else "none"
     peers = None
-    if world > 1 and os.environ.get("C3SC_GATHER", "p2p") == "p2p":
+    gathered = None
+    if world > 1 and gather_mode in ("p2p", "copy"):
         try:
             def _exchange(h):
                 got = [None] * world
                 dist.all_gather_object(got, h)
                 return got
             peers = capi.PeerBuffers(world * F * N * 8, rank, world, _exchange)
-
-            class _Arr:  # zero-copy torch view of the rank's own gathered buffer
-                def __init__(self, ptr, n):
-                    self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<f8", "data": (ptr, False), "version": 3}
-            gathered_p2p = torch.as_tensor(_Arr(peers.own, world * F * N), device=dev)
+            gathered = torch.as_tensor(_Arr(peers.own, world * F * N), device=dev)
             sync_flag = torch.zeros(1, device=dev)
         except Exception as exc:           # no peer access on this box: fall back to NCCL
             if rank == 0:
-                print(f"bench: fused all-gather unavailable ({exc}); using NCCL", file=sys.stderr)
+                print(f"bench: peer-mapped gather unavailable ({exc}); using NCCL", file=sys.stderr)
             peers = None
+            gather_mode = "nccl"
+    if world > 1 and peers is None:
+        gathered = torch.empty(world * F * N, dtype=torch.float64, device=dev)
+    # the rank's own output IS its slot of its gathered buffer (no private copy)
+    out_d = gathered[rank * F * N:(rank + 1) * F * N] if gathered is not None else torch.zeros(F * N, dtype=torch.float64, device=dev)
+    peer_mode = 1 if gather_mode == "copy" else 0
 
-    # N > 1: the rank's fibers go through the pipeline in NSUB sub-batches; the all-gather of sub-batch s
-    # runs on a second stream while sub-batch s+1 computes (gathered layout: [sub-batch][rank][fiber][node])
-    NSUB = 4 if (world > 1 and F % 4 == 0 and F >= 4096) else 1
-    Fs = F // NSUB
-    comm = torch.cuda.Stream(device=dev) if world > 1 else None
-    sub_done = [torch.cuda.Event() for _ in range(NSUB)] if world > 1 else []
+    def peers_struct():
+        o = capi.BatchOut()
+        o.n_peers = world
+        for g, ptr in enumerate(peers.ptrs):
+            o.value_peers[g] = ptr
+        o.peer_offset = rank * F * N
+        o.peer_mode = peer_mode
+        return o
 
     def step_resident():
         if world == 1:
@@ -380,23 +394,31 @@ def main():
         vf.commit(stream=sptr)
         if peers is not None:
             prob.vi_batch_dev(vf, F, dv_d.data_ptr(), fi_d.data_ptr(), N, out_d.data_ptr(), stream=sptr,
-                              peers=peers.ptrs, peer_offset=rank * F * N)
-            dist.all_reduce(sync_flag)                # barrier on the stream: every rank's stores have landed
+                              peers=peers.ptrs, peer_offset=rank * F * N, peer_mode=peer_mode)
+            dist.all_reduce(sync_flag)                # barrier on the stream: every rank's values have landed
             return
-        comm.wait_stream(stream)                      # the previous step's gathers are ordered before reuse
-        for sb in range(NSUB):
-            prob.vi_batch_dev(vf, Fs, dv_d[sb * Fs:].data_ptr(), fi_d[sb * Fs:].data_ptr(), N,
-                              out_d[sb * Fs * N:].data_ptr(), stream=sptr)
-            sub_done[sb].record(stream)
-            comm.wait_event(sub_done[sb])
-            with torch.cuda.stream(comm):
-                dist.all_gather_into_tensor(gathered[sb * world * Fs * N:(sb + 1) * world * Fs * N],
-                                            out_d[sb * Fs * N:(sb + 1) * Fs * N])
-        stream.wait_stream(comm)                      # the step ends when the last gather has landed
+        prob.vi_batch_dev(vf, F, dv_d.data_ptr(), fi_d.data_ptr(), N, out_d.data_ptr(), stream=sptr)
+        dist.all_gather_into_tensor(gathered, out_d)
+
+    ps = peers_struct() if peers is not None else None
 
     def step_e2e():
-        capi.check(capi.lib().c3sc_vi_batch(prob.handle, vf.handle, F, dv_h.data_ptr(), fi_h.data_ptr(), N,
-                                            out_h.data_ptr(), None))
+        """the sharded step through the host-buffer entry: pinned descriptors in, this rank's values back out, cores
+        broadcast and values gathered on the devices (N > 1) -- all inside the call / the timed region"""
+        if world == 1:
+            capi.check(L.c3sc_vi_batch(prob.handle, vf.handle, F, dv_h.data_ptr(), fi_h.data_ptr(), N, out_h.data_ptr(), None))
+            return
+        sharding.broadcast_cores(core_view, src=0)
+        vf.commit(stream=sptr)
+        stream.synchronize()
+        if ps is not None:
+            capi.check(L.c3sc_vi_batch_peers(prob.handle, vf.handle, F, dv_h.data_ptr(), fi_h.data_ptr(), N, out_h.data_ptr(), None,
+                                             ctypes.byref(ps)))
+            dist.all_reduce(sync_flag)
+        else:
+            capi.check(L.c3sc_vi_batch(prob.handle, vf.handle, F, dv_h.data_ptr(), fi_h.data_ptr(), N, out_h.data_ptr(), None))
+            out_d.copy_(out_h, non_blocking=True)
+            dist.all_gather_into_tensor(gathered, out_d)
 
     def timed(fn, steps, warmup):
         for _ in range(warmup):
@@ -424,14 +446,15 @@ def main():
             ms = float(t.item())
         return ms
 
-    if peers is not None:                               # the fused gather must equal an NCCL all-gather
+    if world > 1:                                       # the gather must equal an NCCL all-gather of the ranks' blocks
         step_resident()
         torch.cuda.synchronize(dev)
+        dist.barrier()
         ref_g = torch.empty(world * F * N, dtype=torch.float64, device=dev)
-        dist.all_gather_into_tensor(ref_g, out_d)
+        dist.all_gather_into_tensor(ref_g, out_d.clone())
         torch.cuda.synchronize(dev)
-        if not torch.equal(ref_g, gathered_p2p):
-            raise SystemExit("fused all-gather differs from the NCCL all-gather")
+        if not torch.equal(ref_g, gathered):
+            raise SystemExit("gathered values differ from the NCCL all-gather")
         del ref_g
 
     # The sampler runs from the warm-up on (one NVML query takes ~20 ms on these boxes, about the whole timed
@@ -442,12 +465,11 @@ def main():
     for _ in range(args.warmup):
         step_resident()
     torch.cuda.synchronize(dev)
-    launches0 = capi.lib().c3sc_launch_count()
+    launches0 = L.c3sc_launch_count()
     seen0, wall0 = sampler.count(), time.perf_counter()
     ms_total = timed(step_resident, args.steps, 0)
     wall1 = time.perf_counter()
-    launches = capi.lib().c3sc_launch_count() - launches0
-    # keep the same load running (untimed) until the sampler has seen it a few times
+    launches = L.c3sc_launch_count() - launches0
     in_region, extra = sampler.count_between(wall0, wall1, seen0), 0
     while (extra < 40) if world > 1 else (sampler.count() < 5 and extra < 400):   # fixed count under torchrun: the step has collectives
         step_resident()
@@ -484,50 +506,86 @@ def main():
     value = nodes_per_step * args.steps / (ms_total * 1e-3)
     e2e_value = nodes_per_step * e2e_steps / (ms_e2e * 1e-3)
 
+    # ---- N > 1 extras: strong scaling (the N = 1 batch cut N ways) and the sharded synthetic VI sweep ------------
+    extras = {}
+    if world > 1 and peers is not None:
+        Fs = F // world                                  # this rank's share of a 65 536-fiber batch
+
+        def step_strong():
+            sharding.broadcast_cores(core_view, src=0)
+            vf.commit(stream=sptr)
+            prob.vi_batch_dev(vf, Fs, dv_d.data_ptr(), fi_d.data_ptr(), N, out_d.data_ptr(), stream=sptr,
+                              peers=peers.ptrs, peer_offset=rank * Fs * N, peer_mode=peer_mode)
+            dist.all_reduce(sync_flag)
+        k = max(3, min(args.steps, 10))
+        ms_s = timed(step_strong, k, 2) / k
+        extras["scaling_strong"] = {"fibers_total": Fs * world, "ms_per_step": ms_s, "node_backups_per_s": Fs * world * N / (ms_s * 1e-3),
+                                    "what": "the N = 1 batch split N ways (cores broadcast, values gathered every step)"}
+        if not args.no_sweep:
+            batches = synthetic.sweep_fibers(cfg.ngrid, ranks)
+            shard = []
+            for a, b in batches:
+                a2, b2, _ = sharding.shard_fibers(a, b, world, rank)
+                shard.append((torch.from_numpy(a2).to(dev), torch.from_numpy(b2).to(dev), len(a2)))
+
+            def sweep_sharded():
+                for a, b, f in shard:
+                    prob.vi_batch_dev(vf, f, a.data_ptr(), b.data_ptr(), N, out_d.data_ptr(), stream=sptr,
+                                      peers=peers.ptrs, peer_offset=rank * f * N, peer_mode=peer_mode)
+                    dist.all_reduce(sync_flag)            # the driver needs a core batch's values before it asks for the next
+            ms_sw = timed(sweep_sharded, 10, 3) / 10
+            nodes_sw = sum(len(a) for a, _ in batches) * N
+            extras["vi_sweep_sharded"] = {"seconds": ms_sw * 1e-3, "node_backups": nodes_sw, "core_batches": len(shard),
+                                          "what": "2 x d sequential core batches, each cut N ways, gathered, barrier per batch"}
+
     line = None
     if rank == 0:
         W = contract_flops_per_node(cfg, rank_ft)
-        peak = capi.measure_fp64_peak()
+        peak_dfma = capi.measure_fp64_peak()
+        peak_dmma = capi.measure_fp64_tensor_peak()
         kernel_ms = ms_total / args.steps
-        # stage 1 alone (chains + nodes = the neighbour values, 8r^2 + 4dr algorithmic flops per node): the same
-        # kernels with the node-major cost output instead of the scratch, timed live on a sample of the batch
+        rbar2 = float(np.mean([ranks[k] * ranks[k + 1] for k in range(cfg.dx)]))
+        W1 = 8.0 * rbar2 + 4.0 * cfg.dx * float(max(ranks))
         stage1 = None
         if world == 1:
-            F1 = min(F, 8192)
-            costs_d = torch.empty(F1 * N * (2 * cfg.dx + 1), dtype=torch.float64, device=dev)
-
+            # stage 1 alone (chain stage + node kernel = the neighbour values, 8r^2 + 4dr algorithmic flops per node), launched
+            # exactly as the pipeline launches it (same chunks, lanes and scratch), timed live on the whole batch
             def step_stage1():
-                prob.vi_batch_dev(vf, F1, dv_d.data_ptr(), fi_d.data_ptr(), N, 0, stream=sptr, costs=costs_d.data_ptr())
-            ms1 = timed(step_stage1, max(3, min(args.steps, 10)), 3) / max(3, min(args.steps, 10))
-            rbar2 = float(np.mean([ranks[k] * ranks[k + 1] for k in range(cfg.dx)]))
-            W1 = 8.0 * rbar2 + 4.0 * cfg.dx * float(max(ranks))
-            stage1 = {"kernels": "k_ft_chains + k_ft_nodes", "fibers": F1, "ms": ms1, "flops_per_node": W1,
-                      "achieved": F1 * N * W1 / (ms1 * 1e-3) / 1e12, "unit": "TFLOP/s"}
-            del costs_d
-        achieved = (F * N * W) / (kernel_ms * 1e-3) / 1e12 if world == 1 else (value / world) * W / 1e12
+                prob.stage1_batch_dev(vf, F, dv_d.data_ptr(), fi_d.data_ptr(), N, stream=sptr)
+            k1 = max(3, min(args.steps, 10))
+            ms1 = timed(step_stage1, k1, 3) / k1
+            stage1 = {"kernels": "k_chain_step x (d-1) + k_ft_nodes (k_ft_chains below 4096 fibers)", "fibers": F, "ms": ms1,
+                      "flops_per_node": W1, "achieved": F * N * W1 / (ms1 * 1e-3) / 1e12, "unit": "TFLOP/s"}
+        whole = (F * N * W) / (kernel_ms * 1e-3) / 1e12 if world == 1 else (value / world) * W / 1e12
         hbm_bytes = F * N * 8.0 + F * (cfg.dx + 1) * 4.0 + core_cnt * 8.0
-        hbm_peak = None
         try:
             hbm_peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
         except Exception:
             hbm_peak = 6650.0
+        roof = roofline_record(stage1, whole, peak_dmma, peak_dfma, W, W1, F, kernel_ms, hbm_bytes, hbm_peak)
+        gathers = {"copy": "one bulk copy per pipeline chunk and peer on the copy engines into peer-mapped buffers (CUDA IPC over NVLink) + barrier",
+                   "p2p": "control kernel stores into every rank's peer-mapped buffer (CUDA IPC over NVLink) + barrier",
+                   "nccl": "nccl all_gather_into_tensor"}
         line = {
             "metric": "bellman_node_backups_per_s", "value": value, "unit": "node-backups/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": dict(workload_config(cfg, rank_ft, F, args),
-                           **({"gather": "fused: control kernel stores into every rank's peer-mapped buffer (CUDA IPC over NVLink) + barrier"
-                               if peers is not None else "nccl all_gather_into_tensor, 4 sub-batches overlapped on a second stream"}
-                              if world > 1 else {})),
+                           **({"gather": gathers[gather_mode], "cores": "dist.broadcast of the contiguous core buffer every step",
+                               "cpus_bound_per_rank": ncpus} if world > 1 else {})),
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "node-backups/s",
                     "h2d_bytes_per_step": int(F * (cfg.dx + 1) * 4 * world), "d2h_bytes_per_step": int(F * N * 8 * world),
-                    "ms_per_step": ms_e2e / e2e_steps, "api": "c3sc_vi_batch (host buffers, pinned)"},
+                    "ms_per_step": ms_e2e / e2e_steps,
+                    "api": "c3sc_vi_batch (host buffers, pinned)" if world == 1 else
+                           "c3sc_vi_batch_peers per rank (pinned host buffers) + core broadcast + gather + barrier: the sharded step"},
             "gpu_launches": int(launches),
-            "roofline": roofline_record(stage1, achieved, peak, W, F, kernel_ms, hbm_bytes, hbm_peak),
+            "roofline": roof,
         }
+        line.update(extras)
 
-    if not args.no_sweep and world == 1:
+    sweeps = not args.no_sweep and world == 1
+    if sweeps:
         batches = synthetic.sweep_fibers(cfg.ngrid, ranks)
         dev_b = [(torch.from_numpy(a).to(dev), torch.from_numpy(b).to(dev), len(a)) for a, b in batches]
 
@@ -536,19 +594,14 @@ def main():
                 prob.vi_batch_dev(vf, f, a.data_ptr(), b.data_ptr(), N, out_d.data_ptr(), stream=sptr)
         ms_sw = timed(sweep, 10, 3) / 10
         nodes_sw = sum(f for _, _, f in dev_b) * N
-        if line is not None:
-            line["vi_sweep"] = {"seconds": ms_sw * 1e-3, "node_backups": nodes_sw, "launches": len(dev_b),
-                                "node_backups_per_s": nodes_sw / (ms_sw * 1e-3),
-                                "what": "2 x d sequential core batches of r_k*r_{k+1} fibers (SURVEY §8(d))"}
-
-    if not args.no_sweep and world == 1 and line is not None:
-        # one value-iteration step through the host cross driver (include/c3sc_cross.h): 2 sweeps over the
-        # d cores, every core step = H2D fiber descriptors + pipeline + D2H values + host QR/maxvol
+        line["vi_sweep"] = {"seconds": ms_sw * 1e-3, "node_backups": nodes_sw, "launches": len(dev_b),
+                            "node_backups_per_s": nodes_sw / (ms_sw * 1e-3),
+                            "what": "2 x d sequential core batches of r_k*r_{k+1} fibers (SURVEY §8(d))"}
+        # one value-iteration step through the host cross driver (include/c3sc_cross.h)
         cr = capi.Cross(cfg.ngrid, ranks)
         cr.run_vi(prob, vf, maxiter=1)
         t0 = time.perf_counter()
-        reps = 3
-        nf = 0
+        reps, nf = 3, 0
         for _ in range(reps):
             _, nf, _ = cr.run_vi(prob, vf, maxiter=1)
         dt = (time.perf_counter() - t0) / reps
@@ -556,14 +609,124 @@ def main():
                                  "what": "c3sc_cross_run_vi, one left-right + right-left sweep (host TT-cross with QR + maxvol, "
                                          "one batched operator call per core, host buffers)"}
         cr.close()
+        line["pi_step"] = pi_step(prob, cfg, ranks, vf, dv_h, fi_h, dv_d, fi_d, F, N, dev, timed, timed_host, peak_dmma, W1)
+        line["other_configs"] = other_configs(args, dev, timed)
 
     if rank == 0 and not args.no_cpu_baseline and world == 1:
         line["cpu_baseline"] = cpu_baseline(cfg, rank_ft, args.cpu_seconds)
+        line["parity_check"] = parity_check(cfg, rank_ft, prob, vf, dv_s, fi_s, out_d, N)
     if rank == 0:
         print(json.dumps(line))
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def pi_step(prob, cfg, ranks, vf, dv_h, fi_h, dv_d, fi_d, F, N, dev, timed, timed_host, peak_dmma, W1):
+    """bellman_pi (src/bellman.c:1702-1886), half of every outer solver iteration: one policy improvement (rows from the argmin
+    against the policy value function) + K = 10 sub-iterations against the iterate, rows RESIDENT on the device."""
+    import torch
+    from c3sc_b200 import capi, synthetic
+    L = capi.lib()
+    K = 10
+    RW = 2 * cfg.dx + 3
+    vf_it = capi.ValueF(cfg.ngrid, ranks, synthetic.random_cores(cfg.ngrid, ranks, seed=0xABCD00))
+    rows = torch.empty(F * N * RW, dtype=torch.float64, device=dev)
+    val = torch.empty(F * N, dtype=torch.float64, device=dev)
+    st = torch.cuda.current_stream(dev).cuda_stream
+
+    def improve():
+        prob.pi_batch_dev(vf, vf_it, F, dv_d.data_ptr(), fi_d.data_ptr(), N, 0, rows.data_ptr(), 0, val.data_ptr(), stream=st)
+
+    def subiter():
+        prob.pi_batch_dev(None, vf_it, F, dv_d.data_ptr(), fi_d.data_ptr(), N, 1, rows.data_ptr(), 0, val.data_ptr(), stream=st)
+
+    def whole():
+        improve()
+        for _ in range(K):
+            subiter()
+    ms_imp = timed(improve, 3, 1) / 3
+    ms_sub = timed(subiter, 5, 1) / 5
+    ms_all = timed(whole, 2, 1) / 2
+    out_h = torch.empty(F * N, dtype=torch.float64).pin_memory()
+
+    def e2e_sub():
+        capi.check(L.c3sc_pi_batch_resident(prob.handle, None, vf_it.handle, F, dv_h.data_ptr(), fi_h.data_ptr(), N, 1, rows.data_ptr(),
+                                            out_h.data_ptr()))
+    ms_e2e = timed_host(e2e_sub, 3, 1) / 3
+    nodes = F * N
+    rec = {"what": f"one policy improvement + {K} sub-iterations on {F} fibers, policy rows resident on the device (c3sc_pi_batch_dev)",
+           "ms_improvement": ms_imp, "ms_sub_iteration": ms_sub, "ms_total": ms_all,
+           "node_backups_per_s": nodes * (K + 1) / (ms_all * 1e-3), "sub_iteration_node_evals_per_s": nodes / (ms_sub * 1e-3),
+           "e2e_sub_iteration": {"value": nodes / (ms_e2e * 1e-3), "unit": "node-evaluations/s", "ms": ms_e2e,
+                                 "api": "c3sc_pi_batch_resident (pinned descriptors in, values out, rows stay on the device)",
+                                 "h2d_bytes": int(F * (cfg.dx + 1) * 4), "d2h_bytes": int(F * N * 8)},
+           "roofline": {"bound": "tensor", "basis": "a sub-iteration is stage 1 (8r^2 + 4dr flops per node) + a (2d+1) dot per node",
+                        "achieved": nodes * (W1 + 2.0 * (2 * cfg.dx + 1)) / (ms_sub * 1e-3) / 1e12, "peak": peak_dmma, "unit": "TFLOP/s",
+                        "frac": nodes * (W1 + 2.0 * (2 * cfg.dx + 1)) / (ms_sub * 1e-3) / 1e12 / peak_dmma}}
+    vf_it.close()
+    del rows, val
+    return rec
+
+
+def other_configs(args, dev, timed):
+    """the other BASELINE.json configs at full size, short runs: device-resident rate and the rate through host buffers"""
+    import torch
+    from c3sc_b200 import capi, configs, synthetic
+    L = capi.lib()
+    out = {}
+    for name, F in (("skidding5d", 16384), ("dubinscar_new", 16384), ("double_int", 8192), ("lqg2d_new", 8192)):
+        cfg = configs.get_config(name)
+        prob = capi.Problem(cfg, arith=args.arith)
+        ranks = cfg.ranks()
+        vf = capi.ValueF(cfg.ngrid, ranks, synthetic.random_cores(cfg.ngrid, ranks))
+        dv, fi = synthetic.random_fibers(cfg.ngrid, F)
+        dv_h = torch.from_numpy(np.ascontiguousarray(dv)).pin_memory(); fi_h = torch.from_numpy(np.ascontiguousarray(fi)).pin_memory()
+        dv_d = dv_h.to(dev); fi_d = fi_h.to(dev)
+        N = cfg.n
+        o = torch.empty(F * N, dtype=torch.float64, device=dev)
+        oh = torch.empty(F * N, dtype=torch.float64).pin_memory()
+        st = torch.cuda.current_stream(dev).cuda_stream
+        ms = timed(lambda: prob.vi_batch_dev(vf, F, dv_d.data_ptr(), fi_d.data_ptr(), N, o.data_ptr(), stream=st), 5, 2) / 5
+        t0 = time.perf_counter()
+        for _ in range(3):
+            capi.check(L.c3sc_vi_batch(prob.handle, vf.handle, F, dv_h.data_ptr(), fi_h.data_ptr(), N, oh.data_ptr(), None))
+        ms_h = (time.perf_counter() - t0) / 3 * 1e3
+        out[name] = {"d": cfg.dx, "nodes_per_dim": N, "rank": int(max(ranks)), "n_controls": cfg.nu, "fibers": F,
+                     "node_backups_per_s": F * N / (ms * 1e-3), "ms_per_step": ms,
+                     "e2e_node_backups_per_s": F * N / (ms_h * 1e-3), "contract_flops_per_node": contract_flops_per_node(cfg, int(max(ranks)))}
+        prob.close(); vf.close()
+    return out
+
+
+def parity_check(cfg, rank_ft, prob, vf, dv, fi, out_d, N):
+    """64 fibers of the TIMED batch's output (as left in the device buffer by the last step) against the oracle port"""
+    from c3sc_b200 import synthetic
+    from oracle import pyoracle as po
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from helpers import host_problem
+    if not os.path.exists(po.PORT_PATH):
+        po.build_port()
+    ranks = cfg.ranks(rank_ft)
+    ft = po.FT(cfg.ngrid, ranks, synthetic.random_cores(cfg.ngrid, ranks))
+    xg, h, hmin, h2, t, olb, oub = host_problem(cfg)
+    port = po.Port(cfg, xg, h2, t, olb, oub)
+    F = len(dv)
+    sel = np.unique(np.linspace(0, F - 1, 64).astype(np.int64))
+    got = out_d.cpu().numpy().reshape(F, N)[sel]
+    val2, arg = prob.vi_batch(vf, dv[sel], fi[sel])          # the same fibers as a small batch: argmin for the check
+    oval, oarg = port.vi_batch(ft, dv[sel], fi[sel])
+    worst = 0.0
+    for q, f in enumerate(sel):
+        _, costs = port.neighbor_costs(ft, dv[f], fi[f])
+        sc = np.maximum(np.abs(oval[q, :N]), np.abs(costs).max(axis=1))
+        worst = max(worst, float((np.abs(got[q] - oval[q, :N]) / np.where(sc == 0, 1.0, sc)).max()))
+    return {"fibers_checked": int(sel.size), "against": "oracle port (oracle/c3sc_oracle.c) on the same inputs",
+            "max_rel": worst, "max_rel_scale": "per element: max(|oracle value|, largest |neighbour value| of that node)",
+            "max_rel_batch_scale": float(np.abs(got - oval[:, :N]).max() / np.abs(oval).max()),
+            "argmin_agree": float((arg == oarg).mean()), "timed_output_equals_small_batch": bool(np.array_equal(got, val2[:, :N])),
+            "ok": bool(worst <= 1e-12)}
+
 
 
 def cpu_baseline(cfg, rank_ft, budget_s):

@@ -70,7 +70,7 @@ EXPORTS = [
     "c3sc_multi_create", "c3sc_multi_destroy", "c3sc_multi_device_count", "c3sc_multi_uses_nccl", "c3sc_multi_problem",
     "c3sc_multi_valuef_create", "c3sc_multi_valuef_update", "c3sc_multi_valuef_destroy", "c3sc_multi_valuef_get", "c3sc_multi_shard",
     "c3sc_multi_vi_batch", "c3sc_multi_pi_batch", "c3sc_multi_pi_reset", "c3sc_multi_gathered_count", "c3sc_multi_vi_batch_gathered",
-    "c3sc_cross_run_vi_multi", "c3sc_cross_run_pi_multi", "c3sc_host_alloc", "c3sc_host_free",
+    "c3sc_cross_run_vi_multi", "c3sc_cross_run_pi_multi", "c3sc_host_alloc", "c3sc_host_free", "c3sc_vi_batch_peers",
 ]
 
 _lib = None
@@ -103,6 +103,7 @@ def lib() -> C.CDLL:
         L.c3sc_vi_batch_dev.argtypes = [vp, vp, sz, vp, vp, sz, C.POINTER(BatchOut), vp]
         L.c3sc_pi_batch_dev.argtypes = [vp, vp, vp, sz, vp, vp, sz, i32, vp, vp, vp, vp]
         L.c3sc_vi_batch.argtypes = [vp, vp, sz, vp, vp, sz, vp, vp]
+        L.c3sc_vi_batch_peers.argtypes = [vp, vp, sz, vp, vp, sz, vp, vp, C.POINTER(BatchOut)]
         L.c3sc_vi_batch_debug.argtypes = [vp, vp, sz, vp, vp, sz, vp, vp, vp, vp, vp, vp, vp]
         L.c3sc_fibers_check.argtypes = [vp, sz, vp, vp]
         L.c3sc_stage1_batch_dev.argtypes = [vp, vp, sz, vp, vp, sz, vp]

@@ -946,8 +946,27 @@ int c3sc_vi_batch_debug(c3sc_problem *p, const c3sc_valuef *vf, size_t F, const 
     return finish(p);
 }
 
+static int vi_batch_host(c3sc_problem *p, const c3sc_valuef *vf, size_t F, const int32_t *dim_vary, const int32_t *fixed_ind,
+                         size_t ldo, double *value, int32_t *argmin, const c3sc_batch_out *peers);
+
 int c3sc_vi_batch(c3sc_problem *p, const c3sc_valuef *vf, size_t F, const int32_t *dim_vary,
                   const int32_t *fixed_ind, size_t ldo, double *value, int32_t *argmin)
+{
+    return vi_batch_host(p, vf, F, dim_vary, fixed_ind, ldo, value, argmin, nullptr);
+}
+
+/* c3sc_vi_batch of one rank's block of a sharded batch: host descriptors in, host values out, AND the values gathered
+ * into every rank's peer-mapped device buffer (peers->value_peers / n_peers / peer_offset / peer_mode; the other
+ * fields of *peers are ignored).  The caller orders completion across ranks before reading the gathered buffers. */
+int c3sc_vi_batch_peers(c3sc_problem *p, const c3sc_valuef *vf, size_t F, const int32_t *dim_vary,
+                        const int32_t *fixed_ind, size_t ldo, double *value, int32_t *argmin, const c3sc_batch_out *peers)
+{
+    if (!peers || peers->n_peers == 0 || peers->n_peers > C3SC_MAXPEERS) return fail(C3SC_EINVAL, "no peers given");
+    return vi_batch_host(p, vf, F, dim_vary, fixed_ind, ldo, value, argmin, peers);
+}
+
+static int vi_batch_host(c3sc_problem *p, const c3sc_valuef *vf, size_t F, const int32_t *dim_vary, const int32_t *fixed_ind,
+                         size_t ldo, double *value, int32_t *argmin, const c3sc_batch_out *peers)
 {
     DeviceScope ds_(p ? p->device : c3sc_cur_dev());
     int rc = check_shapes(p, vf, F, ldo);
@@ -985,6 +1004,13 @@ int c3sc_vi_batch(c3sc_problem *p, const c3sc_valuef *vf, size_t F, const int32_
     b.mode = MODE_VI;
     if (mapped) { b.value_peers[0] = mapped; b.n_peers = 1; b.peer_offset = 0; }
     b.copy_stream = p->copy_stream; b.chunk_done = p->chunk_done; b.h_value = mapped ? nullptr : value; b.h_argmin = argmin;
+    if (peers && !mapped) {
+        b.n_peers = (int)peers->n_peers;
+        for (uint32_t g = 0; g < peers->n_peers; g++) b.value_peers[g] = peers->value_peers[g];
+        b.peer_offset = (size_t)peers->peer_offset;
+        b.peer_copy = peers->peer_mode == 1;
+        b.copies_done = p->copies_done;
+    }
     rc = run_batch(p->P, p->model, p->arith, p->scr, &p->grp, vf->ft, b, p->stream);
     if (rc) return rc;
     CK(cudaStreamSynchronize(p->copy_stream));

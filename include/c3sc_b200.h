@@ -218,6 +218,12 @@ int c3sc_pi_batch_dev(c3sc_problem *p, const c3sc_valuef *vf_policy, const c3sc_
 int c3sc_vi_batch(c3sc_problem *p, const c3sc_valuef *vf, size_t F,
                   const int32_t *dim_vary, const int32_t *fixed_ind,
                   size_t ldo, double *value, int32_t *argmin);
+/* One rank's block of a SHARDED batch (one process per GPU): as c3sc_vi_batch, and the values are also gathered into
+ * every rank's peer-mapped device buffer -- peers->value_peers / n_peers / peer_offset / peer_mode as in
+ * c3sc_batch_out, its other fields ignored.  The caller orders completion across ranks (a barrier) before reading. */
+int c3sc_vi_batch_peers(c3sc_problem *p, const c3sc_valuef *vf, size_t F,
+                        const int32_t *dim_vary, const int32_t *fixed_ind,
+                        size_t ldo, double *value, int32_t *argmin, const c3sc_batch_out *peers);
 /* Host-side debugging / parity variant that returns every intermediate.    */
 int c3sc_vi_batch_debug(c3sc_problem *p, const c3sc_valuef *vf, size_t F,
                         const int32_t *dim_vary, const int32_t *fixed_ind, size_t ldo,
