@@ -477,6 +477,7 @@ def main():
         if extra % 8 == 0:
             torch.cuda.synchronize(dev)
     torch.cuda.synchronize(dev)
+    timed_out = out_d.clone() if world == 1 else None       # what the timed steps left behind (later sections reuse out_d)
     clocks = sampler.stop()
     clocks["samples_in_timed_region"] = in_region
     clocks["untimed_steps_of_the_same_load_while_sampling"] = extra
@@ -614,7 +615,7 @@ def main():
 
     if rank == 0 and not args.no_cpu_baseline and world == 1:
         line["cpu_baseline"] = cpu_baseline(cfg, rank_ft, args.cpu_seconds)
-        line["parity_check"] = parity_check(cfg, rank_ft, prob, vf, dv_s, fi_s, out_d, N)
+        line["parity_check"] = parity_check(cfg, rank_ft, prob, vf, dv_s, fi_s, timed_out, N)
     if rank == 0:
         print(json.dumps(line))
     if world > 1:

@@ -197,6 +197,7 @@ struct c3sc_problem {
     int *d_err = nullptr;
     cudaStream_t stream = nullptr;           // host-buffer entry points run here
     cudaStream_t copy_stream = nullptr;      // device->host copies of finished chunks
+    cudaStream_t peer_stream = nullptr;      // bulk copies of finished chunks into the peers' gathered buffers
     cudaEvent_t chunk_done = nullptr, copies_done = nullptr;
     DevBuf b_dv, b_fi, b_val, b_arg, b_abs, b_costs, b_rows, b_nv, b_nf, b_misc[8];
     c3sc_valuef *vf_flags = nullptr;         // rank-1 zero train for the flags-only entry (c3sc_fiber_flags_batch)
@@ -369,6 +370,7 @@ int c3sc_problem_create(const c3sc_problem_desc *d, c3sc_problem **out)
     CKP(cudaMemcpy(p->d_err, k_err_clear, sizeof k_err_clear, cudaMemcpyHostToDevice));
     CKP(cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking));
     CKP(cudaStreamCreateWithFlags(&p->copy_stream, cudaStreamNonBlocking));
+    CKP(cudaStreamCreateWithFlags(&p->peer_stream, cudaStreamNonBlocking));
     CKP(cudaEventCreateWithFlags(&p->chunk_done, cudaEventDisableTiming));
     CKP(cudaEventCreateWithFlags(&p->copies_done, cudaEventDisableTiming));
     P.xgrid = p->d_xgrid; P.obs = p->d_obs; P.utab = p->d_utab; P.err = p->d_err;
@@ -446,6 +448,7 @@ void c3sc_problem_destroy(c3sc_problem *p)
     if (p->vf_flags) c3sc_valuef_destroy(p->vf_flags);
     if (p->stream) cudaStreamDestroy(p->stream);
     if (p->copy_stream) cudaStreamDestroy(p->copy_stream);
+    if (p->peer_stream) cudaStreamDestroy(p->peer_stream);
     if (p->chunk_done) cudaEventDestroy(p->chunk_done);
     if (p->copies_done) cudaEventDestroy(p->copies_done);
     delete p;
@@ -579,7 +582,8 @@ struct BatchArgs {
     double *value_peers[C3SC_MAXPEERS];
     int n_peers;
     size_t peer_offset;
-    int peer_copy;                        // 1: one bulk copy per chunk and peer on copy_stream (copy engines) instead of stores from the kernel
+    int peer_copy;                        // 1: one bulk copy per chunk and peer on peer_stream (copy engines) instead of stores from the kernel
+    cudaStream_t peer_stream;
     cudaEvent_t copies_done;
 };
 
@@ -750,14 +754,18 @@ static int run_batch(const DevProblem &P, int model, int arith, Scratch &scr, co
         if (rc == -1) return fail(C3SC_EUNSUPPORTED, "model %d with dx=%d is not instantiated", model, P.dx);
         if (rc != 0) return fail(C3SC_ECUDA, "control kernel launch: %s", cudaGetErrorString((cudaError_t)rc));
         g_launches++;
-        if (b.copy_stream && b.chunk_done) {
+        if ((b.copy_stream || b.peer_copy) && b.chunk_done) {
             CK(cudaEventRecord(b.chunk_done, st));
-            CK(cudaStreamWaitEvent(b.copy_stream, b.chunk_done, 0));
-            if (b.peer_copy && c.value)                     // the chunk's values into every peer's gathered buffer, off the SMs
+            if (b.peer_copy && c.value && b.peer_stream) {  // the chunk's values into every peer's gathered buffer, off the SMs
+                CK(cudaStreamWaitEvent(b.peer_stream, b.chunk_done, 0));
                 for (int g = 0; g < b.n_peers; g++) {
                     double *dst = b.value_peers[g] + b.peer_offset + n0;
-                    if (dst != c.value) CK(cudaMemcpyAsync(dst, c.value, Fc * b.ldo * 8, cudaMemcpyDefault, b.copy_stream));
+                    if (dst != c.value) CK(cudaMemcpyAsync(dst, c.value, Fc * b.ldo * 8, cudaMemcpyDefault, b.peer_stream));
                 }
+            }
+        }
+        if (b.copy_stream && b.chunk_done && (b.h_value || b.h_argmin)) {
+            CK(cudaStreamWaitEvent(b.copy_stream, b.chunk_done, 0));
             if (b.h_value && c.value) CK(cudaMemcpyAsync(b.h_value + n0, c.value, Fc * b.ldo * 8, cudaMemcpyDeviceToHost, b.copy_stream));
             if (b.h_argmin && c.argmin) CK(cudaMemcpyAsync(b.h_argmin + n0, c.argmin, Fc * b.ldo * 4, cudaMemcpyDeviceToHost, b.copy_stream));
         }
@@ -767,8 +775,8 @@ static int run_batch(const DevProblem &P, int model, int arith, Scratch &scr, co
         CK(cudaEventRecord(scr.lane[l].join, scr.lane[l].stream));
         CK(cudaStreamWaitEvent(st0, scr.lane[l].join, 0));
     }
-    if (b.peer_copy && b.copy_stream && b.copies_done) {    // ... and after the last peer copy
-        CK(cudaEventRecord(b.copies_done, b.copy_stream));
+    if (b.peer_copy && b.peer_stream && b.copies_done) {    // ... and after the last peer copy
+        CK(cudaEventRecord(b.copies_done, b.peer_stream));
         CK(cudaStreamWaitEvent(st0, b.copies_done, 0));
     }
     return C3SC_OK;
@@ -817,8 +825,7 @@ int c3sc_vi_batch_dev(c3sc_problem *p, const c3sc_valuef *vf, size_t F, const in
     if (out->n_peers && out->peer_mode == 1) {
         if (!out->value) return fail(C3SC_EINVAL, "peer_mode 1 (bulk copies) needs the local value buffer");
         b.peer_copy = 1;
-        b.copy_stream = p->copy_stream; b.chunk_done = p->chunk_done; b.copies_done = p->copies_done;
-        // the copy stream must not run ahead of work queued earlier on the caller's stream that still reads the peers' buffers
+        b.peer_stream = p->peer_stream; b.chunk_done = p->chunk_done; b.copies_done = p->copies_done;
     }
     return run_batch(p->P, p->model, p->arith, p->scr, &p->grp, vf->ft, b, (cudaStream_t)stream);
 }
@@ -1009,7 +1016,7 @@ static int vi_batch_host(c3sc_problem *p, const c3sc_valuef *vf, size_t F, const
         for (uint32_t g = 0; g < peers->n_peers; g++) b.value_peers[g] = peers->value_peers[g];
         b.peer_offset = (size_t)peers->peer_offset;
         b.peer_copy = peers->peer_mode == 1;
-        b.copies_done = p->copies_done;
+        b.peer_stream = p->peer_stream; b.copies_done = p->copies_done;
     }
     rc = run_batch(p->P, p->model, p->arith, p->scr, &p->grp, vf->ft, b, p->stream);
     if (rc) return rc;

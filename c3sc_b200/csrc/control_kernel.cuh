@@ -760,14 +760,28 @@ __global__ void __launch_bounds__(CT_NT, grid_minb(ARG)) k_control_grid(const Ct
     }
 }
 
-// policy evaluation (bellman.c:1774-1828,1863-1871): stored rows against the new neighbour values
+// policy evaluation (bellman.c:1774-1828,1863-1871): stored rows against the new neighbour values.
+// The rows are node-major records of 2dx+3 doubles (the reference's layout): a CTA stages the records of PE_NT
+// consecutive nodes in shared memory with coalesced loads (one thread reading its own 184-byte record touches a
+// sector per load and thrashes L1) and every thread then takes its node's record from there (odd stride: no bank
+// conflicts).
+constexpr int PE_NT = 128;
 template <class M, class A>
-__global__ void __launch_bounds__(CT_NT) k_pi_eval(const CtlArgs c)
+__global__ void __launch_bounds__(PE_NT) k_pi_eval(const CtlArgs c)
 {
     constexpr int DX = M::DX, CS = 2 * DX + 1, RW = 2 * DX + 3;
+    __shared__ double srow[PE_NT * RW];
     const DevProblem &P = c.P;
-    const long long stride = (long long)gridDim.x * CT_NT;
-    for (long long id = (long long)blockIdx.x * CT_NT + threadIdx.x; id < c.NS; id += stride) {
+    const int tid = threadIdx.x;
+    for (long long base = (long long)blockIdx.x * PE_NT; base < c.NS; base += (long long)gridDim.x * PE_NT) {
+        const long long left = c.NS - base;
+        const int cnt = left < PE_NT ? (int)left : PE_NT;
+        const double *src = c.rows_in + (size_t)base * RW;
+        __syncthreads();
+        for (int e = tid; e < cnt * RW; e += PE_NT) srow[e] = src[e];
+        __syncthreads();
+        const long long id = base + tid;
+        if (tid >= cnt) continue;
         const int ab = c.flag[id];
         double v;
         if (ab == 2) v = 0.0;                               // padding entry: defined content
@@ -776,7 +790,7 @@ __global__ void __launch_bounds__(CT_NT) k_pi_eval(const CtlArgs c)
             node_state<DX>(c, (int)id, x);
             v = (ab == 1) ? M::boundcost(x, P.mp) : M::obscost(x, P.mp);
         } else {
-            const double *row = c.rows_in + (size_t)id * RW;
+            const double *row = srow + tid * RW;
             double prob[CS], cc[CS];
             load_costs<DX>(c, (int)id, cc);
 #pragma unroll
@@ -841,10 +855,10 @@ int launch_control_t(const CtlArgs &c_in, int pi_eval, cudaStream_t st)
     const CtlLaunchInfo &info = ctl_info();
     CtlArgs c = c_in;
     if (pi_eval) {
-        long long g = (c.NS + CT_NT - 1) / CT_NT;
-        if (g > (long long)info.sms * 16) g = (long long)info.sms * 16;
+        long long g = (c.NS + PE_NT - 1) / PE_NT;
+        if (g > (long long)info.sms * 8) g = (long long)info.sms * 8;
         if (g < 1) return 0;
-        k_pi_eval<M, A><<<(int)g, CT_NT, 0, st>>>(c);
+        k_pi_eval<M, A><<<(int)g, PE_NT, 0, st>>>(c);
         return (int)cudaGetLastError();
     }
     constexpr bool TAB = M::SEP && !A::exact;
