@@ -20,7 +20,13 @@ int launch_group_fibers(const DevProblem &P, int F, int FC, const int *dim_vary,
 int launch_pack_cores(const DevFT &ft, double *baseT, double *baseP, double *baseQ, cudaStream_t st);
 long long ft_padded_layout(DevFT &ft);
 long long ft_compact_layout(DevFT &ft);
-int launch_ft_costs(const FtArgs &a, cudaStream_t st);
+int launch_ft_costs(const FtArgs &a, const CtlArgs *fused, cudaStream_t st);
+int ft_nodes_nsplit(const FtArgs &a);
+long long ft_region_doubles(const DevProblem &P);
+int ft_ring_regions();
+int fused_ok_lqg_lo(int dx, int arith, const CtlArgs &c, int pi_eval);
+int fused_ok_lqg_hi(int dx, int arith, const CtlArgs &c, int pi_eval);
+int fused_ok_misc(int model, int dx, int arith, const CtlArgs &c, int pi_eval);
 int ft_uses_mma(const DevFT &ft);
 int launch_ft_eval_points(const DevProblem &P, const DevFT &ft, int npts, const double *pts, double *out, cudaStream_t st);
 int launch_policy_points(const DevProblem &P, int n, const double *x, double *pts, int *absorbed, cudaStream_t st);
@@ -109,11 +115,14 @@ struct LaneScratch {
 };
 struct Scratch {
     DevBuf perm, cnt, plan_k, plan_t, plan_e;
+    DevBuf ring, ring_flag;                 // fused stage 2: per-CTA regions of neighbour values + their in-use flags
+    bool ring_ready = false;
     LaneScratch lane[MAXLANES];
     cudaEvent_t fork = nullptr;
     void release()
     {
-        perm.release(); cnt.release(); plan_k.release(); plan_t.release(); plan_e.release();
+        perm.release(); cnt.release(); plan_k.release(); plan_t.release(); plan_e.release(); ring.release(); ring_flag.release();
+        ring_ready = false;
         for (LaneScratch &l : lane) l.release();
         if (fork) cudaEventDestroy(fork);
         fork = nullptr;
@@ -722,10 +731,12 @@ static int run_batch(const DevProblem &P, int model, int arith, Scratch &scr, co
         a.sets = mma ? (double *)bsets.p + (c0 - s0) * (size_t)setw : nullptr;
         a.setw = setw; a.rs = rs; a.chains_done = bucketed ? 1 : 0;
         a.task_count = cnt + 33;
-        rc = launch_ft_costs(a, st);
-        if (rc) return fail(C3SC_ECUDA, "FT kernel launch: %s", cudaGetErrorString((cudaError_t)rc));
-        g_launches += 1 + (mma && !bucketed);
-        if (b.mode == MODE_COSTS || b.mode == MODE_STAGE1) continue;
+        if (b.mode == MODE_COSTS || b.mode == MODE_STAGE1) {
+            rc = launch_ft_costs(a, nullptr, st);
+            if (rc) return fail(C3SC_ECUDA, "FT kernel launch: %s", cudaGetErrorString((cudaError_t)rc));
+            g_launches += 1 + (mma && !bucketed);
+            continue;
+        }
         CtlArgs c;
         memset(&c, 0, sizeof c);
         c.P = P; c.F = (int)Fc; c.dim_vary = a.dim_vary; c.fixed_ind = a.fixed_ind; c.ldo = (int)b.ldo; c.NS = a.NS;
@@ -748,12 +759,39 @@ static int run_batch(const DevProblem &P, int model, int arith, Scratch &scr, co
             memcpy(c.gA, grp->gA, sizeof c.gA);
         }
         const int pe_ = b.mode == MODE_PI_EVAL;
-        if (model == C3SC_MODEL_LQGND) rc = (P.dx <= 6) ? launch_control_lqg_lo(P.dx, arith, c, pe_, st)
+        // Fused stage 2: the node kernel walks the control set of its own fibers from a per-CTA region of neighbour values
+        // (no batch-sized scratch through HBM, no second launch) when the model's walk has a fused form, the node kernel
+        // owns whole fibers (large batches) and no node-major cost output is wanted.
+        bool fuse = mma && !a.costs && !getenv("C3SC_NO_FUSE") && ft_nodes_nsplit(a) == 1;
+        if (fuse) {
+            const int fam = model == C3SC_MODEL_LQGND ? (P.dx <= 6 ? 0 : 1) : 2;
+            fuse = fam == 0 ? fused_ok_lqg_lo(P.dx, arith, c, pe_) : (fam == 1 ? fused_ok_lqg_hi(P.dx, arith, c, pe_) : fused_ok_misc(model, P.dx, arith, c, pe_));
+            if (fuse) {
+                const int nring = ft_ring_regions();
+                const long long rd = ft_region_doubles(P);
+                if (scr.ring.cap < (size_t)nring * rd * 8 || !scr.ring_ready) {
+                    CK(cudaStreamSynchronize(st0));                 // (re)allocation: nothing of this problem may be in flight
+                    for (size_t l = 1; l < L; l++) CK(cudaStreamSynchronize(scr.lane[l].stream));
+                    if (scr.ring.reserve((size_t)nring * rd * 8) || scr.ring_flag.reserve((size_t)(nring + 1) * 4))
+                        return fail(C3SC_ECUDA, "cudaMalloc of the fused stage-2 ring failed");
+                    CK(cudaMemset(scr.ring_flag.p, 0, (size_t)(nring + 1) * 4));
+                    scr.ring_ready = true;
+                }
+                a.fused = 1; a.family = fam; a.model = model; a.fuse_pi = pe_; a.fuse_arg = (c.argmin || c.rows) ? 1 : 0;
+                a.ring = (double *)scr.ring.p; a.ring_flag = (int *)scr.ring_flag.p; a.nring = nring; a.region_doubles = rd;
+                a.cst = nullptr; a.flag = nullptr; a.act = nullptr;
+            }
+        }
+        rc = launch_ft_costs(a, fuse ? &c : nullptr, st);
+        if (rc) return fail(C3SC_ECUDA, "FT kernel launch: %s", cudaGetErrorString((cudaError_t)rc));
+        g_launches += 1 + (mma && !bucketed);
+        if (fuse) rc = 0;
+        else if (model == C3SC_MODEL_LQGND) rc = (P.dx <= 6) ? launch_control_lqg_lo(P.dx, arith, c, pe_, st)
                                                         : launch_control_lqg_hi(P.dx, arith, c, pe_, st);
         else rc = launch_control_misc(model, P.dx, arith, c, pe_, st);
         if (rc == -1) return fail(C3SC_EUNSUPPORTED, "model %d with dx=%d is not instantiated", model, P.dx);
         if (rc != 0) return fail(C3SC_ECUDA, "control kernel launch: %s", cudaGetErrorString((cudaError_t)rc));
-        g_launches++;
+        if (!fuse) g_launches++;
         if ((b.copy_stream || b.peer_copy) && b.chunk_done) {
             CK(cudaEventRecord(b.chunk_done, st));
             if (b.peer_copy && c.value && b.peer_stream) {  // the chunk's values into every peer's gathered buffer, off the SMs

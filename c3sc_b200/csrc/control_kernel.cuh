@@ -12,46 +12,11 @@
 #include <cuda_runtime.h>
 #include <math_constants.h>
 #include "dev_types.h"
+#include "ctl_types.cuh"
 #include "arith.cuh"
 #include "models.cuh"
 
 namespace c3sc {
-
-constexpr int CT_NT = 256;
-constexpr int CT_NUDMAX = 6;       // control dimensions of a grid-structured table (3^6 = 729 candidates)
-constexpr int CT_NGMAX = 32;       // candidate groups (distinct normaliser shares) handled by the grouped walk
-
-struct CtlArgs {
-    DevProblem P;
-    int F;                    // fibers of this chunk
-    const int *dim_vary;      // [F]
-    const int *fixed_ind;     // [F*dx]
-    int ldo;
-    long long NS;             // F*ldo
-    const double *cst;        // [(2dx+1)*NS] slot-major neighbour values
-    const signed char *flag;  // [NS]
-    const int *act;           // [NS] non-absorbed node ids
-    const int *act_count;
-    int parts_log2;           // candidate chunks per node = 1 << parts_log2 (<= 32)
-    // separable models, FAST: candidates regrouped by their share of the normaliser (DevProblem::gtab)
-    int ng;                   // number of groups, 0 = plain table walk
-    int gstart[CT_NGMAX + 1]; // first grouped position of every group
-    double gA[CT_NGMAX];      // the group's normaliser share
-    // ... and, when the control table is a full {lo, 0, hi}^NUD grid in C order (last control fastest), its
-    // per-control description for the shared-prefix walk (k_control_grid): candidate (k_0..k_{NUD-1}) adds
-    // gWlo[m]*cost_left(ud m) if k_m = 0, nothing if k_m = 1, gWhi[m]*cost_right if k_m = 2; its normaliser
-    // share and h2*stage_u depend on the number of non-zero controls only (gAg, gHg).
-    int grid_on;
-    double gWlo[CT_NUDMAX], gWhi[CT_NUDMAX], gAg[CT_NUDMAX + 1], gHg[CT_NUDMAX + 1];
-    double *value;            // outputs, any may be NULL
-    int *argmin;
-    double *rows;
-    const double *rows_in;    // k_pi_eval
-    // fused all-gather: values also go to every peer's gathered buffer (peer-mapped memory over NVLink)
-    double *vpeer[C3SC_MAXPEERS];
-    int npeer;
-    long long peer_off;       // element offset of this chunk inside a gathered buffer
-};
 
 // backed-up value of node `id`: the local output and, when the all-gather is fused, every rank's copy
 __device__ __forceinline__ void store_value(const CtlArgs &c, long long id, double v)
@@ -467,13 +432,23 @@ struct Node2 {
     int ibest;
 };
 template <class M>
+__device__ __forceinline__ void node2_from(const CtlArgs &c, const double *x, const double *cc, Node2<M> &n);
+template <class M>
 __device__ __forceinline__ void node2_prepare(const CtlArgs &c, int id, Node2<M> &n)
+{
+    constexpr int DX = M::DX;
+    double x[DX], cc[2 * DX + 1];
+    node_state<DX>(c, id, x);
+    load_costs<DX>(c, id, cc);
+    node2_from<M>(c, x, cc, n);
+}
+// per-node invariants of the separable FAST walk from the node's state and its 2dx+1 neighbour values
+template <class M>
+__device__ __forceinline__ void node2_from(const CtlArgs &c, const double *x, const double *cc, Node2<M> &n)
 {
     constexpr int DX = M::DX, DU = M::DU, NUD = M::NUD;
     const DevProblem &P = c.P;
-    double x[DX], u0[DU], b0[DX], s0[DX], cc[2 * DX + 1];
-    node_state<DX>(c, id, x);
-    load_costs<DX>(c, id, cc);
+    double u0[DU], b0[DX], s0[DX];
 #pragma unroll
     for (int i = 0; i < DU; i++) u0[i] = P.utab[i];
     M::template drift<Fast>(x, u0, P.mp, b0);
@@ -758,6 +733,120 @@ __global__ void __launch_bounds__(CT_NT, grid_minb(ARG)) k_control_grid(const Ct
             for (int m = 0; m < RW; m++) row[m] = 0.0;
         }
     }
+}
+
+// ---------------------------------------------------------------------------
+// FUSED stage 2: the node kernel of stage 1 (ft_mma_kernel.cuh) leaves the neighbour values of ITS OWN fibers in a
+// small per-CTA region (slot-major, written minutes of nanoseconds ago: L2-hot) and calls this walk before it exits --
+// no batch-sized cost scratch through HBM, no second launch.  The call crosses translation units (the node kernel is
+// compiled per rank geometry, the walk per dynamics model): relocatable device code, one dispatcher per model family.
+
+template <class M, bool ARG>
+__device__ void fused_walk_t(const CtlArgs &c, const FusedCta &w)
+{
+    constexpr int DX = M::DX, DU = M::DU, CS = 2 * DX + 1, RW = 2 * DX + 3;
+    constexpr int NUD = M::NUD > 0 ? M::NUD : 1, NG = NUD + 1;
+    const DevProblem &P = c.P;
+    const int nj = w.je - w.jb, total = w.nf * nj, N = P.ngrid[w.k], bk = P.bc[w.k];
+    const double nbh = -P.beta * P.h2;
+    const bool disc = P.beta != 0.0;
+    for (int q = threadIdx.x; q < total; q += blockDim.x) {
+        const int g = q / nj, jj = q - g * nj, j = w.jb + jj;
+        const int ab = w.sAbs[g * w.nmax + j];
+        const long long id = (long long)w.sFid[g] * c.ldo + j;
+        if (ab != 0) {                                      // absorbed (bellman.c:513-532): boundary / obstacle cost, u = 0
+            double x[DX];
+            node_state<DX>(c, (int)id, x);
+            store_value(c, id, (ab == 1) ? M::boundcost(x, P.mp) : M::obscost(x, P.mp));
+            if (c.argmin) c.argmin[id] = -1;
+            if (c.rows) { double *row = c.rows + (size_t)id * RW; for (int m = 0; m < RW; m++) row[m] = 0.0; }
+            continue;
+        }
+        double cc[CS];
+        {
+            int lo, hi;
+            ft_vary_pair(bk, N, j, 0, lo, hi);
+            const double *base = w.reg + g * w.njp + jj, *self = w.reg + (size_t)(2 * DX) * w.RN + g * w.njp;
+#pragma unroll
+            for (int i = 0; i < DX; i++) {
+                cc[2 * i] = __ldcg(i == w.k ? self + (lo - w.jb) : base + (size_t)(2 * i) * w.RN);     // L2, not this SM's L1: the
+                cc[2 * i + 1] = __ldcg(i == w.k ? self + (hi - w.jb) : base + (size_t)(2 * i + 1) * w.RN);   // region is recycled
+            }
+            cc[2 * DX] = __ldcg(self + jj);
+        }
+        if (w.pi_eval) {                                    // bellman.c:1863-1871: the stored row against the new values
+            const double *row = c.rows_in + (size_t)id * RW;
+            double prob[CS];
+#pragma unroll
+            for (int m = 0; m < CS; m++) prob[m] = row[m];
+            store_value(c, id, rhs<DX, Fast>(P, prob, row[CS], row[CS + 1], cc));
+            continue;
+        }
+        if constexpr (M::SEP && M::NUD >= 1 && M::NUD <= CT_NUDMAX) {
+            double x[DX];
+            node_state<DX>(c, (int)id, x);
+            Node2<M> nd;
+            node2_from<M>(c, x, cc, nd);
+            if (nd.norm0 + P.amin < 1e-14) atomicOr(P.err, 1);
+            const bool tiny = P.beta * P.h2 <= 0.00390625 * (nd.norm0 + P.amin);
+            double Tl[NUD], Th[NUD], mn[NG];
+            int am[NG];
+#pragma unroll
+            for (int m = 0; m < NUD; m++) { Tl[m] = c.gWlo[m] * nd.cu[2 * m]; Th[m] = c.gWhi[m] * nd.cu[2 * m + 1]; }
+#pragma unroll
+            for (int gq = 0; gq < NG; gq++) { mn[gq] = CUDART_INF; am[gq] = 0x7fffffff; }
+            GridWalk<NUD, 0, 0, 0, ARG>::go(nd.S0, Tl, Th, mn, am);
+#pragma unroll
+            for (int gq = 0; gq < NG; gq++) {
+                const double rinv = rcp_pos(nd.norm0 + c.gAg[gq]);
+                const double ebt = !disc ? 1.0 : (tiny ? exp_tiny(nbh * rinv) : exp_nonpos(nbh * rinv));
+                const double v = rinv * (fma(ebt, mn[gq], c.gHg[gq]) + nd.hgx);
+                if (v < nd.best || (ARG && v == nd.best && am[gq] < nd.ibest)) { nd.best = v; nd.ibest = am[gq]; }
+            }
+            store_value(c, id, nd.best);
+            if constexpr (ARG) {
+                const int ibest = nd.ibest;
+                if (c.argmin) c.argmin[id] = ibest;
+                if (c.rows) {                               // policy row at u* (bellman.c:1851-1860)
+                    double u[DU], b[DX], sg[DX], prob[CS], dt;
+#pragma unroll
+                    for (int i = 0; i < DU; i++) u[i] = P.utab[(size_t)(ibest < P.nu ? ibest : 0) * DU + i];
+                    M::template drift<Fast>(x, u, P.mp, b);
+                    M::template sigma<Fast>(x, u, P.mp, sg);
+                    const double gs = M::template stage<Fast>(x, u, P.mp);
+                    if (transition_row<DX, Fast>(P, b, sg, prob, dt)) atomicOr(P.err, 1);
+                    double *row = c.rows + (size_t)id * RW;
+#pragma unroll
+                    for (int m = 0; m < CS; m++) row[m] = prob[m];
+                    row[CS] = dt;
+                    row[CS + 1] = gs;
+                }
+            }
+        }
+    }
+    // padding entries j >= ngrid[k] of ragged grids: defined content
+    const int pad = c.ldo - N;
+    if (pad > 0 && w.jb == 0)
+        for (int q = threadIdx.x; q < w.nf * pad; q += blockDim.x) {
+            const int g = q / pad;
+            const long long id = (long long)w.sFid[g] * c.ldo + N + (q - g * pad);
+            store_value(c, id, 0.0);
+            if (c.argmin) c.argmin[id] = -1;
+            if (c.rows) { double *row = c.rows + (size_t)id * RW; for (int m = 0; m < RW; m++) row[m] = 0.0; }
+        }
+}
+template <class M>
+__device__ void fused_walk_m(const CtlArgs &c, const FusedCta &w)
+{
+    if (w.arg && !w.pi_eval) fused_walk_t<M, true>(c, w);
+    else fused_walk_t<M, false>(c, w);
+}
+// can a problem's stage 2 run fused?  (host side; the same test picks the kernel in launch_control_t)
+template <class M>
+inline bool fused_ok_m(int arith, const CtlArgs &c, int pi_eval)
+{
+    if (pi_eval) return arith == C3SC_ARITH_FAST;
+    return arith == C3SC_ARITH_FAST && M::SEP && M::NUD >= 1 && M::NUD <= CT_NUDMAX && c.grid_on && !getenv("C3SC_NO_GRID");
 }
 
 // policy evaluation (bellman.c:1774-1828,1863-1871): stored rows against the new neighbour values.

@@ -160,8 +160,24 @@ int launch_chain_steps(const ChainArgs &a, cudaStream_t st, int *n)
     }
 }
 
+// CTAs per group of the node kernel: small batches split every group over node-tile ranges until the machine is covered
+static int ft_nodes_nsplit_of(const FtArgs &a)
+{
+    ft_device_info();
+    const int grid = (a.F + FT_FBMAX - 1) / FT_FBMAX + a.ft.d;
+    int ntl = 1;
+    for (int k = 0; k < a.ft.d; k++) { const int t = (a.P.ngrid[k] + FTN_T - 1) / FTN_T; ntl = t > ntl ? t : ntl; }
+    int ns = 1;
+    while (ns < ntl && grid * ns * 2 <= 2 * g_sms) ns *= 2;      // stay within one wave of 2 CTAs/SM
+    return ns > ntl ? ntl : ns;
+}
+int ft_nodes_nsplit(const FtArgs &a) { return ft_nodes_nsplit_of(a); }
+// doubles of one region of the fused ring, and the ring size (more regions than CTAs can be resident)
+long long ft_region_doubles(const DevProblem &P) { return (long long)(2 * P.dx + 1) * FT_FBMAX * ft_even_up(P.nmax); }
+int ft_ring_regions() { ft_device_info(); return 2 * g_sms + 32; }
+
 template <int KS>
-static int launch_mma_t(const FtArgs &a, cudaStream_t st)
+static int launch_mma_t(const FtArgs &a, const CtlArgs *fused, cudaStream_t st)
 {
     // chains: one warp per (fiber, side)
     const size_t csm = FtChainPlan<KS>(a.ft).bytes();
@@ -187,26 +203,26 @@ static int launch_mma_t(const FtArgs &a, cudaStream_t st)
     // nodes: one CTA per same-k group
     const size_t smem = FtNodePlan<KS>(a.ft, a.P.nmax).bytes();
     if (smem > (size_t)g_max_optin) return (int)cudaErrorInvalidValue;
-    static size_t attr_dev[C3SC_MAXDEV] = {0};
-    size_t &attr = attr_dev[c3sc_cur_dev()];
+    static size_t attr_dev[C3SC_MAXDEV] = {0}, attrf_dev[C3SC_MAXDEV] = {0};
+    size_t &attr = fused ? attrf_dev[c3sc_cur_dev()] : attr_dev[c3sc_cur_dev()];
     if (smem > attr) {
-        e = cudaFuncSetAttribute(k_ft_nodes<KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        e = fused ? cudaFuncSetAttribute(k_ft_nodes_fused<KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
+                  : cudaFuncSetAttribute(k_ft_nodes<KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return (int)e;
         attr = smem;
     }
     const int grid = (a.F + a.FB - 1) / a.FB + a.ft.d;
     // small batches: several CTAs per group, each a range of node tiles, until the machine is covered twice
     FtArgs b = a;
-    int ntl = 1;
-    for (int k = 0; k < a.ft.d; k++) { const int t = (a.P.ngrid[k] + FTN_T - 1) / FTN_T; ntl = t > ntl ? t : ntl; }
-    b.nsplit = 1;
-    while (b.nsplit < ntl && grid * b.nsplit * 2 <= 2 * g_sms) b.nsplit *= 2;      // stay within one wave of 2 CTAs/SM
-    if (b.nsplit > ntl) b.nsplit = ntl;
-    k_ft_nodes<KS><<<dim3((unsigned)grid, (unsigned)b.nsplit), FTN_NT, smem, st>>>(b, b.sets);
+    b.nsplit = ft_nodes_nsplit_of(a);
+    if (fused) {
+        if (b.nsplit != 1) return (int)cudaErrorInvalidValue;       // the caller asked ft_nodes_nsplit first
+        k_ft_nodes_fused<KS><<<dim3((unsigned)grid, 1u), FTN_NT, smem, st>>>(b, *fused, b.sets);
+    } else k_ft_nodes<KS><<<dim3((unsigned)grid, (unsigned)b.nsplit), FTN_NT, smem, st>>>(b, b.sets);
     return (int)cudaGetLastError();
 }
 
-static int launch_ft_mma(FtArgs a, cudaStream_t st)
+static int launch_ft_mma(FtArgs a, const CtlArgs *fused, cudaStream_t st)
 {
     // group size: 8 fibers fill the DMMA tile (a tile costs the same for 1 fiber as for 8); small
     // batches cover the SMs by splitting every group over node-tile ranges instead (nsplit)
@@ -214,23 +230,23 @@ static int launch_ft_mma(FtArgs a, cudaStream_t st)
     int rmax = 1;
     for (int i = 0; i <= a.ft.d; i++) rmax = a.ft.r[i] > rmax ? a.ft.r[i] : rmax;
     switch ((rmax + 3) / 4) {                                // KS
-    case 1: return launch_mma_t<1>(a, st);
-    case 2: return launch_mma_t<2>(a, st);
-    case 3: return launch_mma_t<3>(a, st);
-    case 4: return launch_mma_t<4>(a, st);
-    case 5: return launch_mma_t<5>(a, st);
-    case 6: return launch_mma_t<6>(a, st);
-    case 7: return launch_mma_t<7>(a, st);
-    default: return launch_mma_t<8>(a, st);
+    case 1: return launch_mma_t<1>(a, fused, st);
+    case 2: return launch_mma_t<2>(a, fused, st);
+    case 3: return launch_mma_t<3>(a, fused, st);
+    case 4: return launch_mma_t<4>(a, fused, st);
+    case 5: return launch_mma_t<5>(a, fused, st);
+    case 6: return launch_mma_t<6>(a, fused, st);
+    case 7: return launch_mma_t<7>(a, fused, st);
+    default: return launch_mma_t<8>(a, fused, st);
     }
 }
 
-static int launch_ft_stage(const FtArgs &a_in, cudaStream_t st);
+static int launch_ft_stage(const FtArgs &a_in, const CtlArgs *fused, cudaStream_t st);
 
-// Stage 1 over one chunk.  a.FB == 0: pick the group size here.
-int launch_ft_costs(const FtArgs &a_in, cudaStream_t st)
+// Stage 1 over one chunk.  a.FB == 0: pick the group size here.  fused != NULL: the node kernel also runs stage 2.
+int launch_ft_costs(const FtArgs &a_in, const CtlArgs *fused, cudaStream_t st)
 {
-    int rc = launch_ft_stage(a_in, st);
+    int rc = launch_ft_stage(a_in, fused, st);
     if (rc || !a_in.costs || a_in.F <= 0) return rc;
     long long g = (a_in.NS + 255) / 256;
     if (g > 4096) g = 4096;
@@ -238,12 +254,13 @@ int launch_ft_costs(const FtArgs &a_in, cudaStream_t st)
     return (int)cudaGetLastError();
 }
 
-static int launch_ft_stage(const FtArgs &a_in, cudaStream_t st)
+static int launch_ft_stage(const FtArgs &a_in, const CtlArgs *fused, cudaStream_t st)
 {
     ft_device_info();
     FtArgs a = a_in;
     if (a.F <= 0) return 0;
-    if (a.sets && ft_uses_mma(a.ft)) return launch_ft_mma(a, st);
+    if (a.sets && ft_uses_mma(a.ft)) return launch_ft_mma(a, fused, st);
+    if (fused) return (int)cudaErrorInvalidValue;               // only the tensor-core node kernel fuses stage 2
     // two CTAs per SM when the carve-up allows it
     const size_t budget = (size_t)g_max_sm / 2 - 1024;
     if (a.FB <= 0) a.FB = ft_pick_fb(a.ft, a.P.nmax, a.F, g_sms, budget);

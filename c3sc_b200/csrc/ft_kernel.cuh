@@ -62,6 +62,15 @@ struct FtArgs {
     int chains_done;          // the records were filled by the bucketed chain steps: skip k_ft_chains
     int *task_count;          // chain kernel: next (fiber, side) task, zeroed by k_group_fibers
     int nsplit;               // k_ft_nodes: CTAs per group, each owning a contiguous range of node tiles (blockIdx.y)
+    // fused stage 2 (k_ft_nodes_fused): the CTA keeps its neighbour values in a region of a small ring and walks the control
+    // set itself before it exits
+    int fused;                // 0 = off
+    int family, model;        // dispatcher of the walk (ctl_types.cuh) and the model id it switches on
+    int fuse_pi, fuse_arg;    // policy evaluation against CtlArgs::rows_in; argmin / policy rows wanted
+    double *ring;             // [nring][region_doubles]
+    int *ring_flag;           // [nring] 0 = free; [nring] = the allocation counter
+    int nring;
+    long long region_doubles; // (2d+1) * FT_FBMAX * even(nmax)
 };
 
 __host__ __device__ inline int ft_even_up(int v) { return (v + 1) & ~1; }

@@ -19,6 +19,7 @@
 #pragma once
 #include "ft_kernel.cuh"
 #include "chain_kernel.cuh"
+#include "ctl_types.cuh"
 
 namespace c3sc {
 
@@ -343,6 +344,7 @@ struct FtNodeCtx {
     const double *sets;
     int ldo;
     bool needSelfFromU;      // k = 0: the self value comes from u . R (vector 0 of the right set)
+    int regionStride;        // > 0: costs go to the CTA's region, fiber g at g*regionStride (fused stage 2); 0: fiber id * ldo
 };
 
 // The node-tile loop with compile-time numbers of 8-wide variant tiles: ML over the left set (1 + 2k vectors, 0 when
@@ -421,7 +423,7 @@ __device__ __forceinline__ void ftn_tile_loop(const FtNodeCtx &c)
     const double *wg0 = c.sW + warp * SW + tig * FTN_TP, *ug0 = c.sU + warp * SW + tig * FTN_TP;
     const int WB = FT_FBMAX * SW;                           // one buffer of w (or u) tiles
     const int jl0 = gid ^ ftn_swz(tig), jl1 = gid ^ ftn_swz(4 + tig);
-    const size_t idf = warp < c.nf ? (size_t)c.sFid[warp] * c.ldo : 0;
+    const size_t idf = c.regionStride > 0 ? (size_t)warp * c.regionStride : (warp < c.nf ? (size_t)c.sFid[warp] * c.ldo : 0);
     const int CS = c.CS;
 
     auto fetch = [&](int j1, int buf) {                     // tid 0: tile starting at node j1 -> buffer buf
@@ -514,8 +516,8 @@ __device__ __forceinline__ void ftn_tile_loop(const FtNodeCtx &c)
     }
 }
 
-template <int KS>
-__global__ void __launch_bounds__(FTN_NT, 2) k_ft_nodes(const FtArgs a, const double *sets)
+template <int KS, bool FUSED>
+__device__ __forceinline__ void ftn_body(const FtArgs &a, const double *sets, const CtlArgs *ctl)
 {
     const DevProblem &P = a.P;
     const DevFT &ft = a.ft;
@@ -571,13 +573,30 @@ __global__ void __launch_bounds__(FTN_NT, 2) k_ft_nodes(const FtArgs a, const do
         }
     }
 
+    // fused stage 2: take a free region of the ring (more regions than CTAs can be resident, so one is always free)
+    __shared__ int s_region;
+    if constexpr (FUSED) {
+        if (tid == 0) {
+            int r;
+            for (;;) {
+                r = (int)((unsigned)atomicAdd(a.ring_flag + a.nring, 1) % (unsigned)a.nring);
+                if (atomicCAS(a.ring_flag + r, 0, 1) == 0) break;
+            }
+            s_region = r;
+        }
+    }
+
     ft_flags_and_indices(a, k, nf, gstart, jb, je, sFid, sWall, sFix, sNf, sAbs, nmax);      // ends with a barrier
 
+    const int njp = ft_even_up(nmax);
+    double *region = FUSED ? a.ring + (size_t)s_region * a.region_doubles : nullptr;
     FtNodeCtx c;
     c.sG = sG; c.sW = sW; c.sU = sU; c.mbar = mbar; c.Gp = Gp; c.sFid = sFid;
     c.GB = GB; c.SW = sp.sw; c.pblk = pblk; c.ldk = ft.ldq[k]; c.jb = jb; c.je = je; c.nf = nf;
     c.nvL = nvL; c.nvR = nvR; c.d = d; c.CS = 2 * d + 1; c.RS = a.rs; c.setw = a.setw;
     c.NS = a.NS; c.cst = a.cst; c.costs = a.costs; c.sets = sets; c.ldo = a.ldo;
+    c.regionStride = 0;
+    if constexpr (FUSED) { c.cst = region; c.NS = (long long)FT_FBMAX * njp; c.costs = nullptr; c.regionStride = njp; }
     c.needSelfFromU = !needW;
     // the tile counts of the variant sets are CTA-uniform run-time values: dispatch to a loop with compile-time
     // counts, so that no predicated-off DMMA (and its fragment load) is issued at all
@@ -591,7 +610,31 @@ __global__ void __launch_bounds__(FTN_NT, 2) k_ft_nodes(const FtArgs a, const do
 #undef C3SC_ND
     }
 
-    ft_active_list(a, nf, jb, je, sFid, sAbs, nmax);
+    if constexpr (!FUSED) ft_active_list(a, nf, jb, je, sFid, sAbs, nmax);
+    else {
+        __syncthreads();                                    // every neighbour value of the group is in the region
+        FusedCta w;
+        w.reg = region; w.RN = FT_FBMAX * njp; w.njp = njp; w.nf = nf; w.jb = jb; w.je = je; w.k = k; w.nmax = nmax;
+        w.sFid = sFid; w.sAbs = sAbs; w.pi_eval = a.fuse_pi; w.arg = a.fuse_arg;
+        switch (a.family) {
+        case 0: fused_walk_lqg_lo(P.dx, *ctl, w); break;
+        case 1: fused_walk_lqg_hi(P.dx, *ctl, w); break;
+        default: fused_walk_misc(a.model, P.dx, *ctl, w); break;
+        }
+        __syncthreads();
+        if (tid == 0) { __threadfence(); atomicExch(a.ring_flag + s_region, 0); }
+    }
+}
+
+template <int KS>
+__global__ void __launch_bounds__(FTN_NT, 2) k_ft_nodes(const FtArgs a, const double *sets)
+{
+    ftn_body<KS, false>(a, sets, nullptr);
+}
+template <int KS>
+__global__ void __launch_bounds__(FTN_NT, 2) k_ft_nodes_fused(const FtArgs a, const CtlArgs ctl, const double *sets)
+{
+    ftn_body<KS, true>(a, sets, &ctl);
 }
 
 }  // namespace c3sc

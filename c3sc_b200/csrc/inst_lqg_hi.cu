@@ -1,6 +1,23 @@
 // explicit instantiations: LQG chain-of-integrators, dx = 8,10,12
 #include "control_kernel.cuh"
 namespace c3sc {
+__device__ void fused_walk_lqg_hi(int dx, const CtlArgs &c, const FusedCta &w)
+{
+    switch (dx) {
+    case 8: fused_walk_m<LqgNd<8>>(c, w); break;
+    case 10: fused_walk_m<LqgNd<10>>(c, w); break;
+    case 12: fused_walk_m<LqgNd<12>>(c, w); break;
+    }
+}
+int fused_ok_lqg_hi(int dx, int arith, const CtlArgs &c, int pi_eval)
+{
+    switch (dx) {
+    case 8: return fused_ok_m<LqgNd<8>>(arith, c, pi_eval);
+    case 10: return fused_ok_m<LqgNd<10>>(arith, c, pi_eval);
+    case 12: return fused_ok_m<LqgNd<12>>(arith, c, pi_eval);
+    }
+    return 0;
+}
 int launch_control_lqg_hi(int dx, int arith, const CtlArgs &a, int pi_eval, cudaStream_t st)
 {
     switch (dx) {

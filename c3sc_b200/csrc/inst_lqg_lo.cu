@@ -1,6 +1,23 @@
 // explicit instantiations: LQG chain-of-integrators, dx = 2,4,6
 #include "control_kernel.cuh"
 namespace c3sc {
+__device__ void fused_walk_lqg_lo(int dx, const CtlArgs &c, const FusedCta &w)
+{
+    switch (dx) {
+    case 2: fused_walk_m<LqgNd<2>>(c, w); break;
+    case 4: fused_walk_m<LqgNd<4>>(c, w); break;
+    case 6: fused_walk_m<LqgNd<6>>(c, w); break;
+    }
+}
+int fused_ok_lqg_lo(int dx, int arith, const CtlArgs &c, int pi_eval)
+{
+    switch (dx) {
+    case 2: return fused_ok_m<LqgNd<2>>(arith, c, pi_eval);
+    case 4: return fused_ok_m<LqgNd<4>>(arith, c, pi_eval);
+    case 6: return fused_ok_m<LqgNd<6>>(arith, c, pi_eval);
+    }
+    return 0;
+}
 int launch_control_lqg_lo(int dx, int arith, const CtlArgs &a, int pi_eval, cudaStream_t st)
 {
     switch (dx) {

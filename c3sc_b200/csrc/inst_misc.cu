@@ -1,6 +1,35 @@
 // explicit instantiations: double integrator (dx 2,3,4), Dubins car, skidding car; transition test kernel
 #include "control_kernel.cuh"
 namespace c3sc {
+__device__ void fused_walk_misc(int model, int dx, const CtlArgs &c, const FusedCta &w)
+{
+    switch (model) {
+    case C3SC_MODEL_DOUBLE_INT:
+        switch (dx) {
+        case 2: fused_walk_m<DoubleInt<2>>(c, w); break;
+        case 3: fused_walk_m<DoubleInt<3>>(c, w); break;
+        case 4: fused_walk_m<DoubleInt<4>>(c, w); break;
+        }
+        break;
+    case C3SC_MODEL_DUBINS: fused_walk_m<Dubins>(c, w); break;
+    case C3SC_MODEL_SKID5D: fused_walk_m<Skid5d>(c, w); break;
+    }
+}
+int fused_ok_misc(int model, int dx, int arith, const CtlArgs &c, int pi_eval)
+{
+    switch (model) {
+    case C3SC_MODEL_DOUBLE_INT:
+        switch (dx) {
+        case 2: return fused_ok_m<DoubleInt<2>>(arith, c, pi_eval);
+        case 3: return fused_ok_m<DoubleInt<3>>(arith, c, pi_eval);
+        case 4: return fused_ok_m<DoubleInt<4>>(arith, c, pi_eval);
+        }
+        return 0;
+    case C3SC_MODEL_DUBINS: return dx == 3 ? fused_ok_m<Dubins>(arith, c, pi_eval) : 0;
+    case C3SC_MODEL_SKID5D: return dx == 5 ? fused_ok_m<Skid5d>(arith, c, pi_eval) : 0;
+    }
+    return 0;
+}
 int launch_control_misc(int model, int dx, int arith, const CtlArgs &a, int pi_eval, cudaStream_t st)
 {
     switch (model) {
