@@ -762,7 +762,10 @@ static int run_batch(const DevProblem &P, int model, int arith, Scratch &scr, co
         // Fused stage 2: the node kernel walks the control set of its own fibers from a per-CTA region of neighbour values
         // (no batch-sized scratch through HBM, no second launch) when the model's walk has a fused form, the node kernel
         // owns whole fibers (large batches) and no node-major cost output is wanted.
-        bool fuse = mma && !a.costs && !getenv("C3SC_NO_FUSE") && ft_nodes_nsplit(a) == 1;
+        // MEASURED SLOWER than the two-kernel pipeline on B200 (2.61 vs 1.94 ms per 65 536-fiber step, profiles/r02_fusion.md:
+        // the fully unrolled walk and the node loop evict each other from the instruction cache and the walk runs at half
+        // the standalone kernel's occupancy), so it is opt-in: C3SC_FUSE=1.
+        bool fuse = mma && !a.costs && getenv("C3SC_FUSE") && ft_nodes_nsplit(a) == 1;
         if (fuse) {
             const int fam = model == C3SC_MODEL_LQGND ? (P.dx <= 6 ? 0 : 1) : 2;
             fuse = fam == 0 ? fused_ok_lqg_lo(P.dx, arith, c, pe_) : (fam == 1 ? fused_ok_lqg_hi(P.dx, arith, c, pe_) : fused_ok_misc(model, P.dx, arith, c, pe_));

@@ -639,6 +639,33 @@ struct GridWalk {
     static constexpr int SPAN = span();      // candidates below a node of depth m
 };
 
+// The same walk for Q nodes of one thread in lock step: Q independent dependency chains per leaf.  Used by the fused
+// walk, which runs inside the node kernel at 16 warps per SM and 128 registers per thread -- latency has to be covered
+// by instruction-level parallelism there, not by occupancy.
+template <int NUD, int m, int cnt, int idx, bool ARG, int Q>
+struct GridWalkQ {
+    static __device__ __forceinline__ void go(const double (&s)[Q], const double (&Tl)[Q][NUD], const double (&Th)[Q][NUD],
+                                              double (&mn)[Q][NUD + 1], int (&am)[Q][NUD + 1])
+    {
+        if constexpr (m == NUD) {
+#pragma unroll
+            for (int q = 0; q < Q; q++)
+                if (s[q] < mn[q][cnt]) {
+                    mn[q][cnt] = s[q];
+                    if constexpr (ARG) am[q][cnt] = idx;
+                }
+        } else {
+            constexpr int stride = GridWalk<NUD, m + 1, 0, 0, ARG>::SPAN;
+            double sl[Q], sh[Q];
+#pragma unroll
+            for (int q = 0; q < Q; q++) { sl[q] = s[q] + Tl[q][m]; sh[q] = s[q] + Th[q][m]; }
+            GridWalkQ<NUD, m + 1, cnt + 1, idx, ARG, Q>::go(sl, Tl, Th, mn, am);
+            GridWalkQ<NUD, m + 1, cnt, idx + stride, ARG, Q>::go(s, Tl, Th, mn, am);
+            GridWalkQ<NUD, m + 1, cnt + 1, idx + 2 * stride, ARG, Q>::go(sh, Tl, Th, mn, am);
+        }
+    }
+};
+
 // Occupancy beats registers here: the walk has no loop-carried state beyond the du+1 running minima, and the
 // 21 neighbour values of a node arrive from L2 -- one node per thread at 4 CTAs/SM (64 registers, ~100 B of
 // spills) measured 4 % faster end to end than two nodes per thread at 2 CTAs/SM (profiles/r01_lanes.md).
@@ -741,29 +768,50 @@ __global__ void __launch_bounds__(CT_NT, grid_minb(ARG)) k_control_grid(const Ct
 // no batch-sized cost scratch through HBM, no second launch.  The call crosses translation units (the node kernel is
 // compiled per rank geometry, the walk per dynamics model): relocatable device code, one dispatcher per model family.
 
+#ifndef C3SC_FUSED_Q
+#define C3SC_FUSED_Q 2         // nodes per thread of the fused walk
+#endif
 template <class M, bool ARG>
 __device__ void fused_walk_t(const CtlArgs &c, const FusedCta &w)
 {
     constexpr int DX = M::DX, DU = M::DU, CS = 2 * DX + 1, RW = 2 * DX + 3;
     constexpr int NUD = M::NUD > 0 ? M::NUD : 1, NG = NUD + 1;
+    constexpr bool GRID = M::SEP && M::NUD >= 1 && M::NUD <= CT_NUDMAX;
+    constexpr int Q = GRID ? C3SC_FUSED_Q : 1;
     const DevProblem &P = c.P;
     const int nj = w.je - w.jb, total = w.nf * nj, N = P.ngrid[w.k], bk = P.bc[w.k];
     const double nbh = -P.beta * P.h2;
     const bool disc = P.beta != 0.0;
-    for (int q = threadIdx.x; q < total; q += blockDim.x) {
-        const int g = q / nj, jj = q - g * nj, j = w.jb + jj;
-        const int ab = w.sAbs[g * w.nmax + j];
-        const long long id = (long long)w.sFid[g] * c.ldo + j;
-        if (ab != 0) {                                      // absorbed (bellman.c:513-532): boundary / obstacle cost, u = 0
+    const int per = (total + Q - 1) / Q;                    // thread t of round r owns nodes it, it + per, ..
+    for (int it = threadIdx.x; it < per; it += blockDim.x) {
+        bool live[Q], tiny[Q];                              // live: a real, non-absorbed node
+        long long id[Q];
+        // what the lock-step walk keeps per node: the control-independent sum, the per-control terms, the running minima
+        double s0[Q], norm0[Q], hgx[Q], Tl[Q][NUD], Th[Q][NUD], mn[Q][NG];
+        int am[Q][NG];
+#pragma unroll
+        for (int u = 0; u < Q; u++) {
+            const int q = it + u * per;
+            live[u] = false; tiny[u] = true;
+            id[u] = 0;
+            s0[u] = 0.0; norm0[u] = 1.0; hgx[u] = 0.0;
+#pragma unroll
+            for (int m = 0; m < NUD; m++) { Tl[u][m] = 0.0; Th[u][m] = 0.0; }
+#pragma unroll
+            for (int gq = 0; gq < NG; gq++) { mn[u][gq] = CUDART_INF; am[u][gq] = 0x7fffffff; }
+            if (q >= total) continue;
+            const int g = q / nj, jj = q - g * nj, j = w.jb + jj;
+            const int ab = w.sAbs[g * w.nmax + j];
+            id[u] = (long long)w.sFid[g] * c.ldo + j;
             double x[DX];
-            node_state<DX>(c, (int)id, x);
-            store_value(c, id, (ab == 1) ? M::boundcost(x, P.mp) : M::obscost(x, P.mp));
-            if (c.argmin) c.argmin[id] = -1;
-            if (c.rows) { double *row = c.rows + (size_t)id * RW; for (int m = 0; m < RW; m++) row[m] = 0.0; }
-            continue;
-        }
-        double cc[CS];
-        {
+            node_state<DX>(c, (int)id[u], x);
+            if (ab != 0) {                                  // absorbed (bellman.c:513-532): boundary / obstacle cost, u = 0
+                store_value(c, id[u], (ab == 1) ? M::boundcost(x, P.mp) : M::obscost(x, P.mp));
+                if (c.argmin) c.argmin[id[u]] = -1;
+                if (c.rows) { double *row = c.rows + (size_t)id[u] * RW; for (int m = 0; m < RW; m++) row[m] = 0.0; }
+                continue;
+            }
+            double cc[CS];
             int lo, hi;
             ft_vary_pair(bk, N, j, 0, lo, hi);
             const double *base = w.reg + g * w.njp + jj, *self = w.reg + (size_t)(2 * DX) * w.RN + g * w.njp;
@@ -773,53 +821,58 @@ __device__ void fused_walk_t(const CtlArgs &c, const FusedCta &w)
                 cc[2 * i + 1] = __ldcg(i == w.k ? self + (hi - w.jb) : base + (size_t)(2 * i + 1) * w.RN);   // region is recycled
             }
             cc[2 * DX] = __ldcg(self + jj);
-        }
-        if (w.pi_eval) {                                    // bellman.c:1863-1871: the stored row against the new values
-            const double *row = c.rows_in + (size_t)id * RW;
-            double prob[CS];
+            if (w.pi_eval) {                                // bellman.c:1863-1871: the stored row against the new values
+                const double *row = c.rows_in + (size_t)id[u] * RW;
+                double prob[CS];
 #pragma unroll
-            for (int m = 0; m < CS; m++) prob[m] = row[m];
-            store_value(c, id, rhs<DX, Fast>(P, prob, row[CS], row[CS + 1], cc));
-            continue;
-        }
-        if constexpr (M::SEP && M::NUD >= 1 && M::NUD <= CT_NUDMAX) {
-            double x[DX];
-            node_state<DX>(c, (int)id, x);
-            Node2<M> nd;
-            node2_from<M>(c, x, cc, nd);
-            if (nd.norm0 + P.amin < 1e-14) atomicOr(P.err, 1);
-            const bool tiny = P.beta * P.h2 <= 0.00390625 * (nd.norm0 + P.amin);
-            double Tl[NUD], Th[NUD], mn[NG];
-            int am[NG];
-#pragma unroll
-            for (int m = 0; m < NUD; m++) { Tl[m] = c.gWlo[m] * nd.cu[2 * m]; Th[m] = c.gWhi[m] * nd.cu[2 * m + 1]; }
-#pragma unroll
-            for (int gq = 0; gq < NG; gq++) { mn[gq] = CUDART_INF; am[gq] = 0x7fffffff; }
-            GridWalk<NUD, 0, 0, 0, ARG>::go(nd.S0, Tl, Th, mn, am);
-#pragma unroll
-            for (int gq = 0; gq < NG; gq++) {
-                const double rinv = rcp_pos(nd.norm0 + c.gAg[gq]);
-                const double ebt = !disc ? 1.0 : (tiny ? exp_tiny(nbh * rinv) : exp_nonpos(nbh * rinv));
-                const double v = rinv * (fma(ebt, mn[gq], c.gHg[gq]) + nd.hgx);
-                if (v < nd.best || (ARG && v == nd.best && am[gq] < nd.ibest)) { nd.best = v; nd.ibest = am[gq]; }
+                for (int m = 0; m < CS; m++) prob[m] = row[m];
+                store_value(c, id[u], rhs<DX, Fast>(P, prob, row[CS], row[CS + 1], cc));
+                continue;
             }
-            store_value(c, id, nd.best);
-            if constexpr (ARG) {
-                const int ibest = nd.ibest;
-                if (c.argmin) c.argmin[id] = ibest;
-                if (c.rows) {                               // policy row at u* (bellman.c:1851-1860)
-                    double u[DU], b[DX], sg[DX], prob[CS], dt;
+            if constexpr (GRID) {
+                Node2<M> nd;
+                node2_from<M>(c, x, cc, nd);
+                if (nd.norm0 + P.amin < 1e-14) atomicOr(P.err, 1);
+                live[u] = true;
+                tiny[u] = P.beta * P.h2 <= 0.00390625 * (nd.norm0 + P.amin);
+                s0[u] = nd.S0; norm0[u] = nd.norm0; hgx[u] = nd.hgx;
 #pragma unroll
-                    for (int i = 0; i < DU; i++) u[i] = P.utab[(size_t)(ibest < P.nu ? ibest : 0) * DU + i];
-                    M::template drift<Fast>(x, u, P.mp, b);
-                    M::template sigma<Fast>(x, u, P.mp, sg);
-                    const double gs = M::template stage<Fast>(x, u, P.mp);
-                    if (transition_row<DX, Fast>(P, b, sg, prob, dt)) atomicOr(P.err, 1);
-                    double *row = c.rows + (size_t)id * RW;
+                for (int m = 0; m < NUD; m++) { Tl[u][m] = c.gWlo[m] * nd.cu[2 * m]; Th[u][m] = c.gWhi[m] * nd.cu[2 * m + 1]; }
+            }
+        }
+        if constexpr (GRID) {
+            if (w.pi_eval) continue;
+            GridWalkQ<NUD, 0, 0, 0, ARG, Q>::go(s0, Tl, Th, mn, am);
 #pragma unroll
-                    for (int m = 0; m < CS; m++) row[m] = prob[m];
-                    row[CS] = dt;
-                    row[CS + 1] = gs;
+            for (int u = 0; u < Q; u++) {
+                if (!live[u]) continue;
+                double best = CUDART_INF;
+                int ibest = 0x7fffffff;
+#pragma unroll
+                for (int gq = 0; gq < NG; gq++) {
+                    const double rinv = rcp_pos(norm0[u] + c.gAg[gq]);
+                    const double ebt = !disc ? 1.0 : (tiny[u] ? exp_tiny(nbh * rinv) : exp_nonpos(nbh * rinv));
+                    const double v = rinv * (fma(ebt, mn[u][gq], c.gHg[gq]) + hgx[u]);
+                    if (v < best || (ARG && v == best && am[u][gq] < ibest)) { best = v; ibest = am[u][gq]; }
+                }
+                store_value(c, id[u], best);
+                if constexpr (ARG) {
+                    if (c.argmin) c.argmin[id[u]] = ibest;
+                    if (c.rows) {                           // policy row at u* (bellman.c:1851-1860)
+                        double x[DX], uu[DU], b[DX], sg[DX], prob[CS], dt;
+                        node_state<DX>(c, (int)id[u], x);
+#pragma unroll
+                        for (int i = 0; i < DU; i++) uu[i] = P.utab[(size_t)(ibest < P.nu ? ibest : 0) * DU + i];
+                        M::template drift<Fast>(x, uu, P.mp, b);
+                        M::template sigma<Fast>(x, uu, P.mp, sg);
+                        const double gs = M::template stage<Fast>(x, uu, P.mp);
+                        if (transition_row<DX, Fast>(P, b, sg, prob, dt)) atomicOr(P.err, 1);
+                        double *row = c.rows + (size_t)id[u] * RW;
+#pragma unroll
+                        for (int m = 0; m < CS; m++) row[m] = prob[m];
+                        row[CS] = dt;
+                        row[CS + 1] = gs;
+                    }
                 }
             }
         }

@@ -612,14 +612,22 @@ __device__ __forceinline__ void ftn_body(const FtArgs &a, const double *sets, co
 
     if constexpr (!FUSED) ft_active_list(a, nf, jb, je, sFid, sAbs, nmax);
     else {
+        // The walk is a real call into another translation unit: its arguments must be addressable.  A kernel parameter
+        // passed by reference would be copied to every thread's local stack (1.7 kB each); one shared copy per CTA instead.
+        __shared__ CtlArgs sctl;
+        {
+            const int *src = reinterpret_cast<const int *>(ctl);
+            int *dst = reinterpret_cast<int *>(&sctl);
+            for (int e = tid; e < (int)(sizeof(CtlArgs) / sizeof(int)); e += FTN_NT) dst[e] = src[e];
+        }
         __syncthreads();                                    // every neighbour value of the group is in the region
         FusedCta w;
         w.reg = region; w.RN = FT_FBMAX * njp; w.njp = njp; w.nf = nf; w.jb = jb; w.je = je; w.k = k; w.nmax = nmax;
         w.sFid = sFid; w.sAbs = sAbs; w.pi_eval = a.fuse_pi; w.arg = a.fuse_arg;
         switch (a.family) {
-        case 0: fused_walk_lqg_lo(P.dx, *ctl, w); break;
-        case 1: fused_walk_lqg_hi(P.dx, *ctl, w); break;
-        default: fused_walk_misc(a.model, P.dx, *ctl, w); break;
+        case 0: fused_walk_lqg_lo(P.dx, sctl, w); break;
+        case 1: fused_walk_lqg_hi(P.dx, sctl, w); break;
+        default: fused_walk_misc(a.model, P.dx, sctl, w); break;
         }
         __syncthreads();
         if (tid == 0) { __threadfence(); atomicExch(a.ring_flag + s_region, 0); }

@@ -252,3 +252,32 @@ def test_bucketed_and_per_fiber_chain_stages_agree(gpu, monkeypatch):
     assert rel_err(v1, v0) <= 1e-13
     assert (a0 != a1).mean() <= 1e-4
     prob.close(); vf.close()
+
+
+@pytest.mark.parametrize("name,n,rank,dx,F", [("lqgnd_reflect", 12, 7, 10, 2600), ("lqgnd", 16, 5, 6, 3000), ("dubinscar_new", 24, 6, None, 2600),
+                                               ("double_int", 40, 5, None, 2500), ("skidding5d", 12, 4, None, 2600)])
+def test_fused_stage2_equals_the_two_kernel_pipeline(gpu, monkeypatch, name, n, rank, dx, F):
+    """C3SC_FUSE=1: the node kernel keeps its fibers' neighbour values in a region of a small ring and runs the control walk
+    (or the policy evaluation) itself through a cross-translation-unit device call.  Opt-in (measured slower on B200), kept
+    correct: value iteration, the improvement step with rows and argmin, and a sub-iteration give the same numbers."""
+    cfg = configs.get_config(name, n=n, rank=rank, dx=dx)
+    prob = capi.Problem(cfg, arith=1)
+    ranks = cfg.ranks()
+    vf = capi.ValueF(cfg.ngrid, ranks, synthetic.random_cores(cfg.ngrid, ranks))
+    vf2 = capi.ValueF(cfg.ngrid, ranks, synthetic.random_cores(cfg.ngrid, ranks, seed=0xABCD00))
+    dv, fi = synthetic.random_fibers(cfg.ngrid, F, seed=13, face_frac=0.2)
+    v0, a0 = prob.vi_batch(vf, dv, fi)
+    p0, rows0, pa0 = prob.pi_batch(vf, vf2, dv, fi)
+    q0, _, _ = prob.pi_batch(None, vf, dv, fi, rows=rows0)
+    monkeypatch.setenv("C3SC_FUSE", "1")
+    n0 = capi.lib().c3sc_launch_count()
+    v1, a1 = prob.vi_batch(vf, dv, fi)
+    launches = capi.lib().c3sc_launch_count() - n0
+    p1, rows1, pa1 = prob.pi_batch(vf, vf2, dv, fi)
+    q1, _, _ = prob.pi_batch(None, vf, dv, fi, rows=rows1)
+    assert rel_err(v1, v0) <= 1e-14 and np.array_equal(a1, a0)
+    assert rel_err(p1, p0) <= 1e-14 and np.array_equal(pa1, pa0) and rel_err(rows1, rows0, scale=1.0) <= 1e-14
+    assert rel_err(q1, q0) <= 1e-14
+    if name != "skidding5d":                        # a grid-structured control set: no control kernel was launched
+        assert launches == 3, launches              # grouping + chains + fused node kernel
+    prob.close(); vf.close(); vf2.close()
