@@ -352,12 +352,13 @@ def main():
     sptr = stream.cuda_stream
 
     # N > 1: every rank's gathered buffer is peer-mapped (CUDA IPC); a rank's values reach the others either as stores
-    # from the control kernel (C3SC_GATHER=p2p) or as one bulk copy per pipeline chunk on the copy engines, overlapped with
-    # the next chunk (C3SC_GATHER=copy, default); a step ends with a barrier.  C3SC_GATHER=nccl: NCCL all-gather.
-    gather_mode = os.environ.get("C3SC_GATHER", "copy") if world > 1 else "none"
+    # from the control kernel (C3SC_GATHER=p2p, default: measured fastest at 8 GPUs), as one bulk copy per pipeline chunk and
+    # peer on the copy engines (copy) or as one small scatter kernel per chunk (scatter), both overlapped with the next chunk;
+    # a step ends with a barrier.  C3SC_GATHER=nccl: NCCL all-gather.
+    gather_mode = os.environ.get("C3SC_GATHER", "p2p") if world > 1 else "none"
     peers = None
     gathered = None
-    if world > 1 and gather_mode in ("p2p", "copy"):
+    if world > 1 and gather_mode in ("p2p", "copy", "scatter"):
         try:
             def _exchange(h):
                 got = [None] * world
@@ -375,7 +376,7 @@ def main():
         gathered = torch.empty(world * F * N, dtype=torch.float64, device=dev)
     # the rank's own output IS its slot of its gathered buffer (no private copy)
     out_d = gathered[rank * F * N:(rank + 1) * F * N] if gathered is not None else torch.zeros(F * N, dtype=torch.float64, device=dev)
-    peer_mode = 1 if gather_mode == "copy" else 0
+    peer_mode = {"copy": 1, "scatter": 2}.get(gather_mode, 0)
 
     def peers_struct():
         o = capi.BatchOut()
@@ -566,6 +567,7 @@ def main():
         roof = roofline_record(stage1, whole, peak_dmma, peak_dfma, W, W1, F, kernel_ms, hbm_bytes, hbm_peak)
         gathers = {"copy": "one bulk copy per pipeline chunk and peer on the copy engines into peer-mapped buffers (CUDA IPC over NVLink) + barrier",
                    "p2p": "control kernel stores into every rank's peer-mapped buffer (CUDA IPC over NVLink) + barrier",
+                   "scatter": "one small kernel per pipeline chunk stores the chunk into every rank's peer-mapped buffer, on a side stream + barrier",
                    "nccl": "nccl all_gather_into_tensor"}
         line = {
             "metric": "bellman_node_backups_per_s", "value": value, "unit": "node-backups/s",

@@ -62,7 +62,7 @@ EXPORTS = [
     "c3sc_neighbor_costs_batch", "c3sc_node_backup_batch", "c3sc_control_value_batch", "c3sc_rhs_batch",
     "c3sc_transition_raw", "c3sc_ft_fiber_nn_batch", "c3sc_valuef_commit",
     "c3sc_cross_create", "c3sc_cross_copy", "c3sc_cross_destroy", "c3sc_cross_ranks", "c3sc_cross_run", "c3sc_cross_run_vi", "c3sc_cross_run_pi",
-    "c3sc_vi_solve", "c3sc_cores_dot", "c3sc_cores_norm", "c3sc_cores_norm2diff",
+    "c3sc_vi_solve", "c3sc_cores_dot", "c3sc_cores_norm", "c3sc_cores_norm2diff", "c3sc_cores_dot_l2", "c3sc_cores_norm_l2", "c3sc_cores_norm2diff_l2",
     "c3sc_valuef_eval_batch", "c3sc_policy_eval_batch",
     "c3sc_cross_index_sets", "c3sc_cores_round", "c3sc_cross_adapt_capacity", "c3sc_cross_set_ranks", "c3sc_cross_run_adapt", "c3sc_cross_run_vi_adapt",
     "c3sc_peer_buffer_create", "c3sc_peer_buffer_open", "c3sc_peer_buffer_close",
@@ -165,8 +165,11 @@ def lib() -> C.CDLL:
                                            c_u64p, c_f64p]
         L.c3sc_cross_run_vi_adapt.argtypes = [vp, vp, vp, C.POINTER(CrossOpts), C.POINTER(AdaptOpts), c_u64p, C.POINTER(c_f64p),
                                               c_u64p, c_f64p]
-        for fn in (L.c3sc_cores_dot, L.c3sc_cores_norm, L.c3sc_cores_norm2diff):
+        for fn in (L.c3sc_cores_dot, L.c3sc_cores_norm, L.c3sc_cores_norm2diff, L.c3sc_cores_dot_l2, L.c3sc_cores_norm_l2, L.c3sc_cores_norm2diff_l2):
             fn.restype = C.c_double
+        L.c3sc_cores_dot_l2.argtypes = [C.c_uint32, c_u64p, C.POINTER(c_f64p), c_u64p, C.POINTER(c_f64p), c_u64p, C.POINTER(c_f64p)]
+        L.c3sc_cores_norm_l2.argtypes = [C.c_uint32, c_u64p, C.POINTER(c_f64p), c_u64p, C.POINTER(c_f64p)]
+        L.c3sc_cores_norm2diff_l2.argtypes = [C.c_uint32, c_u64p, C.POINTER(c_f64p), c_u64p, C.POINTER(c_f64p), c_u64p, C.POINTER(c_f64p)]
         L.c3sc_cores_dot.argtypes = [C.c_uint32, c_u64p, c_u64p, C.POINTER(c_f64p), c_u64p, C.POINTER(c_f64p)]
         L.c3sc_cores_norm.argtypes = [C.c_uint32, c_u64p, c_u64p, C.POINTER(c_f64p)]
         L.c3sc_cores_norm2diff.argtypes = [C.c_uint32, c_u64p, c_u64p, C.POINTER(c_f64p), c_u64p, C.POINTER(c_f64p)]
@@ -572,6 +575,30 @@ def cores_norm(n, ranks, cores) -> float:
     ca = [np.ascontiguousarray(c, dtype=np.float64).reshape(-1) for c in cores]
     aa = (c_f64p * d)(*[c.ctypes.data_as(c_f64p) for c in ca])
     return float(lib().c3sc_cores_norm(d, n.ctypes.data_as(c_u64p), r.ctypes.data_as(c_u64p), aa))
+
+
+def cores_dot_l2(n, xgrid, ranks_a, cores_a, ranks_b, cores_b) -> float:
+    """continuous L2 inner product of two piecewise-linear trains over the box (the reference's function_train_inner on
+    LINELM cores): c3sc_cores_dot_l2"""
+    n = np.ascontiguousarray(n, dtype=np.uint64); d = int(n.size)
+    ra = np.ascontiguousarray(ranks_a, dtype=np.uint64); rb = np.ascontiguousarray(ranks_b, dtype=np.uint64)
+    xg = [np.ascontiguousarray(g, dtype=np.float64) for g in xgrid]
+    ca = [np.ascontiguousarray(c, dtype=np.float64).reshape(-1) for c in cores_a]
+    cb = [np.ascontiguousarray(c, dtype=np.float64).reshape(-1) for c in cores_b]
+    ax = (c_f64p * d)(*[g.ctypes.data_as(c_f64p) for g in xg])
+    aa = (c_f64p * d)(*[c.ctypes.data_as(c_f64p) for c in ca]); ab = (c_f64p * d)(*[c.ctypes.data_as(c_f64p) for c in cb])
+    return float(lib().c3sc_cores_dot_l2(d, n.ctypes.data_as(c_u64p), ax, ra.ctypes.data_as(c_u64p), aa, rb.ctypes.data_as(c_u64p), ab))
+
+
+def cores_norm2diff_l2(n, xgrid, ranks_a, cores_a, ranks_b, cores_b) -> float:
+    n = np.ascontiguousarray(n, dtype=np.uint64); d = int(n.size)
+    ra = np.ascontiguousarray(ranks_a, dtype=np.uint64); rb = np.ascontiguousarray(ranks_b, dtype=np.uint64)
+    xg = [np.ascontiguousarray(g, dtype=np.float64) for g in xgrid]
+    ca = [np.ascontiguousarray(c, dtype=np.float64).reshape(-1) for c in cores_a]
+    cb = [np.ascontiguousarray(c, dtype=np.float64).reshape(-1) for c in cores_b]
+    ax = (c_f64p * d)(*[g.ctypes.data_as(c_f64p) for g in xg])
+    aa = (c_f64p * d)(*[c.ctypes.data_as(c_f64p) for c in ca]); ab = (c_f64p * d)(*[c.ctypes.data_as(c_f64p) for c in cb])
+    return float(lib().c3sc_cores_norm2diff_l2(d, n.ctypes.data_as(c_u64p), ax, ra.ctypes.data_as(c_u64p), aa, rb.ctypes.data_as(c_u64p), ab))
 
 
 class PeerBuffers:

@@ -37,6 +37,7 @@ int chain_bucketed_ok(const DevFT &ft, int nmax);
 int launch_chain_plan(const ChainArgs &a, int FC, cudaStream_t st);
 int launch_chain_steps(const ChainArgs &a, cudaStream_t st, int *n);
 int launch_rows_move(double *dst, const double *src, const int *idx, int F, long long per, int scatter, cudaStream_t st);
+int launch_peer_scatter(const double *src, long long n, double *const *peers, int npeer, long long off, cudaStream_t st);
 int launch_node_backup_lqg_lo(int dx, int arith, const DevProblem &P, int n, const double *x, const double *costs,
                               const int *absorbed, double *value, int *argmin, cudaStream_t st);
 int launch_node_backup_lqg_hi(int dx, int arith, const DevProblem &P, int n, const double *x, const double *costs,
@@ -799,6 +800,11 @@ static int run_batch(const DevProblem &P, int model, int arith, Scratch &scr, co
             CK(cudaEventRecord(b.chunk_done, st));
             if (b.peer_copy && c.value && b.peer_stream) {  // the chunk's values into every peer's gathered buffer, off the SMs
                 CK(cudaStreamWaitEvent(b.peer_stream, b.chunk_done, 0));
+                if (b.peer_copy == 2 && ((b.peer_offset + n0) & 1) == 0 && ((size_t)c.value & 15) == 0) {
+                    int rs_ = launch_peer_scatter(c.value, (long long)(Fc * b.ldo), b.value_peers, b.n_peers, (long long)(b.peer_offset + n0), b.peer_stream);
+                    if (rs_) return fail(C3SC_ECUDA, "peer scatter kernel: %s", cudaGetErrorString((cudaError_t)rs_));
+                    g_launches++;
+                } else
                 for (int g = 0; g < b.n_peers; g++) {
                     double *dst = b.value_peers[g] + b.peer_offset + n0;
                     if (dst != c.value) CK(cudaMemcpyAsync(dst, c.value, Fc * b.ldo * 8, cudaMemcpyDefault, b.peer_stream));
@@ -863,9 +869,9 @@ int c3sc_vi_batch_dev(c3sc_problem *p, const c3sc_valuef *vf, size_t F, const in
     b.n_peers = (int)out->n_peers;
     for (uint32_t g = 0; g < out->n_peers; g++) b.value_peers[g] = out->value_peers[g];
     b.peer_offset = (size_t)out->peer_offset;
-    if (out->n_peers && out->peer_mode == 1) {
-        if (!out->value) return fail(C3SC_EINVAL, "peer_mode 1 (bulk copies) needs the local value buffer");
-        b.peer_copy = 1;
+    if (out->n_peers && out->peer_mode >= 1) {
+        if (!out->value) return fail(C3SC_EINVAL, "peer_mode 1 / 2 (bulk copies) needs the local value buffer");
+        b.peer_copy = (int)out->peer_mode;
         b.peer_stream = p->peer_stream; b.chunk_done = p->chunk_done; b.copies_done = p->copies_done;
     }
     return run_batch(p->P, p->model, p->arith, p->scr, &p->grp, vf->ft, b, (cudaStream_t)stream);
@@ -1056,7 +1062,7 @@ static int vi_batch_host(c3sc_problem *p, const c3sc_valuef *vf, size_t F, const
         b.n_peers = (int)peers->n_peers;
         for (uint32_t g = 0; g < peers->n_peers; g++) b.value_peers[g] = peers->value_peers[g];
         b.peer_offset = (size_t)peers->peer_offset;
-        b.peer_copy = peers->peer_mode == 1;
+        b.peer_copy = peers->peer_mode >= 1 ? (int)peers->peer_mode : 0;
         b.peer_stream = p->peer_stream; b.copies_done = p->copies_done;
     }
     rc = run_batch(p->P, p->model, p->arith, p->scr, &p->grp, vf->ft, b, p->stream);

@@ -299,6 +299,34 @@ int launch_rows_move(double *dst, const double *src, const int *idx, int F, long
     return (int)cudaGetLastError();
 }
 
+// One chunk's values into every peer's gathered buffer with 16-byte stores from a few CTAs (c3sc_batch_out::peer_mode 2):
+// runs on the library's peer stream next to the following chunk's kernels and leaves the control kernel's own stores local.
+struct PeerList { double *p[C3SC_MAXPEERS]; int n; };
+__global__ void __launch_bounds__(256) k_peer_scatter(const double *src, long long n, PeerList peers, long long off)
+{
+    const long long n2 = n >> 1, step = (long long)gridDim.x * blockDim.x;
+    const double2 *s2 = reinterpret_cast<const double2 *>(src);
+    for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < n2; e += step) {
+        const double2 v = s2[e];
+#pragma unroll 1
+        for (int g = 0; g < peers.n; g++) reinterpret_cast<double2 *>(peers.p[g] + off)[e] = v;
+    }
+    if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0)
+        for (int g = 0; g < peers.n; g++) peers.p[g][off + n - 1] = src[n - 1];
+}
+int launch_peer_scatter(const double *src, long long n, double *const *peers, int npeer, long long off, cudaStream_t st)
+{
+    if (n <= 0 || npeer <= 0) return 0;
+    PeerList pl;
+    pl.n = 0;
+    for (int g = 0; g < npeer && g < C3SC_MAXPEERS; g++)
+        if (peers[g] + off != src) pl.p[pl.n++] = peers[g];         // the rank's own slot when it is the output itself
+    if (pl.n == 0) return 0;
+    if (((size_t)src & 15) || (off & 1)) return (int)cudaErrorMisalignedAddress;
+    k_peer_scatter<<<48, 256, 0, st>>>(src, n, pl, off);
+    return (int)cudaGetLastError();
+}
+
 // valuef_eval at npts points (device arrays): piecewise-linear interpolation of the nodal cores
 int launch_ft_eval_points(const DevProblem &P, const DevFT &ft, int npts, const double *pts, double *out, cudaStream_t st)
 {

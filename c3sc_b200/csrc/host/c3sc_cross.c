@@ -538,6 +538,75 @@ double c3sc_cores_norm2diff(uint32_t d, const uint64_t *n, const uint64_t *ra, c
     return sqrt(fabs(aa - 2.0 * ab + bb));
 }
 
+/* ---- continuous L2 inner product of two piecewise-linear (LINELM) function trains ---------------------------------
+ * What the reference's valuef_norm / valuef_norm2diff compute (src/valuefunc.c:315-335 -> C3 function_train_norm2 /
+ * norm2diff on linear elements): <f, g> = integral over the box of f g, f and g the multilinear interpolants of the
+ * nodal cores.  Per dimension the nodal values meet through the mass matrix of the hat functions on the grid,
+ *     M_ii = (h_{i-1} + h_i) / 3,   M_{i,i+1} = M_{i+1,i} = h_i / 6        (h_i = x_{i+1} - x_i, h_{-1} = h_{N-1} = 0),
+ * so the train contraction of c3sc_cores_dot becomes
+ *     Z_{k+1}[a2, b2] = sum_{i,j} M^k_ij sum_{a,b} A_k[i][a, a2] Z_k[a, b] B_k[j][b, b2]
+ * evaluated as T_j = Z_k B_k[j], H_i = sum_j M_ij T_j (three terms), Z_{k+1} += A_k[i]^T H_i.  C3 itself is absent:
+ * pinned against a dense evaluation of the same integral (tests/test_cross_driver.py).  The nodal form (the discrete
+ * l2 of the node values) stays available as c3sc_cores_dot / _norm / _norm2diff. */
+double c3sc_cores_dot_l2(uint32_t d, const uint64_t *n, const double *const *xgrid, const uint64_t *ra, const double *const *A,
+                         const uint64_t *rb, const double *const *B)
+{
+    if (!n || !xgrid || !ra || !A || !rb || !B || d < 1 || d > C3SC_MAXD) return NAN;
+    size_t rmax = 1, nmax = 1;
+    for (uint32_t k = 0; k <= d; k++) { if (ra[k] > rmax) rmax = ra[k]; if (rb[k] > rmax) rmax = rb[k]; }
+    for (uint32_t k = 0; k < d; k++) if (n[k] > nmax) nmax = n[k];
+    const size_t r2 = rmax * rmax;
+    double *Z = (double *)calloc(2 * r2 + (nmax + 1) * r2, sizeof(double));
+    if (!Z) return NAN;
+    double *Zn = Z + r2, *T = Zn + r2;                      /* T[j]: ra[k] x rb[k+1], column-major, all nodes of the dimension */
+    Z[0] = 1.0;
+    for (uint32_t k = 0; k < d; k++) {
+        const size_t a1 = ra[k], a2 = ra[k + 1], b1 = rb[k], b2 = rb[k + 1], N = n[k];
+        const double *x = xgrid[k];
+        /* T_j[a, c] = sum_b Z[a, b] B_k[j][b, c]   (Z column-major a + b*a1, B block column-major b + c*b1) */
+        for (size_t j = 0; j < N; j++) {
+            const double *Bj = B[k] + j * b1 * b2;
+            double *Tj = T + j * a1 * b2;
+            for (size_t c = 0; c < b2; c++)
+                for (size_t a = 0; a < a1; a++) {
+                    double sum = 0.0;
+                    for (size_t b = 0; b < b1; b++) sum += Z[a + b * a1] * Bj[b + c * b1];
+                    Tj[a + c * a1] = sum;
+                }
+        }
+        for (size_t e = 0; e < a2 * b2; e++) Zn[e] = 0.0;
+        double *H = T + N * a1 * b2;                        /* one more block of scratch */
+        for (size_t i = 0; i < N; i++) {
+            const double hl = i > 0 ? x[i] - x[i - 1] : 0.0, hr = i + 1 < N ? x[i + 1] - x[i] : 0.0;
+            const double mc = (hl + hr) / 3.0, ml = hl / 6.0, mr = hr / 6.0;
+            const double *Tc = T + i * a1 * b2, *Tl = i > 0 ? Tc - a1 * b2 : Tc, *Tr = i + 1 < N ? Tc + a1 * b2 : Tc;
+            for (size_t e = 0; e < a1 * b2; e++) H[e] = mc * Tc[e] + ml * Tl[e] + mr * Tr[e];
+            const double *Ai = A[k] + i * a1 * a2;
+            for (size_t c = 0; c < b2; c++)
+                for (size_t q = 0; q < a2; q++) {
+                    double sum = 0.0;
+                    for (size_t a = 0; a < a1; a++) sum += Ai[a + q * a1] * H[a + c * a1];
+                    Zn[q + c * a2] += sum;
+                }
+        }
+        for (size_t e = 0; e < a2 * b2; e++) Z[e] = Zn[e];
+    }
+    const double v = Z[0];
+    free(Z);
+    return v;
+}
+double c3sc_cores_norm_l2(uint32_t d, const uint64_t *n, const double *const *xgrid, const uint64_t *r, const double *const *A)
+{
+    return sqrt(fabs(c3sc_cores_dot_l2(d, n, xgrid, r, A, r, A)));
+}
+double c3sc_cores_norm2diff_l2(uint32_t d, const uint64_t *n, const double *const *xgrid, const uint64_t *ra, const double *const *A,
+                               const uint64_t *rb, const double *const *B)
+{
+    const double aa = c3sc_cores_dot_l2(d, n, xgrid, ra, A, ra, A), ab = c3sc_cores_dot_l2(d, n, xgrid, ra, A, rb, B),
+                 bb = c3sc_cores_dot_l2(d, n, xgrid, rb, B, rb, B);
+    return sqrt(fabs(aa - 2.0 * ab + bb));
+}
+
 int c3sc_cross_run(c3sc_cross *c, c3sc_fiber_batch_fn f, void *arg, const c3sc_cross_opts *opts, double *const *cores,
                    uint64_t *nfibers, double *rel_change)
 {

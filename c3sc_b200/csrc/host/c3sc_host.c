@@ -1045,14 +1045,32 @@ static void vf_u64(const struct ValueF *v, uint64_t *n, uint64_t *r)
     for (size_t k = 0; k < v->d; k++) n[k] = v->N[k];
     for (size_t k = 0; k <= v->d; k++) r[k] = v->ranks[k];
 }
-/* valuef_norm / valuef_norm2diff (src/valuefunc.c:315-335); discrete l2 over the grid nodes */
+/* valuef_norm / valuef_norm2diff (src/valuefunc.c:315-335): the reference's function_train_norm2 / norm2diff, i.e. the
+   continuous L2 norm over the box of the piecewise-linear train (c3sc_cores_*_l2: mass matrices of the hat functions).
+   A value function that does not know its grid (valuef_from_cores without valuef_set_grid) has no such norm: loud. */
 double valuef_norm(struct ValueF *v)
+{
+    uint64_t n[C3SC_MAXD], r[C3SC_MAXD + 1];
+    if (!v->xgrid) die("valuef_norm: the value function has no grid (valuef_set_grid); valuef_norm_nodal needs none");
+    vf_u64(v, n, r);
+    return c3sc_cores_norm_l2((uint32_t)v->d, n, (const double *const *)v->xgrid, r, (const double *const *)v->cores);
+}
+double valuef_norm2diff(struct ValueF *a, struct ValueF *b)
+{
+    uint64_t n[C3SC_MAXD], ra[C3SC_MAXD + 1], rb[C3SC_MAXD + 1];
+    if (!a->xgrid) die("valuef_norm2diff: the value function has no grid (valuef_set_grid); valuef_norm2diff_nodal needs none");
+    vf_u64(a, n, ra); vf_u64(b, n, rb);
+    return c3sc_cores_norm2diff_l2((uint32_t)a->d, n, (const double *const *)a->xgrid, ra, (const double *const *)a->cores, rb,
+                                   (const double *const *)b->cores);
+}
+/* NEW names: the discrete l2 of the node values (what valuef_norm was in the first round of this library) */
+double valuef_norm_nodal(struct ValueF *v)
 {
     uint64_t n[C3SC_MAXD], r[C3SC_MAXD + 1];
     vf_u64(v, n, r);
     return c3sc_cores_norm((uint32_t)v->d, n, r, (const double *const *)v->cores);
 }
-double valuef_norm2diff(struct ValueF *a, struct ValueF *b)
+double valuef_norm2diff_nodal(struct ValueF *a, struct ValueF *b)
 {
     uint64_t n[C3SC_MAXD], ra[C3SC_MAXD + 1], rb[C3SC_MAXD + 1];
     vf_u64(a, n, ra); vf_u64(b, n, rb);

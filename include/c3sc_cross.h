@@ -88,6 +88,18 @@ double c3sc_cores_norm(uint32_t d, const uint64_t *n, const uint64_t *ranks, con
 double c3sc_cores_norm2diff(uint32_t d, const uint64_t *n, const uint64_t *ranks_a, const double *const *a,
                             const uint64_t *ranks_b, const double *const *b);
 
+/* The reference's norms (src/valuefunc.c:315-335: function_train_norm2 / norm2diff on LINELM cores): the CONTINUOUS L2
+ * inner product over the box of the multilinear interpolants of the nodal cores -- the train contraction with the
+ * tridiagonal mass matrix of the hat functions of xgrid[k] in every dimension.  This is what abs_conv_tol of
+ * c3control_vi_solve / pi_solve is measured in (src/bellman.c:2307-2337,2367); the nodal functions above are the
+ * discrete l2 of the node values and are not the reference's quantity. */
+double c3sc_cores_dot_l2(uint32_t d, const uint64_t *n, const double *const *xgrid, const uint64_t *ranks_a,
+                         const double *const *a, const uint64_t *ranks_b, const double *const *b);
+double c3sc_cores_norm_l2(uint32_t d, const uint64_t *n, const double *const *xgrid, const uint64_t *ranks,
+                          const double *const *a);
+double c3sc_cores_norm2diff_l2(uint32_t d, const uint64_t *n, const double *const *xgrid, const uint64_t *ranks_a,
+                               const double *const *a, const uint64_t *ranks_b, const double *const *b);
+
 #ifdef __cplusplus
 }
 #endif

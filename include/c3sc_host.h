@@ -269,8 +269,11 @@ int approx_args_get_adapt(const struct ApproxArgs *);
  * fiber on the host, as the reference does.  Cross approximation: include/c3sc_cross.h.          */
 struct ValueF *valuef_interp(size_t d, int (*f)(size_t, const double *, double *, void *), void *args, const size_t *N,
                              double **grid, struct ValueF *vref, struct ApproxArgs *aargs, int verbose);   /* :603 */
-double valuef_norm(struct ValueF *);                                      /* :315, discrete l2 over the nodes */
-double valuef_norm2diff(struct ValueF *, struct ValueF *);                /* :325 */
+double valuef_norm(struct ValueF *);                                      /* :315: continuous L2 of the piecewise-linear train */
+double valuef_norm2diff(struct ValueF *, struct ValueF *);                /* :325: likewise (the unit of abs_conv_tol) */
+/* NEW names: discrete l2 of the node values (no grid needed); NOT the reference's quantity */
+double valuef_norm_nodal(struct ValueF *);
+double valuef_norm2diff_nodal(struct ValueF *, struct ValueF *);
 double valuef_eval(struct ValueF *, const double *);                      /* :345 */
 /* checkpoint / resume (src/valuefunc.h:51-54).  Own file formats (the reference's are C3's): binary and a
  * 21-digit text form; loading re-samples the cores on the given grid like function_train_create_nodal.

@@ -356,3 +356,50 @@ def test_pivoting_ignores_round_off_of_the_operator(built, name, n, rank, dx, it
     import pivot_stability as ps
     for seed in (2, 5):
         assert ps.run(name, n, rank, dx, iters, seed) <= 1e-10
+
+
+def _dense(n, ranks, cores):
+    """nodal tensor of a train (blocks column-major r_k x r_{k+1})"""
+    d = len(n)
+    t = np.ones((1, 1))
+    for k in range(d):
+        g = np.asarray(cores[k]).reshape(int(n[k]), int(ranks[k + 1]), int(ranks[k])).transpose(2, 0, 1)   # [a, j, b]
+        t = np.tensordot(t, g, axes=([t.ndim - 1], [0]))
+    return t.reshape([int(x) for x in n])
+
+
+@pytest.mark.parametrize("d", [1, 2, 3])
+def test_continuous_l2_inner_product_against_gauss_quadrature(d):
+    """c3sc_cores_dot_l2 (the reference's valuef_norm semantics: integral over the box of the product of the two
+    piecewise-linear interpolants) against 3-point Gauss quadrature of the interpolants cell by cell on non-uniform
+    grids -- an independent evaluation of the same integral (a product of multilinear functions is quadratic per
+    dimension, so the rule is exact)."""
+    rng = np.random.default_rng(5 + d)
+    n = np.array([7, 5, 6][:d], dtype=np.uint64)
+    xg = [np.sort(rng.uniform(-1.0, 2.0, int(m))) for m in n]
+    ra = np.array([1] + [3] * (d - 1) + [1], dtype=np.uint64); rb = np.array([1] + [2] * (d - 1) + [1], dtype=np.uint64)
+    ca = [rng.standard_normal(int(n[k] * ra[k] * ra[k + 1])) for k in range(d)]
+    cb = [rng.standard_normal(int(n[k] * rb[k] * rb[k + 1])) for k in range(d)]
+    A, B = _dense(n, ra, ca), _dense(n, rb, cb)
+    gp, gw = np.polynomial.legendre.leggauss(3)
+    for k in range(d):                                   # interpolate to the Gauss points of every cell, weights along
+        x = xg[k]
+        P = np.zeros((3 * (len(x) - 1), len(x))); w = np.zeros(3 * (len(x) - 1))
+        for c in range(len(x) - 1):
+            h = x[c + 1] - x[c]
+            for q in range(3):
+                t = 0.5 * (gp[q] + 1.0)
+                P[3 * c + q, c] = 1.0 - t; P[3 * c + q, c + 1] = t
+                w[3 * c + q] = 0.5 * h * gw[q]
+        A = np.moveaxis(np.tensordot(P, A, axes=([1], [k])), 0, k)
+        B = np.moveaxis(np.tensordot(P, B, axes=([1], [k])), 0, k)
+        shape = [1] * d; shape[k] = len(w)
+        A = A * w.reshape(shape)
+    want = float((A * B).sum())
+    got = capi.cores_dot_l2(n, xg, ra, ca, rb, cb)
+    assert abs(got - want) <= 1e-12 * max(1.0, abs(want))
+    # norm2diff of a train with itself is 0, with zero it is the norm; and the nodal l2 is a different number
+    assert capi.cores_norm2diff_l2(n, xg, ra, ca, ra, ca) <= 1e-7 * np.sqrt(abs(capi.cores_dot_l2(n, xg, ra, ca, ra, ca)))
+    zero = [np.zeros_like(c) for c in cb]
+    assert abs(capi.cores_norm2diff_l2(n, xg, ra, ca, rb, zero) ** 2 - capi.cores_dot_l2(n, xg, ra, ca, ra, ca)) <= 1e-10
+    assert abs(capi.cores_norm(n, ra, ca) ** 2 - capi.cores_dot_l2(n, xg, ra, ca, ra, ca)) > 1e-3

@@ -342,7 +342,11 @@ def test_vi_solve_fixed_rank_equals_the_cross_driver(gpu):
     assert list(ranks) == list(rg)
     for x, y in zip(cores, cg):
         assert np.array_equal(x, y)
-    assert abs(L.valuef_norm(out) - capi.cores_norm(cfg.ngrid, rg, cg)) <= 1e-12 * L.valuef_norm(out)
+    L.valuef_norm_nodal.restype = dbl; L.valuef_norm_nodal.argtypes = [vp]
+    assert abs(L.valuef_norm_nodal(out) - capi.cores_norm(cfg.ngrid, rg, cg)) <= 1e-12 * L.valuef_norm_nodal(out)
+    # valuef_norm is the reference's quantity: the continuous L2 norm of the piecewise-linear train
+    want = np.sqrt(capi.cores_dot_l2(cfg.ngrid, prob.xgrid, rg, cg, rg, cg))
+    assert abs(L.valuef_norm(out) - want) <= 1e-12 * want
     assert L.valuef_norm2diff(out, v0) > 0
     f = C.create_string_buffer(b"/dev/null")
     assert L.diag_save(head, f) == 0
@@ -438,6 +442,8 @@ def test_pi_regression_norm_from_the_paper(gpu):
     w = np.full(N, 4.0 / (N - 1)); w[0] = w[-1] = 2.0 / (N - 1)    # trapezoid rule on [-2, 2]
     l2 = float(np.sqrt(np.einsum("i,j,ij->", w, w, V * V)))
     assert abs(100.0 - l2) / 100.0 < 0.1, l2
+    # valuef_norm IS that norm now (continuous L2 of the piecewise-linear train, as in tprob_test.c:2346-2348)
+    assert abs(100.0 - L.valuef_norm(cost)) / 100.0 < 0.1 and abs(L.valuef_norm(cost) - l2) < 0.02 * l2
     assert V.min() > 0 and abs(V[N // 2, N // 2] - V.min()) < 0.05 * V.max()      # bowl centred at the origin
     L.valuef_destroy(cost); L.approx_args_free(a); hp.close()
 
