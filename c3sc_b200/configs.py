@@ -15,7 +15,7 @@ from dataclasses import dataclass, field
 
 import numpy as np
 
-MODEL_LQGND, MODEL_DOUBLE_INT, MODEL_DUBINS, MODEL_SKID5D = 1, 2, 3, 4
+MODEL_LQGND, MODEL_DOUBLE_INT, MODEL_DUBINS, MODEL_SKID5D, MODEL_USER = 1, 2, 3, 4, 5
 ABSORB, PERIODIC, REFLECT = 1, 2, 3          # enum EBTYPE, reference src/boundary.h:42-47
 
 
@@ -98,6 +98,10 @@ def get_config(name: str, n: int | None = None, rank: int | None = None, dx: int
         bcv = ABSORB if name == "lqgnd" else REFLECT
         c = Config(name, MODEL_LQGND, d, d // 2, d, 100, np.full(d, -2.0), np.full(d, 2.0),
                    np.full(d, bcv, np.int32), 0.1, _tensor_grid([-1.0, 0.0, 1.0], d // 2), 20)
+    elif name == "user_vdp":         # examples/user_model_vdp.cuh: the example USER model (controlled Van der Pol), not a BASELINE config
+        c = Config(name, MODEL_USER, 2, 1, 2, 40, np.full(2, -3.0), np.full(2, 3.0),
+                   np.array([REFLECT, ABSORB], np.int32), 0.2, c3_linspace(-2.0, 2.0, 9).reshape(-1, 1), 6,
+                   obs_center=np.array([[1.5, 1.5]]), obs_width=np.array([[0.6, 0.6]]))
     else:
         raise KeyError(name)
     if n is not None:

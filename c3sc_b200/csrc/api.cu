@@ -27,6 +27,8 @@ int ft_ring_regions();
 int fused_ok_lqg_lo(int dx, int arith, const CtlArgs &c, int pi_eval);
 int fused_ok_lqg_hi(int dx, int arith, const CtlArgs &c, int pi_eval);
 int fused_ok_misc(int model, int dx, int arith, const CtlArgs &c, int pi_eval);
+int user_model_nud();
+int user_model_dims(int *dx, int *du);
 int ft_uses_mma(const DevFT &ft);
 int launch_ft_eval_points(const DevProblem &P, const DevFT &ft, int npts, const double *pts, double *out, cudaStream_t st);
 int launch_policy_points(const DevProblem &P, int n, const double *x, double *pts, int *absorbed, cudaStream_t st);
@@ -349,9 +351,14 @@ int c3sc_problem_create(const c3sc_problem_desc *d, c3sc_problem **out)
         P.t[2 * i + 1] = d->t[2 * i + 1];
     }
     // model parameter defaults = the reference examples' constants
-    static const double defaults[5][8] = {{0}, {1.0, 1.0, 100.0, 0.0}, {1.0, 1.0, 1000.0, 0.0},
-                                          {1.0, 1e-2, 1.0, 10.0, 0.0}, {0.0}};
-    if (d->model < 0 || d->model > 4) { delete p; return fail(C3SC_EUNSUPPORTED, "model %d unknown", d->model); }
+    static const double defaults[6][8] = {{0}, {1.0, 1.0, 100.0, 0.0}, {1.0, 1.0, 1000.0, 0.0},
+                                          {1.0, 1e-2, 1.0, 10.0, 0.0}, {0.0}, {1.0, 0.5, 0.5, 50.0, 0.0}};
+    if (d->model < 0 || d->model > 5) { delete p; return fail(C3SC_EUNSUPPORTED, "model %d unknown", d->model); }
+    if (d->model == C3SC_MODEL_USER) {
+        int udx = 0, udu = 0;
+        if (user_model_dims(&udx, &udu)) { delete p; return fail(C3SC_EUNSUPPORTED, "the library was built without a user model (make USER_MODEL=...)"); }
+        if ((int)d->dx != udx || (int)d->du != udu) { delete p; return fail(C3SC_EINVAL, "the user model is %d-dimensional with %d controls", udx, udu); }
+    }
     if (geometry_only) P.nu = 0;
     memcpy(P.mp, defaults[d->model], sizeof P.mp);
     for (uint32_t i = 0; i < d->n_model_params && i < 8; i++) P.mp[i] = d->model_params[i];
@@ -387,7 +394,7 @@ int c3sc_problem_create(const c3sc_problem_desc *d, c3sc_problem **out)
     if (!geometry_only) p->h_utab.assign(d->controls, d->controls + (size_t)d->nu * d->du);
     // candidate table of separable models (row stride 2*NUD+2; NUD = dx/2 for LQG, 1 otherwise)
     if (!geometry_only) {
-        const int nud = (d->model == C3SC_MODEL_LQGND) ? (int)d->dx / 2 : (d->model == C3SC_MODEL_SKID5D ? 0 : 1);
+        const int nud = (d->model == C3SC_MODEL_LQGND) ? (int)d->dx / 2 : (d->model == C3SC_MODEL_SKID5D ? 0 : (d->model == C3SC_MODEL_USER ? user_model_nud() : 1));
         const int ct = 2 * nud + 2;
         CKP(cudaMalloc(&p->d_ctab, (size_t)d->nu * ct * sizeof(double)));
         CKP(cudaMemset(p->d_ctab, 0, (size_t)d->nu * ct * sizeof(double)));

@@ -13,7 +13,29 @@ __device__ void fused_walk_misc(int model, int dx, const CtlArgs &c, const Fused
         break;
     case C3SC_MODEL_DUBINS: fused_walk_m<Dubins>(c, w); break;
     case C3SC_MODEL_SKID5D: fused_walk_m<Skid5d>(c, w); break;
+#ifdef C3SC_USER_MODEL_HEADER
+    case C3SC_MODEL_USER: fused_walk_m<UserModel>(c, w); break;
+#endif
     }
+}
+// control dimensions of the USER model's candidate table (0: not separable, no table); -1: no user model compiled in
+int user_model_nud()
+{
+#ifdef C3SC_USER_MODEL_HEADER
+    return UserModel::SEP ? UserModel::NUD : 0;
+#else
+    return -1;
+#endif
+}
+int user_model_dims(int *dx, int *du)
+{
+#ifdef C3SC_USER_MODEL_HEADER
+    *dx = UserModel::DX; *du = UserModel::DU;
+    return 0;
+#else
+    (void)dx; (void)du;
+    return -1;
+#endif
 }
 int fused_ok_misc(int model, int dx, int arith, const CtlArgs &c, int pi_eval)
 {
@@ -27,6 +49,9 @@ int fused_ok_misc(int model, int dx, int arith, const CtlArgs &c, int pi_eval)
         return 0;
     case C3SC_MODEL_DUBINS: return dx == 3 ? fused_ok_m<Dubins>(arith, c, pi_eval) : 0;
     case C3SC_MODEL_SKID5D: return dx == 5 ? fused_ok_m<Skid5d>(arith, c, pi_eval) : 0;
+#ifdef C3SC_USER_MODEL_HEADER
+    case C3SC_MODEL_USER: return dx == UserModel::DX ? fused_ok_m<UserModel>(arith, c, pi_eval) : 0;
+#endif
     }
     return 0;
 }
@@ -42,6 +67,9 @@ int launch_control_misc(int model, int dx, int arith, const CtlArgs &a, int pi_e
         return -1;
     case C3SC_MODEL_DUBINS: return dx == 3 ? launch_control_m<Dubins>(arith, a, pi_eval, st) : -1;
     case C3SC_MODEL_SKID5D: return dx == 5 ? launch_control_m<Skid5d>(arith, a, pi_eval, st) : -1;
+#ifdef C3SC_USER_MODEL_HEADER
+    case C3SC_MODEL_USER: return dx == UserModel::DX ? launch_control_m<UserModel>(arith, a, pi_eval, st) : -1;
+#endif
     }
     return -1;
 }
@@ -58,6 +86,9 @@ int launch_model_eval_misc(int model, int dx, const DevProblem &P, int n, const 
         return -1;
     case C3SC_MODEL_DUBINS: return dx == 3 ? launch_model_eval_t<Dubins>(P, n, x, u, drift, sig, stage, bound, obs, st) : -1;
     case C3SC_MODEL_SKID5D: return dx == 5 ? launch_model_eval_t<Skid5d>(P, n, x, u, drift, sig, stage, bound, obs, st) : -1;
+#ifdef C3SC_USER_MODEL_HEADER
+    case C3SC_MODEL_USER: return dx == UserModel::DX ? launch_model_eval_t<UserModel>(P, n, x, u, drift, sig, stage, bound, obs, st) : -1;
+#endif
     }
     return -1;
 }
@@ -74,6 +105,9 @@ int build_ctab_misc(int model, int dx, const DevProblem &P, double *ctab, cudaSt
         return -1;
     case C3SC_MODEL_DUBINS: return dx == 3 ? build_ctab_t<Dubins>(P, ctab, st) : -1;
     case C3SC_MODEL_SKID5D: return dx == 5 ? 0 : -1;
+#ifdef C3SC_USER_MODEL_HEADER
+    case C3SC_MODEL_USER: return dx == UserModel::DX ? build_ctab_t<UserModel>(P, ctab, st) : -1;
+#endif
     }
     return -1;
 }
@@ -91,6 +125,9 @@ int launch_node_backup_misc(int model, int dx, int arith, const DevProblem &P, i
         return -1;
     case C3SC_MODEL_DUBINS: return dx == 3 ? launch_node_backup_t<Dubins>(arith, P, n, x, costs, absorbed, value, argmin, st) : -1;
     case C3SC_MODEL_SKID5D: return dx == 5 ? launch_node_backup_t<Skid5d>(arith, P, n, x, costs, absorbed, value, argmin, st) : -1;
+#ifdef C3SC_USER_MODEL_HEADER
+    case C3SC_MODEL_USER: return dx == UserModel::DX ? launch_node_backup_t<UserModel>(arith, P, n, x, costs, absorbed, value, argmin, st) : -1;
+#endif
     }
     return -1;
 }
@@ -108,6 +145,9 @@ int launch_control_value_misc(int model, int dx, int arith, const DevProblem &P,
         return -1;
     case C3SC_MODEL_DUBINS: return dx == 3 ? launch_control_value_t<Dubins>(arith, P, n, x, u, costs, value, st) : -1;
     case C3SC_MODEL_SKID5D: return dx == 5 ? launch_control_value_t<Skid5d>(arith, P, n, x, u, costs, value, st) : -1;
+#ifdef C3SC_USER_MODEL_HEADER
+    case C3SC_MODEL_USER: return dx == UserModel::DX ? launch_control_value_t<UserModel>(arith, P, n, x, u, costs, value, st) : -1;
+#endif
     }
     return -1;
 }

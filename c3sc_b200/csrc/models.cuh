@@ -172,3 +172,9 @@ struct Skid5d {
 };
 
 }  // namespace c3sc
+
+// The USER model slot (C3SC_MODEL_USER): a header named at build time (make USER_MODEL=...; default
+// examples/user_model_vdp.cuh) that defines struct c3sc::UserModel with the interface above.
+#ifdef C3SC_USER_MODEL_HEADER
+#include C3SC_USER_MODEL_HEADER
+#endif

@@ -61,7 +61,10 @@ enum c3sc_model {
     C3SC_MODEL_LQGND = 1,
     C3SC_MODEL_DOUBLE_INT = 2,
     C3SC_MODEL_DUBINS = 3,
-    C3SC_MODEL_SKID5D = 4
+    C3SC_MODEL_SKID5D = 4,
+    C3SC_MODEL_USER = 5       /* struct c3sc::UserModel of the header the library was built with (make USER_MODEL=...;
+                                 default examples/user_model_vdp.cuh: controlled Van der Pol oscillator, params
+                                 [mu, s0, s1, boundcost, obscost]) -- INTEGRATION.md, "Adding a device model"     */
 };
 
 /* EXACT reproduces the reference's operation order without fused

@@ -16,12 +16,13 @@ static int    g_model = 0;
 static size_t g_dim = 0;
 static double g_par[8];
 
-static const double k_defaults[5][8] = {
+static const double k_defaults[6][8] = {
     {0},
     {1.0, 1.0, 100.0, 0.0},          /* lqgnd.c:236 ss={1,1}; :164 boundcost 100; :175 ocost 0 */
     {1.0, 1.0, 1000.0, 0.0},         /* double_int.c:147 boundcost 1000 */
     {1.0, 1e-2, 1.0, 10.0, 0.0},     /* dubinscar.c:67-68, :93, :110, :121 */
     {0.0},
+    {1.0, 0.5, 0.5, 50.0, 0.0},      /* user model (Van der Pol): mu, s0, s1, boundcost, obscost */
 };
 
 int orc_model_dims(int model, size_t dx, size_t *du, size_t *dw)
@@ -31,6 +32,7 @@ int orc_model_dims(int model, size_t dx, size_t *du, size_t *dw)
     case ORC_MODEL_DOUBLE_INT: *du = 1; *dw = dx; return 0;                             /* double_int.c:259-261 */
     case ORC_MODEL_DUBINS:     if (dx != 3) return 1; *du = 1; *dw = 3; return 0;
     case ORC_MODEL_SKID5D:     if (dx != 5) return 1; *du = 1; *dw = 5; return 0;
+    case ORC_MODEL_USER:       if (dx != 2) return 1; *du = 1; *dw = 2; return 0;
     }
     return 1;
 }
@@ -82,6 +84,10 @@ static int drift_cb(double t, const double *x, const double *u, double *out, dou
         out[4] = -s * angvel + (ff + ft) / m;
         return 0;
     }
+    case ORC_MODEL_USER:                    /* what a user's host drift callback looks like: controlled Van der Pol */
+        out[0] = x[1];
+        out[1] = g_par[0] * (1.0 - x[0] * x[0]) * x[1] - x[0] + u[0];
+        return 0;
     }
     return 1;
 }
@@ -111,6 +117,9 @@ static int diff_cb(double t, const double *x, const double *u, double *out, doub
                                                without the out-of-bounds store. */
         out[0] = 1e-5; out[6] = 1e-5; out[12] = 1e-5; out[24] = 1e-5;
         return 0;
+    case ORC_MODEL_USER:
+        out[0] = g_par[1]; out[3] = g_par[2];
+        return 0;
     }
     return 1;
 }
@@ -136,6 +145,7 @@ static int stage_cb(double t, const double *x, const double *u, double *out, dou
         *out = g;
         return 0;
     }
+    case ORC_MODEL_USER: *out = x[0] * x[0] + x[1] * x[1] + u[0] * u[0]; return 0;
     }
     return 1;
 }
@@ -153,6 +163,7 @@ static int bound_cb(double t, const double *x, double *out)
         *out = g;
         return 0;
     }
+    case ORC_MODEL_USER:       *out = g_par[3]; return 0;
     }
     return 1;
 }
@@ -165,6 +176,7 @@ static int obs_cb(const double *x, double *out)
     case ORC_MODEL_DOUBLE_INT: *out = g_par[3]; return 0;
     case ORC_MODEL_DUBINS:     *out = g_par[4]; return 0;
     case ORC_MODEL_SKID5D:     *out = g_par[0]; return 0;
+    case ORC_MODEL_USER:       *out = g_par[4]; return 0;
     }
     return 1;
 }

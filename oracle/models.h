@@ -10,7 +10,8 @@
 extern "C" {
 #endif
 /* ids are the values of enum c3sc_model in include/c3sc_b200.h */
-enum { ORC_MODEL_LQGND = 1, ORC_MODEL_DOUBLE_INT = 2, ORC_MODEL_DUBINS = 3, ORC_MODEL_SKID5D = 4 };
+enum { ORC_MODEL_LQGND = 1, ORC_MODEL_DOUBLE_INT = 2, ORC_MODEL_DUBINS = 3, ORC_MODEL_SKID5D = 4,
+       ORC_MODEL_USER = 5 /* examples/user_model_vdp.cuh: the host callbacks of the example user model */ };
 
 /* Select the model the callbacks below evaluate (they read file-static
  * state exactly like the reference examples read their static `dim`).

@@ -17,6 +17,7 @@ SMALL = [
     ("skidding5d", 10, 3, None),
     ("lqgnd", 12, 3, 4),
     ("lqgnd_reflect", 8, 3, 6),
+    ("user_vdp", 24, 4, None),          # the example USER model (examples/user_model_vdp.cuh), general (non-separable) walk
 ]
 
 

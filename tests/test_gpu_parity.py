@@ -88,7 +88,7 @@ def test_policy_rows_bit_exact_in_exact_mode(gpu, name, n, rank, dx):
     sel = (out["argmin"] == oarg) & (oarg >= 0) & valid_mask(cfg, dv)
     assert sel.sum() > 0
     g, o = out["rows"][sel], orows[sel]
-    if cfg.model in (configs.MODEL_LQGND, configs.MODEL_DOUBLE_INT):
+    if cfg.model in (configs.MODEL_LQGND, configs.MODEL_DOUBLE_INT, configs.MODEL_USER):
         assert np.array_equal(g, o)
     else:
         assert rel_err(g[:, :-3], o[:, :-3], scale=1e-3) <= 1e-13      # probabilities
@@ -166,7 +166,7 @@ def test_device_model_equals_host_callbacks(gpu, name, n, rank, dx):
     u = cfg.controls[np.arange(ne) % cfg.nu]
     g = prob.model_eval(x, u)
     o = port.model_eval(x, u)
-    if cfg.model in (configs.MODEL_LQGND, configs.MODEL_DOUBLE_INT):
+    if cfg.model in (configs.MODEL_LQGND, configs.MODEL_DOUBLE_INT, configs.MODEL_USER):
         for a, b in zip(g, o):
             assert np.array_equal(a, b)
     else:

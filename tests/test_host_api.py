@@ -90,7 +90,7 @@ class HostProblem:
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("name,n,rank,dx", [("double_int", 24, 5, None), ("dubinscar_new", 16, 4, None),
-                                             ("skidding5d", 10, 3, None), ("lqgnd_reflect", 8, 3, 6)])
+                                             ("skidding5d", 10, 3, None), ("lqgnd_reflect", 8, 3, 6), ("user_vdp", 20, 3, None)])
 def test_bellman_vi_and_pi_one_fiber_per_call(gpu, name, n, rank, dx):
     L = host_lib()
     cfg = configs.get_config(name, n=n, rank=rank, dx=dx)
