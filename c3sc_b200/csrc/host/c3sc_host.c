@@ -1058,9 +1058,10 @@ double valuef_norm(struct ValueF *v)
 double valuef_norm2diff(struct ValueF *a, struct ValueF *b)
 {
     uint64_t n[C3SC_MAXD], ra[C3SC_MAXD + 1], rb[C3SC_MAXD + 1];
-    if (!a->xgrid) die("valuef_norm2diff: the value function has no grid (valuef_set_grid); valuef_norm2diff_nodal needs none");
+    double **xg = a->xgrid ? a->xgrid : b->xgrid;            /* both functions live on the same grid */
+    if (!xg) die("valuef_norm2diff: neither value function has a grid (valuef_set_grid); valuef_norm2diff_nodal needs none");
     vf_u64(a, n, ra); vf_u64(b, n, rb);
-    return c3sc_cores_norm2diff_l2((uint32_t)a->d, n, (const double *const *)a->xgrid, ra, (const double *const *)a->cores, rb,
+    return c3sc_cores_norm2diff_l2((uint32_t)a->d, n, (const double *const *)xg, ra, (const double *const *)a->cores, rb,
                                    (const double *const *)b->cores);
 }
 /* NEW names: the discrete l2 of the node values (what valuef_norm was in the first round of this library) */
@@ -1342,6 +1343,7 @@ struct ValueF *c3control_vi_solve(struct C3Control *c, size_t maxiter, double ab
                                   struct ApproxArgs *apargs, struct c3Opt *opt, int verbose, struct Diag **diag)
 {
     struct ValueF *start = valuef_copy(vo);
+    if (!start->xgrid) valuef_set_grid(start, c->xgrid);   /* a value function built from bare cores lives on the solver's grid */
     workspace_reset_vi_htable(c->work);
     double stot = 1.0;
     for (size_t j = 0; j < c->dx; j++) stot *= (double)c->ngrid[j];
@@ -1361,6 +1363,7 @@ struct ValueF *c3control_pi_solve(struct C3Control *c, size_t maxiter, double ab
                                   struct ApproxArgs *apargs, struct c3Opt *opt, int verbose, struct Diag **diag)
 {
     struct ValueF *start = valuef_copy(policy);
+    if (!start->xgrid) valuef_set_grid(start, c->xgrid);
     struct PIparam *poli = pi_param_create(1e-10, policy);
     workspace_increment_pi_iter(c->work);
     workspace_reset_pi_prob_htable(c->work);
