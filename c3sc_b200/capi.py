@@ -70,7 +70,7 @@ EXPORTS = [
     "c3sc_multi_create", "c3sc_multi_destroy", "c3sc_multi_device_count", "c3sc_multi_uses_nccl", "c3sc_multi_problem",
     "c3sc_multi_valuef_create", "c3sc_multi_valuef_update", "c3sc_multi_valuef_destroy", "c3sc_multi_valuef_get", "c3sc_multi_shard",
     "c3sc_multi_vi_batch", "c3sc_multi_pi_batch", "c3sc_multi_pi_reset", "c3sc_multi_gathered_count", "c3sc_multi_vi_batch_gathered",
-    "c3sc_cross_run_vi_multi", "c3sc_cross_run_pi_multi", "c3sc_host_alloc", "c3sc_host_free", "c3sc_vi_batch_peers",
+    "c3sc_cross_run_vi_multi", "c3sc_cross_run_pi_multi", "c3sc_host_alloc", "c3sc_host_free", "c3sc_vi_batch_peers", "c3sc_guard_check",
 ]
 
 _lib = None

@@ -82,6 +82,41 @@ static int fail(int code, const char *fmt, ...)
         if (e_ != cudaSuccess) return fail(C3SC_ECUDA, "%s: %s", #call, cudaGetErrorString(e_)); \
     } while (0)
 
+// ---- guard zones (C3SC_GUARD=1): the pool this library is developed on has compute-sanitizer switched off, so the
+// library carries its own check.  Every device allocation gets a 64 kB zone of 0xFF bytes on either side (NaN as a
+// double, -1 as an int): a write outside an allocation damages a zone (c3sc_guard_check counts damaged zones), and a
+// read outside an allocation that reaches a result turns it into NaN, which the parity tests catch.
+constexpr size_t GUARD_BYTES = 64 << 10;
+struct GuardRec { char *raw; size_t bytes; int device; };
+static std::mutex g_guard_mu;
+static std::vector<GuardRec> g_guards;
+static bool guard_on() { static const bool on = getenv("C3SC_GUARD") != nullptr; return on; }
+static cudaError_t dev_malloc(void **p, size_t bytes)
+{
+    if (!guard_on()) return cudaMalloc(p, bytes);
+    char *raw = nullptr;
+    const size_t padded = (bytes + 255) & ~(size_t)255;
+    cudaError_t e = cudaMalloc(&raw, padded + 2 * GUARD_BYTES);
+    if (e != cudaSuccess) return e;
+    e = cudaMemset(raw, 0xFF, padded + 2 * GUARD_BYTES);
+    if (e != cudaSuccess) { cudaFree(raw); return e; }
+    GuardRec r = {raw, padded, 0};
+    cudaGetDevice(&r.device);
+    { std::lock_guard<std::mutex> lk(g_guard_mu); g_guards.push_back(r); }
+    *p = raw + GUARD_BYTES;
+    return cudaSuccess;
+}
+template <class T> static cudaError_t dev_malloc(T **p, size_t bytes) { return dev_malloc((void **)p, bytes); }
+static void dev_free(void *p)
+{
+    if (!p) return;
+    if (!guard_on()) { cudaFree(p); return; }
+    char *raw = (char *)p - GUARD_BYTES;
+    { std::lock_guard<std::mutex> lk(g_guard_mu);
+      for (size_t i = 0; i < g_guards.size(); i++) if (g_guards[i].raw == raw) { g_guards.erase(g_guards.begin() + i); break; } }
+    cudaFree(raw);
+}
+
 // grow-only device scratch
 struct DevBuf {
     void *p = nullptr;
@@ -89,13 +124,13 @@ struct DevBuf {
     int reserve(size_t bytes)
     {
         if (bytes <= cap) return 0;
-        if (p) cudaFree(p);
+        if (p) dev_free(p);
         p = nullptr; cap = 0;
-        if (cudaMalloc(&p, bytes) != cudaSuccess) return 1;
+        if (dev_malloc(&p, bytes) != cudaSuccess) return 1;
         cap = bytes;
         return 0;
     }
-    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+    void release() { if (p) dev_free(p); p = nullptr; cap = 0; }
 };
 
 // per-problem scratch of the two-stage pipeline (one batch in flight per problem, like the
@@ -275,6 +310,30 @@ int c3sc_cuda_init(int device)
     return C3SC_OK;
 }
 
+/* C3SC_GUARD=1 (set before the first allocation): number of guard zones around the library's device allocations that no
+ * longer hold their fill pattern, i.e. allocations something wrote outside of; synchronises the devices.  0 without guards. */
+int c3sc_guard_check(void)
+{
+    if (!guard_on()) return 0;
+    std::lock_guard<std::mutex> lk(g_guard_mu);
+    int prev = 0, damaged = 0;
+    cudaGetDevice(&prev);
+    std::vector<unsigned char> h(GUARD_BYTES);
+    for (const GuardRec &r : g_guards) {
+        cudaSetDevice(r.device);
+        cudaDeviceSynchronize();
+        for (int side = 0; side < 2; side++) {
+            const char *z = side ? r.raw + GUARD_BYTES + r.bytes : r.raw;
+            if (cudaMemcpy(h.data(), z, GUARD_BYTES, cudaMemcpyDeviceToHost) != cudaSuccess) { damaged++; continue; }
+            bool ok = true;
+            for (size_t i = 0; i < GUARD_BYTES && ok; i++) ok = h[i] == 0xFF;
+            if (!ok) damaged++;
+        }
+    }
+    cudaSetDevice(prev);
+    return damaged;
+}
+
 /* page-locked host memory, usable from every device of the process: host buffers handed to the batch entries
  * move at PCIe speed only when they are page-locked (pageable memory goes through the driver's staging copies) */
 int c3sc_host_alloc(size_t bytes, void **ptr)
@@ -375,15 +434,15 @@ int c3sc_problem_create(const c3sc_problem_desc *d, c3sc_problem **out)
         cudaError_t e_ = (call);                                                                     \
         if (e_ != cudaSuccess) { c3sc_problem_destroy(p); return fail(C3SC_ECUDA, "%s: %s", #call, cudaGetErrorString(e_)); } \
     } while (0)
-    CKP(cudaMalloc(&p->d_xgrid, total * sizeof(double)));
+    CKP(dev_malloc(&p->d_xgrid, total * sizeof(double)));
     CKP(cudaMemcpy(p->d_xgrid, xg.data(), total * sizeof(double), cudaMemcpyHostToDevice));
-    CKP(cudaMalloc(&p->d_obs, obs.size() * sizeof(double)));
+    CKP(dev_malloc(&p->d_obs, obs.size() * sizeof(double)));
     CKP(cudaMemcpy(p->d_obs, obs.data(), obs.size() * sizeof(double), cudaMemcpyHostToDevice));
     if (!geometry_only) {
-        CKP(cudaMalloc(&p->d_utab, (size_t)d->nu * d->du * sizeof(double)));
+        CKP(dev_malloc(&p->d_utab, (size_t)d->nu * d->du * sizeof(double)));
         CKP(cudaMemcpy(p->d_utab, d->controls, (size_t)d->nu * d->du * sizeof(double), cudaMemcpyHostToDevice));
     }
-    CKP(cudaMalloc(&p->d_err, 4 * sizeof(int)));
+    CKP(dev_malloc(&p->d_err, 4 * sizeof(int)));
     CKP(cudaMemcpy(p->d_err, k_err_clear, sizeof k_err_clear, cudaMemcpyHostToDevice));
     CKP(cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking));
     CKP(cudaStreamCreateWithFlags(&p->copy_stream, cudaStreamNonBlocking));
@@ -396,7 +455,7 @@ int c3sc_problem_create(const c3sc_problem_desc *d, c3sc_problem **out)
     if (!geometry_only) {
         const int nud = (d->model == C3SC_MODEL_LQGND) ? (int)d->dx / 2 : (d->model == C3SC_MODEL_SKID5D ? 0 : (d->model == C3SC_MODEL_USER ? user_model_nud() : 1));
         const int ct = 2 * nud + 2;
-        CKP(cudaMalloc(&p->d_ctab, (size_t)d->nu * ct * sizeof(double)));
+        CKP(dev_malloc(&p->d_ctab, (size_t)d->nu * ct * sizeof(double)));
         CKP(cudaMemset(p->d_ctab, 0, (size_t)d->nu * ct * sizeof(double)));
         P.ctab = p->d_ctab;
         P.amin = 0.0;
@@ -442,7 +501,7 @@ int c3sc_problem_create(const c3sc_problem_desc *d, c3sc_problem **out)
                 }
                 G.gstart[shares.size()] = (int)pos;
                 G.ng = (int)shares.size();
-                CKP(cudaMalloc(&p->d_gtab, gt.size() * sizeof(double)));
+                CKP(dev_malloc(&p->d_gtab, gt.size() * sizeof(double)));
                 CKP(cudaMemcpy(p->d_gtab, gt.data(), gt.size() * sizeof(double), cudaMemcpyHostToDevice));
                 P.gtab = p->d_gtab;
             }
@@ -457,7 +516,7 @@ void c3sc_problem_destroy(c3sc_problem *p)
 {
     if (!p) return;
     DeviceScope ds_(p->device);
-    cudaFree(p->d_xgrid); cudaFree(p->d_obs); cudaFree(p->d_utab); cudaFree(p->d_err); cudaFree(p->d_ctab); cudaFree(p->d_gtab);
+    dev_free(p->d_xgrid); dev_free(p->d_obs); dev_free(p->d_utab); dev_free(p->d_err); dev_free(p->d_ctab); dev_free(p->d_gtab);
     DevBuf *bufs[] = {&p->b_dv, &p->b_fi, &p->b_val, &p->b_arg, &p->b_abs, &p->b_costs, &p->b_rows, &p->b_nv, &p->b_nf};
     for (DevBuf *b : bufs) b->release();
     for (DevBuf &b : p->b_misc) b.release();
@@ -511,20 +570,20 @@ int c3sc_valuef_create(uint32_t d, const uint64_t *n, const uint64_t *ranks, con
     ft.r[d] = 1;
     if (ft.rmax < 1) ft.rmax = 1;
     vf->count = total;
-    cudaError_t e = cudaMalloc(&vf->d_base, total * sizeof(double));
-    if (e == cudaSuccess) e = cudaMalloc(&vf->d_baseT, total * sizeof(double));
-    if (e != cudaSuccess) { cudaFree(vf->d_base); delete vf; return fail(C3SC_ECUDA, "cudaMalloc cores: %s", cudaGetErrorString(e)); }
+    cudaError_t e = dev_malloc(&vf->d_base, total * sizeof(double));
+    if (e == cudaSuccess) e = dev_malloc(&vf->d_baseT, total * sizeof(double));
+    if (e != cudaSuccess) { dev_free(vf->d_base); delete vf; return fail(C3SC_ECUDA, "cudaMalloc cores: %s", cudaGetErrorString(e)); }
     ft.base = vf->d_base;
     ft.baseT = vf->d_baseT;
     if (ft_uses_mma(ft)) {
         const long long np = ft_padded_layout(ft);
-        e = cudaMalloc(&vf->d_baseP, (size_t)np * sizeof(double));
-        if (e != cudaSuccess) { cudaFree(vf->d_base); cudaFree(vf->d_baseT); delete vf; return fail(C3SC_ECUDA, "cudaMalloc padded cores: %s", cudaGetErrorString(e)); }
+        e = dev_malloc(&vf->d_baseP, (size_t)np * sizeof(double));
+        if (e != cudaSuccess) { dev_free(vf->d_base); dev_free(vf->d_baseT); delete vf; return fail(C3SC_ECUDA, "cudaMalloc padded cores: %s", cudaGetErrorString(e)); }
         ft.baseP = vf->d_baseP;
         const long long nq = ft_compact_layout(ft);
-        e = cudaMalloc(&vf->d_baseQ, (size_t)nq * sizeof(double));
+        e = dev_malloc(&vf->d_baseQ, (size_t)nq * sizeof(double));
         if (e == cudaSuccess) e = cudaMemset(vf->d_baseQ, 0, (size_t)nq * sizeof(double));
-        if (e != cudaSuccess) { cudaFree(vf->d_base); cudaFree(vf->d_baseT); cudaFree(vf->d_baseP); delete vf; return fail(C3SC_ECUDA, "cudaMalloc tile cores: %s", cudaGetErrorString(e)); }
+        if (e != cudaSuccess) { dev_free(vf->d_base); dev_free(vf->d_baseT); dev_free(vf->d_baseP); delete vf; return fail(C3SC_ECUDA, "cudaMalloc tile cores: %s", cudaGetErrorString(e)); }
         ft.baseQ = vf->d_baseQ;
     }
     *out = vf;
@@ -569,10 +628,10 @@ void c3sc_valuef_destroy(c3sc_valuef *vf)
 {
     if (!vf) return;
     DeviceScope ds_(vf->device);
-    cudaFree(vf->d_base);
-    cudaFree(vf->d_baseT);
-    cudaFree(vf->d_baseP);
-    cudaFree(vf->d_baseQ);
+    dev_free(vf->d_base);
+    dev_free(vf->d_baseT);
+    dev_free(vf->d_baseP);
+    dev_free(vf->d_baseQ);
     delete vf;
 }
 
@@ -1162,13 +1221,13 @@ int c3sc_rowstore_reserve(c3sc_rowstore *s, size_t capacity_fibers)
     DeviceScope ds_(s->device);
     const size_t per = s->ldo * (2 * (size_t)s->dx + 3) * sizeof(double);
     double *np = nullptr;
-    if (cudaMalloc(&np, capacity_fibers * per) != cudaSuccess) {
+    if (dev_malloc(&np, capacity_fibers * per) != cudaSuccess) {
         cudaGetLastError();
         return fail(C3SC_ECUDA, "cudaMalloc of the policy-row store (%zu MB) failed", (capacity_fibers * per) >> 20);
     }
     if (s->p) {                                             // growing keeps what is filed
         CK(cudaMemcpy(np, s->p, s->cap_fibers * per, cudaMemcpyDeviceToDevice));
-        cudaFree(s->p);
+        dev_free(s->p);
     }
     s->p = np; s->cap_fibers = capacity_fibers;
     return C3SC_OK;
@@ -1178,7 +1237,7 @@ void c3sc_rowstore_destroy(c3sc_rowstore *s)
 {
     if (!s) return;
     DeviceScope ds_(s->device);
-    cudaFree(s->p);
+    dev_free(s->p);
     delete s;
 }
 

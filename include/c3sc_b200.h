@@ -140,6 +140,13 @@ int c3sc_measure_fp64_peak(double *tflops, int iters, int repeats);
  * the denominator for kernels whose flops run as DMMAs (stage 1).                                            */
 int c3sc_measure_fp64_tensor_peak(double *tflops, int iters, int repeats);
 
+/* The library's own out-of-bounds check (the GPU pool it is developed on has compute-sanitizer switched off).  With
+ * C3SC_GUARD=1 in the environment before the first allocation, every device allocation of the library sits between two
+ * 64 kB zones of 0xFF bytes (NaN as doubles, -1 as ints).  c3sc_guard_check() returns how many zones were damaged (a write
+ * outside an allocation); a READ outside an allocation that reaches a result turns it into NaN, which the parity tests
+ * catch (tests/test_gpu_paths.py::test_guard_zones_*).  Returns 0 when guards are off.                          */
+int c3sc_guard_check(void);
+
 /* Page-locked (pinned, portable) host memory.  The host-buffer entries accept any host pointer, but only page-locked
  * buffers move at PCIe speed and overlap with the kernels (cudaMemcpyAsync from pageable memory is staged by the
  * driver): allocate the fiber descriptors and result arrays of large batches with these.                     */

@@ -281,3 +281,50 @@ def test_fused_stage2_equals_the_two_kernel_pipeline(gpu, monkeypatch, name, n, 
     if name != "skidding5d":                        # a grid-structured control set: no control kernel was launched
         assert launches == 3, launches              # grouping + chains + fused node kernel
     prob.close(); vf.close(); vf2.close()
+
+
+def test_guard_zones_stay_intact_and_nothing_reads_them(gpu):
+    """the library's own memcheck (compute-sanitizer is closed on this GPU pool, profiles/r02_sanitizer_closed.log): in a fresh
+    process with C3SC_GUARD=1 every device allocation sits between 0xFF-filled zones; the parity cases of every kernel family
+    (both chain stages, tensor-core node kernel at odd / mixed ranks, general kernel, grid / grouped / table walks, PI, fused
+    stage 2, off-grid entries, ragged grids) must still match the oracle -- an out-of-bounds read that reached a result would
+    be NaN -- and no zone may be damaged afterwards (an out-of-bounds write)."""
+    import os, subprocess, sys, textwrap
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = textwrap.dedent("""
+        import os, sys
+        sys.path.insert(0, os.path.join(%r, "tests")); sys.path.insert(0, %r)
+        import numpy as np
+        from c3sc_b200 import capi, configs, synthetic
+        import test_gpu_paths as T
+        L = capi.lib(); capi.check(L.c3sc_cuda_init(0))
+        for rank in (1, 7, 20, 31):
+            cfg = configs.get_config("skidding5d", n=12, rank=rank); T._check_costs_and_values(cfg, cfg.ranks(), 24)
+        cfg = configs.get_config("lqgnd", n=9, dx=6)
+        T._check_costs_and_values(cfg, np.array([1, 3, 8, 5, 12, 2, 1], dtype=np.uint64), 67, seed=67)
+        cfg = configs.get_config("dubinscar_new", n=14, rank=40); T._check_costs_and_values(cfg, cfg.ranks(), 40)      # general kernel
+        cfg = configs.get_config("skidding5d", n=12, rank=4); cfg.nvec = np.array([9, 12, 8, 10, 11], dtype=np.uint64)
+        T._check_costs_and_values(cfg, cfg.ranks(), 45)                                                                # ragged
+        os.environ["C3SC_CHAIN_MIN"] = "1"                                                                             # bucketed chains
+        cfg = configs.get_config("lqgnd_reflect", n=16, rank=20, dx=10); T._check_costs_and_values(cfg, cfg.ranks(), 300, face_frac=0.3)
+        cfg = configs.get_config("dubinscar_new", n=14, rank=12); T._check_costs_and_values(cfg, cfg.ranks(), 200)
+        del os.environ["C3SC_CHAIN_MIN"]
+        os.environ["C3SC_FUSE"] = "1"                                                                                  # fused stage 2
+        cfg = configs.get_config("lqgnd_reflect", n=12, rank=7, dx=10)
+        prob = capi.Problem(cfg, arith=1); ranks = cfg.ranks()
+        vf = capi.ValueF(cfg.ngrid, ranks, synthetic.random_cores(cfg.ngrid, ranks))
+        dv, fi = synthetic.random_fibers(cfg.ngrid, 2600, seed=13)
+        v1, a1 = prob.vi_batch(vf, dv, fi); p1, rows, _ = prob.pi_batch(vf, vf, dv, fi)
+        del os.environ["C3SC_FUSE"]
+        v0, a0 = prob.vi_batch(vf, dv, fi)
+        assert np.isfinite(v1).all() and np.isfinite(rows).all() and np.array_equal(a0, a1) and np.abs(v1 - v0).max() <= 1e-14 * np.abs(v0).max()
+        x = cfg.lb + synthetic.uniform01(3, 50 * cfg.dx).reshape(50, cfg.dx) * (cfg.ub - cfg.lb)
+        u, val, ab, costs = prob.policy_eval(vf, x)
+        assert np.isfinite(val).all() and np.isfinite(costs).all()
+        prob.close(); vf.close()
+        print("GUARD_DAMAGED", L.c3sc_guard_check())
+    """ % (root, root))
+    env = dict(os.environ, C3SC_GUARD="1")
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=900, env=env)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
+    assert "GUARD_DAMAGED 0" in r.stdout, r.stdout[-500:]
