@@ -61,7 +61,7 @@ EXPORTS = [
     "c3sc_transition_batch", "c3sc_model_eval", "c3sc_measure_fp64_peak", "c3sc_measure_fp64_tensor_peak",
     "c3sc_neighbor_costs_batch", "c3sc_node_backup_batch", "c3sc_control_value_batch", "c3sc_rhs_batch",
     "c3sc_transition_raw", "c3sc_ft_fiber_nn_batch", "c3sc_valuef_commit",
-    "c3sc_cross_create", "c3sc_cross_copy", "c3sc_cross_destroy", "c3sc_cross_ranks", "c3sc_cross_run", "c3sc_cross_run_vi", "c3sc_cross_run_pi",
+    "c3sc_cross_create", "c3sc_cross_copy", "c3sc_cross_destroy", "c3sc_cross_pin_buffers", "c3sc_cross_ranks", "c3sc_cross_run", "c3sc_cross_run_vi", "c3sc_cross_run_pi",
     "c3sc_vi_solve", "c3sc_cores_dot", "c3sc_cores_norm", "c3sc_cores_norm2diff", "c3sc_cores_dot_l2", "c3sc_cores_norm_l2", "c3sc_cores_norm2diff_l2",
     "c3sc_valuef_eval_batch", "c3sc_policy_eval_batch",
     "c3sc_cross_index_sets", "c3sc_cores_round", "c3sc_cross_adapt_capacity", "c3sc_cross_set_ranks", "c3sc_cross_run_adapt", "c3sc_cross_run_vi_adapt",
@@ -149,6 +149,7 @@ def lib() -> C.CDLL:
         L.c3sc_policy_eval_batch.argtypes = [vp, vp, sz, vp, vp, vp, vp, vp]
         L.c3sc_cross_create.argtypes = [C.c_uint32, c_u64p, c_u64p, C.POINTER(vp)]
         L.c3sc_cross_destroy.argtypes = [vp]
+        L.c3sc_cross_pin_buffers.argtypes = [vp, C.c_int]
         L.c3sc_cross_copy.argtypes = [vp, C.POINTER(vp)]
         L.c3sc_cross_destroy.restype = None
         L.c3sc_cross_ranks.argtypes = [vp, c_u64p]

@@ -16,7 +16,7 @@
  * c3sc_vi_batch / c3sc_pi_batch in c3sc_cross_run_vi / _pi; the parity tests plug the CPU oracle
  * into the same driver).
  */
-#define _POSIX_C_SOURCE 199309L
+#define _GNU_SOURCE
 #include <math.h>
 #include <stdio.h>
 #include <stdint.h>
@@ -31,7 +31,30 @@ struct c3sc_cross {
     /* left index sets I[k]: r[k] multi-indices over dims 0..k-1 (row-major, stride d);
        right index sets J[k]: r[k] multi-indices over dims k..d-1 (stored at their dims) */
     int32_t *I[C3SC_MAXD + 1], *J[C3SC_MAXD + 1];
+    /* what goes to the operator and comes back (fiber descriptors, fiber values), kept between runs; page-locked
+       when the operator is the GPU (c3sc_cross_pin_buffers): pageable memory crosses PCIe through staging copies */
+    void *xbuf; size_t xcap; int xpinned, want_pinned;
 };
+static void exchange_free(c3sc_cross *c)
+{
+    if (c->xbuf) { if (c->xpinned) c3sc_host_free(c->xbuf); else free(c->xbuf); }
+    c->xbuf = NULL; c->xcap = 0; c->xpinned = 0;
+}
+static void *exchange_get(c3sc_cross *c, size_t bytes)
+{
+    if (c->xbuf && c->xcap >= bytes && c->xpinned == c->want_pinned) return c->xbuf;
+    exchange_free(c);
+    if (c->want_pinned && c3sc_host_alloc(bytes, &c->xbuf) == C3SC_OK) c->xpinned = 1;
+    else c->xbuf = malloc(bytes);
+    c->xcap = c->xbuf ? bytes : 0;
+    return c->xbuf;
+}
+int c3sc_cross_pin_buffers(c3sc_cross *c, int on)
+{
+    if (!c) return C3SC_EINVAL;
+    c->want_pinned = on != 0;
+    return C3SC_OK;
+}
 
 /* src/util.c:995-1006 */
 static uint64_t uniform_stride(uint64_t N, uint64_t M)
@@ -86,6 +109,7 @@ void c3sc_cross_destroy(c3sc_cross *c)
 {
     if (!c) return;
     for (uint32_t k = 0; k <= c->d; k++) { free(c->I[k]); free(c->J[k]); }
+    exchange_free(c);
     free(c);
 }
 
@@ -217,94 +241,188 @@ static void qr_explicit_q(double *A, size_t m, size_t n, double *work /* n + m *
     }
 }
 
-/* Orthonormal basis Q (m x n) of the column space of A, by Householder QR with column pivoting; Q
- * overwrites A (column order is immaterial: the cross core B = Q inv(Q[P,:]) only depends on span(Q)).
- * Columns whose remaining norm falls below RANK_EPS times the largest column norm are numerically dependent:
- * a reflector built from them would point wherever the round-off of the operator's values points, and the
- * pivoting after it would follow.  They get no reflector, so their Q columns are H_0..H_{rank-1} e_k -- a
- * completion that depends on the well-determined part only.  Returns the numerical rank. */
+/* ---- the pivoting step of one core: twin rows -> QR basis -> maxvol, by a team of threads ------------------------
+ * One VI sweep is 2(d-1) of these steps in sequence, each on an unfolding of r N x r numbers between two operator
+ * calls: with the backup on the GPU they are what a sweep costs.  The three phases share one OpenMP parallel region
+ * (the reference is an OpenMP library itself, src/bellman.c:1390-1404).  Rows are cut into LA_NB fixed blocks; a
+ * thread owns a contiguous run of blocks and is the only one that ever writes their rows, so the unfolding stays in
+ * its core's cache from the first phase to the last.  Everything that couples rows (column norms, reflector dots,
+ * pivot searches) is reduced per BLOCK, published, and summed by every thread in block order after a barrier: the
+ * numbers depend on LA_NB, never on the number of threads (C3SC_HOST_THREADS, default min(8, omp_get_max_threads())),
+ * and every thread takes the same branches.  Partial results are double-buffered where the next phase would
+ * otherwise overwrite them before a slow thread has read them. */
+#ifdef _OPENMP
+#include <omp.h>
+#include <sched.h>
+#include <stdatomic.h>
+#endif
+#ifndef LA_NB
+#define LA_NB 16
+#endif
 #define RANK_EPS 1e-11
-#define TIE_EPS 1e-8     /* see maxvol */
-static size_t qr_basis(double *A, size_t m, size_t n, double *work /* 3n + m */)
+#define TIE_EPS 1e-8     /* see team_maxvol */
+#define LA_NONE ((size_t)-1)
+
+typedef struct {
+    size_t mcap, ncap;        /* capacity: rows, columns */
+    size_t m, n, bs;          /* this step: rows, columns, rows per block */
+    int threads;
+    double *Q, *B;            /* m x n column-major: unfolding in / orthonormal basis out; cross core Q inv(Q[P]) out */
+    size_t *P;                /* n pivot rows out */
+    char *skip, *used;        /* m */
+    double *part;             /* [2][LA_NB][ncap] partial sums */
+    double *mp;               /* [2][LA_NB][2] pivot search: max over all rows, max over eligible rows */
+    size_t *ip;               /* [3][LA_NB] pivot search: row / entry */
+    double *priv;             /* [threads][8 ncap] */
+    double *S, *aug;          /* n x n, n x 2n (thread 0) */
+    double *k1; int64_t *qk; uint32_t *slot; size_t slotcap;   /* twin rows */
+    size_t sh_bi, sh_bj; double sh_best;                      /* maxvol: masked scan result of thread 0 */
+    int rc;
+#ifdef _OPENMP
+    char pad0[64]; atomic_int bar_count;                      /* sense-reversing barrier of the team, a cache line each */
+    char pad1[60]; atomic_int bar_sense;
+    char pad2[60];
+#endif
+} la_ws;
+typedef struct { int tid, nt, b0, b1, sense; } la_thr;       /* a thread of the team and the blocks it owns */
+
+/* A step has ~150 barriers with a few microseconds of work between them: the team spins (libgomp's barrier parks
+ * threads in the kernel under some team sizes, 50 us a time); a thread that has lost its CPU is waited for with
+ * sched_yield. */
+static inline void la_barrier(la_ws *w, la_thr *t)
 {
-    double *tau = work, *vn2 = work + n, *vref = work + 2 * n, *v = work + 3 * n;
-    size_t rank = n;
-    double ref = 0.0;
-    /* remaining squared column norms, downdated after every reflector (as in LAPACK's dgeqp3) and recomputed
-       exactly once they have lost six digits; the pivot's own norm is always recomputed exactly */
-    for (size_t j = 0; j < n; j++) vn2[j] = vref[j] = dot8(A + j * m, A + j * m, m);
-    for (size_t k = 0; k < n; k++) {
-        size_t p = k; double best = -1.0;
-        for (size_t j = k; j < n; j++) if (vn2[j] > best) { best = vn2[j]; p = j; }
-        for (size_t j = k; j < p; j++) if (vn2[j] >= best * (1.0 - TIE_EPS)) { p = j; break; }
-        if (p != k) {
-            for (size_t i = 0; i < m; i++) { const double t = A[i + k * m]; A[i + k * m] = A[i + p * m]; A[i + p * m] = t; }
-            double t = vn2[k]; vn2[k] = vn2[p]; vn2[p] = t;
-            t = vref[k]; vref[k] = vref[p]; vref[p] = t;
-        }
-        double *ak = A + k * m;
-        const double nrm = sqrt(dot8(ak + k, ak + k, m - k));
-        if (k == 0) ref = nrm;
-        if (nrm <= RANK_EPS * ref || nrm == 0.0) { rank = k; break; }
-        const double alpha = ak[k] >= 0.0 ? -nrm : nrm;
-        const double v0 = ak[k] - alpha;
-        for (size_t i = k + 1; i < m; i++) ak[i] /= v0;
-        tau[k] = -v0 / alpha;
-        ak[k] = alpha;
-        for (size_t j = k + 1; j < n; j++) {
-            double *aj = A + j * m;
-            const double sc = (aj[k] + dot8(ak + k + 1, aj + k + 1, m - k - 1)) * tau[k];
-            aj[k] -= sc;
-            axpy(-sc, ak + k + 1, aj + k + 1, m - k - 1);
-            vn2[j] -= aj[k] * aj[k];
-            if (!(vn2[j] > 1e-6 * vref[j])) vn2[j] = vref[j] = dot8(aj + k + 1, aj + k + 1, m - k - 1);
+#ifdef _OPENMP
+    if (t->nt == 1) return;
+    const int s = !t->sense;
+    t->sense = s;
+    if (atomic_fetch_add_explicit(&w->bar_count, 1, memory_order_acq_rel) == t->nt - 1) {
+        atomic_store_explicit(&w->bar_count, 0, memory_order_relaxed);
+        atomic_store_explicit(&w->bar_sense, s, memory_order_release);
+    } else {
+        for (unsigned spins = 0; atomic_load_explicit(&w->bar_sense, memory_order_acquire) != s; spins++) {
+#if defined(__x86_64__)
+            if (spins < 20000) __builtin_ia32_pause();
+#else
+            if (spins < 20000) continue;
+#endif
+            else sched_yield();
         }
     }
-    for (size_t k = rank; k < n; k++) tau[k] = 0.0;
-    for (size_t kk = n; kk-- > 0;) {
-        double *ak = A + kk * m;
-        v[kk] = 1.0;
-        for (size_t i = kk + 1; i < m; i++) v[i] = ak[i];
-        for (size_t i = 0; i < m; i++) ak[i] = 0.0;
-        ak[kk] = 1.0;
-        if (tau[kk] == 0.0) continue;
-        for (size_t j = kk; j < n; j++) {
-            double *aj = A + j * m;
-            const double sc = dot8(v + kk, aj + kk, m - kk) * tau[kk];
-            axpy(-sc, v + kk, aj + kk, m - kk);
-        }
-    }
-    return rank;
+#else
+    (void)w; (void)t;
+#endif
 }
+#define LA_BARRIER() la_barrier(w, th)
+
+static void la_ws_free(la_ws *w)
+{
+    if (!w) return;
+    free(w->Q); free(w->B); free(w->P); free(w->skip); free(w->used); free(w->part); free(w->mp); free(w->ip); free(w->priv);
+    free(w->S); free(w->aug); free(w->k1); free(w->qk); free(w->slot); free(w);
+}
+
+static int la_threads(void)
+{
+    const char *e = getenv("C3SC_HOST_THREADS");
+    int t = e ? atoi(e) : 0;
+#ifdef _OPENMP
+    if (t <= 0) { t = omp_get_max_threads(); if (t > 8) t = 8; }
+    if (t > LA_NB) t = LA_NB;
+#ifdef __linux__
+    {                                                   /* a spinning team must not outnumber the CPUs it may run on */
+        cpu_set_t set;
+        if (sched_getaffinity(0, sizeof set, &set) == 0 && CPU_COUNT(&set) > 0 && t > CPU_COUNT(&set)) t = CPU_COUNT(&set);
+    }
+#endif
+#else
+    t = 1;
+#endif
+    return t < 1 ? 1 : t;
+}
+
+static la_ws *la_ws_create(size_t mcap, size_t ncap)
+{
+    la_ws *w = (la_ws *)calloc(1, sizeof *w);
+    if (!w) return NULL;
+    w->mcap = mcap; w->ncap = ncap; w->threads = la_threads();
+    w->slotcap = 16;
+    while (w->slotcap < 4 * mcap) w->slotcap <<= 1;
+    w->Q = (double *)malloc(mcap * ncap * sizeof(double));
+    w->B = (double *)malloc(mcap * ncap * sizeof(double));
+    w->P = (size_t *)malloc(ncap * sizeof(size_t));
+    w->skip = (char *)malloc(mcap + 1); w->used = (char *)malloc(mcap + 1);
+    w->part = (double *)malloc(2 * LA_NB * ncap * sizeof(double));
+    w->mp = (double *)malloc(2 * LA_NB * 2 * sizeof(double));
+    w->ip = (size_t *)malloc(3 * LA_NB * sizeof(size_t));
+    w->priv = (double *)malloc((size_t)w->threads * 8 * ncap * sizeof(double));
+    w->S = (double *)malloc(ncap * ncap * sizeof(double));
+    w->aug = (double *)malloc(2 * ncap * ncap * sizeof(double));
+    w->k1 = (double *)malloc(2 * mcap * sizeof(double));
+    w->qk = (int64_t *)malloc(mcap * sizeof(int64_t));
+    w->slot = (uint32_t *)malloc(w->slotcap * sizeof(uint32_t));
+    if (!w->Q || !w->B || !w->P || !w->skip || !w->used || !w->part || !w->mp || !w->ip || !w->priv || !w->S || !w->aug || !w->k1 ||
+        !w->qk || !w->slot) { la_ws_free(w); return NULL; }
+    return w;
+}
+
+/* rows [lo, hi) of block blk that lie at or below row `from` */
+static inline void la_rows(const la_ws *w, int blk, size_t from, size_t *lo, size_t *hi)
+{
+    size_t a = (size_t)blk * w->bs, b = a + w->bs;
+    if (b > w->m) b = w->m;
+    if (a < from) a = from;
+    if (a > b) a = b;
+    *lo = a; *hi = b;
+}
+static inline int la_mine(const la_ws *w, size_t row, int b0, int b1)
+{
+    const int blk = (int)(row / w->bs);
+    return blk >= b0 && blk < b1;
+}
+#define PART(buf, blk, j) part[((size_t)(buf) * LA_NB + (size_t)(blk)) * ncap + (j)]
 
 /* Rows of the unfolding A (m x n, before the QR) that repeat an earlier row to round-off carry no
  * information for the pivoting (absorbing faces with a constant boundary cost produce whole families of
  * them); when the unfolding is rank-deficient the QR completes Q with arbitrary directions and maxvol would
  * happily pick such twins, which makes the NEXT unfolding rank-deficient as well.  skip[i] = 1 withholds
- * row i from the pivoting.  Twins are found through two fixed random projections of the rows. */
-static void mark_twin_rows(const double *A, size_t m, size_t n, char *skip)
+ * row i from the pivoting.  Twins are found through two fixed random projections of the rows (every thread
+ * projects its own rows; thread 0 then walks the rows in order through a hash of the quantised projection while
+ * the others go ahead into the QR, which does not need skip[]). */
+static void team_twin_rows(la_ws *w, la_thr *th)
 {
-    memset(skip, 0, m);
-    size_t H = 16;
-    while (H < 4 * m) H <<= 1;
-    double *k1 = (double *)calloc(2 * m, sizeof(double));
-    uint32_t *slot = (uint32_t *)calloc(H, sizeof(uint32_t));          /* row + 1, keyed by the quantised k1 */
-    int64_t *qk = (int64_t *)malloc(m * sizeof(int64_t));
-    if (!k1 || !slot || !qk) { free(k1); free(slot); free(qk); return; }
-    double *k2 = k1 + m, scale = 0.0;
-    uint64_t st = 0x7F1BE7ull;
-    for (size_t j = 0; j < n; j++) {
-        const double mx = absmax(A + j * m, m);
-        if (mx > scale) scale = mx;
-        st = st * 6364136223846793005ull + 1442695040888963407ull;
-        axpy(0.5 + (double)(st >> 11) / 9007199254740992.0, A + j * m, k1, m);
-        st = st * 6364136223846793005ull + 1442695040888963407ull;
-        axpy(0.5 + (double)(st >> 11) / 9007199254740992.0, A + j * m, k2, m);
+    const int tid = th->tid, b0 = th->b0, b1 = th->b1;
+    const size_t m = w->m, n = w->n, ncap = w->ncap;
+    const double *A = w->Q;
+    double *k1 = w->k1, *k2 = w->k1 + m, *part = w->part;
+    for (int blk = b0; blk < b1; blk++) {
+        size_t lo, hi;
+        la_rows(w, blk, 0, &lo, &hi);
+        double scale = 0.0;
+        uint64_t st = 0x7F1BE7ull;
+        memset(w->skip + lo, 0, hi - lo);
+        for (size_t i = lo; i < hi; i++) k1[i] = k2[i] = 0.0;
+        for (size_t j = 0; j < n; j++) {
+            const double mx = absmax(A + j * m + lo, hi - lo);
+            if (mx > scale) scale = mx;
+            st = st * 6364136223846793005ull + 1442695040888963407ull;
+            axpy(0.5 + (double)(st >> 11) / 9007199254740992.0, A + j * m + lo, k1 + lo, hi - lo);
+            st = st * 6364136223846793005ull + 1442695040888963407ull;
+            axpy(0.5 + (double)(st >> 11) / 9007199254740992.0, A + j * m + lo, k2 + lo, hi - lo);
+        }
+        PART(1, blk, 0) = scale;                        /* buffer 1: the QR starts on buffer 0 */
     }
+    LA_BARRIER();
+    if (tid != 0) return;
+    double scale = 0.0;
+    for (int blk = 0; blk < LA_NB; blk++) if (PART(1, blk, 0) > scale) scale = PART(1, blk, 0);
     const double tol = 1e-12 * scale * (double)n, quantum = 1024.0 * tol;
-    size_t eligible = m;
-    if (!(tol > 0.0)) goto out;                                         /* all-zero unfolding */
-    for (size_t i = 0; i < m; i++) {                                    /* earlier rows stay eligible */
+    if (!(tol > 0.0)) return;                           /* all-zero unfolding */
+    size_t H = 16, eligible = m;
+    while (H < 4 * m) H <<= 1;
+    uint32_t *slot = w->slot;                           /* row + 1, keyed by the quantised k1 */
+    int64_t *qk = w->qk;
+    memset(slot, 0, H * sizeof(uint32_t));
+    for (size_t i = 0; i < m; i++) {                    /* earlier rows stay eligible */
         qk[i] = (int64_t)floor(k1[i] / quantum);
         int twin = 0;
         for (int64_t dq = -1; dq <= 1 && !twin; dq++) {
@@ -314,136 +432,419 @@ static void mark_twin_rows(const double *A, size_t m, size_t n, char *skip)
                 if (qk[r] == q && fabs(k1[i] - k1[r]) <= tol && fabs(k2[i] - k2[r]) <= tol) { twin = 1; break; }
             }
         }
-        if (twin) { skip[i] = 1; eligible--; continue; }
+        if (twin) { w->skip[i] = 1; eligible--; continue; }
         size_t h = (size_t)((uint64_t)qk[i] * 0x9E3779B97F4A7C15ull) & (H - 1);
         while (slot[h]) h = (h + 1) & (H - 1);
         slot[h] = (uint32_t)(i + 1);
     }
-    if (eligible < n) memset(skip, 0, m);                              /* not enough distinct rows: no restriction */
-out:
-    free(k1); free(slot); free(qk);
+    if (eligible < n) memset(w->skip, 0, m);            /* not enough distinct rows: no restriction */
 }
 
-/* Symmetric problems (V(x) = V(-x)) make mirrored rows tie exactly in exact arithmetic; which one wins would
- * then depend on the last bits of the operator's values.  Entries within TIE_EPS of the maximum count as
- * tied and the first in scan order wins, so two operators that agree to round-off pick the same rows. */
-static int maxvol(const double *Q, size_t m, size_t n, const char *skip, size_t *P, double *B, double *work /* n*n + 2n */)
+/* Orthonormal basis Q (m x n) of the column space of A, by Householder QR with column pivoting; Q
+ * overwrites A (column order is immaterial: the cross core B = Q inv(Q[P,:]) only depends on span(Q)).
+ * Columns whose remaining norm falls below RANK_EPS times the largest column norm are numerically dependent:
+ * a reflector built from them would point wherever the round-off of the operator's values points, and the
+ * pivoting after it would follow.  They get no reflector, so their Q columns are H_0..H_{rank-1} e_k -- a
+ * completion that depends on the well-determined part only.
+ * Two barriers per reflector: one for the exact norm of the pivot column, one for its dots with the trailing
+ * columns.  Row k of the trailing columns is read by everyone between the two and written by its owner after
+ * the second; every thread keeps its own copy of tau and of the downdated column norms (LAPACK dgeqp3 style,
+ * recomputed exactly once they have lost six digits). */
+static void team_qr_basis(la_ws *w, la_thr *th)
 {
-    /* start rows: Gaussian elimination with row pivoting on a copy */
-    memcpy(B, Q, m * n * sizeof(double));
-    char *used = (char *)calloc(m, 1);
-    if (!used) return 1;
+    const int tid = th->tid, b0 = th->b0, b1 = th->b1;
+    const size_t m = w->m, n = w->n, ncap = w->ncap;
+    double *A = w->Q, *part = w->part;
+    double *pv = w->priv + (size_t)tid * 8 * ncap;
+    double *tau = pv, *vn2 = pv + ncap, *vref = pv + 2 * ncap, *rowk = pv + 3 * ncap, *sc = pv + 4 * ncap;
+    size_t *redo = (size_t *)(pv + 5 * ncap);
+    int pb = 0;
+    for (int blk = b0; blk < b1; blk++) {
+        size_t lo, hi;
+        la_rows(w, blk, 0, &lo, &hi);
+        for (size_t j = 0; j < n; j++) PART(pb, blk, j) = dot8(A + j * m + lo, A + j * m + lo, hi - lo);
+    }
+    LA_BARRIER();
     for (size_t j = 0; j < n; j++) {
-        size_t piv = 0; double best = -1.0, best_any = 0.0;
-        for (size_t i = 0; i < m; i++) {
-            if (used[i]) continue;
-            const double a = fabs(B[i + j * m]);
-            if (a > best_any) best_any = a;
-            if (!(skip && skip[i]) && a > best) { best = a; piv = i; }
-        }
-        const int all_rows = !skip || best < 1e-6 * best_any;             /* the distinct rows do not reach this direction */
-        if (all_rows && skip) {
-            best = -1.0;
-            for (size_t i = 0; i < m; i++)
-                if (!used[i] && fabs(B[i + j * m]) > best) { best = fabs(B[i + j * m]); piv = i; }
-        }
-        for (size_t i = 0; i < piv; i++)                                 /* TIE_EPS: first row among the near-maximal ones */
-            if (!used[i] && (all_rows || !skip[i]) && fabs(B[i + j * m]) >= best * (1.0 - TIE_EPS)) { piv = i; break; }
-        P[j] = piv; used[piv] = 1;
-        const double pv = B[piv + j * m];
-        if (pv == 0.0) continue;
-        for (size_t c = j + 1; c < n; c++) {
-            const double f = B[piv + c * m] / pv;
-            if (f == 0.0) continue;
-            axpy(-f, B + j * m, B + c * m, m);                           /* rows already used are never read again */
-        }
+        double s = 0.0;
+        for (int blk = 0; blk < LA_NB; blk++) s += PART(pb, blk, j);
+        vn2[j] = vref[j] = s;
     }
-    free(used);
-    /* B = Q inv(Q[P]): invert the n x n block by Gauss-Jordan with partial pivoting on [S | I] */
-    double *S = work, *col = work + n * n;
-    {
-        double *aug = (double *)malloc(2 * n * n * sizeof(double));      /* row-major n x 2n */
-        if (!aug) return 1;
-        for (size_t a = 0; a < n; a++)
-            for (size_t b = 0; b < n; b++) {
-                aug[a * 2 * n + b] = Q[P[a] + b * m];
-                aug[a * 2 * n + n + b] = a == b ? 1.0 : 0.0;
+    pb ^= 1;
+    size_t rank = n;
+    double ref = 0.0;
+    for (size_t k = 0; k < n; k++) {
+        size_t p = k; double best = -1.0;
+        for (size_t j = k; j < n; j++) if (vn2[j] > best) { best = vn2[j]; p = j; }
+        for (size_t j = k; j < p; j++) if (vn2[j] >= best * (1.0 - TIE_EPS)) { p = j; break; }
+        double *ak = A + k * m;
+        if (p != k) {
+            double *ap = A + p * m;
+            for (int blk = b0; blk < b1; blk++) {
+                size_t lo, hi;
+                la_rows(w, blk, 0, &lo, &hi);
+                for (size_t i = lo; i < hi; i++) { const double t = ak[i]; ak[i] = ap[i]; ap[i] = t; }
             }
-        for (size_t k = 0; k < n; k++) {
-            size_t piv = k; double best = fabs(aug[k * 2 * n + k]);
-            for (size_t i = k + 1; i < n; i++)
-                if (fabs(aug[i * 2 * n + k]) > best) { best = fabs(aug[i * 2 * n + k]); piv = i; }
-            if (best == 0.0) { free(aug); return 2; }
-            if (piv != k)
-                for (size_t jx = 0; jx < 2 * n; jx++) { double t = aug[k * 2 * n + jx]; aug[k * 2 * n + jx] = aug[piv * 2 * n + jx]; aug[piv * 2 * n + jx] = t; }
-            const double pv = 1.0 / aug[k * 2 * n + k];
-            for (size_t jx = 0; jx < 2 * n; jx++) aug[k * 2 * n + jx] *= pv;
-            for (size_t i = 0; i < n; i++) {
-                if (i == k) continue;
-                const double fct = aug[i * 2 * n + k];
-                if (fct == 0.0) continue;
-                for (size_t jx = 0; jx < 2 * n; jx++) aug[i * 2 * n + jx] -= fct * aug[k * 2 * n + jx];
+            double t = vn2[k]; vn2[k] = vn2[p]; vn2[p] = t;
+            t = vref[k]; vref[k] = vref[p]; vref[p] = t;
+        }
+        for (int blk = b0; blk < b1; blk++) {
+            size_t lo, hi;
+            la_rows(w, blk, k, &lo, &hi);
+            PART(pb, blk, 0) = dot8(ak + lo, ak + lo, hi - lo);
+        }
+        LA_BARRIER();
+        double nrm = 0.0;
+        for (int blk = 0; blk < LA_NB; blk++) nrm += PART(pb, blk, 0);
+        pb ^= 1;
+        nrm = sqrt(nrm);
+        if (k == 0) ref = nrm;
+        if (nrm <= RANK_EPS * ref || nrm == 0.0) { rank = k; break; }
+        const double akk = ak[k];
+        const double alpha = akk >= 0.0 ? -nrm : nrm;
+        const double v0 = akk - alpha;
+        tau[k] = -v0 / alpha;
+        for (size_t j = k + 1; j < n; j++) rowk[j] = A[k + j * m];
+        for (int blk = b0; blk < b1; blk++) {
+            size_t lo, hi;
+            la_rows(w, blk, k + 1, &lo, &hi);
+            for (size_t i = lo; i < hi; i++) ak[i] /= v0;
+            for (size_t j = k + 1; j < n; j++) PART(pb, blk, j) = dot8(ak + lo, A + j * m + lo, hi - lo);
+        }
+        LA_BARRIER();
+        for (size_t j = k + 1; j < n; j++) {
+            double s = 0.0;
+            for (int blk = 0; blk < LA_NB; blk++) s += PART(pb, blk, j);
+            sc[j] = (rowk[j] + s) * tau[k];
+        }
+        pb ^= 1;
+        if (la_mine(w, k, b0, b1)) {
+            ak[k] = alpha;
+            for (size_t j = k + 1; j < n; j++) A[k + j * m] = rowk[j] - sc[j];
+        }
+        for (int blk = b0; blk < b1; blk++) {
+            size_t lo, hi;
+            la_rows(w, blk, k + 1, &lo, &hi);
+            for (size_t j = k + 1; j < n; j++) axpy(-sc[j], ak + lo, A + j * m + lo, hi - lo);
+        }
+        size_t nre = 0;
+        for (size_t j = k + 1; j < n; j++) {
+            const double ajk = rowk[j] - sc[j];
+            vn2[j] -= ajk * ajk;
+            if (!(vn2[j] > 1e-6 * vref[j])) redo[nre++] = j;
+        }
+        if (nre) {                                       /* the same columns on every thread */
+            for (int blk = b0; blk < b1; blk++) {
+                size_t lo, hi;
+                la_rows(w, blk, k + 1, &lo, &hi);
+                for (size_t q = 0; q < nre; q++) PART(pb, blk, redo[q]) = dot8(A + redo[q] * m + lo, A + redo[q] * m + lo, hi - lo);
             }
+            LA_BARRIER();
+            for (size_t q = 0; q < nre; q++) {
+                double s = 0.0;
+                for (int blk = 0; blk < LA_NB; blk++) s += PART(pb, blk, redo[q]);
+                vn2[redo[q]] = vref[redo[q]] = s;
+            }
+            pb ^= 1;
         }
-        for (size_t a = 0; a < n; a++)
-            for (size_t b = 0; b < n; b++) S[a + b * n] = aug[a * 2 * n + n + b];
-        free(aug);
     }
-    for (size_t b = 0; b < n; b++) {                                    /* B[:,b] = sum_a S[a,b] Q[:,a] */
-        double *bb = B + b * m;
-        for (size_t i = 0; i < m; i++) bb[i] = 0.0;
-        for (size_t a = 0; a < n; a++) axpy(S[a + b * n], Q + a * m, bb, m);
+    for (size_t k = rank; k < n; k++) tau[k] = 0.0;
+    /* accumulate Q = H_0 .. H_{n-1} [I; 0] in place, last reflector first.  Column kk still holds its reflector
+       below the diagonal while the columns after it (already Q columns, zero in rows <= kk) are reflected. */
+    for (size_t kk = n; kk-- > 0;) {
+        double *ak = A + kk * m;
+        const double t = tau[kk];
+        if (t != 0.0 && kk + 1 < n) {
+            for (int blk = b0; blk < b1; blk++) {
+                size_t lo, hi;
+                la_rows(w, blk, kk + 1, &lo, &hi);
+                for (size_t j = kk + 1; j < n; j++) PART(pb, blk, j) = dot8(ak + lo, A + j * m + lo, hi - lo);
+            }
+            LA_BARRIER();
+            for (size_t j = kk + 1; j < n; j++) {
+                double s = 0.0;
+                for (int blk = 0; blk < LA_NB; blk++) s += PART(pb, blk, j);
+                sc[j] = s * t;
+            }
+            pb ^= 1;
+            for (int blk = b0; blk < b1; blk++) {
+                size_t lo, hi;
+                la_rows(w, blk, kk + 1, &lo, &hi);
+                for (size_t j = kk + 1; j < n; j++) axpy(-sc[j], ak + lo, A + j * m + lo, hi - lo);
+            }
+            if (la_mine(w, kk, b0, b1))
+                for (size_t j = kk + 1; j < n; j++) A[kk + j * m] = -sc[j];
+        }
+        for (int blk = b0; blk < b1; blk++) {           /* column kk itself: H_kk e_kk = e_kk - tau v */
+            size_t lo, hi;
+            la_rows(w, blk, 0, &lo, &hi);
+            for (size_t i = lo; i < hi; i++) ak[i] = i < kk ? 0.0 : (i == kk ? 1.0 - t : (t != 0.0 ? -t * ak[i] : 0.0));
+        }
     }
-    /* swaps while some |B[i,j]| > 1 + delta; cmax[j] = max |B[:,j]| is kept up to date by the update pass */
-    double *cmax = col + n;
-    for (size_t j = 0; j < n; j++) cmax[j] = absmax(B + j * m, m);
-    for (int it = 0; it < 200; it++) {
-        size_t bi = 0, bj = 0; double best = 0.0;
-        for (size_t j = 0; j < n; j++) if (cmax[j] > best) best = cmax[j];
-        if (best <= 1.0 + 1e-2) break;
-        int found = 0;                                                   /* first near-maximal entry, column-major order */
-        for (size_t j = 0; j < n && !found; j++) {
-            if (cmax[j] < best * (1.0 - TIE_EPS)) continue;
-            for (size_t i = 0; i < m; i++)
-                if (fabs(B[i + j * m]) >= best * (1.0 - TIE_EPS) && !(skip && skip[i])) { bi = i; bj = j; found = 1; break; }
-        }
-        if (!found) {                                                    /* the maxima sit on withheld rows: masked scan */
-            best = 0.0;
-            for (size_t j = 0; j < n; j++)
-                for (size_t i = 0; i < m; i++)
-                    if (!skip[i] && fabs(B[i + j * m]) > best * (1.0 + TIE_EPS)) { best = fabs(B[i + j * m]); bi = i; bj = j; }
-            if (best <= 1.0 + 1e-2) break;
-        }
-        /* row bi replaces P[bj]:  B <- B - B[:,bj] (B[bi,:] - e_bj) / B[bi,bj] */
-        const double pv = B[bi + bj * m];
-        for (size_t b = 0; b < n; b++) col[b] = (B[bi + b * m] - (b == bj ? 1.0 : 0.0)) / pv;
+}
+
+/* thread 0: S = inv(Q[P,:]) by Gauss-Jordan with partial pivoting on [Q[P] | I] */
+static int invert_pivot_block(la_ws *w)
+{
+    const size_t m = w->m, n = w->n;
+    const double *Q = w->Q;
+    double *aug = w->aug, *S = w->S;                    /* row-major n x 2n */
+    for (size_t a = 0; a < n; a++)
         for (size_t b = 0; b < n; b++) {
-            if (col[b] == 0.0 || b == bj) continue;
-            cmax[b] = axpy_absmax(-col[b], B + bj * m, B + b * m, m);
+            aug[a * 2 * n + b] = Q[w->P[a] + b * m];
+            aug[a * 2 * n + n + b] = a == b ? 1.0 : 0.0;
         }
-        {
-            const double f = 1.0 - col[bj];
-            double *bb = B + bj * m;
-            for (size_t i = 0; i < m; i++) bb[i] *= f;
-            cmax[bj] *= fabs(f);
+    for (size_t k = 0; k < n; k++) {
+        size_t piv = k; double best = fabs(aug[k * 2 * n + k]);
+        for (size_t i = k + 1; i < n; i++)
+            if (fabs(aug[i * 2 * n + k]) > best) { best = fabs(aug[i * 2 * n + k]); piv = i; }
+        if (best == 0.0) return 2;
+        if (piv != k)
+            for (size_t jx = 0; jx < 2 * n; jx++) { double t = aug[k * 2 * n + jx]; aug[k * 2 * n + jx] = aug[piv * 2 * n + jx]; aug[piv * 2 * n + jx] = t; }
+        const double pv = 1.0 / aug[k * 2 * n + k];
+        for (size_t jx = 0; jx < 2 * n; jx++) aug[k * 2 * n + jx] *= pv;
+        for (size_t i = 0; i < n; i++) {
+            if (i == k) continue;
+            const double fct = aug[i * 2 * n + k];
+            if (fct == 0.0) continue;
+            for (size_t jx = 0; jx < 2 * n; jx++) aug[i * 2 * n + jx] -= fct * aug[k * 2 * n + jx];
         }
-        P[bj] = bi;
     }
+    for (size_t a = 0; a < n; a++)
+        for (size_t b = 0; b < n; b++) S[a + b * n] = aug[a * 2 * n + n + b];
     return 0;
 }
 
+/* maxvol: rows P of Q (m x n) with |det Q[P]| locally maximal, and B = Q inv(Q[P]).
+ * Symmetric problems (V(x) = V(-x)) make mirrored rows tie exactly in exact arithmetic; which one wins would
+ * then depend on the last bits of the operator's values.  Entries within TIE_EPS of the maximum count as
+ * tied and the first in scan order wins, so two operators that agree to round-off pick the same rows.
+ * Start rows: Gaussian elimination with row pivoting on a copy (two barriers per column: the block maxima, then
+ * the first near-maximal row); the chosen row is read by everyone and left alone by its owner from then on.
+ * Swaps while some |B[i,j]| > 1 + delta: two barriers per swap (the first near-maximal entry in column-major
+ * order; the per-block column maxima of the updated B).  The owner of the entering row holds its new values back
+ * until the others have read the old ones. */
+static void team_maxvol(la_ws *w, la_thr *th)
+{
+    const int tid = th->tid, b0 = th->b0, b1 = th->b1;
+    const size_t m = w->m, n = w->n, ncap = w->ncap;
+    const double *Q = w->Q;
+    double *B = w->B, *part = w->part, *mp = w->mp;
+    size_t *ip = w->ip;
+    const char *skip = w->skip;
+    char *used = w->used;
+    double *pv = w->priv + (size_t)tid * 8 * ncap;
+    double *f = pv, *cmax = pv + ncap, *col = pv + 2 * ncap, *newrow = pv + 3 * ncap;
+    for (int blk = b0; blk < b1; blk++) {
+        size_t lo, hi;
+        la_rows(w, blk, 0, &lo, &hi);
+        memset(used + lo, 0, hi - lo);
+        for (size_t j = 0; j < n; j++) memcpy(B + j * m + lo, Q + j * m + lo, (hi - lo) * sizeof(double));
+    }
+    for (size_t j = 0; j < n; j++) {
+        const double *bj = B + j * m;
+        for (int blk = b0; blk < b1; blk++) {
+            size_t lo, hi, piv = LA_NONE;
+            la_rows(w, blk, 0, &lo, &hi);
+            double best = -1.0, best_any = 0.0;
+            for (size_t i = lo; i < hi; i++) {
+                if (used[i]) continue;
+                const double a = fabs(bj[i]);
+                if (a > best_any) best_any = a;
+                if (!skip[i] && a > best) { best = a; piv = i; }
+            }
+            mp[(0 * LA_NB + blk) * 2] = best_any; mp[(0 * LA_NB + blk) * 2 + 1] = best; ip[0 * LA_NB + blk] = piv;
+        }
+        LA_BARRIER();
+        size_t piv = 0; double best = -1.0, best_any = 0.0;
+        for (int blk = 0; blk < LA_NB; blk++) {
+            if (mp[blk * 2] > best_any) best_any = mp[blk * 2];
+            if (mp[blk * 2 + 1] > best) { best = mp[blk * 2 + 1]; piv = ip[blk]; }
+        }
+        const int all_rows = best < 1e-6 * best_any;    /* the distinct rows do not reach this direction */
+        if (all_rows) {
+            for (int blk = b0; blk < b1; blk++) {
+                size_t lo, hi, pb_ = LA_NONE;
+                la_rows(w, blk, 0, &lo, &hi);
+                double bb = -1.0;
+                for (size_t i = lo; i < hi; i++)
+                    if (!used[i] && fabs(bj[i]) > bb) { bb = fabs(bj[i]); pb_ = i; }
+                mp[(1 * LA_NB + blk) * 2] = bb; ip[1 * LA_NB + blk] = pb_;
+            }
+            LA_BARRIER();
+            best = -1.0;
+            for (int blk = 0; blk < LA_NB; blk++)
+                if (mp[(LA_NB + blk) * 2] > best) { best = mp[(LA_NB + blk) * 2]; piv = ip[LA_NB + blk]; }
+        }
+        for (int blk = b0; blk < b1; blk++) {           /* TIE_EPS: first row among the near-maximal ones */
+            size_t lo, hi, first = LA_NONE;
+            la_rows(w, blk, 0, &lo, &hi);
+            if (hi > piv) hi = piv;
+            for (size_t i = lo; i < hi; i++)
+                if (!used[i] && (all_rows || !skip[i]) && fabs(bj[i]) >= best * (1.0 - TIE_EPS)) { first = i; break; }
+            ip[2 * LA_NB + blk] = first;
+        }
+        LA_BARRIER();
+        for (int blk = 0; blk < LA_NB; blk++)
+            if (ip[2 * LA_NB + blk] != LA_NONE) { piv = ip[2 * LA_NB + blk]; break; }
+        if (tid == 0) w->P[j] = piv;
+        if (la_mine(w, piv, b0, b1)) used[piv] = 1;
+        const double pvv = bj[piv];
+        if (pvv == 0.0) continue;
+        for (size_t c = j + 1; c < n; c++) f[c] = B[piv + c * m] / pvv;
+        for (int blk = b0; blk < b1; blk++) {
+            size_t lo, hi;
+            la_rows(w, blk, 0, &lo, &hi);
+            for (int seg = 0; seg < 2; seg++) {         /* the pivot row stays as the others read it */
+                size_t s0 = lo, s1 = hi;
+                if (piv >= lo && piv < hi) { if (seg == 0) s1 = piv; else s0 = piv + 1; }
+                else if (seg == 1) break;
+                for (size_t c = j + 1; c < n; c++)
+                    if (f[c] != 0.0) axpy(-f[c], bj + s0, B + c * m + s0, s1 - s0);
+            }
+        }
+    }
+    if (tid == 0) w->rc = invert_pivot_block(w);
+    LA_BARRIER();
+    if (w->rc) return;
+    const double *S = w->S;
+    for (int blk = b0; blk < b1; blk++) {               /* B[:,b] = sum_a S[a,b] Q[:,a] */
+        size_t lo, hi;
+        la_rows(w, blk, 0, &lo, &hi);
+        for (size_t b = 0; b < n; b++) {
+            double *bb = B + b * m;
+            for (size_t i = lo; i < hi; i++) bb[i] = 0.0;
+            for (size_t a = 0; a < n; a++) axpy(S[a + b * n], Q + a * m + lo, bb + lo, hi - lo);
+            PART(0, blk, b) = absmax(bb + lo, hi - lo);
+        }
+    }
+    size_t held = LA_NONE;                               /* entering row whose new values this thread holds back */
+    int it = 0;
+    for (; it < 200; it++) {
+        LA_BARRIER();
+        if (held != LA_NONE) { for (size_t b = 0; b < n; b++) B[held + b * m] = newrow[b]; held = LA_NONE; }
+        double best = 0.0;
+        for (size_t j = 0; j < n; j++) {
+            double c = 0.0;
+            for (int blk = 0; blk < LA_NB; blk++) if (PART(0, blk, j) > c) c = PART(0, blk, j);
+            cmax[j] = c;
+            if (c > best) best = c;
+        }
+        if (best <= 1.0 + 1e-2) break;
+        const double thr = best * (1.0 - TIE_EPS);
+        for (int blk = b0; blk < b1; blk++) {           /* first near-maximal entry, column-major order */
+            size_t lo, hi, key = LA_NONE;
+            la_rows(w, blk, 0, &lo, &hi);
+            for (size_t j = 0; j < n && key == LA_NONE; j++) {
+                if (PART(0, blk, j) < thr) continue;
+                for (size_t i = lo; i < hi; i++)
+                    if (fabs(B[i + j * m]) >= thr && !skip[i]) { key = j * m + i; break; }
+            }
+            ip[blk] = key;
+        }
+        LA_BARRIER();
+        size_t key = LA_NONE;
+        for (int blk = 0; blk < LA_NB; blk++) if (ip[blk] < key) key = ip[blk];
+        size_t bi, bj;
+        if (key != LA_NONE) { bi = key % m; bj = key / m; }
+        else {                                           /* the maxima sit on withheld rows: masked scan */
+            if (tid == 0) {
+                double bm = 0.0; size_t xi = 0, xj = 0;
+                for (size_t j = 0; j < n; j++)
+                    for (size_t i = 0; i < m; i++)
+                        if (!skip[i] && fabs(B[i + j * m]) > bm * (1.0 + TIE_EPS)) { bm = fabs(B[i + j * m]); xi = i; xj = j; }
+                w->sh_best = bm; w->sh_bi = xi; w->sh_bj = xj;
+            }
+            LA_BARRIER();
+            if (w->sh_best <= 1.0 + 1e-2) break;
+            bi = w->sh_bi; bj = w->sh_bj;
+        }
+        /* row bi replaces P[bj]:  B <- B - B[:,bj] (B[bi,:] - e_bj) / B[bi,bj] */
+        const double pvv = B[bi + bj * m];
+        for (size_t b = 0; b < n; b++) col[b] = (B[bi + b * m] - (b == bj ? 1.0 : 0.0)) / pvv;
+        const double fs = 1.0 - col[bj];
+        const int mine = la_mine(w, bi, b0, b1);
+        if (mine) {
+            for (size_t b = 0; b < n; b++)
+                newrow[b] = b == bj ? pvv * fs : (col[b] == 0.0 ? B[bi + b * m] : B[bi + b * m] + (-col[b]) * pvv);
+            held = bi;
+        }
+        for (int blk = b0; blk < b1; blk++) {
+            size_t lo, hi;
+            la_rows(w, blk, 0, &lo, &hi);
+            const int has = bi >= lo && bi < hi;
+            for (size_t b = 0; b < n; b++) {
+                if (b == bj || col[b] == 0.0) continue;
+                double c = has ? fabs(newrow[b]) : 0.0;
+                for (int seg = 0; seg < 2; seg++) {
+                    size_t s0 = lo, s1 = hi;
+                    if (has) { if (seg == 0) s1 = bi; else s0 = bi + 1; }
+                    else if (seg == 1) break;
+                    const double cs = axpy_absmax(-col[b], B + bj * m + s0, B + b * m + s0, s1 - s0);
+                    if (cs > c) c = cs;
+                }
+                PART(0, blk, b) = c;
+            }
+            double *bb = B + bj * m;
+            for (size_t i = lo; i < hi; i++) if (i != bi) bb[i] *= fs;
+            double c;                                    /* row bi still holds the old pivot; its new value is held back */
+            if (has) {
+                c = fabs(newrow[bj]);
+                const double c0 = absmax(bb + lo, bi - lo), c1 = absmax(bb + bi + 1, hi - bi - 1);
+                if (c0 > c) c = c0;
+                if (c1 > c) c = c1;
+            } else c = absmax(bb + lo, hi - lo);
+            PART(0, blk, bj) = c;
+        }
+        if (tid == 0) w->P[bj] = bi;
+    }
+    if (it == 200) {                                     /* swap limit: the last entering row is still held back */
+        LA_BARRIER();
+        if (held != LA_NONE) for (size_t b = 0; b < n; b++) B[held + b * m] = newrow[b];
+    }
+}
+
+/* twin rows + QR basis + maxvol of the unfolding in w->Q (m x n): w->Q <- basis, w->B <- cross core, w->P <- rows */
+static int pivot_step(la_ws *w, size_t m, size_t n)
+{
+    if (m > w->mcap || n > w->ncap || n > m) return 1;
+    w->m = m; w->n = n; w->rc = 0;
+#ifdef _OPENMP
+    atomic_store(&w->bar_count, 0); atomic_store(&w->bar_sense, 0);
+#endif
+    w->bs = ((m + LA_NB - 1) / LA_NB + 7) & ~(size_t)7;
+    int T = m * n < 8192 ? 1 : w->threads;
+    (void)T;
+#ifdef _OPENMP
+#pragma omp parallel num_threads(T) if (T > 1)
+#endif
+    {
+#ifdef _OPENMP
+        const int tid = omp_get_thread_num(), nt = omp_get_num_threads();
+#else
+        const int tid = 0, nt = 1;
+#endif
+        la_thr th = { tid, nt, tid * LA_NB / nt, (tid + 1) * LA_NB / nt, 0 };
+        team_twin_rows(w, &th);
+        team_qr_basis(w, &th);
+        team_maxvol(w, &th);
+    }
+    return w->rc;
+}
+
 /* ---- one core step: all fibers of core k in ONE operator call --------------------------------- */
-static double g_t_eval, g_t_qr, g_t_mv, g_t_dot;
+static double g_t_eval, g_t_piv, g_t_dot;
 static double now_s(void) { struct timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec + 1e-9 * ts.tv_nsec; }
 
+/* all r_k * r_{k+1} fibers of core k in ONE operator call: vals[(a + b*rk) * ldo + j] = T(I_k[a], j, J_{k+1}[b]) */
 static int eval_core(const c3sc_cross *c, uint32_t k, c3sc_fiber_batch_fn f, void *arg, int32_t *dv, int32_t *fi,
-                     double *vals, double *T /* [r_k][N][r_{k+1}] as a + j*rk + b*rk*N */, uint64_t *nfib)
+                     double *vals, uint64_t *nfib)
 {
     const uint32_t d = c->d;
-    const size_t rk = c->r[k], rk1 = c->r[k + 1], N = c->n[k], ldo = c->nmax;
+    const size_t rk = c->r[k], rk1 = c->r[k + 1], ldo = c->nmax;
     const size_t F = rk * rk1;
-    for (size_t a = 0; a < rk; a++)
-        for (size_t b = 0; b < rk1; b++) {
+    for (size_t b = 0; b < rk1; b++)
+        for (size_t a = 0; a < rk; a++) {
             const size_t fidx = a + b * rk;
             dv[fidx] = (int32_t)k;
             for (uint32_t i = 0; i < d; i++)
@@ -454,18 +855,46 @@ static int eval_core(const c3sc_cross *c, uint32_t k, c3sc_fiber_batch_fn f, voi
     g_t_eval += now_s() - t0_;
     if (rc) return rc;
     *nfib += F;
-    for (size_t a = 0; a < rk; a++)
-        for (size_t b = 0; b < rk1; b++)
-            for (size_t j = 0; j < N; j++) T[a + j * rk + b * rk * N] = vals[(a + b * rk) * ldo + j];
     return 0;
 }
-
-/* core tensor T[a + j*rk + b*rk*N] -> valuef_precompute_cores layout: block j column-major */
-static void store_core(const double *T, size_t rk, size_t N, size_t rk1, double *core)
+/* the two unfoldings of a core, straight from the operator's fiber values, and the way back into the
+ * valuef_precompute_cores layout (block j column-major: core[j*rk*rk1 + a + b*rk]) */
+static void unfold_left(const double *vals, size_t ldo, size_t rk, size_t N, size_t rk1, double *Q /* rows (a,j) = a + j*rk, cols b */)
+{
+    for (size_t b = 0; b < rk1; b++)
+        for (size_t a = 0; a < rk; a++) {
+            const double *v = vals + (a + b * rk) * ldo;
+            double *q = Q + a + b * rk * N;
+            for (size_t j = 0; j < N; j++) q[j * rk] = v[j];
+        }
+}
+static void unfold_right(const double *vals, size_t ldo, size_t rk, size_t N, size_t rk1, double *Q /* rows (j,b) = j + b*N, cols a */)
+{
+    for (size_t a = 0; a < rk; a++)
+        for (size_t b = 0; b < rk1; b++) memcpy(Q + b * N + a * N * rk1, vals + (a + b * rk) * ldo, N * sizeof(double));
+}
+static void store_left(const double *B /* (a + j*rk) + b*rk*N */, size_t rk, size_t N, size_t rk1, double *core)
 {
     for (size_t j = 0; j < N; j++)
-        for (size_t b = 0; b < rk1; b++)
-            for (size_t a = 0; a < rk; a++) core[j * rk * rk1 + a + b * rk] = T[a + j * rk + b * rk * N];
+        for (size_t b = 0; b < rk1; b++) memcpy(core + j * rk * rk1 + b * rk, B + j * rk + b * rk * N, rk * sizeof(double));
+}
+static void store_right(const double *B /* (j + b*N) + a*N*rk1 */, size_t rk, size_t N, size_t rk1, double *core)
+{
+    for (size_t a = 0; a < rk; a++)
+        for (size_t b = 0; b < rk1; b++) {
+            const double *s = B + b * N + a * N * rk1;
+            double *t = core + a + b * rk;
+            for (size_t j = 0; j < N; j++) t[j * rk * rk1] = s[j];
+        }
+}
+static void store_vals(const double *vals, size_t ldo, size_t rk, size_t N, size_t rk1, double *core)
+{
+    for (size_t b = 0; b < rk1; b++)
+        for (size_t a = 0; a < rk; a++) {
+            const double *v = vals + (a + b * rk) * ldo;
+            double *t = core + a + b * rk;
+            for (size_t j = 0; j < N; j++) t[j * rk * rk1] = v[j];
+        }
 }
 
 /* <A, B> of two trains in the ValueF layout (discrete inner product over the grid nodes):
@@ -487,21 +916,41 @@ static double tt_dot2(uint32_t d, const uint64_t *n, const uint64_t *ra, double 
     if (!At) return NAN;
     double *Bt = At + cap, *W = At + 2 * cap;
     w1[0] = 1.0;
+    const int T = la_threads();
+    (void)T;
     for (uint32_t k = 0; k < d; k++) {
         const size_t a0 = ra[k], a1 = ra[k + 1], b0 = rb[k], b1 = rb[k + 1], N = n[k];
         const int same = A[k] == B[k] && a0 == b0 && a1 == b1;
-        for (size_t j = 0; j < N; j++)
-            for (size_t e = 0; e < a0 * a1; e++) At[j + e * N] = A[k][j * a0 * a1 + e];
-        if (!same)
-            for (size_t j = 0; j < N; j++)
-                for (size_t e = 0; e < b0 * b1; e++) Bt[j + e * N] = B[k][j * b0 * b1 + e];
         const double *Bu = same ? At : Bt;
-        for (size_t e = 0; e < a0 * N * b1; e++) W[e] = 0.0;
-        for (size_t q = 0; q < b1; q++)
-            for (size_t y = 0; y < b0; y++)
-                for (size_t x = 0; x < a0; x++) axpy(w1[x + y * a0], Bu + (y + q * b0) * N, W + x * N + q * a0 * N, N);
-        for (size_t q = 0; q < b1; q++)
-            for (size_t p = 0; p < a1; p++) w2[p + q * a1] = dot8(At + p * a0 * N, W + q * a0 * N, a0 * N);
+        /* every column q of the carried matrix is one thread's from the transposes to the dots: the same sums
+           in the same order whatever the team size */
+#ifdef _OPENMP
+#pragma omp parallel num_threads(T) if (T > 1 && N * a0 * b0 * b1 >= 32768)
+#endif
+        {
+#ifdef _OPENMP
+#pragma omp for schedule(static)
+#endif
+            for (size_t e = 0; e < a0 * a1; e++)
+                for (size_t j = 0; j < N; j++) At[j + e * N] = A[k][j * a0 * a1 + e];
+            if (!same) {
+#ifdef _OPENMP
+#pragma omp for schedule(static)
+#endif
+                for (size_t e = 0; e < b0 * b1; e++)
+                    for (size_t j = 0; j < N; j++) Bt[j + e * N] = B[k][j * b0 * b1 + e];
+            }
+#ifdef _OPENMP
+#pragma omp for schedule(static)
+#endif
+            for (size_t q = 0; q < b1; q++) {
+                double *Wq = W + q * a0 * N;
+                for (size_t e = 0; e < a0 * N; e++) Wq[e] = 0.0;
+                for (size_t y = 0; y < b0; y++)
+                    for (size_t x = 0; x < a0; x++) axpy(w1[x + y * a0], Bu + (y + q * b0) * N, Wq + x * N, N);
+                for (size_t p = 0; p < a1; p++) w2[p + q * a1] = dot8(At + p * a0 * N, Wq, a0 * N);
+            }
+        }
         memcpy(w1, w2, a1 * b1 * sizeof(double));
     }
     free(At);
@@ -621,20 +1070,26 @@ int c3sc_cross_run(c3sc_cross *c, c3sc_fiber_batch_fn f, void *arg, const c3sc_c
         if (c->r[k] * c->r[k + 1] > fmax) fmax = c->r[k] * c->r[k + 1];
         if (c->r[k] * c->n[k] * c->r[k + 1] > tmax) tmax = c->r[k] * c->n[k] * c->r[k + 1];
     }
-    int32_t *dv = (int32_t *)malloc(fmax * sizeof(int32_t));
-    int32_t *fi = (int32_t *)malloc(fmax * d * sizeof(int32_t));
-    double *vals = (double *)malloc(fmax * c->nmax * sizeof(double));
-    double *T = (double *)malloc(tmax * sizeof(double)), *Q = (double *)malloc(tmax * sizeof(double));
-    double *B = (double *)malloc(tmax * sizeof(double));
-    size_t *P = (size_t *)malloc(rmax * sizeof(size_t));
-    double *work = (double *)malloc((rmax * rmax * 3 + rmax + rmax * c->nmax * rmax + 16) * sizeof(double));
+    (void)tmax;
+    const size_t ldo = c->nmax;
+    double *vals = (double *)exchange_get(c, fmax * ldo * sizeof(double) + fmax * (d + 1) * sizeof(int32_t));
+    int32_t *fi = vals ? (int32_t *)(vals + fmax * ldo) : NULL, *dv = fi ? fi + fmax * d : NULL;
+    double *work = (double *)malloc((rmax * rmax * 3 + 16) * sizeof(double));
     double **prev = (double **)calloc(d, sizeof(double *));
     int32_t *tmpI = (int32_t *)malloc(rmax * d * sizeof(int32_t));
-    char *skip = (char *)malloc(rmax * c->nmax + 1);
+    size_t mcap = 1;
+    for (uint32_t k = 0; k < d; k++) {
+        if (k + 1 < d && c->r[k] * c->n[k] > mcap) mcap = c->r[k] * c->n[k];
+        if (k >= 1 && c->n[k] * c->r[k + 1] > mcap) mcap = c->n[k] * c->r[k + 1];
+    }
+    la_ws *ws = la_ws_create(mcap, rmax);
+    double *Q = ws ? ws->Q : NULL, *B = ws ? ws->B : NULL;
+    size_t *P = ws ? ws->P : NULL;
     int rc = C3SC_OK;
     uint64_t nfib = 0;
     double change = 1.0, prev_norm2 = 0.0;
-    if (!dv || !fi || !vals || !T || !Q || !B || !P || !work || !prev || !tmpI || !skip) { rc = C3SC_EINVAL; goto done; }
+    g_t_eval = g_t_piv = g_t_dot = 0.0;
+    if (!vals || !ws || !work || !prev || !tmpI) { rc = C3SC_EINVAL; goto done; }
     for (uint32_t k = 0; k < d; k++) {
         prev[k] = (double *)calloc(c->r[k] * c->n[k] * c->r[k + 1], sizeof(double));
         if (!prev[k]) { rc = C3SC_EINVAL; goto done; }
@@ -643,12 +1098,10 @@ int c3sc_cross_run(c3sc_cross *c, c3sc_fiber_batch_fn f, void *arg, const c3sc_c
         /* ---- left -> right: fix the left index sets I[1..d-1] ---------------------------------- */
         for (uint32_t k = 0; k + 1 < d; k++) {
             const size_t rk = c->r[k], rk1 = c->r[k + 1], N = c->n[k], m = rk * N;
-            rc = eval_core(c, k, f, arg, dv, fi, vals, T, &nfib);
+            rc = eval_core(c, k, f, arg, dv, fi, vals, &nfib);
             if (rc) goto done;
-            memcpy(Q, T, m * rk1 * sizeof(double));                 /* unfolding (a,j) x b is already column-major */
-            mark_twin_rows(Q, m, rk1, skip);
-            { const double t_ = now_s(); qr_basis(Q, m, rk1, work); g_t_qr += now_s() - t_; }
-            { const double t_ = now_s(); const int mv = maxvol(Q, m, rk1, skip, P, B, work); g_t_mv += now_s() - t_; if (mv) { rc = C3SC_ENUMERIC; goto done; } }
+            unfold_left(vals, ldo, rk, N, rk1, Q);
+            { const double t_ = now_s(); const int mv = pivot_step(ws, m, rk1); g_t_piv += now_s() - t_; if (mv) { rc = C3SC_ENUMERIC; goto done; } }
             for (size_t b = 0; b < rk1; b++) {                      /* new left set: row (a,j) = a + j*rk */
                 const size_t a = P[b] % rk, j = P[b] / rk;
                 for (uint32_t i = 0; i < k; i++) tmpI[b * d + i] = c->I[k][a * d + i];
@@ -656,22 +1109,18 @@ int c3sc_cross_run(c3sc_cross *c, c3sc_fiber_batch_fn f, void *arg, const c3sc_c
             }
             for (size_t b = 0; b < rk1; b++)
                 for (uint32_t i = 0; i <= k; i++) c->I[k + 1][b * d + i] = tmpI[b * d + i];
-            store_core(B, rk, N, rk1, cores[k]);
+            store_left(B, rk, N, rk1, cores[k]);
         }
-        rc = eval_core(c, d - 1, f, arg, dv, fi, vals, T, &nfib);
+        rc = eval_core(c, d - 1, f, arg, dv, fi, vals, &nfib);
         if (rc) goto done;
-        store_core(T, c->r[d - 1], c->n[d - 1], 1, cores[d - 1]);
+        store_vals(vals, ldo, c->r[d - 1], c->n[d - 1], 1, cores[d - 1]);
         /* ---- right -> left: fix the right index sets J[1..d-1] ---------------------------------- */
         for (uint32_t k = d - 1; k >= 1; k--) {
             const size_t rk = c->r[k], rk1 = c->r[k + 1], N = c->n[k], m = N * rk1;
-            rc = eval_core(c, k, f, arg, dv, fi, vals, T, &nfib);
+            rc = eval_core(c, k, f, arg, dv, fi, vals, &nfib);
             if (rc) goto done;
-            for (size_t a = 0; a < rk; a++)                         /* transpose: rows (j,b) = j + b*N, cols a */
-                for (size_t j = 0; j < N; j++)
-                    for (size_t b = 0; b < rk1; b++) Q[(j + b * N) + a * m] = T[a + j * rk + b * rk * N];
-            mark_twin_rows(Q, m, rk, skip);
-            { const double t_ = now_s(); qr_basis(Q, m, rk, work); g_t_qr += now_s() - t_; }
-            { const double t_ = now_s(); const int mv = maxvol(Q, m, rk, skip, P, B, work); g_t_mv += now_s() - t_; if (mv) { rc = C3SC_ENUMERIC; goto done; } }
+            unfold_right(vals, ldo, rk, N, rk1, Q);                 /* rows (j,b) = j + b*N, cols a */
+            { const double t_ = now_s(); const int mv = pivot_step(ws, m, rk); g_t_piv += now_s() - t_; if (mv) { rc = C3SC_ENUMERIC; goto done; } }
             for (size_t a = 0; a < rk; a++) {
                 const size_t j = P[a] % N, b = P[a] / N;
                 tmpI[a * d + k] = (int32_t)j;
@@ -679,14 +1128,11 @@ int c3sc_cross_run(c3sc_cross *c, c3sc_fiber_batch_fn f, void *arg, const c3sc_c
             }
             for (size_t a = 0; a < rk; a++)
                 for (uint32_t i = k; i < d; i++) c->J[k][a * d + i] = tmpI[a * d + i];
-            for (size_t a = 0; a < rk; a++)                         /* back to [a][j][b] */
-                for (size_t j = 0; j < N; j++)
-                    for (size_t b = 0; b < rk1; b++) T[a + j * rk + b * rk * N] = B[(j + b * N) + a * m];
-            store_core(T, rk, N, rk1, cores[k]);
+            store_right(B, rk, N, rk1, cores[k]);
         }
-        rc = eval_core(c, 0, f, arg, dv, fi, vals, T, &nfib);
+        rc = eval_core(c, 0, f, arg, dv, fi, vals, &nfib);
         if (rc) goto done;
-        store_core(T, 1, c->n[0], c->r[1], cores[0]);
+        store_vals(vals, ldo, 1, c->n[0], c->r[1], cores[0]);
         /* ---- change of the train against the previous sweep pair (valuef_norm2diff idea); skipped when
                 nobody asks for it (no tolerance, no output, not verbose): a fifth of a sweep's host time ---- */
         if (tol > 0.0 || rel_change || verbose) {
@@ -699,8 +1145,8 @@ int c3sc_cross_run(c3sc_cross *c, c3sc_fiber_batch_fn f, void *arg, const c3sc_c
             g_t_dot += now_s() - t_;
             const double diff2 = aa - 2.0 * ab + bb;
             change = aa > 0.0 ? sqrt(fabs(diff2) / aa) : 0.0;
-            if (verbose) fprintf(stderr, "c3sc_cross: sweep %u, |T|=%g, rel change %g, fibers %llu; cumulative s: operator %.4f qr %.4f maxvol %.4f norms %.4f\n",
-                                 it, sqrt(aa), change, (unsigned long long)nfib, g_t_eval, g_t_qr, g_t_mv, g_t_dot);
+            if (verbose) fprintf(stderr, "c3sc_cross: sweep %u, |T|=%g, rel change %g, fibers %llu; cumulative s: operator %.4f pivoting (twin rows + qr + maxvol, %d threads) %.4f norms %.4f\n",
+                                 it, sqrt(aa), change, (unsigned long long)nfib, g_t_eval, ws->threads, g_t_piv, g_t_dot);
             for (uint32_t k = 0; k < d; k++) memcpy(prev[k], cores[k], c->r[k] * c->n[k] * c->r[k + 1] * sizeof(double));
             if (tol > 0.0 && change < tol) break;
         }
@@ -709,7 +1155,7 @@ done:
     if (nfibers) *nfibers = nfib;
     if (rel_change) *rel_change = change;
     if (prev) for (uint32_t k = 0; k < d; k++) free(prev[k]);
-    free(prev); free(dv); free(fi); free(vals); free(T); free(Q); free(B); free(P); free(work); free(tmpI); free(skip);
+    free(prev); la_ws_free(ws); free(work); free(tmpI);
     return rc;
 }
 
@@ -1030,6 +1476,8 @@ int c3sc_cross_run_pi(c3sc_cross *c, c3sc_problem *p, const c3sc_valuef *vf_poli
                       uint32_t dx, const c3sc_cross_opts *opts, double *const *cores, uint64_t *nfibers, double *rel_change)
 {
     size_t fmax = 1;
+    if (!c) return C3SC_EINVAL;
+    c->want_pinned = 1;
     for (uint32_t k = 0; k < c->d; k++)
         if (c->r[k] * c->r[k + 1] > fmax) fmax = c->r[k] * c->r[k + 1];
     struct pi_ctx x = {p, vf_policy, vf_iter, NULL, 0};
@@ -1045,6 +1493,8 @@ int c3sc_cross_run_vi(c3sc_cross *c, c3sc_problem *p, const c3sc_valuef *vf, con
                       double *const *cores, uint64_t *nfibers, double *rel_change)
 {
     struct vi_ctx x = {p, vf};
+    if (!c) return C3SC_EINVAL;
+    c->want_pinned = 1;
     return c3sc_cross_run(c, vi_cb, &x, opts, cores, nfibers, rel_change);
 }
 

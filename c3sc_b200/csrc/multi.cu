@@ -410,6 +410,7 @@ int c3sc_cross_run_vi_multi(c3sc_cross *c, c3sc_multi *m, const c3sc_multi_value
 {
     if (!c || !m || !vf) return c3sc_set_error(C3SC_EINVAL, "null argument");
     mvi_ctx x = {m, vf};
+    c3sc_cross_pin_buffers(c, 1);
     return c3sc_cross_run(c, mvi_cb, &x, opts, cores, nfibers, rel_change);
 }
 
@@ -418,6 +419,7 @@ int c3sc_cross_run_pi_multi(c3sc_cross *c, c3sc_multi *m, const c3sc_multi_value
 {
     if (!c || !m || !vf_policy || !vf_iter) return c3sc_set_error(C3SC_EINVAL, "null argument");
     mpi_ctx x = {m, vf_policy, vf_iter};
+    c3sc_cross_pin_buffers(c, 1);
     return c3sc_cross_run(c, mpi_cb, &x, opts, cores, nfibers, rel_change);
 }
 

@@ -31,6 +31,10 @@ typedef struct c3sc_cross c3sc_cross;   /* ranks + left/right index sets, kept b
 int  c3sc_cross_create(uint32_t d, const uint64_t *n, const uint64_t *ranks, c3sc_cross **out);
 int  c3sc_cross_copy(const c3sc_cross *src, c3sc_cross **out);    /* ranks + index sets */
 void c3sc_cross_destroy(c3sc_cross *c);
+/* on != 0: the buffers the driver exchanges with the operator (fiber descriptors out, fiber values back) are
+ * page-locked (c3sc_host_alloc), so a GPU operator copies at PCIe speed; c3sc_cross_run_vi / _pi and their
+ * multi-GPU forms turn it on themselves.  Pageable memory is used where page-locking fails. */
+int  c3sc_cross_pin_buffers(c3sc_cross *c, int on);
 int  c3sc_cross_ranks(const c3sc_cross *c, uint64_t *ranks);
 /* index sets at bond k (0..d): left[r_k*d] over dims 0..k-1, right[r_k*d] over dims k..d-1 (others 0);
  * what ValueF keeps as isl / isr between solver steps (src/valuefunc.c:706-712).  Either may be NULL. */

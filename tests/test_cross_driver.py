@@ -45,6 +45,43 @@ def test_cross_recovers_low_rank_tensor():
     cr.close()
 
 
+def test_pivoting_team_size_does_not_change_the_numbers(monkeypatch):
+    """the pivoting step (twin rows + QR + maxvol) runs on a team of threads over fixed row blocks: cores, index sets and the
+    change norm are bit-identical for 1, 3 and 8 threads (C3SC_HOST_THREADS), on unfoldings big enough to use the team"""
+    n = [64, 48, 64, 56]
+    grids = [np.linspace(-1, 1, m) for m in n]
+
+    def fn(dv, fi):
+        k = int(dv[0])
+        assert (dv == k).all()
+        x = [grids[i][fi[:, i]][:, None] for i in range(4)]
+        x[k] = grids[k][None, :]
+        out = np.zeros((len(dv), max(n)))
+        sm = x[0] + x[1] + x[2] + x[3]
+        out[:, :n[k]] = np.sin(2.0 * sm) + 1.0 / (5.0 + sm) + np.exp(-(x[0] ** 2 + x[1] ** 2 + x[2] ** 2 + x[3] ** 2))
+        return out
+    results = []
+    for threads in ("1", "3", "8"):
+        monkeypatch.setenv("C3SC_HOST_THREADS", threads)
+        cr = capi.Cross(n, [1, 14, 16, 14, 1])
+        cores, nfib, change = cr.run(fn, maxiter=2)
+        sets = [cr.index_sets(k) for k in range(1, 4)] if hasattr(cr, "index_sets") else []
+        results.append((cores, change, sets))
+        cr.close()
+    for cores, change, sets in results[1:]:
+        assert change == results[0][1]
+        for a, b in zip(cores, results[0][0]):
+            assert np.array_equal(np.asarray(a), np.asarray(b))
+        for a, b in zip(sets, results[0][2]):
+            assert all(np.array_equal(x, y) for x, y in zip(a, b))
+    # and the answer is a good approximation (the function has modest TT ranks)
+    X = np.meshgrid(*grids, indexing="ij")
+    sm = X[0] + X[1] + X[2] + X[3]
+    full = np.sin(2.0 * sm) + 1.0 / (5.0 + sm) + np.exp(-(X[0] ** 2 + X[1] ** 2 + X[2] ** 2 + X[3] ** 2))
+    approx = _tt_full(n, [1, 14, 16, 14, 1], results[0][0])
+    assert np.abs(approx - full).max() <= 1e-8 * np.abs(full).max()
+
+
 def test_cross_batches_are_whole_cores():
     """every operator call asks for r_k * r_{k+1} fibers that all vary the same dimension"""
     n = [6, 5, 7]

@@ -1,6 +1,6 @@
 /* micro-benchmark of the host cross driver's dense kernels (QR, maxvol, twin-row marking, TT dot) at the
  * bench shape: unfolding 2000 x 20, d = 10, N = 100, r = 20.
- *   gcc -std=c99 -O3 tools/cross_linalg_bench.c -o build/cross_linalg_bench -lm && build/cross_linalg_bench */
+ *   gcc -std=gnu99 -O3 -fopenmp tools/cross_linalg_bench.c -o build/cross_linalg_bench -lm && C3SC_HOST_THREADS=8 build/cross_linalg_bench [m n] */
 #include "../c3sc_b200/csrc/host/c3sc_cross.c"
 int c3sc_vi_batch(c3sc_problem *p, const c3sc_valuef *v, size_t F, const int32_t *a, const int32_t *b, size_t l, double *o, int32_t *g)
 { (void)p; (void)v; (void)F; (void)a; (void)b; (void)l; (void)o; (void)g; return 1; }
@@ -11,27 +11,29 @@ int c3sc_valuef_create(uint32_t d, const uint64_t *n, const uint64_t *r, const d
 { (void)d; (void)n; (void)r; (void)c; (void)o; return 1; }
 int c3sc_valuef_update(c3sc_valuef *v, const double *const *c) { (void)v; (void)c; return 1; }
 void c3sc_valuef_destroy(c3sc_valuef *v) { (void)v; }
+int c3sc_host_alloc(size_t b, void **p) { (void)b; (void)p; return 1; }
+int c3sc_host_free(void *p) { (void)p; return 0; }
 
-int main(void)
+int main(int argc, char **argv)
 {
-    const size_t m = 2000, n = 20;
-    double *A = malloc(m * n * 8), *Q = malloc(m * n * 8), *B = malloc(m * n * 8), *work = malloc((n * n * 3 + n + m + 16) * 8);
-    size_t P[64];
-    char *skip = calloc(m, 1);
+    const size_t m = argc > 1 ? (size_t)atol(argv[1]) : 2000, n = argc > 2 ? (size_t)atol(argv[2]) : 20;
+    la_ws *w = la_ws_create(m, n);
+    double *A = malloc(m * n * 8);
     srand(1);
     for (size_t i = 0; i < m * n; i++) A[i] = rand() / (double)RAND_MAX - 0.5;
-    double tq = 0, tm = 0, tw = 0, t0;
-    const int reps = 50;
+    double tp = 0, t0;
+    const int reps = 200;
+    unsigned long long h = 1469598103934665603ull;
     for (int rep = 0; rep < reps; rep++) {
-        memcpy(Q, A, m * n * 8);
-        t0 = now_s(); mark_twin_rows(Q, m, n, skip); tw += now_s() - t0;
-        t0 = now_s(); qr_explicit_q(Q, m, n, work); tq += now_s() - t0;
-        t0 = now_s(); maxvol(Q, m, n, skip, P, B, work); tm += now_s() - t0;
+        memcpy(w->Q, A, m * n * 8);
+        t0 = now_s(); pivot_step(w, m, n); tp += now_s() - t0;
     }
-    printf("unfolding %zux%zu: twin rows %.3f ms, qr %.3f ms, maxvol %.3f ms\n", m, n, tw / reps * 1e3, tq / reps * 1e3, tm / reps * 1e3);
+    for (size_t i = 0; i < m * n; i++) { unsigned long long u; memcpy(&u, w->B + i, 8); h = (h ^ u) * 1099511628211ull; }
+    for (size_t j = 0; j < n; j++) h = (h ^ w->P[j]) * 1099511628211ull;
+    printf("unfolding %zux%zu, %d threads: twin rows + qr + maxvol %.3f ms; hash of (B, P) %016llx\n", m, n, w->threads, tp / reps * 1e3, h);
     /* TT dot at d = 10, N = 100, r = 20 */
     uint64_t nn[10], rr[11];
-    double *cores[10], *w = malloc(3 * 400 * 8);
+    double *cores[10], *wk = malloc(3 * 400 * 8);
     for (int k = 0; k <= 10; k++) rr[k] = (k == 0 || k == 10) ? 1 : 20;
     for (int k = 0; k < 10; k++) {
         nn[k] = 100;
@@ -40,7 +42,8 @@ int main(void)
     }
     t0 = now_s();
     double acc = 0;
-    for (int rep = 0; rep < 20; rep++) acc += tt_dot(10, nn, rr, cores, cores, w, w + 400, w + 800);
-    printf("tt_dot: %.3f ms (%g)\n", (now_s() - t0) / 20 * 1e3, acc);
+    for (int rep = 0; rep < 20; rep++) acc += tt_dot(10, nn, rr, cores, cores, wk, wk + 400, wk + 800);
+    printf("tt_dot: %.3f ms (%.17g)\n", (now_s() - t0) / 20 * 1e3, acc);
+    la_ws_free(w);
     return 0;
 }
