@@ -242,6 +242,7 @@ struct c3sc_problem {
     std::vector<double> h_utab;              // host copy of the control table (policy entry returns u, not its index)
     double *d_xgrid = nullptr, *d_obs = nullptr, *d_utab = nullptr, *d_ctab = nullptr;
     int *d_err = nullptr;
+    int *h_err = nullptr;                    // page-locked landing place of the error word (finish_begin / finish_end)
     cudaStream_t stream = nullptr;           // host-buffer entry points run here
     cudaStream_t copy_stream = nullptr;      // device->host copies of finished chunks
     cudaStream_t peer_stream = nullptr;      // bulk copies of finished chunks into the peers' gathered buffers
@@ -268,16 +269,20 @@ struct DeviceScope {
 // device error word of a problem: [0] transition normaliser < 1e-14 seen, [1] a fiber descriptor outside the
 // grid seen (k_group_fibers), [2] smallest such fiber id, [3] spare
 static const int k_err_clear[4] = {0, 0, 0x7fffffff, 0};
-static int read_error_word(c3sc_problem *p)
+static int report_error_word(c3sc_problem *p, const int *w)
 {
-    int w[4] = {0, 0, 0, 0};
-    CK(cudaMemcpy(w, p->d_err, sizeof w, cudaMemcpyDeviceToHost));
     if (!w[0] && !w[1]) return C3SC_OK;
     cudaMemcpy(p->d_err, k_err_clear, sizeof k_err_clear, cudaMemcpyHostToDevice);
     if (w[1])
         return fail(C3SC_EINVAL, "fiber %d: dim_vary or a fixed index lies outside the grid (src/nodeutil.c:437-470 returns non-zero here); "
                     "the batch's results are undefined", w[2]);
     return fail(C3SC_ENUMERIC, "transition normaliser < 1e-14 at some (node, control): the reference asserts here");
+}
+static int read_error_word(c3sc_problem *p)
+{
+    int w[4] = {0, 0, 0, 0};
+    CK(cudaMemcpy(w, p->d_err, sizeof w, cudaMemcpyDeviceToHost));
+    return report_error_word(p, w);
 }
 
 extern "C" {
@@ -444,6 +449,7 @@ int c3sc_problem_create(const c3sc_problem_desc *d, c3sc_problem **out)
     }
     CKP(dev_malloc(&p->d_err, 4 * sizeof(int)));
     CKP(cudaMemcpy(p->d_err, k_err_clear, sizeof k_err_clear, cudaMemcpyHostToDevice));
+    CKP(cudaHostAlloc((void **)&p->h_err, 4 * sizeof(int), cudaHostAllocPortable));
     CKP(cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking));
     CKP(cudaStreamCreateWithFlags(&p->copy_stream, cudaStreamNonBlocking));
     CKP(cudaStreamCreateWithFlags(&p->peer_stream, cudaStreamNonBlocking));
@@ -517,6 +523,7 @@ void c3sc_problem_destroy(c3sc_problem *p)
     if (!p) return;
     DeviceScope ds_(p->device);
     dev_free(p->d_xgrid); dev_free(p->d_obs); dev_free(p->d_utab); dev_free(p->d_err); dev_free(p->d_ctab); dev_free(p->d_gtab);
+    if (p->h_err) cudaFreeHost(p->h_err);
     DevBuf *bufs[] = {&p->b_dv, &p->b_fi, &p->b_val, &p->b_arg, &p->b_abs, &p->b_costs, &p->b_rows, &p->b_nv, &p->b_nf};
     for (DevBuf *b : bufs) b->release();
     for (DevBuf &b : p->b_misc) b.release();
@@ -997,10 +1004,22 @@ static int upload_fibers(c3sc_problem *p, size_t F, const int32_t *dim_vary, con
     return C3SC_OK;
 }
 
-static int finish(c3sc_problem *p)
+/* the batch's error word comes back behind the batch's kernels on the same stream (one round trip, not a
+   synchronize followed by a blocking copy); finish_begin may be issued before waiting on other streams */
+static int finish_begin(c3sc_problem *p)
+{
+    CK(cudaMemcpyAsync(p->h_err, p->d_err, 4 * sizeof(int), cudaMemcpyDeviceToHost, p->stream));
+    return C3SC_OK;
+}
+static int finish_end(c3sc_problem *p)
 {
     CK(cudaStreamSynchronize(p->stream));
-    return read_error_word(p);
+    return report_error_word(p, p->h_err);
+}
+static int finish(c3sc_problem *p)
+{
+    int rc = finish_begin(p);
+    return rc ? rc : finish_end(p);
 }
 
 int c3sc_fibers_check(const c3sc_problem *p, size_t F, const int32_t *dim_vary, const int32_t *fixed_ind)
@@ -1133,8 +1152,10 @@ static int vi_batch_host(c3sc_problem *p, const c3sc_valuef *vf, size_t F, const
     }
     rc = run_batch(p->P, p->model, p->arith, p->scr, &p->grp, vf->ft, b, p->stream);
     if (rc) return rc;
+    rc = finish_begin(p);
+    if (rc) return rc;
     CK(cudaStreamSynchronize(p->copy_stream));
-    return finish(p);
+    return finish_end(p);
 }
 
 int c3sc_pi_batch(c3sc_problem *p, const c3sc_valuef *vf_policy, const c3sc_valuef *vf_iter, size_t F,

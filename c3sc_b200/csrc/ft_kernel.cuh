@@ -160,10 +160,13 @@ __global__ void __launch_bounds__(1024) k_group_fibers(int F, int FC, int d, con
     int *kcount = cnt_all + 64 * blockIdx.x, *kstart = kcount + 16, *act_count = kcount + 32;
     if (tid < MAXD) cnt[tid] = 0;
     __syncthreads();
-    for (int f = tid; f < Fc; f += blockDim.x) {
-        int k = dim_vary[f];
-        k = k < 0 ? 0 : (k >= d ? d - 1 : k);
-        atomicAdd(&cnt[k], 1);
+    // a core batch of the cross driver has ONE k: the counters are bumped once per warp and value (match_any), not 1024 times
+    for (int f0 = 0; f0 < Fc; f0 += blockDim.x) {
+        const int f = f0 + tid;
+        int k = f < Fc ? dim_vary[f] : -1;
+        k = f < Fc ? (k < 0 ? 0 : (k >= d ? d - 1 : k)) : MAXD;
+        const unsigned peers = __match_any_sync(0xffffffffu, k);
+        if (f < Fc && (int)(__ffs(peers) - 1) == (tid & 31)) atomicAdd(&cnt[k], __popc(peers));
     }
     __syncthreads();
     if (tid == 0) {
@@ -174,10 +177,16 @@ __global__ void __launch_bounds__(1024) k_group_fibers(int F, int FC, int d, con
     }
     __syncthreads();
     // the order inside a group does not change any result
-    for (int f = tid; f < Fc; f += blockDim.x) {
-        int k = dim_vary[f];
-        k = k < 0 ? 0 : (k >= d ? d - 1 : k);
-        perm[atomicAdd(&pos[k], 1)] = f;
+    for (int f0 = 0; f0 < Fc; f0 += blockDim.x) {
+        const int f = f0 + tid, lane = tid & 31;
+        int k = f < Fc ? dim_vary[f] : -1;
+        k = f < Fc ? (k < 0 ? 0 : (k >= d ? d - 1 : k)) : MAXD;
+        const unsigned peers = __match_any_sync(0xffffffffu, k);
+        const int leader = __ffs(peers) - 1;
+        int base = 0;
+        if (f < Fc && leader == lane) base = atomicAdd(&pos[k], __popc(peers));
+        base = __shfl_sync(0xffffffffu, base, leader);
+        if (f < Fc) perm[base + __popc(peers & ((1u << lane) - 1u))] = f;
     }
 }
 

@@ -156,7 +156,7 @@ int c3sc_cross_index_sets(const c3sc_cross *c, uint32_t k, int32_t *left, int32_
 
 /* ---- small dense linear algebra (column-major) --------------------------------------------- */
 #if defined(__x86_64__) && defined(__GNUC__) && !defined(__clang__)
-#define C3SC_CLONES __attribute__((target_clones("avx2", "default")))   /* same arithmetic, wider registers (no FMA) */
+#define C3SC_CLONES __attribute__((target_clones("avx512f", "avx2", "default")))   /* same arithmetic, wider registers (no FMA) */
 #else
 #define C3SC_CLONES
 #endif
@@ -243,14 +243,19 @@ static void qr_explicit_q(double *A, size_t m, size_t n, double *work /* n + m *
 
 /* ---- the pivoting step of one core: twin rows -> QR basis -> maxvol, by a team of threads ------------------------
  * One VI sweep is 2(d-1) of these steps in sequence, each on an unfolding of r N x r numbers between two operator
- * calls: with the backup on the GPU they are what a sweep costs.  The three phases share one OpenMP parallel region
+ * calls: with the backup on the GPU they are what a sweep costs.  The phases share one OpenMP parallel region
  * (the reference is an OpenMP library itself, src/bellman.c:1390-1404).  Rows are cut into LA_NB fixed blocks; a
- * thread owns a contiguous run of blocks and is the only one that ever writes their rows, so the unfolding stays in
- * its core's cache from the first phase to the last.  Everything that couples rows (column norms, reflector dots,
- * pivot searches) is reduced per BLOCK, published, and summed by every thread in block order after a barrier: the
- * numbers depend on LA_NB, never on the number of threads (C3SC_HOST_THREADS, default min(8, omp_get_max_threads())),
- * and every thread takes the same branches.  Partial results are double-buffered where the next phase would
- * otherwise overwrite them before a slow thread has read them. */
+ * thread owns a contiguous run of blocks and is the only one that ever writes their rows, from the unfolding of
+ * the operator's values to the store of the cross core, so the data stays in its core's cache.  Everything that
+ * couples rows (column norms, reflector dots, pivot searches) is reduced per BLOCK, published, and combined by
+ * every thread in block order after a barrier: the numbers depend on LA_NB, never on the number of threads
+ * (C3SC_HOST_THREADS, default min(8, omp_get_max_threads(), CPUs of the affinity mask)), and every thread takes
+ * the same branches.  Barriers are what the step costs on a team, so each phase is arranged to need one per
+ * column: the QR takes the dots of the pivot column with ALL columns in one pass (earlier reflectors: the Gram
+ * matrix of the compact WY form; itself: the norm; later columns: the reflection) and forms Q = (I - V T V^T) E
+ * row block by row block with no further exchange; the pivot searches publish, per block, the maximum together
+ * with the block's first near-maximal row.  Published records are double-buffered: a fast thread may already
+ * write the next one while a slow one reads. */
 #ifdef _OPENMP
 #include <omp.h>
 #include <sched.h>
@@ -262,21 +267,31 @@ static void qr_explicit_q(double *A, size_t m, size_t n, double *work /* n + m *
 #define RANK_EPS 1e-11
 #define TIE_EPS 1e-8     /* see team_maxvol */
 #define LA_NONE ((size_t)-1)
+#define LA_SWL 3
+
+/* start rows of maxvol, one column: maxima over the block's unused rows (all of them / those not withheld), the first
+ * row reaching each maximum exactly and the first within TIE_EPS of it */
+typedef struct { double a_max, e_max, a_candval, e_candval; size_t a_arg, e_arg, a_cand, e_cand; } la_erec;
+/* swaps of maxvol: the block's largest eligible |B| and the (at most LA_SWL, ascending) columns within TIE_EPS of it */
+typedef struct { double best; size_t nl, j[LA_SWL], cand[LA_SWL], arg[LA_SWL]; double cm[LA_SWL], candval[LA_SWL]; double pad[7]; } la_srec;   /* 3 cache lines */
 
 typedef struct {
-    size_t mcap, ncap;        /* capacity: rows, columns */
+    size_t mcap, ncap, bscap; /* capacity: rows, columns, rows per block */
+    size_t pstride;           /* doubles between the partial sums of two blocks: whole cache lines */
     size_t m, n, bs;          /* this step: rows, columns, rows per block */
     int threads;
     double *Q, *B;            /* m x n column-major: unfolding in / orthonormal basis out; cross core Q inv(Q[P]) out */
     size_t *P;                /* n pivot rows out */
     char *skip, *used;        /* m */
     double *part;             /* [2][LA_NB][ncap] partial sums */
-    double *mp;               /* [2][LA_NB][2] pivot search: max over all rows, max over eligible rows */
-    size_t *ip;               /* [3][LA_NB] pivot search: row / entry */
-    double *priv;             /* [threads][8 ncap] */
-    double *S, *aug;          /* n x n, n x 2n (thread 0) */
+    la_erec *erec;            /* [2][LA_NB] */
+    la_srec *srec;            /* [2][LA_NB] */
+    double *priv;             /* [threads][privlen] */
+    size_t privlen;
+    double *V1;               /* n x n: the top of the reflector matrix, shared copy */
     double *k1; int64_t *qk; uint32_t *slot; size_t slotcap;   /* twin rows */
-    size_t sh_bi, sh_bj; double sh_best;                      /* maxvol: masked scan result of thread 0 */
+    /* where the unfolding comes from and where the core goes (NULL: w->Q is filled by the caller, w->B read by it) */
+    const double *vals; double *core; size_t ldo, rk, N, rk1; int right;
     int rc;
 #ifdef _OPENMP
     char pad0[64]; atomic_int bar_count;                      /* sense-reversing barrier of the team, a cache line each */
@@ -286,13 +301,20 @@ typedef struct {
 } la_ws;
 typedef struct { int tid, nt, b0, b1, sense; } la_thr;       /* a thread of the team and the blocks it owns */
 
-/* A step has ~150 barriers with a few microseconds of work between them: the team spins (libgomp's barrier parks
+/* A step has ~60 barriers with a few microseconds of work between them: the team spins (libgomp's barrier parks
  * threads in the kernel under some team sizes, 50 us a time); a thread that has lost its CPU is waited for with
  * sched_yield. */
+#ifdef LA_PROFILE
+static double g_bar_wait[64]; static long g_bar_n[64];
+static double now_s(void);
+#endif
 static inline void la_barrier(la_ws *w, la_thr *t)
 {
 #ifdef _OPENMP
     if (t->nt == 1) return;
+#ifdef LA_PROFILE
+    const double t0_ = now_s();
+#endif
     const int s = !t->sense;
     t->sense = s;
     if (atomic_fetch_add_explicit(&w->bar_count, 1, memory_order_acq_rel) == t->nt - 1) {
@@ -308,6 +330,9 @@ static inline void la_barrier(la_ws *w, la_thr *t)
             else sched_yield();
         }
     }
+#ifdef LA_PROFILE
+    g_bar_wait[t->tid] += now_s() - t0_; g_bar_n[t->tid]++;
+#endif
 #else
     (void)w; (void)t;
 #endif
@@ -317,8 +342,8 @@ static inline void la_barrier(la_ws *w, la_thr *t)
 static void la_ws_free(la_ws *w)
 {
     if (!w) return;
-    free(w->Q); free(w->B); free(w->P); free(w->skip); free(w->used); free(w->part); free(w->mp); free(w->ip); free(w->priv);
-    free(w->S); free(w->aug); free(w->k1); free(w->qk); free(w->slot); free(w);
+    free(w->Q); free(w->B); free(w->P); free(w->skip); free(w->used); free(w->part); free(w->erec); free(w->srec); free(w->priv);
+    free(w->V1); free(w->k1); free(w->qk); free(w->slot); free(w);
 }
 
 static int la_threads(void)
@@ -340,27 +365,36 @@ static int la_threads(void)
     return t < 1 ? 1 : t;
 }
 
+static size_t la_block_rows(size_t m) { return ((m + LA_NB - 1) / LA_NB + 7) & ~(size_t)7; }
+
+/* everything two threads may write side by side starts on a cache line of its own */
+static void *la_alloc(size_t bytes) { return aligned_alloc(64, (bytes + 63) & ~(size_t)63); }
+
 static la_ws *la_ws_create(size_t mcap, size_t ncap)
 {
-    la_ws *w = (la_ws *)calloc(1, sizeof *w);
+    la_ws *w = (la_ws *)la_alloc(sizeof *w);
     if (!w) return NULL;
-    w->mcap = mcap; w->ncap = ncap; w->threads = la_threads();
+    memset(w, 0, sizeof *w);
+    w->mcap = mcap; w->ncap = ncap; w->bscap = la_block_rows(mcap); w->threads = la_threads();
+    w->pstride = (ncap + 7) & ~(size_t)7;
     w->slotcap = 16;
     while (w->slotcap < 4 * mcap) w->slotcap <<= 1;
-    w->Q = (double *)malloc(mcap * ncap * sizeof(double));
-    w->B = (double *)malloc(mcap * ncap * sizeof(double));
-    w->P = (size_t *)malloc(ncap * sizeof(size_t));
-    w->skip = (char *)malloc(mcap + 1); w->used = (char *)malloc(mcap + 1);
-    w->part = (double *)malloc(2 * LA_NB * ncap * sizeof(double));
-    w->mp = (double *)malloc(2 * LA_NB * 2 * sizeof(double));
-    w->ip = (size_t *)malloc(3 * LA_NB * sizeof(size_t));
-    w->priv = (double *)malloc((size_t)w->threads * 8 * ncap * sizeof(double));
-    w->S = (double *)malloc(ncap * ncap * sizeof(double));
-    w->aug = (double *)malloc(2 * ncap * ncap * sizeof(double));
-    w->k1 = (double *)malloc(2 * mcap * sizeof(double));
-    w->qk = (int64_t *)malloc(mcap * sizeof(int64_t));
-    w->slot = (uint32_t *)malloc(w->slotcap * sizeof(uint32_t));
-    if (!w->Q || !w->B || !w->P || !w->skip || !w->used || !w->part || !w->mp || !w->ip || !w->priv || !w->S || !w->aug || !w->k1 ||
+    /* per thread: 8 vectors of n, the Gram / T / M / inverse matrices (3 n^2), [Q[P] | I] (2 n^2), the column maxima of its
+       blocks, a row block of reflectors */
+    w->privlen = (8 * ncap + 5 * ncap * ncap + LA_NB * ncap + w->bscap * ncap + 7) & ~(size_t)7;
+    w->Q = (double *)la_alloc(mcap * ncap * sizeof(double));
+    w->B = (double *)la_alloc(mcap * ncap * sizeof(double));
+    w->P = (size_t *)la_alloc(ncap * sizeof(size_t));
+    w->skip = (char *)la_alloc(mcap + 1); w->used = (char *)la_alloc(mcap + 1);
+    w->part = (double *)la_alloc(2 * LA_NB * w->pstride * sizeof(double));
+    w->erec = (la_erec *)la_alloc(2 * LA_NB * sizeof(la_erec));
+    w->srec = (la_srec *)la_alloc(2 * LA_NB * sizeof(la_srec));
+    w->priv = (double *)la_alloc((size_t)w->threads * w->privlen * sizeof(double));
+    w->V1 = (double *)la_alloc(ncap * ncap * sizeof(double));
+    w->k1 = (double *)la_alloc(2 * mcap * sizeof(double));
+    w->qk = (int64_t *)la_alloc(mcap * sizeof(int64_t));
+    w->slot = (uint32_t *)la_alloc(w->slotcap * sizeof(uint32_t));
+    if (!w->Q || !w->B || !w->P || !w->skip || !w->used || !w->part || !w->erec || !w->srec || !w->priv || !w->V1 || !w->k1 ||
         !w->qk || !w->slot) { la_ws_free(w); return NULL; }
     return w;
 }
@@ -374,12 +408,60 @@ static inline void la_rows(const la_ws *w, int blk, size_t from, size_t *lo, siz
     if (a > b) a = b;
     *lo = a; *hi = b;
 }
-static inline int la_mine(const la_ws *w, size_t row, int b0, int b1)
+static inline int la_mine(const la_ws *w, size_t row, const la_thr *th)
 {
     const int blk = (int)(row / w->bs);
-    return blk >= b0 && blk < b1;
+    return blk >= th->b0 && blk < th->b1;
 }
-#define PART(buf, blk, j) part[((size_t)(buf) * LA_NB + (size_t)(blk)) * ncap + (j)]
+#define PART(buf, blk, j) part[((size_t)(buf) * LA_NB + (size_t)(blk)) * pstride + (j)]
+
+/* own rows of the unfolding from the operator's values vals[(a + b*rk) * ldo + j]:
+ * left  unfolding: rows (a,j) = a + j*rk, columns b;  right unfolding: rows (j,b) = j + b*N, columns a */
+static void team_unfold(la_ws *w, la_thr *th)
+{
+    if (!w->vals) return;
+    const size_t m = w->m, rk = w->rk, N = w->N, rk1 = w->rk1, ldo = w->ldo;
+    const double *vals = w->vals;
+    double *Q = w->Q;
+    for (int blk = th->b0; blk < th->b1; blk++) {
+        size_t lo, hi;
+        la_rows(w, blk, 0, &lo, &hi);
+        if (!w->right) {
+            for (size_t b = 0; b < rk1; b++)
+                for (size_t i = lo; i < hi; i++) Q[i + b * m] = vals[(i % rk + b * rk) * ldo + i / rk];
+        } else {
+            for (size_t a = 0; a < rk; a++)
+                for (size_t i = lo; i < hi;) {          /* runs of j inside one b */
+                    const size_t j = i % N, b = i / N;
+                    size_t len = N - j;
+                    if (len > hi - i) len = hi - i;
+                    memcpy(Q + i + a * m, vals + (a + b * rk) * ldo + j, len * sizeof(double));
+                    i += len;
+                }
+        }
+    }
+}
+/* own rows of the cross core into the valuef_precompute_cores layout core[j*rk*rk1 + a + b*rk] */
+static void team_store(la_ws *w, la_thr *th)
+{
+    if (!w->core) return;
+    const size_t m = w->m, rk = w->rk, N = w->N, rk1 = w->rk1;
+    const double *B = w->B;
+    double *core = w->core;
+    for (int blk = th->b0; blk < th->b1; blk++) {
+        size_t lo, hi;
+        la_rows(w, blk, 0, &lo, &hi);
+        if (!w->right) {
+            for (size_t b = 0; b < rk1; b++)
+                for (size_t i = lo; i < hi; i++) core[(i / rk) * rk * rk1 + i % rk + b * rk] = B[i + b * m];
+        } else {
+            for (size_t i = lo; i < hi; i++) {
+                double *t = core + (i % N) * rk * rk1 + (i / N) * rk;
+                for (size_t a = 0; a < rk; a++) t[a] = B[i + a * m];
+            }
+        }
+    }
+}
 
 /* Rows of the unfolding A (m x n, before the QR) that repeat an earlier row to round-off carry no
  * information for the pivoting (absorbing faces with a constant boundary cost produce whole families of
@@ -390,11 +472,10 @@ static inline int la_mine(const la_ws *w, size_t row, int b0, int b1)
  * the others go ahead into the QR, which does not need skip[]). */
 static void team_twin_rows(la_ws *w, la_thr *th)
 {
-    const int tid = th->tid, b0 = th->b0, b1 = th->b1;
-    const size_t m = w->m, n = w->n, ncap = w->ncap;
+    const size_t m = w->m, n = w->n, pstride = w->pstride;
     const double *A = w->Q;
     double *k1 = w->k1, *k2 = w->k1 + m, *part = w->part;
-    for (int blk = b0; blk < b1; blk++) {
+    for (int blk = th->b0; blk < th->b1; blk++) {
         size_t lo, hi;
         la_rows(w, blk, 0, &lo, &hi);
         double scale = 0.0;
@@ -412,7 +493,7 @@ static void team_twin_rows(la_ws *w, la_thr *th)
         PART(1, blk, 0) = scale;                        /* buffer 1: the QR starts on buffer 0 */
     }
     LA_BARRIER();
-    if (tid != 0) return;
+    if (th->tid != 0) return;
     double scale = 0.0;
     for (int blk = 0; blk < LA_NB; blk++) if (PART(1, blk, 0) > scale) scale = PART(1, blk, 0);
     const double tol = 1e-12 * scale * (double)n, quantum = 1024.0 * tol;
@@ -446,18 +527,23 @@ static void team_twin_rows(la_ws *w, la_thr *th)
  * a reflector built from them would point wherever the round-off of the operator's values points, and the
  * pivoting after it would follow.  They get no reflector, so their Q columns are H_0..H_{rank-1} e_k -- a
  * completion that depends on the well-determined part only.
- * Two barriers per reflector: one for the exact norm of the pivot column, one for its dots with the trailing
- * columns.  Row k of the trailing columns is read by everyone between the two and written by its owner after
- * the second; every thread keeps its own copy of tau and of the downdated column norms (LAPACK dgeqp3 style,
- * recomputed exactly once they have lost six digits). */
+ * One barrier per reflector: the pass before it takes the dots of the pivot column a_k (rows below k) with every
+ * column -- with itself for the norm, with the later columns for the reflection (the reflector is a_k / v0, so the
+ * unscaled dots serve), with the earlier reflectors for G = V^T V.  From G and tau every thread builds the
+ * triangular factor T of H_0 .. H_{r-1} = I - V T V^T (LAPACK dlarft, forward columnwise) and M = T V1^T, V1 the top
+ * n x n of V, and then forms its own rows of Q = E - V M.  Row k of the matrix is frozen once reflector k's barrier
+ * has passed (column swaps only touch the rows below), so it can be read by everyone afterwards.  Every thread
+ * keeps its own copy of tau and of the downdated column norms (LAPACK dgeqp3 style, recomputed exactly once they
+ * have lost six digits). */
 static void team_qr_basis(la_ws *w, la_thr *th)
 {
-    const int tid = th->tid, b0 = th->b0, b1 = th->b1;
-    const size_t m = w->m, n = w->n, ncap = w->ncap;
+    const size_t m = w->m, n = w->n, ncap = w->ncap, pstride = w->pstride;
+    const int b0 = th->b0, b1 = th->b1;
     double *A = w->Q, *part = w->part;
-    double *pv = w->priv + (size_t)tid * 8 * ncap;
+    double *pv = w->priv + (size_t)th->tid * w->privlen;
     double *tau = pv, *vn2 = pv + ncap, *vref = pv + 2 * ncap, *rowk = pv + 3 * ncap, *sc = pv + 4 * ncap;
     size_t *redo = (size_t *)(pv + 5 * ncap);
+    double *G = pv + 8 * ncap, *T = G + ncap * ncap, *M = T + ncap * ncap, *Vb = pv + 8 * ncap + 5 * ncap * ncap + LA_NB * ncap;
     int pb = 0;
     for (int blk = b0; blk < b1; blk++) {
         size_t lo, hi;
@@ -482,7 +568,7 @@ static void team_qr_basis(la_ws *w, la_thr *th)
             double *ap = A + p * m;
             for (int blk = b0; blk < b1; blk++) {
                 size_t lo, hi;
-                la_rows(w, blk, 0, &lo, &hi);
+                la_rows(w, blk, k, &lo, &hi);
                 for (size_t i = lo; i < hi; i++) { const double t = ak[i]; ak[i] = ap[i]; ap[i] = t; }
             }
             double t = vn2[k]; vn2[k] = vn2[p]; vn2[p] = t;
@@ -490,41 +576,30 @@ static void team_qr_basis(la_ws *w, la_thr *th)
         }
         for (int blk = b0; blk < b1; blk++) {
             size_t lo, hi;
-            la_rows(w, blk, k, &lo, &hi);
-            PART(pb, blk, 0) = dot8(ak + lo, ak + lo, hi - lo);
+            la_rows(w, blk, k + 1, &lo, &hi);
+            for (size_t j = 0; j < n; j++) PART(pb, blk, j) = dot8(ak + lo, A + j * m + lo, hi - lo);
         }
         LA_BARRIER();
-        double nrm = 0.0;
-        for (int blk = 0; blk < LA_NB; blk++) nrm += PART(pb, blk, 0);
+        for (size_t j = 0; j < n; j++) {
+            double s = 0.0;
+            for (int blk = 0; blk < LA_NB; blk++) s += PART(pb, blk, j);
+            sc[j] = s;
+            rowk[j] = A[k + j * m];
+        }
         pb ^= 1;
-        nrm = sqrt(nrm);
+        const double akk = rowk[k];
+        const double nrm = sqrt(akk * akk + sc[k]);
         if (k == 0) ref = nrm;
         if (nrm <= RANK_EPS * ref || nrm == 0.0) { rank = k; break; }
-        const double akk = ak[k];
         const double alpha = akk >= 0.0 ? -nrm : nrm;
         const double v0 = akk - alpha;
         tau[k] = -v0 / alpha;
-        for (size_t j = k + 1; j < n; j++) rowk[j] = A[k + j * m];
+        for (size_t j = 0; j < k; j++) G[j + k * n] = rowk[j] + sc[j] / v0;               /* v_j . v_k, v_k[k] = 1 */
+        for (size_t j = k + 1; j < n; j++) sc[j] = (rowk[j] + sc[j] / v0) * tau[k];
         for (int blk = b0; blk < b1; blk++) {
             size_t lo, hi;
             la_rows(w, blk, k + 1, &lo, &hi);
             for (size_t i = lo; i < hi; i++) ak[i] /= v0;
-            for (size_t j = k + 1; j < n; j++) PART(pb, blk, j) = dot8(ak + lo, A + j * m + lo, hi - lo);
-        }
-        LA_BARRIER();
-        for (size_t j = k + 1; j < n; j++) {
-            double s = 0.0;
-            for (int blk = 0; blk < LA_NB; blk++) s += PART(pb, blk, j);
-            sc[j] = (rowk[j] + s) * tau[k];
-        }
-        pb ^= 1;
-        if (la_mine(w, k, b0, b1)) {
-            ak[k] = alpha;
-            for (size_t j = k + 1; j < n; j++) A[k + j * m] = rowk[j] - sc[j];
-        }
-        for (int blk = b0; blk < b1; blk++) {
-            size_t lo, hi;
-            la_rows(w, blk, k + 1, &lo, &hi);
             for (size_t j = k + 1; j < n; j++) axpy(-sc[j], ak + lo, A + j * m + lo, hi - lo);
         }
         size_t nre = 0;
@@ -548,50 +623,59 @@ static void team_qr_basis(la_ws *w, la_thr *th)
             pb ^= 1;
         }
     }
-    for (size_t k = rank; k < n; k++) tau[k] = 0.0;
-    /* accumulate Q = H_0 .. H_{n-1} [I; 0] in place, last reflector first.  Column kk still holds its reflector
-       below the diagonal while the columns after it (already Q columns, zero in rows <= kk) are reflected. */
-    for (size_t kk = n; kk-- > 0;) {
-        double *ak = A + kk * m;
-        const double t = tau[kk];
-        if (t != 0.0 && kk + 1 < n) {
-            for (int blk = b0; blk < b1; blk++) {
-                size_t lo, hi;
-                la_rows(w, blk, kk + 1, &lo, &hi);
-                for (size_t j = kk + 1; j < n; j++) PART(pb, blk, j) = dot8(ak + lo, A + j * m + lo, hi - lo);
-            }
-            LA_BARRIER();
-            for (size_t j = kk + 1; j < n; j++) {
-                double s = 0.0;
-                for (int blk = 0; blk < LA_NB; blk++) s += PART(pb, blk, j);
-                sc[j] = s * t;
-            }
-            pb ^= 1;
-            for (int blk = b0; blk < b1; blk++) {
-                size_t lo, hi;
-                la_rows(w, blk, kk + 1, &lo, &hi);
-                for (size_t j = kk + 1; j < n; j++) axpy(-sc[j], ak + lo, A + j * m + lo, hi - lo);
-            }
-            if (la_mine(w, kk, b0, b1))
-                for (size_t j = kk + 1; j < n; j++) A[kk + j * m] = -sc[j];
+    /* the top n x n of V (unit lower triangular in its first `rank` columns), from the owners of those rows */
+    double *V1 = w->V1;
+    for (int blk = b0; blk < b1; blk++) {
+        size_t lo, hi;
+        la_rows(w, blk, 0, &lo, &hi);
+        for (size_t i = lo; i < hi && i < n; i++)
+            for (size_t k = 0; k < rank; k++) V1[i + k * n] = i < k ? 0.0 : (i == k ? 1.0 : A[i + k * m]);
+    }
+    LA_BARRIER();
+    for (size_t k = 0; k < rank; k++) {                 /* T: upper triangular */
+        for (size_t i = 0; i < k; i++) {
+            double z = 0.0;
+            for (size_t l = i; l < k; l++) z += T[i + l * n] * G[l + k * n];
+            T[i + k * n] = -tau[k] * z;
         }
-        for (int blk = b0; blk < b1; blk++) {           /* column kk itself: H_kk e_kk = e_kk - tau v */
-            size_t lo, hi;
-            la_rows(w, blk, 0, &lo, &hi);
-            for (size_t i = lo; i < hi; i++) ak[i] = i < kk ? 0.0 : (i == kk ? 1.0 - t : (t != 0.0 ? -t * ak[i] : 0.0));
+        T[k + k * n] = tau[k];
+    }
+    for (size_t c = 0; c < n; c++)                      /* M[k,c] = sum_j T[k,j] V1[c,j],  k <= j <= min(c, rank-1) */
+        for (size_t k = 0; k < rank; k++) {
+            double s = 0.0;
+            for (size_t j = k; j < rank && j <= c; j++) s += T[k + j * n] * V1[c + j * n];
+            M[k + c * n] = s;
+        }
+    for (int blk = b0; blk < b1; blk++) {               /* own rows of Q = E - V M */
+        size_t lo, hi;
+        la_rows(w, blk, 0, &lo, &hi);
+        const size_t L = hi - lo;
+        if (!L) continue;
+        for (size_t k = 0; k < rank; k++) {
+            double *vb = Vb + k * L;
+            const double *ak = A + k * m;
+            for (size_t i = lo; i < hi; i++) vb[i - lo] = i < k ? 0.0 : (i == k ? 1.0 : ak[i]);
+        }
+        for (size_t c = 0; c < n; c++) {
+            double *qc = A + c * m + lo;
+            for (size_t i = 0; i < L; i++) qc[i] = 0.0;
+            if (c >= lo && c < hi) qc[c - lo] = 1.0;
+            for (size_t k = 0; k < rank; k++) {
+                const double mk = M[k + c * n];
+                if (mk != 0.0) axpy(-mk, Vb + k * L, qc, L);
+            }
         }
     }
 }
 
-/* thread 0: S = inv(Q[P,:]) by Gauss-Jordan with partial pivoting on [Q[P] | I] */
-static int invert_pivot_block(la_ws *w)
+/* S = inv(Q[P,:]) by Gauss-Jordan with partial pivoting on [Q[P] | I] (every thread its own copy) */
+static int invert_pivot_block(const la_ws *w, const size_t *P, double *aug /* n x 2n row-major */, double *S)
 {
     const size_t m = w->m, n = w->n;
     const double *Q = w->Q;
-    double *aug = w->aug, *S = w->S;                    /* row-major n x 2n */
     for (size_t a = 0; a < n; a++)
         for (size_t b = 0; b < n; b++) {
-            aug[a * 2 * n + b] = Q[w->P[a] + b * m];
+            aug[a * 2 * n + b] = Q[P[a] + b * m];
             aug[a * 2 * n + n + b] = a == b ? 1.0 : 0.0;
         }
     for (size_t k = 0; k < n; k++) {
@@ -615,80 +699,131 @@ static int invert_pivot_block(la_ws *w)
     return 0;
 }
 
+/* max |x[i]| over the rows that are not withheld, the held-back row `hold` (or LA_NONE) counted with value hv */
+static double absmax_eligible(const double *x, const char *skip, int any_skip, size_t lo, size_t hi, size_t hold, double hv)
+{
+    double c;
+    if (!any_skip) {
+        if (hold >= lo && hold < hi) {
+            c = fabs(hv);
+            const double c0 = absmax(x + lo, hold - lo), c1 = absmax(x + hold + 1, hi - hold - 1);
+            if (c0 > c) c = c0;
+            if (c1 > c) c = c1;
+        } else c = absmax(x + lo, hi - lo);
+        return c;
+    }
+    c = 0.0;
+    for (size_t i = lo; i < hi; i++) {
+        if (skip[i]) continue;
+        const double a = fabs(i == hold ? hv : x[i]);
+        if (a > c) c = a;
+    }
+    return c;
+}
+
+/* the swap record of a block: its largest eligible |B| and, for the columns within TIE_EPS of it, the first
+ * eligible row within TIE_EPS of the column's maximum and the first row that reaches it */
+static void swap_record(const la_ws *w, int blk, const double *cme /* n */, size_t hold, la_srec *r)
+{
+    const size_t m = w->m, n = w->n;
+    const double *B = w->B;
+    const char *skip = w->skip;
+    size_t lo, hi;
+    la_rows(w, blk, 0, &lo, &hi);
+    double best = 0.0;
+    for (size_t j = 0; j < n; j++) if (cme[j] > best) best = cme[j];
+    r->best = best; r->nl = 0;
+    if (!(best > 1.0)) return;                          /* nothing here can ask for a swap */
+    for (size_t j = 0; j < n && r->nl < LA_SWL; j++) {
+        if (cme[j] < best * (1.0 - TIE_EPS)) continue;
+        const double thr = cme[j] * (1.0 - TIE_EPS);
+        size_t cand = LA_NONE, arg = LA_NONE;
+        for (size_t i = lo; i < hi; i++) {
+            if (skip[i] || i == hold) continue;
+            const double a = fabs(B[i + j * m]);
+            if (cand == LA_NONE && a >= thr) cand = i;
+            if (a == cme[j]) { arg = i; break; }
+        }
+        const size_t l = r->nl++;
+        r->j[l] = j; r->cm[l] = cme[j]; r->cand[l] = cand; r->arg[l] = arg;
+        r->candval[l] = cand == LA_NONE ? -1.0 : fabs(B[cand + j * m]);
+    }
+}
+
 /* maxvol: rows P of Q (m x n) with |det Q[P]| locally maximal, and B = Q inv(Q[P]).
  * Symmetric problems (V(x) = V(-x)) make mirrored rows tie exactly in exact arithmetic; which one wins would
  * then depend on the last bits of the operator's values.  Entries within TIE_EPS of the maximum count as
- * tied and the first in scan order wins, so two operators that agree to round-off pick the same rows.
- * Start rows: Gaussian elimination with row pivoting on a copy (two barriers per column: the block maxima, then
- * the first near-maximal row); the chosen row is read by everyone and left alone by its owner from then on.
- * Swaps while some |B[i,j]| > 1 + delta: two barriers per swap (the first near-maximal entry in column-major
- * order; the per-block column maxima of the updated B).  The owner of the entering row holds its new values back
- * until the others have read the old ones. */
-static void team_maxvol(la_ws *w, la_thr *th)
+ * tied and the first in scan order wins (blocks in order; inside a block the first row within TIE_EPS of the
+ * block's own maximum if that row is within TIE_EPS of the overall one, else the block's maximum), so two
+ * operators that agree to round-off pick the same rows.
+ * Start rows: Gaussian elimination with row pivoting on a copy, one barrier per column; the chosen row is read by
+ * everyone and left alone by its owner from then on.  When the rows that are not withheld do not reach a direction
+ * (their maximum below 1e-6 of the overall one) all rows compete.
+ * Swaps while some eligible |B[i,j]| > 1 + delta: the first near-maximal entry in column-major order enters; one
+ * barrier per swap.  The owner of the entering row holds its new values back until the others have read the old. */
+static int team_maxvol(la_ws *w, la_thr *th)
 {
-    const int tid = th->tid, b0 = th->b0, b1 = th->b1;
     const size_t m = w->m, n = w->n, ncap = w->ncap;
+    const int tid = th->tid, b0 = th->b0, b1 = th->b1;
     const double *Q = w->Q;
-    double *B = w->B, *part = w->part, *mp = w->mp;
-    size_t *ip = w->ip;
+    double *B = w->B;
     const char *skip = w->skip;
     char *used = w->used;
-    double *pv = w->priv + (size_t)tid * 8 * ncap;
-    double *f = pv, *cmax = pv + ncap, *col = pv + 2 * ncap, *newrow = pv + 3 * ncap;
+    double *pv = w->priv + (size_t)tid * w->privlen;
+    double *f = pv, *col = pv + ncap, *newrow = pv + 2 * ncap;
+    size_t *P = (size_t *)(pv + 3 * ncap);
+    double *S = pv + 8 * ncap, *aug = S + ncap * ncap, *cme_all = pv + 8 * ncap + 5 * ncap * ncap;
+#define CME(blk) (cme_all + (size_t)((blk) - b0) * ncap)     /* eligible column maxima of an own block */
+    int any_skip[LA_NB];
+    int pb = 0;
     for (int blk = b0; blk < b1; blk++) {
         size_t lo, hi;
         la_rows(w, blk, 0, &lo, &hi);
         memset(used + lo, 0, hi - lo);
+        any_skip[blk] = 0;
+        for (size_t i = lo; i < hi; i++) any_skip[blk] |= skip[i];
         for (size_t j = 0; j < n; j++) memcpy(B + j * m + lo, Q + j * m + lo, (hi - lo) * sizeof(double));
     }
     for (size_t j = 0; j < n; j++) {
         const double *bj = B + j * m;
         for (int blk = b0; blk < b1; blk++) {
-            size_t lo, hi, piv = LA_NONE;
+            size_t lo, hi;
             la_rows(w, blk, 0, &lo, &hi);
-            double best = -1.0, best_any = 0.0;
+            la_erec r = { -1.0, -1.0, -1.0, -1.0, LA_NONE, LA_NONE, LA_NONE, LA_NONE };
             for (size_t i = lo; i < hi; i++) {
                 if (used[i]) continue;
                 const double a = fabs(bj[i]);
-                if (a > best_any) best_any = a;
-                if (!skip[i] && a > best) { best = a; piv = i; }
+                if (a > r.a_max) { r.a_max = a; r.a_arg = i; }
+                if (!skip[i] && a > r.e_max) { r.e_max = a; r.e_arg = i; }
             }
-            mp[(0 * LA_NB + blk) * 2] = best_any; mp[(0 * LA_NB + blk) * 2 + 1] = best; ip[0 * LA_NB + blk] = piv;
+            for (size_t i = lo; i < hi && (r.a_cand == LA_NONE || (r.e_cand == LA_NONE && r.e_arg != LA_NONE)); i++) {
+                if (used[i]) continue;
+                const double a = fabs(bj[i]);
+                if (r.a_cand == LA_NONE && a >= r.a_max * (1.0 - TIE_EPS)) { r.a_cand = i; r.a_candval = a; }
+                if (r.e_cand == LA_NONE && !skip[i] && a >= r.e_max * (1.0 - TIE_EPS)) { r.e_cand = i; r.e_candval = a; }
+            }
+            w->erec[pb * LA_NB + blk] = r;
         }
         LA_BARRIER();
-        size_t piv = 0; double best = -1.0, best_any = 0.0;
+        const la_erec *er = w->erec + pb * LA_NB;
+        pb ^= 1;
+        double best_any = 0.0, best_e = -1.0;
         for (int blk = 0; blk < LA_NB; blk++) {
-            if (mp[blk * 2] > best_any) best_any = mp[blk * 2];
-            if (mp[blk * 2 + 1] > best) { best = mp[blk * 2 + 1]; piv = ip[blk]; }
+            if (er[blk].a_max > best_any) best_any = er[blk].a_max;
+            if (er[blk].e_max > best_e) best_e = er[blk].e_max;
         }
-        const int all_rows = best < 1e-6 * best_any;    /* the distinct rows do not reach this direction */
-        if (all_rows) {
-            for (int blk = b0; blk < b1; blk++) {
-                size_t lo, hi, pb_ = LA_NONE;
-                la_rows(w, blk, 0, &lo, &hi);
-                double bb = -1.0;
-                for (size_t i = lo; i < hi; i++)
-                    if (!used[i] && fabs(bj[i]) > bb) { bb = fabs(bj[i]); pb_ = i; }
-                mp[(1 * LA_NB + blk) * 2] = bb; ip[1 * LA_NB + blk] = pb_;
-            }
-            LA_BARRIER();
-            best = -1.0;
-            for (int blk = 0; blk < LA_NB; blk++)
-                if (mp[(LA_NB + blk) * 2] > best) { best = mp[(LA_NB + blk) * 2]; piv = ip[LA_NB + blk]; }
+        const int all_rows = best_e < 1e-6 * best_any;  /* the distinct rows do not reach this direction */
+        const double thr = (all_rows ? best_any : best_e) * (1.0 - TIE_EPS);
+        size_t piv = LA_NONE;
+        for (int blk = 0; blk < LA_NB && piv == LA_NONE; blk++) {
+            const double bmax = all_rows ? er[blk].a_max : er[blk].e_max;
+            if (bmax < 0.0 || bmax < thr) continue;
+            if (all_rows) piv = er[blk].a_candval >= thr ? er[blk].a_cand : er[blk].a_arg;
+            else piv = er[blk].e_candval >= thr ? er[blk].e_cand : er[blk].e_arg;
         }
-        for (int blk = b0; blk < b1; blk++) {           /* TIE_EPS: first row among the near-maximal ones */
-            size_t lo, hi, first = LA_NONE;
-            la_rows(w, blk, 0, &lo, &hi);
-            if (hi > piv) hi = piv;
-            for (size_t i = lo; i < hi; i++)
-                if (!used[i] && (all_rows || !skip[i]) && fabs(bj[i]) >= best * (1.0 - TIE_EPS)) { first = i; break; }
-            ip[2 * LA_NB + blk] = first;
-        }
-        LA_BARRIER();
-        for (int blk = 0; blk < LA_NB; blk++)
-            if (ip[2 * LA_NB + blk] != LA_NONE) { piv = ip[2 * LA_NB + blk]; break; }
-        if (tid == 0) w->P[j] = piv;
-        if (la_mine(w, piv, b0, b1)) used[piv] = 1;
+        if (piv == LA_NONE) return 2;                  /* no unused row left: n > m (the same on every thread) */
+        P[j] = piv;
+        if (la_mine(w, piv, th)) used[piv] = 1;
         const double pvv = bj[piv];
         if (pvv == 0.0) continue;
         for (size_t c = j + 1; c < n; c++) f[c] = B[piv + c * m] / pvv;
@@ -704,10 +839,7 @@ static void team_maxvol(la_ws *w, la_thr *th)
             }
         }
     }
-    if (tid == 0) w->rc = invert_pivot_block(w);
-    LA_BARRIER();
-    if (w->rc) return;
-    const double *S = w->S;
+    if (invert_pivot_block(w, P, aug, S)) return 2;
     for (int blk = b0; blk < b1; blk++) {               /* B[:,b] = sum_a S[a,b] Q[:,a] */
         size_t lo, hi;
         la_rows(w, blk, 0, &lo, &hi);
@@ -715,56 +847,34 @@ static void team_maxvol(la_ws *w, la_thr *th)
             double *bb = B + b * m;
             for (size_t i = lo; i < hi; i++) bb[i] = 0.0;
             for (size_t a = 0; a < n; a++) axpy(S[a + b * n], Q + a * m + lo, bb + lo, hi - lo);
-            PART(0, blk, b) = absmax(bb + lo, hi - lo);
+            CME(blk)[b] = absmax_eligible(bb, skip, any_skip[blk], lo, hi, LA_NONE, 0.0);
         }
+        swap_record(w, blk, CME(blk), LA_NONE, w->srec + pb * LA_NB + blk);
     }
     size_t held = LA_NONE;                               /* entering row whose new values this thread holds back */
     int it = 0;
     for (; it < 200; it++) {
         LA_BARRIER();
         if (held != LA_NONE) { for (size_t b = 0; b < n; b++) B[held + b * m] = newrow[b]; held = LA_NONE; }
+        const la_srec *sr = w->srec + pb * LA_NB;
+        pb ^= 1;
         double best = 0.0;
-        for (size_t j = 0; j < n; j++) {
-            double c = 0.0;
-            for (int blk = 0; blk < LA_NB; blk++) if (PART(0, blk, j) > c) c = PART(0, blk, j);
-            cmax[j] = c;
-            if (c > best) best = c;
-        }
+        for (int blk = 0; blk < LA_NB; blk++) if (sr[blk].best > best) best = sr[blk].best;
         if (best <= 1.0 + 1e-2) break;
         const double thr = best * (1.0 - TIE_EPS);
-        for (int blk = b0; blk < b1; blk++) {           /* first near-maximal entry, column-major order */
-            size_t lo, hi, key = LA_NONE;
-            la_rows(w, blk, 0, &lo, &hi);
-            for (size_t j = 0; j < n && key == LA_NONE; j++) {
-                if (PART(0, blk, j) < thr) continue;
-                for (size_t i = lo; i < hi; i++)
-                    if (fabs(B[i + j * m]) >= thr && !skip[i]) { key = j * m + i; break; }
-            }
-            ip[blk] = key;
-        }
-        LA_BARRIER();
-        size_t key = LA_NONE;
-        for (int blk = 0; blk < LA_NB; blk++) if (ip[blk] < key) key = ip[blk];
-        size_t bi, bj;
-        if (key != LA_NONE) { bi = key % m; bj = key / m; }
-        else {                                           /* the maxima sit on withheld rows: masked scan */
-            if (tid == 0) {
-                double bm = 0.0; size_t xi = 0, xj = 0;
-                for (size_t j = 0; j < n; j++)
-                    for (size_t i = 0; i < m; i++)
-                        if (!skip[i] && fabs(B[i + j * m]) > bm * (1.0 + TIE_EPS)) { bm = fabs(B[i + j * m]); xi = i; xj = j; }
-                w->sh_best = bm; w->sh_bi = xi; w->sh_bj = xj;
-            }
-            LA_BARRIER();
-            if (w->sh_best <= 1.0 + 1e-2) break;
-            bi = w->sh_bi; bj = w->sh_bj;
-        }
+        size_t bi = LA_NONE, bj = LA_NONE;              /* first near-maximal entry, column-major order */
+        for (int blk = 0; blk < LA_NB; blk++)
+            for (size_t l = 0; l < sr[blk].nl; l++)
+                if (sr[blk].cm[l] >= thr && (bj == LA_NONE || sr[blk].j[l] < bj)) {
+                    bj = sr[blk].j[l];
+                    bi = sr[blk].candval[l] >= thr ? sr[blk].cand[l] : sr[blk].arg[l];
+                }
+        if (bi == LA_NONE) break;
         /* row bi replaces P[bj]:  B <- B - B[:,bj] (B[bi,:] - e_bj) / B[bi,bj] */
         const double pvv = B[bi + bj * m];
         for (size_t b = 0; b < n; b++) col[b] = (B[bi + b * m] - (b == bj ? 1.0 : 0.0)) / pvv;
         const double fs = 1.0 - col[bj];
-        const int mine = la_mine(w, bi, b0, b1);
-        if (mine) {
+        if (la_mine(w, bi, th)) {
             for (size_t b = 0; b < n; b++)
                 newrow[b] = b == bj ? pvv * fs : (col[b] == 0.0 ? B[bi + b * m] : B[bi + b * m] + (-col[b]) * pvv);
             held = bi;
@@ -773,38 +883,42 @@ static void team_maxvol(la_ws *w, la_thr *th)
             size_t lo, hi;
             la_rows(w, blk, 0, &lo, &hi);
             const int has = bi >= lo && bi < hi;
+            double *bb = B + bj * m;
             for (size_t b = 0; b < n; b++) {
                 if (b == bj || col[b] == 0.0) continue;
-                double c = has ? fabs(newrow[b]) : 0.0;
-                for (int seg = 0; seg < 2; seg++) {
-                    size_t s0 = lo, s1 = hi;
-                    if (has) { if (seg == 0) s1 = bi; else s0 = bi + 1; }
-                    else if (seg == 1) break;
-                    const double cs = axpy_absmax(-col[b], B + bj * m + s0, B + b * m + s0, s1 - s0);
-                    if (cs > c) c = cs;
+                double *xb = B + b * m;
+                if (!any_skip[blk]) {
+                    double c = has ? fabs(newrow[b]) : 0.0;
+                    for (int seg = 0; seg < 2; seg++) {
+                        size_t s0 = lo, s1 = hi;
+                        if (has) { if (seg == 0) s1 = bi; else s0 = bi + 1; }
+                        else if (seg == 1) break;
+                        const double cs = axpy_absmax(-col[b], bb + s0, xb + s0, s1 - s0);
+                        if (cs > c) c = cs;
+                    }
+                    CME(blk)[b] = c;
+                } else {
+                    if (has) { axpy(-col[b], bb + lo, xb + lo, bi - lo); axpy(-col[b], bb + bi + 1, xb + bi + 1, hi - bi - 1); }
+                    else axpy(-col[b], bb + lo, xb + lo, hi - lo);
+                    CME(blk)[b] = absmax_eligible(xb, skip, 1, lo, hi, has ? bi : LA_NONE, has ? newrow[b] : 0.0);
                 }
-                PART(0, blk, b) = c;
             }
-            double *bb = B + bj * m;
             for (size_t i = lo; i < hi; i++) if (i != bi) bb[i] *= fs;
-            double c;                                    /* row bi still holds the old pivot; its new value is held back */
-            if (has) {
-                c = fabs(newrow[bj]);
-                const double c0 = absmax(bb + lo, bi - lo), c1 = absmax(bb + bi + 1, hi - bi - 1);
-                if (c0 > c) c = c0;
-                if (c1 > c) c = c1;
-            } else c = absmax(bb + lo, hi - lo);
-            PART(0, blk, bj) = c;
+            CME(blk)[bj] = absmax_eligible(bb, skip, any_skip[blk], lo, hi, has ? bi : LA_NONE, has ? newrow[bj] : 0.0);
+            swap_record(w, blk, CME(blk), has ? bi : LA_NONE, w->srec + pb * LA_NB + blk);
         }
-        if (tid == 0) w->P[bj] = bi;
+        P[bj] = bi;
     }
     if (it == 200) {                                     /* swap limit: the last entering row is still held back */
         LA_BARRIER();
         if (held != LA_NONE) for (size_t b = 0; b < n; b++) B[held + b * m] = newrow[b];
     }
+    if (tid == 0) for (size_t j = 0; j < n; j++) w->P[j] = P[j];
+    return 0;
+#undef CME
 }
 
-/* twin rows + QR basis + maxvol of the unfolding in w->Q (m x n): w->Q <- basis, w->B <- cross core, w->P <- rows */
+/* twin rows + QR basis + maxvol of an m x n unfolding: w->Q <- basis, w->B <- cross core, w->P <- rows */
 static int pivot_step(la_ws *w, size_t m, size_t n)
 {
     if (m > w->mcap || n > w->ncap || n > m) return 1;
@@ -812,7 +926,7 @@ static int pivot_step(la_ws *w, size_t m, size_t n)
 #ifdef _OPENMP
     atomic_store(&w->bar_count, 0); atomic_store(&w->bar_sense, 0);
 #endif
-    w->bs = ((m + LA_NB - 1) / LA_NB + 7) & ~(size_t)7;
+    w->bs = la_block_rows(m);
     int T = m * n < 8192 ? 1 : w->threads;
     (void)T;
 #ifdef _OPENMP
@@ -825,9 +939,12 @@ static int pivot_step(la_ws *w, size_t m, size_t n)
         const int tid = 0, nt = 1;
 #endif
         la_thr th = { tid, nt, tid * LA_NB / nt, (tid + 1) * LA_NB / nt, 0 };
+        team_unfold(w, &th);
         team_twin_rows(w, &th);
         team_qr_basis(w, &th);
-        team_maxvol(w, &th);
+        const int rc = team_maxvol(w, &th);             /* the same on every thread */
+        if (tid == 0) w->rc = rc;
+        if (!rc) team_store(w, &th);
     }
     return w->rc;
 }
@@ -857,36 +974,7 @@ static int eval_core(const c3sc_cross *c, uint32_t k, c3sc_fiber_batch_fn f, voi
     *nfib += F;
     return 0;
 }
-/* the two unfoldings of a core, straight from the operator's fiber values, and the way back into the
- * valuef_precompute_cores layout (block j column-major: core[j*rk*rk1 + a + b*rk]) */
-static void unfold_left(const double *vals, size_t ldo, size_t rk, size_t N, size_t rk1, double *Q /* rows (a,j) = a + j*rk, cols b */)
-{
-    for (size_t b = 0; b < rk1; b++)
-        for (size_t a = 0; a < rk; a++) {
-            const double *v = vals + (a + b * rk) * ldo;
-            double *q = Q + a + b * rk * N;
-            for (size_t j = 0; j < N; j++) q[j * rk] = v[j];
-        }
-}
-static void unfold_right(const double *vals, size_t ldo, size_t rk, size_t N, size_t rk1, double *Q /* rows (j,b) = j + b*N, cols a */)
-{
-    for (size_t a = 0; a < rk; a++)
-        for (size_t b = 0; b < rk1; b++) memcpy(Q + b * N + a * N * rk1, vals + (a + b * rk) * ldo, N * sizeof(double));
-}
-static void store_left(const double *B /* (a + j*rk) + b*rk*N */, size_t rk, size_t N, size_t rk1, double *core)
-{
-    for (size_t j = 0; j < N; j++)
-        for (size_t b = 0; b < rk1; b++) memcpy(core + j * rk * rk1 + b * rk, B + j * rk + b * rk * N, rk * sizeof(double));
-}
-static void store_right(const double *B /* (j + b*N) + a*N*rk1 */, size_t rk, size_t N, size_t rk1, double *core)
-{
-    for (size_t a = 0; a < rk; a++)
-        for (size_t b = 0; b < rk1; b++) {
-            const double *s = B + b * N + a * N * rk1;
-            double *t = core + a + b * rk;
-            for (size_t j = 0; j < N; j++) t[j * rk * rk1] = s[j];
-        }
-}
+/* an edge core goes straight into the valuef_precompute_cores layout core[j*rk*rk1 + a + b*rk] */
 static void store_vals(const double *vals, size_t ldo, size_t rk, size_t N, size_t rk1, double *core)
 {
     for (size_t b = 0; b < rk1; b++)
@@ -1083,7 +1171,6 @@ int c3sc_cross_run(c3sc_cross *c, c3sc_fiber_batch_fn f, void *arg, const c3sc_c
         if (k >= 1 && c->n[k] * c->r[k + 1] > mcap) mcap = c->n[k] * c->r[k + 1];
     }
     la_ws *ws = la_ws_create(mcap, rmax);
-    double *Q = ws ? ws->Q : NULL, *B = ws ? ws->B : NULL;
     size_t *P = ws ? ws->P : NULL;
     int rc = C3SC_OK;
     uint64_t nfib = 0;
@@ -1100,7 +1187,7 @@ int c3sc_cross_run(c3sc_cross *c, c3sc_fiber_batch_fn f, void *arg, const c3sc_c
             const size_t rk = c->r[k], rk1 = c->r[k + 1], N = c->n[k], m = rk * N;
             rc = eval_core(c, k, f, arg, dv, fi, vals, &nfib);
             if (rc) goto done;
-            unfold_left(vals, ldo, rk, N, rk1, Q);
+            ws->vals = vals; ws->core = cores[k]; ws->ldo = ldo; ws->rk = rk; ws->N = N; ws->rk1 = rk1; ws->right = 0;
             { const double t_ = now_s(); const int mv = pivot_step(ws, m, rk1); g_t_piv += now_s() - t_; if (mv) { rc = C3SC_ENUMERIC; goto done; } }
             for (size_t b = 0; b < rk1; b++) {                      /* new left set: row (a,j) = a + j*rk */
                 const size_t a = P[b] % rk, j = P[b] / rk;
@@ -1109,7 +1196,6 @@ int c3sc_cross_run(c3sc_cross *c, c3sc_fiber_batch_fn f, void *arg, const c3sc_c
             }
             for (size_t b = 0; b < rk1; b++)
                 for (uint32_t i = 0; i <= k; i++) c->I[k + 1][b * d + i] = tmpI[b * d + i];
-            store_left(B, rk, N, rk1, cores[k]);
         }
         rc = eval_core(c, d - 1, f, arg, dv, fi, vals, &nfib);
         if (rc) goto done;
@@ -1119,7 +1205,7 @@ int c3sc_cross_run(c3sc_cross *c, c3sc_fiber_batch_fn f, void *arg, const c3sc_c
             const size_t rk = c->r[k], rk1 = c->r[k + 1], N = c->n[k], m = N * rk1;
             rc = eval_core(c, k, f, arg, dv, fi, vals, &nfib);
             if (rc) goto done;
-            unfold_right(vals, ldo, rk, N, rk1, Q);                 /* rows (j,b) = j + b*N, cols a */
+            ws->vals = vals; ws->core = cores[k]; ws->ldo = ldo; ws->rk = rk; ws->N = N; ws->rk1 = rk1; ws->right = 1;
             { const double t_ = now_s(); const int mv = pivot_step(ws, m, rk); g_t_piv += now_s() - t_; if (mv) { rc = C3SC_ENUMERIC; goto done; } }
             for (size_t a = 0; a < rk; a++) {
                 const size_t j = P[a] % N, b = P[a] / N;
@@ -1128,7 +1214,6 @@ int c3sc_cross_run(c3sc_cross *c, c3sc_fiber_batch_fn f, void *arg, const c3sc_c
             }
             for (size_t a = 0; a < rk; a++)
                 for (uint32_t i = k; i < d; i++) c->J[k][a * d + i] = tmpI[a * d + i];
-            store_right(B, rk, N, rk1, cores[k]);
         }
         rc = eval_core(c, 0, f, arg, dv, fi, vals, &nfib);
         if (rc) goto done;
@@ -1145,7 +1230,7 @@ int c3sc_cross_run(c3sc_cross *c, c3sc_fiber_batch_fn f, void *arg, const c3sc_c
             g_t_dot += now_s() - t_;
             const double diff2 = aa - 2.0 * ab + bb;
             change = aa > 0.0 ? sqrt(fabs(diff2) / aa) : 0.0;
-            if (verbose) fprintf(stderr, "c3sc_cross: sweep %u, |T|=%g, rel change %g, fibers %llu; cumulative s: operator %.4f pivoting (twin rows + qr + maxvol, %d threads) %.4f norms %.4f\n",
+            if (verbose) fprintf(stderr, "c3sc_cross: sweep %u, |T|=%g, rel change %g, fibers %llu; cumulative s: operator %.4f pivoting (unfold + twin rows + qr + maxvol + store, %d threads) %.4f norms %.4f\n",
                                  it, sqrt(aa), change, (unsigned long long)nfib, g_t_eval, ws->threads, g_t_piv, g_t_dot);
             for (uint32_t k = 0; k < d; k++) memcpy(prev[k], cores[k], c->r[k] * c->n[k] * c->r[k + 1] * sizeof(double));
             if (tol > 0.0 && change < tol) break;

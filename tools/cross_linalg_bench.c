@@ -31,6 +31,10 @@ int main(int argc, char **argv)
     for (size_t i = 0; i < m * n; i++) { unsigned long long u; memcpy(&u, w->B + i, 8); h = (h ^ u) * 1099511628211ull; }
     for (size_t j = 0; j < n; j++) h = (h ^ w->P[j]) * 1099511628211ull;
     printf("unfolding %zux%zu, %d threads: twin rows + qr + maxvol %.3f ms; hash of (B, P) %016llx\n", m, n, w->threads, tp / reps * 1e3, h);
+#ifdef LA_PROFILE
+    for (int t = 0; t < w->threads; t++)
+        printf("  thread %d: %.1f barriers per step, %.3f ms per step waiting in them\n", t, (double)g_bar_n[t] / reps, g_bar_wait[t] / reps * 1e3);
+#endif
     /* TT dot at d = 10, N = 100, r = 20 */
     uint64_t nn[10], rr[11];
     double *cores[10], *wk = malloc(3 * 400 * 8);
