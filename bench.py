@@ -608,9 +608,24 @@ def main():
         for _ in range(reps):
             _, nf, _ = cr.run_vi(prob, vf, maxiter=1)
         dt = (time.perf_counter() - t0) / reps
+        # the same with the pivoting step on one host thread (the numbers are identical: fixed row blocks, not thread shares)
+        saved = os.environ.get("C3SC_HOST_THREADS")
+        os.environ["C3SC_HOST_THREADS"] = "1"
+        cr.run_vi(prob, vf, maxiter=1)
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            cr.run_vi(prob, vf, maxiter=1)
+        dt1 = (time.perf_counter() - t0) / reps
+        if saved is None:
+            del os.environ["C3SC_HOST_THREADS"]
+        else:
+            os.environ["C3SC_HOST_THREADS"] = saved
+        ncpu = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
         line["vi_cross_step"] = {"seconds": dt, "fibers": nf, "node_backups": nf * N, "node_backups_per_s": nf * N / dt,
-                                 "what": "c3sc_cross_run_vi, one left-right + right-left sweep (host TT-cross with QR + maxvol, "
-                                         "one batched operator call per core, host buffers)"}
+                                 "seconds_one_host_thread": dt1,
+                                 "host_threads": int(saved) if saved else min(8, ncpu),
+                                 "what": "c3sc_cross_run_vi, one left-right + right-left sweep (host TT-cross: twin rows + QR + maxvol "
+                                         "on a team of host threads, one batched operator call per core, page-locked host buffers)"}
         cr.close()
         line["pi_step"] = pi_step(prob, cfg, ranks, vf, dv_h, fi_h, dv_d, fi_d, F, N, dev, timed, timed_host, peak_dmma, W1)
         line["other_configs"] = other_configs(args, dev, timed)

@@ -290,6 +290,7 @@ typedef struct {
     size_t privlen;
     double *V1;               /* n x n: the top of the reflector matrix, shared copy */
     double *k1; int64_t *qk; uint32_t *slot; size_t slotcap;   /* twin rows */
+    double *twin_scale;       /* [LA_NB] largest |entry| of a block's rows, a cache line each */
     /* where the unfolding comes from and where the core goes (NULL: w->Q is filled by the caller, w->B read by it) */
     const double *vals; double *core; size_t ldo, rk, N, rk1; int right;
     int rc;
@@ -343,7 +344,7 @@ static void la_ws_free(la_ws *w)
 {
     if (!w) return;
     free(w->Q); free(w->B); free(w->P); free(w->skip); free(w->used); free(w->part); free(w->erec); free(w->srec); free(w->priv);
-    free(w->V1); free(w->k1); free(w->qk); free(w->slot); free(w);
+    free(w->V1); free(w->k1); free(w->qk); free(w->slot); free(w->twin_scale); free(w);
 }
 
 static int la_threads(void)
@@ -392,10 +393,11 @@ static la_ws *la_ws_create(size_t mcap, size_t ncap)
     w->priv = (double *)la_alloc((size_t)w->threads * w->privlen * sizeof(double));
     w->V1 = (double *)la_alloc(ncap * ncap * sizeof(double));
     w->k1 = (double *)la_alloc(2 * mcap * sizeof(double));
+    w->twin_scale = (double *)la_alloc(LA_NB * 8 * sizeof(double));
     w->qk = (int64_t *)la_alloc(mcap * sizeof(int64_t));
     w->slot = (uint32_t *)la_alloc(w->slotcap * sizeof(uint32_t));
     if (!w->Q || !w->B || !w->P || !w->skip || !w->used || !w->part || !w->erec || !w->srec || !w->priv || !w->V1 || !w->k1 ||
-        !w->qk || !w->slot) { la_ws_free(w); return NULL; }
+        !w->qk || !w->slot || !w->twin_scale) { la_ws_free(w); return NULL; }
     return w;
 }
 
@@ -468,13 +470,16 @@ static void team_store(la_ws *w, la_thr *th)
  * them); when the unfolding is rank-deficient the QR completes Q with arbitrary directions and maxvol would
  * happily pick such twins, which makes the NEXT unfolding rank-deficient as well.  skip[i] = 1 withholds
  * row i from the pivoting.  Twins are found through two fixed random projections of the rows (every thread
- * projects its own rows; thread 0 then walks the rows in order through a hash of the quantised projection while
- * the others go ahead into the QR, which does not need skip[]). */
-static void team_twin_rows(la_ws *w, la_thr *th)
+ * projects its own rows before the QR overwrites them) and a walk of thread 0 over the rows in order through a
+ * hash of the quantised projection.  The walk is only needed when the QR met a column below TWIN_COND of the
+ * largest: in a well-conditioned unfolding twin rows of Q agree to round-off, a second twin adds no volume, and
+ * among equal candidates the first in scan order wins anyway. */
+#define TWIN_COND 1e-4
+static void team_twin_project(la_ws *w, la_thr *th)
 {
-    const size_t m = w->m, n = w->n, pstride = w->pstride;
+    const size_t m = w->m, n = w->n;
     const double *A = w->Q;
-    double *k1 = w->k1, *k2 = w->k1 + m, *part = w->part;
+    double *k1 = w->k1, *k2 = w->k1 + m;
     for (int blk = th->b0; blk < th->b1; blk++) {
         size_t lo, hi;
         la_rows(w, blk, 0, &lo, &hi);
@@ -490,12 +495,16 @@ static void team_twin_rows(la_ws *w, la_thr *th)
             st = st * 6364136223846793005ull + 1442695040888963407ull;
             axpy(0.5 + (double)(st >> 11) / 9007199254740992.0, A + j * m + lo, k2 + lo, hi - lo);
         }
-        PART(1, blk, 0) = scale;                        /* buffer 1: the QR starts on buffer 0 */
+        w->twin_scale[blk * 8] = scale;
     }
-    LA_BARRIER();
-    if (th->tid != 0) return;
+}
+/* after a barrier that follows team_twin_project on every thread */
+static void twin_walk(la_ws *w)
+{
+    const size_t m = w->m, n = w->n;
+    double *k1 = w->k1, *k2 = w->k1 + m;
     double scale = 0.0;
-    for (int blk = 0; blk < LA_NB; blk++) if (PART(1, blk, 0) > scale) scale = PART(1, blk, 0);
+    for (int blk = 0; blk < LA_NB; blk++) if (w->twin_scale[blk * 8] > scale) scale = w->twin_scale[blk * 8];
     const double tol = 1e-12 * scale * (double)n, quantum = 1024.0 * tol;
     if (!(tol > 0.0)) return;                           /* all-zero unfolding */
     size_t H = 16, eligible = m;
@@ -535,7 +544,7 @@ static void team_twin_rows(la_ws *w, la_thr *th)
  * has passed (column swaps only touch the rows below), so it can be read by everyone afterwards.  Every thread
  * keeps its own copy of tau and of the downdated column norms (LAPACK dgeqp3 style, recomputed exactly once they
  * have lost six digits). */
-static void team_qr_basis(la_ws *w, la_thr *th)
+static double team_qr_basis(la_ws *w, la_thr *th)
 {
     const size_t m = w->m, n = w->n, ncap = w->ncap, pstride = w->pstride;
     const int b0 = th->b0, b1 = th->b1;
@@ -558,7 +567,7 @@ static void team_qr_basis(la_ws *w, la_thr *th)
     }
     pb ^= 1;
     size_t rank = n;
-    double ref = 0.0;
+    double ref = 0.0, cond = 1.0;                         /* smallest pivot column norm over the largest */
     for (size_t k = 0; k < n; k++) {
         size_t p = k; double best = -1.0;
         for (size_t j = k; j < n; j++) if (vn2[j] > best) { best = vn2[j]; p = j; }
@@ -590,7 +599,8 @@ static void team_qr_basis(la_ws *w, la_thr *th)
         const double akk = rowk[k];
         const double nrm = sqrt(akk * akk + sc[k]);
         if (k == 0) ref = nrm;
-        if (nrm <= RANK_EPS * ref || nrm == 0.0) { rank = k; break; }
+        if (nrm <= RANK_EPS * ref || nrm == 0.0) { rank = k; cond = 0.0; break; }
+        if (nrm < cond * ref) cond = nrm / ref;
         const double alpha = akk >= 0.0 ? -nrm : nrm;
         const double v0 = akk - alpha;
         tau[k] = -v0 / alpha;
@@ -665,7 +675,7 @@ static void team_qr_basis(la_ws *w, la_thr *th)
                 if (mk != 0.0) axpy(-mk, Vb + k * L, qc, L);
             }
         }
-    }
+    }    return cond;
 }
 
 /* S = inv(Q[P,:]) by Gauss-Jordan with partial pivoting on [Q[P] | I] (every thread its own copy) */
@@ -940,8 +950,12 @@ static int pivot_step(la_ws *w, size_t m, size_t n)
 #endif
         la_thr th = { tid, nt, tid * LA_NB / nt, (tid + 1) * LA_NB / nt, 0 };
         team_unfold(w, &th);
-        team_twin_rows(w, &th);
-        team_qr_basis(w, &th);
+        team_twin_project(w, &th);
+        const double cond = team_qr_basis(w, &th);     /* the same on every thread */
+        if (cond < TWIN_COND) {
+            if (tid == 0) twin_walk(w);
+            la_barrier(w, &th);
+        }
         const int rc = team_maxvol(w, &th);             /* the same on every thread */
         if (tid == 0) w->rc = rc;
         if (!rc) team_store(w, &th);
