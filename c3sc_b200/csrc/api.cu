@@ -143,12 +143,21 @@ struct LaneScratch {
     DevBuf cst, flag, act, sets;
     cudaStream_t stream = nullptr;          // lane 0 runs on the caller's stream
     cudaEvent_t join = nullptr;
+    // the chain steps of the lane's NEXT super-chunk run on a stream of their own at the highest priority: they are latency-bound
+    // (a few resident warps per SM for 10 us a launch), so their CTAs slip in between the node / control CTAs of the other lane
+    // instead of queueing behind them
+    cudaStream_t chain_stream = nullptr;
+    cudaEvent_t chain_done = nullptr, sets_free = nullptr;
+    bool sets_busy = false;                 // sets_free was recorded for an earlier super-chunk of this batch
     void release()
     {
         cst.release(); flag.release(); act.release(); sets.release();
         if (stream) cudaStreamDestroy(stream);
         if (join) cudaEventDestroy(join);
-        stream = nullptr; join = nullptr;
+        if (chain_stream) cudaStreamDestroy(chain_stream);
+        if (chain_done) cudaEventDestroy(chain_done);
+        if (sets_free) cudaEventDestroy(sets_free);
+        stream = nullptr; join = nullptr; chain_stream = nullptr; chain_done = nullptr; sets_free = nullptr;
     }
 };
 struct Scratch {
@@ -708,6 +717,9 @@ static int run_batch(const DevProblem &P, int model, int arith, Scratch &scr, co
     // several lanes as soon as each (super-)chunk still fills the machine
     const bool multi = g_lanes > 1 && b.mode != MODE_COSTS && b.F * b.ldo >= (size_t)g_lanes * 148 * 1024;
     const size_t L = multi ? (size_t)g_lanes : 1;
+    // chain steps of the lane's next super-chunk on a high-priority stream of their own: measured no gain (1.952 vs 1.939 ms per
+    // 65 536-fiber step, profiles/r02_cross_step.md: the steps are L2-bandwidth work, not idle latency), so opt-in: C3SC_CHAIN_PRIO=1
+    const bool chain_prio = bucketed && multi && getenv("C3SC_CHAIN_PRIO") && atoi(getenv("C3SC_CHAIN_PRIO")) == 1;
     size_t per_chunk = (bucketed ? g_chunk_bytes_b : g_chunk_bytes) / (size_t)g_lanes / (b.ldo * CS * 8);
     if (!multi) per_chunk *= (size_t)g_lanes;
     { const char *pf = getenv("C3SC_CHUNK_FIBERS"); if (pf && atoi(pf) > 0) per_chunk = (size_t)atoi(pf); }    // tests: exact chunk size
@@ -741,6 +753,14 @@ static int run_batch(const DevProblem &P, int model, int arith, Scratch &scr, co
             CK(cudaStreamCreateWithFlags(&ln.stream, cudaStreamNonBlocking));
             CK(cudaEventCreateWithFlags(&ln.join, cudaEventDisableTiming));
         }
+        if (chain_prio && !ln.chain_stream) {
+            int least = 0, greatest = 0;
+            CK(cudaDeviceGetStreamPriorityRange(&least, &greatest));
+            CK(cudaStreamCreateWithPriority(&ln.chain_stream, cudaStreamNonBlocking, greatest));
+            CK(cudaEventCreateWithFlags(&ln.chain_done, cudaEventDisableTiming));
+            CK(cudaEventCreateWithFlags(&ln.sets_free, cudaEventDisableTiming));
+        }
+        ln.sets_busy = false;
     }
     if (L > 1 && !scr.fork) CK(cudaEventCreateWithFlags(&scr.fork, cudaEventDisableTiming));
     {   // every chunk's grouping in one launch; every super-chunk's chain plan in another
@@ -762,6 +782,7 @@ static int run_batch(const DevProblem &P, int model, int arith, Scratch &scr, co
     if (L > 1) {                                            // the other lanes start after everything queued on st so far
         CK(cudaEventRecord(scr.fork, st));
         for (size_t l = 1; l < L; l++) CK(cudaStreamWaitEvent(scr.lane[l].stream, scr.fork, 0));
+        if (chain_prio) for (size_t l = 0; l < L; l++) CK(cudaStreamWaitEvent(scr.lane[l].chain_stream, scr.fork, 0));
     }
     const cudaStream_t st0 = st;
     for (size_t s0 = 0, si = 0; s0 < b.F; s0 += FS, si++) {
@@ -776,9 +797,18 @@ static int run_batch(const DevProblem &P, int model, int arith, Scratch &scr, co
             ca.kst = (int *)scr.plan_k.p + si * pk; ca.tst = (int *)scr.plan_t.p + si * pt; ca.ent = (int *)scr.plan_e.p + si * pe;
             ca.nmax = P.nmax; ca.entstride = (int)(3 * FS);
             int nl = 0;
-            int rc = launch_chain_steps(ca, st, &nl);
+            cudaStream_t cst_ = st;
+            if (chain_prio) {                               // records of this lane are free once its previous super-chunk's nodes are done
+                cst_ = ln.chain_stream;
+                if (ln.sets_busy) CK(cudaStreamWaitEvent(cst_, ln.sets_free, 0));
+            }
+            int rc = launch_chain_steps(ca, cst_, &nl);
             if (rc) return fail(C3SC_ECUDA, "chain step kernel: %s", cudaGetErrorString((cudaError_t)rc));
             g_launches += nl;
+            if (chain_prio) {
+                CK(cudaEventRecord(ln.chain_done, cst_));
+                CK(cudaStreamWaitEvent(st, ln.chain_done, 0));
+            }
         }
         for (size_t c0 = s0; c0 < s0 + Fs; c0 += FC) {
         const size_t Fc = (s0 + Fs - c0 < FC) ? s0 + Fs - c0 : FC;
@@ -809,6 +839,7 @@ static int run_batch(const DevProblem &P, int model, int arith, Scratch &scr, co
             rc = launch_ft_costs(a, nullptr, st);
             if (rc) return fail(C3SC_ECUDA, "FT kernel launch: %s", cudaGetErrorString((cudaError_t)rc));
             g_launches += 1 + (mma && !bucketed);
+            if (chain_prio && c0 + FC >= s0 + Fs) { CK(cudaEventRecord(ln.sets_free, st)); ln.sets_busy = true; }
             continue;
         }
         CtlArgs c;
@@ -862,6 +893,7 @@ static int run_batch(const DevProblem &P, int model, int arith, Scratch &scr, co
         rc = launch_ft_costs(a, fuse ? &c : nullptr, st);
         if (rc) return fail(C3SC_ECUDA, "FT kernel launch: %s", cudaGetErrorString((cudaError_t)rc));
         g_launches += 1 + (mma && !bucketed);
+        if (chain_prio && c0 + FC >= s0 + Fs) { CK(cudaEventRecord(ln.sets_free, st)); ln.sets_busy = true; }   // the last reader of the lane's records
         if (fuse) rc = 0;
         else if (model == C3SC_MODEL_LQGND) rc = (P.dx <= 6) ? launch_control_lqg_lo(P.dx, arith, c, pe_, st)
                                                         : launch_control_lqg_hi(P.dx, arith, c, pe_, st);
