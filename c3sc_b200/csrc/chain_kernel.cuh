@@ -79,6 +79,7 @@ __device__ __forceinline__ int cta_exclusive_scan(int *v, int n, int *wsum)
 // grid (chunks, d), 1024 threads.  Chunk c covers fibers [c*FC, min(F, (c+1)*FC)) of the batch; its plan arrays and
 // records are the c-th slices of the buffers in `a` (strides given).
 struct ChainPlanStrides { long long kst, tst, ent; };
+#ifndef C3SC_FT_KS_UNIT        // compiled once, in ft.cu (ft_ks.cu holds the per-rank-geometry templates)
 __global__ void __launch_bounds__(1024) k_chain_plan(ChainArgs a, int FC, ChainPlanStrides S)
 {
     extern __shared__ int sh[];
@@ -160,6 +161,7 @@ __global__ void __launch_bounds__(1024) k_chain_plan(ChainArgs a, int FC, ChainP
     __syncthreads();
     if (tid == 0) kst[(nmax * 3 + 1) + 3 * N] = fill[(2 * N - 1) * 3 + 2];       // end of side 1's last bucket
 }
+#endif
 
 __device__ __forceinline__ void ch_dmma(double &d0, double &d1, double a, double b)
 {

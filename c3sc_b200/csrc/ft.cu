@@ -16,7 +16,16 @@ static void ft_device_info()
     cudaDeviceGetAttribute(&g_max_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, dev);
 }
 
+// The kernels that are compiled per rank geometry KS = ceil(r_max / 4) (chain steps, per-fiber chains, node kernel) live in
+// ft_ks.cu, one translation unit per KS (built in parallel): their launchers, by name.
+#define C3SC_KS_DECL(n) \
+    int launch_chain_steps_ks##n(const ChainArgs &a, cudaStream_t st); \
+    int launch_mma_ks##n(const FtArgs &a, const CtlArgs *fused, int nsplit, cudaStream_t st);
+C3SC_KS_DECL(1) C3SC_KS_DECL(2) C3SC_KS_DECL(3) C3SC_KS_DECL(4) C3SC_KS_DECL(5) C3SC_KS_DECL(6) C3SC_KS_DECL(7) C3SC_KS_DECL(8)
+#undef C3SC_KS_DECL
+
 int ft_sm_count() { ft_device_info(); return g_sms; }
+int ft_max_optin_smem() { ft_device_info(); return g_max_optin; }
 
 // perm / kcount / kstart / cleared active counters of ALL chunks of a batch.  1 launch.
 int launch_group_fibers(const DevProblem &P, int F, int FC, const int *dim_vary, const int *fixed_ind, int *perm, int *cnt_all,
@@ -118,45 +127,20 @@ int launch_chain_plan(const ChainArgs &a, int FC, cudaStream_t st)
     return (int)cudaGetLastError();
 }
 
-template <int KS>
-static int launch_chain_steps_t(const ChainArgs &a, cudaStream_t st)
-{
-    ft_device_info();
-    const bool g_no_pdl = getenv("C3SC_NO_PDL") != nullptr;
-    // CTAs of a step: the kernel is latency-bound (dependent L2 round trips, a handful of tiles per warp), and while it
-    // holds an SM's registers the other lane's node kernel cannot use that SM
-    int grid = g_sms * 2;
-    { const char *e = getenv("C3SC_CHAIN_GRID"); if (e && atoi(e) > 0) grid = atoi(e); }
-    for (int t = 0; t + 1 < a.ft.d; t++) {
-        const size_t smem = (size_t)(4 * (a.P.ngrid[t] + a.P.ngrid[a.ft.d - 1 - t]) + 4) * sizeof(int);
-        // steps t >= 1 overlap their launch and table prologue with the tail of step t-1 (programmatic dependent
-        // launch; the kernel waits with griddepcontrol.wait before it touches the records)
-        cudaLaunchConfig_t cfg = {};
-        cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(CH_NT); cfg.dynamicSmemBytes = smem; cfg.stream = st;
-        cudaLaunchAttribute attr[1];
-        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-        attr[0].val.programmaticStreamSerializationAllowed = 1;
-        cfg.attrs = attr;
-        cfg.numAttrs = (t > 0 && !g_no_pdl) ? 1 : 0;
-        cudaError_t e = cudaLaunchKernelEx(&cfg, k_chain_step<KS>, a, t);
-        if (e != cudaSuccess) return (int)e;
-    }
-    return 0;
-}
-
 // the d-1 steps of one chunk (a.F = fibers of the chunk, pointers at the chunk's slices); returns the launches via *n
 int launch_chain_steps(const ChainArgs &a, cudaStream_t st, int *n)
 {
     *n = a.ft.d - 1;
+    if (getenv("C3SC_DBG_SKIP_CHAIN")) { *n = 0; return 0; }     // timing experiments only: the records keep stale (finite) data
     switch ((ft_rmax(a.ft) + 3) / 4) {
-    case 1: return launch_chain_steps_t<1>(a, st);
-    case 2: return launch_chain_steps_t<2>(a, st);
-    case 3: return launch_chain_steps_t<3>(a, st);
-    case 4: return launch_chain_steps_t<4>(a, st);
-    case 5: return launch_chain_steps_t<5>(a, st);
-    case 6: return launch_chain_steps_t<6>(a, st);
-    case 7: return launch_chain_steps_t<7>(a, st);
-    default: return launch_chain_steps_t<8>(a, st);
+    case 1: return launch_chain_steps_ks1(a, st);
+    case 2: return launch_chain_steps_ks2(a, st);
+    case 3: return launch_chain_steps_ks3(a, st);
+    case 4: return launch_chain_steps_ks4(a, st);
+    case 5: return launch_chain_steps_ks5(a, st);
+    case 6: return launch_chain_steps_ks6(a, st);
+    case 7: return launch_chain_steps_ks7(a, st);
+    default: return launch_chain_steps_ks8(a, st);
     }
 }
 
@@ -176,52 +160,6 @@ int ft_nodes_nsplit(const FtArgs &a) { return ft_nodes_nsplit_of(a); }
 long long ft_region_doubles(const DevProblem &P) { return (long long)(2 * P.dx + 1) * FT_FBMAX * ft_even_up(P.nmax); }
 int ft_ring_regions() { ft_device_info(); return 2 * g_sms + 32; }
 
-template <int KS>
-static int launch_mma_t(const FtArgs &a, const CtlArgs *fused, cudaStream_t st)
-{
-    // chains: one warp per (fiber, side)
-    const size_t csm = FtChainPlan<KS>(a.ft).bytes();
-    if (csm > (size_t)g_max_optin) return (int)cudaErrorInvalidValue;
-    static size_t cattr_dev[C3SC_MAXDEV] = {0};
-    size_t &cattr = cattr_dev[c3sc_cur_dev()];
-    if (csm > cattr) {
-        cudaError_t e = cudaFuncSetAttribute(k_ft_chains<KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)csm);
-        if (e != cudaSuccess) return (int)e;
-        cattr = csm;
-    }
-    int per_sm = 1;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_ft_chains<KS>, FTC_NT, csm);
-    if (per_sm < 1) per_sm = 1;
-    int cgrid = (2 * a.F + FTC_NT / 32 - 1) / (FTC_NT / 32);
-    if (cgrid > g_sms * per_sm) cgrid = g_sms * per_sm;
-    cudaError_t e = cudaSuccess;
-    if (!a.chains_done) {
-        k_ft_chains<KS><<<cgrid, FTC_NT, csm, st>>>(a, a.sets);
-        e = cudaGetLastError();
-        if (e != cudaSuccess) return (int)e;
-    }
-    // nodes: one CTA per same-k group
-    const size_t smem = FtNodePlan<KS>(a.ft, a.P.nmax).bytes();
-    if (smem > (size_t)g_max_optin) return (int)cudaErrorInvalidValue;
-    static size_t attr_dev[C3SC_MAXDEV] = {0}, attrf_dev[C3SC_MAXDEV] = {0};
-    size_t &attr = fused ? attrf_dev[c3sc_cur_dev()] : attr_dev[c3sc_cur_dev()];
-    if (smem > attr) {
-        e = fused ? cudaFuncSetAttribute(k_ft_nodes_fused<KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
-                  : cudaFuncSetAttribute(k_ft_nodes<KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return (int)e;
-        attr = smem;
-    }
-    const int grid = (a.F + a.FB - 1) / a.FB + a.ft.d;
-    // small batches: several CTAs per group, each a range of node tiles, until the machine is covered twice
-    FtArgs b = a;
-    b.nsplit = ft_nodes_nsplit_of(a);
-    if (fused) {
-        if (b.nsplit != 1) return (int)cudaErrorInvalidValue;       // the caller asked ft_nodes_nsplit first
-        k_ft_nodes_fused<KS><<<dim3((unsigned)grid, 1u), FTN_NT, smem, st>>>(b, *fused, b.sets);
-    } else k_ft_nodes<KS><<<dim3((unsigned)grid, (unsigned)b.nsplit), FTN_NT, smem, st>>>(b, b.sets);
-    return (int)cudaGetLastError();
-}
-
 static int launch_ft_mma(FtArgs a, const CtlArgs *fused, cudaStream_t st)
 {
     // group size: 8 fibers fill the DMMA tile (a tile costs the same for 1 fiber as for 8); small
@@ -229,15 +167,16 @@ static int launch_ft_mma(FtArgs a, const CtlArgs *fused, cudaStream_t st)
     a.FB = FT_FBMAX;
     int rmax = 1;
     for (int i = 0; i <= a.ft.d; i++) rmax = a.ft.r[i] > rmax ? a.ft.r[i] : rmax;
+    const int nsplit = ft_nodes_nsplit_of(a);
     switch ((rmax + 3) / 4) {                                // KS
-    case 1: return launch_mma_t<1>(a, fused, st);
-    case 2: return launch_mma_t<2>(a, fused, st);
-    case 3: return launch_mma_t<3>(a, fused, st);
-    case 4: return launch_mma_t<4>(a, fused, st);
-    case 5: return launch_mma_t<5>(a, fused, st);
-    case 6: return launch_mma_t<6>(a, fused, st);
-    case 7: return launch_mma_t<7>(a, fused, st);
-    default: return launch_mma_t<8>(a, fused, st);
+    case 1: return launch_mma_ks1(a, fused, nsplit, st);
+    case 2: return launch_mma_ks2(a, fused, nsplit, st);
+    case 3: return launch_mma_ks3(a, fused, nsplit, st);
+    case 4: return launch_mma_ks4(a, fused, nsplit, st);
+    case 5: return launch_mma_ks5(a, fused, nsplit, st);
+    case 6: return launch_mma_ks6(a, fused, nsplit, st);
+    case 7: return launch_mma_ks7(a, fused, nsplit, st);
+    default: return launch_mma_ks8(a, fused, nsplit, st);
     }
 }
 

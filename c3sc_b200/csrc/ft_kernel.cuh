@@ -138,6 +138,7 @@ struct FtPlan {
 // error return of the batch, never a read outside the cores.
 struct GridDims { int n[MAXD]; };
 __device__ __forceinline__ int ft_clamp_index(int i0, int n) { return i0 < 0 ? 0 : (i0 >= n ? n - 1 : i0); }
+#ifndef C3SC_FT_KS_UNIT        // compiled once, in ft.cu (ft_ks.cu holds the per-rank-geometry templates)
 __global__ void __launch_bounds__(1024) k_group_fibers(int F, int FC, int d, const int *dim_vary, const int *fixed_ind,
                                                        GridDims ng, int *err, int *perm, int *cnt_all)
 {
@@ -189,10 +190,12 @@ __global__ void __launch_bounds__(1024) k_group_fibers(int F, int FC, int d, con
         if (f < Fc) perm[base + __popc(peers & ((1u << lane) - 1u))] = f;
     }
 }
+#endif
 
 // Derived copies of the cores, rebuilt whenever the cores change (c3sc_valuef_commit):
 //   baseT  every block transposed: baseT[off_k + j*blk + b + a*r_{k+1}] = base[off_k + j*blk + a + b*r_k]
 //   baseP  (optional) zero-padded blocks, leading dimension ldp[k], cpp[k] columns
+#ifndef C3SC_FT_KS_UNIT        // compiled once, in ft.cu (ft_ks.cu holds the per-rank-geometry templates)
 __global__ void k_pack_cores(DevFT ft, double *baseT, double *baseP, double *baseQ)
 {
     const int k = blockIdx.y;
@@ -226,6 +229,7 @@ __global__ void k_pack_cores(DevFT ft, double *baseT, double *baseP, double *bas
         }
     }
 }
+#endif
 
 // ---------------------------------------------------------------------------
 // pieces shared by the general kernel (k_ft_costs) and the tensor-core pair (ft_mma_kernel.cuh)
@@ -359,6 +363,7 @@ __device__ __forceinline__ void ft_active_list(const FtArgs &a, int nf, int jb, 
 // The two neighbours ALONG the fiber (valuefunc.c:514-519) are the fiber's own values at other
 // nodes: stage 1 stores only the self value (slot 2d); the slot-major scratch is completed by its
 // consumer (control_kernel.cuh: load_costs), the node-major `costs` output by this kernel.
+#ifndef C3SC_FT_KS_UNIT        // compiled once, in ft.cu (ft_ks.cu holds the per-rank-geometry templates)
 __global__ void k_costs_along(const FtArgs a)
 {
     const int d = a.ft.d, CS = 2 * d + 1;
@@ -376,8 +381,10 @@ __global__ void k_costs_along(const FtArgs a)
         a.costs[id * CS + 2 * k + 1] = a.costs[(fb + hi) * CS + 2 * d];
     }
 }
+#endif
 
 // ---------------------------------------------------------------------------
+#ifndef C3SC_FT_KS_UNIT        // compiled once, in ft.cu (ft_ks.cu holds the per-rank-geometry templates)
 __global__ void __launch_bounds__(FT_NT, 2) k_ft_costs(const FtArgs a)
 {
     const DevProblem &P = a.P;
@@ -629,6 +636,7 @@ __global__ void __launch_bounds__(FT_NT, 2) k_ft_costs(const FtArgs a)
 
     ft_active_list(a, nf, 0, N, sFid, sAbs, nmax);
 }
+#endif
 
 #endif  // C3SC_FT_TYPES_ONLY
 

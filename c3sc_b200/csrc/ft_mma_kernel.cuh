@@ -25,6 +25,14 @@ namespace c3sc {
 
 constexpr int FTC_NT = 256;      // chain kernel: 8 warps = 8 tasks in flight per CTA
 constexpr int FTN_NT = 256;      // node kernel: 8 warps
+#ifndef C3SC_FTN_PAIR
+#define C3SC_FTN_PAIR 0          // 1: phase 1 on node pairs (no half-empty rank tile when ceil(r/4) is odd): 17 % fewer phase-1 DMMAs at
+                                 // r = 20 but 23 % more instructions (stacked-row addressing); measured 2 % SLOWER on B200
+                                 // (0.831 vs 0.815 ms of node kernels per 65 536 fibers, profiles/r02b_node_kernel.md) -- opt-in
+#endif
+#ifndef C3SC_FTN_SELFSIDE
+#define C3SC_FTN_SELFSIDE 1      // the self value from whichever side saves a variant tile
+#endif
 constexpr int FTN_T = 8;         // nodes per tile (one per warp in the w/u phase)
 constexpr int FTN_TP = 8;        // row stride of a (rank index) row of w / u: 8 nodes, XOR-swizzled (ftn_swz): element
                                  // (rank row a, node j) of a fiber's tile sits at a*8 + (j ^ swz(a)).  With the odd
@@ -294,6 +302,42 @@ __device__ __forceinline__ void node_wu(const double *gj, int offW, int offU, in
     }
 }
 
+// w (or u) of a PAIR of nodes: the two blocks stacked along the free index of the product.  A rank r = 4 (mod 8)
+// pads every node's 8-wide tiles by a half (20 -> 24 rows); 2r rows need ceil(2r/8) <= KS tiles against 2*ceil(r/8),
+// one tile less whenever KS is odd (r = 17..20: 5 instead of 6).  Row R of the stack is row R of the first block for
+// R < r and row R - r of the second; rows beyond 2r read finite data and are not stored.
+// u is computed TRANSPOSED, u^T = G^T L^T: the same instruction stream as w = G R with other strides (row stride ldk and
+// k stride 1 instead of 1 and ldk), the other register operand and the other tile buffer -- one code path for both
+// roles (warps 0..3: w of pairs 0..3, warps 4..7: u), and u's D fragments land in the (rank row, fiber column) form
+// whose stores are conflict-free like w's.
+template <int KS>
+__device__ __forceinline__ void node_pair_wu(const double *g2, int pblk, int rr, int rowstride, int kstride, int tigoff, int jn,
+                                             const double (&Xf)[KS], double *dst, int SW, int tig, int gid)
+{
+    double acc[KS][2];
+    int ld[KS];
+#pragma unroll
+    for (int mt = 0; mt < KS; mt++) {
+        acc[mt][0] = acc[mt][1] = 0.0;
+        const int R = 8 * mt + gid;
+        ld[mt] = tigoff + (R < rr ? R * rowstride : (R < 2 * rr ? pblk + (R - rr) * rowstride : 0));
+    }
+#pragma unroll
+    for (int ks = 0; ks < KS; ks++)
+#pragma unroll
+        for (int mt = 0; mt < KS; mt++) dmma_m8n8k4(acc[mt][0], acc[mt][1], g2[ld[mt] + ks * kstride], Xf[ks]);
+#pragma unroll
+    for (int mt = 0; mt < KS; mt++) {                          // D: stacked row 8mt+gid, cols fiber 2*tig, 2*tig+1
+        const int R = 8 * mt + gid;
+        if (R < 2 * rr) {
+            const int nd = R >= rr, a = R - nd * rr;
+            const int o = a * FTN_TP + ((jn + nd) ^ ftn_swz(a));
+            dst[(2 * tig) * SW + o] = acc[mt][0];
+            dst[(2 * tig + 1) * SW + o] = acc[mt][1];
+        }
+    }
+}
+
 // Shared memory of k_ft_nodes.  Everything the MMA fragments read is zero-padded to the fragment
 // shape, so no fragment load is predicated.  The chain records are NOT staged: every fragment of a fiber's
 // variant sets is loaded from L2 once per CTA and lives in registers for all node tiles.
@@ -343,7 +387,9 @@ struct FtNodeCtx {
     double *cst, *costs;
     const double *sets;
     int ldo;
-    bool needSelfFromU;      // k = 0: the self value comes from u . R (vector 0 of the right set)
+    int vL0, vR0;            // first vector of the left / right set that takes part in the dots: exactly one side keeps its
+                             // vector 0 (the prefix / suffix alone, which gives the SELF value), whichever needs fewer 8-wide tiles
+    int rk, rk1;             // ranks of the varying core
     int regionStride;        // > 0: costs go to the CTA's region, fiber g at g*regionStride (fused stage 2); 0: fiber id * ldo
 };
 
@@ -359,20 +405,25 @@ __device__ __forceinline__ void ftn_tile_loop(const FtNodeCtx &c)
 {
     constexpr int VT = (2 * MAXD + 7) / 8;
     constexpr bool DO_W = ML > 0, DO_U = NR > 0;
+    constexpr bool PAIR = DO_W && DO_U && (KS & 1) && C3SC_FTN_PAIR;     // node pairs in phase 1 (node_pair_w / node_pair_u)
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int gid = lane >> 2, tig = lane & 3;
     const int d = c.d, RS = c.RS;
 
     // ---- register-resident operands ---------------------------------------------------------------
     // phase 1: B fragment of R (row b = 4ks+tig, col fiber gid), A fragment of L (row fiber gid, col a = 4ks+tig)
-    double Rf[KS], Lf[KS];
+    // (node pairs: a warp computes w OR u, so it keeps only R or only L, in Rf)
+    double Rf[KS], Lf[PAIR ? 1 : KS];
     {
         const bool on = gid < c.nf;
         const double *rec = c.sets + (size_t)(on ? c.sFid[gid] : 0) * c.setw;
 #pragma unroll
         for (int ks = 0; ks < KS; ks++) {
-            Rf[ks] = on ? __ldg(rec + (size_t)c.nvL * RS + 4 * ks + tig) : 0.0;
-            Lf[ks] = on ? __ldg(rec + 4 * ks + tig) : 0.0;
+            if constexpr (PAIR) Rf[ks] = on ? __ldg(rec + (warp < 4 ? (size_t)c.nvL * RS : (size_t)0) + 4 * ks + tig) : 0.0;
+            else {
+                Rf[ks] = on ? __ldg(rec + (size_t)c.nvL * RS + 4 * ks + tig) : 0.0;
+                Lf[ks] = on ? __ldg(rec + 4 * ks + tig) : 0.0;
+            }
         }
     }
     // phase 2, fiber g = warp: A fragments of the left set (row v = 8mt+gid, col a = 4ks+tig), B fragments of the
@@ -383,13 +434,13 @@ __device__ __forceinline__ void ftn_tile_loop(const FtNodeCtx &c)
         const double *rec = c.sets + (size_t)(on ? c.sFid[warp] : 0) * c.setw;
 #pragma unroll
         for (int mt = 0; mt < ML; mt++) {
-            const int v = 8 * mt + gid;
+            const int v = c.vL0 + 8 * mt + gid;
 #pragma unroll
             for (int ks = 0; ks < KS; ks++) aL[mt][ks] = (on && v < c.nvL) ? __ldg(rec + (size_t)v * RS + 4 * ks + tig) : 0.0;
         }
 #pragma unroll
         for (int nb = 0; nb < NR; nb++) {
-            const int v = 8 * nb + gid;
+            const int v = c.vR0 + 8 * nb + gid;
 #pragma unroll
             for (int ks = 0; ks < KS; ks++) bR[nb][ks] = (on && v < c.nvR) ? __ldg(rec + (size_t)(c.nvL + v) * RS + 4 * ks + tig) : 0.0;
         }
@@ -398,12 +449,12 @@ __device__ __forceinline__ void ftn_tile_loop(const FtNodeCtx &c)
     int slotL[VT], slotR[VT][2];
 #pragma unroll
     for (int t = 0; t < VT; t++) {
-        const int v = 8 * t + gid;
+        const int v = c.vL0 + 8 * t + gid;
         slotL[t] = v >= c.nvL ? -1 : (v == 0 ? 2 * d : 2 * ((v - 1) >> 1) + ((v - 1) & 1));
 #pragma unroll
         for (int h = 0; h < 2; h++) {
-            const int vv = 8 * t + 2 * tig + h;
-            slotR[t][h] = vv >= c.nvR ? -1 : (vv == 0 ? (c.needSelfFromU ? 2 * d : -1)      // vector 0 is R itself
+            const int vv = c.vR0 + 8 * t + 2 * tig + h;
+            slotR[t][h] = vv >= c.nvR ? -1 : (vv == 0 ? 2 * d                               // vector 0 is R itself: u . R = the self value
                                                        : 2 * (d - 1 - ((vv - 1) >> 1)) + ((vv - 1) & 1));
         }
     }
@@ -420,6 +471,9 @@ __device__ __forceinline__ void ftn_tile_loop(const FtNodeCtx &c)
     }
     const int ldk = c.ldk, SW = c.SW, pblk = c.pblk, GB = c.GB;
     const int offW = tig * ldk + gid, offU = gid * ldk + tig;           // fragment origins inside a node block
+    // node pairs: w = G R walks rows with stride 1 and the contraction index with stride ldk, u^T = G^T L^T the other way round
+    const bool urole = warp >= 4;
+    const int prr = urole ? c.rk1 : c.rk, prow = urole ? ldk : 1, pks = urole ? 4 : 4 * ldk, ptig = urole ? tig : tig * ldk;
     const double *wg0 = c.sW + warp * SW + tig * FTN_TP, *ug0 = c.sU + warp * SW + tig * FTN_TP;
     const int WB = FT_FBMAX * SW;                           // one buffer of w (or u) tiles
     const int jl0 = gid ^ ftn_swz(tig), jl1 = gid ^ ftn_swz(4 + tig);
@@ -443,7 +497,13 @@ __device__ __forceinline__ void ftn_tile_loop(const FtNodeCtx &c)
         // The w / u tiles are double-buffered like the G tiles: phase 1 of tile i+1 writes the other buffer, so the
         // barrier after phase 1 of tile i+1 is also the one that orders phase 2 of tile i before phase 1 of tile i+2
         // re-uses its buffer: ONE CTA barrier per node tile.
-        if (warp < nt) node_wu<KS, DO_W, DO_U>(c.sG + buf * GB + warp * pblk, offW, offU, ldk, Rf, Lf, c.sW + buf * WB, c.sU + buf * WB, SW, tig, gid, warp);
+        if constexpr (PAIR) {
+            const int jn = 2 * (warp & 3);                  // first node of this warp's pair
+            if (jn < nt)
+                node_pair_wu<KS>(c.sG + buf * GB + jn * pblk, pblk, prr, prow, pks, ptig, jn, Rf, (warp < 4 ? c.sW : c.sU) + buf * WB, SW, tig, gid);
+        } else {
+            if (warp < nt) node_wu<KS, DO_W, DO_U>(c.sG + buf * GB + warp * pblk, offW, offU, ldk, Rf, Lf, c.sW + buf * WB, c.sU + buf * WB, SW, tig, gid, warp);
+        }
         __syncthreads();
         const double *wg = wg0 + buf * WB, *ug = ug0 + buf * WB;
         if (tid == 0 && j0 + 2 * FTN_T < c.je) fetch(j0 + 2 * FTN_T, buf);     // this buffer is free: fetch the tile after next
@@ -542,8 +602,13 @@ __device__ __forceinline__ void ftn_body(const FtArgs &a, const double *sets, co
     const int rk1 = ft.r[k + 1];
     const int pblk = ft.ldq[k] * rk1;                                  // compact block (rows even-padded)
     const int nvL = 1 + 2 * k, nvR = 1 + 2 * (d - 1 - k);
-    const bool needU = nvR > 1, needW = nvL > 1 || !needU;            // sides that have neighbour variants (or carry the self value)
-    const int mtL = needW ? (nvL + 7) >> 3 : 0, ntR = needU ? (nvR + 7) >> 3 : 0;   // 8-wide tiles over the variant vectors
+    // Vector 0 of a side is the prefix / suffix alone: against the other side's w / u it gives the SELF value, so only one
+    // side needs it in the dots.  The side whose tile count does not grow keeps it (d = 10: three 8-wide tiles for every k,
+    // against 3.5 on average when the left side always kept it); a side with nothing left to do is dropped altogether.
+    const int tA = ((nvL + 7) >> 3) + ((nvR - 1 + 7) >> 3), tB = ((nvL - 1 + 7) >> 3) + ((nvR + 7) >> 3);
+    const bool selfLeft = C3SC_FTN_SELFSIDE ? (tA <= tB) : (nvL > 1 || nvR <= 1);
+    const int vL0 = selfLeft ? 0 : 1, vR0 = selfLeft ? 1 : 0;
+    const int mtL = (nvL - vL0 + 7) >> 3, ntR = (nvR - vR0 + 7) >> 3;      // 8-wide tiles over the variant vectors
 
     // this CTA's share of the fiber: a contiguous range of node tiles
     const int ntiles = (N + FTN_T - 1) / FTN_T, nsp = a.nsplit > 0 ? a.nsplit : 1;
@@ -597,7 +662,7 @@ __device__ __forceinline__ void ftn_body(const FtArgs &a, const double *sets, co
     c.NS = a.NS; c.cst = a.cst; c.costs = a.costs; c.sets = sets; c.ldo = a.ldo;
     c.regionStride = 0;
     if constexpr (FUSED) { c.cst = region; c.NS = (long long)FT_FBMAX * njp; c.costs = nullptr; c.regionStride = njp; }
-    c.needSelfFromU = !needW;
+    c.vL0 = vL0; c.vR0 = vR0; c.rk = ft.r[k]; c.rk1 = rk1;
     // the tile counts of the variant sets are CTA-uniform run-time values: dispatch to a loop with compile-time
     // counts, so that no predicated-off DMMA (and its fragment load) is issued at all
     switch (mtL * 8 + ntR) {
