@@ -36,7 +36,7 @@ size_t ft_sets_bytes(const DevFT &ft, size_t F);
 void ft_record_geometry(const DevFT &ft, int *setw, int *rs);
 void chain_plan_sizes(const DevFT &ft, int nmax, size_t FC, size_t *kst, size_t *tst, size_t *ent);
 int chain_bucketed_ok(const DevFT &ft, int nmax);
-int launch_chain_plan(const ChainArgs &a, int FC, cudaStream_t st);
+int launch_chain_plan(const ChainArgs &a, int FC, int *cntg, cudaStream_t st);
 int launch_chain_steps(const ChainArgs &a, cudaStream_t st, int *n);
 int launch_rows_move(double *dst, const double *src, const int *idx, int F, long long per, int scatter, cudaStream_t st);
 int launch_peer_scatter(const double *src, long long n, double *const *peers, int npeer, long long off, cudaStream_t st);
@@ -140,7 +140,7 @@ struct DevBuf {
 // the latency-bound chain kernel of one chunk and the tails of every kernel overlap the other chunk's work.
 constexpr int MAXLANES = 4;
 struct LaneScratch {
-    DevBuf cst, flag, act, sets;
+    DevBuf cst, flag, act, sets, xa, xb;    // xa / xb: row buffers of the bucketed chain stage (chain_kernel.cuh)
     cudaStream_t stream = nullptr;          // lane 0 runs on the caller's stream
     cudaEvent_t join = nullptr;
     // the chain steps of the lane's NEXT super-chunk run on a stream of their own at the highest priority: they are latency-bound
@@ -151,7 +151,7 @@ struct LaneScratch {
     bool sets_busy = false;                 // sets_free was recorded for an earlier super-chunk of this batch
     void release()
     {
-        cst.release(); flag.release(); act.release(); sets.release();
+        cst.release(); flag.release(); act.release(); sets.release(); xa.release(); xb.release();
         if (stream) cudaStreamDestroy(stream);
         if (join) cudaEventDestroy(join);
         if (chain_stream) cudaStreamDestroy(chain_stream);
@@ -161,14 +161,22 @@ struct LaneScratch {
     }
 };
 struct Scratch {
-    DevBuf perm, cnt, plan_k, plan_t, plan_e;
+    DevBuf perm, cnt, plan_k, plan_t, plan_e, plan_l, plan_i, plan_c;     // plan_l: row descriptors, plan_i: inverse rows (chain_kernel.cuh)
     DevBuf ring, ring_flag;                 // fused stage 2: per-CTA regions of neighbour values + their in-use flags
     bool ring_ready = false;
     LaneScratch lane[MAXLANES];
     cudaEvent_t fork = nullptr;
+    // the chain plan of super-chunk i (k_chain_plan + k_chain_link: few CTAs, latency-bound) runs on a stream of its own, so only
+    // the first one is exposed; the lanes wait for the plan of the super-chunk they are about to step
+    cudaStream_t plan_stream = nullptr;
+    std::vector<cudaEvent_t> plan_done;
     void release()
     {
-        perm.release(); cnt.release(); plan_k.release(); plan_t.release(); plan_e.release(); ring.release(); ring_flag.release();
+        if (plan_stream) cudaStreamDestroy(plan_stream);
+        plan_stream = nullptr;
+        for (cudaEvent_t e : plan_done) cudaEventDestroy(e);
+        plan_done.clear();
+        perm.release(); cnt.release(); plan_k.release(); plan_t.release(); plan_e.release(); plan_l.release(); plan_i.release(); plan_c.release(); ring.release(); ring_flag.release();
         ring_ready = false;
         for (LaneScratch &l : lane) l.release();
         if (fork) cudaEventDestroy(fork);
@@ -741,13 +749,16 @@ static int run_batch(const DevProblem &P, int model, int arith, Scratch &scr, co
     size_t pk = 0, pt = 0, pe = 0;
     if (bucketed) {
         chain_plan_sizes(ft, P.nmax, FS, &pk, &pt, &pe);
-        if (scr.plan_k.reserve(nsup * pk * 4) || scr.plan_t.reserve(nsup * pt * 4) || scr.plan_e.reserve(nsup * pe * 4))
+        if (scr.plan_k.reserve(nsup * pk * 4) || scr.plan_t.reserve(nsup * pt * 4) || scr.plan_e.reserve(nsup * pe * 4) ||
+            scr.plan_l.reserve(nsup * (d - 1) * (size_t)chain_x_rows((int)d, P.nmax, (long long)FS) * 16) || scr.plan_i.reserve(nsup * pe * 4) || scr.plan_c.reserve(nsup * pk * 4))
             return fail(C3SC_ECUDA, "cudaMalloc chain plan failed");
     }
     for (size_t l = 0; l < L; l++) {
         LaneScratch &ln = scr.lane[l];
         if ((need_cst && ln.cst.reserve(NSmax * CS * 8)) || ln.flag.reserve(NSmax) || ln.act.reserve(NSmax * 4) ||
-            (mma && ln.sets.reserve((size_t)setw * FS * 8)))
+            (mma && ln.sets.reserve((size_t)setw * FS * 8)) ||
+            (bucketed && (ln.xa.reserve((size_t)chain_x_rows((int)d, P.nmax, (long long)FS) * rs * 8) ||
+                          ln.xb.reserve((size_t)chain_x_rows((int)d, P.nmax, (long long)FS) * rs * 8))))
             return fail(C3SC_ECUDA, "cudaMalloc pipeline scratch failed");
         if (l > 0 && !ln.stream) {
             CK(cudaStreamCreateWithFlags(&ln.stream, cudaStreamNonBlocking));
@@ -762,27 +773,57 @@ static int run_batch(const DevProblem &P, int model, int arith, Scratch &scr, co
         }
         ln.sets_busy = false;
     }
-    if (L > 1 && !scr.fork) CK(cudaEventCreateWithFlags(&scr.fork, cudaEventDisableTiming));
-    {   // every chunk's grouping in one launch; every super-chunk's chain plan in another
+    // (measured: the plans of four super-chunks in a row on a side stream take longer than the lanes can wait, 1.40 against 1.28 ms of
+    // stage 1 per 65 536 fibers; opt-in C3SC_PLAN_ASIDE=1)
+    const bool plan_aside = bucketed && nsup > 1 && getenv("C3SC_PLAN_ASIDE");
+    if ((L > 1 || plan_aside) && !scr.fork) CK(cudaEventCreateWithFlags(&scr.fork, cudaEventDisableTiming));
+    if (plan_aside) {
+        if (!scr.plan_stream) CK(cudaStreamCreateWithFlags(&scr.plan_stream, cudaStreamNonBlocking));
+        while (scr.plan_done.size() < nsup) {
+            cudaEvent_t e;
+            CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+            scr.plan_done.push_back(e);
+        }
+    }
+    auto chain_args = [&](size_t si, size_t s0, size_t Fs) {    // the chain stage's view of super-chunk si = fibers [s0, s0 + Fs)
+        ChainArgs ca;
+        memset(&ca, 0, sizeof ca);
+        ca.P = P; ca.ft = ft; ca.F = (int)Fs; ca.dim_vary = b.dim_vary + s0; ca.fixed_ind = b.fixed_ind + s0 * d;
+        ca.nbr_fixed_in = (b.nbr_fixed_in && d > 1) ? b.nbr_fixed_in + s0 * 2 * (d - 1) : nullptr;
+        ca.setw = setw; ca.rs = rs;
+        ca.kst = (int *)scr.plan_k.p + si * pk; ca.tst = (int *)scr.plan_t.p + si * pt; ca.ent = (int *)scr.plan_e.p + si * pe;
+        ca.xrows = chain_x_rows((int)d, P.nmax, (long long)FS);
+        ca.rowd = (int4 *)scr.plan_l.p + si * (d - 1) * (size_t)ca.xrows;
+        ca.inv = (int *)scr.plan_i.p + si * pe; ca.invstride = (int)FS;
+        ca.nmax = P.nmax; ca.entstride = (int)(3 * FS);
+        return ca;
+    };
+    {   // every chunk's grouping in one launch; the chain plans: one launch pair for all super-chunks, or one per super-chunk aside
         int rc = launch_group_fibers(P, (int)b.F, (int)FC, b.dim_vary, b.fixed_ind, (int *)scr.perm.p, (int *)scr.cnt.p, st);
         if (rc) return fail(C3SC_ECUDA, "grouping kernel: %s", cudaGetErrorString((cudaError_t)rc));
         g_launches++;
-        if (bucketed) {
-            ChainArgs ca;
-            memset(&ca, 0, sizeof ca);
-            ca.P = P; ca.ft = ft; ca.F = (int)b.F; ca.dim_vary = b.dim_vary; ca.fixed_ind = b.fixed_ind;
-            ca.nbr_fixed_in = (b.nbr_fixed_in && d > 1) ? b.nbr_fixed_in : nullptr;
-            ca.setw = setw; ca.rs = rs; ca.kst = (int *)scr.plan_k.p; ca.tst = (int *)scr.plan_t.p; ca.ent = (int *)scr.plan_e.p;
-            ca.nmax = P.nmax; ca.entstride = (int)(3 * FS);
-            rc = launch_chain_plan(ca, (int)FS, st);
+        if (bucketed && !plan_aside) {
+            ChainArgs ca = chain_args(0, 0, b.F);
+            rc = launch_chain_plan(ca, (int)FS, (int *)scr.plan_c.p, st);
             if (rc) return fail(C3SC_ECUDA, "chain plan kernel: %s", cudaGetErrorString((cudaError_t)rc));
-            g_launches++;
+            g_launches += 4;
         }
     }
-    if (L > 1) {                                            // the other lanes start after everything queued on st so far
+    if (L > 1 || plan_aside) {                              // the other lanes start after everything queued on st so far
         CK(cudaEventRecord(scr.fork, st));
         for (size_t l = 1; l < L; l++) CK(cudaStreamWaitEvent(scr.lane[l].stream, scr.fork, 0));
         if (chain_prio) for (size_t l = 0; l < L; l++) CK(cudaStreamWaitEvent(scr.lane[l].chain_stream, scr.fork, 0));
+    }
+    if (plan_aside) {                                       // (the plan reads the descriptors only: nothing of the batch before it)
+        CK(cudaStreamWaitEvent(scr.plan_stream, scr.fork, 0));
+        for (size_t s0 = 0, si = 0; s0 < b.F; s0 += FS, si++) {
+            const size_t Fs = (b.F - s0 < FS) ? b.F - s0 : FS;
+            ChainArgs ca = chain_args(si, s0, Fs);
+            int rc = launch_chain_plan(ca, (int)FS, (int *)scr.plan_c.p + si * pk, scr.plan_stream);
+            if (rc) return fail(C3SC_ECUDA, "chain plan kernel: %s", cudaGetErrorString((cudaError_t)rc));
+            g_launches += 4;
+            CK(cudaEventRecord(scr.plan_done[si], scr.plan_stream));
+        }
     }
     const cudaStream_t st0 = st;
     for (size_t s0 = 0, si = 0; s0 < b.F; s0 += FS, si++) {
@@ -790,14 +831,12 @@ static int run_batch(const DevProblem &P, int model, int arith, Scratch &scr, co
         LaneScratch &ln = scr.lane[si % L];
         st = ln.stream ? ln.stream : st0;
         if (bucketed) {
-            ChainArgs ca;
-            memset(&ca, 0, sizeof ca);
-            ca.P = P; ca.ft = ft; ca.F = (int)Fs; ca.dim_vary = b.dim_vary + s0; ca.fixed_ind = b.fixed_ind + s0 * d;
-            ca.sets = (double *)ln.sets.p; ca.setw = setw; ca.rs = rs;
-            ca.kst = (int *)scr.plan_k.p + si * pk; ca.tst = (int *)scr.plan_t.p + si * pt; ca.ent = (int *)scr.plan_e.p + si * pe;
-            ca.nmax = P.nmax; ca.entstride = (int)(3 * FS);
+            ChainArgs ca = chain_args(si, s0, Fs);
+            ca.sets = (double *)ln.sets.p;
+            ca.x[0] = (double *)ln.xa.p; ca.x[1] = (double *)ln.xb.p;
             int nl = 0;
             cudaStream_t cst_ = st;
+            if (plan_aside) CK(cudaStreamWaitEvent(chain_prio ? ln.chain_stream : st, scr.plan_done[si], 0));
             if (chain_prio) {                               // records of this lane are free once its previous super-chunk's nodes are done
                 cst_ = ln.chain_stream;
                 if (ln.sets_busy) CK(cudaStreamWaitEvent(cst_, ln.sets_free, 0));

@@ -14,15 +14,23 @@
 // the two neighbour products), and a block is read once per warp instead of once per fiber.
 //
 //   k_chain_plan   counting sort of the chunk's (fiber, role) entries by (side, dimension, block); roles: centre,
-//                  lower neighbour, upper neighbour.  One CTA per (chunk, dimension).
+//                  lower neighbour, upper neighbour.  One CTA per (chunk, dimension).  Also the inverse: the ROW a
+//                  fiber's centre block / lower / upper slot has in the dimension's bucket order.
+//   k_chain_link   per entry: where the fiber's rows go in the NEXT dimension's bucket order (or -1: the side is done).
 //   k_chain_step   launch t = 0..d-2 advances the left sets through dimension t and the right sets through d-1-t.
+//
+// SCATTER ON WRITE, STREAM ON READ.  The rows a launch works on lie in bucket order in a row buffer X[t & 1]: tile i of
+// the launch is rows [8i, 8i+8) -- one contiguous 8*RS-double piece, fetched by ONE TMA bulk copy (cp.async.bulk +
+// mbarrier) into a per-warp ring of shared-memory slots, four tiles ahead.  Nothing a load needs depends on another
+// load.  The products go where launch t+1 will read them (X[(t+1) & 1], at the rows k_chain_link recorded; a prefix is
+// written three times: into the fiber's centre block and into the two neighbour slots), or, when the fiber's side is
+// complete, into the fiber's record.  (The first version gathered rows through a tag -> row address chain of two
+// dependent L2 round trips per tile and spent 48 % of its issue slots waiting for them, profiles/r02b_chain.md.)
 //
 // Record of fiber f (FtArgs::sets + f*setw, rows of RS = 4*KS doubles, zero beyond the rank):
 //   rows [0, 1+2k)        left set,  row v = vector v          (k = dim_vary)
 //   rows [1+2k, 2d)       right set
-//   rows 2d .. 2d+3       P[side][parity]: the prefix / suffix alone, double-buffered -- the centre product
-//                         rewrites a fiber's rows in place while the neighbour products (other buckets, other
-//                         warps) still read its prefix of the previous step.
+//   rows 2d .. 2d+3       unused (the gathering version kept the double-buffered prefix / suffix there)
 #pragma once
 #include "ft_kernel.cuh"
 
@@ -48,7 +56,18 @@ struct ChainArgs {
     int *tst;                 // [d][2][nmax + 1]    first 8-row tile of block j; [..][N] = number of tiles
     int *ent;                 // [d][entstride]      entries: fiber | k << 24
     int nmax, entstride;      // entstride = 3 * (fibers of a full chunk)
+    int *inv;                 // [d][invstride][3]   row of the fiber's centre block / lower slot / upper slot in dimension m's
+                              //                     bucket order, relative to its side's first row
+    int4 *rowd;               // [d-1][xrows]        per row of launch t's buffer: x = where the product goes (>= 0: row of launch
+                              //                     t+1's buffer; < 0: ~(row of the chunk's records, in units of RS doubles);
+                              //                     INT_MIN: padding row), y / z = the two neighbour slots of launch t+1 that also
+                              //                     take it (a prefix; else -1), w = side * 65536 + block of the row's bucket
+    int invstride;            // fibers of a full chunk
+    double *x[2];             // row buffers of the launches, X[t & 1] read by launch t; xrows rows of RS doubles each
+    long long xrows;
 };
+// rows a launch's buffer must hold: a fiber has at most 2d rows in one launch, every bucket is padded to 8 rows
+__host__ __device__ inline long long chain_x_rows(int d, int nmax, long long F) { return F * 2 * d + 16LL * nmax + 8; }
 
 #ifndef C3SC_FT_TYPES_ONLY
 // exclusive scan of n ints in shared memory by one CTA (n <= 8 * blockDim.x); returns the total
@@ -76,55 +95,77 @@ __device__ __forceinline__ int cta_exclusive_scan(int *v, int n, int *wsum)
     return total;
 }
 
-// grid (chunks, d), 1024 threads.  Chunk c covers fibers [c*FC, min(F, (c+1)*FC)) of the batch; its plan arrays and
-// records are the c-th slices of the buffers in `a` (strides given).
-struct ChainPlanStrides { long long kst, tst, ent; };
-#ifndef C3SC_FT_KS_UNIT        // compiled once, in ft.cu (ft_ks.cu holds the per-rank-geometry templates)
-__global__ void __launch_bounds__(1024) k_chain_plan(ChainArgs a, int FC, ChainPlanStrides S)
+// The plan of a batch: chunk c covers fibers [c*FC, min(F, (c+1)*FC)); its plan arrays are the c-th slices of the buffers
+// in `a` (strides given).  Three launches:
+//   k_chain_count    one CTA per (slice of 1024 fibers, dimension): the (side, block, role) bins, counted in shared memory
+//                    (the first version ran one 1024-thread CTA per (chunk, dimension) with a shared-memory histogram: 40 CTAs
+//                    on 148 SMs and two latency-bound passes over the descriptors, 60 us per 65 536 fibers);
+//   k_chain_scan     one CTA per (chunk, dimension): tiles per block, the exclusive scans -> kst, tst, the running positions;
+//   k_chain_scatter  the same slices again: entries into their bins, and the inverse (rows of the fiber).
+struct ChainPlanStrides { long long kst, tst, ent, inv, rowd; };
+
+// roles of fiber f (batch index) in dimension m; false when m is the varying dimension
+__device__ __forceinline__ bool chain_roles(const ChainArgs &a, int f, int m, int i0raw, int &k, int &side, int &i0, int &lo, int &hi)
+{
+    const int d = a.ft.d, N = a.P.ngrid[m];
+    k = a.dim_vary[f];
+    k = k < 0 ? 0 : (k >= d ? d - 1 : k);
+    if (k == m) return false;
+    side = m < k ? 0 : 1;
+    i0 = ft_clamp_index(i0raw, N);
+    ft_fixed_pair(a.P, m, i0, lo, hi);
+    if (a.nbr_fixed_in) {
+        const int slot = m < k ? m : m - 1;
+        lo = ft_clamp_index(a.nbr_fixed_in[(size_t)f * 2 * (d - 1) + 2 * slot], N);
+        hi = ft_clamp_index(a.nbr_fixed_in[(size_t)f * 2 * (d - 1) + 2 * slot + 1], N);
+    }
+    return true;
+}
+
+#ifndef C3SC_FT_KS_UNIT
+constexpr int CHP_NT = 512, CHP_U = 2, CHP_SLICE = CHP_NT * CHP_U;      // fibers per CTA of the count / scatter kernels
+// grid (slices of a chunk, d, chunks), CHP_NT threads, 6 * nmax ints of shared memory (12 * nmax for the scatter).
+// cntg: [chunk][d][2][nmax*3 + 1] like kst, zero on entry.  A CTA counts its slice of the chunk's fibers in shared memory
+// and adds every non-empty bin to the global count with one atomic.
+__global__ void __launch_bounds__(CHP_NT) k_chain_count(ChainArgs a, int FC, ChainPlanStrides S, int *cntg)
+{
+    extern __shared__ int sh[];
+    const int d = a.ft.d, nmax = a.nmax, m = blockIdx.y, c = blockIdx.z, tid = threadIdx.x;
+    const int N = a.P.ngrid[m], nb = 6 * N;
+    const int f0 = c * FC + blockIdx.x * CHP_SLICE;
+    int fend = (c + 1) * FC < a.F ? (c + 1) * FC : a.F;
+    fend = f0 + CHP_SLICE < fend ? f0 + CHP_SLICE : fend;
+    for (int e = tid; e < nb; e += CHP_NT) sh[e] = 0;
+    __syncthreads();
+#pragma unroll
+    for (int u = 0; u < CHP_U; u++) {
+        const int f = f0 + u * CHP_NT + tid;
+        int k, side, i0, lo, hi;
+        if (f < fend && chain_roles(a, f, m, a.fixed_ind[(size_t)f * d + m], k, side, i0, lo, hi)) {
+            atomicAdd(&sh[(side * N + i0) * 3], 1);
+            atomicAdd(&sh[(side * N + lo) * 3 + 1], 1);
+            atomicAdd(&sh[(side * N + hi) * 3 + 2], 1);
+        }
+    }
+    __syncthreads();
+    int *cg = cntg + c * S.kst + (size_t)m * 2 * (nmax * 3 + 1);
+    for (int e = tid; e < nb; e += CHP_NT)
+        if (sh[e]) atomicAdd(cg + (e / (3 * N)) * (nmax * 3 + 1) + (e % (3 * N)), sh[e]);
+}
+
+// grid (chunks, d), 1024 threads, 14 * nmax ints of shared memory
+__global__ void __launch_bounds__(1024) k_chain_scan(ChainArgs a, ChainPlanStrides S, int *cntg)
 {
     extern __shared__ int sh[];
     __shared__ int wsum[32];
     const int d = a.ft.d, m = blockIdx.y, tid = threadIdx.x, NT = blockDim.x;
-    const int c0 = blockIdx.x * FC, Fc = (a.F - c0 < FC) ? a.F - c0 : FC;
     const int N = a.P.ngrid[m], nmax = a.nmax;
-    const int *dv = a.dim_vary + c0, *fi = a.fixed_ind + (size_t)c0 * d;
-    const int *nfi = a.nbr_fixed_in ? a.nbr_fixed_in + (size_t)c0 * 2 * (d - 1) : nullptr;
     int *kst = a.kst + blockIdx.x * S.kst + (size_t)m * 2 * (nmax * 3 + 1);
     int *tst = a.tst + blockIdx.x * S.tst + (size_t)m * 2 * (nmax + 1);
-    int *ent = a.ent + blockIdx.x * S.ent + (size_t)m * a.entstride;
-    int *cnt = sh, *fill = sh + 2 * 3 * N;                  // [side][j][role]; fill = running positions of the scatter
+    int *cg = cntg + blockIdx.x * S.kst + (size_t)m * 2 * (nmax * 3 + 1);
+    int *cnt = sh, *til = sh + 2 * 3 * N;                   // [side][j][role]; tiles per (side, j)
     const int nb = 2 * 3 * N;
-    for (int e = tid; e < nb; e += NT) cnt[e] = 0;
-    __syncthreads();
-    auto roles = [&](int f, int &side, int &i0, int &lo, int &hi) -> int {      // returns k, or -1 when m is the varying dim
-        int k = dv[f];
-        k = k < 0 ? 0 : (k >= d ? d - 1 : k);
-        if (k == m) return -1;
-        side = m < k ? 0 : 1;
-        i0 = ft_clamp_index(fi[(size_t)f * d + m], N);
-        ft_fixed_pair(a.P, m, i0, lo, hi);
-        if (nfi) {
-            const int slot = m < k ? m : m - 1;
-            lo = ft_clamp_index(nfi[(size_t)f * 2 * (d - 1) + 2 * slot], N);
-            hi = ft_clamp_index(nfi[(size_t)f * 2 * (d - 1) + 2 * slot + 1], N);
-        }
-        return k;
-    };
-    // four fibers per thread and trip: the descriptor loads (a dependent pair per fiber, strided by d) are what this
-    // kernel waits for
-    constexpr int U = 4;
-    for (int f0 = tid; f0 < Fc; f0 += U * NT) {
-        int kk[U], side[U], i0[U], lo[U], hi[U];
-#pragma unroll
-        for (int u = 0; u < U; u++) kk[u] = (f0 + u * NT < Fc) ? roles(f0 + u * NT, side[u], i0[u], lo[u], hi[u]) : -1;
-#pragma unroll
-        for (int u = 0; u < U; u++) {
-            if (kk[u] < 0) continue;
-            atomicAdd(&cnt[(side[u] * N + i0[u]) * 3], 1);
-            atomicAdd(&cnt[(side[u] * N + lo[u]) * 3 + 1], 1);
-            atomicAdd(&cnt[(side[u] * N + hi[u]) * 3 + 2], 1);
-        }
-    }
+    for (int e = tid; e < nb; e += NT) cnt[e] = cg[(e / (3 * N)) * (nmax * 3 + 1) + (e % (3 * N))];
     __syncthreads();
     // tiles per block: ceil((centre * nin + lo + hi) / 8), nin = 1 + 2s vectors before the step; the left sets
     // reach dimension m at step m, the right sets at step d-1-m
@@ -132,34 +173,134 @@ __global__ void __launch_bounds__(1024) k_chain_plan(ChainArgs a, int FC, ChainP
         const int side = e / N;
         const int nin = 1 + 2 * (side ? d - 1 - m : m);
         const int rows = cnt[e * 3] * nin + cnt[e * 3 + 1] + cnt[e * 3 + 2];
-        fill[nb + e] = (rows + 7) >> 3;                     // tile counts behind the two histograms
+        til[e] = (rows + 7) >> 3;
     }
     __syncthreads();
-    cta_exclusive_scan(cnt, nb, wsum);                      // both sides in one list: side 1 starts where side 0 ends
+    const int total = cta_exclusive_scan(cnt, nb, wsum);    // both sides in one list: side 1 starts where side 0 ends
     for (int side = 0; side < 2; side++) {                  // tile prefix per side
-        int *t = fill + nb + side * N;
-        const int total = cta_exclusive_scan(t, N, wsum);
+        int *t = til + side * N;
+        const int tt = cta_exclusive_scan(t, N, wsum);
         for (int e = tid; e < N; e += NT) tst[side * (nmax + 1) + e] = t[e];
-        if (tid == 0) tst[side * (nmax + 1) + N] = total;
+        if (tid == 0) tst[side * (nmax + 1) + N] = tt;
     }
-    for (int e = tid; e < nb; e += NT) { fill[e] = cnt[e]; kst[(e / (3 * N)) * (nmax * 3 + 1) + (e % (3 * N))] = cnt[e]; }
-    if (tid == 0) kst[3 * N] = cnt[3 * N];                  // end of side 0 = start of side 1
+    for (int e = tid; e < nb; e += NT) {
+        const int o = (e / (3 * N)) * (nmax * 3 + 1) + (e % (3 * N));
+        kst[o] = cnt[e];
+        cg[o] = cnt[e];                                     // running positions of the scatter
+    }
+    if (tid == 0) { kst[3 * N] = cnt[3 * N]; kst[(nmax * 3 + 1) + 3 * N] = total; }   // end of side 0 = start of side 1; end of side 1
+}
+
+// Same grid.  The CTA counts its slice again, reserves a range of every non-empty bin with one global atomic, and places
+// its entries inside the ranges with shared-memory atomics; with the position it knows the row, and writes the inverse.
+__global__ void __launch_bounds__(CHP_NT) k_chain_scatter(ChainArgs a, int FC, ChainPlanStrides S, int *cntg)
+{
+    extern __shared__ int sh[];
+    const int d = a.ft.d, nmax = a.nmax, m = blockIdx.y, c = blockIdx.z, tid = threadIdx.x;
+    const int N = a.P.ngrid[m], nb = 6 * N;
+    int *run = sh, *base = sh + nb;
+    const int f0 = c * FC + blockIdx.x * CHP_SLICE;
+    int fend = (c + 1) * FC < a.F ? (c + 1) * FC : a.F;
+    fend = f0 + CHP_SLICE < fend ? f0 + CHP_SLICE : fend;
+    for (int e = tid; e < nb; e += CHP_NT) run[e] = 0;
     __syncthreads();
-    for (int f0 = tid; f0 < Fc; f0 += U * NT) {
-        int kk[U], side[U], i0[U], lo[U], hi[U];
+    int k[CHP_U], side[CHP_U], i0[CHP_U], lo[CHP_U], hi[CHP_U];
+    bool on[CHP_U];
 #pragma unroll
-        for (int u = 0; u < U; u++) kk[u] = (f0 + u * NT < Fc) ? roles(f0 + u * NT, side[u], i0[u], lo[u], hi[u]) : -1;
-#pragma unroll
-        for (int u = 0; u < U; u++) {
-            if (kk[u] < 0) continue;
-            const int tag = (f0 + u * NT) | (kk[u] << 24);
-            ent[atomicAdd(&fill[(side[u] * N + i0[u]) * 3], 1)] = tag;
-            ent[atomicAdd(&fill[(side[u] * N + lo[u]) * 3 + 1], 1)] = tag;
-            ent[atomicAdd(&fill[(side[u] * N + hi[u]) * 3 + 2], 1)] = tag;
+    for (int u = 0; u < CHP_U; u++) {
+        const int f = f0 + u * CHP_NT + tid;
+        on[u] = f < fend && chain_roles(a, f, m, a.fixed_ind[(size_t)f * d + m], k[u], side[u], i0[u], lo[u], hi[u]);
+        if (on[u]) {
+            atomicAdd(&run[(side[u] * N + i0[u]) * 3], 1);
+            atomicAdd(&run[(side[u] * N + lo[u]) * 3 + 1], 1);
+            atomicAdd(&run[(side[u] * N + hi[u]) * 3 + 2], 1);
         }
     }
     __syncthreads();
-    if (tid == 0) kst[(nmax * 3 + 1) + 3 * N] = fill[(2 * N - 1) * 3 + 2];       // end of side 1's last bucket
+    int *cg = cntg + c * S.kst + (size_t)m * 2 * (nmax * 3 + 1);
+    for (int e = tid; e < nb; e += CHP_NT) {
+        const int n = run[e];
+        base[e] = n ? atomicAdd(cg + (e / (3 * N)) * (nmax * 3 + 1) + (e % (3 * N)), n) : 0;
+        run[e] = 0;
+    }
+    __syncthreads();
+    const int *kst = a.kst + c * S.kst + (size_t)m * 2 * (nmax * 3 + 1);
+    const int *tst = a.tst + c * S.tst + (size_t)m * 2 * (nmax + 1);
+    int *ent = a.ent + c * S.ent + (size_t)m * a.entstride;
+#pragma unroll
+    for (int u = 0; u < CHP_U; u++) {
+        if (!on[u]) continue;
+        const int fl = f0 + u * CHP_NT + tid - c * FC;
+        int *inv = a.inv + c * S.inv + ((size_t)m * a.invstride + fl) * 3;
+        const int tag = fl | (k[u] << 24);
+        const int nin = 1 + 2 * (side[u] ? d - 1 - m : m);
+        const int *ks = kst + side[u] * (nmax * 3 + 1), *tpre = tst + side[u] * (nmax + 1);     // first entry / tile of block j
+        {   // centre: the fiber's nin rows start at (entry - first centre entry) * nin inside the block
+            const int b = (side[u] * N + i0[u]) * 3, pos = base[b] + atomicAdd(&run[b], 1);
+            ent[pos] = tag;
+            inv[0] = 8 * tpre[i0[u]] + (pos - ks[3 * i0[u]]) * nin;
+        }
+        {   // neighbour slots follow the block's centre rows, one row per entry, lower entries first
+            const int b = (side[u] * N + lo[u]) * 3 + 1, pos = base[b] + atomicAdd(&run[b], 1);
+            ent[pos] = tag;
+            inv[1] = 8 * tpre[lo[u]] + (ks[3 * lo[u] + 1] - ks[3 * lo[u]]) * nin + (pos - ks[3 * lo[u] + 1]);
+        }
+        {
+            const int b = (side[u] * N + hi[u]) * 3 + 2, pos = base[b] + atomicAdd(&run[b], 1);
+            ent[pos] = tag;
+            inv[2] = 8 * tpre[hi[u]] + (ks[3 * hi[u] + 1] - ks[3 * hi[u]]) * nin + (pos - ks[3 * hi[u] + 1]);
+        }
+    }
+}
+#endif
+
+// grid (chunks, d, Z), 256 threads: the row descriptors.  CTA (c, m, z) walks buckets z, z+Z, .. of dimension m (both sides)
+// and writes, for every row of the bucket, where the row's product goes: the fiber's rows in the next dimension of its side
+// (m+1 left, m-1 right; k_chain_plan's inverse rows), or the fiber's record when the side ends here.
+#ifndef C3SC_FT_KS_UNIT
+constexpr int CH_ROW_PAD = (int)0x80000000;
+__global__ void __launch_bounds__(256) k_chain_link(ChainArgs a, ChainPlanStrides S)
+{
+    const int d = a.ft.d, m = blockIdx.y, nmax = a.nmax;
+    const int N = a.P.ngrid[m];
+    const int *kstm = a.kst + blockIdx.x * S.kst + (size_t)m * 2 * (nmax * 3 + 1);
+    const int *tstm = a.tst + blockIdx.x * S.tst + (size_t)m * 2 * (nmax + 1);
+    const int *tst0 = a.tst + blockIdx.x * S.tst;
+    const int *ent = a.ent + blockIdx.x * S.ent + (size_t)m * a.entstride;
+    const int *inv = a.inv + blockIdx.x * S.inv;
+    int4 *rowd = a.rowd + blockIdx.x * S.rowd;
+    const int recrows = a.setw / a.rs;
+    for (int b = blockIdx.z; b < 2 * N; b += gridDim.z) {
+        const int side = b / N, j = b - side * N;
+        const int t = side ? d - 1 - m : m;                 // the launch that works on this side of dimension m
+        if (t > d - 2) continue;                            // (left side of the last dimension / right side of the first: empty)
+        const int nin = 1 + 2 * t;
+        const int *ks = kstm + side * (nmax * 3 + 1) + 3 * j;
+        const int csc = ks[0], cslo = ks[1], cshi = ks[2], csend = ks[3];
+        const int t0 = tstm[side * (nmax + 1) + j], t1 = tstm[side * (nmax + 1) + j + 1];
+        const int nc = (cslo - csc) * nin, rows = nc + (csend - cslo);
+        // rows of the right side lie behind the left side's tiles, in this launch's buffer and in the next one's
+        const long long here = side ? 8LL * tst0[((size_t)t * 2 + 0) * (nmax + 1) + a.P.ngrid[t]] : 0;
+        const int next = (side && t + 1 <= d - 2) ? 8 * tst0[((size_t)(t + 1) * 2 + 0) * (nmax + 1) + a.P.ngrid[t + 1]] : 0;
+        int4 *out = rowd + (size_t)t * a.xrows + here + 8LL * t0;
+        const int mn = side ? m - 1 : m + 1;
+        for (int r = threadIdx.x; r < 8 * (t1 - t0); r += blockDim.x) {
+            int4 D = make_int4(CH_ROW_PAD, -1, -1, side * 65536 + j);
+            if (r < rows) {
+                int e, v;
+                if (r < nc) { const int q = r / nin; e = csc + q; v = r - q * nin; }
+                else { e = cslo + (r - nc); v = e < cshi ? nin : nin + 1; }
+                const int tag = ent[e], f = tag & 0xffffff, k = tag >> 24;
+                const bool cont = side ? mn > k : mn < k;
+                if (cont) {
+                    const int *iv = inv + ((size_t)mn * a.invstride + f) * 3;
+                    D.x = next + iv[0] + v;
+                    if (r < nc && v == 0) { D.y = next + iv[1]; D.z = next + iv[2]; }
+                } else D.x = ~(f * recrows + (side ? 1 + 2 * k : 0) + v);
+            }
+            out[r] = D;
+        }
+    }
 }
 #endif
 
@@ -168,37 +309,69 @@ __device__ __forceinline__ void ch_dmma(double &d0, double &d1, double a, double
     asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
         : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
 }
+// TMA bulk copy + mbarrier (the node kernel has its own copies of these in ft_mma_kernel.cuh)
+__device__ __forceinline__ unsigned ch_smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void ch_mbar_init(unsigned long long *b, unsigned count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(ch_smem_u32(b)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void ch_fetch(void *dst, const void *src, unsigned bytes, unsigned long long *b)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(ch_smem_u32(b)), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(ch_smem_u32(dst)), "l"(src), "r"(bytes), "r"(ch_smem_u32(b)) : "memory");
+}
+__device__ __forceinline__ void ch_mbar_wait(unsigned long long *b, unsigned parity)
+{
+    asm volatile("{\n"
+                 ".reg .pred P1;\n"
+                 "CH_WAIT:\n"
+                 "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+                 "@P1 bra CH_DONE;\n"
+                 "bra CH_WAIT;\n"
+                 "CH_DONE:\n"
+                 "}" ::"r"(ch_smem_u32(b)), "r"(parity) : "memory");
+}
 
 // One launch = one step of both sides.  Warps own contiguous ranges of 8-row tiles of the concatenated tile list
-// [left buckets of dimension t | right buckets of dimension d-1-t].  The bucket tables of the two dimensions are
-// staged in shared memory once per CTA (one coalesced round trip instead of a dependent chain of L2 loads per warp);
-// a warp's loop is software-pipelined: the entry of tile i+2 and the rows of tile i+1 are in flight while the
-// products of tile i run.
-struct ChainDec { int e, v, sj; unsigned flags; };          // entry position, vector / new row, side*65536 + bucket; flags: 1 valid, 2 centre
+// [left buckets of dimension t | right buckets of dimension d-1-t] = contiguous pieces of the row buffer X[t & 1].
+// A warp keeps CH_SLOTS tiles in flight (TMA bulk copies into its own ring) and the row descriptors of the next tile
+// (only the stores and the choice of the block need them) one tile ahead.  No table, no decoding: everything a row
+// needs is in its descriptor (k_chain_link).
+constexpr int CH_SLOTS = 4;
+
+// dynamic shared memory of k_chain_step: the rings (16-byte aligned), then the mbarriers
+__host__ __device__ inline size_t chain_step_smem(int rs, int *bar_off = nullptr)
+{
+    size_t o = (size_t)(CH_NT / 32) * CH_SLOTS * 8 * rs * sizeof(double);
+    if (bar_off) *bar_off = (int)o;
+    o += (size_t)(CH_NT / 32) * CH_SLOTS * sizeof(unsigned long long);
+    return o;
+}
 
 template <int KS>
 __global__ void __launch_bounds__(CH_NT, 2) k_chain_step(const ChainArgs a, int t)
 {
     constexpr int NT8 = (KS + 1) / 2;                       // 8-wide output tiles
-    extern __shared__ int shs[];
+    extern __shared__ __align__(16) double shd[];
     const DevFT &ft = a.ft;
     const int d = ft.d, nmax = a.nmax, RS = a.rs;
-    const int lane = threadIdx.x & 31, gid = lane >> 2, tig = lane & 3;
-    const int W = gridDim.x * (CH_NT / 32), w = blockIdx.x * (CH_NT / 32) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, gid = lane >> 2, tig = lane & 3;
+    const int W = gridDim.x * (CH_NT / 32), w = blockIdx.x * (CH_NT / 32) + warp;
     const int mL = t, mR = d - 1 - t;
-    const int NL = a.P.ngrid[mL], NR = a.P.ngrid[mR];
-    const int nin = 1 + 2 * t, par = t & 1;
-    // shared: tst of both sides (N+1 each), kst of both sides (3N+1 each)
-    int *sT[2], *sK[2];
-    sT[0] = shs; sT[1] = sT[0] + NL + 1; sK[0] = sT[1] + NR + 1; sK[1] = sK[0] + 3 * NL + 1;
-    {
-        const int *gT0 = a.tst + ((size_t)mL * 2 + 0) * (nmax + 1), *gT1 = a.tst + ((size_t)mR * 2 + 1) * (nmax + 1);
-        const int *gK0 = a.kst + ((size_t)mL * 2 + 0) * (nmax * 3 + 1), *gK1 = a.kst + ((size_t)mR * 2 + 1) * (nmax * 3 + 1);
-        for (int e = threadIdx.x; e <= NL; e += CH_NT) sT[0][e] = __ldg(gT0 + e);
-        for (int e = threadIdx.x; e <= NR; e += CH_NT) sT[1][e] = __ldg(gT1 + e);
-        for (int e = threadIdx.x; e <= 3 * NL; e += CH_NT) sK[0][e] = __ldg(gK0 + e);
-        for (int e = threadIdx.x; e <= 3 * NR; e += CH_NT) sK[1][e] = __ldg(gK1 + e);
+    int bar_off;
+    chain_step_smem(RS, &bar_off);
+    const int TB = 8 * RS;                                  // doubles of a tile
+    double *ring = shd + warp * CH_SLOTS * TB;
+    unsigned long long *bar = reinterpret_cast<unsigned long long *>(reinterpret_cast<char *>(shd) + bar_off) + warp * CH_SLOTS;
+    const int TL = __ldg(a.tst + ((size_t)mL * 2 + 0) * (nmax + 1) + a.P.ngrid[mL]);
+    const int TR = __ldg(a.tst + ((size_t)mR * 2 + 1) * (nmax + 1) + a.P.ngrid[mR]);
+    if (lane == 0) {
+#pragma unroll
+        for (int q = 0; q < CH_SLOTS; q++) ch_mbar_init(bar + q, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
+    __syncwarp();
     // Programmatic dependent launch: steps t >= 1 are launched while step t-1 still runs (ft.cu); everything above
     // reads the plan only.  Let the next step start its own prologue, then wait for the previous step's rows.
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
@@ -215,88 +388,30 @@ __global__ void __launch_bounds__(CH_NT, 2) k_chain_step(const ChainArgs a, int 
             if (k == d - 1) a.sets[(size_t)f * a.setw + (size_t)(1 + 2 * k) * RS + q] = q == 0 ? 1.0 : 0.0;
         }
     }
-    __syncthreads();
-    const int TL = sT[0][NL], TR = sT[1][NR];
     const long long T = (long long)TL + TR;
     int tile = (int)(T * w / W);
     const int tend = (int)(T * (w + 1) / W);
     if (tile >= tend) return;
-    const unsigned magic = (unsigned)((0x100000000ULL + nin - 1) / nin);          // r / nin for r < 2^32 / nin (nin > 1)
+    const double *xin = a.x[t & 1];
+    double *xout = a.x[(t + 1) & 1];
+    const int4 *rowd = a.rowd + (size_t)t * a.xrows + gid;
+    const unsigned tbytes = (unsigned)(TB * sizeof(double));
 
-    // cursor of the decoder: the bucket that holds the tile most recently decoded
-    int cside = -1, cj = 0, cjt0 = 0, cjt1 = 0, csc = 0, cslo = 0, cshi = 0, csend = 0;
-    auto decode = [&](int tl_abs) -> ChainDec {
-        const int sd = tl_abs < TL ? 0 : 1;
-        const int tl = tl_abs - (sd ? TL : 0);
-        bool newb = false;
-        if (sd != cside) {
-            cside = sd;
-            const int N = sd ? NR : NL;
-            int lo = 0, hi = N;                             // largest j with tst[j] <= tl
-            while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (sT[sd][mid] <= tl) lo = mid; else hi = mid; }
-            cj = lo; newb = true;
-        } else if (tl >= cjt1) { cj++; newb = true; }
-        if (newb) {
-            cjt0 = sT[sd][cj]; cjt1 = sT[sd][cj + 1];
-            while (tl >= cjt1) { cj++; cjt0 = cjt1; cjt1 = sT[sd][cj + 1]; }      // empty buckets
-            csc = sK[sd][3 * cj]; cslo = sK[sd][3 * cj + 1]; cshi = sK[sd][3 * cj + 2]; csend = sK[sd][3 * cj + 3];
-        }
-        const int r = (tl - cjt0) * 8 + gid;
-        const int nc = (cslo - csc) * nin, rows = nc + (csend - cslo);
-        ChainDec D;
-        D.flags = (r < rows ? 1u : 0u) | (r < nc ? 2u : 0u);
-        if (r < nc) { const int q = nin == 1 ? r : (int)__umulhi((unsigned)r, magic); D.e = csc + q; D.v = r - q * nin; }
-        else { D.e = cslo + (r - nc); D.v = D.e < cshi ? nin : nin + 1; }
-        D.sj = sd * 65536 + cj;
-        return D;
-    };
-    const int *entS[2] = {a.ent + (size_t)mL * a.entstride, a.ent + (size_t)mR * a.entstride};
-    auto load_tag = [&](const ChainDec &D) -> int { return (D.flags & 1u) ? __ldg(entS[D.sj >> 16] + D.e) : 0; };
-    // pointers of a row: src (read), dst (written), and for the prefix row also row 0 of the set
-    auto row_ptrs = [&](const ChainDec &D, int tag, const double *&src, double *&dst, double *&dst0) {
-        const int f = tag & 0xffffff, k = tag >> 24, side = D.sj >> 16;
-        double *rec = a.sets + (size_t)f * a.setw;
-        double *set = rec + (size_t)(side ? 1 + 2 * k : 0) * RS;
-        const bool centre = (D.flags & 2u) != 0;
-        src = (centre && D.v > 0) ? set + (size_t)D.v * RS : rec + (size_t)(2 * d + 2 * side + par) * RS;
-        dst = (centre && D.v == 0) ? rec + (size_t)(2 * d + 2 * side + (par ^ 1)) * RS : set + (size_t)D.v * RS;
-        dst0 = (centre && D.v == 0) ? set : nullptr;
-    };
-    auto load_rows = [&](const ChainDec &D, const double *src, double (&A)[KS]) {
+    // ring fill: the first CH_SLOTS tiles of this warp's range
+    if (t > 0 && lane == 0) {
 #pragma unroll
-        for (int ks = 0; ks < KS; ks++) {
-            if (t == 0) A[ks] = (4 * ks + tig == 0 && (D.flags & 1u)) ? 1.0 : 0.0;       // every vector of step 0 is e_1
-            else A[ks] = (D.flags & 1u) ? src[4 * ks + tig] : 0.0;
-        }
-    };
-
+        for (int q = 0; q < CH_SLOTS; q++)
+            if (tile + q < tend) ch_fetch(ring + q * TB, xin + (size_t)(tile + q) * TB, tbytes, bar + q);
+    }
     double B[KS][NT8];
     int Bsj = -1;
-    // pipeline fill: tile i decoded + tag + rows; tile i+1 decoded + tag
-    ChainDec D0 = decode(tile), D1;
-    int tag0 = load_tag(D0), tag1 = 0;
-    const double *src0; double *dst0, *dsz0;
-    row_ptrs(D0, tag0, src0, dst0, dsz0);
-    double A0[KS];
-    load_rows(D0, src0, A0);
-    bool have1 = tile + 1 < tend;
-    if (have1) { D1 = decode(tile + 1); tag1 = load_tag(D1); }
-    for (; tile < tend; tile++) {
-        // next tile: pointers from its tag, rows in flight; the tile after: decode + tag in flight
-        const double *src1 = nullptr; double *dst1 = nullptr, *dsz1 = nullptr;
-        double A1[KS];
-        ChainDec D2;
-        int tag2 = 0;
-        bool have2 = false;
-        if (have1) {
-            row_ptrs(D1, tag1, src1, dst1, dsz1);
-            load_rows(D1, src1, A1);
-            have2 = tile + 2 < tend;
-            if (have2) { D2 = decode(tile + 2); tag2 = load_tag(D2); }
-        }
-        // current tile
-        if (D0.sj != Bsj) {
-            Bsj = D0.sj;
+    int4 D0 = __ldg(rowd + (size_t)tile * 8);
+    unsigned phase = 0;                                     // bit q: parity of slot q's next completion
+    for (int it = 0; tile < tend; tile++, it++) {
+        int4 D1 = D0;
+        if (tile + 1 < tend) D1 = __ldg(rowd + (size_t)(tile + 1) * 8);
+        if (D0.w != Bsj) {                                  // (the bucket is the same for the eight rows of a tile)
+            Bsj = D0.w;
             const int side = Bsj >> 16, j = Bsj & 0xffff, m = side ? mR : mL;
             const int rin = side ? ft.r[m + 1] : ft.r[m], rout = side ? ft.r[m] : ft.r[m + 1];
             // B fragments (row q = 4ks+tig of the contraction, column o = 8nt+gid of the output) of block G_m[j]
@@ -311,29 +426,46 @@ __global__ void __launch_bounds__(CH_NT, 2) k_chain_step(const ChainArgs a, int 
                     B[ks][nt] = (q < rin && o < rout) ? __ldg(g + (side ? o + q * rm : q + o * rm)) : 0.0;
                 }
         }
+        // this tile's rows: A fragment (row gid, column 4ks+tig) from the ring slot
+        double A[KS];
+        const int slot = it % CH_SLOTS;
+        if (t == 0) {
+#pragma unroll
+            for (int ks = 0; ks < KS; ks++) A[ks] = (4 * ks + tig == 0) ? 1.0 : 0.0;      // every vector of step 0 is e_1
+        } else {
+            ch_mbar_wait(bar + slot, (phase >> slot) & 1u);
+            phase ^= 1u << slot;
+            const double *row = ring + slot * TB + gid * RS + tig;
+#pragma unroll
+            for (int ks = 0; ks < KS; ks++) A[ks] = row[4 * ks];
+            __syncwarp();                                   // every lane has read the slot: refill it with tile + CH_SLOTS
+            if (lane == 0 && tile + CH_SLOTS < tend)
+                ch_fetch(ring + slot * TB, xin + (size_t)(tile + CH_SLOTS) * TB, tbytes, bar + slot);
+        }
         double acc[NT8][2];
 #pragma unroll
         for (int nt = 0; nt < NT8; nt++) acc[nt][0] = acc[nt][1] = 0.0;
 #pragma unroll
         for (int ks = 0; ks < KS; ks++)
 #pragma unroll
-            for (int nt = 0; nt < NT8; nt++) ch_dmma(acc[nt][0], acc[nt][1], A0[ks], B[ks][nt]);
-        if (D0.flags & 1u) {
+            for (int nt = 0; nt < NT8; nt++) ch_dmma(acc[nt][0], acc[nt][1], A[ks], B[ks][nt]);
+        if (D0.x != (int)0x80000000) {
+            // launch t+1's buffer (plus the two neighbour slots for a prefix), or the fiber's record
+            double *dst = (D0.x >= 0 ? xout + (size_t)D0.x * RS : a.sets + (size_t)(~D0.x) * RS) + 2 * tig;
 #pragma unroll
-            for (int nt = 0; nt < NT8; nt++) {
-                const int o = 8 * nt + 2 * tig;                 // D: row r, columns o, o+1; zero beyond the rank
-                if (o < RS) {
-                    const double2 val = make_double2(acc[nt][0], acc[nt][1]);
-                    *reinterpret_cast<double2 *>(dst0 + o) = val;
-                    if (dsz0) *reinterpret_cast<double2 *>(dsz0 + o) = val;                   // the prefix also lives in row 0
-                }
+            for (int nt = 0; nt < NT8; nt++)
+                if (8 * nt + 2 * tig < RS) *reinterpret_cast<double2 *>(dst + 8 * nt) = make_double2(acc[nt][0], acc[nt][1]);
+            if (D0.y >= 0) {
+                double *dlo = xout + (size_t)D0.y * RS + 2 * tig, *dhi = xout + (size_t)D0.z * RS + 2 * tig;
+#pragma unroll
+                for (int nt = 0; nt < NT8; nt++)
+                    if (8 * nt + 2 * tig < RS) {
+                        *reinterpret_cast<double2 *>(dlo + 8 * nt) = make_double2(acc[nt][0], acc[nt][1]);
+                        *reinterpret_cast<double2 *>(dhi + 8 * nt) = make_double2(acc[nt][0], acc[nt][1]);
+                    }
             }
         }
-        // shift the pipeline
-        D0 = D1; tag0 = tag1; src0 = src1; dst0 = dst1; dsz0 = dsz1;
-#pragma unroll
-        for (int ks = 0; ks < KS; ks++) A0[ks] = A1[ks];
-        D1 = D2; tag1 = tag2; have1 = have2;
+        D0 = D1;
     }
 }
 

@@ -110,22 +110,33 @@ void chain_plan_sizes(const DevFT &ft, int nmax, size_t FC, size_t *kst, size_t 
 {
     *kst = (size_t)ft.d * 2 * ((size_t)nmax * 3 + 1);
     *tst = (size_t)ft.d * 2 * ((size_t)nmax + 1);
-    *ent = (size_t)ft.d * 3 * FC;
+    *ent = (size_t)ft.d * 3 * FC;                           // the inverse rows take another ent ints per chunk
 }
 int chain_bucketed_ok(const DevFT &ft, int nmax) { return ft.d >= 2 && nmax <= CH_NMAX && ft_uses_mma(ft); }
 
 // plan of every chunk of a batch in one launch: a.F = fibers of the batch, FC = fibers per chunk; a.kst / tst / ent /
 // sets point at chunk 0's slices, consecutive chunks follow at the strides of chain_plan_sizes / FC * setw
-int launch_chain_plan(const ChainArgs &a, int FC, cudaStream_t st)
+int launch_chain_plan(const ChainArgs &a, int FC, int *cntg, cudaStream_t st)
 {
     if (a.F <= 0) return 0;
     size_t k, t, e;
     chain_plan_sizes(a.ft, a.nmax, (size_t)FC, &k, &t, &e);
-    ChainPlanStrides S = {(long long)k, (long long)t, (long long)e};
-    const size_t smem = (size_t)14 * a.nmax * sizeof(int);
-    k_chain_plan<<<dim3((unsigned)((a.F + FC - 1) / FC), (unsigned)a.ft.d), 1024, smem, st>>>(a, FC, S);
+    ChainPlanStrides S = {(long long)k, (long long)t, (long long)e, (long long)e, (long long)(a.ft.d - 1) * a.xrows};
+    const unsigned nch = (unsigned)((a.F + FC - 1) / FC);
+    cudaError_t err = cudaMemsetAsync(cntg, 0, (size_t)nch * k * sizeof(int), st);
+    if (err != cudaSuccess) return (int)err;
+    const int fc = a.F < FC ? a.F : FC;
+    const dim3 gs((unsigned)((fc + CHP_SLICE - 1) / CHP_SLICE), (unsigned)a.ft.d, nch);
+    k_chain_count<<<gs, CHP_NT, (size_t)6 * a.nmax * sizeof(int), st>>>(a, FC, S, cntg);
+    k_chain_scan<<<dim3(nch, (unsigned)a.ft.d), 1024, (size_t)8 * a.nmax * sizeof(int), st>>>(a, S, cntg);
+    k_chain_scatter<<<gs, CHP_NT, (size_t)12 * a.nmax * sizeof(int), st>>>(a, FC, S, cntg);
+    // ... and where every row's product goes in the next dimension's bucket order (needs the inverse rows of ALL dimensions;
+    // every bucket of a dimension is a few hundred rows: one CTA per 8 buckets)
+    unsigned gz = (unsigned)((2 * a.nmax + 7) / 8);
+    k_chain_link<<<dim3(nch, (unsigned)a.ft.d, gz), 256, 0, st>>>(a, S);
     return (int)cudaGetLastError();
 }
+constexpr int CHAIN_PLAN_LAUNCHES = 4;
 
 // the d-1 steps of one chunk (a.F = fibers of the chunk, pointers at the chunk's slices); returns the launches via *n
 int launch_chain_steps(const ChainArgs &a, cudaStream_t st, int *n)

@@ -22,8 +22,21 @@ static int launch_chain_steps_t(const ChainArgs &a, cudaStream_t st)
     // holds an SM's registers the other lane's node kernel cannot use that SM
     int grid = ft_sm_count() * 2;
     { const char *e = getenv("C3SC_CHAIN_GRID"); if (e && atoi(e) > 0) grid = atoi(e); }
+    size_t most = 0;
     for (int t = 0; t + 1 < a.ft.d; t++) {
-        const size_t smem = (size_t)(4 * (a.P.ngrid[t] + a.P.ngrid[a.ft.d - 1 - t]) + 4) * sizeof(int);
+        const size_t sm = chain_step_smem(a.rs);
+        most = sm > most ? sm : most;
+    }
+    if (most > (size_t)ft_max_optin_smem()) return (int)cudaErrorInvalidValue;
+    static size_t sattr_dev[C3SC_MAXDEV] = {0};
+    size_t &sattr = sattr_dev[c3sc_cur_dev()];
+    if (most > 48 * 1024 && most > sattr) {
+        cudaError_t e = cudaFuncSetAttribute(k_chain_step<KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)most);
+        if (e != cudaSuccess) return (int)e;
+        sattr = most;
+    }
+    for (int t = 0; t + 1 < a.ft.d; t++) {
+        const size_t smem = chain_step_smem(a.rs);
         // steps t >= 1 overlap their launch and table prologue with the tail of step t-1 (programmatic dependent
         // launch; the kernel waits with griddepcontrol.wait before it touches the records)
         cudaLaunchConfig_t cfg = {};
