@@ -166,16 +166,12 @@ struct Scratch {
     bool ring_ready = false;
     LaneScratch lane[MAXLANES];
     cudaEvent_t fork = nullptr;
-    // the chain plan of super-chunk i (k_chain_plan + k_chain_link: few CTAs, latency-bound) runs on a stream of its own, so only
-    // the first one is exposed; the lanes wait for the plan of the super-chunk they are about to step
-    cudaStream_t plan_stream = nullptr;
-    std::vector<cudaEvent_t> plan_done;
+    cudaEvent_t start = nullptr, grouped = nullptr;     // the grouping kernel on the second lane, next to the chain plan
     void release()
     {
-        if (plan_stream) cudaStreamDestroy(plan_stream);
-        plan_stream = nullptr;
-        for (cudaEvent_t e : plan_done) cudaEventDestroy(e);
-        plan_done.clear();
+        if (start) cudaEventDestroy(start);
+        if (grouped) cudaEventDestroy(grouped);
+        start = grouped = nullptr;
         perm.release(); cnt.release(); plan_k.release(); plan_t.release(); plan_e.release(); plan_l.release(); plan_i.release(); plan_c.release(); ring.release(); ring_flag.release();
         ring_ready = false;
         for (LaneScratch &l : lane) l.release();
@@ -690,7 +686,7 @@ struct BatchArgs {
 static thread_local size_t g_chunk_bytes = (size_t)192 << 20;   // slot-major cost scratch in flight (all lanes) when stage 1a runs per fiber
 static thread_local size_t g_chunk_bytes_b = (size_t)192 << 20; // ... when it runs bucketed (measured: smaller, L2-resident scratch chunks lose more to launch
                                                     // granularity than they gain, gpurun_out/r02_tune*.log -> profiles/r02_tuning.md)
-static thread_local size_t g_chain_fibers = 16384;               // fibers per chain super-chunk (bucketed stage 1a): 63 MB of records, about half the L2
+static thread_local size_t g_chain_fibers = 32768;               // fibers per chain super-chunk (bucketed stage 1a): 126 MB of records (16384: +1.3 % time)
 static thread_local size_t g_chain_min = 4096;                   // smaller batches keep the per-fiber chain kernel
 static thread_local int g_lanes = -1;                            // 2 = alternate (super-)chunks between two streams (default), 1 = one stream
 
@@ -704,7 +700,7 @@ static void read_tuning()
     g_chunk_bytes = (size_t)192 << 20; g_chunk_bytes_b = (size_t)192 << 20;
     if (m && atoi(m) > 0) { g_chunk_bytes = (size_t)atoi(m) << 20; g_chunk_bytes_b = g_chunk_bytes; }
     const char *cf = getenv("C3SC_CHAIN_FIBERS");
-    g_chain_fibers = (cf && atoi(cf) > 0) ? (size_t)atoi(cf) : 16384;
+    g_chain_fibers = (cf && atoi(cf) > 0) ? (size_t)atoi(cf) : 32768;
     const char *cm = getenv("C3SC_CHAIN_MIN");
     g_chain_min = (cm && atoi(cm) >= 0) ? (size_t)atoi(cm) : 4096;
 }
@@ -773,17 +769,10 @@ static int run_batch(const DevProblem &P, int model, int arith, Scratch &scr, co
         }
         ln.sets_busy = false;
     }
-    // (measured: the plans of four super-chunks in a row on a side stream take longer than the lanes can wait, 1.40 against 1.28 ms of
-    // stage 1 per 65 536 fibers; opt-in C3SC_PLAN_ASIDE=1)
-    const bool plan_aside = bucketed && nsup > 1 && getenv("C3SC_PLAN_ASIDE");
-    if ((L > 1 || plan_aside) && !scr.fork) CK(cudaEventCreateWithFlags(&scr.fork, cudaEventDisableTiming));
-    if (plan_aside) {
-        if (!scr.plan_stream) CK(cudaStreamCreateWithFlags(&scr.plan_stream, cudaStreamNonBlocking));
-        while (scr.plan_done.size() < nsup) {
-            cudaEvent_t e;
-            CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-            scr.plan_done.push_back(e);
-        }
+    if (L > 1 && !scr.fork) {
+        CK(cudaEventCreateWithFlags(&scr.fork, cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&scr.start, cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&scr.grouped, cudaEventDisableTiming));
     }
     auto chain_args = [&](size_t si, size_t s0, size_t Fs) {    // the chain stage's view of super-chunk si = fibers [s0, s0 + Fs)
         ChainArgs ca;
@@ -798,32 +787,33 @@ static int run_batch(const DevProblem &P, int model, int arith, Scratch &scr, co
         ca.nmax = P.nmax; ca.entstride = (int)(3 * FS);
         return ca;
     };
-    {   // every chunk's grouping in one launch; the chain plans: one launch pair for all super-chunks, or one per super-chunk aside
-        int rc = launch_group_fibers(P, (int)b.F, (int)FC, b.dim_vary, b.fixed_ind, (int *)scr.perm.p, (int *)scr.cnt.p, st);
+    {   // every chunk's grouping in one launch, every super-chunk's chain plan in four more.  Both read the descriptors only:
+        // with a second lane the grouping runs there, next to the plan (19 of the 123 us before the first chain step can start).
+        // (Tried and measured slower: the plan of a super-chunk queued on its own lane right before its chain steps, 1.30 against
+        // 1.26 ms of stage 1 per 65 536 fibers, and all plans in a row on a third stream, 1.40 ms.)
+        const bool aside = L > 1 && bucketed;
+        cudaStream_t gst = st;
+        if (aside) {
+            gst = scr.lane[1].stream;
+            CK(cudaEventRecord(scr.start, st));
+            CK(cudaStreamWaitEvent(gst, scr.start, 0));
+        }
+        int rc = launch_group_fibers(P, (int)b.F, (int)FC, b.dim_vary, b.fixed_ind, (int *)scr.perm.p, (int *)scr.cnt.p, gst);
         if (rc) return fail(C3SC_ECUDA, "grouping kernel: %s", cudaGetErrorString((cudaError_t)rc));
         g_launches++;
-        if (bucketed && !plan_aside) {
+        if (aside) CK(cudaEventRecord(scr.grouped, gst));
+        if (bucketed) {
             ChainArgs ca = chain_args(0, 0, b.F);
             rc = launch_chain_plan(ca, (int)FS, (int *)scr.plan_c.p, st);
             if (rc) return fail(C3SC_ECUDA, "chain plan kernel: %s", cudaGetErrorString((cudaError_t)rc));
             g_launches += 4;
         }
+        if (aside) CK(cudaStreamWaitEvent(st, scr.grouped, 0));
     }
-    if (L > 1 || plan_aside) {                              // the other lanes start after everything queued on st so far
+    if (L > 1) {                                            // the other lanes start after everything queued on st so far
         CK(cudaEventRecord(scr.fork, st));
         for (size_t l = 1; l < L; l++) CK(cudaStreamWaitEvent(scr.lane[l].stream, scr.fork, 0));
         if (chain_prio) for (size_t l = 0; l < L; l++) CK(cudaStreamWaitEvent(scr.lane[l].chain_stream, scr.fork, 0));
-    }
-    if (plan_aside) {                                       // (the plan reads the descriptors only: nothing of the batch before it)
-        CK(cudaStreamWaitEvent(scr.plan_stream, scr.fork, 0));
-        for (size_t s0 = 0, si = 0; s0 < b.F; s0 += FS, si++) {
-            const size_t Fs = (b.F - s0 < FS) ? b.F - s0 : FS;
-            ChainArgs ca = chain_args(si, s0, Fs);
-            int rc = launch_chain_plan(ca, (int)FS, (int *)scr.plan_c.p + si * pk, scr.plan_stream);
-            if (rc) return fail(C3SC_ECUDA, "chain plan kernel: %s", cudaGetErrorString((cudaError_t)rc));
-            g_launches += 4;
-            CK(cudaEventRecord(scr.plan_done[si], scr.plan_stream));
-        }
     }
     const cudaStream_t st0 = st;
     for (size_t s0 = 0, si = 0; s0 < b.F; s0 += FS, si++) {
@@ -836,7 +826,6 @@ static int run_batch(const DevProblem &P, int model, int arith, Scratch &scr, co
             ca.x[0] = (double *)ln.xa.p; ca.x[1] = (double *)ln.xb.p;
             int nl = 0;
             cudaStream_t cst_ = st;
-            if (plan_aside) CK(cudaStreamWaitEvent(chain_prio ? ln.chain_stream : st, scr.plan_done[si], 0));
             if (chain_prio) {                               // records of this lane are free once its previous super-chunk's nodes are done
                 cst_ = ln.chain_stream;
                 if (ln.sets_busy) CK(cudaStreamWaitEvent(cst_, ln.sets_free, 0));

@@ -284,22 +284,28 @@ __global__ void __launch_bounds__(256) k_chain_link(ChainArgs a, ChainPlanStride
         const int next = (side && t + 1 <= d - 2) ? 8 * tst0[((size_t)(t + 1) * 2 + 0) * (nmax + 1) + a.P.ngrid[t + 1]] : 0;
         int4 *out = rowd + (size_t)t * a.xrows + here + 8LL * t0;
         const int mn = side ? m - 1 : m + 1;
-        for (int r = threadIdx.x; r < 8 * (t1 - t0); r += blockDim.x) {
-            int4 D = make_int4(CH_ROW_PAD, -1, -1, side * 65536 + j);
-            if (r < rows) {
-                int e, v;
-                if (r < nc) { const int q = r / nin; e = csc + q; v = r - q * nin; }
-                else { e = cslo + (r - nc); v = e < cshi ? nin : nin + 1; }
-                const int tag = ent[e], f = tag & 0xffffff, k = tag >> 24;
-                const bool cont = side ? mn > k : mn < k;
-                if (cont) {
-                    const int *iv = inv + ((size_t)mn * a.invstride + f) * 3;
-                    D.x = next + iv[0] + v;
-                    if (r < nc && v == 0) { D.y = next + iv[1]; D.z = next + iv[2]; }
-                } else D.x = ~(f * recrows + (side ? 1 + 2 * k : 0) + v);
+        const int bw = side * 65536 + j;
+        // one thread per ENTRY (tag and inverse rows are loaded once, a centre entry writes its nin rows), then the padding
+        for (int i = threadIdx.x; i < csend - csc; i += blockDim.x) {
+            const int e = csc + i;
+            const int tag = ent[e], f = tag & 0xffffff, k = tag >> 24;
+            const bool cont = side ? mn > k : mn < k;
+            int i0 = 0, i1 = -1, i2 = -1;
+            if (cont) {
+                const int *iv = inv + ((size_t)mn * a.invstride + f) * 3;
+                i0 = next + iv[0];
+                if (e < cslo) { i1 = next + iv[1]; i2 = next + iv[2]; }
+            } else i0 = ~(f * recrows + (side ? 1 + 2 * k : 0));
+            if (e < cslo) {                                 // centre: rows i*nin + v, products keep their vector index
+                int4 *o = out + (size_t)i * nin;
+                o[0] = make_int4(i0, i1, i2, bw);
+                for (int v = 1; v < nin; v++) o[v] = make_int4(cont ? i0 + v : i0 - v, -1, -1, bw);
+            } else {                                        // neighbour: the new vector nin (lower) or nin + 1 (upper)
+                const int v = e < cshi ? nin : nin + 1;
+                out[nc + (e - cslo)] = make_int4(cont ? i0 + v : i0 - v, -1, -1, bw);
             }
-            out[r] = D;
         }
+        for (int r = rows + threadIdx.x; r < 8 * (t1 - t0); r += blockDim.x) out[r] = make_int4(CH_ROW_PAD, -1, -1, bw);
     }
 }
 #endif
