@@ -684,7 +684,7 @@ struct BatchArgs {
 };
 
 static thread_local size_t g_chunk_bytes = (size_t)192 << 20;   // slot-major cost scratch in flight (all lanes) when stage 1a runs per fiber
-static thread_local size_t g_chunk_bytes_b = (size_t)192 << 20; // ... when it runs bucketed (measured: smaller, L2-resident scratch chunks lose more to launch
+static thread_local size_t g_chunk_bytes_b = (size_t)384 << 20; // ... when it runs bucketed (measured: smaller, L2-resident scratch chunks lose more to launch
                                                     // granularity than they gain, gpurun_out/r02_tune*.log -> profiles/r02_tuning.md)
 static thread_local size_t g_chain_fibers = 32768;               // fibers per chain super-chunk (bucketed stage 1a): 126 MB of records (16384: +1.3 % time)
 static thread_local size_t g_chain_min = 4096;                   // smaller batches keep the per-fiber chain kernel
@@ -697,7 +697,7 @@ static void read_tuning()
     if (g_lanes < 1) g_lanes = 1;
     if (g_lanes > MAXLANES) g_lanes = MAXLANES;
     const char *m = getenv("C3SC_CHUNK_MB");                          // tuning aids: cost scratch of all lanes together
-    g_chunk_bytes = (size_t)192 << 20; g_chunk_bytes_b = (size_t)192 << 20;
+    g_chunk_bytes = (size_t)192 << 20; g_chunk_bytes_b = (size_t)384 << 20;
     if (m && atoi(m) > 0) { g_chunk_bytes = (size_t)atoi(m) << 20; g_chunk_bytes_b = g_chunk_bytes; }
     const char *cf = getenv("C3SC_CHAIN_FIBERS");
     g_chain_fibers = (cf && atoi(cf) > 0) ? (size_t)atoi(cf) : 32768;
@@ -782,7 +782,8 @@ static int run_batch(const DevProblem &P, int model, int arith, Scratch &scr, co
         ca.setw = setw; ca.rs = rs;
         ca.kst = (int *)scr.plan_k.p + si * pk; ca.tst = (int *)scr.plan_t.p + si * pt; ca.ent = (int *)scr.plan_e.p + si * pe;
         ca.xrows = chain_x_rows((int)d, P.nmax, (long long)FS);
-        ca.rowd = (int4 *)scr.plan_l.p + si * (d - 1) * (size_t)ca.xrows;
+        ca.rowd = (int2 *)scr.plan_l.p + si * (d - 1) * (size_t)ca.xrows;
+        ca.rowp = (int2 *)scr.plan_l.p + (nsup + si) * (d - 1) * (size_t)ca.xrows;
         ca.inv = (int *)scr.plan_i.p + si * pe; ca.invstride = (int)FS;
         ca.nmax = P.nmax; ca.entstride = (int)(3 * FS);
         return ca;

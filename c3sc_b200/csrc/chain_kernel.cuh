@@ -37,6 +37,7 @@
 namespace c3sc {
 
 constexpr int CH_NT = 256;            // step kernel: 8 warps
+constexpr int CH_PREFIX = 1 << 30;    // ChainArgs::rowd[].y: the row also goes to the two slots in rowp[]
 constexpr int CH_NMAX = 768;          // nodes per dimension the plan kernel's shared-memory histogram covers (14 ints each)
 
 __host__ __device__ inline int ft_rec_rs(int rmax) { return (rmax + 3) & ~3; }                // row stride of a record
@@ -58,10 +59,11 @@ struct ChainArgs {
     int nmax, entstride;      // entstride = 3 * (fibers of a full chunk)
     int *inv;                 // [d][invstride][3]   row of the fiber's centre block / lower slot / upper slot in dimension m's
                               //                     bucket order, relative to its side's first row
-    int4 *rowd;               // [d-1][xrows]        per row of launch t's buffer: x = where the product goes (>= 0: row of launch
+    int2 *rowd;               // [d-1][xrows]        per row of launch t's buffer: x = where the product goes (>= 0: row of launch
                               //                     t+1's buffer; < 0: ~(row of the chunk's records, in units of RS doubles);
-                              //                     INT_MIN: padding row), y / z = the two neighbour slots of launch t+1 that also
-                              //                     take it (a prefix; else -1), w = side * 65536 + block of the row's bucket
+                              //                     INT_MIN: padding row), y = side * 65536 + block of the row's bucket, + CH_PREFIX
+                              //                     when the row is a prefix that two neighbour slots of launch t+1 take as well
+    int2 *rowp;               // [d-1][xrows]        those two slots (rows of launch t+1's buffer), prefix rows only
     int invstride;            // fibers of a full chunk
     double *x[2];             // row buffers of the launches, X[t & 1] read by launch t; xrows rows of RS doubles each
     long long xrows;
@@ -268,7 +270,7 @@ __global__ void __launch_bounds__(256) k_chain_link(ChainArgs a, ChainPlanStride
     const int *tst0 = a.tst + blockIdx.x * S.tst;
     const int *ent = a.ent + blockIdx.x * S.ent + (size_t)m * a.entstride;
     const int *inv = a.inv + blockIdx.x * S.inv;
-    int4 *rowd = a.rowd + blockIdx.x * S.rowd;
+    int2 *rowd = a.rowd + blockIdx.x * S.rowd, *rowp = a.rowp + blockIdx.x * S.rowd;
     const int recrows = a.setw / a.rs;
     for (int b = blockIdx.z; b < 2 * N; b += gridDim.z) {
         const int side = b / N, j = b - side * N;
@@ -282,7 +284,7 @@ __global__ void __launch_bounds__(256) k_chain_link(ChainArgs a, ChainPlanStride
         // rows of the right side lie behind the left side's tiles, in this launch's buffer and in the next one's
         const long long here = side ? 8LL * tst0[((size_t)t * 2 + 0) * (nmax + 1) + a.P.ngrid[t]] : 0;
         const int next = (side && t + 1 <= d - 2) ? 8 * tst0[((size_t)(t + 1) * 2 + 0) * (nmax + 1) + a.P.ngrid[t + 1]] : 0;
-        int4 *out = rowd + (size_t)t * a.xrows + here + 8LL * t0;
+        int2 *out = rowd + (size_t)t * a.xrows + here + 8LL * t0, *outp = rowp + (size_t)t * a.xrows + here + 8LL * t0;
         const int mn = side ? m - 1 : m + 1;
         const int bw = side * 65536 + j;
         // one thread per ENTRY (tag and inverse rows are loaded once, a centre entry writes its nin rows), then the padding
@@ -297,15 +299,16 @@ __global__ void __launch_bounds__(256) k_chain_link(ChainArgs a, ChainPlanStride
                 if (e < cslo) { i1 = next + iv[1]; i2 = next + iv[2]; }
             } else i0 = ~(f * recrows + (side ? 1 + 2 * k : 0));
             if (e < cslo) {                                 // centre: rows i*nin + v, products keep their vector index
-                int4 *o = out + (size_t)i * nin;
-                o[0] = make_int4(i0, i1, i2, bw);
-                for (int v = 1; v < nin; v++) o[v] = make_int4(cont ? i0 + v : i0 - v, -1, -1, bw);
+                int2 *o = out + (size_t)i * nin;
+                o[0] = make_int2(i0, cont ? bw | CH_PREFIX : bw);
+                if (cont) outp[(size_t)i * nin] = make_int2(i1, i2);
+                for (int v = 1; v < nin; v++) o[v] = make_int2(cont ? i0 + v : i0 - v, bw);
             } else {                                        // neighbour: the new vector nin (lower) or nin + 1 (upper)
                 const int v = e < cshi ? nin : nin + 1;
-                out[nc + (e - cslo)] = make_int4(cont ? i0 + v : i0 - v, -1, -1, bw);
+                out[nc + (e - cslo)] = make_int2(cont ? i0 + v : i0 - v, bw);
             }
         }
-        for (int r = rows + threadIdx.x; r < 8 * (t1 - t0); r += blockDim.x) out[r] = make_int4(CH_ROW_PAD, -1, -1, bw);
+        for (int r = rows + threadIdx.x; r < 8 * (t1 - t0); r += blockDim.x) out[r] = make_int2(CH_ROW_PAD, bw);
     }
 }
 #endif
@@ -400,7 +403,7 @@ __global__ void __launch_bounds__(CH_NT, 2) k_chain_step(const ChainArgs a, int 
     if (tile >= tend) return;
     const double *xin = a.x[t & 1];
     double *xout = a.x[(t + 1) & 1];
-    const int4 *rowd = a.rowd + (size_t)t * a.xrows + gid;
+    const int2 *rowd = a.rowd + (size_t)t * a.xrows + gid, *rowp = a.rowp + (size_t)t * a.xrows + gid;
     const unsigned tbytes = (unsigned)(TB * sizeof(double));
 
     // ring fill: the first CH_SLOTS tiles of this warp's range
@@ -411,13 +414,16 @@ __global__ void __launch_bounds__(CH_NT, 2) k_chain_step(const ChainArgs a, int 
     }
     double B[KS][NT8];
     int Bsj = -1;
-    int4 D0 = __ldg(rowd + (size_t)tile * 8);
+    int2 D0 = __ldg(rowd + (size_t)tile * 8);
     unsigned phase = 0;                                     // bit q: parity of slot q's next completion
     for (int it = 0; tile < tend; tile++, it++) {
-        int4 D1 = D0;
+        int2 D1 = D0;
         if (tile + 1 < tend) D1 = __ldg(rowd + (size_t)(tile + 1) * 8);
-        if (D0.w != Bsj) {                                  // (the bucket is the same for the eight rows of a tile)
-            Bsj = D0.w;
+        const int sj0 = D0.y & (CH_PREFIX - 1);
+        int2 P0 = make_int2(-1, -1);                        // a prefix row's two extra destinations: needed by its stores only
+        if (D0.y & CH_PREFIX) P0 = __ldg(rowp + (size_t)tile * 8);
+        if (sj0 != Bsj) {                                   // (the bucket is the same for the eight rows of a tile)
+            Bsj = sj0;
             const int side = Bsj >> 16, j = Bsj & 0xffff, m = side ? mR : mL;
             const int rin = side ? ft.r[m + 1] : ft.r[m], rout = side ? ft.r[m] : ft.r[m + 1];
             // B fragments (row q = 4ks+tig of the contraction, column o = 8nt+gid of the output) of block G_m[j]
@@ -461,8 +467,8 @@ __global__ void __launch_bounds__(CH_NT, 2) k_chain_step(const ChainArgs a, int 
 #pragma unroll
             for (int nt = 0; nt < NT8; nt++)
                 if (8 * nt + 2 * tig < RS) *reinterpret_cast<double2 *>(dst + 8 * nt) = make_double2(acc[nt][0], acc[nt][1]);
-            if (D0.y >= 0) {
-                double *dlo = xout + (size_t)D0.y * RS + 2 * tig, *dhi = xout + (size_t)D0.z * RS + 2 * tig;
+            if (D0.y & CH_PREFIX) {
+                double *dlo = xout + (size_t)P0.x * RS + 2 * tig, *dhi = xout + (size_t)P0.y * RS + 2 * tig;
 #pragma unroll
                 for (int nt = 0; nt < NT8; nt++)
                     if (8 * nt + 2 * tig < RS) {
