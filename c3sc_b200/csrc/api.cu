@@ -724,7 +724,10 @@ static int run_batch(const DevProblem &P, int model, int arith, Scratch &scr, co
     // chain steps of the lane's next super-chunk on a high-priority stream of their own: measured no gain (1.952 vs 1.939 ms per
     // 65 536-fiber step, profiles/r02_cross_step.md: the steps are L2-bandwidth work, not idle latency), so opt-in: C3SC_CHAIN_PRIO=1
     const bool chain_prio = bucketed && multi && getenv("C3SC_CHAIN_PRIO") && atoi(getenv("C3SC_CHAIN_PRIO")) == 1;
-    size_t per_chunk = (bucketed ? g_chunk_bytes_b : g_chunk_bytes) / (size_t)g_lanes / (b.ldo * CS * 8);
+    // host-buffer entries copy a chunk's results out while the next chunk computes; the last chunk's copy of each lane is exposed,
+    // so their chunks stay at the smaller size (e2e 2.58 against 2.78 G node-backups/s with the larger one)
+    const bool host_out = b.copy_stream && (b.h_value || b.h_argmin);
+    size_t per_chunk = ((bucketed && !host_out) ? g_chunk_bytes_b : g_chunk_bytes) / (size_t)g_lanes / (b.ldo * CS * 8);
     if (!multi) per_chunk *= (size_t)g_lanes;
     { const char *pf = getenv("C3SC_CHUNK_FIBERS"); if (pf && atoi(pf) > 0) per_chunk = (size_t)atoi(pf); }    // tests: exact chunk size
     if (per_chunk < 1) per_chunk = 1;

@@ -261,6 +261,7 @@ __global__ void __launch_bounds__(CHP_NT) k_chain_scatter(ChainArgs a, int FC, C
 // (m+1 left, m-1 right; k_chain_plan's inverse rows), or the fiber's record when the side ends here.
 #ifndef C3SC_FT_KS_UNIT
 constexpr int CH_ROW_PAD = (int)0x80000000;
+constexpr int CH_LINK_E = 1024;       // centre entries of a bucket staged per round
 __global__ void __launch_bounds__(256) k_chain_link(ChainArgs a, ChainPlanStrides S)
 {
     const int d = a.ft.d, m = blockIdx.y, nmax = a.nmax;
@@ -272,6 +273,8 @@ __global__ void __launch_bounds__(256) k_chain_link(ChainArgs a, ChainPlanStride
     const int *inv = a.inv + blockIdx.x * S.inv;
     int2 *rowd = a.rowd + blockIdx.x * S.rowd, *rowp = a.rowp + blockIdx.x * S.rowd;
     const int recrows = a.setw / a.rs;
+    __shared__ int s_i0[CH_LINK_E];
+    __shared__ bool s_ct[CH_LINK_E];
     for (int b = blockIdx.z; b < 2 * N; b += gridDim.z) {
         const int side = b / N, j = b - side * N;
         const int t = side ? d - 1 - m : m;                 // the launch that works on this side of dimension m
@@ -287,26 +290,40 @@ __global__ void __launch_bounds__(256) k_chain_link(ChainArgs a, ChainPlanStride
         int2 *out = rowd + (size_t)t * a.xrows + here + 8LL * t0, *outp = rowp + (size_t)t * a.xrows + here + 8LL * t0;
         const int mn = side ? m - 1 : m + 1;
         const int bw = side * 65536 + j;
-        // one thread per ENTRY (tag and inverse rows are loaded once, a centre entry writes its nin rows), then the padding
-        for (int i = threadIdx.x; i < csend - csc; i += blockDim.x) {
-            const int e = csc + i;
+        // where an entry's fiber goes next: loaded once per ENTRY (tag, then the inverse rows of the next dimension)
+        auto entry = [&](int e, bool centre, int &i0, bool &cont) {
             const int tag = ent[e], f = tag & 0xffffff, k = tag >> 24;
-            const bool cont = side ? mn > k : mn < k;
-            int i0 = 0, i1 = -1, i2 = -1;
+            cont = side ? mn > k : mn < k;
             if (cont) {
                 const int *iv = inv + ((size_t)mn * a.invstride + f) * 3;
                 i0 = next + iv[0];
-                if (e < cslo) { i1 = next + iv[1]; i2 = next + iv[2]; }
+                if (centre) outp[(size_t)(e - csc) * nin] = make_int2(next + iv[1], next + iv[2]);      // the prefix's two extra slots
             } else i0 = ~(f * recrows + (side ? 1 + 2 * k : 0));
-            if (e < cslo) {                                 // centre: rows i*nin + v, products keep their vector index
-                int2 *o = out + (size_t)i * nin;
-                o[0] = make_int2(i0, cont ? bw | CH_PREFIX : bw);
-                if (cont) outp[(size_t)i * nin] = make_int2(i1, i2);
-                for (int v = 1; v < nin; v++) o[v] = make_int2(cont ? i0 + v : i0 - v, bw);
-            } else {                                        // neighbour: the new vector nin (lower) or nin + 1 (upper)
-                const int v = e < cshi ? nin : nin + 1;
-                out[nc + (e - cslo)] = make_int2(cont ? i0 + v : i0 - v, bw);
+        };
+        // centre entries, CH_LINK_E at a time: per entry into shared memory, then the entries' nin rows each with consecutive
+        // threads on consecutive rows (products keep their vector index v: row i0 + v of the next buffer, i0 - v of a record)
+        for (int eb = 0; eb < cslo - csc; eb += CH_LINK_E) {
+            const int n = (cslo - csc - eb < CH_LINK_E) ? cslo - csc - eb : CH_LINK_E;
+            __syncthreads();
+            for (int i = threadIdx.x; i < n; i += blockDim.x) {
+                int i0; bool cont;
+                entry(csc + eb + i, true, i0, cont);
+                s_i0[i] = i0; s_ct[i] = cont;
             }
+            __syncthreads();
+            int2 *o = out + (size_t)eb * nin;
+            for (int r = threadIdx.x; r < n * nin; r += blockDim.x) {
+                const int q = r / nin, v = r - q * nin;
+                const bool cont = s_ct[q];
+                o[r] = make_int2(cont ? s_i0[q] + v : s_i0[q] - v, (cont && v == 0) ? bw | CH_PREFIX : bw);
+            }
+        }
+        // neighbour entries: one row each, the new vector nin (lower) or nin + 1 (upper)
+        for (int i = threadIdx.x; i < csend - cslo; i += blockDim.x) {
+            int i0; bool cont;
+            entry(cslo + i, false, i0, cont);
+            const int v = cslo + i < cshi ? nin : nin + 1;
+            out[nc + i] = make_int2(cont ? i0 + v : i0 - v, bw);
         }
         for (int r = rows + threadIdx.x; r < 8 * (t1 - t0); r += blockDim.x) out[r] = make_int2(CH_ROW_PAD, bw);
     }

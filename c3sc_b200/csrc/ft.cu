@@ -131,8 +131,8 @@ int launch_chain_plan(const ChainArgs &a, int FC, int *cntg, cudaStream_t st)
     k_chain_scan<<<dim3(nch, (unsigned)a.ft.d), 1024, (size_t)8 * a.nmax * sizeof(int), st>>>(a, S, cntg);
     k_chain_scatter<<<gs, CHP_NT, (size_t)12 * a.nmax * sizeof(int), st>>>(a, FC, S, cntg);
     // ... and where every row's product goes in the next dimension's bucket order (needs the inverse rows of ALL dimensions;
-    // every bucket of a dimension is a few hundred rows: one CTA per 8 buckets)
-    unsigned gz = (unsigned)((2 * a.nmax + 7) / 8);
+    // every bucket of a dimension is a few hundred rows)
+    unsigned gz = (unsigned)(2 * a.nmax);                   // one CTA per bucket: a bucket is a chain of dependent loads
     k_chain_link<<<dim3(nch, (unsigned)a.ft.d, gz), 256, 0, st>>>(a, S);
     return (int)cudaGetLastError();
 }
