@@ -71,6 +71,7 @@ EXPORTS = [
     "c3sc_multi_valuef_create", "c3sc_multi_valuef_update", "c3sc_multi_valuef_destroy", "c3sc_multi_valuef_get", "c3sc_multi_shard",
     "c3sc_multi_vi_batch", "c3sc_multi_pi_batch", "c3sc_multi_pi_reset", "c3sc_multi_gathered_count", "c3sc_multi_vi_batch_gathered",
     "c3sc_cross_run_vi_multi", "c3sc_cross_run_pi_multi", "c3sc_host_alloc", "c3sc_host_free", "c3sc_vi_batch_peers", "c3sc_guard_check",
+    "c3sc_cross_dim", "c3sc_cross_uses_memo", "c3sc_fiber_memo_create", "c3sc_fiber_memo_call", "c3sc_fiber_memo_stats", "c3sc_fiber_memo_clear", "c3sc_fiber_memo_destroy",
 ]
 
 _lib = None
@@ -153,6 +154,16 @@ def lib() -> C.CDLL:
         L.c3sc_cross_copy.argtypes = [vp, C.POINTER(vp)]
         L.c3sc_cross_destroy.restype = None
         L.c3sc_cross_ranks.argtypes = [vp, c_u64p]
+        L.c3sc_cross_dim.argtypes = [vp]
+        L.c3sc_cross_dim.restype = C.c_uint32
+        L.c3sc_fiber_memo_create.argtypes = [C.c_uint32, FIBER_FN, vp, C.POINTER(vp)]
+        L.c3sc_fiber_memo_call.argtypes = [C.c_size_t, c_i32p, c_i32p, C.c_size_t, c_f64p, vp]
+        L.c3sc_fiber_memo_stats.argtypes = [vp, c_u64p, c_u64p]
+        L.c3sc_fiber_memo_stats.restype = None
+        L.c3sc_fiber_memo_clear.argtypes = [vp]
+        L.c3sc_fiber_memo_clear.restype = None
+        L.c3sc_fiber_memo_destroy.argtypes = [vp]
+        L.c3sc_fiber_memo_destroy.restype = None
         L.c3sc_cross_run.argtypes = [vp, FIBER_FN, vp, C.POINTER(CrossOpts), C.POINTER(c_f64p), c_u64p, c_f64p]
         L.c3sc_cross_run_vi.argtypes = [vp, vp, vp, C.POINTER(CrossOpts), C.POINTER(c_f64p), c_u64p, c_f64p]
         L.c3sc_cross_run_pi.argtypes = [vp, vp, vp, vp, C.c_uint32, C.POINTER(CrossOpts), C.POINTER(c_f64p), c_u64p, c_f64p]
@@ -473,8 +484,9 @@ class Cross:
                                   C.byref(it), C.byref(diff), C.byref(nf)))
         return cores, int(it.value), float(diff.value), int(nf.value)
 
-    def run(self, fn, maxiter=5, tol=0.0, verbose=0):
-        """same driver, operator = Python callable fn(dim_vary[F], fixed_ind[F,d]) -> values[F, nmax]"""
+    def run(self, fn, maxiter=5, tol=0.0, verbose=0, memo=False):
+        """same driver, operator = Python callable fn(dim_vary[F], fixed_ind[F,d]) -> values[F, nmax];
+        memo: behind a c3sc_fiber_memo (every distinct fiber reaches fn once); returns its (requested, computed) as self.memo_stats"""
         nmax = int(self.n.max())
         d = self.d
 
@@ -489,7 +501,19 @@ class Cross:
         cores, arr = self._cores()
         o = CrossOpts(maxiter, tol, verbose)
         nf = C.c_uint64(); ch = C.c_double()
-        check(lib().c3sc_cross_run(self.handle, cb, None, C.byref(o), arr, C.byref(nf), C.byref(ch)))
+        if memo:
+            mh = C.c_void_p()
+            check(lib().c3sc_fiber_memo_create(d, cb, None, C.byref(mh)))
+            try:
+                fptr = C.cast(lib().c3sc_fiber_memo_call, FIBER_FN)
+                check(lib().c3sc_cross_run(self.handle, fptr, mh, C.byref(o), arr, C.byref(nf), C.byref(ch)))
+                rq = C.c_uint64(); cp = C.c_uint64()
+                lib().c3sc_fiber_memo_stats(mh, C.byref(rq), C.byref(cp))
+                self.memo_stats = (int(rq.value), int(cp.value))
+            finally:
+                lib().c3sc_fiber_memo_destroy(mh)
+        else:
+            check(lib().c3sc_cross_run(self.handle, cb, None, C.byref(o), arr, C.byref(nf), C.byref(ch)))
         assert nmax >= 1
         return cores, int(nf.value), float(ch.value)
 

@@ -1553,6 +1553,164 @@ done:
     return rc;
 }
 
+uint32_t c3sc_cross_dim(const c3sc_cross *c) { return c ? c->d : 0; }
+
+/* ---- fiber memo (include/c3sc_cross.h) ---------------------------------------------------------------- */
+struct c3sc_fiber_memo {
+    uint32_t d;
+    c3sc_fiber_batch_fn f;
+    void *arg;
+    size_t ldo;                    /* of the stored rows (fixed by the first call) */
+    /* open-addressing table of slots into the stores */
+    size_t cap, count;             /* cap = 0 or a power of two */
+    int64_t *slot;                 /* -1 = empty */
+    int32_t *keys;                 /* [count][d + 1]: dim_vary, fixed indices with the varying one zeroed */
+    double *vals;                  /* [count][ldo] */
+    size_t store_cap;
+    /* scratch of a call: the descriptors of the misses, compacted */
+    int32_t *mdv, *mfi;
+    int64_t *rslot;                /* per request: its slot */
+    size_t rcap;
+    uint64_t requested, computed;
+};
+
+static uint64_t memo_hash(const int32_t *key, uint32_t n)
+{
+    uint64_t h = 0x9e3779b97f4a7c15ull;
+    for (uint32_t i = 0; i < n; i++) { h ^= (uint64_t)(uint32_t)key[i]; h *= 0xff51afd7ed558ccdull; h ^= h >> 32; }
+    return h;
+}
+
+int c3sc_fiber_memo_create(uint32_t d, c3sc_fiber_batch_fn f, void *arg, c3sc_fiber_memo **out)
+{
+    if (!out || !f || d < 1) return C3SC_EINVAL;
+    c3sc_fiber_memo *m = (c3sc_fiber_memo *)calloc(1, sizeof *m);
+    if (!m) return C3SC_EINVAL;
+    m->d = d; m->f = f; m->arg = arg;
+    *out = m;
+    return C3SC_OK;
+}
+
+void c3sc_fiber_memo_clear(c3sc_fiber_memo *m)
+{
+    if (!m) return;
+    m->count = 0;
+    for (size_t i = 0; i < m->cap; i++) m->slot[i] = -1;
+}
+
+void c3sc_fiber_memo_destroy(c3sc_fiber_memo *m)
+{
+    if (!m) return;
+    free(m->slot); free(m->keys); free(m->vals); free(m->mdv); free(m->mfi); free(m->rslot);
+    free(m);
+}
+
+void c3sc_fiber_memo_stats(const c3sc_fiber_memo *m, uint64_t *requested, uint64_t *computed)
+{
+    if (requested) *requested = m ? m->requested : 0;
+    if (computed) *computed = m ? m->computed : 0;
+}
+
+static int memo_grow_table(c3sc_fiber_memo *m, size_t want)
+{
+    size_t cap = m->cap ? m->cap : 1024;
+    while (cap < 2 * want) cap *= 2;
+    if (cap == m->cap) return 0;
+    int64_t *s = (int64_t *)malloc(cap * sizeof *s);
+    if (!s) return 1;
+    for (size_t i = 0; i < cap; i++) s[i] = -1;
+    for (size_t e = 0; e < m->count; e++) {
+        size_t h = (size_t)memo_hash(m->keys + e * (m->d + 1), m->d + 1) & (cap - 1);
+        while (s[h] >= 0) h = (h + 1) & (cap - 1);
+        s[h] = (int64_t)e;
+    }
+    free(m->slot);
+    m->slot = s; m->cap = cap;
+    return 0;
+}
+
+static int memo_grow_store(c3sc_fiber_memo *m, size_t want)
+{
+    if (want <= m->store_cap) return 0;
+    size_t cap = m->store_cap ? m->store_cap : 1024;
+    while (cap < want) cap *= 2;
+    int32_t *k = (int32_t *)realloc(m->keys, cap * (m->d + 1) * sizeof *k);
+    if (!k) return 1;
+    m->keys = k;
+    double *v = (double *)realloc(m->vals, cap * m->ldo * sizeof *v);
+    if (!v) return 1;
+    m->vals = v; m->store_cap = cap;
+    return 0;
+}
+
+int c3sc_fiber_memo_call(size_t F, const int32_t *dim_vary, const int32_t *fixed_ind, size_t ldo, double *out, void *memo)
+{
+    c3sc_fiber_memo *m = (c3sc_fiber_memo *)memo;
+    if (!m || (F && (!dim_vary || !fixed_ind || !out))) return C3SC_EINVAL;
+    if (F == 0) return C3SC_OK;
+    const uint32_t d = m->d, kw = d + 1;
+    if (m->count == 0) m->ldo = ldo;
+    if (ldo != m->ldo) return C3SC_EINVAL;                     /* one row length per memo */
+    if (F > m->rcap) {
+        free(m->rslot); free(m->mdv); free(m->mfi);
+        m->rslot = (int64_t *)malloc(F * sizeof *m->rslot);
+        m->mdv = (int32_t *)malloc(F * sizeof *m->mdv);
+        m->mfi = (int32_t *)malloc(F * d * sizeof *m->mfi);
+        m->rcap = (m->rslot && m->mdv && m->mfi) ? F : 0;
+        if (!m->rcap) return C3SC_EINVAL;
+    }
+    if (memo_grow_table(m, m->count + F) || memo_grow_store(m, m->count + F)) return C3SC_EINVAL;
+    /* look every request up; a miss takes the next slot at once, so a repeat inside the batch finds it */
+    size_t nmiss = 0;
+    const size_t first_new = m->count;
+    int32_t key[C3SC_MAXD + 1];
+    for (size_t i = 0; i < F; i++) {
+        const int32_t k = dim_vary[i];
+        key[0] = k;
+        for (uint32_t q = 0; q < d; q++) key[1 + q] = ((int32_t)q == k) ? 0 : fixed_ind[i * d + q];
+        size_t h = (size_t)memo_hash(key, kw) & (m->cap - 1);
+        int64_t s;
+        while ((s = m->slot[h]) >= 0 && memcmp(m->keys + (size_t)s * kw, key, kw * sizeof(int32_t)) != 0) h = (h + 1) & (m->cap - 1);
+        if (s < 0) {
+            s = (int64_t)m->count++;
+            m->slot[h] = s;
+            memcpy(m->keys + (size_t)s * kw, key, kw * sizeof(int32_t));
+            m->mdv[nmiss] = k;
+            memcpy(m->mfi + nmiss * d, fixed_ind + i * d, d * sizeof(int32_t));
+            nmiss++;
+        }
+        m->rslot[i] = s;
+    }
+    m->requested += F;
+    m->computed += nmiss;
+    int rc = C3SC_OK;
+    if (nmiss == F) {
+        /* nothing known: the operator writes straight into the caller's buffer (the driver's page-locked one) */
+        rc = m->f(F, dim_vary, fixed_ind, ldo, out, m->arg);
+        if (rc == C3SC_OK) memcpy(m->vals + first_new * ldo, out, F * ldo * sizeof(double));
+    } else if (nmiss > 0) {
+        /* the misses, compacted, through the front of the caller's buffer (nmiss < F rows; the driver's buffer is page-locked,
+           a buffer of the memo's own would have to be page-locked per call, which costs more than a core batch) */
+        rc = m->f(nmiss, m->mdv, m->mfi, ldo, out, m->arg);
+        if (rc == C3SC_OK) memcpy(m->vals + first_new * ldo, out, nmiss * ldo * sizeof(double));
+    }
+    if (rc != C3SC_OK) {                                        /* forget what was not computed */
+        m->count = first_new;
+        for (size_t i = 0; i < m->cap; i++) if (m->slot[i] >= (int64_t)first_new) m->slot[i] = -1;
+        return rc;
+    }
+    if (nmiss < F)
+        for (size_t i = 0; i < F; i++) memcpy(out + i * ldo, m->vals + (size_t)m->rslot[i] * ldo, ldo * sizeof(double));
+    return C3SC_OK;
+}
+
+/* A memo copies every value it stores (out of page-locked memory the device has just written): about 0.1 ms per 400-fiber
+ * core batch, more than the batch costs on the GPU.  It pays when sweeps repeat fibers, i.e. from the second sweep pair on
+ * (index sets that have settled ask for the same fibers again); a single sweep pair goes without.  c3sc_cross_uses_memo is
+ * the rule, for callers that wrap their own operators. */
+int c3sc_cross_uses_memo(const c3sc_cross_opts *opts) { return !opts || opts->maxiter != 1; }
+static int memo_pays(const c3sc_cross_opts *opts) { return c3sc_cross_uses_memo(opts); }
+
 /* ---- the GPU operators behind the driver ---------------------------------------------------------- */
 struct vi_ctx { c3sc_problem *p; const c3sc_valuef *vf; };
 static int vi_cb(size_t F, const int32_t *dv, const int32_t *fi, size_t ldo, double *out, void *arg)
@@ -1582,7 +1740,14 @@ int c3sc_cross_run_pi(c3sc_cross *c, c3sc_problem *p, const c3sc_valuef *vf_poli
     struct pi_ctx x = {p, vf_policy, vf_iter, NULL, 0};
     x.rows = (double *)malloc(fmax * c->nmax * (2 * (size_t)dx + 3) * sizeof(double));
     if (!x.rows) return C3SC_EINVAL;
-    int rc = c3sc_cross_run(c, pi_cb, &x, opts, cores, nfibers, rel_change);
+    c3sc_fiber_memo *memo = NULL;
+    int rc = C3SC_OK;
+    if (!memo_pays(opts)) rc = c3sc_cross_run(c, pi_cb, &x, opts, cores, nfibers, rel_change);
+    else {
+        rc = c3sc_fiber_memo_create(c->d, pi_cb, &x, &memo);
+        if (rc == C3SC_OK) rc = c3sc_cross_run(c, c3sc_fiber_memo_call, memo, opts, cores, nfibers, rel_change);
+        c3sc_fiber_memo_destroy(memo);
+    }
     free(x.rows);
     return rc;
 }
@@ -1594,7 +1759,13 @@ int c3sc_cross_run_vi(c3sc_cross *c, c3sc_problem *p, const c3sc_valuef *vf, con
     struct vi_ctx x = {p, vf};
     if (!c) return C3SC_EINVAL;
     c->want_pinned = 1;
-    return c3sc_cross_run(c, vi_cb, &x, opts, cores, nfibers, rel_change);
+    /* the operator (a backup against the fixed vf) is the same in every sweep of this call: repeated fibers come from the memo */
+    if (!memo_pays(opts)) return c3sc_cross_run(c, vi_cb, &x, opts, cores, nfibers, rel_change);
+    c3sc_fiber_memo *memo = NULL;
+    int rc = c3sc_fiber_memo_create(c->d, vi_cb, &x, &memo);
+    if (rc == C3SC_OK) rc = c3sc_cross_run(c, c3sc_fiber_memo_call, memo, opts, cores, nfibers, rel_change);
+    c3sc_fiber_memo_destroy(memo);
+    return rc;
 }
 
 /* c3control_vi_solve (src/bellman.c:2282-2340): iterate next = cross(bellman_vi(.; current)) until the l2
@@ -1655,5 +1826,9 @@ int c3sc_cross_run_vi_adapt(c3sc_cross *c, c3sc_problem *p, const c3sc_valuef *v
                             double *rel_change)
 {
     struct vi_ctx x = {p, vf};
-    return c3sc_cross_run_adapt(c, vi_cb, &x, opts, aopts, ranks_out, cores, nfibers, rel_change);
+    c3sc_fiber_memo *memo = NULL;                            /* one operator for all the cross runs of the adaptive loop */
+    int rc = c3sc_fiber_memo_create(c->d, vi_cb, &x, &memo);
+    if (rc == C3SC_OK) rc = c3sc_cross_run_adapt(c, c3sc_fiber_memo_call, memo, opts, aopts, ranks_out, cores, nfibers, rel_change);
+    c3sc_fiber_memo_destroy(memo);
+    return rc;
 }

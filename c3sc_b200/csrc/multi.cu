@@ -411,7 +411,12 @@ int c3sc_cross_run_vi_multi(c3sc_cross *c, c3sc_multi *m, const c3sc_multi_value
     if (!c || !m || !vf) return c3sc_set_error(C3SC_EINVAL, "null argument");
     mvi_ctx x = {m, vf};
     c3sc_cross_pin_buffers(c, 1);
-    return c3sc_cross_run(c, mvi_cb, &x, opts, cores, nfibers, rel_change);
+    if (!c3sc_cross_uses_memo(opts)) return c3sc_cross_run(c, mvi_cb, &x, opts, cores, nfibers, rel_change);
+    c3sc_fiber_memo *memo = nullptr;
+    int rc = c3sc_fiber_memo_create(c3sc_cross_dim(c), mvi_cb, &x, &memo);
+    if (rc == C3SC_OK) rc = c3sc_cross_run(c, c3sc_fiber_memo_call, memo, opts, cores, nfibers, rel_change);
+    c3sc_fiber_memo_destroy(memo);
+    return rc;
 }
 
 int c3sc_cross_run_pi_multi(c3sc_cross *c, c3sc_multi *m, const c3sc_multi_valuef *vf_policy, const c3sc_multi_valuef *vf_iter,
@@ -420,7 +425,12 @@ int c3sc_cross_run_pi_multi(c3sc_cross *c, c3sc_multi *m, const c3sc_multi_value
     if (!c || !m || !vf_policy || !vf_iter) return c3sc_set_error(C3SC_EINVAL, "null argument");
     mpi_ctx x = {m, vf_policy, vf_iter};
     c3sc_cross_pin_buffers(c, 1);
-    return c3sc_cross_run(c, mpi_cb, &x, opts, cores, nfibers, rel_change);
+    if (!c3sc_cross_uses_memo(opts)) return c3sc_cross_run(c, mpi_cb, &x, opts, cores, nfibers, rel_change);
+    c3sc_fiber_memo *memo = nullptr;
+    int rc = c3sc_fiber_memo_create(c3sc_cross_dim(c), mpi_cb, &x, &memo);
+    if (rc == C3SC_OK) rc = c3sc_cross_run(c, c3sc_fiber_memo_call, memo, opts, cores, nfibers, rel_change);
+    c3sc_fiber_memo_destroy(memo);
+    return rc;
 }
 
 }  // extern "C"

@@ -36,6 +36,7 @@ void c3sc_cross_destroy(c3sc_cross *c);
  * multi-GPU forms turn it on themselves.  Pageable memory is used where page-locking fails. */
 int  c3sc_cross_pin_buffers(c3sc_cross *c, int on);
 int  c3sc_cross_ranks(const c3sc_cross *c, uint64_t *ranks);
+uint32_t c3sc_cross_dim(const c3sc_cross *c);
 /* index sets at bond k (0..d): left[r_k*d] over dims 0..k-1, right[r_k*d] over dims k..d-1 (others 0);
  * what ValueF keeps as isl / isr between solver steps (src/valuefunc.c:706-712).  Either may be NULL. */
 int  c3sc_cross_index_sets(const c3sc_cross *c, uint32_t k, int32_t *left, int32_t *right);
@@ -43,6 +44,23 @@ int  c3sc_cross_index_sets(const c3sc_cross *c, uint32_t k, int32_t *left, int32
 /* cores[k]: caller-allocated n[k]*r[k]*r[k+1] doubles.  nfibers / rel_change may be NULL. */
 int c3sc_cross_run(c3sc_cross *c, c3sc_fiber_batch_fn f, void *arg, const c3sc_cross_opts *opts,
                    double *const *cores, uint64_t *nfibers, double *rel_change);
+
+/* ---- fiber memo ---------------------------------------------------------------------------------------
+ * The reference memoises backed-up values across the <= 5 sweeps of one cross approximation (hash tables keyed by
+ * node, src/bellman.c:1334-1349, 1383).  Here a backup is a pure function of the fiber, so the
+ * memo works on whole fibers: a wrapper around any fiber operator that computes each distinct
+ * (dim_vary, fixed indices) once -- repeated requests, inside a batch or in a later sweep, are served from the
+ * stored values (bit-identical: the same numbers).  c3sc_cross_run_vi / _pi and their multi-GPU forms use one for
+ * the duration of a call.  The operator behind a memo must not change while the memo holds values. */
+typedef struct c3sc_fiber_memo c3sc_fiber_memo;
+int  c3sc_fiber_memo_create(uint32_t d, c3sc_fiber_batch_fn f, void *arg, c3sc_fiber_memo **out);
+/* a c3sc_fiber_batch_fn: pass it with arg = the memo */
+int  c3sc_fiber_memo_call(size_t F, const int32_t *dim_vary, const int32_t *fixed_ind, size_t ldo, double *out, void *memo);
+void c3sc_fiber_memo_stats(const c3sc_fiber_memo *m, uint64_t *requested, uint64_t *computed);
+void c3sc_fiber_memo_clear(c3sc_fiber_memo *m);
+void c3sc_fiber_memo_destroy(c3sc_fiber_memo *m);
+/* whether c3sc_cross_run_vi / _pi put a memo in front of the GPU operator for these options (more than one sweep pair) */
+int  c3sc_cross_uses_memo(const c3sc_cross_opts *opts);
 
 /* c3control_step_vi / c3control_step_pi (src/bellman.c:2177-2262) on the GPU path */
 int c3sc_cross_run_vi(c3sc_cross *c, c3sc_problem *p, const c3sc_valuef *vf, const c3sc_cross_opts *opts,

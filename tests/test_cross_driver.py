@@ -45,6 +45,44 @@ def test_cross_recovers_low_rank_tensor():
     cr.close()
 
 
+def test_fiber_memo_computes_every_distinct_fiber_once():
+    """c3sc_fiber_memo (the reference's memo tables at fiber level, src/bellman.c:1334-1349): behind the memo the operator sees
+    every distinct (dim_vary, fixed indices) once -- repeats inside a batch and in later sweeps are served from the store --
+    and the driver produces bit-identical cores"""
+    n = [9, 7, 8, 6]
+    grids = [np.linspace(-1, 1, m) for m in n]
+    X = np.meshgrid(*grids, indexing="ij")
+    full = np.sin(X[0] + X[1] + X[2] + X[3]) + 0.3 * X[0] * X[3]
+    seen = []
+
+    def fn(dv, fi):
+        F = len(dv)
+        out = np.zeros((F, max(n)))
+        for f in range(F):
+            idx = [int(v) for v in fi[f]]
+            k = int(dv[f])
+            idx[k] = 0
+            seen.append((k, tuple(idx)))
+            for j in range(n[k]):
+                idx[k] = j
+                out[f, j] = full[tuple(idx)]
+        return out
+    cr = capi.Cross(n, [1, 4, 4, 4, 1])
+    cores0, nfib0, _ = cr.run(fn, maxiter=3)
+    plain_calls = len(seen)
+    cr.close()
+    seen.clear()
+    cr = capi.Cross(n, [1, 4, 4, 4, 1])
+    cores1, nfib1, _ = cr.run(fn, maxiter=3, memo=True)
+    requested, computed = cr.memo_stats
+    cr.close()
+    assert nfib1 == nfib0 == plain_calls == requested
+    assert computed == len(seen) == len(set(seen))            # nothing reached the operator twice
+    assert computed < requested                               # ... and the sweeps of a converged cross do repeat fibers
+    for a, b in zip(cores0, cores1):
+        assert np.array_equal(a, b)
+
+
 def test_pivoting_team_size_does_not_change_the_numbers(monkeypatch):
     """the pivoting step (twin rows + QR + maxvol) runs on a team of threads over fixed row blocks: cores, index sets and the
     change norm are bit-identical for 1, 3 and 8 threads (C3SC_HOST_THREADS), on unfoldings big enough to use the team"""
