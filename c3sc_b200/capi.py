@@ -71,6 +71,7 @@ EXPORTS = [
     "c3sc_multi_valuef_create", "c3sc_multi_valuef_update", "c3sc_multi_valuef_destroy", "c3sc_multi_valuef_get", "c3sc_multi_shard",
     "c3sc_multi_vi_batch", "c3sc_multi_pi_batch", "c3sc_multi_pi_reset", "c3sc_multi_gathered_count", "c3sc_multi_vi_batch_gathered",
     "c3sc_cross_run_vi_multi", "c3sc_cross_run_pi_multi", "c3sc_host_alloc", "c3sc_host_free", "c3sc_vi_batch_peers", "c3sc_guard_check",
+    "c3sc_valuef_dot_l2", "c3sc_valuef_norm_l2", "c3sc_valuef_norm2diff_l2",
     "c3sc_cross_dim", "c3sc_cross_uses_memo", "c3sc_fiber_memo_create", "c3sc_fiber_memo_call", "c3sc_fiber_memo_stats", "c3sc_fiber_memo_clear", "c3sc_fiber_memo_destroy",
 ]
 
@@ -154,6 +155,9 @@ def lib() -> C.CDLL:
         L.c3sc_cross_copy.argtypes = [vp, C.POINTER(vp)]
         L.c3sc_cross_destroy.restype = None
         L.c3sc_cross_ranks.argtypes = [vp, c_u64p]
+        L.c3sc_valuef_dot_l2.argtypes = [vp, vp, C.POINTER(c_f64p), c_f64p]
+        L.c3sc_valuef_norm_l2.argtypes = [vp, C.POINTER(c_f64p), c_f64p]
+        L.c3sc_valuef_norm2diff_l2.argtypes = [vp, vp, C.POINTER(c_f64p), c_f64p]
         L.c3sc_cross_dim.argtypes = [vp]
         L.c3sc_cross_dim.restype = C.c_uint32
         L.c3sc_fiber_memo_create.argtypes = [C.c_uint32, FIBER_FN, vp, C.POINTER(vp)]
@@ -425,6 +429,26 @@ class ValueF:
         p = C.c_void_p(); n = C.c_size_t()
         check(lib().c3sc_valuef_device_buffer(self.handle, C.byref(p), C.byref(n)))
         return p.value, n.value
+
+    # valuef_norm / valuef_norm2diff on the device-resident cores (continuous L2 of the piecewise-linear trains)
+    def _xg(self, xgrid):
+        xg = [np.ascontiguousarray(g, dtype=np.float64) for g in xgrid]
+        return xg, (c_f64p * self.d)(*[g.ctypes.data_as(c_f64p) for g in xg])
+
+    def dot_l2(self, other: "ValueF", xgrid) -> float:
+        keep, ax = self._xg(xgrid); out = C.c_double()
+        check(lib().c3sc_valuef_dot_l2(self.handle, other.handle, ax, C.byref(out)))
+        return float(out.value)
+
+    def norm_l2(self, xgrid) -> float:
+        keep, ax = self._xg(xgrid); out = C.c_double()
+        check(lib().c3sc_valuef_norm_l2(self.handle, ax, C.byref(out)))
+        return float(out.value)
+
+    def norm2diff_l2(self, other: "ValueF", xgrid) -> float:
+        keep, ax = self._xg(xgrid); out = C.c_double()
+        check(lib().c3sc_valuef_norm2diff_l2(self.handle, other.handle, ax, C.byref(out)))
+        return float(out.value)
 
     def commit(self, stream: int = 0):
         """Rebuild the transposed core copy after the device buffer was written directly."""

@@ -3,6 +3,7 @@
 #include <atomic>
 #include <cstdarg>
 #include <cstdio>
+#include <cmath>
 #include <cstring>
 #include <mutex>
 #include <vector>
@@ -10,6 +11,7 @@
 #define C3SC_FT_TYPES_ONLY
 #include "chain_kernel.cuh"     // FtArgs, ChainArgs (host side; the kernels are compiled in ft.cu)
 #include "control_kernel.cuh"   // CtlArgs
+#include "norm_kernel.cuh"      // k_train_dot_l2 (compiled here)
 
 namespace c3sc {
 int launch_control_lqg_lo(int dx, int arith, const CtlArgs &a, int pi_eval, cudaStream_t st);
@@ -644,6 +646,96 @@ int c3sc_valuef_device_buffer(c3sc_valuef *vf, double **dev, size_t *count)
     return C3SC_OK;
 }
 
+}  // extern "C"
+
+// ---- valuef_norm / valuef_norm2diff on the device (norm_kernel.cuh) --------------------------------------------
+namespace {
+struct NormScratch { DevBuf z, x; std::mutex mu; };
+NormScratch g_norm[C3SC_MAXDEV];
+
+// <a,b> (npairs == 1: out[0]) or <a,a>, <a,b>, <b,b> (npairs == 3: out[0..2]) of two value functions on one grid
+int train_dots(const c3sc_valuef *va, const c3sc_valuef *vb, const double *const *xgrid, int npairs, double *out)
+{
+    if (!va || !vb || !xgrid || !out) return fail(C3SC_EINVAL, "null argument");
+    if (va->device != vb->device) return fail(C3SC_EINVAL, "the two value functions live on different devices");
+    const DevFT &fa = va->ft, &fb = vb->ft;
+    if (fa.d != fb.d) return fail(C3SC_EINVAL, "value functions of different dimension");
+    DeviceScope ds_(va->device);
+    NormArgs na;
+    memset(&na, 0, sizeof na);
+    na.d = fa.d; na.npairs = npairs;
+    int rmax = 1, ntot = 0;
+    for (int k = 0; k < fa.d; k++) {
+        if (fa.n[k] != fb.n[k]) return fail(C3SC_EINVAL, "grid size mismatch in dim %d", k);
+        if (!xgrid[k]) return fail(C3SC_EINVAL, "no node coordinates for dim %d", k);
+        na.n[k] = fa.n[k]; na.xoff[k] = ntot; ntot += fa.n[k];
+        na.t[0].off[k] = fa.off[k]; na.t[1].off[k] = fb.off[k];
+    }
+    for (int k = 0; k <= fa.d; k++) {
+        na.t[0].r[k] = fa.r[k]; na.t[1].r[k] = fb.r[k];
+        rmax = fa.r[k] > rmax ? fa.r[k] : rmax; rmax = fb.r[k] > rmax ? fb.r[k] : rmax;
+    }
+    na.t[0].base = fa.base; na.t[1].base = fb.base;
+    na.zstride = rmax * rmax;
+    const size_t smem = (size_t)4 * rmax * rmax * sizeof(double);
+    int dev = 0, optin = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+    if (smem > (size_t)optin) return fail(C3SC_EUNSUPPORTED, "train inner product on the device: rank %d needs %zu bytes of shared memory", rmax, smem);
+    NormScratch &ns = g_norm[c3sc_cur_dev()];
+    std::lock_guard<std::mutex> lock(ns.mu);
+    static size_t attr_dev[C3SC_MAXDEV] = {0};
+    if (smem > 48 * 1024 && smem > attr_dev[c3sc_cur_dev()]) {
+        CK(cudaFuncSetAttribute(k_train_dot_l2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_dev[c3sc_cur_dev()] = smem;
+    }
+    const size_t zbytes = (size_t)2 * npairs * NRM_G * na.zstride * sizeof(double);
+    if (ns.z.reserve(zbytes) || ns.x.reserve((size_t)ntot * sizeof(double))) return fail(C3SC_ECUDA, "cudaMalloc of the norm scratch failed");
+    std::vector<double> hx((size_t)ntot);
+    for (int k = 0; k < fa.d; k++) memcpy(hx.data() + na.xoff[k], xgrid[k], (size_t)fa.n[k] * sizeof(double));
+    CK(cudaMemcpyAsync(ns.x.p, hx.data(), (size_t)ntot * sizeof(double), cudaMemcpyHostToDevice, 0));
+    na.x = (const double *)ns.x.p;
+    double *z0 = (double *)ns.z.p, *z1 = z0 + (size_t)npairs * NRM_G * na.zstride;
+    for (int k = 0; k < fa.d; k++) {
+        k_train_dot_l2<<<dim3(NRM_G, (unsigned)npairs), NRM_NT, smem, 0>>>(na, k, (k & 1) ? z1 : z0, (k & 1) ? z0 : z1);
+        g_launches++;
+    }
+    CK(cudaGetLastError());
+    const double *zl = (fa.d & 1) ? z1 : z0;                // launch d-1 wrote z1 when d-1 is even
+    std::vector<double> part((size_t)npairs * NRM_G);
+    CK(cudaMemcpy2D(part.data(), sizeof(double), zl, (size_t)na.zstride * sizeof(double), sizeof(double), (size_t)npairs * NRM_G,
+                    cudaMemcpyDeviceToHost));
+    for (int p = 0; p < npairs; p++) {
+        double s = 0.0;
+        for (int g = 0; g < NRM_G; g++) s += part[(size_t)p * NRM_G + g];
+        out[p] = s;
+    }
+    return C3SC_OK;
+}
+}  // namespace
+
+extern "C" {
+int c3sc_valuef_dot_l2(const c3sc_valuef *a, const c3sc_valuef *b, const double *const *xgrid, double *out)
+{
+    return train_dots(a, b, xgrid, 1, out);
+}
+int c3sc_valuef_norm_l2(const c3sc_valuef *a, const double *const *xgrid, double *out)
+{
+    double v = 0.0;
+    const int rc = train_dots(a, a, xgrid, 1, &v);
+    if (rc == C3SC_OK && out) *out = sqrt(fabs(v));
+    return rc;
+}
+int c3sc_valuef_norm2diff_l2(const c3sc_valuef *a, const c3sc_valuef *b, const double *const *xgrid, double *out)
+{
+    double v[3] = {0.0, 0.0, 0.0};
+    const int rc = train_dots(a, b, xgrid, 3, v);
+    if (rc == C3SC_OK && out) *out = sqrt(fabs(v[0] - 2.0 * v[1] + v[2]));
+    return rc;
+}
+}  // extern "C"
+
+extern "C" {
 void c3sc_valuef_destroy(c3sc_valuef *vf)
 {
     if (!vf) return;

@@ -1053,6 +1053,9 @@ double valuef_norm(struct ValueF *v)
     uint64_t n[C3SC_MAXD], r[C3SC_MAXD + 1];
     if (!v->xgrid) die("valuef_norm: the value function has no grid (valuef_set_grid); valuef_norm_nodal needs none");
     vf_u64(v, n, r);
+    /* next to the cores on the device; ranks beyond the kernel's shared memory take the host restatement */
+    double out = 0.0;
+    if (v->dev && c3sc_valuef_norm_l2(v->dev, (const double *const *)v->xgrid, &out) == C3SC_OK) return out;
     return c3sc_cores_norm_l2((uint32_t)v->d, n, (const double *const *)v->xgrid, r, (const double *const *)v->cores);
 }
 double valuef_norm2diff(struct ValueF *a, struct ValueF *b)
@@ -1061,6 +1064,8 @@ double valuef_norm2diff(struct ValueF *a, struct ValueF *b)
     double **xg = a->xgrid ? a->xgrid : b->xgrid;            /* both functions live on the same grid */
     if (!xg) die("valuef_norm2diff: neither value function has a grid (valuef_set_grid); valuef_norm2diff_nodal needs none");
     vf_u64(a, n, ra); vf_u64(b, n, rb);
+    double out = 0.0;
+    if (a->dev && b->dev && c3sc_valuef_norm2diff_l2(a->dev, b->dev, (const double *const *)xg, &out) == C3SC_OK) return out;
     return c3sc_cores_norm2diff_l2((uint32_t)a->d, n, (const double *const *)xg, ra, (const double *const *)a->cores, rb,
                                    (const double *const *)b->cores);
 }

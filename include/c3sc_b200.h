@@ -184,6 +184,15 @@ int  c3sc_valuef_device_buffer(c3sc_valuef *vf, double **dev, size_t *count);
 int  c3sc_valuef_commit(c3sc_valuef *vf, void *stream);
 void c3sc_valuef_destroy(c3sc_valuef *vf);
 
+/* valuef_norm / valuef_norm2diff (/root/reference/src/valuefunc.c:315-335 -> C3 function_train_norm2 / norm2diff on LINELM cores)
+ * NEXT TO THE CORES: the continuous L2 inner product of two piecewise-linear function trains whose cores are on the device
+ * (SURVEY 8(f)-3).  xgrid[k]: the n[k] node coordinates of dimension k (host).  One launch per dimension, the node range of a
+ * dimension split over 32 CTAs, partial results summed in a fixed order (run-to-run reproducible); norm2diff shares its launches
+ * between <a,a>, <a,b> and <b,b>.  The host restatement of the same formula is c3sc_cores_dot_l2 (c3sc_cross.h). */
+int c3sc_valuef_dot_l2(const c3sc_valuef *a, const c3sc_valuef *b, const double *const *xgrid, double *out);
+int c3sc_valuef_norm_l2(const c3sc_valuef *a, const double *const *xgrid, double *out);
+int c3sc_valuef_norm2diff_l2(const c3sc_valuef *a, const c3sc_valuef *b, const double *const *xgrid, double *out);
+
 /* ---- fiber descriptors --------------------------------------------------- */
 /* A fiber is (dim_vary, fixed_ind[dx]): what convert_fiber_to_ind (src/nodeutil.c:437-470) decodes from
  * the reference's point list.  Valid means 0 <= dim_vary < dx and 0 <= fixed_ind[i] < ngrid[i] (the slot of

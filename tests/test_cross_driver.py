@@ -478,3 +478,34 @@ def test_continuous_l2_inner_product_against_gauss_quadrature(d):
     zero = [np.zeros_like(c) for c in cb]
     assert abs(capi.cores_norm2diff_l2(n, xg, ra, ca, rb, zero) ** 2 - capi.cores_dot_l2(n, xg, ra, ca, ra, ca)) <= 1e-10
     assert abs(capi.cores_norm(n, ra, ca) ** 2 - capi.cores_dot_l2(n, xg, ra, ca, ra, ca)) > 1e-3
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("d,rmax", [(3, 5), (4, 12), (6, 20), (3, 40)])
+def test_device_l2_inner_products_equal_the_host_restatement(gpu, d, rmax):
+    """c3sc_valuef_dot_l2 / _norm_l2 / _norm2diff_l2 (valuef_norm / valuef_norm2diff next to the device-resident cores, SURVEY
+    8(f)-3) against c3sc_cores_*_l2, the host restatement of the same mass-matrix contraction that is pinned against Gauss
+    quadrature above: non-uniform grids, two trains of different ranks; 1e-12 of the norms' own size (the summation order over the
+    nodes differs: 32 partial sums per dimension)"""
+    rng = np.random.default_rng(17 + d)
+    n = [int(v) for v in rng.integers(7, 23, size=d)]
+    xgrid = [np.sort(rng.uniform(-1.0, 2.0, size=m)) for m in n]
+    ra = [1] + [int(v) for v in rng.integers(2, rmax + 1, size=d - 1)] + [1]
+    rb = [1] + [int(v) for v in rng.integers(1, rmax + 1, size=d - 1)] + [1]
+    ca = [rng.standard_normal(n[k] * ra[k] * ra[k + 1]) for k in range(d)]
+    cb = [rng.standard_normal(n[k] * rb[k] * rb[k + 1]) for k in range(d)]
+    va = capi.ValueF(n, ra, ca); vb = capi.ValueF(n, rb, cb)
+    aa = capi.cores_dot_l2(n, xgrid, ra, ca, ra, ca); ab = capi.cores_dot_l2(n, xgrid, ra, ca, rb, cb); bb = capi.cores_dot_l2(n, xgrid, rb, cb, rb, cb)
+    scale = np.sqrt(aa * bb)
+    assert abs(va.dot_l2(vb, xgrid) - ab) <= 1e-12 * scale
+    assert abs(va.dot_l2(va, xgrid) - aa) <= 1e-12 * aa
+    assert abs(va.norm_l2(xgrid) - np.sqrt(aa)) <= 1e-12 * np.sqrt(aa)
+    host_diff = capi.cores_norm2diff_l2(n, xgrid, ra, ca, rb, cb)
+    assert abs(va.norm2diff_l2(vb, xgrid) - host_diff) <= 1e-10 * (np.sqrt(aa) + np.sqrt(bb))       # a difference of squares
+    # a train against a slightly perturbed copy of itself: the case the solvers' Cauchy criterion meets
+    cc = [c * (1.0 + 1e-6 * rng.standard_normal(c.size)) for c in ca]
+    vc = capi.ValueF(n, ra, cc)
+    dd = va.norm2diff_l2(vc, xgrid); hh = capi.cores_norm2diff_l2(n, xgrid, ra, ca, ra, cc)
+    assert abs(dd - hh) <= 1e-6 * hh + 1e-9 * np.sqrt(aa)
+    assert va.norm2diff_l2(va, xgrid) <= 1e-7 * np.sqrt(aa)      # sqrt of round-off
+    va.close(); vb.close(); vc.close()
