@@ -903,43 +903,84 @@ inline bool fused_ok_m(int arith, const CtlArgs &c, int pi_eval)
 }
 
 // policy evaluation (bellman.c:1774-1828,1863-1871): stored rows against the new neighbour values.
-// The rows are node-major records of 2dx+3 doubles (the reference's layout): a CTA stages the records of PE_NT
-// consecutive nodes in shared memory with coalesced loads (one thread reading its own 184-byte record touches a
-// sector per load and thrashes L1) and every thread then takes its node's record from there (odd stride: no bank
-// conflicts).
+// The rows are node-major records of 2dx+3 doubles (the reference's layout).  The records of PE_NT consecutive nodes are ONE
+// contiguous piece (23.5 kB at dx = 10): a CTA fetches it with one TMA bulk copy (cp.async.bulk + mbarrier) into one of two
+// shared-memory buffers, one tile ahead of the tile it works on, and every thread takes its node's record from there (odd
+// stride in doubles: no bank conflicts).  The kernel is HBM-bound (184 B of rows + 168 B of neighbour values per node); the
+// first version staged the tile with a load -> store loop per thread, four or five loads in flight, and reached 47 % of the
+// DRAM throughput with 81 % of its stall samples on those loads (profiles/r02b_logs/r02b_stalls_k_pi_eval.txt).
 constexpr int PE_NT = 128;
+__device__ __forceinline__ unsigned pe_smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
 template <class M, class A>
 __global__ void __launch_bounds__(PE_NT) k_pi_eval(const CtlArgs c)
 {
     constexpr int DX = M::DX, CS = 2 * DX + 1, RW = 2 * DX + 3;
-    __shared__ double srow[PE_NT * RW];
+    constexpr unsigned TILE_BYTES = PE_NT * RW * sizeof(double);
+    constexpr bool BULK = TILE_BYTES % 16 == 0 && 2 * TILE_BYTES + 64 <= 48 * 1024;
+    __shared__ __align__(16) double srow[(BULK ? 2 : 1) * PE_NT * RW];
+    __shared__ unsigned long long bar[2];
     const DevProblem &P = c.P;
     const int tid = threadIdx.x;
-    for (long long base = (long long)blockIdx.x * PE_NT; base < c.NS; base += (long long)gridDim.x * PE_NT) {
+    const long long tstride = (long long)gridDim.x * PE_NT;
+    const bool aligned = ((size_t)c.rows_in & 15) == 0;
+    auto fetch = [&](long long base, int buf) {             // tid 0: the full tile at `base` -> buffer buf
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(pe_smem_u32(bar + buf)), "r"(TILE_BYTES) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     ::"r"(pe_smem_u32(srow + buf * PE_NT * RW)), "l"(c.rows_in + (size_t)base * RW), "r"(TILE_BYTES),
+                       "r"(pe_smem_u32(bar + buf)) : "memory");
+    };
+    if (BULK && tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(pe_smem_u32(bar)) : "memory");
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(pe_smem_u32(bar + 1)) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        const long long b0 = (long long)blockIdx.x * PE_NT;
+        if (aligned && b0 + PE_NT <= c.NS) fetch(b0, 0);
+    }
+    __syncthreads();
+    unsigned phase = 0;
+    int buf = 0;
+    for (long long base = (long long)blockIdx.x * PE_NT; base < c.NS; base += tstride, buf ^= 1) {
         const long long left = c.NS - base;
         const int cnt = left < PE_NT ? (int)left : PE_NT;
-        const double *src = c.rows_in + (size_t)base * RW;
-        __syncthreads();
-        for (int e = tid; e < cnt * RW; e += PE_NT) srow[e] = src[e];
-        __syncthreads();
-        const long long id = base + tid;
-        if (tid >= cnt) continue;
-        const int ab = c.flag[id];
-        double v;
-        if (ab == 2) v = 0.0;                               // padding entry: defined content
-        else if (ab != 0) {
-            double x[DX];
-            node_state<DX>(c, (int)id, x);
-            v = (ab == 1) ? M::boundcost(x, P.mp) : M::obscost(x, P.mp);
-        } else {
-            const double *row = srow + tid * RW;
-            double prob[CS], cc[CS];
-            load_costs<DX>(c, (int)id, cc);
-#pragma unroll
-            for (int m = 0; m < CS; m++) prob[m] = row[m];
-            v = rhs<DX, A>(P, prob, row[CS], row[CS + 1], cc);
+        const bool bulk = BULK && aligned && cnt == PE_NT;
+        const double *tile = srow + (BULK ? buf : 0) * PE_NT * RW;
+        if (BULK) {
+            // the other buffer was read by the previous trip (barrier at its end): the next full tile goes there now
+            const long long nb = base + tstride;
+            if (tid == 0 && aligned && nb + PE_NT <= c.NS) fetch(nb, buf ^ 1);
         }
-        store_value(c, id, v);
+        if (bulk) {
+            const unsigned par = (phase >> buf) & 1u;
+            asm volatile("{\n.reg .pred P1;\nPE_WAIT:\nmbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n@P1 bra PE_DONE;\nbra PE_WAIT;\nPE_DONE:\n}"
+                         ::"r"(pe_smem_u32(bar + buf)), "r"(par) : "memory");
+            phase ^= 1u << buf;
+        } else {                                            // the ragged last tile (or an unaligned buffer): plain loads
+            const double *src = c.rows_in + (size_t)base * RW;
+            double *dstt = srow + (BULK ? buf : 0) * PE_NT * RW;
+            if (!BULK) __syncthreads();
+            for (int e = tid; e < cnt * RW; e += PE_NT) dstt[e] = src[e];
+            __syncthreads();
+        }
+        const long long id = base + tid;
+        if (tid < cnt) {
+            const int ab = c.flag[id];
+            double v;
+            if (ab == 2) v = 0.0;                           // padding entry: defined content
+            else if (ab != 0) {
+                double x[DX];
+                node_state<DX>(c, (int)id, x);
+                v = (ab == 1) ? M::boundcost(x, P.mp) : M::obscost(x, P.mp);
+            } else {
+                const double *row = tile + tid * RW;
+                double prob[CS], cc[CS];
+                load_costs<DX>(c, (int)id, cc);
+#pragma unroll
+                for (int m = 0; m < CS; m++) prob[m] = row[m];
+                v = rhs<DX, A>(P, prob, row[CS], row[CS + 1], cc);
+            }
+            store_value(c, id, v);
+        }
+        if (BULK) __syncthreads();                          // every thread is done with this buffer
     }
 }
 
