@@ -685,6 +685,8 @@ __global__ void __launch_bounds__(CT_NT, grid_minb(ARG)) k_control_grid(const Ct
     const int tid = threadIdx.x, lane = tid & 31;
     const int nact = *c.act_count, nper = (nact + Q - 1) / Q;
     const long long stride = (long long)gridDim.x * blockDim.x;
+    constexpr bool STAGE = ARG && (size_t)CT_NT * RW * sizeof(double) <= 47 * 1024;     // (dx <= 10; larger records go out directly)
+    __shared__ double srows[STAGE ? CT_NT * RW : 1];        // policy rows of the CTA's nodes on their way out
     const double nbh = -P.beta * P.h2;
     const bool disc = P.beta != 0.0;
     for (long long it0 = (long long)blockIdx.x * blockDim.x + (tid & ~31); it0 < nper; it0 += stride) {
@@ -720,25 +722,41 @@ __global__ void __launch_bounds__(CT_NT, grid_minb(ARG)) k_control_grid(const Ct
         }
 #pragma unroll
         for (int q = 0; q < Q; q++) {
-            if (!valid[q]) continue;
-            store_value(c, id[q], nd[q].best);
+            if (valid[q]) {
+                store_value(c, id[q], nd[q].best);
+                if constexpr (ARG) { if (c.argmin) c.argmin[id[q]] = nd[q].ibest; }
+            }
             if constexpr (ARG) {
-                const int ibest = nd[q].ibest;
-                if (c.argmin) c.argmin[id[q]] = ibest;
                 if (c.rows) {                               // policy row at u* (bellman.c:1851-1860)
-                    double x[DX], u[DU], b[DX], sg[DX], prob[CS], dt;
-                    node_state<DX>(c, id[q], x);
+                    // The rows are node-major records of 2dx+3 doubles: a thread storing its own record issues 2dx+3 stores that
+                    // each touch 32 different sectors.  The warp's records go through shared memory instead and leave row by
+                    // row, 2dx+3 consecutive lanes writing one record (184 contiguous bytes at dx = 10).
+                    double *wr = STAGE ? srows + tid * RW : c.rows + (size_t)(valid[q] ? id[q] : 0) * RW;
+                    if (valid[q]) {
+                        const int ibest = nd[q].ibest;
+                        double x[DX], u[DU], b[DX], sg[DX], prob[CS], dt;
+                        node_state<DX>(c, id[q], x);
 #pragma unroll
-                    for (int i = 0; i < DU; i++) u[i] = P.utab[(size_t)(ibest < P.nu ? ibest : 0) * DU + i];
-                    M::template drift<Fast>(x, u, P.mp, b);
-                    M::template sigma<Fast>(x, u, P.mp, sg);
-                    const double g = M::template stage<Fast>(x, u, P.mp);
-                    if (transition_row<DX, Fast>(P, b, sg, prob, dt)) atomicOr(P.err, 1);
-                    double *row = c.rows + (size_t)id[q] * RW;
+                        for (int i = 0; i < DU; i++) u[i] = P.utab[(size_t)(ibest < P.nu ? ibest : 0) * DU + i];
+                        M::template drift<Fast>(x, u, P.mp, b);
+                        M::template sigma<Fast>(x, u, P.mp, sg);
+                        const double g = M::template stage<Fast>(x, u, P.mp);
+                        if (transition_row<DX, Fast>(P, b, sg, prob, dt)) atomicOr(P.err, 1);
 #pragma unroll
-                    for (int m = 0; m < CS; m++) row[m] = prob[m];
-                    row[CS] = dt;
-                    row[CS + 1] = g;
+                        for (int m = 0; m < CS; m++) wr[m] = prob[m];
+                        wr[CS] = dt;
+                        wr[CS + 1] = g;
+                    }
+                    if constexpr (STAGE) {
+                        __syncwarp();
+                        const int idme = valid[q] ? id[q] : -1;
+                        const double *wsrc = srows + (tid & ~31) * RW;
+                        for (int r = 0; r < 32; r++) {
+                            const int idr = __shfl_sync(0xffffffffu, idme, r);
+                            if (idr >= 0) for (int m = lane; m < RW; m += 32) c.rows[(size_t)idr * RW + m] = wsrc[r * RW + m];
+                        }
+                        __syncwarp();
+                    }
                 }
             }
         }
