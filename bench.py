@@ -351,13 +351,37 @@ def main():
     stream = torch.cuda.current_stream(dev)
     sptr = stream.cuda_stream
 
-    # N > 1: every rank's gathered buffer is peer-mapped (CUDA IPC); a rank's values reach the others either as stores
-    # from the control kernel (C3SC_GATHER=p2p, default: measured fastest at 8 GPUs), as one bulk copy per pipeline chunk and
-    # peer on the copy engines (copy) or as one small scatter kernel per chunk (scatter), both overlapped with the next chunk;
-    # a step ends with a barrier.  C3SC_GATHER=nccl: NCCL all-gather.
-    gather_mode = os.environ.get("C3SC_GATHER", "p2p") if world > 1 else "none"
+    # N > 1: a rank's values reach the others as stores from the control kernel -- to the NVSwitch multicast address of the
+    # ranks' symmetric gathered buffers (C3SC_GATHER=mcast, default: one store per value, replicated by the switch; 1.95 against
+    # 2.06 ms per step at 8 GPUs) or into every rank's peer-mapped buffer (p2p: CUDA IPC, one store per value and peer; also the
+    # fallback without multicast support) --, as one bulk copy per pipeline chunk and peer on the copy engines (copy) or as one
+    # small scatter kernel per chunk (scatter), both overlapped with the next chunk; a step ends with a barrier.
+    # C3SC_GATHER=nccl: NCCL all-gather.
+    gather_mode = os.environ.get("C3SC_GATHER", "mcast") if world > 1 else "none"
     peers = None
     gathered = None
+    mcast = None
+    if world > 1 and gather_mode == "mcast":
+        # NVSwitch multicast (NVLS): the gathered buffers of all ranks are one symmetric allocation with a MULTICAST address;
+        # a store to it is replicated by the switch into every rank's copy, so a value leaves the GPU once instead of once
+        # per peer.  torch's symmetric memory is the plumbing (allocation + rendezvous); the stores are the control kernel's.
+        try:
+            import torch.distributed._symmetric_memory as symm_mem
+            gname = dist.group.WORLD.group_name
+            symt = symm_mem.empty(world * F * N, dtype=torch.float64, device=dev)
+            hdl = symm_mem.rendezvous(symt, gname)
+            mc_ptr = int(hdl.multicast_ptr or 0)
+            if not mc_ptr:
+                raise RuntimeError("no multicast address for the symmetric allocation")
+            gathered = symt
+            mcast = capi.McastPeers(mc_ptr)
+            sync_flag = torch.zeros(1, device=dev)
+        except Exception as exc:
+            if rank == 0:
+                print(f"bench: multicast gather unavailable ({exc}); using peer stores", file=sys.stderr)
+            gather_mode = "p2p"
+            gathered = None
+            mcast = None
     if world > 1 and gather_mode in ("p2p", "copy", "scatter"):
         try:
             def _exchange(h):
@@ -372,6 +396,8 @@ def main():
                 print(f"bench: peer-mapped gather unavailable ({exc}); using NCCL", file=sys.stderr)
             peers = None
             gather_mode = "nccl"
+    if mcast is not None:
+        peers = mcast
     if world > 1 and peers is None:
         gathered = torch.empty(world * F * N, dtype=torch.float64, device=dev)
     # the rank's own output IS its slot of its gathered buffer (no private copy)
@@ -380,19 +406,33 @@ def main():
 
     def peers_struct():
         o = capi.BatchOut()
-        o.n_peers = world
+        o.n_peers = len(peers.ptrs)
         for g, ptr in enumerate(peers.ptrs):
             o.value_peers[g] = ptr
         o.peer_offset = rank * F * N
         o.peer_mode = peer_mode
         return o
 
+    # the broadcast of the cores and the rebuild of their derived copies run on a side stream: the batch's grouping and chain plan
+    # read the descriptors only and go ahead on the main stream; the library waits for the commit (an event of the value
+    # function) right before its first kernel that reads the cores
+    side = torch.cuda.Stream(dev) if world > 1 and os.environ.get("C3SC_BCAST_INLINE") is None else None
+
+    def bcast_cores():
+        if side is None:
+            sharding.broadcast_cores(core_view, src=0)
+            vf.commit(stream=sptr)
+            return
+        side.wait_stream(stream)                      # everything before this step has read the old cores
+        with torch.cuda.stream(side):
+            sharding.broadcast_cores(core_view, src=0)
+            vf.commit(stream=side.cuda_stream)
+
     def step_resident():
         if world == 1:
             prob.vi_batch_dev(vf, F, dv_d.data_ptr(), fi_d.data_ptr(), N, out_d.data_ptr(), stream=sptr)
             return
-        sharding.broadcast_cores(core_view, src=0)
-        vf.commit(stream=sptr)
+        bcast_cores()
         if peers is not None:
             prob.vi_batch_dev(vf, F, dv_d.data_ptr(), fi_d.data_ptr(), N, out_d.data_ptr(), stream=sptr,
                               peers=peers.ptrs, peer_offset=rank * F * N, peer_mode=peer_mode)
@@ -514,8 +554,7 @@ def main():
         Fs = F // world                                  # this rank's share of a 65 536-fiber batch
 
         def step_strong():
-            sharding.broadcast_cores(core_view, src=0)
-            vf.commit(stream=sptr)
+            bcast_cores()
             prob.vi_batch_dev(vf, Fs, dv_d.data_ptr(), fi_d.data_ptr(), N, out_d.data_ptr(), stream=sptr,
                               peers=peers.ptrs, peer_offset=rank * Fs * N, peer_mode=peer_mode)
             dist.all_reduce(sync_flag)
@@ -568,6 +607,7 @@ def main():
         gathers = {"copy": "one bulk copy per pipeline chunk and peer on the copy engines into peer-mapped buffers (CUDA IPC over NVLink) + barrier",
                    "p2p": "control kernel stores into every rank's peer-mapped buffer (CUDA IPC over NVLink) + barrier",
                    "scatter": "one small kernel per pipeline chunk stores the chunk into every rank's peer-mapped buffer, on a side stream + barrier",
+                   "mcast": "stores from the control kernel to the NVSwitch multicast address of the ranks' symmetric gathered buffers (one store per value, replicated by the switch) + barrier",
                    "nccl": "nccl all_gather_into_tensor"}
         line = {
             "metric": "bellman_node_backups_per_s", "value": value, "unit": "node-backups/s",

@@ -677,6 +677,17 @@ class PeerBuffers:
         self.ptrs = []
 
 
+class McastPeers:
+    """The gathered buffers of all ranks behind ONE NVSwitch multicast address (bench.py, C3SC_GATHER=mcast): to the
+    library it is a single `peer` -- a store to it lands in every rank's copy."""
+
+    def __init__(self, mc_ptr: int):
+        self.ptrs = [int(mc_ptr)]
+
+    def close(self):
+        self.ptrs = []
+
+
 def cores_round(n, ranks, cores, eps):
     """function_train_round on nodal cores (c3sc_cores_round): returns (ranks, cores)"""
     n = np.ascontiguousarray(n, dtype=np.uint64); d = int(n.size)

@@ -271,6 +271,11 @@ struct c3sc_valuef {
     int device = 0;
     double *d_base = nullptr, *d_baseT = nullptr, *d_baseP = nullptr, *d_baseQ = nullptr;
     size_t count = 0;
+    // c3sc_valuef_commit on a stream of its own: the event the derived copies are complete at; a batch on ANOTHER stream waits
+    // for it right before its first kernel that reads the cores (the plan of the batch does not, and runs ahead)
+    cudaEvent_t ready = nullptr;
+    cudaStream_t ready_stream = nullptr;
+    bool ready_set = false;
     std::vector<size_t> len;
 };
 
@@ -635,6 +640,10 @@ int c3sc_valuef_commit(c3sc_valuef *vf, void *stream)
     int rc = launch_pack_cores(vf->ft, vf->d_baseT, vf->d_baseP, vf->d_baseQ, (cudaStream_t)stream);
     if (rc) return fail(C3SC_ECUDA, "core packing kernel: %s", cudaGetErrorString((cudaError_t)rc));
     g_launches++;
+    if (!vf->ready) CK(cudaEventCreateWithFlags(&vf->ready, cudaEventDisableTiming));
+    CK(cudaEventRecord(vf->ready, (cudaStream_t)stream));
+    vf->ready_stream = (cudaStream_t)stream;
+    vf->ready_set = true;
     return C3SC_OK;
 }
 
@@ -744,6 +753,7 @@ void c3sc_valuef_destroy(c3sc_valuef *vf)
     dev_free(vf->d_baseT);
     dev_free(vf->d_baseP);
     dev_free(vf->d_baseQ);
+    if (vf->ready) cudaEventDestroy(vf->ready);
     delete vf;
 }
 
@@ -773,6 +783,7 @@ struct BatchArgs {
     int peer_copy;                        // 1: one bulk copy per chunk and peer on peer_stream (copy engines) instead of stores from the kernel
     cudaStream_t peer_stream;
     cudaEvent_t copies_done;
+    cudaEvent_t cores_ready;              // the value function was committed on another stream: wait here before the cores are read
 };
 
 static thread_local size_t g_chunk_bytes = (size_t)192 << 20;   // slot-major cost scratch in flight (all lanes) when stage 1a runs per fiber
@@ -906,6 +917,7 @@ static int run_batch(const DevProblem &P, int model, int arith, Scratch &scr, co
         }
         if (aside) CK(cudaStreamWaitEvent(st, scr.grouped, 0));
     }
+    if (b.cores_ready) CK(cudaStreamWaitEvent(st, b.cores_ready, 0));       // (grouping and plan above read the descriptors only)
     if (L > 1) {                                            // the other lanes start after everything queued on st so far
         CK(cudaEventRecord(scr.fork, st));
         for (size_t l = 1; l < L; l++) CK(cudaStreamWaitEvent(scr.lane[l].stream, scr.fork, 0));
@@ -1103,6 +1115,7 @@ int c3sc_vi_batch_dev(c3sc_problem *p, const c3sc_valuef *vf, size_t F, const in
         b.peer_copy = (int)out->peer_mode;
         b.peer_stream = p->peer_stream; b.chunk_done = p->chunk_done; b.copies_done = p->copies_done;
     }
+    if (vf->ready_set && vf->ready_stream != (cudaStream_t)stream) b.cores_ready = vf->ready;
     return run_batch(p->P, p->model, p->arith, p->scr, &p->grp, vf->ft, b, (cudaStream_t)stream);
 }
 
