@@ -180,7 +180,10 @@ int  c3sc_valuef_update(c3sc_valuef *vf, const double *const *cores);
 /* contiguous device buffer holding all cores (for ncclBroadcast)           */
 int  c3sc_valuef_device_buffer(c3sc_valuef *vf, double **dev, size_t *count);
 /* after writing that buffer on the device (e.g. a broadcast): rebuild the
- * transposed copy the chain kernels read; asynchronous on `stream`.         */
+ * derived copies the kernels read; asynchronous on `stream`.  The value function remembers the event of its last commit: a
+ * c3sc_vi_batch_dev on ANOTHER stream runs its grouping and chain plan (they read the descriptors only) and waits for that
+ * event right before its first kernel that reads the cores -- so a broadcast + commit on a side stream overlaps the plan of
+ * the batch.  (The caller still orders the broadcast after the previous batch's kernels: they read the old cores.)       */
 int  c3sc_valuef_commit(c3sc_valuef *vf, void *stream);
 void c3sc_valuef_destroy(c3sc_valuef *vf);
 
