@@ -36,7 +36,10 @@
 
 namespace c3sc {
 
-constexpr int CH_NT = 256;            // step kernel: 8 warps
+#ifndef C3SC_CH_NT
+#define C3SC_CH_NT 256
+#endif
+constexpr int CH_NT = C3SC_CH_NT;     // step kernel: 8 warps
 constexpr int CH_PREFIX = 1 << 30;    // ChainArgs::rowd[].y: the row also goes to the two slots in rowp[]
 constexpr int CH_NMAX = 768;          // nodes per dimension the plan kernel's shared-memory histogram covers (14 ints each)
 
@@ -364,7 +367,10 @@ __device__ __forceinline__ void ch_mbar_wait(unsigned long long *b, unsigned par
 // A warp keeps CH_SLOTS tiles in flight (TMA bulk copies into its own ring) and the row descriptors of the next tile
 // (only the stores and the choice of the block need them) one tile ahead.  No table, no decoding: everything a row
 // needs is in its descriptor (k_chain_link).
-constexpr int CH_SLOTS = 4;
+#ifndef C3SC_CH_SLOTS
+#define C3SC_CH_SLOTS 4
+#endif
+constexpr int CH_SLOTS = C3SC_CH_SLOTS;
 
 // dynamic shared memory of k_chain_step: the rings (16-byte aligned), then the mbarriers
 __host__ __device__ inline size_t chain_step_smem(int rs, int *bar_off = nullptr)
