@@ -888,8 +888,13 @@ static int run_batch(const DevProblem &P, int model, int arith, Scratch &scr, co
         ca.setw = setw; ca.rs = rs;
         ca.kst = (int *)scr.plan_k.p + si * pk; ca.tst = (int *)scr.plan_t.p + si * pt; ca.ent = (int *)scr.plan_e.p + si * pe;
         ca.xrows = chain_x_rows((int)d, P.nmax, (long long)FS);
-        ca.rowd = (int2 *)scr.plan_l.p + si * (d - 1) * (size_t)ca.xrows;
-        ca.rowp = (int2 *)scr.plan_l.p + (nsup + si) * (d - 1) * (size_t)ca.xrows;
+        {   // plan_l: [nsup] row descriptors (4 B per row) | [nsup] prefix slots (8 B per row) | [nsup] tile buckets (4 B per 8 rows)
+            const size_t per = (d - 1) * (size_t)ca.xrows;
+            char *pl = (char *)scr.plan_l.p;
+            ca.rowd = (int *)pl + si * per;
+            ca.rowp = (int2 *)(pl + nsup * per * 4) + si * per;
+            ca.tileb = (int *)(pl + nsup * per * 12) + si * (per / 8);
+        }
         ca.inv = (int *)scr.plan_i.p + si * pe; ca.invstride = (int)FS;
         ca.nmax = P.nmax; ca.entstride = (int)(3 * FS);
         return ca;

@@ -37,10 +37,10 @@
 namespace c3sc {
 
 #ifndef C3SC_CH_NT
-#define C3SC_CH_NT 256
+#define C3SC_CH_NT 128
 #endif
-constexpr int CH_NT = C3SC_CH_NT;     // step kernel: 8 warps
-constexpr int CH_PREFIX = 1 << 30;    // ChainArgs::rowd[].y: the row also goes to the two slots in rowp[]
+constexpr int CH_NT = C3SC_CH_NT;     // step kernel: 4 warps per CTA, six CTAs per SM (256 x 2 per SM: +1 % time)
+constexpr int CH_PREFIX = 1 << 30;    // ChainArgs::rowd[]: the row (a prefix) also goes to the two slots in rowp[]
 constexpr int CH_NMAX = 768;          // nodes per dimension the plan kernel's shared-memory histogram covers (14 ints each)
 
 __host__ __device__ inline int ft_rec_rs(int rmax) { return (rmax + 3) & ~3; }                // row stride of a record
@@ -62,11 +62,12 @@ struct ChainArgs {
     int nmax, entstride;      // entstride = 3 * (fibers of a full chunk)
     int *inv;                 // [d][invstride][3]   row of the fiber's centre block / lower slot / upper slot in dimension m's
                               //                     bucket order, relative to its side's first row
-    int2 *rowd;               // [d-1][xrows]        per row of launch t's buffer: x = where the product goes (>= 0: row of launch
-                              //                     t+1's buffer; < 0: ~(row of the chunk's records, in units of RS doubles);
-                              //                     INT_MIN: padding row), y = side * 65536 + block of the row's bucket, + CH_PREFIX
-                              //                     when the row is a prefix that two neighbour slots of launch t+1 take as well
+    int *rowd;                // [d-1][xrows]        per row of launch t's buffer, where the product goes: >= 0 a row of launch
+                              //                     t+1's buffer (+ CH_PREFIX when the row is a prefix that two neighbour slots of
+                              //                     launch t+1 take as well), < 0: ~(row of the chunk's records, in units of RS
+                              //                     doubles), INT_MIN: padding row
     int2 *rowp;               // [d-1][xrows]        those two slots (rows of launch t+1's buffer), prefix rows only
+    int *tileb;               // [d-1][xrows / 8]    per tile of launch t: side * 65536 + block of the tile's bucket
     int invstride;            // fibers of a full chunk
     double *x[2];             // row buffers of the launches, X[t & 1] read by launch t; xrows rows of RS doubles each
     long long xrows;
@@ -274,7 +275,8 @@ __global__ void __launch_bounds__(256) k_chain_link(ChainArgs a, ChainPlanStride
     const int *tst0 = a.tst + blockIdx.x * S.tst;
     const int *ent = a.ent + blockIdx.x * S.ent + (size_t)m * a.entstride;
     const int *inv = a.inv + blockIdx.x * S.inv;
-    int2 *rowd = a.rowd + blockIdx.x * S.rowd, *rowp = a.rowp + blockIdx.x * S.rowd;
+    int *rowd = a.rowd + blockIdx.x * S.rowd, *tileb = a.tileb + blockIdx.x * (S.rowd / 8);
+    int2 *rowp = a.rowp + blockIdx.x * S.rowd;
     const int recrows = a.setw / a.rs;
     __shared__ int s_i0[CH_LINK_E];
     __shared__ bool s_ct[CH_LINK_E];
@@ -290,7 +292,9 @@ __global__ void __launch_bounds__(256) k_chain_link(ChainArgs a, ChainPlanStride
         // rows of the right side lie behind the left side's tiles, in this launch's buffer and in the next one's
         const long long here = side ? 8LL * tst0[((size_t)t * 2 + 0) * (nmax + 1) + a.P.ngrid[t]] : 0;
         const int next = (side && t + 1 <= d - 2) ? 8 * tst0[((size_t)(t + 1) * 2 + 0) * (nmax + 1) + a.P.ngrid[t + 1]] : 0;
-        int2 *out = rowd + (size_t)t * a.xrows + here + 8LL * t0, *outp = rowp + (size_t)t * a.xrows + here + 8LL * t0;
+        int *out = rowd + (size_t)t * a.xrows + here + 8LL * t0;
+        int2 *outp = rowp + (size_t)t * a.xrows + here + 8LL * t0;
+        int *outb = tileb + (size_t)t * (a.xrows / 8) + here / 8 + t0;
         const int mn = side ? m - 1 : m + 1;
         const int bw = side * 65536 + j;
         // where an entry's fiber goes next: loaded once per ENTRY (tag, then the inverse rows of the next dimension)
@@ -314,11 +318,11 @@ __global__ void __launch_bounds__(256) k_chain_link(ChainArgs a, ChainPlanStride
                 s_i0[i] = i0; s_ct[i] = cont;
             }
             __syncthreads();
-            int2 *o = out + (size_t)eb * nin;
+            int *o = out + (size_t)eb * nin;
             for (int r = threadIdx.x; r < n * nin; r += blockDim.x) {
                 const int q = r / nin, v = r - q * nin;
                 const bool cont = s_ct[q];
-                o[r] = make_int2(cont ? s_i0[q] + v : s_i0[q] - v, (cont && v == 0) ? bw | CH_PREFIX : bw);
+                o[r] = cont ? (s_i0[q] + v) | (v == 0 ? CH_PREFIX : 0) : s_i0[q] - v;
             }
         }
         // neighbour entries: one row each, the new vector nin (lower) or nin + 1 (upper)
@@ -326,9 +330,10 @@ __global__ void __launch_bounds__(256) k_chain_link(ChainArgs a, ChainPlanStride
             int i0; bool cont;
             entry(cslo + i, false, i0, cont);
             const int v = cslo + i < cshi ? nin : nin + 1;
-            out[nc + i] = make_int2(cont ? i0 + v : i0 - v, bw);
+            out[nc + i] = cont ? i0 + v : i0 - v;
         }
-        for (int r = rows + threadIdx.x; r < 8 * (t1 - t0); r += blockDim.x) out[r] = make_int2(CH_ROW_PAD, bw);
+        for (int r = rows + threadIdx.x; r < 8 * (t1 - t0); r += blockDim.x) out[r] = CH_ROW_PAD;
+        for (int tl = threadIdx.x; tl < t1 - t0; tl += blockDim.x) outb[tl] = bw;
     }
 }
 #endif
@@ -382,7 +387,7 @@ __host__ __device__ inline size_t chain_step_smem(int rs, int *bar_off = nullptr
 }
 
 template <int KS>
-__global__ void __launch_bounds__(CH_NT, 2) k_chain_step(const ChainArgs a, int t)
+__global__ void __launch_bounds__(CH_NT, 512 / CH_NT) k_chain_step(const ChainArgs a, int t)
 {
     constexpr int NT8 = (KS + 1) / 2;                       // 8-wide output tiles
     extern __shared__ __align__(16) double shd[];
@@ -426,7 +431,8 @@ __global__ void __launch_bounds__(CH_NT, 2) k_chain_step(const ChainArgs a, int 
     if (tile >= tend) return;
     const double *xin = a.x[t & 1];
     double *xout = a.x[(t + 1) & 1];
-    const int2 *rowd = a.rowd + (size_t)t * a.xrows + gid, *rowp = a.rowp + (size_t)t * a.xrows + gid;
+    const int *rowd = a.rowd + (size_t)t * a.xrows + gid, *tileb = a.tileb + (size_t)t * (a.xrows / 8);
+    const int2 *rowp = a.rowp + (size_t)t * a.xrows + gid;
     const unsigned tbytes = (unsigned)(TB * sizeof(double));
 
     // ring fill: the first CH_SLOTS tiles of this warp's range
@@ -437,14 +443,15 @@ __global__ void __launch_bounds__(CH_NT, 2) k_chain_step(const ChainArgs a, int 
     }
     double B[KS][NT8];
     int Bsj = -1;
-    int2 D0 = __ldg(rowd + (size_t)tile * 8);
+    int D0 = __ldg(rowd + (size_t)tile * 8), J0 = __ldg(tileb + tile);
     unsigned phase = 0;                                     // bit q: parity of slot q's next completion
     for (int it = 0; tile < tend; tile++, it++) {
-        int2 D1 = D0;
-        if (tile + 1 < tend) D1 = __ldg(rowd + (size_t)(tile + 1) * 8);
-        const int sj0 = D0.y & (CH_PREFIX - 1);
+        int D1 = D0, J1 = J0;
+        if (tile + 1 < tend) { D1 = __ldg(rowd + (size_t)(tile + 1) * 8); J1 = __ldg(tileb + tile + 1); }
+        const int sj0 = J0;
+        const bool prefix = D0 >= 0 && (D0 & CH_PREFIX);
         int2 P0 = make_int2(-1, -1);                        // a prefix row's two extra destinations: needed by its stores only
-        if (D0.y & CH_PREFIX) P0 = __ldg(rowp + (size_t)tile * 8);
+        if (prefix) P0 = __ldg(rowp + (size_t)tile * 8);
         if (sj0 != Bsj) {                                   // (the bucket is the same for the eight rows of a tile)
             Bsj = sj0;
             const int side = Bsj >> 16, j = Bsj & 0xffff, m = side ? mR : mL;
@@ -484,13 +491,13 @@ __global__ void __launch_bounds__(CH_NT, 2) k_chain_step(const ChainArgs a, int 
         for (int ks = 0; ks < KS; ks++)
 #pragma unroll
             for (int nt = 0; nt < NT8; nt++) ch_dmma(acc[nt][0], acc[nt][1], A[ks], B[ks][nt]);
-        if (D0.x != (int)0x80000000) {
+        if (D0 != (int)0x80000000) {
             // launch t+1's buffer (plus the two neighbour slots for a prefix), or the fiber's record
-            double *dst = (D0.x >= 0 ? xout + (size_t)D0.x * RS : a.sets + (size_t)(~D0.x) * RS) + 2 * tig;
+            double *dst = (D0 >= 0 ? xout + (size_t)(D0 & (CH_PREFIX - 1)) * RS : a.sets + (size_t)(~D0) * RS) + 2 * tig;
 #pragma unroll
             for (int nt = 0; nt < NT8; nt++)
                 if (8 * nt + 2 * tig < RS) *reinterpret_cast<double2 *>(dst + 8 * nt) = make_double2(acc[nt][0], acc[nt][1]);
-            if (D0.y & CH_PREFIX) {
+            if (prefix) {
                 double *dlo = xout + (size_t)P0.x * RS + 2 * tig, *dhi = xout + (size_t)P0.y * RS + 2 * tig;
 #pragma unroll
                 for (int nt = 0; nt < NT8; nt++)
@@ -500,7 +507,7 @@ __global__ void __launch_bounds__(CH_NT, 2) k_chain_step(const ChainArgs a, int 
                     }
             }
         }
-        D0 = D1;
+        D0 = D1; J0 = J1;
     }
 }
 

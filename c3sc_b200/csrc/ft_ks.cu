@@ -20,7 +20,7 @@ static int launch_chain_steps_t(const ChainArgs &a, cudaStream_t st)
     const bool g_no_pdl = getenv("C3SC_NO_PDL") != nullptr;
     // CTAs of a step: the kernel is latency-bound (dependent L2 round trips, a handful of tiles per warp), and while it
     // holds an SM's registers the other lane's node kernel cannot use that SM
-    int grid = ft_sm_count() * 2;
+    int grid = ft_sm_count() * (1536 / CH_NT) / 2;         // six 128-thread CTAs per SM
     { const char *e = getenv("C3SC_CHAIN_GRID"); if (e && atoi(e) > 0) grid = atoi(e); }
     size_t most = 0;
     for (int t = 0; t + 1 < a.ft.d; t++) {
