@@ -254,6 +254,53 @@ def test_bucketed_and_per_fiber_chain_stages_agree(gpu, monkeypatch):
     prob.close(); vf.close()
 
 
+def test_commit_on_a_side_stream_is_waited_for_before_the_cores_are_read(gpu):
+    """c3sc_valuef_commit on a stream of its own (bench.py at N > 1: broadcast + commit beside the batch's plan): the value
+    function remembers the event of its last commit and a c3sc_vi_batch_dev on ANOTHER stream waits for it before its first kernel
+    that reads the cores.  New cores are written into the device buffer on a side stream behind a long dummy kernel queue, then
+    committed there; the batch on the main stream must see them -- for the bucketed and the per-fiber chain stage"""
+    import torch
+    cfg = configs.get_config("lqgnd_reflect", n=16, rank=9, dx=6)
+    prob = capi.Problem(cfg, arith=1)
+    ranks = cfg.ranks()
+    c0 = synthetic.random_cores(cfg.ngrid, ranks, seed=1)
+    c1 = synthetic.random_cores(cfg.ngrid, ranks, seed=2)
+    dev = torch.device("cuda", 0)
+    for F in (300, 4500):                                # per-fiber chains / bucketed chains
+        dv, fi = synthetic.random_fibers(cfg.ngrid, F, seed=F)
+        ref = capi.ValueF(cfg.ngrid, ranks, c1)
+        want, _ = prob.vi_batch(ref, dv, fi)
+        ref.close()
+        vf = capi.ValueF(cfg.ngrid, ranks, c0)
+        ptr, count = vf.device_buffer()
+        flat = torch.from_numpy(np.concatenate([np.asarray(c).reshape(-1) for c in c1])).to(dev)
+        assert flat.numel() == count
+        dv_d = torch.from_numpy(np.ascontiguousarray(dv)).to(dev); fi_d = torch.from_numpy(np.ascontiguousarray(fi)).to(dev)
+        out = torch.zeros(F * cfg.n, dtype=torch.float64, device=dev)
+        main = torch.cuda.current_stream(dev); side = torch.cuda.Stream(dev)
+        dst = torch.as_tensor(_DevArr(ptr, count), device=dev)
+        big = torch.empty(64 << 20, dtype=torch.float32, device=dev)
+        torch.cuda.synchronize()
+        with torch.cuda.stream(side):
+            for _ in range(20):
+                big.mul_(1.0001)                         # keeps the side stream busy: the commit below completes late
+            dst.copy_(flat)
+            vf.commit(stream=side.cuda_stream)
+        prob.vi_batch_dev(vf, F, dv_d.data_ptr(), fi_d.data_ptr(), cfg.n, out.data_ptr(), stream=main.cuda_stream)
+        torch.cuda.synchronize()
+        got = out.cpu().numpy().reshape(F, cfg.n)
+        assert np.array_equal(got, np.asarray(want).reshape(F, cfg.n))
+        vf.close()
+    prob.close()
+
+
+class _DevArr:
+    """a device buffer of the library as a __cuda_array_interface__ object (float64)"""
+
+    def __init__(self, ptr, count):
+        self.__cuda_array_interface__ = {"shape": (int(count),), "typestr": "<f8", "data": (int(ptr), False), "version": 3}
+
+
 @pytest.mark.parametrize("name,n,rank,dx,F", [("lqgnd_reflect", 12, 7, 10, 2600), ("lqgnd", 16, 5, 6, 3000), ("dubinscar_new", 24, 6, None, 2600),
                                                ("double_int", 40, 5, None, 2500), ("skidding5d", 12, 4, None, 2600)])
 def test_fused_stage2_equals_the_two_kernel_pipeline(gpu, monkeypatch, name, n, rank, dx, F):
