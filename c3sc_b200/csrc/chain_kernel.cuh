@@ -13,10 +13,12 @@
 // step.  Every DMMA row is a useful vector (the per-fiber kernel k_ft_chains spends a whole 8-row tile on each of
 // the two neighbour products), and a block is read once per warp instead of once per fiber.
 //
-//   k_chain_plan   counting sort of the chunk's (fiber, role) entries by (side, dimension, block); roles: centre,
-//                  lower neighbour, upper neighbour.  One CTA per (chunk, dimension).  Also the inverse: the ROW a
-//                  fiber's centre block / lower / upper slot has in the dimension's bucket order.
-//   k_chain_link   per entry: where the fiber's rows go in the NEXT dimension's bucket order (or -1: the side is done).
+//   k_chain_count / k_chain_scan / k_chain_scatter
+//                  counting sort of the chunk's (fiber, role) entries by (side, dimension, block); roles: centre,
+//                  lower neighbour, upper neighbour.  Also the inverse: the ROW a fiber's centre block / lower /
+//                  upper slot has in the dimension's bucket order.
+//   k_chain_link   per row of every launch: where the row's product goes (the fiber's rows in the NEXT dimension's
+//                  bucket order, or the fiber's record when the side is done), and per tile its bucket.
 //   k_chain_step   launch t = 0..d-2 advances the left sets through dimension t and the right sets through d-1-t.
 //
 // SCATTER ON WRITE, STREAM ON READ.  The rows a launch works on lie in bucket order in a row buffer X[t & 1]: tile i of
@@ -55,7 +57,7 @@ struct ChainArgs {
     const int *nbr_fixed_in;  // optional caller-supplied neighbour pairs [F*2*(d-1)]
     double *sets;             // [F*setw]
     int setw, rs;
-    // plan of this chunk (device, written by k_chain_plan):
+    // plan of this chunk (device, written by k_chain_count / _scan / _scatter / _link):
     int *kst;                 // [d][2][nmax*3 + 1]  start of (block j, role) inside the dimension's entry list
     int *tst;                 // [d][2][nmax + 1]    first 8-row tile of block j; [..][N] = number of tiles
     int *ent;                 // [d][entstride]      entries: fiber | k << 24
@@ -262,7 +264,7 @@ __global__ void __launch_bounds__(CHP_NT) k_chain_scatter(ChainArgs a, int FC, C
 
 // grid (chunks, d, Z), 256 threads: the row descriptors.  CTA (c, m, z) walks buckets z, z+Z, .. of dimension m (both sides)
 // and writes, for every row of the bucket, where the row's product goes: the fiber's rows in the next dimension of its side
-// (m+1 left, m-1 right; k_chain_plan's inverse rows), or the fiber's record when the side ends here.
+// (m+1 left, m-1 right; k_chain_scatter's inverse rows), or the fiber's record when the side ends here.
 #ifndef C3SC_FT_KS_UNIT
 constexpr int CH_ROW_PAD = (int)0x80000000;
 constexpr int CH_LINK_E = 1024;       // centre entries of a bucket staged per round
