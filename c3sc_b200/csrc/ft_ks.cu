@@ -95,7 +95,20 @@ static int launch_mma_t(const FtArgs &a, const CtlArgs *fused, int nsplit, cudaS
     if (fused) {
         if (b.nsplit != 1) return (int)cudaErrorInvalidValue;       // the caller asked ft_nodes_nsplit first
         k_ft_nodes_fused<KS><<<dim3((unsigned)grid, 1u), FTN_NT, smem, st>>>(b, *fused, b.sets);
-    } else k_ft_nodes<KS><<<dim3((unsigned)grid, (unsigned)b.nsplit), FTN_NT, smem, st>>>(b, b.sets);
+    } else {
+        // programmatic dependent launch behind the chain stage (k_ft_chains / the last k_chain_step trigger early; the kernel waits
+        // before it reads their records).  Behind any other kernel the attribute changes nothing: no early trigger, no early start.
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)grid, (unsigned)b.nsplit); cfg.blockDim = dim3(FTN_NT); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = getenv("C3SC_NO_PDL") ? 0 : 1;
+        const double *setsp = b.sets;
+        e = cudaLaunchKernelEx(&cfg, k_ft_nodes<KS>, b, setsp);
+        if (e != cudaSuccess) return (int)e;
+    }
     return (int)cudaGetLastError();
 }
 

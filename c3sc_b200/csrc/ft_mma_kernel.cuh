@@ -98,6 +98,9 @@ __global__ void __launch_bounds__(FTC_NT, KS <= 6 ? C3SC_FTC_MINB : 1) k_ft_chai
     int *sFix = iw, *sNf = iw + d;                   // sNf[2*i], sNf[2*i+1]: pair of dimension i
     const int SETW = a.setw, RS = a.rs;
 
+    // programmatic dependent launch: the node kernel behind this one may start its prologue (tile buffers, flags, first TMA
+    // fetches) now; it waits with griddepcontrol.wait before it reads the records written here
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     // every value a fragment may touch must be finite (padding rows meet zero rows of the block)
     for (int e = lane; e < cp.perWarpDoubles; e += 32) buf0[e] = 0.0;
 
@@ -410,6 +413,9 @@ __device__ __forceinline__ void ftn_tile_loop(const FtNodeCtx &c)
     const int gid = lane >> 2, tig = lane & 3;
     const int d = c.d, RS = c.RS;
 
+    // The chain records are the first thing of the kernel that the preceding launch (chain stage) writes: the kernel is launched
+    // with programmatic stream serialization, everything above (tile buffers, flags, the first tile fetches) overlaps its tail.
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     // ---- register-resident operands ---------------------------------------------------------------
     // phase 1: B fragment of R (row b = 4ks+tig, col fiber gid), A fragment of L (row fiber gid, col a = 4ks+tig)
     // (node pairs: a warp computes w OR u, so it keeps only R or only L, in Rf)
