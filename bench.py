@@ -704,6 +704,10 @@ def pi_step(prob, cfg, ranks, vf, dv_h, fi_h, dv_d, fi_d, F, N, dev, timed, time
         for _ in range(K):
             subiter()
     ms_imp = timed(improve, 3, 1) / 3
+
+    def improve_same():                     # policy function == iterate (the first sub-iteration of a solver step): one stage 1
+        prob.pi_batch_dev(vf_it, vf_it, F, dv_d.data_ptr(), fi_d.data_ptr(), N, 0, rows.data_ptr(), 0, val.data_ptr(), stream=st)
+    ms_imp_same = timed(improve_same, 3, 1) / 3
     ms_sub = timed(subiter, 5, 1) / 5
     ms_all = timed(whole, 2, 1) / 2
     out_h = torch.empty(F * N, dtype=torch.float64).pin_memory()
@@ -714,7 +718,7 @@ def pi_step(prob, cfg, ranks, vf, dv_h, fi_h, dv_d, fi_d, F, N, dev, timed, time
     ms_e2e = timed_host(e2e_sub, 3, 1) / 3
     nodes = F * N
     rec = {"what": f"one policy improvement + {K} sub-iterations on {F} fibers, policy rows resident on the device (c3sc_pi_batch_dev)",
-           "ms_improvement": ms_imp, "ms_sub_iteration": ms_sub, "ms_total": ms_all,
+           "ms_improvement": ms_imp, "ms_improvement_policy_is_iterate": ms_imp_same, "ms_sub_iteration": ms_sub, "ms_total": ms_all,
            "node_backups_per_s": nodes * (K + 1) / (ms_all * 1e-3), "sub_iteration_node_evals_per_s": nodes / (ms_sub * 1e-3),
            "e2e_sub_iteration": {"value": nodes / (ms_e2e * 1e-3), "unit": "node-evaluations/s", "ms": ms_e2e,
                                  "api": "c3sc_pi_batch_resident (pinned descriptors in, values out, rows stay on the device)",

@@ -784,6 +784,8 @@ struct BatchArgs {
     cudaStream_t peer_stream;
     cudaEvent_t copies_done;
     cudaEvent_t cores_ready;              // the value function was committed on another stream: wait here before the cores are read
+    double *eval_value;                   // MODE_VI with rows: after a chunk's improvement, evaluate the rows just written against the
+                                          // SAME neighbour values (policy and iterate are one value function) into this buffer
 };
 
 static thread_local size_t g_chunk_bytes = (size_t)192 << 20;   // slot-major cost scratch in flight (all lanes) when stage 1a runs per fiber
@@ -1042,6 +1044,20 @@ static int run_batch(const DevProblem &P, int model, int arith, Scratch &scr, co
         if (rc == -1) return fail(C3SC_EUNSUPPORTED, "model %d with dx=%d is not instantiated", model, P.dx);
         if (rc != 0) return fail(C3SC_ECUDA, "control kernel launch: %s", cudaGetErrorString((cudaError_t)rc));
         if (!fuse) g_launches++;
+        if (b.eval_value && b.mode == MODE_VI && c.rows && !fuse) {
+            // bellman_pi's first visit of a node (src/bellman.c:1831-1871) is an improvement against the policy function followed
+            // by an evaluation of the new row against the iterate; when the two are the SAME value function the evaluation finds
+            // its neighbour values still in the chunk's scratch -- no second pass of stage 1
+            CtlArgs e = c;
+            e.rows_in = c.rows; e.rows = nullptr; e.argmin = nullptr;
+            e.value = b.eval_value + n0;
+            e.npeer = 0;
+            if (model == C3SC_MODEL_LQGND) rc = (P.dx <= 6) ? launch_control_lqg_lo(P.dx, arith, e, 1, st) : launch_control_lqg_hi(P.dx, arith, e, 1, st);
+            else rc = launch_control_misc(model, P.dx, arith, e, 1, st);
+            if (rc == -1) return fail(C3SC_EUNSUPPORTED, "model %d with dx=%d is not instantiated", model, P.dx);
+            if (rc != 0) return fail(C3SC_ECUDA, "policy evaluation kernel launch: %s", cudaGetErrorString((cudaError_t)rc));
+            g_launches++;
+        }
         if ((b.copy_stream || b.peer_copy) && b.chunk_done) {
             CK(cudaEventRecord(b.chunk_done, st));
             if (b.peer_copy && c.value && b.peer_stream) {  // the chunk's values into every peer's gathered buffer, off the SMs
@@ -1159,6 +1175,10 @@ int c3sc_pi_batch_dev(c3sc_problem *p, const c3sc_valuef *vf_policy, const c3sc_
         b.mode = MODE_VI;
         b.out.rows = d_rows;
         b.out.argmin = d_argmin;
+        if (vf_policy == vf_iter && !getenv("C3SC_FUSE") && !getenv("C3SC_PI_TWO_PASSES")) {
+            b.eval_value = d_value;             // one pass: every chunk's rows are evaluated against the chunk's own scratch
+            return run_batch(p->P, p->model, p->arith, p->scr, &p->grp, vf_policy->ft, b, (cudaStream_t)stream);
+        }
         rc = run_batch(p->P, p->model, p->arith, p->scr, &p->grp, vf_policy->ft, b, (cudaStream_t)stream);
         if (rc) return rc;
     }

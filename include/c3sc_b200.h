@@ -231,7 +231,10 @@ int c3sc_stage1_batch_dev(c3sc_problem *p, const c3sc_valuef *vf, size_t F,
 /* bellman_pi over F fibers (src/bellman.c:1702-1886).  have_rows == 0: pick
  * u* against vf_policy, store the policy rows in d_rows (and argmin if
  * wanted), then evaluate against vf_iter; have_rows != 0: later sub-iteration,
- * reuse d_rows.  d_rows [F*ldo*(2dx+3)].                                   */
+ * reuse d_rows.  d_rows [F*ldo*(2dx+3)].  When vf_policy and vf_iter are the
+ * SAME object (the first sub-iteration of a solver step) the evaluation takes
+ * its neighbour values from the improvement's scratch: one pass of stage 1,
+ * bit-identical results.                                                    */
 int c3sc_pi_batch_dev(c3sc_problem *p, const c3sc_valuef *vf_policy, const c3sc_valuef *vf_iter,
                       size_t F, const int32_t *d_dim_vary, const int32_t *d_fixed_ind,
                       size_t ldo, int have_rows, double *d_rows, int32_t *d_argmin,

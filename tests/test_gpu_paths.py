@@ -294,6 +294,35 @@ def test_commit_on_a_side_stream_is_waited_for_before_the_cores_are_read(gpu):
     prob.close()
 
 
+@pytest.mark.parametrize("name,n,rank,dx,F", [("lqgnd_reflect", 20, 9, 8, 5000), ("lqgnd", 16, 5, 6, 700), ("skidding5d", 12, 4, None, 900)])
+def test_pi_first_visit_in_one_pass_equals_two_passes(gpu, monkeypatch, name, n, rank, dx, F):
+    """bellman_pi's first visit (improvement against the policy function, then evaluation of the new rows against the iterate,
+    src/bellman.c:1831-1871) when both are the SAME value function: the evaluation takes the neighbour values from the chunk's
+    scratch of the improvement instead of a second stage 1 -- rows, argmin and values bit-identical to the two-pass form"""
+    import torch
+    cfg = configs.get_config(name, n=n, rank=rank, dx=dx) if dx else configs.get_config(name, n=n, rank=rank)
+    prob = capi.Problem(cfg, arith=1)
+    ranks = cfg.ranks()
+    vf = capi.ValueF(cfg.ngrid, ranks, synthetic.random_cores(cfg.ngrid, ranks))
+    dv, fi = synthetic.random_fibers(cfg.ngrid, F, seed=3)
+    dev = torch.device("cuda", 0)
+    dv_d = torch.from_numpy(np.ascontiguousarray(dv)).to(dev); fi_d = torch.from_numpy(np.ascontiguousarray(fi)).to(dev)
+    N = cfg.n; RW = 2 * cfg.dx + 3
+    res = []
+    for two in (False, True):
+        if two:
+            monkeypatch.setenv("C3SC_PI_TWO_PASSES", "1")
+        rows = torch.zeros(F * N * RW, dtype=torch.float64, device=dev); val = torch.zeros(F * N, dtype=torch.float64, device=dev)
+        arg = torch.zeros(F * N, dtype=torch.int32, device=dev)
+        prob.pi_batch_dev(vf, vf, F, dv_d.data_ptr(), fi_d.data_ptr(), N, 0, rows.data_ptr(), arg.data_ptr(), val.data_ptr())
+        torch.cuda.synchronize()
+        res.append((rows.cpu().numpy(), val.cpu().numpy(), arg.cpu().numpy()))
+    assert np.array_equal(res[0][0], res[1][0]) and np.array_equal(res[0][2], res[1][2])
+    assert np.array_equal(res[0][1], res[1][1])
+    assert np.abs(res[0][1]).max() > 0
+    prob.close(); vf.close()
+
+
 class _DevArr:
     """a device buffer of the library as a __cuda_array_interface__ object (float64)"""
 
