@@ -670,8 +670,8 @@ struct GridWalkQ {
 // 21 neighbour values of a node arrive from L2 -- one node per thread at 4 CTAs/SM (64 registers, ~100 B of
 // spills) measured 4 % faster end to end than two nodes per thread at 2 CTAs/SM (profiles/r01_lanes.md).
 #ifndef C3SC_GRID_MINB
-#define C3SC_GRID_MINB 4
-#endif
+#define C3SC_GRID_MINB 3          // re-measured with the 10 922-fiber chunks of round 2: 3 CTAs/SM (85 registers, no spills) 1.735 ms per
+#endif                             // 65 536-fiber step, 4 (64 registers) 1.751, 2: 1.801, 5: 1.958 (profiles/r02b_stage1.md)
 #ifndef C3SC_GRID_Q
 #define C3SC_GRID_Q 1          // nodes per thread for large batches
 #endif
