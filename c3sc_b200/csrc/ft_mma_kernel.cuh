@@ -287,7 +287,10 @@ __device__ __forceinline__ void node_wu(const double *gj, int offW, int offU, in
         }
         if constexpr (DO_U) {
 #pragma unroll
-            for (int nb = 0; nb < MT; nb++) dmma_m8n8k4(du[nb][0], du[nb][1], Lf[ks], gj[offU + nb * 8 * ldk + ks * 4]);
+            // u TRANSPOSED, u^T = G^T L^T: the same G elements (the B fragment of G is the A fragment of G^T) and the same L
+            // registers with the operands swapped; the D fragment then is (rank row b, fiber columns) like w's, whose stores
+            // take 2 shared-memory wavefronts instead of 4
+            for (int nb = 0; nb < MT; nb++) dmma_m8n8k4(du[nb][0], du[nb][1], gj[offU + nb * 8 * ldk + ks * 4], Lf[ks]);
         }
     }
 #pragma unroll
@@ -297,10 +300,10 @@ __device__ __forceinline__ void node_wu(const double *gj, int offW, int offU, in
             sW[(2 * tig) * SW + (8 * mt + gid) * FTN_TP + jw] = dw[mt][0];
             sW[(2 * tig + 1) * SW + (8 * mt + gid) * FTN_TP + jw] = dw[mt][1];
         }
-        if constexpr (DO_U) {                                    // D: row fiber gid, cols b = 8nb+2tig, +1
-            const int ju = warp ^ ftn_swz(2 * tig);              // swz(8mt + 2tig + h) = swz(2tig)
-            sU[gid * SW + (8 * mt + 2 * tig) * FTN_TP + ju] = du[mt][0];
-            sU[gid * SW + (8 * mt + 2 * tig + 1) * FTN_TP + ju] = du[mt][1];
+        if constexpr (DO_U) {                                    // D of u^T: row b = 8mt+gid, cols fiber 2*tig, 2*tig+1
+            const int ju = warp ^ ftn_swz(gid);
+            sU[(2 * tig) * SW + (8 * mt + gid) * FTN_TP + ju] = du[mt][0];
+            sU[(2 * tig + 1) * SW + (8 * mt + gid) * FTN_TP + ju] = du[mt][1];
         }
     }
 }
