@@ -17,8 +17,8 @@ namespace c3sc {
 int launch_control_lqg_lo(int dx, int arith, const CtlArgs &a, int pi_eval, cudaStream_t st);
 int launch_control_lqg_hi(int dx, int arith, const CtlArgs &a, int pi_eval, cudaStream_t st);
 int launch_control_misc(int model, int dx, int arith, const CtlArgs &a, int pi_eval, cudaStream_t st);
-int launch_group_fibers(const DevProblem &P, int F, int FC, const int *dim_vary, const int *fixed_ind, int *perm, int *cnt_all,
-                        cudaStream_t st);
+int launch_group_fibers(const DevProblem &P, int F, const ChunkLayout &lay, const int *dim_vary, const int *fixed_ind, int *perm,
+                        int *cnt_all, cudaStream_t st);
 int launch_pack_cores(const DevFT &ft, double *baseT, double *baseP, double *baseQ, cudaStream_t st);
 long long ft_padded_layout(DevFT &ft);
 long long ft_compact_layout(DevFT &ft);
@@ -151,8 +151,16 @@ struct LaneScratch {
     cudaStream_t chain_stream = nullptr;
     cudaEvent_t chain_done = nullptr, sets_free = nullptr;
     bool sets_busy = false;                 // sets_free was recorded for an earlier super-chunk of this batch
+    // host-buffer entries: lanes above 0 copy their finished chunks out on a stream of their own (lane 0 uses the problem's copy
+    // stream).  On ONE copy stream the copies wait for their chunks in the order they were queued -- lane 0's whole super-chunk
+    // before lane 1's first chunk -- and the second lane's copies end up behind the batch instead of under it.
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t copy_done = nullptr;
     void release()
     {
+        if (copy_stream) cudaStreamDestroy(copy_stream);
+        if (copy_done) cudaEventDestroy(copy_done);
+        copy_stream = nullptr; copy_done = nullptr;
         cst.release(); flag.release(); act.release(); sets.release(); xa.release(); xb.release();
         if (stream) cudaStreamDestroy(stream);
         if (join) cudaEventDestroy(join);
@@ -829,10 +837,14 @@ static int run_batch(const DevProblem &P, int model, int arith, Scratch &scr, co
     // chain steps of the lane's next super-chunk on a high-priority stream of their own: measured no gain (1.952 vs 1.939 ms per
     // 65 536-fiber step, profiles/r02_cross_step.md: the steps are L2-bandwidth work, not idle latency), so opt-in: C3SC_CHAIN_PRIO=1
     const bool chain_prio = bucketed && multi && getenv("C3SC_CHAIN_PRIO") && atoi(getenv("C3SC_CHAIN_PRIO")) == 1;
-    // host-buffer entries copy a chunk's results out while the next chunk computes; the last chunk's copy of each lane is exposed,
-    // so their chunks stay at the smaller size (e2e 2.58 against 2.78 G node-backups/s with the larger one)
+    // host-buffer entries copy a chunk's results out while the next chunk computes; the copy of each lane's last chunk is exposed.
+    // TAPERED chunks (default): the large chunks of the device-resident entries, and the last chunk of each lane's last super-chunk
+    // cut into pieces of 1/2, 1/4, 1/4 -- the throughput of the large chunks, the exposed tail of a small one.  C3SC_TAPER=0: equal
+    // chunks of the smaller size (e2e 2.58 against 2.78 G node-backups/s with equal chunks of the larger one).
     const bool host_out = b.copy_stream && (b.h_value || b.h_argmin);
-    size_t per_chunk = ((bucketed && !host_out) ? g_chunk_bytes_b : g_chunk_bytes) / (size_t)g_lanes / (b.ldo * CS * 8);
+    const bool taper_on = !(getenv("C3SC_TAPER") && atoi(getenv("C3SC_TAPER")) == 0);
+    const bool taper_want = host_out && multi && taper_on;
+    size_t per_chunk = ((bucketed && (!host_out || taper_want)) ? g_chunk_bytes_b : g_chunk_bytes) / (size_t)g_lanes / (b.ldo * CS * 8);
     if (!multi) per_chunk *= (size_t)g_lanes;
     { const char *pf = getenv("C3SC_CHUNK_FIBERS"); if (pf && atoi(pf) > 0) per_chunk = (size_t)atoi(pf); }    // tests: exact chunk size
     if (per_chunk < 1) per_chunk = 1;
@@ -846,9 +858,18 @@ static int run_batch(const DevProblem &P, int model, int arith, Scratch &scr, co
     const size_t FS = FC * SC;                                        // fibers per super-chunk
     nsup = (b.F + FS - 1) / FS;
     const size_t NSmax = FC * b.ldo;
+    ChunkLayout lay;
+    memset(&lay, 0, sizeof lay);
+    lay.FS = (int)FS; lay.FC = (int)FC; lay.SC = (int)SC; lay.m = (int)SC; lay.taper_from = 0;
+    if (taper_want && FC >= 4096) {                         // pieces stay above ~1000 fibers (125 node CTAs)
+        lay.m = (int)SC + 2;
+        lay.taper_from = nsup > L ? (int)(nsup - L) : 0;
+        lay.tail[0] = 0; lay.tail[1] = (int)((FC / 2 + 7) & ~(size_t)7); lay.tail[2] = lay.tail[1] + (int)((FC / 4 + 7) & ~(size_t)7);
+    }
+    const size_t nord = nsup * (size_t)lay.m;               // chunk slots of the batch (some empty)
     int setw = 0, rs = 0;
     if (mma) ft_record_geometry(ft, &setw, &rs);
-    if (scr.perm.reserve(b.F * 4) || scr.cnt.reserve(((b.F + FC - 1) / FC) * 64 * 4))
+    if (scr.perm.reserve(b.F * 4) || scr.cnt.reserve(nord * 64 * 4))
         return fail(C3SC_ECUDA, "cudaMalloc pipeline scratch failed");
     size_t pk = 0, pt = 0, pe = 0;
     if (bucketed) {
@@ -874,6 +895,10 @@ static int run_batch(const DevProblem &P, int model, int arith, Scratch &scr, co
             CK(cudaStreamCreateWithPriority(&ln.chain_stream, cudaStreamNonBlocking, greatest));
             CK(cudaEventCreateWithFlags(&ln.chain_done, cudaEventDisableTiming));
             CK(cudaEventCreateWithFlags(&ln.sets_free, cudaEventDisableTiming));
+        }
+        if (l > 0 && host_out && !ln.copy_stream) {
+            CK(cudaStreamCreateWithFlags(&ln.copy_stream, cudaStreamNonBlocking));
+            CK(cudaEventCreateWithFlags(&ln.copy_done, cudaEventDisableTiming));
         }
         ln.sets_busy = false;
     }
@@ -912,7 +937,7 @@ static int run_batch(const DevProblem &P, int model, int arith, Scratch &scr, co
             CK(cudaEventRecord(scr.start, st));
             CK(cudaStreamWaitEvent(gst, scr.start, 0));
         }
-        int rc = launch_group_fibers(P, (int)b.F, (int)FC, b.dim_vary, b.fixed_ind, (int *)scr.perm.p, (int *)scr.cnt.p, gst);
+        int rc = launch_group_fibers(P, (int)b.F, lay, b.dim_vary, b.fixed_ind, (int *)scr.perm.p, (int *)scr.cnt.p, gst);
         if (rc) return fail(C3SC_ECUDA, "grouping kernel: %s", cudaGetErrorString((cudaError_t)rc));
         g_launches++;
         if (aside) CK(cudaEventRecord(scr.grouped, gst));
@@ -953,11 +978,15 @@ static int run_batch(const DevProblem &P, int model, int arith, Scratch &scr, co
                 CK(cudaStreamWaitEvent(st, ln.chain_done, 0));
             }
         }
-        for (size_t c0 = s0; c0 < s0 + Fs; c0 += FC) {
-        const size_t Fc = (s0 + Fs - c0 < FC) ? s0 + Fs - c0 : FC;
+        for (size_t ord = si * (size_t)lay.m; ord < (si + 1) * (size_t)lay.m; ord++) {
+        int c0i, Fci;
+        ft_chunk_range(lay, (int)b.F, (int)ord, &c0i, &Fci);
+        if (Fci <= 0) continue;
+        const size_t c0 = (size_t)c0i, Fc = (size_t)Fci;
+        const bool last_of_super = c0 + Fc >= s0 + Fs;
         const size_t n0 = c0 * b.ldo;
         DevBuf &bcst = ln.cst, &bflag = ln.flag, &bact = ln.act, &bsets = ln.sets;
-        int *cnt = (int *)scr.cnt.p + 64 * (c0 / FC);   // [0,16) kcount, [16,32) kstart, [32] act_count
+        int *cnt = (int *)scr.cnt.p + 64 * ord;         // [0,16) kcount, [16,32) kstart, [32] act_count
         int rc;
         FtArgs a;
         memset(&a, 0, sizeof a);
@@ -982,7 +1011,7 @@ static int run_batch(const DevProblem &P, int model, int arith, Scratch &scr, co
             rc = launch_ft_costs(a, nullptr, st);
             if (rc) return fail(C3SC_ECUDA, "FT kernel launch: %s", cudaGetErrorString((cudaError_t)rc));
             g_launches += 1 + (mma && !bucketed);
-            if (chain_prio && c0 + FC >= s0 + Fs) { CK(cudaEventRecord(ln.sets_free, st)); ln.sets_busy = true; }
+            if (chain_prio && last_of_super) { CK(cudaEventRecord(ln.sets_free, st)); ln.sets_busy = true; }
             continue;
         }
         CtlArgs c;
@@ -1036,7 +1065,7 @@ static int run_batch(const DevProblem &P, int model, int arith, Scratch &scr, co
         rc = launch_ft_costs(a, fuse ? &c : nullptr, st);
         if (rc) return fail(C3SC_ECUDA, "FT kernel launch: %s", cudaGetErrorString((cudaError_t)rc));
         g_launches += 1 + (mma && !bucketed);
-        if (chain_prio && c0 + FC >= s0 + Fs) { CK(cudaEventRecord(ln.sets_free, st)); ln.sets_busy = true; }   // the last reader of the lane's records
+        if (chain_prio && last_of_super) { CK(cudaEventRecord(ln.sets_free, st)); ln.sets_busy = true; }   // the last reader of the lane's records
         if (fuse) rc = 0;
         else if (model == C3SC_MODEL_LQGND) rc = (P.dx <= 6) ? launch_control_lqg_lo(P.dx, arith, c, pe_, st)
                                                         : launch_control_lqg_hi(P.dx, arith, c, pe_, st);
@@ -1074,15 +1103,20 @@ static int run_batch(const DevProblem &P, int model, int arith, Scratch &scr, co
             }
         }
         if (b.copy_stream && b.chunk_done && (b.h_value || b.h_argmin)) {
-            CK(cudaStreamWaitEvent(b.copy_stream, b.chunk_done, 0));
-            if (b.h_value && c.value) CK(cudaMemcpyAsync(b.h_value + n0, c.value, Fc * b.ldo * 8, cudaMemcpyDeviceToHost, b.copy_stream));
-            if (b.h_argmin && c.argmin) CK(cudaMemcpyAsync(b.h_argmin + n0, c.argmin, Fc * b.ldo * 4, cudaMemcpyDeviceToHost, b.copy_stream));
+            const cudaStream_t cps = ln.copy_stream ? ln.copy_stream : b.copy_stream;      // the lane's own copy stream
+            CK(cudaStreamWaitEvent(cps, b.chunk_done, 0));
+            if (b.h_value && c.value) CK(cudaMemcpyAsync(b.h_value + n0, c.value, Fc * b.ldo * 8, cudaMemcpyDeviceToHost, cps));
+            if (b.h_argmin && c.argmin) CK(cudaMemcpyAsync(b.h_argmin + n0, c.argmin, Fc * b.ldo * 4, cudaMemcpyDeviceToHost, cps));
         }
         }
     }
     for (size_t l = 1; l < L; l++) {                        // the caller's stream continues after every lane
         CK(cudaEventRecord(scr.lane[l].join, scr.lane[l].stream));
         CK(cudaStreamWaitEvent(st0, scr.lane[l].join, 0));
+        if (host_out && scr.lane[l].copy_stream) {          // ... and the problem's copy stream after every lane's copies
+            CK(cudaEventRecord(scr.lane[l].copy_done, scr.lane[l].copy_stream));
+            CK(cudaStreamWaitEvent(b.copy_stream, scr.lane[l].copy_done, 0));
+        }
     }
     if (b.peer_copy && b.peer_stream && b.copies_done) {    // ... and after the last peer copy
         CK(cudaEventRecord(b.copies_done, b.peer_stream));

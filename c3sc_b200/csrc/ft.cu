@@ -28,15 +28,16 @@ int ft_sm_count() { ft_device_info(); return g_sms; }
 int ft_max_optin_smem() { ft_device_info(); return g_max_optin; }
 
 // perm / kcount / kstart / cleared active counters of ALL chunks of a batch.  1 launch.
-int launch_group_fibers(const DevProblem &P, int F, int FC, const int *dim_vary, const int *fixed_ind, int *perm, int *cnt_all,
-                        cudaStream_t st)
+int launch_group_fibers(const DevProblem &P, int F, const ChunkLayout &lay, const int *dim_vary, const int *fixed_ind, int *perm,
+                        int *cnt_all, cudaStream_t st)
 {
     if (F <= 0) return 0;
     GridDims ng;
     for (int i = 0; i < MAXD; i++) ng.n[i] = P.ngrid[i];
+    const int FC = lay.FC;
     const int vy = (FC * P.dx + 8191) / 8192 > 16 ? 16 : (FC * P.dx + 8191) / 8192;     // CTAs per chunk for the descriptor check
-    k_group_fibers<<<dim3((unsigned)((F + FC - 1) / FC), (unsigned)(vy < 1 ? 1 : vy)), 1024, 0, st>>>(F, FC, P.dx, dim_vary, fixed_ind, ng, P.err, perm,
-                                                                                                  cnt_all);
+    const unsigned nord = (unsigned)((F + lay.FS - 1) / lay.FS) * (unsigned)lay.m;      // chunk slots of all super-chunks
+    k_group_fibers<<<dim3(nord, (unsigned)(vy < 1 ? 1 : vy)), 1024, 0, st>>>(F, lay, P.dx, dim_vary, fixed_ind, ng, P.err, perm, cnt_all);
     return (int)cudaGetLastError();
 }
 

@@ -75,6 +75,30 @@ struct FtArgs {
 
 __host__ __device__ inline int ft_even_up(int v) { return (v + 1) & ~1; }
 
+// Chunks of a batch.  A super-chunk is FS = FC * SC fibers; it has m >= SC chunk slots.  Super-chunks before `taper_from` (and
+// every one when m == SC) are SC equal chunks of FC fibers, the remaining slots empty.  From `taper_from` on the LAST of the SC
+// chunks is cut into m - SC + 1 pieces starting at tail[0] = 0 < tail[1] < ... (fibers past the first SC - 1 chunks): the
+// host-buffer entries copy a chunk out while the next one computes, and only the copy of a lane's last piece is exposed.
+// Chunk `ord` (= super-chunk * m + slot) owns perm[c0 ..] and the ord-th 64 ints of `cnt`.
+struct ChunkLayout { int FS, FC, SC, m, taper_from; int tail[4]; };
+__host__ __device__ inline void ft_chunk_range(const ChunkLayout &L, int F, int ord, int *c0, int *Fc)
+{
+    const int si = ord / L.m, ci = ord - si * L.m;
+    int lo, hi;
+    if (L.m == L.SC || si < L.taper_from) { lo = ci < L.SC ? ci * L.FC : L.FS; hi = ci < L.SC ? lo + L.FC : L.FS; }
+    else if (ci < L.SC - 1) { lo = ci * L.FC; hi = lo + L.FC; }
+    else {
+        const int t = ci - (L.SC - 1), base = (L.SC - 1) * L.FC;
+        lo = base + L.tail[t];
+        hi = (t + 1 < L.m - L.SC + 1) ? base + L.tail[t + 1] : L.FS;
+    }
+    const long long b = (long long)si * L.FS;
+    long long a0 = b + lo, a1 = b + hi;
+    if (a1 > F) a1 = F;
+    if (a0 > F) a0 = F;
+    *c0 = (int)a0; *Fc = (int)(a1 - a0);
+}
+
 // node-tile size for a varying core with block r_k x r_{k+1}
 __host__ __device__ inline int ft_tile_nodes(int rk, int rk1)
 {
@@ -129,8 +153,8 @@ struct FtPlan {
 #ifndef C3SC_FT_TYPES_ONLY
 // ---------------------------------------------------------------------------
 // Group the fibers of every chunk of a batch by varying dimension: perm = fiber ids (relative to the
-// chunk), k-major.  One CTA per chunk (blockIdx.x); chunk c covers fibers [c*FC, min(F, (c+1)*FC)) and
-// owns perm[c*FC ..], and 64 ints of `cnt`: [0,16) kcount, [16,32) kstart, [32] active-node counter (cleared).
+// chunk), k-major.  One CTA per chunk (blockIdx.x); chunk c covers the fibers ft_chunk_range gives it and
+// owns perm[c0 ..], and 64 ints of `cnt`: [0,16) kcount, [16,32) kstart, [32] active-node counter (cleared).
 //
 // The same pass validates the descriptors (the batch analogue of convert_fiber_to_ind's error returns,
 // src/nodeutil.c:437-470): a dim_vary outside [0, d) or a fixed index outside its grid sets err[1] and records
@@ -139,12 +163,13 @@ struct FtPlan {
 struct GridDims { int n[MAXD]; };
 __device__ __forceinline__ int ft_clamp_index(int i0, int n) { return i0 < 0 ? 0 : (i0 >= n ? n - 1 : i0); }
 #ifndef C3SC_FT_KS_UNIT        // compiled once, in ft.cu (ft_ks.cu holds the per-rank-geometry templates)
-__global__ void __launch_bounds__(1024) k_group_fibers(int F, int FC, int d, const int *dim_vary, const int *fixed_ind,
+__global__ void __launch_bounds__(1024) k_group_fibers(int F, ChunkLayout lay, int d, const int *dim_vary, const int *fixed_ind,
                                                        GridDims ng, int *err, int *perm, int *cnt_all)
 {
     __shared__ int cnt[MAXD], pos[MAXD];
     const int tid = threadIdx.x;
-    const int c0 = blockIdx.x * FC, Fc = (F - c0 < FC) ? F - c0 : FC;
+    int c0, Fc;
+    ft_chunk_range(lay, F, (int)blockIdx.x, &c0, &Fc);
     if (err && fixed_ind) {                                 // validation: the gridDim.y CTAs of a chunk share the scan
         int bad = 0x7fffffff;
         for (int e = blockIdx.y * blockDim.x + tid; e < Fc * d; e += gridDim.y * blockDim.x) {

@@ -91,6 +91,33 @@ def test_large_batch_is_chunked_consistently(gpu):
     prob.close(); vf.close()
 
 
+def test_tapered_host_chunks_equal_the_equal_chunks(gpu, monkeypatch):
+    """c3sc_vi_batch with host buffers cuts the last chunk of each lane into pieces (1/2, 1/4, 1/4: api.cu, ChunkLayout) so that
+    only a small copy-out is exposed.  At the timed workload's geometry and a batch that takes the tapered layout: every fiber
+    is covered exactly once (no result left at its cleared value) and the numbers are those of the equal-chunk layout
+    (C3SC_TAPER=0) bit for bit; a sample of fibers from every piece against the oracle."""
+    cfg = configs.get_config("lqgnd_reflect")
+    prob = capi.Problem(cfg, arith=1)
+    port = make_port(cfg)
+    ranks = cfg.ranks()
+    cores = synthetic.random_cores(cfg.ngrid, ranks)
+    ft = po.FT(cfg.ngrid, ranks, cores)
+    vf = capi.ValueF(cfg.ngrid, ranks, cores)
+    F = 32768 + 40                              # two lanes, chunks of ~5.5 k fibers -> tapered; a ragged last piece
+    dv, fi = synthetic.random_fibers(cfg.ngrid, F, seed=21)
+    v1, a1 = prob.vi_batch(vf, dv, fi)
+    monkeypatch.setenv("C3SC_TAPER", "0")
+    v0, a0 = prob.vi_batch(vf, dv, fi)
+    monkeypatch.delenv("C3SC_TAPER")
+    assert np.array_equal(v1, v0) and np.array_equal(a1, a0)
+    m = valid_mask(cfg, dv)
+    sub = np.unique(np.concatenate([np.arange(0, F, 997), np.arange(F - 48, F), np.arange(16380, 16420)]))
+    oval, oarg = port.vi_batch(ft, dv[sub], fi[sub])
+    assert rel_err(v1[sub], oval, scale=np.abs(oval).max()) <= RTOL
+    assert argmin_mismatches_are_ties(cfg, port, ft, dv[sub], fi[sub], a1[sub], oarg) <= 1e-3 * oarg.size
+    prob.close(); vf.close()
+
+
 def test_device_buffer_commit(gpu):
     """cores written straight into the library's device buffer (what the NCCL broadcast does)
     take effect after c3sc_valuef_commit"""
