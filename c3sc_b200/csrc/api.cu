@@ -818,6 +818,33 @@ static void read_tuning()
     g_chain_min = (cm && atoi(cm) >= 0) ? (size_t)atoi(cm) : 4096;
 }
 
+// Timing aid (C3SC_DBG_TIMELINE=1): events after the plan, every chunk's kernels and every chunk's copy-out; the host-buffer entry
+// prints them (ms since the batch's first event) after the batch.  Not for production: the events are created per batch.
+struct TimelineMark { cudaEvent_t ev; char what[40]; };
+static thread_local std::vector<TimelineMark> g_timeline;
+static bool timeline_on() { static const bool on = getenv("C3SC_DBG_TIMELINE") != nullptr; return on; }
+static void timeline_mark(cudaStream_t st, const char *fmt, int a = 0, int b = 0)
+{
+    if (!timeline_on()) return;
+    TimelineMark m;
+    cudaEventCreate(&m.ev);
+    cudaEventRecord(m.ev, st);
+    snprintf(m.what, sizeof m.what, fmt, a, b);
+    g_timeline.push_back(m);
+}
+static void timeline_print()
+{
+    if (!timeline_on() || g_timeline.empty()) return;
+    for (auto &m : g_timeline) {
+        float ms = 0;
+        cudaEventSynchronize(m.ev);
+        cudaEventElapsedTime(&ms, g_timeline[0].ev, m.ev);
+        fprintf(stderr, "  [timeline] %8.3f ms  %s\n", ms, m.what);
+    }
+    for (auto &m : g_timeline) cudaEventDestroy(m.ev);
+    g_timeline.clear();
+}
+
 // One batch through the pipeline.  Units:
 //   chunk        FC fibers: grouping by varying dimension, node kernel, control kernel, cost scratch
 //   super-chunk  SC consecutive chunks: the bucketed chain stage (chain_kernel.cuh) works on all of them at once,
@@ -828,6 +855,7 @@ static int run_batch(const DevProblem &P, int model, int arith, Scratch &scr, co
 {
     const size_t d = (size_t)P.dx, CS = 2 * d + 1, RW = 2 * d + 3;
     read_tuning();
+    timeline_mark(st, "batch starts on the device");
     const bool need_cst = b.mode != MODE_COSTS;
     const int mma = ft_uses_mma(ft);
     const bool bucketed = mma && chain_bucketed_ok(ft, P.nmax) && b.F >= g_chain_min && !getenv("C3SC_NO_BUCKETS");
@@ -837,12 +865,16 @@ static int run_batch(const DevProblem &P, int model, int arith, Scratch &scr, co
     // chain steps of the lane's next super-chunk on a high-priority stream of their own: measured no gain (1.952 vs 1.939 ms per
     // 65 536-fiber step, profiles/r02_cross_step.md: the steps are L2-bandwidth work, not idle latency), so opt-in: C3SC_CHAIN_PRIO=1
     const bool chain_prio = bucketed && multi && getenv("C3SC_CHAIN_PRIO") && atoi(getenv("C3SC_CHAIN_PRIO")) == 1;
-    // host-buffer entries copy a chunk's results out while the next chunk computes; the copy of each lane's last chunk is exposed.
-    // TAPERED chunks (default): the large chunks of the device-resident entries, and the last chunk of each lane's last super-chunk
-    // cut into pieces of 1/2, 1/4, 1/4 -- the throughput of the large chunks, the exposed tail of a small one.  C3SC_TAPER=0: equal
-    // chunks of the smaller size (e2e 2.58 against 2.78 G node-backups/s with equal chunks of the larger one).
+    // host-buffer entries copy a chunk's results out while the next chunks compute, each lane on a copy stream of its own.  The link
+    // needs ~1.0 ms for a step's values (52 MB at 52 GB/s under load, tools/d2h_under_load.py) and a step's first results appear
+    // after ~1.0 ms (plan, both lanes' chain stages, the first chunk): from there on the link is the bound (C3SC_DBG_TIMELINE=1,
+    // tools/e2e_timeline.py), so these entries keep EQUAL chunks of the smaller size (first results early): 1.97 ms per 65 536-fiber
+    // step.  Measured and not better (profiles/r02c_e2e.md): the large chunks of the device-resident entries with the last chunk of
+    // each lane cut into shrinking pieces (C3SC_TAPER=1: 1.99 ms), the first chunk cut into growing pieces as well
+    // (C3SC_HEAD_CUTS: 2.01-2.06 ms, the small pieces cost the kernels more than the link gains), lanes staggered by one chain stage
+    // (2.05 ms).
     const bool host_out = b.copy_stream && (b.h_value || b.h_argmin);
-    const bool taper_on = !(getenv("C3SC_TAPER") && atoi(getenv("C3SC_TAPER")) == 0);
+    const bool taper_on = getenv("C3SC_TAPER") && atoi(getenv("C3SC_TAPER")) == 1;
     const bool taper_want = host_out && multi && taper_on;
     size_t per_chunk = ((bucketed && (!host_out || taper_want)) ? g_chunk_bytes_b : g_chunk_bytes) / (size_t)g_lanes / (b.ldo * CS * 8);
     if (!multi) per_chunk *= (size_t)g_lanes;
@@ -860,11 +892,32 @@ static int run_batch(const DevProblem &P, int model, int arith, Scratch &scr, co
     const size_t NSmax = FC * b.ldo;
     ChunkLayout lay;
     memset(&lay, 0, sizeof lay);
-    lay.FS = (int)FS; lay.FC = (int)FC; lay.SC = (int)SC; lay.m = (int)SC; lay.taper_from = 0;
-    if (taper_want && FC >= 4096) {                         // pieces stay above ~1000 fibers (125 node CTAs)
-        lay.m = (int)SC + 2;
+    lay.FS = (int)FS; lay.FC = (int)FC; lay.SC = (int)SC; lay.m = (int)SC;
+    if (taper_want && FC >= 4096) {                         // pieces stay above ~350 fibers
+        // The last chunk's pieces shrink by ~0.55, the ratio of the pipeline's fibers per second to the link's: each piece's copy
+        // ends about when the next piece's kernels do.  The first chunk's pieces grow the same way: the link moves a step's values
+        // in ~1 ms of a ~1.8 ms step and must start long before the first large chunk is through (tools/d2h_under_load.py).
+        // C3SC_TAPER_CUTS="a,b,c" / C3SC_HEAD_CUTS="a,b,c": the cuts in thousandths of a chunk (tuning aids; HEAD "0" = no head).
+        auto cuts = [](const char *env, int *cut, int ncut) {
+            const char *tc = getenv(env);
+            if (!tc) return ncut;
+            int a = 0, b_ = 0, c_ = 0;
+            const int got = sscanf(tc, "%d,%d,%d", &a, &b_, &c_);
+            if (got >= 1 && a == 0) return 0;
+            if (got >= 1 && a > 0 && a < 1000 && (got < 2 || (b_ > a && b_ < 1000)) && (got < 3 || (c_ > b_ && c_ < 1000))) {
+                cut[0] = a; cut[1] = b_; cut[2] = c_;
+                return got;
+            }
+            return ncut;
+        };
+        int tcut[3] = {494, 766, 915}, hcut[3] = {85, 234, 506};
+        lay.nt = cuts("C3SC_TAPER_CUTS", tcut, 3);
+        lay.nh = (SC >= 2 && getenv("C3SC_HEAD_CUTS")) ? cuts("C3SC_HEAD_CUTS", hcut, 3) : 0;    // (one chunk per super-chunk: it cannot be both)
+        lay.m = (int)SC + lay.nh + lay.nt;
         lay.taper_from = nsup > L ? (int)(nsup - L) : 0;
-        lay.tail[0] = 0; lay.tail[1] = (int)((FC / 2 + 7) & ~(size_t)7); lay.tail[2] = lay.tail[1] + (int)((FC / 4 + 7) & ~(size_t)7);
+        lay.head_to = (int)L;
+        for (int i = 0; i < lay.nt; i++) lay.tail[i + 1] = (int)((FC * (size_t)tcut[i] / 1000 + 7) & ~(size_t)7);
+        for (int i = 0; i < lay.nh; i++) lay.head[i + 1] = (int)((FC * (size_t)hcut[i] / 1000 + 7) & ~(size_t)7);
     }
     const size_t nord = nsup * (size_t)lay.m;               // chunk slots of the batch (some empty)
     int setw = 0, rs = 0;
@@ -949,6 +1002,7 @@ static int run_batch(const DevProblem &P, int model, int arith, Scratch &scr, co
         }
         if (aside) CK(cudaStreamWaitEvent(st, scr.grouped, 0));
     }
+    timeline_mark(st, "plan + grouping done");
     if (b.cores_ready) CK(cudaStreamWaitEvent(st, b.cores_ready, 0));       // (grouping and plan above read the descriptors only)
     if (L > 1) {                                            // the other lanes start after everything queued on st so far
         CK(cudaEventRecord(scr.fork, st));
@@ -973,6 +1027,7 @@ static int run_batch(const DevProblem &P, int model, int arith, Scratch &scr, co
             int rc = launch_chain_steps(ca, cst_, &nl);
             if (rc) return fail(C3SC_ECUDA, "chain step kernel: %s", cudaGetErrorString((cudaError_t)rc));
             g_launches += nl;
+            timeline_mark(cst_, "lane %d: chain stage of %d fibers", (int)(si % L), (int)Fs);
             if (chain_prio) {
                 CK(cudaEventRecord(ln.chain_done, cst_));
                 CK(cudaStreamWaitEvent(st, ln.chain_done, 0));
@@ -1087,6 +1142,7 @@ static int run_batch(const DevProblem &P, int model, int arith, Scratch &scr, co
             if (rc != 0) return fail(C3SC_ECUDA, "policy evaluation kernel launch: %s", cudaGetErrorString((cudaError_t)rc));
             g_launches++;
         }
+        timeline_mark(st, "lane %d: kernels of a chunk of %d fibers", (int)(si % L), (int)Fc);
         if ((b.copy_stream || b.peer_copy) && b.chunk_done) {
             CK(cudaEventRecord(b.chunk_done, st));
             if (b.peer_copy && c.value && b.peer_stream) {  // the chunk's values into every peer's gathered buffer, off the SMs
@@ -1105,8 +1161,11 @@ static int run_batch(const DevProblem &P, int model, int arith, Scratch &scr, co
         if (b.copy_stream && b.chunk_done && (b.h_value || b.h_argmin)) {
             const cudaStream_t cps = ln.copy_stream ? ln.copy_stream : b.copy_stream;      // the lane's own copy stream
             CK(cudaStreamWaitEvent(cps, b.chunk_done, 0));
+            static const bool dbg_nocopy = getenv("C3SC_DBG_NO_COPYOUT") != nullptr;       // timing aid only: results stay on the device
+            if (dbg_nocopy) continue;
             if (b.h_value && c.value) CK(cudaMemcpyAsync(b.h_value + n0, c.value, Fc * b.ldo * 8, cudaMemcpyDeviceToHost, cps));
             if (b.h_argmin && c.argmin) CK(cudaMemcpyAsync(b.h_argmin + n0, c.argmin, Fc * b.ldo * 4, cudaMemcpyDeviceToHost, cps));
+            timeline_mark(cps, "lane %d: copy-out of %d fibers", (int)(si % L), (int)Fc);
         }
         }
     }
@@ -1383,6 +1442,7 @@ static int vi_batch_host(c3sc_problem *p, const c3sc_valuef *vf, size_t F, const
     rc = finish_begin(p);
     if (rc) return rc;
     CK(cudaStreamSynchronize(p->copy_stream));
+    timeline_print();
     return finish_end(p);
 }
 

@@ -75,22 +75,27 @@ struct FtArgs {
 
 __host__ __device__ inline int ft_even_up(int v) { return (v + 1) & ~1; }
 
-// Chunks of a batch.  A super-chunk is FS = FC * SC fibers; it has m >= SC chunk slots.  Super-chunks before `taper_from` (and
-// every one when m == SC) are SC equal chunks of FC fibers, the remaining slots empty.  From `taper_from` on the LAST of the SC
-// chunks is cut into m - SC + 1 pieces starting at tail[0] = 0 < tail[1] < ... (fibers past the first SC - 1 chunks): the
-// host-buffer entries copy a chunk out while the next one computes, and only the copy of a lane's last piece is exposed.
+// Chunks of a batch.  A super-chunk is FS = FC * SC fibers = SC equal chunks of FC fibers, in m >= SC chunk slots (unused slots are
+// empty).  The host-buffer entries copy a chunk out while the next ones compute: the link is busy from the first finished chunk on
+// and only the copy of a lane's last chunk is exposed, so
+//   * super-chunks before `head_to` (each lane's first) have their FIRST chunk cut into nh + 1 pieces starting at
+//     head[0] = 0 < head[1] < ... (small pieces first: results start to flow early),
+//   * super-chunks from `taper_from` on (each lane's last) have their LAST chunk cut into nt + 1 pieces starting at
+//     tail[0] = 0 < tail[1] < ... fibers past the first SC - 1 chunks (small pieces last).
 // Chunk `ord` (= super-chunk * m + slot) owns perm[c0 ..] and the ord-th 64 ints of `cnt`.
-struct ChunkLayout { int FS, FC, SC, m, taper_from; int tail[4]; };
+struct ChunkLayout { int FS, FC, SC, m, head_to, taper_from, nh, nt; int head[4], tail[4]; };
 __host__ __device__ inline void ft_chunk_range(const ChunkLayout &L, int F, int ord, int *c0, int *Fc)
 {
     const int si = ord / L.m, ci = ord - si * L.m;
-    int lo, hi;
-    if (L.m == L.SC || si < L.taper_from) { lo = ci < L.SC ? ci * L.FC : L.FS; hi = ci < L.SC ? lo + L.FC : L.FS; }
-    else if (ci < L.SC - 1) { lo = ci * L.FC; hi = lo + L.FC; }
+    const int H = (L.nh > 0 && si < L.head_to) ? L.nh : 0, T = (L.nt > 0 && si >= L.taper_from) ? L.nt : 0;
+    int lo = L.FS, hi = L.FS;
+    if (H > 0 && ci <= H) { lo = L.head[ci]; hi = ci < H ? L.head[ci + 1] : L.FC; }
     else {
-        const int t = ci - (L.SC - 1), base = (L.SC - 1) * L.FC;
-        lo = base + L.tail[t];
-        hi = (t + 1 < L.m - L.SC + 1) ? base + L.tail[t + 1] : L.FS;
+        const int cj = ci - H;                               // position among the SC equal chunks
+        if (T > 0 && cj >= L.SC - 1) {
+            const int t = cj - (L.SC - 1), base = (L.SC - 1) * L.FC;
+            if (t <= T) { lo = base + L.tail[t]; hi = t < T ? base + L.tail[t + 1] : L.FS; }
+        } else if (cj < L.SC) { lo = cj * L.FC; hi = lo + L.FC; }
     }
     const long long b = (long long)si * L.FS;
     long long a0 = b + lo, a1 = b + hi;

@@ -92,10 +92,10 @@ def test_large_batch_is_chunked_consistently(gpu):
 
 
 def test_tapered_host_chunks_equal_the_equal_chunks(gpu, monkeypatch):
-    """c3sc_vi_batch with host buffers cuts the last chunk of each lane into pieces (1/2, 1/4, 1/4: api.cu, ChunkLayout) so that
-    only a small copy-out is exposed.  At the timed workload's geometry and a batch that takes the tapered layout: every fiber
-    is covered exactly once (no result left at its cleared value) and the numbers are those of the equal-chunk layout
-    (C3SC_TAPER=0) bit for bit; a sample of fibers from every piece against the oracle."""
+    """The opt-in chunk layouts of the host-buffer entries (api.cu, ChunkLayout: the last chunk of each lane cut into shrinking
+    pieces, C3SC_TAPER=1; the first one into growing pieces as well, C3SC_HEAD_CUTS) at the timed workload's geometry: the
+    numbers are those of the default equal chunks bit for bit (so every fiber is covered exactly once), per-lane copy
+    streams included; a sample of fibers from every piece against the oracle."""
     cfg = configs.get_config("lqgnd_reflect")
     prob = capi.Problem(cfg, arith=1)
     port = make_port(cfg)
@@ -105,10 +105,14 @@ def test_tapered_host_chunks_equal_the_equal_chunks(gpu, monkeypatch):
     vf = capi.ValueF(cfg.ngrid, ranks, cores)
     F = 32768 + 40                              # two lanes, chunks of ~5.5 k fibers -> tapered; a ragged last piece
     dv, fi = synthetic.random_fibers(cfg.ngrid, F, seed=21)
+    monkeypatch.setenv("C3SC_TAPER", "1")
+    monkeypatch.setenv("C3SC_HEAD_CUTS", "85,234,506")
     v1, a1 = prob.vi_batch(vf, dv, fi)
-    monkeypatch.setenv("C3SC_TAPER", "0")
-    v0, a0 = prob.vi_batch(vf, dv, fi)
+    monkeypatch.delenv("C3SC_HEAD_CUTS")
+    v2, a2 = prob.vi_batch(vf, dv, fi)
     monkeypatch.delenv("C3SC_TAPER")
+    v0, a0 = prob.vi_batch(vf, dv, fi)                                     # the default: equal chunks
+    assert np.array_equal(v2, v0) and np.array_equal(a2, a0)
     assert np.array_equal(v1, v0) and np.array_equal(a1, a0)
     m = valid_mask(cfg, dv)
     sub = np.unique(np.concatenate([np.arange(0, F, 997), np.arange(F - 48, F), np.arange(16380, 16420)]))
