@@ -213,7 +213,7 @@ def run_reference(args, cfg, rank_ft):
 
 
 def _ncu_record():
-    for name in ("r02c_traffic.json", "r02b_traffic.json", "r02_traffic.json", "r01_traffic.json"):
+    for name in ("r02e_traffic.json", "r02c_traffic.json", "r02b_traffic.json", "r02_traffic.json", "r01_traffic.json"):
         try:
             return json.load(open(os.path.join(ROOT, "profiles", name)))
         except Exception:

@@ -205,6 +205,14 @@ __device__ __forceinline__ void node_state(const CtlArgs &c, int id, double *x)
     }
 }
 
+#ifndef C3SC_CST_STREAM
+#define C3SC_CST_STREAM 1
+#endif
+#if C3SC_CST_STREAM
+#define C3SC_CST_LD(p) __ldcs(p)
+#else
+#define C3SC_CST_LD(p) (*(p))
+#endif
 // Neighbour values of node `id` from the slot-major scratch.  Stage 1 stores the fixed-dimension
 // neighbours and the node's own value (slot 2dx); the two neighbours ALONG the fiber are the own
 // values of other nodes of the same fiber (valuefunc.c:514-519) and are fetched here.
@@ -220,8 +228,9 @@ __device__ __forceinline__ void load_costs(const CtlArgs &c, int id, double *cc)
     const double vlo = self[lo], vhi = self[hi];
 #pragma unroll
     for (int i = 0; i < DX; i++) {
-        cc[2 * i] = i == k ? vlo : c.cst[(size_t)(2 * i) * c.NS + id];
-        cc[2 * i + 1] = i == k ? vhi : c.cst[(size_t)(2 * i + 1) * c.NS + id];
+        // read once, dead afterwards: evict-first loads (ld.global.cs) keep the chain records and rows in L2 instead
+        cc[2 * i] = i == k ? vlo : C3SC_CST_LD(c.cst + (size_t)(2 * i) * c.NS + id);
+        cc[2 * i + 1] = i == k ? vhi : C3SC_CST_LD(c.cst + (size_t)(2 * i + 1) * c.NS + id);
     }
     cc[2 * DX] = self[j];
 }

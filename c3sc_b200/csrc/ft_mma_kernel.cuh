@@ -406,6 +406,19 @@ struct FtNodeCtx {
 //   phase 2 (warp = fiber of the group) left  C[v][jl] = sum_a A[v][a] W[a][jl],  right C[jl][v] = sum_b U[jl][b] Cv[b][v]
 // The A / Cv fragments (the fiber's variant sets) and R / L are loaded from the chain records ONCE and stay in
 // registers; per tile phase 2 reads only the w / u fragments from shared memory.
+// The slot-major cost scratch is written once here and read once by stage 2 (which reads it with evict-first loads,
+// control_kernel.cuh).  Streaming STORES here as well (-DC3SC_CST_STREAM_ST=1, st.global.cs) were measured and are off: the node
+// kernel gets 1 % slower (875 against 869 us per step, 975 against 953 MB of DRAM writes) for no gain elsewhere.
+#ifndef C3SC_CST_STREAM_ST
+#define C3SC_CST_STREAM_ST 0
+#endif
+#if C3SC_CST_STREAM_ST
+#define C3SC_CST_ST(p, v) __stcs((p), (v))
+#define C3SC_CST_ST2(p, v) __stcs((p), (v))
+#else
+#define C3SC_CST_ST(p, v) (*(p) = (v))
+#define C3SC_CST_ST2(p, v) (*(p) = (v))
+#endif
 template <int KS, int ML, int NR>
 __device__ __forceinline__ void ftn_tile_loop(const FtNodeCtx &c)
 {
@@ -542,12 +555,12 @@ __device__ __forceinline__ void ftn_tile_loop(const FtNodeCtx &c)
                 double *cb = c.cst + idb;
 #pragma unroll
                 for (int mt = 0; mt < ML; mt++)
-                    if (outL[mt] >= 0) *reinterpret_cast<double2 *>(cb + outL[mt]) = make_double2(dl[mt][0], dl[mt][1]);
+                    if (outL[mt] >= 0) C3SC_CST_ST2(reinterpret_cast<double2 *>(cb + outL[mt]), make_double2(dl[mt][0], dl[mt][1]));
 #pragma unroll
                 for (int nb = 0; nb < NR; nb++) {
 #pragma unroll
                     for (int h = 0; h < 2; h++)
-                        if (outR[nb][h] >= 0) cb[outR[nb][h]] = dr[nb][h];
+                        if (outR[nb][h] >= 0) C3SC_CST_ST(cb + outR[nb][h], dr[nb][h]);
                 }
             } else {
 #pragma unroll
